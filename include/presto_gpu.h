@@ -1,0 +1,358 @@
+/*
+ * presto_gpu.h — C ABI of libprestogpu.so: the B200 (sm_100a) operator pipeline that sits behind
+ * prestodb/presto's Operator / OperatorFactory and Page / Block interfaces.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes, and returns an int32 status
+ * (PG_OK == 0).  No torch / C++ types cross this boundary.  A JNI shim binds these
+ * 1:1; the standalone drivers in this repo (pytest, bench.py) bind them with ctypes.
+ *
+ * Reference interfaces each group of functions replaces (paths relative to the presto checkout):
+ *   MB = presto-main-base/src/main/java/com/facebook/presto/
+ *   PC = presto-common/src/main/java/com/facebook/presto/common/
+ *
+ *   pg_block / pg_page ............ PC/block/Block.java:47-403, PC/Page.java:45-498,
+ *                                   LongArrayBlock.java:37-52, IntArrayBlock.java:43-47,
+ *                                   ByteArrayBlock.java:50-54, VariableWidthBlock.java:53-58,
+ *                                   DictionaryBlock.java:59-64, RunLengthEncodedBlock.java:48-49
+ *   pg_operator_* ................. MB/operator/Operator.java:20-102 (needsInput/addInput/getOutput/
+ *                                   finish/isFinished/close), MB/operator/OperatorFactory.java:18-50
+ *   pg_hash_aggregation_create .... MB/operator/HashAggregationOperator.java:56-725 (+ GroupByHash.java:46-59,
+ *                                   BigintGroupByHash.java:44-437, MultiChannelGroupByHash.java:56-872,
+ *                                   aggregation/builder/InMemoryHashAggregationBuilder.java:204-352)
+ *   pg_group_by_hash_* ............ MB/operator/GroupByHash.java:61-89 (addPage/getGroupIds/getGroupCount/
+ *                                   appendValuesTo/contains)
+ *   pg_join_bridge_*, pg_hash_builder_create, pg_lookup_join_create
+ *                                   MB/operator/HashBuilderOperator.java:55-692, PagesIndex.java:202-226,
+ *                                   PagesHash.java:55-181, ArrayPositionLinks.java:38-100, JoinHash.java:81-124,
+ *                                   JoinProbe.java:74-119, LookupJoinOperator.java:212-343,481-616,
+ *                                   JoinBridgeManager / LookupSourceFactory hand-off (LookupJoinOperator.java:127)
+ *   pg_partitioned_output_create .. MB/operator/repartition/OptimizedPartitionedOutputOperator.java:167-179,384-824,
+ *                                   PartitionedOutputOperator.java:394-500, MB/operator/HashGenerator.java:22-29,
+ *                                   MB/operator/InterpretedHashGenerator.java:70-79, PrecomputedHashGenerator.java:31-35
+ *   pg_filter_project_create ...... MB/operator/FilterAndProjectOperator.java:88-99,
+ *                                   MB/operator/project/PageProcessor.java:112-148,180-343, PageFilter.java:27-50,
+ *                                   SelectedPositions.java:23-86
+ *   pg_hash_* (scalar helpers) .... PC/type/AbstractLongType.java:137-141, MB/operator/scalar/CombineHashFunction.java:26-31,
+ *                                   MB/operator/PagesHash.java:236-252
+ */
+#ifndef PRESTO_GPU_H
+#define PRESTO_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * Status codes.  Mirror the PrestoException(StandardErrorCode) / IllegalStateException split of the
+ * reference (SURVEY §8b "Errors"); the JNI shim maps them back.
+ * ---------------------------------------------------------------------------------------------- */
+enum {
+    PG_OK = 0,
+    PG_ERR_INVALID_ARGUMENT = 1,      /* checkArgument(...) failures */
+    PG_ERR_INVALID_STATE = 2,         /* checkState(...): addInput when !needsInput, etc. */
+    PG_ERR_UNSUPPORTED = 3,           /* type / encoding / shape not on the GPU path (no CPU fallback) */
+    PG_ERR_OUT_OF_MEMORY = 4,         /* cudaMalloc failure → EXCEEDED_LOCAL_MEMORY_LIMIT */
+    PG_ERR_INSUFFICIENT_RESOURCES = 5,/* "Size of hash table cannot exceed 1 billion entries" BigintGroupByHash.java:273-276 */
+    PG_ERR_NUMERIC_OVERFLOW = 6,      /* NUMERIC_VALUE_OUT_OF_RANGE: bigint addition overflow (BigintOperators.java:68-78) */
+    PG_ERR_CUDA = 7,                  /* CUDA runtime error; message in pg_last_error */
+    PG_ERR_NO_DEVICE = 8              /* no CUDA device: the product path fails loudly, there is no CPU fallback */
+};
+
+/* ------------------------------------------------------------------------------------------------
+ * Types and block encodings (the subset of PC/type + PC/block on the hot path).
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum {
+    PG_TYPE_BIGINT = 1,   /* LongArrayBlock, 8 B */
+    PG_TYPE_INTEGER = 2,  /* IntArrayBlock, 4 B */
+    PG_TYPE_DOUBLE = 3,   /* LongArrayBlock holding doubleToLongBits, 8 B */
+    PG_TYPE_DATE = 4,     /* IntArrayBlock (days since epoch), 4 B */
+    PG_TYPE_BOOLEAN = 5,  /* ByteArrayBlock, 1 B */
+    PG_TYPE_VARCHAR = 6   /* VariableWidthBlock: bytes + int32 offsets[n+1] */
+} pg_type;
+
+typedef enum {
+    PG_ENC_FLAT = 0,
+    PG_ENC_DICTIONARY = 1, /* DictionaryBlock: ids[n] into a flat dictionary */
+    PG_ENC_RLE = 2         /* RunLengthEncodedBlock: one value repeated n times */
+} pg_encoding;
+
+typedef enum {
+    PG_MEM_HOST = 0,   /* pointers are host addresses (JVM heap via GetPrimitiveArrayCritical, or pinned buffers) */
+    PG_MEM_DEVICE = 1  /* pointers are device addresses on the operator's GPU: chained GPU operators never round-trip */
+} pg_memory;
+
+/* One column.  Equivalent of a presto Block after arrayOffset has been applied to the pointers. */
+typedef struct pg_block {
+    int32_t type;             /* pg_type */
+    int32_t encoding;         /* pg_encoding */
+    int64_t position_count;   /* rows in this block */
+    const void* values;       /* FLAT: position_count values (VARCHAR: the byte slice).
+                                 DICTIONARY/RLE: the dictionary's / the single value's storage */
+    const uint8_t* is_null;   /* boolean[] valueIsNull, one byte per position (of the dictionary for DICTIONARY/RLE); NULL = no nulls */
+    const int32_t* offsets;   /* VARCHAR only: position_count+1 (or dictionary_size+1) offsets into values */
+    const int32_t* ids;       /* DICTIONARY only: position_count dictionary indices */
+    int64_t dictionary_size;  /* DICTIONARY: entries in the dictionary; RLE: 1; FLAT: 0 */
+} pg_block;
+
+/* A batch of rows.  Equivalent of presto Page. */
+typedef struct pg_page {
+    int64_t position_count;
+    int32_t channel_count;
+    int32_t memory;           /* pg_memory: where every pointer of every block lives */
+    pg_block* blocks;         /* channel_count blocks (the array itself is always host memory) */
+} pg_page;
+
+/* ------------------------------------------------------------------------------------------------
+ * Library / device
+ * ---------------------------------------------------------------------------------------------- */
+/* Library version string "presto_b200 <semver> sm_100a". */
+const char* pg_version(void);
+/* Number of visible CUDA devices; returns PG_ERR_NO_DEVICE (and *count = 0) when there is none. */
+int32_t pg_device_count(int32_t* count);
+/* Bind the calling thread's subsequent pg_* calls to a device (cudaSetDevice). */
+int32_t pg_set_device(int32_t device);
+/* Thread-local message of the last failing call on this thread. */
+const char* pg_last_error(void);
+/* Pinned host buffers for the JNI side (direct ByteBuffers) and the benchmarks. */
+int32_t pg_host_alloc(size_t bytes, void** out);
+int32_t pg_host_free(void* p);
+/* Device buffers (used by tests / bench to build device-resident pages without torch). */
+int32_t pg_device_alloc(size_t bytes, void** out);
+int32_t pg_device_free(void* p);
+int32_t pg_memcpy_h2d(void* dst_device, const void* src_host, size_t bytes);
+int32_t pg_memcpy_d2h(void* dst_host, const void* src_device, size_t bytes);
+int32_t pg_device_synchronize(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Scalar hash helpers (host side; bit-exact with the reference; used by tests and by callers that
+ * precompute $hashvalue channels the way HashGenerationOptimizer.java:975-987 would).
+ * ---------------------------------------------------------------------------------------------- */
+int64_t pg_hash_bigint(int64_t value);                 /* AbstractLongType.hash  PC/type/AbstractLongType.java:137-141 */
+int64_t pg_hash_combine(int64_t previous, int64_t h);  /* CombineHashFunction.getHash  :26-31 */
+int64_t pg_hash_murmur3_fmix64(int64_t x);             /* fastutil HashCommon.murmurHash3(long) = PagesHash.java:236-252 */
+int32_t pg_hash_partition(int64_t raw_hash, int32_t partition_count); /* HashGenerator.getPartition  :22-29 */
+int64_t pg_hash_xxhash64(const void* data, size_t len);/* airlift XxHash64.hash(Slice), seed 0 */
+
+/* ------------------------------------------------------------------------------------------------
+ * Operator protocol — MB/operator/Operator.java:20-102.
+ * Every pg_operator* is single-threaded by contract (Driver.java:357-359,404), owns one CUDA stream.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pg_operator pg_operator;
+
+typedef struct pg_operator_stats {   /* MB/operator/OperatorStats.java:40 subset */
+    int64_t input_positions;
+    int64_t input_bytes;
+    int64_t output_positions;
+    int64_t output_bytes;
+    int64_t device_bytes;            /* current device memory held → LocalMemoryContext.setBytes */
+    int64_t kernel_launches;         /* CUDA kernels launched by this operator so far */
+    int64_t group_count;             /* aggregation: groups; join build: positions indexed */
+    int64_t h2d_bytes;
+    int64_t d2h_bytes;
+    double  gpu_ms;                  /* device time accumulated by event-bracketed sections (if enabled) */
+} pg_operator_stats;
+
+/* Options common to all operators. */
+typedef struct pg_operator_options {
+    int32_t device;            /* CUDA device ordinal */
+    int32_t output_memory;     /* pg_memory of pages returned by get_output */
+    void*   cuda_stream;       /* cudaStream_t to run on; NULL = operator creates its own non-blocking stream */
+    int64_t max_output_rows;   /* rows per output page; <=0 = default (1<<20) */
+} pg_operator_options;
+
+int32_t pg_operator_needs_input(pg_operator* op, int32_t* out);
+/* Borrow `page` for the duration of the call (host pages are staged to HBM before return;
+ * device pages are consumed on the operator's stream and must stay valid until the next
+ * pg_operator_* call that synchronises: get_output / finish / stats). */
+int32_t pg_operator_add_input(pg_operator* op, const pg_page* page);
+/* Returns a page with position_count == 0 and channel_count == 0 where Java would return null.
+ * Buffers are owned by the operator and valid until the next get_output / destroy. */
+int32_t pg_operator_get_output(pg_operator* op, pg_page* out);
+int32_t pg_operator_finish(pg_operator* op);
+int32_t pg_operator_is_finished(pg_operator* op, int32_t* out);
+int32_t pg_operator_get_stats(pg_operator* op, pg_operator_stats* out);
+int32_t pg_operator_destroy(pg_operator* op);   /* Operator.close() */
+
+/* ------------------------------------------------------------------------------------------------
+ * HashAggregationOperator
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum {
+    PG_AGG_COUNT_STAR = 0,   /* CountAggregation.java:34-50 */
+    PG_AGG_COUNT_COLUMN = 1, /* CountColumn: count of non-null inputs */
+    PG_AGG_SUM_DOUBLE = 2,   /* DoubleSumAggregation.java:33-61 (NULL when no non-null input) */
+    PG_AGG_SUM_BIGINT = 3,   /* LongSumAggregation.java:33-56 (Math.addExact overflow → PG_ERR_NUMERIC_OVERFLOW) */
+    PG_AGG_AVG_DOUBLE = 4,   /* AverageAggregations.java:41-66 */
+    PG_AGG_AVG_BIGINT = 5,   /* AverageAggregations.java:34-39 */
+    PG_AGG_MIN_DOUBLE = 6, PG_AGG_MAX_DOUBLE = 7,
+    PG_AGG_MIN_BIGINT = 8, PG_AGG_MAX_BIGINT = 9
+} pg_aggregate_function;
+
+typedef enum {              /* AggregationNode.Step */
+    PG_STEP_SINGLE = 0,
+    PG_STEP_PARTIAL = 1,    /* output = intermediate states (sum, count columns) */
+    PG_STEP_FINAL = 2       /* input = intermediate states */
+} pg_aggregation_step;
+
+typedef struct pg_aggregate {
+    int32_t function;       /* pg_aggregate_function */
+    int32_t input_channel;  /* -1 for count(*) */
+    int32_t mask_channel;   /* BOOLEAN channel or -1 (AccumulatorCompiler mask handling) */
+    int32_t reserved;
+} pg_aggregate;
+
+typedef struct pg_hash_aggregation_config {
+    int32_t n_group_channels;
+    const int32_t* group_channels;      /* input channel of each group-by key */
+    const int32_t* group_types;         /* pg_type of each key */
+    const int32_t* group_max_lengths;   /* VARCHAR(n): n (only short keys are on the GPU path); else 0 */
+    int32_t hash_channel;               /* precomputed $hashvalue BIGINT channel or -1 */
+    int32_t n_aggregates;
+    const pg_aggregate* aggregates;
+    int32_t step;                       /* pg_aggregation_step */
+    int32_t expected_groups;            /* expectedSize of GroupByHash.createGroupByHash */
+    pg_operator_options options;
+} pg_hash_aggregation_config;
+
+/* Output page layout = HashAggregationOperator's: group keys [, $hashvalue] , one column per aggregate,
+ * rows in ascending group id = first-appearance order (InMemoryHashAggregationBuilder.java:326-352,400-403). */
+int32_t pg_hash_aggregation_create(const pg_hash_aggregation_config* config, pg_operator** out);
+
+/* ------------------------------------------------------------------------------------------------
+ * GroupByHash (standalone) — MB/operator/GroupByHash.java:61-89
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pg_group_by_hash pg_group_by_hash;
+
+typedef struct pg_group_by_hash_config {
+    int32_t n_channels;
+    const int32_t* channels;
+    const int32_t* types;
+    const int32_t* max_lengths;
+    int32_t hash_channel;      /* inputHashChannel or -1 */
+    int32_t expected_size;
+    pg_operator_options options;
+} pg_group_by_hash_config;
+
+int32_t pg_group_by_hash_create(const pg_group_by_hash_config* config, pg_group_by_hash** out);
+/* addPage: insert the page's keys. */
+int32_t pg_group_by_hash_add_page(pg_group_by_hash* h, const pg_page* page);
+/* getGroupIds: insert + return the dense group id of every row (ids in first-appearance order).
+ * out_group_ids: position_count int64 in page->memory's space (GroupByIdBlock is a BIGINT block). */
+int32_t pg_group_by_hash_get_group_ids(pg_group_by_hash* h, const pg_page* page, int64_t* out_group_ids);
+int32_t pg_group_by_hash_get_group_count(pg_group_by_hash* h, int64_t* out);
+/* contains(position, page): out_flags[position] = 1/0 for every row of the page (host or device per page->memory). */
+int32_t pg_group_by_hash_contains(pg_group_by_hash* h, const pg_page* page, uint8_t* out_flags);
+/* appendValuesTo for groups [0, groupCount): returns a page of the key columns [+ raw hash] in group-id order. */
+int32_t pg_group_by_hash_get_keys(pg_group_by_hash* h, pg_page* out);
+int32_t pg_group_by_hash_destroy(pg_group_by_hash* h);
+
+/* ------------------------------------------------------------------------------------------------
+ * Hash join: HashBuilderOperator → (JoinBridge) → LookupJoinOperator
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pg_join_bridge pg_join_bridge;   /* JoinBridgeManager / LookupSourceFactory */
+
+typedef enum { PG_JOIN_INNER = 0, PG_JOIN_PROBE_OUTER = 1 } pg_join_type; /* LookupJoinOperators.JoinType */
+
+int32_t pg_join_bridge_create(int32_t device, pg_join_bridge** out);
+int32_t pg_join_bridge_destroy(pg_join_bridge* b);
+/* LookupSource statistics once the build finished (PagesHash.getPositionCount / getHashCollisions ... ). */
+int32_t pg_join_bridge_get_position_count(pg_join_bridge* b, int64_t* out);
+
+typedef struct pg_hash_builder_config {
+    int32_t n_channels;                 /* channels of the build pages */
+    const int32_t* types;               /* pg_type per channel */
+    int32_t n_hash_channels;
+    const int32_t* hash_channels;       /* join key channels (BIGINT / INTEGER / DATE) */
+    int32_t n_output_channels;
+    const int32_t* output_channels;     /* build channels appended to join output */
+    int32_t precomputed_hash_channel;   /* $hashvalue channel or -1 */
+    int64_t expected_positions;
+    pg_operator_options options;
+} pg_hash_builder_config;
+
+int32_t pg_hash_builder_create(const pg_hash_builder_config* config, pg_join_bridge* bridge, pg_operator** out);
+
+typedef struct pg_lookup_join_config {
+    int32_t join_type;                  /* pg_join_type */
+    int32_t n_channels;                 /* channels of the probe pages */
+    const int32_t* types;
+    int32_t n_hash_channels;
+    const int32_t* hash_channels;       /* probe join-key channels */
+    int32_t n_output_channels;
+    const int32_t* output_channels;     /* probe channels emitted (probeOutputChannels) */
+    int32_t precomputed_hash_channel;
+    pg_operator_options options;
+} pg_lookup_join_config;
+
+/* Output page = probe output channels followed by build output channels, rows in probe order, matches of one
+ * probe row in PositionLinks order (descending build position; PagesHash.java:108-123, ArrayPositionLinks.java:45-50). */
+int32_t pg_lookup_join_create(const pg_lookup_join_config* config, pg_join_bridge* bridge, pg_operator** out);
+
+/* ------------------------------------------------------------------------------------------------
+ * PartitionedOutputOperator (row repartition)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pg_partitioned_output_config {
+    int32_t n_channels;
+    const int32_t* types;
+    int32_t partition_count;
+    int32_t n_partition_channels;
+    const int32_t* partition_channels;  /* hashed with InterpretedHashGenerator unless hash channel given */
+    int32_t precomputed_hash_channel;   /* PrecomputedHashGenerator channel or -1 */
+    int32_t replicates_any_row;         /* OptimizedPartitionedOutputOperator.java:504-512 */
+    int32_t null_channel;               /* replicate rows whose null_channel is null to every partition; -1 = none */
+    pg_operator_options options;
+} pg_partitioned_output_config;
+
+/* get_output returns, per input page, ONE page holding all partitions back to back (partition p occupies rows
+ * [offsets[p], offsets[p+1]) ), rows inside a partition in input order — what PartitionBuffer.appendData would have
+ * appended.  pg_partitioned_output_get_offsets gives the partition_count+1 row offsets of the page returned last. */
+int32_t pg_partitioned_output_create(const pg_partitioned_output_config* config, pg_operator** out);
+int32_t pg_partitioned_output_get_offsets(pg_operator* op, int64_t* out_offsets /* partition_count+1, host */);
+
+/* ------------------------------------------------------------------------------------------------
+ * FilterAndProjectOperator / PageProcessor
+ * A RowExpression tree is flattened to a register program (one instruction per node).
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum {
+    PG_EX_INPUT = 0,      /* a = channel */
+    PG_EX_CONST_BIGINT = 1, PG_EX_CONST_DOUBLE = 2, PG_EX_CONST_BOOLEAN = 3, PG_EX_CONST_NULL = 4, /* imm */
+    PG_EX_ADD = 10, PG_EX_SUB = 11, PG_EX_MUL = 12, PG_EX_DIV = 13, PG_EX_NEG = 14,
+    PG_EX_EQ = 20, PG_EX_NE = 21, PG_EX_LT = 22, PG_EX_LE = 23, PG_EX_GT = 24, PG_EX_GE = 25,
+    PG_EX_AND = 30, PG_EX_OR = 31, PG_EX_NOT = 32, PG_EX_IS_NULL = 33,
+    PG_EX_CAST_DOUBLE = 40, PG_EX_CAST_BIGINT = 41,
+    PG_EX_BETWEEN = 50,   /* a BETWEEN b AND c */
+    PG_EX_HASH = 60,      /* type hash of a (TypeUtils.hashPosition; NULL → 0) */
+    PG_EX_COMBINE_HASH = 61 /* 31*a + b  (CombineHashFunction) */
+} pg_expr_op;
+
+typedef struct pg_expr_node {
+    int32_t op;        /* pg_expr_op */
+    int32_t type;      /* pg_type of the result */
+    int32_t a, b, c;   /* operand node indices (or channel for INPUT); -1 unused */
+    int32_t reserved;
+    int64_t imm_i;     /* CONST_BIGINT / CONST_BOOLEAN */
+    double  imm_d;     /* CONST_DOUBLE */
+} pg_expr_node;
+
+typedef struct pg_filter_project_config {
+    int32_t n_input_channels;
+    const int32_t* input_types;
+    int32_t n_nodes;
+    const pg_expr_node* nodes;       /* topologically ordered: operands precede users */
+    int32_t filter_node;             /* node index of the BOOLEAN filter, or -1 = select all */
+    int32_t n_projections;
+    const int32_t* projection_nodes; /* node index per output channel */
+    pg_operator_options options;
+} pg_filter_project_config;
+
+int32_t pg_filter_project_create(const pg_filter_project_config* config, pg_operator** out);
+/* SelectedPositions of the last page filtered (PageFilter.positionsArrayToSelectedPositions, PageFilter.java:27-50):
+ * is_list = 0 → positionsRange(0, size) (none or all rows selected), 1 → positionsList of `size` positions. */
+int32_t pg_filter_project_get_last_selection(pg_operator* op, int32_t* is_list, int64_t* size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRESTO_GPU_H */

@@ -1,0 +1,75 @@
+/*
+ * ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_common.h).
+ * C API of liboracle.so: the same shapes as include/presto_gpu.h with the prefix or_ so the python test harness can drive
+ * the oracle and the CUDA product through one marshalling layer.
+ */
+#include "oracle_common.h"
+
+namespace oracle {
+struct JoinBridge;
+Operator* createHashAggregation(const pg_hash_aggregation_config* c);
+JoinBridge* createJoinBridge();
+void destroyJoinBridge(JoinBridge* b);
+int64_t joinBridgePositionCount(JoinBridge* b);
+Operator* createHashBuilder(const pg_hash_builder_config* c, JoinBridge* b);
+Operator* createLookupJoin(const pg_lookup_join_config* c, JoinBridge* b);
+Operator* createPartitionedOutput(const pg_partitioned_output_config* c);
+Operator* createFilterProject(const pg_filter_project_config* c);
+void partitionedOutputOffsets(Operator* op, int64_t* out);
+void filterProjectSelection(Operator* op, int32_t* isList, int64_t* size);
+}
+
+using namespace oracle;
+
+static thread_local std::string g_lastError;
+
+extern "C" {
+
+void or_set_error(const char* msg) { g_lastError = msg; }
+const char* or_last_error(void) { return g_lastError.c_str(); }
+const char* or_version(void) { return "presto oracle (CPU restatement of reference Java operators)"; }
+
+#define OR_TRY try {
+#define OR_CATCH } catch (const OracleError& e) { or_set_error(e.what()); return e.code; } catch (const std::exception& e) { or_set_error(e.what()); return PG_ERR_INVALID_STATE; } return PG_OK;
+
+int64_t or_hash_bigint(int64_t v) { return hashLong(v); }
+int64_t or_hash_combine(int64_t p, int64_t h) { return combineHash(p, h); }
+int64_t or_hash_murmur3_fmix64(int64_t x) { return murmurHash3(x); }
+int32_t or_hash_partition(int64_t rawHash, int32_t partitionCount) { return hashPartition(rawHash, partitionCount); }
+int64_t or_hash_xxhash64(const void* data, size_t len) { return xxHash64((const uint8_t*) data, len); }
+int64_t or_hash_double(double d) { return hashLong(doubleToLongBits(d)); }
+int32_t or_array_size(int64_t expected, int32_t* out) { OR_TRY *out = arraySize(expected, 0.75f); OR_CATCH }
+
+int32_t or_hash_aggregation_create(const pg_hash_aggregation_config* c, void** out) { OR_TRY *out = createHashAggregation(c); OR_CATCH }
+int32_t or_join_bridge_create(int32_t, void** out) { OR_TRY *out = createJoinBridge(); OR_CATCH }
+int32_t or_join_bridge_destroy(void* b) { destroyJoinBridge((JoinBridge*) b); return PG_OK; }
+int32_t or_join_bridge_get_position_count(void* b, int64_t* out) { OR_TRY *out = joinBridgePositionCount((JoinBridge*) b); OR_CATCH }
+int32_t or_hash_builder_create(const pg_hash_builder_config* c, void* bridge, void** out) { OR_TRY *out = createHashBuilder(c, (JoinBridge*) bridge); OR_CATCH }
+int32_t or_lookup_join_create(const pg_lookup_join_config* c, void* bridge, void** out) { OR_TRY *out = createLookupJoin(c, (JoinBridge*) bridge); OR_CATCH }
+int32_t or_partitioned_output_create(const pg_partitioned_output_config* c, void** out) { OR_TRY *out = createPartitionedOutput(c); OR_CATCH }
+int32_t or_partitioned_output_get_offsets(void* op, int64_t* out) { OR_TRY partitionedOutputOffsets((Operator*) op, out); OR_CATCH }
+int32_t or_filter_project_create(const pg_filter_project_config* c, void** out) { OR_TRY *out = createFilterProject(c); OR_CATCH }
+int32_t or_filter_project_get_last_selection(void* op, int32_t* isList, int64_t* size) { OR_TRY filterProjectSelection((Operator*) op, isList, size); OR_CATCH }
+
+int32_t or_operator_needs_input(void* op, int32_t* out) { OR_TRY *out = ((Operator*) op)->needsInput() ? 1 : 0; OR_CATCH }
+int32_t or_operator_add_input(void* op, const pg_page* page)
+{
+    OR_TRY
+    if (page->memory != PG_MEM_HOST) throw OracleError(PG_ERR_INVALID_ARGUMENT, "the oracle only takes host pages");
+    ((Operator*) op)->addInput(page);
+    OR_CATCH
+}
+int32_t or_operator_get_output(void* opv, pg_page* out)
+{
+    OR_TRY
+    auto* op = (Operator*) opv;
+    if (op->getOutput(op->lastOutput)) op->lastOutput.fill(out);
+    else { out->position_count = 0; out->channel_count = 0; out->memory = PG_MEM_HOST; out->blocks = nullptr; }
+    OR_CATCH
+}
+int32_t or_operator_finish(void* op) { OR_TRY ((Operator*) op)->finish(); OR_CATCH }
+int32_t or_operator_is_finished(void* op, int32_t* out) { OR_TRY *out = ((Operator*) op)->isFinished() ? 1 : 0; OR_CATCH }
+int32_t or_operator_get_stats(void* op, pg_operator_stats* out) { OR_TRY *out = ((Operator*) op)->stats; OR_CATCH }
+int32_t or_operator_destroy(void* op) { delete (Operator*) op; return PG_OK; }
+
+}  // extern "C"

@@ -1,0 +1,246 @@
+/*
+ * ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_common.h).
+ *
+ * HashBuilderOperator → PagesIndex → PagesHash (+ArrayPositionLinks) → JoinHash → LookupJoinOperator restated from:
+ *   MB/operator/PagesIndex.java:202-226          (addPage: keep blocks, append synthetic addresses)
+ *   MB/operator/PagesHash.java:55-132,169-181    (build loop / getAddressIndex)
+ *   MB/operator/ArrayPositionLinks.java:38-100   (link / next)
+ *   MB/operator/JoinHash.java:81-124             (getJoinPosition / getNextJoinPosition)
+ *   MB/operator/JoinProbe.java:74-119            (null probe keys never match)
+ *   MB/operator/LookupJoinOperator.java:481-505,567-616 (processProbe / joinCurrentPosition / outerJoinCurrentPosition)
+ *   MB/operator/LookupJoinPageBuilder.java:75-137 (appendRow / appendNullForBuild)
+ *   MB/operator/SimplePagesHashStrategy.java:110-175 (hashPosition = 31*h + typeHash; equality ignore nulls)
+ */
+#include "oracle_common.h"
+
+namespace oracle {
+
+// The build side after finish(): the reference's LookupSource (JoinHash over PagesHash).
+struct LookupSource {
+    // PagesIndex: one flat column per build channel (the reference keeps a list of blocks per channel plus
+    // valueAddresses[i] = pageIndex<<32|position; concatenating the pages makes address == position).
+    std::vector<int> types;
+    std::vector<Column> channels;
+    std::vector<int> hashChannels;
+    std::vector<int> outputChannels;
+    int precomputedHashChannel = -1;
+    int64_t positionCount = 0;
+
+    // PagesHash
+    int32_t mask = 0;
+    std::vector<int32_t> key;
+    std::vector<int8_t> positionToHashes;
+    std::vector<int32_t> positionLinks;    // ArrayPositionLinks (-1 end)
+    bool linksEmpty = true;
+    int64_t hashCollisions = 0;
+    int64_t positionIsNullCount = 0;
+
+    int64_t hashPosition(int64_t position) const   // SimplePagesHashStrategy.hashPosition :110-123
+    {
+        if (precomputedHashChannel >= 0) return channels[precomputedHashChannel].getLong(position);
+        int64_t result = 0;
+        for (int hc : hashChannels) {
+            int64_t h = channels[hc].nulls[position] ? 0 : hashLong(channels[hc].getLong(position));
+            result = result * 31 + h;
+        }
+        return result;
+    }
+    bool isPositionNull(int64_t position) const
+    {
+        for (int hc : hashChannels) if (channels[hc].nulls[position]) return true;
+        return false;
+    }
+    bool positionEqualsPositionIgnoreNulls(int64_t l, int64_t r) const
+    {
+        for (int hc : hashChannels) if (channels[hc].getLong(l) != channels[hc].getLong(r)) return false;
+        return true;
+    }
+    bool positionEqualsRowIgnoreNulls(int64_t l, int64_t rightPosition, const std::vector<BlockView>& probeHashBlocks) const
+    {
+        for (size_t i = 0; i < hashChannels.size(); i++)
+            if (channels[hashChannels[i]].getLong(l) != probeHashBlocks[i].getLong(rightPosition)) return false;
+        return true;
+    }
+
+    void build()   // PagesHash ctor :55-132
+    {
+        int32_t hashSize = arraySize(positionCount, 0.75f);
+        mask = hashSize - 1;
+        key.assign(hashSize, -1);
+        positionToHashes.assign((size_t) positionCount, 0);
+        positionLinks.assign((size_t) positionCount, -1);
+        int64_t positionsInStep = std::min<int64_t>(positionCount + 1, (128 * 1024) / 32);   // CACHE_SIZE / Integer.SIZE :76
+        std::vector<int64_t> positionToFullHashes((size_t) positionsInStep);
+        for (int64_t step = 0; step * positionsInStep < positionCount; step++) {
+            int64_t stepBegin = step * positionsInStep;
+            int64_t stepEnd = std::min((step + 1) * positionsInStep, positionCount);
+            int64_t stepSize = stepEnd - stepBegin;
+            for (int64_t position = 0; position < stepSize; position++) {
+                int64_t realPosition = position + stepBegin;
+                int64_t hash = hashPosition(realPosition);
+                positionToFullHashes[position] = hash;
+                positionToHashes[realPosition] = (int8_t) hash;
+            }
+            for (int64_t position = 0; position < stepSize; position++) {
+                int32_t realPosition = (int32_t) (position + stepBegin);
+                if (isPositionNull(realPosition)) { ++positionIsNullCount; continue; }
+                int64_t hash = positionToFullHashes[position];
+                int32_t pos = (int32_t) (murmurHash3(hash) & mask);
+                while (key[pos] != -1) {
+                    int32_t currentKey = key[pos];
+                    if (((int8_t) hash) == positionToHashes[currentKey] && positionEqualsPositionIgnoreNulls(currentKey, realPosition)) {
+                        // positionLinks.link(realPosition, currentKey): ArrayPositionLinks.java:45-50
+                        positionLinks[realPosition] = currentKey;
+                        linksEmpty = false;
+                        break;
+                    }
+                    pos = (pos + 1) & mask;
+                    hashCollisions++;
+                }
+                key[pos] = realPosition;
+            }
+        }
+    }
+
+    int32_t getAddressIndex(int64_t rightPosition, const std::vector<BlockView>& probeHashBlocks, int64_t rawHash) const   // :169-181
+    {
+        int32_t pos = (int32_t) (murmurHash3(rawHash) & mask);
+        while (key[pos] != -1) {
+            if (positionToHashes[key[pos]] == (int8_t) rawHash && positionEqualsRowIgnoreNulls(key[pos], rightPosition, probeHashBlocks)) return key[pos];
+            pos = (pos + 1) & mask;
+        }
+        return -1;
+    }
+};
+
+struct JoinBridge {
+    std::unique_ptr<LookupSource> lookupSource;   // set when the build finishes (the future completes)
+};
+
+struct HashBuilderOperator : Operator {
+    JoinBridge* bridge;
+    std::unique_ptr<LookupSource> ls;
+    bool finishing = false;
+
+    HashBuilderOperator(const pg_hash_builder_config* c, JoinBridge* b) : bridge(b)
+    {
+        ls = std::make_unique<LookupSource>();
+        ls->types.assign(c->types, c->types + c->n_channels);
+        for (int t : ls->types) ls->channels.emplace_back(t);
+        ls->hashChannels.assign(c->hash_channels, c->hash_channels + c->n_hash_channels);
+        ls->outputChannels.assign(c->output_channels, c->output_channels + c->n_output_channels);
+        ls->precomputedHashChannel = c->precomputed_hash_channel;
+        for (int hc : ls->hashChannels) {
+            int t = ls->types[hc];
+            if (t != PG_TYPE_BIGINT && t != PG_TYPE_INTEGER && t != PG_TYPE_DATE) throw OracleError(PG_ERR_UNSUPPORTED, "join key type");
+        }
+    }
+    bool needsInput() override { return !finishing; }
+    void addInput(const pg_page* page) override   // HashBuilderOperator.addInput :333-349 → PagesIndex.addPage :202-226
+    {
+        if (finishing) throw OracleError(PG_ERR_INVALID_STATE, "Operator is already finishing");
+        for (size_t ch = 0; ch < ls->channels.size(); ch++) {
+            BlockView v(&page->blocks[ch]);
+            for (int64_t p = 0; p < page->position_count; p++) ls->channels[ch].appendFrom(v, p);
+        }
+        ls->positionCount += page->position_count;
+        stats.input_positions += page->position_count;
+    }
+    void finish() override   // finishInput :519-537 → buildLookupSource :642-651
+    {
+        if (finishing) return;
+        finishing = true;
+        ls->build();
+        stats.group_count = ls->positionCount;
+        bridge->lookupSource = std::move(ls);
+    }
+    bool isFinished() override { return finishing; }
+    bool getOutput(OwnedPage&) override { return false; }
+};
+
+struct LookupJoinOperator : Operator {
+    JoinBridge* bridge;
+    int joinType;
+    std::vector<int> types, hashChannels, outputChannels;
+    int precomputedHashChannel;
+    bool finishing = false;
+    bool hasPending = false;
+    OwnedPage pending;
+
+    LookupJoinOperator(const pg_lookup_join_config* c, JoinBridge* b) : bridge(b)
+    {
+        joinType = c->join_type;
+        types.assign(c->types, c->types + c->n_channels);
+        hashChannels.assign(c->hash_channels, c->hash_channels + c->n_hash_channels);
+        outputChannels.assign(c->output_channels, c->output_channels + c->n_output_channels);
+        precomputedHashChannel = c->precomputed_hash_channel;
+    }
+    bool needsInput() override { return !finishing && !hasPending && bridge->lookupSource != nullptr; }   // LookupJoinOperator.java:198-210
+    void addInput(const pg_page* page) override
+    {
+        if (!needsInput()) throw OracleError(PG_ERR_INVALID_STATE, "lookup join does not need input");
+        const LookupSource& ls = *bridge->lookupSource;
+        stats.input_positions += page->position_count;
+        pending.columns.clear();
+        for (int oc : outputChannels) pending.columns.emplace_back(types[oc]);
+        for (int oc : ls.outputChannels) pending.columns.emplace_back(ls.types[oc]);
+        std::vector<BlockView> probeHash;
+        for (int hc : hashChannels) probeHash.emplace_back(&page->blocks[hc]);
+        std::vector<BlockView> probeOut;
+        for (int oc : outputChannels) probeOut.emplace_back(&page->blocks[oc]);
+        BlockView hashBlock;
+        if (precomputedHashChannel >= 0) hashBlock = BlockView(&page->blocks[precomputedHashChannel]);
+        int64_t rows = 0;
+        size_t nProbeOut = outputChannels.size();
+        for (int64_t position = 0; position < page->position_count; position++) {   // processProbe :481-505
+            // JoinProbe.getCurrentJoinPosition :79-90
+            int64_t joinPosition;
+            bool rowNull = false;
+            for (auto& b : probeHash) if (b.isNull(position)) { rowNull = true; break; }
+            if (rowNull) joinPosition = -1;
+            else {
+                int64_t rawHash;
+                if (precomputedHashChannel >= 0) rawHash = hashBlock.getLong(position);
+                else {   // SimplePagesHashStrategy.hashRow :125-136
+                    rawHash = 0;
+                    for (auto& b : probeHash) rawHash = rawHash * 31 + hashLong(b.getLong(position));
+                }
+                joinPosition = ls.getAddressIndex(position, probeHash, rawHash);
+            }
+            bool producedRow = false;
+            while (joinPosition >= 0) {   // joinCurrentPosition :567-586 (no filter function)
+                producedRow = true;
+                for (size_t i = 0; i < nProbeOut; i++) pending.columns[i].appendFrom(probeOut[i], position);
+                for (size_t i = 0; i < ls.outputChannels.size(); i++) pending.columns[nProbeOut + i].appendFrom(ls.channels[ls.outputChannels[i]], joinPosition);
+                rows++;
+                joinPosition = ls.linksEmpty ? -1 : ls.positionLinks[joinPosition];   // JoinHash.getNextJoinPosition :105-111
+            }
+            if (!producedRow && joinType == PG_JOIN_PROBE_OUTER) {   // outerJoinCurrentPosition :608-616 → appendNullForBuild
+                for (size_t i = 0; i < nProbeOut; i++) pending.columns[i].appendFrom(probeOut[i], position);
+                for (size_t i = 0; i < ls.outputChannels.size(); i++) pending.columns[nProbeOut + i].appendNull();
+                rows++;
+            }
+        }
+        pending.positionCount = rows;
+        hasPending = rows > 0;
+        stats.output_positions += rows;
+    }
+    bool getOutput(OwnedPage& out) override
+    {
+        if (!hasPending) return false;
+        out.columns.swap(pending.columns);
+        out.positionCount = pending.positionCount;
+        hasPending = false;
+        return true;
+    }
+    void finish() override { finishing = true; }
+    bool isFinished() override { return finishing && !hasPending; }
+};
+
+JoinBridge* createJoinBridge() { return new JoinBridge(); }
+Operator* createHashBuilder(const pg_hash_builder_config* c, JoinBridge* b) { return new HashBuilderOperator(c, b); }
+Operator* createLookupJoin(const pg_lookup_join_config* c, JoinBridge* b) { return new LookupJoinOperator(c, b); }
+int64_t joinBridgePositionCount(JoinBridge* b) { return b->lookupSource ? b->lookupSource->positionCount : -1; }
+void destroyJoinBridge(JoinBridge* b) { delete b; }
+
+}  // namespace oracle

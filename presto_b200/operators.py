@@ -1,0 +1,305 @@
+"""Host-side mirror of the reference's operator interfaces for the hot path, over the C ABI.
+
+Same names, argument meaning and error behaviour as presto-main-base/src/main/java/com/facebook/presto/operator:
+Operator.java:20-102 (needsInput / addInput / getOutput / finish / isFinished / close), HashAggregationOperator,
+HashBuilderOperator + LookupJoinOperator (joined by a JoinBridge), PartitionedOutputOperator, FilterAndProjectOperator,
+GroupByHash.  Every class takes the ``Backend`` to run on; the default is the CUDA library (no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _abi as abi
+from .page import Block, Page
+
+
+def _default_backend():
+    from ._lib import load
+    return load()
+
+
+def _options(device: int = 0, output_memory: int = abi.MEM_HOST, cuda_stream: int = 0, max_output_rows: int = 0) -> abi.pg_operator_options:
+    o = abi.pg_operator_options()
+    o.device = device
+    o.output_memory = output_memory
+    o.cuda_stream = cuda_stream or None
+    o.max_output_rows = max_output_rows
+    return o
+
+
+class Operator:
+    """MB/operator/Operator.java:20-102."""
+
+    def __init__(self, backend, handle: C.c_void_p):
+        self._b = backend
+        self._h = handle
+        self._closed = False
+
+    def needs_input(self) -> bool:
+        out = C.c_int32()
+        self._b.check(self._b.operator_needs_input(self._h, C.byref(out)))
+        return bool(out.value)
+
+    def add_input(self, page: Page) -> None:
+        cpage, keep = page.as_c()
+        self._b.check(self._b.operator_add_input(self._h, C.byref(cpage)))
+        del keep
+
+    def get_output(self, copy: bool = True) -> Optional[Page]:
+        out = abi.pg_page()
+        self._b.check(self._b.operator_get_output(self._h, C.byref(out)))
+        return Page.from_c(out, self._b, copy=copy)
+
+    def finish(self) -> None:
+        self._b.check(self._b.operator_finish(self._h))
+
+    def is_finished(self) -> bool:
+        out = C.c_int32()
+        self._b.check(self._b.operator_is_finished(self._h, C.byref(out)))
+        return bool(out.value)
+
+    def get_stats(self) -> dict:
+        s = abi.pg_operator_stats()
+        self._b.check(self._b.operator_get_stats(self._h, C.byref(s)))
+        return {name: getattr(s, name) for name, _ in abi.pg_operator_stats._fields_}
+
+    def close(self) -> None:
+        if not self._closed:
+            self._closed = True
+            self._b.operator_destroy(self._h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def to_pages(operator: Operator, input_pages: Sequence[Page]) -> List[Page]:
+    """OperatorAssertion.toPages (presto-main-base/src/test/.../operator/OperatorAssertion.java:78-130): emulate the Driver
+    loop — while needsInput: addInput, drain getOutput; then finish and drain until isFinished."""
+    out: List[Page] = []
+    it = iter(input_pages)
+    pending = next(it, None)
+    for _ in range(10_000_000):
+        if pending is None:
+            break
+        if operator.needs_input():
+            operator.add_input(pending)
+            pending = next(it, None)
+        page = operator.get_output()
+        if page is not None and page.position_count > 0:
+            out.append(page)
+    operator.finish()
+    for _ in range(10_000_000):
+        if operator.is_finished():
+            break
+        page = operator.get_output()
+        if page is not None and page.position_count > 0:
+            out.append(page)
+    assert operator.is_finished(), "Operator did not finish"
+    assert not operator.needs_input(), "Operator still wants input after finish"
+    return out
+
+
+class Aggregate:
+    def __init__(self, function: int, input_channel: int = -1, mask_channel: int = -1):
+        self.function, self.input_channel, self.mask_channel = function, input_channel, mask_channel
+
+
+class HashAggregationOperator(Operator):
+    """HashAggregationOperator.java:56-725 (in-memory builder)."""
+
+    def __init__(self, group_types: Sequence[int], group_channels: Sequence[int], aggregates: Sequence[Aggregate], *,
+                 hash_channel: int = -1, step: int = abi.STEP_SINGLE, expected_groups: int = 10_000,
+                 group_max_lengths: Optional[Sequence[int]] = None, backend=None, **options):
+        backend = backend or _default_backend()
+        cfg = abi.pg_hash_aggregation_config()
+        gc, gt = abi.i32_array(group_channels), abi.i32_array(group_types)
+        gl = abi.i32_array(group_max_lengths if group_max_lengths is not None else [0] * len(group_types))
+        aggs = (abi.pg_aggregate * max(1, len(aggregates)))()
+        for i, a in enumerate(aggregates):
+            aggs[i].function, aggs[i].input_channel, aggs[i].mask_channel = a.function, a.input_channel, a.mask_channel
+        cfg.n_group_channels = len(group_channels)
+        cfg.group_channels, cfg.group_types, cfg.group_max_lengths = gc, gt, gl
+        cfg.hash_channel = hash_channel
+        cfg.n_aggregates = len(aggregates)
+        cfg.aggregates = aggs
+        cfg.step = step
+        cfg.expected_groups = expected_groups
+        cfg.options = _options(**options)
+        handle = C.c_void_p()
+        backend.check(backend.hash_aggregation_create(C.byref(cfg), C.byref(handle)))
+        super().__init__(backend, handle)
+
+
+class GroupByHash:
+    """GroupByHash.java:61-89 — createGroupByHash picks Bigint iff exactly one BIGINT channel (:46-59)."""
+
+    def __init__(self, types: Sequence[int], channels: Sequence[int], *, hash_channel: int = -1, expected_size: int = 100,
+                 max_lengths: Optional[Sequence[int]] = None, backend=None, **options):
+        self._b = backend or _default_backend()
+        cfg = abi.pg_group_by_hash_config()
+        ch, ty = abi.i32_array(channels), abi.i32_array(types)
+        ml = abi.i32_array(max_lengths if max_lengths is not None else [0] * len(types))
+        cfg.n_channels = len(channels)
+        cfg.channels, cfg.types, cfg.max_lengths = ch, ty, ml
+        cfg.hash_channel = hash_channel
+        cfg.expected_size = expected_size
+        cfg.options = _options(**options)
+        self._h = C.c_void_p()
+        self._b.check(self._b.group_by_hash_create(C.byref(cfg), C.byref(self._h)))
+        self._closed = False
+
+    def add_page(self, page: Page) -> None:
+        cpage, keep = page.as_c()
+        self._b.check(self._b.group_by_hash_add_page(self._h, C.byref(cpage)))
+
+    def get_group_ids(self, page: Page) -> np.ndarray:
+        assert not page.on_device
+        cpage, keep = page.as_c()
+        out = np.empty(page.position_count, dtype=np.int64)
+        self._b.check(self._b.group_by_hash_get_group_ids(self._h, C.byref(cpage), out.ctypes.data))
+        return out
+
+    def get_group_count(self) -> int:
+        out = C.c_int64()
+        self._b.check(self._b.group_by_hash_get_group_count(self._h, C.byref(out)))
+        return out.value
+
+    def contains(self, page: Page) -> np.ndarray:
+        cpage, keep = page.as_c()
+        out = np.empty(page.position_count, dtype=np.uint8)
+        self._b.check(self._b.group_by_hash_contains(self._h, C.byref(cpage), out.ctypes.data))
+        return out.astype(bool)
+
+    def get_keys(self) -> Optional[Page]:
+        out = abi.pg_page()
+        self._b.check(self._b.group_by_hash_get_keys(self._h, C.byref(out)))
+        return Page.from_c(out, self._b)
+
+    def close(self) -> None:
+        if not self._closed:
+            self._closed = True
+            self._b.group_by_hash_destroy(self._h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class JoinBridge:
+    """JoinBridgeManager / LookupSourceFactory: the hand-off of the finished LookupSource from build to probe."""
+
+    def __init__(self, device: int = 0, backend=None):
+        self._b = backend or _default_backend()
+        self._h = C.c_void_p()
+        self._b.check(self._b.join_bridge_create(device, C.byref(self._h)))
+        self._closed = False
+
+    def get_position_count(self) -> int:
+        out = C.c_int64()
+        self._b.check(self._b.join_bridge_get_position_count(self._h, C.byref(out)))
+        return out.value
+
+    def close(self) -> None:
+        if not self._closed:
+            self._closed = True
+            self._b.join_bridge_destroy(self._h)
+
+
+class HashBuilderOperator(Operator):
+    """HashBuilderOperator.java:55-692."""
+
+    def __init__(self, bridge: JoinBridge, types: Sequence[int], hash_channels: Sequence[int], output_channels: Sequence[int], *,
+                 precomputed_hash_channel: int = -1, expected_positions: int = 10_000, backend=None, **options):
+        backend = backend or bridge._b
+        cfg = abi.pg_hash_builder_config()
+        ty, hc, oc = abi.i32_array(types), abi.i32_array(hash_channels), abi.i32_array(output_channels)
+        cfg.n_channels, cfg.types = len(types), ty
+        cfg.n_hash_channels, cfg.hash_channels = len(hash_channels), hc
+        cfg.n_output_channels, cfg.output_channels = len(output_channels), oc
+        cfg.precomputed_hash_channel = precomputed_hash_channel
+        cfg.expected_positions = expected_positions
+        cfg.options = _options(**options)
+        handle = C.c_void_p()
+        backend.check(backend.hash_builder_create(C.byref(cfg), bridge._h, C.byref(handle)))
+        super().__init__(backend, handle)
+        self._bridge = bridge
+
+
+class LookupJoinOperator(Operator):
+    """LookupJoinOperator.java:63-760 (INNER and PROBE_OUTER, no filter function)."""
+
+    def __init__(self, bridge: JoinBridge, types: Sequence[int], hash_channels: Sequence[int], output_channels: Sequence[int], *,
+                 join_type: int = abi.JOIN_INNER, precomputed_hash_channel: int = -1, backend=None, **options):
+        backend = backend or bridge._b
+        cfg = abi.pg_lookup_join_config()
+        ty, hc, oc = abi.i32_array(types), abi.i32_array(hash_channels), abi.i32_array(output_channels)
+        cfg.join_type = join_type
+        cfg.n_channels, cfg.types = len(types), ty
+        cfg.n_hash_channels, cfg.hash_channels = len(hash_channels), hc
+        cfg.n_output_channels, cfg.output_channels = len(output_channels), oc
+        cfg.precomputed_hash_channel = precomputed_hash_channel
+        cfg.options = _options(**options)
+        handle = C.c_void_p()
+        backend.check(backend.lookup_join_create(C.byref(cfg), bridge._h, C.byref(handle)))
+        super().__init__(backend, handle)
+        self._bridge = bridge
+
+
+class PartitionedOutputOperator(Operator):
+    """OptimizedPartitionedOutputOperator.java:167-179,384-824 — the partition + copy-by-position step.  get_output returns
+    one page per input page with all partitions back to back; ``get_offsets`` gives the partition boundaries."""
+
+    def __init__(self, types: Sequence[int], partition_count: int, partition_channels: Sequence[int], *,
+                 precomputed_hash_channel: int = -1, replicates_any_row: bool = False, null_channel: int = -1, backend=None, **options):
+        backend = backend or _default_backend()
+        cfg = abi.pg_partitioned_output_config()
+        ty, pc = abi.i32_array(types), abi.i32_array(partition_channels)
+        cfg.n_channels, cfg.types = len(types), ty
+        cfg.partition_count = partition_count
+        cfg.n_partition_channels, cfg.partition_channels = len(partition_channels), pc
+        cfg.precomputed_hash_channel = precomputed_hash_channel
+        cfg.replicates_any_row = int(replicates_any_row)
+        cfg.null_channel = null_channel
+        cfg.options = _options(**options)
+        handle = C.c_void_p()
+        backend.check(backend.partitioned_output_create(C.byref(cfg), C.byref(handle)))
+        super().__init__(backend, handle)
+        self.partition_count = partition_count
+
+    def get_offsets(self) -> np.ndarray:
+        out = np.empty(self.partition_count + 1, dtype=np.int64)
+        self._b.check(self._b.partitioned_output_get_offsets(self._h, out.ctypes.data))
+        return out
+
+
+class FilterAndProjectOperator(Operator):
+    """FilterAndProjectOperator.java:88-99 over a PageProcessor (PageProcessor.java:112-148)."""
+
+    def __init__(self, input_types: Sequence[int], program, *, backend=None, **options):
+        """``program`` is an expressions.Program (flattened RowExpression DAG + filter + projections)."""
+        backend = backend or _default_backend()
+        cfg = abi.pg_filter_project_config()
+        it = abi.i32_array(input_types)
+        nodes = program.c_nodes()
+        proj = abi.i32_array(program.projections)
+        cfg.n_input_channels, cfg.input_types = len(input_types), it
+        cfg.n_nodes, cfg.nodes = len(program.nodes), nodes
+        cfg.filter_node = program.filter
+        cfg.n_projections, cfg.projection_nodes = len(program.projections), proj
+        cfg.options = _options(**options)
+        handle = C.c_void_p()
+        backend.check(backend.filter_project_create(C.byref(cfg), C.byref(handle)))
+        super().__init__(backend, handle)
+
+    def get_last_selection(self):
+        is_list, size = C.c_int32(), C.c_int64()
+        self._b.check(self._b.filter_project_get_last_selection(self._h, C.byref(is_list), C.byref(size)))
+        return bool(is_list.value), size.value

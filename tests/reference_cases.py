@@ -1,0 +1,494 @@
+"""The reference's own behavioural tests for the hot path, re-encoded backend-agnostically.
+
+Each ``case_*`` takes a Backend (the CPU oracle in test_oracle_reference.py, the CUDA library in test_gpu_reference.py)
+and asserts exactly what the cited Java test asserts.  MBT = presto-main-base/src/test/java/com/facebook/presto/.
+Adaptations are stated per case (the GPU join path takes BIGINT/INTEGER/DATE keys, so VARCHAR join keys become BIGINT).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from presto_b200 import (
+    AGG_AVG_BIGINT, AGG_AVG_DOUBLE, AGG_COUNT_COLUMN, AGG_COUNT_STAR, AGG_SUM_BIGINT, AGG_SUM_DOUBLE, BIGINT, BOOLEAN, DATE, DOUBLE,
+    INTEGER, JOIN_INNER, JOIN_PROBE_OUTER, VARCHAR, Aggregate, Block, FilterAndProjectOperator, GroupByHash,
+    HashAggregationOperator, HashBuilderOperator, JoinBridge, LookupJoinOperator, Page, PartitionedOutputOperator, Program, to_pages,
+)
+from presto_b200.hashing import get_hash_block, get_partition, hash_long
+
+from util import (
+    RowPagesBuilder, create_double_sequence_block, create_doubles_block, create_long_sequence_block, create_longs_block,
+    create_string_sequence_block, create_strings_block, rows_close, rows_of,
+)
+
+MAX_GROUP_ID = 500   # MBT/operator/TestGroupByHash.java:58
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# TestGroupByHash
+# ---------------------------------------------------------------------------------------------------------------------
+def case_group_by_hash_add_page(backend, max_group_id=MAX_GROUP_ID, tries_per_value=10):
+    """TestGroupByHash.testAddPage :68-94 — sequential values get groupId == value; re-adding changes nothing."""
+    h = GroupByHash([BIGINT], [0], hash_channel=1, expected_size=100, backend=backend)
+    for tries in range(2):
+        for value in range(max_group_id):
+            block = create_longs_block(value)
+            page = Page([block, get_hash_block([block], backend)])
+            for _ in range(tries_per_value):
+                h.add_page(page)
+                assert h.get_group_count() == (value + 1 if tries == 0 else max_group_id)
+                ids = h.get_group_ids(page)
+                assert h.get_group_count() == (value + 1 if tries == 0 else max_group_id)
+                assert len(ids) == 1 and ids[0] == value
+    h.close()
+
+
+def case_group_by_hash_null_group(backend):
+    """TestGroupByHash.testNullGroup :97-117 — null group, then 132 748 values forcing rehashes; contains(0) is false."""
+    h = GroupByHash([BIGINT], [0], hash_channel=1, expected_size=100, backend=backend)
+    block = create_longs_block(None)
+    h.add_page(Page([block, get_hash_block([block], backend)]))
+    block = create_long_sequence_block(1, 132748)
+    h.add_page(Page([block, get_hash_block([block], backend)]))
+    assert h.get_group_count() == 132748
+    block = create_longs_block(0)
+    assert not h.contains(Page([block, get_hash_block([block], backend)]))[0]
+    block = create_longs_block(None, 5, 132747, 132748)
+    assert list(h.contains(Page([block, get_hash_block([block], backend)]))) == [True, True, True, False]
+    h.close()
+
+
+def case_group_by_hash_get_group_ids(backend, max_group_id=MAX_GROUP_ID, tries_per_value=3):
+    """TestGroupByHash.testGetGroupIds :119-139."""
+    h = GroupByHash([BIGINT], [0], hash_channel=1, expected_size=100, backend=backend)
+    for tries in range(2):
+        for value in range(max_group_id):
+            block = create_longs_block(value)
+            page = Page([block, get_hash_block([block], backend)])
+            for _ in range(tries_per_value):
+                ids = h.get_group_ids(page)
+                assert h.get_group_count() == (value + 1 if tries == 0 else max_group_id)
+                assert len(ids) == 1 and ids[0] == value
+    h.close()
+
+
+def case_group_by_hash_append_to(backend):
+    """TestGroupByHash.testAppendTo :149-176 — VARCHAR keys '0'..'99' + $hashvalue come back in group-id order."""
+    values = create_string_sequence_block(0, 100)
+    hash_block = get_hash_block([values], backend)
+    h = GroupByHash([VARCHAR], [0], hash_channel=1, expected_size=100, max_lengths=[7], backend=backend)
+    ids = h.get_group_ids(Page([values, hash_block]))
+    assert list(ids) == list(range(100))
+    assert h.get_group_count() == 100
+    keys = h.get_keys()
+    assert keys.position_count == 100 and keys.channel_count == 2
+    assert keys.blocks[0].to_pylist() == values.to_pylist()
+    assert keys.blocks[1].to_pylist() == hash_block.to_pylist()
+    h.close()
+
+
+def case_group_by_hash_append_to_multiple_tuples_per_group(backend):
+    """TestGroupByHash.testAppendToMultipleTuplesPerGroup :178-200."""
+    values = create_longs_block([i % 50 for i in range(100)])
+    h = GroupByHash([BIGINT], [0], hash_channel=1, expected_size=100, backend=backend)
+    ids = h.get_group_ids(Page([values, get_hash_block([values], backend)]))
+    assert list(ids) == [i % 50 for i in range(100)]
+    assert h.get_group_count() == 50
+    keys = h.get_keys()
+    assert keys.blocks[0].to_pylist() == list(range(50))
+    assert keys.blocks[1].to_pylist() == [int(x) for x in hash_long(np.arange(50, dtype=np.int64))]
+    h.close()
+
+
+def case_group_by_hash_contains(backend):
+    """TestGroupByHash.testContains :202-217 (DOUBLE key)."""
+    values = create_double_sequence_block(0, 10)
+    h = GroupByHash([DOUBLE], [0], hash_channel=1, expected_size=100, backend=backend)
+    h.get_group_ids(Page([values, get_hash_block([values], backend)]))
+    t = create_doubles_block(3.0)
+    assert h.contains(Page([t, get_hash_block([t], backend)]))[0]
+    t = create_doubles_block(11.0)
+    assert not h.contains(Page([t, get_hash_block([t], backend)]))[0]
+    h.close()
+
+
+def case_group_by_hash_contains_multiple_columns(backend):
+    """TestGroupByHash.testContainsMultipleColumns :219-234 (DOUBLE, VARCHAR)."""
+    values, strings = create_double_sequence_block(0, 10), create_string_sequence_block(0, 10)
+    h = GroupByHash([DOUBLE, VARCHAR], [0, 1], hash_channel=2, expected_size=100, max_lengths=[0, 7], backend=backend)
+    h.get_group_ids(Page([values, strings, get_hash_block([values, strings], backend)]))
+    tv, ts = create_doubles_block(3.0), create_strings_block(b"3")
+    assert h.contains(Page([tv, ts, get_hash_block([tv, ts], backend)]))[0]
+    tv, ts = create_doubles_block(3.0), create_strings_block(b"4")
+    assert not h.contains(Page([tv, ts, get_hash_block([tv, ts], backend)]))[0]
+    h.close()
+
+
+def case_group_by_hash_force_rehash(backend):
+    """TestGroupByHash.testForceRehash :236-250 — expectedSize 4, 100 VARCHAR keys."""
+    values = create_string_sequence_block(0, 100)
+    page = Page([values, get_hash_block([values], backend)])
+    h = GroupByHash([VARCHAR], [0], hash_channel=1, expected_size=4, max_lengths=[7], backend=backend)
+    ids = h.get_group_ids(page)
+    assert list(ids) == list(range(100))
+    assert h.contains(page).all()
+    h.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# TestHashAggregationOperator
+# ---------------------------------------------------------------------------------------------------------------------
+def case_hash_aggregation(backend, hash_enabled: bool, number_of_rows: int = 40_000):
+    """TestHashAggregationOperator.testHashAggregation :162-217 — 3 sequence pages of 40 000 rows, VARCHAR group key;
+    count(*), sum(bigint), avg(bigint), count(varchar), count(boolean).  Adaptation: max(varchar) is dropped (not on the GPU
+    path); the result is compared in group-id order (stricter than the reference's assertPagesEqualIgnoreOrder)."""
+    b = RowPagesBuilder([VARCHAR, VARCHAR, VARCHAR, BIGINT, BOOLEAN], hash_enabled, [1], backend)
+    pages = (b.add_sequence_page(number_of_rows, 100, 0, 100_000, 0, 500)
+              .add_sequence_page(number_of_rows, 100, 0, 200_000, 0, 500)
+              .add_sequence_page(number_of_rows, 100, 0, 300_000, 0, 500).build())
+    op = HashAggregationOperator(
+        [VARCHAR], [1],
+        [Aggregate(AGG_COUNT_STAR), Aggregate(AGG_SUM_BIGINT, 3), Aggregate(AGG_AVG_BIGINT, 3), Aggregate(AGG_COUNT_COLUMN, 0), Aggregate(AGG_COUNT_COLUMN, 4)],
+        hash_channel=b.get_hash_channel(), expected_groups=100_000, group_max_lengths=[7], max_output_rows=16384, backend=backend)
+    out = to_pages(op, pages)
+    assert len(out) > 1, "Expected more than one output page"
+    rows = rows_of(out)
+    expected = []
+    for i in range(number_of_rows):
+        key = str(i).encode()
+        row = (key,)
+        if hash_enabled:
+            row += (backend.hash_xxhash64(key, len(key)),)
+        expected.append(row + (3, 3 * i, float(i), 3, 3))
+    rows_close(rows, expected)
+    op.close()
+
+
+def case_hash_aggregation_null_inputs(backend):
+    """DoubleSumAggregation / AverageAggregations / CountColumn null handling (AccumulatorCompiler.java:462-566): NULL inputs are
+    skipped; sum over no non-null rows is NULL, avg is NULL, count is 0."""
+    keys = Block.from_values(BIGINT, [1, 2, 1, None, 2, None, 3])
+    vals = Block.from_values(DOUBLE, [1.5, None, 2.5, 4.0, None, 6.0, None])
+    longs = Block.from_values(BIGINT, [10, 20, None, 40, None, 60, None])
+    op = HashAggregationOperator(
+        [BIGINT], [0],
+        [Aggregate(AGG_SUM_DOUBLE, 1), Aggregate(AGG_AVG_DOUBLE, 1), Aggregate(AGG_COUNT_COLUMN, 1), Aggregate(AGG_SUM_BIGINT, 2),
+         Aggregate(AGG_AVG_BIGINT, 2), Aggregate(AGG_COUNT_STAR)],
+        expected_groups=16, backend=backend)
+    rows = rows_of(to_pages(op, [Page([keys, vals, longs])]))
+    rows_close(rows, [
+        (1, 4.0, 2.0, 2, 10, 10.0, 2),
+        (2, None, None, 0, 20, 20.0, 2),
+        (None, 10.0, 5.0, 2, 100, 50.0, 2),
+        (3, None, None, 0, None, None, 1),
+    ])
+    op.close()
+
+
+def case_hash_aggregation_mask(backend):
+    """Mask channel handling (TestHashAggregationOperator.testMask): rows whose BOOLEAN mask is false/NULL are not accumulated,
+    but their group still exists."""
+    keys = Block.from_values(BIGINT, [1, 1, 2, 2, 3])
+    vals = Block.from_values(BIGINT, [5, 6, 7, 8, 9])
+    mask = Block.from_values(BOOLEAN, [True, False, False, None, True])
+    op = HashAggregationOperator([BIGINT], [0], [Aggregate(AGG_COUNT_STAR, -1, 2), Aggregate(AGG_SUM_BIGINT, 1, 2)], expected_groups=8, backend=backend)
+    rows = rows_of(to_pages(op, [Page([keys, vals, mask])]))
+    rows_close(rows, [(1, 1, 5), (2, 0, None), (3, 1, 9)])
+    op.close()
+
+
+def case_hash_aggregation_multi_key(backend):
+    """MultiChannelGroupByHash with (BIGINT, DATE, INTEGER) keys — the Q3 shape — null == null grouping
+    (MultiChannelGroupByHash.java:460-466) and first-appearance output order."""
+    k0 = Block.from_values(BIGINT, [7, 7, 8, None, 7, None, 8])
+    k1 = Block.from_values(DATE, [100, 100, 100, 5, 101, 5, 100])
+    k2 = Block.from_values(INTEGER, [0, 0, None, 1, 0, 1, None])
+    v = Block.from_values(DOUBLE, [1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0])
+    op = HashAggregationOperator([BIGINT, DATE, INTEGER], [0, 1, 2], [Aggregate(AGG_SUM_DOUBLE, 3), Aggregate(AGG_COUNT_STAR)], expected_groups=8, backend=backend)
+    rows = rows_of(to_pages(op, [Page([k0, k1, k2, v])]))
+    rows_close(rows, [(7, 100, 0, 3.0, 2), (8, 100, None, 10.0, 2), (None, 5, 1, 10.0, 2), (7, 101, 0, 5.0, 1)])
+    op.close()
+
+
+def case_hash_aggregation_empty(backend):
+    """No input → no output page, operator finishes (HashAggregationOperator.java:451-501 with a null builder)."""
+    op = HashAggregationOperator([BIGINT], [0], [Aggregate(AGG_COUNT_STAR)], backend=backend)
+    assert to_pages(op, []) == []
+    op.close()
+
+
+def case_hash_aggregation_add_after_finish(backend):
+    """checkState(!finishing) in addInput (HashAggregationOperator.java:415)."""
+    from presto_b200 import PrestoException
+    op = HashAggregationOperator([BIGINT], [0], [Aggregate(AGG_COUNT_STAR)], backend=backend)
+    op.add_input(Page([create_longs_block(1, 2)]))
+    op.finish()
+    assert not op.needs_input()
+    try:
+        op.add_input(Page([create_longs_block(3)]))
+    except PrestoException as e:
+        assert e.code == 2
+    else:
+        raise AssertionError("addInput after finish must fail")
+    op.close()
+
+
+def case_bigint_sum_overflow(backend):
+    """LongSumAggregation → BigintOperators.add → Math.addExact (BigintOperators.java:68-78): NUMERIC_VALUE_OUT_OF_RANGE."""
+    from presto_b200 import PrestoException
+    keys = create_longs_block(1, 1)
+    vals = create_longs_block(2 ** 63 - 1, 1)
+    op = HashAggregationOperator([BIGINT], [0], [Aggregate(AGG_SUM_BIGINT, 1)], backend=backend)
+    try:
+        to_pages(op, [Page([keys, vals])])
+    except PrestoException as e:
+        assert e.code == 6
+    else:
+        raise AssertionError("bigint sum overflow must raise")
+    op.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# TestHashJoinOperator (VARCHAR join keys of the reference become BIGINT: 'a','b','c' → 1,2,3; "20".."29" → 20..29)
+# ---------------------------------------------------------------------------------------------------------------------
+def _join(backend, build_pages, build_types, probe_pages, probe_types, join_type, build_hash, probe_hash):
+    bridge = JoinBridge(backend=backend)
+    nb, npr = len(build_types) - (1 if build_hash else 0), len(probe_types) - (1 if probe_hash else 0)
+    builder = HashBuilderOperator(bridge, build_types, [0], list(range(nb)), precomputed_hash_channel=nb if build_hash else -1, backend=backend)
+    probe = LookupJoinOperator(bridge, probe_types, [0], list(range(npr)), join_type=join_type,
+                               precomputed_hash_channel=npr if probe_hash else -1, backend=backend)
+    assert not probe.needs_input(), "probe must wait for the lookup source"
+    assert to_pages(builder, build_pages) == []
+    out = to_pages(probe, probe_pages)
+    rows = rows_of(out)
+    probe.close(); builder.close(); bridge.close()
+    return rows
+
+
+def case_inner_join(backend, probe_hash: bool, build_hash: bool):
+    """TestHashJoinOperator.testInnerJoin :171-207 — ordered expectation."""
+    bp = RowPagesBuilder([BIGINT, BIGINT, BIGINT], build_hash, [0], backend).add_sequence_page(10, 20, 30, 40)
+    pp = RowPagesBuilder([BIGINT, BIGINT, BIGINT], probe_hash, [0], backend).add_sequence_page(1000, 0, 1000, 2000)
+    rows = _join(backend, bp.build(), bp.get_types(), pp.build(), pp.get_types(), JOIN_INNER, build_hash, probe_hash)
+    assert rows == [(20 + i, 1020 + i, 2020 + i, 20 + i, 30 + i, 40 + i) for i in range(10)]
+
+
+def case_inner_join_with_null_probe(backend, probe_hash: bool, build_hash: bool):
+    """testInnerJoinWithNullProbe :712-750."""
+    bp = RowPagesBuilder([BIGINT], build_hash, [0], backend).row(1).row(2).row(3)
+    pp = RowPagesBuilder([BIGINT], probe_hash, [0], backend).row(1).row(None).row(None).row(1).row(2)
+    rows = _join(backend, bp.build(), bp.get_types(), pp.build(), pp.get_types(), JOIN_INNER, build_hash, probe_hash)
+    assert rows == [(1, 1), (1, 1), (2, 2)]
+
+
+def case_inner_join_with_null_build(backend, probe_hash: bool, build_hash: bool):
+    """testInnerJoinWithNullBuild :752-790 — build a,null,null,a,b ; probe a,b,c → (a,a),(a,a),(b,b)."""
+    bp = RowPagesBuilder([BIGINT], build_hash, [0], backend).row(1).row(None).row(None).row(1).row(2)
+    pp = RowPagesBuilder([BIGINT], probe_hash, [0], backend).row(1).row(2).row(3)
+    rows = _join(backend, bp.build(), bp.get_types(), pp.build(), pp.get_types(), JOIN_INNER, build_hash, probe_hash)
+    assert rows == [(1, 1), (1, 1), (2, 2)]
+
+
+def case_inner_join_with_null_on_both_sides(backend, probe_hash: bool, build_hash: bool):
+    """testInnerJoinWithNullOnBothSides :792-830."""
+    bp = RowPagesBuilder([BIGINT], build_hash, [0], backend).row(1).row(None).row(None).row(1).row(2)
+    pp = RowPagesBuilder([BIGINT], probe_hash, [0], backend).row(1).row(2).row(None).row(3)
+    rows = _join(backend, bp.build(), bp.get_types(), pp.build(), pp.get_types(), JOIN_INNER, build_hash, probe_hash)
+    assert rows == [(1, 1), (1, 1), (2, 2)]
+
+
+def case_probe_outer_join(backend, probe_hash: bool, build_hash: bool):
+    """testProbeOuterJoin :833-876."""
+    bp = RowPagesBuilder([BIGINT, BIGINT, BIGINT], build_hash, [0], backend).add_sequence_page(10, 20, 30, 40)
+    pp = RowPagesBuilder([BIGINT, BIGINT, BIGINT], probe_hash, [0], backend).add_sequence_page(15, 20, 1020, 2020)
+    rows = _join(backend, bp.build(), bp.get_types(), pp.build(), pp.get_types(), JOIN_PROBE_OUTER, build_hash, probe_hash)
+    expected = [(20 + i, 1020 + i, 2020 + i, 20 + i, 30 + i, 40 + i) for i in range(10)]
+    expected += [(30 + i, 1030 + i, 2030 + i, None, None, None) for i in range(5)]
+    assert rows == expected
+
+
+def case_outer_join_with_null_on_both_sides(backend, probe_hash: bool, build_hash: bool):
+    """testOuterJoinWithNullOnBothSides :1101-1141 — probe a,b,null,c over build a,null,null,a,b."""
+    bp = RowPagesBuilder([BIGINT], build_hash, [0], backend).row(1).row(None).row(None).row(1).row(2)
+    pp = RowPagesBuilder([BIGINT], probe_hash, [0], backend).row(1).row(2).row(None).row(3)
+    rows = _join(backend, bp.build(), bp.get_types(), pp.build(), pp.get_types(), JOIN_PROBE_OUTER, build_hash, probe_hash)
+    assert rows == [(1, 1), (1, 1), (2, 2), (None, None), (3, None)]
+
+
+def case_probe_outer_join_empty_lookup_source(backend):
+    """testProbeOuterJoinWithEmptyLookupSource :1323+ — empty build: every probe row comes out with NULL build columns."""
+    bridge = JoinBridge(backend=backend)
+    builder = HashBuilderOperator(bridge, [BIGINT], [0], [0], backend=backend)
+    assert to_pages(builder, []) == []
+    probe = LookupJoinOperator(bridge, [BIGINT], [0], [0], join_type=JOIN_PROBE_OUTER, backend=backend)
+    rows = rows_of(to_pages(probe, [Page([create_longs_block(1, 2, None, 3)])]))
+    assert rows == [(1, None), (2, None), (None, None), (3, None)]
+    inner = LookupJoinOperator(bridge, [BIGINT], [0], [0], join_type=JOIN_INNER, backend=backend)
+    assert to_pages(inner, [Page([create_longs_block(1, 2, None, 3)])]) == []
+
+
+def case_join_duplicate_chain_order(backend):
+    """PagesHash.java:108-123 + ArrayPositionLinks.java:45-50: matches of one probe row come out in DESCENDING build position."""
+    build_keys = [5, 7, 5, 9, 5, 7]
+    bp = Page([create_longs_block(build_keys), create_long_sequence_block(100, 106)])
+    pp = Page([create_longs_block(7, 5, 1, 9)])
+    bridge = JoinBridge(backend=backend)
+    builder = HashBuilderOperator(bridge, [BIGINT, BIGINT], [0], [1], backend=backend)
+    to_pages(builder, [bp])
+    probe = LookupJoinOperator(bridge, [BIGINT], [0], [0], backend=backend)
+    rows = rows_of(to_pages(probe, [pp]))
+    assert rows == [(7, 105), (7, 101), (5, 104), (5, 102), (5, 100), (9, 103)]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# PartitionedOutput (TestOptimizedPartitionedOutputOperator: per-partition rows equal the rows the partition function assigns)
+# ---------------------------------------------------------------------------------------------------------------------
+def case_partitioned_output(backend, partition_count: int = 4, n: int = 1000, nulls: bool = False, precomputed: bool = False):
+    """TestOptimizedPartitionedOutputOperator.testPartitionedSinglePagePrimitiveTypes / …WithNulls: every row lands in the
+    partition HashGenerator.getPartition assigns, rows keep input order inside a partition."""
+    rng = np.random.default_rng(11)
+    c0 = rng.integers(-10**12, 10**12, n)
+    c1 = rng.integers(0, 10**6, n).astype(np.int32)
+    c2 = rng.random(n)
+    null0 = (rng.random(n) < 0.1).astype(np.uint8) if nulls else None
+    null2 = (rng.random(n) < 0.2).astype(np.uint8) if nulls else None
+    blocks = [Block.from_numpy(BIGINT, c0, null0), Block.from_numpy(INTEGER, c1), Block.from_numpy(DOUBLE, c2, null2)]
+    types = [BIGINT, INTEGER, DOUBLE]
+    raw = get_hash_block(blocks[:2], backend)
+    hash_channel = -1
+    if precomputed:
+        blocks.append(raw); types.append(BIGINT); hash_channel = 3
+    op = PartitionedOutputOperator(types, partition_count, [0, 1], precomputed_hash_channel=hash_channel, backend=backend)
+    page = Page(blocks)
+    op.add_input(page)
+    out = op.get_output()
+    offsets = op.get_offsets()
+    parts = get_partition(raw.values, partition_count)
+    in_rows = page.rows()
+    out_rows = out.rows()
+    assert offsets[0] == 0 and offsets[-1] == n and out.position_count == n
+    for p in range(partition_count):
+        assert out_rows[offsets[p]:offsets[p + 1]] == [in_rows[i] for i in range(n) if parts[i] == p]
+    op.finish()
+    assert op.is_finished()
+    op.close()
+
+
+def case_partitioned_output_replicates(backend):
+    """OptimizedPartitionedOutputOperator.java:504-530: replicatesAnyRow sends row 0 of the first page to every partition;
+    rows whose nullChannel is NULL go to every partition."""
+    keys = Block.from_values(BIGINT, [10, None, 11, 12, None, 13])
+    vals = create_long_sequence_block(0, 6)
+    op = PartitionedOutputOperator([BIGINT, BIGINT], 3, [0], replicates_any_row=True, null_channel=0, backend=backend)
+    page = Page([keys, vals])
+    op.add_input(page)
+    out = op.get_output()
+    offsets = op.get_offsets()
+    raw = get_hash_block([keys], backend)
+    parts = get_partition(raw.values, 3)
+    in_rows = page.rows()
+    out_rows = out.rows()
+    for p in range(3):
+        expected = [in_rows[0]]
+        for i in range(1, 6):
+            if in_rows[i][0] is None or parts[i] == p:
+                expected.append(in_rows[i])
+        assert out_rows[offsets[p]:offsets[p + 1]] == expected
+    # second page: row 0 is no longer replicated
+    op.add_input(Page([create_longs_block(10), create_longs_block(99)]))
+    out2 = op.get_output()
+    assert out2.position_count == 1
+    op.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# PageProcessor (TestPageProcessor / HandTpchQuery1)
+# ---------------------------------------------------------------------------------------------------------------------
+def case_page_processor_selection(backend):
+    """TestPageProcessor.testSelectAllFilter / testSelectNoneFilter / testPartialFilter(AsList): SelectedPositions is a range
+    when none or all positions are selected and a list otherwise (PageFilter.java:27-50)."""
+    page = Page([create_long_sequence_block(0, 100)])
+    for lo, expect_rows, expect_list in [(0, 100, False), (100, 0, False), (25, 75, True)]:
+        prog = Program([BIGINT])
+        x = prog.input(0)
+        prog.set_filter(x >= lo)
+        prog.project(x)
+        op = FilterAndProjectOperator([BIGINT], prog, backend=backend)
+        rows = rows_of(to_pages(op, [page]))
+        assert rows == [(i,) for i in range(lo, 100)] and len(rows) == expect_rows
+        op2 = FilterAndProjectOperator([BIGINT], prog, backend=backend)
+        op2.add_input(page)
+        is_list, size = op2.get_last_selection()
+        assert (is_list, size) == (expect_list, expect_rows)
+        op.close(); op2.close()
+
+
+def q1_program():
+    """PB/HandTpchQuery1.java:237-330 filterAndProjectRowOriented: shipdate <= 1998-09-02 (day 10471);
+    out = returnflag, linestatus, quantity, extendedprice, ep*(1-d), ep*(1-d)*(1+t), discount.  returnflag/linestatus travel
+    as dictionary-decoded INTEGER codes on the GPU path."""
+    prog = Program([INTEGER, INTEGER, DOUBLE, DOUBLE, DOUBLE, DOUBLE, DATE])
+    rf, ls, qty, ep, disc, tax, ship = [prog.input(i) for i in range(7)]
+    prog.set_filter(ship <= 10471)
+    disc_price = ep * (1.0 - disc)
+    prog.project(rf, ls, qty, ep, disc_price, disc_price * (1.0 + tax), disc)
+    return prog
+
+
+def case_page_processor_q1(backend, n: int = 5000):
+    rng = np.random.default_rng(5)
+    def nullable(a, p=0.05):
+        return (rng.random(n) < p).astype(np.uint8)
+    rf = rng.integers(0, 3, n).astype(np.int32); ls = rng.integers(0, 2, n).astype(np.int32)
+    qty = rng.integers(1, 51, n).astype(np.float64)
+    ep = np.round(rng.random(n) * 1e5, 2); disc = rng.integers(0, 11, n) / 100.0; tax = rng.integers(0, 9, n) / 100.0
+    ship = rng.integers(8035, 10600, n).astype(np.int32)
+    nulls = [None, None, nullable(qty), nullable(ep), nullable(disc), nullable(tax), nullable(ship)]
+    blocks = [Block.from_numpy(t, a, m) for t, a, m in zip([INTEGER, INTEGER, DOUBLE, DOUBLE, DOUBLE, DOUBLE, DATE], [rf, ls, qty, ep, disc, tax, ship], nulls)]
+    op = FilterAndProjectOperator([INTEGER, INTEGER, DOUBLE, DOUBLE, DOUBLE, DOUBLE, DATE], q1_program(), backend=backend)
+    rows = rows_of(to_pages(op, [Page(blocks)]))
+    expected = []
+    for i in range(n):   # HandTpchQuery1.filterAndProjectRowOriented, row by row
+        if nulls[6][i] or ship[i] > 10471:
+            continue
+        q = None if nulls[2][i] else float(qty[i]); e = None if nulls[3][i] else float(ep[i])
+        d = None if nulls[4][i] else float(disc[i]); t = None if nulls[5][i] else float(tax[i])
+        dp = None if e is None or d is None else e * (1 - d)
+        ch = None if dp is None or t is None else e * (1 - d) * (1 + t)
+        expected.append((int(rf[i]), int(ls[i]), q, e, dp, ch, d))
+    assert rows == expected   # IEEE double arithmetic is exact-reproducible: bit-for-bit
+    op.close()
+
+
+def case_page_processor_three_valued_logic(backend):
+    """AND / OR / NOT / IS NULL / BETWEEN over NULLs (SQL three-valued logic)."""
+    a = Block.from_values(BOOLEAN, [True, True, True, False, False, False, None, None, None])
+    b = Block.from_values(BOOLEAN, [True, False, None, True, False, None, True, False, None])
+    x = Block.from_values(BIGINT, [1, 5, 9, None, 3, 7, 10, 0, 5])
+    prog = Program([BOOLEAN, BOOLEAN, BIGINT])
+    ea, eb, ex = prog.input(0), prog.input(1), prog.input(2)
+    prog.project(ea & eb, ea | eb, ~ea, ea.is_null(), ex.between(3, 7), ex + 1, ex * 2 - 3, -ex)
+    op = FilterAndProjectOperator([BOOLEAN, BOOLEAN, BIGINT], prog, backend=backend)
+    rows = rows_of(to_pages(op, [Page([a, b, x])]))
+    T, F, N = True, False, None
+    assert [r[0] for r in rows] == [T, F, N, F, F, F, N, F, N]
+    assert [r[1] for r in rows] == [T, T, T, T, F, N, T, N, N]
+    assert [r[2] for r in rows] == [F, F, F, T, T, T, N, N, N]
+    assert [r[3] for r in rows] == [F, F, F, F, F, F, T, T, T]
+    assert [r[4] for r in rows] == [F, T, F, N, T, T, F, F, T]
+    assert [r[5] for r in rows] == [2, 6, 10, N, 4, 8, 11, 1, 6]
+    assert [r[6] for r in rows] == [-1, 7, 15, N, 3, 11, 17, -3, 7]
+    assert [r[7] for r in rows] == [-1, -5, -9, N, -3, -7, -10, 0, -5]
+    op.close()
+
+
+def case_page_processor_hash_projection(backend):
+    """The $hashvalue projection HashGenerationOptimizer.java:975-987 injects: combine_hash(combine_hash(0, hash(a)), hash(b))."""
+    a = Block.from_values(BIGINT, [1, 2, None, 42])
+    d = Block.from_values(DATE, [10, None, 30, 40])
+    prog = Program([BIGINT, DATE])
+    h = prog.const(0).combine_hash(prog.input(0).hash()).combine_hash(prog.input(1).hash())
+    prog.project(h)
+    op = FilterAndProjectOperator([BIGINT, DATE], prog, backend=backend)
+    rows = rows_of(to_pages(op, [Page([a, d])]))
+    assert [r[0] for r in rows] == get_hash_block([a, d], backend).to_pylist()
+    op.close()
