@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the presto_b200 hot path (BASELINE.json: rows/sec, hash aggregation / hash join).
+
+A "step" = one pass of HashAggregationOperator over the whole synthetic batch resident in HBM:
+  config.workload = "GroupByHash 1B-row synthetic lineitem: bigint key (G groups) + 4 x sum(double)" (BASELINE.json configs[1]),
+  addInput(device page) → finish → getOutput (the result read back to the host).
+value   : rows/s with the inputs already in HBM (CUDA events on the operator's stream, max over ranks)
+e2e     : same metric through the C ABI with HOST (pinned) pages: H2D copies inside the timed region
+roofline: algorithmic bytes (40 B/row: 8 B key + 4 x 8 B doubles) / kernel time, vs MEASURED_PEAKS.json hbm_gbs
+cpu_baseline / --impl reference: the oracle (C++ restatement of the reference's Java operators) on the box's host cores.
+Other cardinalities and the join (configs[2]) are reported in "extra"; they do not change `value`.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_ROW = 40   # 8 (bigint key) + 4 x 8 (double inputs); output negligible
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=1_000_000_000, help="rows per GPU (weak scaling)")
+    ap.add_argument("--groups", type=int, default=4, help="distinct bigint keys of the headline run (4 = TPC-H Q1-like)")
+    ap.add_argument("--e2e-rows", type=int, default=1 << 27, help="rows of the host-resident sample used for the e2e number")
+    ap.add_argument("--cpu-rows", type=int, default=1 << 28, help="rows of the bounded sample the CPU baseline aggregates")
+    ap.add_argument("--extra", type=int, default=1, help="also measure other cardinalities and the join (configs[2])")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx = max(mx, float(s[1]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# =====================================================================================================================
+# CPU arm: the oracle on the host cores
+# =====================================================================================================================
+def cpu_group_by(rows: int, groups: int, threads: int):
+    """All host threads, one oracle HashAggregationOperator per thread over a disjoint slice (= task_concurrency drivers),
+    then a FINAL merge of the per-thread results.  Returns (rows_per_sec, seconds)."""
+    import oracle
+    from presto_b200 import AGG_SUM_DOUBLE, BIGINT, DOUBLE, STEP_FINAL, STEP_PARTIAL, Aggregate, Block, HashAggregationOperator, Page, to_pages
+    from presto_b200.synthetic import double_column_np, group_key_np
+    ob = oracle.backend()
+    per = rows // threads
+    chunk = 1 << 20
+    slices = []
+    for t in range(threads):   # generate outside the timed region
+        start = t * per
+        keys = group_key_np(start, per, groups)
+        cols = [double_column_np(c, start, per) for c in range(4)]
+        slices.append((keys, cols))
+    results = [None] * threads
+
+    def work(t):
+        keys, cols = slices[t]
+        op = HashAggregationOperator([BIGINT], [0], [Aggregate(AGG_SUM_DOUBLE, 1 + c) for c in range(4)], step=STEP_PARTIAL,
+                                     expected_groups=10_000, backend=ob, max_output_rows=1 << 30)
+        for b in range(0, per, chunk):
+            e = min(per, b + chunk)
+            op.add_input(Page([Block.from_numpy(BIGINT, keys[b:e])] + [Block.from_numpy(DOUBLE, c[b:e]) for c in cols]))
+        op.finish()
+        results[t] = op.get_output()
+        op.close()
+
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    final = HashAggregationOperator([BIGINT], [0], [Aggregate(AGG_SUM_DOUBLE, 1 + c) for c in range(4)], step=STEP_FINAL,
+                                    expected_groups=10_000, backend=ob, max_output_rows=1 << 30)
+    out = to_pages(final, [r for r in results if r is not None])
+    dt = time.perf_counter() - t0
+    n_groups = sum(p.position_count for p in out)
+    return per * threads / dt, dt, n_groups
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Java operators cannot run here: no JVM) on all host
+    cores, same metric / config; each step is a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = min(args.cpu_rows, args.rows)
+    sample -= sample % threads
+    times = []
+    for i in range(args.warmup + args.steps):
+        rps, dt, g = cpu_group_by(sample, args.groups, threads)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1000 * float(np.mean(times))
+    value = sample / (ms / 1000)
+    line = {
+        "metric": "rows/sec", "value": value, "unit": "rows/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, sample),
+        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} rows of the same synthetic batch per step, {threads} threads x one oracle operator each + FINAL merge"},
+        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, rows):
+    return {"workload": f"GroupByHash synthetic lineitem: bigint key ({args.groups} groups) + 4 x sum(double), {rows} rows per GPU (BASELINE.json configs[1])",
+            "rows_per_gpu": rows, "groups": args.groups, "l2": "inputs (40 B/row x rows) far exceed the 126 MB L2; no flush needed",
+            "timing": "CUDA events on the operator stream, barrier + synchronize on both sides, max over ranks"}
+
+
+# =====================================================================================================================
+# GPU arm
+# =====================================================================================================================
+def device_page(torch, tensors, types):
+    from presto_b200 import Block, Page
+    n = tensors[0].numel()
+    return Page([Block.device(t, n, x.data_ptr(), keepalive=x) for t, x in zip(types, tensors)])
+
+
+def run_group_by(torch, backend, page, n_rows, groups_hint, steps, warmup, device, dist=None):
+    """Returns dict(ms_per_step, kernel_ms, launches, groups, result_rows)."""
+    from presto_b200 import AGG_SUM_DOUBLE, BIGINT, MEM_HOST, Aggregate, HashAggregationOperator
+    stream = torch.cuda.current_stream()
+    ms, kms, launches, groups = [], [], 0, 0
+    result = None
+    for i in range(warmup + steps):
+        op = HashAggregationOperator([BIGINT], [0], [Aggregate(AGG_SUM_DOUBLE, 1 + c) for c in range(4)], expected_groups=groups_hint,
+                                     backend=backend, device=device, output_memory=MEM_HOST, cuda_stream=stream.cuda_stream, max_output_rows=1 << 30)
+        e0, e1, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        op.add_input(page)
+        e1.record(stream)
+        op.finish()
+        out = op.get_output()
+        e2.record(stream)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        if i >= warmup:
+            ms.append(e0.elapsed_time(e2)); kms.append(e0.elapsed_time(e1))
+            st = op.get_stats()
+            launches = st["kernel_launches"]; groups = st["group_count"]
+        result = out
+        op.close()
+    return {"ms": float(np.mean(ms)), "kernel_ms": float(np.mean(kms)), "launches": int(launches), "groups": int(groups), "result": result}
+
+
+def run_e2e(torch, backend, rows, groups, steps, warmup, device):
+    """Host (pinned) pages through the C ABI: H2D of every column inside the timed region, result read back to the host."""
+    from presto_b200 import AGG_SUM_DOUBLE, BIGINT, DOUBLE, MEM_HOST, Aggregate, Block, HashAggregationOperator, Page
+    from presto_b200.synthetic import double_column_np, group_key_np
+    keys = torch.empty(rows, dtype=torch.int64).pin_memory()
+    cols = [torch.empty(rows, dtype=torch.float64).pin_memory() for _ in range(4)]
+    chunk = 1 << 24
+    for b in range(0, rows, chunk):
+        m = min(chunk, rows - b)
+        keys.numpy()[b:b + m] = group_key_np(b, m, groups)
+        for c in range(4):
+            cols[c].numpy()[b:b + m] = double_column_np(c, b, m)
+    page = Page([Block.from_numpy(BIGINT, keys.numpy())] + [Block.from_numpy(DOUBLE, c.numpy()) for c in cols])
+    times, h2d, d2h = [], 0, 0
+    for i in range(warmup + steps):
+        op = HashAggregationOperator([BIGINT], [0], [Aggregate(AGG_SUM_DOUBLE, 1 + c) for c in range(4)], expected_groups=max(groups, 1024),
+                                     backend=backend, device=device, output_memory=MEM_HOST, max_output_rows=1 << 30)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        op.add_input(page)
+        op.finish()
+        out = op.get_output()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+            st = op.get_stats(); h2d, d2h = st["h2d_bytes"], st["d2h_bytes"]
+        op.close()
+    return rows / float(np.mean(times)), int(h2d), int(d2h), out
+
+
+def run_join(torch, backend, device, build_rows, probe_rows, steps, warmup):
+    """configs[2]: HashBuilder + LookupJoin, orders ⋈ lineitem shape (unique sparse build keys, 1..7 probe rows per key)."""
+    from presto_b200 import BIGINT, DATE, DOUBLE, INTEGER, MEM_DEVICE, Block, HashBuilderOperator, JoinBridge, LookupJoinOperator, Page
+    g = torch.Generator(device=f"cuda:{device}"); g.manual_seed(7)
+    dev = f"cuda:{device}"
+    i = torch.arange(1, build_rows + 1, dtype=torch.int64, device=dev)
+    okey_sorted = ((i >> 3) << 5) + (i & 7)
+    perm = torch.randperm(build_rows, device=dev, generator=g)
+    okey = okey_sorted[perm].contiguous()
+    odate = torch.randint(8035, 10441, (build_rows,), dtype=torch.int32, device=dev, generator=g)
+    oprio = torch.zeros(build_rows, dtype=torch.int32, device=dev)
+    lines = torch.randint(1, 8, (build_rows,), dtype=torch.int64, device=dev, generator=g)
+    lkey = torch.repeat_interleave(okey_sorted, lines)[:probe_rows].contiguous()
+    probe_rows = lkey.numel()
+    del i, perm, lines
+    lprice = torch.rand(probe_rows, dtype=torch.float64, device=dev, generator=g) * 1e5
+    ldisc = torch.randint(0, 11, (probe_rows,), device=dev, generator=g).to(torch.float64) / 100
+    stream = torch.cuda.current_stream()
+    build_page = device_page(torch, [okey, odate, oprio], [BIGINT, DATE, INTEGER])
+    probe_page = device_page(torch, [lkey, lprice, ldisc], [BIGINT, DOUBLE, DOUBLE])
+    bms, pms, out_rows, launches = [], [], 0, 0
+    for it in range(warmup + steps):
+        bridge = JoinBridge(device, backend=backend)
+        builder = HashBuilderOperator(bridge, [BIGINT, DATE, INTEGER], [0], [1, 2], expected_positions=build_rows, backend=backend, device=device, cuda_stream=stream.cuda_stream)
+        probe = LookupJoinOperator(bridge, [BIGINT, DOUBLE, DOUBLE], [0], [0, 1, 2], backend=backend, device=device, output_memory=MEM_DEVICE, cuda_stream=stream.cuda_stream)
+        e0, e1, e2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        torch.cuda.synchronize()
+        e0.record(stream)
+        builder.add_input(build_page); builder.finish()
+        e1.record(stream)
+        probe.add_input(probe_page)
+        out = probe.get_output(copy=False)
+        e2.record(stream)
+        torch.cuda.synchronize()
+        if it >= warmup:
+            bms.append(e0.elapsed_time(e1)); pms.append(e1.elapsed_time(e2))
+            out_rows = out.position_count
+            launches = builder.get_stats()["kernel_launches"] + probe.get_stats()["kernel_launches"]
+        probe.close(); builder.close(); bridge.close()
+    b_ms, p_ms = float(np.mean(bms)), float(np.mean(pms))
+    algo = build_rows * 16 + probe_rows * 24 + out_rows * 32
+    return {"build_rows": build_rows, "probe_rows": probe_rows, "output_rows": int(out_rows), "build_ms": b_ms, "probe_ms": p_ms,
+            "probe_rows_per_s": probe_rows / ((b_ms + p_ms) / 1000), "algorithmic_bytes": algo, "achieved_gbs": algo / ((b_ms + p_ms) / 1000) / 1e9, "launches": int(launches)}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    from presto_b200._lib import load
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        dist = dist_mod
+    backend = load()
+    backend.check(backend.set_device(local))
+    dev = f"cuda:{local}"
+    from presto_b200 import BIGINT, DOUBLE
+    from presto_b200.synthetic import fill_double_column_torch, fill_group_key_torch
+
+    rows = args.rows
+    peak, peak_kind = peaks()
+    # ---- synthetic batch resident in HBM (each rank its own row range: weak scaling) ----
+    row0 = rank * rows
+    keys = torch.empty(rows, dtype=torch.int64, device=dev)
+    cols = [torch.empty(rows, dtype=torch.float64, device=dev) for _ in range(4)]
+    fill_group_key_torch(keys, row0, args.groups)
+    for c in range(4):
+        fill_double_column_torch(cols[c], c, row0)
+    torch.cuda.synchronize()
+    page = device_page(torch, [keys] + cols, [BIGINT] + [DOUBLE] * 4)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    r = run_group_by(torch, backend, page, rows, max(args.groups, 1024), args.steps, args.warmup, local, dist)
+    clocks = sampler.stop() if rank == 0 else None
+    ms, kms = r["ms"], r["kernel_ms"]
+    if dist is not None:
+        t = torch.tensor([ms, kms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, kms = float(t[0]), float(t[1])
+    value = rows * world / (ms / 1000)
+
+    extra = {}
+    e2e = None
+    cpu = None
+    if rank == 0:
+        # ---- end to end through the C ABI with host pages ----
+        e2e_rows = min(args.e2e_rows, rows)
+        e2e_rps, h2d, d2h, _ = run_e2e(torch, backend, e2e_rows, args.groups, max(2, min(args.steps, 3)), 1, local)
+        e2e = {"value": e2e_rps * world, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "sample": f"{e2e_rows} host-resident (pinned) rows per step per GPU, staged in 2^23-row chunks (copy/compute overlapped)"}
+    if rank == 0 and world == 1:
+        # ---- CPU baseline: oracle on the host cores, bounded sample ----
+        threads = os.cpu_count() or 1
+        sample = min(args.cpu_rows, rows); sample -= sample % threads
+        rps, dt, g = cpu_group_by(sample, args.groups, threads)
+        cpu = {"value": rps, "unit": "rows/s", "cores": threads, "kind": "port",
+               "sample": f"{sample} rows of the same batch, {threads} threads x one oracle HashAggregationOperator (PARTIAL) + FINAL merge, {dt:.2f} s"}
+        if args.extra:
+            del page
+            for g_other in (10_000, 3_000_000):
+                if g_other == args.groups:
+                    continue
+                fill_group_key_torch(keys, row0, g_other)
+                torch.cuda.synchronize()
+                pg2 = device_page(torch, [keys] + cols, [BIGINT] + [DOUBLE] * 4)
+                rr = run_group_by(torch, backend, pg2, rows, g_other, max(2, args.steps // 2), 1, local)
+                extra[f"group_by_{g_other}_groups"] = {"rows_per_s": rows / (rr["ms"] / 1000), "ms_per_step": rr["ms"], "groups": rr["groups"],
+                                                      "roofline_frac": ALGO_BYTES_PER_ROW * rows / (rr["kernel_ms"] / 1000) / 1e9 / peak}
+                del pg2
+            del keys, cols
+            torch.cuda.empty_cache()
+            try:
+                scale = min(1.0, rows / 1_000_000_000)
+                extra["hash_join_orders_lineitem"] = run_join(torch, backend, local, int(150_000_000 * scale), int(600_037_902 * scale), 2, 1)
+                extra["hash_join_orders_lineitem"]["roofline_frac"] = extra["hash_join_orders_lineitem"]["achieved_gbs"] / peak
+            except Exception as e:   # the join extra must never take the headline down
+                extra["hash_join_orders_lineitem"] = {"error": str(e)[:200]}
+
+    if rank == 0:
+        achieved = ALGO_BYTES_PER_ROW * rows / (kms / 1000) / 1e9
+        line = {
+            "metric": "rows/sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, rows),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "pg::hashAggKernel<1,4>", "peak_source": peak_kind,
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ROW * rows, "kernel_ms": kms},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": r["launches"], "groups": r["groups"], "clocks": clocks, "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,401 @@
+// presto_b200 — FilterAndProjectOperator / PageProcessor on sm_100a.
+//
+// Replaces (MB = presto-main-base/src/main/java/com/facebook/presto/):
+//   MB/operator/FilterAndProjectOperator.java:88-99, MB/operator/project/PageProcessor.java:112-148,180-343
+//   MB/operator/project/PageFilter.java:27-50 (boolean[] → SelectedPositions), PageProjection.java:24-31
+//   MB/sql/gen/PageFunctionCompiler.java:195-861 — the reference JIT-compiles the RowExpression tree to JVM bytecode;
+//   here the tree arrives as a flat node program (pg_expr_node) and ONE kernel interprets it with warp-uniform control flow.
+//
+//   pass A  every thread evaluates the filter for its row; a warp-unit's selected count goes to counts[unit]
+//   scan    exclusive sum → first output row of every unit (order preserving)
+//   pass B  every selected row re-evaluates the program and writes its projections at offset + rank-in-unit
+// Arithmetic follows MB/type/DoubleOperators.java:62-81 (plain IEEE + - * /) and BigintOperators.java:68-130 (exact, overflow →
+// NUMERIC_VALUE_OUT_OF_RANGE); AND / OR / NOT are SQL three-valued.
+#include "common.cuh"
+#include <cub/device/device_scan.cuh>
+#include <algorithm>
+
+namespace pg {
+
+constexpr int kMaxNodes = 48;
+constexpr int kMaxInputs = 32;
+constexpr int kMaxProjections = 32;
+constexpr int kRowsPerFpUnit = 256;   // rows owned by one warp per step (8 rounds of 32)
+
+enum { FP_ERR_OVERFLOW = 1, FP_ERR_DIV_ZERO = 2 };
+
+struct FpNode { int32_t op, type, a, b, c, isDouble; int64_t immI; };   // immI carries the double's bits for CONST_DOUBLE
+struct FpInput { const void* values; const uint8_t* nulls; int32_t type; };
+struct FpOutput { void* values; uint8_t* nulls; int32_t node; int32_t width; };
+
+struct FpParams {
+    FpNode nodes[kMaxNodes];
+    int32_t nNodes;
+    FpInput inputs[kMaxInputs];
+    int32_t filterNode;
+    FpOutput outs[kMaxProjections];
+    int32_t nOuts;
+    int64_t n, units;
+    uint32_t* counts;          // pass A: [units + 1]
+    const uint32_t* offsets;   // pass B
+    unsigned int* error;
+};
+
+struct Val { uint64_t bits; bool isNull; };
+
+__device__ __forceinline__ double asDouble(const Val& v, bool isDouble) { return isDouble ? __longlong_as_double((long long) v.bits) : (double) (long long) v.bits; }
+
+// Evaluates nodes [0, upTo] for one row; regs live in local memory (L1 resident), the program is warp-uniform.
+__device__ void evalRow(const FpParams& P, int64_t row, int upTo, uint64_t* regs, uint64_t& nullBits)
+{
+    nullBits = 0;
+    for (int k = 0; k <= upTo; k++) {
+        const FpNode& nd = P.nodes[k];
+        Val r{0, false};
+        auto get = [&](int i) -> Val { return Val{regs[i], (bool) ((nullBits >> i) & 1ULL)}; };
+        switch (nd.op) {
+            case PG_EX_INPUT: {
+                const FpInput& in = P.inputs[nd.a];
+                if (in.nulls && in.nulls[row]) r.isNull = true;
+                else switch (in.type) {
+                    case PG_TYPE_BIGINT: case PG_TYPE_DOUBLE: r.bits = ldStream64((const uint64_t*) in.values + row); break;
+                    case PG_TYPE_INTEGER: case PG_TYPE_DATE: r.bits = (uint64_t) (int64_t) (int32_t) ldStream32((const uint32_t*) in.values + row); break;
+                    default: r.bits = ((const uint8_t*) in.values)[row] != 0; break;
+                }
+                break;
+            }
+            case PG_EX_CONST_BIGINT: case PG_EX_CONST_BOOLEAN: case PG_EX_CONST_DOUBLE: r.bits = (uint64_t) nd.immI; break;
+            case PG_EX_CONST_NULL: r.isNull = true; break;
+            case PG_EX_ADD: case PG_EX_SUB: case PG_EX_MUL: case PG_EX_DIV: {
+                const Val x = get(nd.a), y = get(nd.b);
+                if (x.isNull || y.isNull) { r.isNull = true; break; }
+                if (nd.isDouble) {
+                    const double p = asDouble(x, P.nodes[nd.a].isDouble), q = asDouble(y, P.nodes[nd.b].isDouble);
+                    const double z = nd.op == PG_EX_ADD ? p + q : nd.op == PG_EX_SUB ? p - q : nd.op == PG_EX_MUL ? p * q : p / q;
+                    r.bits = (uint64_t) __double_as_longlong(z);
+                }
+                else {
+                    const long long p = (long long) x.bits, q = (long long) y.bits;
+                    long long z = 0;
+                    if (nd.op == PG_EX_ADD) { z = (long long) ((uint64_t) p + (uint64_t) q); if (((p ^ z) & (q ^ z)) < 0) atomicOr(P.error, (unsigned) FP_ERR_OVERFLOW); }
+                    else if (nd.op == PG_EX_SUB) { z = (long long) ((uint64_t) p - (uint64_t) q); if (((p ^ q) & (p ^ z)) < 0) atomicOr(P.error, (unsigned) FP_ERR_OVERFLOW); }
+                    else if (nd.op == PG_EX_MUL) {
+                        z = (long long) ((uint64_t) p * (uint64_t) q);
+                        const long long hi = __mul64hi(p, q);
+                        if (hi != (z >> 63)) atomicOr(P.error, (unsigned) FP_ERR_OVERFLOW);
+                    }
+                    else {
+                        if (q == 0) { atomicOr(P.error, (unsigned) FP_ERR_DIV_ZERO); z = 0; }
+                        else z = (p == LLONG_MIN && q == -1) ? LLONG_MIN : p / q;
+                    }
+                    r.bits = (uint64_t) z;
+                }
+                break;
+            }
+            case PG_EX_NEG: {
+                const Val x = get(nd.a);
+                if (x.isNull) { r.isNull = true; break; }
+                if (nd.isDouble) r.bits = x.bits ^ 0x8000000000000000ULL;
+                else { if ((long long) x.bits == LLONG_MIN) atomicOr(P.error, (unsigned) FP_ERR_OVERFLOW); r.bits = (uint64_t) (-(long long) x.bits); }
+                break;
+            }
+            case PG_EX_EQ: case PG_EX_NE: case PG_EX_LT: case PG_EX_LE: case PG_EX_GT: case PG_EX_GE: {
+                const Val x = get(nd.a), y = get(nd.b);
+                if (x.isNull || y.isNull) { r.isNull = true; break; }
+                bool res;
+                const bool da = P.nodes[nd.a].isDouble, db = P.nodes[nd.b].isDouble;
+                if (da || db) {
+                    const double p = asDouble(x, da), q = asDouble(y, db);
+                    res = nd.op == PG_EX_EQ ? p == q : nd.op == PG_EX_NE ? p != q : nd.op == PG_EX_LT ? p < q : nd.op == PG_EX_LE ? p <= q : nd.op == PG_EX_GT ? p > q : p >= q;
+                }
+                else {
+                    const long long p = (long long) x.bits, q = (long long) y.bits;
+                    res = nd.op == PG_EX_EQ ? p == q : nd.op == PG_EX_NE ? p != q : nd.op == PG_EX_LT ? p < q : nd.op == PG_EX_LE ? p <= q : nd.op == PG_EX_GT ? p > q : p >= q;
+                }
+                r.bits = res;
+                break;
+            }
+            case PG_EX_BETWEEN: {
+                const Val x = get(nd.a), lo = get(nd.b), hi = get(nd.c);
+                const bool da = P.nodes[nd.a].isDouble, db = P.nodes[nd.b].isDouble, dc = P.nodes[nd.c].isDouble;
+                const bool n1 = x.isNull || lo.isNull, n2 = x.isNull || hi.isNull;
+                bool c1 = false, c2 = false;
+                if (!n1) c1 = (da || db) ? asDouble(x, da) >= asDouble(lo, db) : (long long) x.bits >= (long long) lo.bits;
+                if (!n2) c2 = (da || dc) ? asDouble(x, da) <= asDouble(hi, dc) : (long long) x.bits <= (long long) hi.bits;
+                if ((!n1 && !c1) || (!n2 && !c2)) r.bits = 0;
+                else if (n1 || n2) r.isNull = true;
+                else r.bits = 1;
+                break;
+            }
+            case PG_EX_AND: {
+                const Val x = get(nd.a), y = get(nd.b);
+                if ((!x.isNull && !x.bits) || (!y.isNull && !y.bits)) r.bits = 0;
+                else if (x.isNull || y.isNull) r.isNull = true;
+                else r.bits = 1;
+                break;
+            }
+            case PG_EX_OR: {
+                const Val x = get(nd.a), y = get(nd.b);
+                if ((!x.isNull && x.bits) || (!y.isNull && y.bits)) r.bits = 1;
+                else if (x.isNull || y.isNull) r.isNull = true;
+                else r.bits = 0;
+                break;
+            }
+            case PG_EX_NOT: { const Val x = get(nd.a); if (x.isNull) r.isNull = true; else r.bits = !x.bits; break; }
+            case PG_EX_IS_NULL: r.bits = get(nd.a).isNull ? 1 : 0; break;
+            case PG_EX_CAST_DOUBLE: { const Val x = get(nd.a); if (x.isNull) r.isNull = true; else r.bits = (uint64_t) __double_as_longlong(asDouble(x, P.nodes[nd.a].isDouble)); break; }
+            case PG_EX_HASH: {
+                const Val x = get(nd.a);
+                const int t = P.nodes[nd.a].type;
+                if (x.isNull) r.bits = 0;
+                else if (t == PG_TYPE_DOUBLE) r.bits = (uint64_t) hashLong(canonicalDoubleBits((int64_t) x.bits));
+                else if (t == PG_TYPE_BOOLEAN) r.bits = x.bits ? 1231 : 1237;
+                else r.bits = (uint64_t) hashLong((int64_t) x.bits);
+                break;
+            }
+            case PG_EX_COMBINE_HASH: r.bits = 31ULL * get(nd.a).bits + get(nd.b).bits; break;
+            default: break;
+        }
+        regs[k] = r.bits;
+        if (r.isNull) nullBits |= 1ULL << k;
+    }
+}
+
+__global__ void __launch_bounds__(256) fpFilterKernel(const __grid_constant__ FpParams P)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warpId = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+    uint64_t regs[kMaxNodes];
+    for (int64_t unit = warpId; unit < P.units; unit += nWarps) {
+        const int64_t begin = unit * kRowsPerFpUnit, end = min(begin + (int64_t) kRowsPerFpUnit, P.n);
+        uint32_t selected = 0;
+        for (int64_t base = begin; base < end; base += 32) {
+            const int64_t row = base + lane;
+            bool sel = false;
+            if (row < end) {
+                uint64_t nb;
+                evalRow(P, row, P.filterNode, regs, nb);
+                sel = !((nb >> P.filterNode) & 1ULL) && regs[P.filterNode] != 0;   // only TRUE selects
+            }
+            selected += __popc(__ballot_sync(0xffffffffu, sel));
+        }
+        if (lane == 0) P.counts[unit] = selected;
+    }
+}
+
+__global__ void __launch_bounds__(256) fpProjectKernel(const __grid_constant__ FpParams P)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warpId = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+    uint64_t regs[kMaxNodes];
+    for (int64_t unit = warpId; unit < P.units; unit += nWarps) {
+        const int64_t begin = unit * kRowsPerFpUnit, end = min(begin + (int64_t) kRowsPerFpUnit, P.n);
+        uint32_t cursor = P.filterNode >= 0 ? P.offsets[unit] : (uint32_t) begin;
+        for (int64_t base = begin; base < end; base += 32) {
+            const int64_t row = base + lane;
+            bool sel = false;
+            uint64_t nb = 0;
+            if (row < end) {
+                evalRow(P, row, P.nNodes - 1, regs, nb);
+                sel = P.filterNode < 0 || (!((nb >> P.filterNode) & 1ULL) && regs[P.filterNode] != 0);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, sel);
+            if (sel) {
+                const uint32_t dest = cursor + __popc(m & ((1u << lane) - 1));
+                for (int j = 0; j < P.nOuts; j++) {
+                    const FpOutput& o = P.outs[j];
+                    const bool isNull = (nb >> o.node) & 1ULL;
+                    const uint64_t v = isNull ? 0 : regs[o.node];
+                    if (o.width == 8) ((uint64_t*) o.values)[dest] = v;
+                    else if (o.width == 4) ((uint32_t*) o.values)[dest] = (uint32_t) v;
+                    else ((uint8_t*) o.values)[dest] = (uint8_t) v;
+                    if (o.nulls) o.nulls[dest] = isNull ? 1 : 0;
+                }
+            }
+            cursor += __popc(m);
+        }
+    }
+}
+
+class FilterProjectOp : public Operator {
+    std::vector<int> inputTypes, staged;
+    std::vector<pg_expr_node> nodes;
+    std::vector<bool> used;
+    int filterNode;
+    std::vector<int> projections;
+    PageStager stager;
+    bool finishing = false, hasPending = false;
+    DeviceBuffer counts, offsets, scanTemp, errorWord;
+    std::vector<DeviceBuffer> outValues, outNulls;
+    std::vector<PinnedBuffer> hostValues, hostNulls;
+    std::vector<pg_block> outBlocks;
+    int64_t pendingRows = 0;
+    int lastIsList = 0; int64_t lastSize = 0;
+
+public:
+    explicit FilterProjectOp(const pg_filter_project_config* c) : Operator(c->options), stager(this)
+    {
+        PG_CHECK_ARG(c->n_input_channels >= 0 && c->n_input_channels <= kMaxInputs, "at most 32 input channels");
+        PG_CHECK_ARG(c->n_nodes >= 0 && c->n_nodes <= kMaxNodes, "at most 48 expression nodes");
+        PG_CHECK_ARG(c->n_projections >= 0 && c->n_projections <= kMaxProjections, "at most 32 projections");
+        inputTypes.assign(c->input_types, c->input_types + c->n_input_channels);
+        nodes.assign(c->nodes, c->nodes + c->n_nodes);
+        filterNode = c->filter_node;
+        projections.assign(c->projection_nodes, c->projection_nodes + c->n_projections);
+        PG_CHECK_ARG(filterNode < c->n_nodes, "filter node out of range");
+        if (filterNode >= 0) PG_CHECK_ARG(nodes[filterNode].type == PG_TYPE_BOOLEAN, "filter must be BOOLEAN");
+        for (int p : projections) PG_CHECK_ARG(p >= 0 && p < c->n_nodes, "projection node out of range");
+        for (int i = 0; i < c->n_nodes; i++) {
+            const pg_expr_node& n = nodes[i];
+            if (n.type == PG_TYPE_VARCHAR) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR expressions are not on the GPU path");
+            if (n.op == PG_EX_INPUT) {
+                PG_CHECK_ARG(n.a >= 0 && n.a < c->n_input_channels, "input channel out of range");
+                if (inputTypes[n.a] == PG_TYPE_VARCHAR) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR inputs are not on the GPU path");
+                if (std::find(staged.begin(), staged.end(), n.a) == staged.end()) staged.push_back(n.a);
+            }
+            else {
+                for (int o : {n.a, n.b, n.c}) PG_CHECK_ARG(o < i, "expression nodes must be topologically ordered");
+                if (n.op == PG_EX_CAST_BIGINT) throw Error(PG_ERR_UNSUPPORTED, "CAST to BIGINT is not on the GPU path yet");
+            }
+        }
+        for (DeviceBuffer* d : {&counts, &offsets, &scanTemp, &errorWord}) d->accounting = &stats.device_bytes;
+        errorWord.reserve(16);
+        PG_CUDA(cudaMemsetAsync(errorWord.ptr, 0, 16, stream));
+    }
+
+    bool needsInput() override { return !finishing && !hasPending; }
+
+    void addInput(const pg_page* page) override
+    {
+        PG_CHECK_STATE(needsInput(), "filter/project does not need input (finishing or output pending)");
+        const int64_t n = page->position_count;
+        stats.input_positions += n;
+        lastIsList = 0; lastSize = 0;
+        if (n == 0) return;
+        PG_CHECK_ARG(n < (int64_t(1) << 31), "page exceeds 2^31 positions");
+        std::vector<DeviceColumn> cols;
+        int slot = stager.stage(page, staged, cols);
+        FpParams P{};
+        P.nNodes = (int) nodes.size();
+        for (size_t i = 0; i < nodes.size(); i++) {
+            FpNode& d = P.nodes[i]; const pg_expr_node& s = nodes[i];
+            d.op = s.op; d.type = s.type; d.a = s.a; d.b = s.b; d.c = s.c; d.isDouble = s.type == PG_TYPE_DOUBLE;
+            if (s.op == PG_EX_CONST_DOUBLE) memcpy(&d.immI, &s.imm_d, 8); else d.immI = s.imm_i;
+        }
+        std::vector<bool> nullable(nodes.size(), false);
+        for (size_t i = 0; i < staged.size(); i++) {
+            PG_CHECK_ARG(cols[i].type == inputTypes[staged[i]], "input channel type differs from the operator's configuration");
+            P.inputs[staged[i]].values = cols[i].values; P.inputs[staged[i]].nulls = cols[i].nulls; P.inputs[staged[i]].type = cols[i].type;
+        }
+        for (size_t i = 0; i < nodes.size(); i++) {
+            const pg_expr_node& s = nodes[i];
+            switch (s.op) {
+                case PG_EX_INPUT: nullable[i] = P.inputs[s.a].nulls != nullptr; break;
+                case PG_EX_CONST_NULL: nullable[i] = true; break;
+                case PG_EX_CONST_BIGINT: case PG_EX_CONST_DOUBLE: case PG_EX_CONST_BOOLEAN: case PG_EX_IS_NULL: case PG_EX_HASH: case PG_EX_COMBINE_HASH: nullable[i] = false; break;
+                default: nullable[i] = (s.a >= 0 && nullable[s.a]) || (s.b >= 0 && nullable[s.b]) || (s.c >= 0 && nullable[s.c]); break;
+            }
+        }
+        P.filterNode = filterNode; P.n = n; P.units = divUp(n, kRowsPerFpUnit); P.error = errorWord.as<unsigned int>();
+        const int grid = (int) std::min<int64_t>(divUp(P.units, 8), (int64_t) numSMs * 8);
+        int64_t total = n;
+        if (filterNode >= 0) {
+            counts.reserve((size_t) (P.units + 1) * 4); offsets.reserve((size_t) (P.units + 1) * 4);
+            PG_CUDA(cudaMemsetAsync(counts.as<uint32_t>() + P.units, 0, 4, stream));
+            P.counts = counts.as<uint32_t>();
+            PG_LAUNCH(this, fpFilterKernel, grid, 256, 0, P);
+            size_t tb = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tb, counts.as<uint32_t>(), offsets.as<uint32_t>(), (int) (P.units + 1), stream);
+            scanTemp.reserve(tb);
+            cub::DeviceScan::ExclusiveSum(scanTemp.ptr, tb, counts.as<uint32_t>(), offsets.as<uint32_t>(), (int) (P.units + 1), stream);
+            stats.kernel_launches += 2;
+            uint32_t t = 0;
+            PG_CUDA(cudaMemcpyAsync(&t, offsets.as<uint32_t>() + P.units, 4, cudaMemcpyDeviceToHost, stream));
+            PG_CUDA(cudaStreamSynchronize(stream));
+            stats.d2h_bytes += 4;
+            total = t;
+            P.offsets = offsets.as<uint32_t>();
+        }
+        // PageFilter.positionsArrayToSelectedPositions :27-50
+        lastSize = total; lastIsList = (total == 0 || total == n) ? 0 : 1;
+        checkError();
+        if (total == 0) { stager.markCompute(slot); return; }
+        const size_t nOut = projections.size();
+        if (outValues.size() < nOut) { outValues.resize(nOut); outNulls.resize(nOut); for (auto& d : outValues) d.accounting = &stats.device_bytes; for (auto& d : outNulls) d.accounting = &stats.device_bytes; }
+        outBlocks.assign(nOut, pg_block{});
+        P.nOuts = (int) nOut;
+        for (size_t j = 0; j < nOut; j++) {
+            FpOutput& o = P.outs[j];
+            o.node = projections[j]; o.width = typeWidth(nodes[o.node].type);
+            outValues[j].reserve((size_t) total * o.width);
+            o.values = outValues[j].ptr; o.nulls = nullptr;
+            if (nullable[o.node]) { outNulls[j].reserve(total); o.nulls = outNulls[j].as<uint8_t>(); }
+        }
+        if (nOut) PG_LAUNCH(this, fpProjectKernel, grid, 256, 0, P);
+        stager.markCompute(slot);
+        const bool toHost = options.output_memory == PG_MEM_HOST;
+        if (toHost && hostValues.size() < nOut) { hostValues.resize(nOut); hostNulls.resize(nOut); }
+        for (size_t j = 0; j < nOut; j++) {
+            pg_block& b = outBlocks[j];
+            b.type = nodes[projections[j]].type; b.encoding = PG_ENC_FLAT; b.position_count = total;
+            const size_t vbytes = (size_t) total * P.outs[j].width;
+            if (toHost) {
+                hostValues[j].reserve(std::max<size_t>(vbytes, 16));
+                PG_CUDA(cudaMemcpyAsync(hostValues[j].ptr, outValues[j].ptr, vbytes, cudaMemcpyDeviceToHost, stream));
+                b.values = hostValues[j].ptr; b.is_null = nullptr;
+                stats.d2h_bytes += (int64_t) vbytes;
+                if (P.outs[j].nulls) { hostNulls[j].reserve(total); PG_CUDA(cudaMemcpyAsync(hostNulls[j].ptr, outNulls[j].ptr, total, cudaMemcpyDeviceToHost, stream)); b.is_null = hostNulls[j].as<uint8_t>(); stats.d2h_bytes += total; }
+            }
+            else { b.values = outValues[j].ptr; b.is_null = P.outs[j].nulls; }
+            stats.output_bytes += (int64_t) vbytes;
+        }
+        PG_CUDA(cudaStreamSynchronize(stream));
+        checkError();
+        pendingRows = total;
+        hasPending = true;
+        stats.output_positions += total;
+    }
+
+    void checkError()
+    {
+        unsigned int e = 0;
+        PG_CUDA(cudaMemcpyAsync(&e, errorWord.ptr, 4, cudaMemcpyDeviceToHost, stream));
+        PG_CUDA(cudaStreamSynchronize(stream));
+        if (e) PG_CUDA(cudaMemsetAsync(errorWord.ptr, 0, 4, stream));
+        if (e & FP_ERR_OVERFLOW) throw Error(PG_ERR_NUMERIC_OVERFLOW, "bigint arithmetic overflow");
+        if (e & FP_ERR_DIV_ZERO) throw Error(PG_ERR_INVALID_ARGUMENT, "Division by zero");
+    }
+
+    bool getOutput(pg_page* out) override
+    {
+        if (!hasPending) return false;
+        out->position_count = pendingRows; out->channel_count = (int32_t) outBlocks.size(); out->memory = options.output_memory; out->blocks = outBlocks.data();
+        hasPending = false;
+        return true;
+    }
+    void finish() override { finishing = true; }
+    bool isFinished() override { return finishing && !hasPending; }
+    void lastSelection(int32_t* isList, int64_t* size) const { *isList = lastIsList; *size = lastSize; }
+};
+
+}  // namespace pg
+
+extern "C" {
+int32_t pg_filter_project_create(const pg_filter_project_config* config, pg_operator** out)
+{
+    try { *out = (pg_operator*) new pg::FilterProjectOp(config); }
+    catch (const pg::Error& e) { pg::setLastError(e.what()); return e.code; }
+    catch (const std::exception& e) { pg::setLastError(e.what()); return PG_ERR_INVALID_STATE; }
+    return PG_OK;
+}
+int32_t pg_filter_project_get_last_selection(pg_operator* op, int32_t* isList, int64_t* size)
+{
+    try {
+        auto* p = dynamic_cast<pg::FilterProjectOp*>((pg::Operator*) op);
+        if (!p) throw pg::Error(PG_ERR_INVALID_ARGUMENT, "not a filter/project operator");
+        p->lastSelection(isList, size);
+    }
+    catch (const pg::Error& e) { pg::setLastError(e.what()); return e.code; }
+    return PG_OK;
+}
+}

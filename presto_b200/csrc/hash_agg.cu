@@ -1,0 +1,1285 @@
+// presto_b200 — HashAggregationOperator on sm_100a.
+//
+// Replaces (MB = presto-main-base/src/main/java/com/facebook/presto/):
+//   MB/operator/HashAggregationOperator.java:403-501          operator shell
+//   MB/operator/aggregation/builder/InMemoryHashAggregationBuilder.java:204-220  processPage = getGroupIds + one pass per aggregate
+//   MB/operator/BigintGroupByHash.java:222-269 / MultiChannelGroupByHash.java:293-358  putIfAbsent / addNewGroup
+//   MB/operator/aggregation/AccumulatorCompiler.java:462-566  grouped accumulator input loops
+// with ONE fused pass: each row's packed key is found-or-claimed in a per-CTA shared-memory table (warp-aggregated with
+// match/shfl so hot groups cost one shared atomic per warp, not per row) that falls through to the HBM table; accumulators
+// are indexed by slot, never by group id, so group ids never have to be materialised per row.  Group ids = rank of each
+// slot's first-touch row, assigned at output time (InMemoryHashAggregationBuilder.buildResult order :326-352,400-403).
+//
+// Algorithmic HBM bytes per row = key bytes + 8 B per aggregated column; everything else is on-chip.
+#include "common.cuh"
+#include "group_table.cuh"
+#include "key_layout.h"
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <algorithm>
+
+namespace pg {
+
+// accumulator column kinds
+enum { K_F64 = 0, K_F64_FROM_I64 = 1, K_LO32 = 2, K_HI32 = 3, K_COUNT = 4, K_I64_ADD = 5 };
+__host__ __device__ inline bool kindIsFloat(int k) { return k == K_F64 || k == K_F64_FROM_I64; }
+
+struct AccInput {
+    const uint64_t* values;     // 8-byte input column (DOUBLE bits or BIGINT); nullptr for counts
+    const uint8_t* nulls;
+    const uint8_t* mask;        // BOOLEAN mask column or nullptr
+    const uint8_t* maskNulls;
+    int32_t kind;
+    int32_t phys;               // physical accumulator column
+};
+
+template <int MAXV>
+struct AggLaunch {
+    GroupTable t;
+    KeyPlan kp;
+    AccInput acc[MAXV];
+    int32_t nAcc;
+    uint32_t floatMask;          // bit c: accumulator c adds doubles
+    int64_t n;                   // rows in this launch
+    uint64_t rowBase;            // global index of row 0 (first-appearance bookkeeping)
+    const uint32_t* bitmapIn;    // when set: only rows whose bit is set are processed (deferred-row pass)
+    uint32_t* bitmapOut;         // rows that could not claim a slot (table at its limit)
+    uint32_t S;                  // shared table slots (power of two); 0 = no shared table
+    uint32_t sLimit;
+};
+
+constexpr int kAggThreads = 256;
+constexpr int kSharedProbes = 8;
+constexpr int kWarpAggMaxGroups = 8;
+
+template <int MAXV> struct RowsPerThread { static constexpr int value = MAXV <= 4 ? 4 : (MAXV <= 8 ? 2 : 1); };
+
+// ---- shared-memory table ---------------------------------------------------------------------------------------------
+template <int W>
+struct SharedTable {
+    volatile uint64_t* keys;    // [W][S2]
+    volatile uint32_t* state;   // [S2] (W > 1)
+    uint64_t* acc;              // [nAcc][S2]
+    uint32_t* first;            // [S2]
+    uint32_t* count;            // claimed slots
+    uint32_t S, S2, sLimit;
+
+    __device__ __forceinline__ int find(const uint64_t (&kw)[W], uint64_t h) const
+    {
+        uint32_t s = (uint32_t) (h >> 32) & (S - 1);
+        if (W == 1) {
+#pragma unroll 1
+            for (int p = 0; p < kSharedProbes; p++) {
+                uint64_t k = keys[s];
+                if (k == kw[0]) return (int) s;
+                if (k == kEmptyKey) {
+                    if (*(volatile uint32_t*) count >= sLimit) return -1;
+                    uint64_t old = atomicCAS((unsigned long long*) &keys[s], (unsigned long long) kEmptyKey, (unsigned long long) kw[0]);
+                    if (old == kEmptyKey) { atomicAdd(count, 1u); return (int) s; }
+                    if (old == kw[0]) return (int) s;
+                }
+                s = (s + 1) & (S - 1);
+            }
+            return -1;
+        }
+        else {
+            const uint32_t ready = tagOf(h);
+#pragma unroll 1
+            for (int p = 0; p < kSharedProbes; p++) {
+                uint32_t st = state[s];
+                if (st == kStEmpty) {
+                    if (*(volatile uint32_t*) count >= sLimit) return -1;
+                    uint32_t old = atomicCAS((uint32_t*) &state[s], kStEmpty, kStLocked);
+                    if (old == kStEmpty) {
+#pragma unroll
+                        for (int w = 0; w < W; w++) keys[w * S2 + s] = kw[w];
+                        __threadfence_block();
+                        state[s] = ready;
+                        atomicAdd(count, 1u);
+                        return (int) s;
+                    }
+                    st = old;
+                }
+                while (st == kStLocked) st = state[s];
+                if (st == ready) {
+                    bool eq = true;
+#pragma unroll
+                    for (int w = 0; w < W; w++) eq &= keys[w * S2 + s] == kw[w];
+                    if (eq) return (int) s;
+                }
+                s = (s + 1) & (S - 1);
+            }
+            return -1;
+        }
+    }
+};
+
+__device__ __forceinline__ void accAddShared(uint64_t* addr, uint64_t bits, bool isFloat)
+{
+    if (isFloat) atomicAdd((double*) addr, __longlong_as_double((long long) bits));
+    else atomicAdd((unsigned long long*) addr, (unsigned long long) bits);
+}
+__device__ __forceinline__ void accAddGlobal(uint64_t* addr, uint64_t bits, bool isFloat)
+{
+    if (isFloat) atomicAdd((double*) addr, __longlong_as_double((long long) bits));   // REDG.E.ADD.F64
+    else atomicAdd((unsigned long long*) addr, (unsigned long long) bits);
+}
+
+// ---- the fused kernel ---------------------------------------------------------------------------------------------------
+template <int W, int MAXV>
+__global__ void __launch_bounds__(kAggThreads) hashAggKernel(const __grid_constant__ AggLaunch<MAXV> P)
+{
+    constexpr int R = RowsPerThread<MAXV>::value;
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int nAcc = P.nAcc;
+    const GroupTable& T = P.t;
+
+    SharedTable<W> st;
+    st.S = P.S; st.S2 = P.S + 2; st.sLimit = P.sLimit;
+    {
+        unsigned char* p = smemRaw;
+        st.keys = (volatile uint64_t*) p; p += sizeof(uint64_t) * W * st.S2;
+        st.acc = (uint64_t*) p; p += sizeof(uint64_t) * (size_t) nAcc * st.S2;
+        st.first = (uint32_t*) p; p += sizeof(uint32_t) * st.S2;
+        st.state = (volatile uint32_t*) p; p += sizeof(uint32_t) * (W > 1 ? st.S2 : 0);
+        st.count = (uint32_t*) p;
+    }
+    const bool useShared = P.S != 0;
+    if (useShared) {
+        for (uint32_t i = tid; i < W * st.S2; i += kAggThreads) st.keys[i] = kEmptyKey;
+        for (uint32_t i = tid; i < (uint32_t) nAcc * st.S2; i += kAggThreads) st.acc[i] = 0;
+        for (uint32_t i = tid; i < st.S2; i += kAggThreads) { st.first[i] = kNoRow32; if (W > 1) st.state[i] = kStEmpty; }
+        if (tid == 0) *st.count = 0;
+        __syncthreads();
+    }
+
+    bool warpBypass = !useShared;
+    uint32_t warpHits = 0, warpRows = 0;
+    constexpr int TILE = kAggThreads * R;
+    const int64_t nTiles = (P.n + TILE - 1) / TILE;
+
+    for (int64_t tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+        uint64_t kw[R][W];
+        uint64_t contrib[R][MAXV];
+        uint32_t addMask[R];
+        int special[R];
+        bool valid[R];
+        // ---- load phase: all loads of the tile are issued before any is consumed (R x (keys + nAcc) requests in flight) ----
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int64_t row = tile * TILE + (int64_t) r * kAggThreads + tid;
+            bool v = row < P.n;
+            if (v && P.bitmapIn) v = (P.bitmapIn[row >> 5] >> (row & 31)) & 1u;
+            valid[r] = v;
+            addMask[r] = 0;
+            special[r] = 0;
+#pragma unroll
+            for (int w = 0; w < W; w++) kw[r][w] = 0;
+            if (v) {
+                special[r] = packKey<W>(P.kp, row, kw[r]);
+#pragma unroll
+                for (int c = 0; c < MAXV; c++) {
+                    contrib[r][c] = 0;
+                    if (c < nAcc) {
+                        const AccInput& a = P.acc[c];
+                        bool add = true;
+                        if (a.mask) add = a.mask[row] != 0 && !(a.maskNulls && a.maskNulls[row]);
+                        if (add && a.nulls) add = a.nulls[row] == 0;
+                        uint64_t x = 1;
+                        if (a.kind != K_COUNT) {
+                            uint64_t raw = ldStream64(a.values + row);
+                            switch (a.kind) {
+                                case K_F64: case K_I64_ADD: x = raw; break;
+                                case K_F64_FROM_I64: x = (uint64_t) __double_as_longlong((double) (long long) raw); break;
+                                case K_LO32: x = raw & 0xffffffffULL; break;
+                                default: x = (uint64_t) ((long long) raw >> 32); break;   // K_HI32
+                            }
+                        }
+                        contrib[r][c] = x;
+                        if (add) addMask[r] |= 1u << c;
+                    }
+                }
+            }
+        }
+        // ---- accumulate phase ----
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const uint32_t rowIdx = (uint32_t) (tile * TILE + (int64_t) r * kAggThreads + tid);
+            const bool v = valid[r];
+            uint64_t h = 0;
+            int sslot = -1;
+            if (v) {
+                h = hashKeyWords<W>(kw[r]);
+                if (!warpBypass) sslot = special[r] ? (int) st.S + special[r] - 1 : st.find(kw[r], h);
+            }
+            const bool hit = v && sslot >= 0;
+            const unsigned hits = __ballot_sync(0xffffffffu, hit);
+            warpHits += __popc(hits);
+            warpRows += __popc(__ballot_sync(0xffffffffu, v));
+            if (hits) {
+                // group the warp's lanes by shared slot; lanes that missed form singleton groups
+                const int matchKey = hit ? sslot : -1 - lane;
+                const unsigned peers = __match_any_sync(0xffffffffu, matchKey);
+                const bool isLeader = hit && (lane == __ffs(peers) - 1);
+                const unsigned leaders = __ballot_sync(0xffffffffu, isLeader);
+                bool active = hit;
+                uint32_t myAdd = addMask[r];
+                if (__popc(leaders) <= kWarpAggMaxGroups && __popc(hits) > __popc(leaders)) {
+                    // few distinct groups in this warp: reduce each group's lanes with shuffles, one shared atomic per group
+                    uint64_t mine[MAXV];
+#pragma unroll
+                    for (int c = 0; c < MAXV; c++) mine[c] = 0;
+                    uint32_t mineAdd = 0;
+                    unsigned rem = leaders;
+                    while (rem) {
+                        const int gl = __ffs(rem) - 1;
+                        rem &= rem - 1;
+                        const unsigned gmask = __shfl_sync(0xffffffffu, peers, gl);
+                        const bool in = hit && ((gmask >> lane) & 1u);
+#pragma unroll
+                        for (int c = 0; c < MAXV; c++) {
+                            if (c < nAcc) {
+                                const bool adds = in && ((addMask[r] >> c) & 1u);
+                                const unsigned any = __ballot_sync(0xffffffffu, adds);
+                                if (any) {
+                                    uint64_t x = adds ? contrib[r][c] : 0;
+                                    if ((P.floatMask >> c) & 1u) {
+#pragma unroll
+                                        for (int m = 16; m >= 1; m >>= 1)
+                                            x = (uint64_t) __double_as_longlong(__longlong_as_double((long long) x) + __longlong_as_double((long long) shflXor64(x, m)));
+                                    }
+                                    else {
+#pragma unroll
+                                        for (int m = 16; m >= 1; m >>= 1) x += shflXor64(x, m);
+                                    }
+                                    if (lane == gl) { mine[c] = x; mineAdd |= 1u << c; }
+                                }
+                            }
+                        }
+                    }
+                    active = isLeader;
+                    myAdd = mineAdd;
+#pragma unroll
+                    for (int c = 0; c < MAXV; c++) contrib[r][c] = isLeader ? mine[c] : contrib[r][c];
+                }
+                if (active) {
+#pragma unroll
+                    for (int c = 0; c < MAXV; c++)
+                        if (c < nAcc && ((myAdd >> c) & 1u)) accAddShared(&st.acc[c * st.S2 + sslot], contrib[r][c], (P.floatMask >> c) & 1u);
+                    if (rowIdx < *(volatile uint32_t*) &st.first[sslot]) atomicMin(&st.first[sslot], rowIdx);
+                }
+            }
+            if (v && !hit) {
+                // HBM table path (high cardinality, or shared table full)
+                int gslot = special[r] ? (int) T.cap + special[r] - 1 : tableFind<W>(T, kw[r], h, true, false);
+                if (gslot == -2) {
+                    atomicOr(&P.bitmapOut[rowIdx >> 5], 1u << (rowIdx & 31));
+                    atomicAdd(&T.counters[CNT_DEFERRED], 1u);
+                }
+                else {
+                    const uint64_t g = P.rowBase + rowIdx;
+                    if (g < __ldcg(&T.firstRow[gslot])) atomicMin((unsigned long long*) &T.firstRow[gslot], (unsigned long long) g);
+#pragma unroll
+                    for (int c = 0; c < MAXV; c++)
+                        if (c < nAcc && ((addMask[r] >> c) & 1u))
+                            accAddGlobal(&T.acc[(size_t) gslot * T.nvPhys + P.acc[c].phys], contrib[r][c], (P.floatMask >> c) & 1u);
+                }
+            }
+        }
+        // a warp whose rows mostly miss a full shared table stops probing it (high-cardinality input)
+        if (!warpBypass && warpRows >= 256) {
+            if (*(volatile uint32_t*) st.count >= st.sLimit && warpHits * 2 < warpRows) warpBypass = true;
+            warpHits = 0; warpRows = 0;
+        }
+    }
+
+    // ---- flush the CTA's shared table into the HBM table ----
+    if (useShared) {
+        __syncthreads();
+        for (uint32_t s = tid; s < st.S2; s += kAggThreads) {
+            const uint32_t f = st.first[s];
+            if (f == kNoRow32) continue;
+            int gslot;
+            if (s >= st.S) gslot = (int) T.cap + (int) (s - st.S);
+            else {
+                uint64_t kw[W];
+#pragma unroll
+                for (int w = 0; w < W; w++) kw[w] = st.keys[w * st.S2 + s];
+                gslot = tableFind<W>(T, kw, hashKeyWords<W>(kw), true, true);
+            }
+            if (gslot < 0) { atomicOr(&T.counters[CNT_ERROR], 0x80000000u); continue; }   // cannot happen: flush reserve (see HashAggregationOp)
+            const uint64_t g = P.rowBase + f;
+            if (g < __ldcg(&T.firstRow[gslot])) atomicMin((unsigned long long*) &T.firstRow[gslot], (unsigned long long) g);
+            for (int c = 0; c < nAcc; c++) {
+                const uint64_t x = st.acc[c * st.S2 + s];
+                if (x != 0) accAddGlobal(&T.acc[(size_t) gslot * T.nvPhys + P.acc[c].phys], x, (P.floatMask >> c) & 1u);
+            }
+        }
+    }
+}
+
+// ---- table maintenance kernels --------------------------------------------------------------------------------------------
+__global__ void fillU64Kernel(uint64_t* p, uint64_t v, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) p[i] = v;
+}
+
+template <int W>
+__global__ void rehashKernel(GroupTable oldT, GroupTable newT)
+{
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < oldT.capP; s += gridDim.x * blockDim.x) {
+        int ns;
+        if (s >= oldT.cap) {
+            if (oldT.firstRow[s] == kNoRow) continue;
+            ns = (int) newT.cap + (int) (s - oldT.cap);
+        }
+        else {
+            uint64_t kw[W];
+            if (W == 1) { kw[0] = oldT.keys[s]; if (kw[0] == kEmptyKey) continue; }
+            else {
+                if (oldT.state[s] == kStEmpty) continue;
+#pragma unroll
+                for (int w = 0; w < W; w++) kw[w] = oldT.keys[(size_t) w * oldT.capP + s];
+            }
+            ns = tableFind<W>(newT, kw, hashKeyWords<W>(kw), true, true);
+        }
+        newT.firstRow[ns] = oldT.firstRow[s];
+        for (uint32_t c = 0; c < oldT.nvPhys; c++) newT.acc[(size_t) ns * newT.nvPhys + c] = oldT.acc[(size_t) s * oldT.nvPhys + c];
+        if (oldT.gid) newT.gid[ns] = oldT.gid[s];
+    }
+}
+
+// acc[slot][dst] = src >= 0 ? acc[slot][src] : 1   for every touched slot (lazy activation of a per-channel non-null count)
+__global__ void backfillCountKernel(GroupTable t, int dst, int src)
+{
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < t.capP; s += gridDim.x * blockDim.x)
+        if (t.firstRow[s] != kNoRow) t.acc[(size_t) s * t.nvPhys + dst] = src >= 0 ? t.acc[(size_t) s * t.nvPhys + src] : 1;
+}
+
+__global__ void collectSlotsKernel(GroupTable t, uint64_t* sortKeys, uint32_t* sortVals, unsigned int* count)
+{
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < t.capP; s += gridDim.x * blockDim.x) {
+        uint64_t f = t.firstRow[s];
+        if (f != kNoRow) {
+            unsigned int i = atomicAdd(count, 1u);
+            sortKeys[i] = f;
+            sortVals[i] = s;
+        }
+    }
+}
+
+// ---- output ------------------------------------------------------------------------------------------------------------
+struct KeyOut {          // one output key column
+    void* values; uint8_t* nulls; int32_t* lens;   // VARCHAR: lens[g] first, bytes in a second pass
+    int32_t type, word, shift, bits;
+};
+struct AggOut {
+    int32_t function;      // pg_aggregate_function
+    int32_t val0, val1;    // physical value columns (sum; lo/hi for bigint sum)
+    int32_t countCol;      // physical non-null-count column, or -1 = every touched group has >= 1 non-null input
+    int32_t partial;       // PARTIAL step: emit intermediate columns
+    void* out0; uint8_t* null0;   // first output column
+    void* out1;                   // second output column (avg partial: count)
+};
+struct EmitParams {
+    GroupTable t;
+    const uint32_t* order;   // slots in group-id order
+    int32_t nGroups;
+    int32_t W;
+    KeyOut keys[kMaxKeyColumns]; int32_t nKeys; int32_t bigintPath; int32_t nullWord, nullShift;
+    int64_t* hashOut;        // $hashvalue output or nullptr
+    AggOut aggs[32]; int32_t nAggs;
+};
+
+__device__ inline uint64_t fieldOf(const uint64_t* kw, int word, int shift, int bits)
+{
+    uint64_t v = kw[word] >> shift;
+    return bits >= 64 ? v : (v & ((1ULL << bits) - 1));
+}
+
+__global__ void emitKernel(const __grid_constant__ EmitParams P)
+{
+    const GroupTable& T = P.t;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < P.nGroups; g += gridDim.x * blockDim.x) {
+        const uint32_t slot = P.order[g];
+        uint64_t kw[kMaxKeyWords] = {0, 0, 0, 0};
+        bool bigintNull = false;
+        if (slot >= T.cap) { if (slot == T.cap) bigintNull = true; else kw[0] = kEmptyKey; }
+        else for (int w = 0; w < P.W; w++) kw[w] = T.keys[(size_t) w * T.capP + slot];
+        const uint32_t nullMask = P.bigintPath ? (bigintNull ? 1u : 0u) : (uint32_t) fieldOf(kw, P.nullWord, P.nullShift, 8);
+        int64_t rawHash = 0;
+        for (int k = 0; k < P.nKeys; k++) {
+            const KeyOut& ko = P.keys[k];
+            const bool isNull = (nullMask >> k) & 1u;
+            uint64_t v = isNull ? 0 : fieldOf(kw, ko.word, ko.shift, ko.bits);
+            int64_t th = 0;   // TypeUtils.hashPosition: NULL → 0
+            switch (ko.type) {
+                case PG_TYPE_BIGINT: ((int64_t*) ko.values)[g] = (int64_t) v; if (!isNull) th = hashLong((int64_t) v); break;
+                case PG_TYPE_DOUBLE: ((int64_t*) ko.values)[g] = (int64_t) v; if (!isNull) th = hashLong(canonicalDoubleBits((int64_t) v)); break;
+                case PG_TYPE_INTEGER: case PG_TYPE_DATE: ((int32_t*) ko.values)[g] = (int32_t) v; if (!isNull) th = hashLong((int64_t) (int32_t) v); break;
+                case PG_TYPE_BOOLEAN: ((uint8_t*) ko.values)[g] = (uint8_t) v; if (!isNull) th = v ? 1231 : 1237; break;
+                case PG_TYPE_VARCHAR: {
+                    int len = isNull ? 0 : (int) (v & 0xff);
+                    ko.lens[g] = len;
+                    ((uint64_t*) ko.values)[g] = v >> 8;     // packed bytes, expanded by expandVarcharKernel
+                    if (!isNull) th = xxHash64Short(v >> 8, len);
+                    break;
+                }
+            }
+            ko.nulls[g] = isNull ? 1 : 0;
+            rawHash = (int64_t) (31ULL * (uint64_t) rawHash + (uint64_t) th);
+        }
+        if (P.hashOut) P.hashOut[g] = P.bigintPath ? (bigintNull ? 0 : hashLong((int64_t) kw[0])) : rawHash;
+
+        const uint64_t* acc = T.acc + (size_t) slot * T.nvPhys;
+        for (int a = 0; a < P.nAggs; a++) {
+            const AggOut& ao = P.aggs[a];
+            const int64_t count = ao.countCol >= 0 ? (int64_t) acc[ao.countCol] : 1;
+            switch (ao.function) {
+                case PG_AGG_COUNT_STAR: case PG_AGG_COUNT_COLUMN:
+                    ((int64_t*) ao.out0)[g] = (int64_t) acc[ao.val0]; ao.null0[g] = 0; break;
+                case PG_AGG_SUM_DOUBLE:
+                    ((uint64_t*) ao.out0)[g] = count > 0 ? acc[ao.val0] : 0; ao.null0[g] = count > 0 ? 0 : 1; break;
+                case PG_AGG_SUM_BIGINT: {
+                    __int128 total = ((__int128) (int64_t) acc[ao.val1] << 32) + (__int128) acc[ao.val0];
+                    if (total > (__int128) INT64_MAX || total < (__int128) INT64_MIN) { atomicOr(&T.counters[CNT_ERROR], (unsigned int) ERR_BIGINT_OVERFLOW); total = 0; }
+                    ((int64_t*) ao.out0)[g] = count > 0 ? (int64_t) total : 0; ao.null0[g] = count > 0 ? 0 : 1; break;
+                }
+                case PG_AGG_AVG_DOUBLE: case PG_AGG_AVG_BIGINT:
+                    if (ao.partial) { ((uint64_t*) ao.out0)[g] = acc[ao.val0]; ao.null0[g] = 0; ((int64_t*) ao.out1)[g] = count; }
+                    else if (count == 0) { ((uint64_t*) ao.out0)[g] = 0; ao.null0[g] = 1; }
+                    else { ((double*) ao.out0)[g] = __longlong_as_double((long long) acc[ao.val0]) / (double) count; ao.null0[g] = 0; }
+                    break;
+            }
+        }
+    }
+}
+
+__global__ void expandVarcharKernel(const uint64_t* packed, const int32_t* offsets, int32_t n, uint8_t* bytes)
+{
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
+        int32_t o = offsets[g], len = offsets[g + 1] - o;
+        uint64_t v = packed[g];
+        for (int i = 0; i < len; i++) bytes[o + i] = (uint8_t) (v >> (8 * i));
+    }
+}
+
+// ======================================================================================================================
+// Host side
+// ======================================================================================================================
+struct PhysCol { int kind; int channel; int mask; bool lazy; bool active; };
+
+struct AggPlan {
+    pg_aggregate spec;
+    int val0 = -1, val1 = -1;
+    int countCol = -1;        // physical column with the non-null count of (channel, mask); -1 never needed
+    bool countExact = false;  // count value is an output (avg / count) rather than a null flag (sum)
+};
+
+class GroupTableStorage {
+public:
+    DeviceBuffer keys, state, firstRow, acc, gid, counters;
+    uint32_t cap = 0; int W = 1; uint32_t nvPhys = 0; bool withGid = false;
+    uint32_t flushReserve = 0;
+    Operator* op = nullptr;
+
+    GroupTable view() const
+    {
+        GroupTable t{};
+        t.keys = keys.as<uint64_t>(); t.state = W > 1 ? state.as<uint32_t>() : nullptr; t.firstRow = firstRow.as<uint64_t>();
+        t.acc = acc.as<uint64_t>(); t.gid = withGid ? gid.as<int32_t>() : nullptr;
+        t.cap = cap; t.mask = cap - 1; t.capP = cap + 2; t.nvPhys = nvPhys;
+        uint32_t lim = cap / 4 * 3;
+        t.rowClaimLimit = lim;
+        t.counters = counters.as<unsigned int>();
+        return t;
+    }
+    void allocate(uint32_t capacity)
+    {
+        cap = capacity;
+        size_t capP = (size_t) cap + 2;
+        for (DeviceBuffer* b : {&keys, &state, &firstRow, &acc, &gid}) b->accounting = &op->stats.device_bytes;
+        keys.reserve(capP * 8 * W);
+        if (W > 1) state.reserve(capP * 4);
+        firstRow.reserve(capP * 8);
+        acc.reserve(std::max<size_t>(capP * 8 * nvPhys, 8));
+        if (withGid) gid.reserve(capP * 4);
+        cudaStream_t s = op->stream;
+        if (W == 1) { fillU64Kernel<<<1024, 256, 0, s>>>(keys.as<uint64_t>(), kEmptyKey, capP); op->stats.kernel_launches++; }
+        else { PG_CUDA(cudaMemsetAsync(keys.ptr, 0, capP * 8 * W, s)); PG_CUDA(cudaMemsetAsync(state.ptr, 0, capP * 4, s)); }
+        PG_CUDA(cudaMemsetAsync(firstRow.ptr, 0xFF, capP * 8, s));
+        if (nvPhys) PG_CUDA(cudaMemsetAsync(acc.ptr, 0, capP * 8 * nvPhys, s));
+        if (withGid) PG_CUDA(cudaMemsetAsync(gid.ptr, 0xFF, capP * 4, s));
+        PG_CUDA(cudaGetLastError());
+    }
+};
+
+static uint32_t nextPow2(uint64_t v) { uint64_t p = 1; while (p < v) p <<= 1; return (uint32_t) std::min<uint64_t>(p, 1ULL << 31); }
+
+
+// ---- result materialisation shared by HashAggregationOperator and GroupByHash ---------------------------------------------
+struct AggEmit { int function, val0, val1, countCol; bool partial; };
+
+// Slots that were touched, ordered by first-touch row = ascending group id.  Returns the group count.
+static int64_t sortSlotsByFirstRow(Operator* op, const GroupTable& T, DeviceBuffer& order)
+{
+    const size_t capP = T.capP;
+    DeviceBuffer sortKeys, sortVals, sortKeysOut, count, temp;
+    sortKeys.reserve(capP * 8); sortVals.reserve(capP * 4); count.reserve(16);
+    PG_CUDA(cudaMemsetAsync(count.ptr, 0, 16, op->stream));
+    PG_LAUNCH(op, collectSlotsKernel, 1024, 256, 0, T, sortKeys.as<uint64_t>(), sortVals.as<uint32_t>(), count.as<unsigned int>());
+    unsigned int g = 0;
+    PG_CUDA(cudaMemcpyAsync(&g, count.ptr, 4, cudaMemcpyDeviceToHost, op->stream));
+    PG_CUDA(cudaStreamSynchronize(op->stream));
+    if (g == 0) return 0;
+    sortKeysOut.reserve((size_t) g * 8); order.reserve((size_t) g * 4);
+    size_t tempBytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, sortKeys.as<uint64_t>(), sortKeysOut.as<uint64_t>(), sortVals.as<uint32_t>(), order.as<uint32_t>(), (int) g, 0, 64, op->stream);
+    temp.reserve(tempBytes);
+    cub::DeviceRadixSort::SortPairs(temp.ptr, tempBytes, sortKeys.as<uint64_t>(), sortKeysOut.as<uint64_t>(), sortVals.as<uint32_t>(), order.as<uint32_t>(), (int) g, 0, 64, op->stream);
+    op->stats.kernel_launches += 4;
+    PG_CUDA(cudaStreamSynchronize(op->stream));
+    return g;
+}
+
+struct ResultBuilder {
+    std::vector<DeviceBuffer> outBufs;
+    std::vector<PinnedBuffer> outHost;
+    std::vector<pg_block> outBlocks, outSlice;
+    std::vector<int> outTypes;
+
+    // Output schema: group keys [, $hashvalue], aggregates (HashAggregationOperator.java:357 toTypes), `g` rows in `order`.
+    void build(Operator* op, const GroupTable& T, const KeyLayout& layout, const uint32_t* order, int64_t g, bool withHash, const std::vector<AggEmit>& aggs)
+    {
+        cudaStream_t stream = op->stream;
+        EmitParams E{};
+        E.t = T; E.order = order; E.nGroups = (int) g; E.W = layout.W;
+        E.nKeys = layout.nKeys; E.bigintPath = layout.bigintPath; E.nullWord = layout.nullWord < 0 ? 0 : layout.nullWord; E.nullShift = layout.nullShift;
+        outTypes.clear(); outBufs.clear(); outBufs.reserve(64);
+        struct ColBufs { int values, nulls; };
+        std::vector<ColBufs> colBufs;
+        auto newBuf = [&](size_t bytes) { outBufs.emplace_back(); outBufs.back().accounting = &op->stats.device_bytes; outBufs.back().reserve(std::max<size_t>(bytes, 16)); return (int) outBufs.size() - 1; };
+        auto newColumn = [&](int type) {
+            ColBufs cb{-1, -1};
+            int w = typeWidth(type);
+            cb.values = newBuf((size_t) g * (w ? w : 8));
+            cb.nulls = newBuf(g);
+            outTypes.push_back(type); colBufs.push_back(cb);
+            return (int) colBufs.size() - 1;
+        };
+        std::vector<int> varcharLens(layout.nKeys, -1);
+        for (int k = 0; k < layout.nKeys; k++) {
+            int c = newColumn(layout.types[k]);
+            KeyOut& ko = E.keys[k];
+            ko.values = outBufs[colBufs[c].values].ptr; ko.nulls = outBufs[colBufs[c].nulls].as<uint8_t>(); ko.lens = nullptr;
+            ko.type = layout.types[k]; ko.word = layout.word[k]; ko.shift = layout.shift[k]; ko.bits = layout.bits[k];
+            if (layout.types[k] == PG_TYPE_VARCHAR) {
+                varcharLens[k] = newBuf((size_t) (g + 1) * 4);
+                PG_CUDA(cudaMemsetAsync(outBufs[varcharLens[k]].ptr, 0, (size_t) (g + 1) * 4, stream));
+                ko.lens = outBufs[varcharLens[k]].as<int32_t>();
+            }
+        }
+        if (withHash) { int c = newColumn(PG_TYPE_BIGINT); E.hashOut = outBufs[colBufs[c].values].as<int64_t>(); PG_CUDA(cudaMemsetAsync(outBufs[colBufs[c].nulls].ptr, 0, g, stream)); }
+        PG_CHECK_ARG(aggs.size() <= 32, "at most 32 aggregates");
+        E.nAggs = (int) aggs.size();
+        for (size_t i = 0; i < aggs.size(); i++) {
+            const AggEmit& a = aggs[i];
+            AggOut& ao = E.aggs[i];
+            ao.function = a.function; ao.val0 = a.val0; ao.val1 = a.val1; ao.partial = a.partial ? 1 : 0; ao.countCol = a.countCol;
+            int type = (a.function == PG_AGG_SUM_DOUBLE || a.function == PG_AGG_AVG_DOUBLE || a.function == PG_AGG_AVG_BIGINT) ? PG_TYPE_DOUBLE : PG_TYPE_BIGINT;
+            int c = newColumn(type);
+            ao.out0 = outBufs[colBufs[c].values].ptr; ao.null0 = outBufs[colBufs[c].nulls].as<uint8_t>(); ao.out1 = nullptr;
+            if (a.partial && (a.function == PG_AGG_AVG_DOUBLE || a.function == PG_AGG_AVG_BIGINT)) {
+                int c2 = newColumn(PG_TYPE_BIGINT);
+                ao.out1 = outBufs[colBufs[c2].values].ptr;
+                PG_CUDA(cudaMemsetAsync(outBufs[colBufs[c2].nulls].ptr, 0, g, stream));
+            }
+        }
+        PG_LAUNCH(op, emitKernel, (int) std::min<int64_t>(divUp(g, 256), 2048), 256, 0, E);
+        // VARCHAR keys: lens → offsets (exclusive scan) → bytes
+        std::vector<int> varcharBytes(layout.nKeys, -1), varcharOffsets(layout.nKeys, -1);
+        for (int k = 0; k < layout.nKeys; k++) {
+            if (layout.types[k] != PG_TYPE_VARCHAR) continue;
+            int offs = newBuf((size_t) (g + 1) * 4);
+            size_t tb = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tb, outBufs[varcharLens[k]].as<int32_t>(), outBufs[offs].as<int32_t>(), (int) g + 1, stream);
+            DeviceBuffer t2; t2.reserve(tb);
+            cub::DeviceScan::ExclusiveSum(t2.ptr, tb, outBufs[varcharLens[k]].as<int32_t>(), outBufs[offs].as<int32_t>(), (int) g + 1, stream);
+            op->stats.kernel_launches += 2;
+            int bytes = newBuf((size_t) g * 8);
+            PG_LAUNCH(op, expandVarcharKernel, (int) std::min<int64_t>(divUp(g, 256), 2048), 256, 0, (const uint64_t*) outBufs[colBufs[k].values].ptr, outBufs[offs].as<int32_t>(), (int32_t) g, outBufs[bytes].as<uint8_t>());
+            PG_CUDA(cudaStreamSynchronize(stream));
+            varcharBytes[k] = bytes; varcharOffsets[k] = offs;
+        }
+        unsigned int cnt[CNT_COUNT];
+        PG_CUDA(cudaMemcpyAsync(cnt, T.counters, sizeof(cnt), cudaMemcpyDeviceToHost, stream));
+        PG_CUDA(cudaStreamSynchronize(stream));
+        if (cnt[CNT_ERROR] & ERR_BIGINT_OVERFLOW) throw Error(PG_ERR_NUMERIC_OVERFLOW, "bigint addition overflow");
+
+        // describe the full result; slice() hands out row ranges of it
+        outBlocks.assign(colBufs.size(), pg_block{});
+        const bool toHost = op->options.output_memory == PG_MEM_HOST;
+        outHost.clear();
+        outHost.reserve(colBufs.size() * 3 + 4);
+        auto place = [&](const void* dptr, size_t bytes) -> const void* {
+            if (!toHost) return dptr;
+            outHost.emplace_back();
+            outHost.back().reserve(std::max<size_t>(bytes, 16));
+            if (bytes) PG_CUDA(cudaMemcpyAsync(outHost.back().ptr, dptr, bytes, cudaMemcpyDeviceToHost, stream));
+            op->stats.d2h_bytes += (int64_t) bytes;
+            return outHost.back().ptr;
+        };
+        std::vector<int32_t> totalBytes(layout.nKeys, 0);
+        for (int k = 0; k < layout.nKeys; k++)
+            if (varcharOffsets[k] >= 0) PG_CUDA(cudaMemcpyAsync(&totalBytes[k], outBufs[varcharOffsets[k]].as<int32_t>() + g, 4, cudaMemcpyDeviceToHost, stream));
+        PG_CUDA(cudaStreamSynchronize(stream));
+        for (size_t c = 0; c < colBufs.size(); c++) {
+            pg_block& b = outBlocks[c];
+            b.type = outTypes[c]; b.encoding = PG_ENC_FLAT; b.position_count = g; b.dictionary_size = 0; b.ids = nullptr; b.offsets = nullptr;
+            if (outTypes[c] == PG_TYPE_VARCHAR) {
+                int k = (int) c;   // key columns come first
+                b.values = place(outBufs[varcharBytes[k]].ptr, (size_t) totalBytes[k]);
+                b.offsets = (const int32_t*) place(outBufs[varcharOffsets[k]].ptr, (size_t) (g + 1) * 4);
+            }
+            else b.values = place(outBufs[colBufs[c].values].ptr, (size_t) g * typeWidth(outTypes[c]));
+            b.is_null = (const uint8_t*) place(outBufs[colBufs[c].nulls].ptr, g);
+        }
+        PG_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    void slice(int64_t begin, int64_t m, int memory, pg_page* out)
+    {
+        outSlice = outBlocks;
+        for (auto& b : outSlice) {
+            b.position_count = m;
+            if (b.type == PG_TYPE_VARCHAR) b.offsets += begin;   // offsets stay absolute into the shared byte slice
+            else b.values = (const char*) b.values + begin * typeWidth(b.type);
+            b.is_null += begin;
+        }
+        out->position_count = m; out->channel_count = (int32_t) outSlice.size(); out->memory = memory; out->blocks = outSlice.data();
+    }
+};
+
+class HashAggregationOp : public Operator {
+    KeyLayout layout;
+    int hashChannel, step;
+    std::vector<AggPlan> aggs;
+    std::vector<PhysCol> phys;
+    int rowCountCol = -1;
+    GroupTableStorage table;
+    PageStager stager;
+    std::vector<int> stagedChannels;          // input channels the kernels read
+    PinnedBuffer hostCounters;
+    DeviceBuffer bitmapA, bitmapB;
+    uint64_t rowsSeen = 0;
+    int64_t knownGroups = 0;
+    bool finishing = false, finished = false, outputBuilt = false;
+    int gridCTAs = 0; uint32_t sharedSlots = 1024, sharedLimit = 768;
+    int MAXV = 4;
+    // output
+    ResultBuilder result;
+    int64_t outGroups = 0, outNext = 0;
+
+    int physColumn(int kind, int channel, int mask, bool lazy)
+    {
+        for (size_t i = 0; i < phys.size(); i++)
+            if (phys[i].kind == kind && phys[i].channel == channel && phys[i].mask == mask) return (int) i;
+        phys.push_back({kind, channel, mask, lazy, !lazy});
+        return (int) phys.size() - 1;
+    }
+
+public:
+    explicit HashAggregationOp(const pg_hash_aggregation_config* c) : Operator(c->options), stager(this)
+    {
+        PG_CHECK_ARG(c->expected_groups > 0, "expectedSize must be greater than zero");
+        PG_CHECK_ARG(c->n_aggregates >= 0 && c->n_aggregates <= 32, "at most 32 aggregates");
+        layout.plan(c->n_group_channels, c->group_channels, c->group_types, c->group_max_lengths);
+        hashChannel = c->hash_channel;
+        step = c->step;
+        PG_CHECK_ARG(step == PG_STEP_SINGLE || step == PG_STEP_PARTIAL || step == PG_STEP_FINAL, "bad aggregation step");
+        const bool final = step == PG_STEP_FINAL;
+        for (int i = 0; i < c->n_aggregates; i++) {
+            AggPlan a; a.spec = c->aggregates[i];
+            const int ch = a.spec.input_channel, mk = a.spec.mask_channel;
+            PG_CHECK_ARG(!(final && mk >= 0), "FINAL step takes no mask");
+            switch (a.spec.function) {
+                case PG_AGG_COUNT_STAR:
+                    if (final) a.val0 = physColumn(K_I64_ADD, ch, -1, false);
+                    else a.val0 = physColumn(K_COUNT, -1, mk, false);
+                    break;
+                case PG_AGG_COUNT_COLUMN:
+                    if (final) a.val0 = physColumn(K_I64_ADD, ch, -1, false);
+                    else { PG_CHECK_ARG(ch >= 0, "count(column) needs an input channel"); a.val0 = physColumn(K_COUNT, ch, mk, false); }
+                    break;
+                case PG_AGG_SUM_DOUBLE:
+                    a.val0 = physColumn(K_F64, ch, mk, false);
+                    a.countCol = physColumn(K_COUNT, ch, mk, mk < 0);   // lazily activated: only once a page carries NULLs in `ch`
+                    break;
+                case PG_AGG_SUM_BIGINT:
+                    a.val0 = physColumn(K_LO32, ch, mk, false); a.val1 = physColumn(K_HI32, ch, mk, false);
+                    a.countCol = physColumn(K_COUNT, ch, mk, mk < 0);
+                    break;
+                case PG_AGG_AVG_DOUBLE: case PG_AGG_AVG_BIGINT:
+                    a.countExact = true;
+                    if (final) { a.val0 = physColumn(K_F64, ch, -1, false); a.countCol = physColumn(K_I64_ADD, ch + 1, -1, false); }
+                    else {
+                        a.val0 = physColumn(a.spec.function == PG_AGG_AVG_DOUBLE ? K_F64 : K_F64_FROM_I64, ch, mk, false);
+                        a.countCol = physColumn(K_COUNT, ch, mk, mk < 0);
+                    }
+                    break;
+                default: throw Error(PG_ERR_UNSUPPORTED, "aggregate function is not on the GPU path (supported: count, sum, avg over BIGINT/DOUBLE)");
+            }
+            if (a.spec.function != PG_AGG_COUNT_STAR) PG_CHECK_ARG(ch >= 0, "aggregate needs an input channel");
+            aggs.push_back(a);
+        }
+        // exact counts of lazily counted channels fall back on the shared row count until the channel shows a NULL
+        bool needRowCount = false;
+        for (auto& a : aggs) if (a.countExact && a.countCol >= 0 && phys[a.countCol].lazy) needRowCount = true;
+        if (needRowCount) rowCountCol = physColumn(K_COUNT, -1, -1, false);
+        PG_CHECK_ARG(phys.size() <= 16, "too many distinct accumulator columns (max 16)");
+        MAXV = phys.size() <= 4 ? 4 : (phys.size() <= 8 ? 8 : 16);
+
+        // channels to stage: keys, hash channel is not needed (slot function is recomputed from the key), agg inputs, masks
+        auto need = [&](int ch) { if (ch >= 0 && std::find(stagedChannels.begin(), stagedChannels.end(), ch) == stagedChannels.end()) stagedChannels.push_back(ch); };
+        for (int k = 0; k < layout.nKeys; k++) need(layout.channels[k]);
+        for (auto& p : phys) { need(p.channel); need(p.mask); }
+
+        // launch geometry: persistent CTAs, grid = SMs x resident CTAs
+        table.op = this; table.W = layout.W; table.nvPhys = (uint32_t) phys.size();
+        configureGeometry();
+        uint32_t minCap = nextPow2((uint64_t) 8 * gridCTAs * sharedLimit);
+        uint32_t cap = std::max(minCap, nextPow2((uint64_t) c->expected_groups * 2));
+        if (cap > (1u << 30)) throw Error(PG_ERR_INSUFFICIENT_RESOURCES, "Size of hash table cannot exceed 1 billion entries");
+        table.counters.accounting = &stats.device_bytes;
+        table.counters.reserve(CNT_COUNT * sizeof(unsigned int));
+        PG_CUDA(cudaMemsetAsync(table.counters.ptr, 0, CNT_COUNT * sizeof(unsigned int), stream));
+        table.allocate(cap);
+        hostCounters.reserve(CNT_COUNT * sizeof(unsigned int));
+        bitmapA.accounting = bitmapB.accounting = &stats.device_bytes;
+        PG_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    template <int W, int MV> void configureFor()
+    {
+        size_t smem = sharedBytes(sharedSlots);
+        auto kern = hashAggKernel<W, MV>;
+        PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        int perSM = 0;
+        PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kAggThreads, smem));
+        if (perSM < 1) perSM = 1;
+        if (perSM > 4) perSM = 4;
+        gridCTAs = numSMs * perSM;
+    }
+    size_t sharedBytes(uint32_t S) const
+    {
+        size_t S2 = (size_t) S + 2;
+        return 8 * layout.W * S2 + 8 * phys.size() * S2 + 4 * S2 + (layout.W > 1 ? 4 * S2 : 0) + 16;
+    }
+    void configureGeometry()
+    {
+        sharedSlots = 1024;
+        while (sharedBytes(sharedSlots) > 96 * 1024 && sharedSlots > 128) sharedSlots >>= 1;
+        sharedLimit = sharedSlots / 4 * 3;
+        dispatch([&](auto w, auto mv) { configureFor<decltype(w)::value, decltype(mv)::value>(); });
+    }
+    template <typename F> void dispatch(F&& f)
+    {
+        auto withW = [&](auto w) {
+            if (MAXV == 4) f(w, std::integral_constant<int, 4>());
+            else if (MAXV == 8) f(w, std::integral_constant<int, 8>());
+            else f(w, std::integral_constant<int, 16>());
+        };
+        switch (layout.W) {
+            case 1: withW(std::integral_constant<int, 1>()); break;
+            case 2: withW(std::integral_constant<int, 2>()); break;
+            case 3: withW(std::integral_constant<int, 3>()); break;
+            default: withW(std::integral_constant<int, 4>()); break;
+        }
+    }
+
+    bool needsInput() override { return !finishing && !outputBuilt; }
+
+    void readCounters(unsigned int* out)
+    {
+        PG_CUDA(cudaMemcpyAsync(hostCounters.ptr, table.counters.ptr, CNT_COUNT * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+        PG_CUDA(cudaStreamSynchronize(stream));
+        memcpy(out, hostCounters.ptr, CNT_COUNT * sizeof(unsigned int));
+        stats.d2h_bytes += CNT_COUNT * sizeof(unsigned int);
+    }
+    void checkErrors(const unsigned int* cnt)
+    {
+        if (cnt[CNT_ERROR] & ERR_VARCHAR_TOO_LONG) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR group-by key longer than its declared max length (GPU path packs keys of <= 7 bytes)");
+        if (cnt[CNT_ERROR] & 0x80000000u) throw Error(PG_ERR_INVALID_STATE, "internal: shared-table flush could not claim a slot");
+    }
+
+    void grow(uint64_t wantGroups)
+    {
+        uint64_t want = std::max<uint64_t>((uint64_t) table.cap * 2, wantGroups * 4);
+        if (want > (1ULL << 30)) throw Error(PG_ERR_INSUFFICIENT_RESOURCES, "Size of hash table cannot exceed 1 billion entries");
+        GroupTableStorage nt;
+        nt.op = this; nt.W = table.W; nt.nvPhys = table.nvPhys; nt.withGid = false;
+        nt.counters = std::move(table.counters);
+        unsigned int zero = 0;
+        PG_CUDA(cudaMemcpyAsync(nt.counters.as<unsigned int>() + CNT_GROUPS, &zero, sizeof(zero), cudaMemcpyHostToDevice, stream));
+        nt.allocate(nextPow2(want));
+        GroupTable oldV = table.view(); oldV.counters = nt.counters.as<unsigned int>();
+        GroupTable newV = nt.view();
+        switch (table.W) {
+            case 1: PG_LAUNCH(this, rehashKernel<1>, 1024, 256, 0, oldV, newV); break;
+            case 2: PG_LAUNCH(this, rehashKernel<2>, 1024, 256, 0, oldV, newV); break;
+            case 3: PG_LAUNCH(this, rehashKernel<3>, 1024, 256, 0, oldV, newV); break;
+            default: PG_LAUNCH(this, rehashKernel<4>, 1024, 256, 0, oldV, newV); break;
+        }
+        PG_CUDA(cudaStreamSynchronize(stream));
+        table.keys = std::move(nt.keys); table.state = std::move(nt.state); table.firstRow = std::move(nt.firstRow);
+        table.acc = std::move(nt.acc); table.counters = std::move(nt.counters); table.cap = nt.cap;
+    }
+
+    template <int W, int MV>
+    void launchRange(const std::vector<DeviceColumn>& cols, int64_t begin, int64_t n, const uint32_t* bitmapIn, uint32_t* bitmapOut)
+    {
+        AggLaunch<MV> L{};
+        L.t = table.view();
+        auto colOf = [&](int ch) -> const DeviceColumn& {
+            size_t i = std::find(stagedChannels.begin(), stagedChannels.end(), ch) - stagedChannels.begin();
+            return cols[i];
+        };
+        std::vector<DeviceColumn> keyCols;
+        for (int k = 0; k < layout.nKeys; k++) {
+            DeviceColumn kc = colOf(layout.channels[k]);
+            PG_CHECK_ARG(kc.type == layout.types[k], "group-by channel type differs from the operator's configuration");
+            int w = typeWidth(kc.type);
+            if (w) kc.values = (const char*) kc.values + begin * w; else kc.offsets = kc.offsets + begin;
+            if (kc.nulls) kc.nulls += begin;
+            keyCols.push_back(kc);
+        }
+        layout.fill(L.kp, keyCols, table.counters.as<unsigned int>() + CNT_ERROR);
+        int na = 0;
+        for (size_t p = 0; p < phys.size(); p++) {
+            if (!phys[p].active) continue;
+            AccInput& a = L.acc[na];
+            a.kind = phys[p].kind; a.phys = (int) p; a.values = nullptr; a.nulls = nullptr; a.mask = nullptr; a.maskNulls = nullptr;
+            if (phys[p].channel >= 0) {
+                const DeviceColumn& vc = colOf(phys[p].channel);
+                if (phys[p].kind != K_COUNT) {
+                    PG_CHECK_ARG(typeWidth(vc.type) == 8, "sum / avg inputs must be BIGINT or DOUBLE columns");
+                    a.values = (const uint64_t*) vc.values + begin;
+                }
+                a.nulls = vc.nulls ? vc.nulls + begin : nullptr;
+            }
+            if (phys[p].mask >= 0) {
+                const DeviceColumn& mc = colOf(phys[p].mask);
+                PG_CHECK_ARG(mc.type == PG_TYPE_BOOLEAN, "mask channel must be BOOLEAN");
+                a.mask = (const uint8_t*) mc.values + begin; a.maskNulls = mc.nulls ? mc.nulls + begin : nullptr;
+            }
+            if (kindIsFloat(a.kind)) L.floatMask |= 1u << na;
+            na++;
+        }
+        L.nAcc = na;
+        L.n = n; L.rowBase = rowsSeen + (uint64_t) begin;
+        L.bitmapIn = bitmapIn; L.bitmapOut = bitmapOut;
+        L.S = bitmapIn ? 0 : sharedSlots; L.sLimit = sharedLimit;
+        size_t smem = L.S ? sharedBytes(sharedSlots) : 64;
+        int64_t tiles = divUp(n, kAggThreads * RowsPerThread<MV>::value);
+        int grid = (int) std::min<int64_t>(gridCTAs, std::max<int64_t>(tiles, 1));
+        auto kern = hashAggKernel<W, MV>;
+        kern<<<grid, kAggThreads, smem, stream>>>(L);
+        stats.kernel_launches++;
+        PG_CUDA(cudaGetLastError());
+    }
+
+    void activateLazyCounts(const std::vector<DeviceColumn>& cols)
+    {
+        for (size_t p = 0; p < phys.size(); p++) {
+            if (!phys[p].lazy || phys[p].active) continue;
+            size_t i = std::find(stagedChannels.begin(), stagedChannels.end(), phys[p].channel) - stagedChannels.begin();
+            if (cols[i].nulls == nullptr) continue;
+            // first page with NULLs in this channel: every group seen so far has had only non-null inputs
+            PG_LAUNCH(this, backfillCountKernel, 1024, 256, 0, table.view(), (int) p, rowCountCol);
+            phys[p].active = true;
+        }
+    }
+
+    void addInput(const pg_page* page) override
+    {
+        PG_CHECK_STATE(needsInput(), "Operator is already finishing");   // HashAggregationOperator.java:415
+        const int64_t n = page->position_count;
+        stats.input_positions += n;
+        if (n == 0) return;
+        // host pages are staged in sub-chunks so the PCIe copy of chunk k+1 overlaps the kernel of chunk k
+        const int64_t chunk = page->memory == PG_MEM_HOST ? (int64_t(1) << 23) : (int64_t(1) << 30);
+        for (int64_t begin = 0; begin < n; begin += chunk) {
+            const int64_t m = std::min(chunk, n - begin);
+            pg_page sub = *page;
+            std::vector<pg_block> blocks(page->blocks, page->blocks + page->channel_count);
+            sub.blocks = blocks.data(); sub.position_count = m;
+            for (auto& b : blocks) {
+                if (b.encoding == PG_ENC_FLAT) {
+                    int w = typeWidth(b.type);
+                    if (w) b.values = (const char*) b.values + begin * w; else b.offsets = b.offsets + begin;
+                    if (b.is_null) b.is_null += begin;
+                }
+                else if (b.encoding == PG_ENC_DICTIONARY) b.ids += begin;
+                b.position_count = m;
+            }
+            std::vector<DeviceColumn> cols;
+            int slot = stager.stage(&sub, stagedChannels, cols);   // PCIe copy of this chunk overlaps the previous chunk's kernel
+            settle();                                              // previous chunk: counters, deferred rows, growth
+            activateLazyCounts(cols);
+            processChunk(cols, m);
+            stager.markCompute(slot);
+            rowsSeen += (uint64_t) m;
+        }
+        // the borrowed (device) page must not be referenced after return, and deferred rows need its columns: settle now
+        settle();
+    }
+
+    std::vector<DeviceColumn> lastCols; int64_t lastN = 0; uint64_t lastBase = 0; bool lastPending = false;
+
+    void processChunk(const std::vector<DeviceColumn>& cols, int64_t n)
+    {
+        size_t bmBytes = (size_t) divUp(n, 32) * 4;
+        bitmapA.reserve(bmBytes);
+        PG_CUDA(cudaMemsetAsync(bitmapA.ptr, 0, bmBytes, stream));
+        dispatch([&](auto w, auto mv) { launchRange<decltype(w)::value, decltype(mv)::value>(cols, 0, n, nullptr, bitmapA.as<uint32_t>()); });
+        lastCols = cols; lastN = n; lastBase = rowsSeen; lastPending = true;
+    }
+
+    // Wait for the in-flight chunk, re-run rows that found the table at its claim limit after growing it.
+    void settle()
+    {
+        if (!lastPending) return;
+        unsigned int cnt[CNT_COUNT];
+        readCounters(cnt);
+        checkErrors(cnt);
+        uint32_t* in = bitmapA.as<uint32_t>();
+        uint64_t savedRows = rowsSeen;
+        rowsSeen = lastBase;
+        int rounds = 0;
+        while (cnt[CNT_DEFERRED] > 0) {
+            PG_CHECK_STATE(++rounds < 40, "internal: deferred rows did not converge");
+            grow((uint64_t) cnt[CNT_GROUPS] + cnt[CNT_DEFERRED]);
+            size_t bmBytes = (size_t) divUp(lastN, 32) * 4;
+            DeviceBuffer& outB = (in == bitmapA.as<uint32_t>()) ? bitmapB : bitmapA;
+            outB.reserve(bmBytes);
+            PG_CUDA(cudaMemsetAsync(outB.ptr, 0, bmBytes, stream));
+            unsigned int zero = 0;
+            PG_CUDA(cudaMemcpyAsync(table.counters.as<unsigned int>() + CNT_DEFERRED, &zero, sizeof(zero), cudaMemcpyHostToDevice, stream));
+            dispatch([&](auto w, auto mv) { launchRange<decltype(w)::value, decltype(mv)::value>(lastCols, 0, lastN, in, outB.as<uint32_t>()); });
+            in = outB.as<uint32_t>();
+            readCounters(cnt);
+            checkErrors(cnt);
+        }
+        rowsSeen = savedRows;
+        knownGroups = cnt[CNT_GROUPS];
+        if ((uint64_t) knownGroups * 2 > table.cap) grow((uint64_t) knownGroups);
+        lastPending = false;
+    }
+
+    void finish() override { finishing = true; }
+    bool isFinished() override { return finished; }
+    void syncStats() override { if (lastPending) settle(); stats.group_count = knownGroups; }
+
+    // ---- output (buildResult) -------------------------------------------------------------------------------------------
+    void buildOutput()
+    {
+        settle();
+        outputBuilt = true;
+        GroupTable T = table.view();
+        DeviceBuffer order;
+        int64_t g = sortSlotsByFirstRow(this, T, order);
+        outGroups = g; outNext = 0;
+        stats.group_count = g;
+        if (g == 0) return;
+        std::vector<AggEmit> emits;
+        for (auto& a : aggs) {
+            AggEmit e; e.function = a.spec.function; e.val0 = a.val0; e.val1 = a.val1; e.partial = step == PG_STEP_PARTIAL; e.countCol = -1;
+            if (a.countCol >= 0) e.countCol = phys[a.countCol].active ? a.countCol : (a.countExact ? rowCountCol : -1);
+            emits.push_back(e);
+        }
+        result.build(this, T, layout, order.as<uint32_t>(), g, hashChannel >= 0, emits);
+    }
+
+    bool getOutput(pg_page* out) override   // HashAggregationOperator.java:451-501
+    {
+        if (finished || !finishing) return false;
+        if (!outputBuilt) buildOutput();
+        if (outNext >= outGroups) { finished = true; return false; }
+        const int64_t m = std::min<int64_t>(maxOutputRows(), outGroups - outNext);
+        result.slice(outNext, m, options.output_memory, out);
+        outNext += m;
+        stats.output_positions += m;
+        if (outNext >= outGroups) finished = true;
+        return true;
+    }
+};
+
+
+// ======================================================================================================================
+// GroupByHash (standalone) — MB/operator/GroupByHash.java:61-89.  Exact incremental group ids per page:
+//   insert kernel (find-or-claim, atomicMin of the first-touch row of every not-yet-numbered slot, claimers append the slot to
+//   a "new" list) → sort the new slots by first-touch row → gid = nextGroupId + rank → lookup kernel writes the ids.
+// ======================================================================================================================
+template <int W>
+__global__ void gbhInsertKernel(GroupTable T, KeyPlan kp, int64_t n, uint64_t rowBase, uint32_t* newSlots)
+{
+    for (int64_t row = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; row < n; row += (int64_t) gridDim.x * blockDim.x) {
+        uint64_t kw[W];
+        int special = packKey<W>(kp, row, kw);
+        int slot;
+        if (special) slot = (int) T.cap + special - 1;
+        else {
+            bool isNew = false;
+            slot = tableFind<W>(T, kw, hashKeyWords<W>(kw), true, true, &isNew);
+            if (isNew) newSlots[atomicAdd(&T.counters[CNT_NEW], 1u)] = (uint32_t) slot;
+        }
+        if (T.gid[slot] < 0) {
+            const uint64_t g = rowBase + (uint64_t) row;
+            if (g < __ldcg(&T.firstRow[slot])) atomicMin((unsigned long long*) &T.firstRow[slot], (unsigned long long) g);
+        }
+    }
+}
+__global__ void gbhSpecialsKernel(GroupTable T, uint32_t* newSlots)
+{
+    if (threadIdx.x < 2) {
+        uint32_t slot = T.cap + threadIdx.x;
+        if (T.gid[slot] < 0 && T.firstRow[slot] != kNoRow) newSlots[atomicAdd(&T.counters[CNT_NEW], 1u)] = slot;
+    }
+}
+__global__ void gbhGatherFirstRowsKernel(GroupTable T, const uint32_t* newSlots, uint32_t nNew, uint64_t* keysOut)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nNew; i += gridDim.x * blockDim.x) keysOut[i] = T.firstRow[newSlots[i]];
+}
+__global__ void gbhAssignKernel(GroupTable T, const uint32_t* sortedSlots, uint32_t nNew, int32_t nextGroupId, uint32_t* slotOfGid)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nNew; i += gridDim.x * blockDim.x) {
+        uint32_t slot = sortedSlots[i];
+        T.gid[slot] = nextGroupId + (int32_t) i;
+        slotOfGid[nextGroupId + i] = slot;
+    }
+}
+template <int W>
+__global__ void gbhLookupKernel(GroupTable T, KeyPlan kp, int64_t n, int64_t* idsOut, uint8_t* containsOut)
+{
+    for (int64_t row = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; row < n; row += (int64_t) gridDim.x * blockDim.x) {
+        uint64_t kw[W];
+        int special = packKey<W>(kp, row, kw);
+        int slot = special ? (int) T.cap + special - 1 : tableFind<W>(T, kw, hashKeyWords<W>(kw), false, true);
+        int32_t gid = slot >= 0 ? T.gid[slot] : -1;
+        if (idsOut) idsOut[row] = gid;
+        if (containsOut) containsOut[row] = gid >= 0 ? 1 : 0;
+    }
+}
+__global__ void gbhRebuildSlotOfGidKernel(GroupTable T, uint32_t* slotOfGid)
+{
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < T.capP; s += gridDim.x * blockDim.x)
+        if (T.gid[s] >= 0) slotOfGid[T.gid[s]] = s;
+}
+
+class GroupByHashImpl : public Operator {
+    KeyLayout layout;
+    int hashChannel;
+    GroupTableStorage table;
+    PageStager stager;
+    std::vector<int> keyChannels;
+    DeviceBuffer newSlots, slotOfGid, scratchIds, scratchFlags;
+    int64_t nextGroupId = 0;
+    uint64_t rowsSeen = 0;
+    ResultBuilder result;
+
+public:
+    explicit GroupByHashImpl(const pg_group_by_hash_config* c) : Operator(c->options), stager(this)
+    {
+        PG_CHECK_ARG(c->expected_size > 0, "expectedSize must be greater than zero");
+        layout.plan(c->n_channels, c->channels, c->types, c->max_lengths);
+        hashChannel = c->hash_channel;
+        for (int k = 0; k < layout.nKeys; k++) keyChannels.push_back(layout.channels[k]);
+        table.op = this; table.W = layout.W; table.nvPhys = 0; table.withGid = true;
+        table.counters.reserve(CNT_COUNT * sizeof(unsigned int));
+        PG_CUDA(cudaMemsetAsync(table.counters.ptr, 0, CNT_COUNT * sizeof(unsigned int), stream));
+        table.allocate(std::max<uint32_t>(1024, nextPow2((uint64_t) c->expected_size * 2)));
+        PG_CUDA(cudaStreamSynchronize(stream));
+    }
+    bool needsInput() override { return true; }
+    void addInput(const pg_page*) override {}
+    bool getOutput(pg_page*) override { return false; }
+    void finish() override {}
+    bool isFinished() override { return false; }
+
+    void ensureCapacity(int64_t extraRows)
+    {
+        uint64_t need = ((uint64_t) nextGroupId + (uint64_t) extraRows) * 2;
+        if (need <= table.cap) return;
+        if (need > (1ULL << 30)) throw Error(PG_ERR_INSUFFICIENT_RESOURCES, "Size of hash table cannot exceed 1 billion entries");
+        GroupTableStorage nt;
+        nt.op = this; nt.W = table.W; nt.nvPhys = 0; nt.withGid = true;
+        nt.counters = std::move(table.counters);
+        PG_CUDA(cudaMemsetAsync(nt.counters.ptr, 0, CNT_COUNT * sizeof(unsigned int), stream));
+        nt.allocate(nextPow2(need));
+        GroupTable oldV = table.view(); oldV.counters = nt.counters.as<unsigned int>();
+        GroupTable newV = nt.view();
+        switch (table.W) {
+            case 1: PG_LAUNCH(this, rehashKernel<1>, 1024, 256, 0, oldV, newV); break;
+            case 2: PG_LAUNCH(this, rehashKernel<2>, 1024, 256, 0, oldV, newV); break;
+            case 3: PG_LAUNCH(this, rehashKernel<3>, 1024, 256, 0, oldV, newV); break;
+            default: PG_LAUNCH(this, rehashKernel<4>, 1024, 256, 0, oldV, newV); break;
+        }
+        if (nextGroupId > 0) PG_LAUNCH(this, gbhRebuildSlotOfGidKernel, 1024, 256, 0, newV, slotOfGid.as<uint32_t>());
+        PG_CUDA(cudaStreamSynchronize(stream));
+        table.keys = std::move(nt.keys); table.state = std::move(nt.state); table.firstRow = std::move(nt.firstRow);
+        table.acc = std::move(nt.acc); table.gid = std::move(nt.gid); table.counters = std::move(nt.counters); table.cap = nt.cap;
+    }
+
+    template <typename F> void withW(F&& f)
+    {
+        switch (layout.W) {
+            case 1: f(std::integral_constant<int, 1>()); break;
+            case 2: f(std::integral_constant<int, 2>()); break;
+            case 3: f(std::integral_constant<int, 3>()); break;
+            default: f(std::integral_constant<int, 4>()); break;
+        }
+    }
+    void checkErrors()
+    {
+        unsigned int cnt[CNT_COUNT];
+        PG_CUDA(cudaMemcpyAsync(cnt, table.counters.ptr, sizeof(cnt), cudaMemcpyDeviceToHost, stream));
+        PG_CUDA(cudaStreamSynchronize(stream));
+        if (cnt[CNT_ERROR] & ERR_VARCHAR_TOO_LONG) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR group-by key longer than its declared max length (GPU path packs keys of <= 7 bytes)");
+    }
+
+    // addPage (idsOut == nullptr) / getGroupIds.  idsOut lives where the page lives.
+    void insertPage(const pg_page* page, int64_t* idsOut)
+    {
+        const int64_t chunk = int64_t(1) << 24;
+        for (int64_t begin = 0; begin < page->position_count; begin += chunk) {
+            const int64_t n = std::min(chunk, page->position_count - begin);
+            pg_page sub = *page;
+            std::vector<pg_block> blocks(page->blocks, page->blocks + page->channel_count);
+            sub.blocks = blocks.data(); sub.position_count = n;
+            for (auto& b : blocks) {
+                PG_CHECK_ARG(b.encoding == PG_ENC_FLAT || begin == 0, "encoded blocks larger than 2^24 rows");
+                if (b.encoding == PG_ENC_FLAT) {
+                    int w = typeWidth(b.type);
+                    if (w) b.values = (const char*) b.values + begin * w; else b.offsets += begin;
+                    if (b.is_null) b.is_null += begin;
+                }
+                b.position_count = n;
+            }
+            stats.input_positions += n;
+            std::vector<DeviceColumn> cols;
+            stager.stage(&sub, keyChannels, cols);
+            ensureCapacity(n);
+            slotOfGid.accounting = newSlots.accounting = &stats.device_bytes;
+            {   // slotOfGid must hold nextGroupId + n entries, preserving what is there
+                size_t needBytes = ((size_t) nextGroupId + (size_t) n + 2) * 4;
+                if (needBytes > slotOfGid.capacity) {
+                    DeviceBuffer bigger; bigger.accounting = &stats.device_bytes; bigger.reserve(needBytes * 2);
+                    if (nextGroupId) PG_CUDA(cudaMemcpyAsync(bigger.ptr, slotOfGid.ptr, (size_t) nextGroupId * 4, cudaMemcpyDeviceToDevice, stream));
+                    PG_CUDA(cudaStreamSynchronize(stream));
+                    slotOfGid = std::move(bigger);
+                }
+            }
+            newSlots.reserve(((size_t) n + 2) * 4);
+            KeyPlan kp{};
+            layout.fill(kp, cols, table.counters.as<unsigned int>() + CNT_ERROR);
+            GroupTable T = table.view();
+            unsigned int zero = 0;
+            PG_CUDA(cudaMemcpyAsync(T.counters + CNT_NEW, &zero, 4, cudaMemcpyHostToDevice, stream));
+            const int grid = (int) std::min<int64_t>(divUp(n, 256), numSMs * 8);
+            withW([&](auto w) { PG_LAUNCH(this, gbhInsertKernel<decltype(w)::value>, grid, 256, 0, T, kp, n, rowsSeen, newSlots.as<uint32_t>()); });
+            PG_LAUNCH(this, gbhSpecialsKernel, 1, 32, 0, T, newSlots.as<uint32_t>());
+            unsigned int nNew = 0;
+            PG_CUDA(cudaMemcpyAsync(&nNew, T.counters + CNT_NEW, 4, cudaMemcpyDeviceToHost, stream));
+            PG_CUDA(cudaStreamSynchronize(stream));
+            if (nNew) {
+                DeviceBuffer fk, fkOut, sorted, temp;
+                fk.reserve((size_t) nNew * 8); fkOut.reserve((size_t) nNew * 8); sorted.reserve((size_t) nNew * 4);
+                PG_LAUNCH(this, gbhGatherFirstRowsKernel, (int) std::min<int64_t>(divUp(nNew, 256), 1024), 256, 0, T, newSlots.as<uint32_t>(), nNew, fk.as<uint64_t>());
+                size_t tb = 0;
+                cub::DeviceRadixSort::SortPairs(nullptr, tb, fk.as<uint64_t>(), fkOut.as<uint64_t>(), newSlots.as<uint32_t>(), sorted.as<uint32_t>(), (int) nNew, 0, 64, stream);
+                temp.reserve(tb);
+                cub::DeviceRadixSort::SortPairs(temp.ptr, tb, fk.as<uint64_t>(), fkOut.as<uint64_t>(), newSlots.as<uint32_t>(), sorted.as<uint32_t>(), (int) nNew, 0, 64, stream);
+                stats.kernel_launches += 4;
+                PG_LAUNCH(this, gbhAssignKernel, (int) std::min<int64_t>(divUp(nNew, 256), 1024), 256, 0, T, sorted.as<uint32_t>(), nNew, (int32_t) nextGroupId, slotOfGid.as<uint32_t>());
+                PG_CUDA(cudaStreamSynchronize(stream));
+                nextGroupId += nNew;
+            }
+            if (idsOut) lookupInto(cols, n, idsOut + begin, nullptr, page->memory);
+            rowsSeen += (uint64_t) n;
+            checkErrors();
+        }
+        stats.group_count = nextGroupId;
+    }
+
+    void lookupInto(const std::vector<DeviceColumn>& cols, int64_t n, int64_t* idsOut, uint8_t* flagsOut, int memory)
+    {
+        KeyPlan kp{};
+        layout.fill(kp, cols, table.counters.as<unsigned int>() + CNT_ERROR);
+        GroupTable T = table.view();
+        int64_t* dIds = idsOut; uint8_t* dFlags = flagsOut;
+        if (memory == PG_MEM_HOST) {
+            if (idsOut) { scratchIds.reserve((size_t) n * 8); dIds = scratchIds.as<int64_t>(); }
+            if (flagsOut) { scratchFlags.reserve((size_t) n); dFlags = scratchFlags.as<uint8_t>(); }
+        }
+        const int grid = (int) std::min<int64_t>(divUp(n, 256), numSMs * 8);
+        withW([&](auto w) { PG_LAUNCH(this, gbhLookupKernel<decltype(w)::value>, grid, 256, 0, T, kp, n, dIds, dFlags); });
+        if (memory == PG_MEM_HOST) {
+            if (idsOut) { PG_CUDA(cudaMemcpyAsync(idsOut, dIds, (size_t) n * 8, cudaMemcpyDeviceToHost, stream)); stats.d2h_bytes += n * 8; }
+            if (flagsOut) { PG_CUDA(cudaMemcpyAsync(flagsOut, dFlags, (size_t) n, cudaMemcpyDeviceToHost, stream)); stats.d2h_bytes += n; }
+        }
+        PG_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    void contains(const pg_page* page, uint8_t* flagsOut)
+    {
+        if (page->position_count == 0) return;
+        std::vector<DeviceColumn> cols;
+        stager.stage(page, keyChannels, cols);
+        lookupInto(cols, page->position_count, nullptr, flagsOut, page->memory);
+        checkErrors();
+    }
+
+    int64_t groupCount() const { return nextGroupId; }
+
+    void getKeys(pg_page* out)
+    {
+        if (nextGroupId == 0) { out->position_count = 0; out->channel_count = 0; out->memory = options.output_memory; out->blocks = nullptr; return; }
+        result.build(this, table.view(), layout, slotOfGid.as<uint32_t>(), nextGroupId, hashChannel >= 0, {});
+        result.slice(0, nextGroupId, options.output_memory, out);
+    }
+};
+
+Operator* createHashAggregation(const pg_hash_aggregation_config* c) { return new HashAggregationOp(c); }
+
+}  // namespace pg
+
+extern "C" int32_t pg_hash_aggregation_create(const pg_hash_aggregation_config* config, pg_operator** out)
+{
+    try {
+        if (!config || !out) throw pg::Error(PG_ERR_INVALID_ARGUMENT, "null argument");
+        *out = (pg_operator*) pg::createHashAggregation(config);
+    }
+    catch (const pg::Error& e) { pg::setLastError(e.what()); return e.code; }
+    catch (const std::exception& e) { pg::setLastError(e.what()); return PG_ERR_INVALID_STATE; }
+    return PG_OK;
+}
+
+extern "C" {
+#define GBH_TRY try {
+#define GBH_CATCH } catch (const pg::Error& e) { pg::setLastError(e.what()); return e.code; } catch (const std::exception& e) { pg::setLastError(e.what()); return PG_ERR_INVALID_STATE; } return PG_OK;
+
+int32_t pg_group_by_hash_create(const pg_group_by_hash_config* config, pg_group_by_hash** out)
+{
+    GBH_TRY
+    if (!config || !out) throw pg::Error(PG_ERR_INVALID_ARGUMENT, "null argument");
+    *out = (pg_group_by_hash*) new pg::GroupByHashImpl(config);
+    GBH_CATCH
+}
+int32_t pg_group_by_hash_add_page(pg_group_by_hash* h, const pg_page* page) { GBH_TRY auto* g = (pg::GroupByHashImpl*) h; g->bind(); g->insertPage(page, nullptr); GBH_CATCH }
+int32_t pg_group_by_hash_get_group_ids(pg_group_by_hash* h, const pg_page* page, int64_t* out) { GBH_TRY auto* g = (pg::GroupByHashImpl*) h; g->bind(); g->insertPage(page, out); GBH_CATCH }
+int32_t pg_group_by_hash_get_group_count(pg_group_by_hash* h, int64_t* out) { GBH_TRY *out = ((pg::GroupByHashImpl*) h)->groupCount(); GBH_CATCH }
+int32_t pg_group_by_hash_contains(pg_group_by_hash* h, const pg_page* page, uint8_t* out) { GBH_TRY auto* g = (pg::GroupByHashImpl*) h; g->bind(); g->contains(page, out); GBH_CATCH }
+int32_t pg_group_by_hash_get_keys(pg_group_by_hash* h, pg_page* out) { GBH_TRY auto* g = (pg::GroupByHashImpl*) h; g->bind(); g->getKeys(out); GBH_CATCH }
+int32_t pg_group_by_hash_destroy(pg_group_by_hash* h) { GBH_TRY auto* g = (pg::GroupByHashImpl*) h; if (g) { cudaSetDevice(g->options.device); delete g; } GBH_CATCH }
+}

@@ -1,0 +1,525 @@
+// presto_b200 — HashBuilderOperator + LookupJoinOperator on sm_100a.
+//
+// Replaces (MB = presto-main-base/src/main/java/com/facebook/presto/):
+//   MB/operator/HashBuilderOperator.java:333-365,519-537,642-651   addInput / finishInput / buildLookupSource
+//   MB/operator/PagesIndex.java:202-226                             addPage (build columns kept, one address per row)
+//   MB/operator/PagesHash.java:55-132                               open-address int[] key + byte[] positionToHashes build loop
+//   MB/operator/ArrayPositionLinks.java:38-100                      duplicate-key chains
+//   MB/operator/PagesHash.java:169-181, JoinHash.java:81-124        getAddressIndex / getJoinPosition / getNextJoinPosition
+//   MB/operator/JoinProbe.java:74-119, LookupJoinOperator.java:481-505,567-616, LookupJoinPageBuilder.java:75-137
+//
+// Build: the join key of every build row is packed into W words (group_table.cuh) and found-or-claimed in an HBM table in
+// parallel; the slot's `head` is exchanged to the row's position and the row's link takes the previous head.  The reference's
+// sequential loop makes head = the LAST row of a key and links descend (PagesHash.java:108-123); a parallel exchange produces
+// the same set in arbitrary order, so chains of keys with duplicates are re-threaded into descending position order afterwards
+// (skipped entirely when the build side has no duplicate keys — the TPC-H orders case).
+// Probe: pass 1 finds each probe row's chain head and match count, an exclusive scan turns counts into output offsets, pass 2
+// writes probe and build columns straight to their final positions — output rows are in probe order with each probe row's
+// matches in chain order, exactly the order LookupJoinOperator emits (pinned by TestHashJoinOperator).
+#include "common.cuh"
+#include "group_table.cuh"
+#include "key_layout.h"
+#include <cub/device/device_scan.cuh>
+#include <algorithm>
+#include <mutex>
+
+namespace pg {
+
+constexpr int kMaxJoinColumns = 16;
+
+struct JoinTable {
+    GroupTable t;             // keys / state (firstRow, acc unused)
+    int32_t* head;            // [capP] last build position with the slot's key, -1 empty
+    int32_t* links;           // [n]    next (smaller) position with the same key, -1 end
+};
+
+__device__ __forceinline__ bool keyHasNull(const KeyPlan& kp, const uint64_t* kw, int special)
+{
+    if (kp.bigintPath) return special == 1;
+    return ((kw[kp.nullWord] >> kp.nullShift) & 0xff) != 0;
+}
+
+template <int W>
+__global__ void joinBuildKernel(JoinTable J, KeyPlan kp, int64_t n, unsigned long long* stats /* [0]=duplicates [1]=null keys */)
+{
+    for (int64_t pos = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; pos < n; pos += (int64_t) gridDim.x * blockDim.x) {
+        uint64_t kw[W];
+        int special = packKey<W>(kp, pos, kw);
+        if (keyHasNull(kp, kw, special)) { J.links[pos] = -1; atomicAdd(&stats[1], 1ULL); continue; }   // PagesHash.java:99-102
+        int slot = special == 2 ? (int) J.t.cap + 1 : tableFind<W>(J.t, kw, hashKeyWords<W>(kw), true, true);
+        int old = atomicExch(&J.head[slot], (int) pos);
+        J.links[pos] = old;
+        if (old >= 0) atomicAdd(&stats[0], 1ULL);
+    }
+}
+
+// Re-thread every chain longer than one row into descending position order (one thread per slot; chains arrive almost sorted
+// because the exchange order follows the row order, so the tail-append fast path makes this close to linear).
+__global__ void joinSortChainsKernel(JoinTable J)
+{
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < J.t.capP; s += gridDim.x * blockDim.x) {
+        int node = J.head[s];
+        if (node < 0 || J.links[node] < 0) continue;
+        int newHead = -1, newTail = -1;
+        while (node >= 0) {
+            int next = J.links[node];
+            if (newHead < 0) { newHead = newTail = node; J.links[node] = -1; }
+            else if (node < newTail) { J.links[newTail] = node; J.links[node] = -1; newTail = node; }
+            else if (node > newHead) { J.links[node] = newHead; newHead = node; }
+            else {
+                int p = newHead;
+                while (J.links[p] > node) p = J.links[p];
+                J.links[node] = J.links[p];
+                J.links[p] = node;
+            }
+            node = next;
+        }
+        J.head[s] = newHead;
+    }
+}
+
+struct ProbeParams {
+    JoinTable J;
+    KeyPlan kp;
+    int64_t n;
+    int32_t outer;            // PROBE_OUTER: unmatched probe rows emit one row with NULL build columns
+    int32_t hasDuplicates;
+    int32_t* matchHead;       // [n] chain head or -1
+    uint32_t* counts;         // [n+1] output rows per probe row
+};
+
+template <int W>
+__global__ void joinProbeKernel(const __grid_constant__ ProbeParams P)
+{
+    for (int64_t row = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; row < P.n; row += (int64_t) gridDim.x * blockDim.x) {
+        uint64_t kw[W];
+        int special = packKey<W>(P.kp, row, kw);
+        int head = -1;
+        if (!keyHasNull(P.kp, kw, special)) {   // JoinProbe.java:81-84: a NULL probe key never matches
+            int slot = special == 2 ? (int) P.J.t.cap + 1 : tableFind<W>(P.J.t, kw, hashKeyWords<W>(kw), false, true);
+            if (slot >= 0) head = P.J.head[slot];
+        }
+        uint32_t c = 0;
+        if (head >= 0) {
+            c = 1;
+            if (P.hasDuplicates) for (int p = P.J.links[head]; p >= 0; p = P.J.links[p]) c++;
+        }
+        else if (P.outer) c = 1;
+        P.matchHead[row] = head;
+        P.counts[row] = c;
+    }
+}
+
+struct JoinColumn {
+    const void* src; const uint8_t* srcNulls;
+    void* dst; uint8_t* dstNulls;
+    int32_t width;
+};
+struct EmitJoinParams {
+    const int32_t* matchHead; const uint32_t* offsets; const int32_t* links;
+    int64_t n;
+    int32_t hasDuplicates;
+    int32_t nProbe, nBuild;
+    JoinColumn probe[kMaxJoinColumns];
+    JoinColumn build[kMaxJoinColumns];
+};
+
+__device__ __forceinline__ void copyValue(const JoinColumn& c, int64_t from, int64_t to)
+{
+    if (c.width == 8) ((uint64_t*) c.dst)[to] = ((const uint64_t*) c.src)[from];
+    else if (c.width == 4) ((uint32_t*) c.dst)[to] = ((const uint32_t*) c.src)[from];
+    else ((uint8_t*) c.dst)[to] = ((const uint8_t*) c.src)[from];
+    if (c.dstNulls) c.dstNulls[to] = c.srcNulls ? c.srcNulls[from] : 0;
+}
+__device__ __forceinline__ void writeNull(const JoinColumn& c, int64_t to)
+{
+    if (c.width == 8) ((uint64_t*) c.dst)[to] = 0;
+    else if (c.width == 4) ((uint32_t*) c.dst)[to] = 0;
+    else ((uint8_t*) c.dst)[to] = 0;
+    c.dstNulls[to] = 1;
+}
+
+__global__ void joinEmitKernel(const __grid_constant__ EmitJoinParams P)
+{
+    for (int64_t row = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; row < P.n; row += (int64_t) gridDim.x * blockDim.x) {
+        const uint32_t begin = P.offsets[row], end = P.offsets[row + 1];
+        if (begin == end) continue;
+        int pos = P.matchHead[row];
+        for (uint32_t o = begin; o < end; o++) {
+            for (int c = 0; c < P.nProbe; c++) copyValue(P.probe[c], row, o);
+            if (pos >= 0) {
+                for (int c = 0; c < P.nBuild; c++) copyValue(P.build[c], pos, o);
+                pos = P.hasDuplicates ? P.links[pos] : -1;
+            }
+            else for (int c = 0; c < P.nBuild; c++) writeNull(P.build[c], o);   // LookupJoinPageBuilder.appendNullForBuild
+        }
+    }
+}
+
+// ======================================================================================================================
+// Host side
+// ======================================================================================================================
+struct LookupSourceDevice {
+    int device = 0;
+    int64_t positionCount = 0;
+    std::vector<int> types;
+    std::vector<DeviceBuffer> values, nulls;       // per build channel (only channels in `kept`)
+    std::vector<bool> hasNulls;
+    std::vector<int> outputChannels;
+    KeyLayout layout;
+    DeviceBuffer keys, state, head, links, counters;
+    uint32_t cap = 0;
+    bool hasDuplicates = false;
+    int64_t nullKeyCount = 0, duplicateCount = 0;
+    int64_t deviceBytes = 0;
+
+    JoinTable view() const
+    {
+        JoinTable J{};
+        J.t.keys = keys.as<uint64_t>(); J.t.state = layout.W > 1 ? state.as<uint32_t>() : nullptr;
+        J.t.firstRow = nullptr; J.t.acc = nullptr; J.t.gid = nullptr;
+        J.t.cap = cap; J.t.mask = cap - 1; J.t.capP = cap + 2; J.t.nvPhys = 0; J.t.rowClaimLimit = cap;
+        J.t.counters = counters.as<unsigned int>();
+        J.head = head.as<int32_t>(); J.links = links.as<int32_t>();
+        return J;
+    }
+};
+
+struct JoinBridge {
+    int device;
+    std::mutex mu;
+    std::shared_ptr<LookupSourceDevice> lookupSource;   // set when the build finishes (the LookupSourceFactory future completes)
+    std::shared_ptr<LookupSourceDevice> get() { std::lock_guard<std::mutex> l(mu); return lookupSource; }
+    void set(std::shared_ptr<LookupSourceDevice> ls) { std::lock_guard<std::mutex> l(mu); lookupSource = std::move(ls); }
+};
+
+static uint32_t nextPow2u(uint64_t v) { uint64_t p = 2; while (p < v) p <<= 1; return (uint32_t) std::min<uint64_t>(p, 1ULL << 31); }
+__global__ void fillU64KernelJ(uint64_t* p, uint64_t v, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) p[i] = v;
+}
+
+static void checkJoinKeyTypes(const KeyLayout& l)
+{
+    for (int k = 0; k < l.nKeys; k++)
+        if (l.types[k] != PG_TYPE_BIGINT && l.types[k] != PG_TYPE_INTEGER && l.types[k] != PG_TYPE_DATE)
+            throw Error(PG_ERR_UNSUPPORTED, "join keys on the GPU path are BIGINT / INTEGER / DATE channels");
+}
+
+class HashBuilderOp : public Operator {
+    JoinBridge* bridge;
+    std::shared_ptr<LookupSourceDevice> ls;
+    std::vector<int> kept;          // build channels kept on the device (keys + output channels)
+    std::vector<int64_t> capacityRows;
+    PageStager stager;
+    bool finishing = false;
+    int64_t expected;
+
+public:
+    HashBuilderOp(const pg_hash_builder_config* c, JoinBridge* b) : Operator(c->options), bridge(b), stager(this)
+    {
+        PG_CHECK_ARG(b != nullptr, "join bridge is null");
+        PG_CHECK_ARG(c->n_hash_channels >= 1, "hash channels are empty");
+        ls = std::make_shared<LookupSourceDevice>();
+        ls->device = options.device;
+        ls->types.assign(c->types, c->types + c->n_channels);
+        ls->outputChannels.assign(c->output_channels, c->output_channels + c->n_output_channels);
+        PG_CHECK_ARG(c->n_output_channels <= kMaxJoinColumns, "too many build output channels");
+        std::vector<int32_t> keyTypes;
+        for (int i = 0; i < c->n_hash_channels; i++) {
+            PG_CHECK_ARG(c->hash_channels[i] >= 0 && c->hash_channels[i] < c->n_channels, "hash channel out of range");
+            keyTypes.push_back(ls->types[c->hash_channels[i]]);
+        }
+        ls->layout.plan(c->n_hash_channels, c->hash_channels, keyTypes.data(), nullptr);
+        checkJoinKeyTypes(ls->layout);
+        auto keep = [&](int ch) { if (std::find(kept.begin(), kept.end(), ch) == kept.end()) kept.push_back(ch); };
+        for (int k = 0; k < ls->layout.nKeys; k++) keep(ls->layout.channels[k]);
+        for (int oc : ls->outputChannels) {
+            PG_CHECK_ARG(oc >= 0 && oc < c->n_channels, "output channel out of range");
+            if (ls->types[oc] == PG_TYPE_VARCHAR) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR build output channels are not on the GPU path");
+            keep(oc);
+        }
+        ls->values.resize(c->n_channels); ls->nulls.resize(c->n_channels); ls->hasNulls.assign(c->n_channels, false);
+        for (auto& v : ls->values) v.accounting = &ls->deviceBytes;
+        for (auto& v : ls->nulls) v.accounting = &ls->deviceBytes;
+        capacityRows.assign(c->n_channels, 0);
+        expected = std::max<int64_t>(c->expected_positions, 1024);
+    }
+
+    bool needsInput() override { return !finishing; }
+
+    void ensureRows(int ch, int64_t rows, bool withNulls)
+    {
+        int w = typeWidth(ls->types[ch]);
+        if (rows > capacityRows[ch]) {
+            int64_t newCap = std::max<int64_t>({rows, capacityRows[ch] * 2, expected});
+            DeviceBuffer nv; nv.accounting = &ls->deviceBytes; nv.reserve((size_t) newCap * w);
+            if (ls->positionCount) PG_CUDA(cudaMemcpyAsync(nv.ptr, ls->values[ch].ptr, (size_t) ls->positionCount * w, cudaMemcpyDeviceToDevice, stream));
+            DeviceBuffer nn; nn.accounting = &ls->deviceBytes;
+            if (ls->hasNulls[ch] || withNulls) {
+                nn.reserve((size_t) newCap);
+                if (ls->hasNulls[ch] && ls->positionCount) PG_CUDA(cudaMemcpyAsync(nn.ptr, ls->nulls[ch].ptr, (size_t) ls->positionCount, cudaMemcpyDeviceToDevice, stream));
+                else if (ls->positionCount) PG_CUDA(cudaMemsetAsync(nn.ptr, 0, (size_t) ls->positionCount, stream));
+            }
+            PG_CUDA(cudaStreamSynchronize(stream));
+            ls->values[ch] = std::move(nv);
+            ls->nulls[ch] = std::move(nn);
+            capacityRows[ch] = newCap;
+            if (withNulls) ls->hasNulls[ch] = true;
+        }
+        else if (withNulls && !ls->hasNulls[ch]) {
+            ls->nulls[ch].reserve((size_t) capacityRows[ch]);
+            if (ls->positionCount) PG_CUDA(cudaMemsetAsync(ls->nulls[ch].ptr, 0, (size_t) ls->positionCount, stream));
+            ls->hasNulls[ch] = true;
+        }
+    }
+
+    void addInput(const pg_page* page) override   // HashBuilderOperator.addInput :333-349 → PagesIndex.addPage :202-226
+    {
+        PG_CHECK_STATE(!finishing, "Operator is already finishing");
+        const int64_t n = page->position_count;
+        if (n == 0) return;
+        PG_CHECK_ARG(ls->positionCount + n < (int64_t(1) << 31), "build side exceeds 2^31 positions");
+        PG_CHECK_ARG(page->channel_count == (int) ls->types.size(), "build page channel count differs from the operator's configuration");
+        std::vector<DeviceColumn> cols;
+        int slot = stager.stage(page, kept, cols);
+        for (size_t i = 0; i < kept.size(); i++) {
+            int ch = kept[i];
+            PG_CHECK_ARG(cols[i].type == ls->types[ch], "build channel type differs from the operator's configuration");
+            int w = typeWidth(ls->types[ch]);
+            ensureRows(ch, ls->positionCount + n, cols[i].nulls != nullptr);
+            PG_CUDA(cudaMemcpyAsync((char*) ls->values[ch].ptr + (size_t) ls->positionCount * w, cols[i].values, (size_t) n * w, cudaMemcpyDeviceToDevice, stream));
+            if (ls->hasNulls[ch]) {
+                if (cols[i].nulls) PG_CUDA(cudaMemcpyAsync(ls->nulls[ch].as<uint8_t>() + ls->positionCount, cols[i].nulls, (size_t) n, cudaMemcpyDeviceToDevice, stream));
+                else PG_CUDA(cudaMemsetAsync(ls->nulls[ch].as<uint8_t>() + ls->positionCount, 0, (size_t) n, stream));
+            }
+        }
+        stager.markCompute(slot);
+        PG_CUDA(cudaStreamSynchronize(stream));   // the borrowed page is not referenced after return
+        ls->positionCount += n;
+        stats.input_positions += n;
+        stats.device_bytes = ls->deviceBytes;
+    }
+
+    void finish() override   // finishInput :519-537 → buildLookupSource :642-651 → new PagesHash(...)
+    {
+        if (finishing) return;
+        finishing = true;
+        const int64_t n = ls->positionCount;
+        // HashCommon.arraySize(positionCount, 0.75f): power of two >= n / 0.75 (PagesHash.java:67)
+        uint64_t want = (uint64_t) ((double) std::max<int64_t>(n, 1) / 0.75) + 1;
+        if (want > (1ULL << 30)) throw Error(PG_ERR_INSUFFICIENT_RESOURCES, "Too large (hash table cannot exceed 2^30 slots)");
+        ls->cap = nextPow2u(want);
+        const size_t capP = (size_t) ls->cap + 2;
+        const int W = ls->layout.W;
+        for (DeviceBuffer* b : {&ls->keys, &ls->state, &ls->head, &ls->links, &ls->counters}) b->accounting = &ls->deviceBytes;
+        ls->keys.reserve(capP * 8 * W);
+        if (W > 1) { ls->state.reserve(capP * 4); PG_CUDA(cudaMemsetAsync(ls->state.ptr, 0, capP * 4, stream)); PG_CUDA(cudaMemsetAsync(ls->keys.ptr, 0, capP * 8 * W, stream)); }
+        else { fillU64KernelJ<<<1024, 256, 0, stream>>>(ls->keys.as<uint64_t>(), kEmptyKey, capP); stats.kernel_launches++; }
+        ls->head.reserve(capP * 4);
+        PG_CUDA(cudaMemsetAsync(ls->head.ptr, 0xFF, capP * 4, stream));
+        ls->links.reserve(std::max<size_t>((size_t) n * 4, 16));
+        ls->counters.reserve(64);
+        PG_CUDA(cudaMemsetAsync(ls->counters.ptr, 0, 64, stream));
+        if (n > 0) {
+            std::vector<DeviceColumn> keyCols;
+            for (int k = 0; k < ls->layout.nKeys; k++) {
+                int ch = ls->layout.channels[k];
+                DeviceColumn c; c.type = ls->types[ch]; c.n = n; c.values = ls->values[ch].ptr; c.nulls = ls->hasNulls[ch] ? ls->nulls[ch].as<uint8_t>() : nullptr;
+                keyCols.push_back(c);
+            }
+            KeyPlan kp{};
+            ls->layout.fill(kp, keyCols, ls->counters.as<unsigned int>() + CNT_ERROR);
+            JoinTable J = ls->view();
+            unsigned long long* dstats = (unsigned long long*) (ls->counters.as<unsigned int>() + CNT_COUNT);
+            const int grid = (int) std::min<int64_t>(divUp(n, 256), numSMs * 16);
+            switch (W) {
+                case 1: PG_LAUNCH(this, joinBuildKernel<1>, grid, 256, 0, J, kp, n, dstats); break;
+                case 2: PG_LAUNCH(this, joinBuildKernel<2>, grid, 256, 0, J, kp, n, dstats); break;
+                case 3: PG_LAUNCH(this, joinBuildKernel<3>, grid, 256, 0, J, kp, n, dstats); break;
+                default: PG_LAUNCH(this, joinBuildKernel<4>, grid, 256, 0, J, kp, n, dstats); break;
+            }
+            unsigned long long h[2] = {0, 0};
+            PG_CUDA(cudaMemcpyAsync(h, dstats, sizeof(h), cudaMemcpyDeviceToHost, stream));
+            PG_CUDA(cudaStreamSynchronize(stream));
+            ls->duplicateCount = (int64_t) h[0]; ls->nullKeyCount = (int64_t) h[1];
+            ls->hasDuplicates = h[0] > 0;
+            if (ls->hasDuplicates) {
+                PG_LAUNCH(this, joinSortChainsKernel, (int) std::min<int64_t>(divUp((int64_t) capP, 256), numSMs * 16), 256, 0, J);
+                PG_CUDA(cudaStreamSynchronize(stream));
+            }
+        }
+        else PG_CUDA(cudaStreamSynchronize(stream));
+        stats.group_count = n;
+        stats.device_bytes = ls->deviceBytes;
+        bridge->set(ls);
+    }
+    bool isFinished() override { return finishing; }
+    bool getOutput(pg_page*) override { return false; }
+};
+
+class LookupJoinOp : public Operator {
+    JoinBridge* bridge;
+    int joinType;
+    std::vector<int> types, outputChannels, staged;
+    KeyLayout layout;
+    PageStager stager;
+    bool finishing = false, hasPending = false;
+    DeviceBuffer matchHead, counts, offsets, scanTemp;
+    std::vector<DeviceBuffer> outValues, outNulls;
+    std::vector<PinnedBuffer> hostValues, hostNulls;
+    std::vector<pg_block> outBlocks;
+    int64_t pendingRows = 0;
+
+public:
+    LookupJoinOp(const pg_lookup_join_config* c, JoinBridge* b) : Operator(c->options), bridge(b), stager(this)
+    {
+        PG_CHECK_ARG(b != nullptr, "join bridge is null");
+        PG_CHECK_ARG(c->join_type == PG_JOIN_INNER || c->join_type == PG_JOIN_PROBE_OUTER, "join type not on the GPU path (INNER, PROBE_OUTER)");
+        joinType = c->join_type;
+        types.assign(c->types, c->types + c->n_channels);
+        outputChannels.assign(c->output_channels, c->output_channels + c->n_output_channels);
+        PG_CHECK_ARG(c->n_output_channels <= kMaxJoinColumns, "too many probe output channels");
+        std::vector<int32_t> keyTypes;
+        for (int i = 0; i < c->n_hash_channels; i++) {
+            PG_CHECK_ARG(c->hash_channels[i] >= 0 && c->hash_channels[i] < c->n_channels, "hash channel out of range");
+            keyTypes.push_back(types[c->hash_channels[i]]);
+        }
+        layout.plan(c->n_hash_channels, c->hash_channels, keyTypes.data(), nullptr);
+        checkJoinKeyTypes(layout);
+        auto need = [&](int ch) { if (std::find(staged.begin(), staged.end(), ch) == staged.end()) staged.push_back(ch); };
+        for (int k = 0; k < layout.nKeys; k++) need(layout.channels[k]);
+        for (int oc : outputChannels) {
+            PG_CHECK_ARG(oc >= 0 && oc < c->n_channels, "output channel out of range");
+            if (types[oc] == PG_TYPE_VARCHAR) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR probe output channels are not on the GPU path");
+            need(oc);
+        }
+        for (DeviceBuffer* d : {&matchHead, &counts, &offsets, &scanTemp}) d->accounting = &stats.device_bytes;
+    }
+
+    // LookupJoinOperator.needsInput :198-210: blocked until the lookup source future completes
+    bool needsInput() override { return !finishing && !hasPending && bridge->get() != nullptr; }
+
+    void addInput(const pg_page* page) override
+    {
+        PG_CHECK_STATE(needsInput(), "lookup join does not need input (still building, finishing, or output pending)");
+        auto ls = bridge->get();
+        PG_CHECK_ARG(ls->layout.nKeys == layout.nKeys, "probe and build hash channel counts differ");
+        for (int k = 0; k < layout.nKeys; k++) PG_CHECK_ARG(ls->layout.types[k] == layout.types[k], "probe and build join key types differ");
+        const int64_t n = page->position_count;
+        stats.input_positions += n;
+        if (n == 0) return;
+        PG_CHECK_ARG(n < (int64_t(1) << 31), "probe page exceeds 2^31 positions");
+        std::vector<DeviceColumn> cols;
+        int slot = stager.stage(page, staged, cols);
+        auto colOf = [&](int ch) -> const DeviceColumn& { return cols[std::find(staged.begin(), staged.end(), ch) - staged.begin()]; };
+
+        // pass 1: probe
+        matchHead.reserve((size_t) n * 4); counts.reserve((size_t) (n + 1) * 4); offsets.reserve((size_t) (n + 1) * 4);
+        ProbeParams P{};
+        P.J = ls->view();
+        std::vector<DeviceColumn> keyCols;
+        for (int k = 0; k < layout.nKeys; k++) { keyCols.push_back(colOf(layout.channels[k])); PG_CHECK_ARG(keyCols.back().type == layout.types[k], "probe key channel type differs from configuration"); }
+        layout.fill(P.kp, keyCols, ls->counters.as<unsigned int>() + CNT_ERROR);
+        P.n = n; P.outer = joinType == PG_JOIN_PROBE_OUTER; P.hasDuplicates = ls->hasDuplicates; P.matchHead = matchHead.as<int32_t>(); P.counts = counts.as<uint32_t>();
+        PG_CUDA(cudaMemsetAsync(counts.as<uint32_t>() + n, 0, 4, stream));
+        const int grid = (int) std::min<int64_t>(divUp(n, 256), numSMs * 16);
+        switch (layout.W) {
+            case 1: PG_LAUNCH(this, joinProbeKernel<1>, grid, 256, 0, P); break;
+            case 2: PG_LAUNCH(this, joinProbeKernel<2>, grid, 256, 0, P); break;
+            case 3: PG_LAUNCH(this, joinProbeKernel<3>, grid, 256, 0, P); break;
+            default: PG_LAUNCH(this, joinProbeKernel<4>, grid, 256, 0, P); break;
+        }
+        // counts → offsets
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, counts.as<uint32_t>(), offsets.as<uint32_t>(), (int) (n + 1), stream);
+        scanTemp.reserve(tb);
+        cub::DeviceScan::ExclusiveSum(scanTemp.ptr, tb, counts.as<uint32_t>(), offsets.as<uint32_t>(), (int) (n + 1), stream);
+        stats.kernel_launches += 2;
+        uint32_t total = 0;
+        PG_CUDA(cudaMemcpyAsync(&total, offsets.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, stream));
+        PG_CUDA(cudaStreamSynchronize(stream));
+        stats.d2h_bytes += 4;
+        pendingRows = total;
+        if (total == 0) { stager.markCompute(slot); return; }
+
+        // pass 2: write the output columns in place
+        const size_t nOut = outputChannels.size() + ls->outputChannels.size();
+        if (outValues.size() < nOut) { outValues.resize(nOut); outNulls.resize(nOut); for (auto& d : outValues) d.accounting = &stats.device_bytes; for (auto& d : outNulls) d.accounting = &stats.device_bytes; }
+        outBlocks.assign(nOut, pg_block{});
+        EmitJoinParams E{};
+        E.matchHead = matchHead.as<int32_t>(); E.offsets = offsets.as<uint32_t>(); E.links = ls->links.as<int32_t>();
+        E.n = n; E.hasDuplicates = ls->hasDuplicates; E.nProbe = (int) outputChannels.size(); E.nBuild = (int) ls->outputChannels.size();
+        for (size_t i = 0; i < outputChannels.size(); i++) {
+            const DeviceColumn& c = colOf(outputChannels[i]);
+            JoinColumn& jc = E.probe[i];
+            jc.width = typeWidth(c.type); jc.src = c.values; jc.srcNulls = c.nulls;
+            outValues[i].reserve((size_t) total * jc.width);
+            jc.dst = outValues[i].ptr; jc.dstNulls = nullptr;
+            if (c.nulls) { outNulls[i].reserve(total); jc.dstNulls = outNulls[i].as<uint8_t>(); }
+            outBlocks[i].type = c.type;
+        }
+        for (size_t i = 0; i < ls->outputChannels.size(); i++) {
+            const int ch = ls->outputChannels[i];
+            const size_t o = outputChannels.size() + i;
+            JoinColumn& jc = E.build[i];
+            jc.width = typeWidth(ls->types[ch]); jc.src = ls->values[ch].ptr; jc.srcNulls = ls->hasNulls[ch] ? ls->nulls[ch].as<uint8_t>() : nullptr;
+            outValues[o].reserve((size_t) total * jc.width);
+            jc.dst = outValues[o].ptr; jc.dstNulls = nullptr;
+            if (jc.srcNulls || joinType == PG_JOIN_PROBE_OUTER) { outNulls[o].reserve(total); jc.dstNulls = outNulls[o].as<uint8_t>(); }
+            outBlocks[o].type = ls->types[ch];
+        }
+        PG_LAUNCH(this, joinEmitKernel, grid, 256, 0, E);
+        stager.markCompute(slot);
+        const bool toHost = options.output_memory == PG_MEM_HOST;
+        if (toHost && hostValues.size() < nOut) { hostValues.resize(nOut); hostNulls.resize(nOut); }
+        for (size_t i = 0; i < nOut; i++) {
+            pg_block& b = outBlocks[i];
+            const bool hasNulls = (i < outputChannels.size() ? E.probe[i].dstNulls : E.build[i - outputChannels.size()].dstNulls) != nullptr;
+            const size_t vbytes = (size_t) total * typeWidth(b.type);
+            b.encoding = PG_ENC_FLAT; b.position_count = total; b.offsets = nullptr; b.ids = nullptr; b.dictionary_size = 0;
+            if (toHost) {
+                hostValues[i].reserve(vbytes);
+                PG_CUDA(cudaMemcpyAsync(hostValues[i].ptr, outValues[i].ptr, vbytes, cudaMemcpyDeviceToHost, stream));
+                b.values = hostValues[i].ptr; b.is_null = nullptr;
+                stats.d2h_bytes += (int64_t) vbytes;
+                if (hasNulls) { hostNulls[i].reserve(total); PG_CUDA(cudaMemcpyAsync(hostNulls[i].ptr, outNulls[i].ptr, total, cudaMemcpyDeviceToHost, stream)); b.is_null = hostNulls[i].as<uint8_t>(); stats.d2h_bytes += total; }
+            }
+            else { b.values = outValues[i].ptr; b.is_null = hasNulls ? outNulls[i].as<uint8_t>() : nullptr; }
+            stats.output_bytes += (int64_t) vbytes;
+        }
+        PG_CUDA(cudaStreamSynchronize(stream));
+        hasPending = true;
+        stats.output_positions += total;
+    }
+
+    bool getOutput(pg_page* out) override
+    {
+        if (!hasPending) return false;
+        out->position_count = pendingRows; out->channel_count = (int32_t) outBlocks.size(); out->memory = options.output_memory; out->blocks = outBlocks.data();
+        hasPending = false;
+        return true;
+    }
+    void finish() override { finishing = true; }
+    bool isFinished() override { return finishing && !hasPending; }
+};
+
+}  // namespace pg
+
+extern "C" {
+#define J_TRY try {
+#define J_CATCH } catch (const pg::Error& e) { pg::setLastError(e.what()); return e.code; } catch (const std::exception& e) { pg::setLastError(e.what()); return PG_ERR_INVALID_STATE; } return PG_OK;
+
+int32_t pg_join_bridge_create(int32_t device, pg_join_bridge** out)
+{
+    J_TRY
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) throw pg::Error(PG_ERR_NO_DEVICE, "no CUDA device visible: presto_b200 operators only run on the GPU (no CPU fallback)");
+    auto* b = new pg::JoinBridge(); b->device = device; *out = (pg_join_bridge*) b;
+    J_CATCH
+}
+int32_t pg_join_bridge_destroy(pg_join_bridge* b) { J_TRY auto* jb = (pg::JoinBridge*) b; if (jb) { cudaSetDevice(jb->device); delete jb; } J_CATCH }
+int32_t pg_join_bridge_get_position_count(pg_join_bridge* b, int64_t* out) { J_TRY auto ls = ((pg::JoinBridge*) b)->get(); *out = ls ? ls->positionCount : -1; J_CATCH }
+int32_t pg_hash_builder_create(const pg_hash_builder_config* c, pg_join_bridge* bridge, pg_operator** out) { J_TRY *out = (pg_operator*) new pg::HashBuilderOp(c, (pg::JoinBridge*) bridge); J_CATCH }
+int32_t pg_lookup_join_create(const pg_lookup_join_config* c, pg_join_bridge* bridge, pg_operator** out) { J_TRY *out = (pg_operator*) new pg::LookupJoinOp(c, (pg::JoinBridge*) bridge); J_CATCH }
+}

@@ -1,0 +1,297 @@
+// presto_b200 — PartitionedOutputOperator (row repartition) on sm_100a.
+//
+// Replaces (MB = presto-main-base/src/main/java/com/facebook/presto/):
+//   MB/operator/repartition/OptimizedPartitionedOutputOperator.java:487-557  partitionPage: partition function per row →
+//        per-partition position lists (row order), replicate-any-row / null-channel replication
+//   …:664-716 PartitionBuffer.appendData + LongArrayBlockEncodingBuffer.java:154-175  copy values by position list
+//   MB/operator/HashGenerator.java:22-29 getPartition, InterpretedHashGenerator.java:70-79, PrecomputedHashGenerator.java:31-35
+//
+// GPU shape: a stable multisplit.  Every warp owns a contiguous run of rows ("unit").
+//   pass 1  partition id per row (exact HashGenerator.getPartition) → ids[] (2 B/row) + per-unit histogram in shared memory
+//   scan    exclusive sum over (partition-major, unit-minor) histograms = start of every unit's run inside every partition
+//   pass 2  each warp walks its rows in order, ranks lanes of the same partition with match/popc, scatters every column
+// The result is all partitions back to back, rows of a partition in input order = what the reference's position lists give.
+// Across GPUs each partition slab is then the send buffer of one all-to-all peer (presto_b200/exchange.py).
+#include "common.cuh"
+#include <cub/device/device_scan.cuh>
+#include <algorithm>
+
+namespace pg {
+
+constexpr int kMaxPartChannels = 8;
+constexpr int kMaxScatterColumns = 32;
+constexpr int kRowsPerUnit = 2048;       // rows owned by one warp
+constexpr int kPartWarps = 8;
+
+struct HashCol { const void* values; const uint8_t* nulls; int32_t type; };
+
+struct PartitionIdParams {
+    HashCol cols[kMaxPartChannels];
+    int32_t nCols;
+    const int64_t* precomputed;          // $hashvalue channel or nullptr
+    const uint8_t* nullChannelNulls;     // rows whose null channel is NULL go to every partition
+    int32_t replicateRow0;
+    int32_t partitionCount;
+    int64_t n;
+    int64_t units;
+    uint16_t* ids;                       // [n]  partition, or partitionCount = "every partition"
+    uint32_t* hist;                      // [partitionCount][units]
+};
+
+__device__ __forceinline__ int64_t typeHashOf(const HashCol& c, int64_t row)
+{
+    if (c.nulls && c.nulls[row]) return 0;   // TypeUtils.hashPosition: NULL_HASH_CODE
+    switch (c.type) {
+        case PG_TYPE_BIGINT: return hashLong(((const int64_t*) c.values)[row]);
+        case PG_TYPE_DOUBLE: return hashLong(canonicalDoubleBits(((const int64_t*) c.values)[row]));
+        case PG_TYPE_INTEGER: case PG_TYPE_DATE: return hashLong((int64_t) ((const int32_t*) c.values)[row]);
+        default: return ((const uint8_t*) c.values)[row] ? 1231 : 1237;   // BOOLEAN
+    }
+}
+
+__global__ void __launch_bounds__(kPartWarps * 32) partitionIdKernel(const __grid_constant__ PartitionIdParams P)
+{
+    extern __shared__ uint32_t shist[];   // [warps][partitionCount]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int PC = P.partitionCount;
+    uint32_t* h = shist + warp * PC;
+    for (int64_t unit = (int64_t) blockIdx.x * kPartWarps + warp; unit < P.units; unit += (int64_t) gridDim.x * kPartWarps) {
+        for (int p = lane; p < PC; p += 32) h[p] = 0;
+        __syncwarp();
+        const int64_t begin = unit * kRowsPerUnit, end = min(begin + (int64_t) kRowsPerUnit, P.n);
+        for (int64_t base = begin; base < end; base += 32) {
+            const int64_t row = base + lane;
+            int part = -1 - lane;
+            if (row < end) {
+                if ((P.replicateRow0 && row == 0) || (P.nullChannelNulls && P.nullChannelNulls[row])) part = PC;
+                else {
+                    int64_t rawHash;
+                    if (P.precomputed) rawHash = P.precomputed[row];
+                    else {
+                        rawHash = 0;   // InterpretedHashGenerator.hashPosition: CombineHashFunction.getHash(result, typeHash)
+                        for (int c = 0; c < P.nCols; c++) rawHash = (int64_t) (31ULL * (uint64_t) rawHash + (uint64_t) typeHashOf(P.cols[c], row));
+                    }
+                    part = hashPartition(rawHash, PC);
+                }
+                P.ids[row] = (uint16_t) part;
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, part);
+            if (part >= 0 && part < PC && lane == __ffs(peers) - 1) h[part] += __popc(peers);
+            const unsigned rep = __ballot_sync(0xffffffffu, part == PC);
+            if (rep) { __syncwarp(); for (int p = lane; p < PC; p += 32) h[p] += __popc(rep); }
+            __syncwarp();
+        }
+        for (int p = lane; p < PC; p += 32) P.hist[(size_t) p * P.units + unit] = h[p];
+        __syncwarp();
+    }
+}
+
+struct ScatterColumn { const void* src; const uint8_t* srcNulls; void* dst; uint8_t* dstNulls; int32_t width; };
+struct ScatterParams {
+    ScatterColumn cols[kMaxScatterColumns];
+    int32_t nCols;
+    int32_t partitionCount;
+    int64_t n, units;
+    const uint16_t* ids;
+    const uint32_t* base;    // scanned hist
+};
+
+__device__ __forceinline__ void scatterRow(const ScatterParams& P, int64_t row, uint32_t dest)
+{
+    for (int c = 0; c < P.nCols; c++) {
+        const ScatterColumn& sc = P.cols[c];
+        if (sc.width == 8) ((uint64_t*) sc.dst)[dest] = ldStream64((const uint64_t*) sc.src + row);
+        else if (sc.width == 4) ((uint32_t*) sc.dst)[dest] = ldStream32((const uint32_t*) sc.src + row);
+        else ((uint8_t*) sc.dst)[dest] = ((const uint8_t*) sc.src)[row];
+        if (sc.dstNulls) sc.dstNulls[dest] = sc.srcNulls ? sc.srcNulls[row] : 0;
+    }
+}
+
+__global__ void __launch_bounds__(kPartWarps * 32) partitionScatterKernel(const __grid_constant__ ScatterParams P)
+{
+    extern __shared__ uint32_t scursor[];   // [warps][partitionCount]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int PC = P.partitionCount;
+    uint32_t* cur = scursor + warp * PC;
+    const unsigned ltMask = (1u << lane) - 1;
+    for (int64_t unit = (int64_t) blockIdx.x * kPartWarps + warp; unit < P.units; unit += (int64_t) gridDim.x * kPartWarps) {
+        for (int p = lane; p < PC; p += 32) cur[p] = P.base[(size_t) p * P.units + unit];
+        __syncwarp();
+        const int64_t begin = unit * kRowsPerUnit, end = min(begin + (int64_t) kRowsPerUnit, P.n);
+        for (int64_t base = begin; base < end; base += 32) {
+            const int64_t row = base + lane;
+            const int part = row < end ? (int) P.ids[row] : -1 - lane;
+            const unsigned peers = __match_any_sync(0xffffffffu, part);
+            const unsigned rep = __ballot_sync(0xffffffffu, part == PC);
+            if (rep == 0) {
+                uint32_t dest = 0;
+                if (part >= 0) dest = cur[part] + __popc(peers & ltMask);
+                __syncwarp();
+                if (part >= 0 && lane == __ffs(peers) - 1) cur[part] += __popc(peers);
+                if (part >= 0) scatterRow(P, row, dest);
+            }
+            else {
+                // some rows of this round go to every partition: rank inside partition q counts its own rows and the replicated ones
+                for (int q = 0; q < PC; q++) {
+                    const unsigned members = __ballot_sync(0xffffffffu, part == q) | rep;
+                    const bool mine = part == q || part == PC;
+                    const uint32_t dest = cur[q] + __popc(members & ltMask);
+                    __syncwarp();
+                    if (lane == 0) cur[q] += __popc(members);
+                    if (mine) scatterRow(P, row, dest);
+                    __syncwarp();
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+class PartitionedOutputOp : public Operator {
+    std::vector<int> types, partitionChannels, staged;
+    int partitionCount, hashChannel, nullChannel;
+    bool replicatesAnyRow, hasAnyRowBeenReplicated = false;
+    bool finishing = false, hasPending = false;
+    PageStager stager;
+    DeviceBuffer ids, hist, base, scanTemp;
+    std::vector<DeviceBuffer> outValues, outNulls;
+    std::vector<PinnedBuffer> hostValues, hostNulls;
+    std::vector<pg_block> outBlocks;
+    std::vector<int64_t> offsets;
+    int64_t pendingRows = 0;
+
+public:
+    explicit PartitionedOutputOp(const pg_partitioned_output_config* c) : Operator(c->options), stager(this)
+    {
+        PG_CHECK_ARG(c->partition_count >= 1 && c->partition_count <= 4096, "partition count must be in [1, 4096]");
+        PG_CHECK_ARG(c->n_channels >= 1 && c->n_channels <= kMaxScatterColumns, "1..32 channels");
+        PG_CHECK_ARG(c->n_partition_channels <= kMaxPartChannels, "at most 8 partition channels");
+        types.assign(c->types, c->types + c->n_channels);
+        partitionChannels.assign(c->partition_channels, c->partition_channels + c->n_partition_channels);
+        partitionCount = c->partition_count; hashChannel = c->precomputed_hash_channel; nullChannel = c->null_channel;
+        replicatesAnyRow = c->replicates_any_row != 0;
+        for (int t : types) if (t == PG_TYPE_VARCHAR) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR channels are not on the GPU repartition path yet");
+        for (int ch : partitionChannels) PG_CHECK_ARG(ch >= 0 && ch < c->n_channels, "partition channel out of range");
+        PG_CHECK_ARG(hashChannel < c->n_channels && nullChannel < c->n_channels, "channel out of range");
+        PG_CHECK_ARG(hashChannel >= 0 || !partitionChannels.empty() || partitionCount == 1, "no partition channels");
+        if (hashChannel >= 0) PG_CHECK_ARG(types[hashChannel] == PG_TYPE_BIGINT, "precomputed hash channel must be BIGINT");
+        for (int i = 0; i < c->n_channels; i++) staged.push_back(i);
+        offsets.assign(partitionCount + 1, 0);
+        for (DeviceBuffer* d : {&ids, &hist, &base, &scanTemp}) d->accounting = &stats.device_bytes;
+        const size_t smem = (size_t) kPartWarps * partitionCount * 4;
+        PG_CUDA(cudaFuncSetAttribute(partitionIdKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        PG_CUDA(cudaFuncSetAttribute(partitionScatterKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    }
+
+    bool needsInput() override { return !finishing && !hasPending; }
+
+    void addInput(const pg_page* page) override
+    {
+        PG_CHECK_STATE(needsInput(), "partitioned output does not need input (finishing or output pending)");
+        const int64_t n = page->position_count;
+        stats.input_positions += n;
+        if (n == 0) return;
+        PG_CHECK_ARG(n < (int64_t(1) << 31), "page exceeds 2^31 positions");
+        PG_CHECK_ARG(page->channel_count == (int) types.size(), "page channel count differs from the operator's configuration");
+        std::vector<DeviceColumn> cols;
+        int slot = stager.stage(page, staged, cols);
+        for (size_t i = 0; i < cols.size(); i++) PG_CHECK_ARG(cols[i].type == types[i], "channel type differs from the operator's configuration");
+        const int64_t units = divUp(n, kRowsPerUnit);
+        ids.reserve((size_t) n * 2);
+        const size_t histN = (size_t) partitionCount * units + 1;
+        hist.reserve(histN * 4); base.reserve(histN * 4);
+        PartitionIdParams A{};
+        A.nCols = (int) partitionChannels.size();
+        for (int i = 0; i < A.nCols; i++) { const DeviceColumn& c = cols[partitionChannels[i]]; A.cols[i].values = c.values; A.cols[i].nulls = c.nulls; A.cols[i].type = c.type; }
+        A.precomputed = hashChannel >= 0 ? (const int64_t*) cols[hashChannel].values : nullptr;
+        A.nullChannelNulls = nullChannel >= 0 ? cols[nullChannel].nulls : nullptr;
+        A.replicateRow0 = (replicatesAnyRow && !hasAnyRowBeenReplicated) ? 1 : 0;
+        hasAnyRowBeenReplicated = hasAnyRowBeenReplicated || replicatesAnyRow;
+        A.partitionCount = partitionCount; A.n = n; A.units = units; A.ids = ids.as<uint16_t>(); A.hist = hist.as<uint32_t>();
+        PG_CUDA(cudaMemsetAsync(hist.as<uint32_t>() + histN - 1, 0, 4, stream));
+        const size_t smem = (size_t) kPartWarps * partitionCount * 4;
+        const int grid = (int) std::min<int64_t>(divUp(units, kPartWarps), (int64_t) numSMs * 8);
+        PG_LAUNCH(this, partitionIdKernel, grid, kPartWarps * 32, smem, A);
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, hist.as<uint32_t>(), base.as<uint32_t>(), (int) histN, stream);
+        scanTemp.reserve(tb);
+        cub::DeviceScan::ExclusiveSum(scanTemp.ptr, tb, hist.as<uint32_t>(), base.as<uint32_t>(), (int) histN, stream);
+        stats.kernel_launches += 2;
+        // partition boundaries: base[p * units] and the grand total
+        std::vector<uint32_t> hostOffsets(partitionCount + 1);
+        PG_CUDA(cudaMemcpy2DAsync(hostOffsets.data(), 4, base.ptr, (size_t) units * 4, 4, partitionCount, cudaMemcpyDeviceToHost, stream));
+        PG_CUDA(cudaMemcpyAsync(&hostOffsets[partitionCount], base.as<uint32_t>() + histN - 1, 4, cudaMemcpyDeviceToHost, stream));
+        PG_CUDA(cudaStreamSynchronize(stream));
+        stats.d2h_bytes += (partitionCount + 1) * 4;
+        for (int p = 0; p <= partitionCount; p++) offsets[p] = hostOffsets[p];
+        const int64_t total = offsets[partitionCount];
+
+        const size_t nCols = types.size();
+        if (outValues.size() < nCols) { outValues.resize(nCols); outNulls.resize(nCols); for (auto& d : outValues) d.accounting = &stats.device_bytes; for (auto& d : outNulls) d.accounting = &stats.device_bytes; }
+        ScatterParams S{};
+        S.nCols = (int) nCols; S.partitionCount = partitionCount; S.n = n; S.units = units; S.ids = ids.as<uint16_t>(); S.base = base.as<uint32_t>();
+        outBlocks.assign(nCols, pg_block{});
+        for (size_t i = 0; i < nCols; i++) {
+            ScatterColumn& sc = S.cols[i];
+            sc.width = typeWidth(types[i]); sc.src = cols[i].values; sc.srcNulls = cols[i].nulls;
+            outValues[i].reserve((size_t) total * sc.width);
+            sc.dst = outValues[i].ptr; sc.dstNulls = nullptr;
+            if (cols[i].nulls) { outNulls[i].reserve(total); sc.dstNulls = outNulls[i].as<uint8_t>(); }
+        }
+        PG_LAUNCH(this, partitionScatterKernel, grid, kPartWarps * 32, smem, S);
+        stager.markCompute(slot);
+        const bool toHost = options.output_memory == PG_MEM_HOST;
+        if (toHost && hostValues.size() < nCols) { hostValues.resize(nCols); hostNulls.resize(nCols); }
+        for (size_t i = 0; i < nCols; i++) {
+            pg_block& b = outBlocks[i];
+            const size_t vbytes = (size_t) total * typeWidth(types[i]);
+            b.type = types[i]; b.encoding = PG_ENC_FLAT; b.position_count = total;
+            if (toHost) {
+                hostValues[i].reserve(std::max<size_t>(vbytes, 16));
+                PG_CUDA(cudaMemcpyAsync(hostValues[i].ptr, outValues[i].ptr, vbytes, cudaMemcpyDeviceToHost, stream));
+                b.values = hostValues[i].ptr; b.is_null = nullptr;
+                stats.d2h_bytes += (int64_t) vbytes;
+                if (S.cols[i].dstNulls) { hostNulls[i].reserve(total); PG_CUDA(cudaMemcpyAsync(hostNulls[i].ptr, outNulls[i].ptr, total, cudaMemcpyDeviceToHost, stream)); b.is_null = hostNulls[i].as<uint8_t>(); stats.d2h_bytes += total; }
+            }
+            else { b.values = outValues[i].ptr; b.is_null = S.cols[i].dstNulls; }
+            stats.output_bytes += (int64_t) vbytes;
+        }
+        PG_CUDA(cudaStreamSynchronize(stream));
+        pendingRows = total;
+        hasPending = true;
+        stats.output_positions += total;
+    }
+
+    bool getOutput(pg_page* out) override
+    {
+        if (!hasPending) return false;
+        out->position_count = pendingRows; out->channel_count = (int32_t) outBlocks.size(); out->memory = options.output_memory; out->blocks = outBlocks.data();
+        hasPending = false;
+        return true;
+    }
+    void finish() override { finishing = true; }
+    bool isFinished() override { return finishing && !hasPending; }
+    void getOffsets(int64_t* out) const { for (size_t i = 0; i < offsets.size(); i++) out[i] = offsets[i]; }
+};
+
+}  // namespace pg
+
+extern "C" {
+int32_t pg_partitioned_output_create(const pg_partitioned_output_config* config, pg_operator** out)
+{
+    try { *out = (pg_operator*) new pg::PartitionedOutputOp(config); }
+    catch (const pg::Error& e) { pg::setLastError(e.what()); return e.code; }
+    catch (const std::exception& e) { pg::setLastError(e.what()); return PG_ERR_INVALID_STATE; }
+    return PG_OK;
+}
+int32_t pg_partitioned_output_get_offsets(pg_operator* op, int64_t* out)
+{
+    try {
+        auto* p = dynamic_cast<pg::PartitionedOutputOp*>((pg::Operator*) op);
+        if (!p) throw pg::Error(PG_ERR_INVALID_ARGUMENT, "not a partitioned output operator");
+        p->getOffsets(out);
+    }
+    catch (const pg::Error& e) { pg::setLastError(e.what()); return e.code; }
+    return PG_OK;
+}
+}

@@ -1,0 +1,277 @@
+// presto_b200 — runtime: device management, operator base, page staging, scalar hash helpers.
+#include "common.cuh"
+
+namespace pg {
+
+static thread_local std::string g_lastError;
+void setLastError(const std::string& msg) { g_lastError = msg; }
+const char* lastError() { return g_lastError.c_str(); }
+
+// ---- Operator base ----------------------------------------------------------------------------------------------------
+Operator::Operator(const pg_operator_options& o) : options(o)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count < 1)
+        throw Error(PG_ERR_NO_DEVICE, "no CUDA device visible: presto_b200 operators only run on the GPU (no CPU fallback)");
+    PG_CHECK_ARG(o.device >= 0 && o.device < count, "device ordinal out of range");
+    PG_CUDA(cudaSetDevice(o.device));
+    if (o.cuda_stream) { stream = (cudaStream_t) o.cuda_stream; ownsStream = false; }
+    else { PG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)); ownsStream = true; }
+    PG_CUDA(cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking));
+    PG_CUDA(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, o.device));
+}
+
+Operator::~Operator()
+{
+    cudaSetDevice(options.device);
+    if (stream) cudaStreamSynchronize(stream);
+    if (copyStream) { cudaStreamSynchronize(copyStream); cudaStreamDestroy(copyStream); }
+    if (ownsStream && stream) cudaStreamDestroy(stream);
+}
+
+// ---- flatten kernels (DictionaryBlock / RunLengthEncodedBlock → flat) ---------------------------------------------------
+template <typename T>
+__global__ void flattenKernel(const T* __restrict__ dict, const uint8_t* __restrict__ dictNulls, const int32_t* __restrict__ ids,
+                              int64_t n, T* __restrict__ out, uint8_t* __restrict__ outNulls)
+{
+    for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {
+        int32_t id = ids ? ids[i] : 0;
+        out[i] = dict[id];
+        if (outNulls) outNulls[i] = dictNulls[id];
+    }
+}
+
+PageStager::PageStager(Operator* o) : op(o)
+{
+    for (auto& s : slots) {
+        PG_CUDA(cudaEventCreateWithFlags(&s.copyDone, cudaEventDisableTiming));
+        PG_CUDA(cudaEventCreateWithFlags(&s.computeDone, cudaEventDisableTiming));
+    }
+}
+
+PageStager::~PageStager()
+{
+    for (auto& s : slots) {
+        if (s.copyDone) cudaEventDestroy(s.copyDone);
+        if (s.computeDone) cudaEventDestroy(s.computeDone);
+    }
+}
+
+void PageStager::markCompute(int s)
+{
+    PG_CUDA(cudaEventRecord(slots[s].computeDone, op->stream));
+    slots[s].computePending = true;
+}
+
+int PageStager::stage(const pg_page* page, const std::vector<int>& channels, std::vector<DeviceColumn>& cols)
+{
+    int s = next;
+    next = (next + 1) % kSlots;
+    Slot& slot = slots[s];
+    size_t nch = channels.size();
+    if (slot.values.size() < nch) {
+        slot.values.resize(nch); slot.nulls.resize(nch); slot.offsets.resize(nch); slot.scratch.resize(nch);
+        for (size_t i = 0; i < nch; i++)
+            for (DeviceBuffer* b : {&slot.values[i], &slot.nulls[i], &slot.offsets[i], &slot.scratch[i]}) b->accounting = &op->stats.device_bytes;
+    }
+    cols.assign(nch, DeviceColumn());
+    bool host = page->memory == PG_MEM_HOST;
+    // copies into this slot must not overtake kernels still reading it
+    cudaStream_t cs = host ? op->copyStream : op->stream;
+    if (host && slot.computePending) { PG_CUDA(cudaStreamWaitEvent(cs, slot.computeDone, 0)); slot.computePending = false; }
+    bool copied = false;
+    for (size_t i = 0; i < nch; i++) {
+        int ch = channels[i];
+        PG_CHECK_ARG(ch >= 0 && ch < page->channel_count, "channel out of range for the input page");
+        const pg_block& b = page->blocks[ch];
+        PG_CHECK_ARG(b.position_count == page->position_count, "block position count differs from the page's");
+        DeviceColumn& c = cols[i];
+        c.type = b.type; c.n = b.position_count;
+        int w = typeWidth(b.type);
+        bool encoded = b.encoding != PG_ENC_FLAT;
+        PG_CHECK_ARG(b.encoding == PG_ENC_FLAT || b.encoding == PG_ENC_DICTIONARY || b.encoding == PG_ENC_RLE, "unknown block encoding");
+        int64_t entries = encoded ? (b.encoding == PG_ENC_RLE ? 1 : b.dictionary_size) : b.position_count;
+        if (b.type == PG_TYPE_VARCHAR && encoded)
+            throw Error(PG_ERR_UNSUPPORTED, "dictionary / RLE encoded VARCHAR blocks are not on the GPU path yet; flatten before addInput");
+        const void* dValues = b.values; const uint8_t* dNulls = b.is_null; const int32_t* dOffsets = b.offsets; const int32_t* dIds = b.ids;
+        if (host && c.n > 0) {
+            if (b.type == PG_TYPE_VARCHAR) {
+                PG_CHECK_ARG(b.offsets != nullptr, "VARCHAR block without offsets");
+                size_t obytes = (size_t) (entries + 1) * 4;
+                slot.offsets[i].reserve(obytes);
+                PG_CUDA(cudaMemcpyAsync(slot.offsets[i].ptr, b.offsets, obytes, cudaMemcpyHostToDevice, cs));
+                size_t vbytes = (size_t) b.offsets[entries];
+                slot.values[i].reserve(vbytes + 16);
+                if (vbytes) PG_CUDA(cudaMemcpyAsync(slot.values[i].ptr, b.values, vbytes, cudaMemcpyHostToDevice, cs));
+                op->stats.h2d_bytes += (int64_t) (obytes + vbytes);
+                dValues = slot.values[i].ptr; dOffsets = slot.offsets[i].as<int32_t>();
+            }
+            else {
+                size_t vbytes = (size_t) entries * w;
+                DeviceBuffer& vb = encoded ? slot.scratch[i] : slot.values[i];
+                vb.reserve(vbytes + (encoded ? (size_t) c.n * 4 + 16 : 0));
+                PG_CUDA(cudaMemcpyAsync(vb.ptr, b.values, vbytes, cudaMemcpyHostToDevice, cs));
+                op->stats.h2d_bytes += (int64_t) vbytes;
+                dValues = vb.ptr;
+                if (b.encoding == PG_ENC_DICTIONARY) {
+                    size_t off = (vbytes + 15) & ~size_t(15);
+                    PG_CUDA(cudaMemcpyAsync((char*) vb.ptr + off, b.ids, (size_t) c.n * 4, cudaMemcpyHostToDevice, cs));
+                    op->stats.h2d_bytes += c.n * 4;
+                    dIds = (const int32_t*) ((char*) vb.ptr + off);
+                }
+            }
+            if (b.is_null) {
+                DeviceBuffer& nb = slot.nulls[i];
+                // encoded: dictionary nulls first, flat nulls after
+                nb.reserve((size_t) entries + (encoded ? (size_t) c.n + 16 : 0));
+                PG_CUDA(cudaMemcpyAsync(nb.ptr, b.is_null, (size_t) entries, cudaMemcpyHostToDevice, cs));
+                op->stats.h2d_bytes += entries;
+                dNulls = nb.as<uint8_t>();
+            }
+            copied = true;
+        }
+        if (encoded && c.n > 0) {
+            // flatten on the stream the source data lands on
+            slot.values[i].reserve((size_t) c.n * w);
+            uint8_t* outNulls = nullptr;
+            if (dNulls) {
+                if (host) outNulls = slot.nulls[i].as<uint8_t>() + (((size_t) entries + 15) & ~size_t(15));
+                else { slot.nulls[i].reserve((size_t) c.n); outNulls = slot.nulls[i].as<uint8_t>(); }
+            }
+            int grid = (int) std::min<int64_t>(divUp(c.n, 256), 4096);
+            const int32_t* ids = b.encoding == PG_ENC_DICTIONARY ? dIds : nullptr;
+            if (w == 8) flattenKernel<uint64_t><<<grid, 256, 0, cs>>>((const uint64_t*) dValues, dNulls, ids, c.n, slot.values[i].as<uint64_t>(), outNulls);
+            else if (w == 4) flattenKernel<uint32_t><<<grid, 256, 0, cs>>>((const uint32_t*) dValues, dNulls, ids, c.n, slot.values[i].as<uint32_t>(), outNulls);
+            else flattenKernel<uint8_t><<<grid, 256, 0, cs>>>((const uint8_t*) dValues, dNulls, ids, c.n, slot.values[i].as<uint8_t>(), outNulls);
+            op->stats.kernel_launches++;
+            PG_CUDA(cudaGetLastError());
+            dValues = slot.values[i].ptr; dNulls = outNulls;
+        }
+        c.values = dValues; c.nulls = dNulls; c.offsets = dOffsets;
+        op->stats.input_bytes += c.n * (w ? w : 4) + (b.is_null ? c.n : 0);
+    }
+    if (host && copied) {
+        PG_CUDA(cudaEventRecord(slot.copyDone, cs));
+        PG_CUDA(cudaStreamWaitEvent(op->stream, slot.copyDone, 0));
+        // the page's host memory is only borrowed for the duration of addInput
+        PG_CUDA(cudaEventSynchronize(slot.copyDone));
+    }
+    return s;
+}
+
+}  // namespace pg
+
+// ======================================================================================================================
+// C ABI: library / device / scalar helpers
+// ======================================================================================================================
+using namespace pg;
+
+#define PG_TRY try {
+#define PG_CATCH                                                                                          \
+    }                                                                                                     \
+    catch (const pg::Error& e) { pg::setLastError(e.what()); return e.code; }                             \
+    catch (const std::bad_alloc&) { pg::setLastError("host out of memory"); return PG_ERR_OUT_OF_MEMORY; } \
+    catch (const std::exception& e) { pg::setLastError(e.what()); return PG_ERR_INVALID_STATE; }          \
+    return PG_OK;
+
+extern "C" {
+
+const char* pg_version(void) { return "presto_b200 0.1.0 sm_100a"; }
+const char* pg_last_error(void) { return pg::lastError(); }
+
+int32_t pg_device_count(int32_t* count)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n < 1) {
+        *count = 0;
+        pg::setLastError(std::string("no CUDA device visible: ") + cudaGetErrorString(e));
+        cudaGetLastError();
+        return PG_ERR_NO_DEVICE;
+    }
+    *count = n;
+    return PG_OK;
+}
+int32_t pg_set_device(int32_t device) { PG_TRY PG_CUDA(cudaSetDevice(device)); PG_CATCH }
+int32_t pg_host_alloc(size_t bytes, void** out) { PG_TRY PG_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault)); PG_CATCH }
+int32_t pg_host_free(void* p) { PG_TRY PG_CUDA(cudaFreeHost(p)); PG_CATCH }
+int32_t pg_device_alloc(size_t bytes, void** out) { PG_TRY PG_CUDA(cudaMalloc(out, bytes)); PG_CATCH }
+int32_t pg_device_free(void* p) { PG_TRY PG_CUDA(cudaFree(p)); PG_CATCH }
+int32_t pg_memcpy_h2d(void* dst, const void* src, size_t bytes) { PG_TRY PG_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); PG_CATCH }
+int32_t pg_memcpy_d2h(void* dst, const void* src, size_t bytes) { PG_TRY PG_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); PG_CATCH }
+int32_t pg_device_synchronize(void) { PG_TRY PG_CUDA(cudaDeviceSynchronize()); PG_CATCH }
+
+int64_t pg_hash_bigint(int64_t value) { return pg::hashLong(value); }
+int64_t pg_hash_combine(int64_t previous, int64_t h) { return (int64_t) (31ULL * (uint64_t) previous + (uint64_t) h); }
+int64_t pg_hash_murmur3_fmix64(int64_t x) { return (int64_t) pg::murmur64((uint64_t) x); }
+int32_t pg_hash_partition(int64_t rawHash, int32_t partitionCount) { return pg::hashPartition(rawHash, partitionCount); }
+
+int64_t pg_hash_xxhash64(const void* data, size_t len)
+{
+    // XXH64 seed 0 (airlift XxHash64.hash(Slice)); full-length host implementation
+    const uint64_t P1 = 0x9E3779B185EBCA87ULL, P2 = 0xC2B2AE3D27D4EB4FULL, P3 = 0x165667B19E3779F9ULL, P4 = 0x85EBCA77C2B2AE63ULL, P5 = 0x27D4EB2F165667C5ULL;
+    auto rot = [](uint64_t x, int r) { return (x << r) | (x >> (64 - r)); };
+    auto round = [&](uint64_t acc, uint64_t in) { acc += in * P2; acc = rot(acc, 31); return acc * P1; };
+    const uint8_t* p = (const uint8_t*) data;
+    const uint8_t* end = p + len;
+    uint64_t h;
+    if (len >= 32) {
+        uint64_t v1 = P1 + P2, v2 = P2, v3 = 0, v4 = 0 - P1;
+        while (p + 32 <= end) {
+            uint64_t a, b, c, d;
+            memcpy(&a, p, 8); memcpy(&b, p + 8, 8); memcpy(&c, p + 16, 8); memcpy(&d, p + 24, 8);
+            v1 = round(v1, a); v2 = round(v2, b); v3 = round(v3, c); v4 = round(v4, d);
+            p += 32;
+        }
+        h = rot(v1, 1) + rot(v2, 7) + rot(v3, 12) + rot(v4, 18);
+        for (uint64_t v : {v1, v2, v3, v4}) { h ^= round(0, v); h = h * P1 + P4; }
+    }
+    else h = P5;
+    h += (uint64_t) len;
+    while (p + 8 <= end) { uint64_t k; memcpy(&k, p, 8); h ^= round(0, k); h = rot(h, 27) * P1 + P4; p += 8; }
+    if (p + 4 <= end) { uint32_t k; memcpy(&k, p, 4); h ^= (uint64_t) k * P1; h = rot(h, 23) * P2 + P3; p += 4; }
+    while (p < end) { h ^= (uint64_t) (*p) * P5; h = rot(h, 11) * P1; p++; }
+    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+    return (int64_t) h;
+}
+
+// ---- operator protocol ------------------------------------------------------------------------------------------------
+int32_t pg_operator_needs_input(pg_operator* op, int32_t* out) { PG_TRY auto* o = (Operator*) op; o->bind(); *out = o->needsInput() ? 1 : 0; PG_CATCH }
+int32_t pg_operator_add_input(pg_operator* op, const pg_page* page)
+{
+    PG_TRY
+    auto* o = (Operator*) op;
+    o->bind();
+    PG_CHECK_ARG(page != nullptr && page->position_count >= 0, "bad page");
+    o->addInput(page);
+    PG_CATCH
+}
+int32_t pg_operator_get_output(pg_operator* op, pg_page* out)
+{
+    PG_TRY
+    auto* o = (Operator*) op;
+    o->bind();
+    if (!o->getOutput(out)) { out->position_count = 0; out->channel_count = 0; out->memory = o->options.output_memory; out->blocks = nullptr; }
+    PG_CATCH
+}
+int32_t pg_operator_finish(pg_operator* op) { PG_TRY auto* o = (Operator*) op; o->bind(); o->finish(); PG_CATCH }
+int32_t pg_operator_is_finished(pg_operator* op, int32_t* out) { PG_TRY auto* o = (Operator*) op; o->bind(); *out = o->isFinished() ? 1 : 0; PG_CATCH }
+int32_t pg_operator_get_stats(pg_operator* op, pg_operator_stats* out)
+{
+    PG_TRY
+    auto* o = (Operator*) op;
+    o->bind();
+    o->syncStats();
+    *out = o->stats;
+    PG_CATCH
+}
+int32_t pg_operator_destroy(pg_operator* op)
+{
+    PG_TRY
+    auto* o = (Operator*) op;
+    if (o) { cudaSetDevice(o->options.device); delete o; }
+    PG_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+"""Seeded synthetic TPC-H-shaped columns, the same values on the host (numpy) and in HBM (torch, used only
+as the device allocator / elementwise generator for benchmark INPUT data — never on the operator path).
+
+  splitmix64(seed, i) = mix(seed + (i + 1) * 0x9E3779B97F4A7C15)
+  group-by key   = (splitmix64(42, i) >> 11) % G                       (config 2: bigint key, G groups)
+  double column c= (splitmix64(43 + c, i) >> 11) * 2^-53 * 1e5          (config 2: 4 double aggregates)
+"""
+from __future__ import annotations
+
+import numpy as np
+
+_GOLD = 0x9E3779B97F4A7C15
+_M1 = 0xBF58476D1CE4E5B9
+_M2 = 0x94D049BB133111EB
+
+
+def _s64(x: int) -> int:
+    x &= (1 << 64) - 1
+    return x - (1 << 64) if x >= (1 << 63) else x
+
+
+def splitmix64_np(seed: int, start: int, n: int) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        i = np.arange(start + 1, start + 1 + n, dtype=np.uint64)
+        z = np.uint64(seed) + i * np.uint64(_GOLD)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(_M1)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(_M2)
+        return z ^ (z >> np.uint64(31))
+
+
+def group_key_np(start: int, n: int, groups: int, seed: int = 42) -> np.ndarray:
+    return ((splitmix64_np(seed, start, n) >> np.uint64(11)) % np.uint64(groups)).astype(np.int64)
+
+
+def double_column_np(column: int, start: int, n: int, seed: int = 43) -> np.ndarray:
+    return (splitmix64_np(seed + column, start, n) >> np.uint64(11)).astype(np.float64) * (2.0 ** -53 * 1e5)
+
+
+# ---- torch twins (device) -------------------------------------------------------------------------------------------------
+def _lsr(t, k):
+    return (t >> k) & ((1 << (64 - k)) - 1)
+
+
+def splitmix64_torch(seed: int, start: int, n: int, device):
+    import torch
+    i = torch.arange(start + 1, start + 1 + n, dtype=torch.int64, device=device)
+    z = i * _s64(_GOLD) + _s64(seed)
+    z = (z ^ _lsr(z, 30)) * _s64(_M1)
+    z = (z ^ _lsr(z, 27)) * _s64(_M2)
+    return z ^ _lsr(z, 31)
+
+
+def fill_group_key_torch(out, start: int, groups: int, seed: int = 42, chunk: int = 1 << 25) -> None:
+    n = out.numel()
+    for b in range(0, n, chunk):
+        m = min(chunk, n - b)
+        out[b:b + m] = _lsr(splitmix64_torch(seed, start + b, m, out.device), 11) % groups
+
+
+def fill_double_column_torch(out, column: int, start: int, seed: int = 43, chunk: int = 1 << 25) -> None:
+    n = out.numel()
+    for b in range(0, n, chunk):
+        m = min(chunk, n - b)
+        out[b:b + m] = _lsr(splitmix64_torch(seed + column, start + b, m, out.device), 11).to(out.dtype) * (2.0 ** -53 * 1e5)
+
+
+# ---- join (config 3): orders ⋈ lineitem ------------------------------------------------------------------------------------
+def sparse_order_key_np(i: np.ndarray) -> np.ndarray:
+    """dbgen mk_sparse: 8 of every 32 integers are order keys (velox/tpch/gen/dbgen/build.cpp:144-156)."""
+    i = i.astype(np.int64)
+    return ((i >> 3) << 5) + (i & 7)

@@ -1,0 +1,92 @@
+"""CPU-side checks of the drop-in boundary: libprestogpu.so loads and exports every symbol include/presto_gpu.h declares
+(no compute calls without a GPU), the ctypes mirrors match the header's struct layouts, and the product fails loudly — it
+never falls back to a CPU path — when no CUDA device is visible."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "presto_gpu.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    return sorted(set(re.findall(r"\b(pg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from presto_b200._lib import LIB_PATH, load_library
+    assert os.path.exists(LIB_PATH), "build the extension first: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = C.CDLL(LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 40
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"libprestogpu.so does not export {missing}"
+    backend = load_library()
+    assert backend.version().startswith(b"presto_b200")
+
+
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof/offsetof of every ABI struct, computed by the C compiler from the header, equals the ctypes mirror's."""
+    from presto_b200 import _abi as abi
+    structs = ["pg_block", "pg_page", "pg_operator_stats", "pg_operator_options", "pg_aggregate", "pg_hash_aggregation_config",
+               "pg_group_by_hash_config", "pg_hash_builder_config", "pg_lookup_join_config", "pg_partitioned_output_config",
+               "pg_expr_node", "pg_filter_project_config"]
+    src = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
+    for s in structs:
+        cls = getattr(abi, s)
+        src.append(f'printf("{s} %zu", sizeof({s}));')
+        for fname, _ in cls._fields_:
+            src.append(f'printf(" %zu", offsetof({s}, {fname}));')
+        src.append('printf("\\n");')
+    src.append("return 0;}")
+    cfile = tmp_path / "layout.c"
+    cfile.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-o", str(exe), str(cfile)])
+    out = subprocess.check_output([str(exe)]).decode().splitlines()
+    for line in out:
+        parts = line.split()
+        cls = getattr(abi, parts[0])
+        expect = [C.sizeof(cls)] + [getattr(cls, f).offset for f, _ in cls._fields_]
+        assert [int(x) for x in parts[1:]] == expect, f"layout mismatch for {parts[0]}"
+
+
+def test_no_cpu_fallback_without_a_device():
+    """On a box without a GPU every operator constructor must raise NO_DEVICE (this test is skipped where a GPU exists)."""
+    from presto_b200 import AGG_COUNT_STAR, BIGINT, Aggregate, HashAggregationOperator, JoinBridge, PrestoException
+    from presto_b200._lib import load_library
+    b = load_library()
+    n = C.c_int32()
+    if b.device_count(C.byref(n)) == 0 and n.value > 0:
+        pytest.skip("a CUDA device is visible")
+    with pytest.raises(PrestoException) as e:
+        HashAggregationOperator([BIGINT], [0], [Aggregate(AGG_COUNT_STAR)])
+    assert e.value.code == 8
+    with pytest.raises(PrestoException):
+        JoinBridge()
+
+
+def test_product_never_imports_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py may touch oracle/."""
+    pkg = os.path.join(ROOT, "presto_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", text, re.M), f"{f} imports the oracle"
+                assert "liboracle" not in text and "oracle_" not in text, f"{f} references the oracle"
+
+
+def test_host_hash_helpers_match_known_answers():
+    """pg_hash_* host helpers (no GPU needed) against SURVEY.md §8c known answers."""
+    from presto_b200._lib import load_library
+    b = load_library()
+    assert b.hash_bigint(1) == 9155312661752487122 and b.hash_bigint(42) == 1279370338401826588
+    assert b.hash_murmur3_fmix64(1) == -5451962507482445012 and b.hash_murmur3_fmix64(-1) == 7256831767414464289
+    assert [b.hash_partition(b.hash_bigint(v), 8) for v in (0, 1, 42)] == [0, 4, 2]
+    assert b.hash_xxhash64(b"A", 1) == 1371800463213966980 and b.hash_xxhash64(b"", 0) == -1205034819632174695
+    assert b.hash_combine(3, 4) == 97

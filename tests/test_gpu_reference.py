@@ -1,0 +1,57 @@
+"""-m gpu: the reference's behavioural tests (tests/reference_cases.py) against the CUDA product through the C ABI."""
+import pytest
+
+import reference_cases as rc
+
+pytestmark = pytest.mark.gpu
+
+
+def test_group_by_hash_add_page(gpu_backend): rc.case_group_by_hash_add_page(gpu_backend, max_group_id=120, tries_per_value=2)
+def test_group_by_hash_null_group(gpu_backend): rc.case_group_by_hash_null_group(gpu_backend)
+def test_group_by_hash_get_group_ids(gpu_backend): rc.case_group_by_hash_get_group_ids(gpu_backend, max_group_id=120, tries_per_value=2)
+def test_group_by_hash_append_to(gpu_backend): rc.case_group_by_hash_append_to(gpu_backend)
+def test_group_by_hash_append_to_multiple(gpu_backend): rc.case_group_by_hash_append_to_multiple_tuples_per_group(gpu_backend)
+def test_group_by_hash_contains(gpu_backend): rc.case_group_by_hash_contains(gpu_backend)
+def test_group_by_hash_contains_multiple_columns(gpu_backend): rc.case_group_by_hash_contains_multiple_columns(gpu_backend)
+def test_group_by_hash_force_rehash(gpu_backend): rc.case_group_by_hash_force_rehash(gpu_backend)
+
+
+@pytest.mark.parametrize("hash_enabled", [False, True])
+def test_hash_aggregation(gpu_backend, hash_enabled): rc.case_hash_aggregation(gpu_backend, hash_enabled)
+def test_hash_aggregation_null_inputs(gpu_backend): rc.case_hash_aggregation_null_inputs(gpu_backend)
+def test_hash_aggregation_mask(gpu_backend): rc.case_hash_aggregation_mask(gpu_backend)
+def test_hash_aggregation_multi_key(gpu_backend): rc.case_hash_aggregation_multi_key(gpu_backend)
+def test_hash_aggregation_empty(gpu_backend): rc.case_hash_aggregation_empty(gpu_backend)
+def test_hash_aggregation_add_after_finish(gpu_backend): rc.case_hash_aggregation_add_after_finish(gpu_backend)
+def test_bigint_sum_overflow(gpu_backend): rc.case_bigint_sum_overflow(gpu_backend)
+
+
+HASH_FLAGS = [(False, False), (True, True)]
+
+
+@pytest.mark.parametrize("probe_hash,build_hash", HASH_FLAGS)
+def test_inner_join(gpu_backend, probe_hash, build_hash): rc.case_inner_join(gpu_backend, probe_hash, build_hash)
+@pytest.mark.parametrize("probe_hash,build_hash", HASH_FLAGS)
+def test_inner_join_with_null_probe(gpu_backend, probe_hash, build_hash): rc.case_inner_join_with_null_probe(gpu_backend, probe_hash, build_hash)
+@pytest.mark.parametrize("probe_hash,build_hash", HASH_FLAGS)
+def test_inner_join_with_null_build(gpu_backend, probe_hash, build_hash): rc.case_inner_join_with_null_build(gpu_backend, probe_hash, build_hash)
+@pytest.mark.parametrize("probe_hash,build_hash", HASH_FLAGS)
+def test_inner_join_with_null_on_both_sides(gpu_backend, probe_hash, build_hash): rc.case_inner_join_with_null_on_both_sides(gpu_backend, probe_hash, build_hash)
+@pytest.mark.parametrize("probe_hash,build_hash", HASH_FLAGS)
+def test_probe_outer_join(gpu_backend, probe_hash, build_hash): rc.case_probe_outer_join(gpu_backend, probe_hash, build_hash)
+@pytest.mark.parametrize("probe_hash,build_hash", HASH_FLAGS)
+def test_outer_join_with_null_on_both_sides(gpu_backend, probe_hash, build_hash): rc.case_outer_join_with_null_on_both_sides(gpu_backend, probe_hash, build_hash)
+def test_probe_outer_join_empty_lookup_source(gpu_backend): rc.case_probe_outer_join_empty_lookup_source(gpu_backend)
+def test_join_duplicate_chain_order(gpu_backend): rc.case_join_duplicate_chain_order(gpu_backend)
+
+
+@pytest.mark.parametrize("partition_count,nulls,precomputed", [(1, False, False), (4, False, False), (7, True, False), (8, True, True), (256, False, True)])
+def test_partitioned_output(gpu_backend, partition_count, nulls, precomputed):
+    rc.case_partitioned_output(gpu_backend, partition_count, 1000, nulls, precomputed)
+def test_partitioned_output_replicates(gpu_backend): rc.case_partitioned_output_replicates(gpu_backend)
+
+
+def test_page_processor_selection(gpu_backend): rc.case_page_processor_selection(gpu_backend)
+def test_page_processor_q1(gpu_backend): rc.case_page_processor_q1(gpu_backend)
+def test_page_processor_three_valued_logic(gpu_backend): rc.case_page_processor_three_valued_logic(gpu_backend)
+def test_page_processor_hash_projection(gpu_backend): rc.case_page_processor_hash_projection(gpu_backend)
