@@ -46,6 +46,16 @@ inline int typeWidth(int type)
 
 inline int64_t divUp(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// ---- caching allocator ------------------------------------------------------------------------------------------------
+// Operators come and go per query; cudaMalloc / cudaHostAlloc cost milliseconds, so freed blocks are kept per device in size
+// classes (3 significant bits, <= 12.5% slack) and handed out again.  Callers only release a block after the stream that used it
+// has been synchronised (every operator synchronises before it returns to the host).
+void* cachedDeviceAlloc(size_t bytes, size_t* granted);
+void cachedDeviceFree(void* p, size_t granted);
+void* cachedPinnedAlloc(size_t bytes, size_t* granted);
+void cachedPinnedFree(void* p, size_t granted);
+void trimAllocationCaches();
+
 // ---- device buffer (grow-only) -------------------------------------------------------------------------------------
 struct DeviceBuffer {
     void* ptr = nullptr;
@@ -63,7 +73,7 @@ struct DeviceBuffer {
     ~DeviceBuffer() { release(); }
     void release()
     {
-        if (ptr) { cudaFree(ptr); if (accounting) *accounting -= (int64_t) capacity; }
+        if (ptr) { cachedDeviceFree(ptr, capacity); if (accounting) *accounting -= (int64_t) capacity; }
         ptr = nullptr; capacity = 0;
     }
     // Ensure at least `bytes`; contents are NOT preserved when it grows.
@@ -71,9 +81,7 @@ struct DeviceBuffer {
     {
         if (bytes <= capacity) return;
         release();
-        size_t want = (bytes + 255) & ~size_t(255);
-        PG_CUDA(cudaMalloc(&ptr, want));
-        capacity = want;
+        ptr = cachedDeviceAlloc(bytes, &capacity);
         if (accounting) *accounting += (int64_t) capacity;
     }
     template <typename T> T* as() const { return reinterpret_cast<T*>(ptr); }
@@ -82,14 +90,17 @@ struct DeviceBuffer {
 struct PinnedBuffer {
     void* ptr = nullptr;
     size_t capacity = 0;
-    ~PinnedBuffer() { if (ptr) cudaFreeHost(ptr); }
+    PinnedBuffer() = default;
+    PinnedBuffer(const PinnedBuffer&) = delete;
+    PinnedBuffer& operator=(const PinnedBuffer&) = delete;
+    PinnedBuffer(PinnedBuffer&& o) noexcept { ptr = o.ptr; capacity = o.capacity; o.ptr = nullptr; o.capacity = 0; }
+    ~PinnedBuffer() { if (ptr) cachedPinnedFree(ptr, capacity); }
     void reserve(size_t bytes)
     {
         if (bytes <= capacity) return;
-        if (ptr) cudaFreeHost(ptr);
+        if (ptr) cachedPinnedFree(ptr, capacity);
         ptr = nullptr; capacity = 0;
-        PG_CUDA(cudaHostAlloc(&ptr, bytes, cudaHostAllocDefault));
-        capacity = bytes;
+        ptr = cachedPinnedAlloc(bytes, &capacity);
     }
     template <typename T> T* as() const { return reinterpret_cast<T*>(ptr); }
 };

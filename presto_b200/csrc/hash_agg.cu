@@ -46,13 +46,37 @@ struct AggLaunch {
     uint32_t* bitmapOut;         // rows that could not claim a slot (table at its limit)
     uint32_t S;                  // shared table slots (power of two); 0 = no shared table
     uint32_t sLimit;
+    int32_t nAccAlloc;           // accumulator columns the shared table was sized for (>= nAcc)
+    int32_t vec;                 // every 8-byte column pointer is 16-byte aligned: load row pairs with one 128-bit request
 };
 
 constexpr int kAggThreads = 256;
 constexpr int kSharedProbes = 8;
 constexpr int kWarpAggMaxGroups = 8;
 
-template <int MAXV> struct RowsPerThread { static constexpr int value = MAXV <= 4 ? 4 : (MAXV <= 8 ? 2 : 1); };
+template <int MAXV> struct RowsPerThread { static constexpr int value = MAXV <= 4 ? 4 : 2; };   // always even: rows are loaded in pairs
+// Tier 0: the first kTier0Groups groups a CTA claims get per-thread private accumulators in shared memory.
+template <int MAXV> struct Tier0Groups { static constexpr int value = 32 / MAXV; };
+constexpr int kTier0Bytes = 32 * kAggThreads * 8;   // K0 * MAXV == 32 columns of 256 doubles
+
+// shared-memory carve-up, same arithmetic on host and device
+struct SharedLayout {
+    uint32_t keys, acc, first, state, sid, misc, tier0, total;
+    __host__ __device__ SharedLayout(uint32_t S, int W, int nAccAlloc, bool withTier0)
+    {
+        const uint32_t S2 = S + 2;
+        uint32_t o = 0;
+        keys = o; o += 8 * W * S2;
+        acc = o; o += 8 * nAccAlloc * S2;
+        first = o; o += 4 * S2;
+        state = o; o += (W > 1 ? 4 * S2 : 0);
+        sid = o; o += (S2 + 15) & ~15u;
+        misc = o; o += 256;   // claimed count, next tier-0 id, slot of each tier-0 id (<= 32)
+        o = (o + 15) & ~15u;
+        tier0 = o; o += withTier0 ? kTier0Bytes : 0;
+        total = o;
+    }
+};
 
 // ---- shared-memory table ---------------------------------------------------------------------------------------------
 template <int W>
@@ -61,8 +85,19 @@ struct SharedTable {
     volatile uint32_t* state;   // [S2] (W > 1)
     uint64_t* acc;              // [nAcc][S2]
     uint32_t* first;            // [S2]
-    uint32_t* count;            // claimed slots
+    volatile uint8_t* sid;      // [S2] tier-0 id of the slot's group, 0xFF = none
+    uint32_t* count;            // misc[0] claimed slots, misc[1] next tier-0 id, misc[2..] slot of tier-0 id
     uint32_t S, S2, sLimit;
+    int tier0Groups;
+
+    __device__ __forceinline__ void claimed(uint32_t s) const
+    {
+        atomicAdd(count, 1u);
+        if (tier0Groups) {
+            uint32_t id = atomicAdd(count + 1, 1u);
+            if (id < (uint32_t) tier0Groups) { count[2 + id] = s; __threadfence_block(); sid[s] = (uint8_t) id; }
+        }
+    }
 
     __device__ __forceinline__ int find(const uint64_t (&kw)[W], uint64_t h) const
     {
@@ -75,7 +110,7 @@ struct SharedTable {
                 if (k == kEmptyKey) {
                     if (*(volatile uint32_t*) count >= sLimit) return -1;
                     uint64_t old = atomicCAS((unsigned long long*) &keys[s], (unsigned long long) kEmptyKey, (unsigned long long) kw[0]);
-                    if (old == kEmptyKey) { atomicAdd(count, 1u); return (int) s; }
+                    if (old == kEmptyKey) { claimed(s); return (int) s; }
                     if (old == kw[0]) return (int) s;
                 }
                 s = (s + 1) & (S - 1);
@@ -95,7 +130,7 @@ struct SharedTable {
                         for (int w = 0; w < W; w++) keys[w * S2 + s] = kw[w];
                         __threadfence_block();
                         state[s] = ready;
-                        atomicAdd(count, 1u);
+                        claimed(s);
                         return (int) s;
                     }
                     st = old;
@@ -124,38 +159,57 @@ __device__ __forceinline__ void accAddGlobal(uint64_t* addr, uint64_t bits, bool
     if (isFloat) atomicAdd((double*) addr, __longlong_as_double((long long) bits));   // REDG.E.ADD.F64
     else atomicAdd((unsigned long long*) addr, (unsigned long long) bits);
 }
+__device__ __forceinline__ uint64_t contribOf(int kind, uint64_t raw)
+{
+    switch (kind) {
+        case K_COUNT: return 1;
+        case K_F64: case K_I64_ADD: return raw;
+        case K_F64_FROM_I64: return (uint64_t) __double_as_longlong((double) (long long) raw);
+        case K_LO32: return raw & 0xffffffffULL;
+        default: return (uint64_t) ((long long) raw >> 32);   // K_HI32
+    }
+}
 
 // ---- the fused kernel ---------------------------------------------------------------------------------------------------
+// Three tiers, hottest first:
+//   tier 0  the first K0 groups a CTA claims: per-thread private accumulators in shared memory — plain LDS/DADD/STS, no atomics,
+//           no shuffles (TPC-H Q1 has 4 groups: every row ends here)
+//   tier 1  the CTA's shared hash table (up to sLimit groups): warp-aggregated shared atomics
+//   tier 2  the HBM table: find-or-claim + REDG per accumulator (high cardinality)
 template <int W, int MAXV>
 __global__ void __launch_bounds__(kAggThreads) hashAggKernel(const __grid_constant__ AggLaunch<MAXV> P)
 {
     constexpr int R = RowsPerThread<MAXV>::value;
+    constexpr int K0 = Tier0Groups<MAXV>::value;
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int tid = threadIdx.x, lane = tid & 31;
     const int nAcc = P.nAcc;
     const GroupTable& T = P.t;
+    const bool useShared = P.S != 0;
 
     SharedTable<W> st;
-    st.S = P.S; st.S2 = P.S + 2; st.sLimit = P.sLimit;
-    {
-        unsigned char* p = smemRaw;
-        st.keys = (volatile uint64_t*) p; p += sizeof(uint64_t) * W * st.S2;
-        st.acc = (uint64_t*) p; p += sizeof(uint64_t) * (size_t) nAcc * st.S2;
-        st.first = (uint32_t*) p; p += sizeof(uint32_t) * st.S2;
-        st.state = (volatile uint32_t*) p; p += sizeof(uint32_t) * (W > 1 ? st.S2 : 0);
-        st.count = (uint32_t*) p;
-    }
-    const bool useShared = P.S != 0;
+    st.S = P.S; st.S2 = P.S + 2; st.sLimit = P.sLimit; st.tier0Groups = useShared ? K0 : 0;
+    const SharedLayout lay(P.S, W, P.nAccAlloc, true);
+    st.keys = (volatile uint64_t*) (smemRaw + lay.keys);
+    st.acc = (uint64_t*) (smemRaw + lay.acc);
+    st.first = (uint32_t*) (smemRaw + lay.first);
+    st.state = (volatile uint32_t*) (smemRaw + lay.state);
+    st.sid = (volatile uint8_t*) (smemRaw + lay.sid);
+    st.count = (uint32_t*) (smemRaw + lay.misc);
+    uint64_t* tier0 = (uint64_t*) (smemRaw + lay.tier0);     // [K0 * MAXV][256]
     if (useShared) {
         for (uint32_t i = tid; i < W * st.S2; i += kAggThreads) st.keys[i] = kEmptyKey;
-        for (uint32_t i = tid; i < (uint32_t) nAcc * st.S2; i += kAggThreads) st.acc[i] = 0;
-        for (uint32_t i = tid; i < st.S2; i += kAggThreads) { st.first[i] = kNoRow32; if (W > 1) st.state[i] = kStEmpty; }
-        if (tid == 0) *st.count = 0;
+        for (uint32_t i = tid; i < (uint32_t) P.nAccAlloc * st.S2; i += kAggThreads) st.acc[i] = 0;
+        for (uint32_t i = tid; i < st.S2; i += kAggThreads) { st.first[i] = kNoRow32; st.sid[i] = 0xFF; if (W > 1) st.state[i] = kStEmpty; }
+        if (tid < 64) st.count[tid] = 0;
+#pragma unroll
+        for (int i = 0; i < 32; i++) tier0[i * kAggThreads + tid] = 0;
         __syncthreads();
     }
 
     bool warpBypass = !useShared;
     uint32_t warpHits = 0, warpRows = 0;
+    uint32_t seen0 = 0;                       // tier-0 ids this thread has already recorded a first row for
     constexpr int TILE = kAggThreads * R;
     const int64_t nTiles = (P.n + TILE - 1) / TILE;
 
@@ -165,60 +219,95 @@ __global__ void __launch_bounds__(kAggThreads) hashAggKernel(const __grid_consta
         uint32_t addMask[R];
         int special[R];
         bool valid[R];
-        // ---- load phase: all loads of the tile are issued before any is consumed (R x (keys + nAcc) requests in flight) ----
+        uint32_t rowIdxOf[R];
+        // ---- load phase: every load of the tile is issued before any is consumed; 8-byte columns come in as 128-bit pairs ----
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            const int64_t row = tile * TILE + (int64_t) r * kAggThreads + tid;
-            bool v = row < P.n;
-            if (v && P.bitmapIn) v = (P.bitmapIn[row >> 5] >> (row & 31)) & 1u;
-            valid[r] = v;
-            addMask[r] = 0;
-            special[r] = 0;
+        for (int j = 0; j < R / 2; j++) {
+            const int64_t row0 = tile * TILE + (int64_t) j * (2 * kAggThreads) + 2 * tid;
+            bool v0 = row0 < P.n, v1 = row0 + 1 < P.n;
+            if (P.bitmapIn) {
+                if (v0) v0 = (P.bitmapIn[row0 >> 5] >> (row0 & 31)) & 1u;
+                if (v1) v1 = (P.bitmapIn[(row0 + 1) >> 5] >> ((row0 + 1) & 31)) & 1u;
+            }
+            const bool pair = P.vec && v0 && v1;
+            valid[2 * j] = v0; valid[2 * j + 1] = v1;
+            rowIdxOf[2 * j] = (uint32_t) row0; rowIdxOf[2 * j + 1] = (uint32_t) (row0 + 1);
+            addMask[2 * j] = 0; addMask[2 * j + 1] = 0;
+            special[2 * j] = 0; special[2 * j + 1] = 0;
 #pragma unroll
-            for (int w = 0; w < W; w++) kw[r][w] = 0;
-            if (v) {
-                special[r] = packKey<W>(P.kp, row, kw[r]);
+            for (int w = 0; w < W; w++) { kw[2 * j][w] = 0; kw[2 * j + 1][w] = 0; }
+            // keys
+            if (P.kp.bigintPath) {
+                const KeyField& f = P.kp.f[0];
+                uint64_t a = 0, b = 0;
+                if (pair) { const ulonglong2 t = ldStream128((const uint64_t*) f.values + row0); a = t.x; b = t.y; }
+                else { if (v0) a = ldStream64((const uint64_t*) f.values + row0); if (v1) b = ldStream64((const uint64_t*) f.values + row0 + 1); }
+                kw[2 * j][0] = a; kw[2 * j + 1][0] = b;
+                if (v0) special[2 * j] = (f.nulls && f.nulls[row0]) ? 1 : (a == kEmptyKey ? 2 : 0);
+                if (v1) special[2 * j + 1] = (f.nulls && f.nulls[row0 + 1]) ? 1 : (b == kEmptyKey ? 2 : 0);
+            }
+            else {
+                if (v0) special[2 * j] = packKey<W>(P.kp, row0, kw[2 * j]);
+                if (v1) special[2 * j + 1] = packKey<W>(P.kp, row0 + 1, kw[2 * j + 1]);
+            }
+            // accumulator inputs
 #pragma unroll
-                for (int c = 0; c < MAXV; c++) {
-                    contrib[r][c] = 0;
-                    if (c < nAcc) {
-                        const AccInput& a = P.acc[c];
-                        bool add = true;
-                        if (a.mask) add = a.mask[row] != 0 && !(a.maskNulls && a.maskNulls[row]);
-                        if (add && a.nulls) add = a.nulls[row] == 0;
-                        uint64_t x = 1;
-                        if (a.kind != K_COUNT) {
-                            uint64_t raw = ldStream64(a.values + row);
-                            switch (a.kind) {
-                                case K_F64: case K_I64_ADD: x = raw; break;
-                                case K_F64_FROM_I64: x = (uint64_t) __double_as_longlong((double) (long long) raw); break;
-                                case K_LO32: x = raw & 0xffffffffULL; break;
-                                default: x = (uint64_t) ((long long) raw >> 32); break;   // K_HI32
-                            }
-                        }
-                        contrib[r][c] = x;
-                        if (add) addMask[r] |= 1u << c;
+            for (int c = 0; c < MAXV; c++) {
+                contrib[2 * j][c] = 0; contrib[2 * j + 1][c] = 0;
+                if (c < nAcc) {
+                    const AccInput& a = P.acc[c];
+                    bool add0 = v0, add1 = v1;
+                    if (a.mask) {
+                        if (add0) add0 = a.mask[row0] != 0 && !(a.maskNulls && a.maskNulls[row0]);
+                        if (add1) add1 = a.mask[row0 + 1] != 0 && !(a.maskNulls && a.maskNulls[row0 + 1]);
                     }
+                    if (a.nulls) { if (add0) add0 = a.nulls[row0] == 0; if (add1) add1 = a.nulls[row0 + 1] == 0; }
+                    uint64_t r0 = 0, r1 = 0;
+                    if (a.kind != K_COUNT) {
+                        if (pair) { const ulonglong2 t = ldStream128(a.values + row0); r0 = t.x; r1 = t.y; }
+                        else { if (v0) r0 = ldStream64(a.values + row0); if (v1) r1 = ldStream64(a.values + row0 + 1); }
+                    }
+                    contrib[2 * j][c] = contribOf(a.kind, r0); contrib[2 * j + 1][c] = contribOf(a.kind, r1);
+                    if (add0) addMask[2 * j] |= 1u << c;
+                    if (add1) addMask[2 * j + 1] |= 1u << c;
                 }
             }
         }
         // ---- accumulate phase ----
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            const uint32_t rowIdx = (uint32_t) (tile * TILE + (int64_t) r * kAggThreads + tid);
+            const uint32_t rowIdx = rowIdxOf[r];
             const bool v = valid[r];
             uint64_t h = 0;
             int sslot = -1;
+            bool done = false;
             if (v) {
                 h = hashKeyWords<W>(kw[r]);
                 if (!warpBypass) sslot = special[r] ? (int) st.S + special[r] - 1 : st.find(kw[r], h);
+                if (sslot >= 0) {
+                    const uint32_t id = st.sid[sslot];
+                    if (id < (uint32_t) K0) {
+                        // tier 0: this thread's private accumulators of group `id` (bank-conflict free: consecutive threads, consecutive words)
+                        uint64_t* mine = tier0 + (size_t) id * MAXV * kAggThreads + tid;
+#pragma unroll
+                        for (int c = 0; c < MAXV; c++) {
+                            if (c < nAcc && ((addMask[r] >> c) & 1u)) {
+                                uint64_t* p = mine + c * kAggThreads;
+                                if ((P.floatMask >> c) & 1u) *(double*) p = *(double*) p + __longlong_as_double((long long) contrib[r][c]);
+                                else *p = *p + contrib[r][c];
+                            }
+                        }
+                        if (!((seen0 >> id) & 1u)) { seen0 |= 1u << id; atomicMin(&st.first[sslot], rowIdx); }   // rows ascend per thread: first sight = this thread's minimum
+                        done = true;
+                    }
+                }
             }
-            const bool hit = v && sslot >= 0;
+            const bool hit = v && sslot >= 0 && !done;
             const unsigned hits = __ballot_sync(0xffffffffu, hit);
-            warpHits += __popc(hits);
+            warpHits += __popc(__ballot_sync(0xffffffffu, v && sslot >= 0));
             warpRows += __popc(__ballot_sync(0xffffffffu, v));
             if (hits) {
-                // group the warp's lanes by shared slot; lanes that missed form singleton groups
+                // tier 1: group the warp's lanes by shared slot; lanes that missed form singleton groups
                 const int matchKey = hit ? sslot : -1 - lane;
                 const unsigned peers = __match_any_sync(0xffffffffu, matchKey);
                 const bool isLeader = hit && (lane == __ffs(peers) - 1);
@@ -270,8 +359,8 @@ __global__ void __launch_bounds__(kAggThreads) hashAggKernel(const __grid_consta
                     if (rowIdx < *(volatile uint32_t*) &st.first[sslot]) atomicMin(&st.first[sslot], rowIdx);
                 }
             }
-            if (v && !hit) {
-                // HBM table path (high cardinality, or shared table full)
+            if (v && sslot < 0) {
+                // tier 2: HBM table (high cardinality, or the shared table is full)
                 int gslot = special[r] ? (int) T.cap + special[r] - 1 : tableFind<W>(T, kw[r], h, true, false);
                 if (gslot == -2) {
                     atomicOr(&P.bitmapOut[rowIdx >> 5], 1u << (rowIdx & 31));
@@ -294,8 +383,34 @@ __global__ void __launch_bounds__(kAggThreads) hashAggKernel(const __grid_consta
         }
     }
 
-    // ---- flush the CTA's shared table into the HBM table ----
+    // ---- fold tier 0 into the CTA's shared table, then flush that into the HBM table ----
     if (useShared) {
+        __syncthreads();
+        const uint32_t nT0 = min(st.count[1], (uint32_t) K0);
+        const int warp = tid >> 5;
+        for (uint32_t pairIdx = warp; pairIdx < nT0 * (uint32_t) MAXV; pairIdx += kAggThreads / 32) {
+            const uint32_t id = pairIdx / MAXV, c = pairIdx % MAXV;
+            if ((int) c >= nAcc) continue;
+            const uint64_t* src = tier0 + (size_t) pairIdx * kAggThreads;
+            const bool isF = (P.floatMask >> c) & 1u;
+            uint64_t x = 0;
+            if (isF) {
+                double d = 0;
+                for (int i = lane; i < kAggThreads; i += 32) d += __longlong_as_double((long long) src[i]);
+                x = (uint64_t) __double_as_longlong(d);
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) x = (uint64_t) __double_as_longlong(__longlong_as_double((long long) x) + __longlong_as_double((long long) shflXor64(x, m)));
+            }
+            else {
+                for (int i = lane; i < kAggThreads; i += 32) x += src[i];
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) x += shflXor64(x, m);
+            }
+            if (lane == 0) {
+                uint64_t* dst = &st.acc[c * st.S2 + st.count[2 + id]];
+                if (isF) *(double*) dst = *(double*) dst + __longlong_as_double((long long) x); else *dst = *dst + x;
+            }
+        }
         __syncthreads();
         for (uint32_t s = tid; s < st.S2; s += kAggThreads) {
             const uint32_t f = st.first[s];
@@ -315,6 +430,208 @@ __global__ void __launch_bounds__(kAggThreads) hashAggKernel(const __grid_consta
                 const uint64_t x = st.acc[c * st.S2 + s];
                 if (x != 0) accAddGlobal(&T.acc[(size_t) gslot * T.nvPhys + P.acc[c].phys], x, (P.floatMask >> c) & 1u);
             }
+        }
+    }
+}
+
+// ---- specialised kernel: one non-null BIGINT key, NV non-null DOUBLE sums (+ optional row count), no masks ------------------
+// Same three tiers and the same tables as hashAggKernel, but every runtime flag of the generic kernel is a compile-time
+// constant here, and the tile loads are software pipelined (tile t+1's 128-bit loads are in flight while tile t is consumed).
+template <int NV, bool CNT>
+struct FastLaunch {
+    GroupTable t;
+    const uint64_t* key;
+    const uint64_t* vals[NV];
+    int32_t phys[NV + 1];        // physical accumulator column of each value column, then of the row count
+    int64_t n;
+    uint64_t rowBase;
+    uint32_t* bitmapOut;
+    uint32_t S, sLimit;
+    int32_t nAccAlloc;
+};
+
+template <int NV, bool CNT> struct FastGeom {
+    static constexpr int NC = NV + (CNT ? 1 : 0);       // accumulator columns
+    static constexpr int K0 = 32 / NC;                  // tier-0 groups (K0 * NC <= 32 columns of 256 x 8 B = 64 KB)
+};
+
+// Rows that are not tier 0: the CTA's shared table (direct shared atomics) or the HBM table.  Kept out of line so the hot loop stays small.
+template <int NV, bool CNT>
+__device__ __noinline__ void fastSlowRow(const FastLaunch<NV, CNT>& P, const SharedTable<1>& st, int sslot, uint64_t key, uint64_t h,
+                                         const uint64_t (&vals)[NV], uint32_t rowIdx)
+{
+    constexpr int NC = FastGeom<NV, CNT>::NC;
+    if (sslot >= 0) {
+#pragma unroll
+        for (int c = 0; c < NV; c++) atomicAdd((double*) &st.acc[c * st.S2 + sslot], __longlong_as_double((long long) vals[c]));
+        if (CNT) atomicAdd((unsigned long long*) &st.acc[NV * st.S2 + sslot], 1ULL);
+        if (rowIdx < *(volatile uint32_t*) &st.first[sslot]) atomicMin(&st.first[sslot], rowIdx);
+        return;
+    }
+    const GroupTable& T = P.t;
+    uint64_t kw[1] = {key};
+    int gslot = key == kEmptyKey ? (int) T.cap + 1 : tableFind<1>(T, kw, h, true, false);
+    if (gslot == -2) {
+        atomicOr(&P.bitmapOut[rowIdx >> 5], 1u << (rowIdx & 31));
+        atomicAdd(&T.counters[CNT_DEFERRED], 1u);
+        return;
+    }
+    const uint64_t g = P.rowBase + rowIdx;
+    if (g < __ldcg(&T.firstRow[gslot])) atomicMin((unsigned long long*) &T.firstRow[gslot], (unsigned long long) g);
+    uint64_t* acc = T.acc + (size_t) gslot * T.nvPhys;
+#pragma unroll
+    for (int c = 0; c < NV; c++) atomicAdd((double*) &acc[P.phys[c]], __longlong_as_double((long long) vals[c]));
+    if (CNT) atomicAdd((unsigned long long*) &acc[P.phys[NV]], 1ULL);
+    (void) NC;
+}
+
+template <int NV, bool CNT>
+__global__ void __launch_bounds__(kAggThreads, 2) hashAggFastKernel(const __grid_constant__ FastLaunch<NV, CNT> P)
+{
+    constexpr int NC = FastGeom<NV, CNT>::NC;
+    constexpr int K0 = FastGeom<NV, CNT>::K0;
+    constexpr int TILE = kAggThreads * 2;            // one 128-bit pair per thread per column per tile
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const GroupTable& T = P.t;
+
+    SharedTable<1> st;
+    st.S = P.S; st.S2 = P.S + 2; st.sLimit = P.sLimit; st.tier0Groups = K0;
+    const SharedLayout lay(P.S, 1, P.nAccAlloc, true);
+    st.keys = (volatile uint64_t*) (smemRaw + lay.keys);
+    st.acc = (uint64_t*) (smemRaw + lay.acc);
+    st.first = (uint32_t*) (smemRaw + lay.first);
+    st.state = nullptr;
+    st.sid = (volatile uint8_t*) (smemRaw + lay.sid);
+    st.count = (uint32_t*) (smemRaw + lay.misc);
+    uint64_t* tier0 = (uint64_t*) (smemRaw + lay.tier0);     // [K0][NC][256]
+    for (uint32_t i = tid; i < st.S2; i += kAggThreads) { st.keys[i] = kEmptyKey; st.first[i] = kNoRow32; st.sid[i] = 0xFF; }
+    for (uint32_t i = tid; i < (uint32_t) P.nAccAlloc * st.S2; i += kAggThreads) st.acc[i] = 0;
+    if (tid < 64) st.count[tid] = 0;
+#pragma unroll
+    for (int i = 0; i < K0 * NC; i++) tier0[i * kAggThreads + tid] = 0;
+    __syncthreads();
+
+    uint32_t seen0 = 0;
+    uint32_t probeHits = 0, probeMisses = 0;
+    bool bypass = false;
+    const int64_t nTiles = (P.n + TILE - 1) / TILE;
+    const uint64_t* keyBase = P.key;
+
+    // double-buffered tile registers
+    ulonglong2 kA, kB, vA[NV], vB[NV];
+    auto loadTile = [&](int64_t tile, ulonglong2& k, ulonglong2 (&v)[NV]) {
+        const int64_t row0 = tile * TILE + 2 * tid;
+        if (row0 + 1 < P.n) {
+            k = ldStream128(keyBase + row0);
+#pragma unroll
+            for (int c = 0; c < NV; c++) v[c] = ldStream128(P.vals[c] + row0);
+        }
+        else if (row0 < P.n) {
+            k.x = ldStream64(keyBase + row0); k.y = 0;
+#pragma unroll
+            for (int c = 0; c < NV; c++) { v[c].x = ldStream64(P.vals[c] + row0); v[c].y = 0; }
+        }
+    };
+    auto consumeRow = [&](uint64_t key, const uint64_t (&vals)[NV], uint32_t rowIdx) {
+        const uint64_t h = murmur64(key);
+        int sslot = -1;
+        if (key == kEmptyKey) sslot = (int) st.S + 1;      // the sentinel-valued key has its own slot (an empty slot must never match it)
+        else if (!bypass) {
+            const uint32_t s = (uint32_t) (h >> 32) & (st.S - 1);
+            if (st.keys[s] == key) sslot = (int) s;
+            else { uint64_t kw[1] = {key}; sslot = st.find(kw, h); }
+            // a thread whose rows keep missing a full shared table stops probing it (high-cardinality input)
+            if (sslot >= 0) probeHits++; else probeMisses++;
+            if (((probeHits + probeMisses) & 63u) == 0) {
+                if (probeMisses > 3 * probeHits && *(volatile uint32_t*) st.count >= st.sLimit) bypass = true;
+                probeHits = 0; probeMisses = 0;
+            }
+        }
+        uint32_t id = 0xFF;
+        if (sslot >= 0) id = st.sid[sslot];
+        if (id < (uint32_t) K0) {
+            uint64_t* mine = tier0 + (size_t) id * NC * kAggThreads + tid;
+#pragma unroll
+            for (int c = 0; c < NV; c++) {
+                double* p = (double*) (mine + c * kAggThreads);
+                *p = *p + __longlong_as_double((long long) vals[c]);
+            }
+            if (CNT) mine[NV * kAggThreads] += 1;
+            if (!((seen0 >> id) & 1u)) { seen0 |= 1u << id; atomicMin(&st.first[sslot], rowIdx); }
+        }
+        else fastSlowRow<NV, CNT>(P, st, sslot, key, h, vals, rowIdx);
+    };
+    auto consumeTile = [&](int64_t tile, const ulonglong2& k, const ulonglong2 (&v)[NV]) {
+        const int64_t row0 = tile * TILE + 2 * tid;
+        if (row0 < P.n) {
+            uint64_t vals[NV];
+#pragma unroll
+            for (int c = 0; c < NV; c++) vals[c] = v[c].x;
+            consumeRow(k.x, vals, (uint32_t) row0);
+        }
+        if (row0 + 1 < P.n) {
+            uint64_t vals[NV];
+#pragma unroll
+            for (int c = 0; c < NV; c++) vals[c] = v[c].y;
+            consumeRow(k.y, vals, (uint32_t) (row0 + 1));
+        }
+    };
+
+    int64_t tile = blockIdx.x;
+    if (tile < nTiles) loadTile(tile, kA, vA);
+    while (tile < nTiles) {
+        const int64_t t1 = tile + gridDim.x;
+        if (t1 < nTiles) loadTile(t1, kB, vB);
+        consumeTile(tile, kA, vA);
+        if (t1 >= nTiles) break;
+        const int64_t t2 = t1 + gridDim.x;
+        if (t2 < nTiles) loadTile(t2, kA, vA);
+        consumeTile(t1, kB, vB);
+        tile = t2;
+    }
+
+    // ---- fold tier 0 into the shared table, then flush the shared table into the HBM table ----
+    __syncthreads();
+    const uint32_t nT0 = min(st.count[1], (uint32_t) K0);
+    const int warp = tid >> 5;
+    for (uint32_t pairIdx = warp; pairIdx < nT0 * (uint32_t) NC; pairIdx += kAggThreads / 32) {
+        const uint32_t id = pairIdx / NC, c = pairIdx % NC;
+        const uint64_t* src = tier0 + (size_t) pairIdx * kAggThreads;
+        const bool isF = c < (uint32_t) NV;
+        uint64_t x = 0;
+        if (isF) {
+            double d = 0;
+            for (int i = lane; i < kAggThreads; i += 32) d += __longlong_as_double((long long) src[i]);
+            x = (uint64_t) __double_as_longlong(d);
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) x = (uint64_t) __double_as_longlong(__longlong_as_double((long long) x) + __longlong_as_double((long long) shflXor64(x, m)));
+        }
+        else {
+            for (int i = lane; i < kAggThreads; i += 32) x += src[i];
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) x += shflXor64(x, m);
+        }
+        if (lane == 0) {
+            uint64_t* dst = &st.acc[c * st.S2 + st.count[2 + id]];
+            if (isF) *(double*) dst = *(double*) dst + __longlong_as_double((long long) x); else *dst = *dst + x;
+        }
+    }
+    __syncthreads();
+    for (uint32_t s = tid; s < st.S2; s += kAggThreads) {
+        const uint32_t f = st.first[s];
+        if (f == kNoRow32) continue;
+        int gslot;
+        if (s >= st.S) gslot = (int) T.cap + (int) (s - st.S);
+        else { uint64_t kw[1] = {st.keys[s]}; gslot = tableFind<1>(T, kw, murmur64(kw[0]), true, true); }
+        if (gslot < 0) { atomicOr(&T.counters[CNT_ERROR], 0x80000000u); continue; }
+        const uint64_t g = P.rowBase + f;
+        if (g < __ldcg(&T.firstRow[gslot])) atomicMin((unsigned long long*) &T.firstRow[gslot], (unsigned long long) g);
+        uint64_t* acc = T.acc + (size_t) gslot * T.nvPhys;
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            const uint64_t x = st.acc[c * st.S2 + s];
+            if (x != 0) accAddGlobal(&acc[P.phys[c]], x, c < NV);
         }
     }
 }
@@ -767,27 +1084,25 @@ public:
         PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         int perSM = 0;
         PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kAggThreads, smem));
-        if (perSM < 1) perSM = 1;
-        if (perSM > 4) perSM = 4;
-        gridCTAs = numSMs * perSM;
+        (void) perSM;
+        gridCTAs = numSMs * 2;   // the shared-memory budget (tier 0 + table) is sized for two resident CTAs per SM
     }
-    size_t sharedBytes(uint32_t S) const
-    {
-        size_t S2 = (size_t) S + 2;
-        return 8 * layout.W * S2 + 8 * phys.size() * S2 + 4 * S2 + (layout.W > 1 ? 4 * S2 : 0) + 16;
-    }
+    size_t sharedBytes(uint32_t S) const { return SharedLayout(S, layout.W, (int) phys.size(), true).total; }
     void configureGeometry()
     {
         sharedSlots = 1024;
-        while (sharedBytes(sharedSlots) > 96 * 1024 && sharedSlots > 128) sharedSlots >>= 1;
+        while (sharedBytes(sharedSlots) > 112 * 1024 && sharedSlots > 128) sharedSlots >>= 1;   // two CTAs per SM
         sharedLimit = sharedSlots / 4 * 3;
         dispatch([&](auto w, auto mv) { configureFor<decltype(w)::value, decltype(mv)::value>(); });
     }
-    template <typename F> void dispatch(F&& f)
+    template <typename F> void dispatch(F&& f) { dispatchFor(MAXV, f); }
+    // kernels are instantiated for 4 / 8 / 16 accumulator columns; a launch picks the smallest that holds its ACTIVE columns
+    template <typename F> void dispatchActive(F&& f) { int a = activeCount(); dispatchFor(a <= 4 ? 4 : (a <= 8 ? 8 : 16), f); }
+    template <typename F> void dispatchFor(int maxv, F&& f)
     {
         auto withW = [&](auto w) {
-            if (MAXV == 4) f(w, std::integral_constant<int, 4>());
-            else if (MAXV == 8) f(w, std::integral_constant<int, 8>());
+            if (maxv == 4) f(w, std::integral_constant<int, 4>());
+            else if (maxv == 8) f(w, std::integral_constant<int, 8>());
             else f(w, std::integral_constant<int, 16>());
         };
         switch (layout.W) {
@@ -836,6 +1151,61 @@ public:
         table.acc = std::move(nt.acc); table.counters = std::move(nt.counters); table.cap = nt.cap;
     }
 
+    int activeCount() const { int n = 0; for (auto& p : phys) n += p.active ? 1 : 0; return n; }
+
+    // BIGINT key without NULLs, only non-null DOUBLE sums (+ at most one plain row count), 16-byte aligned columns → fast kernel
+    template <int NV, bool CNT>
+    bool launchFastT(const std::vector<DeviceColumn>& cols, int64_t n, uint32_t* bitmapOut, const std::vector<int>& f64Cols, int countCol)
+    {
+        FastLaunch<NV, CNT> L{};
+        L.t = table.view();
+        auto colOf = [&](int ch) -> const DeviceColumn& { return cols[std::find(stagedChannels.begin(), stagedChannels.end(), ch) - stagedChannels.begin()]; };
+        L.key = (const uint64_t*) colOf(layout.channels[0]).values;
+        for (int c = 0; c < NV; c++) { L.vals[c] = (const uint64_t*) colOf(phys[f64Cols[c]].channel).values; L.phys[c] = f64Cols[c]; }
+        L.phys[NV] = CNT ? countCol : 0;
+        L.n = n; L.rowBase = rowsSeen; L.bitmapOut = bitmapOut; L.S = sharedSlots; L.sLimit = sharedLimit; L.nAccAlloc = (int) phys.size();
+        auto kern = hashAggFastKernel<NV, CNT>;
+        const size_t smem = sharedBytes(sharedSlots);
+        static thread_local bool configured = false;
+        if (!configured) { PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
+        int perSM = 0;
+        PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kAggThreads, smem));
+        perSM = std::max(1, std::min(perSM, 2));
+        const int64_t tiles = divUp(n, kAggThreads * 2);
+        const int grid = (int) std::min<int64_t>((int64_t) numSMs * perSM, std::max<int64_t>(tiles, 1));
+        PG_CHECK_STATE((int64_t) grid <= gridCTAs || true, "grid");
+        kern<<<grid, kAggThreads, smem, stream>>>(L);
+        stats.kernel_launches++;
+        PG_CUDA(cudaGetLastError());
+        return true;
+    }
+
+    bool tryLaunchFast(const std::vector<DeviceColumn>& cols, int64_t n, uint32_t* bitmapOut)
+    {
+        if (!layout.bigintPath) return false;
+        auto colOf = [&](int ch) -> const DeviceColumn& { return cols[std::find(stagedChannels.begin(), stagedChannels.end(), ch) - stagedChannels.begin()]; };
+        const DeviceColumn& kc = colOf(layout.channels[0]);
+        if (kc.nulls || ((uintptr_t) kc.values % 16) != 0) return false;
+        std::vector<int> f64Cols; int countCol = -1;
+        for (size_t p = 0; p < phys.size(); p++) {
+            if (!phys[p].active) continue;
+            if (phys[p].kind == K_F64 && phys[p].mask < 0) {
+                const DeviceColumn& vc = colOf(phys[p].channel);
+                if (vc.nulls || ((uintptr_t) vc.values % 16) != 0) return false;
+                f64Cols.push_back((int) p);
+            }
+            else if (phys[p].kind == K_COUNT && phys[p].channel < 0 && phys[p].mask < 0 && countCol < 0) countCol = (int) p;
+            else return false;
+        }
+        const int nv = (int) f64Cols.size();
+        if (nv < 1 || nv > 8) return false;
+        // the shared-memory budget assumes 2 CTAs per SM; flushReserve was sized from gridCTAs >= this grid
+#define PG_FAST_CASE(N) case N: return countCol >= 0 ? launchFastT<N, true>(cols, n, bitmapOut, f64Cols, countCol) : launchFastT<N, false>(cols, n, bitmapOut, f64Cols, countCol);
+        switch (nv) { PG_FAST_CASE(1) PG_FAST_CASE(2) PG_FAST_CASE(3) PG_FAST_CASE(4) PG_FAST_CASE(5) PG_FAST_CASE(6) PG_FAST_CASE(7) PG_FAST_CASE(8) }
+#undef PG_FAST_CASE
+        return false;
+    }
+
     template <int W, int MV>
     void launchRange(const std::vector<DeviceColumn>& cols, int64_t begin, int64_t n, const uint32_t* bitmapIn, uint32_t* bitmapOut)
     {
@@ -880,10 +1250,16 @@ public:
         L.n = n; L.rowBase = rowsSeen + (uint64_t) begin;
         L.bitmapIn = bitmapIn; L.bitmapOut = bitmapOut;
         L.S = bitmapIn ? 0 : sharedSlots; L.sLimit = sharedLimit;
+        L.nAccAlloc = (int) phys.size();
+        bool aligned = true;
+        if (layout.bigintPath) aligned = aligned && ((uintptr_t) L.kp.f[0].values % 16 == 0);
+        for (int c = 0; c < na; c++) if (L.acc[c].values) aligned = aligned && ((uintptr_t) L.acc[c].values % 16 == 0);
+        L.vec = aligned ? 1 : 0;
         size_t smem = L.S ? sharedBytes(sharedSlots) : 64;
         int64_t tiles = divUp(n, kAggThreads * RowsPerThread<MV>::value);
         int grid = (int) std::min<int64_t>(gridCTAs, std::max<int64_t>(tiles, 1));
         auto kern = hashAggKernel<W, MV>;
+        PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         kern<<<grid, kAggThreads, smem, stream>>>(L);
         stats.kernel_launches++;
         PG_CUDA(cudaGetLastError());
@@ -942,7 +1318,8 @@ public:
         size_t bmBytes = (size_t) divUp(n, 32) * 4;
         bitmapA.reserve(bmBytes);
         PG_CUDA(cudaMemsetAsync(bitmapA.ptr, 0, bmBytes, stream));
-        dispatch([&](auto w, auto mv) { launchRange<decltype(w)::value, decltype(mv)::value>(cols, 0, n, nullptr, bitmapA.as<uint32_t>()); });
+        if (!tryLaunchFast(cols, n, bitmapA.as<uint32_t>()))
+            dispatchActive([&](auto w, auto mv) { launchRange<decltype(w)::value, decltype(mv)::value>(cols, 0, n, nullptr, bitmapA.as<uint32_t>()); });
         lastCols = cols; lastN = n; lastBase = rowsSeen; lastPending = true;
     }
 
@@ -966,7 +1343,7 @@ public:
             PG_CUDA(cudaMemsetAsync(outB.ptr, 0, bmBytes, stream));
             unsigned int zero = 0;
             PG_CUDA(cudaMemcpyAsync(table.counters.as<unsigned int>() + CNT_DEFERRED, &zero, sizeof(zero), cudaMemcpyHostToDevice, stream));
-            dispatch([&](auto w, auto mv) { launchRange<decltype(w)::value, decltype(mv)::value>(lastCols, 0, lastN, in, outB.as<uint32_t>()); });
+            dispatchActive([&](auto w, auto mv) { launchRange<decltype(w)::value, decltype(mv)::value>(lastCols, 0, lastN, in, outB.as<uint32_t>()); });
             in = outB.as<uint32_t>();
             readCounters(cnt);
             checkErrors(cnt);
@@ -1281,5 +1658,5 @@ int32_t pg_group_by_hash_get_group_ids(pg_group_by_hash* h, const pg_page* page,
 int32_t pg_group_by_hash_get_group_count(pg_group_by_hash* h, int64_t* out) { GBH_TRY *out = ((pg::GroupByHashImpl*) h)->groupCount(); GBH_CATCH }
 int32_t pg_group_by_hash_contains(pg_group_by_hash* h, const pg_page* page, uint8_t* out) { GBH_TRY auto* g = (pg::GroupByHashImpl*) h; g->bind(); g->contains(page, out); GBH_CATCH }
 int32_t pg_group_by_hash_get_keys(pg_group_by_hash* h, pg_page* out) { GBH_TRY auto* g = (pg::GroupByHashImpl*) h; g->bind(); g->getKeys(out); GBH_CATCH }
-int32_t pg_group_by_hash_destroy(pg_group_by_hash* h) { GBH_TRY auto* g = (pg::GroupByHashImpl*) h; if (g) { cudaSetDevice(g->options.device); delete g; } GBH_CATCH }
+int32_t pg_group_by_hash_destroy(pg_group_by_hash* h) { GBH_TRY auto* g = (pg::GroupByHashImpl*) h; if (g) { cudaSetDevice(g->options.device); if (g->stream) cudaStreamSynchronize(g->stream); delete g; } GBH_CATCH }
 }

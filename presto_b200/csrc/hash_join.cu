@@ -156,6 +156,166 @@ __global__ void joinEmitKernel(const __grid_constant__ EmitJoinParams P)
     }
 }
 
+// ---- dense unique integer keys: bitmap + rank index ------------------------------------------------------------------------
+// When the build keys are unique and span a range of at most kDenseRangeFactor x n (TPC-H order keys: 150 M keys over 600 M), the
+// LookupSource is a succinct index instead of a hash table: one bit per value of the key range (L2 resident: 75 MB at SF100) and a
+// rank directory (exclusive popcount per 256-bit block), with the build OUTPUT columns re-laid in key order.  A probe is one 32-byte
+// bitmap sector (L2) + 4 B of directory → rank → payload[rank]; sorted probe keys (lineitem is clustered by orderkey) make every
+// access sequential.  Results are identical to the hash path (unique keys: at most one match, no chains).
+constexpr int kDenseRangeFactor = 16;
+constexpr int kDenseBlockWords = 4;                  // 4 x 64 bit = one 32-byte sector per block
+
+struct DenseIndex {
+    const uint64_t* bitmap;    // [blocks * 4]
+    const uint32_t* prefix;    // [blocks] set bits before the block
+    int64_t minKey;
+    uint64_t range;            // keys are in [minKey, minKey + range)
+};
+
+struct KeyColumn { const void* values; const uint8_t* nulls; int32_t type; };
+
+__device__ __forceinline__ bool loadKey(const KeyColumn& k, int64_t row, int64_t& key)
+{
+    if (k.nulls && k.nulls[row]) return false;
+    key = k.type == PG_TYPE_BIGINT ? ((const int64_t*) k.values)[row] : (int64_t) ((const int32_t*) k.values)[row];
+    return true;
+}
+
+__global__ void denseMinMaxKernel(KeyColumn k, int64_t n, long long* minMax /* [0]=min [1]=max [2]=non-null count */)
+{
+    long long lo = LLONG_MAX, hi = LLONG_MIN; unsigned long long cnt = 0;
+    for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {
+        int64_t key;
+        if (loadKey(k, i, key)) { lo = min(lo, (long long) key); hi = max(hi, (long long) key); cnt++; }
+    }
+    for (int m = 16; m >= 1; m >>= 1) {
+        lo = min(lo, (long long) shflXor64((uint64_t) lo, m)); hi = max(hi, (long long) shflXor64((uint64_t) hi, m)); cnt += shflXor64(cnt, m);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(&minMax[0], lo); atomicMax(&minMax[1], hi); atomicAdd((unsigned long long*) &minMax[2], cnt); }
+}
+
+__global__ void denseSetBitsKernel(KeyColumn k, int64_t n, int64_t minKey, unsigned long long* bitmap, unsigned int* duplicate)
+{
+    for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {
+        int64_t key;
+        if (!loadKey(k, i, key)) continue;
+        const uint64_t idx = (uint64_t) (key - minKey);
+        const unsigned long long bit = 1ULL << (idx & 63);
+        if (atomicOr(&bitmap[idx >> 6], bit) & bit) *duplicate = 1;   // the same key twice: not unique → hash path
+    }
+}
+
+__global__ void denseBlockCountKernel(const uint64_t* bitmap, int64_t blocks, uint32_t* counts)
+{
+    for (int64_t b = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; b < blocks; b += (int64_t) gridDim.x * blockDim.x) {
+        const uint64_t* w = bitmap + b * kDenseBlockWords;
+        counts[b] = __popcll(w[0]) + __popcll(w[1]) + __popcll(w[2]) + __popcll(w[3]);
+    }
+}
+
+// rank of `key` among the build keys, or -1 when absent
+__device__ __forceinline__ int64_t denseRank(const DenseIndex& D, int64_t key)
+{
+    const uint64_t idx = (uint64_t) (key - D.minKey);
+    if (idx >= D.range) return -1;
+    const uint64_t blk = idx >> 8;
+    const ulonglong4 w = *reinterpret_cast<const ulonglong4*>(D.bitmap + blk * kDenseBlockWords);   // one 32-byte sector
+    const uint32_t wi = (uint32_t) (idx >> 6) & 3u;
+    const uint64_t word = wi == 0 ? w.x : wi == 1 ? w.y : wi == 2 ? w.z : w.w;
+    const uint64_t bit = 1ULL << (idx & 63);
+    if (!(word & bit)) return -1;
+    uint32_t r = D.prefix[blk] + __popcll(word & (bit - 1));
+    if (wi > 0) r += __popcll(w.x);
+    if (wi > 1) r += __popcll(w.y);
+    if (wi > 2) r += __popcll(w.z);
+    return (int64_t) r;
+}
+
+struct DenseGatherParams {
+    KeyColumn key; DenseIndex D; int64_t n;
+    int32_t nCols;
+    JoinColumn cols[kMaxJoinColumns];   // src = build column, dst = the column in key order
+};
+__global__ void denseGatherKernel(const __grid_constant__ DenseGatherParams P)
+{
+    for (int64_t pos = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; pos < P.n; pos += (int64_t) gridDim.x * blockDim.x) {
+        int64_t key;
+        if (!loadKey(P.key, pos, key)) continue;
+        const int64_t r = denseRank(P.D, key);
+        for (int c = 0; c < P.nCols; c++) copyValue(P.cols[c], pos, r);
+    }
+}
+
+constexpr int kProbeTile = 1024;   // rows per CTA step (256 threads x 4)
+
+struct DenseProbeParams {
+    KeyColumn key; DenseIndex D; int64_t n; int64_t tiles;
+    int32_t outer;
+    uint32_t* tileCounts;          // pass A out [tiles + 1]
+    const uint32_t* tileOffsets;   // pass B in
+    int32_t nProbe, nBuild;
+    JoinColumn probe[kMaxJoinColumns];   // src = probe column, dst = output
+    JoinColumn build[kMaxJoinColumns];   // src = build column in key order, dst = output
+};
+
+__global__ void __launch_bounds__(256) denseCountKernel(const __grid_constant__ DenseProbeParams P)
+{
+    __shared__ uint32_t warpCounts[8];
+    for (int64_t tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
+        uint32_t c = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int64_t row = tile * kProbeTile + j * 256 + threadIdx.x;
+            int64_t key;
+            if (row < P.n && loadKey(P.key, row, key) && denseRank(P.D, key) >= 0) c++;
+        }
+        for (int m = 16; m >= 1; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
+        if ((threadIdx.x & 31) == 0) warpCounts[threadIdx.x >> 5] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < 8; w++) t += warpCounts[w]; P.tileCounts[tile] = t; }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) denseEmitKernel(const __grid_constant__ DenseProbeParams P)
+{
+    __shared__ uint32_t partial[32];   // matches of (round j, warp w) at [j * 8 + w]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
+        int64_t rank[4]; bool emit[4]; unsigned ballots[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int64_t row = tile * kProbeTile + j * 256 + threadIdx.x;
+            rank[j] = -1; emit[j] = false;
+            if (row < P.n) {
+                int64_t key;
+                if (loadKey(P.key, row, key)) rank[j] = denseRank(P.D, key);
+                emit[j] = rank[j] >= 0 || P.outer;
+            }
+            ballots[j] = __ballot_sync(0xffffffffu, emit[j]);
+            if (lane == 0) partial[j * 8 + warp] = __popc(ballots[j]);
+        }
+        __syncthreads();
+        if (warp == 0) {   // exclusive scan of the 32 partial counts in (round, warp) order = row order
+            uint32_t v = partial[lane], x = v;
+            for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+            partial[lane] = x - v;
+        }
+        __syncthreads();
+        const uint32_t base = P.outer ? (uint32_t) (tile * kProbeTile) : P.tileOffsets[tile];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (!emit[j]) continue;
+            const int64_t row = tile * kProbeTile + j * 256 + threadIdx.x;
+            const uint32_t o = base + partial[j * 8 + warp] + __popc(ballots[j] & ((1u << lane) - 1));
+            for (int c = 0; c < P.nProbe; c++) copyValue(P.probe[c], row, o);
+            if (rank[j] >= 0) for (int c = 0; c < P.nBuild; c++) copyValue(P.build[c], rank[j], o);
+            else for (int c = 0; c < P.nBuild; c++) writeNull(P.build[c], o);
+        }
+        __syncthreads();
+    }
+}
+
 // ======================================================================================================================
 // Host side
 // ======================================================================================================================
@@ -172,6 +332,12 @@ struct LookupSourceDevice {
     bool hasDuplicates = false;
     int64_t nullKeyCount = 0, duplicateCount = 0;
     int64_t deviceBytes = 0;
+    // dense unique-key index (bitmap + rank) — used instead of the hash table when eligible
+    bool dense = false;
+    int64_t minKey = 0; uint64_t range = 0;
+    DeviceBuffer bitmap, prefix;
+    std::vector<DeviceBuffer> sortedValues, sortedNulls;   // per build OUTPUT channel, in key order
+    DenseIndex denseView() const { DenseIndex D{}; D.bitmap = bitmap.as<uint64_t>(); D.prefix = prefix.as<uint32_t>(); D.minKey = minKey; D.range = range; return D; }
 
     JoinTable view() const
     {
@@ -306,6 +472,12 @@ public:
         if (finishing) return;
         finishing = true;
         const int64_t n = ls->positionCount;
+        if (n > 0 && tryBuildDense()) {
+            stats.group_count = n;
+            stats.device_bytes = ls->deviceBytes;
+            bridge->set(ls);
+            return;
+        }
         // HashCommon.arraySize(positionCount, 0.75f): power of two >= n / 0.75 (PagesHash.java:67)
         uint64_t want = (uint64_t) ((double) std::max<int64_t>(n, 1) / 0.75) + 1;
         if (want > (1ULL << 30)) throw Error(PG_ERR_INSUFFICIENT_RESOURCES, "Too large (hash table cannot exceed 2^30 slots)");
@@ -354,6 +526,71 @@ public:
         stats.device_bytes = ls->deviceBytes;
         bridge->set(ls);
     }
+    // Unique keys over a small range → bitmap + rank index (see DenseIndex).  Returns false to fall back to the hash table.
+    bool tryBuildDense()
+    {
+        if (ls->layout.nKeys != 1) return false;
+        const int64_t n = ls->positionCount;
+        const int kch = ls->layout.channels[0];
+        KeyColumn kc{ls->values[kch].ptr, ls->hasNulls[kch] ? ls->nulls[kch].as<uint8_t>() : nullptr, ls->types[kch]};
+        DeviceBuffer mm; mm.reserve(64);
+        long long init[3] = {LLONG_MAX, LLONG_MIN, 0};
+        PG_CUDA(cudaMemcpyAsync(mm.ptr, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+        const int grid = (int) std::min<int64_t>(divUp(n, 256), numSMs * 16);
+        PG_LAUNCH(this, denseMinMaxKernel, grid, 256, 0, kc, n, mm.as<long long>());
+        long long h[3];
+        PG_CUDA(cudaMemcpyAsync(h, mm.ptr, sizeof(h), cudaMemcpyDeviceToHost, stream));
+        PG_CUDA(cudaStreamSynchronize(stream));
+        const int64_t nonNull = h[2];
+        if (nonNull == 0) return false;
+        const unsigned __int128 span = (unsigned __int128) ((__int128) h[1] - (__int128) h[0]) + 1;
+        if (span > (unsigned __int128) kDenseRangeFactor * (unsigned __int128) nonNull + 4096 || span > ((unsigned __int128) 1 << 36)) return false;
+        const uint64_t range = (uint64_t) span;
+        const int64_t blocks = (int64_t) ((range + 255) >> 8);
+        ls->bitmap.accounting = ls->prefix.accounting = &ls->deviceBytes;
+        ls->bitmap.reserve((size_t) blocks * 32);
+        PG_CUDA(cudaMemsetAsync(ls->bitmap.ptr, 0, (size_t) blocks * 32, stream));
+        DeviceBuffer dup; dup.reserve(16);
+        PG_CUDA(cudaMemsetAsync(dup.ptr, 0, 16, stream));
+        PG_LAUNCH(this, denseSetBitsKernel, grid, 256, 0, kc, n, (int64_t) h[0], ls->bitmap.as<unsigned long long>(), dup.as<unsigned int>());
+        unsigned int isDup = 0;
+        PG_CUDA(cudaMemcpyAsync(&isDup, dup.ptr, 4, cudaMemcpyDeviceToHost, stream));
+        PG_CUDA(cudaStreamSynchronize(stream));
+        if (isDup) { ls->bitmap.release(); return false; }
+        // rank directory
+        DeviceBuffer counts, temp; counts.reserve((size_t) (blocks + 1) * 4);
+        ls->prefix.reserve((size_t) (blocks + 1) * 4);
+        PG_CUDA(cudaMemsetAsync(counts.as<uint32_t>() + blocks, 0, 4, stream));
+        PG_LAUNCH(this, denseBlockCountKernel, (int) std::min<int64_t>(divUp(blocks, 256), numSMs * 16), 256, 0, ls->bitmap.as<uint64_t>(), blocks, counts.as<uint32_t>());
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, counts.as<uint32_t>(), ls->prefix.as<uint32_t>(), (int) (blocks + 1), stream);
+        temp.reserve(tb);
+        cub::DeviceScan::ExclusiveSum(temp.ptr, tb, counts.as<uint32_t>(), ls->prefix.as<uint32_t>(), (int) (blocks + 1), stream);
+        stats.kernel_launches += 2;
+        ls->minKey = h[0]; ls->range = range;
+        // build output columns in key order
+        DenseGatherParams G{};
+        G.key = kc; G.D = ls->denseView(); G.n = n; G.nCols = (int) ls->outputChannels.size();
+        ls->sortedValues.resize(ls->outputChannels.size()); ls->sortedNulls.resize(ls->outputChannels.size());
+        for (size_t i = 0; i < ls->outputChannels.size(); i++) {
+            const int ch = ls->outputChannels[i];
+            JoinColumn& jc = G.cols[i];
+            jc.width = typeWidth(ls->types[ch]); jc.src = ls->values[ch].ptr; jc.srcNulls = ls->hasNulls[ch] ? ls->nulls[ch].as<uint8_t>() : nullptr;
+            ls->sortedValues[i].accounting = ls->sortedNulls[i].accounting = &ls->deviceBytes;
+            ls->sortedValues[i].reserve(std::max<size_t>((size_t) nonNull * jc.width, 16));
+            jc.dst = ls->sortedValues[i].ptr; jc.dstNulls = nullptr;
+            if (jc.srcNulls) { ls->sortedNulls[i].reserve((size_t) nonNull); jc.dstNulls = ls->sortedNulls[i].as<uint8_t>(); }
+        }
+        if (G.nCols) PG_LAUNCH(this, denseGatherKernel, grid, 256, 0, G);
+        PG_CUDA(cudaStreamSynchronize(stream));
+        ls->nullKeyCount = n - nonNull;
+        ls->dense = true;
+        // the unsorted copies of the build columns are no longer needed
+        for (auto& v : ls->values) v.release();
+        for (auto& v : ls->nulls) v.release();
+        return true;
+    }
+
     bool isFinished() override { return finishing; }
     bool getOutput(pg_page*) override { return false; }
 };
@@ -414,6 +651,7 @@ public:
         int slot = stager.stage(page, staged, cols);
         auto colOf = [&](int ch) -> const DeviceColumn& { return cols[std::find(staged.begin(), staged.end(), ch) - staged.begin()]; };
 
+        if (ls->dense) { addInputDense(*ls, cols, slot, n); return; }
         // pass 1: probe
         matchHead.reserve((size_t) n * 4); counts.reserve((size_t) (n + 1) * 4); offsets.reserve((size_t) (n + 1) * 4);
         ProbeParams P{};
@@ -486,6 +724,89 @@ public:
                 if (hasNulls) { hostNulls[i].reserve(total); PG_CUDA(cudaMemcpyAsync(hostNulls[i].ptr, outNulls[i].ptr, total, cudaMemcpyDeviceToHost, stream)); b.is_null = hostNulls[i].as<uint8_t>(); stats.d2h_bytes += total; }
             }
             else { b.values = outValues[i].ptr; b.is_null = hasNulls ? outNulls[i].as<uint8_t>() : nullptr; }
+            stats.output_bytes += (int64_t) vbytes;
+        }
+        PG_CUDA(cudaStreamSynchronize(stream));
+        hasPending = true;
+        stats.output_positions += total;
+    }
+
+    // Probe of the bitmap + rank index: count per tile → scan of the tile counts → write the output columns in place.
+    void addInputDense(const LookupSourceDevice& ls, const std::vector<DeviceColumn>& cols, int slot, int64_t n)
+    {
+        auto colOf = [&](int ch) -> const DeviceColumn& { return cols[std::find(staged.begin(), staged.end(), ch) - staged.begin()]; };
+        const DeviceColumn& kcol = colOf(layout.channels[0]);
+        DenseProbeParams P{};
+        P.key = KeyColumn{kcol.values, kcol.nulls, kcol.type};
+        P.D = ls.denseView(); P.n = n; P.tiles = divUp(n, kProbeTile); P.outer = joinType == PG_JOIN_PROBE_OUTER;
+        const int grid = (int) std::min<int64_t>(P.tiles, (int64_t) numSMs * 8);
+        int64_t total = n;
+        if (!P.outer) {
+            counts.reserve((size_t) (P.tiles + 1) * 4); offsets.reserve((size_t) (P.tiles + 1) * 4);
+            PG_CUDA(cudaMemsetAsync(counts.as<uint32_t>() + P.tiles, 0, 4, stream));
+            P.tileCounts = counts.as<uint32_t>();
+            PG_LAUNCH(this, denseCountKernel, grid, 256, 0, P);
+            size_t tb = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tb, counts.as<uint32_t>(), offsets.as<uint32_t>(), (int) (P.tiles + 1), stream);
+            scanTemp.reserve(tb);
+            cub::DeviceScan::ExclusiveSum(scanTemp.ptr, tb, counts.as<uint32_t>(), offsets.as<uint32_t>(), (int) (P.tiles + 1), stream);
+            stats.kernel_launches += 2;
+            uint32_t t = 0;
+            PG_CUDA(cudaMemcpyAsync(&t, offsets.as<uint32_t>() + P.tiles, 4, cudaMemcpyDeviceToHost, stream));
+            PG_CUDA(cudaStreamSynchronize(stream));
+            stats.d2h_bytes += 4;
+            total = t;
+            P.tileOffsets = offsets.as<uint32_t>();
+        }
+        pendingRows = total;
+        if (total == 0) { stager.markCompute(slot); return; }
+        const size_t nOut = outputChannels.size() + ls.outputChannels.size();
+        if (outValues.size() < nOut) { outValues.resize(nOut); outNulls.resize(nOut); for (auto& d : outValues) d.accounting = &stats.device_bytes; for (auto& d : outNulls) d.accounting = &stats.device_bytes; }
+        outBlocks.assign(nOut, pg_block{});
+        P.nProbe = (int) outputChannels.size(); P.nBuild = (int) ls.outputChannels.size();
+        std::vector<bool> hasNulls(nOut, false);
+        for (size_t i = 0; i < outputChannels.size(); i++) {
+            const DeviceColumn& c = colOf(outputChannels[i]);
+            JoinColumn& jc = P.probe[i];
+            jc.width = typeWidth(c.type); jc.src = c.values; jc.srcNulls = c.nulls;
+            outValues[i].reserve((size_t) total * jc.width);
+            jc.dst = outValues[i].ptr; jc.dstNulls = nullptr;
+            if (c.nulls) { outNulls[i].reserve(total); jc.dstNulls = outNulls[i].as<uint8_t>(); hasNulls[i] = true; }
+            outBlocks[i].type = c.type;
+        }
+        for (size_t i = 0; i < ls.outputChannels.size(); i++) {
+            const int ch = ls.outputChannels[i];
+            const size_t o = outputChannels.size() + i;
+            JoinColumn& jc = P.build[i];
+            jc.width = typeWidth(ls.types[ch]); jc.src = ls.sortedValues[i].ptr; jc.srcNulls = ls.sortedNulls[i].ptr ? ls.sortedNulls[i].as<uint8_t>() : nullptr;
+            outValues[o].reserve((size_t) total * jc.width);
+            jc.dst = outValues[o].ptr; jc.dstNulls = nullptr;
+            if (jc.srcNulls || P.outer) { outNulls[o].reserve(total); jc.dstNulls = outNulls[o].as<uint8_t>(); hasNulls[o] = true; }
+            outBlocks[o].type = ls.types[ch];
+        }
+        PG_LAUNCH(this, denseEmitKernel, grid, 256, 0, P);
+        stager.markCompute(slot);
+        publish(total, hasNulls);
+    }
+
+    // describe (and, for host output, bring back) the `total` output rows sitting in outValues / outNulls
+    void publish(int64_t total, const std::vector<bool>& hasNulls)
+    {
+        const size_t nOut = outBlocks.size();
+        const bool toHost = options.output_memory == PG_MEM_HOST;
+        if (toHost && hostValues.size() < nOut) { hostValues.resize(nOut); hostNulls.resize(nOut); }
+        for (size_t i = 0; i < nOut; i++) {
+            pg_block& b = outBlocks[i];
+            const size_t vbytes = (size_t) total * typeWidth(b.type);
+            b.encoding = PG_ENC_FLAT; b.position_count = total; b.offsets = nullptr; b.ids = nullptr; b.dictionary_size = 0;
+            if (toHost) {
+                hostValues[i].reserve(std::max<size_t>(vbytes, 16));
+                PG_CUDA(cudaMemcpyAsync(hostValues[i].ptr, outValues[i].ptr, vbytes, cudaMemcpyDeviceToHost, stream));
+                b.values = hostValues[i].ptr; b.is_null = nullptr;
+                stats.d2h_bytes += (int64_t) vbytes;
+                if (hasNulls[i]) { hostNulls[i].reserve(total); PG_CUDA(cudaMemcpyAsync(hostNulls[i].ptr, outNulls[i].ptr, total, cudaMemcpyDeviceToHost, stream)); b.is_null = hostNulls[i].as<uint8_t>(); stats.d2h_bytes += total; }
+            }
+            else { b.values = outValues[i].ptr; b.is_null = hasNulls[i] ? outNulls[i].as<uint8_t>() : nullptr; }
             stats.output_bytes += (int64_t) vbytes;
         }
         PG_CUDA(cudaStreamSynchronize(stream));

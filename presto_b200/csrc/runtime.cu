@@ -1,11 +1,85 @@
 // presto_b200 — runtime: device management, operator base, page staging, scalar hash helpers.
 #include "common.cuh"
+#include <map>
+#include <mutex>
 
 namespace pg {
 
 static thread_local std::string g_lastError;
 void setLastError(const std::string& msg) { g_lastError = msg; }
 const char* lastError() { return g_lastError.c_str(); }
+
+// ---- caching allocator ----------------------------------------------------------------------------------------------------
+namespace {
+struct BlockCache {
+    std::mutex mu;
+    std::map<std::pair<int, size_t>, std::vector<void*>> freeBlocks;   // (device, size class) → blocks
+    size_t cachedBytes = 0;
+    size_t limitBytes;
+    bool pinned;
+    BlockCache(size_t limit, bool pin) : limitBytes(limit), pinned(pin) {}
+    static size_t sizeClass(size_t bytes)
+    {
+        if (bytes < 512) return 512;
+        int top = 63 - __builtin_clzll((unsigned long long) bytes);
+        size_t step = size_t(1) << (top - 2);           // 3 significant bits
+        return (bytes + step - 1) & ~(step - 1);
+    }
+    void* alloc(size_t bytes, size_t* granted)
+    {
+        int dev = 0;
+        if (!pinned) PG_CUDA(cudaGetDevice(&dev));
+        const size_t cls = sizeClass(bytes);
+        {
+            std::lock_guard<std::mutex> l(mu);
+            auto it = freeBlocks.find({dev, cls});
+            if (it != freeBlocks.end() && !it->second.empty()) {
+                void* p = it->second.back(); it->second.pop_back(); cachedBytes -= cls; *granted = cls; return p;
+            }
+        }
+        void* p = nullptr;
+        cudaError_t e = pinned ? cudaHostAlloc(&p, cls, cudaHostAllocDefault) : cudaMalloc(&p, cls);
+        if (e == cudaErrorMemoryAllocation) {   // give cached blocks back to the driver and retry once
+            cudaGetLastError();
+            trim();
+            e = pinned ? cudaHostAlloc(&p, cls, cudaHostAllocDefault) : cudaMalloc(&p, cls);
+        }
+        PG_CUDA(e);
+        *granted = cls;
+        return p;
+    }
+    void free(void* p, size_t granted)
+    {
+        int dev = 0;
+        if (!pinned) cudaGetDevice(&dev);
+        {
+            std::lock_guard<std::mutex> l(mu);
+            if (cachedBytes + granted <= limitBytes) { freeBlocks[{dev, granted}].push_back(p); cachedBytes += granted; return; }
+        }
+        if (pinned) cudaFreeHost(p); else cudaFree(p);
+    }
+    void trim()
+    {
+        std::lock_guard<std::mutex> l(mu);
+        int cur = 0; cudaGetDevice(&cur);
+        for (auto& kv : freeBlocks) {
+            if (!pinned) cudaSetDevice(kv.first.first);
+            for (void* p : kv.second) { if (pinned) cudaFreeHost(p); else cudaFree(p); }
+            kv.second.clear();
+        }
+        if (!pinned) cudaSetDevice(cur);
+        cachedBytes = 0;
+    }
+};
+BlockCache& deviceCache() { static BlockCache* c = new BlockCache(size_t(48) << 30, false); return *c; }
+BlockCache& pinnedCache() { static BlockCache* c = new BlockCache(size_t(8) << 30, true); return *c; }
+}  // namespace
+
+void* cachedDeviceAlloc(size_t bytes, size_t* granted) { return deviceCache().alloc(bytes, granted); }
+void cachedDeviceFree(void* p, size_t granted) { deviceCache().free(p, granted); }
+void* cachedPinnedAlloc(size_t bytes, size_t* granted) { return pinnedCache().alloc(bytes, granted); }
+void cachedPinnedFree(void* p, size_t granted) { pinnedCache().free(p, granted); }
+void trimAllocationCaches() { deviceCache().trim(); pinnedCache().trim(); }
 
 // ---- Operator base ----------------------------------------------------------------------------------------------------
 Operator::Operator(const pg_operator_options& o) : options(o)
@@ -270,7 +344,7 @@ int32_t pg_operator_destroy(pg_operator* op)
 {
     PG_TRY
     auto* o = (Operator*) op;
-    if (o) { cudaSetDevice(o->options.device); delete o; }
+    if (o) { cudaSetDevice(o->options.device); if (o->stream) cudaStreamSynchronize(o->stream); if (o->copyStream) cudaStreamSynchronize(o->copyStream); delete o; }
     PG_CATCH
 }
 

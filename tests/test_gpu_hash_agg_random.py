@@ -1,0 +1,149 @@
+"""-m gpu: HashAggregationOperator on seeded random pages vs the oracle — every tier of the kernel (per-thread tier 0, the
+CTA's shared table, the HBM table), the specialised fast kernel and the generic one, table growth and deferred rows.
+Bit-exact keys / counts / group order; doubles within 1e-6 relative (north_star)."""
+import numpy as np
+import pytest
+
+from presto_b200 import (
+    AGG_AVG_BIGINT, AGG_AVG_DOUBLE, AGG_COUNT_COLUMN, AGG_COUNT_STAR, AGG_SUM_BIGINT, AGG_SUM_DOUBLE, BIGINT, DATE, DOUBLE, INTEGER,
+    MEM_DEVICE, STEP_FINAL, STEP_PARTIAL, VARCHAR, Aggregate, Block, HashAggregationOperator, Page, to_pages,
+)
+from util import rows_close, rows_of
+
+pytestmark = pytest.mark.gpu
+
+LONG_MIN = -(2 ** 63)
+
+
+def run(backend, pages, group_types, group_channels, aggs, **kw):
+    op = HashAggregationOperator(group_types, group_channels, aggs, backend=backend, **kw)
+    rows = rows_of(to_pages(op, pages))
+    op.close()
+    return rows
+
+
+def make_pages(rng, n_pages, n, groups, n_vals=4, null_keys=False, null_vals=False, sentinel=False, misalign=False):
+    pages = []
+    for _ in range(n_pages):
+        keys = rng.integers(0, groups, n + 1).astype(np.int64) * 7919 - 3
+        if sentinel:
+            keys[rng.integers(0, n, max(1, n // 50))] = LONG_MIN
+        knull = (rng.random(n + 1) < 0.1).astype(np.uint8) if null_keys else None
+        blocks = []
+        o = 1 if misalign else 0   # a 1-element offset makes the column pointers 8- but not 16-byte aligned
+        blocks.append(Block.from_numpy(BIGINT, keys[o:o + n], None if knull is None else knull[o:o + n]))
+        for c in range(n_vals):
+            v = rng.random(n + 1) * 1e5 - 2e4
+            vn = (rng.random(n + 1) < 0.15).astype(np.uint8) if null_vals else None
+            blocks.append(Block.from_numpy(DOUBLE, v[o:o + n], None if vn is None else vn[o:o + n]))
+        pages.append(Page(blocks))
+    return pages
+
+
+@pytest.mark.parametrize("groups", [1, 4, 9, 700, 5000, 200_000])
+@pytest.mark.parametrize("variant", ["fast", "fast_count", "misaligned", "null_keys", "null_vals", "sentinel"])
+def test_bigint_key_double_sums(gpu_backend, oracle_backend, groups, variant):
+    rng = np.random.default_rng(groups * 31 + len(variant))
+    n = 60_000 if groups < 100_000 else 400_000
+    pages = make_pages(rng, 3, n, groups, null_keys=variant == "null_keys", null_vals=variant == "null_vals",
+                       sentinel=variant == "sentinel", misalign=variant == "misaligned")
+    aggs = [Aggregate(AGG_SUM_DOUBLE, 1 + c) for c in range(4)]
+    if variant != "fast":
+        aggs += [Aggregate(AGG_COUNT_STAR), Aggregate(AGG_AVG_DOUBLE, 2)]
+    got = run(gpu_backend, pages, [BIGINT], [0], aggs, expected_groups=64, max_output_rows=1 << 30)
+    want = run(oracle_backend, pages, [BIGINT], [0], aggs, expected_groups=64, max_output_rows=1 << 30)
+    rows_close(got, want)
+
+
+def test_table_growth_and_deferred_rows(gpu_backend, oracle_backend):
+    """More distinct groups in one page than the table's claim limit: rows are deferred, the table grows, they are re-run."""
+    rng = np.random.default_rng(77)
+    n = 6_000_000
+    keys = rng.permutation(n).astype(np.int64)          # every row its own group, scrambled
+    vals = rng.random(n)
+    page = Page([Block.from_numpy(BIGINT, keys), Block.from_numpy(DOUBLE, vals)])
+    aggs = [Aggregate(AGG_SUM_DOUBLE, 1), Aggregate(AGG_COUNT_STAR)]
+    op = HashAggregationOperator([BIGINT], [0], aggs, backend=gpu_backend, expected_groups=16, max_output_rows=1 << 30)
+    out = to_pages(op, [page, page])
+    assert sum(p.position_count for p in out) == n
+    k = np.concatenate([p.blocks[0].values for p in out]); s = np.concatenate([p.blocks[1].values for p in out]); c = np.concatenate([p.blocks[2].values for p in out])
+    assert (k == keys).all(), "group ids must follow first-appearance order"
+    assert (c == 2).all() and np.allclose(s, 2 * vals, rtol=1e-12)
+    op.close()
+
+
+@pytest.mark.parametrize("groups", [3, 300, 40_000])
+def test_multi_channel_keys(gpu_backend, oracle_backend, groups):
+    """(BIGINT, DATE, INTEGER) keys (TPC-H Q3 shape, W = 3 words) and two varchar(1) keys (Q1 shape, W = 1)."""
+    rng = np.random.default_rng(groups)
+    n = 80_000
+    pages = []
+    for _ in range(2):
+        g = rng.integers(0, groups, n)
+        k0 = Block.from_numpy(BIGINT, g * 1_000_003, (rng.random(n) < 0.02).astype(np.uint8))
+        k1 = Block.from_numpy(DATE, (g % 2500 + 8000).astype(np.int32))
+        k2 = Block.from_numpy(INTEGER, (g % 3).astype(np.int32), (rng.random(n) < 0.02).astype(np.uint8))
+        v = Block.from_numpy(DOUBLE, rng.random(n) * 100)
+        w = Block.from_numpy(BIGINT, rng.integers(-10**9, 10**9, n))
+        pages.append(Page([k0, k1, k2, v, w]))
+    aggs = [Aggregate(AGG_SUM_DOUBLE, 3), Aggregate(AGG_SUM_BIGINT, 4), Aggregate(AGG_AVG_BIGINT, 4), Aggregate(AGG_COUNT_COLUMN, 0), Aggregate(AGG_COUNT_STAR)]
+    got = run(gpu_backend, pages, [BIGINT, DATE, INTEGER], [0, 1, 2], aggs, expected_groups=128, max_output_rows=1 << 30)
+    want = run(oracle_backend, pages, [BIGINT, DATE, INTEGER], [0, 1, 2], aggs, expected_groups=128, max_output_rows=1 << 30)
+    rows_close(got, want)
+
+
+def test_q1_shape_varchar_keys(gpu_backend, oracle_backend):
+    """TPC-H Q1: GROUP BY returnflag, linestatus (varchar(1) each) with the 7 aggregates of PB/HandTpchQuery1.java:113-127."""
+    rng = np.random.default_rng(1)
+    n = 200_000
+    rf = [b"ANR"[i:i + 1] for i in rng.integers(0, 3, n)]
+    ls = [b"FO"[i:i + 1] for i in rng.integers(0, 2, n)]
+    qty = rng.integers(1, 51, n).astype(np.float64); ep = np.round(rng.random(n) * 1e5, 2); disc = rng.integers(0, 11, n) / 100; tax = rng.integers(0, 9, n) / 100
+    page = Page([Block.from_strings(rf), Block.from_strings(ls), Block.from_numpy(DOUBLE, qty), Block.from_numpy(DOUBLE, ep),
+                 Block.from_numpy(DOUBLE, ep * (1 - disc)), Block.from_numpy(DOUBLE, ep * (1 - disc) * (1 + tax)), Block.from_numpy(DOUBLE, disc)])
+    aggs = [Aggregate(AGG_SUM_DOUBLE, 2), Aggregate(AGG_SUM_DOUBLE, 3), Aggregate(AGG_SUM_DOUBLE, 4), Aggregate(AGG_AVG_DOUBLE, 2),
+            Aggregate(AGG_AVG_DOUBLE, 5), Aggregate(AGG_AVG_DOUBLE, 6), Aggregate(AGG_COUNT_STAR)]
+    kw = dict(expected_groups=10_000, group_max_lengths=[1, 1])
+    got = run(gpu_backend, [page], [VARCHAR, VARCHAR], [0, 1], aggs, **kw)
+    want = run(oracle_backend, [page], [VARCHAR, VARCHAR], [0, 1], aggs, **kw)
+    assert len(got) == 6
+    rows_close(got, want)
+
+
+def test_partial_final_equals_single(gpu_backend, oracle_backend):
+    """AggregationNode.Step PARTIAL → FINAL (what P GPUs + one merge do for Q1) equals SINGLE."""
+    rng = np.random.default_rng(9)
+    pages = make_pages(rng, 4, 50_000, 300, n_vals=2, null_vals=True)
+    aggs = [Aggregate(AGG_SUM_DOUBLE, 1), Aggregate(AGG_AVG_DOUBLE, 2), Aggregate(AGG_COUNT_STAR), Aggregate(AGG_COUNT_COLUMN, 1)]
+    single = run(oracle_backend, pages, [BIGINT], [0], aggs, expected_groups=512, max_output_rows=1 << 30)
+    partials = []
+    for half in (pages[:2], pages[2:]):
+        op = HashAggregationOperator([BIGINT], [0], aggs, step=STEP_PARTIAL, backend=gpu_backend, expected_groups=512, max_output_rows=1 << 30)
+        partials += to_pages(op, half)
+        op.close()
+    # FINAL input layout: key, then the intermediate columns of each aggregate in order (sum → 1, avg → 2, count → 1)
+    final_aggs = [Aggregate(AGG_SUM_DOUBLE, 1), Aggregate(AGG_AVG_DOUBLE, 2), Aggregate(AGG_COUNT_STAR, 4), Aggregate(AGG_COUNT_COLUMN, 5)]
+    got = run(gpu_backend, partials, [BIGINT], [0], final_aggs, step=STEP_FINAL, expected_groups=512, max_output_rows=1 << 30)
+    rows_close(sorted(got, key=lambda r: (r[0] is None, r[0])), sorted(single, key=lambda r: (r[0] is None, r[0])))
+
+
+def test_device_resident_pages(gpu_backend, oracle_backend):
+    """Device pages in, device page out: chained GPU operators never round-trip through the host."""
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    n = 100_000
+    keys = rng.integers(0, 50, n).astype(np.int64); vals = rng.random(n)
+    ptrs = []
+    for a in (keys, vals):
+        p = C.c_void_p()
+        gpu_backend.check(gpu_backend.device_alloc(a.nbytes, C.byref(p)))
+        gpu_backend.check(gpu_backend.memcpy_h2d(p, a.ctypes.data, a.nbytes))
+        ptrs.append(p)
+    page = Page([Block.device(BIGINT, n, ptrs[0].value), Block.device(DOUBLE, n, ptrs[1].value)])
+    op = HashAggregationOperator([BIGINT], [0], [Aggregate(AGG_SUM_DOUBLE, 1)], backend=gpu_backend, output_memory=MEM_DEVICE)
+    got = rows_of(to_pages(op, [page]))      # Page.from_c copies the device result back for comparison
+    want = run(oracle_backend, [Page([Block.from_numpy(BIGINT, keys), Block.from_numpy(DOUBLE, vals)])], [BIGINT], [0], [Aggregate(AGG_SUM_DOUBLE, 1)])
+    rows_close(got, want)
+    op.close()
+    for p in ptrs:
+        gpu_backend.device_free(p)
