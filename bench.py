@@ -172,16 +172,25 @@ def device_page(torch, tensors, types):
 
 
 def run_group_by(torch, backend, page, n_rows, groups_hint, steps, warmup, device, dist=None):
-    """Returns dict(ms_per_step, kernel_ms, launches, groups, result_rows)."""
-    from presto_b200 import AGG_SUM_DOUBLE, BIGINT, MEM_HOST, Aggregate, HashAggregationOperator
+    """One step = HashAggregationOperator over the resident batch.  With N > 1 ranks every rank aggregates its shard with a PARTIAL
+    operator, the partial pages (a few hundred bytes) are gathered and rank 0 merges them with a FINAL operator — the Q1 plan
+    (no row exchange).  Returns dict(ms, kernel_ms, launches, groups, result)."""
+    from presto_b200 import AGG_SUM_DOUBLE, BIGINT, MEM_HOST, STEP_FINAL, STEP_PARTIAL, STEP_SINGLE, Aggregate, HashAggregationOperator
+    from presto_b200.exchange import gather_pages_to_root
     stream = torch.cuda.current_stream()
     ms, kms, launches, groups = [], [], 0, 0
     result = None
+    multi = dist is not None
+    aggs = [Aggregate(AGG_SUM_DOUBLE, 1 + c) for c in range(4)]
     for i in range(warmup + steps):
-        op = HashAggregationOperator([BIGINT], [0], [Aggregate(AGG_SUM_DOUBLE, 1 + c) for c in range(4)], expected_groups=groups_hint,
+        op = HashAggregationOperator([BIGINT], [0], aggs, expected_groups=groups_hint, step=STEP_PARTIAL if multi else STEP_SINGLE,
                                      backend=backend, device=device, output_memory=MEM_HOST, cuda_stream=stream.cuda_stream, max_output_rows=1 << 30)
+        final = None
+        if multi and dist.get_rank() == 0:
+            final = HashAggregationOperator([BIGINT], [0], aggs, expected_groups=groups_hint, step=STEP_FINAL, backend=backend, device=device,
+                                            output_memory=MEM_HOST, cuda_stream=stream.cuda_stream, max_output_rows=1 << 30)
         e0, e1, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if dist is not None:
+        if multi:
             dist.barrier()
         torch.cuda.synchronize()
         e0.record(stream)
@@ -189,17 +198,103 @@ def run_group_by(torch, backend, page, n_rows, groups_hint, steps, warmup, devic
         e1.record(stream)
         op.finish()
         out = op.get_output()
+        if multi:
+            partials = gather_pages_to_root(out)
+            if final is not None:
+                for p in partials:
+                    final.add_input(p)
+                final.finish()
+                out = final.get_output()
         e2.record(stream)
         torch.cuda.synchronize()
-        if dist is not None:
+        if multi:
             dist.barrier()
         if i >= warmup:
             ms.append(e0.elapsed_time(e2)); kms.append(e0.elapsed_time(e1))
             st = op.get_stats()
-            launches = st["kernel_launches"]; groups = st["group_count"]
+            launches = st["kernel_launches"] + (final.get_stats()["kernel_launches"] if final is not None else 0)
+            groups = (final or op).get_stats()["group_count"]
         result = out
         op.close()
+        if final is not None:
+            final.close()
     return {"ms": float(np.mean(ms)), "kernel_ms": float(np.mean(kms)), "launches": int(launches), "groups": int(groups), "result": result}
+
+
+def run_partitioned_output(torch, backend, device, rows, partitions, steps, warmup, dist=None):
+    """configs[4] shape: 8 bigint columns, partition on column 0 (InterpretedHashGenerator + HashGenerator.getPartition); with N > 1
+    ranks the partition slabs are exchanged with one all-to-all per column over NCCL."""
+    from presto_b200 import BIGINT, MEM_DEVICE, PartitionedOutputOperator
+    from presto_b200.exchange import all_to_all_pages
+    from presto_b200.synthetic import splitmix64_torch
+    dev = f"cuda:{device}"
+    rank = dist.get_rank() if dist is not None else 0
+    cols = [splitmix64_torch(100 + c, rank * rows, rows, dev) for c in range(8)]
+    page = device_page(torch, cols, [BIGINT] * 8)
+    stream = torch.cuda.current_stream()
+    pms, xms = [], []
+    for it in range(warmup + steps):
+        op = PartitionedOutputOperator([BIGINT] * 8, partitions, [0], backend=backend, device=device, output_memory=MEM_DEVICE, cuda_stream=stream.cuda_stream)
+        e0, e1, e2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        op.add_input(page)
+        out = op.get_output(copy=False)
+        offsets = op.get_offsets()
+        e1.record(stream)
+        received = rows
+        if dist is not None:
+            got = all_to_all_pages(out, offsets, [BIGINT] * 8)
+            received = got.position_count
+            torch.cuda.synchronize()
+        e2.record(stream)
+        torch.cuda.synchronize()
+        if it >= warmup:
+            pms.append(e0.elapsed_time(e1)); xms.append(e1.elapsed_time(e2))
+        op.close()
+    p_ms, x_ms = float(np.mean(pms)), float(np.mean(xms))
+    return {"rows": rows, "partitions": partitions, "partition_ms": p_ms, "exchange_ms": x_ms, "received_rows": int(received),
+            "rows_per_s": rows / ((p_ms + x_ms) / 1000), "partition_gbs": 128 * rows / (p_ms / 1000) / 1e9}
+
+
+def run_page_processor_q1(torch, backend, device, rows, steps, warmup):
+    """TPC-H Q1 filter + project (HandTpchQuery1.java:237-330): shipdate <= 1998-09-02; 7 output columns."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from presto_b200 import DATE, DOUBLE, INTEGER, MEM_DEVICE, FilterAndProjectOperator, Program
+    dev = f"cuda:{device}"
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    rf = torch.randint(0, 3, (rows,), dtype=torch.int32, device=dev, generator=g); ls = torch.randint(0, 2, (rows,), dtype=torch.int32, device=dev, generator=g)
+    qty = torch.randint(1, 51, (rows,), device=dev, generator=g).to(torch.float64)
+    ep = torch.rand(rows, dtype=torch.float64, device=dev, generator=g) * 1e5
+    disc = torch.randint(0, 11, (rows,), device=dev, generator=g).to(torch.float64) / 100
+    tax = torch.randint(0, 9, (rows,), device=dev, generator=g).to(torch.float64) / 100
+    ship = torch.randint(8035, 10600, (rows,), dtype=torch.int32, device=dev, generator=g)
+    types = [INTEGER, INTEGER, DOUBLE, DOUBLE, DOUBLE, DOUBLE, DATE]
+    page = device_page(torch, [rf, ls, qty, ep, disc, tax, ship], types)
+    prog = Program(types)
+    c = [prog.input(i) for i in range(7)]
+    prog.set_filter(c[6] <= 10471)
+    dp = c[3] * (1.0 - c[4])
+    prog.project(c[0], c[1], c[2], c[3], dp, dp * (1.0 + c[5]), c[4])
+    stream = torch.cuda.current_stream()
+    times, out_rows = [], 0
+    for it in range(warmup + steps):
+        op = FilterAndProjectOperator(types, prog, backend=backend, device=device, output_memory=MEM_DEVICE, cuda_stream=stream.cuda_stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        op.add_input(page)
+        out = op.get_output(copy=False)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if it >= warmup:
+            times.append(e0.elapsed_time(e1)); out_rows = out.position_count
+        op.close()
+    ms = float(np.mean(times))
+    algo = rows * 44 + out_rows * 48      # in: 2 x int32 + 4 x double + date; out: 2 x int32 + 5 x double
+    return {"rows": rows, "selected": int(out_rows), "ms": ms, "rows_per_s": rows / (ms / 1000), "achieved_gbs": algo / (ms / 1000) / 1e9}
 
 
 def run_e2e(torch, backend, rows, groups, steps, warmup, device):
@@ -325,14 +420,24 @@ def main():
     value = rows * world / (ms / 1000)
 
     extra = {}
-    e2e = None
     cpu = None
-    if rank == 0:
-        # ---- end to end through the C ABI with host pages ----
-        e2e_rows = min(args.e2e_rows, rows)
-        e2e_rps, h2d, d2h, _ = run_e2e(torch, backend, e2e_rows, args.groups, max(2, min(args.steps, 3)), 1, local)
-        e2e = {"value": e2e_rps * world, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "sample": f"{e2e_rows} host-resident (pinned) rows per step per GPU, staged in 2^23-row chunks (copy/compute overlapped)"}
+    # ---- end to end through the C ABI with host pages (every rank feeds its own GPU over its own PCIe link) ----
+    e2e_rows = min(args.e2e_rows, rows)
+    e2e_rps, h2d, d2h, _ = run_e2e(torch, backend, e2e_rows, args.groups, max(2, min(args.steps, 3)), 1, local)
+    if dist is not None:
+        t = torch.tensor([e2e_rps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        e2e_rps = float(t[0])
+    e2e = {"value": e2e_rps * world, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "sample": f"{e2e_rows} host-resident (pinned) rows per step per GPU, staged in 2^23-row chunks (copy/compute overlapped)"}
+    if world > 1 and args.extra:
+        del page
+        del keys, cols
+        torch.cuda.empty_cache()
+        try:
+            extra["partitioned_output_all_to_all"] = run_partitioned_output(torch, backend, local, min(rows, 1 << 27), world, 2, 1, dist)
+        except Exception as e:
+            extra["partitioned_output_all_to_all"] = {"error": str(e)[:200]}
     if rank == 0 and world == 1:
         # ---- CPU baseline: oracle on the host cores, bounded sample ----
         threads = os.cpu_count() or 1
@@ -354,19 +459,28 @@ def main():
                 del pg2
             del keys, cols
             torch.cuda.empty_cache()
-            try:
-                scale = min(1.0, rows / 1_000_000_000)
-                extra["hash_join_orders_lineitem"] = run_join(torch, backend, local, int(150_000_000 * scale), int(600_037_902 * scale), 2, 1)
-                extra["hash_join_orders_lineitem"]["roofline_frac"] = extra["hash_join_orders_lineitem"]["achieved_gbs"] / peak
-            except Exception as e:   # the join extra must never take the headline down
-                extra["hash_join_orders_lineitem"] = {"error": str(e)[:200]}
+            scale = min(1.0, rows / 1_000_000_000)
+            for name, fn in [
+                ("hash_join_orders_lineitem", lambda: run_join(torch, backend, local, int(150_000_000 * scale), int(600_037_902 * scale), 2, 1)),
+                ("partitioned_output_8_bigint_cols", lambda: run_partitioned_output(torch, backend, local, int((1 << 28) * scale), 8, 2, 1)),
+                ("page_processor_q1", lambda: run_page_processor_q1(torch, backend, local, int((1 << 28) * scale), 2, 1)),
+            ]:
+                try:   # the extras must never take the headline down
+                    extra[name] = fn()
+                    if "achieved_gbs" in extra[name]:
+                        extra[name]["roofline_frac"] = extra[name]["achieved_gbs"] / peak
+                    if "partition_gbs" in extra[name]:
+                        extra[name]["roofline_frac"] = extra[name]["partition_gbs"] / peak
+                except Exception as e:
+                    extra[name] = {"error": str(e)[:200]}
+                torch.cuda.empty_cache()
 
     if rank == 0:
         achieved = ALGO_BYTES_PER_ROW * rows / (kms / 1000) / 1e9
         line = {
             "metric": "rows/sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, rows),
+            "config": dict(workload_config(args, rows), parallelism=(f"{world} ranks: PARTIAL per GPU + FINAL merge on rank 0, no row exchange" if world > 1 else "1 GPU")),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "kernel": "pg::hashAggKernel<1,4>", "peak_source": peak_kind,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ROW * rows, "kernel_ms": kms},

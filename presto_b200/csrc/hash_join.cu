@@ -181,8 +181,9 @@ __device__ __forceinline__ bool loadKey(const KeyColumn& k, int64_t row, int64_t
     return true;
 }
 
-__global__ void denseMinMaxKernel(KeyColumn k, int64_t n, long long* minMax /* [0]=min [1]=max [2]=non-null count */)
+__global__ void __launch_bounds__(256) denseMinMaxKernel(KeyColumn k, int64_t n, long long* minMax /* [0]=min [1]=max [2]=non-null count */)
 {
+    __shared__ long long sLo[8], sHi[8]; __shared__ unsigned long long sCnt[8];
     long long lo = LLONG_MAX, hi = LLONG_MIN; unsigned long long cnt = 0;
     for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {
         int64_t key;
@@ -191,7 +192,12 @@ __global__ void denseMinMaxKernel(KeyColumn k, int64_t n, long long* minMax /* [
     for (int m = 16; m >= 1; m >>= 1) {
         lo = min(lo, (long long) shflXor64((uint64_t) lo, m)); hi = max(hi, (long long) shflXor64((uint64_t) hi, m)); cnt += shflXor64(cnt, m);
     }
-    if ((threadIdx.x & 31) == 0) { atomicMin(&minMax[0], lo); atomicMax(&minMax[1], hi); atomicAdd((unsigned long long*) &minMax[2], cnt); }
+    if ((threadIdx.x & 31) == 0) { sLo[threadIdx.x >> 5] = lo; sHi[threadIdx.x >> 5] = hi; sCnt[threadIdx.x >> 5] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) { lo = min(lo, sLo[w]); hi = max(hi, sHi[w]); cnt += sCnt[w]; }
+        atomicMin(&minMax[0], lo); atomicMax(&minMax[1], hi); atomicAdd((unsigned long long*) &minMax[2], cnt);
+    }
 }
 
 __global__ void denseSetBitsKernel(KeyColumn k, int64_t n, int64_t minKey, unsigned long long* bitmap, unsigned int* duplicate)
@@ -231,10 +237,34 @@ __device__ __forceinline__ int64_t denseRank(const DenseIndex& D, int64_t key)
     return (int64_t) r;
 }
 
+// Build OUTPUT columns are stored row-wise in key order ("payload rows"): one random 8..32-byte write per build row when the index
+// is built, one 8..32-byte read per matching probe row (sequential when the probe keys are clustered).
+constexpr int kMaxPayloadWords = 4;                 // payload rows of up to 32 bytes use the dense index
+struct PayloadColumn { int32_t offset, width, nullOffset; };   // byte offsets inside the row; nullOffset < 0: column has no NULLs
+struct PayloadLayout {
+    int32_t nCols, strideWords;
+    PayloadColumn cols[kMaxJoinColumns];
+};
+
+__device__ __forceinline__ uint64_t loadWidth(const void* base, int64_t i, int width)
+{
+    if (width == 8) return ((const uint64_t*) base)[i];
+    if (width == 4) return ((const uint32_t*) base)[i];
+    return ((const uint8_t*) base)[i];
+}
+__device__ __forceinline__ void storeWidth(void* base, int64_t i, int width, uint64_t v)
+{
+    if (width == 8) ((uint64_t*) base)[i] = v;
+    else if (width == 4) ((uint32_t*) base)[i] = (uint32_t) v;
+    else ((uint8_t*) base)[i] = (uint8_t) v;
+}
+__device__ __forceinline__ uint64_t widthMask(int width) { return width >= 8 ? ~0ULL : ((1ULL << (8 * width)) - 1); }
+
 struct DenseGatherParams {
     KeyColumn key; DenseIndex D; int64_t n;
-    int32_t nCols;
-    JoinColumn cols[kMaxJoinColumns];   // src = build column, dst = the column in key order
+    PayloadLayout L;
+    const void* src[kMaxJoinColumns]; const uint8_t* srcNulls[kMaxJoinColumns];
+    uint64_t* rows;   // [nonNull][strideWords]
 };
 __global__ void denseGatherKernel(const __grid_constant__ DenseGatherParams P)
 {
@@ -242,77 +272,105 @@ __global__ void denseGatherKernel(const __grid_constant__ DenseGatherParams P)
         int64_t key;
         if (!loadKey(P.key, pos, key)) continue;
         const int64_t r = denseRank(P.D, key);
-        for (int c = 0; c < P.nCols; c++) copyValue(P.cols[c], pos, r);
+        uint64_t w[kMaxPayloadWords] = {0, 0, 0, 0};
+        for (int c = 0; c < P.L.nCols; c++) {
+            const PayloadColumn& pc = P.L.cols[c];
+            const uint64_t v = loadWidth(P.src[c], pos, pc.width);
+#pragma unroll
+            for (int k = 0; k < kMaxPayloadWords; k++) if (k == pc.offset >> 3) w[k] |= v << (8 * (pc.offset & 7));
+            if (pc.nullOffset >= 0 && P.srcNulls[c][pos]) {
+#pragma unroll
+                for (int k = 0; k < kMaxPayloadWords; k++) if (k == pc.nullOffset >> 3) w[k] |= 1ULL << (8 * (pc.nullOffset & 7));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kMaxPayloadWords; k++) if (k < P.L.strideWords) P.rows[r * P.L.strideWords + k] = w[k];
     }
 }
 
-constexpr int kProbeTile = 1024;   // rows per CTA step (256 threads x 4)
+constexpr int kUnitRounds = 4;
+constexpr int kUnitRows = 32 * kUnitRounds;     // rows owned by one warp per step
+constexpr int kPreloadCols = 4;                 // probe output columns whose loads are issued before the index lookups
 
 struct DenseProbeParams {
-    KeyColumn key; DenseIndex D; int64_t n; int64_t tiles;
+    KeyColumn key; DenseIndex D; int64_t n; int64_t units;
     int32_t outer;
-    uint32_t* tileCounts;          // pass A out [tiles + 1]
-    const uint32_t* tileOffsets;   // pass B in
+    uint32_t* unitCounts;          // pass A out [units + 1]
+    const uint32_t* unitOffsets;   // pass B in
     int32_t nProbe, nBuild;
-    JoinColumn probe[kMaxJoinColumns];   // src = probe column, dst = output
-    JoinColumn build[kMaxJoinColumns];   // src = build column in key order, dst = output
+    JoinColumn probe[kMaxJoinColumns];   // src = probe column, dst = output column
+    PayloadLayout L; const uint64_t* rows;
+    void* buildDst[kMaxJoinColumns]; uint8_t* buildDstNulls[kMaxJoinColumns];
 };
 
 __global__ void __launch_bounds__(256) denseCountKernel(const __grid_constant__ DenseProbeParams P)
 {
-    __shared__ uint32_t warpCounts[8];
-    for (int64_t tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warpId = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+    for (int64_t unit = warpId; unit < P.units; unit += nWarps) {
+        int64_t key[kUnitRounds]; bool valid[kUnitRounds];
+#pragma unroll
+        for (int j = 0; j < kUnitRounds; j++) {
+            const int64_t row = unit * kUnitRows + j * 32 + lane;
+            valid[j] = row < P.n && loadKey(P.key, row, key[j]);
+        }
         uint32_t c = 0;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int64_t row = tile * kProbeTile + j * 256 + threadIdx.x;
-            int64_t key;
-            if (row < P.n && loadKey(P.key, row, key) && denseRank(P.D, key) >= 0) c++;
-        }
-        for (int m = 16; m >= 1; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
-        if ((threadIdx.x & 31) == 0) warpCounts[threadIdx.x >> 5] = c;
-        __syncthreads();
-        if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < 8; w++) t += warpCounts[w]; P.tileCounts[tile] = t; }
-        __syncthreads();
+        for (int j = 0; j < kUnitRounds; j++) c += __popc(__ballot_sync(0xffffffffu, valid[j] && denseRank(P.D, key[j]) >= 0));
+        if (lane == 0) P.unitCounts[unit] = c;
     }
 }
 
+// One warp per unit of 128 probe rows, no block-level synchronisation: all independent loads of the unit (keys, probe output
+// columns) are in flight before the dependent index lookups, payload reads follow the ranks, output positions come from ballots.
 __global__ void __launch_bounds__(256) denseEmitKernel(const __grid_constant__ DenseProbeParams P)
 {
-    __shared__ uint32_t partial[32];   // matches of (round j, warp w) at [j * 8 + w]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
-        int64_t rank[4]; bool emit[4]; unsigned ballots[4];
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1;
+    const int64_t warpId = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+    for (int64_t unit = warpId; unit < P.units; unit += nWarps) {
+        int64_t key[kUnitRounds]; bool valid[kUnitRounds]; bool inRange[kUnitRounds];
+        uint64_t pv[kUnitRounds][kPreloadCols];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int64_t row = tile * kProbeTile + j * 256 + threadIdx.x;
-            rank[j] = -1; emit[j] = false;
-            if (row < P.n) {
-                int64_t key;
-                if (loadKey(P.key, row, key)) rank[j] = denseRank(P.D, key);
-                emit[j] = rank[j] >= 0 || P.outer;
+        for (int j = 0; j < kUnitRounds; j++) {
+            const int64_t row = unit * kUnitRows + j * 32 + lane;
+            inRange[j] = row < P.n;
+            valid[j] = inRange[j] && loadKey(P.key, row, key[j]);
+#pragma unroll
+            for (int c = 0; c < kPreloadCols; c++) { pv[j][c] = 0; if (c < P.nProbe && inRange[j]) pv[j][c] = loadWidth(P.probe[c].src, row, P.probe[c].width); }
+        }
+        int64_t rank[kUnitRounds];
+#pragma unroll
+        for (int j = 0; j < kUnitRounds; j++) rank[j] = valid[j] ? denseRank(P.D, key[j]) : -1;
+        uint64_t pw[kUnitRounds][kMaxPayloadWords];
+#pragma unroll
+        for (int j = 0; j < kUnitRounds; j++)
+#pragma unroll
+            for (int k = 0; k < kMaxPayloadWords; k++) { pw[j][k] = 0; if (rank[j] >= 0 && k < P.L.strideWords) pw[j][k] = P.rows[rank[j] * P.L.strideWords + k]; }
+        uint32_t cursor = P.outer ? (uint32_t) (unit * kUnitRows) : P.unitOffsets[unit];
+#pragma unroll
+        for (int j = 0; j < kUnitRounds; j++) {
+            const bool emit = inRange[j] && (rank[j] >= 0 || P.outer);
+            const unsigned m = __ballot_sync(0xffffffffu, emit);
+            if (emit) {
+                const int64_t row = unit * kUnitRows + j * 32 + lane;
+                const uint32_t o = cursor + __popc(m & lt);
+#pragma unroll
+                for (int c = 0; c < kPreloadCols; c++) if (c < P.nProbe) storeWidth(P.probe[c].dst, o, P.probe[c].width, pv[j][c]);
+                for (int c = kPreloadCols; c < P.nProbe; c++) storeWidth(P.probe[c].dst, o, P.probe[c].width, loadWidth(P.probe[c].src, row, P.probe[c].width));
+                for (int c = 0; c < P.nProbe; c++) if (P.probe[c].dstNulls) P.probe[c].dstNulls[o] = P.probe[c].srcNulls ? P.probe[c].srcNulls[row] : 0;
+                for (int c = 0; c < P.nBuild; c++) {
+                    const PayloadColumn& pc = P.L.cols[c];
+                    uint64_t word = 0, nullWord = 0;
+#pragma unroll
+                    for (int k = 0; k < kMaxPayloadWords; k++) { if (k == pc.offset >> 3) word = pw[j][k]; if (pc.nullOffset >= 0 && k == pc.nullOffset >> 3) nullWord = pw[j][k]; }
+                    const bool isNull = rank[j] < 0 || (pc.nullOffset >= 0 && ((nullWord >> (8 * (pc.nullOffset & 7))) & 0xff));
+                    storeWidth(P.buildDst[c], o, pc.width, isNull ? 0 : (word >> (8 * (pc.offset & 7))) & widthMask(pc.width));
+                    if (P.buildDstNulls[c]) P.buildDstNulls[c][o] = isNull ? 1 : 0;
+                }
             }
-            ballots[j] = __ballot_sync(0xffffffffu, emit[j]);
-            if (lane == 0) partial[j * 8 + warp] = __popc(ballots[j]);
+            cursor += __popc(m);
         }
-        __syncthreads();
-        if (warp == 0) {   // exclusive scan of the 32 partial counts in (round, warp) order = row order
-            uint32_t v = partial[lane], x = v;
-            for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
-            partial[lane] = x - v;
-        }
-        __syncthreads();
-        const uint32_t base = P.outer ? (uint32_t) (tile * kProbeTile) : P.tileOffsets[tile];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (!emit[j]) continue;
-            const int64_t row = tile * kProbeTile + j * 256 + threadIdx.x;
-            const uint32_t o = base + partial[j * 8 + warp] + __popc(ballots[j] & ((1u << lane) - 1));
-            for (int c = 0; c < P.nProbe; c++) copyValue(P.probe[c], row, o);
-            if (rank[j] >= 0) for (int c = 0; c < P.nBuild; c++) copyValue(P.build[c], rank[j], o);
-            else for (int c = 0; c < P.nBuild; c++) writeNull(P.build[c], o);
-        }
-        __syncthreads();
     }
 }
 
@@ -336,7 +394,8 @@ struct LookupSourceDevice {
     bool dense = false;
     int64_t minKey = 0; uint64_t range = 0;
     DeviceBuffer bitmap, prefix;
-    std::vector<DeviceBuffer> sortedValues, sortedNulls;   // per build OUTPUT channel, in key order
+    DeviceBuffer payloadRows;      // build OUTPUT columns, row-wise, in key order
+    PayloadLayout payload{};
     DenseIndex denseView() const { DenseIndex D{}; D.bitmap = bitmap.as<uint64_t>(); D.prefix = prefix.as<uint32_t>(); D.minKey = minKey; D.range = range; return D; }
 
     JoinTable view() const
@@ -531,6 +590,18 @@ public:
     {
         if (ls->layout.nKeys != 1) return false;
         const int64_t n = ls->positionCount;
+        // payload row layout: widest columns first (natural alignment), then one null byte per nullable column
+        PayloadLayout payloadLayout{};
+        {
+            int off = 0;
+            for (int width : {8, 4, 1})
+                for (size_t i = 0; i < ls->outputChannels.size(); i++)
+                    if (typeWidth(ls->types[ls->outputChannels[i]]) == width) { payloadLayout.cols[i].offset = off; payloadLayout.cols[i].width = width; payloadLayout.cols[i].nullOffset = -1; off += width; }
+            for (size_t i = 0; i < ls->outputChannels.size(); i++)
+                if (ls->hasNulls[ls->outputChannels[i]]) payloadLayout.cols[i].nullOffset = off++;
+            payloadLayout.strideWords = std::max(1, (off + 7) / 8);
+            if (payloadLayout.strideWords > kMaxPayloadWords) return false;   // wide payloads keep the hash-table path
+        }
         const int kch = ls->layout.channels[0];
         KeyColumn kc{ls->values[kch].ptr, ls->hasNulls[kch] ? ls->nulls[kch].as<uint8_t>() : nullptr, ls->types[kch]};
         DeviceBuffer mm; mm.reserve(64);
@@ -568,20 +639,19 @@ public:
         cub::DeviceScan::ExclusiveSum(temp.ptr, tb, counts.as<uint32_t>(), ls->prefix.as<uint32_t>(), (int) (blocks + 1), stream);
         stats.kernel_launches += 2;
         ls->minKey = h[0]; ls->range = range;
-        // build output columns in key order
+        // build output columns as payload rows in key order
         DenseGatherParams G{};
-        G.key = kc; G.D = ls->denseView(); G.n = n; G.nCols = (int) ls->outputChannels.size();
-        ls->sortedValues.resize(ls->outputChannels.size()); ls->sortedNulls.resize(ls->outputChannels.size());
+        G.key = kc; G.D = ls->denseView(); G.n = n;
+        G.L = payloadLayout; G.L.nCols = (int) ls->outputChannels.size();
         for (size_t i = 0; i < ls->outputChannels.size(); i++) {
             const int ch = ls->outputChannels[i];
-            JoinColumn& jc = G.cols[i];
-            jc.width = typeWidth(ls->types[ch]); jc.src = ls->values[ch].ptr; jc.srcNulls = ls->hasNulls[ch] ? ls->nulls[ch].as<uint8_t>() : nullptr;
-            ls->sortedValues[i].accounting = ls->sortedNulls[i].accounting = &ls->deviceBytes;
-            ls->sortedValues[i].reserve(std::max<size_t>((size_t) nonNull * jc.width, 16));
-            jc.dst = ls->sortedValues[i].ptr; jc.dstNulls = nullptr;
-            if (jc.srcNulls) { ls->sortedNulls[i].reserve((size_t) nonNull); jc.dstNulls = ls->sortedNulls[i].as<uint8_t>(); }
+            G.src[i] = ls->values[ch].ptr; G.srcNulls[i] = ls->hasNulls[ch] ? ls->nulls[ch].as<uint8_t>() : nullptr;
         }
-        if (G.nCols) PG_LAUNCH(this, denseGatherKernel, grid, 256, 0, G);
+        ls->payload = G.L;
+        ls->payloadRows.accounting = &ls->deviceBytes;
+        ls->payloadRows.reserve(std::max<size_t>((size_t) nonNull * G.L.strideWords * 8, 16));
+        G.rows = ls->payloadRows.as<uint64_t>();
+        if (G.L.nCols) PG_LAUNCH(this, denseGatherKernel, grid, 256, 0, G);
         PG_CUDA(cudaStreamSynchronize(stream));
         ls->nullKeyCount = n - nonNull;
         ls->dense = true;
@@ -731,32 +801,33 @@ public:
         stats.output_positions += total;
     }
 
-    // Probe of the bitmap + rank index: count per tile → scan of the tile counts → write the output columns in place.
+    // Probe of the bitmap + rank index: count per 128-row unit → scan of the unit counts → write the output columns in place.
     void addInputDense(const LookupSourceDevice& ls, const std::vector<DeviceColumn>& cols, int slot, int64_t n)
     {
         auto colOf = [&](int ch) -> const DeviceColumn& { return cols[std::find(staged.begin(), staged.end(), ch) - staged.begin()]; };
         const DeviceColumn& kcol = colOf(layout.channels[0]);
         DenseProbeParams P{};
         P.key = KeyColumn{kcol.values, kcol.nulls, kcol.type};
-        P.D = ls.denseView(); P.n = n; P.tiles = divUp(n, kProbeTile); P.outer = joinType == PG_JOIN_PROBE_OUTER;
-        const int grid = (int) std::min<int64_t>(P.tiles, (int64_t) numSMs * 8);
+        P.D = ls.denseView(); P.n = n; P.units = divUp(n, kUnitRows); P.outer = joinType == PG_JOIN_PROBE_OUTER;
+        P.L = ls.payload; P.rows = ls.payloadRows.as<uint64_t>();
+        const int grid = (int) std::min<int64_t>(divUp(P.units, 8), (int64_t) numSMs * 8);
         int64_t total = n;
         if (!P.outer) {
-            counts.reserve((size_t) (P.tiles + 1) * 4); offsets.reserve((size_t) (P.tiles + 1) * 4);
-            PG_CUDA(cudaMemsetAsync(counts.as<uint32_t>() + P.tiles, 0, 4, stream));
-            P.tileCounts = counts.as<uint32_t>();
+            counts.reserve((size_t) (P.units + 1) * 4); offsets.reserve((size_t) (P.units + 1) * 4);
+            PG_CUDA(cudaMemsetAsync(counts.as<uint32_t>() + P.units, 0, 4, stream));
+            P.unitCounts = counts.as<uint32_t>();
             PG_LAUNCH(this, denseCountKernel, grid, 256, 0, P);
             size_t tb = 0;
-            cub::DeviceScan::ExclusiveSum(nullptr, tb, counts.as<uint32_t>(), offsets.as<uint32_t>(), (int) (P.tiles + 1), stream);
+            cub::DeviceScan::ExclusiveSum(nullptr, tb, counts.as<uint32_t>(), offsets.as<uint32_t>(), (int) (P.units + 1), stream);
             scanTemp.reserve(tb);
-            cub::DeviceScan::ExclusiveSum(scanTemp.ptr, tb, counts.as<uint32_t>(), offsets.as<uint32_t>(), (int) (P.tiles + 1), stream);
+            cub::DeviceScan::ExclusiveSum(scanTemp.ptr, tb, counts.as<uint32_t>(), offsets.as<uint32_t>(), (int) (P.units + 1), stream);
             stats.kernel_launches += 2;
             uint32_t t = 0;
-            PG_CUDA(cudaMemcpyAsync(&t, offsets.as<uint32_t>() + P.tiles, 4, cudaMemcpyDeviceToHost, stream));
+            PG_CUDA(cudaMemcpyAsync(&t, offsets.as<uint32_t>() + P.units, 4, cudaMemcpyDeviceToHost, stream));
             PG_CUDA(cudaStreamSynchronize(stream));
             stats.d2h_bytes += 4;
             total = t;
-            P.tileOffsets = offsets.as<uint32_t>();
+            P.unitOffsets = offsets.as<uint32_t>();
         }
         pendingRows = total;
         if (total == 0) { stager.markCompute(slot); return; }
@@ -777,11 +848,9 @@ public:
         for (size_t i = 0; i < ls.outputChannels.size(); i++) {
             const int ch = ls.outputChannels[i];
             const size_t o = outputChannels.size() + i;
-            JoinColumn& jc = P.build[i];
-            jc.width = typeWidth(ls.types[ch]); jc.src = ls.sortedValues[i].ptr; jc.srcNulls = ls.sortedNulls[i].ptr ? ls.sortedNulls[i].as<uint8_t>() : nullptr;
-            outValues[o].reserve((size_t) total * jc.width);
-            jc.dst = outValues[o].ptr; jc.dstNulls = nullptr;
-            if (jc.srcNulls || P.outer) { outNulls[o].reserve(total); jc.dstNulls = outNulls[o].as<uint8_t>(); hasNulls[o] = true; }
+            outValues[o].reserve((size_t) total * typeWidth(ls.types[ch]));
+            P.buildDst[i] = outValues[o].ptr; P.buildDstNulls[i] = nullptr;
+            if (ls.payload.cols[i].nullOffset >= 0 || P.outer) { outNulls[o].reserve(total); P.buildDstNulls[i] = outNulls[o].as<uint8_t>(); hasNulls[o] = true; }
             outBlocks[o].type = ls.types[ch];
         }
         PG_LAUNCH(this, denseEmitKernel, grid, 256, 0, P);

@@ -20,7 +20,7 @@ namespace pg {
 
 constexpr int kMaxPartChannels = 8;
 constexpr int kMaxScatterColumns = 32;
-constexpr int kRowsPerUnit = 2048;       // rows owned by one warp
+constexpr int kRowsPerUnit = 1024;       // rows owned by one warp (their output positions live in shared memory during pass 2)
 constexpr int kPartWarps = 8;
 
 struct HashCol { const void* values; const uint8_t* nulls; int32_t type; };
@@ -96,54 +96,107 @@ struct ScatterParams {
     const uint32_t* base;    // scanned hist
 };
 
-__device__ __forceinline__ void scatterRow(const ScatterParams& P, int64_t row, uint32_t dest)
+template <typename T>
+__device__ __forceinline__ void permuteColumn(const T* __restrict__ src, T* __restrict__ dst, const uint32_t* dest, int64_t begin, int count, int lane)
 {
-    for (int c = 0; c < P.nCols; c++) {
-        const ScatterColumn& sc = P.cols[c];
-        if (sc.width == 8) ((uint64_t*) sc.dst)[dest] = ldStream64((const uint64_t*) sc.src + row);
-        else if (sc.width == 4) ((uint32_t*) sc.dst)[dest] = ldStream32((const uint32_t*) sc.src + row);
-        else ((uint8_t*) sc.dst)[dest] = ((const uint8_t*) sc.src)[row];
-        if (sc.dstNulls) sc.dstNulls[dest] = sc.srcNulls ? sc.srcNulls[row] : 0;
+    // the unit's destinations are already in shared memory: every load below is independent → 8 requests in flight per lane
+    int i = lane;
+    for (; i + 7 * 32 < count; i += 8 * 32) {
+        T v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = src[begin + i + k * 32];
+#pragma unroll
+        for (int k = 0; k < 8; k++) dst[dest[i + k * 32]] = v[k];
     }
+    for (; i < count; i += 32) dst[dest[i]] = src[begin + i];
 }
 
+// Pass 2.  Phase A: the warp walks its unit in row order and turns partition ids into output positions (stable: rank inside the
+// partition = rows of the same partition before it) kept in shared memory.  Phase B: one column at a time is permuted through them.
+// Rows that go to EVERY partition (replicate-any-row / NULL partition key) are rare: they are ranked in phase A and copied in a
+// separate epilogue so the common path stays branch-free.
 __global__ void __launch_bounds__(kPartWarps * 32) partitionScatterKernel(const __grid_constant__ ScatterParams P)
 {
-    extern __shared__ uint32_t scursor[];   // [warps][partitionCount]
+    extern __shared__ uint32_t smemU32[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int PC = P.partitionCount;
-    uint32_t* cur = scursor + warp * PC;
+    uint32_t* cur = smemU32 + warp * PC;                                   // [warps][PC]
+    uint32_t* dest = smemU32 + kPartWarps * PC + warp * kRowsPerUnit;      // [warps][kRowsPerUnit]
     const unsigned ltMask = (1u << lane) - 1;
     for (int64_t unit = (int64_t) blockIdx.x * kPartWarps + warp; unit < P.units; unit += (int64_t) gridDim.x * kPartWarps) {
         for (int p = lane; p < PC; p += 32) cur[p] = P.base[(size_t) p * P.units + unit];
         __syncwarp();
         const int64_t begin = unit * kRowsPerUnit, end = min(begin + (int64_t) kRowsPerUnit, P.n);
-        for (int64_t base = begin; base < end; base += 32) {
-            const int64_t row = base + lane;
-            const int part = row < end ? (int) P.ids[row] : -1 - lane;
+        const int count = (int) (end - begin);
+        bool anyReplicated = false;
+        for (int off = 0; off < count; off += 32) {
+            const int i = off + lane;
+            const int part = i < count ? (int) P.ids[begin + i] : -1 - lane;
             const unsigned peers = __match_any_sync(0xffffffffu, part);
             const unsigned rep = __ballot_sync(0xffffffffu, part == PC);
             if (rep == 0) {
-                uint32_t dest = 0;
-                if (part >= 0) dest = cur[part] + __popc(peers & ltMask);
+                uint32_t d = 0;
+                if (part >= 0) d = cur[part] + __popc(peers & ltMask);
                 __syncwarp();
                 if (part >= 0 && lane == __ffs(peers) - 1) cur[part] += __popc(peers);
-                if (part >= 0) scatterRow(P, row, dest);
+                if (i < count) dest[i] = d;
             }
             else {
-                // some rows of this round go to every partition: rank inside partition q counts its own rows and the replicated ones
+                // rows of this round that go to every partition: rank inside partition q counts its own rows and the replicated ones
+                anyReplicated = true;
+                uint32_t d = 0xFFFFFFFFu;
                 for (int q = 0; q < PC; q++) {
                     const unsigned members = __ballot_sync(0xffffffffu, part == q) | rep;
-                    const bool mine = part == q || part == PC;
-                    const uint32_t dest = cur[q] + __popc(members & ltMask);
+                    if (part == q) d = cur[q] + __popc(members & ltMask);
                     __syncwarp();
                     if (lane == 0) cur[q] += __popc(members);
-                    if (mine) scatterRow(P, row, dest);
                     __syncwarp();
                 }
+                if (i < count) dest[i] = d;      // 0xFFFFFFFF marks a replicated row: copied by the epilogue
             }
             __syncwarp();
         }
+        if (!anyReplicated) {
+            for (int c = 0; c < P.nCols; c++) {
+                const ScatterColumn& sc = P.cols[c];
+                if (sc.width == 8) permuteColumn((const uint64_t*) sc.src, (uint64_t*) sc.dst, dest, begin, count, lane);
+                else if (sc.width == 4) permuteColumn((const uint32_t*) sc.src, (uint32_t*) sc.dst, dest, begin, count, lane);
+                else permuteColumn((const uint8_t*) sc.src, (uint8_t*) sc.dst, dest, begin, count, lane);
+                if (sc.dstNulls) {
+                    if (sc.srcNulls) permuteColumn(sc.srcNulls, sc.dstNulls, dest, begin, count, lane);
+                    else for (int i = lane; i < count; i += 32) sc.dstNulls[dest[i]] = 0;
+                }
+            }
+        }
+        else {
+            // slow path for units that contain replicated rows: recompute every row's positions round by round
+            for (int p = lane; p < PC; p += 32) cur[p] = P.base[(size_t) p * P.units + unit];
+            __syncwarp();
+            for (int off = 0; off < count; off += 32) {
+                const int i = off + lane;
+                const int part = i < count ? (int) P.ids[begin + i] : -1 - lane;
+                const unsigned rep = __ballot_sync(0xffffffffu, part == PC);
+                for (int q = 0; q < PC; q++) {
+                    const unsigned members = __ballot_sync(0xffffffffu, part == q) | rep;
+                    const bool mine = part == q || part == PC;
+                    const uint32_t d = cur[q] + __popc(members & ltMask);
+                    __syncwarp();
+                    if (lane == 0) cur[q] += __popc(members);
+                    if (mine) {
+                        const int64_t row = begin + i;
+                        for (int c = 0; c < P.nCols; c++) {
+                            const ScatterColumn& sc = P.cols[c];
+                            if (sc.width == 8) ((uint64_t*) sc.dst)[d] = ((const uint64_t*) sc.src)[row];
+                            else if (sc.width == 4) ((uint32_t*) sc.dst)[d] = ((const uint32_t*) sc.src)[row];
+                            else ((uint8_t*) sc.dst)[d] = ((const uint8_t*) sc.src)[row];
+                            if (sc.dstNulls) sc.dstNulls[d] = sc.srcNulls ? sc.srcNulls[row] : 0;
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -180,7 +233,7 @@ public:
         for (DeviceBuffer* d : {&ids, &hist, &base, &scanTemp}) d->accounting = &stats.device_bytes;
         const size_t smem = (size_t) kPartWarps * partitionCount * 4;
         PG_CUDA(cudaFuncSetAttribute(partitionIdKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        PG_CUDA(cudaFuncSetAttribute(partitionScatterKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        PG_CUDA(cudaFuncSetAttribute(partitionScatterKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (smem + (size_t) kPartWarps * kRowsPerUnit * 4)));
     }
 
     bool needsInput() override { return !finishing && !hasPending; }
@@ -238,7 +291,7 @@ public:
             sc.dst = outValues[i].ptr; sc.dstNulls = nullptr;
             if (cols[i].nulls) { outNulls[i].reserve(total); sc.dstNulls = outNulls[i].as<uint8_t>(); }
         }
-        PG_LAUNCH(this, partitionScatterKernel, grid, kPartWarps * 32, smem, S);
+        PG_LAUNCH(this, partitionScatterKernel, grid, kPartWarps * 32, smem + (size_t) kPartWarps * kRowsPerUnit * 4, S);
         stager.markCompute(slot);
         const bool toHost = options.output_memory == PG_MEM_HOST;
         if (toHost && hostValues.size() < nCols) { hostValues.resize(nCols); hostNulls.resize(nCols); }
