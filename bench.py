@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--e2e-rows", type=int, default=1 << 27, help="rows of the host-resident sample used for the e2e number")
     ap.add_argument("--cpu-rows", type=int, default=1 << 28, help="rows of the bounded sample the CPU baseline aggregates")
     ap.add_argument("--extra", type=int, default=1, help="also measure other cardinalities and the join (configs[2])")
+    ap.add_argument("--only", default="", help="comma separated subset of the extra measurements (names of the extra keys)")
     return ap.parse_args()
 
 
@@ -373,6 +374,39 @@ def run_join(torch, backend, device, build_rows, probe_rows, steps, warmup):
             "probe_rows_per_s": probe_rows / ((b_ms + p_ms) / 1000), "algorithmic_bytes": algo, "achieved_gbs": algo / ((b_ms + p_ms) / 1000) / 1e9, "launches": int(launches)}
 
 
+def run_q3(torch, backend, device, n_orders, steps, warmup):
+    """configs[3] shape on one GPU: TPC-H Q3 filter → join → join → aggregate over device-resident tables (presto_b200/pipelines.py);
+    rows/s counts lineitem rows.  Algorithmic bytes = every input column once (28 B lineitem, 24 B orders, 12 B customer)."""
+    from presto_b200 import BIGINT, DATE, DOUBLE, INTEGER
+    from presto_b200.pipelines import run_q3 as q3
+    from presto_b200.synthetic import q3_tables_torch
+    dev = f"cuda:{device}"
+    customer, orders, lineitem = q3_tables_torch(n_orders, dev)
+    torch.cuda.synchronize()
+    cp = [device_page(torch, list(customer), [BIGINT, INTEGER])]
+    op = [device_page(torch, list(orders), [BIGINT, BIGINT, DATE, INTEGER])]
+    lp = [device_page(torch, list(lineitem), [BIGINT, DOUBLE, DOUBLE, DATE])]
+    n_li = lineitem[0].numel()
+    stream = torch.cuda.current_stream()
+    times, groups, stats = [], 0, {}
+    for it in range(warmup + steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        out = q3(cp, op, lp, backend=backend, device_resident=True, stats=stats, device=device, cuda_stream=stream.cuda_stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if it >= warmup:
+            times.append(e0.elapsed_time(e1)); groups = sum(p.position_count for p in out)
+    ms = float(np.mean(times))
+    # ORDER BY revenue DESC, o_orderdate LIMIT 10 on the host
+    rev = np.concatenate([p.blocks[3].values for p in out]) if out else np.zeros(0)
+    top = float(np.sort(rev)[-1]) if len(rev) else None
+    algo = n_li * 28 + n_orders * 24 + customer[0].numel() * 12
+    return {"orders": n_orders, "lineitem_rows": int(n_li), "joined_rows": int(stats.get("joined_rows", 0)), "groups": int(groups), "ms": ms,
+            "lineitem_rows_per_s": n_li / (ms / 1000), "achieved_gbs": algo / (ms / 1000) / 1e9, "launches": int(stats.get("kernel_launches", 0)), "top_revenue": top}
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -447,8 +481,9 @@ def main():
                "sample": f"{sample} rows of the same batch, {threads} threads x one oracle HashAggregationOperator (PARTIAL) + FINAL merge, {dt:.2f} s"}
         if args.extra:
             del page
+            only = set(x for x in args.only.split(",") if x)
             for g_other in (10_000, 3_000_000):
-                if g_other == args.groups:
+                if g_other == args.groups or (only and f"group_by_{g_other}_groups" not in only):
                     continue
                 fill_group_key_torch(keys, row0, g_other)
                 torch.cuda.synchronize()
@@ -464,7 +499,10 @@ def main():
                 ("hash_join_orders_lineitem", lambda: run_join(torch, backend, local, int(150_000_000 * scale), int(600_037_902 * scale), 2, 1)),
                 ("partitioned_output_8_bigint_cols", lambda: run_partitioned_output(torch, backend, local, int((1 << 28) * scale), 8, 2, 1)),
                 ("page_processor_q1", lambda: run_page_processor_q1(torch, backend, local, int((1 << 28) * scale), 2, 1)),
+                ("q3_pipeline", lambda: run_q3(torch, backend, local, int(150_000_000 * scale), 2, 1)),
             ]:
+                if only and name not in only:
+                    continue
                 try:   # the extras must never take the headline down
                     extra[name] = fn()
                     if "achieved_gbs" in extra[name]:

@@ -12,12 +12,17 @@
 // Arithmetic follows MB/type/DoubleOperators.java:62-81 (plain IEEE + - * /) and BigintOperators.java:68-130 (exact, overflow →
 // NUMERIC_VALUE_OUT_OF_RANGE); AND / OR / NOT are SQL three-valued.
 #include "common.cuh"
+#include "fp_codegen.h"
 #include <cub/device/device_scan.cuh>
+#include <cuda.h>
+#include <dlfcn.h>
 #include <algorithm>
+#include <map>
+#include <mutex>
 
 namespace pg {
 
-constexpr int kMaxNodes = 48;
+constexpr int kMaxNodes = 64;     // one bit per node in the null masks
 constexpr int kMaxInputs = 32;
 constexpr int kMaxProjections = 32;
 constexpr int kRowsPerFpUnit = 256;   // rows owned by one warp per step (8 rounds of 32)
@@ -38,6 +43,8 @@ struct FpParams {
     int64_t n, units;
     uint32_t* counts;          // pass A: [units + 1]
     const uint32_t* offsets;   // pass B
+    uint32_t* selection;       // one bit per row: pass A writes, pass B reads
+    uint64_t needFilter, needProject;   // nodes each pass has to evaluate (sub-DAG of the filter / of the projections)
     unsigned int* error;
 };
 
@@ -45,177 +52,232 @@ struct Val { uint64_t bits; bool isNull; };
 
 __device__ __forceinline__ double asDouble(const Val& v, bool isDouble) { return isDouble ? __longlong_as_double((long long) v.bits) : (double) (long long) v.bits; }
 
-// Evaluates nodes [0, upTo] for one row; regs live in local memory (L1 resident), the program is warp-uniform.
-__device__ void evalRow(const FpParams& P, int64_t row, int upTo, uint64_t* regs, uint64_t& nullBits)
+__device__ __forceinline__ Val evalNode(const FpParams& P, const FpNode& nd, int64_t row, const Val& x, const Val& y, const Val& z)
 {
-    nullBits = 0;
-    for (int k = 0; k <= upTo; k++) {
-        const FpNode& nd = P.nodes[k];
-        Val r{0, false};
-        auto get = [&](int i) -> Val { return Val{regs[i], (bool) ((nullBits >> i) & 1ULL)}; };
-        switch (nd.op) {
-            case PG_EX_INPUT: {
-                const FpInput& in = P.inputs[nd.a];
-                if (in.nulls && in.nulls[row]) r.isNull = true;
-                else switch (in.type) {
-                    case PG_TYPE_BIGINT: case PG_TYPE_DOUBLE: r.bits = ldStream64((const uint64_t*) in.values + row); break;
-                    case PG_TYPE_INTEGER: case PG_TYPE_DATE: r.bits = (uint64_t) (int64_t) (int32_t) ldStream32((const uint32_t*) in.values + row); break;
-                    default: r.bits = ((const uint8_t*) in.values)[row] != 0; break;
-                }
-                break;
+    Val r{0, false};
+    switch (nd.op) {
+        case PG_EX_INPUT: {
+            const FpInput& in = P.inputs[nd.a];
+            if (in.nulls && in.nulls[row]) r.isNull = true;
+            else switch (in.type) {
+                case PG_TYPE_BIGINT: case PG_TYPE_DOUBLE: r.bits = ldStream64((const uint64_t*) in.values + row); break;
+                case PG_TYPE_INTEGER: case PG_TYPE_DATE: r.bits = (uint64_t) (int64_t) (int32_t) ldStream32((const uint32_t*) in.values + row); break;
+                default: r.bits = ((const uint8_t*) in.values)[row] != 0; break;
             }
-            case PG_EX_CONST_BIGINT: case PG_EX_CONST_BOOLEAN: case PG_EX_CONST_DOUBLE: r.bits = (uint64_t) nd.immI; break;
-            case PG_EX_CONST_NULL: r.isNull = true; break;
-            case PG_EX_ADD: case PG_EX_SUB: case PG_EX_MUL: case PG_EX_DIV: {
-                const Val x = get(nd.a), y = get(nd.b);
-                if (x.isNull || y.isNull) { r.isNull = true; break; }
-                if (nd.isDouble) {
-                    const double p = asDouble(x, P.nodes[nd.a].isDouble), q = asDouble(y, P.nodes[nd.b].isDouble);
-                    const double z = nd.op == PG_EX_ADD ? p + q : nd.op == PG_EX_SUB ? p - q : nd.op == PG_EX_MUL ? p * q : p / q;
-                    r.bits = (uint64_t) __double_as_longlong(z);
-                }
-                else {
-                    const long long p = (long long) x.bits, q = (long long) y.bits;
-                    long long z = 0;
-                    if (nd.op == PG_EX_ADD) { z = (long long) ((uint64_t) p + (uint64_t) q); if (((p ^ z) & (q ^ z)) < 0) atomicOr(P.error, (unsigned) FP_ERR_OVERFLOW); }
-                    else if (nd.op == PG_EX_SUB) { z = (long long) ((uint64_t) p - (uint64_t) q); if (((p ^ q) & (p ^ z)) < 0) atomicOr(P.error, (unsigned) FP_ERR_OVERFLOW); }
-                    else if (nd.op == PG_EX_MUL) {
-                        z = (long long) ((uint64_t) p * (uint64_t) q);
-                        const long long hi = __mul64hi(p, q);
-                        if (hi != (z >> 63)) atomicOr(P.error, (unsigned) FP_ERR_OVERFLOW);
-                    }
-                    else {
-                        if (q == 0) { atomicOr(P.error, (unsigned) FP_ERR_DIV_ZERO); z = 0; }
-                        else z = (p == LLONG_MIN && q == -1) ? LLONG_MIN : p / q;
-                    }
-                    r.bits = (uint64_t) z;
-                }
-                break;
-            }
-            case PG_EX_NEG: {
-                const Val x = get(nd.a);
-                if (x.isNull) { r.isNull = true; break; }
-                if (nd.isDouble) r.bits = x.bits ^ 0x8000000000000000ULL;
-                else { if ((long long) x.bits == LLONG_MIN) atomicOr(P.error, (unsigned) FP_ERR_OVERFLOW); r.bits = (uint64_t) (-(long long) x.bits); }
-                break;
-            }
-            case PG_EX_EQ: case PG_EX_NE: case PG_EX_LT: case PG_EX_LE: case PG_EX_GT: case PG_EX_GE: {
-                const Val x = get(nd.a), y = get(nd.b);
-                if (x.isNull || y.isNull) { r.isNull = true; break; }
-                bool res;
-                const bool da = P.nodes[nd.a].isDouble, db = P.nodes[nd.b].isDouble;
-                if (da || db) {
-                    const double p = asDouble(x, da), q = asDouble(y, db);
-                    res = nd.op == PG_EX_EQ ? p == q : nd.op == PG_EX_NE ? p != q : nd.op == PG_EX_LT ? p < q : nd.op == PG_EX_LE ? p <= q : nd.op == PG_EX_GT ? p > q : p >= q;
-                }
-                else {
-                    const long long p = (long long) x.bits, q = (long long) y.bits;
-                    res = nd.op == PG_EX_EQ ? p == q : nd.op == PG_EX_NE ? p != q : nd.op == PG_EX_LT ? p < q : nd.op == PG_EX_LE ? p <= q : nd.op == PG_EX_GT ? p > q : p >= q;
-                }
-                r.bits = res;
-                break;
-            }
-            case PG_EX_BETWEEN: {
-                const Val x = get(nd.a), lo = get(nd.b), hi = get(nd.c);
-                const bool da = P.nodes[nd.a].isDouble, db = P.nodes[nd.b].isDouble, dc = P.nodes[nd.c].isDouble;
-                const bool n1 = x.isNull || lo.isNull, n2 = x.isNull || hi.isNull;
-                bool c1 = false, c2 = false;
-                if (!n1) c1 = (da || db) ? asDouble(x, da) >= asDouble(lo, db) : (long long) x.bits >= (long long) lo.bits;
-                if (!n2) c2 = (da || dc) ? asDouble(x, da) <= asDouble(hi, dc) : (long long) x.bits <= (long long) hi.bits;
-                if ((!n1 && !c1) || (!n2 && !c2)) r.bits = 0;
-                else if (n1 || n2) r.isNull = true;
-                else r.bits = 1;
-                break;
-            }
-            case PG_EX_AND: {
-                const Val x = get(nd.a), y = get(nd.b);
-                if ((!x.isNull && !x.bits) || (!y.isNull && !y.bits)) r.bits = 0;
-                else if (x.isNull || y.isNull) r.isNull = true;
-                else r.bits = 1;
-                break;
-            }
-            case PG_EX_OR: {
-                const Val x = get(nd.a), y = get(nd.b);
-                if ((!x.isNull && x.bits) || (!y.isNull && y.bits)) r.bits = 1;
-                else if (x.isNull || y.isNull) r.isNull = true;
-                else r.bits = 0;
-                break;
-            }
-            case PG_EX_NOT: { const Val x = get(nd.a); if (x.isNull) r.isNull = true; else r.bits = !x.bits; break; }
-            case PG_EX_IS_NULL: r.bits = get(nd.a).isNull ? 1 : 0; break;
-            case PG_EX_CAST_DOUBLE: { const Val x = get(nd.a); if (x.isNull) r.isNull = true; else r.bits = (uint64_t) __double_as_longlong(asDouble(x, P.nodes[nd.a].isDouble)); break; }
-            case PG_EX_HASH: {
-                const Val x = get(nd.a);
-                const int t = P.nodes[nd.a].type;
-                if (x.isNull) r.bits = 0;
-                else if (t == PG_TYPE_DOUBLE) r.bits = (uint64_t) hashLong(canonicalDoubleBits((int64_t) x.bits));
-                else if (t == PG_TYPE_BOOLEAN) r.bits = x.bits ? 1231 : 1237;
-                else r.bits = (uint64_t) hashLong((int64_t) x.bits);
-                break;
-            }
-            case PG_EX_COMBINE_HASH: r.bits = 31ULL * get(nd.a).bits + get(nd.b).bits; break;
-            default: break;
+            break;
         }
-        regs[k] = r.bits;
-        if (r.isNull) nullBits |= 1ULL << k;
+        case PG_EX_CONST_BIGINT: case PG_EX_CONST_BOOLEAN: case PG_EX_CONST_DOUBLE: r.bits = (uint64_t) nd.immI; break;
+        case PG_EX_CONST_NULL: r.isNull = true; break;
+        case PG_EX_ADD: case PG_EX_SUB: case PG_EX_MUL: case PG_EX_DIV: {
+            if (x.isNull || y.isNull) { r.isNull = true; break; }
+            if (nd.isDouble) {
+                const double p = asDouble(x, P.nodes[nd.a].isDouble), q = asDouble(y, P.nodes[nd.b].isDouble);
+                const double v = nd.op == PG_EX_ADD ? p + q : nd.op == PG_EX_SUB ? p - q : nd.op == PG_EX_MUL ? p * q : p / q;
+                r.bits = (uint64_t) __double_as_longlong(v);
+            }
+            else {
+                const long long p = (long long) x.bits, q = (long long) y.bits;
+                long long v = 0;
+                if (nd.op == PG_EX_ADD) { v = (long long) ((uint64_t) p + (uint64_t) q); if (((p ^ v) & (q ^ v)) < 0) atomicOr(P.error, (unsigned) FP_ERR_OVERFLOW); }
+                else if (nd.op == PG_EX_SUB) { v = (long long) ((uint64_t) p - (uint64_t) q); if (((p ^ q) & (p ^ v)) < 0) atomicOr(P.error, (unsigned) FP_ERR_OVERFLOW); }
+                else if (nd.op == PG_EX_MUL) {
+                    v = (long long) ((uint64_t) p * (uint64_t) q);
+                    if (__mul64hi(p, q) != (v >> 63)) atomicOr(P.error, (unsigned) FP_ERR_OVERFLOW);
+                }
+                else {
+                    if (q == 0) { atomicOr(P.error, (unsigned) FP_ERR_DIV_ZERO); v = 0; }
+                    else v = (p == LLONG_MIN && q == -1) ? LLONG_MIN : p / q;
+                }
+                r.bits = (uint64_t) v;
+            }
+            break;
+        }
+        case PG_EX_NEG:
+            if (x.isNull) { r.isNull = true; break; }
+            if (nd.isDouble) r.bits = x.bits ^ 0x8000000000000000ULL;
+            else { if ((long long) x.bits == LLONG_MIN) atomicOr(P.error, (unsigned) FP_ERR_OVERFLOW); r.bits = (uint64_t) (-(long long) x.bits); }
+            break;
+        case PG_EX_EQ: case PG_EX_NE: case PG_EX_LT: case PG_EX_LE: case PG_EX_GT: case PG_EX_GE: {
+            if (x.isNull || y.isNull) { r.isNull = true; break; }
+            bool res;
+            const bool da = P.nodes[nd.a].isDouble, db = P.nodes[nd.b].isDouble;
+            if (da || db) {
+                const double p = asDouble(x, da), q = asDouble(y, db);
+                res = nd.op == PG_EX_EQ ? p == q : nd.op == PG_EX_NE ? p != q : nd.op == PG_EX_LT ? p < q : nd.op == PG_EX_LE ? p <= q : nd.op == PG_EX_GT ? p > q : p >= q;
+            }
+            else {
+                const long long p = (long long) x.bits, q = (long long) y.bits;
+                res = nd.op == PG_EX_EQ ? p == q : nd.op == PG_EX_NE ? p != q : nd.op == PG_EX_LT ? p < q : nd.op == PG_EX_LE ? p <= q : nd.op == PG_EX_GT ? p > q : p >= q;
+            }
+            r.bits = res;
+            break;
+        }
+        case PG_EX_BETWEEN: {
+            const bool da = P.nodes[nd.a].isDouble, db = P.nodes[nd.b].isDouble, dc = P.nodes[nd.c].isDouble;
+            const bool n1 = x.isNull || y.isNull, n2 = x.isNull || z.isNull;
+            bool c1 = false, c2 = false;
+            if (!n1) c1 = (da || db) ? asDouble(x, da) >= asDouble(y, db) : (long long) x.bits >= (long long) y.bits;
+            if (!n2) c2 = (da || dc) ? asDouble(x, da) <= asDouble(z, dc) : (long long) x.bits <= (long long) z.bits;
+            if ((!n1 && !c1) || (!n2 && !c2)) r.bits = 0;
+            else if (n1 || n2) r.isNull = true;
+            else r.bits = 1;
+            break;
+        }
+        case PG_EX_AND:
+            if ((!x.isNull && !x.bits) || (!y.isNull && !y.bits)) r.bits = 0;
+            else if (x.isNull || y.isNull) r.isNull = true;
+            else r.bits = 1;
+            break;
+        case PG_EX_OR:
+            if ((!x.isNull && x.bits) || (!y.isNull && y.bits)) r.bits = 1;
+            else if (x.isNull || y.isNull) r.isNull = true;
+            else r.bits = 0;
+            break;
+        case PG_EX_NOT: if (x.isNull) r.isNull = true; else r.bits = !x.bits; break;
+        case PG_EX_IS_NULL: r.bits = x.isNull ? 1 : 0; break;
+        case PG_EX_CAST_DOUBLE: if (x.isNull) r.isNull = true; else r.bits = (uint64_t) __double_as_longlong(asDouble(x, P.nodes[nd.a].isDouble)); break;
+        case PG_EX_HASH: {
+            const int t = P.nodes[nd.a].type;
+            if (x.isNull) r.bits = 0;
+            else if (t == PG_TYPE_DOUBLE) r.bits = (uint64_t) hashLong(canonicalDoubleBits((int64_t) x.bits));
+            else if (t == PG_TYPE_BOOLEAN) r.bits = x.bits ? 1231 : 1237;
+            else r.bits = (uint64_t) hashLong((int64_t) x.bits);
+            break;
+        }
+        case PG_EX_COMBINE_HASH: r.bits = 31ULL * x.bits + y.bits; break;
+        default: break;
+    }
+    return r;
+}
+
+// Evaluates the nodes of `needMask` for R rows of one thread at once (one switch dispatch per node for R rows); register files
+// live in local memory (L1 resident), the program is warp-uniform.  Rows that are out of range read nothing (active[r] false).
+template <int R>
+__device__ __forceinline__ void evalRows(const FpParams& P, uint64_t needMask, const int64_t (&row)[R], const bool (&active)[R],
+                                         uint64_t (&regs)[kMaxNodes][R], uint64_t (&nullBits)[R])
+{
+#pragma unroll
+    for (int r = 0; r < R; r++) nullBits[r] = 0;
+    for (int k = 0; k < P.nNodes; k++) {
+        if (!((needMask >> k) & 1ULL)) continue;
+        const FpNode& nd = P.nodes[k];
+        const bool isInput = nd.op == PG_EX_INPUT;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            Val x{0, false}, y{0, false}, z{0, false};
+            if (!isInput) {
+                if (nd.a >= 0) x = Val{regs[nd.a][r], (bool) ((nullBits[r] >> nd.a) & 1ULL)};
+                if (nd.b >= 0) y = Val{regs[nd.b][r], (bool) ((nullBits[r] >> nd.b) & 1ULL)};
+                if (nd.c >= 0) z = Val{regs[nd.c][r], (bool) ((nullBits[r] >> nd.c) & 1ULL)};
+            }
+            Val v{0, false};
+            if (active[r]) v = evalNode(P, nd, row[r], x, y, z);
+            regs[k][r] = v.bits;
+            if (v.isNull) nullBits[r] |= 1ULL << k;
+        }
     }
 }
 
+constexpr int kFpRows = 2;   // rows per thread per dispatch
+
+// pass A: selection bitmask (one 32-bit word per 32 rows) + selected count per unit
 __global__ void __launch_bounds__(256) fpFilterKernel(const __grid_constant__ FpParams P)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warpId = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
-    uint64_t regs[kMaxNodes];
+    uint64_t regs[kMaxNodes][kFpRows];
     for (int64_t unit = warpId; unit < P.units; unit += nWarps) {
         const int64_t begin = unit * kRowsPerFpUnit, end = min(begin + (int64_t) kRowsPerFpUnit, P.n);
         uint32_t selected = 0;
-        for (int64_t base = begin; base < end; base += 32) {
-            const int64_t row = base + lane;
-            bool sel = false;
-            if (row < end) {
-                uint64_t nb;
-                evalRow(P, row, P.filterNode, regs, nb);
-                sel = !((nb >> P.filterNode) & 1ULL) && regs[P.filterNode] != 0;   // only TRUE selects
+        for (int64_t base = begin; base < end; base += 32 * kFpRows) {
+            int64_t row[kFpRows]; bool active[kFpRows]; uint64_t nb[kFpRows];
+#pragma unroll
+            for (int r = 0; r < kFpRows; r++) { row[r] = base + r * 32 + lane; active[r] = row[r] < end; }
+            evalRows<kFpRows>(P, P.needFilter, row, active, regs, nb);
+#pragma unroll
+            for (int r = 0; r < kFpRows; r++) {
+                const bool sel = active[r] && !((nb[r] >> P.filterNode) & 1ULL) && regs[P.filterNode][r] != 0;   // only TRUE selects
+                const unsigned m = __ballot_sync(0xffffffffu, sel);
+                if (lane == 0 && base + r * 32 < end) P.selection[(base + r * 32) >> 5] = m;
+                selected += __popc(m);
             }
-            selected += __popc(__ballot_sync(0xffffffffu, sel));
         }
         if (lane == 0) P.counts[unit] = selected;
     }
 }
 
+// pass B: projections of the selected rows, written at offsets[unit] + rank inside the unit
 __global__ void __launch_bounds__(256) fpProjectKernel(const __grid_constant__ FpParams P)
 {
     const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1;
     const int64_t warpId = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
-    uint64_t regs[kMaxNodes];
+    uint64_t regs[kMaxNodes][kFpRows];
     for (int64_t unit = warpId; unit < P.units; unit += nWarps) {
         const int64_t begin = unit * kRowsPerFpUnit, end = min(begin + (int64_t) kRowsPerFpUnit, P.n);
         uint32_t cursor = P.filterNode >= 0 ? P.offsets[unit] : (uint32_t) begin;
-        for (int64_t base = begin; base < end; base += 32) {
-            const int64_t row = base + lane;
-            bool sel = false;
-            uint64_t nb = 0;
-            if (row < end) {
-                evalRow(P, row, P.nNodes - 1, regs, nb);
-                sel = P.filterNode < 0 || (!((nb >> P.filterNode) & 1ULL) && regs[P.filterNode] != 0);
+        for (int64_t base = begin; base < end; base += 32 * kFpRows) {
+            int64_t row[kFpRows]; bool active[kFpRows]; uint64_t nb[kFpRows]; unsigned masks[kFpRows];
+#pragma unroll
+            for (int r = 0; r < kFpRows; r++) {
+                row[r] = base + r * 32 + lane;
+                const bool in = row[r] < end;
+                masks[r] = 0;
+                if (base + r * 32 < end) masks[r] = P.filterNode >= 0 ? P.selection[(base + r * 32) >> 5] : __ballot_sync(0xffffffffu, in);
+                active[r] = in && ((masks[r] >> lane) & 1u);     // unselected rows load nothing
             }
-            const unsigned m = __ballot_sync(0xffffffffu, sel);
-            if (sel) {
-                const uint32_t dest = cursor + __popc(m & ((1u << lane) - 1));
-                for (int j = 0; j < P.nOuts; j++) {
-                    const FpOutput& o = P.outs[j];
-                    const bool isNull = (nb >> o.node) & 1ULL;
-                    const uint64_t v = isNull ? 0 : regs[o.node];
-                    if (o.width == 8) ((uint64_t*) o.values)[dest] = v;
-                    else if (o.width == 4) ((uint32_t*) o.values)[dest] = (uint32_t) v;
-                    else ((uint8_t*) o.values)[dest] = (uint8_t) v;
-                    if (o.nulls) o.nulls[dest] = isNull ? 1 : 0;
+            evalRows<kFpRows>(P, P.needProject, row, active, regs, nb);
+#pragma unroll
+            for (int r = 0; r < kFpRows; r++) {
+                if (active[r]) {
+                    const uint32_t dest = cursor + __popc(masks[r] & lt);
+                    for (int j = 0; j < P.nOuts; j++) {
+                        const FpOutput& o = P.outs[j];
+                        const bool isNull = (nb[r] >> o.node) & 1ULL;
+                        const uint64_t v = isNull ? 0 : regs[o.node][r];
+                        if (o.width == 8) ((uint64_t*) o.values)[dest] = v;
+                        else if (o.width == 4) ((uint32_t*) o.values)[dest] = (uint32_t) v;
+                        else ((uint8_t*) o.values)[dest] = (uint8_t) v;
+                        if (o.nulls) o.nulls[dest] = isNull ? 1 : 0;
+                    }
                 }
+                cursor += __popc(masks[r]);
             }
-            cursor += __popc(m);
         }
     }
 }
+
+// ---- driver-API JIT of generated PTX (libcuda is dlopen'ed: the library still loads on a box without a driver) -----------------
+struct DriverApi {
+    CUresult (*moduleLoadDataEx)(CUmodule*, const void*, unsigned int, CUjit_option*, void**) = nullptr;
+    CUresult (*moduleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*moduleUnload)(CUmodule) = nullptr;
+    CUresult (*launchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
+    bool ok = false;
+    static DriverApi& get()
+    {
+        static DriverApi api;
+        static std::once_flag once;
+        std::call_once(once, [] {
+            void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+            if (!h) return;
+            api.moduleLoadDataEx = (decltype(api.moduleLoadDataEx)) dlsym(h, "cuModuleLoadDataEx");
+            api.moduleGetFunction = (decltype(api.moduleGetFunction)) dlsym(h, "cuModuleGetFunction");
+            api.moduleUnload = (decltype(api.moduleUnload)) dlsym(h, "cuModuleUnload");
+            api.launchKernel = (decltype(api.launchKernel)) dlsym(h, "cuLaunchKernel");
+            api.ok = api.moduleLoadDataEx && api.moduleGetFunction && api.moduleUnload && api.launchKernel;
+        });
+        return api;
+    }
+};
+
+struct JitProgram {
+    CUmodule module = nullptr;
+    CUfunction filter = nullptr, project = nullptr;
+    FpKernelSignature sig;
+    bool ok = false;
+    std::string log;
+};
 
 class FilterProjectOp : public Operator {
     std::vector<int> inputTypes, staged;
@@ -225,18 +287,21 @@ class FilterProjectOp : public Operator {
     std::vector<int> projections;
     PageStager stager;
     bool finishing = false, hasPending = false;
-    DeviceBuffer counts, offsets, scanTemp, errorWord;
+    DeviceBuffer counts, offsets, scanTemp, errorWord, selection;
+    uint64_t needFilter = 0, needProject = 0;
     std::vector<DeviceBuffer> outValues, outNulls;
     std::vector<PinnedBuffer> hostValues, hostNulls;
     std::vector<pg_block> outBlocks;
     int64_t pendingRows = 0;
     int lastIsList = 0; int64_t lastSize = 0;
+    std::map<uint64_t, JitProgram> jitCache;   // keyed by which inputs carry a null map on this page
+    int64_t jitLaunches = 0, interpreterLaunches = 0;
 
 public:
     explicit FilterProjectOp(const pg_filter_project_config* c) : Operator(c->options), stager(this)
     {
         PG_CHECK_ARG(c->n_input_channels >= 0 && c->n_input_channels <= kMaxInputs, "at most 32 input channels");
-        PG_CHECK_ARG(c->n_nodes >= 0 && c->n_nodes <= kMaxNodes, "at most 48 expression nodes");
+        PG_CHECK_ARG(c->n_nodes >= 0 && c->n_nodes <= kMaxNodes, "at most 64 expression nodes");
         PG_CHECK_ARG(c->n_projections >= 0 && c->n_projections <= kMaxProjections, "at most 32 projections");
         inputTypes.assign(c->input_types, c->input_types + c->n_input_channels);
         nodes.assign(c->nodes, c->nodes + c->n_nodes);
@@ -258,12 +323,72 @@ public:
                 if (n.op == PG_EX_CAST_BIGINT) throw Error(PG_ERR_UNSUPPORTED, "CAST to BIGINT is not on the GPU path yet");
             }
         }
-        for (DeviceBuffer* d : {&counts, &offsets, &scanTemp, &errorWord}) d->accounting = &stats.device_bytes;
+        for (DeviceBuffer* d : {&counts, &offsets, &scanTemp, &errorWord, &selection}) d->accounting = &stats.device_bytes;
+        // sub-DAGs: which nodes the filter needs, which the projections need
+        auto closure = [&](std::vector<int> roots) {
+            uint64_t mask = 0;
+            while (!roots.empty()) {
+                int k = roots.back(); roots.pop_back();
+                if (k < 0 || ((mask >> k) & 1ULL)) continue;
+                mask |= 1ULL << k;
+                if (nodes[k].op != PG_EX_INPUT) for (int o : {nodes[k].a, nodes[k].b, nodes[k].c}) roots.push_back(o);
+            }
+            return mask;
+        };
+        if (filterNode >= 0) needFilter = closure({filterNode});
+        needProject = closure(projections);
         errorWord.reserve(16);
         PG_CUDA(cudaMemsetAsync(errorWord.ptr, 0, 16, stream));
     }
 
     bool needsInput() override { return !finishing && !hasPending; }
+
+    // PTX for this program specialised on which inputs carry a null map; compiled once per variant, PG_FP_INTERPRETER=1 disables it
+    JitProgram& getJit(const std::vector<DeviceColumn>& cols)
+    {
+        uint64_t key = 0;
+        for (size_t i = 0; i < staged.size(); i++) if (cols[i].nulls) key |= 1ULL << staged[i];
+        auto it = jitCache.find(key);
+        if (it != jitCache.end()) return it->second;
+        JitProgram& jp = jitCache[key];
+        const char* off = getenv("PG_FP_INTERPRETER");
+        DriverApi& api = DriverApi::get();
+        if ((off && off[0] == '1') || !api.ok) { jp.log = "JIT disabled or libcuda not loadable"; return jp; }
+        FpProgramDesc d;
+        d.nodes = nodes; d.inputTypes = inputTypes; d.filterNode = filterNode; d.projections = projections;
+        d.inputHasNulls.assign(inputTypes.size(), false);
+        for (size_t i = 0; i < staged.size(); i++) d.inputHasNulls[staged[i]] = cols[i].nulls != nullptr;
+        const std::string ptx = generateFilterProjectPtx(d, jp.sig);
+        if (!jp.sig.ok) { jp.log = jp.sig.reason; return jp; }
+        char errLog[4096]; errLog[0] = 0;
+        CUjit_option opts[2] = {CU_JIT_ERROR_LOG_BUFFER, CU_JIT_ERROR_LOG_BUFFER_SIZE_BYTES};
+        void* vals[2] = {errLog, (void*) (uintptr_t) sizeof(errLog)};
+        CUresult r = api.moduleLoadDataEx(&jp.module, ptx.c_str(), 2, opts, vals);
+        if (r != CUDA_SUCCESS) { jp.log = std::string("cuModuleLoadDataEx failed: ") + errLog; jp.module = nullptr; return jp; }
+        bool fine = api.moduleGetFunction(&jp.project, jp.module, "fp_project") == CUDA_SUCCESS;
+        if (filterNode >= 0) fine = fine && api.moduleGetFunction(&jp.filter, jp.module, "fp_filter") == CUDA_SUCCESS;
+        jp.ok = fine;
+        if (!fine) jp.log = "generated module lacks an entry point";
+        return jp;
+    }
+
+    void launchJit(CUfunction f, int grid, std::vector<uint64_t>& values)
+    {
+        std::vector<void*> args(values.size());
+        for (size_t i = 0; i < values.size(); i++) args[i] = &values[i];
+        CUresult r = DriverApi::get().launchKernel(f, (unsigned) grid, 1, 1, 256, 1, 1, 0, (CUstream) stream, args.data(), nullptr);
+        if (r != CUDA_SUCCESS) throw Error(PG_ERR_CUDA, "cuLaunchKernel of a generated filter/project kernel failed (" + std::to_string((int) r) + ")");
+        stats.kernel_launches++;
+        jitLaunches++;
+    }
+    void inputArgs(const JitProgram& jp, const FpParams& P, std::vector<uint64_t>& v) const
+    {
+        v.push_back((uint64_t) P.n); v.push_back((uint64_t) P.units);
+        for (int ch : jp.sig.usedInputs) {
+            v.push_back((uint64_t) (uintptr_t) P.inputs[ch].values);
+            if (P.inputs[ch].nulls) v.push_back((uint64_t) (uintptr_t) P.inputs[ch].nulls);
+        }
+    }
 
     void addInput(const pg_page* page) override
     {
@@ -275,6 +400,7 @@ public:
         PG_CHECK_ARG(n < (int64_t(1) << 31), "page exceeds 2^31 positions");
         std::vector<DeviceColumn> cols;
         int slot = stager.stage(page, staged, cols);
+        JitProgram& jit = getJit(cols);
         FpParams P{};
         P.nNodes = (int) nodes.size();
         for (size_t i = 0; i < nodes.size(); i++) {
@@ -297,13 +423,21 @@ public:
             }
         }
         P.filterNode = filterNode; P.n = n; P.units = divUp(n, kRowsPerFpUnit); P.error = errorWord.as<unsigned int>();
+        P.needFilter = needFilter; P.needProject = needProject;
+        if (filterNode >= 0) { selection.reserve((size_t) divUp(n, 32) * 4 + 16); P.selection = selection.as<uint32_t>(); }
         const int grid = (int) std::min<int64_t>(divUp(P.units, 8), (int64_t) numSMs * 8);
         int64_t total = n;
         if (filterNode >= 0) {
             counts.reserve((size_t) (P.units + 1) * 4); offsets.reserve((size_t) (P.units + 1) * 4);
             PG_CUDA(cudaMemsetAsync(counts.as<uint32_t>() + P.units, 0, 4, stream));
             P.counts = counts.as<uint32_t>();
-            PG_LAUNCH(this, fpFilterKernel, grid, 256, 0, P);
+            if (jit.ok) {
+                std::vector<uint64_t> v;
+                inputArgs(jit, P, v);
+                v.push_back((uint64_t) (uintptr_t) P.selection); v.push_back((uint64_t) (uintptr_t) P.counts); v.push_back((uint64_t) (uintptr_t) P.error);
+                launchJit(jit.filter, grid, v);
+            }
+            else { PG_LAUNCH(this, fpFilterKernel, grid, 256, 0, P); interpreterLaunches++; }
             size_t tb = 0;
             cub::DeviceScan::ExclusiveSum(nullptr, tb, counts.as<uint32_t>(), offsets.as<uint32_t>(), (int) (P.units + 1), stream);
             scanTemp.reserve(tb);
@@ -329,9 +463,16 @@ public:
             o.node = projections[j]; o.width = typeWidth(nodes[o.node].type);
             outValues[j].reserve((size_t) total * o.width);
             o.values = outValues[j].ptr; o.nulls = nullptr;
-            if (nullable[o.node]) { outNulls[j].reserve(total); o.nulls = outNulls[j].as<uint8_t>(); }
+            if (jit.ok ? (bool) jit.sig.projectionNullable[j] : (bool) nullable[o.node]) { outNulls[j].reserve(total); o.nulls = outNulls[j].as<uint8_t>(); }
         }
-        if (nOut) PG_LAUNCH(this, fpProjectKernel, grid, 256, 0, P);
+        if (nOut && jit.ok) {
+            std::vector<uint64_t> v;
+            inputArgs(jit, P, v);
+            for (size_t j = 0; j < nOut; j++) { v.push_back((uint64_t) (uintptr_t) P.outs[j].values); if (jit.sig.projectionNullable[j]) v.push_back((uint64_t) (uintptr_t) P.outs[j].nulls); }
+            v.push_back((uint64_t) (uintptr_t) P.selection); v.push_back((uint64_t) (uintptr_t) P.offsets); v.push_back((uint64_t) (uintptr_t) P.error);
+            launchJit(jit.project, grid, v);
+        }
+        else if (nOut) { PG_LAUNCH(this, fpProjectKernel, grid, 256, 0, P); interpreterLaunches++; }
         stager.markCompute(slot);
         const bool toHost = options.output_memory == PG_MEM_HOST;
         if (toHost && hostValues.size() < nOut) { hostValues.resize(nOut); hostNulls.resize(nOut); }
@@ -365,6 +506,13 @@ public:
         if (e & FP_ERR_OVERFLOW) throw Error(PG_ERR_NUMERIC_OVERFLOW, "bigint arithmetic overflow");
         if (e & FP_ERR_DIV_ZERO) throw Error(PG_ERR_INVALID_ARGUMENT, "Division by zero");
     }
+
+    ~FilterProjectOp() override
+    {
+        for (auto& kv : jitCache) if (kv.second.module) { cudaStreamSynchronize(stream); DriverApi::get().moduleUnload(kv.second.module); }
+    }
+    // 1 = the last page ran through generated PTX, 0 = through the interpreter kernels
+    int usedJit() const { return jitLaunches > 0 && interpreterLaunches == 0 ? 1 : 0; }
 
     bool getOutput(pg_page* out) override
     {

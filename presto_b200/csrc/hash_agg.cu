@@ -456,18 +456,26 @@ template <int NV, bool CNT> struct FastGeom {
 };
 
 // Rows that are not tier 0: the CTA's shared table (direct shared atomics) or the HBM table.  Kept out of line so the hot loop stays small.
-template <int NV, bool CNT>
-__device__ __noinline__ void fastSlowRow(const FastLaunch<NV, CNT>& P, const SharedTable<1>& st, int sslot, uint64_t key, uint64_t h,
-                                         const uint64_t (&vals)[NV], uint32_t rowIdx)
+__device__ __forceinline__ void sharedAddF64(uint64_t* addr, uint64_t bits)
 {
-    constexpr int NC = FastGeom<NV, CNT>::NC;
-    if (sslot >= 0) {
-#pragma unroll
-        for (int c = 0; c < NV; c++) atomicAdd((double*) &st.acc[c * st.S2 + sslot], __longlong_as_double((long long) vals[c]));
-        if (CNT) atomicAdd((unsigned long long*) &st.acc[NV * st.S2 + sslot], 1ULL);
-        if (rowIdx < *(volatile uint32_t*) &st.first[sslot]) atomicMin(&st.first[sslot], rowIdx);
-        return;
-    }
+    const unsigned a = (unsigned) __cvta_generic_to_shared(addr);
+    asm volatile("red.shared.add.f64 [%0], %1;" :: "r"(a), "d"(__longlong_as_double((long long) bits)) : "memory");
+}
+__device__ __forceinline__ void sharedAddU64(uint64_t* addr, uint64_t v)
+{
+    const unsigned a = (unsigned) __cvta_generic_to_shared(addr);
+    asm volatile("red.shared.add.u64 [%0], %1;" :: "r"(a), "l"(v) : "memory");
+}
+__device__ __forceinline__ void sharedMinU32(uint32_t* addr, uint32_t v)
+{
+    const unsigned a = (unsigned) __cvta_generic_to_shared(addr);
+    asm volatile("red.shared.min.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
+}
+
+// Rows that miss the CTA's shared table: the HBM table (tier 2).  Kept out of line so the hot loop stays small.
+template <int NV, bool CNT>
+__device__ __noinline__ void fastGlobalRow(const FastLaunch<NV, CNT>& P, uint64_t key, uint64_t h, const uint64_t (&vals)[NV], uint32_t rowIdx)
+{
     const GroupTable& T = P.t;
     uint64_t kw[1] = {key};
     int gslot = key == kEmptyKey ? (int) T.cap + 1 : tableFind<1>(T, kw, h, true, false);
@@ -482,7 +490,6 @@ __device__ __noinline__ void fastSlowRow(const FastLaunch<NV, CNT>& P, const Sha
 #pragma unroll
     for (int c = 0; c < NV; c++) atomicAdd((double*) &acc[P.phys[c]], __longlong_as_double((long long) vals[c]));
     if (CNT) atomicAdd((unsigned long long*) &acc[P.phys[NV]], 1ULL);
-    (void) NC;
 }
 
 template <int NV, bool CNT>
@@ -560,7 +567,14 @@ __global__ void __launch_bounds__(kAggThreads, 2) hashAggFastKernel(const __grid
             if (CNT) mine[NV * kAggThreads] += 1;
             if (!((seen0 >> id) & 1u)) { seen0 |= 1u << id; atomicMin(&st.first[sslot], rowIdx); }
         }
-        else fastSlowRow<NV, CNT>(P, st, sslot, key, h, vals, rowIdx);
+        else if (sslot >= 0) {
+            // tier 1: the CTA's shared table, shared-space reductions (no return value needed)
+#pragma unroll
+            for (int c = 0; c < NV; c++) sharedAddF64(&st.acc[c * st.S2 + sslot], vals[c]);
+            if (CNT) sharedAddU64(&st.acc[NV * st.S2 + sslot], 1);
+            if (rowIdx < *(volatile uint32_t*) &st.first[sslot]) sharedMinU32(&st.first[sslot], rowIdx);
+        }
+        else fastGlobalRow<NV, CNT>(P, key, h, vals, rowIdx);
     };
     auto consumeTile = [&](int64_t tile, const ulonglong2& k, const ulonglong2 (&v)[NV]) {
         const int64_t row0 = tile * TILE + 2 * tid;

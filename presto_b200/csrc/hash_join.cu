@@ -157,12 +157,13 @@ __global__ void joinEmitKernel(const __grid_constant__ EmitJoinParams P)
 }
 
 // ---- dense unique integer keys: bitmap + rank index ------------------------------------------------------------------------
-// When the build keys are unique and span a range of at most kDenseRangeFactor x n (TPC-H order keys: 150 M keys over 600 M), the
+// When the build keys are unique and span a range of at most kDenseRangeFactor x n (TPC-H order keys: 150 M keys over 600 M; Q3's
+// filtered orders: ~15 M keys over the same 600 M), the
 // LookupSource is a succinct index instead of a hash table: one bit per value of the key range (L2 resident: 75 MB at SF100) and a
 // rank directory (exclusive popcount per 256-bit block), with the build OUTPUT columns re-laid in key order.  A probe is one 32-byte
 // bitmap sector (L2) + 4 B of directory → rank → payload[rank]; sorted probe keys (lineitem is clustered by orderkey) make every
 // access sequential.  Results are identical to the hash path (unique keys: at most one match, no chains).
-constexpr int kDenseRangeFactor = 16;
+constexpr int kDenseRangeFactor = 64;                // keys may cover as little as 1/64 of their range (bitmap: range / 8 bytes)
 constexpr int kDenseBlockWords = 4;                  // 4 x 64 bit = one 32-byte sector per block
 
 struct DenseIndex {
@@ -290,19 +291,27 @@ __global__ void denseGatherKernel(const __grid_constant__ DenseGatherParams P)
 
 constexpr int kUnitRounds = 4;
 constexpr int kUnitRows = 32 * kUnitRounds;     // rows owned by one warp per step
-constexpr int kPreloadCols = 4;                 // probe output columns whose loads are issued before the index lookups
+constexpr int kPreload8 = 4;                    // 8-byte probe output columns whose loads are issued before the index lookups
+
+// Output columns grouped by width so the per-row code has no width switches.
+struct CopyColumn { const void* src; void* dst; };
+struct BuildField { void* dst; uint8_t* dstNulls; int32_t word, shift, nullWord, nullShift; };   // nullWord < 0: never NULL in the build
+struct NullCopy { const uint8_t* src; uint8_t* dst; };
 
 struct DenseProbeParams {
     KeyColumn key; DenseIndex D; int64_t n; int64_t units;
     int32_t outer;
-    uint32_t* unitCounts;          // pass A out [units + 1]
-    const uint32_t* unitOffsets;   // pass B in
-    int32_t nProbe, nBuild;
-    JoinColumn probe[kMaxJoinColumns];   // src = probe column, dst = output column
-    PayloadLayout L; const uint64_t* rows;
-    void* buildDst[kMaxJoinColumns]; uint8_t* buildDstNulls[kMaxJoinColumns];
+    uint32_t* unitCounts;          // pass A out [units + 1]: matches per unit
+    const uint32_t* unitOffsets;   // pass B in: exclusive scan of the counts
+    int32_t nProbe8, nProbe4, nProbe1, nProbeNulls;
+    CopyColumn probe8[kMaxJoinColumns], probe4[kMaxJoinColumns], probe1[kMaxJoinColumns];
+    NullCopy probeNulls[kMaxJoinColumns];
+    int32_t nBuild8, nBuild4, nBuild1;
+    BuildField build8[kMaxJoinColumns], build4[kMaxJoinColumns], build1[kMaxJoinColumns];
+    const uint64_t* rows;          // payload rows in key order
 };
 
+// pass A of the probe: matches per unit (keys + index only; ~9 B of HBM traffic per probe row)
 __global__ void __launch_bounds__(256) denseCountKernel(const __grid_constant__ DenseProbeParams P)
 {
     const int lane = threadIdx.x & 31;
@@ -321,8 +330,18 @@ __global__ void __launch_bounds__(256) denseCountKernel(const __grid_constant__ 
     }
 }
 
-// One warp per unit of 128 probe rows, no block-level synchronisation: all independent loads of the unit (keys, probe output
+template <int SW> __device__ __forceinline__ uint64_t payloadWord(const uint64_t (&w)[SW], int k)
+{
+    if (SW == 1) return w[0];
+    uint64_t r = w[0];
+#pragma unroll
+    for (int i = 1; i < SW; i++) if (k == i) r = w[i];
+    return r;
+}
+
+// One warp per unit of 128 probe rows, no block-level synchronisation: all independent loads of the unit (keys, 8-byte probe output
 // columns) are in flight before the dependent index lookups, payload reads follow the ranks, output positions come from ballots.
+template <int SW>
 __global__ void __launch_bounds__(256) denseEmitKernel(const __grid_constant__ DenseProbeParams P)
 {
     const int lane = threadIdx.x & 31;
@@ -330,23 +349,23 @@ __global__ void __launch_bounds__(256) denseEmitKernel(const __grid_constant__ D
     const int64_t warpId = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
     for (int64_t unit = warpId; unit < P.units; unit += nWarps) {
         int64_t key[kUnitRounds]; bool valid[kUnitRounds]; bool inRange[kUnitRounds];
-        uint64_t pv[kUnitRounds][kPreloadCols];
+        uint64_t pv[kUnitRounds][kPreload8];
 #pragma unroll
         for (int j = 0; j < kUnitRounds; j++) {
             const int64_t row = unit * kUnitRows + j * 32 + lane;
             inRange[j] = row < P.n;
             valid[j] = inRange[j] && loadKey(P.key, row, key[j]);
 #pragma unroll
-            for (int c = 0; c < kPreloadCols; c++) { pv[j][c] = 0; if (c < P.nProbe && inRange[j]) pv[j][c] = loadWidth(P.probe[c].src, row, P.probe[c].width); }
+            for (int c = 0; c < kPreload8; c++) { pv[j][c] = 0; if (c < P.nProbe8 && inRange[j]) pv[j][c] = ldStream64((const uint64_t*) P.probe8[c].src + row); }
         }
         int64_t rank[kUnitRounds];
 #pragma unroll
         for (int j = 0; j < kUnitRounds; j++) rank[j] = valid[j] ? denseRank(P.D, key[j]) : -1;
-        uint64_t pw[kUnitRounds][kMaxPayloadWords];
+        uint64_t pw[kUnitRounds][SW];
 #pragma unroll
         for (int j = 0; j < kUnitRounds; j++)
 #pragma unroll
-            for (int k = 0; k < kMaxPayloadWords; k++) { pw[j][k] = 0; if (rank[j] >= 0 && k < P.L.strideWords) pw[j][k] = P.rows[rank[j] * P.L.strideWords + k]; }
+            for (int k = 0; k < SW; k++) pw[j][k] = rank[j] >= 0 ? P.rows[rank[j] * SW + k] : 0;
         uint32_t cursor = P.outer ? (uint32_t) (unit * kUnitRows) : P.unitOffsets[unit];
 #pragma unroll
         for (int j = 0; j < kUnitRounds; j++) {
@@ -355,18 +374,30 @@ __global__ void __launch_bounds__(256) denseEmitKernel(const __grid_constant__ D
             if (emit) {
                 const int64_t row = unit * kUnitRows + j * 32 + lane;
                 const uint32_t o = cursor + __popc(m & lt);
+                const bool unmatched = rank[j] < 0;
 #pragma unroll
-                for (int c = 0; c < kPreloadCols; c++) if (c < P.nProbe) storeWidth(P.probe[c].dst, o, P.probe[c].width, pv[j][c]);
-                for (int c = kPreloadCols; c < P.nProbe; c++) storeWidth(P.probe[c].dst, o, P.probe[c].width, loadWidth(P.probe[c].src, row, P.probe[c].width));
-                for (int c = 0; c < P.nProbe; c++) if (P.probe[c].dstNulls) P.probe[c].dstNulls[o] = P.probe[c].srcNulls ? P.probe[c].srcNulls[row] : 0;
-                for (int c = 0; c < P.nBuild; c++) {
-                    const PayloadColumn& pc = P.L.cols[c];
-                    uint64_t word = 0, nullWord = 0;
-#pragma unroll
-                    for (int k = 0; k < kMaxPayloadWords; k++) { if (k == pc.offset >> 3) word = pw[j][k]; if (pc.nullOffset >= 0 && k == pc.nullOffset >> 3) nullWord = pw[j][k]; }
-                    const bool isNull = rank[j] < 0 || (pc.nullOffset >= 0 && ((nullWord >> (8 * (pc.nullOffset & 7))) & 0xff));
-                    storeWidth(P.buildDst[c], o, pc.width, isNull ? 0 : (word >> (8 * (pc.offset & 7))) & widthMask(pc.width));
-                    if (P.buildDstNulls[c]) P.buildDstNulls[c][o] = isNull ? 1 : 0;
+                for (int c = 0; c < kPreload8; c++) if (c < P.nProbe8) ((uint64_t*) P.probe8[c].dst)[o] = pv[j][c];
+                for (int c = kPreload8; c < P.nProbe8; c++) ((uint64_t*) P.probe8[c].dst)[o] = ldStream64((const uint64_t*) P.probe8[c].src + row);
+                for (int c = 0; c < P.nProbe4; c++) ((uint32_t*) P.probe4[c].dst)[o] = ldStream32((const uint32_t*) P.probe4[c].src + row);
+                for (int c = 0; c < P.nProbe1; c++) ((uint8_t*) P.probe1[c].dst)[o] = ((const uint8_t*) P.probe1[c].src)[row];
+                for (int c = 0; c < P.nProbeNulls; c++) P.probeNulls[c].dst[o] = P.probeNulls[c].src ? P.probeNulls[c].src[row] : 0;
+                for (int c = 0; c < P.nBuild8; c++) {
+                    const BuildField& f = P.build8[c];
+                    const bool isNull = unmatched || (f.nullWord >= 0 && ((payloadWord<SW>(pw[j], f.nullWord) >> f.nullShift) & 0xff));
+                    ((uint64_t*) f.dst)[o] = isNull ? 0 : payloadWord<SW>(pw[j], f.word);
+                    if (f.dstNulls) f.dstNulls[o] = isNull;
+                }
+                for (int c = 0; c < P.nBuild4; c++) {
+                    const BuildField& f = P.build4[c];
+                    const bool isNull = unmatched || (f.nullWord >= 0 && ((payloadWord<SW>(pw[j], f.nullWord) >> f.nullShift) & 0xff));
+                    ((uint32_t*) f.dst)[o] = isNull ? 0 : (uint32_t) (payloadWord<SW>(pw[j], f.word) >> f.shift);
+                    if (f.dstNulls) f.dstNulls[o] = isNull;
+                }
+                for (int c = 0; c < P.nBuild1; c++) {
+                    const BuildField& f = P.build1[c];
+                    const bool isNull = unmatched || (f.nullWord >= 0 && ((payloadWord<SW>(pw[j], f.nullWord) >> f.nullShift) & 0xff));
+                    ((uint8_t*) f.dst)[o] = isNull ? 0 : (uint8_t) (payloadWord<SW>(pw[j], f.word) >> f.shift);
+                    if (f.dstNulls) f.dstNulls[o] = isNull;
                 }
             }
             cursor += __popc(m);
@@ -600,6 +631,7 @@ public:
             for (size_t i = 0; i < ls->outputChannels.size(); i++)
                 if (ls->hasNulls[ls->outputChannels[i]]) payloadLayout.cols[i].nullOffset = off++;
             payloadLayout.strideWords = std::max(1, (off + 7) / 8);
+            if (payloadLayout.strideWords == 3) payloadLayout.strideWords = 4;
             if (payloadLayout.strideWords > kMaxPayloadWords) return false;   // wide payloads keep the hash-table path
         }
         const int kch = ls->layout.channels[0];
@@ -809,7 +841,7 @@ public:
         DenseProbeParams P{};
         P.key = KeyColumn{kcol.values, kcol.nulls, kcol.type};
         P.D = ls.denseView(); P.n = n; P.units = divUp(n, kUnitRows); P.outer = joinType == PG_JOIN_PROBE_OUTER;
-        P.L = ls.payload; P.rows = ls.payloadRows.as<uint64_t>();
+        P.rows = ls.payloadRows.as<uint64_t>();
         const int grid = (int) std::min<int64_t>(divUp(P.units, 8), (int64_t) numSMs * 8);
         int64_t total = n;
         if (!P.outer) {
@@ -834,26 +866,34 @@ public:
         const size_t nOut = outputChannels.size() + ls.outputChannels.size();
         if (outValues.size() < nOut) { outValues.resize(nOut); outNulls.resize(nOut); for (auto& d : outValues) d.accounting = &stats.device_bytes; for (auto& d : outNulls) d.accounting = &stats.device_bytes; }
         outBlocks.assign(nOut, pg_block{});
-        P.nProbe = (int) outputChannels.size(); P.nBuild = (int) ls.outputChannels.size();
         std::vector<bool> hasNulls(nOut, false);
         for (size_t i = 0; i < outputChannels.size(); i++) {
             const DeviceColumn& c = colOf(outputChannels[i]);
-            JoinColumn& jc = P.probe[i];
-            jc.width = typeWidth(c.type); jc.src = c.values; jc.srcNulls = c.nulls;
-            outValues[i].reserve((size_t) total * jc.width);
-            jc.dst = outValues[i].ptr; jc.dstNulls = nullptr;
-            if (c.nulls) { outNulls[i].reserve(total); jc.dstNulls = outNulls[i].as<uint8_t>(); hasNulls[i] = true; }
+            const int w = typeWidth(c.type);
+            outValues[i].reserve((size_t) total * w);
+            CopyColumn cc{c.values, outValues[i].ptr};
+            if (w == 8) P.probe8[P.nProbe8++] = cc; else if (w == 4) P.probe4[P.nProbe4++] = cc; else P.probe1[P.nProbe1++] = cc;
+            if (c.nulls) { outNulls[i].reserve(total); P.probeNulls[P.nProbeNulls++] = NullCopy{c.nulls, outNulls[i].as<uint8_t>()}; hasNulls[i] = true; }
             outBlocks[i].type = c.type;
         }
         for (size_t i = 0; i < ls.outputChannels.size(); i++) {
             const int ch = ls.outputChannels[i];
             const size_t o = outputChannels.size() + i;
-            outValues[o].reserve((size_t) total * typeWidth(ls.types[ch]));
-            P.buildDst[i] = outValues[o].ptr; P.buildDstNulls[i] = nullptr;
-            if (ls.payload.cols[i].nullOffset >= 0 || P.outer) { outNulls[o].reserve(total); P.buildDstNulls[i] = outNulls[o].as<uint8_t>(); hasNulls[o] = true; }
+            const PayloadColumn& pc = ls.payload.cols[i];
+            outValues[o].reserve((size_t) total * pc.width);
+            BuildField f{};
+            f.dst = outValues[o].ptr; f.dstNulls = nullptr;
+            f.word = pc.offset >> 3; f.shift = 8 * (pc.offset & 7);
+            f.nullWord = pc.nullOffset >= 0 ? pc.nullOffset >> 3 : -1; f.nullShift = pc.nullOffset >= 0 ? 8 * (pc.nullOffset & 7) : 0;
+            if (pc.nullOffset >= 0 || P.outer) { outNulls[o].reserve(total); f.dstNulls = outNulls[o].as<uint8_t>(); hasNulls[o] = true; }
+            if (pc.width == 8) P.build8[P.nBuild8++] = f; else if (pc.width == 4) P.build4[P.nBuild4++] = f; else P.build1[P.nBuild1++] = f;
             outBlocks[o].type = ls.types[ch];
         }
-        PG_LAUNCH(this, denseEmitKernel, grid, 256, 0, P);
+        switch (ls.payload.strideWords) {
+            case 1: PG_LAUNCH(this, denseEmitKernel<1>, grid, 256, 0, P); break;
+            case 2: PG_LAUNCH(this, denseEmitKernel<2>, grid, 256, 0, P); break;
+            default: PG_LAUNCH(this, denseEmitKernel<4>, grid, 256, 0, P); break;
+        }
         stager.markCompute(slot);
         publish(total, hasNulls);
     }

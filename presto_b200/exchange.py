@@ -76,41 +76,86 @@ def all_to_all_pages(page: Page, offsets: Sequence[int], types: Sequence[int], g
     dist.all_to_all_single(rc, sc, group=group)
     recv_counts = [int(x) for x in rc.tolist()]
     total = sum(recv_counts)
+    # null maps travel only for columns where SOME rank has one: one small all_reduce decides for all columns at once
+    srcs = [block_to_tensor(b, dev) for b in page.blocks]
+    src_nulls = [nulls_to_tensor(b, dev) for b in page.blocks]
+    has = torch.tensor([1 if x is not None else 0 for x in src_nulls], dtype=torch.int64, device=dev)
+    dist.all_reduce(has, op=dist.ReduceOp.MAX, group=group)
+    has = [bool(x) for x in has.tolist()]
     blocks: List[Block] = []
-    for t, b in zip(types, page.blocks):
-        src = block_to_tensor(b, dev)
+    for t, src, nulls, with_nulls in zip(types, srcs, src_nulls, has):
         dst = torch.empty(total, dtype=src.dtype, device=dev)
         dist.all_to_all_single(dst, src, output_split_sizes=recv_counts, input_split_sizes=send_counts, group=group)
-        src_nulls = nulls_to_tensor(b, dev)
-        # null maps travel only when some rank has one for this column
-        has = torch.tensor([1 if src_nulls is not None else 0], dtype=torch.int64, device=dev)
-        dist.all_reduce(has, op=dist.ReduceOp.MAX, group=group)
         dst_nulls = None
-        if int(has.item()):
-            if src_nulls is None:
-                src_nulls = torch.zeros(src.numel(), dtype=torch.uint8, device=dev)
+        if with_nulls:
+            if nulls is None:
+                nulls = torch.zeros(src.numel(), dtype=torch.uint8, device=dev)
             dst_nulls = torch.empty(total, dtype=torch.uint8, device=dev)
-            dist.all_to_all_single(dst_nulls, src_nulls, output_split_sizes=recv_counts, input_split_sizes=send_counts, group=group)
+            dist.all_to_all_single(dst_nulls, nulls, output_split_sizes=recv_counts, input_split_sizes=send_counts, group=group)
         blocks.append(tensor_to_block(t, dst, dst_nulls))
     return Page(blocks, total)
 
 
+def _pack_page(page: Optional[Page]) -> np.ndarray:
+    """A small host page of fixed-width columns → one uint8 buffer: [n_cols, n_rows, (type, has_nulls) per column, column data...]."""
+    if page is None or page.position_count == 0:
+        return np.zeros(0, dtype=np.uint8)
+    n = page.position_count
+    head = [len(page.blocks), n]
+    parts = []
+    for b in page.blocks:
+        assert b.type != abi.VARCHAR and b.encoding == abi.ENC_FLAT and not b.on_device, "partial aggregation states are flat fixed-width host columns"
+        head += [b.type, 1 if b.is_null is not None else 0]
+        parts.append(np.ascontiguousarray(b.values).view(np.uint8)[: n * TYPE_WIDTH[b.type]])
+        if b.is_null is not None:
+            parts.append(np.ascontiguousarray(b.is_null, dtype=np.uint8)[:n])
+    return np.concatenate([np.asarray(head, dtype=np.int64).view(np.uint8)] + parts)
+
+
+def _unpack_page(buf: np.ndarray) -> Optional[Page]:
+    if buf.size == 0:
+        return None
+    n_cols, n = [int(x) for x in buf[:16].view(np.int64)]
+    meta = buf[16:16 + 16 * n_cols].view(np.int64)
+    off = 16 + 16 * n_cols
+    blocks = []
+    from .page import _NP_DTYPE
+    for c in range(n_cols):
+        t, has_nulls = int(meta[2 * c]), int(meta[2 * c + 1])
+        nbytes = n * TYPE_WIDTH[t]
+        vals = buf[off:off + nbytes].copy().view(_NP_DTYPE[t]); off += nbytes
+        nulls = None
+        if has_nulls:
+            nulls = buf[off:off + n].copy(); off += n
+        blocks.append(Block(t, n, vals, nulls))
+    return Page(blocks, n)
+
+
 def gather_pages_to_root(page: Optional[Page], group=None, root: int = 0) -> List[Page]:
     """Small host pages (partial aggregation states) from every rank to `root` — the PARTIAL → FINAL hand-off of
-    HashAggregationOperator across GPUs (Q1: a few hundred bytes per rank)."""
+    HashAggregationOperator across GPUs (Q1: a few hundred bytes per rank).  Two fixed-shape collectives (sizes, padded bytes)
+    instead of a pickled object gather."""
+    import torch
     import torch.distributed as dist
-    payload = None
-    if page is not None and page.position_count > 0:
-        payload = [(b.type, b.values, b.is_null, b.offsets) for b in page.blocks]
     world = dist.get_world_size(group)
-    gathered = [None] * world
-    dist.all_gather_object(gathered, payload, group=group)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    buf = _pack_page(page)
+    size = torch.tensor([buf.size], dtype=torch.int64, device=dev)
+    sizes = [torch.empty(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, size, group=group)
+    sizes = [int(x.item()) for x in sizes]
+    cap = max(max(sizes), 1)
+    send = torch.zeros(cap, dtype=torch.uint8, device=dev)
+    if buf.size:
+        send[:buf.size] = torch.from_numpy(buf).to(dev)
+    recv = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(recv, send, group=group)
     if dist.get_rank(group) != root:
         return []
     pages = []
-    for item in gathered:
-        if item is None:
-            continue
-        blocks = [Block(t, len(v) if off is None else len(off) - 1, v, nu, off) for (t, v, nu, off) in item]
-        pages.append(Page(blocks))
+    for r in range(world):
+        p = _unpack_page(recv[r][:sizes[r]].cpu().numpy())
+        if p is not None:
+            pages.append(p)
     return pages

@@ -69,3 +69,50 @@ def sparse_order_key_np(i: np.ndarray) -> np.ndarray:
     """dbgen mk_sparse: 8 of every 32 integers are order keys (velox/tpch/gen/dbgen/build.cpp:144-156)."""
     i = i.astype(np.int64)
     return ((i >> 3) << 5) + (i & 7)
+
+
+# ---- Q3 (config 4): customer / orders / lineitem -----------------------------------------------------------------------------
+def q3_tables_np(n_orders: int, seed: int = 7):
+    """TPC-H-shaped Q3 inputs (numpy, for the parity tests): customer(c_custkey, c_mktsegment code 0..4), orders(o_orderkey sparse,
+    o_custkey, o_orderdate U[8035, 10440], o_shippriority 0) in shuffled order, lineitem clustered by orderkey with 1..7 rows per
+    order (l_orderkey, l_extendedprice, l_discount, l_shipdate = o_orderdate + U[1, 121])."""
+    rng = np.random.default_rng(seed)
+    n_cust = max(n_orders // 10, 10)
+    c_custkey = np.arange(1, n_cust + 1, dtype=np.int64)
+    c_seg = rng.integers(0, 5, n_cust).astype(np.int32)
+    i = np.arange(1, n_orders + 1, dtype=np.int64)
+    okey = sparse_order_key_np(i)
+    odate = rng.integers(8035, 10441, n_orders).astype(np.int32)
+    ocust = rng.integers(1, n_cust + 1, n_orders).astype(np.int64)
+    lines = rng.integers(1, 8, n_orders)
+    idx = np.repeat(np.arange(n_orders), lines)
+    n_li = len(idx)
+    lineitem = (okey[idx], np.round(rng.random(n_li) * 1e5, 2), rng.integers(0, 11, n_li) / 100.0,
+                (odate[idx] + rng.integers(1, 122, n_li)).astype(np.int32))
+    perm = rng.permutation(n_orders)
+    orders = (okey[perm], ocust[perm], odate[perm], np.zeros(n_orders, dtype=np.int32))
+    return (c_custkey, c_seg), orders, lineitem
+
+
+def q3_tables_torch(n_orders: int, device, seed: int = 7):
+    """The same shape generated in HBM with torch (benchmark input only)."""
+    import torch
+    g = torch.Generator(device=device); g.manual_seed(seed)
+    n_cust = max(n_orders // 10, 10)
+    c_custkey = torch.arange(1, n_cust + 1, dtype=torch.int64, device=device)
+    c_seg = torch.randint(0, 5, (n_cust,), dtype=torch.int32, device=device, generator=g)
+    i = torch.arange(1, n_orders + 1, dtype=torch.int64, device=device)
+    okey = ((i >> 3) << 5) + (i & 7)
+    odate = torch.randint(8035, 10441, (n_orders,), dtype=torch.int32, device=device, generator=g)
+    ocust = torch.randint(1, n_cust + 1, (n_orders,), dtype=torch.int64, device=device, generator=g)
+    lines = torch.randint(1, 8, (n_orders,), dtype=torch.int64, device=device, generator=g)
+    idx = torch.repeat_interleave(torch.arange(n_orders, device=device), lines)
+    n_li = idx.numel()
+    l_orderkey = okey[idx]
+    l_ship = (odate[idx] + torch.randint(1, 122, (n_li,), dtype=torch.int32, device=device, generator=g)).to(torch.int32)
+    del idx, lines
+    l_ep = torch.rand(n_li, dtype=torch.float64, device=device, generator=g) * 1e5
+    l_disc = torch.randint(0, 11, (n_li,), device=device, generator=g).to(torch.float64) / 100
+    perm = torch.randperm(n_orders, device=device, generator=g)
+    orders = (okey[perm].contiguous(), ocust[perm].contiguous(), odate[perm].contiguous(), torch.zeros(n_orders, dtype=torch.int32, device=device))
+    return (c_custkey, c_seg), orders, (l_orderkey, l_ep, l_disc, l_ship)
