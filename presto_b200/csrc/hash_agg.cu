@@ -53,6 +53,7 @@ struct AggLaunch {
 constexpr int kAggThreads = 256;
 constexpr int kSharedProbes = 8;
 constexpr int kWarpAggMaxGroups = 8;
+constexpr int kMaxSubsetPasses = 6;      // mid mode gives up (HBM-table atomics) beyond this many hash-subset passes
 
 template <int MAXV> struct RowsPerThread { static constexpr int value = MAXV <= 4 ? 4 : 2; };   // always even: rows are loaded in pairs
 // Tier 0: the first kTier0Groups groups a CTA claims get per-thread private accumulators in shared memory.
@@ -448,6 +449,7 @@ struct FastLaunch {
     uint32_t* bitmapOut;
     uint32_t S, sLimit;
     int32_t nAccAlloc;
+    uint32_t subsetCount, subsetIndex;   // mid mode: this launch aggregates only keys with hashSubset(key) == subsetIndex
 };
 
 template <int NV, bool CNT> struct FastGeom {
@@ -492,19 +494,24 @@ __device__ __noinline__ void fastGlobalRow(const FastLaunch<NV, CNT>& P, uint64_
     if (CNT) atomicAdd((unsigned long long*) &acc[P.phys[NV]], 1ULL);
 }
 
-template <int NV, bool CNT>
-__global__ void __launch_bounds__(kAggThreads, 2) hashAggFastKernel(const __grid_constant__ FastLaunch<NV, CNT> P)
+// MID = false: tiers 0/1/2, 256 threads, two CTAs per SM (few groups: TPC-H Q1).
+// MID = true : no tier 0; one 512-thread CTA per SM owns a 4096-slot shared table and the launch only aggregates the keys of hash
+//              subset P.subsetIndex of P.subsetCount — the host runs subsetCount passes over the chunk so that every pass's groups
+//              fit in shared memory instead of paying 4 L2 atomics per row (10^3 .. 10^5 groups).
+template <int NV, bool CNT, bool MID>
+__global__ void __launch_bounds__(MID ? 512 : kAggThreads, MID ? 1 : 2) hashAggFastKernel(const __grid_constant__ FastLaunch<NV, CNT> P)
 {
+    constexpr int THREADS = MID ? 512 : kAggThreads;
     constexpr int NC = FastGeom<NV, CNT>::NC;
-    constexpr int K0 = FastGeom<NV, CNT>::K0;
-    constexpr int TILE = kAggThreads * 2;            // one 128-bit pair per thread per column per tile
+    constexpr int K0 = MID ? 0 : FastGeom<NV, CNT>::K0;
+    constexpr int TILE = THREADS * 2;            // one 128-bit pair per thread per column per tile
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int tid = threadIdx.x, lane = tid & 31;
     const GroupTable& T = P.t;
 
     SharedTable<1> st;
     st.S = P.S; st.S2 = P.S + 2; st.sLimit = P.sLimit; st.tier0Groups = K0;
-    const SharedLayout lay(P.S, 1, P.nAccAlloc, true);
+    const SharedLayout lay(P.S, 1, P.nAccAlloc, !MID);
     st.keys = (volatile uint64_t*) (smemRaw + lay.keys);
     st.acc = (uint64_t*) (smemRaw + lay.acc);
     st.first = (uint32_t*) (smemRaw + lay.first);
@@ -512,11 +519,13 @@ __global__ void __launch_bounds__(kAggThreads, 2) hashAggFastKernel(const __grid
     st.sid = (volatile uint8_t*) (smemRaw + lay.sid);
     st.count = (uint32_t*) (smemRaw + lay.misc);
     uint64_t* tier0 = (uint64_t*) (smemRaw + lay.tier0);     // [K0][NC][256]
-    for (uint32_t i = tid; i < st.S2; i += kAggThreads) { st.keys[i] = kEmptyKey; st.first[i] = kNoRow32; st.sid[i] = 0xFF; }
-    for (uint32_t i = tid; i < (uint32_t) P.nAccAlloc * st.S2; i += kAggThreads) st.acc[i] = 0;
+    for (uint32_t i = tid; i < st.S2; i += THREADS) { st.keys[i] = kEmptyKey; st.first[i] = kNoRow32; st.sid[i] = 0xFF; }
+    for (uint32_t i = tid; i < (uint32_t) P.nAccAlloc * st.S2; i += THREADS) st.acc[i] = 0;
     if (tid < 64) st.count[tid] = 0;
+    if (!MID) {
 #pragma unroll
-    for (int i = 0; i < K0 * NC; i++) tier0[i * kAggThreads + tid] = 0;
+        for (int i = 0; i < K0 * NC; i++) tier0[i * THREADS + tid] = 0;
+    }
     __syncthreads();
 
     uint32_t seen0 = 0;
@@ -542,6 +551,8 @@ __global__ void __launch_bounds__(kAggThreads, 2) hashAggFastKernel(const __grid
     };
     auto consumeRow = [&](uint64_t key, const uint64_t (&vals)[NV], uint32_t rowIdx) {
         const uint64_t h = murmur64(key);
+        // subset from the LOW hash word (the shared slot index uses bits 32..43: the two must be independent)
+        if (MID && P.subsetCount > 1 && (uint32_t) (((h & 0xffffffffULL) * (uint64_t) P.subsetCount) >> 32) != P.subsetIndex) return;   // another pass owns this key (the caller reconverges the warp)
         int sslot = -1;
         if (key == kEmptyKey) sslot = (int) st.S + 1;      // the sentinel-valued key has its own slot (an empty slot must never match it)
         else if (!bypass) {
@@ -557,14 +568,14 @@ __global__ void __launch_bounds__(kAggThreads, 2) hashAggFastKernel(const __grid
         }
         uint32_t id = 0xFF;
         if (sslot >= 0) id = st.sid[sslot];
-        if (id < (uint32_t) K0) {
-            uint64_t* mine = tier0 + (size_t) id * NC * kAggThreads + tid;
+        if (!MID && id < (uint32_t) K0) {
+            uint64_t* mine = tier0 + (size_t) id * NC * THREADS + tid;
 #pragma unroll
             for (int c = 0; c < NV; c++) {
-                double* p = (double*) (mine + c * kAggThreads);
+                double* p = (double*) (mine + c * THREADS);
                 *p = *p + __longlong_as_double((long long) vals[c]);
             }
-            if (CNT) mine[NV * kAggThreads] += 1;
+            if (CNT) mine[NV * THREADS] += 1;
             if (!((seen0 >> id) & 1u)) { seen0 |= 1u << id; atomicMin(&st.first[sslot], rowIdx); }
         }
         else if (sslot >= 0) {
@@ -598,31 +609,33 @@ __global__ void __launch_bounds__(kAggThreads, 2) hashAggFastKernel(const __grid
         const int64_t t1 = tile + gridDim.x;
         if (t1 < nTiles) loadTile(t1, kB, vB);
         consumeTile(tile, kA, vA);
+        __syncwarp();      // rows take different tiers (or skip: hash subsets); the next tile's 128-bit loads must be issued by whole warps
         if (t1 >= nTiles) break;
         const int64_t t2 = t1 + gridDim.x;
         if (t2 < nTiles) loadTile(t2, kA, vA);
         consumeTile(t1, kB, vB);
+        __syncwarp();
         tile = t2;
     }
 
     // ---- fold tier 0 into the shared table, then flush the shared table into the HBM table ----
     __syncthreads();
-    const uint32_t nT0 = min(st.count[1], (uint32_t) K0);
+    const uint32_t nT0 = MID ? 0u : min(st.count[1], (uint32_t) K0);
     const int warp = tid >> 5;
-    for (uint32_t pairIdx = warp; pairIdx < nT0 * (uint32_t) NC; pairIdx += kAggThreads / 32) {
+    for (uint32_t pairIdx = warp; pairIdx < nT0 * (uint32_t) NC; pairIdx += THREADS / 32) {
         const uint32_t id = pairIdx / NC, c = pairIdx % NC;
-        const uint64_t* src = tier0 + (size_t) pairIdx * kAggThreads;
+        const uint64_t* src = tier0 + (size_t) pairIdx * THREADS;
         const bool isF = c < (uint32_t) NV;
         uint64_t x = 0;
         if (isF) {
             double d = 0;
-            for (int i = lane; i < kAggThreads; i += 32) d += __longlong_as_double((long long) src[i]);
+            for (int i = lane; i < THREADS; i += 32) d += __longlong_as_double((long long) src[i]);
             x = (uint64_t) __double_as_longlong(d);
 #pragma unroll
             for (int m = 16; m >= 1; m >>= 1) x = (uint64_t) __double_as_longlong(__longlong_as_double((long long) x) + __longlong_as_double((long long) shflXor64(x, m)));
         }
         else {
-            for (int i = lane; i < kAggThreads; i += 32) x += src[i];
+            for (int i = lane; i < THREADS; i += 32) x += src[i];
 #pragma unroll
             for (int m = 16; m >= 1; m >>= 1) x += shflXor64(x, m);
         }
@@ -632,7 +645,7 @@ __global__ void __launch_bounds__(kAggThreads, 2) hashAggFastKernel(const __grid
         }
     }
     __syncthreads();
-    for (uint32_t s = tid; s < st.S2; s += kAggThreads) {
+    for (uint32_t s = tid; s < st.S2; s += THREADS) {
         const uint32_t f = st.first[s];
         if (f == kNoRow32) continue;
         int gslot;
@@ -1178,16 +1191,36 @@ public:
         for (int c = 0; c < NV; c++) { L.vals[c] = (const uint64_t*) colOf(phys[f64Cols[c]].channel).values; L.phys[c] = f64Cols[c]; }
         L.phys[NV] = CNT ? countCol : 0;
         L.n = n; L.rowBase = rowsSeen; L.bitmapOut = bitmapOut; L.S = sharedSlots; L.sLimit = sharedLimit; L.nAccAlloc = (int) phys.size();
-        auto kern = hashAggFastKernel<NV, CNT>;
+        L.subsetCount = 1; L.subsetIndex = 0;
+        // ---- mid mode: more groups than the two-CTA shared table holds, few enough for a handful of hash-subset passes ----
+        constexpr int NC = NV + (CNT ? 1 : 0);
+        uint32_t midSlots = 4096;
+        while (SharedLayout(midSlots, 1, NC, false).total > 200 * 1024 && midSlots > 512) midSlots >>= 1;
+        const uint32_t midCapacity = midSlots / 4 * 3;
+        const int64_t passes = (int64_t) ((double) knownGroups * 1.25 / midCapacity) + 1;
+        if (knownGroups > (int64_t) sharedLimit * 9 / 10 && passes <= kMaxSubsetPasses) {
+            auto kern = hashAggFastKernel<NV, CNT, true>;
+            L.S = midSlots; L.sLimit = midCapacity; L.nAccAlloc = NC; L.subsetCount = (uint32_t) passes;
+            const size_t smem = SharedLayout(midSlots, 1, NC, false).total;
+            PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            const int64_t tiles = divUp(n, 512 * 2);
+            const int grid = (int) std::min<int64_t>((int64_t) numSMs, std::max<int64_t>(tiles, 1));
+            for (uint32_t j = 0; j < L.subsetCount; j++) {
+                L.subsetIndex = j;
+                kern<<<grid, 512, smem, stream>>>(L);
+                stats.kernel_launches++;
+            }
+            PG_CUDA(cudaGetLastError());
+            return true;
+        }
+        auto kern = hashAggFastKernel<NV, CNT, false>;
         const size_t smem = sharedBytes(sharedSlots);
-        static thread_local bool configured = false;
-        if (!configured) { PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
+        PG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         int perSM = 0;
         PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kAggThreads, smem));
         perSM = std::max(1, std::min(perSM, 2));
         const int64_t tiles = divUp(n, kAggThreads * 2);
         const int grid = (int) std::min<int64_t>((int64_t) numSMs * perSM, std::max<int64_t>(tiles, 1));
-        PG_CHECK_STATE((int64_t) grid <= gridCTAs || true, "grid");
         kern<<<grid, kAggThreads, smem, stream>>>(L);
         stats.kernel_launches++;
         PG_CUDA(cudaGetLastError());
@@ -1299,8 +1332,10 @@ public:
         if (n == 0) return;
         // host pages are staged in sub-chunks so the PCIe copy of chunk k+1 overlaps the kernel of chunk k
         const int64_t chunk = page->memory == PG_MEM_HOST ? (int64_t(1) << 23) : (int64_t(1) << 30);
-        for (int64_t begin = 0; begin < n; begin += chunk) {
-            const int64_t m = std::min(chunk, n - begin);
+        // a large first page starts with a small probe chunk: its group count picks the kernel mode for the rest
+        const int64_t probe = (rowsSeen == 0 && n > (int64_t(1) << 24)) ? (int64_t(1) << 22) : 0;
+        for (int64_t begin = 0; begin < n;) {
+            const int64_t m = std::min(begin == 0 && probe ? probe : chunk, n - begin);
             pg_page sub = *page;
             std::vector<pg_block> blocks(page->blocks, page->blocks + page->channel_count);
             sub.blocks = blocks.data(); sub.position_count = m;
@@ -1320,6 +1355,7 @@ public:
             processChunk(cols, m);
             stager.markCompute(slot);
             rowsSeen += (uint64_t) m;
+            begin += m;
         }
         // the borrowed (device) page must not be referenced after return, and deferred rows need its columns: settle now
         settle();
