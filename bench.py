@@ -256,8 +256,29 @@ def run_partitioned_output(torch, backend, device, rows, partitions, steps, warm
             pms.append(e0.elapsed_time(e1)); xms.append(e1.elapsed_time(e2))
         op.close()
     p_ms, x_ms = float(np.mean(pms)), float(np.mean(xms))
-    return {"rows": rows, "partitions": partitions, "partition_ms": p_ms, "exchange_ms": x_ms, "received_rows": int(received),
-            "rows_per_s": rows / ((p_ms + x_ms) / 1000), "partition_gbs": 128 * rows / (p_ms / 1000) / 1e9}
+    out = {"rows": rows, "partitions": partitions, "partition_ms": p_ms, "exchange_ms": x_ms, "received_rows": int(received),
+           "rows_per_s": rows / ((p_ms + x_ms) / 1000), "partition_gbs": 128 * rows / (p_ms / 1000) / 1e9}
+    if dist is not None:
+        # the fused path: pass 2 stores every row straight into the destination GPU's receive columns (NVLink peer memory)
+        from presto_b200.exchange import FusedExchange
+        fx = FusedExchange([BIGINT] * 8, rows // partitions * 2 if partitions > 1 else rows, backend=backend)
+        fms = []
+        op = PartitionedOutputOperator([BIGINT] * 8, partitions, [0], backend=backend, device=device, output_memory=MEM_DEVICE, cuda_stream=stream.cuda_stream)
+        for it in range(warmup + steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0.record(stream)
+            got = fx.exchange(op, page)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            if it >= warmup:
+                fms.append(e0.elapsed_time(e1))
+        assert got.position_count == received, "fused exchange and all-to-all disagree on the received row count"
+        op.close(); fx.close()
+        f_ms = float(np.mean(fms))
+        out.update({"fused_scatter_exchange_ms": f_ms, "fused_rows_per_s": rows / (f_ms / 1000), "fused_gbs_per_gpu": 128 * rows / (f_ms / 1000) / 1e9})
+    return out
 
 
 def run_page_processor_q1(torch, backend, device, rows, steps, warmup):
@@ -407,6 +428,54 @@ def run_q3(torch, backend, device, n_orders, steps, warmup):
             "lineitem_rows_per_s": n_li / (ms / 1000), "achieved_gbs": algo / (ms / 1000) / 1e9, "launches": int(stats.get("kernel_launches", 0)), "top_revenue": top}
 
 
+def run_q3_multi(torch, backend, device, n_orders_total, steps, warmup, dist):
+    """configs[3]: Q3 hash-repartitioned across the ranks (presto_b200/pipelines.run_q3_distributed).  Every rank generates the same
+    tables from the same seed and keeps its round-robin shard (rows rank::world), so the union over ranks is the single-GPU input."""
+    from presto_b200 import BIGINT, DATE, DOUBLE, INTEGER
+    from presto_b200.pipelines import run_q3_distributed
+    from presto_b200.synthetic import q3_tables_torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = f"cuda:{device}"
+    customer, orders, lineitem = q3_tables_torch(n_orders_total, dev)
+    shard = lambda cols: [c[rank::world].contiguous() for c in cols]
+    customer, orders, lineitem = shard(customer), shard(orders), shard(lineitem)
+    torch.cuda.empty_cache()
+    torch.cuda.synchronize()
+    cp = [device_page(torch, customer, [BIGINT, INTEGER])]
+    op = [device_page(torch, orders, [BIGINT, BIGINT, DATE, INTEGER])]
+    lp = [device_page(torch, lineitem, [BIGINT, DOUBLE, DOUBLE, DATE])]
+    n_li = torch.tensor([lineitem[0].numel()], dtype=torch.int64, device=dev)
+    dist.all_reduce(n_li)
+    stream = torch.cuda.current_stream()
+    from presto_b200.exchange import FusedExchange
+    # receive columns live as long as the worker's output buffers do: created once, outside the timed region
+    exchanges = (FusedExchange([BIGINT, DATE, INTEGER], orders[0].numel() // 4 + 1024, backend=backend),
+                 FusedExchange([BIGINT, DOUBLE], lineitem[0].numel() * 5 // 8 + 1024, backend=backend))
+    times, nccl_times, stats, groups = [], [], {}, 0
+    for fused in (False, True):
+        for it in range(warmup + steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier(); torch.cuda.synchronize()
+            e0.record(stream)
+            out = run_q3_distributed(cp, op, lp, backend=backend, stats=stats, device=device, cuda_stream=stream.cuda_stream, fused=fused,
+                                     exchanges=exchanges if fused else None)
+            torch.cuda.synchronize()
+            e1.record(stream)
+            torch.cuda.synchronize(); dist.barrier()
+            if it >= warmup:
+                (times if fused else nccl_times).append(e0.elapsed_time(e1)); groups = sum(p.position_count for p in out)
+    for fx in exchanges:
+        fx.close()
+    t = torch.tensor([float(np.mean(times)), float(np.mean(nccl_times))], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    g = torch.tensor([groups, stats.get("exchanged_rows", 0), stats.get("joined_rows", 0)], dtype=torch.int64, device=dev)
+    dist.all_reduce(g)
+    ms = float(t[0])
+    return {"orders": n_orders_total, "lineitem_rows": int(n_li[0]), "groups": int(g[0]), "exchanged_rows": int(g[1]), "joined_rows": int(g[2]), "ms": ms,
+            "ms_with_nccl_all_to_all": float(t[1]), "exchange": "fused scatter into peer receive columns (NVLink P2P)",
+            "lineitem_rows_per_s": int(n_li[0]) / (ms / 1000)}
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -472,6 +541,12 @@ def main():
             extra["partitioned_output_all_to_all"] = run_partitioned_output(torch, backend, local, min(rows, 1 << 27), world, 2, 1, dist)
         except Exception as e:
             extra["partitioned_output_all_to_all"] = {"error": str(e)[:200]}
+        torch.cuda.empty_cache()
+        try:
+            scale = min(1.0, rows / 1_000_000_000)
+            extra["q3_repartitioned"] = run_q3_multi(torch, backend, local, int(150_000_000 * scale), 2, 1, dist)
+        except Exception as e:
+            extra["q3_repartitioned"] = {"error": str(e)[:300]}
     if rank == 0 and world == 1:
         # ---- CPU baseline: oracle on the host cores, bounded sample ----
         threads = os.cpu_count() or 1

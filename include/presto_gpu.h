@@ -311,6 +311,24 @@ typedef struct pg_partitioned_output_config {
 int32_t pg_partitioned_output_create(const pg_partitioned_output_config* config, pg_operator** out);
 int32_t pg_partitioned_output_get_offsets(pg_operator* op, int64_t* out_offsets /* partition_count+1, host */);
 
+/* Fused repartition + exchange across the GPUs of one box (replaces PartitionedOutputBuffer → HTTP → ExchangeClient,
+ * MB/execution/buffer/PartitionedOutputBuffer.java:174-181, MB/operator/ExchangeClient.java:71):
+ *   pg_partitioned_output_count      pass 1 over `page` (partition ids + histograms); returns the rows per partition.  The page must
+ *                                    stay valid until the matching scatter_to call.
+ *   pg_partitioned_output_scatter_to pass 2: partition p's rows are written, in input order, to row offset dst_row_offsets[p] of the
+ *                                    destination columns dst_values[p * n_channels + c] (device addresses that may live on a PEER GPU,
+ *                                    e.g. opened with pg_ipc_import) — the scatter IS the transfer, one NVLink store per value.
+ *                                    dst_nulls entries may be NULL for channels without a null map on any rank.
+ * The caller exchanges the counts (a P x P int64 all-gather) between the two calls and synchronises the ranks afterwards. */
+int32_t pg_partitioned_output_count(pg_operator* op, const pg_page* page, int64_t* out_counts /* partition_count, host */);
+int32_t pg_partitioned_output_scatter_to(pg_operator* op, void* const* dst_values, uint8_t* const* dst_nulls, const int64_t* dst_row_offsets);
+
+/* CUDA IPC plumbing for the above: export a device allocation made with pg_device_alloc, map a peer's allocation. */
+#define PG_IPC_HANDLE_BYTES 64
+int32_t pg_ipc_export(const void* device_ptr, uint8_t* handle /* PG_IPC_HANDLE_BYTES */);
+int32_t pg_ipc_import(const uint8_t* handle, void** out);
+int32_t pg_ipc_close(void* imported);
+
 /* ------------------------------------------------------------------------------------------------
  * FilterAndProjectOperator / PageProcessor
  * A RowExpression tree is flattened to a register program (one instruction per node).

@@ -27,6 +27,7 @@ _STATUS_NAMES = {
 
 # pg_type
 BIGINT, INTEGER, DOUBLE, DATE, BOOLEAN, VARCHAR = 1, 2, 3, 4, 5, 6
+IPC_HANDLE_BYTES = 64
 # pg_encoding
 ENC_FLAT, ENC_DICTIONARY, ENC_RLE = 0, 1, 2
 # pg_memory
@@ -194,6 +195,11 @@ class Backend:
         "memcpy_h2d": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),
         "memcpy_d2h": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),
         "device_synchronize": (C.c_int32, []),
+        "partitioned_output_count": (C.c_int32, [C.c_void_p, C.POINTER(pg_page), C.c_void_p]),
+        "partitioned_output_scatter_to": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+        "ipc_export": (C.c_int32, [C.c_void_p, C.c_void_p]),
+        "ipc_import": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
+        "ipc_close": (C.c_int32, [C.c_void_p]),
     }
 
     def __init__(self, lib: C.CDLL, prefix: str, has_device: bool):

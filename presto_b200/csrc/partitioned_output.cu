@@ -94,7 +94,27 @@ struct ScatterParams {
     int64_t n, units;
     const uint16_t* ids;
     const uint32_t* base;    // scanned hist
+    // fused exchange: partition p's rows go to per-partition destination columns (peer GPU memory) instead of one local slab
+    const uint64_t* remoteValues;   // [nCols][partitionCount] destination column base addresses, or nullptr
+    const uint64_t* remoteNulls;    // [nCols][partitionCount] destination null maps (0 = none)
+    const uint32_t* adjust;         // [partitionCount] destination row offset - start of the partition in the local layout (mod 2^32)
 };
+
+template <typename T>
+__device__ __forceinline__ void permuteColumnRemote(const T* __restrict__ src, const uint64_t* ptrs, const uint32_t* dest, const uint16_t* partOf,
+                                                    int64_t begin, int count, int lane)
+{
+    // the scatter IS the transfer: every store lands in the destination GPU's receive column (NVLink P2P)
+    int i = lane;
+    for (; i + 7 * 32 < count; i += 8 * 32) {
+        T v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = src[begin + i + k * 32];
+#pragma unroll
+        for (int k = 0; k < 8; k++) ((T*) ptrs[partOf[i + k * 32]])[dest[i + k * 32]] = v[k];
+    }
+    for (; i < count; i += 32) ((T*) ptrs[partOf[i]])[dest[i]] = src[begin + i];
+}
 
 template <typename T>
 __device__ __forceinline__ void permuteColumn(const T* __restrict__ src, T* __restrict__ dst, const uint32_t* dest, int64_t begin, int count, int lane)
@@ -122,9 +142,11 @@ __global__ void __launch_bounds__(kPartWarps * 32) partitionScatterKernel(const 
     const int PC = P.partitionCount;
     uint32_t* cur = smemU32 + warp * PC;                                   // [warps][PC]
     uint32_t* dest = smemU32 + kPartWarps * PC + warp * kRowsPerUnit;      // [warps][kRowsPerUnit]
+    uint16_t* partOf = (uint16_t*) (smemU32 + kPartWarps * PC + kPartWarps * kRowsPerUnit) + warp * kRowsPerUnit;   // [warps][kRowsPerUnit]
+    const bool remote = P.remoteValues != nullptr;
     const unsigned ltMask = (1u << lane) - 1;
     for (int64_t unit = (int64_t) blockIdx.x * kPartWarps + warp; unit < P.units; unit += (int64_t) gridDim.x * kPartWarps) {
-        for (int p = lane; p < PC; p += 32) cur[p] = P.base[(size_t) p * P.units + unit];
+        for (int p = lane; p < PC; p += 32) cur[p] = P.base[(size_t) p * P.units + unit] + (remote ? P.adjust[p] : 0u);
         __syncwarp();
         const int64_t begin = unit * kRowsPerUnit, end = min(begin + (int64_t) kRowsPerUnit, P.n);
         const int count = (int) (end - begin);
@@ -139,7 +161,7 @@ __global__ void __launch_bounds__(kPartWarps * 32) partitionScatterKernel(const 
                 if (part >= 0) d = cur[part] + __popc(peers & ltMask);
                 __syncwarp();
                 if (part >= 0 && lane == __ffs(peers) - 1) cur[part] += __popc(peers);
-                if (i < count) dest[i] = d;
+                if (i < count) { dest[i] = d; if (remote) partOf[i] = (uint16_t) part; }
             }
             else {
                 // rows of this round that go to every partition: rank inside partition q counts its own rows and the replicated ones
@@ -156,7 +178,22 @@ __global__ void __launch_bounds__(kPartWarps * 32) partitionScatterKernel(const 
             }
             __syncwarp();
         }
-        if (!anyReplicated) {
+        if (remote) {
+            // (replicated rows are rejected on the host in this mode)
+            for (int c = 0; c < P.nCols; c++) {
+                const ScatterColumn& sc = P.cols[c];
+                const uint64_t* ptrs = P.remoteValues + (size_t) c * PC;
+                if (sc.width == 8) permuteColumnRemote((const uint64_t*) sc.src, ptrs, dest, partOf, begin, count, lane);
+                else if (sc.width == 4) permuteColumnRemote((const uint32_t*) sc.src, ptrs, dest, partOf, begin, count, lane);
+                else permuteColumnRemote((const uint8_t*) sc.src, ptrs, dest, partOf, begin, count, lane);
+                const uint64_t* nptrs = P.remoteNulls + (size_t) c * PC;
+                if (nptrs[0]) {      // a null map travels for this channel (all destinations have one)
+                    if (sc.srcNulls) permuteColumnRemote(sc.srcNulls, nptrs, dest, partOf, begin, count, lane);
+                    else for (int i = lane; i < count; i += 32) ((uint8_t*) nptrs[partOf[i]])[dest[i]] = 0;
+                }
+            }
+        }
+        else if (!anyReplicated) {
             for (int c = 0; c < P.nCols; c++) {
                 const ScatterColumn& sc = P.cols[c];
                 if (sc.width == 8) permuteColumn((const uint64_t*) sc.src, (uint64_t*) sc.dst, dest, begin, count, lane);
@@ -233,38 +270,40 @@ public:
         for (DeviceBuffer* d : {&ids, &hist, &base, &scanTemp}) d->accounting = &stats.device_bytes;
         const size_t smem = (size_t) kPartWarps * partitionCount * 4;
         PG_CUDA(cudaFuncSetAttribute(partitionIdKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        PG_CUDA(cudaFuncSetAttribute(partitionScatterKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (smem + (size_t) kPartWarps * kRowsPerUnit * 4)));
+        PG_CUDA(cudaFuncSetAttribute(partitionScatterKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (smem + (size_t) kPartWarps * kRowsPerUnit * 6)));
     }
 
     bool needsInput() override { return !finishing && !hasPending; }
 
-    void addInput(const pg_page* page) override
+    // ---- pass 1 + scan: partition ids, histograms, partition boundaries (state kept for the scatter) ----
+    std::vector<DeviceColumn> curCols; int curSlot = -1; int64_t curN = 0, curUnits = 0; bool prepared = false;
+    DeviceBuffer remoteTable;
+
+    size_t scatterSmem() const { return (size_t) kPartWarps * partitionCount * 4 + (size_t) kPartWarps * kRowsPerUnit * 6; }
+    int launchGrid() const { return (int) std::min<int64_t>(divUp(curUnits, kPartWarps), (int64_t) numSMs * 8); }
+
+    void prepare(const pg_page* page)
     {
-        PG_CHECK_STATE(needsInput(), "partitioned output does not need input (finishing or output pending)");
         const int64_t n = page->position_count;
-        stats.input_positions += n;
-        if (n == 0) return;
         PG_CHECK_ARG(n < (int64_t(1) << 31), "page exceeds 2^31 positions");
         PG_CHECK_ARG(page->channel_count == (int) types.size(), "page channel count differs from the operator's configuration");
-        std::vector<DeviceColumn> cols;
-        int slot = stager.stage(page, staged, cols);
-        for (size_t i = 0; i < cols.size(); i++) PG_CHECK_ARG(cols[i].type == types[i], "channel type differs from the operator's configuration");
-        const int64_t units = divUp(n, kRowsPerUnit);
+        curSlot = stager.stage(page, staged, curCols);
+        for (size_t i = 0; i < curCols.size(); i++) PG_CHECK_ARG(curCols[i].type == types[i], "channel type differs from the operator's configuration");
+        curN = n; curUnits = divUp(n, kRowsPerUnit);
         ids.reserve((size_t) n * 2);
-        const size_t histN = (size_t) partitionCount * units + 1;
+        const size_t histN = (size_t) partitionCount * curUnits + 1;
         hist.reserve(histN * 4); base.reserve(histN * 4);
         PartitionIdParams A{};
         A.nCols = (int) partitionChannels.size();
-        for (int i = 0; i < A.nCols; i++) { const DeviceColumn& c = cols[partitionChannels[i]]; A.cols[i].values = c.values; A.cols[i].nulls = c.nulls; A.cols[i].type = c.type; }
-        A.precomputed = hashChannel >= 0 ? (const int64_t*) cols[hashChannel].values : nullptr;
-        A.nullChannelNulls = nullChannel >= 0 ? cols[nullChannel].nulls : nullptr;
+        for (int i = 0; i < A.nCols; i++) { const DeviceColumn& c = curCols[partitionChannels[i]]; A.cols[i].values = c.values; A.cols[i].nulls = c.nulls; A.cols[i].type = c.type; }
+        A.precomputed = hashChannel >= 0 ? (const int64_t*) curCols[hashChannel].values : nullptr;
+        A.nullChannelNulls = nullChannel >= 0 ? curCols[nullChannel].nulls : nullptr;
         A.replicateRow0 = (replicatesAnyRow && !hasAnyRowBeenReplicated) ? 1 : 0;
         hasAnyRowBeenReplicated = hasAnyRowBeenReplicated || replicatesAnyRow;
-        A.partitionCount = partitionCount; A.n = n; A.units = units; A.ids = ids.as<uint16_t>(); A.hist = hist.as<uint32_t>();
+        A.partitionCount = partitionCount; A.n = n; A.units = curUnits; A.ids = ids.as<uint16_t>(); A.hist = hist.as<uint32_t>();
         PG_CUDA(cudaMemsetAsync(hist.as<uint32_t>() + histN - 1, 0, 4, stream));
         const size_t smem = (size_t) kPartWarps * partitionCount * 4;
-        const int grid = (int) std::min<int64_t>(divUp(units, kPartWarps), (int64_t) numSMs * 8);
-        PG_LAUNCH(this, partitionIdKernel, grid, kPartWarps * 32, smem, A);
+        PG_LAUNCH(this, partitionIdKernel, launchGrid(), kPartWarps * 32, smem, A);
         size_t tb = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tb, hist.as<uint32_t>(), base.as<uint32_t>(), (int) histN, stream);
         scanTemp.reserve(tb);
@@ -272,17 +311,28 @@ public:
         stats.kernel_launches += 2;
         // partition boundaries: base[p * units] and the grand total
         std::vector<uint32_t> hostOffsets(partitionCount + 1);
-        PG_CUDA(cudaMemcpy2DAsync(hostOffsets.data(), 4, base.ptr, (size_t) units * 4, 4, partitionCount, cudaMemcpyDeviceToHost, stream));
+        PG_CUDA(cudaMemcpy2DAsync(hostOffsets.data(), 4, base.ptr, (size_t) curUnits * 4, 4, partitionCount, cudaMemcpyDeviceToHost, stream));
         PG_CUDA(cudaMemcpyAsync(&hostOffsets[partitionCount], base.as<uint32_t>() + histN - 1, 4, cudaMemcpyDeviceToHost, stream));
         PG_CUDA(cudaStreamSynchronize(stream));
         stats.d2h_bytes += (partitionCount + 1) * 4;
         for (int p = 0; p <= partitionCount; p++) offsets[p] = hostOffsets[p];
-        const int64_t total = offsets[partitionCount];
+        prepared = true;
+    }
 
+    void addInput(const pg_page* page) override
+    {
+        PG_CHECK_STATE(needsInput() && !prepared, "partitioned output does not need input (finishing, output pending or a count awaiting its scatter)");
+        const int64_t n = page->position_count;
+        stats.input_positions += n;
+        if (n == 0) return;
+        prepare(page);
+        prepared = false;
+        const std::vector<DeviceColumn>& cols = curCols;
+        const int64_t total = offsets[partitionCount];
         const size_t nCols = types.size();
         if (outValues.size() < nCols) { outValues.resize(nCols); outNulls.resize(nCols); for (auto& d : outValues) d.accounting = &stats.device_bytes; for (auto& d : outNulls) d.accounting = &stats.device_bytes; }
         ScatterParams S{};
-        S.nCols = (int) nCols; S.partitionCount = partitionCount; S.n = n; S.units = units; S.ids = ids.as<uint16_t>(); S.base = base.as<uint32_t>();
+        S.nCols = (int) nCols; S.partitionCount = partitionCount; S.n = n; S.units = curUnits; S.ids = ids.as<uint16_t>(); S.base = base.as<uint32_t>();
         outBlocks.assign(nCols, pg_block{});
         for (size_t i = 0; i < nCols; i++) {
             ScatterColumn& sc = S.cols[i];
@@ -291,8 +341,8 @@ public:
             sc.dst = outValues[i].ptr; sc.dstNulls = nullptr;
             if (cols[i].nulls) { outNulls[i].reserve(total); sc.dstNulls = outNulls[i].as<uint8_t>(); }
         }
-        PG_LAUNCH(this, partitionScatterKernel, grid, kPartWarps * 32, smem + (size_t) kPartWarps * kRowsPerUnit * 4, S);
-        stager.markCompute(slot);
+        PG_LAUNCH(this, partitionScatterKernel, launchGrid(), kPartWarps * 32, scatterSmem(), S);
+        stager.markCompute(curSlot);
         const bool toHost = options.output_memory == PG_MEM_HOST;
         if (toHost && hostValues.size() < nCols) { hostValues.resize(nCols); hostNulls.resize(nCols); }
         for (size_t i = 0; i < nCols; i++) {
@@ -315,6 +365,47 @@ public:
         stats.output_positions += total;
     }
 
+    // ---- fused repartition + exchange: pass 1 here, pass 2 in scatterTo() straight into (peer) destination columns ----
+    void count(const pg_page* page, int64_t* outCounts)
+    {
+        PG_CHECK_STATE(!finishing && !hasPending && !prepared, "partitioned output: count in the wrong state");
+        PG_CHECK_ARG(!replicatesAnyRow && nullChannel < 0, "replicated rows are not supported by the fused exchange");
+        stats.input_positions += page->position_count;
+        if (page->position_count == 0) { for (int p = 0; p < partitionCount; p++) outCounts[p] = 0; curN = 0; prepared = true; return; }
+        prepare(page);
+        for (int p = 0; p < partitionCount; p++) outCounts[p] = offsets[p + 1] - offsets[p];
+    }
+
+    void scatterTo(void* const* dstValues, uint8_t* const* dstNulls, const int64_t* dstRowOffsets)
+    {
+        PG_CHECK_STATE(prepared, "scatter_to without a preceding count");
+        prepared = false;
+        if (curN == 0) return;
+        const size_t nCols = types.size();
+        // destination tables: [nCols][P] value pointers, [nCols][P] null pointers, [P] row adjustments
+        const size_t words = nCols * partitionCount;
+        std::vector<uint64_t> table(2 * words + (size_t) partitionCount);
+        for (size_t c = 0; c < nCols; c++)
+            for (int p = 0; p < partitionCount; p++) {
+                table[c * partitionCount + p] = (uint64_t) (uintptr_t) dstValues[(size_t) p * nCols + c];
+                table[words + c * partitionCount + p] = dstNulls ? (uint64_t) (uintptr_t) dstNulls[(size_t) p * nCols + c] : 0;
+            }
+        uint32_t* adj = (uint32_t*) &table[2 * words];
+        for (int p = 0; p < partitionCount; p++) adj[p] = (uint32_t) ((uint64_t) dstRowOffsets[p] - (uint64_t) offsets[p]);
+        remoteTable.accounting = &stats.device_bytes;
+        remoteTable.reserve(table.size() * 8);
+        PG_CUDA(cudaMemcpyAsync(remoteTable.ptr, table.data(), table.size() * 8, cudaMemcpyHostToDevice, stream));
+        ScatterParams S{};
+        S.nCols = (int) nCols; S.partitionCount = partitionCount; S.n = curN; S.units = curUnits; S.ids = ids.as<uint16_t>(); S.base = base.as<uint32_t>();
+        S.remoteValues = remoteTable.as<uint64_t>(); S.remoteNulls = remoteTable.as<uint64_t>() + words; S.adjust = (const uint32_t*) (remoteTable.as<uint64_t>() + 2 * words);
+        for (size_t i = 0; i < nCols; i++) { ScatterColumn& sc = S.cols[i]; sc.width = typeWidth(types[i]); sc.src = curCols[i].values; sc.srcNulls = curCols[i].nulls; sc.dst = nullptr; sc.dstNulls = nullptr; }
+        PG_LAUNCH(this, partitionScatterKernel, launchGrid(), kPartWarps * 32, scatterSmem(), S);
+        stager.markCompute(curSlot);
+        PG_CUDA(cudaStreamSynchronize(stream));
+        stats.output_positions += curN;
+        stats.output_bytes += curN * 8 * (int64_t) nCols;
+    }
+
     bool getOutput(pg_page* out) override
     {
         if (!hasPending) return false;
@@ -333,6 +424,30 @@ extern "C" {
 int32_t pg_partitioned_output_create(const pg_partitioned_output_config* config, pg_operator** out)
 {
     try { *out = (pg_operator*) new pg::PartitionedOutputOp(config); }
+    catch (const pg::Error& e) { pg::setLastError(e.what()); return e.code; }
+    catch (const std::exception& e) { pg::setLastError(e.what()); return PG_ERR_INVALID_STATE; }
+    return PG_OK;
+}
+int32_t pg_partitioned_output_count(pg_operator* op, const pg_page* page, int64_t* outCounts)
+{
+    try {
+        auto* p = dynamic_cast<pg::PartitionedOutputOp*>((pg::Operator*) op);
+        if (!p) throw pg::Error(PG_ERR_INVALID_ARGUMENT, "not a partitioned output operator");
+        p->bind();
+        p->count(page, outCounts);
+    }
+    catch (const pg::Error& e) { pg::setLastError(e.what()); return e.code; }
+    catch (const std::exception& e) { pg::setLastError(e.what()); return PG_ERR_INVALID_STATE; }
+    return PG_OK;
+}
+int32_t pg_partitioned_output_scatter_to(pg_operator* op, void* const* dstValues, uint8_t* const* dstNulls, const int64_t* dstRowOffsets)
+{
+    try {
+        auto* p = dynamic_cast<pg::PartitionedOutputOp*>((pg::Operator*) op);
+        if (!p) throw pg::Error(PG_ERR_INVALID_ARGUMENT, "not a partitioned output operator");
+        p->bind();
+        p->scatterTo(dstValues, dstNulls, dstRowOffsets);
+    }
     catch (const pg::Error& e) { pg::setLastError(e.what()); return e.code; }
     catch (const std::exception& e) { pg::setLastError(e.what()); return PG_ERR_INVALID_STATE; }
     return PG_OK;

@@ -275,6 +275,24 @@ int32_t pg_device_free(void* p) { PG_TRY PG_CUDA(cudaFree(p)); PG_CATCH }
 int32_t pg_memcpy_h2d(void* dst, const void* src, size_t bytes) { PG_TRY PG_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); PG_CATCH }
 int32_t pg_memcpy_d2h(void* dst, const void* src, size_t bytes) { PG_TRY PG_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); PG_CATCH }
 int32_t pg_device_synchronize(void) { PG_TRY PG_CUDA(cudaDeviceSynchronize()); PG_CATCH }
+int32_t pg_ipc_export(const void* devicePtr, uint8_t* handle)
+{
+    PG_TRY
+    static_assert(sizeof(cudaIpcMemHandle_t) == PG_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    PG_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(devicePtr)));
+    memcpy(handle, &h, sizeof(h));
+    PG_CATCH
+}
+int32_t pg_ipc_import(const uint8_t* handle, void** out)
+{
+    PG_TRY
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    PG_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    PG_CATCH
+}
+int32_t pg_ipc_close(void* imported) { PG_TRY PG_CUDA(cudaIpcCloseMemHandle(imported)); PG_CATCH }
 
 int64_t pg_hash_bigint(int64_t value) { return pg::hashLong(value); }
 int64_t pg_hash_combine(int64_t previous, int64_t h) { return (int64_t) (31ULL * (uint64_t) previous + (uint64_t) h); }

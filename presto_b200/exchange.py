@@ -50,7 +50,7 @@ def nulls_to_tensor(block: Block, device=None):
     import torch
     if block.on_device:
         p = block.device_ptrs["is_null"]
-        return None if not p else torch.as_tensor(_CudaArray(p, block.position_count, "|u1"), device=device)
+        return None if not p or block.position_count == 0 else torch.as_tensor(_CudaArray(p, block.position_count, "|u1"), device=device)
     return None if block.is_null is None else torch.from_numpy(block.is_null)
 
 
@@ -58,6 +58,18 @@ def tensor_to_block(type_: int, tensor, nulls=None) -> Block:
     if tensor.is_cuda:
         return Block.device(type_, tensor.numel(), tensor.data_ptr(), nulls.data_ptr() if nulls is not None else 0, keepalive=(tensor, nulls))
     return Block.from_numpy(type_, tensor.numpy(), None if nulls is None else nulls.numpy())
+
+
+def page_to_host(page: Page) -> Page:
+    """Copy a device page of flat fixed-width blocks to host numpy blocks (tests and result hand-off)."""
+    if not page.on_device:
+        return page
+    blocks = []
+    for b in page.blocks:
+        v = block_to_tensor(b).cpu().numpy()
+        n = nulls_to_tensor(b)
+        blocks.append(Block.from_numpy(b.type, v, None if n is None else n.cpu().numpy()))
+    return Page(blocks, page.position_count)
 
 
 def all_to_all_pages(page: Page, offsets: Sequence[int], types: Sequence[int], group=None) -> Page:
@@ -94,6 +106,117 @@ def all_to_all_pages(page: Page, offsets: Sequence[int], types: Sequence[int], g
             dist.all_to_all_single(dst_nulls, nulls, output_split_sizes=recv_counts, input_split_sizes=send_counts, group=group)
         blocks.append(tensor_to_block(t, dst, dst_nulls))
     return Page(blocks, total)
+
+
+class FusedExchange:
+    """Repartition and exchange in ONE kernel: pass 2 of PartitionedOutputOperator stores each row straight into the destination
+    GPU's receive column over NVLink (peer memory mapped once through CUDA IPC), so the shuffle costs one scatter instead of a
+    local scatter + an all-to-all copy.  What is left for torch.distributed is one all_gather of the P per-destination row counts
+    (which also fixes every sender's row offset: sender-major, the order all_to_all_pages delivers) and one barrier.
+
+    Replaces PartitionedOutputBuffer → HTTP → ExchangeClient (MB/execution/buffer/PartitionedOutputBuffer.java:174-181,
+    MB/operator/ExchangeClient.java:71) for GPUs of one NVSwitch domain.  The page ``exchange`` returns lives in this object's
+    receive columns and is valid until the next ``exchange`` call on ANY rank: consume it (or copy it) first."""
+
+    def __init__(self, types: Sequence[int], capacity_rows: int, *, with_nulls: bool = False, group=None, backend=None):
+        import torch
+        import torch.distributed as dist
+        from ._lib import load
+        self._b = backend or load()
+        self._group = group
+        self.types = list(types)
+        self.with_nulls = with_nulls
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self._dev = torch.device("cuda", torch.cuda.current_device())
+        self._local, self._imported = [], []
+        self.last_counts = None
+        self._allocate(int(capacity_rows))
+
+    def _allocate(self, capacity: int) -> None:
+        """Collective: receive columns for `capacity` rows on every rank, exported and mapped into every peer."""
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        self.capacity = capacity
+        n_cols = len(self.types)
+        self._local = []        # (values, nulls) device addresses of this rank's receive columns
+        handles = np.zeros((n_cols, 2, abi.IPC_HANDLE_BYTES), dtype=np.uint8)
+        for c, t in enumerate(self.types):
+            ptrs = []
+            for k, nbytes in enumerate((capacity * TYPE_WIDTH[t], capacity if self.with_nulls else 0)):
+                if nbytes == 0:
+                    ptrs.append(0)
+                    continue
+                p = C.c_void_p()
+                self._b.check(self._b.device_alloc(max(nbytes, 2 << 20), C.byref(p)))      # >= one 2 MiB mapping granule: never sub-allocated, so the IPC handle maps exactly this column
+                self._b.check(self._b.ipc_export(p, handles[c, k].ctypes.data))
+                ptrs.append(p.value)
+            self._local.append(tuple(ptrs))
+        mine = torch.from_numpy(handles.reshape(-1)).to(self._dev)
+        everyone = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(everyone, mine, group=self._group)
+        # dst[p][c]: where partition p's rows of channel c go
+        self._values = np.zeros((self.world, n_cols), dtype=np.uint64)
+        self._nulls = np.zeros((self.world, n_cols), dtype=np.uint64) if self.with_nulls else None
+        self._imported = []
+        for r in range(self.world):
+            h = everyone[r].cpu().numpy().reshape(n_cols, 2, abi.IPC_HANDLE_BYTES)
+            for c in range(n_cols):
+                for k in range(2 if self.with_nulls else 1):
+                    if r == self.rank:
+                        addr = self._local[c][k]
+                    else:
+                        p = C.c_void_p()
+                        self._b.check(self._b.ipc_import(np.ascontiguousarray(h[c, k]).ctypes.data, C.byref(p)))
+                        self._imported.append(p.value)
+                        addr = p.value
+                    (self._values if k == 0 else self._nulls)[r, c] = addr
+
+    def _release(self) -> None:
+        """Collective: unmap the peers' columns, then (after everyone unmapped) free this rank's."""
+        import ctypes as C
+        import torch.distributed as dist
+        for p in self._imported:
+            self._b.ipc_close(C.c_void_p(p))
+        done = __import__("torch").zeros(1, dtype=__import__("torch").int32, device=self._dev)
+        dist.all_reduce(done, group=self._group)
+        done.item()
+        for v, n in self._local:
+            for p in (v, n):
+                if p:
+                    self._b.device_free(C.c_void_p(p))
+        self._imported, self._local = [], []
+
+    def exchange(self, op, page: Page) -> Page:
+        """``op`` is a PartitionedOutputOperator with partition_count == world size over ``self.types``."""
+        import torch
+        import torch.distributed as dist
+        assert op.partition_count == self.world, "one partition per rank"
+        counts = op.count(page)
+        mine = torch.from_numpy(counts).to(self._dev)
+        matrix = torch.empty(self.world * self.world, dtype=torch.int64, device=self._dev)
+        # every rank has entered this call once the gather returns, so nobody still reads the previous received page
+        dist.all_gather_into_tensor(matrix, mine, group=self._group)
+        m = matrix.cpu().numpy().reshape(self.world, self.world)          # m[sender][destination]
+        received = m[:, self.rank]
+        total = int(received.sum())
+        need = int(m.sum(axis=0).max())
+        if need > self.capacity:          # every rank sees the same matrix, so every rank regrows together
+            self._release()
+            self._allocate(need + need // 4)
+        row_offsets = m[:self.rank, :].sum(axis=0).astype(np.int64)       # rows lower-ranked senders put before mine, per destination
+        op.scatter_to(self._values, self._nulls, row_offsets)            # returns after the scatter kernel (and its peer stores) completed
+        done = torch.zeros(1, dtype=torch.int32, device=self._dev)
+        dist.all_reduce(done, group=self._group)                          # every sender's rows have landed
+        done.item()
+        self.last_counts = m
+        blocks = [Block.device(t, total, v, n if self._nulls is not None else 0, keepalive=self) for t, (v, n) in zip(self.types, self._local)]
+        return Page(blocks, total)
+
+    def close(self):
+        if self._b is not None:
+            self._release()
+            self._b = None
 
 
 def _pack_page(page: Optional[Page]) -> np.ndarray:

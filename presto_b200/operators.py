@@ -279,6 +279,24 @@ class PartitionedOutputOperator(Operator):
         self._b.check(self._b.partitioned_output_get_offsets(self._h, out.ctypes.data))
         return out
 
+    # ---- fused repartition + exchange (exchange.FusedExchange drives these) ----
+    def count(self, page: Page) -> np.ndarray:
+        """Pass 1 only: rows of ``page`` per partition.  The page stays staged in the operator until ``scatter_to``."""
+        out = np.empty(self.partition_count, dtype=np.int64)
+        cpage, keep = page.as_c()
+        self._b.check(self._b.partitioned_output_count(self._h, C.byref(cpage), out.ctypes.data))
+        self._count_keepalive = (page, keep)
+        return out
+
+    def scatter_to(self, dst_values: np.ndarray, dst_nulls: Optional[np.ndarray], dst_row_offsets: np.ndarray) -> None:
+        """Pass 2: partition p's rows go to ``dst_values[p, c]`` (device addresses, possibly peer-GPU memory) starting at row
+        ``dst_row_offsets[p]``, keeping their input order."""
+        dv = np.ascontiguousarray(dst_values, dtype=np.uint64)
+        dn = None if dst_nulls is None else np.ascontiguousarray(dst_nulls, dtype=np.uint64)
+        ro = np.ascontiguousarray(dst_row_offsets, dtype=np.int64)
+        self._b.check(self._b.partitioned_output_scatter_to(self._h, dv.ctypes.data, None if dn is None else dn.ctypes.data, ro.ctypes.data))
+        self._count_keepalive = None
+
 
 class FilterAndProjectOperator(Operator):
     """FilterAndProjectOperator.java:88-99 over a PageProcessor (PageProcessor.java:112-148)."""

@@ -144,3 +144,138 @@ def run_q3(customer: Sequence[Page], orders: Sequence[Page], lineitem: Sequence[
         op.close()
     bridge1.close(); bridge2.close()
     return result
+
+
+def run_q3_distributed(customer: Sequence[Page], orders: Sequence[Page], lineitem: Sequence[Page], backend=None, stats: Optional[Dict] = None,
+                       group=None, fused: bool = True, exchanges=None, **opts) -> List[Page]:
+    """Q3 across the GPUs of one box (BASELINE.json configs[3]); every rank holds a shard of each table, device resident.
+         customer  : filtered, then REPLICATED (every rank receives all BUILDING customers: PartitionedOutput with one partition per rank
+                     is not needed for a 1/5 x 15 M x 8 B build side — an all-gather of the filtered keys) → build #1 on every rank
+         orders    : filter → probe #1 locally → PartitionedOutput on o_orderkey → all-to-all → build #2 (rank owns its orderkey partition)
+         lineitem  : filter/project → PartitionedOutput on l_orderkey (same partition function) → all-to-all → probe #2 → aggregation
+       The group-by keys start with orderkey, so the aggregation is co-partitioned with the join: no second exchange; every rank returns
+       its own groups (the caller takes the global top-10).  Exactly one all-to-all per repartition boundary, nowhere else.
+       ``fused`` (default): the repartition scatter writes straight into the destination GPU's receive columns (exchange.FusedExchange);
+       otherwise a local PartitionedOutput slab + one all_to_all_single per column (exchange.all_to_all_pages).  ``exchanges`` =
+       (orders FusedExchange, lineitem FusedExchange) reuses long-lived receive columns (a worker's output buffers outlive a query
+       stage); by default they are created and released here."""
+    import torch
+    import torch.distributed as dist
+    from .exchange import FusedExchange, all_to_all_pages, block_to_tensor, tensor_to_block
+    from .operators import PartitionedOutputOperator
+    world = dist.get_world_size(group)
+    mem = abi.MEM_DEVICE
+    o = dict(backend=backend, **opts)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    # ---- customer: filter, replicate the surviving keys, build #1 ----
+    pc = Program([abi.BIGINT, abi.INTEGER])
+    ck, seg = pc.input(0), pc.input(1)
+    pc.set_filter(seg == BUILDING)
+    pc.project(ck)
+    fp_c = FilterAndProjectOperator([abi.BIGINT, abi.INTEGER], pc, output_memory=mem, **o)
+    local_keys = [block_to_tensor(p.blocks[0], dev).clone() for p in _drain(fp_c, customer, False)]
+    mine = torch.cat(local_keys) if local_keys else torch.empty(0, dtype=torch.int64, device=dev)
+    counts = [torch.empty(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([mine.numel()], dtype=torch.int64, device=dev), group=group)
+    cap = max(int(c.item()) for c in counts)
+    padded = torch.zeros(max(cap, 1), dtype=torch.int64, device=dev)
+    padded[:mine.numel()] = mine
+    gathered = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(gathered, padded, group=group)
+    all_keys = torch.cat([g[:int(c.item())] for g, c in zip(gathered, counts)])
+    bridge1 = JoinBridge(opts.get("device", 0), backend=backend)
+    build1 = HashBuilderOperator(bridge1, [abi.BIGINT], [0], [], **o)
+    if all_keys.numel():
+        build1.add_input(Page([tensor_to_block(abi.BIGINT, all_keys)]))
+    build1.finish()
+    # ---- orders: filter → probe #1 → repartition on orderkey → build #2 ----
+    po = Program([abi.BIGINT, abi.BIGINT, abi.DATE, abi.INTEGER])
+    ok, ock, od, sp = [po.input(i) for i in range(4)]
+    po.set_filter(od < Q3_DATE)
+    po.project(ok, ock, od, sp)
+    fp_o = FilterAndProjectOperator([abi.BIGINT, abi.BIGINT, abi.DATE, abi.INTEGER], po, output_memory=mem, **o)
+    probe1 = LookupJoinOperator(bridge1, [abi.BIGINT, abi.BIGINT, abi.DATE, abi.INTEGER], [1], [0, 2, 3], output_memory=mem, **o)
+    part_o = PartitionedOutputOperator([abi.BIGINT, abi.DATE, abi.INTEGER], world, [0], output_memory=mem, **o)
+    bridge2 = JoinBridge(opts.get("device", 0), backend=backend)
+    build2 = HashBuilderOperator(bridge2, [abi.BIGINT, abi.DATE, abi.INTEGER], [0], [1, 2], **o)
+    exchanged = 0
+    order_types = [abi.BIGINT, abi.DATE, abi.INTEGER]
+    line_types = [abi.BIGINT, abi.DOUBLE]
+
+    def empty(types):
+        return Page([tensor_to_block(t, torch.empty(0, dtype=_TORCH[t], device=dev)) for t in types], 0)
+
+    def shuffle(part, fx, page, types):
+        """One repartition boundary for one page (collective: every rank calls it the same number of times)."""
+        if page is None or not page.position_count:
+            page = empty(types)
+        if fx is not None:
+            return fx.exchange(part, page)
+        if not page.position_count:
+            return all_to_all_pages(page, [0] * (world + 1), types, group=group)
+        part.add_input(page)
+        slab = part.get_output(copy=False)
+        return all_to_all_pages(slab, part.get_offsets(), types, group=group)
+
+    _TORCH = {abi.BIGINT: torch.int64, abi.DATE: torch.int32, abi.INTEGER: torch.int32, abi.DOUBLE: torch.float64}
+    cap_o = max([p.position_count for p in orders] + [1])
+    cap_l = max([p.position_count for p in lineitem] + [1])
+    fx_o = fx_l = None
+    if fused and exchanges is not None:
+        fx_o, fx_l = exchanges
+    elif fused:
+        fx_o = FusedExchange(order_types, cap_o // 4 + 1024, group=group, backend=backend)
+        fx_l = FusedExchange(line_types, cap_l + cap_l // 8 + 1024, group=group, backend=backend)
+    for page in orders:            # every rank iterates the same number of pages: the all-to-all is collective
+        fp_o.add_input(page)
+        f = fp_o.get_output(copy=False)
+        j = None
+        if f is not None and f.position_count:
+            probe1.add_input(f)
+            j = probe1.get_output(copy=False)
+        recv = shuffle(part_o, fx_o, j, order_types)
+        exchanged += recv.position_count
+        if recv.position_count:
+            build2.add_input(recv)
+    build2.finish()
+    # ---- lineitem: filter/project → repartition on orderkey → probe #2 → aggregation ----
+    pl = Program([abi.BIGINT, abi.DOUBLE, abi.DOUBLE, abi.DATE])
+    lk, ep, disc, ship = [pl.input(i) for i in range(4)]
+    pl.set_filter(ship > Q3_DATE)
+    pl.project(lk, ep * (1.0 - disc))
+    fp_l = FilterAndProjectOperator([abi.BIGINT, abi.DOUBLE, abi.DOUBLE, abi.DATE], pl, output_memory=mem, **o)
+    part_l = PartitionedOutputOperator([abi.BIGINT, abi.DOUBLE], world, [0], output_memory=mem, **o)
+    probe2 = LookupJoinOperator(bridge2, [abi.BIGINT, abi.DOUBLE], [0], [0, 1], output_memory=mem, **o)
+    agg = HashAggregationOperator([abi.BIGINT, abi.DATE, abi.INTEGER], [0, 2, 3], [Aggregate(abi.AGG_SUM_DOUBLE, 1)], expected_groups=100_000,
+                                  max_output_rows=1 << 30, **o)
+    joined = 0
+    for page in lineitem:
+        fp_l.add_input(page)
+        f = fp_l.get_output(copy=False)
+        recv = shuffle(part_l, fx_l, f, line_types)
+        exchanged += recv.position_count
+        if not recv.position_count:
+            continue
+        probe2.add_input(recv)
+        j = probe2.get_output(copy=False)
+        if j is not None and j.position_count:
+            joined += j.position_count
+            agg.add_input(j)
+    agg.finish()
+    result = []
+    while not agg.is_finished():
+        r = agg.get_output()
+        if r is not None:
+            result.append(r)
+    ops = (fp_c, build1, fp_o, probe1, part_o, build2, fp_l, part_l, probe2, agg)
+    if stats is not None:
+        stats["joined_rows"] = joined
+        stats["exchanged_rows"] = exchanged
+        stats["kernel_launches"] = sum(op.get_stats()["kernel_launches"] for op in ops)
+    for op in ops:
+        op.close()
+    for fx in (fx_o, fx_l):
+        if fx is not None and exchanges is None:
+            fx.close()
+    bridge1.close(); bridge2.close()
+    return result
