@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--e2e-rows", type=int, default=1 << 27, help="rows of the host-resident sample used for the e2e number")
     ap.add_argument("--cpu-rows", type=int, default=1 << 28, help="rows of the bounded sample the CPU baseline aggregates")
     ap.add_argument("--extra", type=int, default=1, help="also measure other cardinalities and the join (configs[2])")
+    ap.add_argument("--extra-scale", type=float, default=0.0, help="size of the extra measurements relative to SF100 (default: rows / 1e9)")
     ap.add_argument("--only", default="", help="comma separated subset of the extra measurements (names of the extra keys)")
     return ap.parse_args()
 
@@ -421,7 +422,8 @@ def run_q3(torch, backend, device, n_orders, steps, warmup):
             times.append(e0.elapsed_time(e1)); groups = sum(p.position_count for p in out)
     ms = float(np.mean(times))
     # ORDER BY revenue DESC, o_orderdate LIMIT 10 on the host
-    rev = np.concatenate([p.blocks[3].values for p in out]) if out else np.zeros(0)
+    from presto_b200.exchange import block_to_tensor
+    rev = torch.cat([block_to_tensor(p.blocks[3]) for p in out]).cpu().numpy() if out else np.zeros(0)
     top = float(np.sort(rev)[-1]) if len(rev) else None
     algo = n_li * 28 + n_orders * 24 + customer[0].numel() * 12
     return {"orders": n_orders, "lineitem_rows": int(n_li), "joined_rows": int(stats.get("joined_rows", 0)), "groups": int(groups), "ms": ms,
@@ -543,7 +545,7 @@ def main():
             extra["partitioned_output_all_to_all"] = {"error": str(e)[:200]}
         torch.cuda.empty_cache()
         try:
-            scale = min(1.0, rows / 1_000_000_000)
+            scale = args.extra_scale or min(1.0, rows / 1_000_000_000)
             extra["q3_repartitioned"] = run_q3_multi(torch, backend, local, int(150_000_000 * scale), 2, 1, dist)
         except Exception as e:
             extra["q3_repartitioned"] = {"error": str(e)[:300]}
@@ -569,7 +571,7 @@ def main():
                 del pg2
             del keys, cols
             torch.cuda.empty_cache()
-            scale = min(1.0, rows / 1_000_000_000)
+            scale = args.extra_scale or min(1.0, rows / 1_000_000_000)
             for name, fn in [
                 ("hash_join_orders_lineitem", lambda: run_join(torch, backend, local, int(150_000_000 * scale), int(600_037_902 * scale), 2, 1)),
                 ("partitioned_output_8_bigint_cols", lambda: run_partitioned_output(torch, backend, local, int((1 << 28) * scale), 8, 2, 1)),
@@ -595,7 +597,7 @@ def main():
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(workload_config(args, rows), parallelism=(f"{world} ranks: PARTIAL per GPU + FINAL merge on rank 0, no row exchange" if world > 1 else "1 GPU")),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "pg::hashAggKernel<1,4>", "peak_source": peak_kind,
+                         "kernel": "pg::hashAggFastKernel<4,0,false>", "peak_source": peak_kind,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ROW * rows, "kernel_ms": kms},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": r["launches"], "groups": r["groups"], "clocks": clocks, "extra": extra,
         }

@@ -369,6 +369,11 @@ int32_t pg_filter_project_create(const pg_filter_project_config* config, pg_oper
 /* SelectedPositions of the last page filtered (PageFilter.positionsArrayToSelectedPositions, PageFilter.java:27-50):
  * is_list = 0 → positionsRange(0, size) (none or all rows selected), 1 → positionsList of `size` positions. */
 int32_t pg_filter_project_get_last_selection(pg_operator* op, int32_t* is_list, int64_t* size);
+/* The PTX the operator would hand to the driver JIT for this program when the input channels in `nullable_inputs` (bit i =
+ * channel i) carry a null map — the counterpart of dumping the bytecode PageFunctionCompiler generates
+ * (MB/sql/gen/PageFunctionCompiler.java:195-861).  Needs no GPU.  *needed = bytes including the terminating NUL; the text is
+ * copied when `capacity` suffices.  PG_ERR_UNSUPPORTED when the program runs on the interpreter kernels instead. */
+int32_t pg_filter_project_explain(const pg_filter_project_config* config, uint64_t nullable_inputs, char* buffer, size_t capacity, size_t* needed);
 
 #ifdef __cplusplus
 }

@@ -200,6 +200,7 @@ class Backend:
         "ipc_export": (C.c_int32, [C.c_void_p, C.c_void_p]),
         "ipc_import": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
         "ipc_close": (C.c_int32, [C.c_void_p]),
+        "filter_project_explain": (C.c_int32, [C.POINTER(pg_filter_project_config), C.c_uint64, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     }
 
     def __init__(self, lib: C.CDLL, prefix: str, has_device: bool):

@@ -536,6 +536,28 @@ int32_t pg_filter_project_create(const pg_filter_project_config* config, pg_oper
     catch (const std::exception& e) { pg::setLastError(e.what()); return PG_ERR_INVALID_STATE; }
     return PG_OK;
 }
+int32_t pg_filter_project_explain(const pg_filter_project_config* c, uint64_t nullableInputs, char* buffer, size_t capacity, size_t* needed)
+{
+    try {
+        PG_CHECK_ARG(c && needed, "null argument");
+        PG_CHECK_ARG(c->n_input_channels >= 0 && c->n_input_channels <= pg::kMaxInputs && c->n_nodes >= 0 && c->n_nodes <= pg::kMaxNodes, "program too large");
+        pg::FpProgramDesc d;
+        d.nodes.assign(c->nodes, c->nodes + c->n_nodes);
+        d.inputTypes.assign(c->input_types, c->input_types + c->n_input_channels);
+        d.filterNode = c->filter_node;
+        d.projections.assign(c->projection_nodes, c->projection_nodes + c->n_projections);
+        d.inputHasNulls.assign(d.inputTypes.size(), false);
+        for (size_t i = 0; i < d.inputTypes.size(); i++) d.inputHasNulls[i] = (nullableInputs >> i) & 1ULL;
+        pg::FpKernelSignature sig;
+        const std::string ptx = pg::generateFilterProjectPtx(d, sig);
+        if (!sig.ok) throw pg::Error(PG_ERR_UNSUPPORTED, "no PTX for this program (interpreter path): " + sig.reason);
+        *needed = ptx.size() + 1;
+        if (buffer && capacity >= ptx.size() + 1) memcpy(buffer, ptx.c_str(), ptx.size() + 1);
+    }
+    catch (const pg::Error& e) { pg::setLastError(e.what()); return e.code; }
+    catch (const std::exception& e) { pg::setLastError(e.what()); return PG_ERR_INVALID_STATE; }
+    return PG_OK;
+}
 int32_t pg_filter_project_get_last_selection(pg_operator* op, int32_t* isList, int64_t* size)
 {
     try {

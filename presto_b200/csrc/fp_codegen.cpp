@@ -280,10 +280,20 @@ std::string prologue(Gen& g, const std::vector<int>& usedInputs, bool filterKern
     return s.str();
 }
 
-const char* kFixedRegs =
-    "    .reg .b64 %n, %units, %unit, %nwarps64, %lane64, %begin, %end, %base, %row, %sel, %off, %cnt, %errp, %w64, %a64, %dest64;\n"
-    "    .reg .b32 %xtid, %xntid, %xctaid, %xnctaid, %gtid, %warp, %lane, %nthr, %nwarps, %lt, %mask, %cur, %t0, %t1, %count;\n"
-    "    .reg .pred %plane0, %perr_ov, %perr_dz, %pdone, %pdr, %pin, %pact, %pbit, %psel;\n";
+// Rounds of 32 rows are generated kJitUnroll times per loop iteration with separate registers, as one straight-line block: the
+// driver's scheduler then issues the loads of all rounds before their uses (memory-level parallelism of kJitUnroll x columns per lane).
+constexpr int kJitUnroll = 4;
+std::string fixedRegs()
+{
+    std::ostringstream s;
+    s << "    .reg .b64 %n, %units, %unit, %nwarps64, %lane64, %begin, %end, %base, %sel, %off, %cnt, %errp, %w64, %a64;\n"
+      << "    .reg .b32 %xtid, %xntid, %xctaid, %xnctaid, %gtid, %warp, %lane, %nthr, %nwarps, %lt, %cur, %t0, %t1, %count;\n"
+      << "    .reg .pred %plane0, %perr_ov, %perr_dz, %pdone, %pdr;\n"
+      << "    .reg .b64 %row<" << kJitUnroll << ">, %dest64_<" << kJitUnroll << ">;\n"
+      << "    .reg .b32 %mask<" << kJitUnroll << ">;\n"
+      << "    .reg .pred %pin<" << kJitUnroll << ">, %pact<" << kJitUnroll << ">, %pbit<" << kJitUnroll << ">, %psel<" << kJitUnroll << ">, %prd<" << kJitUnroll << ">;\n";
+    return s.str();
+}
 
 }  // namespace
 
@@ -321,7 +331,7 @@ std::string generateFilterProjectPtx(const FpProgramDesc& P, FpKernelSignature& 
         g.vals.assign(nNodes, NodeVal()); g.done.assign(nNodes, false);
         g.inValues.assign(P.inputTypes.size(), ""); g.inNulls.assign(P.inputTypes.size(), "");
         for (int ch : sig.usedInputs) { g.inValues[ch] = "%in" + std::to_string(ch) + "v"; if (P.inputHasNulls[ch]) g.inNulls[ch] = "%in" + std::to_string(ch) + "n"; }
-        g.row = "%row"; g.errOverflow = "%perr_ov"; g.errDivZero = "%perr_dz";
+        g.row = "%row0"; g.errOverflow = "%perr_ov"; g.errDivZero = "%perr_dz";
     };
     auto inputRegDecl = [&]() {
         std::ostringstream s;
@@ -330,16 +340,36 @@ std::string generateFilterProjectPtx(const FpProgramDesc& P, FpKernelSignature& 
     };
     auto regDecl = [&](const Gen& g) {
         std::ostringstream s;
-        s << kFixedRegs << inputRegDecl();
+        s << fixedRegs() << inputRegDecl();
         if (g.n64) s << "    .reg .b64 %rd<" << g.n64 << ">;\n";
         if (g.n32) s << "    .reg .b32 %r<" << g.n32 << ">;\n";
         if (g.np) s << "    .reg .pred %p<" << g.np << ">;\n";
         return s.str();
     };
 
+    // INPUT nodes below a set of roots, in node order
+    auto inputNodesOf = [&](std::vector<int> roots) {
+        std::vector<bool> seen(nNodes, false);
+        while (!roots.empty()) {
+            const int k = roots.back(); roots.pop_back();
+            if (k < 0 || k >= nNodes || seen[k]) continue;
+            seen[k] = true;
+            if (P.nodes[k].op != PG_EX_INPUT) for (int o : {P.nodes[k].a, P.nodes[k].b, P.nodes[k].c}) roots.push_back(o);
+        }
+        std::vector<int> in;
+        for (int k = 0; k < nNodes; k++) if (seen[k] && P.nodes[k].op == PG_EX_INPUT) in.push_back(k);
+        return in;
+    };
+    // one evaluation context per unrolled round; all rounds' input loads are generated before any round's arithmetic and stores
+    struct RoundCtx { std::vector<NodeVal> vals; std::vector<bool> done; };
+    auto enter = [&](Gen& g, std::vector<RoundCtx>& ctx, int u, const std::string& guard) {
+        g.vals = ctx[u].vals; g.done = ctx[u].done; g.row = "%row" + std::to_string(u); g.guard = guard + std::to_string(u);
+    };
+    auto leave = [&](Gen& g, std::vector<RoundCtx>& ctx, int u) { ctx[u].vals = g.vals; ctx[u].done = g.done; };
+
     // ---- nullability of the projections (needs one dry generation pass of the projection sub-DAG) ----
     {
-        Gen dry(P); newGen(dry); dry.guard = "%pact";
+        Gen dry(P); newGen(dry); dry.guard = "%pact0";
         sig.projectionNullable.assign(P.projections.size(), false);
         for (size_t j = 0; j < P.projections.size(); j++) sig.projectionNullable[j] = !dry.node(P.projections[j]).nul.empty();
         if (!dry.fail.empty()) { sig.reason = dry.fail; return ""; }
@@ -347,21 +377,36 @@ std::string generateFilterProjectPtx(const FpProgramDesc& P, FpKernelSignature& 
 
     // ---- fp_filter: selection bitmask + per-unit counts ----
     if (P.filterNode >= 0) {
-        Gen g(P); newGen(g); g.guard = "%pin";
-        const NodeVal f = g.node(P.filterNode);
-        if (!g.fail.empty() || f.kind != 'b') { sig.reason = g.fail.empty() ? "filter is not boolean" : g.fail; return ""; }
-        g.emit("and.pred %psel, %pin, " + f.val + ";");
-        if (!f.nul.empty()) g.emit("and.pred %psel, %psel, " + g.notp(f.nul) + ";");      // only TRUE selects
+        Gen g(P); newGen(g);
+        const std::string U = std::to_string(kJitUnroll);
+        std::vector<RoundCtx> ctx(kJitUnroll);
+        for (auto& c : ctx) { c.vals.assign(nNodes, NodeVal()); c.done.assign(nNodes, false); }
+        const std::vector<int> filterInputs = inputNodesOf({P.filterNode});
+        for (int u = 0; u < kJitUnroll; u++) { enter(g, ctx, u, "%pin"); for (int k : filterInputs) g.node(k); leave(g, ctx, u); }
+        for (int u = 0; u < kJitUnroll; u++) {
+            const std::string su = std::to_string(u);
+            enter(g, ctx, u, "%pin");
+            const NodeVal f = g.node(P.filterNode);
+            if (!g.fail.empty() || f.kind != 'b') { sig.reason = g.fail.empty() ? "filter is not boolean" : g.fail; return ""; }
+            g.emit("and.pred %psel" + su + ", %pin" + su + ", " + f.val + ";");
+            if (!f.nul.empty()) g.emit("and.pred %psel" + su + ", %psel" + su + ", " + g.notp(f.nul) + ";");      // only TRUE selects
+        }
         std::ostringstream k;
         k << ".visible .entry fp_filter(\n"; paramList(g, k, true); k << "\n)\n{\n" << regDecl(g) << prologue(g, sig.usedInputs, true)
           << "    ld.param.u64 %sel, [p_sel];\n    cvta.to.global.u64 %sel, %sel;\n    ld.param.u64 %cnt, [p_cnt];\n    cvta.to.global.u64 %cnt, %cnt;\n"
           << "    ld.param.u64 %errp, [p_err];\n    cvta.to.global.u64 %errp, %errp;\n"
           << "F_UNIT:\n    setp.ge.u64 %pdone, %unit, %units;\n    @%pdone bra F_EXIT;\n"
           << "    shl.b64 %begin, %unit, 8;\n    add.u64 %end, %begin, " << kJitUnitRows << ";\n    min.u64 %end, %end, %n;\n    mov.u64 %base, %begin;\n    mov.u32 %count, 0;\n"
-          << "F_ROUND:\n    setp.ge.u64 %pdr, %base, %end;\n    @%pdr bra F_NEXT;\n    add.u64 %row, %base, %lane64;\n    setp.lt.u64 %pin, %row, %end;\n"
-          << g.body.str()
-          << "    vote.sync.ballot.b32 %mask, %psel, 0xffffffff;\n    shr.u64 %w64, %base, 5;\n    mad.lo.u64 %a64, %w64, 4, %sel;\n    @%plane0 st.global.u32 [%a64], %mask;\n"
-          << "    popc.b32 %t0, %mask;\n    add.u32 %count, %count, %t0;\n    add.u64 %base, %base, 32;\n    bra F_ROUND;\n"
+          << "F_ROUND:\n    setp.ge.u64 %pdr, %base, %end;\n    @%pdr bra F_NEXT;\n";
+        for (int u = 0; u < kJitUnroll; u++)
+            k << "    add.u64 %row" << u << ", %base, %lane64;\n    add.u64 %row" << u << ", %row" << u << ", " << 32 * u << ";\n    setp.lt.u64 %pin" << u << ", %row" << u << ", %end;\n";
+        k << g.body.str();
+        for (int u = 0; u < kJitUnroll; u++)
+            k << "    vote.sync.ballot.b32 %mask" << u << ", %psel" << u << ", 0xffffffff;\n"
+              << "    add.u64 %a64, %base, " << 32 * u << ";\n    setp.lt.u64 %prd" << u << ", %a64, %end;\n    and.pred %prd" << u << ", %prd" << u << ", %plane0;\n"
+              << "    shr.u64 %w64, %a64, 5;\n    mad.lo.u64 %a64, %w64, 4, %sel;\n    @%prd" << u << " st.global.u32 [%a64], %mask" << u << ";\n"
+              << "    popc.b32 %t0, %mask" << u << ";\n    add.u32 %count, %count, %t0;\n";
+        k << "    add.u64 %base, %base, " << 32 * kJitUnroll << ";\n    bra F_ROUND;\n"
           << "F_NEXT:\n    mad.lo.u64 %a64, %unit, 4, %cnt;\n    @%plane0 st.global.u32 [%a64], %count;\n    add.u64 %unit, %unit, %nwarps64;\n    bra F_UNIT;\n"
           << "F_EXIT:\n    @%perr_ov red.global.or.b32 [%errp], 1;\n    @%perr_dz red.global.or.b32 [%errp], 2;\n    ret;\n}\n\n";
         ptx << k.str();
@@ -369,39 +414,46 @@ std::string generateFilterProjectPtx(const FpProgramDesc& P, FpKernelSignature& 
 
     // ---- fp_project ----
     {
-        Gen g(P); newGen(g); g.guard = "%pact";
-        std::ostringstream stores;
-        for (size_t j = 0; j < P.projections.size(); j++) {
-            const NodeVal v = g.node(P.projections[j]);
-            if (!g.fail.empty()) break;
-            const int t = P.nodes[P.projections[j]].type;
-            const int w = (t == PG_TYPE_BIGINT || t == PG_TYPE_DOUBLE) ? 8 : (t == PG_TYPE_BOOLEAN ? 1 : 4);
-            if ((w == 1) != (v.kind == 'b')) { g.fail = "projection type / representation mismatch"; break; }
-            const std::string outv = "%out" + std::to_string(j) + "v", outn = "%out" + std::to_string(j) + "n";
-            std::string addr = g.r64();
-            g.emit("mad.lo.u64 " + addr + ", %dest64, " + std::to_string(w) + ", " + outv + ";");
-            if (w == 8) {
-                std::string x = v.val;
-                if (!v.nul.empty()) { x = g.r64(); g.emit("selp.b64 " + x + ", 0, " + v.val + ", " + v.nul + ";"); }
-                g.emit("@%pact st.global.b64 [" + addr + "], " + x + ";");
-            }
-            else if (w == 4) {
-                std::string x = g.r32();
-                g.emit("cvt.u32.u64 " + x + ", " + v.val + ";");
-                if (!v.nul.empty()) g.emit("selp.b32 " + x + ", 0, " + x + ", " + v.nul + ";");
-                g.emit("@%pact st.global.b32 [" + addr + "], " + x + ";");
-            }
-            else {
-                std::string x = g.r32();
-                g.emit("selp.u32 " + x + ", 1, 0, " + v.val + ";");
-                if (!v.nul.empty()) g.emit("selp.b32 " + x + ", 0, " + x + ", " + v.nul + ";");
-                g.emit("@%pact st.global.u8 [" + addr + "], " + x + ";");
-            }
-            if (sig.projectionNullable[j]) {
-                std::string an = g.r64(), x = g.r32();
-                g.emit("add.u64 " + an + ", " + outn + ", %dest64;");
-                g.emit("selp.u32 " + x + ", 1, 0, " + v.nul + ";");
-                g.emit("@%pact st.global.u8 [" + an + "], " + x + ";");
+        Gen g(P); newGen(g);
+        std::vector<RoundCtx> ctx(kJitUnroll);
+        for (auto& c : ctx) { c.vals.assign(nNodes, NodeVal()); c.done.assign(nNodes, false); }
+        const std::vector<int> projectInputs = inputNodesOf(P.projections);
+        for (int u = 0; u < kJitUnroll; u++) { enter(g, ctx, u, "%pact"); for (int k : projectInputs) g.node(k); leave(g, ctx, u); }
+        for (int u = 0; u < kJitUnroll && g.fail.empty(); u++) {
+            const std::string su = std::to_string(u), pact = "%pact" + su, dest = "%dest64_" + su;
+            enter(g, ctx, u, "%pact");
+            for (size_t j = 0; j < P.projections.size(); j++) {
+                const NodeVal v = g.node(P.projections[j]);
+                if (!g.fail.empty()) break;
+                const int t = P.nodes[P.projections[j]].type;
+                const int w = (t == PG_TYPE_BIGINT || t == PG_TYPE_DOUBLE) ? 8 : (t == PG_TYPE_BOOLEAN ? 1 : 4);
+                if ((w == 1) != (v.kind == 'b')) { g.fail = "projection type / representation mismatch"; break; }
+                const std::string outv = "%out" + std::to_string(j) + "v", outn = "%out" + std::to_string(j) + "n";
+                std::string addr = g.r64();
+                g.emit("mad.lo.u64 " + addr + ", " + dest + ", " + std::to_string(w) + ", " + outv + ";");
+                if (w == 8) {
+                    std::string x = v.val;
+                    if (!v.nul.empty()) { x = g.r64(); g.emit("selp.b64 " + x + ", 0, " + v.val + ", " + v.nul + ";"); }
+                    g.emit("@" + pact + " st.global.b64 [" + addr + "], " + x + ";");
+                }
+                else if (w == 4) {
+                    std::string x = g.r32();
+                    g.emit("cvt.u32.u64 " + x + ", " + v.val + ";");
+                    if (!v.nul.empty()) g.emit("selp.b32 " + x + ", 0, " + x + ", " + v.nul + ";");
+                    g.emit("@" + pact + " st.global.b32 [" + addr + "], " + x + ";");
+                }
+                else {
+                    std::string x = g.r32();
+                    g.emit("selp.u32 " + x + ", 1, 0, " + v.val + ";");
+                    if (!v.nul.empty()) g.emit("selp.b32 " + x + ", 0, " + x + ", " + v.nul + ";");
+                    g.emit("@" + pact + " st.global.u8 [" + addr + "], " + x + ";");
+                }
+                if (sig.projectionNullable[j]) {
+                    std::string an = g.r64(), x = g.r32();
+                    g.emit("add.u64 " + an + ", " + outn + ", " + dest + ";");
+                    g.emit("selp.u32 " + x + ", 1, 0, " + v.nul + ";");
+                    g.emit("@" + pact + " st.global.u8 [" + an + "], " + x + ";");
+                }
             }
         }
         if (!g.fail.empty()) { sig.reason = g.fail; return ""; }
@@ -420,13 +472,20 @@ std::string generateFilterProjectPtx(const FpProgramDesc& P, FpKernelSignature& 
           << "    shl.b64 %begin, %unit, 8;\n    add.u64 %end, %begin, " << kJitUnitRows << ";\n    min.u64 %end, %end, %n;\n    mov.u64 %base, %begin;\n";
         if (hasFilter) k << "    mad.lo.u64 %a64, %unit, 4, %off;\n    ld.global.u32 %cur, [%a64];\n";
         else k << "    cvt.u32.u64 %cur, %begin;\n";
-        k << "P_ROUND:\n    setp.ge.u64 %pdr, %base, %end;\n    @%pdr bra P_NEXT;\n    add.u64 %row, %base, %lane64;\n    setp.lt.u64 %pin, %row, %end;\n";
-        if (hasFilter) k << "    shr.u64 %w64, %base, 5;\n    mad.lo.u64 %a64, %w64, 4, %sel;\n    ld.global.u32 %mask, [%a64];\n";
-        else k << "    vote.sync.ballot.b32 %mask, %pin, 0xffffffff;\n";
-        k << "    shr.u32 %t0, %mask, %lane;\n    and.b32 %t0, %t0, 1;\n    setp.ne.u32 %pbit, %t0, 0;\n    and.pred %pact, %pin, %pbit;\n"
-          << "    and.b32 %t1, %mask, %lt;\n    popc.b32 %t1, %t1;\n    add.u32 %t1, %cur, %t1;\n    cvt.u64.u32 %dest64, %t1;\n"
-          << g.body.str()
-          << "    popc.b32 %t0, %mask;\n    add.u32 %cur, %cur, %t0;\n    add.u64 %base, %base, 32;\n    bra P_ROUND;\n"
+        k << "P_ROUND:\n    setp.ge.u64 %pdr, %base, %end;\n    @%pdr bra P_NEXT;\n";
+        for (int u = 0; u < kJitUnroll; u++) {
+            k << "    add.u64 %row" << u << ", %base, %lane64;\n    add.u64 %row" << u << ", %row" << u << ", " << 32 * u << ";\n    setp.lt.u64 %pin" << u << ", %row" << u << ", %end;\n";
+            if (hasFilter)
+                k << "    add.u64 %a64, %base, " << 32 * u << ";\n    setp.lt.u64 %prd" << u << ", %a64, %end;\n    shr.u64 %w64, %a64, 5;\n    mad.lo.u64 %a64, %w64, 4, %sel;\n"
+                  << "    mov.u32 %mask" << u << ", 0;\n    @%prd" << u << " ld.global.u32 %mask" << u << ", [%a64];\n";
+            else k << "    vote.sync.ballot.b32 %mask" << u << ", %pin" << u << ", 0xffffffff;\n";
+        }
+        for (int u = 0; u < kJitUnroll; u++)
+            k << "    shr.u32 %t0, %mask" << u << ", %lane;\n    and.b32 %t0, %t0, 1;\n    setp.ne.u32 %pbit" << u << ", %t0, 0;\n    and.pred %pact" << u << ", %pin" << u << ", %pbit" << u << ";\n"
+              << "    and.b32 %t1, %mask" << u << ", %lt;\n    popc.b32 %t1, %t1;\n    add.u32 %t1, %cur, %t1;\n    cvt.u64.u32 %dest64_" << u << ", %t1;\n"
+              << "    popc.b32 %t0, %mask" << u << ";\n    add.u32 %cur, %cur, %t0;\n";
+        k << g.body.str()
+          << "    add.u64 %base, %base, " << 32 * kJitUnroll << ";\n    bra P_ROUND;\n"
           << "P_NEXT:\n    add.u64 %unit, %unit, %nwarps64;\n    bra P_UNIT;\n"
           << "P_EXIT:\n    @%perr_ov red.global.or.b32 [%errp], 1;\n    @%perr_dz red.global.or.b32 [%errp], 2;\n    ret;\n}\n";
         ptx << k.str();

@@ -238,6 +238,14 @@ __device__ __forceinline__ int64_t denseRank(const DenseIndex& D, int64_t key)
     return (int64_t) r;
 }
 
+// membership only (pass A of the probe): one 8-byte bitmap word, no directory
+__device__ __forceinline__ bool denseContains(const DenseIndex& D, int64_t key)
+{
+    const uint64_t idx = (uint64_t) (key - D.minKey);
+    if (idx >= D.range) return false;
+    return (D.bitmap[idx >> 6] >> (idx & 63)) & 1ULL;
+}
+
 // Build OUTPUT columns are stored row-wise in key order ("payload rows"): one random 8..32-byte write per build row when the index
 // is built, one 8..32-byte read per matching probe row (sequential when the probe keys are clustered).
 constexpr int kMaxPayloadWords = 4;                 // payload rows of up to 32 bytes use the dense index
@@ -289,6 +297,255 @@ __global__ void denseGatherKernel(const __grid_constant__ DenseGatherParams P)
     }
 }
 
+// ---- range-partitioned build of the dense index (large builds) --------------------------------------------------------------
+// Setting one bitmap bit and scattering one payload row per build row, straight from the input order, costs four uncoalesced
+// accesses per row (bit, bitmap sector, directory word, payload row), each a separate L1TEX wavefront (~2 cycles per lane per SM)
+// and a DRAM row miss: ~12 ms for 150 M rows.  Large builds are therefore split first — one tile-staged radix pass on the high
+// bits of (key - min) into up to 1024 key-range buckets — after which ONE CTA owns one bucket: it builds the bucket's bitmap
+// slice and rank directory in shared memory (no global atomics), finds duplicates there, and scatters the payload rows into the
+// bucket's contiguous slice of the payload (a couple of MB: L2 hits, full lines to DRAM).  Records travel as a 32-bit offset
+// inside the bucket plus the packed payload words.
+constexpr int kPartBuckets = 1024;
+constexpr int kPartTile = 4096;                      // rows per CTA tile of the partition pass
+constexpr int kPartThreads = 512;
+constexpr int kPartRowsPerThread = kPartTile / kPartThreads;
+constexpr int kPartMaxShift = 20;                    // bucket = 2^20 key values: 128 KB of bitmap + 16 KB of directory in shared memory
+constexpr int kPartMinShift = 8;                     // a bucket is at least one 256-bit directory block
+constexpr int kFinalThreads = 1024;
+constexpr int64_t kPartBuildMinRows = 1 << 22;       // smaller builds scatter directly (their payload rows fit in L2 anyway)
+
+struct DensePartParams {
+    KeyColumn key; int64_t n, tiles; int64_t minKey; int32_t shift;
+    uint32_t* hist;                 // pass 1 out [kPartBuckets * tiles + 1], bucket-major
+    const uint32_t* base;           // exclusive scan of hist
+    PayloadLayout L;
+    const void* src[kMaxJoinColumns]; const uint8_t* srcNulls[kMaxJoinColumns];
+    uint32_t* recIdx;               // [nonNull] (key - min) & (2^shift - 1), bucket after bucket
+    uint64_t* recPay;               // [strideWords][nonNull] payload word planes
+    int64_t recCap;
+    // final pass
+    uint64_t* bitmap; uint32_t* prefix; int64_t blocks;   // global index: blocks x 256 bits, blocks directory entries
+    uint64_t* rows; unsigned int* duplicate;
+};
+
+// exclusive scan of one value per thread across the CTA (blockDim.x <= 1024); `scratch` has 33 words
+__device__ __forceinline__ uint32_t blockExclusiveScan(uint32_t v, uint32_t* scratch, uint32_t& total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+    if (lane == 31) scratch[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < nWarps ? scratch[lane] : 0, winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, winc, d); if (lane >= d) winc += o; }
+        scratch[lane] = winc - w;
+        if (lane == 31) scratch[32] = winc;
+    }
+    __syncthreads();
+    const uint32_t r = scratch[warp] + inc - v;
+    total = scratch[32];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kPartThreads) densePartHistKernel(const __grid_constant__ DensePartParams P)
+{
+    __shared__ uint32_t hist[kPartBuckets];
+    for (int64_t tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
+        for (int b = threadIdx.x; b < kPartBuckets; b += kPartThreads) hist[b] = 0;
+        __syncthreads();
+        int64_t key[kPartRowsPerThread]; bool valid[kPartRowsPerThread];
+#pragma unroll
+        for (int r = 0; r < kPartRowsPerThread; r++) { const int64_t row = tile * kPartTile + r * kPartThreads + threadIdx.x; valid[r] = row < P.n && loadKey(P.key, row, key[r]); }
+#pragma unroll
+        for (int r = 0; r < kPartRowsPerThread; r++) if (valid[r]) atomicAdd(&hist[(uint64_t) (key[r] - P.minKey) >> P.shift], 1u);
+        __syncthreads();
+        for (int b = threadIdx.x; b < kPartBuckets; b += kPartThreads) P.hist[(size_t) b * P.tiles + tile] = hist[b];
+        __syncthreads();
+    }
+}
+
+template <int SW>
+__global__ void __launch_bounds__(kPartThreads, 2) densePartScatterKernel(const __grid_constant__ DensePartParams P)
+{
+    extern __shared__ __align__(16) unsigned char partSmem[];
+    uint32_t* hist = (uint32_t*) partSmem;                 // [kPartBuckets] counts, then tile-local starts
+    uint32_t* gbase = hist + kPartBuckets;                  // [kPartBuckets] global position of the bucket's first record of this tile - local start
+    uint32_t* scratch = gbase + kPartBuckets;               // [64]
+    uint32_t* sIdx = scratch + 64;                          // [kPartTile]
+    uint16_t* sBucket = (uint16_t*) (sIdx + kPartTile);     // [kPartTile]
+    uint64_t* sPay = (uint64_t*) (sBucket + kPartTile);     // [SW][kPartTile]
+    const uint32_t idxMask = (1u << P.shift) - 1;
+    for (int64_t tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
+        for (int b = threadIdx.x; b < kPartBuckets; b += kPartThreads) hist[b] = 0;
+        __syncthreads();
+        // all independent global loads of the tile first (keys, payload columns, this tile's bucket bases), then the shared-memory ranking
+        int64_t key[kPartRowsPerThread]; bool valid[kPartRowsPerThread];
+        uint64_t w[kPartRowsPerThread][SW];
+#pragma unroll
+        for (int r = 0; r < kPartRowsPerThread; r++) {
+            const int64_t row = tile * kPartTile + r * kPartThreads + threadIdx.x;
+            valid[r] = row < P.n && loadKey(P.key, row, key[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < kPartRowsPerThread; r++)
+#pragma unroll
+            for (int k = 0; k < SW; k++) w[r][k] = 0;
+        for (int c = 0; c < P.L.nCols; c++) {          // column by column: the loads of all rows of the thread are in flight together
+            const PayloadColumn pc = P.L.cols[c];
+            uint64_t v[kPartRowsPerThread]; uint8_t isNull[kPartRowsPerThread];
+#pragma unroll
+            for (int r = 0; r < kPartRowsPerThread; r++) {
+                const int64_t row = tile * kPartTile + r * kPartThreads + threadIdx.x;
+                v[r] = valid[r] ? loadWidth(P.src[c], row, pc.width) : 0;
+                isNull[r] = (valid[r] && pc.nullOffset >= 0) ? P.srcNulls[c][row] : 0;
+            }
+#pragma unroll
+            for (int r = 0; r < kPartRowsPerThread; r++) {
+#pragma unroll
+                for (int k = 0; k < SW; k++) {
+                    if (k == pc.offset >> 3) w[r][k] |= v[r] << (8 * (pc.offset & 7));
+                    if (isNull[r] && k == pc.nullOffset >> 3) w[r][k] |= 1ULL << (8 * (pc.nullOffset & 7));
+                }
+            }
+        }
+        const uint32_t gb0 = P.base[(size_t) (2 * threadIdx.x) * P.tiles + tile], gb1 = P.base[(size_t) (2 * threadIdx.x + 1) * P.tiles + tile];
+        uint32_t idx[kPartRowsPerThread]; uint32_t slot[kPartRowsPerThread];   // slot = bucket << 16 | rank inside (tile, bucket); 0xFFFFFFFF = no record
+#pragma unroll
+        for (int r = 0; r < kPartRowsPerThread; r++) {
+            slot[r] = 0xFFFFFFFFu; idx[r] = 0;
+            if (valid[r]) {
+                const uint64_t full = (uint64_t) (key[r] - P.minKey);
+                const uint32_t b = (uint32_t) (full >> P.shift);
+                idx[r] = (uint32_t) full & idxMask;
+                slot[r] = b << 16 | atomicAdd(&hist[b], 1u);
+            }
+        }
+        __syncthreads();
+        // tile-local starts (2 buckets per thread) and the global position of each bucket's run
+        const uint32_t c0 = hist[2 * threadIdx.x], c1 = hist[2 * threadIdx.x + 1];
+        uint32_t total;
+        const uint32_t start = blockExclusiveScan(c0 + c1, scratch, total);
+        hist[2 * threadIdx.x] = start; hist[2 * threadIdx.x + 1] = start + c0;
+        gbase[2 * threadIdx.x] = gb0 - start;
+        gbase[2 * threadIdx.x + 1] = gb1 - (start + c0);
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kPartRowsPerThread; r++) {
+            if (slot[r] == 0xFFFFFFFFu) continue;
+            const uint32_t b = slot[r] >> 16, pos = hist[b] + (slot[r] & 0xFFFFu);
+            sIdx[pos] = idx[r]; sBucket[pos] = (uint16_t) b;
+#pragma unroll
+            for (int k = 0; k < SW; k++) sPay[k * kPartTile + pos] = w[r][k];
+        }
+        __syncthreads();
+        // write out bucket run after bucket run: neighbouring threads write neighbouring records
+        for (uint32_t j = threadIdx.x; j < total; j += kPartThreads) {
+            const size_t dst = (size_t) gbase[sBucket[j]] + j;
+            P.recIdx[dst] = sIdx[j];
+#pragma unroll
+            for (int k = 0; k < SW; k++) P.recPay[(size_t) k * P.recCap + dst] = sPay[k * kPartTile + j];
+        }
+        __syncthreads();
+    }
+}
+
+// One CTA per bucket: bitmap slice + rank directory built in shared memory from the bucket's records, published to the global index.
+__global__ void __launch_bounds__(kFinalThreads) densePartIndexKernel(const __grid_constant__ DensePartParams P)
+{
+    extern __shared__ __align__(16) unsigned char finalSmem[];
+    const int wordsPerBucket = 1 << (P.shift - 6), blocksPerBucket = 1 << (P.shift - 8);
+    uint64_t* bm = (uint64_t*) finalSmem;                          // [wordsPerBucket]
+    uint32_t* dir = (uint32_t*) (bm + wordsPerBucket);              // [blocksPerBucket] keys of the bucket before the block
+    uint32_t* scratch = dir + blocksPerBucket;                      // [64]
+    uint32_t* bm32 = (uint32_t*) bm;
+    for (int b = blockIdx.x; b < kPartBuckets; b += gridDim.x) {
+        const int64_t firstBlock = (int64_t) b << (P.shift - 8);
+        if (firstBlock >= P.blocks) break;
+        const uint32_t s = P.base[(size_t) b * P.tiles], e = P.base[(size_t) (b + 1) * P.tiles];
+        for (int i = threadIdx.x; i < wordsPerBucket; i += kFinalThreads) bm[i] = 0;
+        __syncthreads();
+        for (uint32_t i0 = s; i0 < e; i0 += 4 * kFinalThreads) {
+            uint32_t idx[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) { const uint32_t i = i0 + q * kFinalThreads + threadIdx.x; idx[q] = i < e ? P.recIdx[i] : 0xFFFFFFFFu; }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (idx[q] == 0xFFFFFFFFu) continue;
+                const uint32_t bit = 1u << (idx[q] & 31);
+                if (atomicOr(&bm32[idx[q] >> 5], bit) & bit) *P.duplicate = 1;   // the same key twice: not unique → hash path
+            }
+        }
+        __syncthreads();
+        // rank directory: exclusive popcount scan over the bucket's 256-bit blocks
+        const int per = (blocksPerBucket + kFinalThreads - 1) / kFinalThreads;
+        uint32_t mine = 0;
+        for (int q = 0; q < per; q++) {
+            const int blk = threadIdx.x * per + q;
+            if (blk < blocksPerBucket) mine += __popcll(bm[4 * blk]) + __popcll(bm[4 * blk + 1]) + __popcll(bm[4 * blk + 2]) + __popcll(bm[4 * blk + 3]);
+        }
+        uint32_t total;
+        uint32_t run = blockExclusiveScan(mine, scratch, total);
+        for (int q = 0; q < per; q++) {
+            const int blk = threadIdx.x * per + q;
+            if (blk < blocksPerBucket) { dir[blk] = run; run += __popcll(bm[4 * blk]) + __popcll(bm[4 * blk + 1]) + __popcll(bm[4 * blk + 2]) + __popcll(bm[4 * blk + 3]); }
+        }
+        __syncthreads();
+        const int64_t liveBlocks = min((int64_t) blocksPerBucket, P.blocks - firstBlock);
+        for (int64_t i = threadIdx.x; i < liveBlocks * 4; i += kFinalThreads) P.bitmap[firstBlock * 4 + i] = bm[i];
+        for (int64_t i = threadIdx.x; i < liveBlocks; i += kFinalThreads) P.prefix[firstBlock + i] = s + dir[i];
+        __syncthreads();
+    }
+}
+
+// kPayloadParts consecutive CTAs per bucket (so the CTAs in flight cover ~20 buckets = ~40 MB of payload rows: L2 resident until the
+// sectors are complete): each stages the bucket's slice of the finished index in shared memory and moves its share of the records'
+// payload words to their ranks.
+constexpr int kPayloadParts = 8;
+template <int SW>
+__global__ void __launch_bounds__(kFinalThreads) densePartPayloadKernel(const __grid_constant__ DensePartParams P)
+{
+    extern __shared__ __align__(16) unsigned char finalSmem[];
+    const int wordsPerBucket = 1 << (P.shift - 6), blocksPerBucket = 1 << (P.shift - 8);
+    uint64_t* bm = (uint64_t*) finalSmem;
+    uint32_t* dir = (uint32_t*) (bm + wordsPerBucket);
+    const int b = blockIdx.x / kPayloadParts, part = blockIdx.x % kPayloadParts;
+    const int64_t firstBlock = (int64_t) b << (P.shift - 8);
+    if (firstBlock >= P.blocks) return;
+    const uint32_t s = P.base[(size_t) b * P.tiles], e = P.base[(size_t) (b + 1) * P.tiles];
+    const uint32_t len = e - s, chunk = (len + kPayloadParts - 1) / kPayloadParts;
+    const uint32_t lo = s + min(len, part * chunk), hi = s + min(len, (part + 1) * chunk);
+    if (lo >= hi) return;
+    const int64_t liveBlocks = min((int64_t) blocksPerBucket, P.blocks - firstBlock);
+    for (int64_t i = threadIdx.x; i < liveBlocks * 4; i += kFinalThreads) bm[i] = P.bitmap[firstBlock * 4 + i];
+    for (int64_t i = threadIdx.x; i < liveBlocks; i += kFinalThreads) dir[i] = P.prefix[firstBlock + i];     // already includes the keys before the bucket
+    __syncthreads();
+    for (uint32_t i0 = lo; i0 < hi; i0 += 4 * kFinalThreads) {
+        uint32_t idx[4]; uint64_t w[4][SW];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t i = i0 + q * kFinalThreads + threadIdx.x;
+            idx[q] = i < hi ? P.recIdx[i] : 0xFFFFFFFFu;
+#pragma unroll
+            for (int k = 0; k < SW; k++) w[q][k] = i < hi ? P.recPay[(size_t) k * P.recCap + i] : 0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (idx[q] == 0xFFFFFFFFu) continue;
+            const uint32_t blk = idx[q] >> 8, wi = (idx[q] >> 6) & 3u;
+            uint32_t r = dir[blk] + __popcll(bm[idx[q] >> 6] & ((1ULL << (idx[q] & 63)) - 1));
+            if (wi > 0) r += __popcll(bm[4 * blk]);
+            if (wi > 1) r += __popcll(bm[4 * blk + 1]);
+            if (wi > 2) r += __popcll(bm[4 * blk + 2]);
+#pragma unroll
+            for (int k = 0; k < SW; k++) P.rows[(size_t) r * SW + k] = w[q][k];
+        }
+    }
+}
+
 constexpr int kUnitRounds = 4;
 constexpr int kUnitRows = 32 * kUnitRounds;     // rows owned by one warp per step
 constexpr int kPreload8 = 4;                    // 8-byte probe output columns whose loads are issued before the index lookups
@@ -302,6 +559,7 @@ struct DenseProbeParams {
     KeyColumn key; DenseIndex D; int64_t n; int64_t units;
     int32_t outer;
     uint32_t* unitCounts;          // pass A out [units + 1]: matches per unit
+    uint32_t* unitMask;            // pass A out / pass B in [units][kUnitRounds]: which lanes of each round matched
     const uint32_t* unitOffsets;   // pass B in: exclusive scan of the counts
     int32_t nProbe8, nProbe4, nProbe1, nProbeNulls;
     CopyColumn probe8[kMaxJoinColumns], probe4[kMaxJoinColumns], probe1[kMaxJoinColumns];
@@ -323,10 +581,15 @@ __global__ void __launch_bounds__(256) denseCountKernel(const __grid_constant__ 
             const int64_t row = unit * kUnitRows + j * 32 + lane;
             valid[j] = row < P.n && loadKey(P.key, row, key[j]);
         }
-        uint32_t c = 0;
+        uint32_t c = 0, mine = 0;
 #pragma unroll
-        for (int j = 0; j < kUnitRounds; j++) c += __popc(__ballot_sync(0xffffffffu, valid[j] && denseRank(P.D, key[j]) >= 0));
+        for (int j = 0; j < kUnitRounds; j++) {
+            const unsigned m = __ballot_sync(0xffffffffu, valid[j] && denseContains(P.D, key[j]));
+            c += __popc(m);
+            if (lane == j) mine = m;
+        }
         if (lane == 0) P.unitCounts[unit] = c;
+        if (lane < kUnitRounds) P.unitMask[unit * kUnitRounds + lane] = mine;
     }
 }
 
@@ -348,15 +611,25 @@ __global__ void __launch_bounds__(256) denseEmitKernel(const __grid_constant__ D
     const unsigned lt = (1u << lane) - 1;
     const int64_t warpId = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
     for (int64_t unit = warpId; unit < P.units; unit += nWarps) {
-        int64_t key[kUnitRounds]; bool valid[kUnitRounds]; bool inRange[kUnitRounds];
+        // inner join: pass A left one match bit per row; units without a match are skipped before any load, and rows without a match
+        // are never loaded (sparse joins touch only the sectors of matching rows)
+        uint32_t mk[kUnitRounds];
+#pragma unroll
+        for (int j = 0; j < kUnitRounds; j++) mk[j] = 0xffffffffu;
+        if (!P.outer) {
+            const uint4 m4 = *reinterpret_cast<const uint4*>(P.unitMask + unit * kUnitRounds);
+            mk[0] = m4.x; mk[1] = m4.y; mk[2] = m4.z; mk[3] = m4.w;
+            if ((m4.x | m4.y | m4.z | m4.w) == 0) continue;
+        }
+        int64_t key[kUnitRounds]; bool valid[kUnitRounds]; bool emit[kUnitRounds];
         uint64_t pv[kUnitRounds][kPreload8];
 #pragma unroll
         for (int j = 0; j < kUnitRounds; j++) {
             const int64_t row = unit * kUnitRows + j * 32 + lane;
-            inRange[j] = row < P.n;
-            valid[j] = inRange[j] && loadKey(P.key, row, key[j]);
+            emit[j] = row < P.n && ((mk[j] >> lane) & 1u);
+            valid[j] = emit[j] && loadKey(P.key, row, key[j]);
 #pragma unroll
-            for (int c = 0; c < kPreload8; c++) { pv[j][c] = 0; if (c < P.nProbe8 && inRange[j]) pv[j][c] = ldStream64((const uint64_t*) P.probe8[c].src + row); }
+            for (int c = 0; c < kPreload8; c++) { pv[j][c] = 0; if (c < P.nProbe8 && emit[j]) pv[j][c] = ldStream64((const uint64_t*) P.probe8[c].src + row); }
         }
         int64_t rank[kUnitRounds];
 #pragma unroll
@@ -367,40 +640,67 @@ __global__ void __launch_bounds__(256) denseEmitKernel(const __grid_constant__ D
 #pragma unroll
             for (int k = 0; k < SW; k++) pw[j][k] = rank[j] >= 0 ? P.rows[rank[j] * SW + k] : 0;
         uint32_t cursor = P.outer ? (uint32_t) (unit * kUnitRows) : P.unitOffsets[unit];
+        uint32_t o[kUnitRounds];
 #pragma unroll
         for (int j = 0; j < kUnitRounds; j++) {
-            const bool emit = inRange[j] && (rank[j] >= 0 || P.outer);
-            const unsigned m = __ballot_sync(0xffffffffu, emit);
-            if (emit) {
-                const int64_t row = unit * kUnitRows + j * 32 + lane;
-                const uint32_t o = cursor + __popc(m & lt);
-                const bool unmatched = rank[j] < 0;
-#pragma unroll
-                for (int c = 0; c < kPreload8; c++) if (c < P.nProbe8) ((uint64_t*) P.probe8[c].dst)[o] = pv[j][c];
-                for (int c = kPreload8; c < P.nProbe8; c++) ((uint64_t*) P.probe8[c].dst)[o] = ldStream64((const uint64_t*) P.probe8[c].src + row);
-                for (int c = 0; c < P.nProbe4; c++) ((uint32_t*) P.probe4[c].dst)[o] = ldStream32((const uint32_t*) P.probe4[c].src + row);
-                for (int c = 0; c < P.nProbe1; c++) ((uint8_t*) P.probe1[c].dst)[o] = ((const uint8_t*) P.probe1[c].src)[row];
-                for (int c = 0; c < P.nProbeNulls; c++) P.probeNulls[c].dst[o] = P.probeNulls[c].src ? P.probeNulls[c].src[row] : 0;
-                for (int c = 0; c < P.nBuild8; c++) {
-                    const BuildField& f = P.build8[c];
-                    const bool isNull = unmatched || (f.nullWord >= 0 && ((payloadWord<SW>(pw[j], f.nullWord) >> f.nullShift) & 0xff));
-                    ((uint64_t*) f.dst)[o] = isNull ? 0 : payloadWord<SW>(pw[j], f.word);
-                    if (f.dstNulls) f.dstNulls[o] = isNull;
-                }
-                for (int c = 0; c < P.nBuild4; c++) {
-                    const BuildField& f = P.build4[c];
-                    const bool isNull = unmatched || (f.nullWord >= 0 && ((payloadWord<SW>(pw[j], f.nullWord) >> f.nullShift) & 0xff));
-                    ((uint32_t*) f.dst)[o] = isNull ? 0 : (uint32_t) (payloadWord<SW>(pw[j], f.word) >> f.shift);
-                    if (f.dstNulls) f.dstNulls[o] = isNull;
-                }
-                for (int c = 0; c < P.nBuild1; c++) {
-                    const BuildField& f = P.build1[c];
-                    const bool isNull = unmatched || (f.nullWord >= 0 && ((payloadWord<SW>(pw[j], f.nullWord) >> f.nullShift) & 0xff));
-                    ((uint8_t*) f.dst)[o] = isNull ? 0 : (uint8_t) (payloadWord<SW>(pw[j], f.word) >> f.shift);
-                    if (f.dstNulls) f.dstNulls[o] = isNull;
-                }
-            }
+            const unsigned m = P.outer ? __ballot_sync(0xffffffffu, emit[j]) : mk[j];
+            o[j] = cursor + __popc(m & lt);
             cursor += __popc(m);
+        }
+        const int64_t row0 = unit * kUnitRows + lane;
+        // column by column, the rounds innermost: pointers and field descriptors are fetched once per unit, not once per round
+#pragma unroll
+        for (int c = 0; c < kPreload8; c++) if (c < P.nProbe8) {
+            uint64_t* dst = (uint64_t*) P.probe8[c].dst;
+#pragma unroll
+            for (int j = 0; j < kUnitRounds; j++) if (emit[j]) dst[o[j]] = pv[j][c];
+        }
+        for (int c = kPreload8; c < P.nProbe8; c++) {
+            const uint64_t* src = (const uint64_t*) P.probe8[c].src; uint64_t* dst = (uint64_t*) P.probe8[c].dst;
+#pragma unroll
+            for (int j = 0; j < kUnitRounds; j++) if (emit[j]) dst[o[j]] = ldStream64(src + row0 + j * 32);
+        }
+        for (int c = 0; c < P.nProbe4; c++) {
+            const uint32_t* src = (const uint32_t*) P.probe4[c].src; uint32_t* dst = (uint32_t*) P.probe4[c].dst;
+#pragma unroll
+            for (int j = 0; j < kUnitRounds; j++) if (emit[j]) dst[o[j]] = ldStream32(src + row0 + j * 32);
+        }
+        for (int c = 0; c < P.nProbe1; c++) {
+            const uint8_t* src = (const uint8_t*) P.probe1[c].src; uint8_t* dst = (uint8_t*) P.probe1[c].dst;
+#pragma unroll
+            for (int j = 0; j < kUnitRounds; j++) if (emit[j]) dst[o[j]] = src[row0 + j * 32];
+        }
+        for (int c = 0; c < P.nProbeNulls; c++) {
+            const uint8_t* src = P.probeNulls[c].src; uint8_t* dst = P.probeNulls[c].dst;
+#pragma unroll
+            for (int j = 0; j < kUnitRounds; j++) if (emit[j]) dst[o[j]] = src ? src[row0 + j * 32] : 0;
+        }
+        for (int c = 0; c < P.nBuild8; c++) {
+            const BuildField f = P.build8[c];
+#pragma unroll
+            for (int j = 0; j < kUnitRounds; j++) if (emit[j]) {
+                const bool isNull = rank[j] < 0 || (f.nullWord >= 0 && ((payloadWord<SW>(pw[j], f.nullWord) >> f.nullShift) & 0xff));
+                ((uint64_t*) f.dst)[o[j]] = isNull ? 0 : payloadWord<SW>(pw[j], f.word);
+                if (f.dstNulls) f.dstNulls[o[j]] = isNull;
+            }
+        }
+        for (int c = 0; c < P.nBuild4; c++) {
+            const BuildField f = P.build4[c];
+#pragma unroll
+            for (int j = 0; j < kUnitRounds; j++) if (emit[j]) {
+                const bool isNull = rank[j] < 0 || (f.nullWord >= 0 && ((payloadWord<SW>(pw[j], f.nullWord) >> f.nullShift) & 0xff));
+                ((uint32_t*) f.dst)[o[j]] = isNull ? 0 : (uint32_t) (payloadWord<SW>(pw[j], f.word) >> f.shift);
+                if (f.dstNulls) f.dstNulls[o[j]] = isNull;
+            }
+        }
+        for (int c = 0; c < P.nBuild1; c++) {
+            const BuildField f = P.build1[c];
+#pragma unroll
+            for (int j = 0; j < kUnitRounds; j++) if (emit[j]) {
+                const bool isNull = rank[j] < 0 || (f.nullWord >= 0 && ((payloadWord<SW>(pw[j], f.nullWord) >> f.nullShift) & 0xff));
+                ((uint8_t*) f.dst)[o[j]] = isNull ? 0 : (uint8_t) (payloadWord<SW>(pw[j], f.word) >> f.shift);
+                if (f.dstNulls) f.dstNulls[o[j]] = isNull;
+            }
         }
     }
 }
@@ -655,25 +955,19 @@ public:
         PG_CUDA(cudaMemsetAsync(ls->bitmap.ptr, 0, (size_t) blocks * 32, stream));
         DeviceBuffer dup; dup.reserve(16);
         PG_CUDA(cudaMemsetAsync(dup.ptr, 0, 16, stream));
-        PG_LAUNCH(this, denseSetBitsKernel, grid, 256, 0, kc, n, (int64_t) h[0], ls->bitmap.as<unsigned long long>(), dup.as<unsigned int>());
-        unsigned int isDup = 0;
-        PG_CUDA(cudaMemcpyAsync(&isDup, dup.ptr, 4, cudaMemcpyDeviceToHost, stream));
-        PG_CUDA(cudaStreamSynchronize(stream));
-        if (isDup) { ls->bitmap.release(); return false; }
-        // rank directory
-        DeviceBuffer counts, temp; counts.reserve((size_t) (blocks + 1) * 4);
+        // large builds with a payload over a range of at most 2^30: range-partition first (see DensePartParams)
+        int64_t partMinRows = kPartBuildMinRows;
+        if (const char* e = getenv("PG_JOIN_BUCKET_MIN_ROWS")) partMinRows = atoll(e);     // tests force the partitioned build on small inputs
+        int shift = kPartMinShift;
+        while (((range - 1) >> shift) >= (uint64_t) kPartBuckets) shift++;
+        // (the partitioned build stages range/8 bytes of bitmap per pass: it pays only for reasonably dense key sets)
+        const bool partitioned = n >= partMinRows && !ls->outputChannels.empty() && shift <= kPartMaxShift && range <= (uint64_t) 16 * (uint64_t) nonNull;
+        if (!partitioned) PG_LAUNCH(this, denseSetBitsKernel, grid, 256, 0, kc, n, (int64_t) h[0], ls->bitmap.as<unsigned long long>(), dup.as<unsigned int>());
         ls->prefix.reserve((size_t) (blocks + 1) * 4);
-        PG_CUDA(cudaMemsetAsync(counts.as<uint32_t>() + blocks, 0, 4, stream));
-        PG_LAUNCH(this, denseBlockCountKernel, (int) std::min<int64_t>(divUp(blocks, 256), numSMs * 16), 256, 0, ls->bitmap.as<uint64_t>(), blocks, counts.as<uint32_t>());
-        size_t tb = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tb, counts.as<uint32_t>(), ls->prefix.as<uint32_t>(), (int) (blocks + 1), stream);
-        temp.reserve(tb);
-        cub::DeviceScan::ExclusiveSum(temp.ptr, tb, counts.as<uint32_t>(), ls->prefix.as<uint32_t>(), (int) (blocks + 1), stream);
-        stats.kernel_launches += 2;
         ls->minKey = h[0]; ls->range = range;
         // build output columns as payload rows in key order
         DenseGatherParams G{};
-        G.key = kc; G.D = ls->denseView(); G.n = n;
+        G.key = kc; G.n = n;
         G.L = payloadLayout; G.L.nCols = (int) ls->outputChannels.size();
         for (size_t i = 0; i < ls->outputChannels.size(); i++) {
             const int ch = ls->outputChannels[i];
@@ -683,8 +977,68 @@ public:
         ls->payloadRows.accounting = &ls->deviceBytes;
         ls->payloadRows.reserve(std::max<size_t>((size_t) nonNull * G.L.strideWords * 8, 16));
         G.rows = ls->payloadRows.as<uint64_t>();
-        if (G.L.nCols) PG_LAUNCH(this, denseGatherKernel, grid, 256, 0, G);
-        PG_CUDA(cudaStreamSynchronize(stream));
+        auto failOnDuplicate = [&]() {
+            unsigned int isDup = 0;
+            PG_CUDA(cudaMemcpyAsync(&isDup, dup.ptr, 4, cudaMemcpyDeviceToHost, stream));
+            PG_CUDA(cudaStreamSynchronize(stream));
+            if (isDup) { ls->bitmap.release(); ls->prefix.release(); ls->payloadRows.release(); }
+            return isDup != 0;
+        };
+        if (partitioned) {
+            DensePartParams B{};
+            DeviceBuffer hist, base, temp, recIdx, recPay;
+            B.key = kc; B.n = n; B.tiles = divUp(n, kPartTile); B.minKey = (int64_t) h[0]; B.shift = shift;
+            const size_t histN = (size_t) kPartBuckets * B.tiles + 1;
+            hist.reserve(histN * 4); base.reserve(histN * 4);
+            B.hist = hist.as<uint32_t>(); B.base = base.as<uint32_t>();
+            PG_CUDA(cudaMemsetAsync(B.hist + histN - 1, 0, 4, stream));
+            const int SW = G.L.strideWords;
+            // tile staging: counts/starts + global bases + scan scratch + idx + bucket + payload planes
+            const size_t partSmem = (size_t) kPartBuckets * 8 + 256 + (size_t) kPartTile * (4 + 2 + 8 * SW);
+            const size_t finalSmem = ((size_t) 1 << (shift - 3)) + ((size_t) 4 << (shift - 8)) + 256;
+            const int pgrid = (int) std::min<int64_t>(B.tiles, (int64_t) numSMs * (partSmem > 100 * 1024 ? 1 : partSmem > 70 * 1024 ? 2 : 3));
+            PG_LAUNCH(this, densePartHistKernel, (int) std::min<int64_t>(B.tiles, numSMs * 4), kPartThreads, 0, B);
+            size_t tb = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tb, B.hist, base.as<uint32_t>(), (int) histN, stream);
+            temp.reserve(tb);
+            cub::DeviceScan::ExclusiveSum(temp.ptr, tb, B.hist, base.as<uint32_t>(), (int) histN, stream);
+            stats.kernel_launches += 2;
+            recIdx.reserve((size_t) nonNull * 4); recPay.reserve((size_t) nonNull * SW * 8);
+            B.recIdx = recIdx.as<uint32_t>(); B.recPay = recPay.as<uint64_t>(); B.recCap = nonNull;
+            B.L = G.L;
+            for (int i = 0; i < G.L.nCols; i++) { B.src[i] = G.src[i]; B.srcNulls[i] = G.srcNulls[i]; }
+            B.bitmap = ls->bitmap.as<uint64_t>(); B.prefix = ls->prefix.as<uint32_t>(); B.blocks = blocks;
+            B.rows = G.rows; B.duplicate = dup.as<unsigned int>();
+            const int usedBuckets = (int) (((range - 1) >> shift) + 1);
+            const int fgrid = usedBuckets;
+#define PG_PART_BUILD(SWV) do { \
+                PG_CUDA(cudaFuncSetAttribute(densePartScatterKernel<SWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) partSmem)); \
+                PG_CUDA(cudaFuncSetAttribute(densePartIndexKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) finalSmem)); \
+                PG_CUDA(cudaFuncSetAttribute(densePartPayloadKernel<SWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) finalSmem)); \
+                PG_LAUNCH(this, densePartScatterKernel<SWV>, pgrid, kPartThreads, partSmem, B); \
+                PG_LAUNCH(this, densePartIndexKernel, fgrid, kFinalThreads, finalSmem, B); \
+                PG_LAUNCH(this, densePartPayloadKernel<SWV>, fgrid * kPayloadParts, kFinalThreads, finalSmem, B); } while (0)
+            if (SW == 1) PG_PART_BUILD(1); else if (SW == 2) PG_PART_BUILD(2); else PG_PART_BUILD(4);
+#undef PG_PART_BUILD
+            const uint32_t total = (uint32_t) nonNull;
+            PG_CUDA(cudaMemcpyAsync(ls->prefix.as<uint32_t>() + blocks, &total, 4, cudaMemcpyHostToDevice, stream));
+            if (failOnDuplicate()) return false;     // (also waits for the kernels: the temporaries above are released on return)
+        }
+        else {
+            if (failOnDuplicate()) return false;
+            // rank directory
+            DeviceBuffer counts, temp; counts.reserve((size_t) (blocks + 1) * 4);
+            PG_CUDA(cudaMemsetAsync(counts.as<uint32_t>() + blocks, 0, 4, stream));
+            PG_LAUNCH(this, denseBlockCountKernel, (int) std::min<int64_t>(divUp(blocks, 256), numSMs * 16), 256, 0, ls->bitmap.as<uint64_t>(), blocks, counts.as<uint32_t>());
+            size_t tb = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tb, counts.as<uint32_t>(), ls->prefix.as<uint32_t>(), (int) (blocks + 1), stream);
+            temp.reserve(tb);
+            cub::DeviceScan::ExclusiveSum(temp.ptr, tb, counts.as<uint32_t>(), ls->prefix.as<uint32_t>(), (int) (blocks + 1), stream);
+            stats.kernel_launches += 2;
+            G.D = ls->denseView();
+            if (G.L.nCols) PG_LAUNCH(this, denseGatherKernel, grid, 256, 0, G);
+            PG_CUDA(cudaStreamSynchronize(stream));
+        }
         ls->nullKeyCount = n - nonNull;
         ls->dense = true;
         // the unsorted copies of the build columns are no longer needed
@@ -704,7 +1058,7 @@ class LookupJoinOp : public Operator {
     KeyLayout layout;
     PageStager stager;
     bool finishing = false, hasPending = false;
-    DeviceBuffer matchHead, counts, offsets, scanTemp;
+    DeviceBuffer matchHead, counts, offsets, scanTemp, unitMask;
     std::vector<DeviceBuffer> outValues, outNulls;
     std::vector<PinnedBuffer> hostValues, hostNulls;
     std::vector<pg_block> outBlocks;
@@ -733,7 +1087,7 @@ public:
             if (types[oc] == PG_TYPE_VARCHAR) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR probe output channels are not on the GPU path");
             need(oc);
         }
-        for (DeviceBuffer* d : {&matchHead, &counts, &offsets, &scanTemp}) d->accounting = &stats.device_bytes;
+        for (DeviceBuffer* d : {&matchHead, &counts, &offsets, &scanTemp, &unitMask}) d->accounting = &stats.device_bytes;
     }
 
     // LookupJoinOperator.needsInput :198-210: blocked until the lookup source future completes
@@ -848,6 +1202,8 @@ public:
             counts.reserve((size_t) (P.units + 1) * 4); offsets.reserve((size_t) (P.units + 1) * 4);
             PG_CUDA(cudaMemsetAsync(counts.as<uint32_t>() + P.units, 0, 4, stream));
             P.unitCounts = counts.as<uint32_t>();
+            unitMask.reserve((size_t) P.units * kUnitRounds * 4);
+            P.unitMask = unitMask.as<uint32_t>();
             PG_LAUNCH(this, denseCountKernel, grid, 256, 0, P);
             size_t tb = 0;
             cub::DeviceScan::ExclusiveSum(nullptr, tb, counts.as<uint32_t>(), offsets.as<uint32_t>(), (int) (P.units + 1), stream);

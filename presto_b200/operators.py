@@ -317,6 +317,29 @@ class FilterAndProjectOperator(Operator):
         backend.check(backend.filter_project_create(C.byref(cfg), C.byref(handle)))
         super().__init__(backend, handle)
 
+    @staticmethod
+    def explain(input_types: Sequence[int], program, nullable_inputs: Sequence[int] = (), backend=None) -> str:
+        """The PTX generated for ``program`` when the channels in ``nullable_inputs`` carry null maps (no GPU needed)."""
+        if backend is None:
+            from ._lib import load_library
+            backend = load_library()
+        cfg = abi.pg_filter_project_config()
+        it = abi.i32_array(input_types)
+        nodes = program.c_nodes()
+        proj = abi.i32_array(program.projections)
+        cfg.n_input_channels, cfg.input_types = len(input_types), it
+        cfg.n_nodes, cfg.nodes = len(program.nodes), nodes
+        cfg.filter_node = program.filter
+        cfg.n_projections, cfg.projection_nodes = len(program.projections), proj
+        mask = 0
+        for ch in nullable_inputs:
+            mask |= 1 << ch
+        need = C.c_size_t()
+        backend.check(backend.filter_project_explain(C.byref(cfg), mask, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        backend.check(backend.filter_project_explain(C.byref(cfg), mask, buf, need.value, C.byref(need)))
+        return buf.value.decode()
+
     def get_last_selection(self):
         is_list, size = C.c_int32(), C.c_int64()
         self._b.check(self._b.filter_project_get_last_selection(self._h, C.byref(is_list), C.byref(size)))

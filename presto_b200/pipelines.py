@@ -33,6 +33,16 @@ def _drain(op, pages: Sequence[Page], copy: bool) -> List[Page]:
     return out
 
 
+def _detach(page: Page) -> Page:
+    """A device page that outlives the operator that produced it: one device-to-device copy per block into torch-owned memory."""
+    from .exchange import block_to_tensor, nulls_to_tensor, tensor_to_block
+    blocks = []
+    for b in page.blocks:
+        n = nulls_to_tensor(b)
+        blocks.append(tensor_to_block(b.type, block_to_tensor(b).clone(), None if n is None else n.clone()))
+    return Page(blocks, page.position_count)
+
+
 def q1_program() -> Program:
     """HandTpchQuery1.filterAndProjectRowOriented :237-330 (returnflag / linestatus as dictionary codes)."""
     prog = Program([abi.INTEGER, abi.INTEGER, abi.DOUBLE, abi.DOUBLE, abi.DOUBLE, abi.DOUBLE, abi.DATE])
@@ -119,7 +129,7 @@ def run_q3(customer: Sequence[Page], orders: Sequence[Page], lineitem: Sequence[
     fp_l = FilterAndProjectOperator([abi.BIGINT, abi.DOUBLE, abi.DOUBLE, abi.DATE], pl, output_memory=mem, **o)
     probe2 = LookupJoinOperator(bridge2, [abi.BIGINT, abi.DOUBLE], [0], [0, 1], output_memory=mem, **o)
     agg = HashAggregationOperator([abi.BIGINT, abi.DATE, abi.INTEGER], [0, 2, 3], [Aggregate(abi.AGG_SUM_DOUBLE, 1)], expected_groups=100_000,
-                                  max_output_rows=1 << 30, **o)
+                                  max_output_rows=1 << 30, output_memory=mem, **o)
     joined = 0
     for page in lineitem:
         fp_l.add_input(page)
@@ -134,9 +144,9 @@ def run_q3(customer: Sequence[Page], orders: Sequence[Page], lineitem: Sequence[
     agg.finish()
     result = []
     while not agg.is_finished():
-        r = agg.get_output()
+        r = agg.get_output(copy=copy)
         if r is not None:
-            result.append(r)
+            result.append(_detach(r) if device_resident else r)     # the operator's buffers die with close() below
     if stats is not None:
         stats["joined_rows"] = joined
         stats["kernel_launches"] = sum(op.get_stats()["kernel_launches"] for op in (fp_c, build1, fp_o, probe1, build2, fp_l, probe2, agg))

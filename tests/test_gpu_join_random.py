@@ -94,3 +94,37 @@ def test_int32_join_keys(gpu_backend, oracle_backend, key_type):
     probe = Page([Block.from_numpy(key_type, pk)])
     args = ([build], [key_type, BIGINT], [probe], [key_type], JOIN_PROBE_OUTER, [1], [0])
     assert join(gpu_backend, *args) == join(oracle_backend, *args)
+
+
+@pytest.mark.parametrize("payload", ["date", "date_int", "double_nullable_date", "bigint_double_nullable_int"])
+@pytest.mark.parametrize("with_duplicate", [False, True])
+def test_range_partitioned_build_of_the_dense_index(gpu_backend, oracle_backend, monkeypatch, payload, with_duplicate):
+    """Large dense builds first split the rows into key-range buckets (hash_join.cu DenseBucketParams); forced here on a small
+    build.  Payload rows of 1, 2 and 4 words, NULL keys and NULL payload values, a range that is not a multiple of the bucket
+    width, and a duplicate key detected by the partitioning pass (→ falls back to the hash table, same result)."""
+    monkeypatch.setenv("PG_JOIN_BUCKET_MIN_ROWS", "1")
+    rng = np.random.default_rng(len(payload) * 2 + int(with_duplicate))
+    nb = 70_001
+    keys, nb = build_side(rng, "dense_unique", nb, BIGINT)
+    keys = keys + 12345
+    if with_duplicate:
+        keys[nb // 2] = keys[7]
+    knull = (rng.random(nb) < 0.02).astype(np.uint8)
+    cols = {"date": (DATE, rng.integers(8000, 10500, nb).astype(np.int32), None),
+            "int": (INTEGER, rng.integers(-5, 5, nb).astype(np.int32), None),
+            "double_nullable": (DOUBLE, rng.random(nb), (rng.random(nb) < 0.1).astype(np.uint8)),
+            "bigint": (BIGINT, rng.integers(-2**62, 2**62, nb), None),
+            "nullable_int": (INTEGER, rng.integers(0, 1000, nb).astype(np.int32), (rng.random(nb) < 0.3).astype(np.uint8))}
+    chosen = {"date": ["date"], "date_int": ["date", "int"], "double_nullable_date": ["double_nullable", "date"],
+              "bigint_double_nullable_int": ["bigint", "double_nullable", "nullable_int"]}[payload]
+    types = [BIGINT] + [cols[c][0] for c in chosen]
+    cuts = [0, nb // 3, nb]
+    build_pages = [Page([Block.from_numpy(BIGINT, keys[a:b], knull[a:b])] + [Block.from_numpy(cols[c][0], cols[c][1][a:b], None if cols[c][2] is None else cols[c][2][a:b]) for c in chosen])
+                   for a, b in zip(cuts[:-1], cuts[1:])]
+    npr = 120_000
+    pk = np.where(rng.random(npr) < 0.6, keys[rng.integers(0, nb, npr)], rng.integers(0, int(keys.max()) + 1000, npr))
+    probe_pages = [Page([Block.from_numpy(BIGINT, pk), Block.from_numpy(DOUBLE, rng.random(npr))])]
+    args = (build_pages, types, probe_pages, [BIGINT, DOUBLE], JOIN_INNER, list(range(1, len(types))), [0, 1])
+    got = join(gpu_backend, *args)
+    want = join(oracle_backend, *args)
+    assert len(got) > 0 and got == want

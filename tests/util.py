@@ -116,6 +116,9 @@ def flatten(b: Block) -> Block:
 def rows_of(pages: Sequence[Page]) -> List[tuple]:
     out: List[tuple] = []
     for p in pages:
+        if p.on_device:
+            from presto_b200.exchange import page_to_host
+            p = page_to_host(p)
         out.extend(p.rows())
     return out
 
