@@ -177,7 +177,7 @@ def run_group_by(torch, backend, page, n_rows, groups_hint, steps, warmup, devic
     """One step = HashAggregationOperator over the resident batch.  With N > 1 ranks every rank aggregates its shard with a PARTIAL
     operator, the partial pages (a few hundred bytes) are gathered and rank 0 merges them with a FINAL operator — the Q1 plan
     (no row exchange).  Returns dict(ms, kernel_ms, launches, groups, result)."""
-    from presto_b200 import AGG_SUM_DOUBLE, BIGINT, MEM_HOST, STEP_FINAL, STEP_PARTIAL, STEP_SINGLE, Aggregate, HashAggregationOperator
+    from presto_b200 import AGG_SUM_DOUBLE, BIGINT, MEM_DEVICE, MEM_HOST, STEP_FINAL, STEP_PARTIAL, STEP_SINGLE, Aggregate, HashAggregationOperator
     from presto_b200.exchange import gather_pages_to_root
     stream = torch.cuda.current_stream()
     ms, kms, launches, groups = [], [], 0, 0
@@ -185,8 +185,11 @@ def run_group_by(torch, backend, page, n_rows, groups_hint, steps, warmup, devic
     multi = dist is not None
     aggs = [Aggregate(AGG_SUM_DOUBLE, 1 + c) for c in range(4)]
     for i in range(warmup + steps):
+        # the result page stays in HBM like the input (the e2e leg is the one that crosses PCIe); partial states of the multi-GPU plan
+        # go to the host because they travel through the gather
         op = HashAggregationOperator([BIGINT], [0], aggs, expected_groups=groups_hint, step=STEP_PARTIAL if multi else STEP_SINGLE,
-                                     backend=backend, device=device, output_memory=MEM_HOST, cuda_stream=stream.cuda_stream, max_output_rows=1 << 30)
+                                     backend=backend, device=device, output_memory=MEM_HOST if multi else MEM_DEVICE, cuda_stream=stream.cuda_stream,
+                                     max_output_rows=1 << 30)
         final = None
         if multi and dist.get_rank() == 0:
             final = HashAggregationOperator([BIGINT], [0], aggs, expected_groups=groups_hint, step=STEP_FINAL, backend=backend, device=device,
@@ -199,7 +202,7 @@ def run_group_by(torch, backend, page, n_rows, groups_hint, steps, warmup, devic
         op.add_input(page)
         e1.record(stream)
         op.finish()
-        out = op.get_output()
+        out = op.get_output(copy=multi)
         if multi:
             partials = gather_pages_to_root(out)
             if final is not None:
@@ -216,7 +219,7 @@ def run_group_by(torch, backend, page, n_rows, groups_hint, steps, warmup, devic
             st = op.get_stats()
             launches = st["kernel_launches"] + (final.get_stats()["kernel_launches"] if final is not None else 0)
             groups = (final or op).get_stats()["group_count"]
-        result = out
+        result = None if out is None else (out if multi else out.position_count)
         op.close()
         if final is not None:
             final.close()

@@ -52,6 +52,18 @@ __device__ __forceinline__ uint64_t hashKeyWords(const uint64_t (&kw)[W])
     return h;
 }
 
+// One group-counter increment per inserting row, issued once per set of lanes that reach it together (warp-aggregated): with
+// millions of new groups per page a per-row atomic on this single address is the insert path's bottleneck.
+__device__ __forceinline__ unsigned int claimGroupNumber(unsigned int* counter)
+{
+    const unsigned m = __activemask();
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    unsigned int base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned int) __popc(m));
+    base = __shfl_sync(m, base, leader);
+    return base + __popc(m & ((1u << lane) - 1));
+}
+
 // ---- global table -----------------------------------------------------------------------------------------------------
 // Returns the slot of the key; inserting it when absent and `insert`.  -1: absent and !insert.  -2: table at its claim limit
 // (the caller defers the row).  `fromFlush` claims are exempt from the row claim limit.
@@ -66,7 +78,7 @@ __device__ __forceinline__ int tableFind(const GroupTable& t, const uint64_t (&k
             if (k == kw[0]) return (int) slot;
             if (k == kEmptyKey) {
                 if (!insert) return -1;
-                unsigned int c = atomicAdd(&t.counters[CNT_GROUPS], 1u);
+                unsigned int c = claimGroupNumber(&t.counters[CNT_GROUPS]);
                 if (!fromFlush && c >= t.rowClaimLimit) { atomicSub(&t.counters[CNT_GROUPS], 1u); return -2; }
                 uint64_t old = atomicCAS(&keys[slot], (unsigned long long) kEmptyKey, (unsigned long long) kw[0]);
                 if (old == kEmptyKey) { if (isNew) *isNew = true; return (int) slot; }
@@ -85,7 +97,7 @@ __device__ __forceinline__ int tableFind(const GroupTable& t, const uint64_t (&k
             uint32_t st = state[slot];
             if (st == kStEmpty) {
                 if (!insert) return -1;
-                unsigned int c = atomicAdd(&t.counters[CNT_GROUPS], 1u);
+                unsigned int c = claimGroupNumber(&t.counters[CNT_GROUPS]);
                 if (!fromFlush && c >= t.rowClaimLimit) { atomicSub(&t.counters[CNT_GROUPS], 1u); return -2; }
                 uint32_t old = atomicCAS(&t.state[slot], kStEmpty, kStLocked);
                 if (old == kStEmpty) {

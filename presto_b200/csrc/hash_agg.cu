@@ -53,7 +53,7 @@ struct AggLaunch {
 constexpr int kAggThreads = 256;
 constexpr int kSharedProbes = 8;
 constexpr int kWarpAggMaxGroups = 8;
-constexpr int kMaxSubsetPasses = 6;      // mid mode gives up (HBM-table atomics) beyond this many hash-subset passes
+constexpr int kMaxSubsetPasses = 1;      // mid mode (47 G rows/s at 1000 groups) loses to direct mode (~28 G rows/s flat) from the second hash-subset pass on
 
 template <int MAXV> struct RowsPerThread { static constexpr int value = MAXV <= 4 ? 4 : 2; };   // always even: rows are loaded in pairs
 // Tier 0: the first kTier0Groups groups a CTA claims get per-thread private accumulators in shared memory.
@@ -450,6 +450,7 @@ struct FastLaunch {
     uint32_t S, sLimit;
     int32_t nAccAlloc;
     uint32_t subsetCount, subsetIndex;   // mid mode: this launch aggregates only keys with hashSubset(key) == subsetIndex
+    uint32_t capBits;                    // direct mode: log2(t.cap); subsets are contiguous slot ranges of the HBM table
 };
 
 template <int NV, bool CNT> struct FastGeom {
@@ -492,6 +493,106 @@ __device__ __noinline__ void fastGlobalRow(const FastLaunch<NV, CNT>& P, uint64_
 #pragma unroll
     for (int c = 0; c < NV; c++) atomicAdd((double*) &acc[P.phys[c]], __longlong_as_double((long long) vals[c]));
     if (CNT) atomicAdd((unsigned long long*) &acc[P.phys[NV]], 1ULL);
+}
+
+// ---- direct mode: every row goes straight to the HBM table (10^4 .. 10^7 groups) ---------------------------------------------
+// Past a few thousand groups a shared-memory table stops catching rows, and each row costs its L2 atomics anyway: one key probe, NV
+// native f64 REDs (REDG.ADD.F64), one firstRow min.  What is left to engineer is WHERE those atomics land: the launch aggregates
+// only the keys whose home slot lies in slot range `subsetIndex` of `subsetCount` (contiguous ranges of the table), the host running
+// as many passes over the chunk as it takes for one range's keys + accumulators to stay L2 resident — the streamed input is loaded
+// with an evict-first policy so that it does not wash the table out of L2.  Per pass the kernel reads every key (8 B/row) and the
+// value sectors of the rows it owns.
+__device__ __forceinline__ ulonglong2 ldStreamEvictFirst128(const uint64_t* p, uint64_t policy)
+{
+    ulonglong2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u64 {%0,%1}, [%2], %3;" : "=l"(v.x), "=l"(v.y) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ uint64_t ldStreamEvictFirst64(const uint64_t* p, uint64_t policy)
+{
+    uint64_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(policy));
+    return v;
+}
+
+// Each warp scans keys (two per lane per step, software pipelined) and queues the rows it owns in shared memory; whenever 32 are
+// queued the whole warp aggregates them, one row per lane — so with 1/8 of the rows owned the dependent chain (value loads, key
+// probe, firstRow, REDs) runs once per ~256 scanned rows instead of once per 64, with every lane busy.
+constexpr int kDirectQueue = 96;      // per warp: up to 31 left over + 64 new entries
+template <int NV, bool CNT>
+__global__ void __launch_bounds__(256, 4) hashAggDirectKernel(const __grid_constant__ FastLaunch<NV, CNT> P)
+{
+    constexpr int THREADS = 256, TILE = THREADS * 2;
+    __shared__ uint64_t qKey[THREADS / 32][kDirectQueue];
+    __shared__ uint32_t qRow[THREADS / 32][kDirectQueue];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt = (1u << lane) - 1;
+    const GroupTable& T = P.t;
+    uint64_t streamPolicy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(streamPolicy));
+    const int64_t nTiles = (P.n + TILE - 1) / TILE;
+    ulonglong2 kA, kB;
+    auto loadKeys = [&](int64_t tile, ulonglong2& k) {
+        const int64_t row0 = tile * TILE + 2 * tid;
+        k.x = 0; k.y = 0;
+        if (row0 + 1 < P.n) k = ldStreamEvictFirst128(P.key + row0, streamPolicy);
+        else if (row0 < P.n) k.x = ldStreamEvictFirst64(P.key + row0, streamPolicy);
+    };
+    auto owns = [&](uint64_t h) {
+        return P.subsetCount <= 1 || (uint32_t) (((uint64_t) ((uint32_t) h & T.mask) * P.subsetCount) >> P.capBits) == P.subsetIndex;
+    };
+    auto aggregateRow = [&](uint64_t key, uint32_t rowIdx) {
+        uint64_t vals[NV];
+#pragma unroll
+        for (int c = 0; c < NV; c++) vals[c] = ldStreamEvictFirst64(P.vals[c] + rowIdx, streamPolicy);
+        uint64_t kw[1] = {key};
+        const int gslot = key == kEmptyKey ? (int) T.cap + 1 : tableFind<1>(T, kw, murmur64(key), true, false);
+        if (gslot == -2) {
+            atomicOr(&P.bitmapOut[rowIdx >> 5], 1u << (rowIdx & 31));
+            atomicAdd(&T.counters[CNT_DEFERRED], 1u);
+            return;
+        }
+        const uint64_t g = P.rowBase + rowIdx;
+        if (g < __ldcg(&T.firstRow[gslot])) atomicMin((unsigned long long*) &T.firstRow[gslot], (unsigned long long) g);
+        uint64_t* acc = T.acc + (size_t) gslot * T.nvPhys;
+#pragma unroll
+        for (int c = 0; c < NV; c++) atomicAdd((double*) &acc[P.phys[c]], __longlong_as_double((long long) vals[c]));
+        if (CNT) atomicAdd((unsigned long long*) &acc[P.phys[NV]], 1ULL);
+    };
+    uint32_t qCount = 0;       // warp-uniform
+    auto push = [&](bool mine, uint64_t key, uint32_t rowIdx) {
+        const unsigned m = __ballot_sync(0xffffffffu, mine);
+        if (mine) { const uint32_t at = qCount + __popc(m & lt); qKey[warp][at] = key; qRow[warp][at] = rowIdx; }
+        qCount += __popc(m);
+    };
+    auto drain = [&](uint32_t keep) {       // aggregate queued rows, 32 at a time, until at most `keep` are left
+        __syncwarp();
+        while (qCount > keep) {
+            const uint32_t take = min(32u, qCount), at = qCount - take + lane;
+            if (lane < take) aggregateRow(qKey[warp][at], qRow[warp][at]);
+            qCount -= take;
+            __syncwarp();
+        }
+    };
+    auto consumeTile = [&](int64_t tile, const ulonglong2& k) {
+        const int64_t row0 = tile * TILE + 2 * tid;
+        push(row0 < P.n && owns(murmur64(k.x)), k.x, (uint32_t) row0);
+        push(row0 + 1 < P.n && owns(murmur64(k.y)), k.y, (uint32_t) (row0 + 1));
+        if (qCount >= 32) drain(31);
+    };
+    int64_t tile = blockIdx.x;
+    if (tile < nTiles) loadKeys(tile, kA);
+    while (tile < nTiles) {
+        const int64_t t1 = tile + gridDim.x;
+        if (t1 < nTiles) loadKeys(t1, kB);
+        consumeTile(tile, kA);
+        if (t1 >= nTiles) break;
+        const int64_t t2 = t1 + gridDim.x;
+        if (t2 < nTiles) loadKeys(t2, kA);
+        consumeTile(t1, kB);
+        tile = t2;
+    }
+    drain(0);
 }
 
 // MID = false: tiers 0/1/2, 256 threads, two CTAs per SM (few groups: TPC-H Q1).
@@ -1198,7 +1299,9 @@ public:
         while (SharedLayout(midSlots, 1, NC, false).total > 200 * 1024 && midSlots > 512) midSlots >>= 1;
         const uint32_t midCapacity = midSlots / 4 * 3;
         const int64_t passes = (int64_t) ((double) knownGroups * 1.25 / midCapacity) + 1;
-        if (knownGroups > (int64_t) sharedLimit * 9 / 10 && passes <= kMaxSubsetPasses) {
+        const char* modeEnv0 = getenv("PG_AGG_MODE");
+        const bool forceDirect = modeEnv0 && !strcmp(modeEnv0, "direct");
+        if (!forceDirect && knownGroups > (int64_t) sharedLimit * 9 / 10 && passes <= kMaxSubsetPasses) {   // one pass; beyond that direct mode is faster
             auto kern = hashAggFastKernel<NV, CNT, true>;
             L.S = midSlots; L.sLimit = midCapacity; L.nAccAlloc = NC; L.subsetCount = (uint32_t) passes;
             const size_t smem = SharedLayout(midSlots, 1, NC, false).total;
@@ -1208,6 +1311,27 @@ public:
             for (uint32_t j = 0; j < L.subsetCount; j++) {
                 L.subsetIndex = j;
                 kern<<<grid, 512, smem, stream>>>(L);
+                stats.kernel_launches++;
+            }
+            PG_CUDA(cudaGetLastError());
+            return true;
+        }
+        // ---- direct mode: too many groups for shared-memory tables: straight to the HBM table, one L2-resident slot range per pass ----
+        const char* modeEnv = getenv("PG_AGG_MODE");
+        if ((knownGroups > (int64_t) sharedLimit * 9 / 10 && !(modeEnv && !strcmp(modeEnv, "tiered"))) || (modeEnv && !strcmp(modeEnv, "direct"))) {
+            auto kern = hashAggDirectKernel<NV, CNT>;
+            int64_t budgetMB = 96;
+            if (const char* e = getenv("PG_AGG_L2_BUDGET_MB")) budgetMB = std::max<int64_t>(1, atoll(e));
+            // bytes the probes and atomics of one full pass touch: every key slot (probing reads empty slots too), firstRow + accumulators of live groups
+            const double live = std::min<double>((double) table.cap, (double) std::max<int64_t>(knownGroups, 1) * 1.25);
+            const double footprint = (double) table.cap * 8.0 + live * (32.0 + 8.0 * table.nvPhys);
+            L.subsetCount = (uint32_t) std::min<double>(64.0, std::max<double>(1.0, std::ceil(footprint / ((double) budgetMB * 1048576.0))));
+            L.capBits = 0; while ((1u << L.capBits) < table.cap) L.capBits++;
+            const int64_t tiles = divUp(n, 512);
+            const int grid = (int) std::min<int64_t>((int64_t) numSMs * 4, std::max<int64_t>(tiles, 1));
+            for (uint32_t j = 0; j < L.subsetCount; j++) {
+                L.subsetIndex = j;
+                kern<<<grid, 256, 0, stream>>>(L);
                 stats.kernel_launches++;
             }
             PG_CUDA(cudaGetLastError());
