@@ -61,8 +61,31 @@ class ClockSampler:
         self.index, self.samples, self.proc = index, [], None
 
     def start(self):
+        # NVML in-process (same counters nvidia-smi prints) every 2 ms, so that even a 50 ms timed region gets a few dozen samples;
+        # falls back to an nvidia-smi subprocess
+        self.stopFlag = False
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            bits = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+
+            def poll():
+                while not self.stopFlag:
+                    try:
+                        sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.samples.append([str(sm), str(mx), "", *["Active" if r & b else "Not Active" for _, b in bits]])
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+            threading.Thread(target=poll, daemon=True).start()
+            return
+        except Exception:
+            pass
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -73,6 +96,7 @@ class ClockSampler:
             self.samples.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        self.stopFlag = True
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], 0, set()
@@ -354,6 +378,37 @@ def run_e2e(torch, backend, rows, groups, steps, warmup, device):
     return rows / float(np.mean(times)), int(h2d), int(d2h), out
 
 
+def run_q1_pipeline(torch, backend, device, rows, steps, warmup):
+    """BASELINE.json configs[0] shape at SF100 size on one GPU: TPC-H Q1 = PageProcessor filter/project → HashAggregationOperator over
+    (returnflag, linestatus) with 4 sums, 3 avgs and count(*) (HandTpchQuery1.java:99-127), lineitem device resident.  Algorithmic
+    bytes = the 7 input columns once (46 B/row); the 4-group result is negligible."""
+    from presto_b200 import DATE, DOUBLE, INTEGER
+    from presto_b200.pipelines import run_q1
+    dev = f"cuda:{device}"
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    rf = torch.randint(0, 3, (rows,), dtype=torch.int32, device=dev, generator=g); ls = torch.randint(0, 2, (rows,), dtype=torch.int32, device=dev, generator=g)
+    qty = torch.randint(1, 51, (rows,), device=dev, generator=g).to(torch.float64)
+    ep = torch.rand(rows, dtype=torch.float64, device=dev, generator=g) * 1e5
+    disc = torch.randint(0, 11, (rows,), device=dev, generator=g).to(torch.float64) / 100
+    tax = torch.randint(0, 9, (rows,), device=dev, generator=g).to(torch.float64) / 100
+    ship = torch.randint(8035, 10600, (rows,), dtype=torch.int32, device=dev, generator=g)
+    types = [INTEGER, INTEGER, DOUBLE, DOUBLE, DOUBLE, DOUBLE, DATE]
+    page = device_page(torch, [rf, ls, qty, ep, disc, tax, ship], types)
+    stream = torch.cuda.current_stream()
+    times, groups = [], 0
+    for it in range(warmup + steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        out = run_q1([page], backend=backend, device_resident=True, device=device, cuda_stream=stream.cuda_stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if it >= warmup:
+            times.append(e0.elapsed_time(e1)); groups = sum(p.position_count for p in out)
+    ms = float(np.mean(times))
+    return {"rows": rows, "groups": int(groups), "ms": ms, "rows_per_s": rows / (ms / 1000), "achieved_gbs": 46 * rows / (ms / 1000) / 1e9}
+
+
 def run_join(torch, backend, device, build_rows, probe_rows, steps, warmup):
     """configs[2]: HashBuilder + LookupJoin, orders ⋈ lineitem shape (unique sparse build keys, 1..7 probe rows per key)."""
     from presto_b200 import BIGINT, DATE, DOUBLE, INTEGER, MEM_DEVICE, Block, HashBuilderOperator, JoinBridge, LookupJoinOperator, Page
@@ -579,6 +634,7 @@ def main():
                 ("hash_join_orders_lineitem", lambda: run_join(torch, backend, local, int(150_000_000 * scale), int(600_037_902 * scale), 2, 1)),
                 ("partitioned_output_8_bigint_cols", lambda: run_partitioned_output(torch, backend, local, int((1 << 28) * scale), 8, 2, 1)),
                 ("page_processor_q1", lambda: run_page_processor_q1(torch, backend, local, int((1 << 28) * scale), 2, 1)),
+                ("q1_pipeline", lambda: run_q1_pipeline(torch, backend, local, int(600_037_902 * scale), 2, 1)),
                 ("q3_pipeline", lambda: run_q3(torch, backend, local, int(150_000_000 * scale), 2, 1)),
             ]:
                 if only and name not in only:

@@ -78,6 +78,9 @@ __device__ __forceinline__ int tableFind(const GroupTable& t, const uint64_t (&k
             if (k == kw[0]) return (int) slot;
             if (k == kEmptyKey) {
                 if (!insert) return -1;
+                // once the table is at its claim limit every new key is deferred: find that out with a load, not with two atomics on
+                // the one counter every deferred row of the page would otherwise hammer
+                if (!fromFlush && __ldcg(&t.counters[CNT_GROUPS]) >= t.rowClaimLimit) return -2;
                 unsigned int c = claimGroupNumber(&t.counters[CNT_GROUPS]);
                 if (!fromFlush && c >= t.rowClaimLimit) { atomicSub(&t.counters[CNT_GROUPS], 1u); return -2; }
                 uint64_t old = atomicCAS(&keys[slot], (unsigned long long) kEmptyKey, (unsigned long long) kw[0]);
@@ -97,6 +100,7 @@ __device__ __forceinline__ int tableFind(const GroupTable& t, const uint64_t (&k
             uint32_t st = state[slot];
             if (st == kStEmpty) {
                 if (!insert) return -1;
+                if (!fromFlush && __ldcg(&t.counters[CNT_GROUPS]) >= t.rowClaimLimit) return -2;
                 unsigned int c = claimGroupNumber(&t.counters[CNT_GROUPS]);
                 if (!fromFlush && c >= t.rowClaimLimit) { atomicSub(&t.counters[CNT_GROUPS], 1u); return -2; }
                 uint32_t old = atomicCAS(&t.state[slot], kStEmpty, kStLocked);

@@ -57,8 +57,9 @@ constexpr int kMaxSubsetPasses = 1;      // mid mode (47 G rows/s at 1000 groups
 
 template <int MAXV> struct RowsPerThread { static constexpr int value = MAXV <= 4 ? 4 : 2; };   // always even: rows are loaded in pairs
 // Tier 0: the first kTier0Groups groups a CTA claims get per-thread private accumulators in shared memory.
-template <int MAXV> struct Tier0Groups { static constexpr int value = 32 / MAXV; };
-constexpr int kTier0Bytes = 32 * kAggThreads * 8;   // K0 * MAXV == 32 columns of 256 doubles
+constexpr int kTier0Columns = 40;                  // per-thread private accumulator columns of one CTA (Q1: 6 groups x 6 columns = 36)
+template <int MAXV> struct Tier0Groups { static constexpr int value = kTier0Columns / MAXV; };
+constexpr int kTier0Bytes = kTier0Columns * kAggThreads * 8;   // K0 * MAXV <= 40 columns of 256 doubles = 80 KB
 
 // shared-memory carve-up, same arithmetic on host and device
 struct SharedLayout {
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(kAggThreads) hashAggKernel(const __grid_consta
         for (uint32_t i = tid; i < st.S2; i += kAggThreads) { st.first[i] = kNoRow32; st.sid[i] = 0xFF; if (W > 1) st.state[i] = kStEmpty; }
         if (tid < 64) st.count[tid] = 0;
 #pragma unroll
-        for (int i = 0; i < 32; i++) tier0[i * kAggThreads + tid] = 0;
+        for (int i = 0; i < kTier0Columns; i++) tier0[i * kAggThreads + tid] = 0;
         __syncthreads();
     }
 
@@ -451,11 +452,32 @@ struct FastLaunch {
     int32_t nAccAlloc;
     uint32_t subsetCount, subsetIndex;   // mid mode: this launch aggregates only keys with hashSubset(key) == subsetIndex
     uint32_t capBits;                    // direct mode: log2(t.cap); subsets are contiguous slot ranges of the HBM table
+    // packed-key mode (keyMode 1): two 32-bit key columns without NULLs on this page (Q1: returnflag, linestatus).  Inside the kernel
+    // the key is (col1 << 32 | col0); at the HBM table it is re-packed into the table's W = 2 layout (KeyLayout: word / shift per column).
+    int32_t keyMode;
+    const uint32_t* key32[2];
+    int32_t kWord[2], kShift[2];
 };
+
+// slot of a fast-kernel key in the HBM table (insert)
+template <int NV, bool CNT>
+__device__ __forceinline__ int fastGlobalFind(const FastLaunch<NV, CNT>& P, uint64_t key, bool fromFlush)
+{
+    if (P.keyMode == 0) {
+        if (key == kEmptyKey) return (int) P.t.cap + 1;
+        uint64_t kw[1] = {key};
+        return tableFind<1>(P.t, kw, murmur64(key), true, fromFlush);
+    }
+    uint64_t kw[2] = {0, 0};
+    const uint64_t v0 = key & 0xffffffffULL, v1 = key >> 32;
+    if (P.kWord[0] == 0) kw[0] |= v0 << P.kShift[0]; else kw[1] |= v0 << P.kShift[0];
+    if (P.kWord[1] == 0) kw[0] |= v1 << P.kShift[1]; else kw[1] |= v1 << P.kShift[1];
+    return tableFind<2>(P.t, kw, hashKeyWords<2>(kw), true, fromFlush);
+}
 
 template <int NV, bool CNT> struct FastGeom {
     static constexpr int NC = NV + (CNT ? 1 : 0);       // accumulator columns
-    static constexpr int K0 = 32 / NC;                  // tier-0 groups (K0 * NC <= 32 columns of 256 x 8 B = 64 KB)
+    static constexpr int K0 = (kTier0Columns / NC) > 31 ? 31 : (kTier0Columns / NC);   // tier-0 groups (K0 * NC <= 40 columns of 256 x 8 B = 80 KB; ids live in a 32-bit mask)
 };
 
 // Rows that are not tier 0: the CTA's shared table (direct shared atomics) or the HBM table.  Kept out of line so the hot loop stays small.
@@ -640,12 +662,19 @@ __global__ void __launch_bounds__(MID ? 512 : kAggThreads, MID ? 1 : 2) hashAggF
     auto loadTile = [&](int64_t tile, ulonglong2& k, ulonglong2 (&v)[NV]) {
         const int64_t row0 = tile * TILE + 2 * tid;
         if (row0 + 1 < P.n) {
-            k = ldStream128(keyBase + row0);
+            if (P.keyMode == 0) k = ldStream128(keyBase + row0);
+            else {      // two rows of each 32-bit key column in one 64-bit load; key = col1 << 32 | col0
+                const uint64_t a = ldStream64((const uint64_t*) (P.key32[0] + row0)), b = ldStream64((const uint64_t*) (P.key32[1] + row0));
+                k.x = (a & 0xffffffffULL) | (b << 32);
+                k.y = (a >> 32) | (b & 0xffffffff00000000ULL);
+            }
 #pragma unroll
             for (int c = 0; c < NV; c++) v[c] = ldStream128(P.vals[c] + row0);
         }
         else if (row0 < P.n) {
-            k.x = ldStream64(keyBase + row0); k.y = 0;
+            if (P.keyMode == 0) k.x = ldStream64(keyBase + row0);
+            else k.x = (uint64_t) ldStream32(P.key32[0] + row0) | ((uint64_t) ldStream32(P.key32[1] + row0) << 32);
+            k.y = 0;
 #pragma unroll
             for (int c = 0; c < NV; c++) { v[c].x = ldStream64(P.vals[c] + row0); v[c].y = 0; }
         }
@@ -749,9 +778,8 @@ __global__ void __launch_bounds__(MID ? 512 : kAggThreads, MID ? 1 : 2) hashAggF
     for (uint32_t s = tid; s < st.S2; s += THREADS) {
         const uint32_t f = st.first[s];
         if (f == kNoRow32) continue;
-        int gslot;
-        if (s >= st.S) gslot = (int) T.cap + (int) (s - st.S);
-        else { uint64_t kw[1] = {st.keys[s]}; gslot = tableFind<1>(T, kw, murmur64(kw[0]), true, true); }
+        // (slot S + 1 holds the key whose value equals the empty sentinel; slot S, the NULL key, is never used by this kernel)
+        const int gslot = fastGlobalFind<NV, CNT>(P, s >= st.S ? kEmptyKey : (uint64_t) st.keys[s], true);
         if (gslot < 0) { atomicOr(&T.counters[CNT_ERROR], 0x80000000u); continue; }
         const uint64_t g = P.rowBase + f;
         if (g < __ldcg(&T.firstRow[gslot])) atomicMin((unsigned long long*) &T.firstRow[gslot], (unsigned long long) g);
@@ -1289,6 +1317,9 @@ public:
         L.t = table.view();
         auto colOf = [&](int ch) -> const DeviceColumn& { return cols[std::find(stagedChannels.begin(), stagedChannels.end(), ch) - stagedChannels.begin()]; };
         L.key = (const uint64_t*) colOf(layout.channels[0]).values;
+        L.keyMode = layout.bigintPath ? 0 : 1;
+        if (L.keyMode == 1)
+            for (int k = 0; k < 2; k++) { L.key32[k] = (const uint32_t*) colOf(layout.channels[k]).values; L.kWord[k] = layout.word[k]; L.kShift[k] = layout.shift[k]; }
         for (int c = 0; c < NV; c++) { L.vals[c] = (const uint64_t*) colOf(phys[f64Cols[c]].channel).values; L.phys[c] = f64Cols[c]; }
         L.phys[NV] = CNT ? countCol : 0;
         L.n = n; L.rowBase = rowsSeen; L.bitmapOut = bitmapOut; L.S = sharedSlots; L.sLimit = sharedLimit; L.nAccAlloc = (int) phys.size();
@@ -1353,10 +1384,16 @@ public:
 
     bool tryLaunchFast(const std::vector<DeviceColumn>& cols, int64_t n, uint32_t* bitmapOut)
     {
-        if (!layout.bigintPath) return false;
         auto colOf = [&](int ch) -> const DeviceColumn& { return cols[std::find(stagedChannels.begin(), stagedChannels.end(), ch) - stagedChannels.begin()]; };
-        const DeviceColumn& kc = colOf(layout.channels[0]);
-        if (kc.nulls || ((uintptr_t) kc.values % 16) != 0) return false;
+        // key: one BIGINT column, or two 32-bit columns (INTEGER / DATE: Q1's returnflag, linestatus codes); no NULL keys on this page
+        const bool packed32 = !layout.bigintPath && layout.nKeys == 2 && layout.W == 2 && layout.bits[0] == 32 && layout.bits[1] == 32
+                              && layout.types[0] != PG_TYPE_VARCHAR && layout.types[1] != PG_TYPE_VARCHAR;
+        if (!layout.bigintPath && !packed32) return false;
+        for (int k = 0; k < layout.nKeys; k++) {
+            const DeviceColumn& kc = colOf(layout.channels[k]);
+            if (kc.nulls || ((uintptr_t) kc.values % 16) != 0) return false;
+        }
+        if (packed32 && knownGroups > (int64_t) sharedLimit * 9 / 10) return false;    // mid / direct modes address the W = 1 table
         std::vector<int> f64Cols; int countCol = -1;
         for (size_t p = 0; p < phys.size(); p++) {
             if (!phys[p].active) continue;

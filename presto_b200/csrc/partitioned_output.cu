@@ -279,7 +279,8 @@ public:
     std::vector<DeviceColumn> curCols; int curSlot = -1; int64_t curN = 0, curUnits = 0; bool prepared = false;
     DeviceBuffer remoteTable;
 
-    size_t scatterSmem() const { return (size_t) kPartWarps * partitionCount * 4 + (size_t) kPartWarps * kRowsPerUnit * 6; }
+    // ranks (4 B per row of a unit) and, for the fused exchange only, the partition of each row (2 B)
+    size_t scatterSmem(bool remote) const { return (size_t) kPartWarps * partitionCount * 4 + (size_t) kPartWarps * kRowsPerUnit * (remote ? 6 : 4); }
     int launchGrid() const { return (int) std::min<int64_t>(divUp(curUnits, kPartWarps), (int64_t) numSMs * 8); }
 
     void prepare(const pg_page* page)
@@ -341,7 +342,7 @@ public:
             sc.dst = outValues[i].ptr; sc.dstNulls = nullptr;
             if (cols[i].nulls) { outNulls[i].reserve(total); sc.dstNulls = outNulls[i].as<uint8_t>(); }
         }
-        PG_LAUNCH(this, partitionScatterKernel, launchGrid(), kPartWarps * 32, scatterSmem(), S);
+        PG_LAUNCH(this, partitionScatterKernel, launchGrid(), kPartWarps * 32, scatterSmem(false), S);
         stager.markCompute(curSlot);
         const bool toHost = options.output_memory == PG_MEM_HOST;
         if (toHost && hostValues.size() < nCols) { hostValues.resize(nCols); hostNulls.resize(nCols); }
@@ -399,7 +400,7 @@ public:
         S.nCols = (int) nCols; S.partitionCount = partitionCount; S.n = curN; S.units = curUnits; S.ids = ids.as<uint16_t>(); S.base = base.as<uint32_t>();
         S.remoteValues = remoteTable.as<uint64_t>(); S.remoteNulls = remoteTable.as<uint64_t>() + words; S.adjust = (const uint32_t*) (remoteTable.as<uint64_t>() + 2 * words);
         for (size_t i = 0; i < nCols; i++) { ScatterColumn& sc = S.cols[i]; sc.width = typeWidth(types[i]); sc.src = curCols[i].values; sc.srcNulls = curCols[i].nulls; sc.dst = nullptr; sc.dstNulls = nullptr; }
-        PG_LAUNCH(this, partitionScatterKernel, launchGrid(), kPartWarps * 32, scatterSmem(), S);
+        PG_LAUNCH(this, partitionScatterKernel, launchGrid(), kPartWarps * 32, scatterSmem(true), S);
         stager.markCompute(curSlot);
         PG_CUDA(cudaStreamSynchronize(stream));
         stats.output_positions += curN;
