@@ -533,6 +533,7 @@ def run_q3_multi(torch, backend, device, n_orders_total, steps, warmup, dist):
     ms = float(t[0])
     return {"orders": n_orders_total, "lineitem_rows": int(n_li[0]), "groups": int(g[0]), "exchanged_rows": int(g[1]), "joined_rows": int(g[2]), "ms": ms,
             "ms_with_nccl_all_to_all": float(t[1]), "exchange": "fused scatter into peer receive columns (NVLink P2P)",
+            **({"trace_ms_rank0": stats["trace_ms"]} if "trace_ms" in stats else {}),
             "lineitem_rows_per_s": int(n_li[0]) / (ms / 1000)}
 
 

@@ -164,6 +164,7 @@ __global__ void joinEmitKernel(const __grid_constant__ EmitJoinParams P)
 // bitmap sector (L2) + 4 B of directory → rank → payload[rank]; sorted probe keys (lineitem is clustered by orderkey) make every
 // access sequential.  Results are identical to the hash path (unique keys: at most one match, no chains).
 constexpr int kDenseRangeFactor = 64;                // keys may cover as little as 1/64 of their range (bitmap: range / 8 bytes)
+constexpr int kDenseSmallRangeBits = 31;             // ranges up to 2^31 (256 MB bitmap + 32 MB directory) use the index at any density
 constexpr int kDenseBlockWords = 4;                  // 4 x 64 bit = one 32-byte sector per block
 
 struct DenseIndex {
@@ -947,7 +948,11 @@ public:
         const int64_t nonNull = h[2];
         if (nonNull == 0) return false;
         const unsigned __int128 span = (unsigned __int128) ((__int128) h[1] - (__int128) h[0]) + 1;
-        if (span > (unsigned __int128) kDenseRangeFactor * (unsigned __int128) nonNull + 4096 || span > ((unsigned __int128) 1 << 36)) return false;
+        // dense enough (bitmap <= 8 x the key column), or small in absolute terms: a hash-partitioned build side keeps the full key range
+        // on every rank with 1/P of the keys — the bitmap (range / 8 bytes: 75 MB for TPC-H SF100 order keys) still fits L2
+        const bool denseEnough = span <= (unsigned __int128) kDenseRangeFactor * (unsigned __int128) nonNull + 4096;
+        const bool smallEnough = span <= ((unsigned __int128) 1 << kDenseSmallRangeBits);
+        if ((!denseEnough && !smallEnough) || span > ((unsigned __int128) 1 << 36)) return false;
         const uint64_t range = (uint64_t) span;
         const int64_t blocks = (int64_t) ((range + 255) >> 8);
         ls->bitmap.accounting = ls->prefix.accounting = &ls->deviceBytes;

@@ -189,15 +189,21 @@ class FusedExchange:
 
     def exchange(self, op, page: Page) -> Page:
         """``op`` is a PartitionedOutputOperator with partition_count == world size over ``self.types``."""
+        import os
+        import time
         import torch
         import torch.distributed as dist
         assert op.partition_count == self.world, "one partition per rank"
+        trace = os.environ.get("PG_Q3_TRACE")
+        t = [time.perf_counter()] if trace else None
         counts = op.count(page)
+        if trace: t.append(time.perf_counter())
         mine = torch.from_numpy(counts).to(self._dev)
         matrix = torch.empty(self.world * self.world, dtype=torch.int64, device=self._dev)
         # every rank has entered this call once the gather returns, so nobody still reads the previous received page
         dist.all_gather_into_tensor(matrix, mine, group=self._group)
         m = matrix.cpu().numpy().reshape(self.world, self.world)          # m[sender][destination]
+        if trace: t.append(time.perf_counter())
         received = m[:, self.rank]
         total = int(received.sum())
         need = int(m.sum(axis=0).max())
@@ -206,11 +212,15 @@ class FusedExchange:
             self._allocate(need + need // 4)
         row_offsets = m[:self.rank, :].sum(axis=0).astype(np.int64)       # rows lower-ranked senders put before mine, per destination
         op.scatter_to(self._values, self._nulls, row_offsets)            # returns after the scatter kernel (and its peer stores) completed
+        if trace: t.append(time.perf_counter())
         done = torch.zeros(1, dtype=torch.int32, device=self._dev)
         dist.all_reduce(done, group=self._group)                          # every sender's rows have landed
         done.item()
+        if trace:
+            t.append(time.perf_counter())
+            self.trace_ms = [round((b - a) * 1e3, 3) for a, b in zip(t[:-1], t[1:])]     # count, count all-gather, scatter, barrier
         self.last_counts = m
-        blocks = [Block.device(t, total, v, n if self._nulls is not None else 0, keepalive=self) for t, (v, n) in zip(self.types, self._local)]
+        blocks = [Block.device(t_, total, v, n if self._nulls is not None else 0, keepalive=self) for t_, (v, n) in zip(self.types, self._local)]
         return Page(blocks, total)
 
     def close(self):

@@ -169,11 +169,20 @@ def run_q3_distributed(customer: Sequence[Page], orders: Sequence[Page], lineite
        otherwise a local PartitionedOutput slab + one all_to_all_single per column (exchange.all_to_all_pages).  ``exchanges`` =
        (orders FusedExchange, lineitem FusedExchange) reuses long-lived receive columns (a worker's output buffers outlive a query
        stage); by default they are created and released here."""
+    import os
+    import time
     import torch
     import torch.distributed as dist
     from .exchange import FusedExchange, all_to_all_pages, block_to_tensor, tensor_to_block
     from .operators import PartitionedOutputOperator
     world = dist.get_world_size(group)
+    trace = [] if os.environ.get("PG_Q3_TRACE") else None      # wall-clock per phase (rank-local), printed by the caller
+
+    def mark(name):
+        if trace is not None:
+            torch.cuda.synchronize()
+            trace.append((name, time.perf_counter()))
+    mark("start")
     mem = abi.MEM_DEVICE
     o = dict(backend=backend, **opts)
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -198,6 +207,7 @@ def run_q3_distributed(customer: Sequence[Page], orders: Sequence[Page], lineite
     if all_keys.numel():
         build1.add_input(Page([tensor_to_block(abi.BIGINT, all_keys)]))
     build1.finish()
+    mark("customer filter + replicate + build1")
     # ---- orders: filter → probe #1 → repartition on orderkey → build #2 ----
     po = Program([abi.BIGINT, abi.BIGINT, abi.DATE, abi.INTEGER])
     ok, ock, od, sp = [po.input(i) for i in range(4)]
@@ -248,6 +258,7 @@ def run_q3_distributed(customer: Sequence[Page], orders: Sequence[Page], lineite
         if recv.position_count:
             build2.add_input(recv)
     build2.finish()
+    mark("orders filter + probe1 + exchange + build2")
     # ---- lineitem: filter/project → repartition on orderkey → probe #2 → aggregation ----
     pl = Program([abi.BIGINT, abi.DOUBLE, abi.DOUBLE, abi.DATE])
     lk, ep, disc, ship = [pl.input(i) for i in range(4)]
@@ -257,26 +268,31 @@ def run_q3_distributed(customer: Sequence[Page], orders: Sequence[Page], lineite
     part_l = PartitionedOutputOperator([abi.BIGINT, abi.DOUBLE], world, [0], output_memory=mem, **o)
     probe2 = LookupJoinOperator(bridge2, [abi.BIGINT, abi.DOUBLE], [0], [0, 1], output_memory=mem, **o)
     agg = HashAggregationOperator([abi.BIGINT, abi.DATE, abi.INTEGER], [0, 2, 3], [Aggregate(abi.AGG_SUM_DOUBLE, 1)], expected_groups=100_000,
-                                  max_output_rows=1 << 30, **o)
+                                  max_output_rows=1 << 30, output_memory=mem, **o)
     joined = 0
     for page in lineitem:
         fp_l.add_input(page)
         f = fp_l.get_output(copy=False)
+        mark("lineitem filter/project")
         recv = shuffle(part_l, fx_l, f, line_types)
+        mark("lineitem exchange " + (str(getattr(fx_l, "trace_ms", "")) if fx_l is not None else "(nccl)"))
         exchanged += recv.position_count
         if not recv.position_count:
             continue
         probe2.add_input(recv)
         j = probe2.get_output(copy=False)
+        mark("lineitem probe2")
         if j is not None and j.position_count:
             joined += j.position_count
             agg.add_input(j)
+    mark("lineitem filter + exchange + probe2 + aggregation input")
     agg.finish()
     result = []
     while not agg.is_finished():
-        r = agg.get_output()
+        r = agg.get_output(copy=False)
         if r is not None:
-            result.append(r)
+            result.append(_detach(r))      # device resident; the operator's buffers die with close() below
+    mark("aggregation output")
     ops = (fp_c, build1, fp_o, probe1, part_o, build2, fp_l, part_l, probe2, agg)
     if stats is not None:
         stats["joined_rows"] = joined
@@ -288,4 +304,7 @@ def run_q3_distributed(customer: Sequence[Page], orders: Sequence[Page], lineite
         if fx is not None and exchanges is None:
             fx.close()
     bridge1.close(); bridge2.close()
+    mark("close")
+    if stats is not None and trace is not None:
+        stats["trace_ms"] = [(b[0], round((b[1] - a[1]) * 1e3, 3)) for a, b in zip(trace[:-1], trace[1:])]
     return result

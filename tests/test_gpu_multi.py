@@ -47,7 +47,8 @@ def _worker(rank, world, port, out_dir, fused):
     stats = {}
     out = run_q3_distributed(shard_pages([BIGINT, INTEGER], customer, 1), shard_pages([BIGINT, BIGINT, DATE, INTEGER], orders, 2),
                              shard_pages([BIGINT, DOUBLE, DOUBLE, DATE], lineitem, 3), backend=backend, stats=stats, device=rank, fused=fused)
-    rows = [r for p in out for r in p.rows()]
+    from presto_b200.exchange import page_to_host
+    rows = [r for p in out for r in page_to_host(p).rows()]
     with open(os.path.join(out_dir, f"q3_{rank}.pkl"), "wb") as f:
         pickle.dump({"rows": rows, "stats": stats}, f)
     dist.barrier()
