@@ -27,6 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+NCU_DRAM_BYTES_PER_ROW = 40.01   # measured, see roofline.traffic
 ALGO_BYTES_PER_ROW = 40   # 8 (bigint key) + 4 x 8 (double inputs); output negligible
 
 
@@ -656,7 +657,10 @@ def main():
             "metric": "rows/sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(workload_config(args, rows), parallelism=(f"{world} ranks: PARTIAL per GPU + FINAL merge on rank 0, no row exchange" if world > 1 else "1 GPU")),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel: 39.84 GB for the 995.8 M rows of its launch
+                         # (profiles/r01_ncu_hashagg_fast_1b.txt, one ncu --set full capture) = 40.01 B/row; only quoted for that workload
+                         "traffic": NCU_DRAM_BYTES_PER_ROW * rows if (args.groups == 4 and rows >= 100_000_000) else None,
                          "kernel": "pg::hashAggFastKernel<4,0,false>", "peak_source": peak_kind,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ROW * rows, "kernel_ms": kms},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": r["launches"], "groups": r["groups"], "clocks": clocks, "extra": extra,
