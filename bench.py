@@ -310,6 +310,36 @@ def run_partitioned_output(torch, backend, device, rows, partitions, steps, warm
     return out
 
 
+def run_serialized_page(torch, backend, device, rows, steps, warmup):
+    """PagesSerde over a device-resident page of 8 bigint columns (the PartitionedOutput row shape): serialize to a
+    device wire buffer, deserialize it back to device columns.  Algorithmic bytes: 64 B/row read + 64 B/row written, each way."""
+    from presto_b200 import BIGINT, MEM_DEVICE, PagesSerde
+    from presto_b200.synthetic import splitmix64_torch
+    dev = f"cuda:{device}"
+    cols = [splitmix64_torch(200 + c, 0, rows, dev) for c in range(8)]
+    page = device_page(torch, cols, [BIGINT] * 8)
+    stream = torch.cuda.current_stream()
+    ser = PagesSerde(backend=backend, device=device, output_memory=MEM_DEVICE, cuda_stream=stream.cuda_stream)
+    de = PagesSerde(backend=backend, device=device, output_memory=MEM_DEVICE, cuda_stream=stream.cuda_stream)
+    sms, dms, size = [], [], 0
+    for it in range(warmup + steps):
+        e0, e1, e2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        torch.cuda.synchronize()
+        e0.record(stream)
+        addr, size = ser.serialize(page, copy=False)
+        e1.record(stream)
+        back = de.deserialize(addr, [BIGINT] * 8, size=size, memory=MEM_DEVICE, copy=False)
+        e2.record(stream)
+        torch.cuda.synchronize()
+        assert back.position_count == rows
+        if it >= warmup:
+            sms.append(e0.elapsed_time(e1)); dms.append(e1.elapsed_time(e2))
+    ser.close(); de.close()
+    s_ms, d_ms = float(np.mean(sms)), float(np.mean(dms))
+    return {"rows": rows, "wire_bytes": int(size), "serialize_ms": s_ms, "deserialize_ms": d_ms, "serialize_gbs": 128 * rows / (s_ms / 1000) / 1e9,
+            "deserialize_gbs": 128 * rows / (d_ms / 1000) / 1e9, "achieved_gbs": 256 * rows / ((s_ms + d_ms) / 1000) / 1e9}
+
+
 def run_page_processor_q1(torch, backend, device, rows, steps, warmup):
     """TPC-H Q1 filter + project (HandTpchQuery1.java:237-330): shipdate <= 1998-09-02; 7 output columns."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -636,6 +666,7 @@ def main():
                 ("hash_join_orders_lineitem", lambda: run_join(torch, backend, local, int(150_000_000 * scale), int(600_037_902 * scale), 2, 1)),
                 ("partitioned_output_8_bigint_cols", lambda: run_partitioned_output(torch, backend, local, int((1 << 28) * scale), 8, 2, 1)),
                 ("page_processor_q1", lambda: run_page_processor_q1(torch, backend, local, int((1 << 28) * scale), 2, 1)),
+                ("serialized_page_8_bigint_cols", lambda: run_serialized_page(torch, backend, local, int((1 << 24) * scale), 3, 2)),
                 ("q1_pipeline", lambda: run_q1_pipeline(torch, backend, local, int(600_037_902 * scale), 2, 1)),
                 ("q3_pipeline", lambda: run_q3(torch, backend, local, int(150_000_000 * scale), 2, 1)),
             ]:

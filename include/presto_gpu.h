@@ -375,6 +375,39 @@ int32_t pg_filter_project_get_last_selection(pg_operator* op, int32_t* is_list, 
  * copied when `capacity` suffices.  PG_ERR_UNSUPPORTED when the program runs on the interpreter kernels instead. */
 int32_t pg_filter_project_explain(const pg_filter_project_config* config, uint64_t nullable_inputs, char* buffer, size_t capacity, size_t* needed);
 
+/* ------------------------------------------------------------------------------------------------
+ * SerializedPage wire format: what PartitionedOutput hands to an OutputBuffer and an
+ * ExchangeClient receives when pages leave the box.
+ *   PagesSerde.serialize / deserialize            presto-spi/.../spi/page/PagesSerde.java:67-156
+ *   PagesSerdeUtil.writeSerializedPage / read...   presto-spi/.../spi/page/PagesSerdeUtil.java:45-120
+ *   block encodings                                presto-common/.../common/block/{LongArray,IntArray,ByteArray,VariableWidth,
+ *                                                  RunLength,Dictionary}BlockEncoding.java, EncoderUtil.java:31-100
+ * Wire bytes: [positionCount i32][markers u8][uncompressedSize i32][size i32][checksum i64] (21 bytes, little endian) then the raw
+ * page: [channelCount i32] and per channel [name length i32][encoding name][positionCount i32][mayHaveNull u8][null bits, MSB first]
+ * [non-null values].  Compression and encryption markers are not produced and are rejected with PG_ERR_UNSUPPORTED.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pg_pages_serde pg_pages_serde;
+typedef struct pg_pages_serde_config {
+    int32_t checksum_enabled;      /* PagesSerde.checksumEnabled: CHECKSUMMED marker + CRC32 over data, markers, positionCount, uncompressedSize */
+    pg_operator_options options;   /* device; output_memory = where serialized bytes AND deserialized pages are returned; cuda_stream */
+} pg_pages_serde_config;
+#define PG_SERIALIZED_PAGE_HEADER_BYTES 21
+#define PG_PAGE_MARKER_COMPRESSED 1
+#define PG_PAGE_MARKER_ENCRYPTED 2
+#define PG_PAGE_MARKER_CHECKSUMMED 4
+
+int32_t pg_pages_serde_create(const pg_pages_serde_config* config, pg_pages_serde** out);
+/* serialize(Page) + writeSerializedPage.  FLAT blocks → LONG_ARRAY / INT_ARRAY / BYTE_ARRAY / VARIABLE_WIDTH, RLE blocks → RLE,
+ * DICTIONARY blocks are written flat (the reference writes the compacted dictionary; a reader sees the same rows).
+ * *bytes (in options.output_memory) stays valid until the next call on this serde. */
+int32_t pg_pages_serde_serialize(pg_pages_serde* serde, const pg_page* page, const uint8_t** bytes, int64_t* size);
+/* readSerializedPage + deserialize.  `memory` = where `bytes` live; `types` gives the SQL type of every channel (the wire only
+ * carries encodings).  RLE / DICTIONARY channels come back as blocks of those encodings.  A CHECKSUMMED page whose CRC32 does not
+ * match fails with PG_ERR_INVALID_ARGUMENT.  out->blocks (in options.output_memory) stay valid until the next call. */
+int32_t pg_pages_serde_deserialize(pg_pages_serde* serde, const uint8_t* bytes, int64_t size, int32_t memory,
+                                   const int32_t* types, int32_t n_types, pg_page* out);
+int32_t pg_pages_serde_destroy(pg_pages_serde* serde);
+
 #ifdef __cplusplus
 }
 #endif

@@ -147,6 +147,14 @@ def i32_array(values):
     return (C.c_int32 * max(1, len(values)))(*values)
 
 
+class pg_pages_serde_config(C.Structure):
+    _fields_ = [("checksum_enabled", C.c_int32), ("options", pg_operator_options)]
+
+
+SERIALIZED_PAGE_HEADER_BYTES = 21
+PAGE_MARKER_COMPRESSED, PAGE_MARKER_ENCRYPTED, PAGE_MARKER_CHECKSUMMED = 1, 2, 4
+
+
 class Backend:
     """Entry points of one shared library, bound by prefix (``pg_`` for the CUDA product)."""
 
@@ -183,6 +191,10 @@ class Backend:
         "partitioned_output_get_offsets": (C.c_int32, [C.c_void_p, C.c_void_p]),
         "filter_project_create": (C.c_int32, [C.POINTER(pg_filter_project_config), C.POINTER(C.c_void_p)]),
         "filter_project_get_last_selection": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+        "pages_serde_create": (C.c_int32, [C.POINTER(pg_pages_serde_config), C.POINTER(C.c_void_p)]),
+        "pages_serde_serialize": (C.c_int32, [C.c_void_p, C.POINTER(pg_page), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+        "pages_serde_deserialize": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(pg_page)]),
+        "pages_serde_destroy": (C.c_int32, [C.c_void_p]),
     }
     # only the CUDA product exports these
     _DEVICE_SIGNATURES = {

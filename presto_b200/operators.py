@@ -344,3 +344,50 @@ class FilterAndProjectOperator(Operator):
         is_list, size = C.c_int32(), C.c_int64()
         self._b.check(self._b.filter_project_get_last_selection(self._h, C.byref(is_list), C.byref(size)))
         return bool(is_list.value), size.value
+
+
+class PagesSerde:
+    """PagesSerde (presto-spi/.../spi/page/PagesSerde.java:67-156) + PagesSerdeUtil.writeSerializedPage / readSerializedPage
+    (:64-88): pages to and from the SerializedPage wire bytes (21-byte header + raw page)."""
+
+    def __init__(self, *, checksum_enabled: bool = False, backend=None, **options):
+        self._b = backend or _default_backend()
+        cfg = abi.pg_pages_serde_config()
+        cfg.checksum_enabled = int(checksum_enabled)
+        cfg.options = _options(**options)
+        self._memory = cfg.options.output_memory
+        self._h = C.c_void_p()
+        self._b.check(self._b.pages_serde_create(C.byref(cfg), C.byref(self._h)))
+
+    def serialize(self, page: Page, copy: bool = True):
+        """The wire bytes of ``page``: a numpy uint8 array (copy=True) or (address, size) of serde-owned memory in the serde's
+        output memory (valid until the next call)."""
+        cpage, keep = page.as_c()
+        ptr, size = C.c_void_p(), C.c_int64()
+        self._b.check(self._b.pages_serde_serialize(self._h, C.byref(cpage), C.byref(ptr), C.byref(size)))
+        del keep
+        if not copy:
+            return ptr.value, size.value
+        out = np.empty(size.value, dtype=np.uint8)
+        if self._memory == abi.MEM_DEVICE:
+            self._b.check(self._b.memcpy_d2h(out.ctypes.data, ptr, size.value))
+        else:
+            C.memmove(out.ctypes.data, ptr, size.value)
+        return out
+
+    def deserialize(self, data, types: Sequence[int], *, size: Optional[int] = None, memory: int = abi.MEM_HOST, copy: bool = True) -> Page:
+        """``data``: numpy uint8 array (host) or an address (with ``size`` and ``memory``)."""
+        if isinstance(data, np.ndarray):
+            data = np.ascontiguousarray(data, dtype=np.uint8)
+            ptr, size, memory = data.ctypes.data, data.size, abi.MEM_HOST
+        else:
+            ptr = int(data)
+        ty = abi.i32_array(types)
+        out = abi.pg_page()
+        self._b.check(self._b.pages_serde_deserialize(self._h, C.c_void_p(ptr), size, memory, ty, len(types), C.byref(out)))
+        return Page.from_c(out, self._b, copy=copy)
+
+    def close(self) -> None:
+        if self._h:
+            self._b.pages_serde_destroy(self._h)
+            self._h = C.c_void_p()

@@ -212,15 +212,24 @@ class Page:
                     C.memmove(out.ctypes.data, ptr, nbytes)
                 return out
 
-            is_null = fetch(b.is_null, n, np.uint8) if b.is_null else None
+            # storage positions: the block's own rows (FLAT), the dictionary's entries, or the single RLE value
+            enc = int(b.encoding)
+            m = n if enc == abi.ENC_FLAT else (int(b.dictionary_size) if enc == abi.ENC_DICTIONARY else 1)
+            is_null = fetch(b.is_null, m, np.uint8) if b.is_null else None
             if t == abi.VARCHAR:
-                offsets = fetch(b.offsets, 4 * (n + 1), np.int32)
-                total = int(offsets[-1]) if n else 0
+                offsets = fetch(b.offsets, 4 * (m + 1), np.int32)
+                total = int(offsets[-1]) if m else 0
                 data = fetch(b.values, total, np.uint8) if total else np.zeros(1, dtype=np.uint8)
-                blocks.append(Block(t, n, data, is_null, offsets))
+                storage = Block(t, m, data, is_null, offsets)
             else:
-                vals = fetch(b.values, n * TYPE_WIDTH[t], _NP_DTYPE[t])
-                blocks.append(Block(t, n, vals, is_null))
+                vals = fetch(b.values, m * TYPE_WIDTH[t], _NP_DTYPE[t])
+                storage = Block(t, m, vals, is_null)
+            if enc == abi.ENC_DICTIONARY:
+                blocks.append(Block.dictionary(storage, fetch(b.ids, 4 * int(b.position_count), np.int32)))
+            elif enc == abi.ENC_RLE:
+                blocks.append(Block.rle(storage, int(b.position_count)))
+            else:
+                blocks.append(storage)
         return Page(blocks, n)
 
 
