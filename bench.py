@@ -174,7 +174,8 @@ def run_reference(args):
     line = {
         "metric": "rows/sec", "value": value, "unit": "rows/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, sample),
+        "config": dict(workload_config(args, sample), timing="host wall clock (time.perf_counter) around each step; no GPU involved",
+                       l2="host arm: not applicable"),
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} rows of the same synthetic batch per step, {threads} threads x one oracle operator each + FINAL merge"},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -1,5 +1,6 @@
 // presto_b200 — runtime: device management, operator base, page staging, scalar hash helpers.
 #include "common.cuh"
+#include <cub/device/device_scan.cuh>
 #include <map>
 #include <mutex>
 
@@ -116,6 +117,28 @@ __global__ void flattenKernel(const T* __restrict__ dict, const uint8_t* __restr
     }
 }
 
+// VARCHAR dictionaries (DictionaryBlock over a VariableWidthBlock — how low-cardinality strings usually arrive): row lengths, then
+// (after an inclusive scan of the lengths into the flat offsets) the bytes of every row
+__global__ void flattenVarcharLengthsKernel(const int32_t* __restrict__ dictOffsets, const int32_t* __restrict__ ids, int64_t n, int32_t* __restrict__ outOffsets)
+{
+    for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {
+        const int32_t id = ids ? ids[i] : 0;
+        outOffsets[i + 1] = dictOffsets[id + 1] - dictOffsets[id];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) outOffsets[0] = 0;
+}
+__global__ void flattenVarcharBytesKernel(const uint8_t* __restrict__ dictBytes, const int32_t* __restrict__ dictOffsets, const uint8_t* __restrict__ dictNulls,
+                                          const int32_t* __restrict__ ids, int64_t n, const int32_t* __restrict__ outOffsets, uint8_t* __restrict__ outBytes,
+                                          uint8_t* __restrict__ outNulls)
+{
+    for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {
+        const int32_t id = ids ? ids[i] : 0;
+        const int32_t src = dictOffsets[id], len = dictOffsets[id + 1] - src, dst = outOffsets[i];
+        for (int32_t k = 0; k < len; k++) outBytes[dst + k] = dictBytes[src + k];
+        if (outNulls) outNulls[i] = dictNulls[id];
+    }
+}
+
 PageStager::PageStager(Operator* o) : op(o)
 {
     for (auto& s : slots) {
@@ -166,20 +189,33 @@ int PageStager::stage(const pg_page* page, const std::vector<int>& channels, std
         bool encoded = b.encoding != PG_ENC_FLAT;
         PG_CHECK_ARG(b.encoding == PG_ENC_FLAT || b.encoding == PG_ENC_DICTIONARY || b.encoding == PG_ENC_RLE, "unknown block encoding");
         int64_t entries = encoded ? (b.encoding == PG_ENC_RLE ? 1 : b.dictionary_size) : b.position_count;
-        if (b.type == PG_TYPE_VARCHAR && encoded)
-            throw Error(PG_ERR_UNSUPPORTED, "dictionary / RLE encoded VARCHAR blocks are not on the GPU path yet; flatten before addInput");
         const void* dValues = b.values; const uint8_t* dNulls = b.is_null; const int32_t* dOffsets = b.offsets; const int32_t* dIds = b.ids;
         if (host && c.n > 0) {
             if (b.type == PG_TYPE_VARCHAR) {
                 PG_CHECK_ARG(b.offsets != nullptr, "VARCHAR block without offsets");
                 size_t obytes = (size_t) (entries + 1) * 4;
-                slot.offsets[i].reserve(obytes);
-                PG_CUDA(cudaMemcpyAsync(slot.offsets[i].ptr, b.offsets, obytes, cudaMemcpyHostToDevice, cs));
                 size_t vbytes = (size_t) b.offsets[entries];
-                slot.values[i].reserve(vbytes + 16);
-                if (vbytes) PG_CUDA(cudaMemcpyAsync(slot.values[i].ptr, b.values, vbytes, cudaMemcpyHostToDevice, cs));
+                // encoded: the dictionary goes to the scratch buffer (bytes, then offsets, then ids); the flat column is built below
+                DeviceBuffer& vb = encoded ? slot.scratch[i] : slot.values[i];
+                const size_t offAt = (vbytes + 15) & ~size_t(15), idsAt = (offAt + obytes + 15) & ~size_t(15);
+                vb.reserve(encoded ? idsAt + (size_t) c.n * 4 + 16 : vbytes + 16);
+                if (vbytes) PG_CUDA(cudaMemcpyAsync(vb.ptr, b.values, vbytes, cudaMemcpyHostToDevice, cs));
                 op->stats.h2d_bytes += (int64_t) (obytes + vbytes);
-                dValues = slot.values[i].ptr; dOffsets = slot.offsets[i].as<int32_t>();
+                dValues = vb.ptr;
+                if (!encoded) {
+                    slot.offsets[i].reserve(obytes);
+                    PG_CUDA(cudaMemcpyAsync(slot.offsets[i].ptr, b.offsets, obytes, cudaMemcpyHostToDevice, cs));
+                    dOffsets = slot.offsets[i].as<int32_t>();
+                }
+                else {
+                    PG_CUDA(cudaMemcpyAsync((char*) vb.ptr + offAt, b.offsets, obytes, cudaMemcpyHostToDevice, cs));
+                    dOffsets = (const int32_t*) ((char*) vb.ptr + offAt);
+                    if (b.encoding == PG_ENC_DICTIONARY) {
+                        PG_CUDA(cudaMemcpyAsync((char*) vb.ptr + idsAt, b.ids, (size_t) c.n * 4, cudaMemcpyHostToDevice, cs));
+                        op->stats.h2d_bytes += c.n * 4;
+                        dIds = (const int32_t*) ((char*) vb.ptr + idsAt);
+                    }
+                }
             }
             else {
                 size_t vbytes = (size_t) entries * w;
@@ -205,7 +241,34 @@ int PageStager::stage(const pg_page* page, const std::vector<int>& channels, std
             }
             copied = true;
         }
-        if (encoded && c.n > 0) {
+        if (encoded && c.n > 0 && b.type == PG_TYPE_VARCHAR) {
+            // lengths → inclusive scan → offsets; then the bytes (and nulls) row by row
+            PG_CHECK_ARG(dOffsets != nullptr, "VARCHAR block without offsets");
+            const int32_t* ids = b.encoding == PG_ENC_DICTIONARY ? dIds : nullptr;
+            slot.offsets[i].reserve((size_t) (c.n + 1) * 4);
+            int32_t* outOff = slot.offsets[i].as<int32_t>();
+            const int grid = (int) std::min<int64_t>(divUp(c.n, 256), 4096);
+            flattenVarcharLengthsKernel<<<grid, 256, 0, cs>>>(dOffsets, ids, c.n, outOff);
+            size_t tb = 0;
+            cub::DeviceScan::InclusiveSum(nullptr, tb, outOff + 1, outOff + 1, (int) c.n, cs);
+            DeviceBuffer scanTmp; scanTmp.reserve(tb);
+            cub::DeviceScan::InclusiveSum(scanTmp.ptr, tb, outOff + 1, outOff + 1, (int) c.n, cs);
+            int32_t totalBytes = 0;
+            PG_CUDA(cudaMemcpyAsync(&totalBytes, outOff + c.n, 4, cudaMemcpyDeviceToHost, cs));
+            PG_CUDA(cudaStreamSynchronize(cs));
+            slot.values[i].reserve((size_t) totalBytes + 16);
+            uint8_t* outNulls = nullptr;
+            if (dNulls) {
+                if (host) outNulls = slot.nulls[i].as<uint8_t>() + (((size_t) entries + 15) & ~size_t(15));
+                else { slot.nulls[i].reserve((size_t) c.n); outNulls = slot.nulls[i].as<uint8_t>(); }
+            }
+            flattenVarcharBytesKernel<<<grid, 256, 0, cs>>>((const uint8_t*) dValues, dOffsets, dNulls, ids, c.n, outOff, slot.values[i].as<uint8_t>(), outNulls);
+            op->stats.kernel_launches += 4;
+            PG_CUDA(cudaGetLastError());
+            PG_CUDA(cudaStreamSynchronize(cs));      // scanTmp dies here
+            dValues = slot.values[i].ptr; dNulls = outNulls; dOffsets = outOff;
+        }
+        else if (encoded && c.n > 0) {
             // flatten on the stream the source data lands on
             slot.values[i].reserve((size_t) c.n * w);
             uint8_t* outNulls = nullptr;
