@@ -57,8 +57,8 @@ def test_generated_ptx_assembles_for_sm_100a(make, nullable, tmp_path):
     ptx = FilterAndProjectOperator.explain(types, program, nullable_inputs=nullable)
     assert ".target sm_100a" in ptx and ".entry fp_project" in ptx
     assert (".entry fp_filter" in ptx) == (program.filter >= 0)
-    # four rounds of 32 rows per loop iteration, each with its own registers (the loads of all of them are issued together)
-    assert "%row3" in ptx and "%row4" not in ptx
+    # eight rounds of 32 rows (one 256-row unit) per loop iteration, each with its own registers: the loads of all of them are issued together
+    assert "%row7" in ptx and "%row8" not in ptx
     src = tmp_path / "k.ptx"
     src.write_text(ptx)
     r = subprocess.run([PTXAS, "-arch=sm_100a", "-v", "-o", str(tmp_path / "k.cubin"), str(src)], capture_output=True, text=True)
