@@ -53,6 +53,7 @@ struct AggLaunch {
 constexpr int kAggThreads = 256;
 constexpr int kSharedProbes = 8;
 constexpr int kWarpAggMaxGroups = 8;
+constexpr int kMidMinGroups = 40;        // from here on the CTA-per-SM shared table beats tier 0 + a small tier-1 table (see launchFastT)
 constexpr int kMaxSubsetPasses = 1;      // mid mode (47 G rows/s at 1000 groups) loses to direct mode (~28 G rows/s flat) from the second hash-subset pass on
 
 template <int MAXV> struct RowsPerThread { static constexpr int value = MAXV <= 4 ? 4 : 2; };   // always even: rows are loaded in pairs
@@ -1332,7 +1333,10 @@ public:
         const int64_t passes = (int64_t) ((double) knownGroups * 1.25 / midCapacity) + 1;
         const char* modeEnv0 = getenv("PG_AGG_MODE");
         const bool forceDirect = modeEnv0 && !strcmp(modeEnv0, "direct");
-        if (!forceDirect && knownGroups > (int64_t) sharedLimit * 9 / 10 && passes <= kMaxSubsetPasses) {   // one pass; beyond that direct mode is faster
+        const bool forceMid = modeEnv0 && !strcmp(modeEnv0, "mid");
+        // measured (256 M rows, 4 sums, G rows/s): tiers 0/1 — 109 up to 10 groups (all tier 0), 44 / 39 / 34 / 33 / 18 at 11 / 16 / 32 / 64 / 128;
+        // one 4096-slot table per SM — 22 / 27 / 36 / 44 / 47 / 49 at 11 / 16 / 32 / 64 / 128 / 256..1000 (fewer threads per hot address)
+        if (!forceDirect && (knownGroups > kMidMinGroups || forceMid) && passes <= kMaxSubsetPasses) {   // one pass; beyond that direct mode is faster
             auto kern = hashAggFastKernel<NV, CNT, true>;
             L.S = midSlots; L.sLimit = midCapacity; L.nAccAlloc = NC; L.subsetCount = (uint32_t) passes;
             const size_t smem = SharedLayout(midSlots, 1, NC, false).total;
