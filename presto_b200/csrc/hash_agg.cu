@@ -11,6 +11,13 @@
 // slot's first-touch row, assigned at output time (InMemoryHashAggregationBuilder.buildResult order :326-352,400-403).
 //
 // Algorithmic HBM bytes per row = key bytes + 8 B per aggregated column; everything else is on-chip.
+//
+// Where a row's accumulators live depends on how many groups the page has (learned from a probe chunk of the first page):
+//   <= 10 groups      tier 0: per-thread private accumulators in shared memory, no atomics            (hashAggFastKernel)
+//   11 .. 40          warp mode: per-warp accumulator sets, same-group lanes resolved in rounds         (hashAggFastKernel, warpGroups > 0)
+//   .. ~3000          one 4096-slot shared table per SM, shared-memory reductions                       (hashAggFastKernel<.., MID = true>)
+//   more              direct mode: native f64 REDs on the HBM table, one L2-resident slot range per pass (hashAggDirectKernel)
+// Keys that are not one BIGINT / two 32-bit columns, NULLs, masks, bigint sums: hashAggKernel<W, MAXV> (tiers 0 / 1 / 2).
 #include "common.cuh"
 #include "group_table.cuh"
 #include "key_layout.h"
@@ -53,6 +60,8 @@ struct AggLaunch {
 constexpr int kAggThreads = 256;
 constexpr int kSharedProbes = 8;
 constexpr int kWarpAggMaxGroups = 8;
+constexpr int kWarpMaxGroups = 40;       // up to here: per-warp accumulator sets (47 / 41 G rows/s at 16 / 32 groups vs 39 / 34 on tiers 0/1; beyond, the
+                                         // 512-slot table of this geometry fills up and the 4096-slot table per SM wins: 44+ G rows/s)
 constexpr int kMidMinGroups = 40;        // from here on the CTA-per-SM shared table beats tier 0 + a small tier-1 table (see launchFastT)
 constexpr int kMaxSubsetPasses = 1;      // mid mode (47 G rows/s at 1000 groups) loses to direct mode (~28 G rows/s flat) from the second hash-subset pass on
 
@@ -74,7 +83,7 @@ struct SharedLayout {
         first = o; o += 4 * S2;
         state = o; o += (W > 1 ? 4 * S2 : 0);
         sid = o; o += (S2 + 15) & ~15u;
-        misc = o; o += 256;   // claimed count, next tier-0 id, slot of each tier-0 id (<= 32)
+        misc = o; o += 1280;  // claimed count, next tier-0 / warp-table id, slot of each id (<= 254)
         o = (o + 15) & ~15u;
         tier0 = o; o += withTier0 ? kTier0Bytes : 0;
         total = o;
@@ -455,6 +464,7 @@ struct FastLaunch {
     uint32_t capBits;                    // direct mode: log2(t.cap); subsets are contiguous slot ranges of the HBM table
     // packed-key mode (keyMode 1): two 32-bit key columns without NULLs on this page (Q1: returnflag, linestatus).  Inside the kernel
     // the key is (col1 << 32 | col0); at the HBM table it is re-packed into the table's W = 2 layout (KeyLayout: word / shift per column).
+    int32_t warpGroups;                  // > 0: warp-private accumulator sets for the first warpGroups group ids instead of tier 0 (11 .. ~250 groups)
     int32_t keyMode;
     const uint32_t* key32[2];
     int32_t kWord[2], kShift[2];
@@ -634,7 +644,11 @@ __global__ void __launch_bounds__(MID ? 512 : kAggThreads, MID ? 1 : 2) hashAggF
     const GroupTable& T = P.t;
 
     SharedTable<1> st;
-    st.S = P.S; st.S2 = P.S + 2; st.sLimit = P.sLimit; st.tier0Groups = K0;
+    // warp mode (host decides: more groups than tier 0 holds, few enough for per-warp sets): the tier-0 region holds, per warp,
+    // [NC accumulator columns + firstRow][KW] instead; a warp updates its own set with plain LDS / DADD / STS, resolving lanes that
+    // hit the same group in rounds (rank among the __match_any_sync peers) — no CAS loops, no contention across warps
+    const int KW = MID ? 0 : P.warpGroups;
+    st.S = P.S; st.S2 = P.S + 2; st.sLimit = P.sLimit; st.tier0Groups = KW > 0 ? KW : K0;
     const SharedLayout lay(P.S, 1, P.nAccAlloc, !MID);
     st.keys = (volatile uint64_t*) (smemRaw + lay.keys);
     st.acc = (uint64_t*) (smemRaw + lay.acc);
@@ -645,10 +659,16 @@ __global__ void __launch_bounds__(MID ? 512 : kAggThreads, MID ? 1 : 2) hashAggF
     uint64_t* tier0 = (uint64_t*) (smemRaw + lay.tier0);     // [K0][NC][256]
     for (uint32_t i = tid; i < st.S2; i += THREADS) { st.keys[i] = kEmptyKey; st.first[i] = kNoRow32; st.sid[i] = 0xFF; }
     for (uint32_t i = tid; i < (uint32_t) P.nAccAlloc * st.S2; i += THREADS) st.acc[i] = 0;
-    if (tid < 64) st.count[tid] = 0;
+    for (int i = tid; i < 320; i += THREADS) st.count[i] = 0;
+    uint64_t* wtab = tier0 + (size_t) (tid >> 5) * (NC + 1) * (KW > 0 ? KW : 1);    // this warp's [NC + 1][KW]
     if (!MID) {
+        if (KW > 0) {
+            for (int i = tid; i < (THREADS / 32) * (NC + 1) * KW; i += THREADS) tier0[i] = ((i / KW) % (NC + 1)) == NC ? ~0ULL : 0ULL;
+        }
+        else {
 #pragma unroll
-        for (int i = 0; i < K0 * NC; i++) tier0[i * THREADS + tid] = 0;
+            for (int i = 0; i < K0 * NC; i++) tier0[i * THREADS + tid] = 0;
+        }
     }
     __syncthreads();
 
@@ -680,11 +700,9 @@ __global__ void __launch_bounds__(MID ? 512 : kAggThreads, MID ? 1 : 2) hashAggF
             for (int c = 0; c < NV; c++) { v[c].x = ldStream64(P.vals[c] + row0); v[c].y = 0; }
         }
     };
-    auto consumeRow = [&](uint64_t key, const uint64_t (&vals)[NV], uint32_t rowIdx) {
-        const uint64_t h = murmur64(key);
-        // subset from the LOW hash word (the shared slot index uses bits 32..43: the two must be independent)
-        if (MID && P.subsetCount > 1 && (uint32_t) (((h & 0xffffffffULL) * (uint64_t) P.subsetCount) >> 32) != P.subsetIndex) return;   // another pass owns this key (the caller reconverges the warp)
-        int sslot = -1;
+    // shared-table slot and group id of a key (sslot < 0: not in the CTA's table)
+    auto lookup = [&](uint64_t key, uint64_t h, int& sslot, uint32_t& id) {
+        sslot = -1;
         if (key == kEmptyKey) sslot = (int) st.S + 1;      // the sentinel-valued key has its own slot (an empty slot must never match it)
         else if (!bypass) {
             const uint32_t s = (uint32_t) (h >> 32) & (st.S - 1);
@@ -697,8 +715,26 @@ __global__ void __launch_bounds__(MID ? 512 : kAggThreads, MID ? 1 : 2) hashAggF
                 probeHits = 0; probeMisses = 0;
             }
         }
-        uint32_t id = 0xFF;
+        id = 0xFF;
         if (sslot >= 0) id = st.sid[sslot];
+    };
+    // tiers 1 and 2
+    auto applyShared = [&](uint64_t key, uint64_t h, const uint64_t (&vals)[NV], uint32_t rowIdx, int sslot) {
+        if (sslot >= 0) {
+            // tier 1: the CTA's shared table, shared-space reductions (no return value needed)
+#pragma unroll
+            for (int c = 0; c < NV; c++) sharedAddF64(&st.acc[c * st.S2 + sslot], vals[c]);
+            if (CNT) sharedAddU64(&st.acc[NV * st.S2 + sslot], 1);
+            if (rowIdx < *(volatile uint32_t*) &st.first[sslot]) sharedMinU32(&st.first[sslot], rowIdx);
+        }
+        else fastGlobalRow<NV, CNT>(P, key, h, vals, rowIdx);
+    };
+    auto consumeRow = [&](uint64_t key, const uint64_t (&vals)[NV], uint32_t rowIdx) {
+        const uint64_t h = murmur64(key);
+        // subset from the LOW hash word (the shared slot index uses bits 32..43: the two must be independent)
+        if (MID && P.subsetCount > 1 && (uint32_t) (((h & 0xffffffffULL) * (uint64_t) P.subsetCount) >> 32) != P.subsetIndex) return;   // another pass owns this key (the caller reconverges the warp)
+        int sslot; uint32_t id;
+        lookup(key, h, sslot, id);
         if (!MID && id < (uint32_t) K0) {
             uint64_t* mine = tier0 + (size_t) id * NC * THREADS + tid;
 #pragma unroll
@@ -709,17 +745,47 @@ __global__ void __launch_bounds__(MID ? 512 : kAggThreads, MID ? 1 : 2) hashAggF
             if (CNT) mine[NV * THREADS] += 1;
             if (!((seen0 >> id) & 1u)) { seen0 |= 1u << id; atomicMin(&st.first[sslot], rowIdx); }
         }
-        else if (sslot >= 0) {
-            // tier 1: the CTA's shared table, shared-space reductions (no return value needed)
+        else applyShared(key, h, vals, rowIdx, sslot);
+    };
+    // warp mode: the whole warp takes one row per lane together (live = the lane has a row)
+    auto consumeRowWarp = [&](bool live, uint64_t key, const uint64_t (&vals)[NV], uint32_t rowIdx) {
+        const uint64_t h = murmur64(key);
+        int sslot = -1; uint32_t id = 0xFF;
+        if (live) lookup(key, h, sslot, id);
+        __syncwarp();
+        const bool mine = live && id < (uint32_t) KW;
+        const int wid = mine ? (int) id : -1 - lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, wid);
+        const int rank = __popc(peers & ((1u << lane) - 1));
+        const int rounds = (int) __reduce_max_sync(0xffffffffu, mine ? (unsigned) __popc(peers) : 0u);
+        for (int r = 0; r < rounds; r++) {
+            if (mine && rank == r) {
+                volatile uint64_t* w = wtab + wid;
 #pragma unroll
-            for (int c = 0; c < NV; c++) sharedAddF64(&st.acc[c * st.S2 + sslot], vals[c]);
-            if (CNT) sharedAddU64(&st.acc[NV * st.S2 + sslot], 1);
-            if (rowIdx < *(volatile uint32_t*) &st.first[sslot]) sharedMinU32(&st.first[sslot], rowIdx);
+                for (int c = 0; c < NV; c++) {
+                    const double cur = __longlong_as_double((long long) w[c * KW]);
+                    w[c * KW] = (uint64_t) __double_as_longlong(cur + __longlong_as_double((long long) vals[c]));
+                }
+                if (CNT) w[NV * KW] = w[NV * KW] + 1;
+                if ((uint64_t) rowIdx < w[NC * KW]) w[NC * KW] = rowIdx;
+            }
+            __syncwarp();
         }
-        else fastGlobalRow<NV, CNT>(P, key, h, vals, rowIdx);
+        if (live && !mine) applyShared(key, h, vals, rowIdx, sslot);
+        __syncwarp();
     };
     auto consumeTile = [&](int64_t tile, const ulonglong2& k, const ulonglong2 (&v)[NV]) {
         const int64_t row0 = tile * TILE + 2 * tid;
+        if (KW > 0) {
+            uint64_t vals[NV];
+#pragma unroll
+            for (int c = 0; c < NV; c++) vals[c] = v[c].x;
+            consumeRowWarp(row0 < P.n, k.x, vals, (uint32_t) row0);
+#pragma unroll
+            for (int c = 0; c < NV; c++) vals[c] = v[c].y;
+            consumeRowWarp(row0 + 1 < P.n, k.y, vals, (uint32_t) (row0 + 1));
+            return;
+        }
         if (row0 < P.n) {
             uint64_t vals[NV];
 #pragma unroll
@@ -749,9 +815,33 @@ __global__ void __launch_bounds__(MID ? 512 : kAggThreads, MID ? 1 : 2) hashAggF
         tile = t2;
     }
 
-    // ---- fold tier 0 into the shared table, then flush the shared table into the HBM table ----
+    // ---- fold tier 0 (or the warp sets) into the shared table, then flush the shared table into the HBM table ----
     __syncthreads();
-    const uint32_t nT0 = MID ? 0u : min(st.count[1], (uint32_t) K0);
+    if (KW > 0) {
+        const uint32_t nIds = min(st.count[1], (uint32_t) KW);
+        for (uint32_t i = tid; i < nIds * (uint32_t) (NC + 1); i += THREADS) {
+            const uint32_t id = i / (NC + 1), c = i % (NC + 1);
+            const uint32_t slot = st.count[2 + id];
+            if (c == (uint32_t) NC) {
+                uint64_t f = ~0ULL;
+                for (int w = 0; w < THREADS / 32; w++) f = min(f, tier0[((size_t) w * (NC + 1) + c) * KW + id]);
+                if (f != ~0ULL) st.first[slot] = min(st.first[slot], (uint32_t) f);
+            }
+            else if (c < (uint32_t) NV) {
+                double d = 0;
+                for (int w = 0; w < THREADS / 32; w++) d += __longlong_as_double((long long) tier0[((size_t) w * (NC + 1) + c) * KW + id]);
+                double* dst = (double*) &st.acc[c * st.S2 + slot];
+                *dst = *dst + d;
+            }
+            else {
+                uint64_t x = 0;
+                for (int w = 0; w < THREADS / 32; w++) x += tier0[((size_t) w * (NC + 1) + c) * KW + id];
+                st.acc[c * st.S2 + slot] += x;
+            }
+        }
+        __syncthreads();
+    }
+    const uint32_t nT0 = (MID || KW > 0) ? 0u : min(st.count[1], (uint32_t) K0);
     const int warp = tid >> 5;
     for (uint32_t pairIdx = warp; pairIdx < nT0 * (uint32_t) NC; pairIdx += THREADS / 32) {
         const uint32_t id = pairIdx / NC, c = pairIdx % NC;
@@ -1334,9 +1424,15 @@ public:
         const char* modeEnv0 = getenv("PG_AGG_MODE");
         const bool forceDirect = modeEnv0 && !strcmp(modeEnv0, "direct");
         const bool forceMid = modeEnv0 && !strcmp(modeEnv0, "mid");
+        // warp-private accumulator sets: more groups than tier 0 holds (K0), at most what the per-warp sets hold (KW)
+        constexpr int K0host = FastGeom<NV, CNT>::K0;
+        const int KWcap = std::min<int>(254, kTier0Bytes / ((kAggThreads / 32) * (NC + 1) * 8));
+        const bool forceWarp = modeEnv0 && !strcmp(modeEnv0, "warp");
+        const bool warpMode = !forceMid && !forceDirect && !(modeEnv0 && !strcmp(modeEnv0, "tiered")) && knownGroups > K0host && (knownGroups <= kWarpMaxGroups || forceWarp) && knownGroups <= KWcap;
+        L.warpGroups = warpMode ? KWcap : 0;
         // measured (256 M rows, 4 sums, G rows/s): tiers 0/1 — 109 up to 10 groups (all tier 0), 44 / 39 / 34 / 33 / 18 at 11 / 16 / 32 / 64 / 128;
         // one 4096-slot table per SM — 22 / 27 / 36 / 44 / 47 / 49 at 11 / 16 / 32 / 64 / 128 / 256..1000 (fewer threads per hot address)
-        if (!forceDirect && (knownGroups > kMidMinGroups || forceMid) && passes <= kMaxSubsetPasses) {   // one pass; beyond that direct mode is faster
+        if (!forceDirect && !warpMode && (knownGroups > kMidMinGroups || forceMid) && passes <= kMaxSubsetPasses) {   // one pass; beyond that direct mode is faster
             auto kern = hashAggFastKernel<NV, CNT, true>;
             L.S = midSlots; L.sLimit = midCapacity; L.nAccAlloc = NC; L.subsetCount = (uint32_t) passes;
             const size_t smem = SharedLayout(midSlots, 1, NC, false).total;

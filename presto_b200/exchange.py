@@ -108,6 +108,26 @@ def all_to_all_pages(page: Page, offsets: Sequence[int], types: Sequence[int], g
     return Page(blocks, total)
 
 
+def serialize_partitions(serde, page: Page, offsets: Sequence[int]) -> List[np.ndarray]:
+    """Off-box leg of a repartition: one SerializedPage (wire bytes) per partition of a PartitionedOutputOperator output page
+    (partition p = rows offsets[p]:offsets[p+1]) — what OptimizedPartitionedOutputOperator.flush hands to OutputBuffer.enqueue
+    (MB/operator/repartition/OptimizedPartitionedOutputOperator.java:774-797).  Device pages are sliced by pointer arithmetic; the
+    serde runs on the GPU."""
+    out = []
+    for p in range(len(offsets) - 1):
+        lo, hi = int(offsets[p]), int(offsets[p + 1])
+        blocks = []
+        for b in page.blocks:
+            w = TYPE_WIDTH[b.type]
+            if b.on_device:
+                nulls = b.device_ptrs["is_null"]
+                blocks.append(Block.device(b.type, hi - lo, b.device_ptrs["values"] + lo * w, (nulls + lo) if nulls else 0, keepalive=b))
+            else:
+                blocks.append(Block.from_numpy(b.type, b.values[lo:hi], None if b.is_null is None else b.is_null[lo:hi]))
+        out.append(serde.serialize(Page(blocks, hi - lo)))
+    return out
+
+
 class FusedExchange:
     """Repartition and exchange in ONE kernel: pass 2 of PartitionedOutputOperator stores each row straight into the destination
     GPU's receive column over NVLink (peer memory mapped once through CUDA IPC), so the shuffle costs one scatter instead of a

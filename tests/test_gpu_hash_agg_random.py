@@ -40,7 +40,7 @@ def make_pages(rng, n_pages, n, groups, n_vals=4, null_keys=False, null_vals=Fal
     return pages
 
 
-@pytest.mark.parametrize("groups", [1, 4, 9, 700, 5000, 200_000])
+@pytest.mark.parametrize("groups", [1, 4, 9, 30, 180, 700, 5000, 200_000])
 @pytest.mark.parametrize("variant", ["fast", "fast_count", "misaligned", "null_keys", "null_vals", "sentinel"])
 def test_bigint_key_double_sums(gpu_backend, oracle_backend, groups, variant):
     rng = np.random.default_rng(groups * 31 + len(variant))

@@ -27,7 +27,8 @@ def column(page, i):
     return block_to_tensor(page.blocks[i])
 
 
-@pytest.mark.parametrize("groups", [4, 1000, 100_000, 2_000_000], ids=["tier0", "shared_table", "direct_one_pass", "direct_slot_range_passes"])
+@pytest.mark.parametrize("groups", [4, 60, 250, 1000, 100_000, 2_000_000],
+                         ids=["tier0", "warp_private_sets", "warp_private_sets_full", "shared_table", "direct_one_pass", "direct_slot_range_passes"])
 def test_group_by_sums_counts_and_first_appearance_order(gpu_backend, groups):
     n = 1 << 25
     g = torch.Generator(device="cuda"); g.manual_seed(groups)

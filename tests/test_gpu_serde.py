@@ -101,3 +101,26 @@ def test_rejects_what_it_does_not_speak(gpu_backend):
     with pytest.raises(Exception, match="checksum"):
         g.deserialize(flipped, [BIGINT])
     g.close()
+
+
+def test_partitioned_output_to_serialized_pages(gpu_backend, oracle_backend):
+    """PartitionedOutputOperator → one SerializedPage per partition (the off-box leg): decoded by the oracle, every partition holds
+    exactly the rows the oracle's partitioned output puts there, in the same order."""
+    from presto_b200 import MEM_DEVICE, PartitionedOutputOperator
+    from presto_b200.exchange import serialize_partitions
+    rng = np.random.default_rng(8)
+    n, parts = 20_011, 5
+    page = Page([Block.from_numpy(BIGINT, rng.integers(-1000, 1000, n), (rng.random(n) < 0.1).astype(np.uint8)), Block.from_numpy(DOUBLE, rng.random(n))])
+    op = PartitionedOutputOperator([BIGINT, DOUBLE], parts, [0], backend=gpu_backend, output_memory=MEM_DEVICE)
+    op.add_input(page)
+    out, offs = op.get_output(copy=False), op.get_offsets()
+    g = PagesSerde(checksum_enabled=True, backend=gpu_backend)
+    wires = serialize_partitions(g, out, offs)
+    ref = PartitionedOutputOperator([BIGINT, DOUBLE], parts, [0], backend=oracle_backend)
+    ref.add_input(page)
+    want, woffs = ref.get_output().rows(), ref.get_offsets()
+    o = PagesSerde(checksum_enabled=True, backend=oracle_backend)
+    assert list(offs) == list(woffs)
+    for p in range(parts):
+        assert o.deserialize(wires[p], [BIGINT, DOUBLE]).rows() == want[woffs[p]:woffs[p + 1]]
+    op.close(); ref.close(); g.close(); o.close()
