@@ -125,6 +125,9 @@ int32_t pg_device_free(void* p);
 int32_t pg_memcpy_h2d(void* dst_device, const void* src_host, size_t bytes);
 int32_t pg_memcpy_d2h(void* dst_host, const void* src_device, size_t bytes);
 int32_t pg_device_synchronize(void);
+/* Give the device / pinned blocks the library keeps cached for reuse back to the driver (operators allocate through a caching
+ * allocator; nothing an operator currently owns is touched). */
+int32_t pg_release_cached_memory(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Scalar hash helpers (host side; bit-exact with the reference; used by tests and by callers that

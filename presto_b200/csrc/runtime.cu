@@ -338,6 +338,7 @@ int32_t pg_device_free(void* p) { PG_TRY PG_CUDA(cudaFree(p)); PG_CATCH }
 int32_t pg_memcpy_h2d(void* dst, const void* src, size_t bytes) { PG_TRY PG_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); PG_CATCH }
 int32_t pg_memcpy_d2h(void* dst, const void* src, size_t bytes) { PG_TRY PG_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); PG_CATCH }
 int32_t pg_device_synchronize(void) { PG_TRY PG_CUDA(cudaDeviceSynchronize()); PG_CATCH }
+int32_t pg_release_cached_memory(void) { PG_TRY PG_CUDA(cudaDeviceSynchronize()); pg::trimAllocationCaches(); PG_CATCH }
 int32_t pg_ipc_export(const void* devicePtr, uint8_t* handle)
 {
     PG_TRY
