@@ -237,6 +237,98 @@ __global__ void __launch_bounds__(kPartWarps * 32) partitionScatterKernel(const 
     }
 }
 
+// Pass 2 of the fused exchange.  Stores to a peer GPU travel as NVLink write packets: 8-byte stores that hop between destinations
+// every few lanes become 32-byte packets (measured ~300–400 GB/s per GPU).  Here the rows of a unit are first ordered by destination
+// in shared memory (stable, the ranks of phase A), so that consecutive lanes store consecutive addresses of ONE destination — 256
+// contiguous bytes per warp instruction.
+constexpr int kRemoteWarps = 4;
+__global__ void __launch_bounds__(kRemoteWarps * 32) partitionScatterStagedKernel(const __grid_constant__ ScatterParams P)
+{
+    extern __shared__ __align__(16) unsigned char remoteSmem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int PC = P.partitionCount;
+    const unsigned ltMask = (1u << lane) - 1;
+    unsigned char* mine = remoteSmem + (size_t) warp * (8192 + 3 * 2048);
+    uint64_t* stage = (uint64_t*) mine;                       // [kRowsPerUnit] values of one column in destination order
+    uint32_t* dest = (uint32_t*) mine;                        // phase A only (aliases stage)
+    uint16_t* sortedPos = (uint16_t*) (mine + 8192);          // row i of the unit → position in destination order
+    uint16_t* partSorted = sortedPos + kRowsPerUnit;          // position in destination order → partition
+    uint16_t* partOf = partSorted + kRowsPerUnit;             // row i → partition
+    uint32_t* cur = (uint32_t*) (remoteSmem + (size_t) kRemoteWarps * (8192 + 3 * 2048)) + (size_t) warp * 3 * PC;
+    uint32_t* unitBase = cur + PC;                            // destination row of the unit's first row of partition p
+    uint32_t* localStart = unitBase + PC;                     // first position of partition p in the unit's destination order
+    for (int64_t unit = (int64_t) blockIdx.x * kRemoteWarps + warp; unit < P.units; unit += (int64_t) gridDim.x * kRemoteWarps) {
+        for (int p = lane; p < PC; p += 32) { const uint32_t b = P.base[(size_t) p * P.units + unit] + P.adjust[p]; cur[p] = b; unitBase[p] = b; }
+        __syncwarp();
+        const int64_t begin = unit * kRowsPerUnit, end = min(begin + (int64_t) kRowsPerUnit, P.n);
+        const int count = (int) (end - begin);
+        // phase A: stable ranks (as in partitionScatterKernel)
+        for (int off = 0; off < count; off += 32) {
+            const int i = off + lane;
+            const int part = i < count ? (int) P.ids[begin + i] : -1 - lane;
+            const unsigned peers = __match_any_sync(0xffffffffu, part);
+            uint32_t d = 0;
+            if (part >= 0) d = cur[part] + __popc(peers & ltMask);
+            __syncwarp();
+            if (part >= 0 && lane == __ffs(peers) - 1) cur[part] += __popc(peers);
+            if (i < count) { dest[i] = d; partOf[i] = (uint16_t) part; }
+            __syncwarp();
+        }
+        // positions of the partitions in the unit's destination order: exclusive scan of the unit's per-partition counts
+        uint32_t running = 0;
+        for (int p0 = 0; p0 < PC; p0 += 32) {
+            const int p = p0 + lane;
+            const uint32_t c = p < PC ? cur[p] - unitBase[p] : 0;
+            uint32_t inc = c;
+#pragma unroll
+            for (int dlt = 1; dlt < 32; dlt <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, dlt); if (lane >= dlt) inc += o; }
+            if (p < PC) localStart[p] = running + inc - c;
+            running += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        __syncwarp();
+        for (int i = lane; i < count; i += 32) {
+            const int p = partOf[i];
+            const uint32_t sp = localStart[p] + (dest[i] - unitBase[p]);
+            sortedPos[i] = (uint16_t) sp;
+            partSorted[sp] = (uint16_t) p;
+        }
+        __syncwarp();       // dest[] is dead from here on: its storage becomes the staging buffer
+        // phase B: one column at a time through the staging buffer
+        auto moveColumn = [&](auto typeTag, const void* srcV, const uint64_t* ptrs, bool zeros) {
+            using T = decltype(typeTag);
+            const T* src = (const T*) srcV;
+            T* st = (T*) stage;
+            int i = lane;
+            if (zeros) { for (; i < count; i += 32) st[i] = (T) 0; }
+            else {
+                for (; i + 7 * 32 < count; i += 8 * 32) {
+                    T v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) v[k] = src[begin + i + k * 32];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) st[sortedPos[i + k * 32]] = v[k];
+                }
+                for (; i < count; i += 32) st[sortedPos[i]] = src[begin + i];
+            }
+            __syncwarp();
+            for (int j = lane; j < count; j += 32) {
+                const int p = partSorted[j];
+                ((T*) ptrs[p])[unitBase[p] + ((uint32_t) j - localStart[p])] = st[j];
+            }
+            __syncwarp();
+        };
+        for (int c = 0; c < P.nCols; c++) {
+            const ScatterColumn& sc = P.cols[c];
+            const uint64_t* ptrs = P.remoteValues + (size_t) c * PC;
+            if (sc.width == 8) moveColumn((uint64_t) 0, sc.src, ptrs, false);
+            else if (sc.width == 4) moveColumn((uint32_t) 0, sc.src, ptrs, false);
+            else moveColumn((uint8_t) 0, sc.src, ptrs, false);
+            const uint64_t* nptrs = P.remoteNulls + (size_t) c * PC;
+            if (nptrs[0]) moveColumn((uint8_t) 0, sc.srcNulls, nptrs, sc.srcNulls == nullptr);
+        }
+    }
+}
+
 class PartitionedOutputOp : public Operator {
     std::vector<int> types, partitionChannels, staged;
     int partitionCount, hashChannel, nullChannel;
@@ -400,7 +492,15 @@ public:
         S.nCols = (int) nCols; S.partitionCount = partitionCount; S.n = curN; S.units = curUnits; S.ids = ids.as<uint16_t>(); S.base = base.as<uint32_t>();
         S.remoteValues = remoteTable.as<uint64_t>(); S.remoteNulls = remoteTable.as<uint64_t>() + words; S.adjust = (const uint32_t*) (remoteTable.as<uint64_t>() + 2 * words);
         for (size_t i = 0; i < nCols; i++) { ScatterColumn& sc = S.cols[i]; sc.width = typeWidth(types[i]); sc.src = curCols[i].values; sc.srcNulls = curCols[i].nulls; sc.dst = nullptr; sc.dstNulls = nullptr; }
-        PG_LAUNCH(this, partitionScatterKernel, launchGrid(), kPartWarps * 32, scatterSmem(true), S);
+        // destination-ordered staging in shared memory → contiguous peer stores (PG_REMOTE_SCATTER=direct keeps the unstaged variant)
+        const char* rs = getenv("PG_REMOTE_SCATTER");
+        const size_t smem = (size_t) kRemoteWarps * (8192 + 3 * 2048) + (size_t) kRemoteWarps * 3 * partitionCount * 4;
+        if ((rs && !strcmp(rs, "direct")) || smem > 200 * 1024) PG_LAUNCH(this, partitionScatterKernel, launchGrid(), kPartWarps * 32, scatterSmem(true), S);
+        else {
+            PG_CUDA(cudaFuncSetAttribute(partitionScatterStagedKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            const int grid = (int) std::min<int64_t>(divUp(curUnits, kRemoteWarps), (int64_t) numSMs * 8);
+            PG_LAUNCH(this, partitionScatterStagedKernel, grid, kRemoteWarps * 32, smem, S);
+        }
         stager.markCompute(curSlot);
         PG_CUDA(cudaStreamSynchronize(stream));
         stats.output_positions += curN;

@@ -105,6 +105,9 @@ def all_to_all_pages(page: Page, offsets: Sequence[int], types: Sequence[int], g
             dst_nulls = torch.empty(total, dtype=torch.uint8, device=dev)
             dist.all_to_all_single(dst_nulls, nulls, output_split_sizes=recv_counts, input_split_sizes=send_counts, group=group)
         blocks.append(tensor_to_block(t, dst, dst_nulls))
+    if on_device:
+        # the collectives ran on torch's stream; the operators that consume the page run on their own streams
+        torch.cuda.current_stream().synchronize()
     return Page(blocks, total)
 
 

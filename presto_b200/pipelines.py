@@ -202,6 +202,7 @@ def run_q3_distributed(customer: Sequence[Page], orders: Sequence[Page], lineite
     gathered = [torch.empty_like(padded) for _ in range(world)]
     dist.all_gather(gathered, padded, group=group)
     all_keys = torch.cat([g[:int(c.item())] for g, c in zip(gathered, counts)])
+    torch.cuda.current_stream().synchronize()      # torch produced the keys on its stream; the operators run on their own
     bridge1 = JoinBridge(opts.get("device", 0), backend=backend)
     build1 = HashBuilderOperator(bridge1, [abi.BIGINT], [0], [], **o)
     if all_keys.numel():
