@@ -951,7 +951,7 @@ public:
         // dense enough (bitmap <= 8 x the key column), or small in absolute terms: a hash-partitioned build side keeps the full key range
         // on every rank with 1/P of the keys — the bitmap (range / 8 bytes: 75 MB for TPC-H SF100 order keys) still fits L2
         const bool denseEnough = span <= (unsigned __int128) kDenseRangeFactor * (unsigned __int128) nonNull + 4096;
-        const bool smallEnough = span <= ((unsigned __int128) 1 << kDenseSmallRangeBits);
+        const bool smallEnough = span <= ((unsigned __int128) 1 << kDenseSmallRangeBits) && nonNull >= 65536 && span <= (unsigned __int128) 4096 * (unsigned __int128) nonNull;   // (not for a handful of far-apart keys)
         if ((!denseEnough && !smallEnough) || span > ((unsigned __int128) 1 << 36)) return false;
         const uint64_t range = (uint64_t) span;
         const int64_t blocks = (int64_t) ((range + 255) >> 8);
