@@ -128,7 +128,10 @@ def run_q3(customer: Sequence[Page], orders: Sequence[Page], lineitem: Sequence[
     pl.project(lk, ep * (1.0 - disc))
     fp_l = FilterAndProjectOperator([abi.BIGINT, abi.DOUBLE, abi.DOUBLE, abi.DATE], pl, output_memory=mem, **o)
     probe2 = LookupJoinOperator(bridge2, [abi.BIGINT, abi.DOUBLE], [0], [0, 1], output_memory=mem, **o)
-    agg = HashAggregationOperator([abi.BIGINT, abi.DATE, abi.INTEGER], [0, 2, 3], [Aggregate(abi.AGG_SUM_DOUBLE, 1)], expected_groups=100_000,
+    # the planner's group-count estimate (Q3: about one group per 500 lineitem rows — 1.1 M at SF100) sizes the table so that it
+    # does not have to grow mid-page
+    agg = HashAggregationOperator([abi.BIGINT, abi.DATE, abi.INTEGER], [0, 2, 3], [Aggregate(abi.AGG_SUM_DOUBLE, 1)],
+                                  expected_groups=max(100_000, sum(p.position_count for p in lineitem) // 500),
                                   max_output_rows=1 << 30, output_memory=mem, **o)
     joined = 0
     for page in lineitem:
