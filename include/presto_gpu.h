@@ -293,6 +293,20 @@ typedef struct pg_lookup_join_config {
  * probe row in PositionLinks order (descending build position; PagesHash.java:108-123, ArrayPositionLinks.java:45-50). */
 int32_t pg_lookup_join_create(const pg_lookup_join_config* config, pg_join_bridge* bridge, pg_operator** out);
 
+/* HashSemiJoinOperator (MB/operator/HashSemiJoinOperator.java:142-192) over the ChannelSet a SetBuilderOperator builds
+ * (MB/operator/SetBuilderOperator.java, ChannelSet.java:33-77).  The set is a pg_join_bridge fed by a
+ * pg_hash_builder whose only hash channel is the set channel and which has no output channels.  Output page = every input channel
+ * + one BOOLEAN channel: NULL probe value → NULL (false when the set has no rows at all); otherwise contained → true, not
+ * contained → NULL when the set holds a NULL, else false.  Input channels are fixed width. */
+typedef struct pg_semi_join_config {
+    int32_t n_channels;
+    const int32_t* types;
+    int32_t probe_join_channel;
+    int32_t precomputed_hash_channel;   /* accepted and ignored (the slot function is recomputed from the key) */
+    pg_operator_options options;
+} pg_semi_join_config;
+int32_t pg_hash_semi_join_create(const pg_semi_join_config* config, pg_join_bridge* set, pg_operator** out);
+
 /* ------------------------------------------------------------------------------------------------
  * PartitionedOutputOperator (row repartition)
  * ---------------------------------------------------------------------------------------------- */

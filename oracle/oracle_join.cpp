@@ -237,7 +237,65 @@ struct LookupJoinOperator : Operator {
     bool isFinished() override { return finishing && !hasPending; }
 };
 
+// HashSemiJoinOperator.addInput (MB/operator/HashSemiJoinOperator.java:142-192).  The reference probes a ChannelSet (a GroupByHash
+// over the set channel, ChannelSet.java:33-77); membership is the same question the PagesHash above answers, so the set is the
+// LookupSource a HashBuilderOperator built from the set channel: isEmpty() = no rows at all (NULL is a group of its own in the
+// GroupByHash), containsNull() = some set row was NULL.
+struct SemiJoinOperator : Operator {
+    JoinBridge* bridge;
+    std::vector<int> types;
+    int probeChannel;
+    bool finishing = false, hasPending = false;
+    OwnedPage pending;
+
+    SemiJoinOperator(const pg_semi_join_config* c, JoinBridge* b) : bridge(b)
+    {
+        types.assign(c->types, c->types + c->n_channels);
+        probeChannel = c->probe_join_channel;
+    }
+    bool needsInput() override { return !finishing && !hasPending && bridge->lookupSource != nullptr; }
+    void addInput(const pg_page* page) override
+    {
+        if (!needsInput()) throw OracleError(PG_ERR_INVALID_STATE, "semi join does not need input (set not built, finishing, or output pending)");
+        const LookupSource& set = *bridge->lookupSource;
+        const bool setEmpty = set.positionCount == 0, setHasNull = set.positionIsNullCount > 0;
+        stats.input_positions += page->position_count;
+        pending.columns.clear();
+        for (int t : types) pending.columns.emplace_back(t);
+        pending.columns.emplace_back(PG_TYPE_BOOLEAN);
+        std::vector<BlockView> in;
+        for (size_t ch = 0; ch < types.size(); ch++) in.emplace_back(&page->blocks[ch]);
+        std::vector<BlockView> probe{BlockView(&page->blocks[probeChannel])};
+        Column& flag = pending.columns.back();
+        for (int64_t position = 0; position < page->position_count; position++) {
+            for (size_t ch = 0; ch < types.size(); ch++) pending.columns[ch].appendFrom(in[ch], position);      // page.appendColumn keeps the input
+            if (probe[0].isNull(position)) {                                  // :161-168
+                if (setEmpty) flag.appendLong(0); else flag.appendNull();
+            }
+            else {
+                const bool contains = !setEmpty && set.getAddressIndex(position, probe, hashLong(probe[0].getLong(position))) >= 0;   // :170-177
+                if (!contains && setHasNull) flag.appendNull();               // :178-183
+                else flag.appendLong(contains ? 1 : 0);
+            }
+        }
+        pending.positionCount = page->position_count;
+        hasPending = page->position_count > 0;
+        stats.output_positions += page->position_count;
+    }
+    bool getOutput(OwnedPage& out) override
+    {
+        if (!hasPending) return false;
+        out.columns.swap(pending.columns);
+        out.positionCount = pending.positionCount;
+        hasPending = false;
+        return true;
+    }
+    void finish() override { finishing = true; }
+    bool isFinished() override { return finishing && !hasPending; }
+};
+
 JoinBridge* createJoinBridge() { return new JoinBridge(); }
+Operator* createSemiJoin(const pg_semi_join_config* c, JoinBridge* b) { return new SemiJoinOperator(c, b); }
 Operator* createHashBuilder(const pg_hash_builder_config* c, JoinBridge* b) { return new HashBuilderOperator(c, b); }
 Operator* createLookupJoin(const pg_lookup_join_config* c, JoinBridge* b) { return new LookupJoinOperator(c, b); }
 int64_t joinBridgePositionCount(JoinBridge* b) { return b->lookupSource ? b->lookupSource->positionCount : -1; }

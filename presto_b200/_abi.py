@@ -147,6 +147,11 @@ def i32_array(values):
     return (C.c_int32 * max(1, len(values)))(*values)
 
 
+class pg_semi_join_config(C.Structure):
+    _fields_ = [("n_channels", C.c_int32), ("types", _I32P), ("probe_join_channel", C.c_int32), ("precomputed_hash_channel", C.c_int32),
+                ("options", pg_operator_options)]
+
+
 class pg_pages_serde_config(C.Structure):
     _fields_ = [("checksum_enabled", C.c_int32), ("options", pg_operator_options)]
 
@@ -187,6 +192,7 @@ class Backend:
         "join_bridge_get_position_count": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64)]),
         "hash_builder_create": (C.c_int32, [C.POINTER(pg_hash_builder_config), C.c_void_p, C.POINTER(C.c_void_p)]),
         "lookup_join_create": (C.c_int32, [C.POINTER(pg_lookup_join_config), C.c_void_p, C.POINTER(C.c_void_p)]),
+        "hash_semi_join_create": (C.c_int32, [C.POINTER(pg_semi_join_config), C.c_void_p, C.POINTER(C.c_void_p)]),
         "partitioned_output_create": (C.c_int32, [C.POINTER(pg_partitioned_output_config), C.POINTER(C.c_void_p)]),
         "partitioned_output_get_offsets": (C.c_int32, [C.c_void_p, C.c_void_p]),
         "filter_project_create": (C.c_int32, [C.POINTER(pg_filter_project_config), C.POINTER(C.c_void_p)]),

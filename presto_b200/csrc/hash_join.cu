@@ -1295,6 +1295,146 @@ public:
     bool isFinished() override { return finishing && !hasPending; }
 };
 
+// ---- HashSemiJoinOperator (MB/operator/HashSemiJoinOperator.java:142-192) -------------------------------------------------------
+// flag = contains(set, key) with SQL's three values: NULL key → NULL (false for a set without rows); absent → NULL if the set holds a NULL
+__device__ __forceinline__ void semiResult(bool keyIsNull, bool contains, int setEmpty, int setHasNull, int64_t row, uint8_t* val, uint8_t* isNull)
+{
+    bool n, v;
+    if (keyIsNull) { n = !setEmpty; v = false; }
+    else if (!contains && setHasNull) { n = true; v = false; }
+    else { n = false; v = contains; }
+    val[row] = v ? 1 : 0; isNull[row] = n ? 1 : 0;
+}
+__global__ void semiJoinDenseKernel(KeyColumn key, DenseIndex D, int64_t n, int setEmpty, int setHasNull, uint8_t* val, uint8_t* isNull)
+{
+    for (int64_t row = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; row < n; row += (int64_t) gridDim.x * blockDim.x) {
+        int64_t k;
+        const bool have = loadKey(key, row, k);
+        semiResult(!have, have && denseContains(D, k), setEmpty, setHasNull, row, val, isNull);
+    }
+}
+template <int W>
+__global__ void semiJoinHashKernel(const __grid_constant__ ProbeParams P, int setEmpty, int setHasNull, uint8_t* val, uint8_t* isNull)
+{
+    for (int64_t row = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; row < P.n; row += (int64_t) gridDim.x * blockDim.x) {
+        uint64_t kw[W];
+        const int special = packKey<W>(P.kp, row, kw);
+        const bool keyIsNull = keyHasNull(P.kp, kw, special);
+        bool contains = false;
+        if (!keyIsNull && !setEmpty) {
+            const int slot = special == 2 ? (int) P.J.t.cap + 1 : tableFind<W>(P.J.t, kw, hashKeyWords<W>(kw), false, true);
+            contains = slot >= 0 && P.J.head[slot] >= 0;
+        }
+        semiResult(keyIsNull, contains, setEmpty, setHasNull, row, val, isNull);
+    }
+}
+
+class SemiJoinOp : public Operator {
+    JoinBridge* bridge;
+    std::vector<int> types, staged;
+    int probeChannel;
+    KeyLayout layout;
+    PageStager stager;
+    bool finishing = false, hasPending = false;
+    std::vector<DeviceBuffer> outValues, outNulls;
+    std::vector<PinnedBuffer> hostValues, hostNulls;
+    std::vector<pg_block> outBlocks;
+    int64_t pendingRows = 0;
+
+public:
+    SemiJoinOp(const pg_semi_join_config* c, JoinBridge* b) : Operator(c->options), bridge(b), stager(this)
+    {
+        PG_CHECK_ARG(b != nullptr, "set bridge is null");
+        PG_CHECK_ARG(c->n_channels >= 1 && c->n_channels < kMaxJoinColumns, "too many channels");
+        types.assign(c->types, c->types + c->n_channels);
+        probeChannel = c->probe_join_channel;
+        PG_CHECK_ARG(probeChannel >= 0 && probeChannel < c->n_channels, "probe join channel out of range");
+        for (int t : types) if (t == PG_TYPE_VARCHAR) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR channels are not on the GPU semi-join path");
+        int32_t kt = types[probeChannel];
+        layout.plan(1, &probeChannel, &kt, nullptr);
+        checkJoinKeyTypes(layout);
+        for (int i = 0; i < c->n_channels; i++) staged.push_back(i);
+        const size_t nOut = types.size() + 1;
+        outValues.resize(nOut); outNulls.resize(nOut);
+        for (auto& d : outValues) d.accounting = &stats.device_bytes;
+        for (auto& d : outNulls) d.accounting = &stats.device_bytes;
+    }
+    bool needsInput() override { return !finishing && !hasPending && bridge->get() != nullptr; }   // "Set has not been built yet"
+
+    void addInput(const pg_page* page) override
+    {
+        PG_CHECK_STATE(needsInput(), "semi join does not need input (set not built, finishing, or output pending)");
+        auto ls = bridge->get();
+        PG_CHECK_ARG(ls->layout.nKeys == 1 && ls->layout.types[0] == layout.types[0], "probe and set key types differ");
+        const int64_t n = page->position_count;
+        stats.input_positions += n;
+        if (n == 0) return;
+        PG_CHECK_ARG(n < (int64_t(1) << 31), "probe page exceeds 2^31 positions");
+        PG_CHECK_ARG(page->channel_count == (int) types.size(), "page channel count differs from the operator's configuration");
+        std::vector<DeviceColumn> cols;
+        const int slot = stager.stage(page, staged, cols);
+        const size_t flag = types.size();
+        outValues[flag].reserve((size_t) n); outNulls[flag].reserve((size_t) n);
+        const int setEmpty = ls->positionCount == 0, setHasNull = ls->nullKeyCount > 0;
+        const int grid = (int) std::min<int64_t>(divUp(n, 256), (int64_t) numSMs * 16);
+        const DeviceColumn& kc = cols[(size_t) probeChannel];
+        PG_CHECK_ARG(kc.type == layout.types[0], "probe key channel type differs from configuration");
+        if (ls->dense)
+            PG_LAUNCH(this, semiJoinDenseKernel, grid, 256, 0, KeyColumn{kc.values, kc.nulls, kc.type}, ls->denseView(), n, setEmpty, setHasNull, outValues[flag].as<uint8_t>(), outNulls[flag].as<uint8_t>());
+        else {
+            ProbeParams P{};
+            P.J = ls->view();
+            std::vector<DeviceColumn> keyCols{kc};
+            layout.fill(P.kp, keyCols, ls->counters.as<unsigned int>() + CNT_ERROR);
+            P.n = n;
+            switch (layout.W) {
+                case 1: PG_LAUNCH(this, semiJoinHashKernel<1>, grid, 256, 0, P, setEmpty, setHasNull, outValues[flag].as<uint8_t>(), outNulls[flag].as<uint8_t>()); break;
+                default: PG_LAUNCH(this, semiJoinHashKernel<2>, grid, 256, 0, P, setEmpty, setHasNull, outValues[flag].as<uint8_t>(), outNulls[flag].as<uint8_t>()); break;
+            }
+        }
+        // the input channels travel with the page (Page.appendColumn in the reference; here: device copies owned by the operator)
+        outBlocks.assign(flag + 1, pg_block{});
+        std::vector<bool> hasNulls(flag + 1, false);
+        for (size_t i = 0; i < flag; i++) {
+            const int w = typeWidth(types[i]);
+            outValues[i].reserve((size_t) n * w);
+            PG_CUDA(cudaMemcpyAsync(outValues[i].ptr, cols[i].values, (size_t) n * w, cudaMemcpyDeviceToDevice, stream));
+            if (cols[i].nulls) { outNulls[i].reserve((size_t) n); PG_CUDA(cudaMemcpyAsync(outNulls[i].ptr, cols[i].nulls, (size_t) n, cudaMemcpyDeviceToDevice, stream)); hasNulls[i] = true; }
+            outBlocks[i].type = types[i];
+        }
+        outBlocks[flag].type = PG_TYPE_BOOLEAN; hasNulls[flag] = true;
+        stager.markCompute(slot);
+        const bool toHost = options.output_memory == PG_MEM_HOST;
+        if (toHost && hostValues.size() < flag + 1) { hostValues.resize(flag + 1); hostNulls.resize(flag + 1); }
+        for (size_t i = 0; i <= flag; i++) {
+            pg_block& b = outBlocks[i];
+            const size_t vbytes = (size_t) n * typeWidth(b.type);
+            b.encoding = PG_ENC_FLAT; b.position_count = n; b.offsets = nullptr; b.ids = nullptr; b.dictionary_size = 0;
+            if (toHost) {
+                hostValues[i].reserve(std::max<size_t>(vbytes, 16));
+                PG_CUDA(cudaMemcpyAsync(hostValues[i].ptr, outValues[i].ptr, vbytes, cudaMemcpyDeviceToHost, stream));
+                b.values = hostValues[i].ptr; b.is_null = nullptr;
+                stats.d2h_bytes += (int64_t) vbytes;
+                if (hasNulls[i]) { hostNulls[i].reserve((size_t) n); PG_CUDA(cudaMemcpyAsync(hostNulls[i].ptr, outNulls[i].ptr, (size_t) n, cudaMemcpyDeviceToHost, stream)); b.is_null = hostNulls[i].as<uint8_t>(); stats.d2h_bytes += n; }
+            }
+            else { b.values = outValues[i].ptr; b.is_null = hasNulls[i] ? outNulls[i].as<uint8_t>() : nullptr; }
+            stats.output_bytes += (int64_t) vbytes;
+        }
+        PG_CUDA(cudaStreamSynchronize(stream));
+        pendingRows = n; hasPending = true;
+        stats.output_positions += n;
+    }
+    bool getOutput(pg_page* out) override
+    {
+        if (!hasPending) return false;
+        out->position_count = pendingRows; out->channel_count = (int32_t) outBlocks.size(); out->memory = options.output_memory; out->blocks = outBlocks.data();
+        hasPending = false;
+        return true;
+    }
+    void finish() override { finishing = true; }
+    bool isFinished() override { return finishing && !hasPending; }
+};
+
 }  // namespace pg
 
 extern "C" {
@@ -1313,4 +1453,5 @@ int32_t pg_join_bridge_destroy(pg_join_bridge* b) { J_TRY auto* jb = (pg::JoinBr
 int32_t pg_join_bridge_get_position_count(pg_join_bridge* b, int64_t* out) { J_TRY auto ls = ((pg::JoinBridge*) b)->get(); *out = ls ? ls->positionCount : -1; J_CATCH }
 int32_t pg_hash_builder_create(const pg_hash_builder_config* c, pg_join_bridge* bridge, pg_operator** out) { J_TRY *out = (pg_operator*) new pg::HashBuilderOp(c, (pg::JoinBridge*) bridge); J_CATCH }
 int32_t pg_lookup_join_create(const pg_lookup_join_config* c, pg_join_bridge* bridge, pg_operator** out) { J_TRY *out = (pg_operator*) new pg::LookupJoinOp(c, (pg::JoinBridge*) bridge); J_CATCH }
+int32_t pg_hash_semi_join_create(const pg_semi_join_config* c, pg_join_bridge* set, pg_operator** out) { J_TRY *out = (pg_operator*) new pg::SemiJoinOp(c, (pg::JoinBridge*) set); J_CATCH }
 }

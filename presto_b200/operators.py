@@ -253,6 +253,23 @@ class LookupJoinOperator(Operator):
         self._bridge = bridge
 
 
+class HashSemiJoinOperator(Operator):
+    """HashSemiJoinOperator.java:142-192: every input channel + a BOOLEAN "probe value is in the set" channel (SQL three-valued).
+    The set (SetBuilderOperator / ChannelSet) is a JoinBridge filled by ``HashBuilderOperator(bridge, [type], [0], [])``."""
+
+    def __init__(self, bridge: "JoinBridge", types: Sequence[int], probe_join_channel: int, *, backend=None, **options):
+        backend = backend or _default_backend()
+        cfg = abi.pg_semi_join_config()
+        ty = abi.i32_array(types)
+        cfg.n_channels, cfg.types = len(types), ty
+        cfg.probe_join_channel = probe_join_channel
+        cfg.precomputed_hash_channel = -1
+        cfg.options = _options(**options)
+        handle = C.c_void_p()
+        backend.check(backend.hash_semi_join_create(C.byref(cfg), bridge._h, C.byref(handle)))
+        super().__init__(backend, handle)
+
+
 class PartitionedOutputOperator(Operator):
     """OptimizedPartitionedOutputOperator.java:167-179,384-824 — the partition + copy-by-position step.  get_output returns
     one page per input page with all partitions back to back; ``get_offsets`` gives the partition boundaries."""

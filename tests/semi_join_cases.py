@@ -1,0 +1,31 @@
+"""TestHashSemiJoinOperator (presto-main-base/src/test/java/com/facebook/presto/operator/TestHashSemiJoinOperator.java) re-encoded:
+(set rows, probe rows as (key, other...) tuples, expected output rows)."""
+REFERENCE_CASES = {
+    # testSemiJoin :92-153
+    "testSemiJoin": ([10, 30, 30, 35, 36, 37, 50], [(30 + i, i) for i in range(10)],
+                     [(30, 0, True), (31, 1, False), (32, 2, False), (33, 3, False), (34, 4, False), (35, 5, True), (36, 6, True), (37, 7, True),
+                      (38, 8, False), (39, 9, False)]),
+    # testBuildSideNulls :250-305: a NULL in the set turns "absent" into NULL
+    "testBuildSideNulls": ([0, 1, 2, 2, 3, None], [(1,), (2,), (3,), (4,)], [(1, True), (2, True), (3, True), (4, None)]),
+    # testProbeSideNulls :308-363
+    "testProbeSideNulls": ([0, 1, 3], [(0,), (None,), (1,), (2,)], [(0, True), (None, None), (1, True), (2, False)]),
+    # testProbeAndBuildNulls :366-422
+    "testProbeAndBuildNulls": ([0, 1, None, 3], [(0,), (None,), (1,), (2,)], [(0, True), (None, None), (1, True), (2, None)]),
+}
+
+
+def run_semi_join(backend, set_values, probe_rows, set_pages=1):
+    import numpy as np
+    from presto_b200 import BIGINT, Block, HashBuilderOperator, HashSemiJoinOperator, JoinBridge, Page, to_pages
+    bridge = JoinBridge(backend=backend)
+    builder = HashBuilderOperator(bridge, [BIGINT], [0], [], backend=backend)
+    cuts = np.linspace(0, len(set_values), set_pages + 1).astype(int)
+    pages = [Page([Block.from_values(BIGINT, set_values[a:b], [v is None for v in set_values[a:b]])], b - a) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert to_pages(builder, pages) == []
+    width = len(probe_rows[0]) if probe_rows else 1
+    op = HashSemiJoinOperator(bridge, [BIGINT] * width, 0, backend=backend)
+    cols = [[r[c] for r in probe_rows] for c in range(width)]
+    probe = Page([Block.from_values(BIGINT, col, [v is None for v in col]) for col in cols], len(probe_rows))
+    out = [r for p in to_pages(op, [probe]) for r in p.rows()]
+    op.close(); builder.close(); bridge.close()
+    return out

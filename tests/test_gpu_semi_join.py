@@ -1,0 +1,44 @@
+"""-m gpu: HashSemiJoinOperator on the CUDA backend vs the oracle: the reference's own cases, both LookupSource structures (dense
+index for unique keys, hash table with duplicate chains), NULLs on either side, the empty set, multi-page sets."""
+import numpy as np
+import pytest
+
+from semi_join_cases import REFERENCE_CASES, run_semi_join
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", sorted(REFERENCE_CASES))
+def test_reference_case(gpu_backend, name):
+    set_values, probe, expected = REFERENCE_CASES[name]
+    assert run_semi_join(gpu_backend, set_values, probe) == expected
+
+
+def test_empty_set(gpu_backend):
+    assert run_semi_join(gpu_backend, [], [(1,), (None,)]) == [(1, False), (None, False)]
+
+
+@pytest.mark.parametrize("kind", ["unique_dense", "duplicates", "sparse"])
+@pytest.mark.parametrize("set_nulls", [False, True])
+def test_random(gpu_backend, oracle_backend, kind, set_nulls):
+    rng = np.random.default_rng(len(kind) + int(set_nulls))
+    n = 20_000
+    if kind == "unique_dense":
+        values = list(rng.permutation(n) * 3)
+    elif kind == "duplicates":
+        values = list(rng.integers(0, n // 4, n))
+    else:
+        values = list(rng.choice(1 << 40, n, replace=False))
+    values = [int(v) for v in values]
+    if set_nulls:
+        for i in rng.integers(0, n, 50):
+            values[i] = None
+    pool = [v for v in values if v is not None]
+    probe = []
+    for i in range(30_000):
+        r = rng.random()
+        key = None if r < 0.05 else (pool[rng.integers(0, len(pool))] if r < 0.6 else int(rng.integers(-100, 1 << 41)))
+        probe.append((key, i, None if i % 7 == 0 else i * 2))
+    got = run_semi_join(gpu_backend, values, probe, set_pages=3)
+    want = run_semi_join(oracle_backend, values, probe, set_pages=3)
+    assert got == want and any(r[-1] is True for r in got) and any(r[-1] is False or r[-1] is None for r in got)
