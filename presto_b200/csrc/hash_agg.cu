@@ -107,6 +107,9 @@ struct SharedTable {
         atomicAdd(count, 1u);
         if (tier0Groups) {
             uint32_t id = atomicAdd(count + 1, 1u);
+            // sid[s] is published last and read without a barrier by other threads (compute-sanitizer racecheck flags it): a reader that
+            // still sees 0xFF sends its row to tier 1 (st.acc of the same slot), one that sees the id uses the private / per-warp
+            // accumulators — both are folded into the slot before the flush, so either outcome is correct
             if (id < (uint32_t) tier0Groups) { count[2 + id] = s; __threadfence_block(); sid[s] = (uint8_t) id; }
         }
     }
