@@ -413,6 +413,9 @@ typedef struct pg_pages_serde_config {
 #define PG_PAGE_MARKER_ENCRYPTED 2
 #define PG_PAGE_MARKER_CHECKSUMMED 4
 
+/* The host half of the page checksum: CRC-32 (java.util.zip.CRC32) of a host buffer computed as the serde does — one CRC per
+ * `chunk` bytes (0 = 4096), combined with the zero-extension operator.  Needs no GPU; exists so that the combine logic is testable. */
+int64_t pg_hash_crc32_chunked(const void* data, size_t len, size_t chunk);
 int32_t pg_pages_serde_create(const pg_pages_serde_config* config, pg_pages_serde** out);
 /* serialize(Page) + writeSerializedPage.  FLAT blocks → LONG_ARRAY / INT_ARRAY / BYTE_ARRAY / VARIABLE_WIDTH, RLE blocks → RLE,
  * DICTIONARY blocks are written flat (the reference writes the compacted dictionary; a reader sees the same rows).

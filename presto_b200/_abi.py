@@ -214,6 +214,7 @@ class Backend:
         "memcpy_d2h": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t]),
         "device_synchronize": (C.c_int32, []),
         "release_cached_memory": (C.c_int32, []),
+        "hash_crc32_chunked": (C.c_int64, [C.c_void_p, C.c_size_t, C.c_size_t]),
         "partitioned_output_count": (C.c_int32, [C.c_void_p, C.POINTER(pg_page), C.c_void_p]),
         "partitioned_output_scatter_to": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
         "ipc_export": (C.c_int32, [C.c_void_p, C.c_void_p]),

@@ -1,5 +1,6 @@
 // presto_b200 — runtime: device management, operator base, page staging, scalar hash helpers.
 #include "common.cuh"
+#include "crc32_host.h"
 #include <cub/device/device_scan.cuh>
 #include <map>
 #include <mutex>
@@ -338,6 +339,7 @@ int32_t pg_device_free(void* p) { PG_TRY PG_CUDA(cudaFree(p)); PG_CATCH }
 int32_t pg_memcpy_h2d(void* dst, const void* src, size_t bytes) { PG_TRY PG_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); PG_CATCH }
 int32_t pg_memcpy_d2h(void* dst, const void* src, size_t bytes) { PG_TRY PG_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); PG_CATCH }
 int32_t pg_device_synchronize(void) { PG_TRY PG_CUDA(cudaDeviceSynchronize()); PG_CATCH }
+int64_t pg_hash_crc32_chunked(const void* data, size_t len, size_t chunk) { return (int64_t) (uint64_t) pg::crc32ChunkedHost((const uint8_t*) data, len, chunk ? chunk : 4096); }
 int32_t pg_release_cached_memory(void) { PG_TRY PG_CUDA(cudaDeviceSynchronize()); pg::trimAllocationCaches(); PG_CATCH }
 int32_t pg_ipc_export(const void* devicePtr, uint8_t* handle)
 {

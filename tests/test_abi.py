@@ -90,3 +90,19 @@ def test_host_hash_helpers_match_known_answers():
     assert [b.hash_partition(b.hash_bigint(v), 8) for v in (0, 1, 42)] == [0, 4, 2]
     assert b.hash_xxhash64(b"A", 1) == 1371800463213966980 and b.hash_xxhash64(b"", 0) == -1205034819632174695
     assert b.hash_combine(3, 4) == 97
+
+
+def test_chunked_crc32_combine_equals_zlib():
+    """The host half of the SerializedPage checksum (csrc/crc32_host.h): per-chunk CRCs combined with the zero-extension operator
+    must equal java.util.zip.CRC32 (= zlib.crc32) of the whole buffer, for chunk counts of 1, 2, many, and ragged last chunks."""
+    import zlib
+
+    import numpy as np
+    from presto_b200._lib import load_library
+    lib = load_library()
+    rng = np.random.default_rng(5)
+    data = rng.integers(0, 256, 1_000_003, dtype=np.uint8)
+    for n in (0, 1, 4095, 4096, 4097, 8192, 12_289, 100_000, 1_000_003):
+        for chunk in (4096, 1000, 65536):
+            got = lib.hash_crc32_chunked(data.ctypes.data, n, chunk)
+            assert got == zlib.crc32(data[:n].tobytes()), (n, chunk)
