@@ -147,3 +147,24 @@ def test_device_resident_pages(gpu_backend, oracle_backend):
     op.close()
     for p in ptrs:
         gpu_backend.device_free(p)
+
+
+@pytest.mark.parametrize("groups", [6, 25, 200, 5000], ids=["tier0", "warp_sets", "shared_table_per_sm", "generic_kernel"])
+def test_two_32_bit_key_columns_on_the_fast_path(gpu_backend, oracle_backend, groups):
+    """Q1's key shape (two INTEGER / DATE codes, no NULLs) with double sums + count(*): the specialised kernel packs the two columns
+    into one 64-bit key and re-packs it into the table's two-word layout at the HBM table; beyond ~350 groups the generic kernel
+    takes over.  Includes the pair (0, INT_MIN) whose packed value equals the kernel's empty-slot sentinel."""
+    rng = np.random.default_rng(groups)
+    n = 120_000
+    pages = []
+    for _ in range(2):
+        g = rng.integers(0, groups, n)
+        a = (g % 97 - 3).astype(np.int32)
+        b = (g // 97 + 9000).astype(np.int32)
+        a[:50] = 0; b[:50] = -2**31                       # col1 << 32 | col0 == 0x8000000000000000
+        pages.append(Page([Block.from_numpy(INTEGER, a), Block.from_numpy(DATE, b), Block.from_numpy(DOUBLE, rng.random(n) * 10), Block.from_numpy(DOUBLE, rng.random(n))]))
+    aggs = [Aggregate(AGG_SUM_DOUBLE, 2), Aggregate(AGG_SUM_DOUBLE, 3), Aggregate(AGG_AVG_DOUBLE, 2), Aggregate(AGG_COUNT_STAR)]
+    got = run(gpu_backend, pages, [INTEGER, DATE], [0, 1], aggs, expected_groups=groups, max_output_rows=1 << 30)
+    want = run(oracle_backend, pages, [INTEGER, DATE], [0, 1], aggs, expected_groups=groups, max_output_rows=1 << 30)
+    assert len(want) >= min(groups, 6)
+    rows_close(got, want)
