@@ -138,6 +138,10 @@ int64_t pg_hash_combine(int64_t previous, int64_t h);  /* CombineHashFunction.ge
 int64_t pg_hash_murmur3_fmix64(int64_t x);             /* fastutil HashCommon.murmurHash3(long) = PagesHash.java:236-252 */
 int32_t pg_hash_partition(int64_t raw_hash, int32_t partition_count); /* HashGenerator.getPartition  :22-29 */
 int64_t pg_hash_xxhash64(const void* data, size_t len);/* airlift XxHash64.hash(Slice), seed 0 */
+int64_t pg_hash_double(double value);                  /* DoubleType.hash → TypeUtils.doubleHashCode  PC/type/TypeUtils.java:232-238 (-0.0 == +0.0, one NaN) */
+/* LocalPartitionGenerator.getPartition(rawHash)  MB/operator/exchange/LocalPartitionGenerator.java:43-63:
+ * (int) XxHash64.hash(Long.reverse(rawHash)) & (partitionCount - 1); partitionCount must be a power of two (-1 otherwise). */
+int32_t pg_hash_local_partition(int64_t raw_hash, int32_t partition_count);
 
 /* ------------------------------------------------------------------------------------------------
  * Operator protocol — MB/operator/Operator.java:20-102.
@@ -310,6 +314,12 @@ int32_t pg_hash_semi_join_create(const pg_semi_join_config* config, pg_join_brid
 /* ------------------------------------------------------------------------------------------------
  * PartitionedOutputOperator (row repartition)
  * ---------------------------------------------------------------------------------------------- */
+typedef enum {
+    PG_PARTITION_HASH_GENERATOR = 0, /* HashGenerator.getPartition (MB/operator/HashGenerator.java:22-29): between tasks / GPUs */
+    PG_PARTITION_LOCAL = 1           /* LocalPartitionGenerator (MB/operator/exchange/LocalPartitionGenerator.java:43-63): LocalExchange and
+                                        PartitionedLookupSource inside one task; partition_count must be a power of two */
+} pg_partition_function;
+
 typedef struct pg_partitioned_output_config {
     int32_t n_channels;
     const int32_t* types;
@@ -319,6 +329,7 @@ typedef struct pg_partitioned_output_config {
     int32_t precomputed_hash_channel;   /* PrecomputedHashGenerator channel or -1 */
     int32_t replicates_any_row;         /* OptimizedPartitionedOutputOperator.java:504-512 */
     int32_t null_channel;               /* replicate rows whose null_channel is null to every partition; -1 = none */
+    int32_t partition_function;         /* pg_partition_function */
     pg_operator_options options;
 } pg_partitioned_output_config;
 

@@ -34,8 +34,6 @@ def backend() -> abi.Backend:
         _backend = abi.Backend(lib, "or_", has_device=False)
         lib.or_group_by_hash_get_capacity.restype = C.c_int32
         lib.or_group_by_hash_get_capacity.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
-        lib.or_hash_double.restype = C.c_int64
-        lib.or_hash_double.argtypes = [C.c_double]
         lib.or_array_size.restype = C.c_int32
         lib.or_array_size.argtypes = [C.c_int64, C.POINTER(C.c_int32)]
     return _backend

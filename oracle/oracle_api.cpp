@@ -38,7 +38,12 @@ int64_t or_hash_combine(int64_t p, int64_t h) { return combineHash(p, h); }
 int64_t or_hash_murmur3_fmix64(int64_t x) { return murmurHash3(x); }
 int32_t or_hash_partition(int64_t rawHash, int32_t partitionCount) { return hashPartition(rawHash, partitionCount); }
 int64_t or_hash_xxhash64(const void* data, size_t len) { return xxHash64((const uint8_t*) data, len); }
-int64_t or_hash_double(double d) { return hashLong(doubleToLongBits(d)); }
+int64_t or_hash_double(double d) { return doubleHashCode(d); }
+int32_t or_hash_local_partition(int64_t rawHash, int32_t partitionCount)
+{
+    if (partitionCount <= 0 || (partitionCount & (partitionCount - 1)) != 0) return -1;
+    return localPartition(rawHash, partitionCount);
+}
 int32_t or_array_size(int64_t expected, int32_t* out) { OR_TRY *out = arraySize(expected, 0.75f); OR_CATCH }
 
 int32_t or_hash_aggregation_create(const pg_hash_aggregation_config* c, void** out) { OR_TRY *out = createHashAggregation(c); OR_CATCH }

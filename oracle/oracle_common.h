@@ -125,11 +125,30 @@ inline int64_t xxHash64(const uint8_t* p, size_t len)
     return (int64_t) h;
 }
 
+// LocalPartitionGenerator.getPartition(rawHash)  MB/operator/exchange/LocalPartitionGenerator.java:43-63:
+//   processRawHash = (int) XxHash64.hash(Long.reverse(rawHash)); partition = processRawHash & (partitionCount - 1)
+// airlift XxHash64.hash(long) restated as XXH64 (seed 0) of the value's 8 little-endian bytes (cross-checked vs python xxhash).
+inline int32_t localPartition(int64_t rawHash, int32_t partitionCount)
+{
+    uint64_t x = (uint64_t) rawHash, r = 0;
+    for (int i = 0; i < 64; i++) { r = (r << 1) | (x & 1); x >>= 1; }     // Long.reverse
+    uint8_t le[8];
+    for (int i = 0; i < 8; i++) le[i] = (uint8_t) (r >> (8 * i));
+    return (int32_t) xxHash64(le, 8) & (partitionCount - 1);
+}
+
 // Double.doubleToLongBits: canonical NaN
 inline int64_t doubleToLongBits(double d)
 {
     if (d != d) return 0x7ff8000000000000LL;
     int64_t b; memcpy(&b, &d, 8); return b;
+}
+
+// TypeUtils.doubleHashCode  PC/type/TypeUtils.java:232-238 (DoubleType.DOUBLE = new DoubleType(true): DoubleType.java:37,92-100)
+inline int64_t doubleHashCode(double d)
+{
+    if (d == 0) d = 0;      // value == -0 ? 0 : value
+    return hashLong(doubleToLongBits(d));
 }
 
 // fastutil HashCommon.arraySize(expected, f): max(2, nextPowerOfTwo(ceil(expected / f))), > 2^30 → IllegalArgumentException
@@ -184,7 +203,7 @@ inline int64_t typeHashPosition(int type, const BlockView& v, int64_t pos)
     if (v.isNull(pos)) return 0;
     switch (type) {
         case PG_TYPE_BIGINT: case PG_TYPE_INTEGER: case PG_TYPE_DATE: return hashLong(v.getLong(pos));
-        case PG_TYPE_DOUBLE: return hashLong(doubleToLongBits(v.getDouble(pos)));   // PC/type/DoubleType.java:92-100 (legacy NaN definition)
+        case PG_TYPE_DOUBLE: return doubleHashCode(v.getDouble(pos));   // PC/type/DoubleType.java:92-100 → TypeUtils.doubleHashCode
         case PG_TYPE_BOOLEAN: return v.getLong(pos) != 0 ? 1231 : 1237;              // PC/type/BooleanType.java:121-125
         case PG_TYPE_VARCHAR: return xxHash64(v.slicePtr(pos), (size_t) v.sliceLength(pos)); // AbstractVariableWidthBlock.java:102-106
     }

@@ -229,10 +229,11 @@ struct MultiChannelGroupByHash : GroupByHash {
                 if (ll != rl || memcmp(left.data.data() + left.offsets[address], right.slicePtr(position), (size_t) ll) != 0) return false;
             }
             else if (hashTypes[i] == PG_TYPE_DOUBLE) {
-                // DoubleType.equalTo legacy semantics (DoubleType.java:80-90): leftValue == rightValue on the doubles
+                // DoubleComparisonOperators.DoubleDistinctFromOperator :105-140 → notEqual → TypeUtils.doubleEquals (TypeUtils.java:223-230;
+                // use-new-nan-definition defaults to true, FunctionsConfig.java:39): +0 == -0, NaN == NaN
                 double a, b; int64_t la = left.getLong(address), lb = right.getLong(position);
                 memcpy(&a, &la, 8); memcpy(&b, &lb, 8);
-                if (!(a == b)) return false;
+                if (!(a == b || doubleToLongBits(a) == doubleToLongBits(b))) return false;
             }
             else if (left.getLong(address) != right.getLong(position)) return false;
         }

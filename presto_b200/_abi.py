@@ -124,8 +124,11 @@ class pg_partitioned_output_config(C.Structure):
     _fields_ = [
         ("n_channels", C.c_int32), ("types", _I32P), ("partition_count", C.c_int32), ("n_partition_channels", C.c_int32),
         ("partition_channels", _I32P), ("precomputed_hash_channel", C.c_int32), ("replicates_any_row", C.c_int32),
-        ("null_channel", C.c_int32), ("options", pg_operator_options),
+        ("null_channel", C.c_int32), ("partition_function", C.c_int32), ("options", pg_operator_options),
     ]
+
+
+PARTITION_HASH_GENERATOR, PARTITION_LOCAL = 0, 1
 
 
 class pg_expr_node(C.Structure):
@@ -172,6 +175,8 @@ class Backend:
         "hash_murmur3_fmix64": (C.c_int64, [C.c_int64]),
         "hash_partition": (C.c_int32, [C.c_int64, C.c_int32]),
         "hash_xxhash64": (C.c_int64, [C.c_void_p, C.c_size_t]),
+        "hash_double": (C.c_int64, [C.c_double]),
+        "hash_local_partition": (C.c_int32, [C.c_int64, C.c_int32]),
         "operator_needs_input": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32)]),
         "operator_add_input": (C.c_int32, [C.c_void_p, C.POINTER(pg_page)]),
         "operator_get_output": (C.c_int32, [C.c_void_p, C.POINTER(pg_page)]),

@@ -187,10 +187,45 @@ __host__ __device__ __forceinline__ int32_t hashPartition(int64_t rawHash, int32
     uint32_t folded = (uint32_t) ((uint64_t) rawHash ^ ((uint64_t) rawHash >> 32));
     return (int32_t) (((uint64_t) folded * (uint64_t) (uint32_t) partitionCount) >> 32);
 }
+// airlift XxHash64.hash(long) = XXH64 (seed 0) of the value's 8 little-endian bytes
+__host__ __device__ __forceinline__ int64_t xxHash64Long(uint64_t value)
+{
+    const uint64_t P1 = 0x9E3779B185EBCA87ULL, P2 = 0xC2B2AE3D27D4EB4FULL, P3 = 0x165667B19E3779F9ULL, P4 = 0x85EBCA77C2B2AE63ULL, P5 = 0x27D4EB2F165667C5ULL;
+    uint64_t h = P5 + 8;
+    uint64_t k = value * P2; k = (k << 31) | (k >> 33); k *= P1;
+    h ^= k; h = ((h << 27) | (h >> 37)) * P1 + P4;
+    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+    return (int64_t) h;
+}
+__host__ __device__ __forceinline__ uint64_t reverseBits64(uint64_t x)
+{
+#ifdef __CUDA_ARCH__
+    return __brevll(x);
+#else
+    x = ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
+    x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
+    x = ((x >> 8) & 0x00FF00FF00FF00FFULL) | ((x & 0x00FF00FF00FF00FFULL) << 8);
+    x = ((x >> 16) & 0x0000FFFF0000FFFFULL) | ((x & 0x0000FFFF0000FFFFULL) << 16);
+    return (x >> 32) | (x << 32);
+#endif
+}
+// LocalPartitionGenerator.getPartition(rawHash)  MB/operator/exchange/LocalPartitionGenerator.java:43-63 (partitionCount: power of two)
+__host__ __device__ __forceinline__ int32_t localPartition(int64_t rawHash, int32_t partitionCount)
+{
+    return (int32_t) xxHash64Long(reverseBits64((uint64_t) rawHash)) & (partitionCount - 1);
+}
 // Double.doubleToLongBits (canonical NaN)
 __host__ __device__ __forceinline__ int64_t canonicalDoubleBits(int64_t bits)
 {
     return ((bits & 0x7fffffffffffffffLL) > 0x7ff0000000000000LL) ? 0x7ff8000000000000LL : bits;
+}
+// TypeUtils.doubleHashCode (PC/type/TypeUtils.java:232-238; DoubleType.DOUBLE = new DoubleType(true), DoubleType.java:37,92-100):
+// -0.0 hashes like +0.0, every NaN like the canonical NaN
+__host__ __device__ __forceinline__ int64_t doubleHashBits(int64_t bits)
+{
+    const int64_t c = canonicalDoubleBits(bits);
+    return c == (int64_t) 0x8000000000000000LL ? 0 : c;
 }
 // XXH64 (seed 0) of a short (< 32 byte) slice held in registers: `lo` = bytes 0..7 little endian, len <= 8
 __host__ __device__ inline int64_t xxHash64Short(uint64_t lo, int len)

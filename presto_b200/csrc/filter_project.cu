@@ -86,7 +86,8 @@ __device__ __forceinline__ Val evalNode(const FpParams& P, const FpNode& nd, int
                 }
                 else {
                     if (q == 0) { atomicOr(P.error, (unsigned) FP_ERR_DIV_ZERO); v = 0; }
-                    else v = (p == LLONG_MIN && q == -1) ? LLONG_MIN : p / q;
+                    else if (p == LLONG_MIN && q == -1) { atomicOr(P.error, (unsigned) FP_ERR_OVERFLOW); v = 0; }   // BigintOperators.divide :106-117
+                    else v = p / q;
                 }
                 r.bits = (uint64_t) v;
             }
@@ -139,7 +140,7 @@ __device__ __forceinline__ Val evalNode(const FpParams& P, const FpNode& nd, int
         case PG_EX_HASH: {
             const int t = P.nodes[nd.a].type;
             if (x.isNull) r.bits = 0;
-            else if (t == PG_TYPE_DOUBLE) r.bits = (uint64_t) hashLong(canonicalDoubleBits((int64_t) x.bits));
+            else if (t == PG_TYPE_DOUBLE) r.bits = (uint64_t) hashLong(doubleHashBits((int64_t) x.bits));
             else if (t == PG_TYPE_BOOLEAN) r.bits = x.bits ? 1231 : 1237;
             else r.bits = (uint64_t) hashLong((int64_t) x.bits);
             break;

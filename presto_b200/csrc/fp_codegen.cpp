@@ -104,11 +104,13 @@ struct Gen {
         if (a.kind == 'b') emit("selp.b64 " + r.val + ", 1231, 1237, " + a.val + ";");
         else {
             std::string v = a.val;
-            if (type == PG_TYPE_DOUBLE) {   // Double.doubleToLongBits: canonical NaN
-                std::string p = pr(), c = r64();
+            if (type == PG_TYPE_DOUBLE) {   // TypeUtils.doubleHashCode: -0.0 → +0.0, then Double.doubleToLongBits (canonical NaN)
+                std::string p = pr(), c = r64(), z = pr(), c2 = r64();
                 emit("setp.nan.f64 " + p + ", " + a.val + ", " + a.val + ";");
                 emit("selp.b64 " + c + ", 0x7ff8000000000000, " + a.val + ", " + p + ";");
-                v = c;
+                emit("setp.eq.b64 " + z + ", " + c + ", 0x8000000000000000;");
+                emit("selp.b64 " + c2 + ", 0, " + c + ", " + z + ";");
+                v = c2;
             }
             std::string t = r64(), x = r64(), y = r64();
             emit("mul.lo.u64 " + t + ", " + v + ", 0xC2B2AE3D27D4EB4F;");
@@ -204,8 +206,9 @@ struct Gen {
                         emit("setp.eq.b64 " + pm + ", " + a.val + ", 0x8000000000000000;");
                         emit("setp.eq.s64 " + pm2 + ", " + b.val + ", -1;");
                         emit("and.pred " + pm + ", " + pm + ", " + pm2 + ";");
+                        raise(errOverflow, pm, r.nul);                                    // BigintOperators.divide :106-117: MIN / -1 → NUMERIC_VALUE_OUT_OF_RANGE
                         emit("or.pred " + pm + ", " + pm + ", " + pz + ";");
-                        emit("selp.b64 " + d + ", 1, " + b.val + ", " + pm + ";");     // x / 0 → flagged; MIN / -1 → MIN (Java)
+                        emit("selp.b64 " + d + ", 1, " + b.val + ", " + pm + ";");     // x / 0 and MIN / -1 are flagged; the division itself must not trap
                         emit("div.s64 " + r.val + ", " + a.val + ", " + d + ";");
                         emit("selp.b64 " + r.val + ", 0, " + r.val + ", " + pz + ";");
                     }

@@ -22,6 +22,11 @@ constexpr uint64_t kNoRow = 0xFFFFFFFFFFFFFFFFULL;
 constexpr uint32_t kNoRow32 = 0xFFFFFFFFu;
 constexpr uint32_t kStEmpty = 0, kStLocked = 1;
 constexpr int kMaxKeyWords = 4;
+// firstRow word of a slot = (global row index << 8) | spelling mask of that row: bit k set = DOUBLE key column k of the row was -0.0
+// (DoubleType.equalTo groups -0.0 with +0.0, but the reference's key pages keep the bits of the FIRST row of the group:
+// MultiChannelGroupByHash.addNewGroup :324-358 appends the current row).  atomicMin keeps the smallest row, hence its spelling.
+constexpr int kFirstRowShift = 8;
+__host__ __device__ __forceinline__ uint64_t firstRowWord(uint64_t globalRow, uint32_t spelling = 0) { return (globalRow << kFirstRowShift) | spelling; }
 constexpr int kMaxKeyColumns = 8;
 
 // counters[] indices
@@ -150,7 +155,7 @@ enum { ERR_BIGINT_OVERFLOW = 1, ERR_VARCHAR_TOO_LONG = 2 };
 
 // Packs the key of `row`.  Returns 0 = ordinary key, 1 = NULL key of the Bigint path, 2 = key equal to the W==1 sentinel.
 template <int W>
-__device__ __forceinline__ int packKey(const KeyPlan& kp, int64_t row, uint64_t (&kw)[W])
+__device__ __forceinline__ int packKey(const KeyPlan& kp, int64_t row, uint64_t (&kw)[W], uint32_t* spelling = nullptr)
 {
 #pragma unroll
     for (int w = 0; w < W; w++) kw[w] = 0;
@@ -170,7 +175,8 @@ __device__ __forceinline__ int packKey(const KeyPlan& kp, int64_t row, uint64_t 
                 case PG_TYPE_BIGINT: v = ((const uint64_t*) f.values)[row]; break;
                 case PG_TYPE_DOUBLE: {
                     int64_t b = canonicalDoubleBits(((const int64_t*) f.values)[row]);
-                    v = (b == (int64_t) 0x8000000000000000LL) ? 0 : (uint64_t) b;   // -0.0 groups with +0.0 (DoubleType.equalTo: a == b)
+                    v = (uint64_t) b;
+                    if (b == (int64_t) 0x8000000000000000LL) { v = 0; if (spelling) *spelling |= 1u << k; }   // -0.0 groups with +0.0 (DoubleType.equalTo: a == b)
                     break;
                 }
                 case PG_TYPE_INTEGER: case PG_TYPE_DATE: v = ((const uint32_t*) f.values)[row]; break;

@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(kAggThreads) hashAggKernel(const __grid_consta
         uint64_t contrib[R][MAXV];
         uint32_t addMask[R];
         int special[R];
+        uint32_t spell[R];            // -0.0 spelling mask of the row's DOUBLE key columns (rare: such rows go straight to the HBM table)
         bool valid[R];
         uint32_t rowIdxOf[R];
         // ---- load phase: every load of the tile is issued before any is consumed; 8-byte columns come in as 128-bit pairs ----
@@ -249,6 +250,7 @@ __global__ void __launch_bounds__(kAggThreads) hashAggKernel(const __grid_consta
             rowIdxOf[2 * j] = (uint32_t) row0; rowIdxOf[2 * j + 1] = (uint32_t) (row0 + 1);
             addMask[2 * j] = 0; addMask[2 * j + 1] = 0;
             special[2 * j] = 0; special[2 * j + 1] = 0;
+            spell[2 * j] = 0; spell[2 * j + 1] = 0;
 #pragma unroll
             for (int w = 0; w < W; w++) { kw[2 * j][w] = 0; kw[2 * j + 1][w] = 0; }
             // keys
@@ -262,8 +264,8 @@ __global__ void __launch_bounds__(kAggThreads) hashAggKernel(const __grid_consta
                 if (v1) special[2 * j + 1] = (f.nulls && f.nulls[row0 + 1]) ? 1 : (b == kEmptyKey ? 2 : 0);
             }
             else {
-                if (v0) special[2 * j] = packKey<W>(P.kp, row0, kw[2 * j]);
-                if (v1) special[2 * j + 1] = packKey<W>(P.kp, row0 + 1, kw[2 * j + 1]);
+                if (v0) special[2 * j] = packKey<W>(P.kp, row0, kw[2 * j], &spell[2 * j]);
+                if (v1) special[2 * j + 1] = packKey<W>(P.kp, row0 + 1, kw[2 * j + 1], &spell[2 * j + 1]);
             }
             // accumulator inputs
 #pragma unroll
@@ -298,7 +300,7 @@ __global__ void __launch_bounds__(kAggThreads) hashAggKernel(const __grid_consta
             bool done = false;
             if (v) {
                 h = hashKeyWords<W>(kw[r]);
-                if (!warpBypass) sslot = special[r] ? (int) st.S + special[r] - 1 : st.find(kw[r], h);
+                if (!warpBypass && !spell[r]) sslot = special[r] ? (int) st.S + special[r] - 1 : st.find(kw[r], h);
                 if (sslot >= 0) {
                     const uint32_t id = st.sid[sslot];
                     if (id < (uint32_t) K0) {
@@ -382,7 +384,7 @@ __global__ void __launch_bounds__(kAggThreads) hashAggKernel(const __grid_consta
                     atomicAdd(&T.counters[CNT_DEFERRED], 1u);
                 }
                 else {
-                    const uint64_t g = P.rowBase + rowIdx;
+                    const uint64_t g = firstRowWord(P.rowBase + rowIdx, spell[r]);
                     if (g < __ldcg(&T.firstRow[gslot])) atomicMin((unsigned long long*) &T.firstRow[gslot], (unsigned long long) g);
 #pragma unroll
                     for (int c = 0; c < MAXV; c++)
@@ -439,7 +441,7 @@ __global__ void __launch_bounds__(kAggThreads) hashAggKernel(const __grid_consta
                 gslot = tableFind<W>(T, kw, hashKeyWords<W>(kw), true, true);
             }
             if (gslot < 0) { atomicOr(&T.counters[CNT_ERROR], 0x80000000u); continue; }   // cannot happen: flush reserve (see HashAggregationOp)
-            const uint64_t g = P.rowBase + f;
+            const uint64_t g = firstRowWord(P.rowBase + f);
             if (g < __ldcg(&T.firstRow[gslot])) atomicMin((unsigned long long*) &T.firstRow[gslot], (unsigned long long) g);
             for (int c = 0; c < nAcc; c++) {
                 const uint64_t x = st.acc[c * st.S2 + s];
@@ -523,7 +525,7 @@ __device__ __noinline__ void fastGlobalRow(const FastLaunch<NV, CNT>& P, uint64_
         atomicAdd(&T.counters[CNT_DEFERRED], 1u);
         return;
     }
-    const uint64_t g = P.rowBase + rowIdx;
+    const uint64_t g = firstRowWord(P.rowBase + rowIdx);
     if (g < __ldcg(&T.firstRow[gslot])) atomicMin((unsigned long long*) &T.firstRow[gslot], (unsigned long long) g);
     uint64_t* acc = T.acc + (size_t) gslot * T.nvPhys;
 #pragma unroll
@@ -588,7 +590,7 @@ __global__ void __launch_bounds__(256, 4) hashAggDirectKernel(const __grid_const
             atomicAdd(&T.counters[CNT_DEFERRED], 1u);
             return;
         }
-        const uint64_t g = P.rowBase + rowIdx;
+        const uint64_t g = firstRowWord(P.rowBase + rowIdx);
         if (g < __ldcg(&T.firstRow[gslot])) atomicMin((unsigned long long*) &T.firstRow[gslot], (unsigned long long) g);
         uint64_t* acc = T.acc + (size_t) gslot * T.nvPhys;
 #pragma unroll
@@ -875,7 +877,7 @@ __global__ void __launch_bounds__(MID ? 512 : kAggThreads, MID ? 1 : 2) hashAggF
         // (slot S + 1 holds the key whose value equals the empty sentinel; slot S, the NULL key, is never used by this kernel)
         const int gslot = fastGlobalFind<NV, CNT>(P, s >= st.S ? kEmptyKey : (uint64_t) st.keys[s], true);
         if (gslot < 0) { atomicOr(&T.counters[CNT_ERROR], 0x80000000u); continue; }
-        const uint64_t g = P.rowBase + f;
+        const uint64_t g = firstRowWord(P.rowBase + f);
         if (g < __ldcg(&T.firstRow[gslot])) atomicMin((unsigned long long*) &T.firstRow[gslot], (unsigned long long) g);
         uint64_t* acc = T.acc + (size_t) gslot * T.nvPhys;
 #pragma unroll
@@ -975,6 +977,7 @@ __global__ void emitKernel(const __grid_constant__ EmitParams P)
         if (slot >= T.cap) { if (slot == T.cap) bigintNull = true; else kw[0] = kEmptyKey; }
         else for (int w = 0; w < P.W; w++) kw[w] = T.keys[(size_t) w * T.capP + slot];
         const uint32_t nullMask = P.bigintPath ? (bigintNull ? 1u : 0u) : (uint32_t) fieldOf(kw, P.nullWord, P.nullShift, 8);
+        const uint32_t spelling = (uint32_t) T.firstRow[slot] & ((1u << kFirstRowShift) - 1);   // -0.0 spelling of the group's first row
         int64_t rawHash = 0;
         for (int k = 0; k < P.nKeys; k++) {
             const KeyOut& ko = P.keys[k];
@@ -983,7 +986,11 @@ __global__ void emitKernel(const __grid_constant__ EmitParams P)
             int64_t th = 0;   // TypeUtils.hashPosition: NULL → 0
             switch (ko.type) {
                 case PG_TYPE_BIGINT: ((int64_t*) ko.values)[g] = (int64_t) v; if (!isNull) th = hashLong((int64_t) v); break;
-                case PG_TYPE_DOUBLE: ((int64_t*) ko.values)[g] = (int64_t) v; if (!isNull) th = hashLong(canonicalDoubleBits((int64_t) v)); break;
+                case PG_TYPE_DOUBLE:
+                    if (!isNull) th = hashLong(doubleHashBits((int64_t) v));
+                    if (!isNull && v == 0 && ((spelling >> k) & 1u)) v = 0x8000000000000000ULL;     // the first row of the group spelled it -0.0
+                    ((int64_t*) ko.values)[g] = (int64_t) v;
+                    break;
                 case PG_TYPE_INTEGER: case PG_TYPE_DATE: ((int32_t*) ko.values)[g] = (int32_t) v; if (!isNull) th = hashLong((int64_t) (int32_t) v); break;
                 case PG_TYPE_BOOLEAN: ((uint8_t*) ko.values)[g] = (uint8_t) v; if (!isNull) th = v ? 1231 : 1237; break;
                 case PG_TYPE_VARCHAR: {
@@ -1494,6 +1501,7 @@ public:
         if (!layout.bigintPath && !packed32) return false;
         for (int k = 0; k < layout.nKeys; k++) {
             const DeviceColumn& kc = colOf(layout.channels[k]);
+            PG_CHECK_ARG(kc.type == layout.types[k], "group-by channel type differs from the operator's configuration");
             if (kc.nulls || ((uintptr_t) kc.values % 16) != 0) return false;
         }
         if (packed32 && knownGroups > (int64_t) sharedLimit * 9 / 10) return false;    // mid / direct modes address the W = 1 table
@@ -1502,6 +1510,7 @@ public:
             if (!phys[p].active) continue;
             if (phys[p].kind == K_F64 && phys[p].mask < 0) {
                 const DeviceColumn& vc = colOf(phys[p].channel);
+                PG_CHECK_ARG(typeWidth(vc.type) == 8, "sum / avg inputs must be BIGINT or DOUBLE columns");
                 if (vc.nulls || ((uintptr_t) vc.values % 16) != 0) return false;
                 f64Cols.push_back((int) p);
             }
@@ -1717,7 +1726,8 @@ __global__ void gbhInsertKernel(GroupTable T, KeyPlan kp, int64_t n, uint64_t ro
 {
     for (int64_t row = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; row < n; row += (int64_t) gridDim.x * blockDim.x) {
         uint64_t kw[W];
-        int special = packKey<W>(kp, row, kw);
+        uint32_t spelling = 0;
+        int special = packKey<W>(kp, row, kw, &spelling);
         int slot;
         if (special) slot = (int) T.cap + special - 1;
         else {
@@ -1726,7 +1736,7 @@ __global__ void gbhInsertKernel(GroupTable T, KeyPlan kp, int64_t n, uint64_t ro
             if (isNew) newSlots[atomicAdd(&T.counters[CNT_NEW], 1u)] = (uint32_t) slot;
         }
         if (T.gid[slot] < 0) {
-            const uint64_t g = rowBase + (uint64_t) row;
+            const uint64_t g = firstRowWord(rowBase + (uint64_t) row, spelling);
             if (g < __ldcg(&T.firstRow[slot])) atomicMin((unsigned long long*) &T.firstRow[slot], (unsigned long long) g);
         }
     }

@@ -86,11 +86,13 @@ struct ProbeParams {
     int32_t hasDuplicates;
     int32_t* matchHead;       // [n] chain head or -1
     uint32_t* counts;         // [n+1] output rows per probe row
+    unsigned long long* total;   // exact 64-bit sum of counts (a skewed join can emit more than 2^32 rows for one probe page)
 };
 
 template <int W>
 __global__ void joinProbeKernel(const __grid_constant__ ProbeParams P)
 {
+    unsigned long long mine = 0;
     for (int64_t row = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; row < P.n; row += (int64_t) gridDim.x * blockDim.x) {
         uint64_t kw[W];
         int special = packKey<W>(P.kp, row, kw);
@@ -107,7 +109,11 @@ __global__ void joinProbeKernel(const __grid_constant__ ProbeParams P)
         else if (P.outer) c = 1;
         P.matchHead[row] = head;
         P.counts[row] = c;
+        mine += c;
     }
+    // every thread of the warp gets here (no early exits): one 64-bit atomic per warp
+    for (int s = 16; s >= 1; s >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, s);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(P.total, mine);
 }
 
 struct JoinColumn {
@@ -1063,7 +1069,7 @@ class LookupJoinOp : public Operator {
     KeyLayout layout;
     PageStager stager;
     bool finishing = false, hasPending = false;
-    DeviceBuffer matchHead, counts, offsets, scanTemp, unitMask;
+    DeviceBuffer matchHead, counts, offsets, scanTemp, unitMask, exactTotal;
     std::vector<DeviceBuffer> outValues, outNulls;
     std::vector<PinnedBuffer> hostValues, hostNulls;
     std::vector<pg_block> outBlocks;
@@ -1122,6 +1128,9 @@ public:
         layout.fill(P.kp, keyCols, ls->counters.as<unsigned int>() + CNT_ERROR);
         P.n = n; P.outer = joinType == PG_JOIN_PROBE_OUTER; P.hasDuplicates = ls->hasDuplicates; P.matchHead = matchHead.as<int32_t>(); P.counts = counts.as<uint32_t>();
         PG_CUDA(cudaMemsetAsync(counts.as<uint32_t>() + n, 0, 4, stream));
+        exactTotal.reserve(16);
+        PG_CUDA(cudaMemsetAsync(exactTotal.ptr, 0, 8, stream));
+        P.total = exactTotal.as<unsigned long long>();
         const int grid = (int) std::min<int64_t>(divUp(n, 256), numSMs * 16);
         switch (layout.W) {
             case 1: PG_LAUNCH(this, joinProbeKernel<1>, grid, 256, 0, P); break;
@@ -1136,9 +1145,17 @@ public:
         cub::DeviceScan::ExclusiveSum(scanTemp.ptr, tb, counts.as<uint32_t>(), offsets.as<uint32_t>(), (int) (n + 1), stream);
         stats.kernel_launches += 2;
         uint32_t total = 0;
+        unsigned long long total64 = 0;
         PG_CUDA(cudaMemcpyAsync(&total, offsets.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, stream));
+        PG_CUDA(cudaMemcpyAsync(&total64, exactTotal.ptr, 8, cudaMemcpyDeviceToHost, stream));
         PG_CUDA(cudaStreamSynchronize(stream));
-        stats.d2h_bytes += 4;
+        stats.d2h_bytes += 12;
+        // the 32-bit scan wraps silently beyond 2^32 output rows; a Page holds < 2^31 positions (the reference bounds every output page
+        // through LookupJoinPageBuilder; here the caller has to feed smaller probe pages)
+        if (total64 >= (1ULL << 31)) {
+            stager.markCompute(slot);
+            throw Error(PG_ERR_INSUFFICIENT_RESOURCES, "join output of one probe page exceeds 2^31 positions (" + std::to_string(total64) + "): feed smaller probe pages");
+        }
         pendingRows = total;
         if (total == 0) { stager.markCompute(slot); return; }
 

@@ -32,6 +32,7 @@ struct PartitionIdParams {
     const uint8_t* nullChannelNulls;     // rows whose null channel is NULL go to every partition
     int32_t replicateRow0;
     int32_t partitionCount;
+    int32_t localFunction;               // 1: LocalPartitionGenerator instead of HashGenerator.getPartition
     int64_t n;
     int64_t units;
     uint16_t* ids;                       // [n]  partition, or partitionCount = "every partition"
@@ -43,7 +44,7 @@ __device__ __forceinline__ int64_t typeHashOf(const HashCol& c, int64_t row)
     if (c.nulls && c.nulls[row]) return 0;   // TypeUtils.hashPosition: NULL_HASH_CODE
     switch (c.type) {
         case PG_TYPE_BIGINT: return hashLong(((const int64_t*) c.values)[row]);
-        case PG_TYPE_DOUBLE: return hashLong(canonicalDoubleBits(((const int64_t*) c.values)[row]));
+        case PG_TYPE_DOUBLE: return hashLong(doubleHashBits(((const int64_t*) c.values)[row]));
         case PG_TYPE_INTEGER: case PG_TYPE_DATE: return hashLong((int64_t) ((const int32_t*) c.values)[row]);
         default: return ((const uint8_t*) c.values)[row] ? 1231 : 1237;   // BOOLEAN
     }
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(kPartWarps * 32) partitionIdKernel(const __gri
                         rawHash = 0;   // InterpretedHashGenerator.hashPosition: CombineHashFunction.getHash(result, typeHash)
                         for (int c = 0; c < P.nCols; c++) rawHash = (int64_t) (31ULL * (uint64_t) rawHash + (uint64_t) typeHashOf(P.cols[c], row));
                     }
-                    part = hashPartition(rawHash, PC);
+                    part = P.localFunction ? localPartition(rawHash, PC) : hashPartition(rawHash, PC);
                 }
                 P.ids[row] = (uint16_t) part;
             }
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(kRemoteWarps * 32) partitionScatterStagedKerne
 
 class PartitionedOutputOp : public Operator {
     std::vector<int> types, partitionChannels, staged;
-    int partitionCount, hashChannel, nullChannel;
+    int partitionCount, hashChannel, nullChannel, partitionFunction;
     bool replicatesAnyRow, hasAnyRowBeenReplicated = false;
     bool finishing = false, hasPending = false;
     PageStager stager;
@@ -352,6 +353,10 @@ public:
         partitionChannels.assign(c->partition_channels, c->partition_channels + c->n_partition_channels);
         partitionCount = c->partition_count; hashChannel = c->precomputed_hash_channel; nullChannel = c->null_channel;
         replicatesAnyRow = c->replicates_any_row != 0;
+        partitionFunction = c->partition_function;
+        PG_CHECK_ARG(partitionFunction == PG_PARTITION_HASH_GENERATOR || partitionFunction == PG_PARTITION_LOCAL, "unknown partition function");
+        if (partitionFunction == PG_PARTITION_LOCAL)
+            PG_CHECK_ARG((partitionCount & (partitionCount - 1)) == 0, "partitionCount must be a power of 2");   // LocalPartitionGenerator.java:33
         for (int t : types) if (t == PG_TYPE_VARCHAR) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR channels are not on the GPU repartition path yet");
         for (int ch : partitionChannels) PG_CHECK_ARG(ch >= 0 && ch < c->n_channels, "partition channel out of range");
         PG_CHECK_ARG(hashChannel < c->n_channels && nullChannel < c->n_channels, "channel out of range");
@@ -393,7 +398,7 @@ public:
         A.nullChannelNulls = nullChannel >= 0 ? curCols[nullChannel].nulls : nullptr;
         A.replicateRow0 = (replicatesAnyRow && !hasAnyRowBeenReplicated) ? 1 : 0;
         hasAnyRowBeenReplicated = hasAnyRowBeenReplicated || replicatesAnyRow;
-        A.partitionCount = partitionCount; A.n = n; A.units = curUnits; A.ids = ids.as<uint16_t>(); A.hist = hist.as<uint32_t>();
+        A.partitionCount = partitionCount; A.localFunction = partitionFunction == PG_PARTITION_LOCAL ? 1 : 0; A.n = n; A.units = curUnits; A.ids = ids.as<uint16_t>(); A.hist = hist.as<uint32_t>();
         PG_CUDA(cudaMemsetAsync(hist.as<uint32_t>() + histN - 1, 0, 4, stream));
         const size_t smem = (size_t) kPartWarps * partitionCount * 4;
         PG_LAUNCH(this, partitionIdKernel, launchGrid(), kPartWarps * 32, smem, A);

@@ -364,6 +364,12 @@ int64_t pg_hash_bigint(int64_t value) { return pg::hashLong(value); }
 int64_t pg_hash_combine(int64_t previous, int64_t h) { return (int64_t) (31ULL * (uint64_t) previous + (uint64_t) h); }
 int64_t pg_hash_murmur3_fmix64(int64_t x) { return (int64_t) pg::murmur64((uint64_t) x); }
 int32_t pg_hash_partition(int64_t rawHash, int32_t partitionCount) { return pg::hashPartition(rawHash, partitionCount); }
+int64_t pg_hash_double(double value) { int64_t b; memcpy(&b, &value, 8); return pg::hashLong(pg::doubleHashBits(b)); }
+int32_t pg_hash_local_partition(int64_t rawHash, int32_t partitionCount)
+{
+    if (partitionCount <= 0 || (partitionCount & (partitionCount - 1)) != 0) return -1;   // checkArgument(Integer.bitCount(partitionCount) == 1)
+    return pg::localPartition(rawHash, partitionCount);
+}
 
 int64_t pg_hash_xxhash64(const void* data, size_t len)
 {

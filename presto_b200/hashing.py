@@ -50,6 +50,7 @@ def type_hash(block: Block, backend=None) -> np.ndarray:
         d = block.values.astype(np.float64)
         bits = d.view(np.int64).copy()
         bits[np.isnan(d)] = 0x7FF8000000000000
+        bits[d == 0] = 0          # TypeUtils.doubleHashCode: -0.0 hashes like +0.0
         h = hash_long(bits)
     elif t == abi.BOOLEAN:
         h = np.where(block.values != 0, 1231, 1237).astype(np.int64)
@@ -82,3 +83,27 @@ def get_partition(raw_hash: np.ndarray, partition_count: int) -> np.ndarray:
     u = raw_hash.astype(np.int64).view(np.uint64)
     folded = (u ^ (u >> np.uint64(32))) & np.uint64(0xFFFFFFFF)
     return ((folded * np.uint64(partition_count)) >> np.uint64(32)).astype(np.int32)
+
+
+def local_partition(raw_hash: np.ndarray, partition_count: int) -> np.ndarray:
+    """LocalPartitionGenerator.getPartition  MB/operator/exchange/LocalPartitionGenerator.java:43-63:
+    (int) XxHash64.hash(Long.reverse(rawHash)) & (partitionCount - 1), numpy restatement (XXH64 seed 0 of the 8 LE bytes)."""
+    assert partition_count > 0 and partition_count & (partition_count - 1) == 0, "partitionCount must be a power of 2"
+    M = np.uint64(0xFFFFFFFFFFFFFFFF)
+    x = raw_hash.astype(np.int64).view(np.uint64).copy()
+    r = np.zeros_like(x)
+    for _ in range(64):                       # Long.reverse
+        r = (r << np.uint64(1)) | (x & np.uint64(1))
+        x = x >> np.uint64(1)
+    P1, P2, P3, P4, P5 = (np.uint64(v) for v in (0x9E3779B185EBCA87, 0xC2B2AE3D27D4EB4F, 0x165667B19E3779F9, 0x85EBCA77C2B2AE63, 0x27D4EB2F165667C5))
+
+    def rotl(v, k):
+        return ((v << np.uint64(k)) | (v >> np.uint64(64 - k))) & M
+    with np.errstate(over="ignore"):
+        h = P5 + np.uint64(8)
+        k = rotl(r * P2, 31) * P1
+        h = rotl(h ^ k, 27) * P1 + P4
+        h ^= h >> np.uint64(33); h = h * P2
+        h ^= h >> np.uint64(29); h = h * P3
+        h ^= h >> np.uint64(32)
+    return (h & np.uint64(partition_count - 1)).astype(np.int32)

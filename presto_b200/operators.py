@@ -275,9 +275,11 @@ class PartitionedOutputOperator(Operator):
     one page per input page with all partitions back to back; ``get_offsets`` gives the partition boundaries."""
 
     def __init__(self, types: Sequence[int], partition_count: int, partition_channels: Sequence[int], *,
-                 precomputed_hash_channel: int = -1, replicates_any_row: bool = False, null_channel: int = -1, backend=None, **options):
+                 precomputed_hash_channel: int = -1, replicates_any_row: bool = False, null_channel: int = -1,
+                 partition_function: int = abi.PARTITION_HASH_GENERATOR, backend=None, **options):
         backend = backend or _default_backend()
         cfg = abi.pg_partitioned_output_config()
+        cfg.partition_function = partition_function
         ty, pc = abi.i32_array(types), abi.i32_array(partition_channels)
         cfg.n_channels, cfg.types = len(types), ty
         cfg.partition_count = partition_count

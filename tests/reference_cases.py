@@ -13,7 +13,7 @@ from presto_b200 import (
     INTEGER, JOIN_INNER, JOIN_PROBE_OUTER, VARCHAR, Aggregate, Block, FilterAndProjectOperator, GroupByHash,
     HashAggregationOperator, HashBuilderOperator, JoinBridge, LookupJoinOperator, Page, PartitionedOutputOperator, Program, to_pages,
 )
-from presto_b200.hashing import get_hash_block, get_partition, hash_long
+from presto_b200.hashing import get_hash_block, get_partition, hash_long, local_partition
 
 from util import (
     RowPagesBuilder, create_double_sequence_block, create_doubles_block, create_long_sequence_block, create_longs_block,
@@ -342,7 +342,7 @@ def case_join_duplicate_chain_order(backend):
 # ---------------------------------------------------------------------------------------------------------------------
 # PartitionedOutput (TestOptimizedPartitionedOutputOperator: per-partition rows equal the rows the partition function assigns)
 # ---------------------------------------------------------------------------------------------------------------------
-def case_partitioned_output(backend, partition_count: int = 4, n: int = 1000, nulls: bool = False, precomputed: bool = False):
+def case_partitioned_output(backend, partition_count: int = 4, n: int = 1000, nulls: bool = False, precomputed: bool = False, local: bool = False):
     """TestOptimizedPartitionedOutputOperator.testPartitionedSinglePagePrimitiveTypes / …WithNulls: every row lands in the
     partition HashGenerator.getPartition assigns, rows keep input order inside a partition."""
     rng = np.random.default_rng(11)
@@ -357,12 +357,15 @@ def case_partitioned_output(backend, partition_count: int = 4, n: int = 1000, nu
     hash_channel = -1
     if precomputed:
         blocks.append(raw); types.append(BIGINT); hash_channel = 3
-    op = PartitionedOutputOperator(types, partition_count, [0, 1], precomputed_hash_channel=hash_channel, backend=backend)
+    # local = LocalPartitionGenerator (LocalExchange / PartitionedLookupSource, LocalPartitionGenerator.java:43-63) instead of
+    # HashGenerator.getPartition; the expectation comes from the numpy restatement (cross-checked against python xxhash in test_abi)
+    op = PartitionedOutputOperator(types, partition_count, [0, 1], precomputed_hash_channel=hash_channel, backend=backend,
+                                   partition_function=1 if local else 0)
     page = Page(blocks)
     op.add_input(page)
     out = op.get_output()
     offsets = op.get_offsets()
-    parts = get_partition(raw.values, partition_count)
+    parts = local_partition(raw.values, partition_count) if local else get_partition(raw.values, partition_count)
     in_rows = page.rows()
     out_rows = out.rows()
     assert offsets[0] == 0 and offsets[-1] == n and out.position_count == n
@@ -370,6 +373,27 @@ def case_partitioned_output(backend, partition_count: int = 4, n: int = 1000, nu
         assert out_rows[offsets[p]:offsets[p + 1]] == [in_rows[i] for i in range(n) if parts[i] == p]
     op.finish()
     assert op.is_finished()
+    op.close()
+
+
+def case_partitioned_output_double_zero_keys(backend):
+    """DoubleType.hash → TypeUtils.doubleHashCode (PC/type/TypeUtils.java:232-238): -0.0 and +0.0 are equal keys, so they must reach the
+    same partition (hash 0 → partition 0), as must every NaN payload."""
+    import struct
+    nan2 = struct.unpack("<d", struct.pack("<Q", 0x7FF0000000000123))[0]
+    keys = Block.from_numpy(DOUBLE, np.array([0.0, -0.0, 1.5, float("nan"), nan2, -0.0, 2.5], dtype=np.float64))
+    vals = create_long_sequence_block(0, 7)
+    op = PartitionedOutputOperator([DOUBLE, BIGINT], 8, [0], backend=backend)
+    op.add_input(Page([keys, vals]))
+    out = op.get_output()
+    offsets = op.get_offsets()
+    seq = [r[1] for r in out.rows()]
+    part_of = {}
+    for p in range(8):
+        for v in seq[offsets[p]:offsets[p + 1]]:
+            part_of[v] = p
+    assert part_of[0] == part_of[1] == part_of[5] == 0
+    assert part_of[3] == part_of[4]
     op.close()
 
 

@@ -90,6 +90,36 @@ def test_host_hash_helpers_match_known_answers():
     assert [b.hash_partition(b.hash_bigint(v), 8) for v in (0, 1, 42)] == [0, 4, 2]
     assert b.hash_xxhash64(b"A", 1) == 1371800463213966980 and b.hash_xxhash64(b"", 0) == -1205034819632174695
     assert b.hash_combine(3, 4) == 97
+    # TypeUtils.doubleHashCode (PC/type/TypeUtils.java:232-238): -0.0 is canonicalised to +0.0 (hash(0) = 0), every NaN to the canonical NaN
+    assert b.hash_double(-0.0) == b.hash_double(0.0) == 0
+    import struct
+    nan_payload = struct.unpack("<d", struct.pack("<Q", 0x7FF0000000000123))[0]
+    assert b.hash_double(float("nan")) == b.hash_double(nan_payload) == b.hash_bigint(0x7FF8000000000000)
+    assert b.hash_double(1.5) == b.hash_bigint(struct.unpack("<q", struct.pack("<d", 1.5))[0])
+
+
+def test_local_partition_generator_known_answers(oracle_backend):
+    """LocalPartitionGenerator.getPartition (MB/operator/exchange/LocalPartitionGenerator.java:43-63) =
+    (int) XxHash64.hash(Long.reverse(rawHash)) & (P - 1): the product helper, the oracle and an independent restatement through the
+    python xxhash package (XXH64 of the 8 little-endian bytes) agree; P must be a power of two."""
+    import struct
+
+    import numpy as np
+    from presto_b200._lib import load_library
+    from presto_b200.hashing import hash_long, local_partition
+    xxhash = pytest.importorskip("xxhash")
+    b = load_library()
+    rng = np.random.default_rng(3)
+    raw = np.concatenate([np.array([0, 1, -1, 42, 1 << 62, -(1 << 63)], dtype=np.int64), hash_long(rng.integers(-10**12, 10**12, 200))])
+    for P in (1, 2, 8, 64, 1024):
+        want = []
+        for v in raw.tolist():
+            rev = int(format(v & 0xFFFFFFFFFFFFFFFF, "064b")[::-1], 2)
+            want.append(xxhash.xxh64(struct.pack("<Q", rev)).intdigest() & (P - 1))
+        assert [b.hash_local_partition(v, P) for v in raw.tolist()] == want
+        assert [oracle_backend.hash_local_partition(v, P) for v in raw.tolist()] == want
+        assert local_partition(raw, P).tolist() == want
+    assert b.hash_local_partition(5, 6) == -1 and oracle_backend.hash_local_partition(5, 0) == -1
 
 
 def test_chunked_crc32_combine_equals_zlib():

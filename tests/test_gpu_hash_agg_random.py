@@ -168,3 +168,39 @@ def test_two_32_bit_key_columns_on_the_fast_path(gpu_backend, oracle_backend, gr
     want = run(oracle_backend, pages, [INTEGER, DATE], [0, 1], aggs, expected_groups=groups, max_output_rows=1 << 30)
     assert len(want) >= min(groups, 6)
     rows_close(got, want)
+
+
+def double_key_pages(rng):
+    """DOUBLE group keys with both spellings of zero and NaN; the first row of the zero group is -0.0 on page 1 of column a and +0.0 of column b."""
+    pages = []
+    for p in range(3):
+        n = 5000
+        a = rng.integers(-3, 4, n).astype(np.float64)
+        a[rng.random(n) < 0.3] = -0.0
+        b = rng.integers(0, 3, n).astype(np.float64) * 0.5
+        b[rng.random(n) < 0.2] = -0.0
+        if p == 0:
+            a[0], b[0] = -0.0, 0.0
+            a[1], b[1] = 0.0, -0.0
+        a[rng.random(n) < 0.05] = np.nan
+        pages.append(Page([Block.from_numpy(DOUBLE, a), Block.from_numpy(DOUBLE, b), Block.from_numpy(DOUBLE, rng.random(n))]))
+    return pages
+
+
+def key_bits(rows, n_keys):
+    import struct
+    return [tuple(None if v is None else struct.unpack("<q", struct.pack("<d", v))[0] for v in r[:n_keys]) for r in rows]
+
+
+def test_double_keys_keep_the_first_rows_zero_spelling(gpu_backend, oracle_backend):
+    """DoubleType.equalTo groups -0.0 with +0.0, and the reference's key pages keep the FIRST row's bits
+    (MultiChannelGroupByHash.addNewGroup :324-358): the output key column must match the oracle bit for bit, not just as a double."""
+    rng = np.random.default_rng(2024)
+    pages = double_key_pages(rng)
+    aggs = [Aggregate(AGG_SUM_DOUBLE, 2), Aggregate(AGG_COUNT_STAR)]
+    for types, channels in (([DOUBLE, DOUBLE], [0, 1]), ([DOUBLE], [0])):
+        got = run(gpu_backend, pages, types, channels, aggs, expected_groups=64, max_output_rows=1 << 30)
+        want = run(oracle_backend, pages, types, channels, aggs, expected_groups=64, max_output_rows=1 << 30)
+        rows_close(got, want)
+        assert key_bits(got, len(types)) == key_bits(want, len(types))
+        assert any(b == (-(1 << 63),) * 1 or (-(1 << 63)) in b for b in key_bits(want, len(types))), "the case must contain a -0.0 first row"

@@ -92,12 +92,14 @@ def test_random_expressions(gpu_backend, oracle_backend, mode, seed):
 
 def test_overflow_and_division_by_zero_are_reported(gpu_backend, mode):
     from presto_b200 import PrestoException
-    for build, code in [(lambda x: x * x * x * x * x, 6), (lambda x: x / (x - x), 1)]:
+    # x^5 overflows; x / 0; Long.MIN_VALUE / -1 (BigintOperators.divide :106-117: NUMERIC_VALUE_OUT_OF_RANGE)
+    for build, code, vals in [(lambda x: x * x * x * x * x, 6, [3, 100000, 7]), (lambda x: x / (x - x), 1, [3, 100000, 7]),
+                              (lambda x: x / -1, 6, [3, -(1 << 63), 7])]:
         prog = Program([BIGINT])
         prog.project(build(prog.input(0)))
         op = FilterAndProjectOperator([BIGINT], prog, backend=gpu_backend)
         with pytest.raises(PrestoException) as e:
-            op.add_input(Page([Block.from_values(BIGINT, [3, 100000, 7])]))
+            op.add_input(Page([Block.from_values(BIGINT, vals)]))
         assert e.value.code == code
         op.close()
     # NULL operands and filtered-out rows never raise

@@ -49,6 +49,11 @@ def test_join_duplicate_chain_order(gpu_backend): rc.case_join_duplicate_chain_o
 def test_partitioned_output(gpu_backend, partition_count, nulls, precomputed):
     rc.case_partitioned_output(gpu_backend, partition_count, 1000, nulls, precomputed)
 def test_partitioned_output_replicates(gpu_backend): rc.case_partitioned_output_replicates(gpu_backend)
+def test_partitioned_output_double_zero_keys(gpu_backend): rc.case_partitioned_output_double_zero_keys(gpu_backend)
+@pytest.mark.parametrize("partition_count", [1, 2, 8, 64])
+def test_partitioned_output_local_partition_generator(gpu_backend, partition_count):
+    rc.case_partitioned_output(gpu_backend, partition_count, 1000, True, False, local=True)
+    rc.case_partitioned_output(gpu_backend, partition_count, 1000, False, True, local=True)
 
 
 def test_page_processor_selection(gpu_backend): rc.case_page_processor_selection(gpu_backend)
