@@ -410,7 +410,7 @@ def run_e2e(torch, backend, rows, groups, steps, warmup, device):
     return rows / float(np.mean(times)), int(h2d), int(d2h), out
 
 
-def run_q1_pipeline(torch, backend, device, rows, steps, warmup):
+def run_q1_pipeline(torch, backend, device, rows, steps, warmup, fused=True):
     """BASELINE.json configs[0] shape at SF100 size on one GPU: TPC-H Q1 = PageProcessor filter/project → HashAggregationOperator over
     (returnflag, linestatus) with 4 sums, 3 avgs and count(*) (HandTpchQuery1.java:99-127), lineitem device resident.  Algorithmic
     bytes = the 7 input columns once (46 B/row); the 4-group result is negligible."""
@@ -432,13 +432,15 @@ def run_q1_pipeline(torch, backend, device, rows, steps, warmup):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record(stream)
-        out = run_q1([page], backend=backend, device_resident=True, device=device, cuda_stream=stream.cuda_stream)
+        info = {}
+        out = run_q1([page], backend=backend, device_resident=True, fused=fused, info=info, device=device, cuda_stream=stream.cuda_stream)
         e1.record(stream)
         torch.cuda.synchronize()
         if it >= warmup:
             times.append(e0.elapsed_time(e1)); groups = sum(p.position_count for p in out)
     ms = float(np.mean(times))
-    return {"rows": rows, "groups": int(groups), "ms": ms, "rows_per_s": rows / (ms / 1000), "achieved_gbs": 46 * rows / (ms / 1000) / 1e9}
+    return {"rows": rows, "groups": int(groups), "ms": ms, "rows_per_s": rows / (ms / 1000), "achieved_gbs": 44 * rows / (ms / 1000) / 1e9, "fused": bool(fused),
+            "bytes_per_row": 44, **{k: info[k] for k in ("fused_pages", "unfused_pages", "registers", "kernel_paths", "kernel_launches") if k in info}}
 
 
 def run_join(torch, backend, device, build_rows, probe_rows, steps, warmup):
@@ -486,7 +488,7 @@ def run_join(torch, backend, device, build_rows, probe_rows, steps, warmup):
             "probe_rows_per_s": probe_rows / ((b_ms + p_ms) / 1000), "algorithmic_bytes": algo, "achieved_gbs": algo / ((b_ms + p_ms) / 1000) / 1e9, "launches": int(launches)}
 
 
-def run_q3(torch, backend, device, n_orders, steps, warmup):
+def run_q3(torch, backend, device, n_orders, steps, warmup, fused=True):
     """configs[3] shape on one GPU: TPC-H Q3 filter → join → join → aggregate over device-resident tables (presto_b200/pipelines.py);
     rows/s counts lineitem rows.  Algorithmic bytes = every input column once (28 B lineitem, 24 B orders, 12 B customer)."""
     from presto_b200 import BIGINT, DATE, DOUBLE, INTEGER
@@ -505,7 +507,7 @@ def run_q3(torch, backend, device, n_orders, steps, warmup):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record(stream)
-        out = q3(cp, op, lp, backend=backend, device_resident=True, stats=stats, device=device, cuda_stream=stream.cuda_stream)
+        out = q3(cp, op, lp, backend=backend, device_resident=True, stats=stats, fused=fused, device=device, cuda_stream=stream.cuda_stream)
         e1.record(stream)
         torch.cuda.synchronize()
         if it >= warmup:
@@ -517,7 +519,8 @@ def run_q3(torch, backend, device, n_orders, steps, warmup):
     top = float(np.sort(rev)[-1]) if len(rev) else None
     algo = n_li * 28 + n_orders * 24 + customer[0].numel() * 12
     return {"orders": n_orders, "lineitem_rows": int(n_li), "joined_rows": int(stats.get("joined_rows", 0)), "groups": int(groups), "ms": ms,
-            "lineitem_rows_per_s": n_li / (ms / 1000), "achieved_gbs": algo / (ms / 1000) / 1e9, "launches": int(stats.get("kernel_launches", 0)), "top_revenue": top}
+            "lineitem_rows_per_s": n_li / (ms / 1000), "achieved_gbs": algo / (ms / 1000) / 1e9, "launches": int(stats.get("kernel_launches", 0)), "top_revenue": top,
+            "fused": bool(fused), **{k: v for k, v in stats.items() if k.startswith("fused_") or k == "kernel_paths"}}
 
 
 def run_q3_multi(torch, backend, device, n_orders_total, steps, warmup, dist):
@@ -669,8 +672,10 @@ def main():
                 ("partitioned_output_8_bigint_cols", lambda: run_partitioned_output(torch, backend, local, int((1 << 28) * scale), 8, 2, 1)),
                 ("page_processor_q1", lambda: run_page_processor_q1(torch, backend, local, int((1 << 28) * scale), 2, 1)),
                 ("serialized_page_8_bigint_cols", lambda: run_serialized_page(torch, backend, local, int((1 << 24) * scale), 3, 2)),
-                ("q1_pipeline", lambda: run_q1_pipeline(torch, backend, local, int(600_037_902 * scale), 2, 1)),
-                ("q3_pipeline", lambda: run_q3(torch, backend, local, int(150_000_000 * scale), 2, 1)),
+                ("q1_pipeline", lambda: run_q1_pipeline(torch, backend, local, int(600_037_902 * scale), 3, 2)),
+                ("q1_pipeline_unfused", lambda: run_q1_pipeline(torch, backend, local, int(600_037_902 * scale), 2, 1, fused=False)),
+                ("q3_pipeline", lambda: run_q3(torch, backend, local, int(150_000_000 * scale), 3, 2)),
+                ("q3_pipeline_unfused", lambda: run_q3(torch, backend, local, int(150_000_000 * scale), 2, 1, fused=False)),
             ]:
                 if only and name not in only:
                     continue

@@ -38,8 +38,10 @@
 #ifndef PRESTO_GPU_H
 #define PRESTO_GPU_H
 
+#ifndef __CUDACC_RTC__   /* NVRTC (fused pipeline kernels compile this header for its enums): the including file provides the integer types */
 #include <stddef.h>
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -160,7 +162,19 @@ typedef struct pg_operator_stats {   /* MB/operator/OperatorStats.java:40 subset
     int64_t h2d_bytes;
     int64_t d2h_bytes;
     double  gpu_ms;                  /* device time accumulated by event-bracketed sections (if enabled) */
+    int64_t kernel_paths;            /* aggregation: bit mask of pg_kernel_path — which kernels this operator's rows went through */
 } pg_operator_stats;
+
+typedef enum {                       /* pg_operator_stats.kernel_paths */
+    PG_PATH_AGG_FAST = 1,            /* hashAggFastKernel tiers 0/1/2 (few groups) */
+    PG_PATH_AGG_WARP = 2,            /* per-warp accumulator sets (11..40 groups) */
+    PG_PATH_AGG_MID = 4,             /* one shared table per SM (.. ~3000 groups) */
+    PG_PATH_AGG_DIRECT = 8,          /* straight to the HBM table, L2-resident slot ranges */
+    PG_PATH_AGG_GENERIC = 16,        /* hashAggKernel<W, MAXV>: NULLs, masks, bigint sums, wide keys */
+    PG_PATH_FUSED_TIERS = 32,        /* generated fused pipeline kernel, on-chip tiers */
+    PG_PATH_FUSED_DIRECT = 64,       /* generated fused pipeline kernel, HBM table */
+    PG_PATH_UNFUSED_CHAIN = 128      /* fused operator that ran its fragment operator by operator (fragment not fusable for that page) */
+} pg_kernel_path;
 
 /* Options common to all operators. */
 typedef struct pg_operator_options {
@@ -402,6 +416,42 @@ int32_t pg_filter_project_get_last_selection(pg_operator* op, int32_t* is_list, 
  * (MB/sql/gen/PageFunctionCompiler.java:195-861).  Needs no GPU.  *needed = bytes including the terminating NUL; the text is
  * copied when `capacity` suffices.  PG_ERR_UNSUPPORTED when the program runs on the interpreter kernels instead. */
 int32_t pg_filter_project_explain(const pg_filter_project_config* config, uint64_t nullable_inputs, char* buffer, size_t capacity, size_t* needed);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused pipeline fragment: FilterAndProjectOperator → LookupJoinOperator* → HashAggregationOperator as ONE operator.
+ * The reference chains these operators inside one Driver and hands <= 1 MB pages between them in the CPU cache
+ * (MB/operator/Driver.java:402-536; planner sites LocalExecutionPlanner.java:1633-1666, 2650-2686, 3544-3640; scan + filter + project
+ * are already a single operator there: ScanFilterAndProjectOperator).  On the GPU the intermediate pages would cross HBM, so the
+ * Gpu*OperatorFactory for such a chain creates this operator instead: the PageProcessor's expressions, the probes of the joins' dense
+ * LookupSources and the aggregation's key packing are generated as one row program, compiled at run time (NVRTC, like the reference
+ * compiles them to bytecode) and run in a single pass over the raw input page.  Results are those of the three operators chained:
+ * when the fragment cannot be fused for a page (LookupSource with duplicate keys, nullable aggregate inputs, bigint sums, masks, ...)
+ * the operator runs the chain operator by operator on the GPU instead (pg_operator_stats.kernel_paths tells which).
+ *   page_processor   over the raw input page; its projections are the layout the first join / the aggregation sees
+ *   joins[k]         INNER lookup joins, each over the previous layout; output layout = probe output channels, then the
+ *                    bridge's build output channels (LookupJoinOperator's page layout)
+ *   aggregation      over the last layout; step SINGLE or PARTIAL
+ * needs_input is false until every bridge's build has finished (LookupJoinOperator.java:198-210).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pg_fused_aggregation_config {
+    pg_filter_project_config page_processor;
+    int32_t n_joins;                          /* 0..2 */
+    const pg_lookup_join_config* joins;
+    pg_join_bridge* const* bridges;
+    pg_hash_aggregation_config aggregation;   /* its options are the operator's */
+} pg_fused_aggregation_config;
+int32_t pg_fused_aggregation_create(const pg_fused_aggregation_config* config, pg_operator** out);
+/* Pages that ran fused / operator by operator so far, the registers per thread of the generated kernel (0 before the first fused
+ * page) and, when a page was not fused, why (copied into reason when capacity allows). */
+int32_t pg_fused_aggregation_get_info(pg_operator* op, int64_t* fused_pages, int64_t* unfused_pages, int32_t* registers, char* reason, size_t capacity);
+/* The CUDA C++ the operator would hand to NVRTC for this fragment when the raw input channels in `nullable_inputs` (bit i = channel
+ * i) carry a null map — the counterpart of dumping generated bytecode.  Needs no GPU; join build sides are described by
+ * `build_types` / `build_nullable` (per join: the bridge's output channel types, since no LookupSource exists yet): payload rows are
+ * laid out as HashBuilderOperator would.  PG_ERR_UNSUPPORTED (reason in pg_last_error) when the fragment is not fusable. */
+int32_t pg_fused_aggregation_explain(const pg_fused_aggregation_config* config, uint64_t nullable_inputs, const int32_t* const* build_types,
+                                     const int32_t* n_build_types, char* buffer, size_t capacity, size_t* needed);
+/* NVRTC compile check of a CUDA C++ source against the embedded device headers (no GPU needed): cubin size or the compiler log. */
+int32_t pg_jit_compile_check(const char* source, char* log_buffer, size_t capacity, int64_t* cubin_bytes);
 
 /* ------------------------------------------------------------------------------------------------
  * SerializedPage wire format: what PartitionedOutput hands to an OutputBuffer and an

@@ -74,8 +74,11 @@ class pg_operator_stats(C.Structure):
     _fields_ = [
         ("input_positions", C.c_int64), ("input_bytes", C.c_int64), ("output_positions", C.c_int64), ("output_bytes", C.c_int64),
         ("device_bytes", C.c_int64), ("kernel_launches", C.c_int64), ("group_count", C.c_int64), ("h2d_bytes", C.c_int64),
-        ("d2h_bytes", C.c_int64), ("gpu_ms", C.c_double),
+        ("d2h_bytes", C.c_int64), ("gpu_ms", C.c_double), ("kernel_paths", C.c_int64),
     ]
+
+
+PATH_AGG_FAST, PATH_AGG_WARP, PATH_AGG_MID, PATH_AGG_DIRECT, PATH_AGG_GENERIC, PATH_FUSED_TIERS, PATH_FUSED_DIRECT, PATH_UNFUSED_CHAIN = 1, 2, 4, 8, 16, 32, 64, 128
 
 
 class pg_operator_options(C.Structure):
@@ -143,6 +146,11 @@ class pg_filter_project_config(C.Structure):
         ("n_input_channels", C.c_int32), ("input_types", _I32P), ("n_nodes", C.c_int32), ("nodes", C.POINTER(pg_expr_node)),
         ("filter_node", C.c_int32), ("n_projections", C.c_int32), ("projection_nodes", _I32P), ("options", pg_operator_options),
     ]
+
+
+class pg_fused_aggregation_config(C.Structure):
+    _fields_ = [("page_processor", pg_filter_project_config), ("n_joins", C.c_int32), ("joins", C.POINTER(pg_lookup_join_config)),
+                ("bridges", C.POINTER(C.c_void_p)), ("aggregation", pg_hash_aggregation_config)]
 
 
 def i32_array(values):
@@ -226,6 +234,11 @@ class Backend:
         "ipc_import": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
         "ipc_close": (C.c_int32, [C.c_void_p]),
         "filter_project_explain": (C.c_int32, [C.POINTER(pg_filter_project_config), C.c_uint64, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+        "fused_aggregation_create": (C.c_int32, [C.POINTER(pg_fused_aggregation_config), C.POINTER(C.c_void_p)]),
+        "fused_aggregation_get_info": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_char_p, C.c_size_t]),
+        "fused_aggregation_explain": (C.c_int32, [C.POINTER(pg_fused_aggregation_config), C.c_uint64, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32),
+                                                  C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+        "jit_compile_check": (C.c_int32, [C.c_char_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_int64)]),
     }
 
     def __init__(self, lib: C.CDLL, prefix: str, has_device: bool):

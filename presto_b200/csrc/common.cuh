@@ -1,5 +1,16 @@
 // presto_b200 — common host/device infrastructure for libprestogpu.so (sm_100a only).
+//
+// The device helpers at the bottom (and group_table.cuh, agg_tiers.cuh, dense_index.cuh, fused_agg.cuh on top of them) are also
+// compiled at run time by NVRTC for fused pipeline kernels (jit_runtime.h): under __CUDACC_RTC__ the host half is skipped and the
+// fixed-width integer types come from the prelude below.
 #pragma once
+#ifdef __CUDACC_RTC__
+typedef signed char int8_t; typedef unsigned char uint8_t; typedef short int16_t; typedef unsigned short uint16_t;
+typedef int int32_t; typedef unsigned int uint32_t; typedef long long int64_t; typedef unsigned long long uint64_t;
+typedef unsigned long long uintptr_t;
+#define LLONG_MIN (-9223372036854775807LL - 1)
+#define LLONG_MAX 9223372036854775807LL
+#else
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -8,9 +19,11 @@
 #include <string>
 #include <vector>
 #include <memory>
+#endif
 #include "../../include/presto_gpu.h"
 
 namespace pg {
+#ifndef __CUDACC_RTC__
 
 // ---- errors ---------------------------------------------------------------------------------------------------------
 struct Error : std::runtime_error {
@@ -163,6 +176,8 @@ struct PageStager {
         (op)->stats.kernel_launches++;                                                        \
         PG_CUDA(cudaGetLastError());                                                          \
     } while (0)
+
+#endif  // !__CUDACC_RTC__
 
 // ---- device helpers --------------------------------------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -14,8 +14,8 @@
 #include "common.cuh"
 #include "fp_codegen.h"
 #include <cub/device/device_scan.cuh>
-#include <cuda.h>
-#include <dlfcn.h>
+#include "jit_runtime.h"
+#include "operators_internal.h"
 #include <algorithm>
 #include <map>
 #include <mutex>
@@ -248,30 +248,7 @@ __global__ void __launch_bounds__(256) fpProjectKernel(const __grid_constant__ F
     }
 }
 
-// ---- driver-API JIT of generated PTX (libcuda is dlopen'ed: the library still loads on a box without a driver) -----------------
-struct DriverApi {
-    CUresult (*moduleLoadDataEx)(CUmodule*, const void*, unsigned int, CUjit_option*, void**) = nullptr;
-    CUresult (*moduleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
-    CUresult (*moduleUnload)(CUmodule) = nullptr;
-    CUresult (*launchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
-    bool ok = false;
-    static DriverApi& get()
-    {
-        static DriverApi api;
-        static std::once_flag once;
-        std::call_once(once, [] {
-            void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
-            if (!h) return;
-            api.moduleLoadDataEx = (decltype(api.moduleLoadDataEx)) dlsym(h, "cuModuleLoadDataEx");
-            api.moduleGetFunction = (decltype(api.moduleGetFunction)) dlsym(h, "cuModuleGetFunction");
-            api.moduleUnload = (decltype(api.moduleUnload)) dlsym(h, "cuModuleUnload");
-            api.launchKernel = (decltype(api.launchKernel)) dlsym(h, "cuLaunchKernel");
-            api.ok = api.moduleLoadDataEx && api.moduleGetFunction && api.moduleUnload && api.launchKernel;
-        });
-        return api;
-    }
-};
-
+// ---- driver-API JIT of generated PTX (DriverApi: jit_runtime.h; libcuda is dlopen'ed so the library still loads without a driver) ----
 struct JitProgram {
     CUmodule module = nullptr;
     CUfunction filter = nullptr, project = nullptr;
@@ -526,6 +503,8 @@ public:
     bool isFinished() override { return finishing && !hasPending; }
     void lastSelection(int32_t* isList, int64_t* size) const { *isList = lastIsList; *size = lastSize; }
 };
+
+Operator* createFilterProject(const pg_filter_project_config* c) { return new FilterProjectOp(c); }
 
 }  // namespace pg
 

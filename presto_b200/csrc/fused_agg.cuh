@@ -1,0 +1,225 @@
+// presto_b200 — the kernel skeleton of a fused pipeline fragment: FilterAndProject → LookupJoin* → HashAggregation in ONE pass over
+// the raw input page (reference: the operators of one Driver, MB/operator/Driver.java:402-536 chained by
+// LocalExecutionPlanner.java:1633-1666 / 2650-2686 / 3544-3640; InMemoryHashAggregationBuilder.processPage :204-220 as the sink).
+//
+// This header is compiled twice: by nvcc into libprestogpu.so (FusedParams is the launch ABI the host fills) and by NVRTC at run time
+// together with a generated `struct Prog` (fused_codegen.cpp) — the row program of the fragment: tile loads, filter, dense-index
+// probes, key packing.  What is fixed lives here: the persistent tile loop with a register double buffer, and the aggregation sink
+// with the same three tiers as hashAggFastKernel (hash_agg.cu): per-thread private accumulators in shared memory for the first groups
+// a CTA sees (TPC-H Q1: every row ends there), the CTA's shared table, the HBM table.
+#pragma once
+#include "agg_tiers.cuh"
+#include "dense_index.cuh"
+
+namespace pg {
+
+constexpr int kFusedMaxInputs = 32;
+constexpr int kFusedMaxJoins = 2;
+constexpr int kFusedMaxSums = 8;
+
+struct FusedJoinView {
+    DenseIndex D;
+    const uint64_t* rows;            // payload rows in key order (strideWords words each); nullptr when the join has no build output
+};
+
+struct FusedParams {
+    GroupTable t;
+    int64_t n;                       // rows of this launch
+    uint64_t rowBase;                // global index of row 0 (first-appearance bookkeeping)
+    const uint32_t* bitmapIn;        // when set: only rows whose bit is set are processed (deferred-row pass)
+    uint32_t* bitmapOut;             // rows that found the table at its claim limit
+    uint32_t S, sLimit;              // shared table slots / fill limit (W == 1, !direct)
+    int32_t nAccAlloc;               // accumulator columns the shared table was sized for
+    int32_t direct;                  // 1: no on-chip tiers, every row goes to the HBM table (many groups, or W > 1)
+    int32_t phys[kFusedMaxSums + 1]; // physical accumulator column of each sum, then of the row count
+    const void* values[kFusedMaxInputs];     // raw input channels: fixed-width values or VARCHAR bytes
+    const uint8_t* nulls[kFusedMaxInputs];
+    const int32_t* offsets[kFusedMaxInputs]; // VARCHAR
+    FusedJoinView joins[kFusedMaxJoins];
+    unsigned int* fpError;           // bit 0 overflow, bit 1 division by zero (PageProcessor), bit 2 VARCHAR key longer than declared
+};
+
+#ifdef __CUDACC__
+// ---- the aggregation sink -----------------------------------------------------------------------------------------------------
+// The on-chip tiers work on ONE 64-bit word per group: the packed key itself when W == 1, otherwise (Prog::TIERS) the key's fields
+// squeezed together by the generated Prog::tierKey — e.g. Q1's two INTEGER codes, which the W-word layout spreads over two words to
+// make room for the NULL flags no row of the page uses.  Prog::expandKey restores the W-word key when a group is flushed to the HBM table.
+template <class Prog>
+struct FusedAggSink {
+    static constexpr int W = Prog::W, NV = Prog::NV, THREADS = Prog::THREADS;
+    static constexpr bool CNT = Prog::CNT;
+    static constexpr int NC = NV + (CNT ? 1 : 0);
+    static constexpr int NVA = NV > 0 ? NV : 1;
+    static constexpr int K0 = (kTier0Columns / NC) > 31 ? 31 : (kTier0Columns / NC);
+    const FusedParams& P;
+    SharedTable<1> st;
+    uint64_t* tier0;                 // [K0][NC][THREADS]
+    uint32_t seen0, probeHits, probeMisses;
+    bool bypass, tiers;
+    int tid;
+
+    __device__ __forceinline__ FusedAggSink(const FusedParams& p) : P(p) {}
+
+    __device__ __forceinline__ void init(unsigned char* smemRaw)
+    {
+        tid = threadIdx.x;
+        seen0 = 0; probeHits = 0; probeMisses = 0; bypass = false;
+        tiers = Prog::TIERS && !P.direct;
+        if (!tiers) return;
+        st.S = P.S; st.S2 = P.S + 2; st.sLimit = P.sLimit; st.tier0Groups = K0;
+        const SharedLayout lay(P.S, 1, P.nAccAlloc, true);
+        st.keys = (volatile uint64_t*) (smemRaw + lay.keys);
+        st.acc = (uint64_t*) (smemRaw + lay.acc);
+        st.first = (uint32_t*) (smemRaw + lay.first);
+        st.state = nullptr;
+        st.sid = (volatile uint8_t*) (smemRaw + lay.sid);
+        st.count = (uint32_t*) (smemRaw + lay.misc);
+        tier0 = (uint64_t*) (smemRaw + lay.tier0);
+        for (uint32_t i = tid; i < st.S2; i += THREADS) { st.keys[i] = kEmptyKey; st.first[i] = kNoRow32; st.sid[i] = 0xFF; }
+        for (uint32_t i = tid; i < (uint32_t) P.nAccAlloc * st.S2; i += THREADS) st.acc[i] = 0;
+        for (int i = tid; i < 320; i += THREADS) st.count[i] = 0;
+#pragma unroll
+        for (int i = 0; i < K0 * NC; i++) tier0[i * THREADS + tid] = 0;
+    }
+
+    // the HBM table (tier 2 / direct mode)
+    __device__ __forceinline__ void addGlobal(const uint64_t (&kw)[W], int special, uint32_t spell, const uint64_t (&vals)[NVA], uint32_t rowIdx)
+    {
+        const GroupTable& T = P.t;
+        const int gslot = special ? (int) T.cap + special - 1 : tableFind<W>(T, kw, hashKeyWords<W>(kw), true, false);
+        if (gslot == -2) {
+            atomicOr(&P.bitmapOut[rowIdx >> 5], 1u << (rowIdx & 31));
+            atomicAdd(&T.counters[CNT_DEFERRED], 1u);
+            return;
+        }
+        const uint64_t g = firstRowWord(P.rowBase + rowIdx, spell);
+        if (g < __ldcg(&T.firstRow[gslot])) atomicMin((unsigned long long*) &T.firstRow[gslot], (unsigned long long) g);
+        uint64_t* acc = T.acc + (size_t) gslot * T.nvPhys;
+#pragma unroll
+        for (int c = 0; c < NV; c++) atomicAdd((double*) &acc[P.phys[c]], __longlong_as_double((long long) vals[c]));
+        if (CNT) atomicAdd((unsigned long long*) &acc[P.phys[NV]], 1ULL);
+    }
+
+    __device__ __forceinline__ void add(const uint64_t (&kw)[W], int special, uint32_t spell, const uint64_t (&vals)[NVA], uint32_t rowIdx)
+    {
+        if (!Prog::TIERS || !tiers || spell) { addGlobal(kw, special, spell, vals, rowIdx); return; }
+        const uint64_t key = Prog::tierKey(kw);
+        if (W > 1 && key == kEmptyKey) { addGlobal(kw, special, spell, vals, rowIdx); return; }     // a squeezed key that looks like an empty slot
+        const uint64_t h = murmur64(key);
+        int sslot = -1;
+        if (special) sslot = (int) st.S + special - 1;        // NULL key of the Bigint path / the key equal to the empty sentinel: dedicated slots
+        else if (!bypass) {
+            const uint32_t s = (uint32_t) (h >> 32) & (st.S - 1);
+            if (st.keys[s] == key) sslot = (int) s;
+            else { uint64_t k1[1] = {key}; sslot = st.find(k1, h); }
+            // a thread whose rows keep missing a full shared table stops probing it (high-cardinality input)
+            if (sslot >= 0) probeHits++; else probeMisses++;
+            if (((probeHits + probeMisses) & 63u) == 0) {
+                if (probeMisses > 3 * probeHits && *(volatile uint32_t*) st.count >= st.sLimit) bypass = true;
+                probeHits = 0; probeMisses = 0;
+            }
+        }
+        if (sslot < 0) { addGlobal(kw, special, spell, vals, rowIdx); return; }
+        const uint32_t id = st.sid[sslot];       // the two dedicated slots never get a tier-0 id: their rows take tier 1
+        if (id < (uint32_t) K0) {
+            // tier 0: this thread's private accumulators of group `id` (consecutive threads, consecutive words: no bank conflicts)
+            uint64_t* mine = tier0 + (size_t) id * NC * THREADS + tid;
+#pragma unroll
+            for (int c = 0; c < NV; c++) {
+                double* p = (double*) (mine + c * THREADS);
+                *p = *p + __longlong_as_double((long long) vals[c]);
+            }
+            if (CNT) mine[NV * THREADS] += 1;
+            if (!((seen0 >> id) & 1u)) { seen0 |= 1u << id; atomicMin(&st.first[sslot], rowIdx); }    // rows ascend per thread
+            return;
+        }
+        // tier 1: the CTA's shared table, shared-space reductions
+#pragma unroll
+        for (int c = 0; c < NV; c++) sharedAddF64(&st.acc[c * st.S2 + sslot], vals[c]);
+        if (CNT) sharedAddU64(&st.acc[NV * st.S2 + sslot], 1);
+        if (rowIdx < *(volatile uint32_t*) &st.first[sslot]) sharedMinU32(&st.first[sslot], rowIdx);
+    }
+
+    // fold tier 0 into the CTA's shared table, then the shared table into the HBM table
+    __device__ __forceinline__ void flush()
+    {
+        if (!tiers) return;
+        __syncthreads();
+        const GroupTable& T = P.t;
+        const int lane = tid & 31, warp = tid >> 5;
+        const uint32_t nT0 = min(st.count[1], (uint32_t) K0);
+        for (uint32_t pairIdx = warp; pairIdx < nT0 * (uint32_t) NC; pairIdx += THREADS / 32) {
+            const uint32_t id = pairIdx / NC, c = pairIdx % NC;
+            const uint64_t* src = tier0 + (size_t) pairIdx * THREADS;
+            const bool isF = c < (uint32_t) NV;
+            uint64_t x = 0;
+            if (isF) {
+                double d = 0;
+                for (int i = lane; i < THREADS; i += 32) d += __longlong_as_double((long long) src[i]);
+                x = (uint64_t) __double_as_longlong(d);
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) x = (uint64_t) __double_as_longlong(__longlong_as_double((long long) x) + __longlong_as_double((long long) shflXor64(x, m)));
+            }
+            else {
+                for (int i = lane; i < THREADS; i += 32) x += src[i];
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) x += shflXor64(x, m);
+            }
+            if (lane == 0) {
+                uint64_t* dst = &st.acc[c * st.S2 + st.count[2 + id]];
+                if (isF) *(double*) dst = *(double*) dst + __longlong_as_double((long long) x); else *dst = *dst + x;
+            }
+        }
+        __syncthreads();
+        for (uint32_t s = tid; s < st.S2; s += THREADS) {
+            const uint32_t f = st.first[s];
+            if (f == kNoRow32) continue;
+            int gslot;
+            if (s >= st.S) gslot = (int) T.cap + (int) (s - st.S);
+            else { uint64_t kw[W]; Prog::expandKey((uint64_t) st.keys[s], kw); gslot = tableFind<W>(T, kw, hashKeyWords<W>(kw), true, true); }
+            if (gslot < 0) { atomicOr(&T.counters[CNT_ERROR], 0x80000000u); continue; }
+            const uint64_t g = firstRowWord(P.rowBase + f);
+            if (g < __ldcg(&T.firstRow[gslot])) atomicMin((unsigned long long*) &T.firstRow[gslot], (unsigned long long) g);
+            uint64_t* acc = T.acc + (size_t) gslot * T.nvPhys;
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const uint64_t x = st.acc[c * st.S2 + s];
+                if (x != 0) {
+                    if (c < NV) atomicAdd((double*) &acc[P.phys[c]], __longlong_as_double((long long) x));
+                    else atomicAdd((unsigned long long*) &acc[P.phys[c]], (unsigned long long) x);
+                }
+            }
+        }
+    }
+};
+
+// ---- the kernel body: persistent CTAs, tiles of THREADS * R rows, the next tile's loads in flight while this one is consumed ----
+template <class Prog>
+__device__ __forceinline__ void fusedAggBody(const FusedParams& P)
+{
+    extern __shared__ __align__(16) unsigned char fusedSmem[];
+    FusedAggSink<Prog> sink(P);
+    sink.init(fusedSmem);
+    __syncthreads();
+    constexpr int TILE = Prog::THREADS * Prog::R;
+    const long long nTiles = (P.n + TILE - 1) / TILE;
+    typename Prog::Tile tA, tB;
+    long long tile = blockIdx.x;
+    if (tile < nTiles) Prog::load(P, tile * TILE, tA);
+    while (tile < nTiles) {
+        const long long t1 = tile + gridDim.x;
+        if (t1 < nTiles) Prog::load(P, t1 * TILE, tB);
+        Prog::process(P, tA, tile * TILE, sink);
+        __syncwarp();      // rows take different paths (filter, probe miss, tiers): the next tile's vector loads are issued by whole warps
+        if (t1 >= nTiles) break;
+        const long long t2 = t1 + gridDim.x;
+        if (t2 < nTiles) Prog::load(P, t2 * TILE, tA);
+        Prog::process(P, tB, t1 * TILE, sink);
+        __syncwarp();
+        tile = t2;
+    }
+    sink.flush();
+}
+#endif  // __CUDACC__
+
+}  // namespace pg

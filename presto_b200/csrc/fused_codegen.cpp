@@ -1,0 +1,555 @@
+// presto_b200 — pipeline fragment → CUDA C++ (see fused_codegen.h).
+//
+// The generated translation unit defines `struct Prog` with
+//   Tile                 the eagerly loaded columns of one tile, R rows per thread (registers; double buffered by the kernel)
+//   load(P, base, t)     128-bit / 64-bit streaming loads of those columns
+//   process(P, t, base, sink)   the row program, emitted stage by stage with the R rows of a thread unrolled INSIDE each stage:
+//         A  validity, deferred-row bitmap, the filter                        (PageProcessor.java:118-148 / PageFilter.java:27-50)
+//         B  per join: probe key, bitmap sector + directory word loads of all R rows, then ranks, then payload rows
+//                                                                             (JoinProbe.java:74-119, PagesHash.java:169-181)
+//         C  group key packing + aggregate inputs → sink.add(...)             (MultiChannelGroupByHash.putIfAbsent / AccumulatorCompiler loops)
+//    so that the independent loads of all R rows of a stage are in flight together, and columns that only surviving rows need are
+//    loaded after the filter / the probe (a 1 %-selective join never touches 99 % of its payload sectors).
+// Arithmetic is the PageProcessor's: IEEE double through __dadd_rn / __dmul_rn … (never contracted), exact BIGINT with overflow /
+// division-by-zero flags, SQL three-valued logic — the same semantics as fp_codegen.cpp's PTX and the interpreter kernels.
+#include "fused_codegen.h"
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+
+namespace pg {
+namespace {
+
+struct Val {
+    char kind = 'i';        // 'i' long long, 'd' double, 'b' bool, 's' VARCHAR slice (pass-through only)
+    std::string v;          // C++ expression / variable holding the value
+    std::string z;          // bool variable "is NULL"; empty = never NULL
+    int channel = -1;       // 's': raw input channel
+};
+
+struct ChanRef { int kind = 0; int node = -1; int join = -1; int col = -1; };   // kind 0: expression node of the PageProcessor, 1: build column
+
+std::string hex64(uint64_t v) { char b[40]; snprintf(b, sizeof b, "0x%016llxULL", (unsigned long long) v); return b; }
+int widthOf(int t) { return (t == PG_TYPE_BIGINT || t == PG_TYPE_DOUBLE) ? 8 : (t == PG_TYPE_BOOLEAN ? 1 : (t == PG_TYPE_VARCHAR ? 0 : 4)); }
+
+struct Gen {
+    const FusedProgramDesc& D;
+    const FpProgramDesc& P;
+    int R = 2;
+    std::vector<bool> eager;                 // per raw input channel
+    std::ostringstream out;                  // current stage's code
+    std::vector<std::vector<Val>> vals;      // [row slot][node]
+    std::vector<std::vector<bool>> done;
+    std::string fail;
+    bool usesErr = false;
+
+    explicit Gen(const FusedProgramDesc& d) : D(d), P(d.fp) {}
+    void emit(const std::string& s) { out << "        " << s << "\n"; }
+    static std::string sfx(int k, int u) { return std::to_string(k) + "_" + std::to_string(u); }
+    std::string orz(const std::string& a, const std::string& b, const std::string& name)
+    {
+        if (a.empty() && b.empty()) return "";
+        if (a.empty()) return b;
+        if (b.empty()) return a;
+        emit("const bool " + name + " = " + a + " || " + b + ";");
+        return name;
+    }
+    std::string asDouble(const Val& x)
+    {
+        if (x.kind == 'd') return x.v;
+        if (x.kind != 'i') { fail = "boolean operand in arithmetic"; return x.v; }
+        return "__ll2double_rn(" + x.v + ")";
+    }
+    // raise an error flag for rows that are evaluated (guard) and whose operands are not NULL
+    void raise(const char* flag, const std::string& cond, const std::string& z, const std::string& guard)
+    {
+        usesErr = true;
+        emit(std::string(flag) + " |= " + guard + " && (" + cond + ")" + (z.empty() ? "" : " && !" + z) + ";");
+    }
+
+    Val compare(int op, const Val& a, const Val& b, const std::string& id)
+    {
+        Val r; r.kind = 'b'; r.v = "v" + id;
+        r.z = orz(a.z, b.z, "z" + id);
+        if (a.kind == 's' || b.kind == 's') { fail = "VARCHAR comparison"; return r; }
+        if (a.kind == 'b' || b.kind == 'b') {
+            if (a.kind != 'b' || b.kind != 'b' || (op != PG_EX_EQ && op != PG_EX_NE)) { fail = "boolean comparison"; return r; }
+            emit("const bool " + r.v + " = " + a.v + (op == PG_EX_EQ ? " == " : " != ") + b.v + ";");
+            return r;
+        }
+        const char* cc = op == PG_EX_EQ ? "==" : op == PG_EX_NE ? "!=" : op == PG_EX_LT ? "<" : op == PG_EX_LE ? "<=" : op == PG_EX_GT ? ">" : ">=";
+        if (a.kind == 'd' || b.kind == 'd') emit("const bool " + r.v + " = " + asDouble(a) + " " + cc + " " + asDouble(b) + ";");
+        else emit("const bool " + r.v + " = " + a.v + " " + cc + " " + b.v + ";");
+        return r;
+    }
+    Val logic(bool isOr, const Val& a, const Val& b, const std::string& id)
+    {
+        Val r; r.kind = 'b'; r.v = "v" + id;
+        if (a.kind != 'b' || b.kind != 'b') { fail = "AND/OR over non-boolean"; return r; }
+        if (a.z.empty() && b.z.empty()) { emit("const bool " + r.v + " = " + a.v + (isOr ? " || " : " && ") + b.v + ";"); return r; }
+        // decided: an operand that is not NULL and alone fixes the result (OR: true, AND: false)
+        auto decided = [&](const Val& x) { return std::string("(") + (x.z.empty() ? "" : "!" + x.z + " && ") + (isOr ? "" : "!") + x.v + ")"; };
+        emit("const bool y" + id + " = " + decided(a) + " || " + decided(b) + ";");
+        r.z = "z" + id;
+        emit("const bool " + r.z + " = (" + (a.z.empty() ? "false" : a.z) + " || " + (b.z.empty() ? "false" : b.z) + ") && !y" + id + ";");
+        emit("const bool " + r.v + " = y" + id + " ? " + (isOr ? "true" : "false") + " : (" + a.v + (isOr ? " || " : " && ") + b.v + ");");
+        return r;
+    }
+
+    // Evaluates node k for row slot u under `guard` (a bool variable that is true when the row is still alive).
+    const Val& node(int k, int u, const std::string& guard)
+    {
+        if (done[u][k]) return vals[u][k];
+        const pg_expr_node& nd = P.nodes[k];
+        const std::string id = sfx(k, u);
+        const std::string row = "row" + std::to_string(u);
+        Val r;
+        auto A = [&]() -> Val { return node(nd.a, u, guard); };
+        auto B = [&]() -> Val { return node(nd.b, u, guard); };
+        switch (nd.op) {
+            case PG_EX_INPUT: {
+                const int ch = nd.a, t = P.inputTypes[ch], w = widthOf(t);
+                const std::string cs = std::to_string(ch), us = std::to_string(u);
+                if (t == PG_TYPE_VARCHAR) { r.kind = 's'; r.channel = ch; r.v = ""; }
+                else {
+                    std::string raw;
+                    if (eager[ch]) raw = "t.c" + cs + "[" + us + "]";
+                    else {
+                        raw = "w" + id;
+                        const char* ty = w == 8 ? "unsigned long long" : (w == 4 ? "unsigned int" : "unsigned char");
+                        const char* ld = w == 8 ? "ldStream64((const uint64_t*) P.values[" : (w == 4 ? "ldStream32((const uint32_t*) P.values[" : "((const uint8_t*) P.values[");
+                        if (w == 1) emit(std::string("const ") + ty + " " + raw + " = " + guard + " ? " + ld + cs + "])[" + row + "] : (unsigned char) 0;");
+                        else emit(std::string("const ") + ty + " " + raw + " = " + guard + " ? " + ld + cs + "] + " + row + ") : 0;");
+                    }
+                    r.v = "v" + id;
+                    if (t == PG_TYPE_DOUBLE) { r.kind = 'd'; emit("const double " + r.v + " = __longlong_as_double((long long) " + raw + ");"); }
+                    else if (t == PG_TYPE_BIGINT) { r.kind = 'i'; emit("const long long " + r.v + " = (long long) " + raw + ";"); }
+                    else if (t == PG_TYPE_BOOLEAN) { r.kind = 'b'; emit("const bool " + r.v + " = " + raw + " != 0;"); }
+                    else { r.kind = 'i'; emit("const long long " + r.v + " = (long long) (int) " + raw + ";"); }
+                }
+                if (P.inputHasNulls[ch]) { r.z = "z" + id; emit("const bool " + r.z + " = " + guard + " && P.nulls[" + cs + "][" + row + "] != 0;"); }
+                break;
+            }
+            case PG_EX_CONST_BIGINT: r.kind = 'i'; r.v = "((long long) " + hex64((uint64_t) nd.imm_i) + ")"; break;
+            case PG_EX_CONST_DOUBLE: { uint64_t b; memcpy(&b, &nd.imm_d, 8); r.kind = 'd'; r.v = "__longlong_as_double((long long) " + hex64(b) + ")"; break; }
+            case PG_EX_CONST_BOOLEAN: r.kind = 'b'; r.v = nd.imm_i ? "true" : "false"; break;
+            case PG_EX_CONST_NULL:
+                r.z = "true";
+                if (nd.type == PG_TYPE_BOOLEAN) { r.kind = 'b'; r.v = "false"; }
+                else if (nd.type == PG_TYPE_DOUBLE) { r.kind = 'd'; r.v = "0.0"; }
+                else { r.kind = 'i'; r.v = "0LL"; }
+                break;
+            case PG_EX_ADD: case PG_EX_SUB: case PG_EX_MUL: case PG_EX_DIV: {
+                const Val a = A(), b = B();
+                r.z = orz(a.z, b.z, "z" + id); r.v = "v" + id;
+                if (nd.type == PG_TYPE_DOUBLE) {
+                    r.kind = 'd';
+                    const char* fn = nd.op == PG_EX_ADD ? "__dadd_rn" : nd.op == PG_EX_SUB ? "__dsub_rn" : nd.op == PG_EX_MUL ? "__dmul_rn" : "__ddiv_rn";
+                    emit("const double " + r.v + " = " + fn + "(" + asDouble(a) + ", " + asDouble(b) + ");");
+                }
+                else {
+                    if (a.kind != 'i' || b.kind != 'i') { fail = "integer arithmetic over non-integer operands"; break; }
+                    r.kind = 'i';
+                    if (nd.op == PG_EX_ADD) {
+                        emit("const long long " + r.v + " = (long long) ((unsigned long long) " + a.v + " + (unsigned long long) " + b.v + ");");
+                        raise("errOv", "((" + a.v + " ^ " + r.v + ") & (" + b.v + " ^ " + r.v + ")) < 0", r.z, guard);
+                    }
+                    else if (nd.op == PG_EX_SUB) {
+                        emit("const long long " + r.v + " = (long long) ((unsigned long long) " + a.v + " - (unsigned long long) " + b.v + ");");
+                        raise("errOv", "((" + a.v + " ^ " + b.v + ") & (" + a.v + " ^ " + r.v + ")) < 0", r.z, guard);
+                    }
+                    else if (nd.op == PG_EX_MUL) {
+                        emit("const long long " + r.v + " = (long long) ((unsigned long long) " + a.v + " * (unsigned long long) " + b.v + ");");
+                        raise("errOv", "__mul64hi(" + a.v + ", " + b.v + ") != (" + r.v + " >> 63)", r.z, guard);
+                    }
+                    else {
+                        raise("errDz", b.v + " == 0", r.z, guard);
+                        raise("errOv", a.v + " == LLONG_MIN && " + b.v + " == -1", r.z, guard);     // BigintOperators.divide :106-117
+                        emit("const long long " + r.v + " = (" + b.v + " == 0 || (" + a.v + " == LLONG_MIN && " + b.v + " == -1)) ? 0 : " + a.v + " / " + b.v + ";");
+                    }
+                }
+                break;
+            }
+            case PG_EX_NEG: {
+                const Val a = A();
+                r.z = a.z; r.kind = a.kind; r.v = "v" + id;
+                if (a.kind == 'd') emit("const double " + r.v + " = __longlong_as_double(__double_as_longlong(" + a.v + ") ^ (long long) 0x8000000000000000ULL);");
+                else if (a.kind == 'i') {
+                    raise("errOv", a.v + " == LLONG_MIN", r.z, guard);
+                    emit("const long long " + r.v + " = (long long) (0ULL - (unsigned long long) " + a.v + ");");
+                }
+                else fail = "negation of a non-number";
+                break;
+            }
+            case PG_EX_EQ: case PG_EX_NE: case PG_EX_LT: case PG_EX_LE: case PG_EX_GT: case PG_EX_GE: { const Val a = A(), b = B(); r = compare(nd.op, a, b, id); break; }
+            case PG_EX_BETWEEN: {
+                const Val x = A(), lo = B(), hi = node(nd.c, u, guard);
+                const Val c1 = compare(PG_EX_GE, x, lo, id + "a"), c2 = compare(PG_EX_LE, x, hi, id + "b");
+                r = logic(false, c1, c2, id);
+                break;
+            }
+            case PG_EX_AND: { const Val a = A(), b = B(); r = logic(false, a, b, id); break; }
+            case PG_EX_OR: { const Val a = A(), b = B(); r = logic(true, a, b, id); break; }
+            case PG_EX_NOT: {
+                const Val a = A();
+                if (a.kind != 'b') { fail = "NOT over non-boolean"; break; }
+                r.kind = 'b'; r.z = a.z; r.v = "v" + id;
+                emit("const bool " + r.v + " = !" + a.v + ";");
+                break;
+            }
+            case PG_EX_IS_NULL: { const Val a = A(); r.kind = 'b'; r.v = a.z.empty() ? "false" : a.z; break; }
+            case PG_EX_CAST_DOUBLE: {
+                const Val a = A();
+                r.kind = 'd'; r.z = a.z; r.v = "v" + id;
+                emit("const double " + r.v + " = " + asDouble(a) + ";");
+                break;
+            }
+            case PG_EX_HASH: {
+                const Val a = A();
+                r.kind = 'i'; r.v = "v" + id;
+                std::string h;
+                if (a.kind == 'b') h = "(" + a.v + " ? 1231LL : 1237LL)";
+                else if (a.kind == 'd') h = "hashLong(doubleHashBits(__double_as_longlong(" + a.v + ")))";
+                else if (a.kind == 'i') h = "hashLong(" + a.v + ")";
+                else { fail = "hash of a VARCHAR expression"; break; }
+                emit("const long long " + r.v + " = " + (a.z.empty() ? h : a.z + " ? 0LL : " + h) + ";");      // TypeUtils.hashPosition: NULL → 0
+                break;
+            }
+            case PG_EX_COMBINE_HASH: {
+                const Val a = A(), b = B();
+                if (a.kind != 'i' || b.kind != 'i') { fail = "combine_hash over non-integers"; break; }
+                r.kind = 'i'; r.v = "v" + id;
+                emit("const long long " + r.v + " = (long long) (31ULL * (unsigned long long) " + a.v + " + (unsigned long long) " + b.v + ");");
+                break;
+            }
+            default: fail = "expression op " + std::to_string(nd.op) + " cannot be fused"; break;
+        }
+        vals[u][k] = r; done[u][k] = true;
+        return vals[u][k];
+    }
+};
+
+}  // namespace
+
+std::string generateFusedAggSource(const FusedProgramDesc& D, FusedKernelInfo& info)
+{
+    info = FusedKernelInfo();
+    const FpProgramDesc& P = D.fp;
+    const int nNodes = (int) P.nodes.size(), nIn = (int) P.inputTypes.size();
+    auto decline = [&](const std::string& why) { info.ok = false; info.reason = why; return std::string(); };
+    if (D.accs.size() > 8) return decline("more than 8 sum columns");
+    if (D.accs.empty() && !D.countRows) return decline("no aggregate");
+    if (D.joins.size() > 2) return decline("more than two joins");
+    if (D.W < 1 || D.W > 4) return decline("key width");
+
+    // ---- layouts: which expression / build column every channel of every stage is ----
+    std::vector<std::vector<ChanRef>> layouts(1);
+    for (int p : P.projections) { ChanRef c; c.kind = 0; c.node = p; layouts[0].push_back(c); }
+    for (size_t j = 0; j < D.joins.size(); j++) {
+        const FusedJoinDesc& J = D.joins[j];
+        const std::vector<ChanRef>& in = layouts.back();
+        std::vector<ChanRef> next;
+        if (J.keyChannel < 0 || J.keyChannel >= (int) in.size()) return decline("join key channel out of range");
+        for (int c : J.probeOutputChannels) { if (c < 0 || c >= (int) in.size()) return decline("probe output channel out of range"); next.push_back(in[c]); }
+        for (size_t c = 0; c < J.buildOutputs.size(); c++) { ChanRef r; r.kind = 1; r.join = (int) j; r.col = (int) c; next.push_back(r); }
+        layouts.push_back(next);
+    }
+    const std::vector<ChanRef>& fin = layouts.back();
+    for (const auto& k : D.keys) if (k.channel < 0 || k.channel >= (int) fin.size()) return decline("group-by channel out of range");
+    for (const auto& a : D.accs) if (a.channel < 0 || a.channel >= (int) fin.size()) return decline("aggregate channel out of range");
+
+    // ---- which raw inputs are read, which of them eagerly ----
+    auto closure = [&](std::vector<int> roots) {
+        std::vector<bool> seen(nNodes, false);
+        while (!roots.empty()) {
+            const int k = roots.back(); roots.pop_back();
+            if (k < 0 || k >= nNodes || seen[k]) continue;
+            seen[k] = true;
+            if (P.nodes[k].op != PG_EX_INPUT) for (int o : {P.nodes[k].a, P.nodes[k].b, P.nodes[k].c}) roots.push_back(o);
+        }
+        return seen;
+    };
+    auto inputsOf = [&](const std::vector<bool>& seen) {
+        std::vector<bool> in(nIn, false);
+        for (int k = 0; k < nNodes; k++) if (seen[k] && P.nodes[k].op == PG_EX_INPUT) in[P.nodes[k].a] = true;
+        return in;
+    };
+    std::vector<int> allRoots;
+    if (P.filterNode >= 0) allRoots.push_back(P.filterNode);
+    auto rootOf = [&](const ChanRef& c) { if (c.kind == 0) allRoots.push_back(c.node); };
+    for (size_t j = 0; j < D.joins.size(); j++) rootOf(layouts[j][D.joins[j].keyChannel]);
+    for (const auto& k : D.keys) rootOf(fin[k.channel]);
+    for (const auto& a : D.accs) rootOf(fin[a.channel]);
+    const std::vector<bool> used = inputsOf(closure(allRoots));
+    std::vector<bool> eager(nIn, false);
+    {
+        std::vector<int> eagerRoots;
+        if (P.filterNode >= 0) eagerRoots.push_back(P.filterNode);
+        if (!D.joins.empty()) { const ChanRef& c = layouts[0][D.joins[0].keyChannel]; if (c.kind == 0) eagerRoots.push_back(c.node); }
+        else eagerRoots = allRoots;     // no join: (almost) every row reaches the aggregation, load everything up front
+        eager = inputsOf(closure(eagerRoots));
+        if (P.filterNode < 0 && D.joins.empty()) eager = used;
+    }
+    int eagerBytes = 0;
+    for (int c = 0; c < nIn; c++) {
+        if (P.inputTypes[c] == PG_TYPE_VARCHAR) eager[c] = false;       // slices are read where they are used
+        if (eager[c]) eagerBytes += widthOf(P.inputTypes[c]);
+    }
+    for (int c = 0; c < nIn; c++) if (used[c]) info.usedInputs.push_back(c);
+    for (int c = 0; c < nIn; c++) if (eager[c]) info.eagerInputs.push_back(c);
+    const int R = eagerBytes <= 16 ? 4 : 2;
+    info.rowsPerThread = R; info.nv = (int) D.accs.size(); info.cnt = D.countRows;
+    const int NV = (int) D.accs.size();
+    const int THREADS = 256;
+
+    Gen g(D);
+    g.R = R; g.eager = eager;
+    g.vals.assign(R, std::vector<Val>(nNodes)); g.done.assign(R, std::vector<bool>(nNodes, false));
+
+    std::ostringstream src;
+    src << "// generated by presto_b200 fused_codegen: FilterAndProject -> LookupJoin* -> HashAggregation as one row program\n"
+        << "#include \"fused_agg.cuh\"\nnamespace pg {\nstruct Prog {\n"
+        << "    static constexpr int THREADS = " << THREADS << ", MIN_CTAS = 2, R = " << R << ", W = " << D.W << ", NV = " << NV << ";\n"
+        << "    static constexpr bool CNT = " << (D.countRows ? "true" : "false") << ";\n"
+        << "    static constexpr int NEAGER = " << info.eagerInputs.size() << ";\n";
+    // ---- the 64-bit word the on-chip tiers identify a group by ----
+    {
+        bool keyNullable = false;     // decided below, once the key channels' nullability is known: a dry evaluation of the key channels
+        Gen dry(D); dry.R = 1; dry.eager = eager; dry.vals.assign(1, std::vector<Val>(nNodes)); dry.done.assign(1, std::vector<bool>(nNodes, false));
+        for (const auto& k : D.keys) {
+            const ChanRef& c = fin[k.channel];
+            if (c.kind == 0) { if (!dry.node(c.node, 0, "g").z.empty()) keyNullable = true; }
+            else if (D.joins[c.join].buildOutputs[c.col].nullWord >= 0) keyNullable = true;
+        }
+        int totalBits = 0;
+        for (const auto& k : D.keys) totalBits += k.bits;
+        const bool squeeze = D.W > 1 && !D.bigintPath && !keyNullable && totalBits <= 64;
+        src << "    static constexpr bool TIERS = " << ((D.W == 1 || squeeze) ? "true" : "false") << ";\n";
+        src << "    static __device__ __forceinline__ unsigned long long tierKey(const unsigned long long (&kw)[W])\n    {\n";
+        if (D.W == 1 || !squeeze) src << "        return kw[0];\n";
+        else {
+            src << "        unsigned long long t = 0;\n";
+            int off = 0;
+            for (const auto& k : D.keys) {
+                src << "        t |= ((kw[" << k.word << "] >> " << k.shift << ")" << (k.bits < 64 ? " & " + hex64((1ULL << k.bits) - 1) : std::string()) << ") << " << off << ";\n";
+                off += k.bits;
+            }
+            src << "        return t;\n";
+        }
+        src << "    }\n    static __device__ __forceinline__ void expandKey(unsigned long long t, unsigned long long (&kw)[W])\n    {\n";
+        for (int w = 0; w < D.W; w++) src << "        kw[" << w << "] = 0;\n";
+        if (D.W == 1 || !squeeze) src << "        kw[0] = t;\n";
+        else {
+            int off = 0;
+            for (const auto& k : D.keys) {
+                src << "        kw[" << k.word << "] |= ((t >> " << off << ")" << (k.bits < 64 ? " & " + hex64((1ULL << k.bits) - 1) : std::string()) << ") << " << k.shift << ";\n";
+                off += k.bits;
+            }
+        }
+        src << "    }\n";
+    }
+    // ---- Tile + load ----
+    src << "    struct Tile {\n";
+    for (int c : info.eagerInputs) {
+        const int w = widthOf(P.inputTypes[c]);
+        src << "        " << (w == 8 ? "unsigned long long" : w == 4 ? "unsigned int" : "unsigned char") << " c" << c << "[R];\n";
+    }
+    if (info.eagerInputs.empty()) src << "        int unused;\n";
+    src << "    };\n";
+    src << "    static __device__ __forceinline__ void load(const FusedParams& P, long long base, Tile& t)\n    {\n";
+    for (int p = 0; p < R / 2; p++) {
+        src << "        {\n            const long long r0 = base + " << p * 2 * THREADS << " + 2 * (long long) threadIdx.x;\n"
+            << "            if (r0 + 1 < P.n) {\n";
+        for (int c : info.eagerInputs) {
+            const int w = widthOf(P.inputTypes[c]);
+            if (w == 8) src << "                { const ulonglong2 x = ldStream128((const uint64_t*) P.values[" << c << "] + r0); t.c" << c << "[" << 2 * p << "] = x.x; t.c" << c << "[" << 2 * p + 1 << "] = x.y; }\n";
+            else if (w == 4) src << "                { const uint64_t x = ldStream64((const uint32_t*) P.values[" << c << "] + r0); t.c" << c << "[" << 2 * p << "] = (unsigned int) x; t.c" << c << "[" << 2 * p + 1 << "] = (unsigned int) (x >> 32); }\n";
+            else src << "                { const unsigned short x = *((const unsigned short*) ((const uint8_t*) P.values[" << c << "] + r0)); t.c" << c << "[" << 2 * p << "] = (unsigned char) x; t.c" << c << "[" << 2 * p + 1 << "] = (unsigned char) (x >> 8); }\n";
+        }
+        src << "            }\n            else {\n";
+        for (int c : info.eagerInputs) {
+            const int w = widthOf(P.inputTypes[c]);
+            const char* ty = w == 8 ? "uint64_t" : w == 4 ? "uint32_t" : "uint8_t";
+            src << "                t.c" << c << "[" << 2 * p << "] = r0 < P.n ? ((const " << ty << "*) P.values[" << c << "])[r0] : 0; t.c" << c << "[" << 2 * p + 1 << "] = 0;\n";
+        }
+        src << "            }\n        }\n";
+    }
+    src << "    }\n";
+
+    // ---- process ----
+    std::ostringstream body;
+    auto flush = [&]() { body << g.out.str(); g.out.str(""); g.out.clear(); };
+    body << "        bool errOv = false, errDz = false;\n";
+    // stage A: validity + filter
+    for (int u = 0; u < R; u++) {
+        const std::string us = std::to_string(u);
+        const int p = u / 2, q = u % 2;
+        g.emit("const long long row" + us + " = base + " + std::to_string(p * 2 * THREADS + q) + " + 2 * (long long) threadIdx.x;");
+        g.emit("bool live" + us + " = row" + us + " < P.n;");
+        g.emit("if (P.bitmapIn && live" + us + ") live" + us + " = (P.bitmapIn[row" + us + " >> 5] >> (row" + us + " & 31)) & 1u;");
+    }
+    flush();
+    if (P.filterNode >= 0) {
+        for (int u = 0; u < R; u++) {
+            const std::string us = std::to_string(u), guard = "live" + us;
+            // the filter's inputs are evaluated under the validity guard; a copy of the guard keeps `live` assignable
+            g.emit("const bool in" + us + " = live" + us + ";");
+            const Val f = g.node(P.filterNode, u, "in" + us);
+            if (!g.fail.empty()) return decline(g.fail);
+            if (f.kind != 'b') return decline("filter is not boolean");
+            g.emit(guard + " = in" + us + " && " + f.v + (f.z.empty() ? "" : " && !" + f.z) + ";");      // only TRUE selects
+        }
+        flush();
+    }
+    // a channel's value for row slot u (evaluated lazily under `guard`)
+    auto chanVal = [&](const ChanRef& c, int u, const std::string& guard) -> Val {
+        if (c.kind == 0) return g.node(c.node, u, guard);
+        const FusedBuildColumn& bc = D.joins[c.join].buildOutputs[c.col];
+        const std::string us = std::to_string(u), js = std::to_string(c.join), id = "b" + js + "_" + std::to_string(c.col) + "_" + us;
+        Val r;
+        const std::string word = "pw" + js + "_" + us + "[" + std::to_string(bc.word) + "]";
+        const std::string rawBits = bc.width == 8 ? word : "((" + word + " >> " + std::to_string(bc.shift) + ") & " + hex64(bc.width == 4 ? 0xffffffffULL : 0xffULL) + ")";
+        r.v = "v" + id;
+        if (bc.type == PG_TYPE_DOUBLE) { r.kind = 'd'; g.emit("const double " + r.v + " = __longlong_as_double((long long) " + rawBits + ");"); }
+        else if (bc.type == PG_TYPE_BIGINT) { r.kind = 'i'; g.emit("const long long " + r.v + " = (long long) " + rawBits + ";"); }
+        else if (bc.type == PG_TYPE_BOOLEAN) { r.kind = 'b'; g.emit("const bool " + r.v + " = " + rawBits + " != 0;"); }
+        else if (bc.type == PG_TYPE_INTEGER || bc.type == PG_TYPE_DATE) { r.kind = 'i'; g.emit("const long long " + r.v + " = (long long) (int) (unsigned int) " + rawBits + ";"); }
+        else { g.fail = "VARCHAR build column"; return r; }
+        if (bc.nullWord >= 0) {
+            r.z = "z" + id;
+            g.emit("const bool " + r.z + " = ((pw" + js + "_" + us + "[" + std::to_string(bc.nullWord) + "] >> " + std::to_string(bc.nullShift) + ") & 0xff) != 0;");
+        }
+        return r;
+    };
+    // stage B: joins
+    for (size_t j = 0; j < D.joins.size(); j++) {
+        const FusedJoinDesc& J = D.joins[j];
+        const std::string js = std::to_string(j);
+        const ChanRef& keyRef = layouts[j][J.keyChannel];
+        const bool membershipOnly = J.strideWords == 0;
+        // B1: keys, index loads of all R rows
+        for (int u = 0; u < R; u++) {
+            const std::string us = std::to_string(u), guard = "live" + us;
+            g.emit("const bool in" + js + "_" + us + " = live" + us + ";");
+            const Val k = chanVal(keyRef, u, "in" + js + "_" + us);
+            if (!g.fail.empty()) return decline(g.fail);
+            if (k.kind != 'i') return decline("join key must be an integer channel");
+            g.emit("const unsigned long long ix" + js + "_" + us + " = (unsigned long long) (" + k.v + " - P.joins[" + js + "].D.minKey);");
+            g.emit("const bool ir" + js + "_" + us + " = in" + js + "_" + us + (k.z.empty() ? "" : " && !" + k.z) + " && ix" + js + "_" + us + " < P.joins[" + js + "].D.range;");
+            if (membershipOnly)
+                g.emit("const unsigned long long bw" + js + "_" + us + " = ir" + js + "_" + us + " ? __ldg(P.joins[" + js + "].D.bitmap + (ix" + js + "_" + us + " >> 6)) : 0ULL;");
+            else {
+                g.emit("ulonglong4 bs" + js + "_" + us + " = make_ulonglong4(0, 0, 0, 0); unsigned int pf" + js + "_" + us + " = 0;");
+                g.emit("if (ir" + js + "_" + us + ") { const ulonglong2* bp = (const ulonglong2*) (P.joins[" + js + "].D.bitmap + (ix" + js + "_" + us + " >> 8) * 4); const ulonglong2 lo = __ldg(bp), hi = __ldg(bp + 1); "
+                       "bs" + js + "_" + us + " = make_ulonglong4(lo.x, lo.y, hi.x, hi.y); pf" + js + "_" + us + " = __ldg(P.joins[" + js + "].D.prefix + (ix" + js + "_" + us + " >> 8)); }");
+            }
+            (void) guard;
+        }
+        flush();
+        // B2: membership / rank, narrow `live`, payload loads
+        for (int u = 0; u < R; u++) {
+            const std::string us = std::to_string(u), s = js + "_" + us;
+            if (membershipOnly) g.emit("live" + us + " = ir" + s + " && ((bw" + s + " >> (ix" + s + " & 63)) & 1ULL);");
+            else {
+                g.emit("const unsigned int wi" + s + " = (unsigned int) (ix" + s + " >> 6) & 3u;");
+                g.emit("const unsigned long long wd" + s + " = wi" + s + " == 0 ? bs" + s + ".x : wi" + s + " == 1 ? bs" + s + ".y : wi" + s + " == 2 ? bs" + s + ".z : bs" + s + ".w;");
+                g.emit("const unsigned long long bt" + s + " = 1ULL << (ix" + s + " & 63);");
+                g.emit("live" + us + " = ir" + s + " && (wd" + s + " & bt" + s + ") != 0;");
+                g.emit("unsigned int rk" + s + " = pf" + s + " + __popcll(wd" + s + " & (bt" + s + " - 1));");
+                g.emit("if (wi" + s + " > 0) rk" + s + " += __popcll(bs" + s + ".x); if (wi" + s + " > 1) rk" + s + " += __popcll(bs" + s + ".y); if (wi" + s + " > 2) rk" + s + " += __popcll(bs" + s + ".z);");
+                g.emit("unsigned long long pw" + s + "[" + std::to_string(J.strideWords) + "];");
+                for (int k = 0; k < J.strideWords; k++)
+                    g.emit("pw" + s + "[" + std::to_string(k) + "] = live" + us + " ? __ldg(P.joins[" + js + "].rows + (unsigned long long) rk" + s + " * " + std::to_string(J.strideWords) + " + " + std::to_string(k) + ") : 0ULL;");
+            }
+        }
+        flush();
+    }
+    // stage C1: aggregate inputs and key fields of all rows (lazy loads in flight together)
+    struct KeyEval { Val v; };
+    std::vector<std::vector<Val>> keyVals(R), accVals(R);
+    for (int u = 0; u < R; u++) {
+        const std::string us = std::to_string(u);
+        g.emit("const bool go" + us + " = live" + us + ";");
+        for (const auto& a : D.accs) {
+            Val v = chanVal(fin[a.channel], u, "go" + us);
+            if (!g.fail.empty()) return decline(g.fail);
+            if (!v.z.empty()) return decline("nullable aggregate input");
+            if (a.fromBigint ? v.kind != 'i' : v.kind != 'd') return decline("aggregate input type");
+            accVals[u].push_back(v);
+        }
+        for (const auto& k : D.keys) {
+            Val v = chanVal(fin[k.channel], u, "go" + us);
+            if (!g.fail.empty()) return decline(g.fail);
+            if (v.kind == 's') {
+                // VARCHAR(n <= 7) key: [length byte][bytes] exactly as group_table.cuh packKey packs it
+                const std::string id = "k" + std::to_string(&k - &D.keys[0]) + "_" + us, cs = std::to_string(v.channel);
+                g.emit("unsigned long long s" + id + " = 0;");
+                g.emit("if (go" + us + (v.z.empty() ? "" : " && !" + v.z) + ") { const int o = P.offsets[" + cs + "][row" + us + "]; int len = P.offsets[" + cs + "][row" + us + " + 1] - o; "
+                       "if (len > " + std::to_string(k.maxLen) + ") { errLen = true; len = " + std::to_string(k.maxLen) + "; } "
+                       "const uint8_t* b = (const uint8_t*) P.values[" + cs + "] + o; s" + id + " = (unsigned long long) (unsigned int) len; "
+                       "for (int i = 0; i < len && i < 7; i++) s" + id + " |= (unsigned long long) b[i] << (8 * (i + 1)); }");
+                v.v = "s" + id;
+            }
+            keyVals[u].push_back(v);
+        }
+    }
+    flush();
+    // stage C2: pack keys, hand the row to the aggregation
+    for (int u = 0; u < R; u++) {
+        const std::string us = std::to_string(u);
+        body << "        if (go" << us << ") {\n";
+        body << "            unsigned long long kw[" << D.W << "]; int special = 0; unsigned int spell = 0;\n";
+        for (int w = 0; w < D.W; w++) body << "            kw[" << w << "] = 0;\n";
+        if (D.bigintPath) {
+            const Val& v = keyVals[u][0];
+            if (v.kind != 'i') return decline("BIGINT key expected");
+            body << "            kw[0] = (unsigned long long) " << v.v << ";\n";
+            if (!v.z.empty()) body << "            if (" << v.z << ") { special = 1; kw[0] = 0; } else\n";
+            body << "            if (kw[0] == kEmptyKey) special = 2;\n";
+        }
+        else {
+            body << "            unsigned int nullMask = 0;\n";
+            for (size_t k = 0; k < D.keys.size(); k++) {
+                const FusedKeyField& f = D.keys[k];
+                const Val& v = keyVals[u][k];
+                std::string bits;
+                switch (f.type) {
+                    case PG_TYPE_BIGINT: if (v.kind != 'i') return decline("key type"); bits = "(unsigned long long) " + v.v; break;
+                    case PG_TYPE_INTEGER: case PG_TYPE_DATE: if (v.kind != 'i') return decline("key type"); bits = "(unsigned long long) (unsigned int) " + v.v; break;
+                    case PG_TYPE_BOOLEAN: if (v.kind != 'b') return decline("key type"); bits = "(" + v.v + " ? 1ULL : 0ULL)"; break;
+                    case PG_TYPE_VARCHAR: if (v.kind != 's') return decline("VARCHAR keys must be input columns passed through"); bits = v.v; break;
+                    case PG_TYPE_DOUBLE: {
+                        if (v.kind != 'd') return decline("key type");
+                        body << "            unsigned long long d" << k << " = (unsigned long long) canonicalDoubleBits(__double_as_longlong(" << v.v << "));\n"
+                             << "            if (d" << k << " == 0x8000000000000000ULL) { d" << k << " = 0; spell |= " << (1u << k) << "u; }\n";
+                        bits = "d" + std::to_string(k);
+                        break;
+                    }
+                    default: return decline("group-by key type");
+                }
+                if (!v.z.empty()) body << "            if (" << v.z << ") nullMask |= " << (1u << k) << "u; else\n";
+                body << "            kw[" << f.word << "] |= (" << bits << ") << " << f.shift << ";\n";
+            }
+            body << "            kw[" << D.nullWord << "] |= (unsigned long long) nullMask << " << D.nullShift << ";\n";
+            if (D.W == 1) body << "            if (kw[0] == kEmptyKey) special = 2;\n";
+        }
+        body << "            unsigned long long vals[" << (NV > 0 ? NV : 1) << "];\n";
+        for (int c = 0; c < NV; c++) {
+            const Val& v = accVals[u][c];
+            if (D.accs[c].fromBigint) body << "            vals[" << c << "] = (unsigned long long) __double_as_longlong(__ll2double_rn(" << v.v << "));\n";
+            else body << "            vals[" << c << "] = (unsigned long long) __double_as_longlong(" << v.v << ");\n";
+        }
+        body << "            sink.add(kw, special, spell, vals, (unsigned int) row" << us << ");\n        }\n";
+    }
+    if (!g.fail.empty()) return decline(g.fail);
+
+    src << "    template <class Sink>\n    static __device__ __forceinline__ void process(const FusedParams& P, const Tile& t, long long base, Sink& sink)\n    {\n"
+        << "        bool errLen = false;\n" << body.str()
+        << "        if (errOv) atomicOr(P.fpError, 1u);\n        if (errDz) atomicOr(P.fpError, 2u);\n        if (errLen) atomicOr(P.fpError, 4u);\n"
+        << "    }\n};\n}  // namespace pg\n"
+        << "extern \"C\" __global__ void __launch_bounds__(pg::Prog::THREADS, pg::Prog::MIN_CTAS) fused_kernel(const __grid_constant__ pg::FusedParams P) { pg::fusedAggBody<pg::Prog>(P); }\n";
+    info.ok = true;
+    return src.str();
+}
+
+}  // namespace pg

@@ -30,7 +30,7 @@ __host__ __device__ __forceinline__ uint64_t firstRowWord(uint64_t globalRow, ui
 constexpr int kMaxKeyColumns = 8;
 
 // counters[] indices
-enum { CNT_GROUPS = 0, CNT_DEFERRED = 1, CNT_ERROR = 2, CNT_NEW = 3, CNT_COUNT = 8 };
+enum { CNT_GROUPS = 0, CNT_DEFERRED = 1, CNT_ERROR = 2, CNT_NEW = 3, CNT_FPERR = 4, CNT_COUNT = 8 };
 
 struct GroupTable {          // device view (passed by value to kernels)
     uint64_t* keys;          // [W][capP]

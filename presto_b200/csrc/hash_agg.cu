@@ -21,9 +21,15 @@
 #include "common.cuh"
 #include "group_table.cuh"
 #include "key_layout.h"
+#include "agg_tiers.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <algorithm>
+#include <functional>
+#include <map>
+#include "fused_agg.cuh"
+#include "jit_runtime.h"
+#include "operators_internal.h"
 
 namespace pg {
 
@@ -55,113 +61,6 @@ struct AggLaunch {
     uint32_t sLimit;
     int32_t nAccAlloc;           // accumulator columns the shared table was sized for (>= nAcc)
     int32_t vec;                 // every 8-byte column pointer is 16-byte aligned: load row pairs with one 128-bit request
-};
-
-constexpr int kAggThreads = 256;
-constexpr int kSharedProbes = 8;
-constexpr int kWarpAggMaxGroups = 8;
-constexpr int kWarpMaxGroups = 40;       // up to here: per-warp accumulator sets (47 / 41 G rows/s at 16 / 32 groups vs 39 / 34 on tiers 0/1; beyond, the
-                                         // 512-slot table of this geometry fills up and the 4096-slot table per SM wins: 44+ G rows/s)
-constexpr int kMidMinGroups = 40;        // from here on the CTA-per-SM shared table beats tier 0 + a small tier-1 table (see launchFastT)
-constexpr int kMaxSubsetPasses = 1;      // mid mode (47 G rows/s at 1000 groups) loses to direct mode (~28 G rows/s flat) from the second hash-subset pass on
-
-template <int MAXV> struct RowsPerThread { static constexpr int value = MAXV <= 4 ? 4 : 2; };   // always even: rows are loaded in pairs
-// Tier 0: the first kTier0Groups groups a CTA claims get per-thread private accumulators in shared memory.
-constexpr int kTier0Columns = 40;                  // per-thread private accumulator columns of one CTA (Q1: 6 groups x 6 columns = 36)
-template <int MAXV> struct Tier0Groups { static constexpr int value = kTier0Columns / MAXV; };
-constexpr int kTier0Bytes = kTier0Columns * kAggThreads * 8;   // K0 * MAXV <= 40 columns of 256 doubles = 80 KB
-
-// shared-memory carve-up, same arithmetic on host and device
-struct SharedLayout {
-    uint32_t keys, acc, first, state, sid, misc, tier0, total;
-    __host__ __device__ SharedLayout(uint32_t S, int W, int nAccAlloc, bool withTier0)
-    {
-        const uint32_t S2 = S + 2;
-        uint32_t o = 0;
-        keys = o; o += 8 * W * S2;
-        acc = o; o += 8 * nAccAlloc * S2;
-        first = o; o += 4 * S2;
-        state = o; o += (W > 1 ? 4 * S2 : 0);
-        sid = o; o += (S2 + 15) & ~15u;
-        misc = o; o += 1280;  // claimed count, next tier-0 / warp-table id, slot of each id (<= 254)
-        o = (o + 15) & ~15u;
-        tier0 = o; o += withTier0 ? kTier0Bytes : 0;
-        total = o;
-    }
-};
-
-// ---- shared-memory table ---------------------------------------------------------------------------------------------
-template <int W>
-struct SharedTable {
-    volatile uint64_t* keys;    // [W][S2]
-    volatile uint32_t* state;   // [S2] (W > 1)
-    uint64_t* acc;              // [nAcc][S2]
-    uint32_t* first;            // [S2]
-    volatile uint8_t* sid;      // [S2] tier-0 id of the slot's group, 0xFF = none
-    uint32_t* count;            // misc[0] claimed slots, misc[1] next tier-0 id, misc[2..] slot of tier-0 id
-    uint32_t S, S2, sLimit;
-    int tier0Groups;
-
-    __device__ __forceinline__ void claimed(uint32_t s) const
-    {
-        atomicAdd(count, 1u);
-        if (tier0Groups) {
-            uint32_t id = atomicAdd(count + 1, 1u);
-            // sid[s] is published last and read without a barrier by other threads (compute-sanitizer racecheck flags it): a reader that
-            // still sees 0xFF sends its row to tier 1 (st.acc of the same slot), one that sees the id uses the private / per-warp
-            // accumulators — both are folded into the slot before the flush, so either outcome is correct
-            if (id < (uint32_t) tier0Groups) { count[2 + id] = s; __threadfence_block(); sid[s] = (uint8_t) id; }
-        }
-    }
-
-    __device__ __forceinline__ int find(const uint64_t (&kw)[W], uint64_t h) const
-    {
-        uint32_t s = (uint32_t) (h >> 32) & (S - 1);
-        if (W == 1) {
-#pragma unroll 1
-            for (int p = 0; p < kSharedProbes; p++) {
-                uint64_t k = keys[s];
-                if (k == kw[0]) return (int) s;
-                if (k == kEmptyKey) {
-                    if (*(volatile uint32_t*) count >= sLimit) return -1;
-                    uint64_t old = atomicCAS((unsigned long long*) &keys[s], (unsigned long long) kEmptyKey, (unsigned long long) kw[0]);
-                    if (old == kEmptyKey) { claimed(s); return (int) s; }
-                    if (old == kw[0]) return (int) s;
-                }
-                s = (s + 1) & (S - 1);
-            }
-            return -1;
-        }
-        else {
-            const uint32_t ready = tagOf(h);
-#pragma unroll 1
-            for (int p = 0; p < kSharedProbes; p++) {
-                uint32_t st = state[s];
-                if (st == kStEmpty) {
-                    if (*(volatile uint32_t*) count >= sLimit) return -1;
-                    uint32_t old = atomicCAS((uint32_t*) &state[s], kStEmpty, kStLocked);
-                    if (old == kStEmpty) {
-#pragma unroll
-                        for (int w = 0; w < W; w++) keys[w * S2 + s] = kw[w];
-                        __threadfence_block();
-                        state[s] = ready;
-                        claimed(s);
-                        return (int) s;
-                    }
-                    st = old;
-                }
-                while (st == kStLocked) st = state[s];
-                if (st == ready) {
-                    bool eq = true;
-#pragma unroll
-                    for (int w = 0; w < W; w++) eq &= keys[w * S2 + s] == kw[w];
-                    if (eq) return (int) s;
-                }
-                s = (s + 1) & (S - 1);
-            }
-            return -1;
-        }
-    }
 };
 
 __device__ __forceinline__ void accAddShared(uint64_t* addr, uint64_t bits, bool isFloat)
@@ -489,28 +388,6 @@ __device__ __forceinline__ int fastGlobalFind(const FastLaunch<NV, CNT>& P, uint
     if (P.kWord[0] == 0) kw[0] |= v0 << P.kShift[0]; else kw[1] |= v0 << P.kShift[0];
     if (P.kWord[1] == 0) kw[0] |= v1 << P.kShift[1]; else kw[1] |= v1 << P.kShift[1];
     return tableFind<2>(P.t, kw, hashKeyWords<2>(kw), true, fromFlush);
-}
-
-template <int NV, bool CNT> struct FastGeom {
-    static constexpr int NC = NV + (CNT ? 1 : 0);       // accumulator columns
-    static constexpr int K0 = (kTier0Columns / NC) > 31 ? 31 : (kTier0Columns / NC);   // tier-0 groups (K0 * NC <= 40 columns of 256 x 8 B = 80 KB; ids live in a 32-bit mask)
-};
-
-// Rows that are not tier 0: the CTA's shared table (direct shared atomics) or the HBM table.  Kept out of line so the hot loop stays small.
-__device__ __forceinline__ void sharedAddF64(uint64_t* addr, uint64_t bits)
-{
-    const unsigned a = (unsigned) __cvta_generic_to_shared(addr);
-    asm volatile("red.shared.add.f64 [%0], %1;" :: "r"(a), "d"(__longlong_as_double((long long) bits)) : "memory");
-}
-__device__ __forceinline__ void sharedAddU64(uint64_t* addr, uint64_t v)
-{
-    const unsigned a = (unsigned) __cvta_generic_to_shared(addr);
-    asm volatile("red.shared.add.u64 [%0], %1;" :: "r"(a), "l"(v) : "memory");
-}
-__device__ __forceinline__ void sharedMinU32(uint32_t* addr, uint32_t v)
-{
-    const unsigned a = (unsigned) __cvta_generic_to_shared(addr);
-    asm volatile("red.shared.min.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
 }
 
 // Rows that miss the CTA's shared table: the HBM table (tier 2).  Kept out of line so the hot loop stays small.
@@ -1235,7 +1112,66 @@ struct ResultBuilder {
     }
 };
 
+// GroupByHash.createGroupByHash + the accumulator factories of one HashAggregationOperator, planned on the host: the packed key layout
+// and the physical accumulator columns (one per distinct (kind, channel, mask)) every aggregate reads.  Needs no device.
+static void planAggregation(const pg_hash_aggregation_config* c, KeyLayout& layout, std::vector<AggPlan>& aggs, std::vector<PhysCol>& phys, int& rowCountCol)
+{
+    auto physColumn = [&](int kind, int channel, int mask, bool lazy) {
+        for (size_t i = 0; i < phys.size(); i++)
+            if (phys[i].kind == kind && phys[i].channel == channel && phys[i].mask == mask) return (int) i;
+        phys.push_back({kind, channel, mask, lazy, !lazy});
+        return (int) phys.size() - 1;
+    };
+    PG_CHECK_ARG(c->expected_groups > 0, "expectedSize must be greater than zero");
+    PG_CHECK_ARG(c->n_aggregates >= 0 && c->n_aggregates <= 32, "at most 32 aggregates");
+    layout.plan(c->n_group_channels, c->group_channels, c->group_types, c->group_max_lengths);
+    const int step = c->step;
+    PG_CHECK_ARG(step == PG_STEP_SINGLE || step == PG_STEP_PARTIAL || step == PG_STEP_FINAL, "bad aggregation step");
+    const bool final = step == PG_STEP_FINAL;
+    for (int i = 0; i < c->n_aggregates; i++) {
+        AggPlan a; a.spec = c->aggregates[i];
+        const int ch = a.spec.input_channel, mk = a.spec.mask_channel;
+        PG_CHECK_ARG(!(final && mk >= 0), "FINAL step takes no mask");
+        switch (a.spec.function) {
+            case PG_AGG_COUNT_STAR:
+                if (final) a.val0 = physColumn(K_I64_ADD, ch, -1, false);
+                else a.val0 = physColumn(K_COUNT, -1, mk, false);
+                break;
+            case PG_AGG_COUNT_COLUMN:
+                if (final) a.val0 = physColumn(K_I64_ADD, ch, -1, false);
+                else { PG_CHECK_ARG(ch >= 0, "count(column) needs an input channel"); a.val0 = physColumn(K_COUNT, ch, mk, false); }
+                break;
+            case PG_AGG_SUM_DOUBLE:
+                a.val0 = physColumn(K_F64, ch, mk, false);
+                a.countCol = physColumn(K_COUNT, ch, mk, mk < 0);   // lazily activated: only once a page carries NULLs in `ch`
+                break;
+            case PG_AGG_SUM_BIGINT:
+                a.val0 = physColumn(K_LO32, ch, mk, false); a.val1 = physColumn(K_HI32, ch, mk, false);
+                a.countCol = physColumn(K_COUNT, ch, mk, mk < 0);
+                break;
+            case PG_AGG_AVG_DOUBLE: case PG_AGG_AVG_BIGINT:
+                a.countExact = true;
+                if (final) { a.val0 = physColumn(K_F64, ch, -1, false); a.countCol = physColumn(K_I64_ADD, ch + 1, -1, false); }
+                else {
+                    a.val0 = physColumn(a.spec.function == PG_AGG_AVG_DOUBLE ? K_F64 : K_F64_FROM_I64, ch, mk, false);
+                    a.countCol = physColumn(K_COUNT, ch, mk, mk < 0);
+                }
+                break;
+            default: throw Error(PG_ERR_UNSUPPORTED, "aggregate function is not on the GPU path (supported: count, sum, avg over BIGINT/DOUBLE)");
+        }
+        if (a.spec.function != PG_AGG_COUNT_STAR) PG_CHECK_ARG(ch >= 0, "aggregate needs an input channel");
+        aggs.push_back(a);
+    }
+    // exact counts of lazily counted channels fall back on the shared row count until the channel shows a NULL
+    bool needRowCount = false;
+    for (auto& a : aggs) if (a.countExact && a.countCol >= 0 && phys[a.countCol].lazy) needRowCount = true;
+    if (needRowCount) rowCountCol = physColumn(K_COUNT, -1, -1, false);
+    PG_CHECK_ARG(phys.size() <= 16, "too many distinct accumulator columns (max 16)");
+
+}
+
 class HashAggregationOp : public Operator {
+protected:
     KeyLayout layout;
     int hashChannel, step;
     std::vector<AggPlan> aggs;
@@ -1254,64 +1190,18 @@ class HashAggregationOp : public Operator {
     // output
     ResultBuilder result;
     int64_t outGroups = 0, outNext = 0;
-
-    int physColumn(int kind, int channel, int mask, bool lazy)
-    {
-        for (size_t i = 0; i < phys.size(); i++)
-            if (phys[i].kind == kind && phys[i].channel == channel && phys[i].mask == mask) return (int) i;
-        phys.push_back({kind, channel, mask, lazy, !lazy});
-        return (int) phys.size() - 1;
-    }
+    // fused pipeline input (FusedAggregationOp below): while set, addInput stages the RAW page's channels and every chunk runs through
+    // `fusedLaunch` (filter / project / probe / aggregate in one kernel) instead of the aggregation kernels
+    const std::vector<int>* inputChannels = nullptr;
+    std::function<void(const std::vector<DeviceColumn>&, int64_t, const uint32_t*, uint32_t*)> fusedLaunch;
+    bool lastFused = false;
 
 public:
     explicit HashAggregationOp(const pg_hash_aggregation_config* c) : Operator(c->options), stager(this)
     {
-        PG_CHECK_ARG(c->expected_groups > 0, "expectedSize must be greater than zero");
-        PG_CHECK_ARG(c->n_aggregates >= 0 && c->n_aggregates <= 32, "at most 32 aggregates");
-        layout.plan(c->n_group_channels, c->group_channels, c->group_types, c->group_max_lengths);
+        planAggregation(c, layout, aggs, phys, rowCountCol);
         hashChannel = c->hash_channel;
         step = c->step;
-        PG_CHECK_ARG(step == PG_STEP_SINGLE || step == PG_STEP_PARTIAL || step == PG_STEP_FINAL, "bad aggregation step");
-        const bool final = step == PG_STEP_FINAL;
-        for (int i = 0; i < c->n_aggregates; i++) {
-            AggPlan a; a.spec = c->aggregates[i];
-            const int ch = a.spec.input_channel, mk = a.spec.mask_channel;
-            PG_CHECK_ARG(!(final && mk >= 0), "FINAL step takes no mask");
-            switch (a.spec.function) {
-                case PG_AGG_COUNT_STAR:
-                    if (final) a.val0 = physColumn(K_I64_ADD, ch, -1, false);
-                    else a.val0 = physColumn(K_COUNT, -1, mk, false);
-                    break;
-                case PG_AGG_COUNT_COLUMN:
-                    if (final) a.val0 = physColumn(K_I64_ADD, ch, -1, false);
-                    else { PG_CHECK_ARG(ch >= 0, "count(column) needs an input channel"); a.val0 = physColumn(K_COUNT, ch, mk, false); }
-                    break;
-                case PG_AGG_SUM_DOUBLE:
-                    a.val0 = physColumn(K_F64, ch, mk, false);
-                    a.countCol = physColumn(K_COUNT, ch, mk, mk < 0);   // lazily activated: only once a page carries NULLs in `ch`
-                    break;
-                case PG_AGG_SUM_BIGINT:
-                    a.val0 = physColumn(K_LO32, ch, mk, false); a.val1 = physColumn(K_HI32, ch, mk, false);
-                    a.countCol = physColumn(K_COUNT, ch, mk, mk < 0);
-                    break;
-                case PG_AGG_AVG_DOUBLE: case PG_AGG_AVG_BIGINT:
-                    a.countExact = true;
-                    if (final) { a.val0 = physColumn(K_F64, ch, -1, false); a.countCol = physColumn(K_I64_ADD, ch + 1, -1, false); }
-                    else {
-                        a.val0 = physColumn(a.spec.function == PG_AGG_AVG_DOUBLE ? K_F64 : K_F64_FROM_I64, ch, mk, false);
-                        a.countCol = physColumn(K_COUNT, ch, mk, mk < 0);
-                    }
-                    break;
-                default: throw Error(PG_ERR_UNSUPPORTED, "aggregate function is not on the GPU path (supported: count, sum, avg over BIGINT/DOUBLE)");
-            }
-            if (a.spec.function != PG_AGG_COUNT_STAR) PG_CHECK_ARG(ch >= 0, "aggregate needs an input channel");
-            aggs.push_back(a);
-        }
-        // exact counts of lazily counted channels fall back on the shared row count until the channel shows a NULL
-        bool needRowCount = false;
-        for (auto& a : aggs) if (a.countExact && a.countCol >= 0 && phys[a.countCol].lazy) needRowCount = true;
-        if (needRowCount) rowCountCol = physColumn(K_COUNT, -1, -1, false);
-        PG_CHECK_ARG(phys.size() <= 16, "too many distinct accumulator columns (max 16)");
         MAXV = phys.size() <= 4 ? 4 : (phys.size() <= 8 ? 8 : 16);
 
         // channels to stage: keys, hash channel is not needed (slot function is recomputed from the key), agg inputs, masks
@@ -1383,6 +1273,10 @@ public:
     {
         if (cnt[CNT_ERROR] & ERR_VARCHAR_TOO_LONG) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR group-by key longer than its declared max length (GPU path packs keys of <= 7 bytes)");
         if (cnt[CNT_ERROR] & 0x80000000u) throw Error(PG_ERR_INVALID_STATE, "internal: shared-table flush could not claim a slot");
+        // the PageProcessor half of a fused fragment
+        if (cnt[CNT_FPERR] & 4u) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR group-by key longer than its declared max length (GPU path packs keys of <= 7 bytes)");
+        if (cnt[CNT_FPERR] & 1u) throw Error(PG_ERR_NUMERIC_OVERFLOW, "bigint arithmetic overflow");
+        if (cnt[CNT_FPERR] & 2u) throw Error(PG_ERR_INVALID_ARGUMENT, "Division by zero");
     }
 
     void grow(uint64_t wantGroups)
@@ -1622,9 +1516,9 @@ public:
                 b.position_count = m;
             }
             std::vector<DeviceColumn> cols;
-            int slot = stager.stage(&sub, stagedChannels, cols);   // PCIe copy of this chunk overlaps the previous chunk's kernel
+            int slot = stager.stage(&sub, inputChannels ? *inputChannels : stagedChannels, cols);   // PCIe copy of this chunk overlaps the previous chunk's kernel
             settle();                                              // previous chunk: counters, deferred rows, growth
-            activateLazyCounts(cols);
+            if (!fusedLaunch) activateLazyCounts(cols);
             processChunk(cols, m);
             stager.markCompute(slot);
             rowsSeen += (uint64_t) m;
@@ -1641,9 +1535,10 @@ public:
         size_t bmBytes = (size_t) divUp(n, 32) * 4;
         bitmapA.reserve(bmBytes);
         PG_CUDA(cudaMemsetAsync(bitmapA.ptr, 0, bmBytes, stream));
-        if (!tryLaunchFast(cols, n, bitmapA.as<uint32_t>()))
+        if (fusedLaunch) fusedLaunch(cols, n, nullptr, bitmapA.as<uint32_t>());
+        else if (!tryLaunchFast(cols, n, bitmapA.as<uint32_t>()))
             dispatchActive([&](auto w, auto mv) { launchRange<decltype(w)::value, decltype(mv)::value>(cols, 0, n, nullptr, bitmapA.as<uint32_t>()); });
-        lastCols = cols; lastN = n; lastBase = rowsSeen; lastPending = true;
+        lastCols = cols; lastN = n; lastBase = rowsSeen; lastPending = true; lastFused = (bool) fusedLaunch;
     }
 
     // Wait for the in-flight chunk, re-run rows that found the table at its claim limit after growing it.
@@ -1666,7 +1561,8 @@ public:
             PG_CUDA(cudaMemsetAsync(outB.ptr, 0, bmBytes, stream));
             unsigned int zero = 0;
             PG_CUDA(cudaMemcpyAsync(table.counters.as<unsigned int>() + CNT_DEFERRED, &zero, sizeof(zero), cudaMemcpyHostToDevice, stream));
-            dispatchActive([&](auto w, auto mv) { launchRange<decltype(w)::value, decltype(mv)::value>(lastCols, 0, lastN, in, outB.as<uint32_t>()); });
+            if (lastFused) fusedLaunch(lastCols, lastN, in, outB.as<uint32_t>());     // the fragment's row program again, restricted to the deferred rows
+            else dispatchActive([&](auto w, auto mv) { launchRange<decltype(w)::value, decltype(mv)::value>(lastCols, 0, lastN, in, outB.as<uint32_t>()); });
             in = outB.as<uint32_t>();
             readCounters(cnt);
             checkErrors(cnt);
@@ -1951,7 +1847,253 @@ public:
     }
 };
 
+
+struct FusedJoinShape { int joinType; std::vector<int32_t> hashChannels, outputChannels; };
+
+// Describes a FilterAndProject → LookupJoin* → HashAggregation fragment for the code generator; false + why when it has to run
+// operator by operator.  Host only (also behind pg_fused_aggregation_explain, which needs no device).
+static bool describeFragment(FusedProgramDesc& D, const std::vector<int32_t>& inputTypes, const std::vector<pg_expr_node>& nodes, int filterNode,
+                             const std::vector<int32_t>& projections, const std::vector<FusedJoinShape>& joins, const std::vector<LookupSourceView>& views,
+                             const KeyLayout& layout, const std::vector<PhysCol>& phys, const std::vector<bool>& inputHasNulls, std::string& why)
+{
+    D = FusedProgramDesc();
+    D.fp.nodes = nodes; D.fp.inputTypes.assign(inputTypes.begin(), inputTypes.end()); D.fp.inputHasNulls = inputHasNulls;
+    D.fp.filterNode = filterNode; D.fp.projections.assign(projections.begin(), projections.end());
+    for (size_t j = 0; j < joins.size(); j++) {
+        const FusedJoinShape& J = joins[j];
+        const LookupSourceView& v = views[j];
+        if (J.joinType != PG_JOIN_INNER) { why = "outer join"; return false; }
+        if (J.hashChannels.size() != 1 || v.nKeys != 1) { why = "multi-column join key"; return false; }
+        if (!v.dense) { why = "lookup source is a hash table (duplicate or sparse keys), not the dense index"; return false; }
+        FusedJoinDesc fj;
+        fj.keyChannel = J.hashChannels[0];
+        fj.probeOutputChannels.assign(J.outputChannels.begin(), J.outputChannels.end());
+        fj.buildOutputs = v.buildOutputs; fj.strideWords = v.strideWords;
+        D.joins.push_back(fj);
+    }
+    for (int k = 0; k < layout.nKeys; k++) {
+        FusedKeyField f; f.channel = layout.channels[k]; f.type = layout.types[k]; f.word = layout.word[k]; f.shift = layout.shift[k]; f.bits = layout.bits[k]; f.maxLen = layout.maxLens[k];
+        D.keys.push_back(f);
+    }
+    D.bigintPath = layout.bigintPath; D.W = layout.W; D.nullWord = layout.nullWord < 0 ? 0 : layout.nullWord; D.nullShift = layout.nullShift;
+    for (size_t p = 0; p < phys.size(); p++) {
+        if (!phys[p].active) continue;
+        if ((phys[p].kind == K_F64 || phys[p].kind == K_F64_FROM_I64) && phys[p].mask < 0) D.accs.push_back({phys[p].channel, phys[p].kind == K_F64_FROM_I64});
+        else if (phys[p].kind == K_COUNT && phys[p].channel < 0 && phys[p].mask < 0 && !D.countRows) D.countRows = true;
+        else { why = "aggregate outside the fused set (sums / averages of doubles and count(*))"; return false; }
+    }
+    return true;
+}
+
+// ======================================================================================================================
+// FusedAggregationOp — FilterAndProject → LookupJoin* → HashAggregation as one operator (include/presto_gpu.h, fused_agg.cuh,
+// fused_codegen.cpp).  It IS the HashAggregationOperator of the chain (same group table, same output path); only the way rows get
+// into the table differs: one generated kernel over the raw page instead of three operators and two intermediate pages.
+// ======================================================================================================================
+class FusedAggregationOp : public HashAggregationOp {
+    struct JoinCfg {
+        JoinBridge* bridge; int joinType; std::vector<int32_t> types, hashChannels, outputChannels; int precomputedHash;
+    };
+    std::vector<int32_t> inputTypes, projections;
+    std::vector<pg_expr_node> nodes;
+    int filterNode;
+    std::vector<JoinCfg> joins;
+    std::vector<int> rawChannels;                       // raw input channels the fragment reads (staged for the fused kernel)
+    struct Compiled { const JitKernel* kernel = nullptr; FusedKernelInfo info; std::string reason; };
+    std::map<uint64_t, Compiled> compiled;              // by null signature of the raw page
+    std::unique_ptr<Operator> fpOp;
+    std::vector<std::unique_ptr<Operator>> joinOps;
+    int64_t fusedPages = 0, unfusedPages = 0;
+    int lastRegisters = 0;
+    std::string lastReason;
+    std::vector<LookupSourceView> views;
+
+public:
+    explicit FusedAggregationOp(const pg_fused_aggregation_config* c) : HashAggregationOp(&c->aggregation)
+    {
+        const pg_filter_project_config& f = c->page_processor;
+        PG_CHECK_ARG(f.n_input_channels >= 0 && f.n_input_channels <= kFusedMaxInputs, "at most 32 input channels");
+        PG_CHECK_ARG(f.n_nodes >= 0 && f.n_nodes <= 64 && f.n_projections >= 0 && f.n_projections <= 32, "page processor program too large");
+        PG_CHECK_ARG(c->n_joins >= 0 && c->n_joins <= kFusedMaxJoins, "at most 2 joins in a fused fragment");
+        inputTypes.assign(f.input_types, f.input_types + f.n_input_channels);
+        nodes.assign(f.nodes, f.nodes + f.n_nodes);
+        filterNode = f.filter_node;
+        projections.assign(f.projection_nodes, f.projection_nodes + f.n_projections);
+        PG_CHECK_ARG(filterNode < f.n_nodes, "filter node out of range");
+        for (int p : projections) PG_CHECK_ARG(p >= 0 && p < f.n_nodes, "projection node out of range");
+        for (int i = 0; i < f.n_nodes; i++) {
+            const pg_expr_node& n = nodes[i];
+            if (n.op == PG_EX_INPUT) PG_CHECK_ARG(n.a >= 0 && n.a < f.n_input_channels, "input channel out of range");
+            else for (int o : {n.a, n.b, n.c}) PG_CHECK_ARG(o < i, "expression nodes must be topologically ordered");
+        }
+        for (int j = 0; j < c->n_joins; j++) {
+            const pg_lookup_join_config& jc = c->joins[j];
+            PG_CHECK_ARG(c->bridges && c->bridges[j], "join bridge is null");
+            JoinCfg J;
+            J.bridge = (JoinBridge*) c->bridges[j]; J.joinType = jc.join_type; J.precomputedHash = jc.precomputed_hash_channel;
+            J.types.assign(jc.types, jc.types + jc.n_channels);
+            J.hashChannels.assign(jc.hash_channels, jc.hash_channels + jc.n_hash_channels);
+            J.outputChannels.assign(jc.output_channels, jc.output_channels + jc.n_output_channels);
+            joins.push_back(J);
+        }
+        PG_CHECK_ARG(step != PG_STEP_FINAL, "a fused fragment aggregates raw rows: step must be SINGLE or PARTIAL");
+        for (int ch = 0; ch < f.n_input_channels; ch++) {
+            bool used = false;
+            for (const auto& n : nodes) if (n.op == PG_EX_INPUT && n.a == ch) used = true;
+            if (used) rawChannels.push_back(ch);
+        }
+        views.resize(joins.size());
+    }
+
+    // LookupJoinOperator.needsInput :198-210: blocked until every lookup source future completes
+    bool needsInput() override
+    {
+        if (!HashAggregationOp::needsInput()) return false;
+        for (size_t j = 0; j < joins.size(); j++) { if (!views[j].ready) describeLookupSource(joins[j].bridge, views[j]); if (!views[j].ready) return false; }
+        return true;
+    }
+
+    // Describes the fragment for the code generator; false + why when it has to run operator by operator.
+    bool describe(FusedProgramDesc& D, const std::vector<bool>& inputHasNulls, std::string& why) const
+    {
+        std::vector<FusedJoinShape> shapes;
+        for (const auto& J : joins) shapes.push_back({J.joinType, J.hashChannels, J.outputChannels});
+        return describeFragment(D, inputTypes, nodes, filterNode, projections, shapes, views, layout, phys, inputHasNulls, why);
+    }
+    void physMapping(int32_t (&out)[kFusedMaxSums + 1]) const
+    {
+        int nv = 0, cnt = -1;
+        for (size_t p = 0; p < phys.size(); p++) {
+            if (!phys[p].active) continue;
+            if (phys[p].kind == K_F64 || phys[p].kind == K_F64_FROM_I64) out[nv++] = (int) p; else cnt = (int) p;
+        }
+        out[nv] = cnt < 0 ? 0 : cnt;
+    }
+
+    Compiled& kernelFor(const pg_page* page)
+    {
+        uint64_t sig = 0;
+        std::vector<bool> hasNulls(inputTypes.size(), false);
+        for (int ch : rawChannels) if (page->blocks[ch].is_null) { sig |= 1ULL << ch; hasNulls[ch] = true; }
+        auto it = compiled.find(sig);
+        if (it != compiled.end()) return it->second;
+        Compiled& c = compiled[sig];
+        const char* off = getenv("PG_FUSED");
+        if (off && off[0] == '0') { c.reason = "PG_FUSED=0"; return c; }
+        FusedProgramDesc D;
+        if (!describe(D, hasNulls, c.reason)) return c;
+        const std::string src = generateFusedAggSource(D, c.info);
+        if (!c.info.ok) { c.reason = c.info.reason; return c; }
+        std::string err;
+        c.kernel = getOrCompileKernel(options.device, src, "fused_kernel", &err);
+        if (!c.kernel) c.reason = err;
+        return c;
+    }
+
+    void addInput(const pg_page* page) override
+    {
+        PG_CHECK_STATE(needsInput(), "fused aggregation does not need input (lookup sources still building, or already finishing)");
+        PG_CHECK_ARG(page->channel_count == (int) inputTypes.size(), "page channel count differs from the page processor's input types");
+        if (page->position_count == 0) return;
+        for (int ch : rawChannels) PG_CHECK_ARG(page->blocks[ch].type == inputTypes[ch], "input channel type differs from the operator's configuration");
+        Compiled& c = kernelFor(page);
+        bool fusable = c.kernel != nullptr;
+        if (fusable && page->memory == PG_MEM_DEVICE) {
+            // eagerly loaded columns come in as 128-bit pairs: device pages must be 16-byte aligned (staged host pages always are)
+            for (int ch : c.info.eagerInputs) if (((uintptr_t) page->blocks[ch].values % 16) != 0 || page->blocks[ch].encoding != PG_ENC_FLAT) { fusable = false; lastReason = "misaligned or encoded device column"; }
+        }
+        if (!fusable) { if (!c.reason.empty()) lastReason = c.reason; addInputUnfused(page); return; }
+        lastRegisters = c.kernel->registers;
+        int32_t physMap[kFusedMaxSums + 1] = {0};
+        physMapping(physMap);
+        const CUfunction fn = c.kernel->function;
+        DriverApi& api = DriverApi::get();
+        fusedLaunch = [&, fn](const std::vector<DeviceColumn>& cols, int64_t n, const uint32_t* bitmapIn, uint32_t* bitmapOut) {
+            FusedParams L{};
+            L.t = table.view();
+            L.n = n; L.rowBase = rowsSeen; L.bitmapIn = bitmapIn; L.bitmapOut = bitmapOut;
+            L.S = sharedSlots; L.sLimit = sharedLimit; L.nAccAlloc = (int) phys.size();
+            L.direct = (layout.W != 1 || bitmapIn != nullptr || knownGroups > (int64_t) sharedLimit * 9 / 10) ? 1 : 0;
+            memcpy(L.phys, physMap, sizeof(physMap));
+            for (size_t i = 0; i < rawChannels.size(); i++) {
+                L.values[rawChannels[i]] = cols[i].values; L.nulls[rawChannels[i]] = cols[i].nulls; L.offsets[rawChannels[i]] = cols[i].offsets;
+            }
+            for (size_t j = 0; j < joins.size(); j++) { L.joins[j].D = views[j].D; L.joins[j].rows = views[j].rows; }
+            L.fpError = table.counters.as<unsigned int>() + CNT_FPERR;
+            const size_t smem = L.direct ? 64 : sharedBytes(sharedSlots);
+            if (api.funcSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, 200 * 1024) != CUDA_SUCCESS) throw Error(PG_ERR_CUDA, "cuFuncSetAttribute failed for a fused pipeline kernel");
+            int perSM = 0;
+            api.occupancyMaxActiveBlocks(&perSM, fn, 256, smem);
+            perSM = std::max(1, std::min(perSM, L.direct ? 8 : 2));    // flushReserve of the table was sized for 2 resident CTAs per SM with a shared table
+            const int64_t tiles = divUp(n, 256 * c.info.rowsPerThread);
+            const unsigned grid = (unsigned) std::min<int64_t>((int64_t) numSMs * perSM, std::max<int64_t>(tiles, 1));
+            void* args[1] = {&L};
+            const CUresult r = api.launchKernel(fn, grid, 1, 1, 256, 1, 1, (unsigned) smem, (CUstream) stream, args, nullptr);
+            if (r != CUDA_SUCCESS) throw Error(PG_ERR_CUDA, "cuLaunchKernel of a fused pipeline kernel failed (" + std::to_string((int) r) + ")");
+            stats.kernel_launches++;
+            stats.kernel_paths |= L.direct ? PG_PATH_FUSED_DIRECT : PG_PATH_FUSED_TIERS;
+        };
+        inputChannels = &rawChannels;
+        struct Reset { FusedAggregationOp* o; ~Reset() { o->fusedLaunch = nullptr; o->inputChannels = nullptr; } } reset{this};
+        HashAggregationOp::addInput(page);      // chunking, staging, deferred rows and growth are the aggregation's own
+        fusedPages++;
+    }
+
+    // The same fragment operator by operator (still on the GPU): FilterAndProjectOperator → LookupJoinOperator* → this aggregation.
+    void addInputUnfused(const pg_page* page)
+    {
+        pg_operator_options o = options;
+        o.output_memory = PG_MEM_DEVICE; o.cuda_stream = (void*) stream;
+        if (!fpOp) {
+            pg_filter_project_config f{};
+            f.n_input_channels = (int) inputTypes.size(); f.input_types = inputTypes.data(); f.n_nodes = (int) nodes.size(); f.nodes = nodes.data();
+            f.filter_node = filterNode; f.n_projections = (int) projections.size(); f.projection_nodes = projections.data(); f.options = o;
+            fpOp.reset(createFilterProject(&f));
+            for (auto& J : joins) {
+                pg_lookup_join_config jc{};
+                jc.join_type = J.joinType; jc.n_channels = (int) J.types.size(); jc.types = J.types.data();
+                jc.n_hash_channels = (int) J.hashChannels.size(); jc.hash_channels = J.hashChannels.data();
+                jc.n_output_channels = (int) J.outputChannels.size(); jc.output_channels = J.outputChannels.data();
+                jc.precomputed_hash_channel = J.precomputedHash; jc.options = o;
+                joinOps.emplace_back(createLookupJoin(&jc, J.bridge));
+            }
+        }
+        unfusedPages++;
+        stats.kernel_paths |= PG_PATH_UNFUSED_CHAIN;
+        const int64_t before = stats.input_positions;
+        fpOp->addInput(page);
+        pg_page cur{};
+        bool has = fpOp->getOutput(&cur);
+        for (auto& j : joinOps) {
+            if (!has || cur.position_count == 0) break;
+            j->addInput(&cur);
+            has = j->getOutput(&cur);
+        }
+        if (has && cur.position_count > 0) HashAggregationOp::addInput(&cur);
+        stats.input_positions = before + page->position_count;     // rows of the RAW page, like the fused path
+    }
+
+    void syncStats() override
+    {
+        HashAggregationOp::syncStats();
+    }
+    int64_t chainLaunches() const
+    {
+        int64_t n = fpOp ? fpOp->stats.kernel_launches : 0;
+        for (auto& j : joinOps) n += j->stats.kernel_launches;
+        return n;
+    }
+    void info(int64_t* fused, int64_t* unfused, int32_t* regs, char* reason, size_t cap) const
+    {
+        if (fused) *fused = fusedPages;
+        if (unfused) *unfused = unfusedPages;
+        if (regs) *regs = lastRegisters;
+        if (reason && cap) snprintf(reason, cap, "%s", lastReason.c_str());
+    }
+};
+
 Operator* createHashAggregation(const pg_hash_aggregation_config* c) { return new HashAggregationOp(c); }
+Operator* createFusedAggregation(const pg_fused_aggregation_config* c) { return new FusedAggregationOp(c); }
 
 }  // namespace pg
 
@@ -1960,6 +2102,69 @@ extern "C" int32_t pg_hash_aggregation_create(const pg_hash_aggregation_config* 
     try {
         if (!config || !out) throw pg::Error(PG_ERR_INVALID_ARGUMENT, "null argument");
         *out = (pg_operator*) pg::createHashAggregation(config);
+    }
+    catch (const pg::Error& e) { pg::setLastError(e.what()); return e.code; }
+    catch (const std::exception& e) { pg::setLastError(e.what()); return PG_ERR_INVALID_STATE; }
+    return PG_OK;
+}
+
+extern "C" int32_t pg_fused_aggregation_create(const pg_fused_aggregation_config* config, pg_operator** out)
+{
+    try {
+        if (!config || !out) throw pg::Error(PG_ERR_INVALID_ARGUMENT, "null argument");
+        *out = (pg_operator*) pg::createFusedAggregation(config);
+    }
+    catch (const pg::Error& e) { pg::setLastError(e.what()); return e.code; }
+    catch (const std::exception& e) { pg::setLastError(e.what()); return PG_ERR_INVALID_STATE; }
+    return PG_OK;
+}
+extern "C" int32_t pg_fused_aggregation_get_info(pg_operator* op, int64_t* fused, int64_t* unfused, int32_t* registers, char* reason, size_t capacity)
+{
+    try {
+        auto* p = dynamic_cast<pg::FusedAggregationOp*>((pg::Operator*) op);
+        if (!p) throw pg::Error(PG_ERR_INVALID_ARGUMENT, "not a fused aggregation operator");
+        p->info(fused, unfused, registers, reason, capacity);
+    }
+    catch (const pg::Error& e) { pg::setLastError(e.what()); return e.code; }
+    return PG_OK;
+}
+
+// Payload row layout HashBuilderOperator gives a dense index (hash_join.cu tryBuildDense): widest columns first, no NULL bytes here.
+extern "C" int32_t pg_fused_aggregation_explain(const pg_fused_aggregation_config* c, uint64_t nullableInputs, const int32_t* const* buildTypes,
+                                                const int32_t* nBuildTypes, char* buffer, size_t capacity, size_t* needed)
+{
+    try {
+        using namespace pg;
+        PG_CHECK_ARG(c && needed, "null argument");
+        const pg_filter_project_config& f = c->page_processor;
+        std::vector<int32_t> inputTypes(f.input_types, f.input_types + f.n_input_channels), projections(f.projection_nodes, f.projection_nodes + f.n_projections);
+        std::vector<pg_expr_node> nodes(f.nodes, f.nodes + f.n_nodes);
+        std::vector<FusedJoinShape> shapes; std::vector<LookupSourceView> views;
+        for (int j = 0; j < c->n_joins; j++) {
+            const pg_lookup_join_config& jc = c->joins[j];
+            shapes.push_back({jc.join_type, std::vector<int32_t>(jc.hash_channels, jc.hash_channels + jc.n_hash_channels), std::vector<int32_t>(jc.output_channels, jc.output_channels + jc.n_output_channels)});
+            LookupSourceView v; v.ready = true; v.dense = true; v.nKeys = 1; v.keyType = PG_TYPE_BIGINT;
+            int off = 0;
+            const int nb = nBuildTypes ? nBuildTypes[j] : 0;
+            v.buildOutputs.resize(nb);
+            for (int width : {8, 4, 1})
+                for (int i = 0; i < nb; i++)
+                    if (typeWidth(buildTypes[j][i]) == width) { FusedBuildColumn& b = v.buildOutputs[i]; b.type = buildTypes[j][i]; b.width = width; b.word = off >> 3; b.shift = 8 * (off & 7); off += width; }
+            v.strideWords = nb ? std::max(1, (off + 7) / 8) : 0;
+            if (v.strideWords == 3) v.strideWords = 4;
+            views.push_back(v);
+        }
+        KeyLayout layout; std::vector<AggPlan> aggs; std::vector<PhysCol> phys; int rowCountCol = -1;
+        planAggregation(&c->aggregation, layout, aggs, phys, rowCountCol);
+        std::vector<bool> hasNulls(inputTypes.size(), false);
+        for (size_t i = 0; i < inputTypes.size(); i++) hasNulls[i] = (nullableInputs >> i) & 1ULL;
+        FusedProgramDesc D; std::string why;
+        if (!describeFragment(D, inputTypes, nodes, f.filter_node, projections, shapes, views, layout, phys, hasNulls, why)) throw Error(PG_ERR_UNSUPPORTED, "fragment is not fusable: " + why);
+        FusedKernelInfo info;
+        const std::string src = generateFusedAggSource(D, info);
+        if (!info.ok) throw Error(PG_ERR_UNSUPPORTED, "fragment is not fusable: " + info.reason);
+        *needed = src.size() + 1;
+        if (buffer && capacity >= src.size() + 1) memcpy(buffer, src.c_str(), src.size() + 1);
     }
     catch (const pg::Error& e) { pg::setLastError(e.what()); return e.code; }
     catch (const std::exception& e) { pg::setLastError(e.what()); return PG_ERR_INVALID_STATE; }

@@ -19,6 +19,8 @@
 #include "common.cuh"
 #include "group_table.cuh"
 #include "key_layout.h"
+#include "dense_index.cuh"
+#include "operators_internal.h"
 #include <cub/device/device_scan.cuh>
 #include <algorithm>
 #include <mutex>
@@ -171,14 +173,6 @@ __global__ void joinEmitKernel(const __grid_constant__ EmitJoinParams P)
 // access sequential.  Results are identical to the hash path (unique keys: at most one match, no chains).
 constexpr int kDenseRangeFactor = 64;                // keys may cover as little as 1/64 of their range (bitmap: range / 8 bytes)
 constexpr int kDenseSmallRangeBits = 31;             // ranges up to 2^31 (256 MB bitmap + 32 MB directory) use the index at any density
-constexpr int kDenseBlockWords = 4;                  // 4 x 64 bit = one 32-byte sector per block
-
-struct DenseIndex {
-    const uint64_t* bitmap;    // [blocks * 4]
-    const uint32_t* prefix;    // [blocks] set bits before the block
-    int64_t minKey;
-    uint64_t range;            // keys are in [minKey, minKey + range)
-};
 
 struct KeyColumn { const void* values; const uint8_t* nulls; int32_t type; };
 
@@ -225,32 +219,6 @@ __global__ void denseBlockCountKernel(const uint64_t* bitmap, int64_t blocks, ui
         const uint64_t* w = bitmap + b * kDenseBlockWords;
         counts[b] = __popcll(w[0]) + __popcll(w[1]) + __popcll(w[2]) + __popcll(w[3]);
     }
-}
-
-// rank of `key` among the build keys, or -1 when absent
-__device__ __forceinline__ int64_t denseRank(const DenseIndex& D, int64_t key)
-{
-    const uint64_t idx = (uint64_t) (key - D.minKey);
-    if (idx >= D.range) return -1;
-    const uint64_t blk = idx >> 8;
-    const ulonglong4 w = *reinterpret_cast<const ulonglong4*>(D.bitmap + blk * kDenseBlockWords);   // one 32-byte sector
-    const uint32_t wi = (uint32_t) (idx >> 6) & 3u;
-    const uint64_t word = wi == 0 ? w.x : wi == 1 ? w.y : wi == 2 ? w.z : w.w;
-    const uint64_t bit = 1ULL << (idx & 63);
-    if (!(word & bit)) return -1;
-    uint32_t r = D.prefix[blk] + __popcll(word & (bit - 1));
-    if (wi > 0) r += __popcll(w.x);
-    if (wi > 1) r += __popcll(w.y);
-    if (wi > 2) r += __popcll(w.z);
-    return (int64_t) r;
-}
-
-// membership only (pass A of the probe): one 8-byte bitmap word, no directory
-__device__ __forceinline__ bool denseContains(const DenseIndex& D, int64_t key)
-{
-    const uint64_t idx = (uint64_t) (key - D.minKey);
-    if (idx >= D.range) return false;
-    return (D.bitmap[idx >> 6] >> (idx & 63)) & 1ULL;
 }
 
 // Build OUTPUT columns are stored row-wise in key order ("payload rows"): one random 8..32-byte write per build row when the index
@@ -1311,6 +1279,31 @@ public:
     void finish() override { finishing = true; }
     bool isFinished() override { return finishing && !hasPending; }
 };
+
+Operator* createLookupJoin(const pg_lookup_join_config* c, JoinBridge* bridge) { return new LookupJoinOp(c, bridge); }
+
+void describeLookupSource(JoinBridge* bridge, LookupSourceView& out)
+{
+    out = LookupSourceView();
+    auto ls = bridge->get();
+    if (!ls) return;
+    out.ready = true;
+    out.nKeys = ls->layout.nKeys;
+    out.keyType = ls->layout.types[0];
+    out.dense = ls->dense;
+    if (!ls->dense) return;
+    out.D = ls->denseView();
+    out.rows = ls->payloadRows.as<uint64_t>();
+    out.strideWords = ls->outputChannels.empty() ? 0 : ls->payload.strideWords;
+    for (size_t i = 0; i < ls->outputChannels.size(); i++) {
+        const PayloadColumn& pc = ls->payload.cols[i];
+        FusedBuildColumn b;
+        b.type = ls->types[ls->outputChannels[i]]; b.width = pc.width;
+        b.word = pc.offset >> 3; b.shift = 8 * (pc.offset & 7);
+        b.nullWord = pc.nullOffset >= 0 ? pc.nullOffset >> 3 : -1; b.nullShift = pc.nullOffset >= 0 ? 8 * (pc.nullOffset & 7) : 0;
+        out.buildOutputs.push_back(b);
+    }
+}
 
 // ---- HashSemiJoinOperator (MB/operator/HashSemiJoinOperator.java:142-192) -------------------------------------------------------
 // flag = contains(set, key) with SQL's three values: NULL key → NULL (false for a set without rows); absent → NULL if the set holds a NULL

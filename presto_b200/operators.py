@@ -365,6 +365,149 @@ class FilterAndProjectOperator(Operator):
         return bool(is_list.value), size.value
 
 
+class FusedJoin:
+    """One INNER LookupJoinOperator of a fused fragment: probes ``bridge`` with channel ``hash_channels`` of the incoming layout."""
+
+    def __init__(self, bridge: "JoinBridge", types: Sequence[int], hash_channels: Sequence[int], output_channels: Sequence[int]):
+        self.bridge, self.types, self.hash_channels, self.output_channels = bridge, list(types), list(hash_channels), list(output_channels)
+
+
+class FusedAggregationOperator(Operator):
+    """FilterAndProjectOperator → LookupJoinOperator* → HashAggregationOperator of one Driver as ONE operator
+    (include/presto_gpu.h pg_fused_aggregation_create): on the CUDA backend the fragment is generated as a single kernel; on any
+    other backend (the tests' oracle) the three reference operators are simply chained — the results are the same by definition."""
+
+    def __init__(self, input_types: Sequence[int], program, joins: Sequence[FusedJoin], group_types: Sequence[int], group_channels: Sequence[int],
+                 aggregates: Sequence[Aggregate], *, step: int = abi.STEP_SINGLE, expected_groups: int = 10_000,
+                 group_max_lengths: Optional[Sequence[int]] = None, hash_channel: int = -1, backend=None, **options):
+        backend = backend or _default_backend()
+        self._chain = None
+        if not backend.has_device:
+            chain_opts = {k: v for k, v in options.items() if k in ("max_output_rows",)}
+            fp = FilterAndProjectOperator(input_types, program, backend=backend)
+            js = [LookupJoinOperator(j.bridge, j.types, j.hash_channels, j.output_channels, backend=backend) for j in joins]
+            agg = HashAggregationOperator(group_types, group_channels, aggregates, step=step, expected_groups=expected_groups,
+                                          group_max_lengths=group_max_lengths, hash_channel=hash_channel, backend=backend, **chain_opts)
+            self._chain = (fp, js, agg)
+            self._b, self._h, self._closed = backend, None, False
+            return
+        cfg, self._keep = self._config(input_types, program, joins, group_types, group_channels, aggregates, step, expected_groups,
+                                       group_max_lengths, hash_channel, options)
+        handle = C.c_void_p()
+        backend.check(backend.fused_aggregation_create(C.byref(cfg), C.byref(handle)))
+        super().__init__(backend, handle)
+
+    @staticmethod
+    def _config(input_types, program, joins, group_types, group_channels, aggregates, step, expected_groups, group_max_lengths, hash_channel, options):
+        cfg = abi.pg_fused_aggregation_config()
+        keep = []
+        it, nodes, proj = abi.i32_array(input_types), program.c_nodes(), abi.i32_array(program.projections)
+        f = cfg.page_processor
+        f.n_input_channels, f.input_types = len(input_types), it
+        f.n_nodes, f.nodes = len(program.nodes), nodes
+        f.filter_node = program.filter
+        f.n_projections, f.projection_nodes = len(program.projections), proj
+        keep += [it, nodes, proj]
+        jarr = (abi.pg_lookup_join_config * max(1, len(joins)))()
+        barr = (C.c_void_p * max(1, len(joins)))()
+        for i, j in enumerate(joins):
+            ty, hc, oc = abi.i32_array(j.types), abi.i32_array(j.hash_channels), abi.i32_array(j.output_channels)
+            jarr[i].join_type = abi.JOIN_INNER
+            jarr[i].n_channels, jarr[i].types = len(j.types), ty
+            jarr[i].n_hash_channels, jarr[i].hash_channels = len(j.hash_channels), hc
+            jarr[i].n_output_channels, jarr[i].output_channels = len(j.output_channels), oc
+            jarr[i].precomputed_hash_channel = -1
+            barr[i] = j.bridge._h if j.bridge is not None else None
+            keep += [ty, hc, oc]
+        cfg.n_joins, cfg.joins, cfg.bridges = len(joins), jarr, barr
+        keep += [jarr, barr]
+        a = cfg.aggregation
+        gc, gt = abi.i32_array(group_channels), abi.i32_array(group_types)
+        gl = abi.i32_array(group_max_lengths if group_max_lengths is not None else [0] * len(group_types))
+        aggs = (abi.pg_aggregate * max(1, len(aggregates)))()
+        for i, g in enumerate(aggregates):
+            aggs[i].function, aggs[i].input_channel, aggs[i].mask_channel = g.function, g.input_channel, g.mask_channel
+        a.n_group_channels = len(group_channels)
+        a.group_channels, a.group_types, a.group_max_lengths = gc, gt, gl
+        a.hash_channel = hash_channel
+        a.n_aggregates, a.aggregates = len(aggregates), aggs
+        a.step, a.expected_groups = step, expected_groups
+        a.options = _options(**options)
+        keep += [gc, gt, gl, aggs]
+        return cfg, keep
+
+    @staticmethod
+    def explain(input_types, program, joins, build_types, group_types, group_channels, aggregates, *, nullable_inputs=(), step: int = abi.STEP_SINGLE,
+                group_max_lengths=None, backend=None) -> str:
+        """The CUDA C++ generated for the fragment (no GPU needed); ``build_types[j]`` = types of join j's build output channels."""
+        if backend is None:
+            from ._lib import load_library
+            backend = load_library()
+        cfg, keep = FusedAggregationOperator._config(input_types, program, joins, group_types, group_channels, aggregates, step, 1000,
+                                                     group_max_lengths, -1, {})
+        bt = [abi.i32_array(t) for t in build_types]
+        bptr = (C.POINTER(C.c_int32) * max(1, len(bt)))(*[C.cast(b, C.POINTER(C.c_int32)) for b in bt])
+        nb = abi.i32_array([len(t) for t in build_types])
+        mask = 0
+        for ch in nullable_inputs:
+            mask |= 1 << ch
+        need = C.c_size_t()
+        backend.check(backend.fused_aggregation_explain(C.byref(cfg), mask, bptr, nb, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        backend.check(backend.fused_aggregation_explain(C.byref(cfg), mask, bptr, nb, buf, need.value, C.byref(need)))
+        return buf.value.decode()
+
+    def get_info(self) -> dict:
+        if self._chain is not None:
+            return {"fused_pages": 0, "unfused_pages": 0, "registers": 0, "reason": "reference operators chained"}
+        f, u, r = C.c_int64(), C.c_int64(), C.c_int32()
+        buf = C.create_string_buffer(2048)
+        self._b.check(self._b.fused_aggregation_get_info(self._h, C.byref(f), C.byref(u), C.byref(r), buf, 2048))
+        return {"fused_pages": f.value, "unfused_pages": u.value, "registers": r.value, "reason": buf.value.decode()}
+
+    # ---- the reference chain (non-CUDA backends) ----
+    def needs_input(self) -> bool:
+        if self._chain is None:
+            return super().needs_input()
+        fp, js, agg = self._chain
+        return agg.needs_input() and all(j.needs_input() or True for j in js)
+
+    def add_input(self, page: Page) -> None:
+        if self._chain is None:
+            return super().add_input(page)
+        fp, js, agg = self._chain
+        fp.add_input(page)
+        cur = fp.get_output()
+        for j in js:
+            if cur is None or not cur.position_count:
+                break
+            j.add_input(cur)
+            cur = j.get_output()
+        if cur is not None and cur.position_count:
+            agg.add_input(cur)
+
+    def get_output(self, copy: bool = True):
+        return super().get_output(copy) if self._chain is None else self._chain[2].get_output(copy)
+
+    def finish(self) -> None:
+        return super().finish() if self._chain is None else self._chain[2].finish()
+
+    def is_finished(self) -> bool:
+        return super().is_finished() if self._chain is None else self._chain[2].is_finished()
+
+    def get_stats(self) -> dict:
+        return super().get_stats() if self._chain is None else self._chain[2].get_stats()
+
+    def close(self) -> None:
+        if self._chain is None:
+            return super().close()
+        if not self._closed:
+            self._closed = True
+            fp, js, agg = self._chain
+            for op in [fp, *js, agg]:
+                op.close()
+
+
 class PagesSerde:
     """PagesSerde (presto-spi/.../spi/page/PagesSerde.java:67-156) + PagesSerdeUtil.writeSerializedPage / readSerializedPage
     (:64-88): pages to and from the SerializedPage wire bytes (21-byte header + raw page)."""

@@ -10,7 +10,8 @@ from typing import Dict, List, Optional, Sequence
 
 from . import _abi as abi
 from .expressions import Program
-from .operators import (Aggregate, FilterAndProjectOperator, HashAggregationOperator, HashBuilderOperator, JoinBridge, LookupJoinOperator)
+from .operators import (Aggregate, FilterAndProjectOperator, FusedAggregationOperator, FusedJoin, HashAggregationOperator, HashBuilderOperator, JoinBridge,
+                        LookupJoinOperator)
 from .page import Page
 
 BUILDING = 1                 # dictionary code of c_mktsegment = 'BUILDING'
@@ -53,10 +54,43 @@ def q1_program() -> Program:
     return prog
 
 
-def run_q1(lineitem_pages: Sequence[Page], backend=None, device_resident: bool = False, **opts) -> List[Page]:
+Q1_AGGREGATES = [Aggregate(abi.AGG_SUM_DOUBLE, 2), Aggregate(abi.AGG_SUM_DOUBLE, 3), Aggregate(abi.AGG_SUM_DOUBLE, 4), Aggregate(abi.AGG_SUM_DOUBLE, 5),
+                 Aggregate(abi.AGG_AVG_DOUBLE, 2), Aggregate(abi.AGG_AVG_DOUBLE, 3), Aggregate(abi.AGG_AVG_DOUBLE, 6), Aggregate(abi.AGG_COUNT_STAR)]
+
+
+def q1_program_typed(key_type: int) -> Program:
+    """q1_program with returnflag / linestatus of ``key_type``: INTEGER dictionary codes, or VARCHAR(1) — the reference's own types
+    (HandTpchQuery1.java:99-108) — passed through the PageProcessor to become the group-by keys."""
+    prog = Program([key_type, key_type, abi.DOUBLE, abi.DOUBLE, abi.DOUBLE, abi.DOUBLE, abi.DATE])
+    rf, ls, qty, ep, disc, tax, ship = [prog.input(i) for i in range(7)]
+    prog.set_filter(ship <= Q1_DATE)
+    dp = ep * (1.0 - disc)
+    prog.project(rf, ls, qty, ep, dp, dp * (1.0 + tax), disc)
+    return prog
+
+
+def run_q1(lineitem_pages: Sequence[Page], backend=None, device_resident: bool = False, fused: bool = False, key_type: int = abi.INTEGER,
+           info: Optional[Dict] = None, **opts) -> List[Page]:
     """lineitem(returnflag, linestatus, quantity, extendedprice, discount, tax, shipdate) → filter/project → GROUP BY returnflag,
-    linestatus: sum(qty), sum(ep), sum(disc_price), sum(charge), avg(qty), avg(ep), avg(disc), count(*) (HandTpchQuery1.java:99-127)."""
+    linestatus: sum(qty), sum(ep), sum(disc_price), sum(charge), avg(qty), avg(ep), avg(disc), count(*) (HandTpchQuery1.java:99-127).
+    ``fused``: the whole Driver pipeline as one FusedAggregationOperator (one generated kernel on the CUDA backend)."""
     mem = abi.MEM_DEVICE if device_resident else abi.MEM_HOST
+    if fused:
+        types = [key_type, key_type, abi.DOUBLE, abi.DOUBLE, abi.DOUBLE, abi.DOUBLE, abi.DATE]
+        op = FusedAggregationOperator(types, q1_program_typed(key_type), [], [key_type, key_type], [0, 1], Q1_AGGREGATES, expected_groups=10_000,
+                                      group_max_lengths=[1, 1] if key_type == abi.VARCHAR else None, backend=backend, max_output_rows=1 << 30, **opts)
+        for page in lineitem_pages:
+            op.add_input(page)
+        op.finish()
+        result = []
+        while not op.is_finished():
+            o = op.get_output()
+            if o is not None:
+                result.append(o)
+        if info is not None:
+            info.update(op.get_info()); info.update(op.get_stats())
+        op.close()
+        return result
     fp = FilterAndProjectOperator([abi.INTEGER, abi.INTEGER, abi.DOUBLE, abi.DOUBLE, abi.DOUBLE, abi.DOUBLE, abi.DATE], q1_program(),
                                   backend=backend, output_memory=mem, **opts)
     agg = HashAggregationOperator([abi.INTEGER, abi.INTEGER], [0, 1],
@@ -80,7 +114,7 @@ def run_q1(lineitem_pages: Sequence[Page], backend=None, device_resident: bool =
 
 
 def run_q3(customer: Sequence[Page], orders: Sequence[Page], lineitem: Sequence[Page], backend=None, device_resident: bool = False,
-           stats: Optional[Dict] = None, **opts) -> List[Page]:
+           stats: Optional[Dict] = None, fused: bool = False, **opts) -> List[Page]:
     """Q3 without the final ORDER BY / LIMIT (done on the host by the caller):
          customer(c_custkey BIGINT, c_mktsegment INTEGER code)   → filter mktsegment = BUILDING           → build #1 (custkey)
          orders(o_orderkey, o_custkey, o_orderdate DATE, o_shippriority INTEGER) → filter o_orderdate < 1995-03-15
@@ -126,6 +160,29 @@ def run_q3(customer: Sequence[Page], orders: Sequence[Page], lineitem: Sequence[
     lk, ep, disc, ship = [pl.input(i) for i in range(4)]
     pl.set_filter(ship > Q3_DATE)
     pl.project(lk, ep * (1.0 - disc))
+    if fused:
+        # the lineitem Driver (filter/project → probe → aggregate) as ONE operator: no filtered page, no joined page
+        fa = FusedAggregationOperator([abi.BIGINT, abi.DOUBLE, abi.DOUBLE, abi.DATE], pl, [FusedJoin(bridge2, [abi.BIGINT, abi.DOUBLE], [0], [0, 1])],
+                                      [abi.BIGINT, abi.DATE, abi.INTEGER], [0, 2, 3], [Aggregate(abi.AGG_SUM_DOUBLE, 1)],
+                                      expected_groups=max(100_000, sum(p.position_count for p in lineitem) // 500),
+                                      max_output_rows=1 << 30, output_memory=mem, **o)
+        for page in lineitem:
+            fa.add_input(page)
+        fa.finish()
+        result = []
+        while not fa.is_finished():
+            r = fa.get_output(copy=copy)
+            if r is not None:
+                result.append(_detach(r) if device_resident else r)
+        if stats is not None:
+            stats["joined_rows"] = -1
+            stats["kernel_launches"] = sum(op.get_stats()["kernel_launches"] for op in (fp_c, build1, fp_o, probe1, build2, fa))
+            stats.update({"fused_" + k: v for k, v in fa.get_info().items()})
+            stats["kernel_paths"] = fa.get_stats()["kernel_paths"]
+        for op in (fp_c, build1, fp_o, probe1, build2, fa):
+            op.close()
+        bridge1.close(); bridge2.close()
+        return result
     fp_l = FilterAndProjectOperator([abi.BIGINT, abi.DOUBLE, abi.DOUBLE, abi.DATE], pl, output_memory=mem, **o)
     probe2 = LookupJoinOperator(bridge2, [abi.BIGINT, abi.DOUBLE], [0], [0, 1], output_memory=mem, **o)
     # the planner's group-count estimate (Q3: about one group per 500 lineitem rows — 1.1 M at SF100) sizes the table so that it
