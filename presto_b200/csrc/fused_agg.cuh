@@ -65,6 +65,7 @@ struct FusedAggSink {
         tid = threadIdx.x;
         seen0 = 0; probeHits = 0; probeMisses = 0; bypass = false;
         tiers = Prog::TIERS && !P.direct;
+        if (Prog::QUEUE) initQueue(smemRaw + (tiers ? SharedLayout(P.S, 1, P.nAccAlloc, true).total : 0));
         if (!tiers) return;
         st.S = P.S; st.S2 = P.S + 2; st.sLimit = P.sLimit; st.tier0Groups = K0;
         const SharedLayout lay(P.S, 1, P.nAccAlloc, true);
@@ -100,18 +101,28 @@ struct FusedAggSink {
         if (CNT) atomicAdd((unsigned long long*) &acc[P.phys[NV]], 1ULL);
     }
 
-    __device__ __forceinline__ void add(const uint64_t (&kw)[W], int special, uint32_t spell, const uint64_t (&vals)[NVA], uint32_t rowIdx)
+    // Slot function of the CTA's shared table.  Nothing observable depends on it (group ids come from first-touch rows), so it is the
+    // cheapest mix that separates small codes in either half of the key: two 32-bit multiplies (murmur64 costs ~25 instructions per row).
+    __device__ __forceinline__ static uint64_t tierHash(uint64_t key)
+    {
+        const uint32_t m = ((uint32_t) key * 0x9E3779B1u) ^ ((uint32_t) (key >> 32) * 0x85EBCA6Bu);
+        return (uint64_t) (m ^ (m >> 15)) << 32;        // SharedTable::find takes the slot from bits 32.. of the hash
+    }
+
+    // Everything that is not "the key sits in its home slot of the shared table and owns a tier-0 id": probing / claiming a shared
+    // slot, tier 1 (shared-space reductions), the HBM table.  (Inlined: a noinline member would force the whole sink — table pointers,
+    // counters, the row arrays — into local memory, which cost 2x on Q1.)
+    __device__ __forceinline__ void addSlow(const uint64_t (&kw)[W], int special, uint32_t spell, const uint64_t (&vals)[NVA], uint32_t rowIdx)
     {
         if (!Prog::TIERS || !tiers || spell) { addGlobal(kw, special, spell, vals, rowIdx); return; }
         const uint64_t key = Prog::tierKey(kw);
         if (W > 1 && key == kEmptyKey) { addGlobal(kw, special, spell, vals, rowIdx); return; }     // a squeezed key that looks like an empty slot
-        const uint64_t h = murmur64(key);
+        const uint64_t h = tierHash(key);
         int sslot = -1;
         if (special) sslot = (int) st.S + special - 1;        // NULL key of the Bigint path / the key equal to the empty sentinel: dedicated slots
         else if (!bypass) {
-            const uint32_t s = (uint32_t) (h >> 32) & (st.S - 1);
-            if (st.keys[s] == key) sslot = (int) s;
-            else { uint64_t k1[1] = {key}; sslot = st.find(k1, h); }
+            uint64_t k1[1] = {key};
+            sslot = st.find(k1, h);
             // a thread whose rows keep missing a full shared table stops probing it (high-cardinality input)
             if (sslot >= 0) probeHits++; else probeMisses++;
             if (((probeHits + probeMisses) & 63u) == 0) {
@@ -121,18 +132,7 @@ struct FusedAggSink {
         }
         if (sslot < 0) { addGlobal(kw, special, spell, vals, rowIdx); return; }
         const uint32_t id = st.sid[sslot];       // the two dedicated slots never get a tier-0 id: their rows take tier 1
-        if (id < (uint32_t) K0) {
-            // tier 0: this thread's private accumulators of group `id` (consecutive threads, consecutive words: no bank conflicts)
-            uint64_t* mine = tier0 + (size_t) id * NC * THREADS + tid;
-#pragma unroll
-            for (int c = 0; c < NV; c++) {
-                double* p = (double*) (mine + c * THREADS);
-                *p = *p + __longlong_as_double((long long) vals[c]);
-            }
-            if (CNT) mine[NV * THREADS] += 1;
-            if (!((seen0 >> id) & 1u)) { seen0 |= 1u << id; atomicMin(&st.first[sslot], rowIdx); }    // rows ascend per thread
-            return;
-        }
+        if (id < (uint32_t) K0) { addTier0(id, (uint32_t) sslot, vals, rowIdx); return; }
         // tier 1: the CTA's shared table, shared-space reductions
 #pragma unroll
         for (int c = 0; c < NV; c++) sharedAddF64(&st.acc[c * st.S2 + sslot], vals[c]);
@@ -140,9 +140,85 @@ struct FusedAggSink {
         if (rowIdx < *(volatile uint32_t*) &st.first[sslot]) sharedMinU32(&st.first[sslot], rowIdx);
     }
 
+    // tier 0: this thread's private accumulators of group `id` (consecutive threads, consecutive words: no bank conflicts)
+    __device__ __forceinline__ void addTier0(uint32_t id, uint32_t sslot, const uint64_t (&vals)[NVA], uint32_t rowIdx)
+    {
+        uint64_t* mine = tier0 + (size_t) id * NC * THREADS + tid;
+#pragma unroll
+        for (int c = 0; c < NV; c++) {
+            double* p = (double*) (mine + c * THREADS);
+            *p = *p + __longlong_as_double((long long) vals[c]);
+        }
+        if (CNT) mine[NV * THREADS] += 1;
+        if (Prog::QUEUE) { if (rowIdx < *(volatile uint32_t*) &st.first[sslot]) atomicMin(&st.first[sslot], rowIdx); }   // rows reach a thread in queue order
+        else if (!((seen0 >> id) & 1u)) { seen0 |= 1u << id; atomicMin(&st.first[sslot], rowIdx); }                      // rows ascend per thread: first sight = its minimum
+    }
+
+    __device__ __forceinline__ void add(const uint64_t (&kw)[W], int special, uint32_t spell, const uint64_t (&vals)[NVA], uint32_t rowIdx)
+    {
+        if (Prog::TIERS && tiers) {
+            const uint64_t key = Prog::tierKey(kw);
+            const uint32_t s = (uint32_t) (tierHash(key) >> 32) & (st.S - 1);
+            if (!special && !spell && st.keys[s] == key && (!Prog::TIERKEY_CAN_BE_EMPTY || key != kEmptyKey)) {
+                const uint32_t id = st.sid[s];
+                if (id < (uint32_t) K0) { addTier0(id, s, vals, rowIdx); return; }
+            }
+        }
+        addSlow(kw, special, spell, vals, rowIdx);
+    }
+
+    // ---- survivor queue (Prog::QUEUE: fragments with joins) ----------------------------------------------------------------------
+    // After a selective probe only a few lanes of a warp still hold a row; running the aggregation (a table probe plus atomics) under
+    // that divergence costs a full warp instruction stream per survivor.  Survivors are queued per warp in shared memory instead and
+    // aggregated 32 at a time with every lane busy (the same idea as hashAggDirectKernel's owned-row queue).
+    static constexpr int kQueueSlots = 64;             // up to 31 left over + 32 new per push
+    struct QueueEntry { uint64_t kw[W]; uint64_t vals[NVA]; uint32_t rowIdx; uint32_t meta; };   // meta = special | spell << 8
+    QueueEntry* queue;                                 // this warp's slots
+    uint32_t qCount;                                   // warp-uniform
+
+    __device__ __forceinline__ static size_t queueBytes() { return Prog::QUEUE ? sizeof(QueueEntry) * kQueueSlots * (THREADS / 32) : 0; }
+    __device__ __forceinline__ void initQueue(unsigned char* base) { queue = (QueueEntry*) base + (size_t) (tid >> 5) * kQueueSlots; qCount = 0; }
+
+    __device__ __forceinline__ void drain(uint32_t keep)
+    {
+        __syncwarp();
+        const int lane = tid & 31;
+        while (qCount > keep) {
+            const uint32_t take = min(32u, qCount), at = qCount - take + lane;
+            if (lane < (int) take) {
+                const QueueEntry& e = queue[at];
+                uint64_t kw[W], vals[NVA];
+#pragma unroll
+                for (int w = 0; w < W; w++) kw[w] = e.kw[w];
+#pragma unroll
+                for (int c = 0; c < NVA; c++) vals[c] = e.vals[c];
+                add(kw, (int) (e.meta & 0xff), e.meta >> 8, vals, e.rowIdx);
+            }
+            qCount -= take;
+            __syncwarp();
+        }
+    }
+    // called by ALL lanes of the warp (live = this lane has a surviving row)
+    __device__ __forceinline__ void push(bool live, const uint64_t (&kw)[W], int special, uint32_t spell, const uint64_t (&vals)[NVA], uint32_t rowIdx)
+    {
+        const unsigned m = __ballot_sync(0xffffffffu, live);
+        if (m == 0) return;
+        if (live) {
+            QueueEntry& e = queue[qCount + __popc(m & ((1u << (tid & 31)) - 1))];
+#pragma unroll
+            for (int w = 0; w < W; w++) e.kw[w] = kw[w];
+#pragma unroll
+            for (int c = 0; c < NVA; c++) e.vals[c] = vals[c];
+            e.rowIdx = rowIdx; e.meta = (uint32_t) special | (spell << 8);
+        }
+        qCount += __popc(m);
+        if (qCount >= 32) drain(31);
+    }
+
     // fold tier 0 into the CTA's shared table, then the shared table into the HBM table
     __device__ __forceinline__ void flush()
     {
+        if (Prog::QUEUE) drain(0);
         if (!tiers) return;
         __syncthreads();
         const GroupTable& T = P.t;

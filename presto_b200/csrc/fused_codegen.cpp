@@ -324,6 +324,11 @@ std::string generateFusedAggSource(const FusedProgramDesc& D, FusedKernelInfo& i
         int totalBits = 0;
         for (const auto& k : D.keys) totalBits += k.bits;
         const bool squeeze = D.W > 1 && !D.bigintPath && !keyNullable && totalBits <= 64;
+        info.tiers = D.W == 1 || squeeze;
+        info.queue = !D.joins.empty();
+        info.queueBytes = info.queue ? (size_t) (8 * D.W + 8 * (D.accs.empty() ? 1 : (int) D.accs.size()) + 8) * 64 * (256 / 32) : 0;     // fused_agg.cuh QueueEntry x kQueueSlots x warps
+        src << "    static constexpr bool QUEUE = " << (info.queue ? "true" : "false") << ";      // survivors of the probes are aggregated 32 at a time\n";
+        src << "    static constexpr bool TIERKEY_CAN_BE_EMPTY = " << ((squeeze && totalBits == 64) ? "true" : "false") << ";\n";
         src << "    static constexpr bool TIERS = " << ((D.W == 1 || squeeze) ? "true" : "false") << ";\n";
         src << "    static __device__ __forceinline__ unsigned long long tierKey(const unsigned long long (&kw)[W])\n    {\n";
         if (D.W == 1 || !squeeze) src << "        return kw[0];\n";
@@ -497,7 +502,7 @@ std::string generateFusedAggSource(const FusedProgramDesc& D, FusedKernelInfo& i
     // stage C2: pack keys, hand the row to the aggregation
     for (int u = 0; u < R; u++) {
         const std::string us = std::to_string(u);
-        body << "        if (go" << us << ") {\n";
+        body << (info.queue ? "        {\n" : "        if (go" + us + ") {\n");
         body << "            unsigned long long kw[" << D.W << "]; int special = 0; unsigned int spell = 0;\n";
         for (int w = 0; w < D.W; w++) body << "            kw[" << w << "] = 0;\n";
         if (D.bigintPath) {
@@ -539,7 +544,8 @@ std::string generateFusedAggSource(const FusedProgramDesc& D, FusedKernelInfo& i
             if (D.accs[c].fromBigint) body << "            vals[" << c << "] = (unsigned long long) __double_as_longlong(__ll2double_rn(" << v.v << "));\n";
             else body << "            vals[" << c << "] = (unsigned long long) __double_as_longlong(" << v.v << ");\n";
         }
-        body << "            sink.add(kw, special, spell, vals, (unsigned int) row" << us << ");\n        }\n";
+        if (info.queue) body << "            sink.push(go" << us << ", kw, special, spell, vals, (unsigned int) row" << us << ");\n        }\n";
+        else body << "            sink.add(kw, special, spell, vals, (unsigned int) row" << us << ");\n        }\n";
     }
     if (!g.fail.empty()) return decline(g.fail);
 

@@ -49,6 +49,9 @@ struct FusedKernelInfo {
     int rowsPerThread = 2;
     int nv = 0;
     bool cnt = false;
+    bool queue = false;            // survivors of the probes are queued per warp and aggregated 32 at a time (fragments with joins)
+    size_t queueBytes = 0;         // shared memory of the queues (per CTA)
+    bool tiers = false;            // the on-chip tiers are available (one-word key, or a key whose fields squeeze into 64 bits)
 };
 
 // Returns the CUDA C++ translation unit (#include "fused_agg.cuh" + struct Prog + an explicit kernel instantiation named

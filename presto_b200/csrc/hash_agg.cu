@@ -2013,14 +2013,14 @@ public:
             L.t = table.view();
             L.n = n; L.rowBase = rowsSeen; L.bitmapIn = bitmapIn; L.bitmapOut = bitmapOut;
             L.S = sharedSlots; L.sLimit = sharedLimit; L.nAccAlloc = (int) phys.size();
-            L.direct = (layout.W != 1 || bitmapIn != nullptr || knownGroups > (int64_t) sharedLimit * 9 / 10) ? 1 : 0;
+            L.direct = (!c.info.tiers || bitmapIn != nullptr || knownGroups > (int64_t) sharedLimit * 9 / 10) ? 1 : 0;
             memcpy(L.phys, physMap, sizeof(physMap));
             for (size_t i = 0; i < rawChannels.size(); i++) {
                 L.values[rawChannels[i]] = cols[i].values; L.nulls[rawChannels[i]] = cols[i].nulls; L.offsets[rawChannels[i]] = cols[i].offsets;
             }
             for (size_t j = 0; j < joins.size(); j++) { L.joins[j].D = views[j].D; L.joins[j].rows = views[j].rows; }
             L.fpError = table.counters.as<unsigned int>() + CNT_FPERR;
-            const size_t smem = L.direct ? 64 : sharedBytes(sharedSlots);
+            const size_t smem = (L.direct ? 64 : sharedBytes(sharedSlots)) + c.info.queueBytes;
             if (api.funcSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, 200 * 1024) != CUDA_SUCCESS) throw Error(PG_ERR_CUDA, "cuFuncSetAttribute failed for a fused pipeline kernel");
             int perSM = 0;
             api.occupancyMaxActiveBlocks(&perSM, fn, 256, smem);
