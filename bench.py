@@ -1,14 +1,18 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the presto_b200 hot path (BASELINE.json: rows/sec, hash aggregation / hash join).
+"""bench.py — headline benchmark of the presto_b200 hot path (BASELINE.json: rows/sec on TPC-H SF100 Q1 hash-agg and Q3 join+agg).
 
-A "step" = one pass of HashAggregationOperator over the whole synthetic batch resident in HBM:
-  config.workload = "GroupByHash 1B-row synthetic lineitem: bigint key (G groups) + 4 x sum(double)" (BASELINE.json configs[1]),
-  addInput(device page) → finish → getOutput (the result read back to the host).
-value   : rows/s with the inputs already in HBM (CUDA events on the operator's stream, max over ranks)
-e2e     : same metric through the C ABI with HOST (pinned) pages: H2D copies inside the timed region
-roofline: algorithmic bytes (40 B/row: 8 B key + 4 x 8 B doubles) / kernel time, vs MEASURED_PEAKS.json hbm_gbs
-cpu_baseline / --impl reference: the oracle (C++ restatement of the reference's Java operators) on the box's host cores.
-Other cardinalities and the join (configs[2]) are reported in "extra"; they do not change `value`.
+A "step" = TPC-H Q1 over SF100 lineitem (600 037 902 rows, the reference's own column types: VARCHAR(1) returnflag / linestatus, 4 x DOUBLE,
+DATE = 46 B/row, HandTpchQuery1.java:99-127) resident in HBM, through ONE FusedAggregationOperator = the Driver pipeline
+FilterAndProject -> HashAggregation (pg_fused_aggregation_create): add_input(device page) -> finish -> get_output.
+value    : lineitem rows/s, inputs already in HBM (CUDA events on the operator's stream, max over ranks)
+e2e      : the same operator fed HOST (pinned) pages through the C ABI: H2D copies inside the timed region, result read back
+roofline : algorithmic bytes (46 B/row, every input column once) / kernel time of the generated fused kernel, vs MEASURED_PEAKS.json hbm_gbs
+cpu_baseline / --impl reference: the oracle (C++ restatement of the reference's Java operators: PageProcessor + HashAggregation) on all
+           host cores, one operator chain per thread over thread-local (first-touched) slices + FINAL merge.
+parity   : the GPU result of the full 600 M rows is compared with the oracle's on the same rows (counts exact, sums 1e-6) before timing.
+Q3 (join + agg, SF100), the INTEGER-coded Q1, the BASELINE configs[1] group-by kernels, the join and the repartition are in "extra".
+N > 1    : every rank holds its own SF100 lineitem shard (weak scaling): PARTIAL fused pipeline per GPU, one all-gather of the partial
+           pages, FINAL merge on rank 0 — Q1 has no row exchange; the repartitioned Q3 (configs[3]) and configs[4] are in "extra".
 """
 from __future__ import annotations
 
@@ -37,12 +41,14 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rows", type=int, default=1_000_000_000, help="rows per GPU (weak scaling)")
-    ap.add_argument("--groups", type=int, default=4, help="distinct bigint keys of the headline run (4 = TPC-H Q1-like)")
+    ap.add_argument("--rows", type=int, default=600_037_902, help="lineitem rows per GPU (SF100; weak scaling)")
+    ap.add_argument("--keys", default="varchar", choices=["varchar", "integer"], help="returnflag / linestatus as VARCHAR(1) (the reference's types) or INTEGER codes")
+    ap.add_argument("--parity", type=int, default=1, help="compare the full-size GPU result with the oracle before timing (rank 0, N = 1)")
+    ap.add_argument("--groups", type=int, default=4, help="(extras) distinct bigint keys")
     ap.add_argument("--e2e-rows", type=int, default=1 << 27, help="rows of the host-resident sample used for the e2e number")
     ap.add_argument("--cpu-rows", type=int, default=1 << 28, help="rows of the bounded sample the CPU baseline aggregates")
     ap.add_argument("--extra", type=int, default=1, help="also measure other cardinalities and the join (configs[2])")
-    ap.add_argument("--extra-scale", type=float, default=0.0, help="size of the extra measurements relative to SF100 (default: rows / 1e9)")
+    ap.add_argument("--extra-scale", type=float, default=0.0, help="size of the extra measurements relative to SF100 (default: rows / 600 037 902)")
     ap.add_argument("--only", default="", help="comma separated subset of the extra measurements (names of the extra keys)")
     return ap.parse_args()
 
@@ -153,35 +159,6 @@ def cpu_group_by(rows: int, groups: int, threads: int):
     dt = time.perf_counter() - t0
     n_groups = sum(p.position_count for p in out)
     return per * threads / dt, dt, n_groups
-
-
-def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port; the Java operators cannot run here: no JVM) on all host
-    cores, same metric / config; each step is a bounded sample of the workload."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    threads = os.cpu_count() or 1
-    sample = min(args.cpu_rows, args.rows)
-    sample -= sample % threads
-    times = []
-    for i in range(args.warmup + args.steps):
-        rps, dt, g = cpu_group_by(sample, args.groups, threads)
-        if i >= args.warmup:
-            times.append(dt)
-    ms = 1000 * float(np.mean(times))
-    value = sample / (ms / 1000)
-    line = {
-        "metric": "rows/sec", "value": value, "unit": "rows/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": dict(workload_config(args, sample), timing="host wall clock (time.perf_counter) around each step; no GPU involved",
-                       l2="host arm: not applicable"),
-        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} rows of the same synthetic batch per step, {threads} threads x one oracle operator each + FINAL merge"},
-        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print(json.dumps(line), flush=True)
 
 
 def workload_config(args, rows):
@@ -572,6 +549,305 @@ def run_q3_multi(torch, backend, device, n_orders_total, steps, warmup, dist):
             "lineitem_rows_per_s": int(n_li[0]) / (ms / 1000)}
 
 
+# =====================================================================================================================
+# Headline: TPC-H Q1 over SF100 lineitem
+# =====================================================================================================================
+Q1_SF100_ROWS = 600_037_902
+Q1_BYTES_PER_ROW = {"varchar": 46, "integer": 44}     # 2 x (4 B offset + 1 B) or 2 x 4 B codes, 4 x 8 B doubles, 4 B date
+
+
+def gen_q1_lineitem(torch, dev, rows, seed, key_kind="varchar"):
+    """TPC-H-shaped lineitem columns of Q1 in HBM (synthetic, seeded): shipdate U[1992-01-01, 1998-12-31); linestatus = 'O' iff
+    shipdate > 1995-06-17, returnflag = 'N' iff receiptdate (= shipdate + U[1, 30]) > 1995-06-17 else 'R' / 'A' — the four groups of
+    the real query ((A,F), (N,F), (N,O), (R,F)); quantity U{1..50}, extendedprice, discount {0.00..0.10}, tax {0.00..0.08} as DOUBLE."""
+    g = torch.Generator(device=dev); g.manual_seed(seed)
+    ship = torch.randint(8035, 10592, (rows,), dtype=torch.int32, device=dev, generator=g)
+    receipt = ship + torch.randint(1, 31, (rows,), dtype=torch.int32, device=dev, generator=g)
+    coin = torch.randint(0, 2, (rows,), dtype=torch.int32, device=dev, generator=g)
+    rf = torch.where(receipt > 9298, torch.full_like(coin, 1), coin * 2)          # 0 = 'A', 1 = 'N', 2 = 'R'
+    ls = (ship > 9298).to(torch.int32)                                            # 0 = 'F', 1 = 'O'
+    del receipt, coin
+    qty = torch.randint(1, 51, (rows,), device=dev, generator=g).to(torch.float64)
+    ep = torch.rand(rows, dtype=torch.float64, device=dev, generator=g) * 1e5
+    disc = torch.randint(0, 11, (rows,), device=dev, generator=g).to(torch.float64) / 100
+    tax = torch.randint(0, 9, (rows,), device=dev, generator=g).to(torch.float64) / 100
+    cols = {"qty": qty, "ep": ep, "disc": disc, "tax": tax, "ship": ship}
+    if key_kind == "varchar":
+        cols["rf"] = torch.tensor([65, 78, 82], dtype=torch.uint8, device=dev)[rf.long()]      # 'A' 'N' 'R'
+        cols["ls"] = torch.tensor([70, 79], dtype=torch.uint8, device=dev)[ls.long()]          # 'F' 'O'
+        cols["offsets"] = torch.arange(rows + 1, dtype=torch.int32, device=dev)                 # every slice is one byte long
+    else:
+        cols["rf"], cols["ls"] = rf, ls
+    return cols
+
+
+def q1_device_page(cols, key_kind, begin=0, end=None):
+    from presto_b200 import DATE, DOUBLE, INTEGER, VARCHAR, Block, Page
+    n = cols["ship"].numel() if end is None else end
+    m = n - begin
+    blocks = []
+    for k in ("rf", "ls"):
+        if key_kind == "varchar":
+            blocks.append(Block.device(VARCHAR, m, cols[k].data_ptr(), offsets_ptr=cols["offsets"].data_ptr() + 4 * begin, keepalive=[cols[k], cols["offsets"]]))
+        else:
+            blocks.append(Block.device(INTEGER, m, cols[k].data_ptr() + 4 * begin, keepalive=cols[k]))
+    for k in ("qty", "ep", "disc", "tax"):
+        blocks.append(Block.device(DOUBLE, m, cols[k].data_ptr() + 8 * begin, keepalive=cols[k]))
+    blocks.append(Block.device(DATE, m, cols["ship"].data_ptr() + 4 * begin, keepalive=cols["ship"]))
+    return Page(blocks, m)
+
+
+def q1_host_page(arrays, key_kind, b, e):
+    """Host page of rows [b, e) from numpy arrays (the CPU arm / the e2e leg)."""
+    from presto_b200 import DATE, DOUBLE, INTEGER, VARCHAR, Block, Page
+    blocks = []
+    for k in ("rf", "ls"):
+        if key_kind == "varchar":
+            blocks.append(Block(VARCHAR, e - b, arrays[k][b:e], None, arrays["offsets"][:e - b + 1]))
+        else:
+            blocks.append(Block.from_numpy(INTEGER, arrays[k][b:e]))
+    for k in ("qty", "ep", "disc", "tax"):
+        blocks.append(Block.from_numpy(DOUBLE, arrays[k][b:e]))
+    blocks.append(Block.from_numpy(DATE, arrays["ship"][b:e]))
+    return Page(blocks, e - b)
+
+
+def q1_operator(backend, key_kind, step, **opts):
+    from presto_b200 import INTEGER, VARCHAR, FusedAggregationOperator
+    from presto_b200.pipelines import Q1_AGGREGATES, q1_program_typed
+    kt = VARCHAR if key_kind == "varchar" else INTEGER
+    types = [kt, kt] + [3, 3, 3, 3, 4]
+    return FusedAggregationOperator(types, q1_program_typed(kt), [], [kt, kt], [0, 1], Q1_AGGREGATES, step=step, expected_groups=1024,
+                                    group_max_lengths=[1, 1] if key_kind == "varchar" else None, backend=backend, max_output_rows=1 << 30, **opts)
+
+
+def cpu_q1(torch, cols, key_kind, row_begin, row_end, threads, chunk=1 << 20):
+    """The reference's Q1 operators (oracle: FilterAndProject -> HashAggregation PARTIAL) on `threads` host threads over rows
+    [row_begin, row_end) of the device columns, then one FINAL merge.  Every thread copies ITS slice from the GPU into memory it
+    allocates and first-touches itself (NUMA-local pages), outside the timed region.  Returns (rows/s, seconds, result rows, host GB/s)."""
+    import oracle
+    from presto_b200 import STEP_FINAL, STEP_PARTIAL, HashAggregationOperator, INTEGER, VARCHAR, to_pages
+    from presto_b200.pipelines import Q1_AGGREGATES
+    ob = oracle.backend()
+    n = row_end - row_begin
+    per = (n + threads - 1) // threads
+    slices = [None] * threads
+    results = [None] * threads
+    start = threading.Barrier(threads + 1)
+    done = threading.Barrier(threads + 1)
+
+    def work(t):
+        b, e = row_begin + min(n, t * per), row_begin + min(n, (t + 1) * per)
+        local = {}
+        for k, v in cols.items():
+            if k == "offsets":
+                local[k] = np.arange(min(chunk, max(e - b, 1)) + 1, dtype=np.int32)
+                continue
+            a = np.empty(e - b, dtype={torch.uint8: np.uint8, torch.int32: np.int32, torch.float64: np.float64}[v.dtype])
+            if e > b:
+                torch.from_numpy(a).copy_(v[b:e])          # D2H into pages this thread touches first
+            local[k] = a
+        slices[t] = local
+        start.wait()
+        op = q1_operator(ob, key_kind, STEP_PARTIAL)
+        for c in range(0, e - b, chunk):
+            op.add_input(q1_host_page(local, key_kind, c, min(e - b, c + chunk)))
+        op.finish()
+        results[t] = op.get_output()
+        op.close()
+        done.wait()
+
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    [t.start() for t in ths]
+    start.wait()
+    t0 = time.perf_counter()
+    done.wait()
+    kt = VARCHAR if key_kind == "varchar" else INTEGER
+    # FINAL over the partial pages: keys, then (sum) / (sum, count) intermediate columns in aggregate order
+    from presto_b200 import AGG_AVG_DOUBLE, AGG_COUNT_STAR, AGG_SUM_DOUBLE, Aggregate
+    final_aggs, ch = [], 2
+    for a in Q1_AGGREGATES:
+        final_aggs.append(Aggregate(a.function, ch))
+        ch += 2 if a.function == AGG_AVG_DOUBLE else 1
+    final = HashAggregationOperator([kt, kt], [0, 1], final_aggs, step=STEP_FINAL, expected_groups=1024, group_max_lengths=[1, 1] if key_kind == "varchar" else None,
+                                    backend=ob, max_output_rows=1 << 30)
+    out = to_pages(final, [r for r in results if r is not None and r.position_count])
+    dt = time.perf_counter() - t0
+    [t.join() for t in ths]
+    rows = [r for p in out for r in p.rows()]
+    final.close()
+    return n / dt, dt, rows, n * Q1_BYTES_PER_ROW[key_kind] / dt / 1e9
+
+
+def merge_partials_on_root(torch, dist, page, backend, key_kind, device, stream):
+    """PARTIAL -> FINAL across ranks (Q1 has no row exchange): every rank's partial page (a few rows) travels in ONE fixed-size
+    all-gather; rank 0 feeds the concatenation to a FINAL HashAggregationOperator as a single page."""
+    from presto_b200 import AGG_AVG_DOUBLE, MEM_HOST, STEP_FINAL, Aggregate, HashAggregationOperator, INTEGER, VARCHAR
+    from presto_b200.exchange import _pack_page, _unpack_page
+    from presto_b200.pipelines import Q1_AGGREGATES
+    world, rank = dist.get_world_size(), dist.get_rank()
+    CAP = 1 << 14
+    buf = _pack_page(page)
+    assert buf.size + 8 <= CAP, "partial page larger than the merge buffer"
+    send = np.zeros(CAP, dtype=np.uint8)
+    send[:8] = np.frombuffer(np.int64(buf.size).tobytes(), dtype=np.uint8)
+    send[8:8 + buf.size] = buf
+    dev = torch.device("cuda", device)
+    s = torch.from_numpy(send).to(dev, non_blocking=True)
+    recv = torch.empty(world * CAP, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(recv, s)
+    if rank != 0:
+        return None
+    host = recv.cpu().numpy()
+    pages = []
+    for r in range(world):
+        size = int(np.frombuffer(host[r * CAP:r * CAP + 8].tobytes(), dtype=np.int64)[0])
+        p = _unpack_page(host[r * CAP + 8:r * CAP + 8 + size])
+        if p is not None:
+            pages.append(p)
+    kt = VARCHAR if key_kind == "varchar" else INTEGER
+    final_aggs, ch = [], 2
+    for a in Q1_AGGREGATES:
+        final_aggs.append(Aggregate(a.function, ch))
+        ch += 2 if a.function == AGG_AVG_DOUBLE else 1
+    final = HashAggregationOperator([kt, kt], [0, 1], final_aggs, step=STEP_FINAL, expected_groups=1024, group_max_lengths=[1, 1] if key_kind == "varchar" else None,
+                                    backend=backend, device=device, output_memory=MEM_HOST, cuda_stream=stream, max_output_rows=1 << 30)
+    for p in pages:
+        final.add_input(p)
+    final.finish()
+    out = final.get_output()
+    launches = final.get_stats()["kernel_launches"]
+    final.close()
+    return out, launches
+
+
+def run_q1_headline(torch, backend, cols, key_kind, steps, warmup, device, dist=None):
+    """One step = Q1 over the resident lineitem shard through the fused operator (+ the PARTIAL -> FINAL merge when N > 1)."""
+    from presto_b200 import MEM_DEVICE, MEM_HOST, STEP_PARTIAL, STEP_SINGLE
+    page = q1_device_page(cols, key_kind)
+    stream = torch.cuda.current_stream()
+    multi = dist is not None
+    ms, kms, launches, info, result = [], [], 0, {}, None
+    for i in range(warmup + steps):
+        # the result page (4 groups) is read back to the host inside the timed region
+        op = q1_operator(backend, key_kind, STEP_PARTIAL if multi else STEP_SINGLE, device=device, output_memory=MEM_HOST, cuda_stream=stream.cuda_stream)
+        e0, e1, e2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        op.add_input(page)
+        e1.record(stream)
+        op.finish()
+        out = op.get_output()
+        extra_launches = 0
+        if multi:
+            merged = merge_partials_on_root(torch, dist, out, backend, key_kind, device, stream.cuda_stream)
+            if merged is not None:
+                out, extra_launches = merged
+        e2.record(stream)
+        torch.cuda.synchronize()
+        if multi:
+            dist.barrier()
+        if i >= warmup:
+            ms.append(e0.elapsed_time(e2)); kms.append(e0.elapsed_time(e1))
+            st = op.get_stats()
+            launches = st["kernel_launches"] + extra_launches
+            info = dict(op.get_info(), kernel_paths=st["kernel_paths"], groups=st["group_count"])
+        if out is not None:
+            result = out.rows()
+        op.close()
+    return {"ms": float(np.mean(ms)), "kernel_ms": float(np.mean(kms)), "launches": int(launches), "info": info, "result": result}
+
+
+def run_q1_e2e(torch, backend, cols, key_kind, rows, steps, warmup, device):
+    """The same operator fed HOST (pinned) pages through the C ABI: every column crosses PCIe inside the timed region (staged in 2^23-row
+    chunks, copy / compute overlapped), the result page is read back."""
+    from presto_b200 import MEM_HOST, STEP_SINGLE
+    host = {}
+    for k, v in cols.items():
+        if k == "offsets":
+            host[k] = torch.arange(rows + 1, dtype=torch.int32).pin_memory().numpy()
+        else:
+            t = torch.empty(rows, dtype=v.dtype).pin_memory()
+            t.copy_(v[:rows])
+            host[k] = t.numpy()
+            host["_keep_" + k] = t
+    page = q1_host_page(host, key_kind, 0, rows)
+    times, h2d, d2h = [], 0, 0
+    for i in range(warmup + steps):
+        op = q1_operator(backend, key_kind, STEP_SINGLE, device=device, output_memory=MEM_HOST)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        op.add_input(page)
+        op.finish()
+        out = op.get_output()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+            st = op.get_stats(); h2d, d2h = st["h2d_bytes"], st["d2h_bytes"]
+        op.close()
+    return rows / float(np.mean(times)), int(h2d), int(d2h), out.rows()
+
+
+def rows_match(got, want, rel=1e-6):
+    """Keys / counts exact, double aggregates within `rel` (north_star); rows in the same (first-appearance) order."""
+    if got is None or want is None or len(got) != len(want):
+        return False
+    for g, w in zip(got, want):
+        if len(g) != len(w):
+            return False
+        for x, y in zip(g, w):
+            if isinstance(y, float):
+                if not (abs(x - y) <= rel * max(abs(x), abs(y)) or x == y):
+                    return False
+            elif x != y:
+                return False
+    return True
+
+
+def q1_config(args, key_kind):
+    rows = args.rows
+    return {"workload": f"TPC-H Q1 (filter/project -> hash aggregation, 4 groups, 8 aggregates) over SF100-sized lineitem: {rows} rows per GPU, "
+                        f"{'VARCHAR(1)' if key_kind == 'varchar' else 'INTEGER-coded'} returnflag / linestatus, {Q1_BYTES_PER_ROW[key_kind]} B/row (BASELINE.json metric; configs[0] shape at SF100)",
+            "rows_per_gpu": rows, "key_columns": key_kind, "bytes_per_row": Q1_BYTES_PER_ROW[key_kind],
+            "l2": "inputs (46 B/row x rows = 27.6 GB) far exceed the 126 MB L2; no flush needed",
+            "timing": "CUDA events on the operator stream, barrier + synchronize on both sides, max over ranks"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU operators for the same workload (oracle port; the Java operators cannot run here: no JVM)
+    on all host cores; each step is a bounded sample of the workload.  The sample is generated on the GPU (same generator as the GPU
+    arm) and copied to thread-local host memory before the clock starts."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    sample = min(args.cpu_rows, args.rows)
+    dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+    cols = gen_q1_lineitem(torch, dev, sample, 1, args.keys)
+    times, gbs = [], 0.0
+    for i in range(args.warmup + args.steps):
+        rps, dt, rows, gbs = cpu_q1(torch, cols, args.keys, 0, sample, threads)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1000 * float(np.mean(times))
+    value = sample / (ms / 1000)
+    line = {
+        "metric": "rows/sec", "value": value, "unit": "rows/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": q1_config(args, args.keys),
+        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port", "host_gbs": sample * Q1_BYTES_PER_ROW[args.keys] / (ms / 1000) / 1e9,
+                         "sample": f"{sample} rows of the workload per step, {threads} threads x (oracle FilterAndProject -> HashAggregation PARTIAL over thread-local, "
+                                   f"first-touched slices in 2^20-row pages) + FINAL merge; host wall clock, no GPU in the timed region"},
+        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -591,25 +867,33 @@ def main():
     backend = load()
     backend.check(backend.set_device(local))
     dev = f"cuda:{local}"
-    from presto_b200 import BIGINT, DOUBLE
-    from presto_b200.synthetic import fill_double_column_torch, fill_group_key_torch
-
-    rows = args.rows
+    rows, kk = args.rows, args.keys
     peak, peak_kind = peaks()
-    # ---- synthetic batch resident in HBM (each rank its own row range: weak scaling) ----
-    row0 = rank * rows
-    keys = torch.empty(rows, dtype=torch.int64, device=dev)
-    cols = [torch.empty(rows, dtype=torch.float64, device=dev) for _ in range(4)]
-    fill_group_key_torch(keys, row0, args.groups)
-    for c in range(4):
-        fill_double_column_torch(cols[c], c, row0)
+    bpr = Q1_BYTES_PER_ROW[kk]
+
+    # ---- SF100 lineitem shard resident in HBM (each rank its own seed: weak scaling) ----
+    cols = gen_q1_lineitem(torch, dev, rows, 1 + rank, kk)
     torch.cuda.synchronize()
-    page = device_page(torch, [keys] + cols, [BIGINT] + [DOUBLE] * 4)
+
+    # ---- parity at the BASELINE size: the GPU's result over ALL rows vs the oracle's over the same rows (before any timing) ----
+    parity = None
+    if rank == 0 and args.parity:
+        threads = os.cpu_count() or 1
+        r0 = run_q1_headline(torch, backend, cols, kk, 1, 0, local, None)
+        _, dt, want, _ = cpu_q1(torch, cols, kk, 0, rows, threads)
+        ok = rows_match(r0["result"], want)
+        parity = {"checked": True, "ok": bool(ok), "rows": rows, "groups": len(want), "against": f"oracle operators on {threads} host threads over the same {rows} rows ({dt:.1f} s)",
+                  "rule": "group keys, group order and count(*) exact; sums / averages within 1e-6 relative"}
+        if not ok:
+            print(json.dumps({"error": "GPU result differs from the oracle at the BASELINE size", "gpu": r0["result"], "oracle": want}), file=sys.stderr, flush=True)
+            raise SystemExit(3)
+    if dist is not None:
+        dist.barrier()
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    r = run_group_by(torch, backend, page, rows, max(args.groups, 1024), args.steps, args.warmup, local, dist)
+    r = run_q1_headline(torch, backend, cols, kk, args.steps, args.warmup, local, dist)
     clocks = sampler.stop() if rank == 0 else None
     ms, kms = r["ms"], r["kernel_ms"]
     if dist is not None:
@@ -617,92 +901,111 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, kms = float(t[0]), float(t[1])
     value = rows * world / (ms / 1000)
+    if dist is not None and rank == 0 and args.parity:
+        # N > 1: the merged result must account for every selected row of every rank (count(*) summed) — checked against torch reductions
+        pass
+    sel = torch.tensor([int((cols["ship"] <= 10471).sum())], dtype=torch.int64, device=dev)
+    if dist is not None:
+        dist.all_reduce(sel)
+    multi_parity = None
+    if rank == 0 and r["result"] is not None:
+        counted = sum(row[-1] for row in r["result"])
+        multi_parity = {"count_star_total": int(counted), "selected_rows_all_ranks": int(sel[0]), "ok": int(counted) == int(sel[0])}
+        if not multi_parity["ok"]:
+            print(json.dumps({"error": "count(*) over the groups differs from the rows the filter selects", **multi_parity}), file=sys.stderr, flush=True)
+            raise SystemExit(3)
 
-    extra = {}
-    cpu = None
     # ---- end to end through the C ABI with host pages (every rank feeds its own GPU over its own PCIe link) ----
     e2e_rows = min(args.e2e_rows, rows)
-    e2e_rps, h2d, d2h, _ = run_e2e(torch, backend, e2e_rows, args.groups, max(2, min(args.steps, 3)), 1, local)
+    e2e_rps, h2d, d2h, e2e_result = run_q1_e2e(torch, backend, cols, kk, e2e_rows, max(2, min(args.steps, 3)), 1, local)
     if dist is not None:
         t = torch.tensor([e2e_rps], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         e2e_rps = float(t[0])
     e2e = {"value": e2e_rps * world, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "sample": f"{e2e_rows} host-resident (pinned) rows per step per GPU, staged in 2^23-row chunks (copy/compute overlapped)"}
+           "sample": f"{e2e_rows} host-resident (pinned) rows per step per GPU through pg_operator_add_input, staged in 2^23-row chunks (copy / compute overlapped)"}
+
+    extra, cpu = {}, None
+    only = set(x for x in args.only.split(",") if x)
+    scale = args.extra_scale or min(1.0, rows / Q1_SF100_ROWS)
+    if rank == 0 and world == 1:
+        threads = os.cpu_count() or 1
+        sample = min(args.cpu_rows, rows)
+        rps, dt, _, gbs = cpu_q1(torch, cols, kk, 0, sample, threads)
+        cpu = {"value": rps, "unit": "rows/s", "cores": threads, "kind": "port", "host_gbs": gbs,
+               "sample": f"{sample} rows of the same lineitem, {threads} threads x (oracle FilterAndProject -> HashAggregation PARTIAL over thread-local first-touched slices) + FINAL merge, {dt:.2f} s"}
+    del cols
+    torch.cuda.empty_cache()
+    backend.release_cached_memory()
     if world > 1 and args.extra:
-        del page
-        del keys, cols
-        torch.cuda.empty_cache()
         try:
             extra["partitioned_output_all_to_all"] = run_partitioned_output(torch, backend, local, min(rows, 1 << 27), world, 2, 1, dist)
         except Exception as e:
             extra["partitioned_output_all_to_all"] = {"error": str(e)[:200]}
         torch.cuda.empty_cache()
         try:
-            scale = args.extra_scale or min(1.0, rows / 1_000_000_000)
             extra["q3_repartitioned"] = run_q3_multi(torch, backend, local, int(150_000_000 * scale), 2, 1, dist)
         except Exception as e:
             extra["q3_repartitioned"] = {"error": str(e)[:300]}
-    if rank == 0 and world == 1:
-        # ---- CPU baseline: oracle on the host cores, bounded sample ----
-        threads = os.cpu_count() or 1
-        sample = min(args.cpu_rows, rows); sample -= sample % threads
-        rps, dt, g = cpu_group_by(sample, args.groups, threads)
-        cpu = {"value": rps, "unit": "rows/s", "cores": threads, "kind": "port",
-               "sample": f"{sample} rows of the same batch, {threads} threads x one oracle HashAggregationOperator (PARTIAL) + FINAL merge, {dt:.2f} s"}
-        if args.extra:
-            del page
-            only = set(x for x in args.only.split(",") if x)
-            for g_other in (10_000, 3_000_000):
-                if g_other == args.groups or (only and f"group_by_{g_other}_groups" not in only):
-                    continue
-                fill_group_key_torch(keys, row0, g_other)
+    if rank == 0 and world == 1 and args.extra:
+        from presto_b200 import BIGINT, DOUBLE
+        from presto_b200.synthetic import fill_double_column_torch, fill_group_key_torch
+
+        def group_by_kernels():
+            """BASELINE configs[1]: GroupByHash over 1 B synthetic rows (bigint key, 4 x sum(double), 40 B/row) at 4 / 10^4 / 3 x 10^6 groups."""
+            n = int(1_000_000_000 * scale)
+            keys = torch.empty(n, dtype=torch.int64, device=dev)
+            vals = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(4)]
+            for c in range(4):
+                fill_double_column_torch(vals[c], c, 0)
+            out = {}
+            for g in (4, 10_000, 3_000_000):
+                fill_group_key_torch(keys, 0, g)
                 torch.cuda.synchronize()
-                pg2 = device_page(torch, [keys] + cols, [BIGINT] + [DOUBLE] * 4)
-                rr = run_group_by(torch, backend, pg2, rows, g_other, max(2, args.steps // 2), 1, local)
-                extra[f"group_by_{g_other}_groups"] = {"rows_per_s": rows / (rr["ms"] / 1000), "ms_per_step": rr["ms"], "groups": rr["groups"],
-                                                      "roofline_frac": ALGO_BYTES_PER_ROW * rows / (rr["kernel_ms"] / 1000) / 1e9 / peak}
-                del pg2
-            del keys, cols
+                pg = device_page(torch, [keys] + vals, [BIGINT] + [DOUBLE] * 4)
+                rr = run_group_by(torch, backend, pg, n, max(g, 1024), 3, 2, local)
+                out[f"{g}_groups"] = {"rows": n, "rows_per_s": n / (rr["ms"] / 1000), "ms_per_step": rr["ms"], "groups": rr["groups"],
+                                      "roofline_frac": ALGO_BYTES_PER_ROW * n / (rr["kernel_ms"] / 1000) / 1e9 / peak}
+            return out
+
+        for name, fn in [
+            ("q3_pipeline", lambda: run_q3(torch, backend, local, int(150_000_000 * scale), 3, 2)),
+            ("q1_pipeline_integer_keys", lambda: run_q1_pipeline(torch, backend, local, int(Q1_SF100_ROWS * scale), 3, 2)),
+            ("group_by_1b_rows", group_by_kernels),
+            ("hash_join_orders_lineitem", lambda: run_join(torch, backend, local, int(150_000_000 * scale), int(600_037_902 * scale), 2, 1)),
+            ("partitioned_output_8_bigint_cols", lambda: run_partitioned_output(torch, backend, local, int((1 << 28) * scale), 8, 2, 1)),
+            ("page_processor_q1", lambda: run_page_processor_q1(torch, backend, local, int((1 << 28) * scale), 2, 1)),
+            ("serialized_page_8_bigint_cols", lambda: run_serialized_page(torch, backend, local, int((1 << 24) * scale), 3, 2)),
+            ("q1_pipeline_unfused", lambda: run_q1_pipeline(torch, backend, local, int(Q1_SF100_ROWS * scale), 2, 1, fused=False)),
+            ("q3_pipeline_unfused", lambda: run_q3(torch, backend, local, int(150_000_000 * scale), 2, 1, fused=False)),
+        ]:
+            if only and name not in only:
+                continue
+            try:   # the extras must never take the headline down
+                extra[name] = fn()
+                if "achieved_gbs" in extra[name]:
+                    extra[name]["roofline_frac"] = extra[name]["achieved_gbs"] / peak
+                if "partition_gbs" in extra[name]:
+                    extra[name]["roofline_frac"] = extra[name]["partition_gbs"] / peak
+            except Exception as e:
+                extra[name] = {"error": str(e)[:200]}
             torch.cuda.empty_cache()
-            backend.release_cached_memory()
-            scale = args.extra_scale or min(1.0, rows / 1_000_000_000)
-            for name, fn in [
-                ("hash_join_orders_lineitem", lambda: run_join(torch, backend, local, int(150_000_000 * scale), int(600_037_902 * scale), 2, 1)),
-                ("partitioned_output_8_bigint_cols", lambda: run_partitioned_output(torch, backend, local, int((1 << 28) * scale), 8, 2, 1)),
-                ("page_processor_q1", lambda: run_page_processor_q1(torch, backend, local, int((1 << 28) * scale), 2, 1)),
-                ("serialized_page_8_bigint_cols", lambda: run_serialized_page(torch, backend, local, int((1 << 24) * scale), 3, 2)),
-                ("q1_pipeline", lambda: run_q1_pipeline(torch, backend, local, int(600_037_902 * scale), 3, 2)),
-                ("q1_pipeline_unfused", lambda: run_q1_pipeline(torch, backend, local, int(600_037_902 * scale), 2, 1, fused=False)),
-                ("q3_pipeline", lambda: run_q3(torch, backend, local, int(150_000_000 * scale), 3, 2)),
-                ("q3_pipeline_unfused", lambda: run_q3(torch, backend, local, int(150_000_000 * scale), 2, 1, fused=False)),
-            ]:
-                if only and name not in only:
-                    continue
-                try:   # the extras must never take the headline down
-                    extra[name] = fn()
-                    if "achieved_gbs" in extra[name]:
-                        extra[name]["roofline_frac"] = extra[name]["achieved_gbs"] / peak
-                    if "partition_gbs" in extra[name]:
-                        extra[name]["roofline_frac"] = extra[name]["partition_gbs"] / peak
-                except Exception as e:
-                    extra[name] = {"error": str(e)[:200]}
-                torch.cuda.empty_cache()
-                backend.release_cached_memory()      # each measurement starts from an empty block cache, like the isolated runs
+            backend.release_cached_memory()      # each measurement starts from an empty block cache, like the isolated runs
 
     if rank == 0:
-        achieved = ALGO_BYTES_PER_ROW * rows / (kms / 1000) / 1e9
+        achieved = bpr * rows / (kms / 1000) / 1e9
         line = {
             "metric": "rows/sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(args, rows), parallelism=(f"{world} ranks: PARTIAL per GPU + FINAL merge on rank 0, no row exchange" if world > 1 else "1 GPU")),
+            "config": dict(q1_config(args, kk), parallelism=(f"{world} ranks: PARTIAL fused pipeline per GPU + one all-gather of the partial pages + FINAL merge on rank 0, no row exchange" if world > 1 else "1 GPU")),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel: 39.84 GB for the 995.8 M rows of its launch
-                         # (profiles/r01_ncu_hashagg_fast_1b.txt, one ncu --set full capture) = 40.01 B/row; only quoted for that workload
-                         "traffic": NCU_DRAM_BYTES_PER_ROW * rows if (args.groups == 4 and rows >= 100_000_000) else None,
-                         "kernel": "pg::hashAggFastKernel<4,0,false>", "peak_source": peak_kind,
-                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ROW * rows, "kernel_ms": kms},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": r["launches"], "groups": r["groups"], "clocks": clocks, "extra": extra,
+                         # dram__bytes of the fused kernel from the ncu --set full capture in profiles/ (quoted, not re-measured per run)
+                         "traffic": None, "traffic_note": "see profiles/r02_ncu_q1_fused.txt (dram__bytes_read + write of the same kernel, per launch)",
+                         "kernel": "fused_kernel (generated: fused_codegen.cpp + fused_agg.cuh, NVRTC sm_100a)", "peak_source": peak_kind,
+                         "algorithmic_bytes_per_launch": bpr * rows, "kernel_ms": kms},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": r["launches"], "groups": len(r["result"] or []), "result": r["result"],
+            "fused": r["info"], "parity_checked": bool(parity and parity["ok"]) if world == 1 else bool(multi_parity and multi_parity["ok"]),
+            "parity": parity, "parity_counts": multi_parity, "clocks": clocks, "extra": extra,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

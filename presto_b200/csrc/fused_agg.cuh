@@ -198,11 +198,9 @@ struct FusedAggSink {
             __syncwarp();
         }
     }
-    // called by ALL lanes of the warp (live = this lane has a surviving row)
-    __device__ __forceinline__ void push(bool live, const uint64_t (&kw)[W], int special, uint32_t spell, const uint64_t (&vals)[NVA], uint32_t rowIdx)
+    // called by ALL lanes of the warp (live = this lane has a surviving row; m = the warp's ballot of `live`, not zero)
+    __device__ __forceinline__ void push(unsigned m, bool live, const uint64_t (&kw)[W], int special, uint32_t spell, const uint64_t (&vals)[NVA], uint32_t rowIdx)
     {
-        const unsigned m = __ballot_sync(0xffffffffu, live);
-        if (m == 0) return;
         if (live) {
             QueueEntry& e = queue[qCount + __popc(m & ((1u << (tid & 31)) - 1))];
 #pragma unroll

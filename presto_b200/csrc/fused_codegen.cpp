@@ -441,50 +441,48 @@ std::string generateFusedAggSource(const FusedProgramDesc& D, FusedKernelInfo& i
             if (k.kind != 'i') return decline("join key must be an integer channel");
             g.emit("const unsigned long long ix" + js + "_" + us + " = (unsigned long long) (" + k.v + " - P.joins[" + js + "].D.minKey);");
             g.emit("const bool ir" + js + "_" + us + " = in" + js + "_" + us + (k.z.empty() ? "" : " && !" + k.z) + " && ix" + js + "_" + us + " < P.joins[" + js + "].D.range;");
-            if (membershipOnly)
-                g.emit("const unsigned long long bw" + js + "_" + us + " = ir" + js + "_" + us + " ? __ldg(P.joins[" + js + "].D.bitmap + (ix" + js + "_" + us + " >> 6)) : 0ULL;");
-            else {
-                g.emit("ulonglong4 bs" + js + "_" + us + " = make_ulonglong4(0, 0, 0, 0); unsigned int pf" + js + "_" + us + " = 0;");
-                g.emit("if (ir" + js + "_" + us + ") { const ulonglong2* bp = (const ulonglong2*) (P.joins[" + js + "].D.bitmap + (ix" + js + "_" + us + " >> 8) * 4); const ulonglong2 lo = __ldg(bp), hi = __ldg(bp + 1); "
-                       "bs" + js + "_" + us + " = make_ulonglong4(lo.x, lo.y, hi.x, hi.y); pf" + js + "_" + us + " = __ldg(P.joins[" + js + "].D.prefix + (ix" + js + "_" + us + " >> 8)); }");
-            }
+            // one 8-byte bitmap word decides membership (L2 resident: range / 8 bytes); the rest of the 32-byte block, the rank directory
+            // and the payload row are only touched by the rows that matched
+            g.emit("const unsigned long long bw" + js + "_" + us + " = ir" + js + "_" + us + " ? __ldg(P.joins[" + js + "].D.bitmap + (ix" + js + "_" + us + " >> 6)) : 0ULL;");
             (void) guard;
         }
         flush();
-        // B2: membership / rank, narrow `live`, payload loads
+        // B2: membership narrows `live`; matched rows fetch their rank (block popcounts + directory word) and payload row
         for (int u = 0; u < R; u++) {
             const std::string us = std::to_string(u), s = js + "_" + us;
-            if (membershipOnly) g.emit("live" + us + " = ir" + s + " && ((bw" + s + " >> (ix" + s + " & 63)) & 1ULL);");
-            else {
-                g.emit("const unsigned int wi" + s + " = (unsigned int) (ix" + s + " >> 6) & 3u;");
-                g.emit("const unsigned long long wd" + s + " = wi" + s + " == 0 ? bs" + s + ".x : wi" + s + " == 1 ? bs" + s + ".y : wi" + s + " == 2 ? bs" + s + ".z : bs" + s + ".w;");
-                g.emit("const unsigned long long bt" + s + " = 1ULL << (ix" + s + " & 63);");
-                g.emit("live" + us + " = ir" + s + " && (wd" + s + " & bt" + s + ") != 0;");
-                g.emit("unsigned int rk" + s + " = pf" + s + " + __popcll(wd" + s + " & (bt" + s + " - 1));");
-                g.emit("if (wi" + s + " > 0) rk" + s + " += __popcll(bs" + s + ".x); if (wi" + s + " > 1) rk" + s + " += __popcll(bs" + s + ".y); if (wi" + s + " > 2) rk" + s + " += __popcll(bs" + s + ".z);");
-                g.emit("unsigned long long pw" + s + "[" + std::to_string(J.strideWords) + "];");
-                for (int k = 0; k < J.strideWords; k++)
-                    g.emit("pw" + s + "[" + std::to_string(k) + "] = live" + us + " ? __ldg(P.joins[" + js + "].rows + (unsigned long long) rk" + s + " * " + std::to_string(J.strideWords) + " + " + std::to_string(k) + ") : 0ULL;");
+            g.emit("const unsigned long long bt" + s + " = 1ULL << (ix" + s + " & 63);");
+            g.emit("live" + us + " = ir" + s + " && (bw" + s + " & bt" + s + ") != 0;");
+            if (!membershipOnly) {
+                std::string init = "unsigned long long pw" + s + "[" + std::to_string(J.strideWords) + "] = {";
+                for (int k = 0; k < J.strideWords; k++) init += k ? ", 0" : "0";
+                g.emit(init + "};");
+                std::string code = "if (live" + us + ") { const unsigned long long* bp = P.joins[" + js + "].D.bitmap + (ix" + s + " >> 8) * 4; const unsigned int wi = (unsigned int) (ix" + s + " >> 6) & 3u; "
+                                   "unsigned int rk = __ldg(P.joins[" + js + "].D.prefix + (ix" + s + " >> 8)) + __popcll(bw" + s + " & (bt" + s + " - 1)); "
+                                   "if (wi > 0) rk += __popcll(__ldg(bp)); if (wi > 1) rk += __popcll(__ldg(bp + 1)); if (wi > 2) rk += __popcll(__ldg(bp + 2)); "
+                                   "const unsigned long long* pr = P.joins[" + js + "].rows + (unsigned long long) rk * " + std::to_string(J.strideWords) + "; ";
+                for (int k = 0; k < J.strideWords; k++) code += "pw" + s + "[" + std::to_string(k) + "] = __ldg(pr + " + std::to_string(k) + "); ";
+                g.emit(code + "}");
             }
         }
         flush();
     }
-    // stage C1: aggregate inputs and key fields of all rows (lazy loads in flight together)
-    struct KeyEval { Val v; };
+    // stage C: aggregate inputs and key fields (C1), key packing + hand-over to the aggregation (C2).
+    //   without joins: C1 of all R rows first (their lazy loads in flight together), then C2 under `if (go)`;
+    //   with joins (survivor queue): per row slot, everything inside `if (any lane of the warp still holds a row)` — after a selective
+    //   probe most warps skip the whole stage.
     std::vector<std::vector<Val>> keyVals(R), accVals(R);
-    for (int u = 0; u < R; u++) {
+    auto emitC1 = [&](int u) -> bool {
         const std::string us = std::to_string(u);
-        g.emit("const bool go" + us + " = live" + us + ";");
         for (const auto& a : D.accs) {
             Val v = chanVal(fin[a.channel], u, "go" + us);
-            if (!g.fail.empty()) return decline(g.fail);
-            if (!v.z.empty()) return decline("nullable aggregate input");
-            if (a.fromBigint ? v.kind != 'i' : v.kind != 'd') return decline("aggregate input type");
+            if (!g.fail.empty()) return false;
+            if (!v.z.empty()) { g.fail = "nullable aggregate input"; return false; }
+            if (a.fromBigint ? v.kind != 'i' : v.kind != 'd') { g.fail = "aggregate input type"; return false; }
             accVals[u].push_back(v);
         }
         for (const auto& k : D.keys) {
             Val v = chanVal(fin[k.channel], u, "go" + us);
-            if (!g.fail.empty()) return decline(g.fail);
+            if (!g.fail.empty()) return false;
             if (v.kind == 's') {
                 // VARCHAR(n <= 7) key: [length byte][bytes] exactly as group_table.cuh packKey packs it
                 const std::string id = "k" + std::to_string(&k - &D.keys[0]) + "_" + us, cs = std::to_string(v.channel);
@@ -497,17 +495,16 @@ std::string generateFusedAggSource(const FusedProgramDesc& D, FusedKernelInfo& i
             }
             keyVals[u].push_back(v);
         }
-    }
-    flush();
-    // stage C2: pack keys, hand the row to the aggregation
-    for (int u = 0; u < R; u++) {
+        return true;
+    };
+    auto emitC2 = [&](int u, std::ostringstream& body) -> bool {
         const std::string us = std::to_string(u);
         body << (info.queue ? "        {\n" : "        if (go" + us + ") {\n");
         body << "            unsigned long long kw[" << D.W << "]; int special = 0; unsigned int spell = 0;\n";
         for (int w = 0; w < D.W; w++) body << "            kw[" << w << "] = 0;\n";
         if (D.bigintPath) {
             const Val& v = keyVals[u][0];
-            if (v.kind != 'i') return decline("BIGINT key expected");
+            if (v.kind != 'i') { g.fail = "BIGINT key expected"; return false; }
             body << "            kw[0] = (unsigned long long) " << v.v << ";\n";
             if (!v.z.empty()) body << "            if (" << v.z << ") { special = 1; kw[0] = 0; } else\n";
             body << "            if (kw[0] == kEmptyKey) special = 2;\n";
@@ -519,18 +516,18 @@ std::string generateFusedAggSource(const FusedProgramDesc& D, FusedKernelInfo& i
                 const Val& v = keyVals[u][k];
                 std::string bits;
                 switch (f.type) {
-                    case PG_TYPE_BIGINT: if (v.kind != 'i') return decline("key type"); bits = "(unsigned long long) " + v.v; break;
-                    case PG_TYPE_INTEGER: case PG_TYPE_DATE: if (v.kind != 'i') return decline("key type"); bits = "(unsigned long long) (unsigned int) " + v.v; break;
-                    case PG_TYPE_BOOLEAN: if (v.kind != 'b') return decline("key type"); bits = "(" + v.v + " ? 1ULL : 0ULL)"; break;
-                    case PG_TYPE_VARCHAR: if (v.kind != 's') return decline("VARCHAR keys must be input columns passed through"); bits = v.v; break;
+                    case PG_TYPE_BIGINT: if (v.kind != 'i') { g.fail = "key type"; return false; } bits = "(unsigned long long) " + v.v; break;
+                    case PG_TYPE_INTEGER: case PG_TYPE_DATE: if (v.kind != 'i') { g.fail = "key type"; return false; } bits = "(unsigned long long) (unsigned int) " + v.v; break;
+                    case PG_TYPE_BOOLEAN: if (v.kind != 'b') { g.fail = "key type"; return false; } bits = "(" + v.v + " ? 1ULL : 0ULL)"; break;
+                    case PG_TYPE_VARCHAR: if (v.kind != 's') { g.fail = "VARCHAR keys must be input columns passed through"; return false; } bits = v.v; break;
                     case PG_TYPE_DOUBLE: {
-                        if (v.kind != 'd') return decline("key type");
+                        if (v.kind != 'd') { g.fail = "key type"; return false; }
                         body << "            unsigned long long d" << k << " = (unsigned long long) canonicalDoubleBits(__double_as_longlong(" << v.v << "));\n"
                              << "            if (d" << k << " == 0x8000000000000000ULL) { d" << k << " = 0; spell |= " << (1u << k) << "u; }\n";
                         bits = "d" + std::to_string(k);
                         break;
                     }
-                    default: return decline("group-by key type");
+                    default: g.fail = "group-by key type"; return false;
                 }
                 if (!v.z.empty()) body << "            if (" << v.z << ") nullMask |= " << (1u << k) << "u; else\n";
                 body << "            kw[" << f.word << "] |= (" << bits << ") << " << f.shift << ";\n";
@@ -539,13 +536,30 @@ std::string generateFusedAggSource(const FusedProgramDesc& D, FusedKernelInfo& i
             if (D.W == 1) body << "            if (kw[0] == kEmptyKey) special = 2;\n";
         }
         body << "            unsigned long long vals[" << (NV > 0 ? NV : 1) << "];\n";
+        if (NV == 0) body << "            vals[0] = 0;\n";
         for (int c = 0; c < NV; c++) {
             const Val& v = accVals[u][c];
             if (D.accs[c].fromBigint) body << "            vals[" << c << "] = (unsigned long long) __double_as_longlong(__ll2double_rn(" << v.v << "));\n";
             else body << "            vals[" << c << "] = (unsigned long long) __double_as_longlong(" << v.v << ");\n";
         }
-        if (info.queue) body << "            sink.push(go" << us << ", kw, special, spell, vals, (unsigned int) row" << us << ");\n        }\n";
+        if (info.queue) body << "            sink.push(m" << us << ", go" << us << ", kw, special, spell, vals, (unsigned int) row" << us << ");\n        }\n";
         else body << "            sink.add(kw, special, spell, vals, (unsigned int) row" << us << ");\n        }\n";
+        return true;
+    };
+    if (!info.queue) {
+        for (int u = 0; u < R; u++) { g.emit("const bool go" + std::to_string(u) + " = live" + std::to_string(u) + ";"); if (!emitC1(u)) return decline(g.fail); }
+        flush();
+        for (int u = 0; u < R; u++) if (!emitC2(u, body)) return decline(g.fail);
+    }
+    else {
+        for (int u = 0; u < R; u++) {
+            const std::string us = std::to_string(u);
+            body << "        const bool go" << us << " = live" << us << ";\n        const unsigned int m" << us << " = __ballot_sync(0xffffffffu, go" << us << ");\n        if (m" << us << ") {\n";
+            if (!emitC1(u)) return decline(g.fail);
+            flush();
+            if (!emitC2(u, body)) return decline(g.fail);
+            body << "        }\n";
+        }
     }
     if (!g.fail.empty()) return decline(g.fail);
 

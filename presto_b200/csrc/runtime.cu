@@ -195,14 +195,17 @@ int PageStager::stage(const pg_page* page, const std::vector<int>& channels, std
             if (b.type == PG_TYPE_VARCHAR) {
                 PG_CHECK_ARG(b.offsets != nullptr, "VARCHAR block without offsets");
                 size_t obytes = (size_t) (entries + 1) * 4;
-                size_t vbytes = (size_t) b.offsets[entries];
+                // only the bytes this block's offsets cover travel (a sub-range of a larger block shares the byte slice: offsets stay
+                // absolute, so the device base pointer is moved back by the first offset instead of rebasing every offset)
+                const size_t first = encoded ? 0 : (size_t) b.offsets[0];
+                size_t vbytes = (size_t) b.offsets[entries] - first;
                 // encoded: the dictionary goes to the scratch buffer (bytes, then offsets, then ids); the flat column is built below
                 DeviceBuffer& vb = encoded ? slot.scratch[i] : slot.values[i];
                 const size_t offAt = (vbytes + 15) & ~size_t(15), idsAt = (offAt + obytes + 15) & ~size_t(15);
                 vb.reserve(encoded ? idsAt + (size_t) c.n * 4 + 16 : vbytes + 16);
-                if (vbytes) PG_CUDA(cudaMemcpyAsync(vb.ptr, b.values, vbytes, cudaMemcpyHostToDevice, cs));
+                if (vbytes) PG_CUDA(cudaMemcpyAsync(vb.ptr, (const char*) b.values + first, vbytes, cudaMemcpyHostToDevice, cs));
                 op->stats.h2d_bytes += (int64_t) (obytes + vbytes);
-                dValues = vb.ptr;
+                dValues = (const char*) vb.ptr - first;
                 if (!encoded) {
                     slot.offsets[i].reserve(obytes);
                     PG_CUDA(cudaMemcpyAsync(slot.offsets[i].ptr, b.offsets, obytes, cudaMemcpyHostToDevice, cs));

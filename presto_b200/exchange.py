@@ -260,9 +260,16 @@ def _pack_page(page: Optional[Page]) -> np.ndarray:
     head = [len(page.blocks), n]
     parts = []
     for b in page.blocks:
-        assert b.type != abi.VARCHAR and b.encoding == abi.ENC_FLAT and not b.on_device, "partial aggregation states are flat fixed-width host columns"
+        assert b.encoding == abi.ENC_FLAT and not b.on_device, "partial aggregation states are flat host columns"
         head += [b.type, 1 if b.is_null is not None else 0]
-        parts.append(np.ascontiguousarray(b.values).view(np.uint8)[: n * TYPE_WIDTH[b.type]])
+        if b.type == abi.VARCHAR:      # (group keys) offsets rebased to 0, then the byte count, then the bytes
+            offs = np.ascontiguousarray(b.offsets[: n + 1], dtype=np.int32)
+            lo, hi = int(offs[0]), int(offs[n])
+            parts.append((offs - lo).astype(np.int32).view(np.uint8))
+            parts.append(np.asarray([hi - lo], dtype=np.int64).view(np.uint8))
+            parts.append(np.ascontiguousarray(b.values).view(np.uint8)[lo:hi])
+        else:
+            parts.append(np.ascontiguousarray(b.values).view(np.uint8)[: n * TYPE_WIDTH[b.type]])
         if b.is_null is not None:
             parts.append(np.ascontiguousarray(b.is_null, dtype=np.uint8)[:n])
     return np.concatenate([np.asarray(head, dtype=np.int64).view(np.uint8)] + parts)
@@ -278,12 +285,18 @@ def _unpack_page(buf: np.ndarray) -> Optional[Page]:
     from .page import _NP_DTYPE
     for c in range(n_cols):
         t, has_nulls = int(meta[2 * c]), int(meta[2 * c + 1])
-        nbytes = n * TYPE_WIDTH[t]
-        vals = buf[off:off + nbytes].copy().view(_NP_DTYPE[t]); off += nbytes
+        offsets = None
+        if t == abi.VARCHAR:
+            offsets = buf[off:off + 4 * (n + 1)].copy().view(np.int32); off += 4 * (n + 1)
+            nbytes = int(buf[off:off + 8].copy().view(np.int64)[0]); off += 8
+            vals = buf[off:off + nbytes].copy() if nbytes else np.zeros(1, dtype=np.uint8); off += nbytes
+        else:
+            nbytes = n * TYPE_WIDTH[t]
+            vals = buf[off:off + nbytes].copy().view(_NP_DTYPE[t]); off += nbytes
         nulls = None
         if has_nulls:
             nulls = buf[off:off + n].copy(); off += n
-        blocks.append(Block(t, n, vals, nulls))
+        blocks.append(Block(t, n, vals, nulls, offsets))
     return Page(blocks, n)
 
 
