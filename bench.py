@@ -674,7 +674,7 @@ def cpu_q1(torch, cols, key_kind, row_begin, row_end, threads, chunk=1 << 20):
     out = to_pages(final, [r for r in results if r is not None and r.position_count])
     dt = time.perf_counter() - t0
     [t.join() for t in ths]
-    rows = [r for p in out for r in p.rows()]
+    rows = [tuple(v.decode() if isinstance(v, bytes) else v for v in r) for p in out for r in p.rows()]
     final.close()
     return n / dt, dt, rows, n * Q1_BYTES_PER_ROW[key_kind] / dt / 1e9
 
@@ -755,7 +755,7 @@ def run_q1_headline(torch, backend, cols, key_kind, steps, warmup, device, dist=
             launches = st["kernel_launches"] + extra_launches
             info = dict(op.get_info(), kernel_paths=st["kernel_paths"], groups=st["group_count"])
         if out is not None:
-            result = out.rows()
+            result = [tuple(v.decode() if isinstance(v, bytes) else v for v in row) for row in out.rows()]
         op.close()
     return {"ms": float(np.mean(ms)), "kernel_ms": float(np.mean(kms)), "launches": int(launches), "info": info, "result": result}
 

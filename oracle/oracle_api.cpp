@@ -20,6 +20,43 @@ void partitionedOutputOffsets(Operator* op, int64_t* out);
 void filterProjectSelection(Operator* op, int32_t* isList, int64_t* size);
 }
 
+namespace oracle {
+// The operators of one Driver chained the way Driver.processInternal does (MB/operator/Driver.java:402-536): a page is pushed through
+// FilterAndProjectOperator -> LookupJoinOperator* -> HashAggregationOperator, each operator's output page being the next one's input.
+// This is the reference semantics of include/presto_gpu.h's pg_fused_aggregation_create (which the product runs as one kernel).
+struct DriverChain : Operator {
+    std::unique_ptr<Operator> fp;
+    std::vector<std::unique_ptr<Operator>> joins;
+    std::unique_ptr<Operator> agg;
+    OwnedPage a, b;
+    explicit DriverChain(const pg_fused_aggregation_config* c)
+    {
+        fp.reset(createFilterProject(&c->page_processor));
+        for (int j = 0; j < c->n_joins; j++) joins.emplace_back(createLookupJoin(&c->joins[j], (JoinBridge*) c->bridges[j]));
+        agg.reset(createHashAggregation(&c->aggregation));
+    }
+    bool needsInput() override { return agg->needsInput(); }
+    void addInput(const pg_page* page) override
+    {
+        stats.input_positions += page->position_count;
+        fp->addInput(page);
+        OwnedPage* cur = &a; OwnedPage* next = &b;
+        if (!fp->getOutput(*cur) || cur->positionCount == 0) return;
+        for (auto& j : joins) {
+            pg_page in{}; cur->fill(&in);
+            j->addInput(&in);
+            if (!j->getOutput(*next) || next->positionCount == 0) return;
+            std::swap(cur, next);
+        }
+        pg_page in{}; cur->fill(&in);
+        agg->addInput(&in);
+    }
+    bool getOutput(OwnedPage& out) override { return agg->getOutput(out); }
+    void finish() override { agg->finish(); }
+    bool isFinished() override { return agg->isFinished(); }
+};
+}
+
 using namespace oracle;
 
 static thread_local std::string g_lastError;
@@ -57,6 +94,8 @@ int32_t or_partitioned_output_create(const pg_partitioned_output_config* c, void
 int32_t or_partitioned_output_get_offsets(void* op, int64_t* out) { OR_TRY partitionedOutputOffsets((Operator*) op, out); OR_CATCH }
 int32_t or_filter_project_create(const pg_filter_project_config* c, void** out) { OR_TRY *out = createFilterProject(c); OR_CATCH }
 int32_t or_filter_project_get_last_selection(void* op, int32_t* isList, int64_t* size) { OR_TRY filterProjectSelection((Operator*) op, isList, size); OR_CATCH }
+
+int32_t or_fused_aggregation_create(const pg_fused_aggregation_config* c, void** out) { OR_TRY *out = new DriverChain(c); OR_CATCH }
 
 int32_t or_operator_needs_input(void* op, int32_t* out) { OR_TRY *out = ((Operator*) op)->needsInput() ? 1 : 0; OR_CATCH }
 int32_t or_operator_add_input(void* op, const pg_page* page)

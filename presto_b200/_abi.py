@@ -210,6 +210,7 @@ class Backend:
         "partitioned_output_get_offsets": (C.c_int32, [C.c_void_p, C.c_void_p]),
         "filter_project_create": (C.c_int32, [C.POINTER(pg_filter_project_config), C.POINTER(C.c_void_p)]),
         "filter_project_get_last_selection": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+        "fused_aggregation_create": (C.c_int32, [C.POINTER(pg_fused_aggregation_config), C.POINTER(C.c_void_p)]),
         "pages_serde_create": (C.c_int32, [C.POINTER(pg_pages_serde_config), C.POINTER(C.c_void_p)]),
         "pages_serde_serialize": (C.c_int32, [C.c_void_p, C.POINTER(pg_page), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
         "pages_serde_deserialize": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(pg_page)]),
@@ -234,7 +235,6 @@ class Backend:
         "ipc_import": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
         "ipc_close": (C.c_int32, [C.c_void_p]),
         "filter_project_explain": (C.c_int32, [C.POINTER(pg_filter_project_config), C.c_uint64, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
-        "fused_aggregation_create": (C.c_int32, [C.POINTER(pg_fused_aggregation_config), C.POINTER(C.c_void_p)]),
         "fused_aggregation_get_info": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_char_p, C.c_size_t]),
         "fused_aggregation_explain": (C.c_int32, [C.POINTER(pg_fused_aggregation_config), C.c_uint64, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32),
                                                   C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -374,23 +374,13 @@ class FusedJoin:
 
 class FusedAggregationOperator(Operator):
     """FilterAndProjectOperator → LookupJoinOperator* → HashAggregationOperator of one Driver as ONE operator
-    (include/presto_gpu.h pg_fused_aggregation_create): on the CUDA backend the fragment is generated as a single kernel; on any
-    other backend (the tests' oracle) the three reference operators are simply chained — the results are the same by definition."""
+    (include/presto_gpu.h pg_fused_aggregation_create): on the CUDA backend the fragment is generated as a single kernel; the tests'
+    oracle chains the three reference operators the way Driver.processInternal does — the results are the same by definition."""
 
     def __init__(self, input_types: Sequence[int], program, joins: Sequence[FusedJoin], group_types: Sequence[int], group_channels: Sequence[int],
                  aggregates: Sequence[Aggregate], *, step: int = abi.STEP_SINGLE, expected_groups: int = 10_000,
                  group_max_lengths: Optional[Sequence[int]] = None, hash_channel: int = -1, backend=None, **options):
         backend = backend or _default_backend()
-        self._chain = None
-        if not backend.has_device:
-            chain_opts = {k: v for k, v in options.items() if k in ("max_output_rows",)}
-            fp = FilterAndProjectOperator(input_types, program, backend=backend)
-            js = [LookupJoinOperator(j.bridge, j.types, j.hash_channels, j.output_channels, backend=backend) for j in joins]
-            agg = HashAggregationOperator(group_types, group_channels, aggregates, step=step, expected_groups=expected_groups,
-                                          group_max_lengths=group_max_lengths, hash_channel=hash_channel, backend=backend, **chain_opts)
-            self._chain = (fp, js, agg)
-            self._b, self._h, self._closed = backend, None, False
-            return
         cfg, self._keep = self._config(input_types, program, joins, group_types, group_channels, aggregates, step, expected_groups,
                                        group_max_lengths, hash_channel, options)
         handle = C.c_void_p()
@@ -458,54 +448,12 @@ class FusedAggregationOperator(Operator):
         return buf.value.decode()
 
     def get_info(self) -> dict:
-        if self._chain is not None:
+        if not self._b.has_device:
             return {"fused_pages": 0, "unfused_pages": 0, "registers": 0, "reason": "reference operators chained"}
         f, u, r = C.c_int64(), C.c_int64(), C.c_int32()
         buf = C.create_string_buffer(2048)
         self._b.check(self._b.fused_aggregation_get_info(self._h, C.byref(f), C.byref(u), C.byref(r), buf, 2048))
         return {"fused_pages": f.value, "unfused_pages": u.value, "registers": r.value, "reason": buf.value.decode()}
-
-    # ---- the reference chain (non-CUDA backends) ----
-    def needs_input(self) -> bool:
-        if self._chain is None:
-            return super().needs_input()
-        fp, js, agg = self._chain
-        return agg.needs_input() and all(j.needs_input() or True for j in js)
-
-    def add_input(self, page: Page) -> None:
-        if self._chain is None:
-            return super().add_input(page)
-        fp, js, agg = self._chain
-        fp.add_input(page)
-        cur = fp.get_output()
-        for j in js:
-            if cur is None or not cur.position_count:
-                break
-            j.add_input(cur)
-            cur = j.get_output()
-        if cur is not None and cur.position_count:
-            agg.add_input(cur)
-
-    def get_output(self, copy: bool = True):
-        return super().get_output(copy) if self._chain is None else self._chain[2].get_output(copy)
-
-    def finish(self) -> None:
-        return super().finish() if self._chain is None else self._chain[2].finish()
-
-    def is_finished(self) -> bool:
-        return super().is_finished() if self._chain is None else self._chain[2].is_finished()
-
-    def get_stats(self) -> dict:
-        return super().get_stats() if self._chain is None else self._chain[2].get_stats()
-
-    def close(self) -> None:
-        if self._chain is None:
-            return super().close()
-        if not self._closed:
-            self._closed = True
-            fp, js, agg = self._chain
-            for op in [fp, *js, agg]:
-                op.close()
 
 
 class PagesSerde:
