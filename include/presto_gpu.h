@@ -450,6 +450,22 @@ int32_t pg_fused_aggregation_get_info(pg_operator* op, int64_t* fused_pages, int
  * laid out as HashBuilderOperator would.  PG_ERR_UNSUPPORTED (reason in pg_last_error) when the fragment is not fusable. */
 int32_t pg_fused_aggregation_explain(const pg_fused_aggregation_config* config, uint64_t nullable_inputs, const int32_t* const* build_types,
                                      const int32_t* n_build_types, char* buffer, size_t capacity, size_t* needed);
+/* The same fragment WITHOUT the aggregation: FilterAndProjectOperator → LookupJoinOperator* (INNER) as one operator whose output pages
+ * are the last operator's (rows in input order; layout = last join's probe output channels then its bridge's build output channels, or
+ * the projections when there is no join).  One generated row program, launched twice (selection pass, emit pass); fragments outside the
+ * fused set (hash-table LookupSource, VARCHAR channels) run operator by operator.  get_output returns one page per input page. */
+typedef struct pg_fused_page_config {
+    pg_filter_project_config page_processor;
+    int32_t n_joins;                          /* 0..2 */
+    const pg_lookup_join_config* joins;
+    pg_join_bridge* const* bridges;
+    pg_operator_options options;
+} pg_fused_page_config;
+int32_t pg_fused_page_create(const pg_fused_page_config* config, pg_operator** out);
+int32_t pg_fused_page_get_info(pg_operator* op, int64_t* fused_pages, int64_t* unfused_pages, char* reason, size_t capacity);
+int32_t pg_fused_page_explain(const pg_fused_page_config* config, uint64_t nullable_inputs, const int32_t* const* build_types, const int32_t* n_build_types,
+                              char* buffer, size_t capacity, size_t* needed);
+
 /* NVRTC compile check of a CUDA C++ source against the embedded device headers (no GPU needed): cubin size or the compiler log. */
 int32_t pg_jit_compile_check(const char* source, char* log_buffer, size_t capacity, int64_t* cubin_bytes);
 

@@ -29,13 +29,20 @@ struct DriverChain : Operator {
     std::vector<std::unique_ptr<Operator>> joins;
     std::unique_ptr<Operator> agg;
     OwnedPage a, b;
+    bool finishing = false, hasPending = false;
+    OwnedPage pending;
     explicit DriverChain(const pg_fused_aggregation_config* c)
     {
         fp.reset(createFilterProject(&c->page_processor));
         for (int j = 0; j < c->n_joins; j++) joins.emplace_back(createLookupJoin(&c->joins[j], (JoinBridge*) c->bridges[j]));
         agg.reset(createHashAggregation(&c->aggregation));
     }
-    bool needsInput() override { return agg->needsInput(); }
+    explicit DriverChain(const pg_fused_page_config* c)      // no aggregation: the chain's output is the last operator's page
+    {
+        fp.reset(createFilterProject(&c->page_processor));
+        for (int j = 0; j < c->n_joins; j++) joins.emplace_back(createLookupJoin(&c->joins[j], (JoinBridge*) c->bridges[j]));
+    }
+    bool needsInput() override { return agg ? agg->needsInput() : (!finishing && !hasPending); }
     void addInput(const pg_page* page) override
     {
         stats.input_positions += page->position_count;
@@ -48,12 +55,19 @@ struct DriverChain : Operator {
             if (!j->getOutput(*next) || next->positionCount == 0) return;
             std::swap(cur, next);
         }
+        if (!agg) { pending.columns.swap(cur->columns); pending.positionCount = cur->positionCount; hasPending = true; return; }
         pg_page in{}; cur->fill(&in);
         agg->addInput(&in);
     }
-    bool getOutput(OwnedPage& out) override { return agg->getOutput(out); }
-    void finish() override { agg->finish(); }
-    bool isFinished() override { return agg->isFinished(); }
+    bool getOutput(OwnedPage& out) override
+    {
+        if (agg) return agg->getOutput(out);
+        if (!hasPending) return false;
+        out.columns.swap(pending.columns); out.positionCount = pending.positionCount; hasPending = false;
+        return true;
+    }
+    void finish() override { if (agg) agg->finish(); else finishing = true; }
+    bool isFinished() override { return agg ? agg->isFinished() : (finishing && !hasPending); }
 };
 }
 
@@ -96,6 +110,7 @@ int32_t or_filter_project_create(const pg_filter_project_config* c, void** out) 
 int32_t or_filter_project_get_last_selection(void* op, int32_t* isList, int64_t* size) { OR_TRY filterProjectSelection((Operator*) op, isList, size); OR_CATCH }
 
 int32_t or_fused_aggregation_create(const pg_fused_aggregation_config* c, void** out) { OR_TRY *out = new DriverChain(c); OR_CATCH }
+int32_t or_fused_page_create(const pg_fused_page_config* c, void** out) { OR_TRY *out = new DriverChain(c); OR_CATCH }
 
 int32_t or_operator_needs_input(void* op, int32_t* out) { OR_TRY *out = ((Operator*) op)->needsInput() ? 1 : 0; OR_CATCH }
 int32_t or_operator_add_input(void* op, const pg_page* page)

@@ -11,7 +11,7 @@ from ._abi import (  # noqa: F401
 from .page import Block, Page  # noqa: F401
 from .expressions import Program  # noqa: F401
 from .operators import (  # noqa: F401
-    Aggregate, FilterAndProjectOperator, FusedAggregationOperator, FusedJoin, GroupByHash, HashAggregationOperator, HashBuilderOperator, HashSemiJoinOperator, JoinBridge,
+    Aggregate, FilterAndProjectOperator, FusedAggregationOperator, FusedJoin, FusedPageOperator, GroupByHash, HashAggregationOperator, HashBuilderOperator, HashSemiJoinOperator, JoinBridge,
     LookupJoinOperator, Operator, PagesSerde, PartitionedOutputOperator, to_pages,
 )
 

@@ -153,6 +153,11 @@ class pg_fused_aggregation_config(C.Structure):
                 ("bridges", C.POINTER(C.c_void_p)), ("aggregation", pg_hash_aggregation_config)]
 
 
+class pg_fused_page_config(C.Structure):
+    _fields_ = [("page_processor", pg_filter_project_config), ("n_joins", C.c_int32), ("joins", C.POINTER(pg_lookup_join_config)),
+                ("bridges", C.POINTER(C.c_void_p)), ("options", pg_operator_options)]
+
+
 def i32_array(values):
     values = list(values)
     return (C.c_int32 * max(1, len(values)))(*values)
@@ -211,6 +216,7 @@ class Backend:
         "filter_project_create": (C.c_int32, [C.POINTER(pg_filter_project_config), C.POINTER(C.c_void_p)]),
         "filter_project_get_last_selection": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
         "fused_aggregation_create": (C.c_int32, [C.POINTER(pg_fused_aggregation_config), C.POINTER(C.c_void_p)]),
+        "fused_page_create": (C.c_int32, [C.POINTER(pg_fused_page_config), C.POINTER(C.c_void_p)]),
         "pages_serde_create": (C.c_int32, [C.POINTER(pg_pages_serde_config), C.POINTER(C.c_void_p)]),
         "pages_serde_serialize": (C.c_int32, [C.c_void_p, C.POINTER(pg_page), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
         "pages_serde_deserialize": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(pg_page)]),
@@ -238,6 +244,9 @@ class Backend:
         "fused_aggregation_get_info": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_char_p, C.c_size_t]),
         "fused_aggregation_explain": (C.c_int32, [C.POINTER(pg_fused_aggregation_config), C.c_uint64, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32),
                                                   C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+        "fused_page_get_info": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_char_p, C.c_size_t]),
+        "fused_page_explain": (C.c_int32, [C.POINTER(pg_fused_page_config), C.c_uint64, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32),
+                                           C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
         "jit_compile_check": (C.c_int32, [C.c_char_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_int64)]),
     }
 

@@ -39,7 +39,54 @@ struct FusedParams {
     unsigned int* fpError;           // bit 0 overflow, bit 1 division by zero (PageProcessor), bit 2 VARCHAR key longer than declared
 };
 
+// ---- page sink: FilterAndProject → LookupJoin* materialised as an output page, rows in input order --------------------------------
+// Two launches of the same generated row program: the selection pass leaves, per 64-row unit (one warp, one row pair per lane), the
+// survivors among its even and odd rows and their count; after an exclusive scan of the counts the emit pass re-runs the probes for
+// the survivors only and stores every output channel at its final position — the compacted page is the only thing written to HBM.
+struct FusedPageParams {
+    int64_t n;
+    const void* values[kFusedMaxInputs];
+    const uint8_t* nulls[kFusedMaxInputs];
+    const int32_t* offsets[kFusedMaxInputs];
+    FusedJoinView joins[kFusedMaxJoins];
+    unsigned int* fpError;
+    uint32_t* masks;                 // [units][2]
+    uint32_t* counts;                // [units + 1]
+    const uint32_t* unitOffsets;     // emit pass: exclusive scan of counts
+    void* outValues[kFusedMaxInputs];
+    uint8_t* outNulls[kFusedMaxInputs];
+};
+
 #ifdef __CUDACC__
+template <class Prog>
+__device__ __forceinline__ void fusedSelectBody(const FusedPageParams& P)
+{
+    constexpr int TILE = Prog::THREADS * Prog::R;
+    const long long nTiles = (P.n + TILE - 1) / TILE;
+    typename Prog::Tile tA, tB;
+    long long tile = blockIdx.x;
+    if (tile < nTiles) Prog::load(P, tile * TILE, tA);
+    while (tile < nTiles) {
+        const long long t1 = tile + gridDim.x;
+        if (t1 < nTiles) Prog::load(P, t1 * TILE, tB);
+        Prog::select(P, tA, tile * TILE);
+        __syncwarp();
+        if (t1 >= nTiles) break;
+        const long long t2 = t1 + gridDim.x;
+        if (t2 < nTiles) Prog::load(P, t2 * TILE, tA);
+        Prog::select(P, tB, t1 * TILE);
+        __syncwarp();
+        tile = t2;
+    }
+}
+template <class Prog>
+__device__ __forceinline__ void fusedEmitBody(const FusedPageParams& P)
+{
+    constexpr int TILE = Prog::THREADS * Prog::R;
+    const long long nTiles = (P.n + TILE - 1) / TILE;
+    for (long long tile = blockIdx.x; tile < nTiles; tile += gridDim.x) { Prog::emit(P, tile * TILE); __syncwarp(); }
+}
+
 // ---- the aggregation sink -----------------------------------------------------------------------------------------------------
 // The on-chip tiers work on ONE 64-bit word per group: the packed key itself when W == 1, otherwise (Prog::TIERS) the key's fields
 // squeezed together by the generated Prog::tierKey — e.g. Q1's two INTEGER codes, which the W-word layout spreads over two words to

@@ -229,37 +229,40 @@ struct Gen {
     }
 };
 
-}  // namespace
 
-std::string generateFusedAggSource(const FusedProgramDesc& D, FusedKernelInfo& info)
-{
-    info = FusedKernelInfo();
-    const FpProgramDesc& P = D.fp;
-    const int nNodes = (int) P.nodes.size(), nIn = (int) P.inputTypes.size();
-    auto decline = [&](const std::string& why) { info.ok = false; info.reason = why; return std::string(); };
-    if (D.accs.size() > 8) return decline("more than 8 sum columns");
-    if (D.accs.empty() && !D.countRows) return decline("no aggregate");
-    if (D.joins.size() > 2) return decline("more than two joins");
-    if (D.W < 1 || D.W > 4) return decline("key width");
+// ---- what both sinks (aggregation, page) share: layouts, eager / lazy inputs, the tile loads, stages A (filter) and B (probes) ----
+struct Frag {
+    const FusedProgramDesc& D;
+    const FpProgramDesc& P;
+    int nNodes, nIn;
+    std::vector<std::vector<ChanRef>> layouts;
+    std::vector<bool> used, eager;
+    std::vector<int> usedInputs, eagerInputs;
+    int R = 2;
+    static constexpr int THREADS = 256;
+    Gen g;
+    std::string fail;
 
-    // ---- layouts: which expression / build column every channel of every stage is ----
-    std::vector<std::vector<ChanRef>> layouts(1);
-    for (int p : P.projections) { ChanRef c; c.kind = 0; c.node = p; layouts[0].push_back(c); }
-    for (size_t j = 0; j < D.joins.size(); j++) {
-        const FusedJoinDesc& J = D.joins[j];
-        const std::vector<ChanRef>& in = layouts.back();
-        std::vector<ChanRef> next;
-        if (J.keyChannel < 0 || J.keyChannel >= (int) in.size()) return decline("join key channel out of range");
-        for (int c : J.probeOutputChannels) { if (c < 0 || c >= (int) in.size()) return decline("probe output channel out of range"); next.push_back(in[c]); }
-        for (size_t c = 0; c < J.buildOutputs.size(); c++) { ChanRef r; r.kind = 1; r.join = (int) j; r.col = (int) c; next.push_back(r); }
-        layouts.push_back(next);
+    explicit Frag(const FusedProgramDesc& d) : D(d), P(d.fp), nNodes((int) d.fp.nodes.size()), nIn((int) d.fp.inputTypes.size()), g(d) {}
+    const std::vector<ChanRef>& fin() const { return layouts.back(); }
+
+    bool buildLayouts()
+    {
+        layouts.assign(1, {});
+        for (int p : P.projections) { ChanRef c; c.kind = 0; c.node = p; layouts[0].push_back(c); }
+        for (size_t j = 0; j < D.joins.size(); j++) {
+            const FusedJoinDesc& J = D.joins[j];
+            const std::vector<ChanRef>& in = layouts.back();
+            std::vector<ChanRef> next;
+            if (J.keyChannel < 0 || J.keyChannel >= (int) in.size()) { fail = "join key channel out of range"; return false; }
+            for (int c : J.probeOutputChannels) { if (c < 0 || c >= (int) in.size()) { fail = "probe output channel out of range"; return false; } next.push_back(in[c]); }
+            for (size_t c = 0; c < J.buildOutputs.size(); c++) { ChanRef r; r.kind = 1; r.join = (int) j; r.col = (int) c; next.push_back(r); }
+            layouts.push_back(next);
+        }
+        return true;
     }
-    const std::vector<ChanRef>& fin = layouts.back();
-    for (const auto& k : D.keys) if (k.channel < 0 || k.channel >= (int) fin.size()) return decline("group-by channel out of range");
-    for (const auto& a : D.accs) if (a.channel < 0 || a.channel >= (int) fin.size()) return decline("aggregate channel out of range");
-
-    // ---- which raw inputs are read, which of them eagerly ----
-    auto closure = [&](std::vector<int> roots) {
+    std::vector<bool> closure(std::vector<int> roots) const
+    {
         std::vector<bool> seen(nNodes, false);
         while (!roots.empty()) {
             const int k = roots.back(); roots.pop_back();
@@ -268,43 +271,199 @@ std::string generateFusedAggSource(const FusedProgramDesc& D, FusedKernelInfo& i
             if (P.nodes[k].op != PG_EX_INPUT) for (int o : {P.nodes[k].a, P.nodes[k].b, P.nodes[k].c}) roots.push_back(o);
         }
         return seen;
-    };
-    auto inputsOf = [&](const std::vector<bool>& seen) {
+    }
+    std::vector<bool> inputsOf(const std::vector<bool>& seen) const
+    {
         std::vector<bool> in(nIn, false);
         for (int k = 0; k < nNodes; k++) if (seen[k] && P.nodes[k].op == PG_EX_INPUT) in[P.nodes[k].a] = true;
         return in;
-    };
-    std::vector<int> allRoots;
-    if (P.filterNode >= 0) allRoots.push_back(P.filterNode);
-    auto rootOf = [&](const ChanRef& c) { if (c.kind == 0) allRoots.push_back(c.node); };
-    for (size_t j = 0; j < D.joins.size(); j++) rootOf(layouts[j][D.joins[j].keyChannel]);
-    for (const auto& k : D.keys) rootOf(fin[k.channel]);
-    for (const auto& a : D.accs) rootOf(fin[a.channel]);
-    const std::vector<bool> used = inputsOf(closure(allRoots));
-    std::vector<bool> eager(nIn, false);
+    }
+    // `finalChannels`: channels of the last layout the sink consumes.  Inputs of the filter and of the first probe key are loaded
+    // eagerly (for every row, ahead of time); everything else after the filter / the probes, for surviving rows only — unless there is
+    // no join and `allEagerWithoutJoins` (aggregation sink: almost every row reaches it).
+    void planInputs(const std::vector<int>& finalChannels, bool allEagerWithoutJoins)
     {
+        std::vector<int> allRoots;
+        if (P.filterNode >= 0) allRoots.push_back(P.filterNode);
+        auto rootOf = [&](const ChanRef& c) { if (c.kind == 0) allRoots.push_back(c.node); };
+        for (size_t j = 0; j < D.joins.size(); j++) rootOf(layouts[j][D.joins[j].keyChannel]);
+        for (int c : finalChannels) rootOf(fin()[c]);
+        used = inputsOf(closure(allRoots));
         std::vector<int> eagerRoots;
         if (P.filterNode >= 0) eagerRoots.push_back(P.filterNode);
         if (!D.joins.empty()) { const ChanRef& c = layouts[0][D.joins[0].keyChannel]; if (c.kind == 0) eagerRoots.push_back(c.node); }
-        else eagerRoots = allRoots;     // no join: (almost) every row reaches the aggregation, load everything up front
+        else if (allEagerWithoutJoins) eagerRoots = allRoots;
         eager = inputsOf(closure(eagerRoots));
-        if (P.filterNode < 0 && D.joins.empty()) eager = used;
+        if (P.filterNode < 0 && D.joins.empty() && allEagerWithoutJoins) eager = used;
+        int eagerBytes = 0;
+        for (int c = 0; c < nIn; c++) {
+            if (P.inputTypes[c] == PG_TYPE_VARCHAR) eager[c] = false;       // slices are read where they are used
+            if (eager[c]) eagerBytes += widthOf(P.inputTypes[c]);
+        }
+        usedInputs.clear(); eagerInputs.clear();
+        for (int c = 0; c < nIn; c++) if (used[c]) usedInputs.push_back(c);
+        for (int c = 0; c < nIn; c++) if (eager[c]) eagerInputs.push_back(c);
+        R = eagerBytes <= 16 ? 4 : 2;
+        resetGen();
     }
-    int eagerBytes = 0;
-    for (int c = 0; c < nIn; c++) {
-        if (P.inputTypes[c] == PG_TYPE_VARCHAR) eager[c] = false;       // slices are read where they are used
-        if (eager[c]) eagerBytes += widthOf(P.inputTypes[c]);
+    void resetGen()
+    {
+        g.R = R; g.eager = eager;
+        g.vals.assign(R, std::vector<Val>(nNodes)); g.done.assign(R, std::vector<bool>(nNodes, false));
+        g.out.str(""); g.out.clear();
     }
-    for (int c = 0; c < nIn; c++) if (used[c]) info.usedInputs.push_back(c);
-    for (int c = 0; c < nIn; c++) if (eager[c]) info.eagerInputs.push_back(c);
-    const int R = eagerBytes <= 16 ? 4 : 2;
+    void flush(std::ostringstream& body) { body << g.out.str(); g.out.str(""); g.out.clear(); }
+
+    void emitTileAndLoad(std::ostringstream& src, const char* paramsType)
+    {
+        src << "    struct Tile {\n";
+        for (int c : eagerInputs) {
+            const int w = widthOf(P.inputTypes[c]);
+            src << "        " << (w == 8 ? "unsigned long long" : w == 4 ? "unsigned int" : "unsigned char") << " c" << c << "[R];\n";
+        }
+        if (eagerInputs.empty()) src << "        int unused;\n";
+        src << "    };\n";
+        src << "    static __device__ __forceinline__ void load(const " << paramsType << "& P, long long base, Tile& t)\n    {\n";
+        for (int p = 0; p < R / 2; p++) {
+            src << "        {\n            const long long r0 = base + " << p * 2 * THREADS << " + 2 * (long long) threadIdx.x;\n"
+                << "            if (r0 + 1 < P.n) {\n";
+            for (int c : eagerInputs) {
+                const int w = widthOf(P.inputTypes[c]);
+                if (w == 8) src << "                { const ulonglong2 x = ldStream128((const uint64_t*) P.values[" << c << "] + r0); t.c" << c << "[" << 2 * p << "] = x.x; t.c" << c << "[" << 2 * p + 1 << "] = x.y; }\n";
+                else if (w == 4) src << "                { const uint64_t x = ldStream64((const uint32_t*) P.values[" << c << "] + r0); t.c" << c << "[" << 2 * p << "] = (unsigned int) x; t.c" << c << "[" << 2 * p + 1 << "] = (unsigned int) (x >> 32); }\n";
+                else src << "                { const unsigned short x = *((const unsigned short*) ((const uint8_t*) P.values[" << c << "] + r0)); t.c" << c << "[" << 2 * p << "] = (unsigned char) x; t.c" << c << "[" << 2 * p + 1 << "] = (unsigned char) (x >> 8); }\n";
+            }
+            src << "            }\n            else {\n";
+            for (int c : eagerInputs) {
+                const int w = widthOf(P.inputTypes[c]);
+                const char* ty = w == 8 ? "uint64_t" : w == 4 ? "uint32_t" : "uint8_t";
+                src << "                t.c" << c << "[" << 2 * p << "] = r0 < P.n ? ((const " << ty << "*) P.values[" << c << "])[r0] : 0; t.c" << c << "[" << 2 * p + 1 << "] = 0;\n";
+            }
+            src << "            }\n        }\n";
+        }
+        src << "    }\n";
+    }
+
+    // stage A: row index and validity of every row slot (+ the deferred-row bitmap of the aggregation sink)
+    void stageValidity(std::ostringstream& body, bool withBitmapIn)
+    {
+        for (int u = 0; u < R; u++) {
+            const std::string us = std::to_string(u);
+            const int p = u / 2, q = u % 2;
+            g.emit("const long long row" + us + " = base + " + std::to_string(p * 2 * THREADS + q) + " + 2 * (long long) threadIdx.x;");
+            g.emit("bool live" + us + " = row" + us + " < P.n;");
+            if (withBitmapIn) g.emit("if (P.bitmapIn && live" + us + ") live" + us + " = (P.bitmapIn[row" + us + " >> 5] >> (row" + us + " & 31)) & 1u;");
+        }
+        flush(body);
+    }
+    bool stageFilter(std::ostringstream& body)
+    {
+        if (P.filterNode < 0) return true;
+        for (int u = 0; u < R; u++) {
+            const std::string us = std::to_string(u), guard = "live" + us;
+            // the filter's inputs are evaluated under the validity guard; a copy of the guard keeps `live` assignable
+            g.emit("const bool in" + us + " = live" + us + ";");
+            const Val f = g.node(P.filterNode, u, "in" + us);
+            if (!g.fail.empty()) { fail = g.fail; return false; }
+            if (f.kind != 'b') { fail = "filter is not boolean"; return false; }
+            g.emit(guard + " = in" + us + " && " + f.v + (f.z.empty() ? "" : " && !" + f.z) + ";");      // only TRUE selects
+        }
+        flush(body);
+        return true;
+    }
+    // a channel's value for row slot u (evaluated lazily under `guard`)
+    Val chanVal(const ChanRef& c, int u, const std::string& guard)
+    {
+        if (c.kind == 0) return g.node(c.node, u, guard);
+        const FusedBuildColumn& bc = D.joins[c.join].buildOutputs[c.col];
+        const std::string us = std::to_string(u), js = std::to_string(c.join), id = "b" + js + "_" + std::to_string(c.col) + "_" + us;
+        Val r;
+        const std::string word = "pw" + js + "_" + us + "[" + std::to_string(bc.word) + "]";
+        const std::string rawBits = bc.width == 8 ? word : "((" + word + " >> " + std::to_string(bc.shift) + ") & " + hex64(bc.width == 4 ? 0xffffffffULL : 0xffULL) + ")";
+        r.v = "v" + id;
+        if (bc.type == PG_TYPE_DOUBLE) { r.kind = 'd'; g.emit("const double " + r.v + " = __longlong_as_double((long long) " + rawBits + ");"); }
+        else if (bc.type == PG_TYPE_BIGINT) { r.kind = 'i'; g.emit("const long long " + r.v + " = (long long) " + rawBits + ";"); }
+        else if (bc.type == PG_TYPE_BOOLEAN) { r.kind = 'b'; g.emit("const bool " + r.v + " = " + rawBits + " != 0;"); }
+        else if (bc.type == PG_TYPE_INTEGER || bc.type == PG_TYPE_DATE) { r.kind = 'i'; g.emit("const long long " + r.v + " = (long long) (int) (unsigned int) " + rawBits + ";"); }
+        else { g.fail = "VARCHAR build column"; return r; }
+        if (bc.nullWord >= 0) {
+            r.z = "z" + id;
+            g.emit("const bool " + r.z + " = ((pw" + js + "_" + us + "[" + std::to_string(bc.nullWord) + "] >> " + std::to_string(bc.nullShift) + ") & 0xff) != 0;");
+        }
+        return r;
+    }
+    // stage B: the probes.  withPayload = false: membership only (the selection pass of the page sink).
+    bool stageJoins(std::ostringstream& body, bool withPayload)
+    {
+        for (size_t j = 0; j < D.joins.size(); j++) {
+            const FusedJoinDesc& J = D.joins[j];
+            const std::string js = std::to_string(j);
+            const ChanRef& keyRef = layouts[j][J.keyChannel];
+            const bool membershipOnly = J.strideWords == 0 || !withPayload;
+            // B1: keys, one bitmap word per row of all R rows
+            for (int u = 0; u < R; u++) {
+                const std::string us = std::to_string(u);
+                g.emit("const bool in" + js + "_" + us + " = live" + us + ";");
+                const Val k = chanVal(keyRef, u, "in" + js + "_" + us);
+                if (!g.fail.empty()) { fail = g.fail; return false; }
+                if (k.kind != 'i') { fail = "join key must be an integer channel"; return false; }
+                g.emit("const unsigned long long ix" + js + "_" + us + " = (unsigned long long) (" + k.v + " - P.joins[" + js + "].D.minKey);");
+                g.emit("const bool ir" + js + "_" + us + " = in" + js + "_" + us + (k.z.empty() ? "" : " && !" + k.z) + " && ix" + js + "_" + us + " < P.joins[" + js + "].D.range;");
+                // one 8-byte bitmap word decides membership (L2 resident: range / 8 bytes); the rest of the 32-byte block, the rank directory
+                // and the payload row are only touched by the rows that matched
+                g.emit("const unsigned long long bw" + js + "_" + us + " = ir" + js + "_" + us + " ? __ldg(P.joins[" + js + "].D.bitmap + (ix" + js + "_" + us + " >> 6)) : 0ULL;");
+            }
+            flush(body);
+            // B2: membership narrows `live`; matched rows fetch their rank (block popcounts + directory word) and payload row
+            for (int u = 0; u < R; u++) {
+                const std::string us = std::to_string(u), s = js + "_" + us;
+                g.emit("const unsigned long long bt" + s + " = 1ULL << (ix" + s + " & 63);");
+                g.emit("live" + us + " = ir" + s + " && (bw" + s + " & bt" + s + ") != 0;");
+                if (!membershipOnly) {
+                    std::string init = "unsigned long long pw" + s + "[" + std::to_string(J.strideWords) + "] = {";
+                    for (int k = 0; k < J.strideWords; k++) init += k ? ", 0" : "0";
+                    g.emit(init + "};");
+                    std::string code = "if (live" + us + ") { const unsigned long long* bp = P.joins[" + js + "].D.bitmap + (ix" + s + " >> 8) * 4; const unsigned int wi = (unsigned int) (ix" + s + " >> 6) & 3u; "
+                                       "unsigned int rk = __ldg(P.joins[" + js + "].D.prefix + (ix" + s + " >> 8)) + __popcll(bw" + s + " & (bt" + s + " - 1)); "
+                                       "if (wi > 0) rk += __popcll(__ldg(bp)); if (wi > 1) rk += __popcll(__ldg(bp + 1)); if (wi > 2) rk += __popcll(__ldg(bp + 2)); "
+                                       "const unsigned long long* pr = P.joins[" + js + "].rows + (unsigned long long) rk * " + std::to_string(J.strideWords) + "; ";
+                    for (int k = 0; k < J.strideWords; k++) code += "pw" + s + "[" + std::to_string(k) + "] = __ldg(pr + " + std::to_string(k) + "); ";
+                    g.emit(code + "}");
+                }
+            }
+            flush(body);
+        }
+        return true;
+    }
+};
+
+}  // namespace
+
+std::string generateFusedAggSource(const FusedProgramDesc& D, FusedKernelInfo& info)
+{
+    info = FusedKernelInfo();
+    const FpProgramDesc& P = D.fp;
+    const int nNodes = (int) P.nodes.size();
+    auto decline = [&](const std::string& why) { info.ok = false; info.reason = why; return std::string(); };
+    if (D.accs.size() > 8) return decline("more than 8 sum columns");
+    if (D.accs.empty() && !D.countRows) return decline("no aggregate");
+    if (D.joins.size() > 2) return decline("more than two joins");
+    if (D.W < 1 || D.W > 4) return decline("key width");
+
+    Frag F(D);
+    if (!F.buildLayouts()) return decline(F.fail);
+    const std::vector<ChanRef>& fin = F.fin();
+    std::vector<int> finalChannels;
+    for (const auto& k : D.keys) { if (k.channel < 0 || k.channel >= (int) fin.size()) return decline("group-by channel out of range"); finalChannels.push_back(k.channel); }
+    for (const auto& a : D.accs) { if (a.channel < 0 || a.channel >= (int) fin.size()) return decline("aggregate channel out of range"); finalChannels.push_back(a.channel); }
+    F.planInputs(finalChannels, true);
+    info.usedInputs = F.usedInputs; info.eagerInputs = F.eagerInputs;
+    const int R = F.R;
     info.rowsPerThread = R; info.nv = (int) D.accs.size(); info.cnt = D.countRows;
     const int NV = (int) D.accs.size();
-    const int THREADS = 256;
-
-    Gen g(D);
-    g.R = R; g.eager = eager;
-    g.vals.assign(R, std::vector<Val>(nNodes)); g.done.assign(R, std::vector<bool>(nNodes, false));
+    const int THREADS = Frag::THREADS;
+    Gen& g = F.g;
+    const std::vector<bool>& eager = F.eager;
 
     std::ostringstream src;
     src << "// generated by presto_b200 fused_codegen: FilterAndProject -> LookupJoin* -> HashAggregation as one row program\n"
@@ -314,7 +473,7 @@ std::string generateFusedAggSource(const FusedProgramDesc& D, FusedKernelInfo& i
         << "    static constexpr int NEAGER = " << info.eagerInputs.size() << ";\n";
     // ---- the 64-bit word the on-chip tiers identify a group by ----
     {
-        bool keyNullable = false;     // decided below, once the key channels' nullability is known: a dry evaluation of the key channels
+        bool keyNullable = false;     // a dry evaluation of the key channels tells whether any of them can be NULL on this page
         Gen dry(D); dry.R = 1; dry.eager = eager; dry.vals.assign(1, std::vector<Val>(nNodes)); dry.done.assign(1, std::vector<bool>(nNodes, false));
         for (const auto& k : D.keys) {
             const ChanRef& c = fin[k.channel];
@@ -353,119 +512,16 @@ std::string generateFusedAggSource(const FusedProgramDesc& D, FusedKernelInfo& i
         }
         src << "    }\n";
     }
-    // ---- Tile + load ----
-    src << "    struct Tile {\n";
-    for (int c : info.eagerInputs) {
-        const int w = widthOf(P.inputTypes[c]);
-        src << "        " << (w == 8 ? "unsigned long long" : w == 4 ? "unsigned int" : "unsigned char") << " c" << c << "[R];\n";
-    }
-    if (info.eagerInputs.empty()) src << "        int unused;\n";
-    src << "    };\n";
-    src << "    static __device__ __forceinline__ void load(const FusedParams& P, long long base, Tile& t)\n    {\n";
-    for (int p = 0; p < R / 2; p++) {
-        src << "        {\n            const long long r0 = base + " << p * 2 * THREADS << " + 2 * (long long) threadIdx.x;\n"
-            << "            if (r0 + 1 < P.n) {\n";
-        for (int c : info.eagerInputs) {
-            const int w = widthOf(P.inputTypes[c]);
-            if (w == 8) src << "                { const ulonglong2 x = ldStream128((const uint64_t*) P.values[" << c << "] + r0); t.c" << c << "[" << 2 * p << "] = x.x; t.c" << c << "[" << 2 * p + 1 << "] = x.y; }\n";
-            else if (w == 4) src << "                { const uint64_t x = ldStream64((const uint32_t*) P.values[" << c << "] + r0); t.c" << c << "[" << 2 * p << "] = (unsigned int) x; t.c" << c << "[" << 2 * p + 1 << "] = (unsigned int) (x >> 32); }\n";
-            else src << "                { const unsigned short x = *((const unsigned short*) ((const uint8_t*) P.values[" << c << "] + r0)); t.c" << c << "[" << 2 * p << "] = (unsigned char) x; t.c" << c << "[" << 2 * p + 1 << "] = (unsigned char) (x >> 8); }\n";
-        }
-        src << "            }\n            else {\n";
-        for (int c : info.eagerInputs) {
-            const int w = widthOf(P.inputTypes[c]);
-            const char* ty = w == 8 ? "uint64_t" : w == 4 ? "uint32_t" : "uint8_t";
-            src << "                t.c" << c << "[" << 2 * p << "] = r0 < P.n ? ((const " << ty << "*) P.values[" << c << "])[r0] : 0; t.c" << c << "[" << 2 * p + 1 << "] = 0;\n";
-        }
-        src << "            }\n        }\n";
-    }
-    src << "    }\n";
+    F.emitTileAndLoad(src, "FusedParams");
 
     // ---- process ----
     std::ostringstream body;
-    auto flush = [&]() { body << g.out.str(); g.out.str(""); g.out.clear(); };
+    auto flush = [&]() { F.flush(body); };
+    auto chanVal = [&](const ChanRef& c, int u, const std::string& guard) { return F.chanVal(c, u, guard); };
     body << "        bool errOv = false, errDz = false;\n";
-    // stage A: validity + filter
-    for (int u = 0; u < R; u++) {
-        const std::string us = std::to_string(u);
-        const int p = u / 2, q = u % 2;
-        g.emit("const long long row" + us + " = base + " + std::to_string(p * 2 * THREADS + q) + " + 2 * (long long) threadIdx.x;");
-        g.emit("bool live" + us + " = row" + us + " < P.n;");
-        g.emit("if (P.bitmapIn && live" + us + ") live" + us + " = (P.bitmapIn[row" + us + " >> 5] >> (row" + us + " & 31)) & 1u;");
-    }
-    flush();
-    if (P.filterNode >= 0) {
-        for (int u = 0; u < R; u++) {
-            const std::string us = std::to_string(u), guard = "live" + us;
-            // the filter's inputs are evaluated under the validity guard; a copy of the guard keeps `live` assignable
-            g.emit("const bool in" + us + " = live" + us + ";");
-            const Val f = g.node(P.filterNode, u, "in" + us);
-            if (!g.fail.empty()) return decline(g.fail);
-            if (f.kind != 'b') return decline("filter is not boolean");
-            g.emit(guard + " = in" + us + " && " + f.v + (f.z.empty() ? "" : " && !" + f.z) + ";");      // only TRUE selects
-        }
-        flush();
-    }
-    // a channel's value for row slot u (evaluated lazily under `guard`)
-    auto chanVal = [&](const ChanRef& c, int u, const std::string& guard) -> Val {
-        if (c.kind == 0) return g.node(c.node, u, guard);
-        const FusedBuildColumn& bc = D.joins[c.join].buildOutputs[c.col];
-        const std::string us = std::to_string(u), js = std::to_string(c.join), id = "b" + js + "_" + std::to_string(c.col) + "_" + us;
-        Val r;
-        const std::string word = "pw" + js + "_" + us + "[" + std::to_string(bc.word) + "]";
-        const std::string rawBits = bc.width == 8 ? word : "((" + word + " >> " + std::to_string(bc.shift) + ") & " + hex64(bc.width == 4 ? 0xffffffffULL : 0xffULL) + ")";
-        r.v = "v" + id;
-        if (bc.type == PG_TYPE_DOUBLE) { r.kind = 'd'; g.emit("const double " + r.v + " = __longlong_as_double((long long) " + rawBits + ");"); }
-        else if (bc.type == PG_TYPE_BIGINT) { r.kind = 'i'; g.emit("const long long " + r.v + " = (long long) " + rawBits + ";"); }
-        else if (bc.type == PG_TYPE_BOOLEAN) { r.kind = 'b'; g.emit("const bool " + r.v + " = " + rawBits + " != 0;"); }
-        else if (bc.type == PG_TYPE_INTEGER || bc.type == PG_TYPE_DATE) { r.kind = 'i'; g.emit("const long long " + r.v + " = (long long) (int) (unsigned int) " + rawBits + ";"); }
-        else { g.fail = "VARCHAR build column"; return r; }
-        if (bc.nullWord >= 0) {
-            r.z = "z" + id;
-            g.emit("const bool " + r.z + " = ((pw" + js + "_" + us + "[" + std::to_string(bc.nullWord) + "] >> " + std::to_string(bc.nullShift) + ") & 0xff) != 0;");
-        }
-        return r;
-    };
-    // stage B: joins
-    for (size_t j = 0; j < D.joins.size(); j++) {
-        const FusedJoinDesc& J = D.joins[j];
-        const std::string js = std::to_string(j);
-        const ChanRef& keyRef = layouts[j][J.keyChannel];
-        const bool membershipOnly = J.strideWords == 0;
-        // B1: keys, index loads of all R rows
-        for (int u = 0; u < R; u++) {
-            const std::string us = std::to_string(u), guard = "live" + us;
-            g.emit("const bool in" + js + "_" + us + " = live" + us + ";");
-            const Val k = chanVal(keyRef, u, "in" + js + "_" + us);
-            if (!g.fail.empty()) return decline(g.fail);
-            if (k.kind != 'i') return decline("join key must be an integer channel");
-            g.emit("const unsigned long long ix" + js + "_" + us + " = (unsigned long long) (" + k.v + " - P.joins[" + js + "].D.minKey);");
-            g.emit("const bool ir" + js + "_" + us + " = in" + js + "_" + us + (k.z.empty() ? "" : " && !" + k.z) + " && ix" + js + "_" + us + " < P.joins[" + js + "].D.range;");
-            // one 8-byte bitmap word decides membership (L2 resident: range / 8 bytes); the rest of the 32-byte block, the rank directory
-            // and the payload row are only touched by the rows that matched
-            g.emit("const unsigned long long bw" + js + "_" + us + " = ir" + js + "_" + us + " ? __ldg(P.joins[" + js + "].D.bitmap + (ix" + js + "_" + us + " >> 6)) : 0ULL;");
-            (void) guard;
-        }
-        flush();
-        // B2: membership narrows `live`; matched rows fetch their rank (block popcounts + directory word) and payload row
-        for (int u = 0; u < R; u++) {
-            const std::string us = std::to_string(u), s = js + "_" + us;
-            g.emit("const unsigned long long bt" + s + " = 1ULL << (ix" + s + " & 63);");
-            g.emit("live" + us + " = ir" + s + " && (bw" + s + " & bt" + s + ") != 0;");
-            if (!membershipOnly) {
-                std::string init = "unsigned long long pw" + s + "[" + std::to_string(J.strideWords) + "] = {";
-                for (int k = 0; k < J.strideWords; k++) init += k ? ", 0" : "0";
-                g.emit(init + "};");
-                std::string code = "if (live" + us + ") { const unsigned long long* bp = P.joins[" + js + "].D.bitmap + (ix" + s + " >> 8) * 4; const unsigned int wi = (unsigned int) (ix" + s + " >> 6) & 3u; "
-                                   "unsigned int rk = __ldg(P.joins[" + js + "].D.prefix + (ix" + s + " >> 8)) + __popcll(bw" + s + " & (bt" + s + " - 1)); "
-                                   "if (wi > 0) rk += __popcll(__ldg(bp)); if (wi > 1) rk += __popcll(__ldg(bp + 1)); if (wi > 2) rk += __popcll(__ldg(bp + 2)); "
-                                   "const unsigned long long* pr = P.joins[" + js + "].rows + (unsigned long long) rk * " + std::to_string(J.strideWords) + "; ";
-                for (int k = 0; k < J.strideWords; k++) code += "pw" + s + "[" + std::to_string(k) + "] = __ldg(pr + " + std::to_string(k) + "); ";
-                g.emit(code + "}");
-            }
-        }
-        flush();
-    }
+    F.stageValidity(body, true);
+    if (!F.stageFilter(body)) return decline(F.fail);
+    if (!F.stageJoins(body, true)) return decline(F.fail);
     // stage C: aggregate inputs and key fields (C1), key packing + hand-over to the aggregation (C2).
     //   without joins: C1 of all R rows first (their lazy loads in flight together), then C2 under `if (go)`;
     //   with joins (survivor queue): per row slot, everything inside `if (any lane of the warp still holds a row)` — after a selective
@@ -568,6 +624,114 @@ std::string generateFusedAggSource(const FusedProgramDesc& D, FusedKernelInfo& i
         << "        if (errOv) atomicOr(P.fpError, 1u);\n        if (errDz) atomicOr(P.fpError, 2u);\n        if (errLen) atomicOr(P.fpError, 4u);\n"
         << "    }\n};\n}  // namespace pg\n"
         << "extern \"C\" __global__ void __launch_bounds__(pg::Prog::THREADS, pg::Prog::MIN_CTAS) fused_kernel(const __grid_constant__ pg::FusedParams P) { pg::fusedAggBody<pg::Prog>(P); }\n";
+    info.ok = true;
+    return src.str();
+}
+
+}  // namespace pg
+
+namespace pg {
+
+std::string generateFusedPageSource(const FusedProgramDesc& D, FusedPageInfo& info)
+{
+    info = FusedPageInfo();
+    const FpProgramDesc& P = D.fp;
+    auto decline = [&](const std::string& why) { info.ok = false; info.reason = why; return std::string(); };
+    if (D.joins.size() > 2) return decline("more than two joins");
+    const int THREADS = Frag::THREADS;
+
+    // ---- selection pass: filter + membership probes ----
+    Frag A(D);
+    if (!A.buildLayouts()) return decline(A.fail);
+    const size_t nOut = A.fin().size();
+    if (nOut == 0 || nOut > 32) return decline("output channel count");
+    std::vector<int> finalChannels;
+    for (size_t c = 0; c < nOut; c++) finalChannels.push_back((int) c);
+    A.planInputs(finalChannels, false);
+    info.usedInputs = A.usedInputs; info.eagerInputs = A.eagerInputs; info.rowsPerThread = A.R;
+    const int R = A.R;
+    std::ostringstream src;
+    src << "// generated by presto_b200 fused_codegen: FilterAndProject -> LookupJoin* materialised as a page (selection pass + emit pass)\n"
+        << "#include \"fused_agg.cuh\"\nnamespace pg {\nstruct Prog {\n"
+        << "    static constexpr int THREADS = " << THREADS << ", MIN_CTAS = 2, R = " << R << ";\n";
+    A.emitTileAndLoad(src, "FusedPageParams");
+    {
+        std::ostringstream body;
+        body << "        bool errOv = false, errDz = false;\n        const int lane = threadIdx.x & 31;\n";
+        A.stageValidity(body, false);
+        if (!A.stageFilter(body)) return decline(A.fail);
+        if (!A.stageJoins(body, false)) return decline(A.fail);
+        for (int p = 0; p < R / 2; p++) {
+            body << "        {\n            const unsigned int m0 = __ballot_sync(0xffffffffu, live" << 2 * p << "), m1 = __ballot_sync(0xffffffffu, live" << 2 * p + 1 << ");\n"
+                 << "            const long long unit = (base + " << p * 2 * THREADS << " + 64 * (long long) (threadIdx.x >> 5)) >> 6;\n"
+                 << "            if (lane == 0 && unit * 64 < P.n) { P.masks[2 * unit] = m0; P.masks[2 * unit + 1] = m1; P.counts[unit] = __popc(m0) + __popc(m1); }\n        }\n";
+        }
+        src << "    static __device__ __forceinline__ void select(const FusedPageParams& P, const Tile& t, long long base)\n    {\n" << body.str()
+            << "        if (errOv) atomicOr(P.fpError, 1u);\n        if (errDz) atomicOr(P.fpError, 2u);\n    }\n";
+    }
+    // ---- emit pass: survivors only; nothing is loaded ahead of time ----
+    Frag B(D);
+    B.buildLayouts();
+    B.planInputs(finalChannels, false);
+    B.R = R;
+    std::fill(B.eager.begin(), B.eager.end(), false);
+    B.resetGen();
+    {
+        std::ostringstream body;
+        body << "        bool errOv = false, errDz = false;\n        const int lane = threadIdx.x & 31;\n        const unsigned int lt = (1u << lane) - 1;\n";
+        for (int p = 0; p < R / 2; p++) {
+            const std::string e = std::to_string(2 * p), o = std::to_string(2 * p + 1), ps = std::to_string(p);
+            body << "        const long long unit" << ps << " = (base + " << p * 2 * THREADS << " + 64 * (long long) (threadIdx.x >> 5)) >> 6;\n"
+                 << "        unsigned int ma" << ps << " = 0, mb" << ps << " = 0, off" << ps << " = 0;\n"
+                 << "        if (unit" << ps << " * 64 < P.n) { const uint2 mm = *(const uint2*) (P.masks + 2 * unit" << ps << "); ma" << ps << " = mm.x; mb" << ps << " = mm.y; off" << ps << " = P.unitOffsets[unit" << ps << "]; }\n"
+                 << "        const long long row" << e << " = base + " << p * 2 * THREADS << " + 2 * (long long) threadIdx.x, row" << o << " = row" << e << " + 1;\n"
+                 << "        bool live" << e << " = (ma" << ps << " >> lane) & 1u, live" << o << " = (mb" << ps << " >> lane) & 1u;\n"
+                 << "        const unsigned int dest" << e << " = off" << ps << " + __popc(ma" << ps << " & lt) + __popc(mb" << ps << " & lt), dest" << o << " = dest" << e << " + (live" << e << " ? 1u : 0u);\n";
+        }
+        // everything below runs under `if (any survivor in this warp's units)`: most warps of a selective fragment skip it
+        std::string any;
+        for (int p = 0; p < R / 2; p++) any += (p ? " | " : "") + std::string("ma") + std::to_string(p) + " | mb" + std::to_string(p);
+        body << "        if ((" << any << ") == 0) return;\n";
+        if (!B.stageJoins(body, true)) return decline(B.fail);
+        info.outputTypes.assign(nOut, 0); info.outputNullable.assign(nOut, false);
+        std::vector<std::vector<Val>> outVals(R);
+        for (int u = 0; u < R; u++) {
+            const std::string us = std::to_string(u);
+            B.g.emit("const bool go" + us + " = live" + us + ";");
+            for (size_t c = 0; c < nOut; c++) {
+                const ChanRef& ref = B.fin()[c];
+                const int type = ref.kind == 0 ? P.nodes[ref.node].type : D.joins[ref.join].buildOutputs[ref.col].type;
+                if (type == PG_TYPE_VARCHAR) return decline("VARCHAR output channel");
+                const Val v = B.chanVal(ref, u, "go" + us);
+                if (!B.g.fail.empty()) return decline(B.g.fail);
+                const int w = widthOf(type);
+                if ((w == 1) != (v.kind == 'b') || (type == PG_TYPE_DOUBLE) != (v.kind == 'd')) return decline("output channel type / representation mismatch");
+                info.outputTypes[c] = type;
+                if (!v.z.empty()) info.outputNullable[c] = true;
+                outVals[u].push_back(v);
+                const std::string cs = std::to_string(c);
+                std::string bits = v.kind == 'd' ? "(unsigned long long) __double_as_longlong(" + v.v + ")" : v.kind == 'b' ? "(" + v.v + " ? 1u : 0u)" : "(unsigned long long) " + v.v;
+                if (!v.z.empty()) bits = "(" + v.z + " ? 0 : " + bits + ")";
+                const char* ty = w == 8 ? "unsigned long long" : w == 4 ? "unsigned int" : "unsigned char";
+                B.g.emit("if (go" + us + ") ((" + ty + "*) P.outValues[" + cs + "])[dest" + us + "] = (" + ty + ") " + bits + ";");
+            }
+        }
+        // nullability is a per-channel property: a channel that is nullable for one row slot is nullable for all (same expressions)
+        for (int u = 0; u < R; u++) {
+            const std::string us = std::to_string(u);
+            for (size_t c = 0; c < nOut; c++) {
+                if (!info.outputNullable[c]) continue;
+                const Val& v = outVals[u][c];
+                B.g.emit("if (go" + us + ") P.outNulls[" + std::to_string(c) + "][dest" + us + "] = " + (v.z.empty() ? std::string("0") : "(" + v.z + " ? 1 : 0)") + ";");
+            }
+        }
+        B.flush(body);
+        src << "    static __device__ __forceinline__ void emit(const FusedPageParams& P, long long base)\n    {\n" << body.str()
+            << "        if (errOv) atomicOr(P.fpError, 1u);\n        if (errDz) atomicOr(P.fpError, 2u);\n    }\n";
+    }
+    src << "};\n}  // namespace pg\n"
+        << "extern \"C\" __global__ void __launch_bounds__(pg::Prog::THREADS, pg::Prog::MIN_CTAS) fused_select(const __grid_constant__ pg::FusedPageParams P) { pg::fusedSelectBody<pg::Prog>(P); }\n"
+        << "extern \"C\" __global__ void __launch_bounds__(pg::Prog::THREADS, pg::Prog::MIN_CTAS) fused_emit(const __grid_constant__ pg::FusedPageParams P) { pg::fusedEmitBody<pg::Prog>(P); }\n";
     info.ok = true;
     return src.str();
 }

@@ -58,4 +58,16 @@ struct FusedKernelInfo {
 // `fused_kernel`); empty when the fragment is not fusable (info.reason says why).
 std::string generateFusedAggSource(const FusedProgramDesc& d, FusedKernelInfo& info);
 
+// FilterAndProject → LookupJoin* materialised as a page (the aggregation fields of `d` are ignored): two kernels, `fused_select` and
+// `fused_emit` (fused_agg.cuh, page sink).  info.outputTypes / outputNullable describe the channels of the output page.
+struct FusedPageInfo {
+    bool ok = false;
+    std::string reason;
+    std::vector<int> usedInputs, eagerInputs;
+    int rowsPerThread = 2;
+    std::vector<int> outputTypes;
+    std::vector<bool> outputNullable;
+};
+std::string generateFusedPageSource(const FusedProgramDesc& d, FusedPageInfo& info);
+
 }  // namespace pg

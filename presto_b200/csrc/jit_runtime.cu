@@ -100,24 +100,31 @@ std::vector<char> compileCudaToCubin(const std::string& source, const std::strin
 
 const JitKernel* getOrCompileKernel(int device, const std::string& source, const char* entry, std::string* error)
 {
+    struct Module { CUmodule module = nullptr; std::map<std::string, JitKernel> kernels; };
     static std::mutex mu;
-    static std::map<std::pair<int, std::string>, JitKernel> cache;
+    static std::map<std::pair<int, std::string>, Module> cache;
     static std::map<std::pair<int, std::string>, std::string> failures;
     std::lock_guard<std::mutex> lock(mu);
     const auto key = std::make_pair(device, source);
-    auto it = cache.find(key);
-    if (it != cache.end()) return &it->second;
     auto f = failures.find(key);
     if (f != failures.end()) { if (error) *error = f->second; return nullptr; }
     try {
         DriverApi& api = DriverApi::get();
         if (!api.ok) throw Error(PG_ERR_UNSUPPORTED, "libcuda.so.1 cannot be loaded");
-        const std::vector<char> cubin = compileCudaToCubin(source, "fused_pipeline.cu");
-        JitKernel k;
-        if (api.moduleLoadData(&k.module, cubin.data()) != CUDA_SUCCESS) throw Error(PG_ERR_CUDA, "cuModuleLoadData of a generated pipeline kernel failed");
-        if (api.moduleGetFunction(&k.function, k.module, entry) != CUDA_SUCCESS) throw Error(PG_ERR_CUDA, "generated module lacks its entry point");
-        api.funcGetAttribute(&k.registers, CU_FUNC_ATTRIBUTE_NUM_REGS, k.function);
-        return &(cache[key] = k);
+        auto it = cache.find(key);
+        if (it == cache.end()) {
+            const std::vector<char> cubin = compileCudaToCubin(source, "fused_pipeline.cu");
+            Module m;
+            if (api.moduleLoadData(&m.module, cubin.data()) != CUDA_SUCCESS) throw Error(PG_ERR_CUDA, "cuModuleLoadData of a generated pipeline kernel failed");
+            it = cache.emplace(key, m).first;
+        }
+        Module& m = it->second;
+        auto k = m.kernels.find(entry);
+        if (k != m.kernels.end()) return &k->second;
+        JitKernel jk; jk.module = m.module;
+        if (api.moduleGetFunction(&jk.function, m.module, entry) != CUDA_SUCCESS) throw Error(PG_ERR_CUDA, std::string("generated module lacks the entry point ") + entry);
+        api.funcGetAttribute(&jk.registers, CU_FUNC_ATTRIBUTE_NUM_REGS, jk.function);
+        return &(m.kernels[entry] = jk);
     }
     catch (const std::exception& e) {
         failures[key] = e.what();

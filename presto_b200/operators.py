@@ -456,6 +456,72 @@ class FusedAggregationOperator(Operator):
         return {"fused_pages": f.value, "unfused_pages": u.value, "registers": r.value, "reason": buf.value.decode()}
 
 
+class FusedPageOperator(Operator):
+    """FilterAndProjectOperator → LookupJoinOperator* of one Driver as ONE operator (include/presto_gpu.h pg_fused_page_create); its
+    output pages are the last operator's.  The oracle chains the reference operators."""
+
+    def __init__(self, input_types: Sequence[int], program, joins: Sequence[FusedJoin], *, backend=None, **options):
+        backend = backend or _default_backend()
+        cfg, self._keep = self._config(input_types, program, joins, options)
+        handle = C.c_void_p()
+        backend.check(backend.fused_page_create(C.byref(cfg), C.byref(handle)))
+        super().__init__(backend, handle)
+
+    @staticmethod
+    def explain(input_types, program, joins, build_types, *, nullable_inputs=(), backend=None) -> str:
+        """The CUDA C++ of the selection and emit passes (no GPU needed); ``build_types[j]`` = types of join j's build output channels."""
+        if backend is None:
+            from ._lib import load_library
+            backend = load_library()
+        cfg, keep = FusedPageOperator._config(input_types, program, joins, {})
+        bt = [abi.i32_array(t) for t in build_types]
+        bptr = (C.POINTER(C.c_int32) * max(1, len(bt)))(*[C.cast(b, C.POINTER(C.c_int32)) for b in bt])
+        nb = abi.i32_array([len(t) for t in build_types])
+        mask = 0
+        for ch in nullable_inputs:
+            mask |= 1 << ch
+        need = C.c_size_t()
+        backend.check(backend.fused_page_explain(C.byref(cfg), mask, bptr, nb, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        backend.check(backend.fused_page_explain(C.byref(cfg), mask, bptr, nb, buf, need.value, C.byref(need)))
+        return buf.value.decode()
+
+    @staticmethod
+    def _config(input_types, program, joins, options):
+        cfg = abi.pg_fused_page_config()
+        self = type("K", (), {})()
+        it, nodes, proj = abi.i32_array(input_types), program.c_nodes(), abi.i32_array(program.projections)
+        f = cfg.page_processor
+        f.n_input_channels, f.input_types = len(input_types), it
+        f.n_nodes, f.nodes = len(program.nodes), nodes
+        f.filter_node = program.filter
+        f.n_projections, f.projection_nodes = len(program.projections), proj
+        self._keep = [it, nodes, proj]
+        jarr = (abi.pg_lookup_join_config * max(1, len(joins)))()
+        barr = (C.c_void_p * max(1, len(joins)))()
+        for i, j in enumerate(joins):
+            ty, hc, oc = abi.i32_array(j.types), abi.i32_array(j.hash_channels), abi.i32_array(j.output_channels)
+            jarr[i].join_type = abi.JOIN_INNER
+            jarr[i].n_channels, jarr[i].types = len(j.types), ty
+            jarr[i].n_hash_channels, jarr[i].hash_channels = len(j.hash_channels), hc
+            jarr[i].n_output_channels, jarr[i].output_channels = len(j.output_channels), oc
+            jarr[i].precomputed_hash_channel = -1
+            barr[i] = j.bridge._h if j.bridge is not None else None
+            self._keep += [ty, hc, oc]
+        cfg.n_joins, cfg.joins, cfg.bridges = len(joins), jarr, barr
+        self._keep += [jarr, barr]
+        cfg.options = _options(**options)
+        return cfg, self._keep
+
+    def get_info(self) -> dict:
+        if not self._b.has_device:
+            return {"fused_pages": 0, "unfused_pages": 0, "reason": "reference operators chained"}
+        f, u = C.c_int64(), C.c_int64()
+        buf = C.create_string_buffer(2048)
+        self._b.check(self._b.fused_page_get_info(self._h, C.byref(f), C.byref(u), buf, 2048))
+        return {"fused_pages": f.value, "unfused_pages": u.value, "reason": buf.value.decode()}
+
+
 class PagesSerde:
     """PagesSerde (presto-spi/.../spi/page/PagesSerde.java:67-156) + PagesSerdeUtil.writeSerializedPage / readSerializedPage
     (:64-88): pages to and from the SerializedPage wire bytes (21-byte header + raw page)."""

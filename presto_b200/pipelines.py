@@ -10,8 +10,8 @@ from typing import Dict, List, Optional, Sequence
 
 from . import _abi as abi
 from .expressions import Program
-from .operators import (Aggregate, FilterAndProjectOperator, FusedAggregationOperator, FusedJoin, HashAggregationOperator, HashBuilderOperator, JoinBridge,
-                        LookupJoinOperator)
+from .operators import (Aggregate, FilterAndProjectOperator, FusedAggregationOperator, FusedJoin, FusedPageOperator, HashAggregationOperator,
+                        HashBuilderOperator, JoinBridge, LookupJoinOperator)
 from .page import Page
 
 BUILDING = 1                 # dictionary code of c_mktsegment = 'BUILDING'
@@ -141,19 +141,32 @@ def run_q3(customer: Sequence[Page], orders: Sequence[Page], lineitem: Sequence[
     ok, ock, od, sp = [po.input(i) for i in range(4)]
     po.set_filter(od < Q3_DATE)
     po.project(ok, ock, od, sp)
-    fp_o = FilterAndProjectOperator([abi.BIGINT, abi.BIGINT, abi.DATE, abi.INTEGER], po, output_memory=mem, **o)
-    probe1 = LookupJoinOperator(bridge1, [abi.BIGINT, abi.BIGINT, abi.DATE, abi.INTEGER], [1], [0, 2, 3], output_memory=mem, **o)
     bridge2 = JoinBridge(opts.get("device", 0), backend=backend)
     build2 = HashBuilderOperator(bridge2, [abi.BIGINT, abi.DATE, abi.INTEGER], [0], [1, 2], **o)
-    for page in orders:
-        fp_o.add_input(page)
-        f = fp_o.get_output(copy=copy)
-        if f is None or not f.position_count:
-            continue
-        probe1.add_input(f)
-        j = probe1.get_output(copy=copy)
-        if j is not None and j.position_count:
-            build2.add_input(j)
+    if fused:
+        # the orders Driver (filter → probe the BUILDING customers) as ONE operator feeding the build of the second join
+        fp_o = FusedPageOperator([abi.BIGINT, abi.BIGINT, abi.DATE, abi.INTEGER], po, [FusedJoin(bridge1, [abi.BIGINT, abi.BIGINT, abi.DATE, abi.INTEGER], [1], [0, 2, 3])],
+                                 output_memory=mem, **o)
+        probe1 = fp_o
+        for page in orders:
+            fp_o.add_input(page)
+            j = fp_o.get_output(copy=copy)
+            if j is not None and j.position_count:
+                build2.add_input(j)
+        if stats is not None:
+            stats.update({"orders_" + k: v for k, v in fp_o.get_info().items()})
+    else:
+        fp_o = FilterAndProjectOperator([abi.BIGINT, abi.BIGINT, abi.DATE, abi.INTEGER], po, output_memory=mem, **o)
+        probe1 = LookupJoinOperator(bridge1, [abi.BIGINT, abi.BIGINT, abi.DATE, abi.INTEGER], [1], [0, 2, 3], output_memory=mem, **o)
+        for page in orders:
+            fp_o.add_input(page)
+            f = fp_o.get_output(copy=copy)
+            if f is None or not f.position_count:
+                continue
+            probe1.add_input(f)
+            j = probe1.get_output(copy=copy)
+            if j is not None and j.position_count:
+                build2.add_input(j)
     build2.finish()
     # lineitem → probe #2 → aggregation
     pl = Program([abi.BIGINT, abi.DOUBLE, abi.DOUBLE, abi.DATE])
@@ -176,10 +189,10 @@ def run_q3(customer: Sequence[Page], orders: Sequence[Page], lineitem: Sequence[
                 result.append(_detach(r) if device_resident else r)
         if stats is not None:
             stats["joined_rows"] = -1
-            stats["kernel_launches"] = sum(op.get_stats()["kernel_launches"] for op in (fp_c, build1, fp_o, probe1, build2, fa))
+            stats["kernel_launches"] = sum(op.get_stats()["kernel_launches"] for op in (fp_c, build1, fp_o, build2, fa))
             stats.update({"fused_" + k: v for k, v in fa.get_info().items()})
             stats["kernel_paths"] = fa.get_stats()["kernel_paths"]
-        for op in (fp_c, build1, fp_o, probe1, build2, fa):
+        for op in (fp_c, build1, fp_o, build2, fa):
             op.close()
         bridge1.close(); bridge2.close()
         return result

@@ -82,3 +82,25 @@ def test_unfusable_fragments_are_declined_with_a_reason():
         with pytest.raises(PrestoException) as e:
             FusedAggregationOperator.explain(types, prog, [], [], [BIGINT], [0], aggs, nullable_inputs=nullable)
         assert e.value.code == 3 and why in str(e.value)
+
+
+def test_page_sink_fragment_compiles():
+    """Q3's orders Driver: filter on orderdate -> probe the customer key set (no payload: pure membership) -> (orderkey, orderdate, shippriority)
+    page; and a fragment whose join contributes payload columns with a nullable probe-side projection."""
+    from presto_b200 import FusedPageOperator
+    types = [BIGINT, BIGINT, DATE, INTEGER]
+    po = Program(types)
+    ok, ock, od, sp = [po.input(i) for i in range(4)]
+    po.set_filter(od < Q3_DATE)
+    po.project(ok, ock, od, sp)
+    src = FusedPageOperator.explain(types, po, [join([BIGINT, BIGINT, DATE, INTEGER], [1], [0, 2, 3])], [[]])
+    assert "fused_select" in src and "fused_emit" in src and ", R = 4;" in src and "P.outValues[2]" in src and "P.outValues[3]" not in src
+    assert compile_check(src) > 10_000
+    types = [BIGINT, DOUBLE, INTEGER]
+    p2 = Program(types)
+    k, v, i = [p2.input(c) for c in range(3)]
+    p2.set_filter(v > 0.5)
+    p2.project(k, v * 2.0, i + 1)
+    src = FusedPageOperator.explain(types, p2, [join([BIGINT, DOUBLE, BIGINT], [0], [0, 1, 2])], [[DOUBLE, INTEGER]], nullable_inputs=[2])
+    assert "P.outNulls[2]" in src and "P.outValues[4]" in src and "errOv" in src
+    assert compile_check(src) > 10_000

@@ -282,3 +282,66 @@ def test_device_resident_pages(gpu_backend, oracle_backend):
         assert info["fused_pages"] == expect_fused, info
     for p in keep:
         gpu_backend.device_free(p)
+
+
+def run_page_op(backend, pages, types, prog, joins, info=None):
+    from presto_b200 import FusedPageOperator
+    op = FusedPageOperator(types, prog, joins, backend=backend)
+    rows = rows_of(to_pages(op, pages))
+    if info is not None:
+        info.update(op.get_info())
+    op.close()
+    return rows
+
+
+def test_page_sink_filter_join_pages(gpu_backend, oracle_backend):
+    """FusedPageOperator: filter → probe → output page, rows in input order, bit-exact against the chained reference operators: pure
+    membership join (Q3's orders ⋈ BUILDING customers), payload join with NULLs on both sides, no join at all, a page of all misses."""
+    rng = np.random.default_rng(33)
+    n = 150_000
+
+    def run(backend, info=None):
+        out = []
+        b1 = JoinBridge(backend=backend); b2 = JoinBridge(backend=backend)
+        h1 = HashBuilderOperator(b1, [BIGINT], [0], [], backend=backend)
+        to_pages(h1, [Page([Block.from_numpy(BIGINT, (rng2.permutation(40_000)[:9000] + 7).astype(np.int64))])])
+        pay_nulls = (rng2.random(5000) < 0.2).astype(np.uint8)
+        h2 = HashBuilderOperator(b2, [BIGINT, DOUBLE, INTEGER], [0], [1, 2], backend=backend)
+        to_pages(h2, [Page([Block.from_numpy(BIGINT, (rng2.permutation(20_000)[:5000] * 2).astype(np.int64)), Block.from_numpy(DOUBLE, rng2.random(5000), pay_nulls),
+                            Block.from_numpy(INTEGER, rng2.integers(0, 9, 5000).astype(np.int32))])])
+        # (1) membership join, Q3 orders shape
+        types = [BIGINT, BIGINT, DATE, INTEGER]
+        prog = Program(types)
+        ok, ck, od, sp = [prog.input(i) for i in range(4)]
+        prog.set_filter(od < 9204)
+        prog.project(ok, ck, od, sp)
+        pages = [Page([Block.from_numpy(BIGINT, rng2.integers(0, 10**9, m)), Block.from_numpy(BIGINT, rng2.integers(0, 45_000, m)),
+                       Block.from_numpy(DATE, rng2.integers(8035, 10441, m).astype(np.int32)), Block.from_numpy(INTEGER, np.zeros(m, dtype=np.int32))]) for m in (n, 777, 1)]
+        i1 = {}
+        out.append(run_page_op(backend, pages, types, prog, [FusedJoin(b1, types, [1], [0, 2, 3])], i1))
+        # (2) payload join, nullable probe key and a computed probe-side column
+        types2 = [BIGINT, DOUBLE, INTEGER]
+        prog2 = Program(types2)
+        k, v, c = [prog2.input(i) for i in range(3)]
+        prog2.set_filter((v > 0.25) | c.is_null())
+        prog2.project(k, v * 2.0, c + 1)
+        kn = (rng2.random(n) < 0.05).astype(np.uint8); cn = (rng2.random(n) < 0.1).astype(np.uint8)
+        pages2 = [Page([Block.from_numpy(BIGINT, rng2.integers(0, 45_000, n), kn), Block.from_numpy(DOUBLE, rng2.random(n)), Block.from_numpy(INTEGER, rng2.integers(0, 100, n).astype(np.int32), cn)])]
+        i2 = {}
+        out.append(run_page_op(backend, pages2, types2, prog2, [FusedJoin(b2, [BIGINT, DOUBLE, BIGINT], [0], [0, 1, 2])], i2))
+        # (3) no join: plain filter / project; (4) every probe misses
+        i3 = {}
+        out.append(run_page_op(backend, pages2, types2, prog2, [], i3))
+        miss = [Page([Block.from_numpy(BIGINT, np.full(1000, 10**12, dtype=np.int64)), Block.from_numpy(DOUBLE, np.ones(1000)), Block.from_numpy(INTEGER, np.ones(1000, dtype=np.int32))])]
+        out.append(run_page_op(backend, miss, types2, prog2, [FusedJoin(b2, [BIGINT, DOUBLE, BIGINT], [0], [0, 1, 2])]))
+        for x in (h1, h2): x.close()
+        b1.close(); b2.close()
+        if info is not None:
+            info.update({"i1": i1, "i2": i2, "i3": i3})
+        return out
+    rng2 = np.random.default_rng(34); want = run(oracle_backend)
+    rng2 = np.random.default_rng(34); info = {}; got = run(gpu_backend, info)
+    assert [len(x) for x in want] == [len(x) for x in got] and len(want[0]) > 1000 and len(want[1]) > 1000 and len(want[3]) == 0
+    for g, w in zip(got, want):
+        rows_close(g, w, rel=0.0)
+    assert info["i1"]["fused_pages"] == 3 and info["i2"]["fused_pages"] == 1 and info["i3"]["fused_pages"] == 1, info
