@@ -621,7 +621,7 @@ def q1_operator(backend, key_kind, step, **opts):
                                     group_max_lengths=[1, 1] if key_kind == "varchar" else None, backend=backend, max_output_rows=1 << 30, **opts)
 
 
-def cpu_q1(torch, cols, key_kind, row_begin, row_end, threads, chunk=1 << 20):
+def cpu_q1(torch, cols, key_kind, row_begin, row_end, threads, chunk=1 << 16):
     """The reference's Q1 operators (oracle: FilterAndProject -> HashAggregation PARTIAL) on `threads` host threads over rows
     [row_begin, row_end) of the device columns, then one FINAL merge.  Every thread copies ITS slice from the GPU into memory it
     allocates and first-touches itself (NUMA-local pages), outside the timed region.  Returns (rows/s, seconds, result rows, host GB/s)."""
@@ -841,7 +841,7 @@ def run_reference(args):
         "config": q1_config(args, args.keys),
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port", "host_gbs": sample * Q1_BYTES_PER_ROW[args.keys] / (ms / 1000) / 1e9,
                          "sample": f"{sample} rows of the workload per step, {threads} threads x (oracle FilterAndProject -> HashAggregation PARTIAL over thread-local, "
-                                   f"first-touched slices in 2^20-row pages) + FINAL merge; host wall clock, no GPU in the timed region"},
+                                   f"first-touched slices in 2^16-row pages) + FINAL merge; host wall clock, no GPU in the timed region"},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -893,6 +893,11 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        t_wait = time.time()
+        while not sampler.samples and time.time() - t_wait < 10:      # NVML initialisation can take longer than the whole timed region
+            time.sleep(0.01)
+    if dist is not None:
+        dist.barrier()
     r = run_q1_headline(torch, backend, cols, kk, args.steps, args.warmup, local, dist)
     clocks = sampler.stop() if rank == 0 else None
     ms, kms = r["ms"], r["kernel_ms"]

@@ -73,6 +73,17 @@ struct DriverChain : Operator {
 
 using namespace oracle;
 
+// The operators build every output page in fresh std::vectors.  With glibc's defaults each of those (> 128 KB) is its own mmap / page
+// fault / munmap cycle, and 128 driver threads doing that serialise on the process's mm lock (measured: 0.3 M rows/s per thread instead
+// of 3.7 M).  Keep freed blocks in the arenas instead — the JVM's heap does the same for the reference.
+#include <malloc.h>
+__attribute__((constructor)) static void oracleMallocSetup()
+{
+    mallopt(M_MMAP_THRESHOLD, 1 << 30);
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
+    mallopt(M_ARENA_MAX, 256);
+}
+
 static thread_local std::string g_lastError;
 
 extern "C" {

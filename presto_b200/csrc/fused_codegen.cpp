@@ -237,6 +237,7 @@ struct Frag {
     int nNodes, nIn;
     std::vector<std::vector<ChanRef>> layouts;
     std::vector<bool> used, eager;
+    std::vector<bool> eagerOffsets;          // VARCHAR channels whose offsets ride in the tile (the slices themselves are read by the row program)
     std::vector<int> usedInputs, eagerInputs;
     int R = 2;
     static constexpr int THREADS = 256;
@@ -300,6 +301,11 @@ struct Frag {
             if (P.inputTypes[c] == PG_TYPE_VARCHAR) eager[c] = false;       // slices are read where they are used
             if (eager[c]) eagerBytes += widthOf(P.inputTypes[c]);
         }
+        // VARCHAR inputs of a fragment without joins (every row reaches the sink): their offsets are loaded with the tile, so that only
+        // ONE dependent load (the bytes) is left when the row is processed
+        eagerOffsets.assign(nIn, false);
+        if (D.joins.empty() && allEagerWithoutJoins)
+            for (int c = 0; c < nIn; c++) if (used[c] && P.inputTypes[c] == PG_TYPE_VARCHAR) eagerOffsets[c] = true;
         usedInputs.clear(); eagerInputs.clear();
         for (int c = 0; c < nIn; c++) if (used[c]) usedInputs.push_back(c);
         for (int c = 0; c < nIn; c++) if (eager[c]) eagerInputs.push_back(c);
@@ -321,6 +327,7 @@ struct Frag {
             const int w = widthOf(P.inputTypes[c]);
             src << "        " << (w == 8 ? "unsigned long long" : w == 4 ? "unsigned int" : "unsigned char") << " c" << c << "[R];\n";
         }
+        for (int c = 0; c < nIn; c++) if (eagerOffsets[c]) src << "        int o" << c << "[R / 2][3];\n";
         if (eagerInputs.empty()) src << "        int unused;\n";
         src << "    };\n";
         src << "    static __device__ __forceinline__ void load(const " << paramsType << "& P, long long base, Tile& t)\n    {\n";
@@ -333,12 +340,16 @@ struct Frag {
                 else if (w == 4) src << "                { const uint64_t x = ldStream64((const uint32_t*) P.values[" << c << "] + r0); t.c" << c << "[" << 2 * p << "] = (unsigned int) x; t.c" << c << "[" << 2 * p + 1 << "] = (unsigned int) (x >> 32); }\n";
                 else src << "                { const unsigned short x = *((const unsigned short*) ((const uint8_t*) P.values[" << c << "] + r0)); t.c" << c << "[" << 2 * p << "] = (unsigned char) x; t.c" << c << "[" << 2 * p + 1 << "] = (unsigned char) (x >> 8); }\n";
             }
+            for (int c = 0; c < nIn; c++) if (eagerOffsets[c])
+                src << "                { const int* op = P.offsets[" << c << "] + r0; t.o" << c << "[" << p << "][0] = __ldg(op); t.o" << c << "[" << p << "][1] = __ldg(op + 1); t.o" << c << "[" << p << "][2] = __ldg(op + 2); }\n";
             src << "            }\n            else {\n";
             for (int c : eagerInputs) {
                 const int w = widthOf(P.inputTypes[c]);
                 const char* ty = w == 8 ? "uint64_t" : w == 4 ? "uint32_t" : "uint8_t";
                 src << "                t.c" << c << "[" << 2 * p << "] = r0 < P.n ? ((const " << ty << "*) P.values[" << c << "])[r0] : 0; t.c" << c << "[" << 2 * p + 1 << "] = 0;\n";
             }
+            for (int c = 0; c < nIn; c++) if (eagerOffsets[c])
+                src << "                { const bool in = r0 < P.n; t.o" << c << "[" << p << "][0] = in ? P.offsets[" << c << "][r0] : 0; t.o" << c << "[" << p << "][1] = in ? P.offsets[" << c << "][r0 + 1] : 0; t.o" << c << "[" << p << "][2] = t.o" << c << "[" << p << "][1]; }\n";
             src << "            }\n        }\n";
         }
         src << "    }\n";
@@ -392,11 +403,13 @@ struct Frag {
         }
         return r;
     }
-    // stage B: the probes.  withPayload = false: membership only (the selection pass of the page sink).
-    bool stageJoins(std::ostringstream& body, bool withPayload)
+    // stage B: the probes.  withPayload = false: membership only (the selection pass of the page sink).  survivorsOnly: the rows are
+    // known to match every join (emit pass): joins without build output are not probed again.
+    bool stageJoins(std::ostringstream& body, bool withPayload, bool survivorsOnly = false)
     {
         for (size_t j = 0; j < D.joins.size(); j++) {
             const FusedJoinDesc& J = D.joins[j];
+            if (survivorsOnly && J.strideWords == 0) continue;
             const std::string js = std::to_string(j);
             const ChanRef& keyRef = layouts[j][J.keyChannel];
             const bool membershipOnly = J.strideWords == 0 || !withPayload;
@@ -543,7 +556,10 @@ std::string generateFusedAggSource(const FusedProgramDesc& D, FusedKernelInfo& i
                 // VARCHAR(n <= 7) key: [length byte][bytes] exactly as group_table.cuh packKey packs it
                 const std::string id = "k" + std::to_string(&k - &D.keys[0]) + "_" + us, cs = std::to_string(v.channel);
                 g.emit("unsigned long long s" + id + " = 0;");
-                g.emit("if (go" + us + (v.z.empty() ? "" : " && !" + v.z) + ") { const int o = P.offsets[" + cs + "][row" + us + "]; int len = P.offsets[" + cs + "][row" + us + " + 1] - o; "
+                const std::string offs = F.eagerOffsets[v.channel]
+                    ? "const int o = t.o" + cs + "[" + std::to_string(u / 2) + "][" + std::to_string(u % 2) + "]; int len = t.o" + cs + "[" + std::to_string(u / 2) + "][" + std::to_string(u % 2 + 1) + "] - o; "
+                    : "const int o = P.offsets[" + cs + "][row" + us + "]; int len = P.offsets[" + cs + "][row" + us + " + 1] - o; ";
+                g.emit("if (go" + us + (v.z.empty() ? "" : " && !" + v.z) + ") { " + offs +
                        "if (len > " + std::to_string(k.maxLen) + ") { errLen = true; len = " + std::to_string(k.maxLen) + "; } "
                        "const uint8_t* b = (const uint8_t*) P.values[" + cs + "] + o; s" + id + " = (unsigned long long) (unsigned int) len; "
                        "for (int i = 0; i < len && i < 7; i++) s" + id + " |= (unsigned long long) b[i] << (8 * (i + 1)); }");
@@ -692,7 +708,7 @@ std::string generateFusedPageSource(const FusedProgramDesc& D, FusedPageInfo& in
         std::string any;
         for (int p = 0; p < R / 2; p++) any += (p ? " | " : "") + std::string("ma") + std::to_string(p) + " | mb" + std::to_string(p);
         body << "        if ((" << any << ") == 0) return;\n";
-        if (!B.stageJoins(body, true)) return decline(B.fail);
+        if (!B.stageJoins(body, true, true)) return decline(B.fail);
         info.outputTypes.assign(nOut, 0); info.outputNullable.assign(nOut, false);
         std::vector<std::vector<Val>> outVals(R);
         for (int u = 0; u < R; u++) {
