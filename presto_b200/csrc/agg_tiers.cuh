@@ -22,7 +22,10 @@ constexpr int kTier0Bytes = kTier0Columns * kAggThreads * 8;   // K0 * MAXV <= 4
 // shared-memory carve-up, same arithmetic on host and device
 struct SharedLayout {
     uint32_t keys, acc, first, state, sid, misc, tier0, total;
-    __host__ __device__ SharedLayout(uint32_t S, int W, int nAccAlloc, bool withTier0)
+    __host__ __device__ SharedLayout(uint32_t S, int W, int nAccAlloc, bool withTier0) { plan(S, W, nAccAlloc, withTier0 ? (uint32_t) kTier0Bytes : 0u); }
+    // explicit tier-0 size (fused kernels size it for the groups the page actually has, to leave room for a TMA staging ring)
+    __host__ __device__ SharedLayout(uint32_t S, int W, int nAccAlloc, uint32_t tier0Bytes, int) { plan(S, W, nAccAlloc, tier0Bytes); }
+    __host__ __device__ void plan(uint32_t S, int W, int nAccAlloc, uint32_t tier0Bytes)
     {
         const uint32_t S2 = S + 2;
         uint32_t o = 0;
@@ -33,7 +36,7 @@ struct SharedLayout {
         sid = o; o += (S2 + 15) & ~15u;
         misc = o; o += 1280;  // claimed count, next tier-0 / warp-table id, slot of each id (<= 254)
         o = (o + 15) & ~15u;
-        tier0 = o; o += withTier0 ? kTier0Bytes : 0;
+        tier0 = o; o += tier0Bytes;
         total = o;
     }
 };

@@ -31,6 +31,9 @@ struct FusedParams {
     uint32_t S, sLimit;              // shared table slots / fill limit (W == 1, !direct)
     int32_t nAccAlloc;               // accumulator columns the shared table was sized for
     int32_t direct;                  // 1: no on-chip tiers, every row goes to the HBM table (many groups, or W > 1)
+    int32_t t0Groups;                // groups that get per-thread private accumulators (tier 0): <= kTier0Columns / accumulator columns
+    int32_t tmaStages;               // > 0: eager columns arrive through a cp.async.bulk ring of this many stages (fused_kernel_tma)
+    int64_t tmaTiles;                // tiles [0, tmaTiles) come through the ring; the tail (and partial tiles) through direct loads
     int32_t phys[kFusedMaxSums + 1]; // physical accumulator column of each sum, then of the row count
     const void* values[kFusedMaxInputs];     // raw input channels: fixed-width values or VARCHAR bytes
     const uint8_t* nulls[kFusedMaxInputs];
@@ -97,8 +100,9 @@ struct FusedAggSink {
     static constexpr bool CNT = Prog::CNT;
     static constexpr int NC = NV + (CNT ? 1 : 0);
     static constexpr int NVA = NV > 0 ? NV : 1;
-    static constexpr int K0 = (kTier0Columns / NC) > 31 ? 31 : (kTier0Columns / NC);
+    static constexpr int K0MAX = (kTier0Columns / NC) > 31 ? 31 : (kTier0Columns / NC);
     const FusedParams& P;
+    int K0;                          // tier-0 groups of this launch (P.t0Groups)
     SharedTable<1> st;
     uint64_t* tier0;                 // [K0][NC][THREADS]
     uint32_t seen0, probeHits, probeMisses;
@@ -112,10 +116,11 @@ struct FusedAggSink {
         tid = threadIdx.x;
         seen0 = 0; probeHits = 0; probeMisses = 0; bypass = false;
         tiers = Prog::TIERS && !P.direct;
-        if (Prog::QUEUE) initQueue(smemRaw + (tiers ? SharedLayout(P.S, 1, P.nAccAlloc, true).total : 0));
+        K0 = min(max(P.t0Groups, 0), K0MAX);
+        const SharedLayout lay(P.S, 1, P.nAccAlloc, (uint32_t) (K0 * NC * THREADS * 8), 0);
+        if (Prog::QUEUE) initQueue(smemRaw + (tiers ? lay.total : 0));
         if (!tiers) return;
         st.S = P.S; st.S2 = P.S + 2; st.sLimit = P.sLimit; st.tier0Groups = K0;
-        const SharedLayout lay(P.S, 1, P.nAccAlloc, true);
         st.keys = (volatile uint64_t*) (smemRaw + lay.keys);
         st.acc = (uint64_t*) (smemRaw + lay.acc);
         st.first = (uint32_t*) (smemRaw + lay.first);
@@ -123,12 +128,15 @@ struct FusedAggSink {
         st.sid = (volatile uint8_t*) (smemRaw + lay.sid);
         st.count = (uint32_t*) (smemRaw + lay.misc);
         tier0 = (uint64_t*) (smemRaw + lay.tier0);
-        for (uint32_t i = tid; i < st.S2; i += THREADS) { st.keys[i] = kEmptyKey; st.first[i] = kNoRow32; st.sid[i] = 0xFF; }
-        for (uint32_t i = tid; i < (uint32_t) P.nAccAlloc * st.S2; i += THREADS) st.acc[i] = 0;
-        for (int i = tid; i < 320; i += THREADS) st.count[i] = 0;
-#pragma unroll
-        for (int i = 0; i < K0 * NC; i++) tier0[i * THREADS + tid] = 0;
+        if (tid < THREADS) {
+            for (uint32_t i = tid; i < st.S2; i += THREADS) { st.keys[i] = kEmptyKey; st.first[i] = kNoRow32; st.sid[i] = 0xFF; }
+            for (uint32_t i = tid; i < (uint32_t) P.nAccAlloc * st.S2; i += THREADS) st.acc[i] = 0;
+            for (int i = tid; i < 320; i += THREADS) st.count[i] = 0;
+        }
+        if (tid < THREADS) for (int i = 0; i < K0 * NC; i++) tier0[i * THREADS + tid] = 0;
     }
+    // bytes of the tier layout of this launch (a TMA ring, when used, starts behind it)
+    __device__ __forceinline__ uint32_t layoutBytes() const { return tiers ? SharedLayout(P.S, 1, P.nAccAlloc, (uint32_t) (K0 * NC * THREADS * 8), 0).total : 0; }
 
     // the HBM table (tier 2 / direct mode)
     __device__ __forceinline__ void addGlobal(const uint64_t (&kw)[W], int special, uint32_t spell, const uint64_t (&vals)[NVA], uint32_t rowIdx)
@@ -269,7 +277,7 @@ struct FusedAggSink {
         const GroupTable& T = P.t;
         const int lane = tid & 31, warp = tid >> 5;
         const uint32_t nT0 = min(st.count[1], (uint32_t) K0);
-        for (uint32_t pairIdx = warp; pairIdx < nT0 * (uint32_t) NC; pairIdx += THREADS / 32) {
+        for (uint32_t pairIdx = warp; pairIdx < nT0 * (uint32_t) NC && tid < THREADS; pairIdx += THREADS / 32) {
             const uint32_t id = pairIdx / NC, c = pairIdx % NC;
             const uint64_t* src = tier0 + (size_t) pairIdx * THREADS;
             const bool isF = c < (uint32_t) NV;
@@ -292,7 +300,7 @@ struct FusedAggSink {
             }
         }
         __syncthreads();
-        for (uint32_t s = tid; s < st.S2; s += THREADS) {
+        for (uint32_t s = tid; s < st.S2 && tid < THREADS; s += THREADS) {
             const uint32_t f = st.first[s];
             if (f == kNoRow32) continue;
             int gslot;
@@ -313,6 +321,79 @@ struct FusedAggSink {
         }
     }
 };
+
+// ---- TMA staging ring (north_star: "TMA bulk staging of page data into shared memory") ----------------------------------------------
+// cp.async.bulk (the 1-D form of TMA: no tensor map) copies one tile of every eagerly loaded column from HBM into a shared-memory stage
+// and signals an mbarrier with the byte count; a dedicated producer warp keeps `stages` tiles in flight while the 8 consumer warps
+// move a landed tile into registers (Prog::loadSmem), release the stage and run the row program.  Compared with the register double
+// buffer of fusedAggBody the prefetch depth no longer costs registers and the consumers issue no global loads for these columns.
+__device__ __forceinline__ uint32_t smemU32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smemU32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smemU32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbarArrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smemU32(bar)) : "memory"); }
+__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}" :: "r"(smemU32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulkCopyToShared(void* dstSmem, const void* srcGlobal, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smemU32(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(smemU32(bar)) : "memory");
+}
+
+template <class Prog>
+__device__ __forceinline__ void fusedAggBodyTma(const FusedParams& P)
+{
+    extern __shared__ __align__(16) unsigned char fusedSmem[];
+    constexpr int THREADS = Prog::THREADS;            // consumer threads; the block has THREADS + 32 (the producer warp)
+    constexpr int TILE = THREADS * Prog::R;
+    FusedAggSink<Prog> sink(P);
+    sink.init(fusedSmem);
+    const int stages = P.tmaStages;
+    unsigned char* ring = fusedSmem + ((sink.layoutBytes() + 127u) & ~127u);
+    uint64_t* full = (uint64_t*) (ring + (size_t) stages * Prog::STAGE_BYTES);
+    uint64_t* empty = full + stages;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; s++) { mbarInit(&full[s], 1); mbarInit(&empty[s], THREADS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const long long nTiles = (P.n + TILE - 1) / TILE;
+    const long long tmaTiles = min((long long) P.tmaTiles, nTiles);
+    if (threadIdx.x >= THREADS) {
+        // ---- producer warp: one lane issues the bulk copies of tile k into stage k % stages once the consumers released it ----
+        if (threadIdx.x == THREADS) {
+            long long k = 0;
+            for (long long tile = blockIdx.x; tile < tmaTiles; tile += gridDim.x, k++) {
+                const int s = (int) (k % stages);
+                if (k >= stages) mbarWait(&empty[s], (uint32_t) ((k / stages - 1) & 1));
+                mbarExpectTx(&full[s], Prog::STAGE_TX_BYTES);
+                Prog::issueStage(P, tile * TILE, ring + (size_t) s * Prog::STAGE_BYTES, &full[s]);
+            }
+        }
+    }
+    else {
+        // ---- consumers ----
+        typename Prog::Tile t;
+        long long k = 0;
+        for (long long tile = blockIdx.x; tile < tmaTiles; tile += gridDim.x, k++) {
+            const int s = (int) (k % stages);
+            mbarWait(&full[s], (uint32_t) ((k / stages) & 1));
+            Prog::loadSmem(ring + (size_t) s * Prog::STAGE_BYTES, t);
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbarArrive(&empty[s]);      // the stage is free as soon as the tile sits in registers
+            Prog::process(P, t, tile * TILE, sink);
+            __syncwarp();
+        }
+        // the tail: the last full tile and the partial one come through direct loads (a bulk copy must not read past a column's end)
+        for (long long tile = tmaTiles + blockIdx.x; tile < nTiles; tile += gridDim.x) {
+            Prog::load(P, tile * TILE, t);
+            Prog::process(P, t, tile * TILE, sink);
+            __syncwarp();
+        }
+    }
+    sink.flush();
+}
 
 // ---- the kernel body: persistent CTAs, tiles of THREADS * R rows, the next tile's loads in flight while this one is consumed ----
 template <class Prog>

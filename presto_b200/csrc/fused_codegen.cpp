@@ -355,6 +355,41 @@ struct Frag {
         src << "    }\n";
     }
 
+    // The cp.async.bulk ring's view of a tile (fused_agg.cuh fusedAggBodyTma): every eager column's TILE rows back to back in one
+    // shared-memory stage.  Returns the stage size in bytes.
+    int emitTma(std::ostringstream& src, const char* paramsType)
+    {
+        const int TILE = THREADS * R;
+        struct Part { int ch; int width; bool offsets; int at; int bytes; };
+        std::vector<Part> parts;
+        int at = 0;
+        for (int c : eagerInputs) { const int w = widthOf(P.inputTypes[c]); parts.push_back({c, w, false, at, TILE * w}); at += (TILE * w + 15) & ~15; }
+        for (int c = 0; c < nIn; c++) if (eagerOffsets[c]) { parts.push_back({c, 4, true, at, TILE * 4 + 16}); at += TILE * 4 + 16; }
+        const int stageBytes = (at + 127) & ~127;
+        src << "    static constexpr int STAGE_BYTES = " << stageBytes << ";\n";
+        src << "    static __device__ __forceinline__ void issueStage(const " << paramsType << "& P, long long base, unsigned char* stage, uint64_t* bar)\n    {\n";
+        int tx = 0;
+        for (const Part& p : parts) {
+            if (p.offsets) src << "        bulkCopyToShared(stage + " << p.at << ", (const char*) (P.offsets[" << p.ch << "] + base), " << p.bytes << ", bar);\n";
+            else src << "        bulkCopyToShared(stage + " << p.at << ", (const char*) P.values[" << p.ch << "] + base * " << p.width << ", " << p.bytes << ", bar);\n";
+            tx += p.bytes;
+        }
+        src << "    }\n    static constexpr int STAGE_TX_BYTES = " << tx << ";\n";
+        src << "    static __device__ __forceinline__ void loadSmem(const unsigned char* stage, Tile& t)\n    {\n";
+        for (int p = 0; p < R / 2; p++) {
+            src << "        {\n            const int r = " << p * 2 * THREADS << " + 2 * (int) threadIdx.x;\n";
+            for (const Part& q : parts) {
+                if (q.offsets) src << "            { const int* op = (const int*) (stage + " << q.at << ") + r; const int2 a = *(const int2*) op; t.o" << q.ch << "[" << p << "][0] = a.x; t.o" << q.ch << "[" << p << "][1] = a.y; t.o" << q.ch << "[" << p << "][2] = op[2]; }\n";
+                else if (q.width == 8) src << "            { const ulonglong2 x = *(const ulonglong2*) (stage + " << q.at << " + r * 8); t.c" << q.ch << "[" << 2 * p << "] = x.x; t.c" << q.ch << "[" << 2 * p + 1 << "] = x.y; }\n";
+                else if (q.width == 4) src << "            { const uint2 x = *(const uint2*) (stage + " << q.at << " + r * 4); t.c" << q.ch << "[" << 2 * p << "] = x.x; t.c" << q.ch << "[" << 2 * p + 1 << "] = x.y; }\n";
+                else src << "            { const unsigned short x = *(const unsigned short*) (stage + " << q.at << " + r); t.c" << q.ch << "[" << 2 * p << "] = (unsigned char) x; t.c" << q.ch << "[" << 2 * p + 1 << "] = (unsigned char) (x >> 8); }\n";
+            }
+            src << "        }\n";
+        }
+        src << "    }\n";
+        return stageBytes;
+    }
+
     // stage A: row index and validity of every row slot (+ the deferred-row bitmap of the aggregation sink)
     void stageValidity(std::ostringstream& body, bool withBitmapIn)
     {
@@ -526,6 +561,8 @@ std::string generateFusedAggSource(const FusedProgramDesc& D, FusedKernelInfo& i
         src << "    }\n";
     }
     F.emitTileAndLoad(src, "FusedParams");
+    info.tma = D.joins.empty() && !F.eagerInputs.empty();
+    if (info.tma) info.tmaStageBytes = F.emitTma(src, "FusedParams");
 
     // ---- process ----
     std::ostringstream body;
@@ -640,6 +677,8 @@ std::string generateFusedAggSource(const FusedProgramDesc& D, FusedKernelInfo& i
         << "        if (errOv) atomicOr(P.fpError, 1u);\n        if (errDz) atomicOr(P.fpError, 2u);\n        if (errLen) atomicOr(P.fpError, 4u);\n"
         << "    }\n};\n}  // namespace pg\n"
         << "extern \"C\" __global__ void __launch_bounds__(pg::Prog::THREADS, pg::Prog::MIN_CTAS) fused_kernel(const __grid_constant__ pg::FusedParams P) { pg::fusedAggBody<pg::Prog>(P); }\n";
+    if (info.tma)
+        src << "extern \"C\" __global__ void __launch_bounds__(pg::Prog::THREADS + 32, pg::Prog::MIN_CTAS) fused_kernel_tma(const __grid_constant__ pg::FusedParams P) { pg::fusedAggBodyTma<pg::Prog>(P); }\n";
     info.ok = true;
     return src.str();
 }

@@ -51,6 +51,8 @@ struct FusedKernelInfo {
     bool cnt = false;
     bool queue = false;            // survivors of the probes are queued per warp and aggregated 32 at a time (fragments with joins)
     size_t queueBytes = 0;         // shared memory of the queues (per CTA)
+    bool tma = false;              // the translation unit also holds `fused_kernel_tma` (eager columns through a cp.async.bulk ring)
+    int tmaStageBytes = 0;
     bool tiers = false;            // the on-chip tiers are available (one-word key, or a key whose fields squeeze into 64 bits)
 };
 

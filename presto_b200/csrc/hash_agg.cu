@@ -1899,7 +1899,7 @@ class FusedAggregationOp : public HashAggregationOp {
     int filterNode;
     std::vector<JoinCfg> joins;
     std::vector<int> rawChannels;                       // raw input channels the fragment reads (staged for the fused kernel)
-    struct Compiled { const JitKernel* kernel = nullptr; FusedKernelInfo info; std::string reason; };
+    struct Compiled { const JitKernel* kernel = nullptr; const JitKernel* kernelTma = nullptr; FusedKernelInfo info; std::string reason; };
     std::map<uint64_t, Compiled> compiled;              // by null signature of the raw page
     std::unique_ptr<Operator> fpOp;
     std::vector<std::unique_ptr<Operator>> joinOps;
@@ -1987,6 +1987,8 @@ public:
         std::string err;
         c.kernel = getOrCompileKernel(options.device, src, "fused_kernel", &err);
         if (!c.kernel) c.reason = err;
+        const char* tmaOff = getenv("PG_FUSED_TMA");
+        if (c.kernel && c.info.tma && !(tmaOff && tmaOff[0] == '0')) c.kernelTma = getOrCompileKernel(options.device, src, "fused_kernel_tma", &err);
         return c;
     }
 
@@ -2008,7 +2010,9 @@ public:
         physMapping(physMap);
         const CUfunction fn = c.kernel->function;
         DriverApi& api = DriverApi::get();
-        fusedLaunch = [&, fn](const std::vector<DeviceColumn>& cols, int64_t n, const uint32_t* bitmapIn, uint32_t* bitmapOut) {
+        int smemPerSM = 0;
+        PG_CUDA(cudaDeviceGetAttribute(&smemPerSM, cudaDevAttrMaxSharedMemoryPerMultiprocessor, options.device));
+        fusedLaunch = [&, fn, smemPerSM](const std::vector<DeviceColumn>& cols, int64_t n, const uint32_t* bitmapIn, uint32_t* bitmapOut) {
             FusedParams L{};
             L.t = table.view();
             L.n = n; L.rowBase = rowsSeen; L.bitmapIn = bitmapIn; L.bitmapOut = bitmapOut;
@@ -2020,18 +2024,37 @@ public:
             }
             for (size_t j = 0; j < joins.size(); j++) { L.joins[j].D = views[j].D; L.joins[j].rows = views[j].rows; }
             L.fpError = table.counters.as<unsigned int>() + CNT_FPERR;
-            const size_t smem = (L.direct ? 64 : sharedBytes(sharedSlots)) + c.info.queueBytes;
-            if (api.funcSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, 200 * 1024) != CUDA_SUCCESS) throw Error(PG_ERR_CUDA, "cuFuncSetAttribute failed for a fused pipeline kernel");
-            int perSM = 0;
-            api.occupancyMaxActiveBlocks(&perSM, fn, 256, smem);
-            perSM = std::max(1, std::min(perSM, L.direct ? 8 : 2));    // flushReserve of the table was sized for 2 resident CTAs per SM with a shared table
+            const int NC = c.info.nv + (c.info.cnt ? 1 : 0);
+            const int k0max = std::min(31, kTier0Columns / std::max(NC, 1));
+            L.t0Groups = k0max;
             const int64_t tiles = divUp(n, 256 * c.info.rowsPerThread);
+            // ---- TMA ring: once the page's group count is known (probe chunk), tier 0 is sized for exactly those groups and the rest of
+            // the shared-memory budget of two resident CTAs becomes cp.async.bulk stages for the eager columns ----
+            CUfunction launchFn = fn;
+            unsigned block = 256;
+            size_t smem = (L.direct ? 64 : sharedBytes(sharedSlots)) + c.info.queueBytes;
+            if (c.kernelTma && !L.direct && knownGroups >= 1 && knownGroups <= k0max && tiles > 4 * (int64_t) numSMs) {
+                const int t0 = (int) knownGroups;
+                const size_t lay = (SharedLayout(sharedSlots, 1, (int) phys.size(), (uint32_t) (t0 * NC * 256 * 8), 0).total + 127) & ~size_t(127);
+                const size_t budget = (size_t) smemPerSM / 2 - 1024 - 64;
+                const int stages = lay < budget ? (int) std::min<size_t>(4, (budget - lay) / ((size_t) c.info.tmaStageBytes + 16)) : 0;
+                if (stages >= 2) {
+                    L.t0Groups = t0; L.tmaStages = stages; L.tmaTiles = n / (256 * c.info.rowsPerThread) - 1;
+                    launchFn = c.kernelTma->function; block = 256 + 32;
+                    smem = lay + (size_t) stages * ((size_t) c.info.tmaStageBytes + 16);
+                }
+            }
+            if (api.funcSetAttribute(launchFn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, 200 * 1024) != CUDA_SUCCESS) throw Error(PG_ERR_CUDA, "cuFuncSetAttribute failed for a fused pipeline kernel");
+            int perSM = 0;
+            api.occupancyMaxActiveBlocks(&perSM, launchFn, (int) block, smem);
+            perSM = std::max(1, std::min(perSM, L.direct ? 8 : 2));    // flushReserve of the table was sized for 2 resident CTAs per SM with a shared table
             const unsigned grid = (unsigned) std::min<int64_t>((int64_t) numSMs * perSM, std::max<int64_t>(tiles, 1));
             void* args[1] = {&L};
-            const CUresult r = api.launchKernel(fn, grid, 1, 1, 256, 1, 1, (unsigned) smem, (CUstream) stream, args, nullptr);
+            const CUresult r = api.launchKernel(launchFn, grid, 1, 1, block, 1, 1, (unsigned) smem, (CUstream) stream, args, nullptr);
             if (r != CUDA_SUCCESS) throw Error(PG_ERR_CUDA, "cuLaunchKernel of a fused pipeline kernel failed (" + std::to_string((int) r) + ")");
             stats.kernel_launches++;
-            stats.kernel_paths |= L.direct ? PG_PATH_FUSED_DIRECT : PG_PATH_FUSED_TIERS;
+            stats.kernel_paths |= L.direct ? PG_PATH_FUSED_DIRECT : (L.tmaStages ? PG_PATH_FUSED_TMA : PG_PATH_FUSED_TIERS);
+            lastRegisters = L.tmaStages ? c.kernelTma->registers : c.kernel->registers;
         };
         inputChannels = &rawChannels;
         struct Reset { FusedAggregationOp* o; ~Reset() { o->fusedLaunch = nullptr; o->inputChannels = nullptr; } } reset{this};

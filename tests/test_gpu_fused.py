@@ -345,3 +345,26 @@ def test_page_sink_filter_join_pages(gpu_backend, oracle_backend):
     for g, w in zip(got, want):
         rows_close(g, w, rel=0.0)
     assert info["i1"]["fused_pages"] == 3 and info["i2"]["fused_pages"] == 1 and info["i3"]["fused_pages"] == 1, info
+
+
+@pytest.mark.parametrize("key_type", [INTEGER, VARCHAR])
+def test_tma_ring_path(gpu_backend, oracle_backend, key_type):
+    """Pages large enough for the cp.async.bulk staging ring (fused_kernel_tma: eager columns land in shared-memory stages, a producer
+    warp keeps them in flight): same rows as the oracle, and the operator reports that the ring kernel ran.  Page sizes that are not a
+    multiple of the 512-row tile exercise the direct-load tail."""
+    rng = np.random.default_rng(77)
+    pages = [Page(q1_arrays(rng, n, key_type)) for n in (330_001, 400_000, 512 * 700, 1023)]
+    want = rows_of(run_q1(pages, backend=oracle_backend, fused=True, key_type=key_type))
+    info = {}
+    got = rows_of(run_q1(pages, backend=gpu_backend, fused=True, key_type=key_type, info=info))
+    rows_close(got, want)
+    assert info["fused_pages"] == 4 and info["kernel_paths"] & abi.PATH_FUSED_TMA, info
+    os.environ["PG_FUSED_TMA"] = "0"
+    try:
+        # a fresh program signature is not needed: the switch is read when the fragment is compiled per operator
+        info2 = {}
+        got2 = rows_of(run_q1(pages, backend=gpu_backend, fused=True, key_type=key_type, info=info2))
+        rows_close(got2, want)
+        assert not (info2["kernel_paths"] & abi.PATH_FUSED_TMA), info2
+    finally:
+        del os.environ["PG_FUSED_TMA"]
