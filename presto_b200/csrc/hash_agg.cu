@@ -2035,11 +2035,15 @@ public:
             size_t smem = (L.direct ? 64 : sharedBytes(sharedSlots)) + c.info.queueBytes;
             if (c.kernelTma && !L.direct && knownGroups >= 1 && knownGroups <= k0max && tiles > 4 * (int64_t) numSMs) {
                 const int t0 = (int) knownGroups;
-                const size_t lay = (SharedLayout(sharedSlots, 1, (int) phys.size(), (uint32_t) (t0 * NC * 256 * 8), 0).total + 127) & ~size_t(127);
+                // a handful of groups does not need the full shared table: 4 slots per known group leave the ring more room
+                uint32_t slots = 64;
+                while (slots < 4 * (uint32_t) t0 && slots < sharedSlots) slots <<= 1;
+                const size_t lay = (SharedLayout(slots, 1, (int) phys.size(), (uint32_t) (t0 * NC * 256 * 8), 0).total + 127) & ~size_t(127);
                 const size_t budget = (size_t) smemPerSM / 2 - 1024 - 64;
                 const int stages = lay < budget ? (int) std::min<size_t>(4, (budget - lay) / ((size_t) c.info.tmaStageBytes + 16)) : 0;
                 if (stages >= 2) {
                     L.t0Groups = t0; L.tmaStages = stages; L.tmaTiles = n / (256 * c.info.rowsPerThread) - 1;
+                    L.S = slots; L.sLimit = slots / 4 * 3;
                     launchFn = c.kernelTma->function; block = 256 + 32;
                     smem = lay + (size_t) stages * ((size_t) c.info.tmaStageBytes + 16);
                 }

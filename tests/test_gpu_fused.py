@@ -30,8 +30,8 @@ def run_fused(backend, pages, *args, info=None, **kw):
     return rows
 
 
-def q1_arrays(rng, n, key_type):
-    rf, ls = rng.integers(0, 3, n), rng.integers(0, 2, n)
+def q1_arrays(rng, n, key_type, flags=3):
+    rf, ls = rng.integers(0, flags, n), rng.integers(0, 2, n)
     if key_type == VARCHAR:
         keys = [Block.from_strings([b"ANR"[i:i + 1] for i in rf]), Block.from_strings([b"FO"[i:i + 1] for i in ls])]
     else:
@@ -353,10 +353,11 @@ def test_tma_ring_path(gpu_backend, oracle_backend, key_type):
     warp keeps them in flight): same rows as the oracle, and the operator reports that the ring kernel ran.  Page sizes that are not a
     multiple of the 512-row tile exercise the direct-load tail."""
     rng = np.random.default_rng(77)
-    pages = [Page(q1_arrays(rng, n, key_type)) for n in (330_001, 400_000, 512 * 700, 1023)]
+    pages = [Page(q1_arrays(rng, n, key_type, flags=2)) for n in (330_001, 400_000, 512 * 700, 1023)]     # 4 groups, like TPC-H's Q1
     want = rows_of(run_q1(pages, backend=oracle_backend, fused=True, key_type=key_type))
     info = {}
     got = rows_of(run_q1(pages, backend=gpu_backend, fused=True, key_type=key_type, info=info))
+    assert len(want) == 4
     rows_close(got, want)
     assert info["fused_pages"] == 4 and info["kernel_paths"] & abi.PATH_FUSED_TMA, info
     os.environ["PG_FUSED_TMA"] = "0"
