@@ -679,14 +679,49 @@ def cpu_q1(torch, cols, key_kind, row_begin, row_end, threads, chunk=1 << 16):
     return n / dt, dt, rows, n * Q1_BYTES_PER_ROW[key_kind] / dt / 1e9
 
 
-def merge_partials_on_root(torch, dist, page, backend, key_kind, device, stream):
-    """PARTIAL -> FINAL across ranks (Q1 has no row exchange): every rank's partial page (a few rows) travels in ONE fixed-size
-    all-gather; rank 0 feeds the concatenation to a FINAL HashAggregationOperator as a single page."""
+def q1_final_operator(backend, key_kind, device, stream):
+    """The FINAL HashAggregationOperator of the Q1 plan (rank 0): its inputs are the PARTIAL operators' intermediate columns."""
     from presto_b200 import AGG_AVG_DOUBLE, MEM_HOST, STEP_FINAL, Aggregate, HashAggregationOperator, INTEGER, VARCHAR
-    from presto_b200.exchange import _pack_page, _unpack_page
     from presto_b200.pipelines import Q1_AGGREGATES
+    kt = VARCHAR if key_kind == "varchar" else INTEGER
+    final_aggs, ch = [], 2
+    for a in Q1_AGGREGATES:
+        final_aggs.append(Aggregate(a.function, ch))
+        ch += 2 if a.function == AGG_AVG_DOUBLE else 1
+    return HashAggregationOperator([kt, kt], [0, 1], final_aggs, step=STEP_FINAL, expected_groups=1024, group_max_lengths=[1, 1] if key_kind == "varchar" else None,
+                                   backend=backend, device=device, output_memory=MEM_HOST, cuda_stream=stream, max_output_rows=1 << 30)
+
+
+def concat_host_pages(pages):
+    """Small host pages with the same channels -> one page (VARCHAR: bytes concatenated, offsets rebased)."""
+    from presto_b200 import VARCHAR, Block, Page
+    blocks = []
+    for c in range(len(pages[0].blocks)):
+        bs = [p.blocks[c] for p in pages]
+        t, n = bs[0].type, sum(b.position_count for b in bs)
+        nulls = None
+        if any(b.is_null is not None for b in bs):
+            nulls = np.concatenate([b.is_null[:b.position_count] if b.is_null is not None else np.zeros(b.position_count, dtype=np.uint8) for b in bs])
+        if t == VARCHAR:
+            data, offs, base = [], [np.zeros(1, dtype=np.int32)], 0
+            for b in bs:
+                o = np.asarray(b.offsets[:b.position_count + 1], dtype=np.int64)
+                data.append(np.asarray(b.values, dtype=np.uint8)[int(o[0]):int(o[-1])])
+                offs.append((o[1:] - o[0] + base).astype(np.int32))
+                base += int(o[-1] - o[0])
+            vals = np.concatenate(data) if base else np.zeros(1, dtype=np.uint8)
+            blocks.append(Block(t, n, vals, nulls, np.concatenate(offs)))
+        else:
+            blocks.append(Block(t, n, np.concatenate([b.values[:b.position_count] for b in bs]), nulls))
+    return Page(blocks, sum(p.position_count for p in pages))
+
+
+def merge_partials_on_root(torch, dist, page, final, device):
+    """PARTIAL -> FINAL across ranks (Q1 has no row exchange): every rank's partial page (a few rows) travels in ONE fixed-size
+    all-gather; rank 0 feeds the concatenation to the FINAL HashAggregationOperator as a single page."""
+    from presto_b200.exchange import _pack_page, _unpack_page
     world, rank = dist.get_world_size(), dist.get_rank()
-    CAP = 1 << 14
+    CAP = 1 << 13
     buf = _pack_page(page)
     assert buf.size + 8 <= CAP, "partial page larger than the merge buffer"
     send = np.zeros(CAP, dtype=np.uint8)
@@ -705,20 +740,9 @@ def merge_partials_on_root(torch, dist, page, backend, key_kind, device, stream)
         p = _unpack_page(host[r * CAP + 8:r * CAP + 8 + size])
         if p is not None:
             pages.append(p)
-    kt = VARCHAR if key_kind == "varchar" else INTEGER
-    final_aggs, ch = [], 2
-    for a in Q1_AGGREGATES:
-        final_aggs.append(Aggregate(a.function, ch))
-        ch += 2 if a.function == AGG_AVG_DOUBLE else 1
-    final = HashAggregationOperator([kt, kt], [0, 1], final_aggs, step=STEP_FINAL, expected_groups=1024, group_max_lengths=[1, 1] if key_kind == "varchar" else None,
-                                    backend=backend, device=device, output_memory=MEM_HOST, cuda_stream=stream, max_output_rows=1 << 30)
-    for p in pages:
-        final.add_input(p)
+    final.add_input(concat_host_pages(pages))
     final.finish()
-    out = final.get_output()
-    launches = final.get_stats()["kernel_launches"]
-    final.close()
-    return out, launches
+    return final.get_output(), final.get_stats()["kernel_launches"]
 
 
 def run_q1_headline(torch, backend, cols, key_kind, steps, warmup, device, dist=None):
@@ -731,6 +755,7 @@ def run_q1_headline(torch, backend, cols, key_kind, steps, warmup, device, dist=
     for i in range(warmup + steps):
         # the result page (4 groups) is read back to the host inside the timed region
         op = q1_operator(backend, key_kind, STEP_PARTIAL if multi else STEP_SINGLE, device=device, output_memory=MEM_HOST, cuda_stream=stream.cuda_stream)
+        final = q1_final_operator(backend, key_kind, device, stream.cuda_stream) if multi and dist.get_rank() == 0 else None
         e0, e1, e2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         if multi:
             dist.barrier()
@@ -742,7 +767,7 @@ def run_q1_headline(torch, backend, cols, key_kind, steps, warmup, device, dist=
         out = op.get_output()
         extra_launches = 0
         if multi:
-            merged = merge_partials_on_root(torch, dist, out, backend, key_kind, device, stream.cuda_stream)
+            merged = merge_partials_on_root(torch, dist, out, final, device)
             if merged is not None:
                 out, extra_launches = merged
         e2.record(stream)
@@ -757,6 +782,8 @@ def run_q1_headline(torch, backend, cols, key_kind, steps, warmup, device, dist=
         if out is not None:
             result = [tuple(v.decode() if isinstance(v, bytes) else v for v in row) for row in out.rows()]
         op.close()
+        if final is not None:
+            final.close()
     return {"ms": float(np.mean(ms)), "kernel_ms": float(np.mean(kms)), "launches": int(launches), "info": info, "result": result}
 
 

@@ -234,10 +234,11 @@ def run_q3_distributed(customer: Sequence[Page], orders: Sequence[Page], lineite
     """Q3 across the GPUs of one box (BASELINE.json configs[3]); every rank holds a shard of each table, device resident.
          customer  : filtered, then REPLICATED (every rank receives all BUILDING customers: PartitionedOutput with one partition per rank
                      is not needed for a 1/5 x 15 M x 8 B build side — an all-gather of the filtered keys) → build #1 on every rank
-         orders    : filter → probe #1 locally → PartitionedOutput on o_orderkey → all-to-all → build #2 (rank owns its orderkey partition)
-         lineitem  : filter/project → PartitionedOutput on l_orderkey (same partition function) → all-to-all → probe #2 → aggregation
+         orders    : [filter → probe #1] (one FusedPageOperator) → PartitionedOutput on o_orderkey → exchange → build #2 (rank owns its partition)
+         lineitem  : [filter/project] (FusedPageOperator) → PartitionedOutput on l_orderkey (same partition function) → exchange →
+                     [probe #2 → aggregation] (one FusedAggregationOperator)
        The group-by keys start with orderkey, so the aggregation is co-partitioned with the join: no second exchange; every rank returns
-       its own groups (the caller takes the global top-10).  Exactly one all-to-all per repartition boundary, nowhere else.
+       its own groups (the caller takes the global top-10).  Exactly one exchange per repartition boundary, nowhere else.
        ``fused`` (default): the repartition scatter writes straight into the destination GPU's receive columns (exchange.FusedExchange);
        otherwise a local PartitionedOutput slab + one all_to_all_single per column (exchange.all_to_all_pages).  ``exchanges`` =
        (orders FusedExchange, lineitem FusedExchange) reuses long-lived receive columns (a worker's output buffers outlive a query
@@ -259,6 +260,7 @@ def run_q3_distributed(customer: Sequence[Page], orders: Sequence[Page], lineite
     mem = abi.MEM_DEVICE
     o = dict(backend=backend, **opts)
     dev = torch.device("cuda", torch.cuda.current_device())
+    _TORCH = {abi.BIGINT: torch.int64, abi.DATE: torch.int32, abi.INTEGER: torch.int32, abi.DOUBLE: torch.float64}
     # ---- customer: filter, replicate the surviving keys, build #1 ----
     pc = Program([abi.BIGINT, abi.INTEGER])
     ck, seg = pc.input(0), pc.input(1)
@@ -267,14 +269,21 @@ def run_q3_distributed(customer: Sequence[Page], orders: Sequence[Page], lineite
     fp_c = FilterAndProjectOperator([abi.BIGINT, abi.INTEGER], pc, output_memory=mem, **o)
     local_keys = [block_to_tensor(p.blocks[0], dev).clone() for p in _drain(fp_c, customer, False)]
     mine = torch.cat(local_keys) if local_keys else torch.empty(0, dtype=torch.int64, device=dev)
-    counts = [torch.empty(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(counts, torch.tensor([mine.numel()], dtype=torch.int64, device=dev), group=group)
-    cap = max(int(c.item()) for c in counts)
-    padded = torch.zeros(max(cap, 1), dtype=torch.int64, device=dev)
-    padded[:mine.numel()] = mine
-    gathered = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(gathered, padded, group=group)
-    all_keys = torch.cat([g[:int(c.item())] for g, c in zip(gathered, counts)])
+    # one fixed-shape all-gather: [count, keys...] padded to the shard size (the filter keeps ~1/5)
+    cap = max(sum(p.position_count for p in customer), 1)
+    send = torch.zeros(cap + 1, dtype=torch.int64, device=dev)
+    send[0] = mine.numel()
+    send[1:1 + mine.numel()] = mine
+    caps = torch.tensor([cap + 1], dtype=torch.int64, device=dev)
+    dist.all_reduce(caps, op=dist.ReduceOp.MAX, group=group)
+    width = int(caps.item())
+    if width > send.numel():
+        send = torch.cat([send, torch.zeros(width - send.numel(), dtype=torch.int64, device=dev)])
+    gathered = torch.empty(world * width, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(gathered, send, group=group)
+    gathered = gathered.view(world, width)
+    counts = gathered[:, 0].cpu().tolist()
+    all_keys = torch.cat([gathered[r, 1:1 + int(counts[r])] for r in range(world)])
     torch.cuda.current_stream().synchronize()      # torch produced the keys on its stream; the operators run on their own
     bridge1 = JoinBridge(opts.get("device", 0), backend=backend)
     build1 = HashBuilderOperator(bridge1, [abi.BIGINT], [0], [], **o)
@@ -282,13 +291,13 @@ def run_q3_distributed(customer: Sequence[Page], orders: Sequence[Page], lineite
         build1.add_input(Page([tensor_to_block(abi.BIGINT, all_keys)]))
     build1.finish()
     mark("customer filter + replicate + build1")
-    # ---- orders: filter → probe #1 → repartition on orderkey → build #2 ----
+    # ---- orders: [filter → probe #1] → repartition on orderkey → build #2 ----
     po = Program([abi.BIGINT, abi.BIGINT, abi.DATE, abi.INTEGER])
     ok, ock, od, sp = [po.input(i) for i in range(4)]
     po.set_filter(od < Q3_DATE)
     po.project(ok, ock, od, sp)
-    fp_o = FilterAndProjectOperator([abi.BIGINT, abi.BIGINT, abi.DATE, abi.INTEGER], po, output_memory=mem, **o)
-    probe1 = LookupJoinOperator(bridge1, [abi.BIGINT, abi.BIGINT, abi.DATE, abi.INTEGER], [1], [0, 2, 3], output_memory=mem, **o)
+    fo = FusedPageOperator([abi.BIGINT, abi.BIGINT, abi.DATE, abi.INTEGER], po, [FusedJoin(bridge1, [abi.BIGINT, abi.BIGINT, abi.DATE, abi.INTEGER], [1], [0, 2, 3])],
+                           output_memory=mem, **o)
     part_o = PartitionedOutputOperator([abi.BIGINT, abi.DATE, abi.INTEGER], world, [0], output_memory=mem, **o)
     bridge2 = JoinBridge(opts.get("device", 0), backend=backend)
     build2 = HashBuilderOperator(bridge2, [abi.BIGINT, abi.DATE, abi.INTEGER], [0], [1, 2], **o)
@@ -311,7 +320,6 @@ def run_q3_distributed(customer: Sequence[Page], orders: Sequence[Page], lineite
         slab = part.get_output(copy=False)
         return all_to_all_pages(slab, part.get_offsets(), types, group=group)
 
-    _TORCH = {abi.BIGINT: torch.int64, abi.DATE: torch.int32, abi.INTEGER: torch.int32, abi.DOUBLE: torch.float64}
     cap_o = max([p.position_count for p in orders] + [1])
     cap_l = max([p.position_count for p in lineitem] + [1])
     fx_o = fx_l = None
@@ -320,58 +328,53 @@ def run_q3_distributed(customer: Sequence[Page], orders: Sequence[Page], lineite
     elif fused:
         fx_o = FusedExchange(order_types, cap_o // 4 + 1024, group=group, backend=backend)
         fx_l = FusedExchange(line_types, cap_l + cap_l // 8 + 1024, group=group, backend=backend)
-    for page in orders:            # every rank iterates the same number of pages: the all-to-all is collective
-        fp_o.add_input(page)
-        f = fp_o.get_output(copy=False)
-        j = None
-        if f is not None and f.position_count:
-            probe1.add_input(f)
-            j = probe1.get_output(copy=False)
+    for page in orders:            # every rank iterates the same number of pages: the exchange is collective
+        fo.add_input(page)
+        j = fo.get_output(copy=False)
         recv = shuffle(part_o, fx_o, j, order_types)
         exchanged += recv.position_count
         if recv.position_count:
             build2.add_input(recv)
     build2.finish()
-    mark("orders filter + probe1 + exchange + build2")
-    # ---- lineitem: filter/project → repartition on orderkey → probe #2 → aggregation ----
+    mark("orders [filter + probe1] + exchange + build2")
+    # ---- lineitem: [filter/project] → repartition on orderkey → [probe #2 → aggregation] ----
     pl = Program([abi.BIGINT, abi.DOUBLE, abi.DOUBLE, abi.DATE])
     lk, ep, disc, ship = [pl.input(i) for i in range(4)]
     pl.set_filter(ship > Q3_DATE)
     pl.project(lk, ep * (1.0 - disc))
-    fp_l = FilterAndProjectOperator([abi.BIGINT, abi.DOUBLE, abi.DOUBLE, abi.DATE], pl, output_memory=mem, **o)
+    fl = FusedPageOperator([abi.BIGINT, abi.DOUBLE, abi.DOUBLE, abi.DATE], pl, [], output_memory=mem, **o)
     part_l = PartitionedOutputOperator([abi.BIGINT, abi.DOUBLE], world, [0], output_memory=mem, **o)
-    probe2 = LookupJoinOperator(bridge2, [abi.BIGINT, abi.DOUBLE], [0], [0, 1], output_memory=mem, **o)
-    agg = HashAggregationOperator([abi.BIGINT, abi.DATE, abi.INTEGER], [0, 2, 3], [Aggregate(abi.AGG_SUM_DOUBLE, 1)], expected_groups=100_000,
+    # after the exchange: probe #2 and the aggregation as ONE operator over the received (orderkey, revenue) rows
+    pr = Program([abi.BIGINT, abi.DOUBLE])
+    pr.project(pr.input(0), pr.input(1))
+    fa = FusedAggregationOperator([abi.BIGINT, abi.DOUBLE], pr, [FusedJoin(bridge2, [abi.BIGINT, abi.DOUBLE], [0], [0, 1])],
+                                  [abi.BIGINT, abi.DATE, abi.INTEGER], [0, 2, 3], [Aggregate(abi.AGG_SUM_DOUBLE, 1)],
+                                  expected_groups=max(100_000, sum(p.position_count for p in lineitem) // 400),
                                   max_output_rows=1 << 30, output_memory=mem, **o)
-    joined = 0
     for page in lineitem:
-        fp_l.add_input(page)
-        f = fp_l.get_output(copy=False)
+        fl.add_input(page)
+        f = fl.get_output(copy=False)
         mark("lineitem filter/project")
         recv = shuffle(part_l, fx_l, f, line_types)
         mark("lineitem exchange " + (str(getattr(fx_l, "trace_ms", "")) if fx_l is not None else "(nccl)"))
         exchanged += recv.position_count
         if not recv.position_count:
             continue
-        probe2.add_input(recv)
-        j = probe2.get_output(copy=False)
-        mark("lineitem probe2")
-        if j is not None and j.position_count:
-            joined += j.position_count
-            agg.add_input(j)
-    mark("lineitem filter + exchange + probe2 + aggregation input")
-    agg.finish()
+        fa.add_input(recv)
+        mark("lineitem [probe2 + aggregation]")
+    fa.finish()
     result = []
-    while not agg.is_finished():
-        r = agg.get_output(copy=False)
+    while not fa.is_finished():
+        r = fa.get_output(copy=False)
         if r is not None:
             result.append(_detach(r))      # device resident; the operator's buffers die with close() below
     mark("aggregation output")
-    ops = (fp_c, build1, fp_o, probe1, part_o, build2, fp_l, part_l, probe2, agg)
+    ops = (fp_c, build1, fo, part_o, build2, fl, part_l, fa)
     if stats is not None:
-        stats["joined_rows"] = joined
+        stats["joined_rows"] = -1
         stats["exchanged_rows"] = exchanged
         stats["kernel_launches"] = sum(op.get_stats()["kernel_launches"] for op in ops)
+        stats.update({"fused_" + k: v for k, v in fa.get_info().items()})
     for op in ops:
         op.close()
     for fx in (fx_o, fx_l):
