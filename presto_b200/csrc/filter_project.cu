@@ -248,6 +248,55 @@ __global__ void __launch_bounds__(256) fpProjectKernel(const __grid_constant__ F
     }
 }
 
+// ---- VARCHAR input references (InputPageProjection, MB/operator/project/InputPageProjection.java): the selected positions' slices pass
+// through.  The fixed-width machinery above never sees them: pass 1 writes the selected rows' lengths at their output positions, a scan
+// turns them into the output offsets, pass 2 copies the bytes.  `selection` == nullptr: every row is selected (dest = row).
+__global__ void varcharSelectLensKernel(const uint32_t* selection, const uint32_t* unitOffsets, const int32_t* inOffsets, const uint8_t* inNulls, int64_t n,
+                                        int32_t* outLens, uint8_t* outNulls)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1;
+    const int64_t warpId = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+    const int64_t units = (n + kRowsPerFpUnit - 1) / kRowsPerFpUnit;
+    for (int64_t unit = warpId; unit < units; unit += nWarps) {
+        const int64_t begin = unit * kRowsPerFpUnit, end = min(begin + (int64_t) kRowsPerFpUnit, n);
+        uint32_t cursor = selection ? unitOffsets[unit] : (uint32_t) begin;
+        for (int64_t base = begin; base < end; base += 32) {
+            const int64_t row = base + lane;
+            const unsigned m = selection ? selection[base >> 5] : __ballot_sync(0xffffffffu, row < end);
+            if (row < end && ((m >> lane) & 1u)) {
+                const uint32_t dest = cursor + __popc(m & lt);
+                const bool isNull = inNulls && inNulls[row];
+                outLens[dest] = isNull ? 0 : inOffsets[row + 1] - inOffsets[row];
+                if (outNulls) outNulls[dest] = isNull ? 1 : 0;
+            }
+            cursor += __popc(m);
+        }
+    }
+}
+__global__ void varcharSelectCopyKernel(const uint32_t* selection, const uint32_t* unitOffsets, const uint8_t* inBytes, const int32_t* inOffsets, const uint8_t* inNulls,
+                                        int64_t n, const int32_t* outOffsets, uint8_t* outBytes)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1;
+    const int64_t warpId = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+    const int64_t units = (n + kRowsPerFpUnit - 1) / kRowsPerFpUnit;
+    for (int64_t unit = warpId; unit < units; unit += nWarps) {
+        const int64_t begin = unit * kRowsPerFpUnit, end = min(begin + (int64_t) kRowsPerFpUnit, n);
+        uint32_t cursor = selection ? unitOffsets[unit] : (uint32_t) begin;
+        for (int64_t base = begin; base < end; base += 32) {
+            const int64_t row = base + lane;
+            const unsigned m = selection ? selection[base >> 5] : __ballot_sync(0xffffffffu, row < end);
+            if (row < end && ((m >> lane) & 1u) && !(inNulls && inNulls[row])) {
+                const uint32_t dest = cursor + __popc(m & lt);
+                const int32_t from = inOffsets[row], len = inOffsets[row + 1] - from, to = outOffsets[dest];
+                for (int32_t i = 0; i < len; i++) outBytes[to + i] = inBytes[from + i];
+            }
+            cursor += __popc(m);
+        }
+    }
+}
+
 // ---- driver-API JIT of generated PTX (DriverApi: jit_runtime.h; libcuda is dlopen'ed so the library still loads without a driver) ----
 struct JitProgram {
     CUmodule module = nullptr;
@@ -262,7 +311,14 @@ class FilterProjectOp : public Operator {
     std::vector<pg_expr_node> nodes;
     std::vector<bool> used;
     int filterNode;
-    std::vector<int> projections;
+    std::vector<int> projections;              // the fixed-width projections (what the generated / interpreter kernels evaluate)
+    struct OutSlot { bool varchar; int index; };   // output channel → fixed-width projection index, or VARCHAR pass-through index
+    std::vector<OutSlot> outSlots;
+    std::vector<int> varcharChannels;          // input channel of each VARCHAR pass-through output
+    std::vector<DeviceBuffer> vcLens, vcOffsets, vcBytes, vcNulls;
+    std::vector<PinnedBuffer> vcHostBytes, vcHostOffsets, vcHostNulls;
+    DeviceBuffer vcScanTemp;
+    std::vector<pg_block> publicBlocks;
     PageStager stager;
     bool finishing = false, hasPending = false;
     DeviceBuffer counts, offsets, scanTemp, errorWord, selection;
@@ -284,16 +340,26 @@ public:
         inputTypes.assign(c->input_types, c->input_types + c->n_input_channels);
         nodes.assign(c->nodes, c->nodes + c->n_nodes);
         filterNode = c->filter_node;
-        projections.assign(c->projection_nodes, c->projection_nodes + c->n_projections);
         PG_CHECK_ARG(filterNode < c->n_nodes, "filter node out of range");
         if (filterNode >= 0) PG_CHECK_ARG(nodes[filterNode].type == PG_TYPE_BOOLEAN, "filter must be BOOLEAN");
-        for (int p : projections) PG_CHECK_ARG(p >= 0 && p < c->n_nodes, "projection node out of range");
+        // VARCHAR: input references only (InputPageProjection: the selected positions' slices pass through); they are split off here and
+        // never reach the expression kernels
+        for (int j = 0; j < c->n_projections; j++) {
+            const int p = c->projection_nodes[j];
+            PG_CHECK_ARG(p >= 0 && p < c->n_nodes, "projection node out of range");
+            if (nodes[p].type == PG_TYPE_VARCHAR) {
+                if (nodes[p].op != PG_EX_INPUT) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR expressions other than input references are not on the GPU path");
+                outSlots.push_back({true, (int) varcharChannels.size()});
+                varcharChannels.push_back(nodes[p].a);
+            }
+            else { outSlots.push_back({false, (int) projections.size()}); projections.push_back(p); }
+        }
         for (int i = 0; i < c->n_nodes; i++) {
             const pg_expr_node& n = nodes[i];
-            if (n.type == PG_TYPE_VARCHAR) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR expressions are not on the GPU path");
+            if (n.type == PG_TYPE_VARCHAR && n.op != PG_EX_INPUT) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR expressions other than input references are not on the GPU path");
             if (n.op == PG_EX_INPUT) {
                 PG_CHECK_ARG(n.a >= 0 && n.a < c->n_input_channels, "input channel out of range");
-                if (inputTypes[n.a] == PG_TYPE_VARCHAR) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR inputs are not on the GPU path");
+                PG_CHECK_ARG(inputTypes[n.a] == n.type, "input node type differs from the channel's type");
                 if (std::find(staged.begin(), staged.end(), n.a) == staged.end()) staged.push_back(n.a);
             }
             else {
@@ -451,6 +517,38 @@ public:
             launchJit(jit.project, grid, v);
         }
         else if (nOut) { PG_LAUNCH(this, fpProjectKernel, grid, 256, 0, P); interpreterLaunches++; }
+        // VARCHAR pass-through channels: lengths of the selected rows → output offsets (scan) → bytes
+        const size_t nVc = varcharChannels.size();
+        std::vector<int32_t> vcTotalBytes(nVc, 0);
+        std::vector<bool> vcHasNulls(nVc, false);
+        if (nVc) {
+            if (vcLens.size() < nVc) {
+                vcLens.resize(nVc); vcOffsets.resize(nVc); vcBytes.resize(nVc); vcNulls.resize(nVc);
+                for (auto* vec : {&vcLens, &vcOffsets, &vcBytes, &vcNulls}) for (auto& d : *vec) d.accounting = &stats.device_bytes;
+            }
+            const uint32_t* sel = filterNode >= 0 ? selection.as<uint32_t>() : nullptr;
+            for (size_t v = 0; v < nVc; v++) {
+                const DeviceColumn& vc = cols[std::find(staged.begin(), staged.end(), varcharChannels[v]) - staged.begin()];
+                PG_CHECK_ARG(vc.offsets != nullptr, "VARCHAR block without offsets");
+                vcLens[v].reserve((size_t) (total + 1) * 4); vcOffsets[v].reserve((size_t) (total + 1) * 4);
+                PG_CUDA(cudaMemsetAsync(vcLens[v].as<int32_t>() + total, 0, 4, stream));
+                uint8_t* on = nullptr;
+                if (vc.nulls) { vcNulls[v].reserve((size_t) total); on = vcNulls[v].as<uint8_t>(); vcHasNulls[v] = true; }
+                PG_LAUNCH(this, varcharSelectLensKernel, grid, 256, 0, sel, P.offsets, vc.offsets, vc.nulls, n, vcLens[v].as<int32_t>(), on);
+                size_t tb = 0;
+                cub::DeviceScan::ExclusiveSum(nullptr, tb, vcLens[v].as<int32_t>(), vcOffsets[v].as<int32_t>(), (int) (total + 1), stream);
+                vcScanTemp.reserve(tb);
+                cub::DeviceScan::ExclusiveSum(vcScanTemp.ptr, tb, vcLens[v].as<int32_t>(), vcOffsets[v].as<int32_t>(), (int) (total + 1), stream);
+                stats.kernel_launches += 2;
+                PG_CUDA(cudaMemcpyAsync(&vcTotalBytes[v], vcOffsets[v].as<int32_t>() + total, 4, cudaMemcpyDeviceToHost, stream));
+            }
+            PG_CUDA(cudaStreamSynchronize(stream));
+            for (size_t v = 0; v < nVc; v++) {
+                const DeviceColumn& vc = cols[std::find(staged.begin(), staged.end(), varcharChannels[v]) - staged.begin()];
+                vcBytes[v].reserve((size_t) vcTotalBytes[v] + 16);
+                PG_LAUNCH(this, varcharSelectCopyKernel, grid, 256, 0, sel, P.offsets, (const uint8_t*) vc.values, vc.offsets, vc.nulls, n, vcOffsets[v].as<int32_t>(), vcBytes[v].as<uint8_t>());
+            }
+        }
         stager.markCompute(slot);
         const bool toHost = options.output_memory == PG_MEM_HOST;
         if (toHost && hostValues.size() < nOut) { hostValues.resize(nOut); hostNulls.resize(nOut); }
@@ -467,6 +565,25 @@ public:
             }
             else { b.values = outValues[j].ptr; b.is_null = P.outs[j].nulls; }
             stats.output_bytes += (int64_t) vbytes;
+        }
+        // the public page: fixed-width and VARCHAR channels in the order the projections were given
+        if (toHost && vcHostBytes.size() < nVc) { vcHostBytes.resize(nVc); vcHostOffsets.resize(nVc); vcHostNulls.resize(nVc); }
+        publicBlocks.assign(outSlots.size(), pg_block{});
+        for (size_t c = 0; c < outSlots.size(); c++) {
+            if (!outSlots[c].varchar) { publicBlocks[c] = outBlocks[outSlots[c].index]; continue; }
+            const int v = outSlots[c].index;
+            pg_block& b = publicBlocks[c];
+            b.type = PG_TYPE_VARCHAR; b.encoding = PG_ENC_FLAT; b.position_count = total;
+            if (toHost) {
+                vcHostBytes[v].reserve((size_t) vcTotalBytes[v] + 16); vcHostOffsets[v].reserve((size_t) (total + 1) * 4);
+                if (vcTotalBytes[v]) PG_CUDA(cudaMemcpyAsync(vcHostBytes[v].ptr, vcBytes[v].ptr, (size_t) vcTotalBytes[v], cudaMemcpyDeviceToHost, stream));
+                PG_CUDA(cudaMemcpyAsync(vcHostOffsets[v].ptr, vcOffsets[v].ptr, (size_t) (total + 1) * 4, cudaMemcpyDeviceToHost, stream));
+                b.values = vcHostBytes[v].ptr; b.offsets = vcHostOffsets[v].as<int32_t>(); b.is_null = nullptr;
+                if (vcHasNulls[v]) { vcHostNulls[v].reserve((size_t) total); PG_CUDA(cudaMemcpyAsync(vcHostNulls[v].ptr, vcNulls[v].ptr, (size_t) total, cudaMemcpyDeviceToHost, stream)); b.is_null = vcHostNulls[v].as<uint8_t>(); }
+                stats.d2h_bytes += (int64_t) vcTotalBytes[v] + (total + 1) * 4;
+            }
+            else { b.values = vcBytes[v].ptr; b.offsets = vcOffsets[v].as<int32_t>(); b.is_null = vcHasNulls[v] ? vcNulls[v].as<uint8_t>() : nullptr; }
+            stats.output_bytes += (int64_t) vcTotalBytes[v] + (total + 1) * 4;
         }
         PG_CUDA(cudaStreamSynchronize(stream));
         checkError();
@@ -495,7 +612,7 @@ public:
     bool getOutput(pg_page* out) override
     {
         if (!hasPending) return false;
-        out->position_count = pendingRows; out->channel_count = (int32_t) outBlocks.size(); out->memory = options.output_memory; out->blocks = outBlocks.data();
+        out->position_count = pendingRows; out->channel_count = (int32_t) publicBlocks.size(); out->memory = options.output_memory; out->blocks = publicBlocks.data();
         hasPending = false;
         return true;
     }
@@ -525,7 +642,8 @@ int32_t pg_filter_project_explain(const pg_filter_project_config* c, uint64_t nu
         d.nodes.assign(c->nodes, c->nodes + c->n_nodes);
         d.inputTypes.assign(c->input_types, c->input_types + c->n_input_channels);
         d.filterNode = c->filter_node;
-        d.projections.assign(c->projection_nodes, c->projection_nodes + c->n_projections);
+        for (int j = 0; j < c->n_projections; j++)      // VARCHAR input references pass through outside the generated kernels
+            if (c->nodes[c->projection_nodes[j]].type != PG_TYPE_VARCHAR) d.projections.push_back(c->projection_nodes[j]);
         d.inputHasNulls.assign(d.inputTypes.size(), false);
         for (size_t i = 0; i < d.inputTypes.size(); i++) d.inputHasNulls[i] = (nullableInputs >> i) & 1ULL;
         pg::FpKernelSignature sig;

@@ -307,7 +307,18 @@ std::string generateFilterProjectPtx(const FpProgramDesc& P, FpKernelSignature& 
     const int nNodes = (int) P.nodes.size();
     // which inputs are referenced at all
     std::vector<bool> used(P.inputTypes.size(), false);
-    for (const auto& nd : P.nodes) if (nd.op == PG_EX_INPUT) used[nd.a] = true;
+    {   // inputs reachable from the filter or a projection (VARCHAR input references that only pass through are not among them)
+        std::vector<int> roots(P.projections.begin(), P.projections.end());
+        if (P.filterNode >= 0) roots.push_back(P.filterNode);
+        std::vector<bool> seen(nNodes, false);
+        while (!roots.empty()) {
+            const int k = roots.back(); roots.pop_back();
+            if (k < 0 || k >= nNodes || seen[k]) continue;
+            seen[k] = true;
+            if (P.nodes[k].op == PG_EX_INPUT) used[P.nodes[k].a] = true;
+            else for (int o : {P.nodes[k].a, P.nodes[k].b, P.nodes[k].c}) roots.push_back(o);
+        }
+    }
     sig.usedInputs.clear();
     for (size_t c = 0; c < used.size(); c++) if (used[c]) sig.usedInputs.push_back((int) c);
     for (int ch : sig.usedInputs) if (P.inputTypes[ch] == PG_TYPE_VARCHAR) { sig.reason = "VARCHAR input"; return ""; }

@@ -973,10 +973,13 @@ static uint32_t nextPow2(uint64_t v) { uint64_t p = 1; while (p < v) p <<= 1; re
 struct AggEmit { int function, val0, val1, countCol; bool partial; };
 
 // Slots that were touched, ordered by first-touch row = ascending group id.  Returns the group count.
-static int64_t sortSlotsByFirstRow(Operator* op, const GroupTable& T, DeviceBuffer& order)
+// `scratch` keeps the sort's temporaries alive until the caller's next synchronisation (blocks go back to the caching allocator only
+// after the stream that used them was synchronised): no sync is needed here beyond reading the group count.
+static int64_t sortSlotsByFirstRow(Operator* op, const GroupTable& T, DeviceBuffer& order, std::vector<DeviceBuffer>& scratch)
 {
     const size_t capP = T.capP;
-    DeviceBuffer sortKeys, sortVals, sortKeysOut, count, temp;
+    scratch.clear(); scratch.resize(5);
+    DeviceBuffer& sortKeys = scratch[0]; DeviceBuffer& sortVals = scratch[1]; DeviceBuffer& sortKeysOut = scratch[2]; DeviceBuffer& count = scratch[3]; DeviceBuffer& temp = scratch[4];
     sortKeys.reserve(capP * 8); sortVals.reserve(capP * 4); count.reserve(16);
     PG_CUDA(cudaMemsetAsync(count.ptr, 0, 16, op->stream));
     PG_LAUNCH(op, collectSlotsKernel, 1024, 256, 0, T, sortKeys.as<uint64_t>(), sortVals.as<uint32_t>(), count.as<unsigned int>());
@@ -990,7 +993,6 @@ static int64_t sortSlotsByFirstRow(Operator* op, const GroupTable& T, DeviceBuff
     temp.reserve(tempBytes);
     cub::DeviceRadixSort::SortPairs(temp.ptr, tempBytes, sortKeys.as<uint64_t>(), sortKeysOut.as<uint64_t>(), sortVals.as<uint32_t>(), order.as<uint32_t>(), (int) g, 0, 64, op->stream);
     op->stats.kernel_launches += 4;
-    PG_CUDA(cudaStreamSynchronize(op->stream));
     return g;
 }
 
@@ -1055,18 +1057,15 @@ struct ResultBuilder {
             int offs = newBuf((size_t) (g + 1) * 4);
             size_t tb = 0;
             cub::DeviceScan::ExclusiveSum(nullptr, tb, outBufs[varcharLens[k]].as<int32_t>(), outBufs[offs].as<int32_t>(), (int) g + 1, stream);
-            DeviceBuffer t2; t2.reserve(tb);
-            cub::DeviceScan::ExclusiveSum(t2.ptr, tb, outBufs[varcharLens[k]].as<int32_t>(), outBufs[offs].as<int32_t>(), (int) g + 1, stream);
+            const int t2 = newBuf(tb);       // (lives in outBufs until the next build: no synchronisation needed to release it)
+            cub::DeviceScan::ExclusiveSum(outBufs[t2].ptr, tb, outBufs[varcharLens[k]].as<int32_t>(), outBufs[offs].as<int32_t>(), (int) g + 1, stream);
             op->stats.kernel_launches += 2;
             int bytes = newBuf((size_t) g * 8);
             PG_LAUNCH(op, expandVarcharKernel, (int) std::min<int64_t>(divUp(g, 256), 2048), 256, 0, (const uint64_t*) outBufs[colBufs[k].values].ptr, outBufs[offs].as<int32_t>(), (int32_t) g, outBufs[bytes].as<uint8_t>());
-            PG_CUDA(cudaStreamSynchronize(stream));
             varcharBytes[k] = bytes; varcharOffsets[k] = offs;
         }
         unsigned int cnt[CNT_COUNT];
         PG_CUDA(cudaMemcpyAsync(cnt, T.counters, sizeof(cnt), cudaMemcpyDeviceToHost, stream));
-        PG_CUDA(cudaStreamSynchronize(stream));
-        if (cnt[CNT_ERROR] & ERR_BIGINT_OVERFLOW) throw Error(PG_ERR_NUMERIC_OVERFLOW, "bigint addition overflow");
 
         // describe the full result; slice() hands out row ranges of it
         outBlocks.assign(colBufs.size(), pg_block{});
@@ -1084,7 +1083,8 @@ struct ResultBuilder {
         std::vector<int32_t> totalBytes(layout.nKeys, 0);
         for (int k = 0; k < layout.nKeys; k++)
             if (varcharOffsets[k] >= 0) PG_CUDA(cudaMemcpyAsync(&totalBytes[k], outBufs[varcharOffsets[k]].as<int32_t>() + g, 4, cudaMemcpyDeviceToHost, stream));
-        PG_CUDA(cudaStreamSynchronize(stream));
+        PG_CUDA(cudaStreamSynchronize(stream));      // the error counters and the VARCHAR byte totals arrive together
+        if (cnt[CNT_ERROR] & ERR_BIGINT_OVERFLOW) throw Error(PG_ERR_NUMERIC_OVERFLOW, "bigint addition overflow");
         for (size_t c = 0; c < colBufs.size(); c++) {
             pg_block& b = outBlocks[c];
             b.type = outTypes[c]; b.encoding = PG_ENC_FLAT; b.position_count = g; b.dictionary_size = 0; b.ids = nullptr; b.offsets = nullptr;
@@ -1189,6 +1189,8 @@ protected:
     int MAXV = 4;
     // output
     ResultBuilder result;
+    DeviceBuffer order;
+    std::vector<DeviceBuffer> sortScratch;
     int64_t outGroups = 0, outNext = 0;
     // fused pipeline input (FusedAggregationOp below): while set, addInput stages the RAW page's channels and every chunk runs through
     // `fusedLaunch` (filter / project / probe / aggregate in one kernel) instead of the aggregation kernels
@@ -1583,8 +1585,7 @@ public:
         settle();
         outputBuilt = true;
         GroupTable T = table.view();
-        DeviceBuffer order;
-        int64_t g = sortSlotsByFirstRow(this, T, order);
+        int64_t g = sortSlotsByFirstRow(this, T, order, sortScratch);
         outGroups = g; outNext = 0;
         stats.group_count = g;
         if (g == 0) return;

@@ -91,12 +91,10 @@ def run_q1(lineitem_pages: Sequence[Page], backend=None, device_resident: bool =
             info.update(op.get_info()); info.update(op.get_stats())
         op.close()
         return result
-    fp = FilterAndProjectOperator([abi.INTEGER, abi.INTEGER, abi.DOUBLE, abi.DOUBLE, abi.DOUBLE, abi.DOUBLE, abi.DATE], q1_program(),
+    fp = FilterAndProjectOperator([key_type, key_type, abi.DOUBLE, abi.DOUBLE, abi.DOUBLE, abi.DOUBLE, abi.DATE], q1_program_typed(key_type),
                                   backend=backend, output_memory=mem, **opts)
-    agg = HashAggregationOperator([abi.INTEGER, abi.INTEGER], [0, 1],
-                                  [Aggregate(abi.AGG_SUM_DOUBLE, 2), Aggregate(abi.AGG_SUM_DOUBLE, 3), Aggregate(abi.AGG_SUM_DOUBLE, 4), Aggregate(abi.AGG_SUM_DOUBLE, 5),
-                                   Aggregate(abi.AGG_AVG_DOUBLE, 2), Aggregate(abi.AGG_AVG_DOUBLE, 3), Aggregate(abi.AGG_AVG_DOUBLE, 6), Aggregate(abi.AGG_COUNT_STAR)],
-                                  expected_groups=10_000, backend=backend, max_output_rows=1 << 30, **opts)
+    agg = HashAggregationOperator([key_type, key_type], [0, 1], Q1_AGGREGATES, expected_groups=10_000, backend=backend, max_output_rows=1 << 30,
+                                  group_max_lengths=[1, 1] if key_type == abi.VARCHAR else None, **opts)
     for page in lineitem_pages:
         fp.add_input(page)
         out = fp.get_output(copy=not device_resident)

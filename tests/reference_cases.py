@@ -483,6 +483,29 @@ def case_page_processor_q1(backend, n: int = 5000):
     op.close()
 
 
+def case_page_processor_varchar_pass_through(backend):
+    """InputPageProjection (MB/operator/project/InputPageProjection.java): VARCHAR input references pass the selected positions' slices
+    through unchanged — with and without a filter, with NULL slices, empty strings and multi-byte values, between computed channels."""
+    rng = np.random.default_rng(8)
+    n = 3000
+    words = [b"", b"A", b"BUILDING", b"AUTOMOBILE", "\u00e9t\u00e9".encode(), b"x" * 40]
+    strs = [None if rng.random() < 0.1 else words[rng.integers(len(words))] for _ in range(n)]
+    s_block = Block.from_strings(strs)
+    v = rng.integers(-50, 50, n)
+    page = Page([s_block, Block.from_numpy(BIGINT, v), Block.from_strings([b"k%d" % (i % 7) for i in range(n)])])
+    for with_filter in (True, False):
+        prog = Program([VARCHAR, BIGINT, VARCHAR])
+        a, b, c = prog.input(0), prog.input(1), prog.input(2)
+        if with_filter:
+            prog.set_filter(b > 0)
+        prog.project(c, b * 2, a, b)
+        op = FilterAndProjectOperator([VARCHAR, BIGINT, VARCHAR], prog, backend=backend)
+        rows = rows_of(to_pages(op, [page, page]))
+        expected = [(b"k%d" % (i % 7), int(v[i]) * 2, strs[i], int(v[i])) for i in range(n) if (not with_filter or v[i] > 0)] * 2
+        assert rows == expected
+        op.close()
+
+
 def case_page_processor_three_valued_logic(backend):
     """AND / OR / NOT / IS NULL / BETWEEN over NULLs (SQL three-valued logic)."""
     a = Block.from_values(BOOLEAN, [True, True, True, False, False, False, None, None, None])

@@ -29,6 +29,7 @@ def test_reference_cases_both_modes(gpu_backend, mode):
     rc.case_page_processor_q1(gpu_backend, n=20_000)
     rc.case_page_processor_three_valued_logic(gpu_backend)
     rc.case_page_processor_hash_projection(gpu_backend)
+    rc.case_page_processor_varchar_pass_through(gpu_backend)
 
 
 def random_program(rng, types):

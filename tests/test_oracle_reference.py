@@ -119,3 +119,4 @@ def test_page_processor_selection(oracle_backend): rc.case_page_processor_select
 def test_page_processor_q1(oracle_backend): rc.case_page_processor_q1(oracle_backend)
 def test_page_processor_three_valued_logic(oracle_backend): rc.case_page_processor_three_valued_logic(oracle_backend)
 def test_page_processor_hash_projection(oracle_backend): rc.case_page_processor_hash_projection(oracle_backend)
+def test_page_processor_varchar_pass_through(oracle_backend): rc.case_page_processor_varchar_pass_through(oracle_backend)
