@@ -53,6 +53,35 @@ def parse_args():
     return ap.parse_args()
 
 
+def host_cpu_info():
+    """What the host arm really runs on: logical CPUs visible, the scheduler affinity of this process and the cgroup CPU quota (a
+    container limited to a fraction of the box cannot use all the threads it sees)."""
+    info = {"logical": os.cpu_count()}
+    try:
+        info["affinity"] = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                info["cgroup_cpus"] = None if txt[0] == "max" else round(int(txt[0]) / int(txt[1]), 2)
+            else:
+                q = int(txt[0]); p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                info["cgroup_cpus"] = None if q < 0 else round(q / p, 2)
+            break
+        except Exception:
+            continue
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                info["model"] = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return info
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -866,7 +895,7 @@ def run_reference(args):
         "metric": "rows/sec", "value": value, "unit": "rows/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": q1_config(args, args.keys),
-        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port", "host_gbs": sample * Q1_BYTES_PER_ROW[args.keys] / (ms / 1000) / 1e9,
+        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port", "host_gbs": sample * Q1_BYTES_PER_ROW[args.keys] / (ms / 1000) / 1e9, "host": host_cpu_info(),
                          "sample": f"{sample} rows of the workload per step, {threads} threads x (oracle FilterAndProject -> HashAggregation PARTIAL over thread-local, "
                                    f"first-touched slices in 2^16-row pages) + FINAL merge; host wall clock, no GPU in the timed region"},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -964,7 +993,7 @@ def main():
         threads = os.cpu_count() or 1
         sample = min(args.cpu_rows, rows)
         rps, dt, _, gbs = cpu_q1(torch, cols, kk, 0, sample, threads)
-        cpu = {"value": rps, "unit": "rows/s", "cores": threads, "kind": "port", "host_gbs": gbs,
+        cpu = {"value": rps, "unit": "rows/s", "cores": threads, "kind": "port", "host_gbs": gbs, "host": host_cpu_info(),
                "sample": f"{sample} rows of the same lineitem, {threads} threads x (oracle FilterAndProject -> HashAggregation PARTIAL over thread-local first-touched slices) + FINAL merge, {dt:.2f} s"}
     del cols
     torch.cuda.empty_cache()

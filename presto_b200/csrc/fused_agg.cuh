@@ -350,7 +350,7 @@ __device__ __forceinline__ void fusedAggBodyTma(const FusedParams& P)
     FusedAggSink<Prog> sink(P);
     sink.init(fusedSmem);
     const int stages = P.tmaStages;
-    unsigned char* ring = fusedSmem + ((sink.layoutBytes() + 127u) & ~127u);
+    unsigned char* ring = fusedSmem + ((sink.layoutBytes() + (uint32_t) FusedAggSink<Prog>::queueBytes() + 127u) & ~127u);
     uint64_t* full = (uint64_t*) (ring + (size_t) stages * Prog::STAGE_BYTES);
     uint64_t* empty = full + stages;
     if (threadIdx.x == 0) {

@@ -561,7 +561,7 @@ std::string generateFusedAggSource(const FusedProgramDesc& D, FusedKernelInfo& i
         src << "    }\n";
     }
     F.emitTileAndLoad(src, "FusedParams");
-    info.tma = D.joins.empty() && !F.eagerInputs.empty();
+    info.tma = !F.eagerInputs.empty();
     if (info.tma) info.tmaStageBytes = F.emitTma(src, "FusedParams");
 
     // ---- process ----
@@ -599,7 +599,7 @@ std::string generateFusedAggSource(const FusedProgramDesc& D, FusedKernelInfo& i
                 g.emit("if (go" + us + (v.z.empty() ? "" : " && !" + v.z) + ") { " + offs +
                        "if (len > " + std::to_string(k.maxLen) + ") { errLen = true; len = " + std::to_string(k.maxLen) + "; } "
                        "const uint8_t* b = (const uint8_t*) P.values[" + cs + "] + o; s" + id + " = (unsigned long long) (unsigned int) len; "
-                       "for (int i = 0; i < len && i < 7; i++) s" + id + " |= (unsigned long long) b[i] << (8 * (i + 1)); }");
+                       + [&]() { std::string u8; for (int i = 0; i < k.maxLen && i < 7; i++) u8 += "if (len > " + std::to_string(i) + ") s" + id + " |= (unsigned long long) __ldg(b + " + std::to_string(i) + ") << " + std::to_string(8 * (i + 1)) + "; "; return u8; }() + "}");      // declared length: straight-line predicated byte loads
                 v.v = "s" + id;
             }
             keyVals[u].push_back(v);

@@ -2034,7 +2034,15 @@ public:
             CUfunction launchFn = fn;
             unsigned block = 256;
             size_t smem = (L.direct ? 64 : sharedBytes(sharedSlots)) + c.info.queueBytes;
-            if (c.kernelTma && !L.direct && knownGroups >= 1 && knownGroups <= k0max && tiles > 4 * (int64_t) numSMs) {
+            if (c.kernelTma && L.direct && !bitmapIn && tiles > 4 * (int64_t) numSMs) {
+                // direct mode (every survivor goes to the HBM table): no tier layout, only the survivor queue sits in front of the ring
+                const size_t lay = (c.info.queueBytes + 127) & ~size_t(127);
+                const int stages = 4;
+                L.tmaStages = stages; L.tmaTiles = n / (256 * c.info.rowsPerThread) - 1;
+                launchFn = c.kernelTma->function; block = 256 + 32;
+                smem = lay + (size_t) stages * ((size_t) c.info.tmaStageBytes + 16);
+            }
+            else if (c.kernelTma && !L.direct && knownGroups >= 1 && knownGroups <= k0max && tiles > 4 * (int64_t) numSMs) {
                 const int t0 = (int) knownGroups;
                 // a handful of groups does not need the full shared table: 4 slots per known group leave the ring more room
                 uint32_t slots = 64;
@@ -2058,7 +2066,7 @@ public:
             const CUresult r = api.launchKernel(launchFn, grid, 1, 1, block, 1, 1, (unsigned) smem, (CUstream) stream, args, nullptr);
             if (r != CUDA_SUCCESS) throw Error(PG_ERR_CUDA, "cuLaunchKernel of a fused pipeline kernel failed (" + std::to_string((int) r) + ")");
             stats.kernel_launches++;
-            stats.kernel_paths |= L.direct ? PG_PATH_FUSED_DIRECT : (L.tmaStages ? PG_PATH_FUSED_TMA : PG_PATH_FUSED_TIERS);
+            stats.kernel_paths |= (L.direct ? PG_PATH_FUSED_DIRECT : PG_PATH_FUSED_TIERS) | (L.tmaStages ? PG_PATH_FUSED_TMA : 0);
             lastRegisters = L.tmaStages ? c.kernelTma->registers : c.kernel->registers;
         };
         inputChannels = &rawChannels;
