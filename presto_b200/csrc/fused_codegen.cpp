@@ -14,6 +14,7 @@
 // division-by-zero flags, SQL three-valued logic — the same semantics as fp_codegen.cpp's PTX and the interpreter kernels.
 #include "fused_codegen.h"
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
 
@@ -516,7 +517,8 @@ std::string generateFusedAggSource(const FusedProgramDesc& D, FusedKernelInfo& i
     std::ostringstream src;
     src << "// generated by presto_b200 fused_codegen: FilterAndProject -> LookupJoin* -> HashAggregation as one row program\n"
         << "#include \"fused_agg.cuh\"\nnamespace pg {\nstruct Prog {\n"
-        << "    static constexpr int THREADS = " << THREADS << ", MIN_CTAS = 2, R = " << R << ", W = " << D.W << ", NV = " << NV << ";\n"
+        // fragments with joins are latency bound on the probes' L2 loads: PG_FUSED_MIN_CTAS trades registers for resident warps
+        << "    static constexpr int THREADS = " << THREADS << ", MIN_CTAS = " << (D.joins.empty() ? 2 : (getenv("PG_FUSED_MIN_CTAS") ? atoi(getenv("PG_FUSED_MIN_CTAS")) : 3)) << ", R = " << R << ", W = " << D.W << ", NV = " << NV << ";\n"
         << "    static constexpr bool CNT = " << (D.countRows ? "true" : "false") << ";\n"
         << "    static constexpr int NEAGER = " << info.eagerInputs.size() << ";\n";
     // ---- the 64-bit word the on-chip tiers identify a group by ----
@@ -599,7 +601,7 @@ std::string generateFusedAggSource(const FusedProgramDesc& D, FusedKernelInfo& i
                 g.emit("if (go" + us + (v.z.empty() ? "" : " && !" + v.z) + ") { " + offs +
                        "if (len > " + std::to_string(k.maxLen) + ") { errLen = true; len = " + std::to_string(k.maxLen) + "; } "
                        "const uint8_t* b = (const uint8_t*) P.values[" + cs + "] + o; s" + id + " = (unsigned long long) (unsigned int) len; "
-                       + [&]() { std::string u8; for (int i = 0; i < k.maxLen && i < 7; i++) u8 += "if (len > " + std::to_string(i) + ") s" + id + " |= (unsigned long long) __ldg(b + " + std::to_string(i) + ") << " + std::to_string(8 * (i + 1)) + "; "; return u8; }() + "}");      // declared length: straight-line predicated byte loads
+                       "for (int i = 0; i < len && i < 7; i++) s" + id + " |= (unsigned long long) b[i] << (8 * (i + 1)); }");
                 v.v = "s" + id;
             }
             keyVals[u].push_back(v);

@@ -2034,7 +2034,10 @@ public:
             CUfunction launchFn = fn;
             unsigned block = 256;
             size_t smem = (L.direct ? 64 : sharedBytes(sharedSlots)) + c.info.queueBytes;
-            if (c.kernelTma && L.direct && !bitmapIn && tiles > 4 * (int64_t) numSMs) {
+            // (measured on Q3's lineitem fragment: the ring is SLOWER than the register double buffer in direct mode — 3.46 vs 2.78 ms; the
+            // consumers of a selective fragment stall on the probe's L2 loads, not on the tile loads — so it stays opt-in there)
+            const char* tmaJoins = getenv("PG_FUSED_TMA_DIRECT");
+            if (c.kernelTma && L.direct && !bitmapIn && tiles > 4 * (int64_t) numSMs && tmaJoins && tmaJoins[0] == '1') {
                 // direct mode (every survivor goes to the HBM table): no tier layout, only the survivor queue sits in front of the ring
                 const size_t lay = (c.info.queueBytes + 127) & ~size_t(127);
                 const int stages = 4;
