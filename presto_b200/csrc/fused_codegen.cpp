@@ -518,7 +518,7 @@ std::string generateFusedAggSource(const FusedProgramDesc& D, FusedKernelInfo& i
     src << "// generated by presto_b200 fused_codegen: FilterAndProject -> LookupJoin* -> HashAggregation as one row program\n"
         << "#include \"fused_agg.cuh\"\nnamespace pg {\nstruct Prog {\n"
         // fragments with joins are latency bound on the probes' L2 loads: PG_FUSED_MIN_CTAS trades registers for resident warps
-        << "    static constexpr int THREADS = " << THREADS << ", MIN_CTAS = " << (D.joins.empty() ? 2 : (getenv("PG_FUSED_MIN_CTAS") ? atoi(getenv("PG_FUSED_MIN_CTAS")) : 3)) << ", R = " << R << ", W = " << D.W << ", NV = " << NV << ";\n"
+        << "    static constexpr int THREADS = " << THREADS << ", MIN_CTAS = " << (D.joins.empty() ? 2 : (getenv("PG_FUSED_MIN_CTAS") ? atoi(getenv("PG_FUSED_MIN_CTAS")) : 4)) << ", R = " << R << ", W = " << D.W << ", NV = " << NV << ";\n"
         << "    static constexpr bool CNT = " << (D.countRows ? "true" : "false") << ";\n"
         << "    static constexpr int NEAGER = " << info.eagerInputs.size() << ";\n";
     // ---- the 64-bit word the on-chip tiers identify a group by ----
