@@ -186,6 +186,10 @@ typedef struct pg_operator_options {
 } pg_operator_options;
 
 int32_t pg_operator_needs_input(pg_operator* op, int32_t* out);
+/* Operator.isBlocked() (MB/operator/Operator.java:32; default NOT_BLOCKED): *out = 1 while the operator waits for something another
+ * Driver produces — a LookupJoin / semi join / fused fragment whose LookupSource is still being built (LookupJoinOperator.java:198-210:
+ * the lookupSourceProviderFuture) — 0 otherwise.  The JNI shim turns this into the ListenableFuture the Driver polls. */
+int32_t pg_operator_is_blocked(pg_operator* op, int32_t* out);
 /* Borrow `page` for the duration of the call (host pages are staged to HBM before return;
  * device pages are consumed on the operator's stream and must stay valid until the next
  * pg_operator_* call that synchronises: get_output / finish / stats). */

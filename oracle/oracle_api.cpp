@@ -124,6 +124,7 @@ int32_t or_fused_aggregation_create(const pg_fused_aggregation_config* c, void**
 int32_t or_fused_page_create(const pg_fused_page_config* c, void** out) { OR_TRY *out = new DriverChain(c); OR_CATCH }
 
 int32_t or_operator_needs_input(void* op, int32_t* out) { OR_TRY *out = ((Operator*) op)->needsInput() ? 1 : 0; OR_CATCH }
+int32_t or_operator_is_blocked(void* op, int32_t* out) { OR_TRY *out = ((Operator*) op)->isBlocked() ? 1 : 0; OR_CATCH }
 int32_t or_operator_add_input(void* op, const pg_page* page)
 {
     OR_TRY

@@ -296,6 +296,7 @@ struct Operator {
     virtual bool getOutput(OwnedPage& out) = 0;   // false = null
     virtual void finish() = 0;
     virtual bool isFinished() = 0;
+    virtual bool isBlocked() { return false; }    // Operator.isBlocked() (Operator.java:32)
     OwnedPage lastOutput;
     pg_operator_stats stats{};
 };

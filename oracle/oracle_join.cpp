@@ -176,6 +176,7 @@ struct LookupJoinOperator : Operator {
         precomputedHashChannel = c->precomputed_hash_channel;
     }
     bool needsInput() override { return !finishing && !hasPending && bridge->lookupSource != nullptr; }   // LookupJoinOperator.java:198-210
+    bool isBlocked() override { return bridge->lookupSource == nullptr; }      // the lookupSourceProviderFuture
     void addInput(const pg_page* page) override
     {
         if (!needsInput()) throw OracleError(PG_ERR_INVALID_STATE, "lookup join does not need input");
@@ -254,6 +255,7 @@ struct SemiJoinOperator : Operator {
         probeChannel = c->probe_join_channel;
     }
     bool needsInput() override { return !finishing && !hasPending && bridge->lookupSource != nullptr; }
+    bool isBlocked() override { return bridge->lookupSource == nullptr; }
     void addInput(const pg_page* page) override
     {
         if (!needsInput()) throw OracleError(PG_ERR_INVALID_STATE, "semi join does not need input (set not built, finishing, or output pending)");

@@ -192,6 +192,7 @@ class Backend:
         "hash_double": (C.c_int64, [C.c_double]),
         "hash_local_partition": (C.c_int32, [C.c_int64, C.c_int32]),
         "operator_needs_input": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32)]),
+        "operator_is_blocked": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32)]),
         "operator_add_input": (C.c_int32, [C.c_void_p, C.POINTER(pg_page)]),
         "operator_get_output": (C.c_int32, [C.c_void_p, C.POINTER(pg_page)]),
         "operator_finish": (C.c_int32, [C.c_void_p]),

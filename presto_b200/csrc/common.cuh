@@ -143,6 +143,7 @@ struct Operator {
     virtual bool getOutput(pg_page* out) = 0;     // false → Java null
     virtual void finish() = 0;
     virtual bool isFinished() = 0;
+    virtual bool isBlocked() { return false; }    // Operator.isBlocked(): waiting on another Driver (a LookupSource under construction)
     virtual void syncStats() {}
     void bind() const { PG_CUDA(cudaSetDevice(options.device)); }
     int64_t maxOutputRows() const { return options.max_output_rows > 0 ? options.max_output_rows : (int64_t(1) << 20); }

@@ -76,6 +76,11 @@ public:
         PG_CUDA(cudaMemsetAsync(errorWord.ptr, 0, 16, stream));
     }
 
+    bool isBlocked() override
+    {
+        for (size_t j = 0; j < joins.size(); j++) { if (!views[j].ready) describeLookupSource(joins[j].bridge, views[j]); if (!views[j].ready) return true; }
+        return false;
+    }
     bool needsInput() override
     {
         if (finishing || hasPending) return false;

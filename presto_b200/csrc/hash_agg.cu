@@ -1946,6 +1946,11 @@ public:
         views.resize(joins.size());
     }
 
+    bool isBlocked() override
+    {
+        for (size_t j = 0; j < joins.size(); j++) { if (!views[j].ready) describeLookupSource(joins[j].bridge, views[j]); if (!views[j].ready) return true; }
+        return false;
+    }
     // LookupJoinOperator.needsInput :198-210: blocked until every lookup source future completes
     bool needsInput() override
     {

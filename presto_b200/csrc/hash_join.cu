@@ -1071,6 +1071,7 @@ public:
 
     // LookupJoinOperator.needsInput :198-210: blocked until the lookup source future completes
     bool needsInput() override { return !finishing && !hasPending && bridge->get() != nullptr; }
+    bool isBlocked() override { return bridge->get() == nullptr; }
 
     void addInput(const pg_page* page) override
     {
@@ -1370,6 +1371,7 @@ public:
         for (auto& d : outNulls) d.accounting = &stats.device_bytes;
     }
     bool needsInput() override { return !finishing && !hasPending && bridge->get() != nullptr; }   // "Set has not been built yet"
+    bool isBlocked() override { return bridge->get() == nullptr; }
 
     void addInput(const pg_page* page) override
     {

@@ -405,6 +405,7 @@ int64_t pg_hash_xxhash64(const void* data, size_t len)
 
 // ---- operator protocol ------------------------------------------------------------------------------------------------
 int32_t pg_operator_needs_input(pg_operator* op, int32_t* out) { PG_TRY auto* o = (Operator*) op; o->bind(); *out = o->needsInput() ? 1 : 0; PG_CATCH }
+int32_t pg_operator_is_blocked(pg_operator* op, int32_t* out) { PG_TRY auto* o = (Operator*) op; *out = o->isBlocked() ? 1 : 0; PG_CATCH }
 int32_t pg_operator_add_input(pg_operator* op, const pg_page* page)
 {
     PG_TRY

@@ -43,6 +43,12 @@ class Operator:
         self._b.check(self._b.operator_needs_input(self._h, C.byref(out)))
         return bool(out.value)
 
+    def is_blocked(self) -> bool:
+        """Operator.isBlocked() (Operator.java:32): True while the operator waits for another Driver (a LookupSource still being built)."""
+        out = C.c_int32()
+        self._b.check(self._b.operator_is_blocked(self._h, C.byref(out)))
+        return bool(out.value)
+
     def add_input(self, page: Page) -> None:
         cpage, keep = page.as_c()
         self._b.check(self._b.operator_add_input(self._h, C.byref(cpage)))

@@ -376,6 +376,24 @@ def case_partitioned_output(backend, partition_count: int = 4, n: int = 1000, nu
     op.close()
 
 
+def case_lookup_join_is_blocked_until_the_build_finishes(backend):
+    """Operator.isBlocked() (Operator.java:32) as LookupJoinOperator uses it (:198-210): the probe is blocked — and does not need input —
+    until HashBuilderOperator.finish() has published the LookupSource; every other operator is never blocked."""
+    bridge = JoinBridge(backend=backend)
+    build = HashBuilderOperator(bridge, [BIGINT, BIGINT], [0], [1], backend=backend)
+    probe = LookupJoinOperator(bridge, [BIGINT], [0], [0], backend=backend)
+    assert probe.is_blocked() and not probe.needs_input() and not build.is_blocked()
+    build.add_input(Page([create_long_sequence_block(0, 10), create_long_sequence_block(100, 110)]))
+    assert probe.is_blocked()
+    build.finish()
+    assert not probe.is_blocked() and probe.needs_input()
+    probe.add_input(Page([create_longs_block(3, 11, 7)]))
+    assert probe.get_output().rows() == [(3, 103), (7, 107)]
+    for op in (build, probe):
+        op.close()
+    bridge.close()
+
+
 def case_partitioned_output_double_zero_keys(backend):
     """DoubleType.hash → TypeUtils.doubleHashCode (PC/type/TypeUtils.java:232-238): -0.0 and +0.0 are equal keys, so they must reach the
     same partition (hash 0 → partition 0), as must every NaN payload."""
