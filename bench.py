@@ -82,6 +82,16 @@ def host_cpu_info():
     return info
 
 
+def host_threads():
+    """Threads the host arm uses: every CPU this process may actually run on — the smaller of the visible CPUs, the scheduler affinity and
+    the cgroup CPU quota (128 threads on a 16-CPU quota only buy throttling)."""
+    info = host_cpu_info()
+    n = info.get("affinity") or info.get("logical") or 1
+    if info.get("cgroup_cpus"):
+        n = min(n, max(1, int(info["cgroup_cpus"] + 0.999)))
+    return max(1, int(n))
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -880,7 +890,7 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     sample = min(args.cpu_rows, args.rows)
     dev = "cuda:0" if torch.cuda.is_available() else "cpu"
     cols = gen_q1_lineitem(torch, dev, sample, 1, args.keys)
@@ -934,7 +944,7 @@ def main():
     # ---- parity at the BASELINE size: the GPU's result over ALL rows vs the oracle's over the same rows (before any timing) ----
     parity = None
     if rank == 0 and args.parity:
-        threads = os.cpu_count() or 1
+        threads = host_threads()
         r0 = run_q1_headline(torch, backend, cols, kk, 1, 0, local, None)
         _, dt, want, _ = cpu_q1(torch, cols, kk, 0, rows, threads)
         ok = rows_match(r0["result"], want)
@@ -990,7 +1000,7 @@ def main():
     only = set(x for x in args.only.split(",") if x)
     scale = args.extra_scale or min(1.0, rows / Q1_SF100_ROWS)
     if rank == 0 and world == 1:
-        threads = os.cpu_count() or 1
+        threads = host_threads()
         sample = min(args.cpu_rows, rows)
         rps, dt, _, gbs = cpu_q1(torch, cols, kk, 0, sample, threads)
         cpu = {"value": rps, "unit": "rows/s", "cores": threads, "kind": "port", "host_gbs": gbs, "host": host_cpu_info(),
