@@ -383,6 +383,29 @@ struct GroupedAccumulator {
         return r;
     }
 
+    // TypeUtils.doubleCompare (PC/type/TypeUtils.java:240-261): NaN is larger than everything, +0 == -0
+    static int doubleCompare(double a, double b)
+    {
+        if (a < b) return -1;
+        if (a > b) return 1;
+        if (a == b) return 0;
+        const int64_t x = doubleToLongBits(a), y = doubleToLongBits(b);
+        return x < y ? -1 : (x > y ? 1 : 0);
+    }
+    // AbstractMinMaxAggregationFunction.compareAndUpdateState :256-287 with the type's LESS_THAN / GREATER_THAN operator
+    // (DoubleComparisonOperators.java: doubleCompare(left, right) < 0 / > 0; BigintOperators: plain < / >)
+    void minMaxLong(int64_t g, int64_t value, bool isMin)
+    {
+        if (isNull[g]) { isNull[g] = 0; longs[g] = value; return; }
+        if (isMin ? value < longs[g] : value > longs[g]) longs[g] = value;
+    }
+    void minMaxDouble(int64_t g, double value, bool isMin)
+    {
+        if (isNull[g]) { isNull[g] = 0; doubles[g] = value; return; }
+        const int c = doubleCompare(value, doubles[g]);
+        if (isMin ? c < 0 : c > 0) doubles[g] = value;
+    }
+
     // Number of input channels the FINAL step consumes for this aggregate (our intermediate layout):
     // sum → 1 (nullable value), count → 1, avg → 2 (sum double, count bigint)
     static int intermediateChannels(int fn) { return (fn == PG_AGG_AVG_DOUBLE || fn == PG_AGG_AVG_BIGINT) ? 2 : 1; }
@@ -412,6 +435,8 @@ struct GroupedAccumulator {
                     longs[g] = longs[g] + 1; doubles[g] = doubles[g] + in.getDouble(p); break;
                 case PG_AGG_AVG_BIGINT:   // AverageAggregations.input(long) :34-39
                     longs[g] = longs[g] + 1; doubles[g] = doubles[g] + (double) in.getLong(p); break;
+                case PG_AGG_MIN_BIGINT: case PG_AGG_MAX_BIGINT: minMaxLong(g, in.getLong(p), spec.function == PG_AGG_MIN_BIGINT); break;      // AbstractMinMaxAggregationFunction.input :199-202
+                case PG_AGG_MIN_DOUBLE: case PG_AGG_MAX_DOUBLE: minMaxDouble(g, in.getDouble(p), spec.function == PG_AGG_MIN_DOUBLE); break;  // :194-197
                 default: throw OracleError(PG_ERR_UNSUPPORTED, "aggregate function not in the oracle");
             }
         }
@@ -440,6 +465,12 @@ struct GroupedAccumulator {
                     BlockView c(&page->blocks[channel + 1]);
                     longs[g] += c.getLong(p); doubles[g] += a.getDouble(p); break;
                 }
+                case PG_AGG_MIN_BIGINT: case PG_AGG_MAX_BIGINT:      // AbstractMinMaxAggregationFunction.combine :225-228 (NULL intermediate states are skipped)
+                    if (!a.isNull(p)) minMaxLong(g, a.getLong(p), spec.function == PG_AGG_MIN_BIGINT);
+                    break;
+                case PG_AGG_MIN_DOUBLE: case PG_AGG_MAX_DOUBLE:
+                    if (!a.isNull(p)) minMaxDouble(g, a.getDouble(p), spec.function == PG_AGG_MIN_DOUBLE);
+                    break;
                 default: throw OracleError(PG_ERR_UNSUPPORTED, "aggregate function not in the oracle");
             }
         }
@@ -449,8 +480,8 @@ struct GroupedAccumulator {
     {
         bool partial = step == PG_STEP_PARTIAL;
         switch (spec.function) {
-            case PG_AGG_COUNT_STAR: case PG_AGG_COUNT_COLUMN: case PG_AGG_SUM_BIGINT: out.push_back(PG_TYPE_BIGINT); break;
-            case PG_AGG_SUM_DOUBLE: out.push_back(PG_TYPE_DOUBLE); break;
+            case PG_AGG_COUNT_STAR: case PG_AGG_COUNT_COLUMN: case PG_AGG_SUM_BIGINT: case PG_AGG_MIN_BIGINT: case PG_AGG_MAX_BIGINT: out.push_back(PG_TYPE_BIGINT); break;
+            case PG_AGG_SUM_DOUBLE: case PG_AGG_MIN_DOUBLE: case PG_AGG_MAX_DOUBLE: out.push_back(PG_TYPE_DOUBLE); break;
             case PG_AGG_AVG_DOUBLE: case PG_AGG_AVG_BIGINT:
                 out.push_back(PG_TYPE_DOUBLE); if (partial) out.push_back(PG_TYPE_BIGINT); break;
             default: throw OracleError(PG_ERR_UNSUPPORTED, "aggregate function not in the oracle");
@@ -462,8 +493,8 @@ struct GroupedAccumulator {
         bool partial = step == PG_STEP_PARTIAL;
         switch (spec.function) {
             case PG_AGG_COUNT_STAR: case PG_AGG_COUNT_COLUMN: out[offset++].appendLong(longs[g]); break;
-            case PG_AGG_SUM_DOUBLE: if (isNull[g]) out[offset++].appendNull(); else out[offset++].appendDouble(doubles[g]); break;
-            case PG_AGG_SUM_BIGINT: if (isNull[g]) out[offset++].appendNull(); else out[offset++].appendLong(longs[g]); break;
+            case PG_AGG_SUM_DOUBLE: case PG_AGG_MIN_DOUBLE: case PG_AGG_MAX_DOUBLE: if (isNull[g]) out[offset++].appendNull(); else out[offset++].appendDouble(doubles[g]); break;
+            case PG_AGG_SUM_BIGINT: case PG_AGG_MIN_BIGINT: case PG_AGG_MAX_BIGINT: if (isNull[g]) out[offset++].appendNull(); else out[offset++].appendLong(longs[g]); break;
             case PG_AGG_AVG_DOUBLE: case PG_AGG_AVG_BIGINT:
                 if (partial) { out[offset++].appendDouble(doubles[g]); out[offset++].appendLong(longs[g]); }
                 else if (longs[g] == 0) out[offset++].appendNull();                       // AverageAggregations.output :55-66

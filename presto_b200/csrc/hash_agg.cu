@@ -34,8 +34,24 @@
 namespace pg {
 
 // accumulator column kinds
-enum { K_F64 = 0, K_F64_FROM_I64 = 1, K_LO32 = 2, K_HI32 = 3, K_COUNT = 4, K_I64_ADD = 5 };
+enum { K_F64 = 0, K_F64_FROM_I64 = 1, K_LO32 = 2, K_HI32 = 3, K_COUNT = 4, K_I64_ADD = 5, K_MIN_F64 = 6, K_MAX_F64 = 7, K_MIN_I64 = 8, K_MAX_I64 = 9 };
 __host__ __device__ inline bool kindIsFloat(int k) { return k == K_F64 || k == K_F64_FROM_I64; }
+// min / max (MB/operator/aggregation/AbstractMinMaxAggregationFunction.java: state = value if it compares better) are ONE combine rule
+// here: every value is mapped to an unsigned word whose order is the type's order (`ordered`), MIN stores its complement, and the
+// accumulator takes the unsigned maximum.  The all-zero word every accumulator starts from is the identity of that rule, so table
+// initialisation, growth (rehash) and the tier folding need nothing special.  DOUBLE: NaN is canonical and sorts above +Infinity
+// (TypeUtils.doubleCompare: the new NaN definition); -0.0 sorts below +0.0 (the reference keeps whichever zero came first).
+__host__ __device__ inline bool kindIsMax(int k) { return k >= K_MIN_F64 && k <= K_MAX_I64; }
+__host__ __device__ inline uint64_t orderedOfI64(uint64_t v) { return v ^ 0x8000000000000000ULL; }
+__host__ __device__ inline uint64_t orderedOfF64(uint64_t bits)
+{
+    bits = (uint64_t) canonicalDoubleBits((int64_t) bits);
+    return (bits >> 63) ? ~bits : (bits ^ 0x8000000000000000ULL);
+}
+__host__ __device__ inline uint64_t i64OfOrdered(uint64_t o) { return o ^ 0x8000000000000000ULL; }
+__host__ __device__ inline uint64_t f64OfOrdered(uint64_t o) { return (o >> 63) ? (o ^ 0x8000000000000000ULL) : ~o; }
+// combine rule of an accumulator column: 0 integer add, 1 double add, 2 unsigned max
+enum { OP_ADD_I64 = 0, OP_ADD_F64 = 1, OP_MAX_U64 = 2 };
 
 struct AccInput {
     const uint64_t* values;     // 8-byte input column (DOUBLE bits or BIGINT); nullptr for counts
@@ -53,6 +69,7 @@ struct AggLaunch {
     AccInput acc[MAXV];
     int32_t nAcc;
     uint32_t floatMask;          // bit c: accumulator c adds doubles
+    uint32_t maxMask;            // bit c: accumulator c takes the unsigned maximum (min / max aggregates)
     int64_t n;                   // rows in this launch
     uint64_t rowBase;            // global index of row 0 (first-appearance bookkeeping)
     const uint32_t* bitmapIn;    // when set: only rows whose bit is set are processed (deferred-row pass)
@@ -63,15 +80,23 @@ struct AggLaunch {
     int32_t vec;                 // every 8-byte column pointer is 16-byte aligned: load row pairs with one 128-bit request
 };
 
-__device__ __forceinline__ void accAddShared(uint64_t* addr, uint64_t bits, bool isFloat)
+__device__ __forceinline__ void accAddShared(uint64_t* addr, uint64_t bits, int op)
 {
-    if (isFloat) atomicAdd((double*) addr, __longlong_as_double((long long) bits));
+    if (op == OP_ADD_F64) atomicAdd((double*) addr, __longlong_as_double((long long) bits));
+    else if (op == OP_MAX_U64) atomicMax((unsigned long long*) addr, (unsigned long long) bits);
     else atomicAdd((unsigned long long*) addr, (unsigned long long) bits);
 }
-__device__ __forceinline__ void accAddGlobal(uint64_t* addr, uint64_t bits, bool isFloat)
+__device__ __forceinline__ void accAddGlobal(uint64_t* addr, uint64_t bits, int op)
 {
-    if (isFloat) atomicAdd((double*) addr, __longlong_as_double((long long) bits));   // REDG.E.ADD.F64
+    if (op == OP_ADD_F64) atomicAdd((double*) addr, __longlong_as_double((long long) bits));   // REDG.E.ADD.F64
+    else if (op == OP_MAX_U64) atomicMax((unsigned long long*) addr, (unsigned long long) bits);
     else atomicAdd((unsigned long long*) addr, (unsigned long long) bits);
+}
+__device__ __forceinline__ uint64_t combineAcc(uint64_t a, uint64_t b, int op)
+{
+    if (op == OP_ADD_F64) return (uint64_t) __double_as_longlong(__longlong_as_double((long long) a) + __longlong_as_double((long long) b));
+    if (op == OP_MAX_U64) return a > b ? a : b;
+    return a + b;
 }
 __device__ __forceinline__ uint64_t contribOf(int kind, uint64_t raw)
 {
@@ -80,6 +105,10 @@ __device__ __forceinline__ uint64_t contribOf(int kind, uint64_t raw)
         case K_F64: case K_I64_ADD: return raw;
         case K_F64_FROM_I64: return (uint64_t) __double_as_longlong((double) (long long) raw);
         case K_LO32: return raw & 0xffffffffULL;
+        case K_MAX_I64: return orderedOfI64(raw);
+        case K_MIN_I64: return ~orderedOfI64(raw);
+        case K_MAX_F64: return orderedOfF64(raw);
+        case K_MIN_F64: return ~orderedOfF64(raw);
         default: return (uint64_t) ((long long) raw >> 32);   // K_HI32
     }
 }
@@ -100,6 +129,7 @@ __global__ void __launch_bounds__(kAggThreads) hashAggKernel(const __grid_consta
     const int nAcc = P.nAcc;
     const GroupTable& T = P.t;
     const bool useShared = P.S != 0;
+    auto opOf = [&](int c) { return ((P.maxMask >> c) & 1u) ? OP_MAX_U64 : (((P.floatMask >> c) & 1u) ? OP_ADD_F64 : OP_ADD_I64); };
 
     SharedTable<W> st;
     st.S = P.S; st.S2 = P.S + 2; st.sLimit = P.sLimit; st.tier0Groups = useShared ? K0 : 0;
@@ -209,8 +239,7 @@ __global__ void __launch_bounds__(kAggThreads) hashAggKernel(const __grid_consta
                         for (int c = 0; c < MAXV; c++) {
                             if (c < nAcc && ((addMask[r] >> c) & 1u)) {
                                 uint64_t* p = mine + c * kAggThreads;
-                                if ((P.floatMask >> c) & 1u) *(double*) p = *(double*) p + __longlong_as_double((long long) contrib[r][c]);
-                                else *p = *p + contrib[r][c];
+                                *p = combineAcc(*p, contrib[r][c], opOf(c));
                             }
                         }
                         if (!((seen0 >> id) & 1u)) { seen0 |= 1u << id; atomicMin(&st.first[sslot], rowIdx); }   // rows ascend per thread: first sight = this thread's minimum
@@ -248,16 +277,10 @@ __global__ void __launch_bounds__(kAggThreads) hashAggKernel(const __grid_consta
                                 const bool adds = in && ((addMask[r] >> c) & 1u);
                                 const unsigned any = __ballot_sync(0xffffffffu, adds);
                                 if (any) {
-                                    uint64_t x = adds ? contrib[r][c] : 0;
-                                    if ((P.floatMask >> c) & 1u) {
+                                    uint64_t x = adds ? contrib[r][c] : 0;       // 0 is the identity of all three combine rules
+                                    const int op = opOf(c);
 #pragma unroll
-                                        for (int m = 16; m >= 1; m >>= 1)
-                                            x = (uint64_t) __double_as_longlong(__longlong_as_double((long long) x) + __longlong_as_double((long long) shflXor64(x, m)));
-                                    }
-                                    else {
-#pragma unroll
-                                        for (int m = 16; m >= 1; m >>= 1) x += shflXor64(x, m);
-                                    }
+                                    for (int m = 16; m >= 1; m >>= 1) x = combineAcc(x, shflXor64(x, m), op);
                                     if (lane == gl) { mine[c] = x; mineAdd |= 1u << c; }
                                 }
                             }
@@ -271,7 +294,7 @@ __global__ void __launch_bounds__(kAggThreads) hashAggKernel(const __grid_consta
                 if (active) {
 #pragma unroll
                     for (int c = 0; c < MAXV; c++)
-                        if (c < nAcc && ((myAdd >> c) & 1u)) accAddShared(&st.acc[c * st.S2 + sslot], contrib[r][c], (P.floatMask >> c) & 1u);
+                        if (c < nAcc && ((myAdd >> c) & 1u)) accAddShared(&st.acc[c * st.S2 + sslot], contrib[r][c], opOf(c));
                     if (rowIdx < *(volatile uint32_t*) &st.first[sslot]) atomicMin(&st.first[sslot], rowIdx);
                 }
             }
@@ -288,7 +311,7 @@ __global__ void __launch_bounds__(kAggThreads) hashAggKernel(const __grid_consta
 #pragma unroll
                     for (int c = 0; c < MAXV; c++)
                         if (c < nAcc && ((addMask[r] >> c) & 1u))
-                            accAddGlobal(&T.acc[(size_t) gslot * T.nvPhys + P.acc[c].phys], contrib[r][c], (P.floatMask >> c) & 1u);
+                            accAddGlobal(&T.acc[(size_t) gslot * T.nvPhys + P.acc[c].phys], contrib[r][c], opOf(c));
                 }
             }
         }
@@ -308,23 +331,14 @@ __global__ void __launch_bounds__(kAggThreads) hashAggKernel(const __grid_consta
             const uint32_t id = pairIdx / MAXV, c = pairIdx % MAXV;
             if ((int) c >= nAcc) continue;
             const uint64_t* src = tier0 + (size_t) pairIdx * kAggThreads;
-            const bool isF = (P.floatMask >> c) & 1u;
+            const int op = opOf((int) c);
             uint64_t x = 0;
-            if (isF) {
-                double d = 0;
-                for (int i = lane; i < kAggThreads; i += 32) d += __longlong_as_double((long long) src[i]);
-                x = (uint64_t) __double_as_longlong(d);
+            for (int i = lane; i < kAggThreads; i += 32) x = combineAcc(x, src[i], op);
 #pragma unroll
-                for (int m = 16; m >= 1; m >>= 1) x = (uint64_t) __double_as_longlong(__longlong_as_double((long long) x) + __longlong_as_double((long long) shflXor64(x, m)));
-            }
-            else {
-                for (int i = lane; i < kAggThreads; i += 32) x += src[i];
-#pragma unroll
-                for (int m = 16; m >= 1; m >>= 1) x += shflXor64(x, m);
-            }
+            for (int m = 16; m >= 1; m >>= 1) x = combineAcc(x, shflXor64(x, m), op);
             if (lane == 0) {
                 uint64_t* dst = &st.acc[c * st.S2 + st.count[2 + id]];
-                if (isF) *(double*) dst = *(double*) dst + __longlong_as_double((long long) x); else *dst = *dst + x;
+                *dst = combineAcc(*dst, x, op);
             }
         }
         __syncthreads();
@@ -344,7 +358,7 @@ __global__ void __launch_bounds__(kAggThreads) hashAggKernel(const __grid_consta
             if (g < __ldcg(&T.firstRow[gslot])) atomicMin((unsigned long long*) &T.firstRow[gslot], (unsigned long long) g);
             for (int c = 0; c < nAcc; c++) {
                 const uint64_t x = st.acc[c * st.S2 + s];
-                if (x != 0) accAddGlobal(&T.acc[(size_t) gslot * T.nvPhys + P.acc[c].phys], x, (P.floatMask >> c) & 1u);
+                if (x != 0) accAddGlobal(&T.acc[(size_t) gslot * T.nvPhys + P.acc[c].phys], x, opOf(c));
             }
         }
     }
@@ -897,6 +911,12 @@ __global__ void emitKernel(const __grid_constant__ EmitParams P)
                     if (total > (__int128) INT64_MAX || total < (__int128) INT64_MIN) { atomicOr(&T.counters[CNT_ERROR], (unsigned int) ERR_BIGINT_OVERFLOW); total = 0; }
                     ((int64_t*) ao.out0)[g] = count > 0 ? (int64_t) total : 0; ao.null0[g] = count > 0 ? 0 : 1; break;
                 }
+                case PG_AGG_MIN_DOUBLE: case PG_AGG_MAX_DOUBLE: case PG_AGG_MIN_BIGINT: case PG_AGG_MAX_BIGINT: {
+                    const bool isMin = ao.function == PG_AGG_MIN_DOUBLE || ao.function == PG_AGG_MIN_BIGINT;
+                    const uint64_t o = isMin ? ~acc[ao.val0] : acc[ao.val0];
+                    const uint64_t v = (ao.function == PG_AGG_MIN_DOUBLE || ao.function == PG_AGG_MAX_DOUBLE) ? f64OfOrdered(o) : i64OfOrdered(o);
+                    ((uint64_t*) ao.out0)[g] = count > 0 ? v : 0; ao.null0[g] = count > 0 ? 0 : 1; break;
+                }
                 case PG_AGG_AVG_DOUBLE: case PG_AGG_AVG_BIGINT:
                     if (ao.partial) { ((uint64_t*) ao.out0)[g] = acc[ao.val0]; ao.null0[g] = 0; ((int64_t*) ao.out1)[g] = count; }
                     else if (count == 0) { ((uint64_t*) ao.out0)[g] = 0; ao.null0[g] = 1; }
@@ -1040,7 +1060,8 @@ struct ResultBuilder {
             const AggEmit& a = aggs[i];
             AggOut& ao = E.aggs[i];
             ao.function = a.function; ao.val0 = a.val0; ao.val1 = a.val1; ao.partial = a.partial ? 1 : 0; ao.countCol = a.countCol;
-            int type = (a.function == PG_AGG_SUM_DOUBLE || a.function == PG_AGG_AVG_DOUBLE || a.function == PG_AGG_AVG_BIGINT) ? PG_TYPE_DOUBLE : PG_TYPE_BIGINT;
+            int type = (a.function == PG_AGG_SUM_DOUBLE || a.function == PG_AGG_AVG_DOUBLE || a.function == PG_AGG_AVG_BIGINT || a.function == PG_AGG_MIN_DOUBLE
+                        || a.function == PG_AGG_MAX_DOUBLE) ? PG_TYPE_DOUBLE : PG_TYPE_BIGINT;
             int c = newColumn(type);
             ao.out0 = outBufs[colBufs[c].values].ptr; ao.null0 = outBufs[colBufs[c].nulls].as<uint8_t>(); ao.out1 = nullptr;
             if (a.partial && (a.function == PG_AGG_AVG_DOUBLE || a.function == PG_AGG_AVG_BIGINT)) {
@@ -1157,7 +1178,16 @@ static void planAggregation(const pg_hash_aggregation_config* c, KeyLayout& layo
                     a.countCol = physColumn(K_COUNT, ch, mk, mk < 0);
                 }
                 break;
-            default: throw Error(PG_ERR_UNSUPPORTED, "aggregate function is not on the GPU path (supported: count, sum, avg over BIGINT/DOUBLE)");
+            case PG_AGG_MIN_DOUBLE: case PG_AGG_MAX_DOUBLE: case PG_AGG_MIN_BIGINT: case PG_AGG_MAX_BIGINT: {
+                // AbstractMinMaxAggregationFunction: NULL inputs are skipped, a group without a non-null input yields NULL; the intermediate
+                // state (PARTIAL -> FINAL) is the value itself, so the FINAL step is the same function over the intermediate channel
+                const int kind = a.spec.function == PG_AGG_MIN_DOUBLE ? K_MIN_F64 : a.spec.function == PG_AGG_MAX_DOUBLE ? K_MAX_F64
+                               : a.spec.function == PG_AGG_MIN_BIGINT ? K_MIN_I64 : K_MAX_I64;
+                a.val0 = physColumn(kind, ch, final ? -1 : mk, false);
+                a.countCol = physColumn(K_COUNT, ch, final ? -1 : mk, (final ? -1 : mk) < 0);
+                break;
+            }
+            default: throw Error(PG_ERR_UNSUPPORTED, "aggregate function is not on the GPU path (supported: count, sum, avg, min, max over BIGINT/DOUBLE)");
         }
         if (a.spec.function != PG_AGG_COUNT_STAR) PG_CHECK_ARG(ch >= 0, "aggregate needs an input channel");
         aggs.push_back(a);
@@ -1460,6 +1490,7 @@ public:
                 a.mask = (const uint8_t*) mc.values + begin; a.maskNulls = mc.nulls ? mc.nulls + begin : nullptr;
             }
             if (kindIsFloat(a.kind)) L.floatMask |= 1u << na;
+            if (kindIsMax(a.kind)) L.maxMask |= 1u << na;
             na++;
         }
         L.nAcc = na;

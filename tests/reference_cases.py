@@ -376,6 +376,37 @@ def case_partitioned_output(backend, partition_count: int = 4, n: int = 1000, nu
     op.close()
 
 
+def case_min_max_aggregates(backend):
+    """min / max over BIGINT and DOUBLE (AbstractMinMaxAggregationFunction.java:194-287): NULL inputs are skipped, a group whose inputs are
+    all NULL yields NULL, NaN is the largest DOUBLE (TypeUtils.doubleCompare), SINGLE equals PARTIAL -> FINAL; expectations computed here
+    from the definition, independent of both implementations."""
+    from presto_b200 import AGG_MAX_BIGINT, AGG_MAX_DOUBLE, AGG_MIN_BIGINT, AGG_MIN_DOUBLE, STEP_FINAL, STEP_PARTIAL
+    keys = [1, 2, 1, 3, 2, 1, 3, 4, 4]
+    longs = [5, None, -7, None, 9, 2**62, None, -(2**63), 2**63 - 1]
+    dbls = [1.5, float("nan"), -2.25, None, 7.0, None, None, float("-inf"), 3.0]
+    page = Page([Block.from_values(BIGINT, keys), Block.from_values(BIGINT, longs), Block.from_values(DOUBLE, dbls)])
+    aggs = [Aggregate(AGG_MIN_BIGINT, 1), Aggregate(AGG_MAX_BIGINT, 1), Aggregate(AGG_MIN_DOUBLE, 2), Aggregate(AGG_MAX_DOUBLE, 2), Aggregate(AGG_COUNT_STAR)]
+    op = HashAggregationOperator([BIGINT], [0], aggs, backend=backend)
+    rows = rows_of(to_pages(op, [page]))
+    op.close()
+    nan = float("nan")
+    expected = [(1, -7, 2**62, -2.25, 1.5, 3), (2, 9, 9, 7.0, nan, 2), (3, None, None, None, None, 2), (4, -(2**63), 2**63 - 1, float("-inf"), 3.0, 2)]
+    rows_close(rows, expected, rel=0.0)
+    # PARTIAL per page, FINAL over the intermediate pages (channels: key, then one per aggregate)
+    partials = []
+    for half in (page_slice(page, 0, 4), page_slice(page, 4, 9)):
+        p = HashAggregationOperator([BIGINT], [0], aggs, step=STEP_PARTIAL, backend=backend)
+        partials += to_pages(p, [half])
+        p.close()
+    f = HashAggregationOperator([BIGINT], [0], [Aggregate(a.function, 1 + i) for i, a in enumerate(aggs)], step=STEP_FINAL, backend=backend)
+    rows_close(rows_of(to_pages(f, partials)), expected, rel=0.0)
+    f.close()
+
+
+def page_slice(page: Page, begin: int, end: int) -> Page:
+    return Page([Block.from_values(b.type, b.to_pylist()[begin:end]) for b in page.blocks])
+
+
 def case_lookup_join_is_blocked_until_the_build_finishes(backend):
     """Operator.isBlocked() (Operator.java:32) as LookupJoinOperator uses it (:198-210): the probe is blocked — and does not need input —
     until HashBuilderOperator.finish() has published the LookupSource; every other operator is never blocked."""
