@@ -563,6 +563,7 @@ def run_q3_multi(torch, backend, device, n_orders_total, steps, warmup, dist):
     exchanges = (FusedExchange([BIGINT, DATE, INTEGER], orders[0].numel() // 4 + 1024, backend=backend),
                  FusedExchange([BIGINT, DOUBLE], lineitem[0].numel() * 5 // 8 + 1024, backend=backend))
     times, nccl_times, stats, groups = [], [], {}, 0
+    digest = {}
     for fused in (False, True):
         for it in range(warmup + steps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -575,8 +576,21 @@ def run_q3_multi(torch, backend, device, n_orders_total, steps, warmup, dist):
             torch.cuda.synchronize(); dist.barrier()
             if it >= warmup:
                 (times if fused else nccl_times).append(e0.elapsed_time(e1)); groups = sum(p.position_count for p in out)
+        # parity between the two exchange arms (and, through tests/test_gpu_multi.py, with the single-GPU plan): the groups a rank owns and
+        # their revenue must not depend on how the rows travelled — order-independent digest of (orderkey, orderdate, shippriority, revenue)
+        from presto_b200.exchange import block_to_tensor
+        if out:
+            keys = torch.cat([block_to_tensor(p.blocks[0]) for p in out])
+            rev = torch.cat([block_to_tensor(p.blocks[3]) for p in out])
+            d = torch.stack([torch.tensor(float(keys.numel()), dtype=torch.float64, device=dev), keys.to(torch.float64).sum(), (keys % 1000003).to(torch.float64).sum(), rev.sum()])
+        else:
+            d = torch.zeros(4, dtype=torch.float64, device=dev)
+        dist.all_reduce(d)
+        digest[fused] = d.cpu().tolist()
     for fx in exchanges:
         fx.close()
+    a, b_ = digest[False], digest[True]
+    same = a[0] == b_[0] and a[1] == b_[1] and a[2] == b_[2] and abs(a[3] - b_[3]) <= 1e-9 * abs(a[3])
     t = torch.tensor([float(np.mean(times)), float(np.mean(nccl_times))], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     g = torch.tensor([groups, stats.get("exchanged_rows", 0), stats.get("joined_rows", 0)], dtype=torch.int64, device=dev)
@@ -584,6 +598,7 @@ def run_q3_multi(torch, backend, device, n_orders_total, steps, warmup, dist):
     ms = float(t[0])
     return {"orders": n_orders_total, "lineitem_rows": int(n_li[0]), "groups": int(g[0]), "exchanged_rows": int(g[1]), "joined_rows": int(g[2]), "ms": ms,
             "ms_with_nccl_all_to_all": float(t[1]), "exchange": "fused scatter into peer receive columns (NVLink P2P)",
+            "parity_checked": bool(same), "parity": {"fused_vs_nccl_digest": [a, b_], "rule": "group count, key checksums exact; total revenue 1e-9"},
             **({"trace_ms_rank0": stats["trace_ms"]} if "trace_ms" in stats else {}),
             "lineitem_rows_per_s": int(n_li[0]) / (ms / 1000)}
 

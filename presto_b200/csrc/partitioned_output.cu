@@ -330,6 +330,23 @@ __global__ void __launch_bounds__(kRemoteWarps * 32) partitionScatterStagedKerne
     }
 }
 
+// ---- VARCHAR channels (VariableWidthBlockEncodingBuffer.java:1-293: per partition the selected positions' offsets and slice bytes are
+// appended) ride on the fixed-width machinery: a slice's length and its start offset are scattered as two synthetic 4-byte columns (so
+// stable order, replicated rows and NULL maps need nothing new); a scan of the scattered lengths gives the output offsets and one
+// pass copies the bytes.
+__global__ void varcharLengthsKernel(const int32_t* offsets, const uint8_t* nulls, int64_t n, int32_t* lens)
+{
+    for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
+        lens[i] = (nulls && nulls[i]) ? 0 : offsets[i + 1] - offsets[i];
+}
+__global__ void varcharGatherBytesKernel(const uint8_t* inBytes, const int32_t* starts, const int32_t* outOffsets, int64_t total, uint8_t* outBytes)
+{
+    for (int64_t j = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; j < total; j += (int64_t) gridDim.x * blockDim.x) {
+        const int32_t to = outOffsets[j], len = outOffsets[j + 1] - to, from = starts[j];
+        for (int32_t i = 0; i < len; i++) outBytes[to + i] = inBytes[from + i];
+    }
+}
+
 class PartitionedOutputOp : public Operator {
     std::vector<int> types, partitionChannels, staged;
     int partitionCount, hashChannel, nullChannel, partitionFunction;
@@ -342,6 +359,11 @@ class PartitionedOutputOp : public Operator {
     std::vector<pg_block> outBlocks;
     std::vector<int64_t> offsets;
     int64_t pendingRows = 0;
+    // VARCHAR channels: scattered lengths / starts, output offsets and bytes
+    std::vector<DeviceBuffer> vcLens, vcOutLens, vcOutStarts, vcOutOffsets, vcOutBytes;
+    std::vector<PinnedBuffer> vcHostBytes, vcHostOffsets;
+    DeviceBuffer vcScanTemp;
+    bool hasVarchar = false;
 
 public:
     explicit PartitionedOutputOp(const pg_partitioned_output_config* c) : Operator(c->options), stager(this)
@@ -357,8 +379,13 @@ public:
         PG_CHECK_ARG(partitionFunction == PG_PARTITION_HASH_GENERATOR || partitionFunction == PG_PARTITION_LOCAL, "unknown partition function");
         if (partitionFunction == PG_PARTITION_LOCAL)
             PG_CHECK_ARG((partitionCount & (partitionCount - 1)) == 0, "partitionCount must be a power of 2");   // LocalPartitionGenerator.java:33
-        for (int t : types) if (t == PG_TYPE_VARCHAR) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR channels are not on the GPU repartition path yet");
-        for (int ch : partitionChannels) PG_CHECK_ARG(ch >= 0 && ch < c->n_channels, "partition channel out of range");
+        int internalColumns = 0;
+        for (int t : types) { if (t == PG_TYPE_VARCHAR) { hasVarchar = true; internalColumns += 2; } else internalColumns++; }
+        PG_CHECK_ARG(internalColumns <= kMaxScatterColumns, "too many channels (a VARCHAR channel counts twice)");
+        for (int ch : partitionChannels) {
+            PG_CHECK_ARG(ch >= 0 && ch < c->n_channels, "partition channel out of range");
+            if (types[ch] == PG_TYPE_VARCHAR) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR partition channels are not hashed on the GPU path: pass a precomputed $hashvalue channel");
+        }
         PG_CHECK_ARG(hashChannel < c->n_channels && nullChannel < c->n_channels, "channel out of range");
         PG_CHECK_ARG(hashChannel >= 0 || !partitionChannels.empty() || partitionCount == 1, "no partition channels");
         if (hashChannel >= 0) PG_CHECK_ARG(types[hashChannel] == PG_TYPE_BIGINT, "precomputed hash channel must be BIGINT");
@@ -430,32 +457,92 @@ public:
         const size_t nCols = types.size();
         if (outValues.size() < nCols) { outValues.resize(nCols); outNulls.resize(nCols); for (auto& d : outValues) d.accounting = &stats.device_bytes; for (auto& d : outNulls) d.accounting = &stats.device_bytes; }
         ScatterParams S{};
-        S.nCols = (int) nCols; S.partitionCount = partitionCount; S.n = n; S.units = curUnits; S.ids = ids.as<uint16_t>(); S.base = base.as<uint32_t>();
+        S.partitionCount = partitionCount; S.n = n; S.units = curUnits; S.ids = ids.as<uint16_t>(); S.base = base.as<uint32_t>();
         outBlocks.assign(nCols, pg_block{});
+        const size_t nVc = (size_t) std::count(types.begin(), types.end(), (int) PG_TYPE_VARCHAR);
+        if (vcLens.size() < nVc) {
+            vcLens.resize(nVc); vcOutLens.resize(nVc); vcOutStarts.resize(nVc); vcOutOffsets.resize(nVc); vcOutBytes.resize(nVc);
+            for (auto* vec : {&vcLens, &vcOutLens, &vcOutStarts, &vcOutOffsets, &vcOutBytes}) for (auto& d : *vec) d.accounting = &stats.device_bytes;
+        }
+        std::vector<uint8_t*> dstNullsOf(nCols, nullptr);
+        int k = 0;
+        size_t v = 0;
         for (size_t i = 0; i < nCols; i++) {
-            ScatterColumn& sc = S.cols[i];
+            if (types[i] == PG_TYPE_VARCHAR) {
+                PG_CHECK_ARG(cols[i].offsets != nullptr, "VARCHAR block without offsets");
+                vcLens[v].reserve((size_t) n * 4); vcOutLens[v].reserve((size_t) (total + 1) * 4); vcOutStarts[v].reserve((size_t) total * 4);
+                PG_LAUNCH(this, varcharLengthsKernel, (int) std::min<int64_t>(divUp(n, 256), 4096), 256, 0, cols[i].offsets, cols[i].nulls, n, vcLens[v].as<int32_t>());
+                PG_CUDA(cudaMemsetAsync(vcOutLens[v].as<int32_t>() + total, 0, 4, stream));
+                ScatterColumn& sl = S.cols[k++];
+                sl.width = 4; sl.src = vcLens[v].ptr; sl.srcNulls = cols[i].nulls; sl.dst = vcOutLens[v].ptr; sl.dstNulls = nullptr;
+                if (cols[i].nulls) { outNulls[i].reserve(total); sl.dstNulls = outNulls[i].as<uint8_t>(); }
+                dstNullsOf[i] = sl.dstNulls;
+                ScatterColumn& ss = S.cols[k++];
+                ss.width = 4; ss.src = cols[i].offsets; ss.srcNulls = nullptr; ss.dst = vcOutStarts[v].ptr; ss.dstNulls = nullptr;
+                v++;
+                continue;
+            }
+            ScatterColumn& sc = S.cols[k++];
             sc.width = typeWidth(types[i]); sc.src = cols[i].values; sc.srcNulls = cols[i].nulls;
             outValues[i].reserve((size_t) total * sc.width);
             sc.dst = outValues[i].ptr; sc.dstNulls = nullptr;
             if (cols[i].nulls) { outNulls[i].reserve(total); sc.dstNulls = outNulls[i].as<uint8_t>(); }
+            dstNullsOf[i] = sc.dstNulls;
         }
+        S.nCols = k;
         PG_LAUNCH(this, partitionScatterKernel, launchGrid(), kPartWarps * 32, scatterSmem(false), S);
+        // VARCHAR: scattered lengths → output offsets → bytes
+        std::vector<int32_t> vcTotalBytes(nVc, 0);
+        v = 0;
+        for (size_t i = 0; i < nCols; i++) {
+            if (types[i] != PG_TYPE_VARCHAR) continue;
+            vcOutOffsets[v].reserve((size_t) (total + 1) * 4);
+            size_t tb = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tb, vcOutLens[v].as<int32_t>(), vcOutOffsets[v].as<int32_t>(), (int) (total + 1), stream);
+            vcScanTemp.reserve(tb);
+            cub::DeviceScan::ExclusiveSum(vcScanTemp.ptr, tb, vcOutLens[v].as<int32_t>(), vcOutOffsets[v].as<int32_t>(), (int) (total + 1), stream);
+            stats.kernel_launches += 2;
+            PG_CUDA(cudaMemcpyAsync(&vcTotalBytes[v], vcOutOffsets[v].as<int32_t>() + total, 4, cudaMemcpyDeviceToHost, stream));
+            v++;
+        }
+        if (nVc) {
+            PG_CUDA(cudaStreamSynchronize(stream));
+            v = 0;
+            for (size_t i = 0; i < nCols; i++) {
+                if (types[i] != PG_TYPE_VARCHAR) continue;
+                vcOutBytes[v].reserve((size_t) vcTotalBytes[v] + 16);
+                PG_LAUNCH(this, varcharGatherBytesKernel, (int) std::min<int64_t>(divUp(total, 256), 4096), 256, 0, (const uint8_t*) cols[i].values, vcOutStarts[v].as<int32_t>(),
+                          vcOutOffsets[v].as<int32_t>(), total, vcOutBytes[v].as<uint8_t>());
+                v++;
+            }
+        }
         stager.markCompute(curSlot);
         const bool toHost = options.output_memory == PG_MEM_HOST;
         if (toHost && hostValues.size() < nCols) { hostValues.resize(nCols); hostNulls.resize(nCols); }
+        if (toHost && vcHostBytes.size() < nVc) { vcHostBytes.resize(nVc); vcHostOffsets.resize(nVc); }
+        v = 0;
         for (size_t i = 0; i < nCols; i++) {
             pg_block& b = outBlocks[i];
-            const size_t vbytes = (size_t) total * typeWidth(types[i]);
             b.type = types[i]; b.encoding = PG_ENC_FLAT; b.position_count = total;
+            const bool isVc = types[i] == PG_TYPE_VARCHAR;
+            const size_t vbytes = isVc ? (size_t) vcTotalBytes[v] : (size_t) total * typeWidth(types[i]);
+            const void* dValues = isVc ? vcOutBytes[v].ptr : outValues[i].ptr;
             if (toHost) {
-                hostValues[i].reserve(std::max<size_t>(vbytes, 16));
-                PG_CUDA(cudaMemcpyAsync(hostValues[i].ptr, outValues[i].ptr, vbytes, cudaMemcpyDeviceToHost, stream));
-                b.values = hostValues[i].ptr; b.is_null = nullptr;
+                PinnedBuffer& hv = isVc ? vcHostBytes[v] : hostValues[i];
+                hv.reserve(std::max<size_t>(vbytes, 16));
+                if (vbytes) PG_CUDA(cudaMemcpyAsync(hv.ptr, dValues, vbytes, cudaMemcpyDeviceToHost, stream));
+                b.values = hv.ptr; b.is_null = nullptr;
                 stats.d2h_bytes += (int64_t) vbytes;
-                if (S.cols[i].dstNulls) { hostNulls[i].reserve(total); PG_CUDA(cudaMemcpyAsync(hostNulls[i].ptr, outNulls[i].ptr, total, cudaMemcpyDeviceToHost, stream)); b.is_null = hostNulls[i].as<uint8_t>(); stats.d2h_bytes += total; }
+                if (isVc) {
+                    vcHostOffsets[v].reserve((size_t) (total + 1) * 4);
+                    PG_CUDA(cudaMemcpyAsync(vcHostOffsets[v].ptr, vcOutOffsets[v].ptr, (size_t) (total + 1) * 4, cudaMemcpyDeviceToHost, stream));
+                    b.offsets = vcHostOffsets[v].as<int32_t>();
+                }
+                if (dstNullsOf[i]) { hostNulls[i].reserve(total); PG_CUDA(cudaMemcpyAsync(hostNulls[i].ptr, outNulls[i].ptr, total, cudaMemcpyDeviceToHost, stream)); b.is_null = hostNulls[i].as<uint8_t>(); stats.d2h_bytes += total; }
             }
-            else { b.values = outValues[i].ptr; b.is_null = S.cols[i].dstNulls; }
+            else { b.values = dValues; b.is_null = dstNullsOf[i]; if (isVc) b.offsets = vcOutOffsets[v].as<int32_t>(); }
             stats.output_bytes += (int64_t) vbytes;
+            if (isVc) v++;
         }
         PG_CUDA(cudaStreamSynchronize(stream));
         pendingRows = total;
@@ -468,6 +555,7 @@ public:
     {
         PG_CHECK_STATE(!finishing && !hasPending && !prepared, "partitioned output: count in the wrong state");
         PG_CHECK_ARG(!replicatesAnyRow && nullChannel < 0, "replicated rows are not supported by the fused exchange");
+        if (hasVarchar) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR channels are not supported by the fused (peer-memory) exchange");
         stats.input_positions += page->position_count;
         if (page->position_count == 0) { for (int p = 0; p < partitionCount; p++) outCounts[p] = 0; curN = 0; prepared = true; return; }
         prepare(page);

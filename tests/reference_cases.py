@@ -425,6 +425,37 @@ def case_lookup_join_is_blocked_until_the_build_finishes(backend):
     bridge.close()
 
 
+def case_partitioned_output_varchar_channels(backend, partition_count: int = 5, replicate: bool = False):
+    """TestOptimizedPartitionedOutputOperator.testPartitionedSinglePageVariableWidthTypes (VariableWidthBlockEncodingBuffer.java:1-293): VARCHAR
+    channels travel with the row — every row lands in its partition with its slices intact, input order kept inside a partition; NULL
+    slices, empty strings, multi-byte values; partition key = a BIGINT channel (or the precomputed $hashvalue)."""
+    rng = np.random.default_rng(17)
+    n = 4000
+    words = [b"", b"A", b"BUILDING", b"AUTOMOBILE", "\u00e9t\u00e9".encode(), b"y" * 33]
+    s1 = [None if rng.random() < 0.15 else words[rng.integers(len(words))] + (b"%d" % i) for i in range(n)]
+    s2 = [words[rng.integers(len(words))] for _ in range(n)]
+    k = rng.integers(-10**9, 10**9, n)
+    kn = (rng.random(n) < 0.05).astype(np.uint8) if replicate else None
+    v = rng.random(n)
+    blocks = [Block.from_strings(s1), Block.from_numpy(BIGINT, k, kn), Block.from_strings(s2), Block.from_numpy(DOUBLE, v)]
+    types = [VARCHAR, BIGINT, VARCHAR, DOUBLE]
+    raw = get_hash_block([blocks[1]], backend)
+    op = PartitionedOutputOperator(types, partition_count, [1], backend=backend, replicates_any_row=replicate, null_channel=1 if replicate else -1)
+    page = Page(blocks)
+    op.add_input(page)
+    out = op.get_output()
+    offsets = op.get_offsets()
+    parts = get_partition(raw.values, partition_count)
+    in_rows, out_rows = page.rows(), out.rows()
+    for p in range(partition_count):
+        if replicate:
+            expected = [in_rows[i] for i in range(n) if i == 0 or in_rows[i][1] is None or parts[i] == p]
+        else:
+            expected = [in_rows[i] for i in range(n) if parts[i] == p]
+        assert out_rows[offsets[p]:offsets[p + 1]] == expected
+    op.close()
+
+
 def case_partitioned_output_double_zero_keys(backend):
     """DoubleType.hash → TypeUtils.doubleHashCode (PC/type/TypeUtils.java:232-238): -0.0 and +0.0 are equal keys, so they must reach the
     same partition (hash 0 → partition 0), as must every NaN payload."""

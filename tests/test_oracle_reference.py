@@ -108,6 +108,8 @@ def test_join_duplicate_chain_order(oracle_backend): rc.case_join_duplicate_chai
 def test_partitioned_output(oracle_backend, partition_count, nulls, precomputed):
     rc.case_partitioned_output(oracle_backend, partition_count, 1000, nulls, precomputed)
 def test_partitioned_output_replicates(oracle_backend): rc.case_partitioned_output_replicates(oracle_backend)
+@pytest.mark.parametrize("replicate", [False, True])
+def test_partitioned_output_varchar_channels(oracle_backend, replicate): rc.case_partitioned_output_varchar_channels(oracle_backend, 5, replicate)
 def test_min_max_aggregates(oracle_backend): rc.case_min_max_aggregates(oracle_backend)
 def test_lookup_join_is_blocked_until_the_build_finishes(oracle_backend): rc.case_lookup_join_is_blocked_until_the_build_finishes(oracle_backend)
 def test_partitioned_output_double_zero_keys(oracle_backend): rc.case_partitioned_output_double_zero_keys(oracle_backend)
