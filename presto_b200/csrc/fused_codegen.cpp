@@ -311,6 +311,7 @@ struct Frag {
         for (int c = 0; c < nIn; c++) if (used[c]) usedInputs.push_back(c);
         for (int c = 0; c < nIn; c++) if (eager[c]) eagerInputs.push_back(c);
         R = eagerBytes <= 16 ? 4 : 2;
+        if (const char* e = getenv("PG_FUSED_ROWS")) { const int r = atoi(e); if (r == 2 || r == 4 || r == 8) R = r; }     // experiment knob: rows per thread per tile
         resetGen();
     }
     void resetGen()

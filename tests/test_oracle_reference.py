@@ -124,3 +124,28 @@ def test_page_processor_q1(oracle_backend): rc.case_page_processor_q1(oracle_bac
 def test_page_processor_three_valued_logic(oracle_backend): rc.case_page_processor_three_valued_logic(oracle_backend)
 def test_page_processor_hash_projection(oracle_backend): rc.case_page_processor_hash_projection(oracle_backend)
 def test_page_processor_varchar_pass_through(oracle_backend): rc.case_page_processor_varchar_pass_through(oracle_backend)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_page_processor_vectorised_equals_row_at_a_time(oracle_backend, seed, monkeypatch):
+    """The oracle evaluates expressions node by node over a page (evalNodes); OR_ROW_AT_A_TIME=1 switches to the row-at-a-time
+    statement of the same semantics (evalRow).  Random DAGs with nulls: identical rows, or the same error."""
+    from presto_b200 import BIGINT, BOOLEAN, DATE, DOUBLE, INTEGER, Block, FilterAndProjectOperator, Page, PrestoException, to_pages
+    from test_gpu_page_processor import random_program
+    from util import rows_of
+    rng = np.random.default_rng(7000 + seed)
+    n = 3000
+    types = [BIGINT, INTEGER, DOUBLE, DOUBLE, DATE, BOOLEAN]
+    def nulls(p): return (rng.random(n) < p).astype(np.uint8) if p else None
+    page = Page([Block.from_numpy(BIGINT, rng.integers(-100, 100, n), nulls(0.1)), Block.from_numpy(INTEGER, rng.integers(-100, 100, n).astype(np.int32), nulls(0.0)),
+                 Block.from_numpy(DOUBLE, np.round(rng.normal(0, 50, n), 3), nulls(0.2)), Block.from_numpy(DOUBLE, rng.integers(-3, 4, n).astype(np.float64), nulls(0.0)),
+                 Block.from_numpy(DATE, rng.integers(8000, 8100, n).astype(np.int32), nulls(0.05)), Block.from_numpy(BOOLEAN, rng.integers(0, 2, n).astype(np.int8), nulls(0.1))])
+    prog = random_program(rng, types)
+    def run():
+        try:
+            return rows_of(to_pages(FilterAndProjectOperator(types, prog, backend=oracle_backend), [page]))
+        except PrestoException as e:
+            return ("error", e.code)
+    vectorised = run()
+    monkeypatch.setenv("OR_ROW_AT_A_TIME", "1")
+    assert repr(run()) == repr(vectorised)       # repr: NaN results compare equal to themselves
