@@ -770,12 +770,17 @@ def concat_host_pages(pages):
     return Page(blocks, sum(p.position_count for p in pages))
 
 
-def merge_partials_on_root(torch, dist, page, final, device):
+def merge_partials_on_root(torch, dist, page, final, device, trace=None):
     """PARTIAL -> FINAL across ranks (Q1 has no row exchange): every rank's partial page (a few rows) travels in ONE fixed-size
     all-gather; rank 0 feeds the concatenation to the FINAL HashAggregationOperator as a single page."""
     from presto_b200.exchange import _pack_page, _unpack_page
     world, rank = dist.get_world_size(), dist.get_rank()
     CAP = 1 << 13
+    def mark(what):
+        if trace is not None:
+            torch.cuda.synchronize()
+            trace.append((what, time.perf_counter()))
+    mark("partial output")
     buf = _pack_page(page)
     assert buf.size + 8 <= CAP, "partial page larger than the merge buffer"
     send = np.zeros(CAP, dtype=np.uint8)
@@ -784,19 +789,27 @@ def merge_partials_on_root(torch, dist, page, final, device):
     dev = torch.device("cuda", device)
     s = torch.from_numpy(send).to(dev, non_blocking=True)
     recv = torch.empty(world * CAP, dtype=torch.uint8, device=dev)
+    mark("pack + h2d")
     dist.all_gather_into_tensor(recv, s)
+    mark("all_gather")
     if rank != 0:
         return None
     host = recv.cpu().numpy()
+    mark("d2h")
     pages = []
     for r in range(world):
         size = int(np.frombuffer(host[r * CAP:r * CAP + 8].tobytes(), dtype=np.int64)[0])
         p = _unpack_page(host[r * CAP + 8:r * CAP + 8 + size])
         if p is not None:
             pages.append(p)
-    final.add_input(concat_host_pages(pages))
+    merged = concat_host_pages(pages)
+    mark("unpack + concat")
+    final.add_input(merged)
+    mark("final add_input")
     final.finish()
-    return final.get_output(), final.get_stats()["kernel_launches"]
+    out = final.get_output()
+    mark("final finish + output")
+    return out, final.get_stats()["kernel_launches"]
 
 
 def run_q1_headline(torch, backend, cols, key_kind, steps, warmup, device, dist=None):
@@ -815,13 +828,18 @@ def run_q1_headline(torch, backend, cols, key_kind, steps, warmup, device, dist=
             dist.barrier()
         torch.cuda.synchronize()
         e0.record(stream)
+        trace = [("start", time.perf_counter())] if multi and os.environ.get("PG_Q1_TRACE") and i == warmup + steps - 1 else None
         op.add_input(page)
         e1.record(stream)
+        if trace is not None:
+            torch.cuda.synchronize(); trace.append(("fused kernel", time.perf_counter()))
         op.finish()
         out = op.get_output()
         extra_launches = 0
         if multi:
-            merged = merge_partials_on_root(torch, dist, out, final, device)
+            merged = merge_partials_on_root(torch, dist, out, final, device, trace)
+            if trace is not None and dist.get_rank() == 0:
+                print("Q1 trace (ms): " + ", ".join("%s %.3f" % (w, (t - trace[k][1]) * 1e3) for k, (w, t) in enumerate(trace[1:])), file=sys.stderr)
             if merged is not None:
                 out, extra_launches = merged
         e2.record(stream)

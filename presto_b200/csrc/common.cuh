@@ -156,8 +156,10 @@ struct PageStager {
     Operator* op;
     struct Slot {
         std::vector<DeviceBuffer> values, nulls, offsets, scratch;
+        DeviceBuffer arena;              // small host pages: every column of the page in one buffer, one copy
+        PinnedBuffer arenaHost;
         cudaEvent_t copyDone = nullptr, computeDone = nullptr;
-        bool computePending = false;
+        bool computePending = false, arenaCopyPending = false;
     } slots[kSlots];
     int next = 0;
 
@@ -166,6 +168,10 @@ struct PageStager {
     // Stage the listed channels of `page`.  Returns the slot used; cols[i] describes channel channels[i].
     // On return host memory of the page is no longer referenced; the compute stream has been made to wait for the copies.
     int stage(const pg_page* page, const std::vector<int>& channels, std::vector<DeviceColumn>& cols);
+    // Host pages of FLAT blocks up to kSmallPageBytes (the reference's pages are ≤ 1 MB: PageProcessor MAX_PAGE_SIZE_IN_BYTES) are
+    // gathered into one pinned arena and cross PCIe in ONE copy instead of two or three per column.
+    static constexpr size_t kSmallPageBytes = 1 << 20;
+    bool stageSmall(const pg_page* page, const std::vector<int>& channels, std::vector<DeviceColumn>& cols, Slot& slot);
     // Call after enqueueing the kernels that read slot `s` on op->stream.
     void markCompute(int s);
 };

@@ -1017,8 +1017,18 @@ static int64_t sortSlotsByFirstRow(Operator* op, const GroupTable& T, DeviceBuff
 }
 
 struct ResultBuilder {
-    std::vector<DeviceBuffer> outBufs;
+    struct Buf {
+        void* ptr = nullptr;
+        template <typename T> T* as() const { return reinterpret_cast<T*>(ptr); }
+    };
+    std::vector<Buf> outBufs;
+    std::vector<DeviceBuffer> owned;
     std::vector<PinnedBuffer> outHost;
+    // Small results bound for the host (a partial aggregation's few groups, a Q1 answer) are built inside ONE device arena and cross
+    // PCIe in one copy with the error counters: one synchronisation instead of two, one copy instead of two or three per column.
+    static constexpr size_t kArenaBytes = 1 << 20;
+    DeviceBuffer arena;
+    PinnedBuffer arenaHost;
     std::vector<pg_block> outBlocks, outSlice;
     std::vector<int> outTypes;
 
@@ -1029,10 +1039,37 @@ struct ResultBuilder {
         EmitParams E{};
         E.t = T; E.order = order; E.nGroups = (int) g; E.W = layout.W;
         E.nKeys = layout.nKeys; E.bigintPath = layout.bigintPath; E.nullWord = layout.nullWord < 0 ? 0 : layout.nullWord; E.nullShift = layout.nullShift;
-        outTypes.clear(); outBufs.clear(); outBufs.reserve(64);
+        outTypes.clear(); outBufs.clear(); outBufs.reserve(64); owned.clear(); owned.reserve(64);
         struct ColBufs { int values, nulls; };
         std::vector<ColBufs> colBufs;
-        auto newBuf = [&](size_t bytes) { outBufs.emplace_back(); outBufs.back().accounting = &op->stats.device_bytes; outBufs.back().reserve(std::max<size_t>(bytes, 16)); return (int) outBufs.size() - 1; };
+        const bool toHost = op->options.output_memory == PG_MEM_HOST;
+        auto align = [](size_t v) { return (v + 255) & ~size_t(255); };
+        size_t scanTemp = 0, bound = 0, arenaUsed = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, scanTemp, (const int32_t*) nullptr, (int32_t*) nullptr, (int) g + 1, stream);
+        {
+            size_t nCols = (size_t) layout.nKeys + (withHash ? 1 : 0), nVarchar = 0;
+            for (const AggEmit& a : aggs) nCols += (a.partial && (a.function == PG_AGG_AVG_DOUBLE || a.function == PG_AGG_AVG_BIGINT)) ? 2 : 1;
+            for (int k = 0; k < layout.nKeys; k++) nVarchar += layout.types[k] == PG_TYPE_VARCHAR;
+            bound = nCols * (align((size_t) g * 8 + 16) + align((size_t) g + 16)) + nVarchar * (2 * align((size_t) (g + 1) * 4) + align(scanTemp + 16) + align((size_t) g * 8 + 16));
+        }
+        const bool arenaMode = toHost && g > 0 && bound <= kArenaBytes;
+        if (arenaMode) {
+            arena.accounting = &op->stats.device_bytes;
+            arena.reserve(bound);
+            PG_CUDA(cudaMemsetAsync(arena.ptr, 0, bound, stream));      // every null vector / length column starts at zero
+        }
+        auto newBuf = [&](size_t bytes) {
+            bytes = std::max<size_t>(bytes, 16);
+            Buf b;
+            if (arenaMode) {
+                PG_CHECK_STATE(arenaUsed + align(bytes) <= bound, "result arena bound too small");
+                b.ptr = (char*) arena.ptr + arenaUsed; arenaUsed += align(bytes);
+            }
+            else { owned.emplace_back(); owned.back().accounting = &op->stats.device_bytes; owned.back().reserve(bytes); b.ptr = owned.back().ptr; }
+            outBufs.push_back(b);
+            return (int) outBufs.size() - 1;
+        };
+        auto zero = [&](void* p, size_t bytes) { if (!arenaMode) PG_CUDA(cudaMemsetAsync(p, 0, bytes, stream)); };
         auto newColumn = [&](int type) {
             ColBufs cb{-1, -1};
             int w = typeWidth(type);
@@ -1049,11 +1086,11 @@ struct ResultBuilder {
             ko.type = layout.types[k]; ko.word = layout.word[k]; ko.shift = layout.shift[k]; ko.bits = layout.bits[k];
             if (layout.types[k] == PG_TYPE_VARCHAR) {
                 varcharLens[k] = newBuf((size_t) (g + 1) * 4);
-                PG_CUDA(cudaMemsetAsync(outBufs[varcharLens[k]].ptr, 0, (size_t) (g + 1) * 4, stream));
+                zero(outBufs[varcharLens[k]].ptr, (size_t) (g + 1) * 4);
                 ko.lens = outBufs[varcharLens[k]].as<int32_t>();
             }
         }
-        if (withHash) { int c = newColumn(PG_TYPE_BIGINT); E.hashOut = outBufs[colBufs[c].values].as<int64_t>(); PG_CUDA(cudaMemsetAsync(outBufs[colBufs[c].nulls].ptr, 0, g, stream)); }
+        if (withHash) { int c = newColumn(PG_TYPE_BIGINT); E.hashOut = outBufs[colBufs[c].values].as<int64_t>(); zero(outBufs[colBufs[c].nulls].ptr, g); }
         PG_CHECK_ARG(aggs.size() <= 32, "at most 32 aggregates");
         E.nAggs = (int) aggs.size();
         for (size_t i = 0; i < aggs.size(); i++) {
@@ -1067,7 +1104,7 @@ struct ResultBuilder {
             if (a.partial && (a.function == PG_AGG_AVG_DOUBLE || a.function == PG_AGG_AVG_BIGINT)) {
                 int c2 = newColumn(PG_TYPE_BIGINT);
                 ao.out1 = outBufs[colBufs[c2].values].ptr;
-                PG_CUDA(cudaMemsetAsync(outBufs[colBufs[c2].nulls].ptr, 0, g, stream));
+                zero(outBufs[colBufs[c2].nulls].ptr, g);
             }
         }
         PG_LAUNCH(op, emitKernel, (int) std::min<int64_t>(divUp(g, 256), 2048), 256, 0, E);
@@ -1090,11 +1127,16 @@ struct ResultBuilder {
 
         // describe the full result; slice() hands out row ranges of it
         outBlocks.assign(colBufs.size(), pg_block{});
-        const bool toHost = op->options.output_memory == PG_MEM_HOST;
         outHost.clear();
         outHost.reserve(colBufs.size() * 3 + 4);
+        if (arenaMode) {
+            arenaHost.reserve(arenaUsed + 16);
+            PG_CUDA(cudaMemcpyAsync(arenaHost.ptr, arena.ptr, arenaUsed, cudaMemcpyDeviceToHost, stream));
+            op->stats.d2h_bytes += (int64_t) arenaUsed;
+        }
         auto place = [&](const void* dptr, size_t bytes) -> const void* {
             if (!toHost) return dptr;
+            if (arenaMode) return (const char*) arenaHost.ptr + ((const char*) dptr - (const char*) arena.ptr);
             outHost.emplace_back();
             outHost.back().reserve(std::max<size_t>(bytes, 16));
             if (bytes) PG_CUDA(cudaMemcpyAsync(outHost.back().ptr, dptr, bytes, cudaMemcpyDeviceToHost, stream));
@@ -1103,8 +1145,8 @@ struct ResultBuilder {
         };
         std::vector<int32_t> totalBytes(layout.nKeys, 0);
         for (int k = 0; k < layout.nKeys; k++)
-            if (varcharOffsets[k] >= 0) PG_CUDA(cudaMemcpyAsync(&totalBytes[k], outBufs[varcharOffsets[k]].as<int32_t>() + g, 4, cudaMemcpyDeviceToHost, stream));
-        PG_CUDA(cudaStreamSynchronize(stream));      // the error counters and the VARCHAR byte totals arrive together
+            if (varcharOffsets[k] >= 0 && !arenaMode) PG_CUDA(cudaMemcpyAsync(&totalBytes[k], outBufs[varcharOffsets[k]].as<int32_t>() + g, 4, cudaMemcpyDeviceToHost, stream));
+        PG_CUDA(cudaStreamSynchronize(stream));      // the error counters and the VARCHAR byte totals (arena: the whole result) arrive together
         if (cnt[CNT_ERROR] & ERR_BIGINT_OVERFLOW) throw Error(PG_ERR_NUMERIC_OVERFLOW, "bigint addition overflow");
         for (size_t c = 0; c < colBufs.size(); c++) {
             pg_block& b = outBlocks[c];
@@ -1117,7 +1159,7 @@ struct ResultBuilder {
             else b.values = place(outBufs[colBufs[c].values].ptr, (size_t) g * typeWidth(outTypes[c]));
             b.is_null = (const uint8_t*) place(outBufs[colBufs[c].nulls].ptr, g);
         }
-        PG_CUDA(cudaStreamSynchronize(stream));
+        if (!arenaMode) PG_CUDA(cudaStreamSynchronize(stream));
     }
 
     void slice(int64_t begin, int64_t m, int memory, pg_page* out)

@@ -162,11 +162,68 @@ void PageStager::markCompute(int s)
     slots[s].computePending = true;
 }
 
+bool PageStager::stageSmall(const pg_page* page, const std::vector<int>& channels, std::vector<DeviceColumn>& cols, Slot& slot)
+{
+    const size_t nch = channels.size();
+    if (page->memory != PG_MEM_HOST || page->position_count <= 0 || nch == 0) return false;
+    struct Piece { const void* src; size_t bytes, at; };
+    std::vector<Piece> pieces;
+    pieces.reserve(nch * 3);
+    size_t total = 0;
+    auto add = [&](const void* src, size_t bytes) { pieces.push_back({src, bytes, total}); total += (bytes + 15) & ~size_t(15); return pieces.back().at; };
+    struct Where { size_t values = 0, nulls = 0, offsets = 0, first = 0; bool hasNulls = false; };
+    std::vector<Where> where(nch);
+    const int64_t n = page->position_count;
+    for (size_t i = 0; i < nch; i++) {
+        const int ch = channels[i];
+        if (ch < 0 || ch >= page->channel_count) return false;       // the general path reports it
+        const pg_block& b = page->blocks[ch];
+        if (b.encoding != PG_ENC_FLAT || b.position_count != n) return false;
+        Where& w = where[i];
+        if (b.type == PG_TYPE_VARCHAR) {
+            if (!b.offsets) return false;
+            w.first = (size_t) b.offsets[0];
+            w.values = add((const char*) b.values + w.first, (size_t) b.offsets[n] - w.first);
+            w.offsets = add(b.offsets, (size_t) (n + 1) * 4);
+        }
+        else w.values = add(b.values, (size_t) n * typeWidth(b.type));
+        if (b.is_null) { w.hasNulls = true; w.nulls = add(b.is_null, (size_t) n); }
+        if (total > kSmallPageBytes) return false;
+    }
+    // the arena of this slot may still be travelling (the previous page staged through it did not wait for its copy)
+    if (slot.arenaCopyPending) { PG_CUDA(cudaEventSynchronize(slot.copyDone)); slot.arenaCopyPending = false; }
+    if (slot.computePending) { PG_CUDA(cudaStreamWaitEvent(op->copyStream, slot.computeDone, 0)); slot.computePending = false; }
+    slot.arena.accounting = &op->stats.device_bytes;
+    slot.arena.reserve(total + 16);
+    slot.arenaHost.reserve(total + 16);
+    for (const Piece& p : pieces) if (p.bytes) memcpy((char*) slot.arenaHost.ptr + p.at, p.src, p.bytes);
+    PG_CUDA(cudaMemcpyAsync(slot.arena.ptr, slot.arenaHost.ptr, total, cudaMemcpyHostToDevice, op->copyStream));
+    PG_CUDA(cudaEventRecord(slot.copyDone, op->copyStream));
+    PG_CUDA(cudaStreamWaitEvent(op->stream, slot.copyDone, 0));
+    slot.arenaCopyPending = true;            // the page's own memory is no longer referenced: no wait here
+    cols.assign(nch, DeviceColumn());
+    const char* base = (const char*) slot.arena.ptr;
+    for (size_t i = 0; i < nch; i++) {
+        const pg_block& b = page->blocks[channels[i]];
+        const Where& w = where[i];
+        DeviceColumn& c = cols[i];
+        c.type = b.type; c.n = n;
+        c.values = base + w.values - w.first;
+        c.offsets = b.type == PG_TYPE_VARCHAR ? (const int32_t*) (base + w.offsets) : nullptr;
+        c.nulls = w.hasNulls ? (const uint8_t*) (base + w.nulls) : nullptr;
+        const int width = typeWidth(b.type);
+        op->stats.input_bytes += n * (width ? width : 4) + (w.hasNulls ? n : 0);
+    }
+    op->stats.h2d_bytes += (int64_t) total;
+    return true;
+}
+
 int PageStager::stage(const pg_page* page, const std::vector<int>& channels, std::vector<DeviceColumn>& cols)
 {
     int s = next;
     next = (next + 1) % kSlots;
     Slot& slot = slots[s];
+    if (stageSmall(page, channels, cols, slot)) return s;
     size_t nch = channels.size();
     if (slot.values.size() < nch) {
         slot.values.resize(nch); slot.nulls.resize(nch); slot.offsets.resize(nch); slot.scratch.resize(nch);
