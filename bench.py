@@ -11,8 +11,9 @@ cpu_baseline / --impl reference: the oracle (C++ restatement of the reference's 
            host cores, one operator chain per thread over thread-local (first-touched) slices + FINAL merge.
 parity   : the GPU result of the full 600 M rows is compared with the oracle's on the same rows (counts exact, sums 1e-6) before timing.
 Q3 (join + agg, SF100), the INTEGER-coded Q1, the BASELINE configs[1] group-by kernels, the join and the repartition are in "extra".
-N > 1    : every rank holds its own SF100 lineitem shard (weak scaling): PARTIAL fused pipeline per GPU, one all-gather of the partial
-           pages, FINAL merge on rank 0 — Q1 has no row exchange; the repartitioned Q3 (configs[3]) and configs[4] are in "extra".
+N > 1    : every rank holds its own SF100 lineitem shard (weak scaling): fused pipeline per GPU, the group tables compacted on the
+           device, one all-gather over NVLink, merge kernels into rank 0's operator — Q1 has no row exchange; the repartitioned Q3
+           (configs[3]) and configs[4] are in "extra".
 """
 from __future__ import annotations
 
@@ -733,115 +734,42 @@ def cpu_q1(torch, cols, key_kind, row_begin, row_end, threads, chunk=1 << 16):
     return n / dt, dt, rows, n * Q1_BYTES_PER_ROW[key_kind] / dt / 1e9
 
 
-def q1_final_operator(backend, key_kind, device, stream):
-    """The FINAL HashAggregationOperator of the Q1 plan (rank 0): its inputs are the PARTIAL operators' intermediate columns."""
-    from presto_b200 import AGG_AVG_DOUBLE, MEM_HOST, STEP_FINAL, Aggregate, HashAggregationOperator, INTEGER, VARCHAR
-    from presto_b200.pipelines import Q1_AGGREGATES
-    kt = VARCHAR if key_kind == "varchar" else INTEGER
-    final_aggs, ch = [], 2
-    for a in Q1_AGGREGATES:
-        final_aggs.append(Aggregate(a.function, ch))
-        ch += 2 if a.function == AGG_AVG_DOUBLE else 1
-    return HashAggregationOperator([kt, kt], [0, 1], final_aggs, step=STEP_FINAL, expected_groups=1024, group_max_lengths=[1, 1] if key_kind == "varchar" else None,
-                                   backend=backend, device=device, output_memory=MEM_HOST, cuda_stream=stream, max_output_rows=1 << 30)
-
-
-def concat_host_pages(pages):
-    """Small host pages with the same channels -> one page (VARCHAR: bytes concatenated, offsets rebased)."""
-    from presto_b200 import VARCHAR, Block, Page
-    blocks = []
-    for c in range(len(pages[0].blocks)):
-        bs = [p.blocks[c] for p in pages]
-        t, n = bs[0].type, sum(b.position_count for b in bs)
-        nulls = None
-        if any(b.is_null is not None for b in bs):
-            nulls = np.concatenate([b.is_null[:b.position_count] if b.is_null is not None else np.zeros(b.position_count, dtype=np.uint8) for b in bs])
-        if t == VARCHAR:
-            data, offs, base = [], [np.zeros(1, dtype=np.int32)], 0
-            for b in bs:
-                o = np.asarray(b.offsets[:b.position_count + 1], dtype=np.int64)
-                data.append(np.asarray(b.values, dtype=np.uint8)[int(o[0]):int(o[-1])])
-                offs.append((o[1:] - o[0] + base).astype(np.int32))
-                base += int(o[-1] - o[0])
-            vals = np.concatenate(data) if base else np.zeros(1, dtype=np.uint8)
-            blocks.append(Block(t, n, vals, nulls, np.concatenate(offs)))
-        else:
-            blocks.append(Block(t, n, np.concatenate([b.values[:b.position_count] for b in bs]), nulls))
-    return Page(blocks, sum(p.position_count for p in pages))
-
-
-def merge_partials_on_root(torch, dist, page, final, device, trace=None):
-    """PARTIAL -> FINAL across ranks (Q1 has no row exchange): every rank's partial page (a few rows) travels in ONE fixed-size
-    all-gather; rank 0 feeds the concatenation to the FINAL HashAggregationOperator as a single page."""
-    from presto_b200.exchange import _pack_page, _unpack_page
-    world, rank = dist.get_world_size(), dist.get_rank()
-    CAP = 1 << 13
-    def mark(what):
-        if trace is not None:
-            torch.cuda.synchronize()
-            trace.append((what, time.perf_counter()))
-    mark("partial output")
-    buf = _pack_page(page)
-    assert buf.size + 8 <= CAP, "partial page larger than the merge buffer"
-    send = np.zeros(CAP, dtype=np.uint8)
-    send[:8] = np.frombuffer(np.int64(buf.size).tobytes(), dtype=np.uint8)
-    send[8:8 + buf.size] = buf
-    dev = torch.device("cuda", device)
-    s = torch.from_numpy(send).to(dev, non_blocking=True)
-    recv = torch.empty(world * CAP, dtype=torch.uint8, device=dev)
-    mark("pack + h2d")
-    dist.all_gather_into_tensor(recv, s)
-    mark("all_gather")
-    if rank != 0:
-        return None
-    host = recv.cpu().numpy()
-    mark("d2h")
-    pages = []
-    for r in range(world):
-        size = int(np.frombuffer(host[r * CAP:r * CAP + 8].tobytes(), dtype=np.int64)[0])
-        p = _unpack_page(host[r * CAP + 8:r * CAP + 8 + size])
-        if p is not None:
-            pages.append(p)
-    merged = concat_host_pages(pages)
-    mark("unpack + concat")
-    final.add_input(merged)
-    mark("final add_input")
-    final.finish()
-    out = final.get_output()
-    mark("final finish + output")
-    return out, final.get_stats()["kernel_launches"]
-
-
 def run_q1_headline(torch, backend, cols, key_kind, steps, warmup, device, dist=None):
-    """One step = Q1 over the resident lineitem shard through the fused operator (+ the PARTIAL -> FINAL merge when N > 1)."""
-    from presto_b200 import MEM_DEVICE, MEM_HOST, STEP_PARTIAL, STEP_SINGLE
+    """One step = Q1 over the resident lineitem shard through the fused operator.  N > 1: every rank's operator aggregates its shard;
+    the PARTIAL -> FINAL hand-off is the operators' group tables compacted on the device, ONE all-gather over NVLink, and the merge
+    into rank 0's operator (presto_b200.exchange.merge_aggregation_states) — no intermediate page, nothing through the host."""
+    from presto_b200 import MEM_HOST, STEP_PARTIAL, STEP_SINGLE
+    from presto_b200.exchange import merge_aggregation_states
     page = q1_device_page(cols, key_kind)
     stream = torch.cuda.current_stream()
     multi = dist is not None
+    root = not multi or dist.get_rank() == 0
     ms, kms, launches, info, result = [], [], 0, {}, None
     for i in range(warmup + steps):
         # the result page (4 groups) is read back to the host inside the timed region
-        op = q1_operator(backend, key_kind, STEP_PARTIAL if multi else STEP_SINGLE, device=device, output_memory=MEM_HOST, cuda_stream=stream.cuda_stream)
-        final = q1_final_operator(backend, key_kind, device, stream.cuda_stream) if multi and dist.get_rank() == 0 else None
+        op = q1_operator(backend, key_kind, STEP_SINGLE if root else STEP_PARTIAL, device=device, output_memory=MEM_HOST, cuda_stream=stream.cuda_stream)
         e0, e1, e2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         if multi:
             dist.barrier()
         torch.cuda.synchronize()
         e0.record(stream)
         trace = [("start", time.perf_counter())] if multi and os.environ.get("PG_Q1_TRACE") and i == warmup + steps - 1 else None
+        def mark(what):
+            if trace is not None:
+                torch.cuda.synchronize(); trace.append((what, time.perf_counter()))
         op.add_input(page)
         e1.record(stream)
-        if trace is not None:
-            torch.cuda.synchronize(); trace.append(("fused kernel", time.perf_counter()))
-        op.finish()
-        out = op.get_output()
-        extra_launches = 0
+        mark("fused kernel")
         if multi:
-            merged = merge_partials_on_root(torch, dist, out, final, device, trace)
-            if trace is not None and dist.get_rank() == 0:
-                print("Q1 trace (ms): " + ", ".join("%s %.3f" % (w, (t - trace[k][1]) * 1e3) for k, (w, t) in enumerate(trace[1:])), file=sys.stderr)
-            if merged is not None:
-                out, extra_launches = merged
+            merge_aggregation_states(op, max_groups=1024)
+            mark("export + all-gather + merge")
+        out = None
+        if root:
+            op.finish()
+            out = op.get_output()
+            mark("finish + output")
+        if trace is not None and root:
+            print("Q1 trace (ms): " + ", ".join("%s %.3f" % (w, (t - trace[k][1]) * 1e3) for k, (w, t) in enumerate(trace[1:])), file=sys.stderr)
         e2.record(stream)
         torch.cuda.synchronize()
         if multi:
@@ -849,13 +777,11 @@ def run_q1_headline(torch, backend, cols, key_kind, steps, warmup, device, dist=
         if i >= warmup:
             ms.append(e0.elapsed_time(e2)); kms.append(e0.elapsed_time(e1))
             st = op.get_stats()
-            launches = st["kernel_launches"] + extra_launches
+            launches = st["kernel_launches"]
             info = dict(op.get_info(), kernel_paths=st["kernel_paths"], groups=st["group_count"])
         if out is not None:
             result = [tuple(v.decode() if isinstance(v, bytes) else v for v in row) for row in out.rows()]
         op.close()
-        if final is not None:
-            final.close()
     return {"ms": float(np.mean(ms)), "kernel_ms": float(np.mean(kms)), "launches": int(launches), "info": info, "result": result}
 
 
@@ -1101,7 +1027,7 @@ def main():
         line = {
             "metric": "rows/sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(q1_config(args, kk), parallelism=(f"{world} ranks: PARTIAL fused pipeline per GPU + one all-gather of the partial pages + FINAL merge on rank 0, no row exchange" if world > 1 else "1 GPU")),
+            "config": dict(q1_config(args, kk), parallelism=(f"{world} ranks: fused pipeline per GPU, group tables compacted on the device + ONE all-gather over NVLink + merge kernels into rank 0's operator (no intermediate pages, no row exchange)" if world > 1 else "1 GPU")),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          # dram__bytes of the fused kernel from the ncu --set full capture in profiles/ (quoted, not re-measured per run)
                          "traffic": None, "traffic_note": "see profiles/r02_ncu_q1_fused.txt (dram__bytes_read + write of the same kernel, per launch)",

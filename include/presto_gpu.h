@@ -246,6 +246,25 @@ typedef struct pg_hash_aggregation_config {
  * rows in ascending group id = first-appearance order (InMemoryHashAggregationBuilder.java:326-352,400-403). */
 int32_t pg_hash_aggregation_create(const pg_hash_aggregation_config* config, pg_operator** out);
 
+/* PARTIAL -> FINAL hand-off between GPUs without intermediate pages.  The reference ships a PARTIAL operator's groups as pages of
+ * intermediate states through an exchange to the FINAL operator (HashAggregationOperator.java:451-501 getOutput -> ... -> addInput
+ * of the FINAL step: GroupedAccumulator.addIntermediate, InMemoryHashAggregationBuilder.java:204-260).  Here the state of a source
+ * operator (hash aggregation or fused aggregation) is compacted into a fixed-capacity buffer in ITS GPU's memory, the buffers travel
+ * in one collective (all-gather over NVLink), and the destination — an operator created from the same configuration, step aside —
+ * merges them into its own group table: packed keys + physical accumulators, i.e. exactly the intermediate states.
+ *   state_bytes   size of one state buffer able to hold max_groups groups
+ *   export_state  asynchronous on the operator's stream; the operator itself is unchanged (it may go on aggregating or produce output);
+ *                 more than max_groups groups -> the state is marked overflowed and merge_states rejects it (PG_ERR_INSUFFICIENT_RESOURCES)
+ *   merge_states  `count` states `stride` bytes apart (state j at device_buffers + j * stride), written on this operator's stream or
+ *                 on work it has been ordered after; all-zero states are skipped (an unused slot of the gather).  Source j's groups
+ *                 order after this operator's own input and after sources < j (first-appearance order = the order in which the
+ *                 FINAL operator would have received the sources' pages); order_base + j tags the source (order_base >= 1 when the
+ *                 operator has input of its own).  DOUBLE sums are added source by source: reproducible.
+ *                 PG_ERR_INVALID_ARGUMENT for a state of a differently planned operator. */
+int32_t pg_hash_aggregation_state_bytes(pg_operator* op, int64_t max_groups, size_t* bytes);
+int32_t pg_hash_aggregation_export_state(pg_operator* op, void* device_buffer, size_t capacity, int64_t max_groups);
+int32_t pg_hash_aggregation_merge_states(pg_operator* op, const void* device_buffers, int32_t count, size_t stride, int64_t max_groups, int32_t order_base);
+
 /* ------------------------------------------------------------------------------------------------
  * GroupByHash (standalone) — MB/operator/GroupByHash.java:61-89
  * ---------------------------------------------------------------------------------------------- */

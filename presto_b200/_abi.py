@@ -243,6 +243,9 @@ class Backend:
         "ipc_import": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
         "ipc_close": (C.c_int32, [C.c_void_p]),
         "filter_project_explain": (C.c_int32, [C.POINTER(pg_filter_project_config), C.c_uint64, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+        "hash_aggregation_state_bytes": (C.c_int32, [C.c_void_p, C.c_int64, C.POINTER(C.c_size_t)]),
+        "hash_aggregation_export_state": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64]),
+        "hash_aggregation_merge_states": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_size_t, C.c_int64, C.c_int32]),
         "fused_aggregation_get_info": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_char_p, C.c_size_t]),
         "fused_aggregation_explain": (C.c_int32, [C.POINTER(pg_fused_aggregation_config), C.c_uint64, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32),
                                                   C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),

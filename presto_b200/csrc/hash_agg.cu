@@ -817,6 +817,96 @@ __global__ void backfillCountKernel(GroupTable t, int dst, int src)
         if (t.firstRow[s] != kNoRow) t.acc[(size_t) s * t.nvPhys + dst] = src >= 0 ? t.acc[(size_t) s * t.nvPhys + src] : 1;
 }
 
+// ---- aggregation state hand-off (PARTIAL → FINAL between GPUs without pages) ----------------------------------------------------
+// The reference ships a PARTIAL HashAggregationOperator's groups as intermediate pages through an exchange to the FINAL operator
+// (HashAggregationOperator.java:451-501 getOutput → PartitionedOutput/ExchangeClient → addInput of the FINAL step, which runs
+// GroupedAccumulator.addIntermediate).  Between GPUs of one NVSwitch domain the same hand-off is: every source table compacted into a
+// fixed-capacity wire buffer in HBM (one kernel, no host round trip), ONE all-gather of those buffers, one merge kernel per source on
+// the destination.  The wire carries the packed key words and the physical accumulator columns, i.e. exactly the intermediate state.
+struct AggStateHeader {
+    uint32_t magic, W, nvPhys, maxGroups;
+    uint32_t nGroups, overflow;          // written by the export kernel
+    uint64_t configHash;                 // key layout + accumulator kinds: a state only merges into an operator planned identically
+    uint64_t pad[4];
+};
+static_assert(sizeof(AggStateHeader) == 64, "wire header is 64 bytes");
+constexpr uint32_t kAggStateMagic = 0x50474153;   // "PGAS"
+struct AggStateView {
+    AggStateHeader* header;
+    uint64_t* keys;       // [W][maxGroups]
+    uint64_t* firstRow;   // [maxGroups]
+    uint64_t* special;    // [maxGroups] 0 ordinary key, 1 the Bigint path's NULL key, 2 the key equal to the W == 1 sentinel
+    uint64_t* acc;        // [maxGroups][nvPhys]
+    uint32_t maxGroups;
+};
+static size_t aggStateBytes(int W, uint32_t nvPhys, uint64_t maxGroups) { return sizeof(AggStateHeader) + (size_t) maxGroups * 8 * ((size_t) W + 2 + nvPhys); }
+static AggStateView aggStateView(void* buffer, int W, uint32_t nvPhys, uint32_t maxGroups)
+{
+    AggStateView v;
+    char* p = (char*) buffer;
+    v.header = (AggStateHeader*) p; p += sizeof(AggStateHeader);
+    v.keys = (uint64_t*) p; p += (size_t) maxGroups * 8 * W;
+    v.firstRow = (uint64_t*) p; p += (size_t) maxGroups * 8;
+    v.special = (uint64_t*) p; p += (size_t) maxGroups * 8;
+    v.acc = (uint64_t*) p;
+    v.maxGroups = maxGroups;
+    return v;
+}
+
+// inactiveMask: lazily activated non-null counts that never saw a NULL hold nothing yet; their value is the group's row count
+// (column countSrc), or 1 when no row count is kept (then only "> 0" is ever asked of them) — backfillCountKernel's rule
+template <int W>
+__global__ void exportStateKernel(GroupTable T, AggStateView out, uint64_t configHash, uint32_t inactiveMask, int countSrc)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        out.header->magic = kAggStateMagic; out.header->W = W; out.header->nvPhys = T.nvPhys; out.header->maxGroups = out.maxGroups;
+        out.header->configHash = configHash;
+    }
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < T.capP; s += gridDim.x * blockDim.x) {
+        const uint64_t f = T.firstRow[s];
+        if (f == kNoRow) continue;
+        const uint32_t i = atomicAdd(&out.header->nGroups, 1u);
+        if (i >= out.maxGroups) { out.header->overflow = 1; continue; }
+#pragma unroll
+        for (int w = 0; w < W; w++) out.keys[(size_t) w * out.maxGroups + i] = s < T.cap ? T.keys[(size_t) w * T.capP + s] : 0;
+        out.firstRow[i] = f;
+        out.special[i] = s < T.cap ? 0 : (uint64_t) (s - T.cap + 1);
+        for (uint32_t c = 0; c < T.nvPhys; c++) {
+            uint64_t v = T.acc[(size_t) s * T.nvPhys + c];
+            if ((inactiveMask >> c) & 1u) v = countSrc >= 0 ? T.acc[(size_t) s * T.nvPhys + countSrc] : 1;
+            out.acc[(size_t) i * T.nvPhys + c] = v;
+        }
+    }
+}
+
+// One source state into the table: every group occurs once per state and the states are merged by consecutive launches, so each
+// accumulator receives its contributions in a fixed order (source 0, 1, 2 ...: DOUBLE sums are reproducible).  `orderTag` goes on top
+// of the first-row words so that first-appearance order across sources is (source, row) — the order the FINAL operator would see the
+// sources' pages in.
+template <int W>
+__global__ void mergeStateKernel(GroupTable T, AggStateView in, uint32_t nGroups, uint64_t orderTag, uint32_t floatMask, uint32_t maxMask)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nGroups; i += gridDim.x * blockDim.x) {
+        const uint64_t special = in.special[i];
+        int slot;
+        if (special) slot = (int) T.cap + (int) special - 1;
+        else {
+            uint64_t kw[W];
+#pragma unroll
+            for (int w = 0; w < W; w++) kw[w] = in.keys[(size_t) w * in.maxGroups + i];
+            slot = tableFind<W>(T, kw, hashKeyWords<W>(kw), true, true);
+            if (slot < 0) { atomicOr(&T.counters[CNT_ERROR], 0x80000000u); continue; }
+        }
+        const uint64_t f = in.firstRow[i] | orderTag;
+        if (f < T.firstRow[slot]) T.firstRow[slot] = f;
+        for (uint32_t c = 0; c < T.nvPhys; c++) {
+            uint64_t* p = &T.acc[(size_t) slot * T.nvPhys + c];
+            const int op = ((maxMask >> c) & 1u) ? OP_MAX_U64 : (((floatMask >> c) & 1u) ? OP_ADD_F64 : OP_ADD_I64);
+            *p = combineAcc(*p, in.acc[(size_t) i * T.nvPhys + c], op);
+        }
+    }
+}
+
 __global__ void collectSlotsKernel(GroupTable t, uint64_t* sortKeys, uint32_t* sortVals, unsigned int* count)
 {
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < t.capP; s += gridDim.x * blockDim.x) {
@@ -1648,6 +1738,95 @@ public:
         lastPending = false;
     }
 
+    // ---- state hand-off (see exportStateKernel) ---------------------------------------------------------------------------
+    uint64_t stateConfigHash() const
+    {
+        uint64_t h = 0xcbf29ce484222325ULL;
+        auto mix = [&](uint64_t v) { h = (h ^ v) * 0x100000001b3ULL; };
+        mix(layout.W); mix(layout.nKeys); mix(layout.bigintPath);
+        for (int k = 0; k < layout.nKeys; k++) { mix(layout.types[k]); mix(layout.word[k]); mix(layout.shift[k]); mix(layout.bits[k]); }
+        mix(phys.size());
+        for (auto& p : phys) mix(p.kind);
+        return h;
+    }
+    size_t stateBytes(int64_t maxGroups) const
+    {
+        PG_CHECK_ARG(maxGroups >= 1 && maxGroups <= (int64_t(1) << 30), "max_groups out of range");
+        return aggStateBytes(layout.W, (uint32_t) phys.size(), (uint64_t) maxGroups);
+    }
+    // Everything this operator has aggregated so far, compacted into `buffer` (device memory of this operator's GPU) on its stream;
+    // asynchronous — a consumer on another stream orders itself after the operator's stream.  The operator itself is unchanged.
+    void exportState(void* buffer, size_t capacity, int64_t maxGroups)
+    {
+        PG_CHECK_ARG(buffer != nullptr && capacity >= stateBytes(maxGroups), "state buffer smaller than pg_hash_aggregation_state_bytes(max_groups)");
+        PG_CHECK_STATE(!outputBuilt, "the operator has already produced output");
+        settle();
+        uint32_t inactive = 0;
+        for (size_t p = 0; p < phys.size(); p++) if (phys[p].lazy && !phys[p].active) inactive |= 1u << p;
+        const AggStateView v = aggStateView(buffer, layout.W, (uint32_t) phys.size(), (uint32_t) maxGroups);
+        PG_CUDA(cudaMemsetAsync(buffer, 0, sizeof(AggStateHeader), stream));
+        const GroupTable T = table.view();
+        const int grid = (int) std::min<int64_t>(divUp(T.capP, 256), 8 * numSMs);
+        const uint64_t hash = stateConfigHash();
+        switch (layout.W) {
+            case 1: PG_LAUNCH(this, exportStateKernel<1>, grid, 256, 0, T, v, hash, inactive, rowCountCol); break;
+            case 2: PG_LAUNCH(this, exportStateKernel<2>, grid, 256, 0, T, v, hash, inactive, rowCountCol); break;
+            case 3: PG_LAUNCH(this, exportStateKernel<3>, grid, 256, 0, T, v, hash, inactive, rowCountCol); break;
+            default: PG_LAUNCH(this, exportStateKernel<4>, grid, 256, 0, T, v, hash, inactive, rowCountCol); break;
+        }
+    }
+    // `count` states of identically planned operators, `stride` bytes apart in this GPU's memory (an all-gather's receive buffer),
+    // written before this call was made or by work this operator's stream has been ordered after.  Source j is merged as if its rows
+    // followed those of source j-1 (and this operator's own input when orderBase > 0).
+    void mergeStates(const void* buffers, int32_t count, size_t stride, int64_t maxGroups, int32_t orderBase)
+    {
+        PG_CHECK_ARG(buffers != nullptr && count >= 1 && count <= 200 && orderBase >= 0 && orderBase + count <= 255, "between 1 and 200 states, order tags below 255");
+        PG_CHECK_ARG(stride >= stateBytes(maxGroups), "stride smaller than one state");
+        PG_CHECK_STATE(needsInput(), "Operator is already finishing");
+        settle();
+        // one strided copy brings every header; the group counts size the table, the hashes guard against a mismatched plan
+        hostCounters.reserve(std::max<size_t>((size_t) count * sizeof(AggStateHeader), CNT_COUNT * sizeof(unsigned int)));
+        PG_CUDA(cudaMemcpy2DAsync(hostCounters.ptr, sizeof(AggStateHeader), buffers, stride, sizeof(AggStateHeader), (size_t) count, cudaMemcpyDeviceToHost, stream));
+        PG_CUDA(cudaStreamSynchronize(stream));
+        stats.d2h_bytes += (int64_t) count * (int64_t) sizeof(AggStateHeader);
+        std::vector<AggStateHeader> headers((const AggStateHeader*) hostCounters.ptr, (const AggStateHeader*) hostCounters.ptr + count);
+        uint64_t incoming = 0;
+        for (const AggStateHeader& h : headers) {
+            if (h.magic == 0 && h.nGroups == 0) continue;       // an unused slot of the gather
+            PG_CHECK_ARG(h.magic == kAggStateMagic && h.W == (uint32_t) layout.W && h.nvPhys == phys.size() && h.maxGroups == (uint32_t) maxGroups
+                         && h.configHash == stateConfigHash(), "aggregation state of a differently planned operator");
+            if (h.overflow || h.nGroups > h.maxGroups)
+                throw Error(PG_ERR_INSUFFICIENT_RESOURCES, "aggregation state holds " + std::to_string(h.nGroups) + " groups, its buffer only " + std::to_string(h.maxGroups));
+            incoming += h.nGroups;
+        }
+        if (((uint64_t) knownGroups + incoming) * 2 > table.cap) grow((uint64_t) knownGroups + incoming);
+        uint32_t floatMask = 0, maxMask = 0;
+        for (size_t p = 0; p < phys.size(); p++) {
+            if (kindIsFloat(phys[p].kind)) floatMask |= 1u << p;
+            if (kindIsMax(phys[p].kind)) maxMask |= 1u << p;
+            if (phys[p].lazy && !phys[p].active) {      // the states carry every count explicitly
+                PG_LAUNCH(this, backfillCountKernel, 1024, 256, 0, table.view(), (int) p, rowCountCol);
+                phys[p].active = true;
+            }
+        }
+        const GroupTable T = table.view();
+        for (int32_t j = 0; j < count; j++) {
+            const AggStateHeader& h = headers[j];
+            if (h.nGroups == 0) continue;
+            const AggStateView v = aggStateView((char*) buffers + (size_t) j * stride, layout.W, (uint32_t) phys.size(), (uint32_t) maxGroups);
+            const uint64_t tag = (uint64_t) (orderBase + j) << 56;
+            const int grid = (int) std::min<int64_t>(divUp(h.nGroups, 256), 8 * numSMs);
+            switch (layout.W) {
+                case 1: PG_LAUNCH(this, mergeStateKernel<1>, grid, 256, 0, T, v, h.nGroups, tag, floatMask, maxMask); break;
+                case 2: PG_LAUNCH(this, mergeStateKernel<2>, grid, 256, 0, T, v, h.nGroups, tag, floatMask, maxMask); break;
+                case 3: PG_LAUNCH(this, mergeStateKernel<3>, grid, 256, 0, T, v, h.nGroups, tag, floatMask, maxMask); break;
+                default: PG_LAUNCH(this, mergeStateKernel<4>, grid, 256, 0, T, v, h.nGroups, tag, floatMask, maxMask); break;
+            }
+        }
+        knownGroups += (int64_t) incoming;       // an upper bound until the next settle() reads the counter
+        stats.input_positions += (int64_t) incoming;
+    }
+
     void finish() override { finishing = true; }
     bool isFinished() override { return finished; }
     void syncStats() override { if (lastPending) settle(); stats.group_count = knownGroups; }
@@ -2219,6 +2398,41 @@ extern "C" int32_t pg_hash_aggregation_create(const pg_hash_aggregation_config* 
     try {
         if (!config || !out) throw pg::Error(PG_ERR_INVALID_ARGUMENT, "null argument");
         *out = (pg_operator*) pg::createHashAggregation(config);
+    }
+    catch (const pg::Error& e) { pg::setLastError(e.what()); return e.code; }
+    catch (const std::exception& e) { pg::setLastError(e.what()); return PG_ERR_INVALID_STATE; }
+    return PG_OK;
+}
+
+extern "C" int32_t pg_hash_aggregation_state_bytes(pg_operator* op, int64_t max_groups, size_t* bytes)
+{
+    try {
+        auto* p = dynamic_cast<pg::HashAggregationOp*>((pg::Operator*) op);
+        if (!p || !bytes) throw pg::Error(PG_ERR_INVALID_ARGUMENT, "not a hash aggregation operator");
+        *bytes = p->stateBytes(max_groups);
+    }
+    catch (const pg::Error& e) { pg::setLastError(e.what()); return e.code; }
+    return PG_OK;
+}
+extern "C" int32_t pg_hash_aggregation_export_state(pg_operator* op, void* device_buffer, size_t capacity, int64_t max_groups)
+{
+    try {
+        auto* p = dynamic_cast<pg::HashAggregationOp*>((pg::Operator*) op);
+        if (!p) throw pg::Error(PG_ERR_INVALID_ARGUMENT, "not a hash aggregation operator");
+        p->bind();
+        p->exportState(device_buffer, capacity, max_groups);
+    }
+    catch (const pg::Error& e) { pg::setLastError(e.what()); return e.code; }
+    catch (const std::exception& e) { pg::setLastError(e.what()); return PG_ERR_INVALID_STATE; }
+    return PG_OK;
+}
+extern "C" int32_t pg_hash_aggregation_merge_states(pg_operator* op, const void* device_buffers, int32_t count, size_t stride, int64_t max_groups, int32_t order_base)
+{
+    try {
+        auto* p = dynamic_cast<pg::HashAggregationOp*>((pg::Operator*) op);
+        if (!p) throw pg::Error(PG_ERR_INVALID_ARGUMENT, "not a hash aggregation operator");
+        p->bind();
+        p->mergeStates(device_buffers, count, stride, max_groups, order_base);
     }
     catch (const pg::Error& e) { pg::setLastError(e.what()); return e.code; }
     catch (const std::exception& e) { pg::setLastError(e.what()); return PG_ERR_INVALID_STATE; }

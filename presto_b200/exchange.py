@@ -328,3 +328,38 @@ def gather_pages_to_root(page: Optional[Page], group=None, root: int = 0) -> Lis
         if p is not None:
             pages.append(p)
     return pages
+
+
+def merge_aggregation_states(op, group=None, root: int = 0, max_groups: int = 4096) -> bool:
+    """Device-side PARTIAL → FINAL hand-off of a (fused) hash aggregation across the GPUs of one node: every rank but `root` compacts
+    its operator's group table into a fixed-capacity device buffer (pg_hash_aggregation_export_state: one kernel, no host round trip),
+    ONE all_gather_into_tensor moves the buffers over NVLink, and `root` merges them into ITS operator's table
+    (pg_hash_aggregation_merge_states: one small header read + one kernel per source).  The operators must come from the same
+    configuration (the root's step decides what its output holds: STEP_SINGLE for final values).  Returns True on `root`, whose
+    operator then finishes / outputs as usual; the other ranks' operators are simply closed.
+
+    Replaces gather_pages_to_root for operators on GPUs: no page is built, serialised, or copied through the host."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    stride = (op.state_bytes(max_groups) + 255) // 256 * 256
+    send = torch.empty(stride, dtype=torch.uint8, device=dev)
+    recv = torch.empty(world * stride, dtype=torch.uint8, device=dev)
+    shared_stream = op.cuda_stream != 0 and op.cuda_stream == torch.cuda.current_stream().cuda_stream
+    if rank == root:
+        send[:64].zero_()                 # an all-zero header: "no state in this slot"
+    else:
+        if not shared_stream:
+            torch.cuda.current_stream().synchronize()      # `send` exists before the operator's stream writes it
+        op.export_state(send.data_ptr(), stride, max_groups)
+        if not shared_stream:
+            torch.cuda.synchronize()
+    dist.all_gather_into_tensor(recv, send, group=group)
+    if rank != root:
+        return False
+    if not shared_stream:
+        torch.cuda.current_stream().synchronize()          # the operator's own stream reads `recv`
+    op.merge_states(recv.data_ptr(), world, stride, max_groups, order_base=1)
+    op._keep_states = recv                # the merge kernels are asynchronous: keep the buffer until the operator is gone
+    return True

@@ -116,7 +116,24 @@ class Aggregate:
         self.function, self.input_channel, self.mask_channel = function, input_channel, mask_channel
 
 
-class HashAggregationOperator(Operator):
+class _AggregationState:
+    """PARTIAL -> FINAL hand-off between GPUs without intermediate pages (include/presto_gpu.h pg_hash_aggregation_*_state): the
+    operator's group table compacted into a device buffer, merged by an identically configured operator on another GPU."""
+
+    def state_bytes(self, max_groups: int) -> int:
+        out = C.c_size_t()
+        self._b.check(self._b.hash_aggregation_state_bytes(self._h, max_groups, C.byref(out)))
+        return int(out.value)
+
+    def export_state(self, device_pointer: int, capacity: int, max_groups: int) -> None:
+        """Asynchronous on the operator's stream."""
+        self._b.check(self._b.hash_aggregation_export_state(self._h, C.c_void_p(device_pointer), capacity, max_groups))
+
+    def merge_states(self, device_pointer: int, count: int, stride: int, max_groups: int, order_base: int = 1) -> None:
+        self._b.check(self._b.hash_aggregation_merge_states(self._h, C.c_void_p(device_pointer), count, stride, max_groups, order_base))
+
+
+class HashAggregationOperator(_AggregationState, Operator):
     """HashAggregationOperator.java:56-725 (in-memory builder)."""
 
     def __init__(self, group_types: Sequence[int], group_channels: Sequence[int], aggregates: Sequence[Aggregate], *,
@@ -140,6 +157,7 @@ class HashAggregationOperator(Operator):
         handle = C.c_void_p()
         backend.check(backend.hash_aggregation_create(C.byref(cfg), C.byref(handle)))
         super().__init__(backend, handle)
+        self.cuda_stream = int(options.get("cuda_stream", 0) or 0)
 
 
 class GroupByHash:
@@ -378,7 +396,7 @@ class FusedJoin:
         self.bridge, self.types, self.hash_channels, self.output_channels = bridge, list(types), list(hash_channels), list(output_channels)
 
 
-class FusedAggregationOperator(Operator):
+class FusedAggregationOperator(_AggregationState, Operator):
     """FilterAndProjectOperator → LookupJoinOperator* → HashAggregationOperator of one Driver as ONE operator
     (include/presto_gpu.h pg_fused_aggregation_create): on the CUDA backend the fragment is generated as a single kernel; the tests'
     oracle chains the three reference operators the way Driver.processInternal does — the results are the same by definition."""
@@ -392,6 +410,7 @@ class FusedAggregationOperator(Operator):
         handle = C.c_void_p()
         backend.check(backend.fused_aggregation_create(C.byref(cfg), C.byref(handle)))
         super().__init__(backend, handle)
+        self.cuda_stream = int(options.get("cuda_stream", 0) or 0)
 
     @staticmethod
     def _config(input_types, program, joins, group_types, group_channels, aggregates, step, expected_groups, group_max_lengths, hash_channel, options):
