@@ -192,3 +192,67 @@ def test_count_then_scatter_to_matches_add_input(gpu_backend):
     for a in allocs:
         gpu_backend.device_free(a)
     op.close(); ref.close()
+
+
+def _q1_pages(seed, n):
+    from presto_b200 import DATE, DOUBLE, Block, Page
+    rng = np.random.default_rng(seed)
+    rf = [b"ANR"[i:i + 1] for i in rng.integers(0, 3, n)]; ls = [b"FO"[i:i + 1] for i in rng.integers(0, 2, n)]
+    return Page([Block.from_strings(rf), Block.from_strings(ls), Block.from_numpy(DOUBLE, rng.integers(1, 51, n).astype(np.float64)),
+                 Block.from_numpy(DOUBLE, np.round(rng.random(n) * 1e5, 2)), Block.from_numpy(DOUBLE, rng.integers(0, 11, n) / 100),
+                 Block.from_numpy(DOUBLE, rng.integers(0, 9, n) / 100), Block.from_numpy(DATE, rng.integers(8035, 10592, n).astype(np.int32))])
+
+
+def _q1_operator(backend, step, **kw):
+    from presto_b200 import DATE, DOUBLE, VARCHAR, FusedAggregationOperator
+    from presto_b200.pipelines import Q1_AGGREGATES, q1_program_typed
+    types = [VARCHAR, VARCHAR, DOUBLE, DOUBLE, DOUBLE, DOUBLE, DATE]
+    return FusedAggregationOperator(types, q1_program_typed(VARCHAR), [], [VARCHAR, VARCHAR], [0, 1], Q1_AGGREGATES, step=step, expected_groups=1024,
+                                    group_max_lengths=[1, 1], backend=backend, max_output_rows=1 << 30, **kw)
+
+
+def _state_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    from presto_b200 import STEP_PARTIAL, STEP_SINGLE
+    from presto_b200._lib import load
+    from presto_b200.exchange import merge_aggregation_states
+    backend = load()
+    backend.check(backend.set_device(rank))
+    rows = {}
+    for shared in (False, True):          # the operator on its own stream / on torch's current stream
+        kw = dict(cuda_stream=torch.cuda.current_stream().cuda_stream) if shared else {}
+        op = _q1_operator(backend, STEP_SINGLE if rank == 0 else STEP_PARTIAL, device=rank, **kw)
+        op.add_input(_q1_pages(100 + rank, 40_000 + 10_000 * rank))
+        if merge_aggregation_states(op, max_groups=64):
+            op.finish()
+            rows[shared] = op.get_output().rows()
+        torch.cuda.synchronize()
+        op.close()
+    with open(os.path.join(out_dir, f"s_{rank}.pkl"), "wb") as f:
+        pickle.dump(rows, f)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_aggregation_states_merge_across_two_gpus(gpu_backend, oracle_backend, tmp_path):
+    """Q1 on two GPUs: each aggregates its shard, rank 1's group table travels as a device-side state (one all-gather) and is merged
+    into rank 0's operator — equal to ONE operator over rank 0's page then rank 1's (the oracle, SINGLE step)."""
+    import ctypes as C
+    from presto_b200 import STEP_SINGLE, to_pages
+    from util import rows_close, rows_of
+    n = C.c_int32()
+    gpu_backend.check(gpu_backend.device_count(C.byref(n)))
+    if n.value < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_state_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    want = rows_of(to_pages(_q1_operator(oracle_backend, STEP_SINGLE), [_q1_pages(100, 40_000), _q1_pages(101, 50_000)]))
+    got = pickle.load(open(tmp_path / "s_0.pkl", "rb"))
+    assert pickle.load(open(tmp_path / "s_1.pkl", "rb")) == {}
+    for shared in (False, True):
+        rows_close(got[shared], want)
