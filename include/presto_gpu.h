@@ -494,6 +494,36 @@ int32_t pg_fused_page_explain(const pg_fused_page_config* config, uint64_t nulla
 int32_t pg_jit_compile_check(const char* source, char* log_buffer, size_t capacity, int64_t* cubin_bytes);
 
 /* ------------------------------------------------------------------------------------------------
+ * OperatorFactory — MB/operator/OperatorFactory.java:19-51.  A factory owns a deep copy of one plan node's configuration (the
+ * caller's structs may be freed after create); every Driver asks it for its own operator.
+ *   create_operator      OperatorFactory.createOperator(DriverContext) :21 — `options` is the Driver's part (device, stream, output
+ *                        memory, page size), NULL = the options of the configuration.  PG_ERR_INVALID_STATE "Factory is already
+ *                        closed" after no_more_operators (HashAggregationOperator.java:222).
+ *   no_more_operators    :33 (HashAggregationOperator.java:249-252)
+ *   duplicate            :50 — a new OPEN factory over the same plan (HashAggregationOperator.java:255-275); join factories share
+ *                        the bridge (JoinBridgeManager), they do not copy it
+ * `bridge` is required for PG_FACTORY_HASH_BUILDER / LOOKUP_JOIN / HASH_SEMI_JOIN and ignored otherwise (fused configurations carry
+ * their bridges).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pg_operator_factory pg_operator_factory;
+typedef enum {
+    PG_FACTORY_HASH_AGGREGATION = 1,   /* config: pg_hash_aggregation_config */
+    PG_FACTORY_FILTER_PROJECT = 2,     /* pg_filter_project_config */
+    PG_FACTORY_HASH_BUILDER = 3,       /* pg_hash_builder_config */
+    PG_FACTORY_LOOKUP_JOIN = 4,        /* pg_lookup_join_config */
+    PG_FACTORY_HASH_SEMI_JOIN = 5,     /* pg_semi_join_config */
+    PG_FACTORY_PARTITIONED_OUTPUT = 6, /* pg_partitioned_output_config */
+    PG_FACTORY_FUSED_AGGREGATION = 7,  /* pg_fused_aggregation_config */
+    PG_FACTORY_FUSED_PAGE = 8          /* pg_fused_page_config */
+} pg_operator_kind;
+int32_t pg_operator_factory_create(int32_t kind, const void* config, pg_join_bridge* bridge, pg_operator_factory** out);
+int32_t pg_operator_factory_create_operator(pg_operator_factory* factory, const pg_operator_options* options, pg_operator** out);
+int32_t pg_operator_factory_no_more_operators(pg_operator_factory* factory);
+int32_t pg_operator_factory_duplicate(pg_operator_factory* factory, pg_operator_factory** out);
+int32_t pg_operator_factory_get_created_count(pg_operator_factory* factory, int64_t* count);
+int32_t pg_operator_factory_destroy(pg_operator_factory* factory);
+
+/* ------------------------------------------------------------------------------------------------
  * SerializedPage wire format: what PartitionedOutput hands to an OutputBuffer and an
  * ExchangeClient receives when pages leave the box.
  *   PagesSerde.serialize / deserialize            presto-spi/.../spi/page/PagesSerde.java:67-156

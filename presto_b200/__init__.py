@@ -12,7 +12,7 @@ from .page import Block, Page  # noqa: F401
 from .expressions import Program  # noqa: F401
 from .operators import (  # noqa: F401
     Aggregate, FilterAndProjectOperator, FusedAggregationOperator, FusedJoin, FusedPageOperator, GroupByHash, HashAggregationOperator, HashBuilderOperator, HashSemiJoinOperator, JoinBridge,
-    LookupJoinOperator, Operator, PagesSerde, PartitionedOutputOperator, to_pages,
+    LookupJoinOperator, Operator, OperatorFactory, PagesSerde, PartitionedOutputOperator, to_pages,
 )
 
 __version__ = "0.1.0"

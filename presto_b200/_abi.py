@@ -252,6 +252,12 @@ class Backend:
         "fused_page_get_info": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_char_p, C.c_size_t]),
         "fused_page_explain": (C.c_int32, [C.POINTER(pg_fused_page_config), C.c_uint64, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32),
                                            C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+        "operator_factory_create": (C.c_int32, [C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+        "operator_factory_create_operator": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+        "operator_factory_no_more_operators": (C.c_int32, [C.c_void_p]),
+        "operator_factory_duplicate": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
+        "operator_factory_get_created_count": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64)]),
+        "operator_factory_destroy": (C.c_int32, [C.c_void_p]),
         "jit_compile_check": (C.c_int32, [C.c_char_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_int64)]),
     }
 

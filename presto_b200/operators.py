@@ -136,10 +136,12 @@ class _AggregationState:
 class HashAggregationOperator(_AggregationState, Operator):
     """HashAggregationOperator.java:56-725 (in-memory builder)."""
 
-    def __init__(self, group_types: Sequence[int], group_channels: Sequence[int], aggregates: Sequence[Aggregate], *,
-                 hash_channel: int = -1, step: int = abi.STEP_SINGLE, expected_groups: int = 10_000,
-                 group_max_lengths: Optional[Sequence[int]] = None, backend=None, **options):
-        backend = backend or _default_backend()
+    FACTORY_KIND = 1
+
+    @staticmethod
+    def _config(group_types: Sequence[int], group_channels: Sequence[int], aggregates: Sequence[Aggregate], *,
+                hash_channel: int = -1, step: int = abi.STEP_SINGLE, expected_groups: int = 10_000,
+                group_max_lengths: Optional[Sequence[int]] = None, **options):
         cfg = abi.pg_hash_aggregation_config()
         gc, gt = abi.i32_array(group_channels), abi.i32_array(group_types)
         gl = abi.i32_array(group_max_lengths if group_max_lengths is not None else [0] * len(group_types))
@@ -154,10 +156,15 @@ class HashAggregationOperator(_AggregationState, Operator):
         cfg.step = step
         cfg.expected_groups = expected_groups
         cfg.options = _options(**options)
+        return cfg, (gc, gt, gl, aggs), None
+
+    def __init__(self, group_types: Sequence[int], group_channels: Sequence[int], aggregates: Sequence[Aggregate], *, backend=None, **kwargs):
+        backend = backend or _default_backend()
+        cfg, keep, _ = self._config(group_types, group_channels, aggregates, **kwargs)
         handle = C.c_void_p()
         backend.check(backend.hash_aggregation_create(C.byref(cfg), C.byref(handle)))
         super().__init__(backend, handle)
-        self.cuda_stream = int(options.get("cuda_stream", 0) or 0)
+        self.cuda_stream = int(kwargs.get("cuda_stream", 0) or 0)
 
 
 class GroupByHash:
@@ -240,9 +247,11 @@ class JoinBridge:
 class HashBuilderOperator(Operator):
     """HashBuilderOperator.java:55-692."""
 
-    def __init__(self, bridge: JoinBridge, types: Sequence[int], hash_channels: Sequence[int], output_channels: Sequence[int], *,
-                 precomputed_hash_channel: int = -1, expected_positions: int = 10_000, backend=None, **options):
-        backend = backend or bridge._b
+    FACTORY_KIND = 3
+
+    @staticmethod
+    def _config(bridge: JoinBridge, types: Sequence[int], hash_channels: Sequence[int], output_channels: Sequence[int], *,
+                precomputed_hash_channel: int = -1, expected_positions: int = 10_000, **options):
         cfg = abi.pg_hash_builder_config()
         ty, hc, oc = abi.i32_array(types), abi.i32_array(hash_channels), abi.i32_array(output_channels)
         cfg.n_channels, cfg.types = len(types), ty
@@ -251,6 +260,11 @@ class HashBuilderOperator(Operator):
         cfg.precomputed_hash_channel = precomputed_hash_channel
         cfg.expected_positions = expected_positions
         cfg.options = _options(**options)
+        return cfg, (ty, hc, oc), bridge
+
+    def __init__(self, bridge: JoinBridge, types: Sequence[int], hash_channels: Sequence[int], output_channels: Sequence[int], *, backend=None, **kwargs):
+        backend = backend or bridge._b
+        cfg, keep, _ = self._config(bridge, types, hash_channels, output_channels, **kwargs)
         handle = C.c_void_p()
         backend.check(backend.hash_builder_create(C.byref(cfg), bridge._h, C.byref(handle)))
         super().__init__(backend, handle)
@@ -260,9 +274,11 @@ class HashBuilderOperator(Operator):
 class LookupJoinOperator(Operator):
     """LookupJoinOperator.java:63-760 (INNER and PROBE_OUTER, no filter function)."""
 
-    def __init__(self, bridge: JoinBridge, types: Sequence[int], hash_channels: Sequence[int], output_channels: Sequence[int], *,
-                 join_type: int = abi.JOIN_INNER, precomputed_hash_channel: int = -1, backend=None, **options):
-        backend = backend or bridge._b
+    FACTORY_KIND = 4
+
+    @staticmethod
+    def _config(bridge: JoinBridge, types: Sequence[int], hash_channels: Sequence[int], output_channels: Sequence[int], *,
+                join_type: int = abi.JOIN_INNER, precomputed_hash_channel: int = -1, **options):
         cfg = abi.pg_lookup_join_config()
         ty, hc, oc = abi.i32_array(types), abi.i32_array(hash_channels), abi.i32_array(output_channels)
         cfg.join_type = join_type
@@ -271,6 +287,11 @@ class LookupJoinOperator(Operator):
         cfg.n_output_channels, cfg.output_channels = len(output_channels), oc
         cfg.precomputed_hash_channel = precomputed_hash_channel
         cfg.options = _options(**options)
+        return cfg, (ty, hc, oc), bridge
+
+    def __init__(self, bridge: JoinBridge, types: Sequence[int], hash_channels: Sequence[int], output_channels: Sequence[int], *, backend=None, **kwargs):
+        backend = backend or bridge._b
+        cfg, keep, _ = self._config(bridge, types, hash_channels, output_channels, **kwargs)
         handle = C.c_void_p()
         backend.check(backend.lookup_join_create(C.byref(cfg), bridge._h, C.byref(handle)))
         super().__init__(backend, handle)
@@ -344,9 +365,10 @@ class PartitionedOutputOperator(Operator):
 class FilterAndProjectOperator(Operator):
     """FilterAndProjectOperator.java:88-99 over a PageProcessor (PageProcessor.java:112-148)."""
 
-    def __init__(self, input_types: Sequence[int], program, *, backend=None, **options):
-        """``program`` is an expressions.Program (flattened RowExpression DAG + filter + projections)."""
-        backend = backend or _default_backend()
+    FACTORY_KIND = 2
+
+    @staticmethod
+    def _config(input_types: Sequence[int], program, **options):
         cfg = abi.pg_filter_project_config()
         it = abi.i32_array(input_types)
         nodes = program.c_nodes()
@@ -356,6 +378,12 @@ class FilterAndProjectOperator(Operator):
         cfg.filter_node = program.filter
         cfg.n_projections, cfg.projection_nodes = len(program.projections), proj
         cfg.options = _options(**options)
+        return cfg, (it, nodes, proj), None
+
+    def __init__(self, input_types: Sequence[int], program, *, backend=None, **options):
+        """``program`` is an expressions.Program (flattened RowExpression DAG + filter + projections)."""
+        backend = backend or _default_backend()
+        cfg, keep, _ = self._config(input_types, program, **options)
         handle = C.c_void_p()
         backend.check(backend.filter_project_create(C.byref(cfg), C.byref(handle)))
         super().__init__(backend, handle)
@@ -545,6 +573,54 @@ class FusedPageOperator(Operator):
         buf = C.create_string_buffer(2048)
         self._b.check(self._b.fused_page_get_info(self._h, C.byref(f), C.byref(u), buf, 2048))
         return {"fused_pages": f.value, "unfused_pages": u.value, "reason": buf.value.decode()}
+
+
+class OperatorFactory:
+    """OperatorFactory.java:19-51 over the C ABI's pg_operator_factory_*: ``OperatorFactory(HashAggregationOperator, group_types, ...)``
+    takes the operator class and the arguments its constructor takes (the plan node's part; the factory keeps a deep copy), and
+    ``create_operator(**driver_options)`` hands out one operator per Driver (device / cuda_stream / output_memory / max_output_rows)."""
+
+    def __init__(self, operator_class, *args, backend=None, _handle=None, **kwargs):
+        self._cls = operator_class
+        self._closed = False
+        if _handle is not None:
+            self._b, self._h, self._bridge = backend, _handle, kwargs.get("_bridge")
+            return
+        cfg, keep, bridge = operator_class._config(*args, **kwargs)
+        self._b = backend or (bridge._b if bridge is not None else _default_backend())
+        self._bridge = bridge
+        self._h = C.c_void_p()
+        self._b.check(self._b.operator_factory_create(operator_class.FACTORY_KIND, C.byref(cfg), bridge._h if bridge is not None else None, C.byref(self._h)))
+        del keep          # the factory copied every array
+
+    def create_operator(self, **options) -> Operator:
+        handle = C.c_void_p()
+        opts = _options(**options) if options else None
+        self._b.check(self._b.operator_factory_create_operator(self._h, C.byref(opts) if opts is not None else None, C.byref(handle)))
+        op = self._cls.__new__(self._cls)
+        Operator.__init__(op, self._b, handle)
+        op.cuda_stream = int(options.get("cuda_stream", 0) or 0)
+        op._bridge = self._bridge
+        return op
+
+    def no_more_operators(self) -> None:
+        self._b.check(self._b.operator_factory_no_more_operators(self._h))
+
+    def duplicate(self) -> "OperatorFactory":
+        handle = C.c_void_p()
+        self._b.check(self._b.operator_factory_duplicate(self._h, C.byref(handle)))
+        return OperatorFactory(self._cls, backend=self._b, _handle=handle, _bridge=self._bridge)
+
+    @property
+    def created_count(self) -> int:
+        out = C.c_int64()
+        self._b.check(self._b.operator_factory_get_created_count(self._h, C.byref(out)))
+        return int(out.value)
+
+    def close(self) -> None:
+        if not self._closed:
+            self._b.operator_factory_destroy(self._h)
+            self._closed = True
 
 
 class PagesSerde:
