@@ -72,7 +72,12 @@ typedef enum {
     PG_TYPE_DOUBLE = 3,   /* LongArrayBlock holding doubleToLongBits, 8 B */
     PG_TYPE_DATE = 4,     /* IntArrayBlock (days since epoch), 4 B */
     PG_TYPE_BOOLEAN = 5,  /* ByteArrayBlock, 1 B */
-    PG_TYPE_VARCHAR = 6   /* VariableWidthBlock: bytes + int32 offsets[n+1] */
+    PG_TYPE_VARCHAR = 6,  /* VariableWidthBlock: bytes + int32 offsets[n+1] (VARBINARY travels in the same block: the intermediate state of
+                             sum(decimal)) */
+    PG_TYPE_LONG_DECIMAL = 7 /* Int128ArrayBlock (PC/block/Int128ArrayBlock.java), 16 B per position: decimal(19..38) unscaled values in
+                                UnscaledDecimal128Arithmetic's sign-magnitude form — long 0 = low 64 bits of the magnitude, long 1 = high 63
+                                bits | sign << 63 (UnscaledDecimal128Arithmetic.java:46-58,172-180).  Short decimals (precision <= 18) are
+                                plain longs: PG_TYPE_BIGINT. */
 } pg_type;
 
 typedef enum {
@@ -213,7 +218,13 @@ typedef enum {
     PG_AGG_AVG_DOUBLE = 4,   /* AverageAggregations.java:41-66 */
     PG_AGG_AVG_BIGINT = 5,   /* AverageAggregations.java:34-39 */
     PG_AGG_MIN_DOUBLE = 6, PG_AGG_MAX_DOUBLE = 7,
-    PG_AGG_MIN_BIGINT = 8, PG_AGG_MAX_BIGINT = 9
+    PG_AGG_MIN_BIGINT = 8, PG_AGG_MAX_BIGINT = 9,
+    /* DecimalSumAggregation.java:60-185: sum(decimal(p,s)) -> decimal(38,s).  SHORT: the input channel holds unscaled longs (PG_TYPE_BIGINT
+     * blocks, inputShortDecimal :145-153); LONG: PG_TYPE_LONG_DECIMAL blocks (inputLongDecimal :155-163).  Output PG_TYPE_LONG_DECIMAL, NULL
+     * without a non-null input; PG_ERR_NUMERIC_OVERFLOW when the sum leaves decimal(38) (outputLongDecimal :179-185).  Intermediate state
+     * (PARTIAL output / FINAL input) = one VARBINARY of 3 longs {overflow, low, high} per group
+     * (LongDecimalWithOverflowStateSerializer.java:37-49), NULL for a group without input. */
+    PG_AGG_SUM_SHORT_DECIMAL = 10, PG_AGG_SUM_LONG_DECIMAL = 11
 } pg_aggregate_function;
 
 typedef enum {              /* AggregationNode.Step */

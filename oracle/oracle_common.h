@@ -37,6 +37,7 @@ inline int typeWidth(int type)
         case PG_TYPE_INTEGER: case PG_TYPE_DATE: return 4;
         case PG_TYPE_BOOLEAN: return 1;
         case PG_TYPE_VARCHAR: return 0;
+        case PG_TYPE_LONG_DECIMAL: return 16;
     }
     throw OracleError(PG_ERR_UNSUPPORTED, "unknown type");
 }
@@ -193,6 +194,7 @@ struct BlockView {
         throw OracleError(PG_ERR_UNSUPPORTED, "getLong on variable width block");
     }
     inline double getDouble(int64_t pos) const { int64_t v = getLong(pos); double d; memcpy(&d, &v, 8); return d; }
+    inline const int64_t* int128Ptr(int64_t pos) const { return (const int64_t*) b->values + 2 * dictPos(pos); }
     inline const uint8_t* slicePtr(int64_t pos) const { return (const uint8_t*) b->values + b->offsets[dictPos(pos)]; }
     inline int32_t sliceLength(int64_t pos) const { int64_t p = dictPos(pos); return b->offsets[p + 1] - b->offsets[p]; }
 };
@@ -236,6 +238,12 @@ struct Column {
         nulls.push_back(0); n++;
     }
     void appendDouble(double d) { int64_t v; memcpy(&v, &d, 8); appendLong(v); }
+    void appendInt128(int64_t low, int64_t high)     // Int128ArrayBlockBuilder.writeLong x2
+    {
+        size_t o = data.size(); data.resize(o + 16);
+        memcpy(&data[o], &low, 8); memcpy(&data[o + 8], &high, 8);
+        nulls.push_back(0); n++;
+    }
     void appendSlice(const uint8_t* p, int32_t len)
     {
         data.insert(data.end(), p, p + len);
@@ -246,12 +254,15 @@ struct Column {
     void appendFrom(const BlockView& v, int64_t pos)
     {
         if (v.isNull(pos)) { appendNull(); return; }
-        if (type == PG_TYPE_VARCHAR) appendSlice(v.slicePtr(pos), v.sliceLength(pos)); else appendLong(v.getLong(pos));
+        if (type == PG_TYPE_VARCHAR) appendSlice(v.slicePtr(pos), v.sliceLength(pos));
+        else if (type == PG_TYPE_LONG_DECIMAL) { const int64_t* w = v.int128Ptr(pos); appendInt128(w[0], w[1]); }
+        else appendLong(v.getLong(pos));
     }
     void appendFrom(const Column& c, int64_t pos)
     {
         if (c.nulls[pos]) { appendNull(); return; }
         if (type == PG_TYPE_VARCHAR) appendSlice(c.data.data() + c.offsets[pos], c.offsets[pos + 1] - c.offsets[pos]);
+        else if (type == PG_TYPE_LONG_DECIMAL) { int64_t w[2]; memcpy(w, &c.data[pos * 16], 16); appendInt128(w[0], w[1]); }
         else appendLong(c.getLong(pos));
     }
     int64_t getLong(int64_t pos) const

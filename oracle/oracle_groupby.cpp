@@ -372,6 +372,7 @@ struct GroupedAccumulator {
             doubles.resize(groupCount, 0.0);
             longs.resize(groupCount, 0);
             isNull.resize(groupCount, 1);
+            if (spec.function == PG_AGG_SUM_SHORT_DECIMAL || spec.function == PG_AGG_SUM_LONG_DECIMAL) { decimals.resize(groupCount); overflows.resize(groupCount, 0); }
         }
     }
 
@@ -406,6 +407,61 @@ struct GroupedAccumulator {
         if (isMin ? c < 0 : c > 0) doubles[g] = value;
     }
 
+    // ---- DecimalSumAggregation: LongDecimalWithOverflowState = {Slice longDecimal (null until the first input), long overflow} ----
+    // 128-bit unscaled decimals in UnscaledDecimal128Arithmetic's sign-magnitude form: low = long 0, high = long 1 (bit 63 = sign).
+    struct Decimal128 { uint64_t low = 0, high = 0; };     // `high` carries the sign bit
+    static constexpr uint64_t kSignMask = 0x8000000000000000ULL;
+    std::vector<Decimal128> decimals;
+    std::vector<int64_t> overflows;
+    static Decimal128 unscaledDecimal(int64_t v)           // UnscaledDecimal128Arithmetic.unscaledDecimal(long) :170-183
+    {
+        Decimal128 d;
+        if (v < 0) { d.low = (uint64_t) 0 - (uint64_t) v; d.high = kSignMask; } else d.low = (uint64_t) v;
+        return d;
+    }
+    // UnscaledDecimal128Arithmetic.addWithOverflow :312-337 (addUnsignedReturnOverflow :371-407, subtractUnsigned :409-447,
+    // compareAbsolute :693-708): sign-magnitude addition; the magnitude keeps 127 bits, what spills over is returned as +-1.
+    static int64_t addWithOverflow(const Decimal128& l, const Decimal128& r, Decimal128& out)
+    {
+        const bool ln = (l.high & kSignMask) != 0, rn = (r.high & kSignMask) != 0;
+        const unsigned __int128 lm = ((unsigned __int128) (l.high & ~kSignMask) << 64) | l.low, rm = ((unsigned __int128) (r.high & ~kSignMask) << 64) | r.low;
+        int64_t overflow = 0;
+        unsigned __int128 m; bool negative;
+        if (ln == rn) {
+            m = lm + rm;                                            // < 2^128: no wrap
+            overflow = (int64_t) (uint64_t) (m >> 127);             // :401 `intermediateResult >> 31` of the top int
+            m &= ~((unsigned __int128) 1 << 127);
+            negative = ln;
+            if (ln) overflow = -overflow;
+        }
+        else if (lm > rm) { m = lm - rm; negative = ln; }
+        else if (lm < rm) { m = rm - lm; negative = !ln; }
+        else { m = 0; negative = false; }                           // setToZero
+        out.low = (uint64_t) m; out.high = (uint64_t) (m >> 64) | (negative ? kSignMask : 0);
+        return overflow;
+    }
+    void decimalInput(int64_t g, const Decimal128& v)               // DecimalSumAggregation.inputShortDecimal / inputLongDecimal :145-163
+    {
+        if (isNull[g]) { isNull[g] = 0; decimals[g] = Decimal128(); }
+        overflows[g] += addWithOverflow(decimals[g], v, decimals[g]);
+    }
+    void decimalCombine(int64_t g, int64_t otherOverflow, const Decimal128& other)     // DecimalSumAggregation.combine :165-177
+    {
+        int64_t toAdd = otherOverflow;
+        if (isNull[g]) { isNull[g] = 0; decimals[g] = other; }
+        else toAdd += addWithOverflow(decimals[g], other, decimals[g]);
+        overflows[g] += toAdd;
+    }
+    // UnscaledDecimal128Arithmetic.exceedsOrEqualTenToThirtyEight :1671-1686 (getLong(decimal, 1) is the high long without its sign)
+    static bool exceedsOrEqualTenToThirtyEight(const Decimal128& d)
+    {
+        const int64_t high = (int64_t) (d.high & ~kSignMask);
+        if (high >= 0 && high < 0x4b3b4ca85a86c47aLL) return false;
+        if (high != 0x4b3b4ca85a86c47aLL) return true;
+        const int64_t low = (int64_t) d.low;
+        return low < 0 || low >= 0x098a224000000000LL;
+    }
+
     // Number of input channels the FINAL step consumes for this aggregate (our intermediate layout):
     // sum → 1 (nullable value), count → 1, avg → 2 (sum double, count bigint)
     static int intermediateChannels(int fn) { return (fn == PG_AGG_AVG_DOUBLE || fn == PG_AGG_AVG_BIGINT) ? 2 : 1; }
@@ -435,6 +491,8 @@ struct GroupedAccumulator {
                     longs[g] = longs[g] + 1; doubles[g] = doubles[g] + in.getDouble(p); break;
                 case PG_AGG_AVG_BIGINT:   // AverageAggregations.input(long) :34-39
                     longs[g] = longs[g] + 1; doubles[g] = doubles[g] + (double) in.getLong(p); break;
+                case PG_AGG_SUM_SHORT_DECIMAL: decimalInput(g, unscaledDecimal(in.getLong(p))); break;
+                case PG_AGG_SUM_LONG_DECIMAL: { const int64_t* w = in.int128Ptr(p); Decimal128 d; d.low = (uint64_t) w[0]; d.high = (uint64_t) w[1]; decimalInput(g, d); break; }
                 case PG_AGG_MIN_BIGINT: case PG_AGG_MAX_BIGINT: minMaxLong(g, in.getLong(p), spec.function == PG_AGG_MIN_BIGINT); break;      // AbstractMinMaxAggregationFunction.input :199-202
                 case PG_AGG_MIN_DOUBLE: case PG_AGG_MAX_DOUBLE: minMaxDouble(g, in.getDouble(p), spec.function == PG_AGG_MIN_DOUBLE); break;  // :194-197
                 default: throw OracleError(PG_ERR_UNSUPPORTED, "aggregate function not in the oracle");
@@ -465,6 +523,14 @@ struct GroupedAccumulator {
                     BlockView c(&page->blocks[channel + 1]);
                     longs[g] += c.getLong(p); doubles[g] += a.getDouble(p); break;
                 }
+                case PG_AGG_SUM_SHORT_DECIMAL: case PG_AGG_SUM_LONG_DECIMAL: {     // LongDecimalWithOverflowStateSerializer.deserialize :52-66
+                    if (a.isNull(p)) break;
+                    if (a.sliceLength(p) != 24) throw OracleError(PG_ERR_INVALID_STATE, "Unexpected serialized state size: " + std::to_string(a.sliceLength(p)));
+                    int64_t w[3]; memcpy(w, a.slicePtr(p), 24);
+                    Decimal128 d; d.low = (uint64_t) w[1]; d.high = (uint64_t) w[2];
+                    decimalCombine(g, w[0], d);
+                    break;
+                }
                 case PG_AGG_MIN_BIGINT: case PG_AGG_MAX_BIGINT:      // AbstractMinMaxAggregationFunction.combine :225-228 (NULL intermediate states are skipped)
                     if (!a.isNull(p)) minMaxLong(g, a.getLong(p), spec.function == PG_AGG_MIN_BIGINT);
                     break;
@@ -484,6 +550,7 @@ struct GroupedAccumulator {
             case PG_AGG_SUM_DOUBLE: case PG_AGG_MIN_DOUBLE: case PG_AGG_MAX_DOUBLE: out.push_back(PG_TYPE_DOUBLE); break;
             case PG_AGG_AVG_DOUBLE: case PG_AGG_AVG_BIGINT:
                 out.push_back(PG_TYPE_DOUBLE); if (partial) out.push_back(PG_TYPE_BIGINT); break;
+            case PG_AGG_SUM_SHORT_DECIMAL: case PG_AGG_SUM_LONG_DECIMAL: out.push_back(partial ? PG_TYPE_VARCHAR : PG_TYPE_LONG_DECIMAL); break;
             default: throw OracleError(PG_ERR_UNSUPPORTED, "aggregate function not in the oracle");
         }
     }
@@ -499,6 +566,17 @@ struct GroupedAccumulator {
                 if (partial) { out[offset++].appendDouble(doubles[g]); out[offset++].appendLong(longs[g]); }
                 else if (longs[g] == 0) out[offset++].appendNull();                       // AverageAggregations.output :55-66
                 else out[offset++].appendDouble(doubles[g] / (double) longs[g]);
+                break;
+            case PG_AGG_SUM_SHORT_DECIMAL: case PG_AGG_SUM_LONG_DECIMAL:
+                if (isNull[g]) { out[offset++].appendNull(); break; }
+                if (partial) {      // LongDecimalWithOverflowStateSerializer.serialize :37-49
+                    const int64_t w[3] = {overflows[g], (int64_t) decimals[g].low, (int64_t) decimals[g].high};
+                    out[offset++].appendSlice((const uint8_t*) w, 24);
+                }
+                else {              // DecimalSumAggregation.outputLongDecimal :179-193
+                    if (overflows[g] != 0 || exceedsOrEqualTenToThirtyEight(decimals[g])) throw OracleError(PG_ERR_NUMERIC_OVERFLOW, "Decimal overflow");
+                    out[offset++].appendInt128((int64_t) decimals[g].low, (int64_t) decimals[g].high);
+                }
                 break;
             default: throw OracleError(PG_ERR_UNSUPPORTED, "aggregate function not in the oracle");
         }

@@ -26,7 +26,7 @@ _STATUS_NAMES = {
 }
 
 # pg_type
-BIGINT, INTEGER, DOUBLE, DATE, BOOLEAN, VARCHAR = 1, 2, 3, 4, 5, 6
+BIGINT, INTEGER, DOUBLE, DATE, BOOLEAN, VARCHAR, LONG_DECIMAL = 1, 2, 3, 4, 5, 6, 7
 IPC_HANDLE_BYTES = 64
 # pg_encoding
 ENC_FLAT, ENC_DICTIONARY, ENC_RLE = 0, 1, 2
@@ -35,6 +35,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 # pg_aggregate_function
 AGG_COUNT_STAR, AGG_COUNT_COLUMN, AGG_SUM_DOUBLE, AGG_SUM_BIGINT, AGG_AVG_DOUBLE, AGG_AVG_BIGINT = 0, 1, 2, 3, 4, 5
 AGG_MIN_DOUBLE, AGG_MAX_DOUBLE, AGG_MIN_BIGINT, AGG_MAX_BIGINT = 6, 7, 8, 9
+AGG_SUM_SHORT_DECIMAL, AGG_SUM_LONG_DECIMAL = 10, 11
 # pg_aggregation_step
 STEP_SINGLE, STEP_PARTIAL, STEP_FINAL = 0, 1, 2
 # pg_join_type

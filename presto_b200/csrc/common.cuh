@@ -53,6 +53,7 @@ inline int typeWidth(int type)
         case PG_TYPE_INTEGER: case PG_TYPE_DATE: return 4;
         case PG_TYPE_BOOLEAN: return 1;
         case PG_TYPE_VARCHAR: return 0;
+        case PG_TYPE_LONG_DECIMAL: return 16;
     }
     throw Error(PG_ERR_UNSUPPORTED, "unknown pg_type " + std::to_string(type));
 }

@@ -151,7 +151,7 @@ struct KeyPlan {
     unsigned int* errorFlag;   // CNT_ERROR word
 };
 
-enum { ERR_BIGINT_OVERFLOW = 1, ERR_VARCHAR_TOO_LONG = 2 };
+enum { ERR_BIGINT_OVERFLOW = 1, ERR_VARCHAR_TOO_LONG = 2, ERR_DECIMAL_OVERFLOW = 4 };
 
 // Packs the key of `row`.  Returns 0 = ordinary key, 1 = NULL key of the Bigint path, 2 = key equal to the W==1 sentinel.
 template <int W>

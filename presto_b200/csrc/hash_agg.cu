@@ -34,7 +34,13 @@
 namespace pg {
 
 // accumulator column kinds
-enum { K_F64 = 0, K_F64_FROM_I64 = 1, K_LO32 = 2, K_HI32 = 3, K_COUNT = 4, K_I64_ADD = 5, K_MIN_F64 = 6, K_MAX_F64 = 7, K_MIN_I64 = 8, K_MAX_I64 = 9 };
+enum { K_F64 = 0, K_F64_FROM_I64 = 1, K_LO32 = 2, K_HI32 = 3, K_COUNT = 4, K_I64_ADD = 5, K_MIN_F64 = 6, K_MAX_F64 = 7, K_MIN_I64 = 8, K_MAX_I64 = 9,
+       // sum(decimal): the 128-bit value as four 32-bit limbs, each summed in its own 64-bit accumulator (exact for 2^31 rows per group;
+       // limb 3 is signed).  K_DEC_*: a PG_TYPE_LONG_DECIMAL input (sign-magnitude, 16 B); K_DST_*: a serialized state {overflow, low,
+       // high} (24 B inside a VARBINARY block), i.e. overflow * 2^127 + value.  Short decimals are plain longs: K_LO32 / K_HI32.
+       K_DEC_L0 = 10, K_DEC_L1 = 11, K_DEC_L2 = 12, K_DEC_L3 = 13, K_DST_L0 = 14, K_DST_L1 = 15, K_DST_L2 = 16, K_DST_L3 = 17 };
+__host__ __device__ inline bool kindIsDecimal(int k) { return k >= K_DEC_L0 && k <= K_DEC_L3; }
+__host__ __device__ inline bool kindIsDecimalState(int k) { return k >= K_DST_L0 && k <= K_DST_L3; }
 __host__ __device__ inline bool kindIsFloat(int k) { return k == K_F64 || k == K_F64_FROM_I64; }
 // min / max (MB/operator/aggregation/AbstractMinMaxAggregationFunction.java: state = value if it compares better) are ONE combine rule
 // here: every value is mapped to an unsigned word whose order is the type's order (`ordered`), MIN stores its complement, and the
@@ -58,6 +64,7 @@ struct AccInput {
     const uint8_t* nulls;
     const uint8_t* mask;        // BOOLEAN mask column or nullptr
     const uint8_t* maskNulls;
+    const int32_t* offsets;     // K_DST_*: offsets of the VARBINARY block holding the states (`values` = its bytes)
     int32_t kind;
     int32_t phys;               // physical accumulator column
 };
@@ -111,6 +118,31 @@ __device__ __forceinline__ uint64_t contribOf(int kind, uint64_t raw)
         case K_MIN_F64: return ~orderedOfF64(raw);
         default: return (uint64_t) ((long long) raw >> 32);   // K_HI32
     }
+}
+
+// Limb `kind - base` of a 128-bit two's complement value (limbs 0..2 unsigned, limb 3 signed).
+__device__ __forceinline__ uint64_t limbOf(__int128 v, int limb)
+{
+    return limb == 3 ? (uint64_t) (int64_t) (v >> 96) : (uint64_t) ((unsigned __int128) v >> (32 * limb)) & 0xffffffffULL;
+}
+// sign-magnitude (UnscaledDecimal128Arithmetic) -> two's complement
+__device__ __forceinline__ __int128 decimalOfSignMagnitude(uint64_t low, uint64_t high)
+{
+    const __int128 m = (__int128) (((unsigned __int128) (high & 0x7fffffffffffffffULL) << 64) | low);
+    return (high >> 63) ? -m : m;
+}
+__device__ __forceinline__ uint64_t decimalContrib(const AccInput& a, int64_t row)
+{
+    if (kindIsDecimal(a.kind)) {
+        const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(a.values + 2 * row);
+        return limbOf(decimalOfSignMagnitude(t.x, t.y), a.kind - K_DEC_L0);
+    }
+    // a state: {overflow, low, high}, value = overflow * 2^127 + (low, high); the overflow lands in limb 3 as overflow << 31
+    const unsigned char* p = (const unsigned char*) a.values + a.offsets[row];
+    uint64_t w[3];
+    for (int i = 0; i < 3; i++) { uint64_t x = 0; for (int b = 0; b < 8; b++) x |= (uint64_t) p[8 * i + b] << (8 * b); w[i] = x; }
+    const uint64_t limb = limbOf(decimalOfSignMagnitude(w[1], w[2]), a.kind - K_DST_L0);
+    return a.kind == K_DST_L3 ? limb + ((uint64_t) (int64_t) w[0] << 31) : limb;
 }
 
 // ---- the fused kernel ---------------------------------------------------------------------------------------------------
@@ -209,11 +241,17 @@ __global__ void __launch_bounds__(kAggThreads) hashAggKernel(const __grid_consta
                     }
                     if (a.nulls) { if (add0) add0 = a.nulls[row0] == 0; if (add1) add1 = a.nulls[row0 + 1] == 0; }
                     uint64_t r0 = 0, r1 = 0;
-                    if (a.kind != K_COUNT) {
-                        if (pair) { const ulonglong2 t = ldStream128(a.values + row0); r0 = t.x; r1 = t.y; }
-                        else { if (v0) r0 = ldStream64(a.values + row0); if (v1) r1 = ldStream64(a.values + row0 + 1); }
+                    if (a.kind >= K_DEC_L0) {      // sum(decimal) over 16-byte values / serialized states: rows whose input is NULL hold no bytes
+                        if (add0) contrib[2 * j][c] = decimalContrib(a, row0);
+                        if (add1) contrib[2 * j + 1][c] = decimalContrib(a, row0 + 1);
                     }
-                    contrib[2 * j][c] = contribOf(a.kind, r0); contrib[2 * j + 1][c] = contribOf(a.kind, r1);
+                    else {
+                        if (a.kind != K_COUNT) {
+                            if (pair) { const ulonglong2 t = ldStream128(a.values + row0); r0 = t.x; r1 = t.y; }
+                            else { if (v0) r0 = ldStream64(a.values + row0); if (v1) r1 = ldStream64(a.values + row0 + 1); }
+                        }
+                        contrib[2 * j][c] = contribOf(a.kind, r0); contrib[2 * j + 1][c] = contribOf(a.kind, r1);
+                    }
                     if (add0) addMask[2 * j] |= 1u << c;
                     if (add1) addMask[2 * j + 1] |= 1u << c;
                 }
@@ -927,10 +965,11 @@ struct KeyOut {          // one output key column
 struct AggOut {
     int32_t function;      // pg_aggregate_function
     int32_t val0, val1;    // physical value columns (sum; lo/hi for bigint sum)
+    int32_t val2, val3;    // sum(decimal) over 128-bit inputs: limbs 2 and 3 (-1: a short decimal, lo/hi only)
     int32_t countCol;      // physical non-null-count column, or -1 = every touched group has >= 1 non-null input
     int32_t partial;       // PARTIAL step: emit intermediate columns
     void* out0; uint8_t* null0;   // first output column
-    void* out1;                   // second output column (avg partial: count)
+    void* out1;                   // second output column (avg partial: count; sum(decimal) partial: the state block's offsets)
 };
 struct EmitParams {
     GroupTable t;
@@ -1001,6 +1040,55 @@ __global__ void emitKernel(const __grid_constant__ EmitParams P)
                     if (total > (__int128) INT64_MAX || total < (__int128) INT64_MIN) { atomicOr(&T.counters[CNT_ERROR], (unsigned int) ERR_BIGINT_OVERFLOW); total = 0; }
                     ((int64_t*) ao.out0)[g] = count > 0 ? (int64_t) total : 0; ao.null0[g] = count > 0 ? 0 : 1; break;
                 }
+                case PG_AGG_SUM_SHORT_DECIMAL: case PG_AGG_SUM_LONG_DECIMAL: {
+                    // exact total of the limb sums in 192 bits (t2 : t1 : t0, t2 signed); DecimalSumAggregation keeps 127 bits of
+                    // magnitude + an overflow count, i.e. the same number as overflow * 2^127 + value
+                    unsigned __int128 lowPart = (unsigned __int128) acc[ao.val0];
+                    __int128 top = 0;                 // multiples of 2^64
+                    auto addShifted = [&](__int128 v, int shift) {        // += v << shift   (shift = 32 or 96 handled by splitting)
+                        // v fits 65 bits (a signed / unsigned 64-bit sum)
+                        const unsigned __int128 lo = (unsigned __int128) v << shift;          // low 128 bits of v << shift
+                        const __int128 hi = v >> (128 - shift);                                // what fell off the top (arithmetic)
+                        const unsigned __int128 before = lowPart;
+                        lowPart += lo;
+                        top += hi + (lowPart < before ? 1 : 0);
+                    };
+                    // `top` counts multiples of 2^128 here
+                    if (ao.val2 < 0) addShifted((__int128) (int64_t) acc[ao.val1], 32);
+                    else {
+                        addShifted((__int128) (unsigned __int128) acc[ao.val1], 32);
+                        addShifted((__int128) (unsigned __int128) acc[ao.val2], 64);
+                        addShifted((__int128) (int64_t) acc[ao.val3], 96);
+                    }
+                    // value = top * 2^128 + lowPart (two's complement over 192+ bits): magnitude and sign
+                    bool negative = top < 0;
+                    unsigned __int128 magLow = lowPart; __int128 magTop = top;
+                    if (negative) { magLow = ~lowPart + 1; magTop = ~top + (magLow == 0 ? 1 : 0); }
+                    const uint64_t mLow = (uint64_t) magLow, mHigh = (uint64_t) (magLow >> 64);
+                    const bool isNull = count <= 0;
+                    if (ao.partial) {
+                        // {overflow, low, high}: magnitude split at 2^127 (any split with |value| < 2^127 is the same number)
+                        const __int128 over = (magTop << 1) | (__int128) (mHigh >> 63);
+                        int64_t* st = (int64_t*) ao.out0 + 3 * (size_t) g;
+                        st[0] = isNull ? 0 : (int64_t) (negative ? -over : over);
+                        st[1] = isNull ? 0 : (int64_t) mLow;
+                        st[2] = isNull ? 0 : (int64_t) ((mHigh & 0x7fffffffffffffffULL) | (negative && (mLow | (mHigh & 0x7fffffffffffffffULL)) ? 0x8000000000000000ULL : 0));
+                        int32_t* offs = (int32_t*) ao.out1;
+                        offs[g + 1] = 24 * (g + 1);
+                        if (g == 0) offs[0] = 0;
+                        ao.null0[g] = isNull ? 1 : 0;
+                    }
+                    else {
+                        // outputLongDecimal: overflow != 0 or |value| >= 10^38 -> "Decimal overflow"
+                        const bool tooBig = magTop != 0 || mHigh > 0x4b3b4ca85a86c47aULL || (mHigh == 0x4b3b4ca85a86c47aULL && mLow >= 0x098a224000000000ULL);
+                        if (!isNull && tooBig) atomicOr(&T.counters[CNT_ERROR], (unsigned int) ERR_DECIMAL_OVERFLOW);
+                        uint64_t* o = (uint64_t*) ao.out0 + 2 * (size_t) g;
+                        o[0] = isNull || tooBig ? 0 : mLow;
+                        o[1] = isNull || tooBig ? 0 : (mHigh | (negative && (mLow | mHigh) ? 0x8000000000000000ULL : 0));
+                        ao.null0[g] = isNull ? 1 : 0;
+                    }
+                    break;
+                }
                 case PG_AGG_MIN_DOUBLE: case PG_AGG_MAX_DOUBLE: case PG_AGG_MIN_BIGINT: case PG_AGG_MAX_BIGINT: {
                     const bool isMin = ao.function == PG_AGG_MIN_DOUBLE || ao.function == PG_AGG_MIN_BIGINT;
                     const uint64_t o = isMin ? ~acc[ao.val0] : acc[ao.val0];
@@ -1033,7 +1121,7 @@ struct PhysCol { int kind; int channel; int mask; bool lazy; bool active; };
 
 struct AggPlan {
     pg_aggregate spec;
-    int val0 = -1, val1 = -1;
+    int val0 = -1, val1 = -1, val2 = -1, val3 = -1;
     int countCol = -1;        // physical column with the non-null count of (channel, mask); -1 never needed
     bool countExact = false;  // count value is an output (avg / count) rather than a null flag (sum)
 };
@@ -1080,7 +1168,7 @@ static uint32_t nextPow2(uint64_t v) { uint64_t p = 1; while (p < v) p <<= 1; re
 
 
 // ---- result materialisation shared by HashAggregationOperator and GroupByHash ---------------------------------------------
-struct AggEmit { int function, val0, val1, countCol; bool partial; };
+struct AggEmit { int function, val0, val1, countCol; bool partial; int val2 = -1, val3 = -1; };
 
 // Slots that were touched, ordered by first-touch row = ascending group id.  Returns the group count.
 // `scratch` keeps the sort's temporaries alive until the caller's next synchronisation (blocks go back to the caching allocator only
@@ -1140,7 +1228,10 @@ struct ResultBuilder {
             size_t nCols = (size_t) layout.nKeys + (withHash ? 1 : 0), nVarchar = 0;
             for (const AggEmit& a : aggs) nCols += (a.partial && (a.function == PG_AGG_AVG_DOUBLE || a.function == PG_AGG_AVG_BIGINT)) ? 2 : 1;
             for (int k = 0; k < layout.nKeys; k++) nVarchar += layout.types[k] == PG_TYPE_VARCHAR;
-            bound = nCols * (align((size_t) g * 8 + 16) + align((size_t) g + 16)) + nVarchar * (2 * align((size_t) (g + 1) * 4) + align(scanTemp + 16) + align((size_t) g * 8 + 16));
+            size_t nDecimal = 0;
+            for (const AggEmit& a : aggs) nDecimal += a.function == PG_AGG_SUM_SHORT_DECIMAL || a.function == PG_AGG_SUM_LONG_DECIMAL;
+            bound = nCols * (align((size_t) g * 8 + 16) + align((size_t) g + 16)) + nVarchar * (2 * align((size_t) (g + 1) * 4) + align(scanTemp + 16) + align((size_t) g * 8 + 16))
+                  + nDecimal * (align((size_t) g * 24 + 16) + align((size_t) (g + 1) * 4 + 16));
         }
         const bool arenaMode = toHost && g > 0 && bound <= kArenaBytes;
         if (arenaMode) {
@@ -1169,6 +1260,7 @@ struct ResultBuilder {
             return (int) colBufs.size() - 1;
         };
         std::vector<int> varcharLens(layout.nKeys, -1);
+        std::map<int, int> stateOffsets;          // output column -> buffer with the offsets of its VARBINARY states
         for (int k = 0; k < layout.nKeys; k++) {
             int c = newColumn(layout.types[k]);
             KeyOut& ko = E.keys[k];
@@ -1186,7 +1278,21 @@ struct ResultBuilder {
         for (size_t i = 0; i < aggs.size(); i++) {
             const AggEmit& a = aggs[i];
             AggOut& ao = E.aggs[i];
-            ao.function = a.function; ao.val0 = a.val0; ao.val1 = a.val1; ao.partial = a.partial ? 1 : 0; ao.countCol = a.countCol;
+            ao.function = a.function; ao.val0 = a.val0; ao.val1 = a.val1; ao.val2 = a.val2; ao.val3 = a.val3; ao.partial = a.partial ? 1 : 0; ao.countCol = a.countCol;
+            if (a.function == PG_AGG_SUM_SHORT_DECIMAL || a.function == PG_AGG_SUM_LONG_DECIMAL) {
+                if (!a.partial) {
+                    int c = newColumn(PG_TYPE_LONG_DECIMAL);
+                    ao.out0 = outBufs[colBufs[c].values].ptr; ao.null0 = outBufs[colBufs[c].nulls].as<uint8_t>(); ao.out1 = nullptr;
+                }
+                else {      // one 24-byte state per group in a VARBINARY column (null groups keep their 24 zero bytes: offsets stay 24 * g)
+                    ColBufs cb{newBuf((size_t) g * 24), newBuf(g)};
+                    outTypes.push_back(PG_TYPE_VARCHAR); colBufs.push_back(cb);
+                    const int offs = newBuf((size_t) (g + 1) * 4);
+                    stateOffsets[(int) colBufs.size() - 1] = offs;
+                    ao.out0 = outBufs[cb.values].ptr; ao.null0 = outBufs[cb.nulls].as<uint8_t>(); ao.out1 = outBufs[offs].ptr;
+                }
+                continue;
+            }
             int type = (a.function == PG_AGG_SUM_DOUBLE || a.function == PG_AGG_AVG_DOUBLE || a.function == PG_AGG_AVG_BIGINT || a.function == PG_AGG_MIN_DOUBLE
                         || a.function == PG_AGG_MAX_DOUBLE) ? PG_TYPE_DOUBLE : PG_TYPE_BIGINT;
             int c = newColumn(type);
@@ -1238,10 +1344,15 @@ struct ResultBuilder {
             if (varcharOffsets[k] >= 0 && !arenaMode) PG_CUDA(cudaMemcpyAsync(&totalBytes[k], outBufs[varcharOffsets[k]].as<int32_t>() + g, 4, cudaMemcpyDeviceToHost, stream));
         PG_CUDA(cudaStreamSynchronize(stream));      // the error counters and the VARCHAR byte totals (arena: the whole result) arrive together
         if (cnt[CNT_ERROR] & ERR_BIGINT_OVERFLOW) throw Error(PG_ERR_NUMERIC_OVERFLOW, "bigint addition overflow");
+        if (cnt[CNT_ERROR] & ERR_DECIMAL_OVERFLOW) throw Error(PG_ERR_NUMERIC_OVERFLOW, "Decimal overflow");
         for (size_t c = 0; c < colBufs.size(); c++) {
             pg_block& b = outBlocks[c];
             b.type = outTypes[c]; b.encoding = PG_ENC_FLAT; b.position_count = g; b.dictionary_size = 0; b.ids = nullptr; b.offsets = nullptr;
-            if (outTypes[c] == PG_TYPE_VARCHAR) {
+            if (outTypes[c] == PG_TYPE_VARCHAR && stateOffsets.count((int) c)) {
+                b.values = place(outBufs[colBufs[c].values].ptr, (size_t) g * 24);
+                b.offsets = (const int32_t*) place(outBufs[stateOffsets[(int) c]].ptr, (size_t) (g + 1) * 4);
+            }
+            else if (outTypes[c] == PG_TYPE_VARCHAR) {
                 int k = (int) c;   // key columns come first
                 b.values = place(outBufs[varcharBytes[k]].ptr, (size_t) totalBytes[k]);
                 b.offsets = (const int32_t*) place(outBufs[varcharOffsets[k]].ptr, (size_t) (g + 1) * 4);
@@ -1302,6 +1413,13 @@ static void planAggregation(const pg_hash_aggregation_config* c, KeyLayout& layo
                 a.val0 = physColumn(K_LO32, ch, mk, false); a.val1 = physColumn(K_HI32, ch, mk, false);
                 a.countCol = physColumn(K_COUNT, ch, mk, mk < 0);
                 break;
+            case PG_AGG_SUM_SHORT_DECIMAL: case PG_AGG_SUM_LONG_DECIMAL:
+                // DecimalSumAggregation: exact 128-bit sums as 32-bit limbs (see K_DEC_*); FINAL reads the serialized states
+                if (final) { a.val0 = physColumn(K_DST_L0, ch, -1, false); a.val1 = physColumn(K_DST_L1, ch, -1, false); a.val2 = physColumn(K_DST_L2, ch, -1, false); a.val3 = physColumn(K_DST_L3, ch, -1, false); }
+                else if (a.spec.function == PG_AGG_SUM_SHORT_DECIMAL) { a.val0 = physColumn(K_LO32, ch, mk, false); a.val1 = physColumn(K_HI32, ch, mk, false); }
+                else { a.val0 = physColumn(K_DEC_L0, ch, mk, false); a.val1 = physColumn(K_DEC_L1, ch, mk, false); a.val2 = physColumn(K_DEC_L2, ch, mk, false); a.val3 = physColumn(K_DEC_L3, ch, mk, false); }
+                a.countCol = physColumn(K_COUNT, ch, final ? -1 : mk, (final ? -1 : mk) < 0);
+                break;
             case PG_AGG_AVG_DOUBLE: case PG_AGG_AVG_BIGINT:
                 a.countExact = true;
                 if (final) { a.val0 = physColumn(K_F64, ch, -1, false); a.countCol = physColumn(K_I64_ADD, ch + 1, -1, false); }
@@ -1319,7 +1437,7 @@ static void planAggregation(const pg_hash_aggregation_config* c, KeyLayout& layo
                 a.countCol = physColumn(K_COUNT, ch, final ? -1 : mk, (final ? -1 : mk) < 0);
                 break;
             }
-            default: throw Error(PG_ERR_UNSUPPORTED, "aggregate function is not on the GPU path (supported: count, sum, avg, min, max over BIGINT/DOUBLE)");
+            default: throw Error(PG_ERR_UNSUPPORTED, "aggregate function is not on the GPU path (supported: count, sum, avg, min, max over BIGINT/DOUBLE, sum over decimals)");
         }
         if (a.spec.function != PG_AGG_COUNT_STAR) PG_CHECK_ARG(ch >= 0, "aggregate needs an input channel");
         aggs.push_back(a);
@@ -1607,10 +1725,18 @@ public:
         for (size_t p = 0; p < phys.size(); p++) {
             if (!phys[p].active) continue;
             AccInput& a = L.acc[na];
-            a.kind = phys[p].kind; a.phys = (int) p; a.values = nullptr; a.nulls = nullptr; a.mask = nullptr; a.maskNulls = nullptr;
+            a.kind = phys[p].kind; a.phys = (int) p; a.values = nullptr; a.nulls = nullptr; a.mask = nullptr; a.maskNulls = nullptr; a.offsets = nullptr;
             if (phys[p].channel >= 0) {
                 const DeviceColumn& vc = colOf(phys[p].channel);
-                if (phys[p].kind != K_COUNT) {
+                if (kindIsDecimal(a.kind)) {
+                    PG_CHECK_ARG(vc.type == PG_TYPE_LONG_DECIMAL && (uintptr_t) vc.values % 16 == 0, "sum(long decimal) needs a 16-byte aligned PG_TYPE_LONG_DECIMAL column");
+                    a.values = (const uint64_t*) vc.values + 2 * begin;
+                }
+                else if (kindIsDecimalState(a.kind)) {
+                    PG_CHECK_ARG(vc.type == PG_TYPE_VARCHAR && vc.offsets, "the FINAL step of sum(decimal) reads VARBINARY states");
+                    a.values = (const uint64_t*) vc.values; a.offsets = vc.offsets + begin;
+                }
+                else if (phys[p].kind != K_COUNT) {
                     PG_CHECK_ARG(typeWidth(vc.type) == 8, "sum / avg inputs must be BIGINT or DOUBLE columns");
                     a.values = (const uint64_t*) vc.values + begin;
                 }
@@ -1632,7 +1758,7 @@ public:
         L.nAccAlloc = (int) phys.size();
         bool aligned = true;
         if (layout.bigintPath) aligned = aligned && ((uintptr_t) L.kp.f[0].values % 16 == 0);
-        for (int c = 0; c < na; c++) if (L.acc[c].values) aligned = aligned && ((uintptr_t) L.acc[c].values % 16 == 0);
+        for (int c = 0; c < na; c++) if (L.acc[c].values && L.acc[c].kind < K_DEC_L0) aligned = aligned && ((uintptr_t) L.acc[c].values % 16 == 0);
         L.vec = aligned ? 1 : 0;
         size_t smem = L.S ? sharedBytes(sharedSlots) : 64;
         int64_t tiles = divUp(n, kAggThreads * RowsPerThread<MV>::value);
@@ -1843,7 +1969,7 @@ public:
         if (g == 0) return;
         std::vector<AggEmit> emits;
         for (auto& a : aggs) {
-            AggEmit e; e.function = a.spec.function; e.val0 = a.val0; e.val1 = a.val1; e.partial = step == PG_STEP_PARTIAL; e.countCol = -1;
+            AggEmit e; e.function = a.spec.function; e.val0 = a.val0; e.val1 = a.val1; e.val2 = a.val2; e.val3 = a.val3; e.partial = step == PG_STEP_PARTIAL; e.countCol = -1;
             if (a.countCol >= 0) e.countCol = phys[a.countCol].active ? a.countCol : (a.countExact ? rowCountCol : -1);
             emits.push_back(e);
         }

@@ -246,6 +246,7 @@ int PageStager::stage(const pg_page* page, const std::vector<int>& channels, std
         int w = typeWidth(b.type);
         bool encoded = b.encoding != PG_ENC_FLAT;
         PG_CHECK_ARG(b.encoding == PG_ENC_FLAT || b.encoding == PG_ENC_DICTIONARY || b.encoding == PG_ENC_RLE, "unknown block encoding");
+        if (encoded && b.type == PG_TYPE_LONG_DECIMAL) throw Error(PG_ERR_UNSUPPORTED, "dictionary / RLE encoded Int128 blocks are not on the GPU path");
         int64_t entries = encoded ? (b.encoding == PG_ENC_RLE ? 1 : b.dictionary_size) : b.position_count;
         const void* dValues = b.values; const uint8_t* dNulls = b.is_null; const int32_t* dOffsets = b.offsets; const int32_t* dIds = b.ids;
         if (host && c.n > 0) {

@@ -15,8 +15,9 @@ import numpy as np
 
 from . import _abi as abi
 
-_NP_DTYPE = {abi.BIGINT: np.int64, abi.DOUBLE: np.float64, abi.INTEGER: np.int32, abi.DATE: np.int32, abi.BOOLEAN: np.int8}
-TYPE_WIDTH = {abi.BIGINT: 8, abi.DOUBLE: 8, abi.INTEGER: 4, abi.DATE: 4, abi.BOOLEAN: 1, abi.VARCHAR: 0}
+_NP_DTYPE = {abi.BIGINT: np.int64, abi.DOUBLE: np.float64, abi.INTEGER: np.int32, abi.DATE: np.int32, abi.BOOLEAN: np.int8,
+             abi.LONG_DECIMAL: np.uint64}     # LONG_DECIMAL: two uint64 per position (low, high | sign << 63)
+TYPE_WIDTH = {abi.BIGINT: 8, abi.DOUBLE: 8, abi.INTEGER: 4, abi.DATE: 4, abi.BOOLEAN: 1, abi.VARCHAR: 0, abi.LONG_DECIMAL: 16}
 
 
 def _ptr(a: Optional[np.ndarray]) -> Optional[int]:
@@ -85,6 +86,23 @@ class Block:
         return Block(abi.VARCHAR, n, data, is_null if is_null.any() else None, offsets)
 
     @staticmethod
+    def from_decimals(values: Sequence[Optional[int]]) -> "Block":
+        """Int128ArrayBlock of unscaled decimal(19..38) values (python ints, None for NULL): UnscaledDecimal128Arithmetic's sign-magnitude
+        layout, low 64 bits then high 63 bits | sign << 63 (UnscaledDecimal128Arithmetic.java:172-180)."""
+        n = len(values)
+        arr = np.zeros(2 * n, dtype=np.uint64)
+        is_null = np.zeros(n, dtype=np.uint8)
+        for i, v in enumerate(values):
+            if v is None:
+                is_null[i] = 1
+                continue
+            m = abs(int(v))
+            assert m < (1 << 127), "magnitude needs 127 bits"
+            arr[2 * i] = m & 0xFFFFFFFFFFFFFFFF
+            arr[2 * i + 1] = (m >> 64) | ((1 << 63) if v < 0 else 0)
+        return Block(abi.LONG_DECIMAL, n, arr, is_null if is_null.any() else None)
+
+    @staticmethod
     def dictionary(dictionary: "Block", ids: np.ndarray) -> "Block":
         ids = np.ascontiguousarray(ids, dtype=np.int32)
         return Block(dictionary.type, int(ids.shape[0]), dictionary.values, dictionary.is_null, dictionary.offsets, ids,
@@ -125,6 +143,10 @@ class Block:
                 out.append(None)
             elif self.type == abi.VARCHAR:
                 out.append(bytes(self.values[self.offsets[q]:self.offsets[q + 1]]))
+            elif self.type == abi.LONG_DECIMAL:
+                low, high = int(self.values[2 * q]), int(self.values[2 * q + 1])
+                m = ((high & 0x7FFFFFFFFFFFFFFF) << 64) | low
+                out.append(-m if high >> 63 else m)
             elif self.type == abi.DOUBLE:
                 out.append(float(self.values[q]))
             elif self.type == abi.BOOLEAN:

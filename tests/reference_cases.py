@@ -7,6 +7,7 @@ Adaptations are stated per case (the GPU join path takes BIGINT/INTEGER/DATE key
 from __future__ import annotations
 
 import numpy as np
+import pytest
 
 from presto_b200 import (
     AGG_AVG_BIGINT, AGG_AVG_DOUBLE, AGG_COUNT_COLUMN, AGG_COUNT_STAR, AGG_SUM_BIGINT, AGG_SUM_DOUBLE, BIGINT, BOOLEAN, DATE, DOUBLE,
@@ -404,7 +405,87 @@ def case_min_max_aggregates(backend):
 
 
 def page_slice(page: Page, begin: int, end: int) -> Page:
-    return Page([Block.from_values(b.type, b.to_pylist()[begin:end]) for b in page.blocks])
+    from presto_b200 import LONG_DECIMAL
+    return Page([Block.from_decimals(b.to_pylist()[begin:end]) if b.type == LONG_DECIMAL else Block.from_values(b.type, b.to_pylist()[begin:end]) for b in page.blocks])
+
+
+def _decimal_state(overflow: int, value: int) -> bytes:
+    """LongDecimalWithOverflowStateSerializer.serialize :37-49: {overflow, low, high | sign << 63} as three little-endian longs."""
+    import struct
+    m = abs(value)
+    return struct.pack("<qQQ", overflow, m & (2**64 - 1), (m >> 64) | ((1 << 63) if value < 0 else 0))
+
+
+def _state_value(state: bytes) -> int:
+    import struct
+    overflow, low, high = struct.unpack("<qQQ", state)
+    m = ((high & (2**63 - 1)) << 64) | low
+    return overflow * 2**127 + (-m if high >> 63 else m)
+
+
+def case_decimal_sum(backend):
+    """sum(decimal) (DecimalSumAggregation.java:145-193): short decimals are unscaled longs, long decimals Int128 values; NULL inputs are
+    skipped, a group without input is NULL; the result is decimal(38): exact python integers here.  SINGLE equals PARTIAL -> FINAL through
+    the VARBINARY states {overflow, low, high} (LongDecimalWithOverflowStateSerializer.java:37-66)."""
+    from presto_b200 import AGG_SUM_LONG_DECIMAL, AGG_SUM_SHORT_DECIMAL, STEP_FINAL, STEP_PARTIAL
+    keys = [1, 2, 1, 3, 2, 1, 3, 4, 4, 4]
+    shorts = [10**18 - 1, -5, 10**18 - 1, None, 7, -(10**18 - 1), None, 2**62, 2**62, 2**62]
+    longs = [10**37, -(10**30), 8 * 10**37, None, 10**30, -3, None, -(10**38 - 1), 10**38 - 1, None]
+    page = Page([Block.from_values(BIGINT, keys), Block.from_values(BIGINT, shorts), Block.from_decimals(longs)])
+    aggs = [Aggregate(AGG_SUM_SHORT_DECIMAL, 1), Aggregate(AGG_SUM_LONG_DECIMAL, 2), Aggregate(AGG_COUNT_STAR)]
+    expected = [(1, 10**18 - 1, 9 * 10**37 - 3, 3), (2, 2, 0, 2), (3, None, None, 2), (4, 3 * 2**62, 0, 3)]
+    op = HashAggregationOperator([BIGINT], [0], aggs, backend=backend)
+    assert rows_of(to_pages(op, [page])) == expected
+    op.close()
+    partials = []
+    for half in (page_slice(page, 0, 4), page_slice(page, 4, 10)):
+        p = HashAggregationOperator([BIGINT], [0], aggs, step=STEP_PARTIAL, backend=backend)
+        out = to_pages(p, [half])
+        for pg in out:      # the intermediate states are what the reference serialises: 24 bytes, the number they denote is the partial sum
+            for row in pg.rows():
+                assert all(s is None or len(s) == 24 for s in row[1:3])
+        partials += out
+        p.close()
+    first = {r[0]: r for r in partials[0].rows()}
+    assert _state_value(first[1][1]) == 2 * (10**18 - 1) and _state_value(first[1][2]) == 9 * 10**37 and first[3][1] is None
+    f = HashAggregationOperator([BIGINT], [0], [Aggregate(a.function, 1 + i) for i, a in enumerate(aggs)], step=STEP_FINAL, backend=backend)
+    assert rows_of(to_pages(f, partials)) == expected
+    f.close()
+
+
+def case_decimal_sum_overflow(backend):
+    """TestDecimalSumAggregation.java:46-127: 2^126 + 2^126 leaves the 127-bit magnitude (overflow = 1, value = 0) and the output throws
+    (testOverflowOnOutput); two such states combine to overflow 1 + value 2^126 (testCombineOverflow); a sum of magnitude >= 10^38 throws
+    too (outputLongDecimal -> throwIfOverflows)."""
+    from presto_b200 import AGG_SUM_LONG_DECIMAL, PrestoException, STEP_FINAL, STEP_PARTIAL
+    two = 2
+    def single(values):
+        op = HashAggregationOperator([BIGINT], [0], [Aggregate(AGG_SUM_LONG_DECIMAL, 1)], backend=backend)
+        try:
+            return rows_of(to_pages(op, [Page([Block.from_values(BIGINT, [7] * len(values)), Block.from_decimals(values)])]))
+        finally:
+            op.close()
+    for values in ([two**126, two**126], [-(two**126), -(two**126)], [9 * 10**37, 10**37], [-(9 * 10**37), -(10**37)]):
+        with pytest.raises(PrestoException) as e:
+            single(values)
+        assert "Decimal overflow" in str(e.value)
+    assert single([9 * 10**37, 10**37 - 1]) == [(7, 10**38 - 1)]
+    # testUnderflowAfterOverflow: the overflow count goes back to 0 and the result is exact
+    assert single([two**126, two**126, two**125, -(two**126), -(two**126), -(two**126)]) == [(7, -(two**125))]
+    # testCombineOverflow through the operators: states (0, 2^125 + 2^126) twice -> FINAL holds overflow 1, value 2^126 -> throws on output
+    p = HashAggregationOperator([BIGINT], [0], [Aggregate(AGG_SUM_LONG_DECIMAL, 1)], step=STEP_PARTIAL, backend=backend)
+    state_pages = to_pages(p, [Page([Block.from_values(BIGINT, [7, 7]), Block.from_decimals([two**125, two**126])])])
+    p.close()
+    assert _state_value(state_pages[0].rows()[0][1]) == 3 * two**125
+    f = HashAggregationOperator([BIGINT], [0], [Aggregate(AGG_SUM_LONG_DECIMAL, 1)], step=STEP_FINAL, backend=backend)
+    with pytest.raises(PrestoException):
+        to_pages(f, state_pages + state_pages)
+    f.close()
+    # a hand-written state with an overflow count that a negative state cancels (FINAL only sees states)
+    f = HashAggregationOperator([BIGINT], [0], [Aggregate(AGG_SUM_LONG_DECIMAL, 1)], step=STEP_FINAL, backend=backend)
+    states = Page([Block.from_values(BIGINT, [7, 7, 7]), Block.from_strings([_decimal_state(1, 5), _decimal_state(-1, -2), None])])
+    assert rows_of(to_pages(f, [states])) == [(7, 3)]
+    f.close()
 
 
 def case_lookup_join_is_blocked_until_the_build_finishes(backend):

@@ -226,3 +226,37 @@ def test_min_max_random(gpu_backend, oracle_backend, groups):
     want = run(oracle_backend, pages, [BIGINT], [0], aggs, expected_groups=16, max_output_rows=1 << 30)
     rows_close(got, want)
     assert [r[:5] for r in got] == [r[:5] for r in want] or all((x == y) or (x != x and y != y) for g, w in zip(got, want) for x, y in zip(g[:5], w[:5]))
+
+
+@pytest.mark.parametrize("groups", [5, 400, 30_000])
+def test_decimal_sums_random(gpu_backend, oracle_backend, groups):
+    """sum(decimal): short (unscaled longs over the whole 18-digit range) and long (Int128, up to 10^36 so that 10^5 rows stay inside
+    decimal(38)) with NULLs, one and three key words; SINGLE and PARTIAL -> FINAL through the serialized states.  Exact integers."""
+    from presto_b200 import AGG_SUM_LONG_DECIMAL, AGG_SUM_SHORT_DECIMAL
+    rng = np.random.default_rng(groups + 17)
+    n = 50_000
+    pages = []
+    for _ in range(3):
+        g = rng.integers(0, groups, n)
+        shorts = rng.integers(-(10**18) + 1, 10**18, n)
+        longs = [int(a) * 10**18 + int(b) for a, b in zip(rng.integers(-(10**17), 10**17, n), rng.integers(0, 10**18, n))]
+        longs = [None if rng.random() < 0.1 else v for v in longs]
+        pages.append(Page([Block.from_numpy(BIGINT, g * 1_000_003), Block.from_numpy(DATE, (g % 2500 + 8000).astype(np.int32)),
+                           Block.from_numpy(BIGINT, shorts, (rng.random(n) < 0.1).astype(np.uint8)), Block.from_decimals(longs)]))
+    aggs = [Aggregate(AGG_SUM_SHORT_DECIMAL, 2), Aggregate(AGG_SUM_LONG_DECIMAL, 3), Aggregate(AGG_COUNT_COLUMN, 3)]
+    for types, channels in (([BIGINT], [0]), ([BIGINT, DATE], [0, 1])):
+        got = run(gpu_backend, pages, types, channels, aggs, expected_groups=64, max_output_rows=1 << 30)
+        want = run(oracle_backend, pages, types, channels, aggs, expected_groups=64, max_output_rows=1 << 30)
+        assert got == want
+        partials = []
+        for half in (pages[:1], pages[1:]):
+            op = HashAggregationOperator(types, channels, aggs, step=STEP_PARTIAL, backend=gpu_backend, expected_groups=64, max_output_rows=1 << 30)
+            partials += to_pages(op, half)
+            op.close()
+        k = len(channels)
+        final_aggs = [Aggregate(AGG_SUM_SHORT_DECIMAL, k), Aggregate(AGG_SUM_LONG_DECIMAL, k + 1), Aggregate(AGG_COUNT_COLUMN, k + 2)]
+        final = run(gpu_backend, partials, types, list(range(k)), final_aggs, step=STEP_FINAL, expected_groups=64, max_output_rows=1 << 30)
+        assert sorted(final, key=repr) == sorted(want, key=repr)
+        # and the oracle's FINAL accepts the GPU's states (the wire format of the intermediate column is the reference's)
+        mixed = run(oracle_backend, partials, types, list(range(k)), final_aggs, step=STEP_FINAL, expected_groups=64, max_output_rows=1 << 30)
+        assert sorted(mixed, key=repr) == sorted(want, key=repr)

@@ -52,6 +52,8 @@ def test_partitioned_output_replicates(gpu_backend): rc.case_partitioned_output_
 @pytest.mark.parametrize("replicate", [False, True])
 def test_partitioned_output_varchar_channels(gpu_backend, replicate): rc.case_partitioned_output_varchar_channels(gpu_backend, 5, replicate)
 def test_min_max_aggregates(gpu_backend): rc.case_min_max_aggregates(gpu_backend)
+def test_decimal_sum(gpu_backend): rc.case_decimal_sum(gpu_backend)
+def test_decimal_sum_overflow(gpu_backend): rc.case_decimal_sum_overflow(gpu_backend)
 def test_lookup_join_is_blocked_until_the_build_finishes(gpu_backend): rc.case_lookup_join_is_blocked_until_the_build_finishes(gpu_backend)
 def test_partitioned_output_double_zero_keys(gpu_backend): rc.case_partitioned_output_double_zero_keys(gpu_backend)
 @pytest.mark.parametrize("partition_count", [1, 2, 8, 64])

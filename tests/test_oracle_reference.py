@@ -111,6 +111,8 @@ def test_partitioned_output_replicates(oracle_backend): rc.case_partitioned_outp
 @pytest.mark.parametrize("replicate", [False, True])
 def test_partitioned_output_varchar_channels(oracle_backend, replicate): rc.case_partitioned_output_varchar_channels(oracle_backend, 5, replicate)
 def test_min_max_aggregates(oracle_backend): rc.case_min_max_aggregates(oracle_backend)
+def test_decimal_sum(oracle_backend): rc.case_decimal_sum(oracle_backend)
+def test_decimal_sum_overflow(oracle_backend): rc.case_decimal_sum_overflow(oracle_backend)
 def test_lookup_join_is_blocked_until_the_build_finishes(oracle_backend): rc.case_lookup_join_is_blocked_until_the_build_finishes(oracle_backend)
 def test_partitioned_output_double_zero_keys(oracle_backend): rc.case_partitioned_output_double_zero_keys(oracle_backend)
 @pytest.mark.parametrize("partition_count", [1, 2, 8, 64])
