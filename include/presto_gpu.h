@@ -309,7 +309,12 @@ int32_t pg_group_by_hash_destroy(pg_group_by_hash* h);
  * ---------------------------------------------------------------------------------------------- */
 typedef struct pg_join_bridge pg_join_bridge;   /* JoinBridgeManager / LookupSourceFactory */
 
-typedef enum { PG_JOIN_INNER = 0, PG_JOIN_PROBE_OUTER = 1 } pg_join_type; /* LookupJoinOperators.JoinType */
+typedef enum {       /* LookupJoinOperators.JoinType (MB/operator/LookupJoinOperators.java:30-36) */
+    PG_JOIN_INNER = 0,
+    PG_JOIN_PROBE_OUTER = 1,
+    PG_JOIN_LOOKUP_OUTER = 2,  /* RIGHT join: the probe behaves like INNER; the bridge tracks visited build positions */
+    PG_JOIN_FULL_OUTER = 3     /* the probe behaves like PROBE_OUTER; the bridge tracks visited build positions */
+} pg_join_type;
 
 int32_t pg_join_bridge_create(int32_t device, pg_join_bridge** out);
 int32_t pg_join_bridge_destroy(pg_join_bridge* b);
@@ -345,6 +350,25 @@ typedef struct pg_lookup_join_config {
 /* Output page = probe output channels followed by build output channels, rows in probe order, matches of one
  * probe row in PositionLinks order (descending build position; PagesHash.java:108-123, ArrayPositionLinks.java:45-50). */
 int32_t pg_lookup_join_create(const pg_lookup_join_config* config, pg_join_bridge* bridge, pg_operator** out);
+
+/* Build-outer joins (RIGHT / FULL OUTER).  OuterLookupSource.java:36-203: every build position a probe appends is marked visited
+ * (appendTo :100-105); LookupOuterOperator.java:109-225 is the SOURCE operator that, once every probe operator is done, emits the
+ * positions nobody visited — ascending build position — as NULL probe channels + the build output channels.
+ *   pg_join_bridge_set_outer                 before the build finishes (PartitionedLookupSourceFactory(outer = true)): the LookupSource keeps
+ *                                            its position-ordered columns and a visited map; LOOKUP_OUTER / FULL_OUTER probes need it
+ *   pg_join_bridge_no_more_probe_operators   the probe OperatorFactory is closed (JoinBridgeManager.probeOperatorFactoryClosed); together
+ *                                            with every probe operator having finished / been destroyed this completes the
+ *                                            outerPositionsFuture: the outer operator stops being blocked
+ *   pg_lookup_outer_create                   needs_input is always false; get_output returns nothing while blocked, then pages of at most
+ *                                            max_output_rows rows; finish() terminates the output (LookupOuterOperator.finish :155-160). */
+typedef struct pg_lookup_outer_config {
+    int32_t n_probe_output_channels;
+    const int32_t* probe_output_types;   /* pg_type of the probe's output channels (all NULL in the output) */
+    pg_operator_options options;
+} pg_lookup_outer_config;
+int32_t pg_join_bridge_set_outer(pg_join_bridge* bridge);
+int32_t pg_join_bridge_no_more_probe_operators(pg_join_bridge* bridge);
+int32_t pg_lookup_outer_create(const pg_lookup_outer_config* config, pg_join_bridge* bridge, pg_operator** out);
 
 /* HashSemiJoinOperator (MB/operator/HashSemiJoinOperator.java:142-192) over the ChannelSet a SetBuilderOperator builds
  * (MB/operator/SetBuilderOperator.java, ChannelSet.java:33-77).  The set is a pg_join_bridge fed by a

@@ -13,6 +13,9 @@ void destroyJoinBridge(JoinBridge* b);
 int64_t joinBridgePositionCount(JoinBridge* b);
 Operator* createHashBuilder(const pg_hash_builder_config* c, JoinBridge* b);
 Operator* createLookupJoin(const pg_lookup_join_config* c, JoinBridge* b);
+Operator* createLookupOuter(const pg_lookup_outer_config* c, JoinBridge* b);
+void joinBridgeSetOuter(JoinBridge* b);
+void joinBridgeNoMoreProbes(JoinBridge* b);
 Operator* createSemiJoin(const pg_semi_join_config* c, JoinBridge* b);
 Operator* createPartitionedOutput(const pg_partitioned_output_config* c);
 Operator* createFilterProject(const pg_filter_project_config* c);
@@ -113,6 +116,9 @@ int32_t or_join_bridge_create(int32_t, void** out) { OR_TRY *out = createJoinBri
 int32_t or_join_bridge_destroy(void* b) { destroyJoinBridge((JoinBridge*) b); return PG_OK; }
 int32_t or_join_bridge_get_position_count(void* b, int64_t* out) { OR_TRY *out = joinBridgePositionCount((JoinBridge*) b); OR_CATCH }
 int32_t or_hash_builder_create(const pg_hash_builder_config* c, void* bridge, void** out) { OR_TRY *out = createHashBuilder(c, (JoinBridge*) bridge); OR_CATCH }
+int32_t or_join_bridge_set_outer(void* b) { OR_TRY joinBridgeSetOuter((JoinBridge*) b); OR_CATCH }
+int32_t or_join_bridge_no_more_probe_operators(void* b) { OR_TRY joinBridgeNoMoreProbes((JoinBridge*) b); OR_CATCH }
+int32_t or_lookup_outer_create(const pg_lookup_outer_config* c, void* bridge, void** out) { OR_TRY *out = createLookupOuter(c, (JoinBridge*) bridge); OR_CATCH }
 int32_t or_lookup_join_create(const pg_lookup_join_config* c, void* bridge, void** out) { OR_TRY *out = createLookupJoin(c, (JoinBridge*) bridge); OR_CATCH }
 int32_t or_hash_semi_join_create(const pg_semi_join_config* c, void* set, void** out) { OR_TRY *out = createSemiJoin(c, (JoinBridge*) set); OR_CATCH }
 int32_t or_partitioned_output_create(const pg_partitioned_output_config* c, void** out) { OR_TRY *out = createPartitionedOutput(c); OR_CATCH }

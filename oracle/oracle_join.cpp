@@ -115,6 +115,12 @@ struct LookupSource {
 
 struct JoinBridge {
     std::unique_ptr<LookupSource> lookupSource;   // set when the build finishes (the future completes)
+    // OuterLookupSource.OuterPositionTracker :165-203 (boolean[] visitedPositions) + the outerPositionsFuture of
+    // PartitionedLookupSourceFactory: complete once the probe factory is closed and every probe operator is done
+    bool outer = false, noMoreProbes = false;
+    int liveProbes = 0;
+    std::vector<uint8_t> visitedPositions;
+    bool outerPositionsReady() const { return lookupSource != nullptr && noMoreProbes && liveProbes == 0; }
 };
 
 struct HashBuilderOperator : Operator {
@@ -152,6 +158,7 @@ struct HashBuilderOperator : Operator {
         finishing = true;
         ls->build();
         stats.group_count = ls->positionCount;
+        if (bridge->outer) bridge->visitedPositions.assign((size_t) ls->positionCount, 0);
         bridge->lookupSource = std::move(ls);
     }
     bool isFinished() override { return finishing; }
@@ -167,9 +174,15 @@ struct LookupJoinOperator : Operator {
     bool hasPending = false;
     OwnedPage pending;
 
+    bool tracked = false;
+    ~LookupJoinOperator() override { if (tracked) bridge->liveProbes--; }
     LookupJoinOperator(const pg_lookup_join_config* c, JoinBridge* b) : bridge(b)
     {
-        joinType = c->join_type;
+        if ((c->join_type == PG_JOIN_LOOKUP_OUTER || c->join_type == PG_JOIN_FULL_OUTER) && !b->outer)
+            throw OracleError(PG_ERR_INVALID_ARGUMENT, "LOOKUP_OUTER / FULL_OUTER joins need an outer bridge");
+        // LookupJoinOperators.java:30-39: the probe of LOOKUP_OUTER joins like INNER, of FULL_OUTER like PROBE_OUTER
+        joinType = (c->join_type == PG_JOIN_PROBE_OUTER || c->join_type == PG_JOIN_FULL_OUTER) ? PG_JOIN_PROBE_OUTER : PG_JOIN_INNER;
+        if (b->outer) { tracked = true; b->liveProbes++; }
         types.assign(c->types, c->types + c->n_channels);
         hashChannels.assign(c->hash_channels, c->hash_channels + c->n_hash_channels);
         outputChannels.assign(c->output_channels, c->output_channels + c->n_output_channels);
@@ -213,6 +226,7 @@ struct LookupJoinOperator : Operator {
                 producedRow = true;
                 for (size_t i = 0; i < nProbeOut; i++) pending.columns[i].appendFrom(probeOut[i], position);
                 for (size_t i = 0; i < ls.outputChannels.size(); i++) pending.columns[nProbeOut + i].appendFrom(ls.channels[ls.outputChannels[i]], joinPosition);
+                if (bridge->outer) bridge->visitedPositions[joinPosition] = 1;     // OuterLookupSource.appendTo :100-105
                 rows++;
                 joinPosition = ls.linksEmpty ? -1 : ls.positionLinks[joinPosition];   // JoinHash.getNextJoinPosition :105-111
             }
@@ -234,8 +248,49 @@ struct LookupJoinOperator : Operator {
         hasPending = false;
         return true;
     }
-    void finish() override { finishing = true; }
+    void finish() override { finishing = true; if (tracked) { tracked = false; bridge->liveProbes--; } }
     bool isFinished() override { return finishing && !hasPending; }
+};
+
+// LookupOuterOperator (MB/operator/LookupOuterOperator.java:109-225) over SharedLookupOuterPositionIterator.appendToNext
+// (OuterLookupSource.java:139-151): unvisited build positions in ascending order, NULL probe channels + build output channels.
+struct LookupOuterOperator : Operator {
+    JoinBridge* bridge;
+    std::vector<int> probeTypes;
+    int64_t currentPosition = 0, maxRows;
+    bool closed = false;
+    LookupOuterOperator(const pg_lookup_outer_config* c, JoinBridge* b) : bridge(b)
+    {
+        if (!b->outer) throw OracleError(PG_ERR_INVALID_ARGUMENT, "the bridge was not created for outer tracking");
+        probeTypes.assign(c->probe_output_types, c->probe_output_types + c->n_probe_output_channels);
+        maxRows = c->options.max_output_rows > 0 ? c->options.max_output_rows : (int64_t(1) << 20);
+    }
+    bool needsInput() override { return false; }
+    void addInput(const pg_page*) override { throw OracleError(PG_ERR_UNSUPPORTED, "LookupOuterOperator is a source operator"); }
+    bool isBlocked() override { return !closed && !bridge->outerPositionsReady(); }
+    void finish() override { closed = true; }
+    bool isFinished() override { return closed; }
+    bool getOutput(OwnedPage& out) override
+    {
+        if (closed || !bridge->outerPositionsReady()) return false;
+        const LookupSource& ls = *bridge->lookupSource;
+        out.columns.clear();
+        for (int t : probeTypes) out.columns.emplace_back(t);
+        for (int oc : ls.outputChannels) out.columns.emplace_back(ls.types[oc]);
+        int64_t rows = 0;
+        while (rows < maxRows && currentPosition < (int64_t) bridge->visitedPositions.size()) {      // pageBuilder.isFull() stands in for maxRows
+            if (!bridge->visitedPositions[currentPosition]) {
+                for (size_t i = 0; i < probeTypes.size(); i++) out.columns[i].appendNull();
+                for (size_t i = 0; i < ls.outputChannels.size(); i++) out.columns[probeTypes.size() + i].appendFrom(ls.channels[ls.outputChannels[i]], currentPosition);
+                rows++;
+            }
+            currentPosition++;
+        }
+        if (currentPosition >= (int64_t) bridge->visitedPositions.size()) closed = true;      // outputPositionsFinished -> close()
+        out.positionCount = rows;
+        stats.output_positions += rows;
+        return rows > 0;
+    }
 };
 
 // HashSemiJoinOperator.addInput (MB/operator/HashSemiJoinOperator.java:142-192).  The reference probes a ChannelSet (a GroupByHash
@@ -300,6 +355,9 @@ JoinBridge* createJoinBridge() { return new JoinBridge(); }
 Operator* createSemiJoin(const pg_semi_join_config* c, JoinBridge* b) { return new SemiJoinOperator(c, b); }
 Operator* createHashBuilder(const pg_hash_builder_config* c, JoinBridge* b) { return new HashBuilderOperator(c, b); }
 Operator* createLookupJoin(const pg_lookup_join_config* c, JoinBridge* b) { return new LookupJoinOperator(c, b); }
+Operator* createLookupOuter(const pg_lookup_outer_config* c, JoinBridge* b) { return new LookupOuterOperator(c, b); }
+void joinBridgeSetOuter(JoinBridge* b) { if (b->lookupSource) throw OracleError(PG_ERR_INVALID_STATE, "the build side has already finished"); b->outer = true; }
+void joinBridgeNoMoreProbes(JoinBridge* b) { b->noMoreProbes = true; }
 int64_t joinBridgePositionCount(JoinBridge* b) { return b->lookupSource ? b->lookupSource->positionCount : -1; }
 void destroyJoinBridge(JoinBridge* b) { delete b; }
 

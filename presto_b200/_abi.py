@@ -39,7 +39,7 @@ AGG_SUM_SHORT_DECIMAL, AGG_SUM_LONG_DECIMAL = 10, 11
 # pg_aggregation_step
 STEP_SINGLE, STEP_PARTIAL, STEP_FINAL = 0, 1, 2
 # pg_join_type
-JOIN_INNER, JOIN_PROBE_OUTER = 0, 1
+JOIN_INNER, JOIN_PROBE_OUTER, JOIN_LOOKUP_OUTER, JOIN_FULL_OUTER = 0, 1, 2, 3
 # pg_expr_op
 EX_INPUT, EX_CONST_BIGINT, EX_CONST_DOUBLE, EX_CONST_BOOLEAN, EX_CONST_NULL = 0, 1, 2, 3, 4
 EX_ADD, EX_SUB, EX_MUL, EX_DIV, EX_NEG = 10, 11, 12, 13, 14
@@ -123,6 +123,10 @@ class pg_lookup_join_config(C.Structure):
         ("n_output_channels", C.c_int32), ("output_channels", _I32P), ("precomputed_hash_channel", C.c_int32),
         ("options", pg_operator_options),
     ]
+
+
+class pg_lookup_outer_config(C.Structure):
+    _fields_ = [("n_probe_output_channels", C.c_int32), ("probe_output_types", _I32P), ("options", pg_operator_options)]
 
 
 class pg_partitioned_output_config(C.Structure):
@@ -213,6 +217,9 @@ class Backend:
         "join_bridge_get_position_count": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64)]),
         "hash_builder_create": (C.c_int32, [C.POINTER(pg_hash_builder_config), C.c_void_p, C.POINTER(C.c_void_p)]),
         "lookup_join_create": (C.c_int32, [C.POINTER(pg_lookup_join_config), C.c_void_p, C.POINTER(C.c_void_p)]),
+        "join_bridge_set_outer": (C.c_int32, [C.c_void_p]),
+        "join_bridge_no_more_probe_operators": (C.c_int32, [C.c_void_p]),
+        "lookup_outer_create": (C.c_int32, [C.POINTER(pg_lookup_outer_config), C.c_void_p, C.POINTER(C.c_void_p)]),
         "hash_semi_join_create": (C.c_int32, [C.POINTER(pg_semi_join_config), C.c_void_p, C.POINTER(C.c_void_p)]),
         "partitioned_output_create": (C.c_int32, [C.POINTER(pg_partitioned_output_config), C.POINTER(C.c_void_p)]),
         "partitioned_output_get_offsets": (C.c_int32, [C.c_void_p, C.c_void_p]),

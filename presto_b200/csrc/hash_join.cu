@@ -128,6 +128,7 @@ struct EmitJoinParams {
     int64_t n;
     int32_t hasDuplicates;
     int32_t nProbe, nBuild;
+    uint8_t* visited;          // OuterLookupSource.appendTo :100-105: positionVisited(position); nullptr when the join is not build-outer
     JoinColumn probe[kMaxJoinColumns];
     JoinColumn build[kMaxJoinColumns];
 };
@@ -157,6 +158,7 @@ __global__ void joinEmitKernel(const __grid_constant__ EmitJoinParams P)
             for (int c = 0; c < P.nProbe; c++) copyValue(P.probe[c], row, o);
             if (pos >= 0) {
                 for (int c = 0; c < P.nBuild; c++) copyValue(P.build[c], pos, o);
+                if (P.visited) P.visited[pos] = 1;
                 pos = P.hasDuplicates ? P.links[pos] : -1;
             }
             else for (int c = 0; c < P.nBuild; c++) writeNull(P.build[c], o);   // LookupJoinPageBuilder.appendNullForBuild
@@ -701,6 +703,7 @@ struct LookupSourceDevice {
     int64_t minKey = 0; uint64_t range = 0;
     DeviceBuffer bitmap, prefix;
     DeviceBuffer payloadRows;      // build OUTPUT columns, row-wise, in key order
+    DeviceBuffer visited;          // outer bridges: one byte per build position, set by the probes' emit kernels (OuterPositionTracker)
     PayloadLayout payload{};
     DenseIndex denseView() const { DenseIndex D{}; D.bitmap = bitmap.as<uint64_t>(); D.prefix = prefix.as<uint32_t>(); D.minKey = minKey; D.range = range; return D; }
 
@@ -720,8 +723,16 @@ struct JoinBridge {
     int device;
     std::mutex mu;
     std::shared_ptr<LookupSourceDevice> lookupSource;   // set when the build finishes (the LookupSourceFactory future completes)
+    // build-outer joins (OuterLookupSource.java:36-203): the lookup source remembers which build positions a probe emitted; the
+    // LookupOuterOperator may read them once every probe operator is done (PartitionedLookupSourceFactory's outerPositionsFuture)
+    bool outer = false, noMoreProbes = false;
+    int liveProbes = 0;
     std::shared_ptr<LookupSourceDevice> get() { std::lock_guard<std::mutex> l(mu); return lookupSource; }
     void set(std::shared_ptr<LookupSourceDevice> ls) { std::lock_guard<std::mutex> l(mu); lookupSource = std::move(ls); }
+    bool isOuter() { std::lock_guard<std::mutex> l(mu); return outer; }
+    void probeOpened() { std::lock_guard<std::mutex> l(mu); liveProbes++; }
+    void probeClosed() { std::lock_guard<std::mutex> l(mu); liveProbes--; }
+    bool outerPositionsReady() { std::lock_guard<std::mutex> l(mu); return lookupSource != nullptr && noMoreProbes && liveProbes == 0; }
 };
 
 static uint32_t nextPow2u(uint64_t v) { uint64_t p = 2; while (p < v) p <<= 1; return (uint32_t) std::min<uint64_t>(p, 1ULL << 31); }
@@ -837,7 +848,12 @@ public:
         if (finishing) return;
         finishing = true;
         const int64_t n = ls->positionCount;
-        if (n > 0 && tryBuildDense()) {
+        if (bridge->isOuter()) {       // the outer operator walks build POSITIONS: keep the position-ordered PagesIndex columns + hash table
+            ls->visited.accounting = &ls->deviceBytes;
+            ls->visited.reserve((size_t) std::max<int64_t>(n, 1));
+            PG_CUDA(cudaMemsetAsync(ls->visited.ptr, 0, (size_t) std::max<int64_t>(n, 1), stream));
+        }
+        if (n > 0 && !bridge->isOuter() && tryBuildDense()) {
             stats.group_count = n;
             stats.device_bytes = ls->deviceBytes;
             bridge->set(ls);
@@ -1042,13 +1058,20 @@ class LookupJoinOp : public Operator {
     std::vector<PinnedBuffer> hostValues, hostNulls;
     std::vector<pg_block> outBlocks;
     int64_t pendingRows = 0;
+    bool trackedByBridge = false;     // counted in bridge->liveProbes until finish() / destruction
 
 public:
+    ~LookupJoinOp() override { if (trackedByBridge) bridge->probeClosed(); }
     LookupJoinOp(const pg_lookup_join_config* c, JoinBridge* b) : Operator(c->options), bridge(b), stager(this)
     {
         PG_CHECK_ARG(b != nullptr, "join bridge is null");
-        PG_CHECK_ARG(c->join_type == PG_JOIN_INNER || c->join_type == PG_JOIN_PROBE_OUTER, "join type not on the GPU path (INNER, PROBE_OUTER)");
-        joinType = c->join_type;
+        PG_CHECK_ARG(c->join_type >= PG_JOIN_INNER && c->join_type <= PG_JOIN_FULL_OUTER, "unknown join type");
+        if ((c->join_type == PG_JOIN_LOOKUP_OUTER || c->join_type == PG_JOIN_FULL_OUTER) && !b->isOuter())
+            throw Error(PG_ERR_INVALID_ARGUMENT, "LOOKUP_OUTER / FULL_OUTER joins need a bridge created for outer tracking (pg_join_bridge_set_outer)");
+        // the probe side of LOOKUP_OUTER behaves like INNER, of FULL_OUTER like PROBE_OUTER (LookupJoinOperators.java: probeOuterJoin / fullOuterJoin)
+        joinType = (c->join_type == PG_JOIN_PROBE_OUTER || c->join_type == PG_JOIN_FULL_OUTER) ? PG_JOIN_PROBE_OUTER : PG_JOIN_INNER;
+        trackedByBridge = b->isOuter();
+        if (trackedByBridge) b->probeOpened();
         types.assign(c->types, c->types + c->n_channels);
         outputChannels.assign(c->output_channels, c->output_channels + c->n_output_channels);
         PG_CHECK_ARG(c->n_output_channels <= kMaxJoinColumns, "too many probe output channels");
@@ -1135,6 +1158,7 @@ public:
         EmitJoinParams E{};
         E.matchHead = matchHead.as<int32_t>(); E.offsets = offsets.as<uint32_t>(); E.links = ls->links.as<int32_t>();
         E.n = n; E.hasDuplicates = ls->hasDuplicates; E.nProbe = (int) outputChannels.size(); E.nBuild = (int) ls->outputChannels.size();
+        E.visited = ls->visited.as<uint8_t>();
         for (size_t i = 0; i < outputChannels.size(); i++) {
             const DeviceColumn& c = colOf(outputChannels[i]);
             JoinColumn& jc = E.probe[i];
@@ -1277,8 +1301,149 @@ public:
         hasPending = false;
         return true;
     }
-    void finish() override { finishing = true; }
+    void finish() override
+    {
+        finishing = true;
+        if (trackedByBridge) { trackedByBridge = false; bridge->probeClosed(); }     // this probe will visit no more positions
+    }
     bool isFinished() override { return finishing && !hasPending; }
+};
+
+// ======================================================================================================================
+// LookupOuterOperator (MB/operator/LookupOuterOperator.java:109-225): the source operator of RIGHT / FULL OUTER joins.  Once every probe
+// operator is done it emits the build positions none of them visited — ascending position (SharedLookupOuterPositionIterator.appendToNext
+// :139-151) — as rows of NULL probe channels + the build output channels.
+// ======================================================================================================================
+__global__ void outerUnvisitedKernel(const uint8_t* visited, int64_t n, uint32_t* flags)
+{
+    for (int64_t p = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; p <= n; p += (int64_t) gridDim.x * blockDim.x) flags[p] = (p < n && !visited[p]) ? 1u : 0u;
+}
+struct OuterEmitParams {
+    const uint8_t* visited; const uint32_t* offsets; int64_t n;
+    int32_t nProbe, nBuild;
+    JoinColumn probe[kMaxJoinColumns];      // dst only: all NULL
+    JoinColumn build[kMaxJoinColumns];
+};
+__global__ void outerEmitKernel(const __grid_constant__ OuterEmitParams P)
+{
+    for (int64_t p = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; p < P.n; p += (int64_t) gridDim.x * blockDim.x) {
+        if (P.visited[p]) continue;
+        const int64_t o = P.offsets[p];
+        for (int c = 0; c < P.nProbe; c++) writeNull(P.probe[c], o);
+        for (int c = 0; c < P.nBuild; c++) copyValue(P.build[c], p, o);
+    }
+}
+
+class LookupOuterOp : public Operator {
+    JoinBridge* bridge;
+    std::vector<int> probeTypes;
+    bool built = false, closed = false;
+    int64_t total = 0, next = 0;
+    std::vector<DeviceBuffer> outValues, outNulls;
+    std::vector<PinnedBuffer> hostValues, hostNulls;
+    std::vector<pg_block> outBlocks, slice;
+    DeviceBuffer flags, offsets, scanTemp;
+
+public:
+    LookupOuterOp(const pg_lookup_outer_config* c, JoinBridge* b) : Operator(c->options), bridge(b)
+    {
+        PG_CHECK_ARG(b != nullptr, "join bridge is null");
+        PG_CHECK_ARG(b->isOuter(), "the bridge was not created for outer tracking (pg_join_bridge_set_outer)");
+        PG_CHECK_ARG(c->n_probe_output_channels >= 0 && c->n_probe_output_channels <= kMaxJoinColumns, "too many probe output channels");
+        probeTypes.assign(c->probe_output_types, c->probe_output_types + c->n_probe_output_channels);
+        for (int t : probeTypes) if (t == PG_TYPE_VARCHAR) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR probe output channels are not on the GPU path");
+    }
+    bool needsInput() override { return false; }
+    void addInput(const pg_page*) override { throw Error(PG_ERR_UNSUPPORTED, "LookupOuterOperator is a source operator"); }    // :171-175
+    bool isBlocked() override { return !closed && !bridge->outerPositionsReady(); }     // the outerPositionsFuture :149-153
+    void finish() override { closed = true; }                                            // :155-160: a source operator just terminates
+    bool isFinished() override { return closed; }
+
+    void build()
+    {
+        built = true;
+        auto ls = bridge->get();
+        const int64_t n = ls->positionCount;
+        if (n == 0) return;
+        PG_CHECK_ARG(n < (int64_t(1) << 31), "build side exceeds 2^31 positions");
+        flags.reserve((size_t) (n + 1) * 4); offsets.reserve((size_t) (n + 1) * 4);
+        const int grid = (int) std::min<int64_t>(divUp(n + 1, 256), numSMs * 16);
+        PG_LAUNCH(this, outerUnvisitedKernel, grid, 256, 0, ls->visited.as<uint8_t>(), n, flags.as<uint32_t>());
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, flags.as<uint32_t>(), offsets.as<uint32_t>(), (int) (n + 1), stream);
+        scanTemp.reserve(tb);
+        cub::DeviceScan::ExclusiveSum(scanTemp.ptr, tb, flags.as<uint32_t>(), offsets.as<uint32_t>(), (int) (n + 1), stream);
+        stats.kernel_launches += 2;
+        uint32_t t = 0;
+        PG_CUDA(cudaMemcpyAsync(&t, offsets.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, stream));
+        PG_CUDA(cudaStreamSynchronize(stream));
+        stats.d2h_bytes += 4;
+        total = t;
+        if (total == 0) return;
+        const size_t nOut = probeTypes.size() + ls->outputChannels.size();
+        outValues.resize(nOut); outNulls.resize(nOut);
+        for (auto& d : outValues) d.accounting = &stats.device_bytes;
+        for (auto& d : outNulls) d.accounting = &stats.device_bytes;
+        outBlocks.assign(nOut, pg_block{});
+        OuterEmitParams E{};
+        E.visited = ls->visited.as<uint8_t>(); E.offsets = offsets.as<uint32_t>(); E.n = n;
+        E.nProbe = (int) probeTypes.size(); E.nBuild = (int) ls->outputChannels.size();
+        std::vector<bool> hasNulls(nOut, false);
+        for (size_t i = 0; i < probeTypes.size(); i++) {
+            JoinColumn& jc = E.probe[i];
+            jc.width = typeWidth(probeTypes[i]); jc.src = nullptr; jc.srcNulls = nullptr;
+            outValues[i].reserve((size_t) total * jc.width); outNulls[i].reserve(total);
+            jc.dst = outValues[i].ptr; jc.dstNulls = outNulls[i].as<uint8_t>();
+            outBlocks[i].type = probeTypes[i]; hasNulls[i] = true;
+        }
+        for (size_t i = 0; i < ls->outputChannels.size(); i++) {
+            const int ch = ls->outputChannels[i];
+            const size_t o = probeTypes.size() + i;
+            JoinColumn& jc = E.build[i];
+            jc.width = typeWidth(ls->types[ch]); jc.src = ls->values[ch].ptr; jc.srcNulls = ls->hasNulls[ch] ? ls->nulls[ch].as<uint8_t>() : nullptr;
+            outValues[o].reserve((size_t) total * jc.width);
+            jc.dst = outValues[o].ptr; jc.dstNulls = nullptr;
+            if (jc.srcNulls) { outNulls[o].reserve(total); jc.dstNulls = outNulls[o].as<uint8_t>(); hasNulls[o] = true; }
+            outBlocks[o].type = ls->types[ch];
+        }
+        PG_LAUNCH(this, outerEmitKernel, grid, 256, 0, E);
+        const bool toHost = options.output_memory == PG_MEM_HOST;
+        if (toHost) { hostValues.resize(nOut); hostNulls.resize(nOut); }
+        for (size_t i = 0; i < nOut; i++) {
+            pg_block& b = outBlocks[i];
+            const size_t vbytes = (size_t) total * typeWidth(b.type);
+            b.encoding = PG_ENC_FLAT; b.position_count = total; b.offsets = nullptr; b.ids = nullptr; b.dictionary_size = 0;
+            if (toHost) {
+                hostValues[i].reserve(std::max<size_t>(vbytes, 16));
+                PG_CUDA(cudaMemcpyAsync(hostValues[i].ptr, outValues[i].ptr, vbytes, cudaMemcpyDeviceToHost, stream));
+                b.values = hostValues[i].ptr; b.is_null = nullptr;
+                stats.d2h_bytes += (int64_t) vbytes;
+                if (hasNulls[i]) { hostNulls[i].reserve(total); PG_CUDA(cudaMemcpyAsync(hostNulls[i].ptr, outNulls[i].ptr, total, cudaMemcpyDeviceToHost, stream)); b.is_null = hostNulls[i].as<uint8_t>(); stats.d2h_bytes += total; }
+            }
+            else { b.values = outValues[i].ptr; b.is_null = hasNulls[i] ? outNulls[i].as<uint8_t>() : nullptr; }
+            stats.output_bytes += (int64_t) vbytes;
+        }
+        PG_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    bool getOutput(pg_page* out) override      // :183-214
+    {
+        if (closed || !bridge->outerPositionsReady()) return false;       // tryGetFutureValue(outerPositionsFuture) == null -> return null
+        if (!built) build();
+        if (next >= total) { closed = true; return false; }
+        const int64_t m = std::min<int64_t>(maxOutputRows(), total - next);
+        slice = outBlocks;
+        for (auto& b : slice) {
+            b.position_count = m;
+            b.values = (const char*) b.values + next * typeWidth(b.type);
+            if (b.is_null) b.is_null += next;
+        }
+        out->position_count = m; out->channel_count = (int32_t) slice.size(); out->memory = options.output_memory; out->blocks = slice.data();
+        next += m;
+        stats.output_positions += m;
+        if (next >= total) closed = true;
+        return true;
+    }
 };
 
 Operator* createLookupJoin(const pg_lookup_join_config* c, JoinBridge* bridge) { return new LookupJoinOp(c, bridge); }
@@ -1465,5 +1630,8 @@ int32_t pg_join_bridge_destroy(pg_join_bridge* b) { J_TRY auto* jb = (pg::JoinBr
 int32_t pg_join_bridge_get_position_count(pg_join_bridge* b, int64_t* out) { J_TRY auto ls = ((pg::JoinBridge*) b)->get(); *out = ls ? ls->positionCount : -1; J_CATCH }
 int32_t pg_hash_builder_create(const pg_hash_builder_config* c, pg_join_bridge* bridge, pg_operator** out) { J_TRY *out = (pg_operator*) new pg::HashBuilderOp(c, (pg::JoinBridge*) bridge); J_CATCH }
 int32_t pg_lookup_join_create(const pg_lookup_join_config* c, pg_join_bridge* bridge, pg_operator** out) { J_TRY *out = (pg_operator*) new pg::LookupJoinOp(c, (pg::JoinBridge*) bridge); J_CATCH }
+int32_t pg_join_bridge_set_outer(pg_join_bridge* b) { J_TRY PG_CHECK_ARG(b != nullptr, "null argument"); auto* jb = (pg::JoinBridge*) b; PG_CHECK_STATE(jb->get() == nullptr, "the build side has already finished"); std::lock_guard<std::mutex> l(jb->mu); jb->outer = true; J_CATCH }
+int32_t pg_join_bridge_no_more_probe_operators(pg_join_bridge* b) { J_TRY PG_CHECK_ARG(b != nullptr, "null argument"); auto* jb = (pg::JoinBridge*) b; std::lock_guard<std::mutex> l(jb->mu); jb->noMoreProbes = true; J_CATCH }
+int32_t pg_lookup_outer_create(const pg_lookup_outer_config* c, pg_join_bridge* bridge, pg_operator** out) { J_TRY PG_CHECK_ARG(c && out, "null argument"); *out = (pg_operator*) new pg::LookupOuterOp(c, (pg::JoinBridge*) bridge); J_CATCH }
 int32_t pg_hash_semi_join_create(const pg_semi_join_config* c, pg_join_bridge* set, pg_operator** out) { J_TRY *out = (pg_operator*) new pg::SemiJoinOp(c, (pg::JoinBridge*) set); J_CATCH }
 }

@@ -227,11 +227,20 @@ class GroupByHash:
 class JoinBridge:
     """JoinBridgeManager / LookupSourceFactory: the hand-off of the finished LookupSource from build to probe."""
 
-    def __init__(self, device: int = 0, backend=None):
+    def __init__(self, device: int = 0, backend=None, outer: bool = False):
+        """``outer``: the build side is an outer side (RIGHT / FULL OUTER): the LookupSource tracks the build positions the probes emit
+        (OuterLookupSource.java:100-105) for a LookupOuterOperator."""
         self._b = backend or _default_backend()
         self._h = C.c_void_p()
         self._b.check(self._b.join_bridge_create(device, C.byref(self._h)))
         self._closed = False
+        if outer:
+            self._b.check(self._b.join_bridge_set_outer(self._h))
+
+    def no_more_probe_operators(self) -> None:
+        """The probe OperatorFactory is closed (JoinBridgeManager.probeOperatorFactoryClosed): once the live probe operators have
+        finished, the LookupOuterOperator is unblocked."""
+        self._b.check(self._b.join_bridge_no_more_probe_operators(self._h))
 
     def get_position_count(self) -> int:
         out = C.c_int64()
@@ -294,6 +303,22 @@ class LookupJoinOperator(Operator):
         cfg, keep, _ = self._config(bridge, types, hash_channels, output_channels, **kwargs)
         handle = C.c_void_p()
         backend.check(backend.lookup_join_create(C.byref(cfg), bridge._h, C.byref(handle)))
+        super().__init__(backend, handle)
+        self._bridge = bridge
+
+
+class LookupOuterOperator(Operator):
+    """LookupOuterOperator.java:109-225: source operator emitting the build positions no probe visited (NULL probe channels + build
+    output channels), unblocked once every probe operator of the (outer) bridge is done."""
+
+    def __init__(self, bridge: JoinBridge, probe_output_types: Sequence[int], *, backend=None, **options):
+        backend = backend or bridge._b
+        cfg = abi.pg_lookup_outer_config()
+        ty = abi.i32_array(probe_output_types)
+        cfg.n_probe_output_channels, cfg.probe_output_types = len(probe_output_types), ty
+        cfg.options = _options(**options)
+        handle = C.c_void_p()
+        backend.check(backend.lookup_outer_create(C.byref(cfg), bridge._h, C.byref(handle)))
         super().__init__(backend, handle)
         self._bridge = bridge
 

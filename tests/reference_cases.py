@@ -327,6 +327,71 @@ def case_probe_outer_join_empty_lookup_source(backend):
     assert to_pages(inner, [Page([create_longs_block(1, 2, None, 3)])]) == []
 
 
+def case_lookup_outer_join_empty_lookup_source(backend):
+    """testLookupOuterJoinWithEmptyLookupSource :1285-1320 (RIGHT join, empty build): the probe produces nothing, and so does the outer
+    operator; testFullOuterJoinWithEmptyLookupSource :1363-1402: every probe row comes out with NULL build columns.  (BIGINT keys for the
+    reference's VARCHAR, like the other join cases.)"""
+    from presto_b200 import JOIN_FULL_OUTER, JOIN_LOOKUP_OUTER, LookupOuterOperator
+    for join_type, expected in ((JOIN_LOOKUP_OUTER, []), (JOIN_FULL_OUTER, [(1, None), (2, None), (None, None), (3, None)])):
+        bridge = JoinBridge(backend=backend, outer=True)
+        builder = HashBuilderOperator(bridge, [BIGINT], [0], [0], backend=backend)
+        assert to_pages(builder, []) == []
+        probe = LookupJoinOperator(bridge, [BIGINT], [0], [0], join_type=join_type, backend=backend)
+        outer = LookupOuterOperator(bridge, [BIGINT], backend=backend)
+        assert rows_of(to_pages(probe, [Page([create_longs_block(1, 2, None, 3)])])) == expected
+        bridge.no_more_probe_operators()
+        assert not outer.is_blocked() and outer.get_output() is None
+        for op in (probe, outer, builder):
+            op.close()
+        bridge.close()
+
+
+def case_lookup_outer_operator(backend):
+    """RIGHT / FULL OUTER joins: LookupOuterOperator.java:183-214 + OuterLookupSource.java:100-151.  Two probe operators share the
+    bridge; the outer operator is blocked (and returns no page) until the probe factory is closed AND both probes finished; then the
+    build rows nobody matched come out in ascending build position with NULL probe channels.  Build keys include a NULL (never matches:
+    stays unvisited) and duplicates (one visit marks only the positions actually emitted)."""
+    from presto_b200 import JOIN_FULL_OUTER, JOIN_LOOKUP_OUTER, LookupOuterOperator
+    build_keys = [5, 7, None, 9, 5, 11, 13]
+    bp = Page([create_longs_block(*build_keys), create_long_sequence_block(100, 107)])
+    for join_type in (JOIN_LOOKUP_OUTER, JOIN_FULL_OUTER):
+        bridge = JoinBridge(backend=backend, outer=True)
+        builder = HashBuilderOperator(bridge, [BIGINT, BIGINT], [0], [0, 1], backend=backend)
+        probes = [LookupJoinOperator(bridge, [BIGINT, BIGINT], [0], [0, 1], join_type=join_type, backend=backend) for _ in range(2)]
+        outer = LookupOuterOperator(bridge, [BIGINT, BIGINT], backend=backend, max_output_rows=2)
+        assert outer.is_blocked() and not outer.needs_input() and outer.get_output() is None
+        to_pages(builder, [bp])
+        assert outer.is_blocked()                       # built, but the probes are still running
+        r0 = rows_of(to_pages(probes[0], [Page([create_longs_block(7, 1, None), create_longs_block(70, 10, 0)])]))
+        if join_type == JOIN_LOOKUP_OUTER:
+            assert r0 == [(7, 70, 7, 101)]
+        else:
+            assert r0 == [(7, 70, 7, 101), (1, 10, None, None), (None, 0, None, None)]
+        bridge.no_more_probe_operators()
+        assert outer.is_blocked() and outer.get_output() is None      # probes[1] has not finished
+        r1 = rows_of(to_pages(probes[1], [Page([create_longs_block(5, 13), create_longs_block(50, 130)])]))
+        assert r1 == [(5, 50, 5, 104), (5, 50, 5, 100), (13, 130, 13, 106)]
+        assert not outer.is_blocked()
+        pages = []
+        while not outer.is_finished():
+            p = outer.get_output()
+            if p is not None:
+                pages.append(p)
+        assert [p.position_count for p in pages] == [2, 1]            # pages of max_output_rows
+        assert rows_of(pages) == [(None, None, None, 102), (None, None, 9, 103), (None, None, 11, 105)]
+        for op in probes + [outer, builder]:
+            op.close()
+        bridge.close()
+    # a LOOKUP_OUTER probe over a bridge without tracking is refused
+    from presto_b200 import PrestoException
+    bridge = JoinBridge(backend=backend)
+    with pytest.raises(PrestoException):
+        LookupJoinOperator(bridge, [BIGINT], [0], [0], join_type=JOIN_LOOKUP_OUTER, backend=backend)
+    with pytest.raises(PrestoException):
+        LookupOuterOperator(bridge, [BIGINT], backend=backend)
+    bridge.close()
+
+
 def case_join_duplicate_chain_order(backend):
     """PagesHash.java:108-123 + ArrayPositionLinks.java:45-50: matches of one probe row come out in DESCENDING build position."""
     build_keys = [5, 7, 5, 9, 5, 7]

@@ -128,3 +128,47 @@ def test_range_partitioned_build_of_the_dense_index(gpu_backend, oracle_backend,
     got = join(gpu_backend, *args)
     want = join(oracle_backend, *args)
     assert len(got) > 0 and got == want
+
+
+@pytest.mark.parametrize("kind", ["dense_unique", "sparse_unique", "duplicates"])
+@pytest.mark.parametrize("full", [False, True], ids=["lookup_outer", "full_outer"])
+def test_build_outer_joins_match_oracle(gpu_backend, oracle_backend, kind, full):
+    """RIGHT / FULL OUTER: two probe operators over one outer bridge, then the LookupOuterOperator's pages — bit-exact vs the oracle,
+    output order included (unvisited build positions ascending).  `dense_unique` keys would pick the bitmap index for an inner join;
+    an outer bridge keeps the position-ordered hash path."""
+    from presto_b200 import JOIN_FULL_OUTER, JOIN_LOOKUP_OUTER, LookupOuterOperator
+    rng = np.random.default_rng(sum(map(ord, kind)) + int(full))
+    keys, nb = build_side(rng, kind, 40_000, BIGINT)
+    knull = (rng.random(nb) < 0.05).astype(np.uint8)
+    pay = rng.random(nb); pnull = (rng.random(nb) < 0.1).astype(np.uint8)
+    cut = nb // 3
+    build_pages = [Page([Block.from_numpy(BIGINT, keys[s], knull[s]), Block.from_numpy(DOUBLE, pay[s], pnull[s])]) for s in (slice(0, cut), slice(cut, nb))]
+    probe_pages = []
+    for _ in range(2):
+        npr = 30_000
+        pk = np.where(rng.random(npr) < 0.5, keys[rng.integers(0, nb // 2, npr)], rng.integers(-1000, 1 << 41, npr))      # half of the build side is never probed
+        probe_pages.append(Page([Block.from_numpy(BIGINT, pk, (rng.random(npr) < 0.05).astype(np.uint8)), Block.from_numpy(INTEGER, rng.integers(0, 100, npr).astype(np.int32))]))
+
+    def run(backend):
+        bridge = JoinBridge(backend=backend, outer=True)
+        builder = HashBuilderOperator(bridge, [BIGINT, DOUBLE], [0], [0, 1], backend=backend)
+        assert to_pages(builder, build_pages) == []
+        jt = JOIN_FULL_OUTER if full else JOIN_LOOKUP_OUTER
+        probes = [LookupJoinOperator(bridge, [BIGINT, INTEGER], [0], [1, 0], join_type=jt, backend=backend) for _ in range(2)]
+        outer = LookupOuterOperator(bridge, [INTEGER, BIGINT], backend=backend, max_output_rows=7000)
+        bridge.no_more_probe_operators()
+        rows = [rows_of(to_pages(op, [p])) for op, p in zip(probes, probe_pages)]
+        assert not outer.is_blocked()
+        pages = []
+        while not outer.is_finished():
+            p = outer.get_output()
+            if p is not None:
+                pages.append(p)
+        rows.append(rows_of(pages))
+        for op in probes + [outer, builder]:
+            op.close()
+        bridge.close()
+        return rows
+    got, want = run(gpu_backend), run(oracle_backend)
+    assert got == want
+    assert len(want[2]) > nb // 3

@@ -43,6 +43,8 @@ def test_probe_outer_join(gpu_backend, probe_hash, build_hash): rc.case_probe_ou
 def test_outer_join_with_null_on_both_sides(gpu_backend, probe_hash, build_hash): rc.case_outer_join_with_null_on_both_sides(gpu_backend, probe_hash, build_hash)
 def test_probe_outer_join_empty_lookup_source(gpu_backend): rc.case_probe_outer_join_empty_lookup_source(gpu_backend)
 def test_join_duplicate_chain_order(gpu_backend): rc.case_join_duplicate_chain_order(gpu_backend)
+def test_lookup_outer_join_empty_lookup_source(gpu_backend): rc.case_lookup_outer_join_empty_lookup_source(gpu_backend)
+def test_lookup_outer_operator(gpu_backend): rc.case_lookup_outer_operator(gpu_backend)
 
 
 @pytest.mark.parametrize("partition_count,nulls,precomputed", [(1, False, False), (4, False, False), (7, True, False), (8, True, True), (256, False, True)])

@@ -102,6 +102,8 @@ def test_probe_outer_join(oracle_backend, probe_hash, build_hash): rc.case_probe
 def test_outer_join_with_null_on_both_sides(oracle_backend, probe_hash, build_hash): rc.case_outer_join_with_null_on_both_sides(oracle_backend, probe_hash, build_hash)
 def test_probe_outer_join_empty_lookup_source(oracle_backend): rc.case_probe_outer_join_empty_lookup_source(oracle_backend)
 def test_join_duplicate_chain_order(oracle_backend): rc.case_join_duplicate_chain_order(oracle_backend)
+def test_lookup_outer_join_empty_lookup_source(oracle_backend): rc.case_lookup_outer_join_empty_lookup_source(oracle_backend)
+def test_lookup_outer_operator(oracle_backend): rc.case_lookup_outer_operator(oracle_backend)
 
 
 @pytest.mark.parametrize("partition_count,nulls,precomputed", [(1, False, False), (4, False, False), (7, True, False), (8, True, True), (256, False, True)])
