@@ -331,6 +331,13 @@ typedef struct pg_hash_builder_config {
     int32_t precomputed_hash_channel;   /* $hashvalue channel or -1 */
     int64_t expected_positions;
     pg_operator_options options;
+    /* JoinFilterFunction (MB/operator/JoinFilterFunction.java; compiled by MB/sql/gen/JoinFilterFunctionCompiler.java:97-250 and handed to
+     * the BUILD side: HashBuilderOperator's filterFunctionFactory -> JoinHash.isJoinPositionEligible :113-118): the non-equi part of the
+     * join condition, a BOOLEAN expression whose inputs are the build pages' channels [0, n_channels) followed by the probe page's
+     * channels (LocalExecutionPlanner.createJoinSourcesLayout); only TRUE keeps a candidate (LookupJoinOperator.joinCurrentPosition
+     * :567-586; a PROBE_OUTER row without an eligible candidate is emitted once with NULL build columns).  Only nodes / filter_node /
+     * n_input_channels / input_types of the pg_filter_project_config (declared further down) are read.  NULL = no filter function. */
+    const struct pg_filter_project_config* filter;
 } pg_hash_builder_config;
 
 int32_t pg_hash_builder_create(const pg_hash_builder_config* config, pg_join_bridge* bridge, pg_operator** out);

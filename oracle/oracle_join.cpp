@@ -113,7 +113,15 @@ struct LookupSource {
     }
 };
 
+// oracle_exchange_project.cpp: the RowExpression interpreter evaluating a JoinFilterFunction
+struct JoinFilterEvaluator;
+JoinFilterEvaluator* createJoinFilter(const pg_filter_project_config* c, int buildChannels);
+void destroyJoinFilter(JoinFilterEvaluator* e);
+bool joinFilterEligible(JoinFilterEvaluator* e, const pg_page* buildThenProbe, int64_t buildPosition, int64_t probePosition);
+
 struct JoinBridge {
+    JoinFilterEvaluator* filter = nullptr;        // JoinHash.filterFunction (handed over by the build side's factory)
+    ~JoinBridge() { if (filter) destroyJoinFilter(filter); }
     std::unique_ptr<LookupSource> lookupSource;   // set when the build finishes (the future completes)
     // OuterLookupSource.OuterPositionTracker :165-203 (boolean[] visitedPositions) + the outerPositionsFuture of
     // PartitionedLookupSourceFactory: complete once the probe factory is closed and every probe operator is done
@@ -136,6 +144,7 @@ struct HashBuilderOperator : Operator {
         ls->hashChannels.assign(c->hash_channels, c->hash_channels + c->n_hash_channels);
         ls->outputChannels.assign(c->output_channels, c->output_channels + c->n_output_channels);
         ls->precomputedHashChannel = c->precomputed_hash_channel;
+        if (c->filter && c->filter->filter_node >= 0) bridge->filter = createJoinFilter(c->filter, c->n_channels);
         for (int hc : ls->hashChannels) {
             int t = ls->types[hc];
             if (t != PG_TYPE_BIGINT && t != PG_TYPE_INTEGER && t != PG_TYPE_DATE) throw OracleError(PG_ERR_UNSUPPORTED, "join key type");
@@ -206,6 +215,14 @@ struct LookupJoinOperator : Operator {
         if (precomputedHashChannel >= 0) hashBlock = BlockView(&page->blocks[precomputedHashChannel]);
         int64_t rows = 0;
         size_t nProbeOut = outputChannels.size();
+        // the filter function's view: build channels, then all probe channels (createJoinSourcesLayout)
+        std::vector<pg_block> filterBlocks;
+        pg_page filterPage{};
+        if (bridge->filter) {
+            for (const Column& c : ls.channels) filterBlocks.push_back(c.asBlock());
+            for (int ch = 0; ch < page->channel_count; ch++) filterBlocks.push_back(page->blocks[ch]);
+            filterPage.blocks = filterBlocks.data(); filterPage.channel_count = (int32_t) filterBlocks.size(); filterPage.position_count = page->position_count;
+        }
         for (int64_t position = 0; position < page->position_count; position++) {   // processProbe :481-505
             // JoinProbe.getCurrentJoinPosition :79-90
             int64_t joinPosition;
@@ -222,7 +239,11 @@ struct LookupJoinOperator : Operator {
                 joinPosition = ls.getAddressIndex(position, probeHash, rawHash);
             }
             bool producedRow = false;
-            while (joinPosition >= 0) {   // joinCurrentPosition :567-586 (no filter function)
+            while (joinPosition >= 0) {   // joinCurrentPosition :567-586
+                if (bridge->filter && !joinFilterEligible(bridge->filter, &filterPage, joinPosition, position)) {   // JoinHash.isJoinPositionEligible :113-118
+                    joinPosition = ls.linksEmpty ? -1 : ls.positionLinks[joinPosition];
+                    continue;
+                }
                 producedRow = true;
                 for (size_t i = 0; i < nProbeOut; i++) pending.columns[i].appendFrom(probeOut[i], position);
                 for (size_t i = 0; i < ls.outputChannels.size(); i++) pending.columns[nProbeOut + i].appendFrom(ls.channels[ls.outputChannels[i]], joinPosition);

@@ -114,6 +114,7 @@ class pg_hash_builder_config(C.Structure):
         ("n_channels", C.c_int32), ("types", _I32P), ("n_hash_channels", C.c_int32), ("hash_channels", _I32P),
         ("n_output_channels", C.c_int32), ("output_channels", _I32P), ("precomputed_hash_channel", C.c_int32),
         ("expected_positions", C.c_int64), ("options", pg_operator_options),
+        ("filter", C.c_void_p),      # const pg_filter_project_config* (the JoinFilterFunction) or NULL
     ]
 
 

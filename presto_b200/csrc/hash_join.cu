@@ -17,6 +17,7 @@
 // writes probe and build columns straight to their final positions — output rows are in probe order with each probe row's
 // matches in chain order, exactly the order LookupJoinOperator emits (pinned by TestHashJoinOperator).
 #include "common.cuh"
+#include "fp_interp.cuh"
 #include "group_table.cuh"
 #include "key_layout.h"
 #include "dense_index.cuh"
@@ -80,6 +81,39 @@ __global__ void joinSortChainsKernel(JoinTable J)
     }
 }
 
+// ---- JoinFilterFunction (MB/operator/JoinFilterFunction.java, MB/sql/gen/JoinFilterFunctionCompiler.java:97-250) --------------------
+// The non-equi part of a join condition: a BOOLEAN RowExpression over the build row at `buildPosition` (inputs [0, nBuildInputs): the
+// build pages' channels) and the probe row at `probePosition` (the remaining inputs: the probe page's channels) — the layout
+// LocalExecutionPlanner.createJoinSourcesLayout gives it.  JoinHash.isJoinPositionEligible :113-118 asks it for every candidate of a
+// chain; only TRUE keeps the match.  Evaluated by the RowExpression interpreter (fp_interp.cuh) inside the probe / emit kernels.
+constexpr int kMaxJoinFilterNodes = 32;
+struct JoinFilterProgram {
+    FpNode nodes[kMaxJoinFilterNodes];
+    FpInput inputs[kMaxInputs];
+    int32_t nNodes, filterNode, nBuildInputs;
+    unsigned int* error;
+};
+__device__ __forceinline__ bool joinPositionEligible(const JoinFilterProgram* F, int64_t buildPosition, int64_t probePosition)
+{
+    uint64_t regs[kMaxJoinFilterNodes];
+    uint32_t nullBits = 0;
+    for (int k = 0; k < F->nNodes; k++) {
+        const FpNode& nd = F->nodes[k];
+        Val x{0, false}, y{0, false}, z{0, false};
+        int64_t row = 0;
+        if (nd.op == PG_EX_INPUT) row = nd.a < F->nBuildInputs ? buildPosition : probePosition;
+        else {
+            if (nd.a >= 0) x = Val{regs[nd.a], (bool) ((nullBits >> nd.a) & 1u)};
+            if (nd.b >= 0) y = Val{regs[nd.b], (bool) ((nullBits >> nd.b) & 1u)};
+            if (nd.c >= 0) z = Val{regs[nd.c], (bool) ((nullBits >> nd.c) & 1u)};
+        }
+        const Val v = evalNodeAt(F->nodes, F->inputs, F->error, nd, row, x, y, z);
+        regs[k] = v.bits;
+        if (v.isNull) nullBits |= 1u << k;
+    }
+    return !((nullBits >> F->filterNode) & 1u) && regs[F->filterNode] != 0;
+}
+
 struct ProbeParams {
     JoinTable J;
     KeyPlan kp;
@@ -89,6 +123,7 @@ struct ProbeParams {
     int32_t* matchHead;       // [n] chain head or -1
     uint32_t* counts;         // [n+1] output rows per probe row
     unsigned long long* total;   // exact 64-bit sum of counts (a skewed join can emit more than 2^32 rows for one probe page)
+    const JoinFilterProgram* filter;   // device memory; nullptr = no filter function
 };
 
 template <int W>
@@ -104,7 +139,11 @@ __global__ void joinProbeKernel(const __grid_constant__ ProbeParams P)
             if (slot >= 0) head = P.J.head[slot];
         }
         uint32_t c = 0;
-        if (head >= 0) {
+        if (head >= 0 && P.filter) {        // LookupJoinOperator.joinCurrentPosition :567-586: only eligible positions produce rows
+            for (int p = head; p >= 0; p = P.hasDuplicates ? P.J.links[p] : -1) c += joinPositionEligible(P.filter, p, row) ? 1u : 0u;
+            if (c == 0 && P.outer) c = 1;
+        }
+        else if (head >= 0) {
             c = 1;
             if (P.hasDuplicates) for (int p = P.J.links[head]; p >= 0; p = P.J.links[p]) c++;
         }
@@ -129,6 +168,7 @@ struct EmitJoinParams {
     int32_t hasDuplicates;
     int32_t nProbe, nBuild;
     uint8_t* visited;          // OuterLookupSource.appendTo :100-105: positionVisited(position); nullptr when the join is not build-outer
+    const JoinFilterProgram* filter;
     JoinColumn probe[kMaxJoinColumns];
     JoinColumn build[kMaxJoinColumns];
 };
@@ -154,6 +194,21 @@ __global__ void joinEmitKernel(const __grid_constant__ EmitJoinParams P)
         const uint32_t begin = P.offsets[row], end = P.offsets[row + 1];
         if (begin == end) continue;
         int pos = P.matchHead[row];
+        if (P.filter) {
+            uint32_t o = begin;
+            for (; pos >= 0 && o < end; pos = P.hasDuplicates ? P.links[pos] : -1) {
+                if (!joinPositionEligible(P.filter, pos, row)) continue;
+                for (int c = 0; c < P.nProbe; c++) copyValue(P.probe[c], row, o);
+                for (int c = 0; c < P.nBuild; c++) copyValue(P.build[c], pos, o);
+                if (P.visited) P.visited[pos] = 1;
+                o++;
+            }
+            if (o == begin) {      // PROBE_OUTER and no eligible position
+                for (int c = 0; c < P.nProbe; c++) copyValue(P.probe[c], row, o);
+                for (int c = 0; c < P.nBuild; c++) writeNull(P.build[c], o);
+            }
+            continue;
+        }
         for (uint32_t o = begin; o < end; o++) {
             for (int c = 0; c < P.nProbe; c++) copyValue(P.probe[c], row, o);
             if (pos >= 0) {
@@ -703,6 +758,9 @@ struct LookupSourceDevice {
     int64_t minKey = 0; uint64_t range = 0;
     DeviceBuffer bitmap, prefix;
     DeviceBuffer payloadRows;      // build OUTPUT columns, row-wise, in key order
+    // JoinFilterFunction handed to the build side (HashBuilderOperator's filterFunctionFactory → JoinHash.filterFunction)
+    std::vector<pg_expr_node> filterNodes; int filterNode = -1; std::vector<int> filterInputTypes; int filterBuildInputs = 0;
+    bool hasFilter() const { return filterNode >= 0; }
     DeviceBuffer visited;          // outer bridges: one byte per build position, set by the probes' emit kernels (OuterPositionTracker)
     PayloadLayout payload{};
     DenseIndex denseView() const { DenseIndex D{}; D.bitmap = bitmap.as<uint64_t>(); D.prefix = prefix.as<uint32_t>(); D.minKey = minKey; D.range = range; return D; }
@@ -781,6 +839,24 @@ public:
             if (ls->types[oc] == PG_TYPE_VARCHAR) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR build output channels are not on the GPU path");
             keep(oc);
         }
+        if (c->filter && c->filter->filter_node >= 0) {
+            const pg_filter_project_config& f = *c->filter;
+            PG_CHECK_ARG(f.n_input_channels >= c->n_channels && f.n_input_channels <= kMaxInputs, "the join filter's inputs are the build channels followed by the probe channels (at most 32)");
+            PG_CHECK_ARG(f.n_nodes >= 1 && f.n_nodes <= kMaxJoinFilterNodes && f.filter_node < f.n_nodes, "join filter: between 1 and 32 expression nodes");
+            ls->filterNodes.assign(f.nodes, f.nodes + f.n_nodes);
+            ls->filterInputTypes.assign(f.input_types, f.input_types + f.n_input_channels);
+            ls->filterNode = f.filter_node; ls->filterBuildInputs = c->n_channels;
+            PG_CHECK_ARG(ls->filterNodes[ls->filterNode].type == PG_TYPE_BOOLEAN, "filter must be BOOLEAN");
+            for (int i = 0; i < f.n_nodes; i++) {
+                const pg_expr_node& n = ls->filterNodes[i];
+                if (n.op == PG_EX_INPUT) {
+                    PG_CHECK_ARG(n.a >= 0 && n.a < f.n_input_channels && ls->filterInputTypes[n.a] == n.type, "join filter: input node does not match its channel");
+                    if (n.type == PG_TYPE_VARCHAR || n.type == PG_TYPE_LONG_DECIMAL) throw Error(PG_ERR_UNSUPPORTED, "join filter inputs are fixed-width channels of at most 8 bytes on the GPU path");
+                    if (n.a < c->n_channels) { PG_CHECK_ARG(ls->types[n.a] == n.type, "join filter: build input type differs from the build channel's"); keep(n.a); }
+                }
+                else for (int o : {n.a, n.b, n.c}) PG_CHECK_ARG(o < i, "expression nodes must be topologically ordered");
+            }
+        }
         ls->values.resize(c->n_channels); ls->nulls.resize(c->n_channels); ls->hasNulls.assign(c->n_channels, false);
         for (auto& v : ls->values) v.accounting = &ls->deviceBytes;
         for (auto& v : ls->nulls) v.accounting = &ls->deviceBytes;
@@ -853,7 +929,7 @@ public:
             ls->visited.reserve((size_t) std::max<int64_t>(n, 1));
             PG_CUDA(cudaMemsetAsync(ls->visited.ptr, 0, (size_t) std::max<int64_t>(n, 1), stream));
         }
-        if (n > 0 && !bridge->isOuter() && tryBuildDense()) {
+        if (n > 0 && !bridge->isOuter() && !ls->hasFilter() && tryBuildDense()) {
             stats.group_count = n;
             stats.device_bytes = ls->deviceBytes;
             bridge->set(ls);
@@ -1059,6 +1135,8 @@ class LookupJoinOp : public Operator {
     std::vector<pg_block> outBlocks;
     int64_t pendingRows = 0;
     bool trackedByBridge = false;     // counted in bridge->liveProbes until finish() / destruction
+    DeviceBuffer filterDev;           // JoinFilterProgram + its error word, rebuilt per page (the probe columns move)
+    bool filterChannelsStaged = false;
 
 public:
     ~LookupJoinOp() override { if (trackedByBridge) bridge->probeClosed(); }
@@ -1106,11 +1184,42 @@ public:
         stats.input_positions += n;
         if (n == 0) return;
         PG_CHECK_ARG(n < (int64_t(1) << 31), "probe page exceeds 2^31 positions");
+        if (ls->hasFilter() && !filterChannelsStaged) {      // the filter function reads probe channels of its own
+            PG_CHECK_ARG((int) ls->filterInputTypes.size() == ls->filterBuildInputs + (int) types.size(), "the join filter's inputs are the build channels followed by the probe channels");
+            for (const pg_expr_node& nd : ls->filterNodes)
+                if (nd.op == PG_EX_INPUT && nd.a >= ls->filterBuildInputs) {
+                    const int ch = nd.a - ls->filterBuildInputs;
+                    PG_CHECK_ARG(types[ch] == nd.type, "join filter: probe input type differs from the probe channel's");
+                    if (std::find(staged.begin(), staged.end(), ch) == staged.end()) staged.push_back(ch);
+                }
+            filterChannelsStaged = true;
+        }
         std::vector<DeviceColumn> cols;
         int slot = stager.stage(page, staged, cols);
         auto colOf = [&](int ch) -> const DeviceColumn& { return cols[std::find(staged.begin(), staged.end(), ch) - staged.begin()]; };
 
         if (ls->dense) { addInputDense(*ls, cols, slot, n); return; }
+        const JoinFilterProgram* filterProgram = nullptr;
+        if (ls->hasFilter()) {
+            JoinFilterProgram F{};
+            F.nNodes = (int) ls->filterNodes.size(); F.filterNode = ls->filterNode; F.nBuildInputs = ls->filterBuildInputs;
+            for (int i = 0; i < F.nNodes; i++) {
+                FpNode& d = F.nodes[i]; const pg_expr_node& sn = ls->filterNodes[i];
+                d.op = sn.op; d.type = sn.type; d.a = sn.a; d.b = sn.b; d.c = sn.c; d.isDouble = sn.type == PG_TYPE_DOUBLE;
+                if (sn.op == PG_EX_CONST_DOUBLE) memcpy(&d.immI, &sn.imm_d, 8); else d.immI = sn.imm_i;
+                if (sn.op != PG_EX_INPUT) continue;
+                FpInput& in = F.inputs[sn.a];
+                in.type = sn.type;
+                if (sn.a < F.nBuildInputs) { in.values = ls->values[sn.a].ptr; in.nulls = ls->hasNulls[sn.a] ? ls->nulls[sn.a].as<uint8_t>() : nullptr; }
+                else { const DeviceColumn& c = colOf(sn.a - F.nBuildInputs); in.values = c.values; in.nulls = c.nulls; }
+            }
+            filterDev.accounting = &stats.device_bytes;
+            filterDev.reserve(sizeof(JoinFilterProgram) + 16);
+            F.error = (unsigned int*) ((char*) filterDev.ptr + sizeof(JoinFilterProgram));
+            PG_CUDA(cudaMemsetAsync(F.error, 0, 4, stream));
+            PG_CUDA(cudaMemcpyAsync(filterDev.ptr, &F, sizeof(F), cudaMemcpyHostToDevice, stream));     // (pageable source: staged before the call returns)
+            filterProgram = (const JoinFilterProgram*) filterDev.ptr;
+        }
         // pass 1: probe
         matchHead.reserve((size_t) n * 4); counts.reserve((size_t) (n + 1) * 4); offsets.reserve((size_t) (n + 1) * 4);
         ProbeParams P{};
@@ -1123,6 +1232,7 @@ public:
         exactTotal.reserve(16);
         PG_CUDA(cudaMemsetAsync(exactTotal.ptr, 0, 8, stream));
         P.total = exactTotal.as<unsigned long long>();
+        P.filter = filterProgram;
         const int grid = (int) std::min<int64_t>(divUp(n, 256), numSMs * 16);
         switch (layout.W) {
             case 1: PG_LAUNCH(this, joinProbeKernel<1>, grid, 256, 0, P); break;
@@ -1140,8 +1250,15 @@ public:
         unsigned long long total64 = 0;
         PG_CUDA(cudaMemcpyAsync(&total, offsets.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, stream));
         PG_CUDA(cudaMemcpyAsync(&total64, exactTotal.ptr, 8, cudaMemcpyDeviceToHost, stream));
+        unsigned int filterError = 0;
+        if (filterProgram) PG_CUDA(cudaMemcpyAsync(&filterError, (const char*) filterDev.ptr + sizeof(JoinFilterProgram), 4, cudaMemcpyDeviceToHost, stream));
         PG_CUDA(cudaStreamSynchronize(stream));
         stats.d2h_bytes += 12;
+        if (filterError) {
+            stager.markCompute(slot);
+            if (filterError & FP_ERR_OVERFLOW) throw Error(PG_ERR_NUMERIC_OVERFLOW, "bigint arithmetic overflow in the join filter");
+            throw Error(PG_ERR_INVALID_ARGUMENT, "Division by zero");
+        }
         // the 32-bit scan wraps silently beyond 2^32 output rows; a Page holds < 2^31 positions (the reference bounds every output page
         // through LookupJoinPageBuilder; here the caller has to feed smaller probe pages)
         if (total64 >= (1ULL << 31)) {
@@ -1159,6 +1276,7 @@ public:
         E.matchHead = matchHead.as<int32_t>(); E.offsets = offsets.as<uint32_t>(); E.links = ls->links.as<int32_t>();
         E.n = n; E.hasDuplicates = ls->hasDuplicates; E.nProbe = (int) outputChannels.size(); E.nBuild = (int) ls->outputChannels.size();
         E.visited = ls->visited.as<uint8_t>();
+        E.filter = filterProgram;
         for (size_t i = 0; i < outputChannels.size(); i++) {
             const DeviceColumn& c = colOf(outputChannels[i]);
             JoinColumn& jc = E.probe[i];

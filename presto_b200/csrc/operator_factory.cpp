@@ -82,6 +82,11 @@ struct Plan {
                 builder.types = keep(arena, s.types, s.n_channels);
                 builder.hash_channels = keep(arena, s.hash_channels, s.n_hash_channels);
                 builder.output_channels = keep(arena, s.output_channels, s.n_output_channels);
+                if (s.filter) {      // the join filter function belongs to the build side's plan node
+                    pg_filter_project_config f{};
+                    copyFilterProject(f, *s.filter);
+                    builder.filter = keep(arena, &f, 1);
+                }
                 break;
             }
             case PG_FACTORY_LOOKUP_JOIN: copyJoin(join, *(const pg_lookup_join_config*) config); break;

@@ -260,7 +260,9 @@ class HashBuilderOperator(Operator):
 
     @staticmethod
     def _config(bridge: JoinBridge, types: Sequence[int], hash_channels: Sequence[int], output_channels: Sequence[int], *,
-                precomputed_hash_channel: int = -1, expected_positions: int = 10_000, **options):
+                precomputed_hash_channel: int = -1, expected_positions: int = 10_000, filter_program=None, **options):
+        """``filter_program``: the JoinFilterFunction — an expressions.Program over the build channels followed by the probe channels whose
+        filter is the non-equi part of the join condition (JoinFilterFunctionCompiler; it belongs to the build side like in the reference)."""
         cfg = abi.pg_hash_builder_config()
         ty, hc, oc = abi.i32_array(types), abi.i32_array(hash_channels), abi.i32_array(output_channels)
         cfg.n_channels, cfg.types = len(types), ty
@@ -269,7 +271,18 @@ class HashBuilderOperator(Operator):
         cfg.precomputed_hash_channel = precomputed_hash_channel
         cfg.expected_positions = expected_positions
         cfg.options = _options(**options)
-        return cfg, (ty, hc, oc), bridge
+        fkeep = None
+        if filter_program is not None:
+            assert filter_program.filter >= 0, "the join filter program needs set_filter(...)"
+            fcfg = abi.pg_filter_project_config()
+            it, nodes = abi.i32_array(filter_program.input_types), filter_program.c_nodes()
+            fcfg.n_input_channels, fcfg.input_types = len(filter_program.input_types), it
+            fcfg.n_nodes, fcfg.nodes = len(filter_program.nodes), nodes
+            fcfg.filter_node = filter_program.filter
+            fcfg.n_projections = 0
+            cfg.filter = C.cast(C.pointer(fcfg), C.c_void_p)
+            fkeep = (fcfg, it, nodes)
+        return cfg, (ty, hc, oc, fkeep), bridge
 
     def __init__(self, bridge: JoinBridge, types: Sequence[int], hash_channels: Sequence[int], output_channels: Sequence[int], *, backend=None, **kwargs):
         backend = backend or bridge._b

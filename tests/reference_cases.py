@@ -251,10 +251,11 @@ def case_bigint_sum_overflow(backend):
 # ---------------------------------------------------------------------------------------------------------------------
 # TestHashJoinOperator (VARCHAR join keys of the reference become BIGINT: 'a','b','c' → 1,2,3; "20".."29" → 20..29)
 # ---------------------------------------------------------------------------------------------------------------------
-def _join(backend, build_pages, build_types, probe_pages, probe_types, join_type, build_hash, probe_hash):
+def _join(backend, build_pages, build_types, probe_pages, probe_types, join_type, build_hash, probe_hash, filter_program=None):
     bridge = JoinBridge(backend=backend)
     nb, npr = len(build_types) - (1 if build_hash else 0), len(probe_types) - (1 if probe_hash else 0)
-    builder = HashBuilderOperator(bridge, build_types, [0], list(range(nb)), precomputed_hash_channel=nb if build_hash else -1, backend=backend)
+    builder = HashBuilderOperator(bridge, build_types, [0], list(range(nb)), precomputed_hash_channel=nb if build_hash else -1, backend=backend,
+                                  filter_program=filter_program)
     probe = LookupJoinOperator(bridge, probe_types, [0], list(range(npr)), join_type=join_type,
                                precomputed_hash_channel=npr if probe_hash else -1, backend=backend)
     assert not probe.needs_input(), "probe must wait for the lookup source"
@@ -313,6 +314,78 @@ def case_outer_join_with_null_on_both_sides(backend, probe_hash: bool, build_has
     pp = RowPagesBuilder([BIGINT], probe_hash, [0], backend).row(1).row(2).row(None).row(3)
     rows = _join(backend, bp.build(), bp.get_types(), pp.build(), pp.get_types(), JOIN_PROBE_OUTER, build_hash, probe_hash)
     assert rows == [(1, 1), (1, 1), (2, 2), (None, None), (3, None)]
+
+
+def _join_filter(build_types, probe_types, make):
+    """A JoinFilterFunction: a Program over the build channels followed by the probe channels (createJoinSourcesLayout); `make(build,
+    probe)` gets the two lists of input expressions and returns the BOOLEAN filter."""
+    from presto_b200 import Program
+    prog = Program(list(build_types) + list(probe_types))
+    ins = [prog.input(i) for i in range(len(build_types) + len(probe_types))]
+    prog.set_filter(make(ins[:len(build_types)], ins[len(build_types):]))
+    return prog
+
+
+def case_probe_outer_join_with_filter_function(backend, probe_hash: bool, build_hash: bool):
+    """testProbeOuterJoinWithFilterFunction :879-925 — filter `probe.channel1 >= 1025`: matches below it lose their build side."""
+    bp = RowPagesBuilder([BIGINT, BIGINT, BIGINT], build_hash, [0], backend).add_sequence_page(10, 20, 30, 40)
+    pp = RowPagesBuilder([BIGINT, BIGINT, BIGINT], probe_hash, [0], backend).add_sequence_page(15, 20, 1020, 2020)
+    f = _join_filter(bp.get_types(), pp.get_types(), lambda build, probe: probe[1] >= 1025)
+    rows = _join(backend, bp.build(), bp.get_types(), pp.build(), pp.get_types(), JOIN_PROBE_OUTER, build_hash, probe_hash, filter_program=f)
+    expected = [(20 + i, 1020 + i, 2020 + i, None, None, None) for i in range(5)]
+    expected += [(25 + i, 1025 + i, 2025 + i, 25 + i, 35 + i, 45 + i) for i in range(5)]
+    expected += [(30 + i, 1030 + i, 2030 + i, None, None, None) for i in range(5)]
+    assert rows == expected
+    # the same filter on an INNER join keeps the five eligible matches only
+    rows = _join(backend, bp.build(), bp.get_types(), pp.build(), pp.get_types(), JOIN_INNER, build_hash, probe_hash, filter_program=f)
+    assert rows == [(25 + i, 1025 + i, 2025 + i, 25 + i, 35 + i, 45 + i) for i in range(5)]
+
+
+def case_outer_join_with_nulls_and_filter_function(backend, probe_hash: bool, build_hash: bool):
+    """testOuterJoinWithNullProbeAndFilterFunction :970-1011, ...NullBuild... :1056-1098, ...NullOnBothSides... :1143-1187: the filter
+    `probe.key = 'a'` (here: = 1) on top of the NULL-key rules; b -> 2, c -> 3."""
+    def f(bt, pt):
+        return _join_filter(bt, pt, lambda build, probe: probe[0] == 1)
+    bp = RowPagesBuilder([BIGINT], build_hash, [0], backend).row(1).row(2).row(3)
+    pp = RowPagesBuilder([BIGINT], probe_hash, [0], backend).row(1).row(None).row(None).row(1).row(2)
+    rows = _join(backend, bp.build(), bp.get_types(), pp.build(), pp.get_types(), JOIN_PROBE_OUTER, build_hash, probe_hash, filter_program=f(bp.get_types(), pp.get_types()))
+    assert rows == [(1, 1), (None, None), (None, None), (1, 1), (2, None)]
+    bp = RowPagesBuilder([BIGINT], build_hash, [0], backend).row(1).row(None).row(None).row(1).row(2)
+    pp = RowPagesBuilder([BIGINT], probe_hash, [0], backend).row(1).row(2).row(3)
+    rows = _join(backend, bp.build(), bp.get_types(), pp.build(), pp.get_types(), JOIN_PROBE_OUTER, build_hash, probe_hash, filter_program=f(bp.get_types(), pp.get_types()))
+    assert rows == [(1, 1), (1, 1), (2, None), (3, None)]
+    pp = RowPagesBuilder([BIGINT], probe_hash, [0], backend).row(1).row(2).row(None).row(3)
+    rows = _join(backend, bp.build(), bp.get_types(), pp.build(), pp.get_types(), JOIN_PROBE_OUTER, build_hash, probe_hash, filter_program=f(bp.get_types(), pp.get_types()))
+    assert rows == [(1, 1), (1, 1), (2, None), (None, None), (3, None)]
+
+
+def case_join_filter_over_both_sides(backend):
+    """A filter reading BOTH rows (the reference's own tests only look at the probe row): build.payload + 5 < probe.payload * 2.0 over
+    duplicate chains, NULL payloads (NULL filter result = not eligible) — expectation from the definition of the join."""
+    build_keys = [5, 7, 5, 9, 5, 7]
+    build_pay = [10, 11, None, 13, 14, 15]
+    probe_keys = [7, 5, 1, 9, 5]
+    probe_pay = [9.0, 8.0, 1.0, None, 10.0]
+    bp = Page([create_longs_block(*build_keys), create_longs_block(*build_pay)])
+    pp = Page([create_longs_block(*probe_keys), Block.from_values(DOUBLE, probe_pay)])
+    f = _join_filter([BIGINT, BIGINT], [BIGINT, DOUBLE], lambda build, probe: (build[1] + 5) < probe[1] * 2.0)
+    def expect(outer):
+        rows = []
+        for pk, pv in zip(probe_keys, probe_pay):
+            n = 0
+            for pos in reversed(range(len(build_keys))):      # PositionLinks order: descending build position
+                if build_keys[pos] == pk and build_pay[pos] is not None and pv is not None and build_pay[pos] + 5 < pv * 2.0:
+                    rows.append((pk, pv, build_pay[pos])); n += 1
+            if n == 0 and outer:
+                rows.append((pk, pv, None))
+        return rows
+    for jt in (JOIN_INNER, JOIN_PROBE_OUTER):
+        bridge = JoinBridge(backend=backend)
+        builder = HashBuilderOperator(bridge, [BIGINT, BIGINT], [0], [1], backend=backend, filter_program=f)
+        to_pages(builder, [bp])
+        probe = LookupJoinOperator(bridge, [BIGINT, DOUBLE], [0], [0, 1], join_type=jt, backend=backend)
+        assert rows_of(to_pages(probe, [pp])) == expect(jt == JOIN_PROBE_OUTER)
+        probe.close(); builder.close(); bridge.close()
 
 
 def case_probe_outer_join_empty_lookup_source(backend):

@@ -171,4 +171,4 @@ def test_build_outer_joins_match_oracle(gpu_backend, oracle_backend, kind, full)
         return rows
     got, want = run(gpu_backend), run(oracle_backend)
     assert got == want
-    assert len(want[2]) > nb // 3
+    assert len(want[2]) > nb // 8
