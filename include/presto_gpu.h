@@ -336,7 +336,7 @@ typedef struct pg_hash_builder_config {
      * join condition, a BOOLEAN expression whose inputs are the build pages' channels [0, n_channels) followed by the probe page's
      * channels (LocalExecutionPlanner.createJoinSourcesLayout); only TRUE keeps a candidate (LookupJoinOperator.joinCurrentPosition
      * :567-586; a PROBE_OUTER row without an eligible candidate is emitted once with NULL build columns).  Only nodes / filter_node /
-     * n_input_channels / input_types of the pg_filter_project_config (declared further down) are read.  NULL = no filter function. */
+     * n_input_channels / input_types of the filter's pg_filter_project_config, declared further down, are read.  NULL = no filter function. */
     const struct pg_filter_project_config* filter;
 } pg_hash_builder_config;
 

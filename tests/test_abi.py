@@ -35,7 +35,7 @@ def test_struct_layouts_match_header(tmp_path):
     structs = ["pg_block", "pg_page", "pg_operator_stats", "pg_operator_options", "pg_aggregate", "pg_hash_aggregation_config",
                "pg_group_by_hash_config", "pg_hash_builder_config", "pg_lookup_join_config", "pg_partitioned_output_config",
                "pg_expr_node", "pg_filter_project_config", "pg_fused_aggregation_config", "pg_fused_page_config", "pg_semi_join_config",
-               "pg_pages_serde_config"]
+               "pg_pages_serde_config", "pg_lookup_outer_config"]
     src = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for s in structs:
         cls = getattr(abi, s)
