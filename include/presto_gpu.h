@@ -591,7 +591,8 @@ typedef struct pg_pages_serde_config {
 int64_t pg_hash_crc32_chunked(const void* data, size_t len, size_t chunk);
 int32_t pg_pages_serde_create(const pg_pages_serde_config* config, pg_pages_serde** out);
 /* serialize(Page) + writeSerializedPage.  FLAT blocks → LONG_ARRAY / INT_ARRAY / BYTE_ARRAY / VARIABLE_WIDTH, RLE blocks → RLE,
- * DICTIONARY blocks are written flat (the reference writes the compacted dictionary; a reader sees the same rows).
+ * DICTIONARY blocks -> DICTIONARY of the compacted dictionary (DictionaryBlockEncoding.writeBlock :34-54 over DictionaryBlock.compact
+ * :584-628: referenced entries in order of first reference, remapped ids) + a per-dictionary instance id.
  * *bytes (in options.output_memory) stays valid until the next call on this serde. */
 int32_t pg_pages_serde_serialize(pg_pages_serde* serde, const pg_page* page, const uint8_t** bytes, int64_t* size);
 /* readSerializedPage + deserialize.  `memory` = where `bytes` live; `types` gives the SQL type of every channel (the wire only

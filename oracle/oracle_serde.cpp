@@ -100,26 +100,48 @@ static void writeBlock(Writer& w, const pg_block& b)
         writeFlat(w, b.type, 1, b.values, b.is_null, b.offsets);
         return;
     }
-    if (b.encoding == PG_ENC_DICTIONARY) {   // written flat (header: DICTIONARY inputs are flattened; same rows for a reader)
-        const int64_t n = b.position_count;
-        std::vector<uint8_t> nulls; bool any = false;
-        if (b.is_null) { nulls.resize(n); for (int64_t p = 0; p < n; p++) { nulls[p] = b.is_null[b.ids[p]]; any |= nulls[p] != 0; } }
-        if (b.type == PG_TYPE_VARCHAR) {
-            std::vector<int32_t> off(n + 1, 0); std::vector<uint8_t> bytes;
-            for (int64_t p = 0; p < n; p++) {
-                const int32_t o = b.offsets[b.ids[p]], len = b.offsets[b.ids[p] + 1] - o;
-                bytes.insert(bytes.end(), (const uint8_t*) b.values + o, (const uint8_t*) b.values + o + len);
-                off[p + 1] = off[p] + len;
+    if (b.encoding == PG_ENC_DICTIONARY) {
+        // DictionaryBlockEncoding.writeBlock :34-54: the dictionary is compacted first (DictionaryBlock.compact :584-628: referenced
+        // entries only, renumbered in order of first reference; untouched when every entry is referenced), then position count, the
+        // dictionary block, the ids, the dictionary instance id (DictionaryId.randomDictionaryId :29-32: this node's UUID + a sequence)
+        const int64_t n = b.position_count, dictSize = b.dictionary_size;
+        std::vector<int32_t> remap((size_t) dictSize, -1), keep, ids((size_t) n);
+        for (int64_t p = 0; p < n; p++) {
+            const int32_t id = b.ids[p];
+            if (id < 0 || id >= dictSize) throw OracleError(PG_ERR_INVALID_ARGUMENT, "reference to a non-existent key");
+            if (remap[id] == -1) { remap[id] = (int32_t) keep.size(); keep.push_back(id); }
+        }
+        w.name("DICTIONARY");
+        w.i32((int32_t) n);
+        if ((int64_t) keep.size() == dictSize) {
+            writeFlat(w, b.type, dictSize, b.values, b.is_null, b.offsets);
+            for (int64_t p = 0; p < n; p++) ids[p] = b.ids[p];
+        }
+        else {      // dictionary.copyPositions(dictionaryPositionsToCopy)
+            const int64_t m = (int64_t) keep.size();
+            std::vector<uint8_t> nulls;
+            if (b.is_null) { nulls.resize((size_t) m + 1); for (int64_t k = 0; k < m; k++) nulls[k] = b.is_null[keep[k]]; }     // (+1: a null array exists even for 0 entries)
+            if (b.type == PG_TYPE_VARCHAR) {
+                std::vector<int32_t> off((size_t) m + 1, 0); std::vector<uint8_t> bytes;
+                for (int64_t k = 0; k < m; k++) {
+                    const int32_t o = b.offsets[keep[k]], len = b.offsets[keep[k] + 1] - o;
+                    bytes.insert(bytes.end(), (const uint8_t*) b.values + o, (const uint8_t*) b.values + o + len);
+                    off[k + 1] = off[k] + len;
+                }
+                writeFlat(w, b.type, m, bytes.data(), b.is_null ? nulls.data() : nullptr, off.data());
             }
-            writeFlat(w, b.type, n, bytes.data(), b.is_null ? nulls.data() : nullptr, off.data());
+            else {
+                const int width = typeWidth(b.type);
+                std::vector<uint8_t> vals((size_t) m * width);
+                for (int64_t k = 0; k < m; k++) memcpy(&vals[(size_t) k * width], (const uint8_t*) b.values + (size_t) keep[k] * width, width);
+                writeFlat(w, b.type, m, vals.data(), b.is_null ? nulls.data() : nullptr, nullptr);
+            }
+            for (int64_t p = 0; p < n; p++) ids[p] = remap[b.ids[p]];
         }
-        else {
-            const int width = typeWidth(b.type);
-            std::vector<uint8_t> vals((size_t) n * width);
-            for (int64_t p = 0; p < n; p++) memcpy(&vals[(size_t) p * width], (const uint8_t*) b.values + (size_t) b.ids[p] * width, width);
-            writeFlat(w, b.type, n, vals.data(), b.is_null ? nulls.data() : nullptr, nullptr);
-        }
-        (void) any;
+        w.bytes(ids.data(), (size_t) n * 4);
+        static const uint64_t nodeId[2] = {0x6f7261636c652d6eULL, 0x6f64652d69640000ULL};     // "oracle-node-id": one per process, like the JVM's random UUID
+        static int64_t sequence = 0;
+        w.i64((int64_t) nodeId[0]); w.i64((int64_t) nodeId[1]); w.i64(sequence++);
         return;
     }
     writeFlat(w, b.type, b.position_count, b.values, b.is_null, b.offsets);

@@ -4,7 +4,7 @@
 //   SPI/PagesSerde.java:67-156          serialize / deserialize / wrapSlice (no compressor, no cipher)
 //   SPI/PagesSerdeUtil.java:45-120      writeRawPage / readRawPage, page metadata (21 bytes), CRC32 checksum
 //   PC/{LongArray,IntArray,ByteArray}BlockEncoding.java, PC/VariableWidthBlockEncoding.java:35-75, PC/RunLengthBlockEncoding.java:30-55,
-//   PC/DictionaryBlockEncoding.java:57-80 (read side), PC/EncoderUtil.java:31-100 (null bits, MSB first)
+//   PC/DictionaryBlockEncoding.java:34-80 (write: the compacted dictionary, DictionaryBlock.java:584-628; read), PC/EncoderUtil.java:31-100 (null bits, MSB first)
 //
 // The wire is a byte stream without alignment: a LONG_ARRAY's values typically start at offset 44.  Everything that touches it goes
 // through one primitive, copyBytesKernel, that moves a byte range between arbitrarily aligned addresses with aligned 16-byte stores
@@ -15,7 +15,11 @@
 #include "common.cuh"
 #include "crc32_host.h"
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
+#include <atomic>
 #include <cstring>
+#include <memory>
+#include <random>
 #include <string>
 
 namespace pg {
@@ -129,6 +133,44 @@ __global__ void __launch_bounds__(128) crcChunksKernel(const uint8_t* __restrict
     }
 }
 
+// ---- DictionaryBlock.compact (PC/block/DictionaryBlock.java:584-628) on the device: the referenced dictionary entries, renumbered in
+// order of first reference ---------------------------------------------------------------------------------------------------------
+__global__ void dictFillKernel(uint32_t* p, uint32_t v, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void dictFirstUseKernel(const int32_t* __restrict__ ids, int64_t n, int64_t dictSize, uint32_t* firstUse, unsigned int* flags /* [0]=bad id */)
+{
+    for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {
+        const int32_t id = ids[i];
+        if (id < 0 || id >= dictSize) { atomicOr(flags, 1u); continue; }
+        if ((uint32_t) i < firstUse[id]) atomicMin(&firstUse[id], (uint32_t) i);
+    }
+}
+__global__ void dictCountUsedKernel(const uint32_t* firstUse, int64_t dictSize, unsigned int* used, uint32_t* iota)
+{
+    unsigned int mine = 0;
+    for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < dictSize; i += (int64_t) gridDim.x * blockDim.x) { mine += firstUse[i] != 0xFFFFFFFFu; iota[i] = (uint32_t) i; }
+    if (mine) atomicAdd(used, mine);
+}
+__global__ void dictRemapKernel(const uint32_t* order, int64_t used, int32_t* remap)
+{
+    for (int64_t r = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; r < used; r += (int64_t) gridDim.x * blockDim.x) remap[order[r]] = (int32_t) r;
+}
+__global__ void dictApplyRemapKernel(const int32_t* __restrict__ ids, int64_t n, const int32_t* __restrict__ remap, int32_t* __restrict__ out)
+{
+    for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) out[i] = remap[ids[i]];
+}
+
+// DictionaryId.randomDictionaryId (PC/block/DictionaryId.java:29-32): this process's random node id + a sequence number; a reader keys
+// its per-dictionary caches on it, so every written dictionary gets its own
+static void nextDictionaryId(int64_t (&id)[3])
+{
+    static const std::pair<int64_t, int64_t> node = [] { std::random_device rd; auto r = [&] { return ((uint64_t) rd() << 32) | rd(); }; return std::make_pair((int64_t) r(), (int64_t) r()); }();
+    static std::atomic<int64_t> sequence{0};
+    id[0] = node.first; id[1] = node.second; id[2] = sequence.fetch_add(1);
+}
+
 // ---- the serde -----------------------------------------------------------------------------------------------------------------
 static const char* flatEncodingName(int type)
 {
@@ -231,8 +273,17 @@ public:
     }
 
     // ================================================================== serialize ==================================================================
+    struct ChannelPlan;
+    std::vector<std::unique_ptr<PageStager>> dictStagers;      // staging areas of the dictionaries of one call
+
+    // DictionaryBlockEncoding.writeBlock :34-54 writes dictionaryBlock.compact(): bring ids + dictionary to the device, find the
+    // referenced entries and their order of first reference, renumber.  Leaves the (compacted) dictionary in P.values / nulls /
+    // offsets (P.n entries) and the ids to write in P.ids.
+    void planDictionary(const pg_page* page, int c, ChannelPlan& P);
+
     struct ChannelPlan {
         bool rle = false; int32_t run = 0;          // RLE: run length; the value block is planned like a 1-row flat block
+        bool dict = false; const int32_t* ids = nullptr; int64_t idsAt = 0;     // DICTIONARY: `run` = position count, the (compacted) dictionary is planned like a flat block of n entries
         int type = 0; int width = 0; int64_t n = 0;
         const void* values = nullptr; const uint8_t* nulls = nullptr; const int32_t* offsets = nullptr;     // device
         bool mayHaveNull = false;                   // Block.mayHaveNull(): a null map exists (even for 0 rows)
@@ -242,6 +293,7 @@ public:
 
     void serialize(const pg_page* page, const uint8_t** bytes, int64_t* size)
     {
+        dictStagers.clear();
         const int64_t n = page->position_count;
         PG_CHECK_ARG(n >= 0 && n < (int64_t(1) << 31), "page exceeds 2^31 positions");
         const int nch = page->channel_count;
@@ -256,6 +308,7 @@ public:
             const pg_block& b = page->blocks[c];
             plan[c].type = b.type; plan[c].width = typeWidth(b.type); plan[c].mayHaveNull = b.is_null != nullptr;
             if (b.encoding == PG_ENC_RLE) { plan[c].rle = true; plan[c].run = (int32_t) b.position_count; plan[c].n = 1; }
+            else if (b.encoding == PG_ENC_DICTIONARY) { plan[c].dict = true; plan[c].run = (int32_t) n; plan[c].n = b.dictionary_size; }
             else { plan[c].n = n; flatOf[c] = (int) flatBlocks.size(); flatBlocks.push_back(b); }
         }
         std::vector<DeviceColumn> cols; int slot = -1;
@@ -286,6 +339,7 @@ public:
                 else P.values = upload(b.values, (size_t) P.width);
                 P.nulls = b.is_null ? (const uint8_t*) upload(b.is_null, 1) : nullptr;
             }
+            else if (P.dict) planDictionary(page, c, P);
             else if (n > 0) { const DeviceColumn& dc = cols[(size_t) flatOf[c]]; P.values = dc.values; P.nulls = dc.nulls; P.offsets = dc.offsets; }
         }
         // ---- sizes that depend on the data: non-null counts, varchar byte totals ----
@@ -315,12 +369,14 @@ public:
             ChannelPlan& P = plan[c];
             P.fixedAt = at;
             if (P.rle) at += 4 + 3 + 4;                            // "RLE", run length
+            if (P.dict) at += 4 + 10 + 4;                          // "DICTIONARY", position count
             at += 4 + (int64_t) strlen(flatEncodingName(P.type)) + 4;   // name, position count
             if (P.type == PG_TYPE_VARCHAR) { P.endsAt = at; at += 4 * P.n; }
             P.nullFlagAt = at; at += 1;
             P.bitsAt = at; if (P.mayHaveNull) at += (P.n + 7) / 8;
             if (P.type == PG_TYPE_VARCHAR) { P.totalAt = at; at += 4; P.valuesAt = at; at += P.varcharBytes; }
             else { P.valuesAt = at; at += P.nonNull * P.width; }
+            if (P.dict) { P.idsAt = at; at += 4 * (int64_t) P.run + 24; }     // ids, dictionary instance id
             P.end = at;
         }
         const int64_t total = at;
@@ -337,12 +393,17 @@ public:
         };
         auto le32 = [](int32_t v) { return std::string((const char*) &v, 4); };
         auto named = [&](const char* s) { return le32((int32_t) strlen(s)) + s; };
-        hostScratch.reserve((size_t) (64 + 96 * nch));
+        hostScratch.reserve((size_t) (64 + 160 * nch));
         hs = hostScratch.as<uint8_t>();
         for (int c = 0; c < nch; c++) {
             const ChannelPlan& P = plan[c];
             std::string head;
             if (P.rle) head += named("RLE") + le32(P.run);
+            if (P.dict) {
+                head += named("DICTIONARY") + le32(P.run);
+                int64_t id[3]; nextDictionaryId(id);
+                patch(P.idsAt + 4 * (int64_t) P.run, std::string((const char*) id, 24));
+            }
             head += named(flatEncodingName(P.type)) + le32((int32_t) P.n);
             patch(P.fixedAt, head);
             patch(P.nullFlagAt, std::string(1, P.mayHaveNull ? '\1' : '\0'));
@@ -351,6 +412,7 @@ public:
         // ---- data ----
         for (int c = 0; c < nch; c++) {
             const ChannelPlan& P = plan[c];
+            if (P.dict) copyBytes(W + P.idsAt, (const uint8_t*) P.ids, 4 * (int64_t) P.run);
             if (P.n == 0) continue;
             if (P.nulls) PG_LAUNCH(this, packNullBitsKernel, gridFor((P.n + 7) / 8), 256, 0, P.nulls, P.n, W + P.bitsAt);
             if (P.type == PG_TYPE_VARCHAR) {
@@ -384,7 +446,7 @@ public:
         }
         else *bytes = W;
         PG_CUDA(cudaStreamSynchronize(stream));
-        temps.clear();
+        temps.clear(); dictStagers.clear();
         *size = total;
     }
 
@@ -548,6 +610,71 @@ public:
         stats.output_positions += positionCount;
     }
 };
+
+void PagesSerde::planDictionary(const pg_page* page, int c, ChannelPlan& P)
+{
+    const pg_block& b = page->blocks[c];
+    const int64_t n = b.position_count, D = b.dictionary_size;
+    PG_CHECK_ARG(D >= 0 && D < (int64_t(1) << 31) && b.ids != nullptr, "DICTIONARY block without ids");
+    const bool host = page->memory == PG_MEM_HOST;
+    // ids on the device
+    const int32_t* ids = b.ids;
+    if (host) {
+        temps.emplace_back(); DeviceBuffer& t = temps.back(); t.reserve(std::max<size_t>((size_t) n * 4, 16));
+        PG_CUDA(cudaMemcpyAsync(t.ptr, b.ids, (size_t) n * 4, cudaMemcpyHostToDevice, stream));
+        stats.h2d_bytes += n * 4;
+        ids = t.as<int32_t>();
+    }
+    // the dictionary itself as a flat column of D entries
+    auto stageFlat = [&](const pg_block& blk, int64_t rows, int memory, DeviceColumn& out) {
+        dictStagers.emplace_back(new PageStager(this));
+        pg_block one = blk; one.position_count = rows;
+        pg_page shadow{}; shadow.position_count = rows; shadow.channel_count = 1; shadow.memory = memory; shadow.blocks = &one;
+        std::vector<DeviceColumn> cols;
+        if (rows > 0) { dictStagers.back()->stage(&shadow, std::vector<int>{0}, cols); out = cols[0]; }
+        else { out = DeviceColumn(); out.type = blk.type; }
+    };
+    pg_block flatDict = b; flatDict.encoding = PG_ENC_FLAT; flatDict.ids = nullptr; flatDict.dictionary_size = 0;
+    DeviceColumn dict;
+    stageFlat(flatDict, D, page->memory, dict);
+    // first reference of every entry
+    temps.emplace_back(); DeviceBuffer& firstUse = temps.back(); firstUse.reserve(std::max<size_t>((size_t) D * 4, 16));
+    temps.emplace_back(); DeviceBuffer& iota = temps.back(); iota.reserve(std::max<size_t>((size_t) D * 4, 16));
+    temps.emplace_back(); DeviceBuffer& flags = temps.back(); flags.reserve(16);
+    PG_CUDA(cudaMemsetAsync(flags.ptr, 0, 8, stream));
+    if (D > 0) PG_LAUNCH(this, dictFillKernel, gridFor(D), 256, 0, firstUse.as<uint32_t>(), 0xFFFFFFFFu, D);
+    PG_LAUNCH(this, dictFirstUseKernel, gridFor(n), 256, 0, ids, n, D, firstUse.as<uint32_t>(), flags.as<unsigned int>());
+    if (D > 0) PG_LAUNCH(this, dictCountUsedKernel, gridFor(D), 256, 0, firstUse.as<uint32_t>(), D, flags.as<unsigned int>() + 1, iota.as<uint32_t>());
+    unsigned int h[2] = {0, 0};
+    PG_CUDA(cudaMemcpyAsync(h, flags.ptr, 8, cudaMemcpyDeviceToHost, stream));
+    PG_CUDA(cudaStreamSynchronize(stream));
+    stats.d2h_bytes += 8;
+    if (h[0]) throw Error(PG_ERR_INVALID_ARGUMENT, "reference to a non-existent key");      // DictionaryBlock.compact :615-617
+    const int64_t used = h[1];
+    P.ids = ids;
+    if (used == D) { P.values = dict.values; P.nulls = dict.nulls; P.offsets = dict.offsets; P.n = D; P.mayHaveNull = b.is_null != nullptr; return; }      // entire dictionary is referenced :607-609
+    // order of first reference → new numbering
+    temps.emplace_back(); DeviceBuffer& keysOut = temps.back(); keysOut.reserve((size_t) D * 4);
+    temps.emplace_back(); DeviceBuffer& order = temps.back(); order.reserve((size_t) D * 4);
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, firstUse.as<uint32_t>(), keysOut.as<uint32_t>(), iota.as<uint32_t>(), order.as<uint32_t>(), (int) D, 0, 32, stream);
+    temps.emplace_back(); DeviceBuffer& sortTemp = temps.back(); sortTemp.reserve(tb);
+    cub::DeviceRadixSort::SortPairs(sortTemp.ptr, tb, firstUse.as<uint32_t>(), keysOut.as<uint32_t>(), iota.as<uint32_t>(), order.as<uint32_t>(), (int) D, 0, 32, stream);
+    stats.kernel_launches += 3;
+    temps.emplace_back(); DeviceBuffer& remap = temps.back(); remap.reserve((size_t) D * 4);
+    temps.emplace_back(); DeviceBuffer& newIds = temps.back(); newIds.reserve(std::max<size_t>((size_t) n * 4, 16));
+    PG_LAUNCH(this, dictRemapKernel, gridFor(used), 256, 0, order.as<uint32_t>(), used, remap.as<int32_t>());
+    PG_LAUNCH(this, dictApplyRemapKernel, gridFor(n), 256, 0, ids, n, remap.as<int32_t>(), newIds.as<int32_t>());
+    P.ids = newIds.as<int32_t>();
+    // dictionary.copyPositions(referenced entries in that order): a DICTIONARY view over the staged dictionary, flattened by the stager
+    pg_block view{};
+    view.type = b.type; view.encoding = PG_ENC_DICTIONARY; view.position_count = used; view.values = dict.values; view.is_null = dict.nulls;
+    view.offsets = dict.offsets; view.ids = (const int32_t*) order.ptr; view.dictionary_size = D;
+    DeviceColumn compacted;
+    stageFlat(view, used, PG_MEM_DEVICE, compacted);
+    P.values = compacted.values; P.nulls = compacted.nulls; P.offsets = compacted.offsets; P.n = used;
+    P.mayHaveNull = b.is_null != nullptr;      // copyPositions keeps a null array when its source has one (LongArrayBlock.copyPositions)
+}
 
 }  // namespace pg
 

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from presto_b200 import BIGINT, DOUBLE, INTEGER, MEM_DEVICE, Block, Page, PagesSerde
-from serde_cases import HEADER, header_of, java_checksum, name, random_page, types_of
+from serde_cases import dictionary_id_ranges, dictionary_pages, same_wire_up_to_dictionary_ids, HEADER, header_of, java_checksum, name, random_page, types_of
 
 pytestmark = pytest.mark.gpu
 
@@ -44,12 +44,29 @@ def test_rle_and_dictionary_channels(gpu_backend, oracle_backend):
     ids = np.array([2, 2, 0, 1, 0], dtype=np.int32)
     page = Page([Block.rle(value, 5), Block.dictionary(dictionary, ids)], 5)
     wire = g.serialize(page)
-    assert (wire == o.serialize(page)).all()
+    assert same_wire_up_to_dictionary_ids(wire, o.serialize(page))
     assert g.deserialize(wire, [DOUBLE, BIGINT]).rows() == page.rows()
     raw = (struct.pack("<i", 1) + name("DICTIONARY") + struct.pack("<i", 5) + name("LONG_ARRAY") + struct.pack("<i", 3) + b"\x01" + bytes([0x40])
            + struct.pack("<qq", 10, 30) + ids.tobytes() + struct.pack("<qqq", 1, 2, 3))
     java_wire = np.frombuffer(struct.pack("<iBiiq", 5, 0, len(raw), len(raw), 0) + raw, dtype=np.uint8)
     assert g.deserialize(java_wire, [BIGINT]).rows() == [(30,), (30,), (10,), (None,), (10,)]
+    g.close(); o.close()
+
+
+@pytest.mark.parametrize("checksum", [False, True])
+def test_dictionary_blocks_are_written_compacted(gpu_backend, oracle_backend, checksum):
+    """DICTIONARY channels: the GPU writer's bytes equal the oracle's (compacted dictionary in order of first reference, remapped ids) up to
+    the dictionary instance ids; both read each other's pages; ids are unique per written dictionary."""
+    g, o = PagesSerde(checksum_enabled=checksum, backend=gpu_backend), PagesSerde(checksum_enabled=checksum, backend=oracle_backend)
+    seen = set()
+    for page in dictionary_pages(np.random.default_rng(11)):
+        wg, wo = g.serialize(page), o.serialize(page)
+        assert same_wire_up_to_dictionary_ids(wg, wo)
+        assert g.deserialize(wo, types_of(page)).rows() == page.rows() == o.deserialize(wg, types_of(page)).rows()
+        for lo, hi in dictionary_id_ranges(wg):
+            ident = wg[lo:hi].tobytes()
+            assert ident not in seen
+            seen.add(ident)
     g.close(); o.close()
 
 

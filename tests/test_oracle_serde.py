@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from presto_b200 import BIGINT, DOUBLE, INTEGER, VARCHAR, Block, Page, PagesSerde
-from serde_cases import HEADER, header_of, java_checksum, name, random_page, types_of
+from serde_cases import dictionary_id_ranges, dictionary_pages, same_wire_up_to_dictionary_ids, HEADER, header_of, java_checksum, name, random_page, types_of
 
 
 @pytest.fixture
@@ -73,7 +73,7 @@ def test_rle_and_dictionary_blocks(serde):
     ids = np.array([2, 2, 0, 1, 0], dtype=np.int32)
     page = Page([Block.rle(value, 5), Block.dictionary(dictionary, ids)], 5)
     wire = serde.serialize(page)
-    assert name("RLE") in wire.tobytes() and name("DICTIONARY") not in wire.tobytes()      # dictionaries are written flat
+    assert name("RLE") in wire.tobytes() and name("DICTIONARY") in wire.tobytes()
     back = serde.deserialize(wire, [DOUBLE, BIGINT])
     assert back.rows() == page.rows() == [(2.5, 30), (2.5, 30), (2.5, 10), (2.5, None), (2.5, 10)]
     # a DICTIONARY block as the Java writer lays it out (DictionaryBlockEncoding.writeBlock :30-52)
@@ -81,6 +81,29 @@ def test_rle_and_dictionary_blocks(serde):
            + struct.pack("<qq", 10, 30) + ids.tobytes() + struct.pack("<qqq", 1, 2, 3))
     wire = np.frombuffer(struct.pack("<iBiiq", 5, 0, len(raw), len(raw), 0) + raw, dtype=np.uint8)
     assert serde.deserialize(wire, [BIGINT]).rows() == [(30,), (30,), (10,), (None,), (10,)]
+    # and that is, up to the dictionary instance id, what the writer produces for the same block (every entry referenced: no compaction)
+    assert same_wire_up_to_dictionary_ids(serde.serialize(Page([Block.dictionary(dictionary, ids)], 5)), wire)
+
+
+def test_dictionary_blocks_are_written_compacted(serde):
+    """DictionaryBlockEncoding.writeBlock :34-54 writes dictionaryBlock.compact() (DictionaryBlock.java:584-628): only referenced entries,
+    renumbered in order of first reference; every written dictionary carries its own instance id."""
+    d = Block.from_numpy(BIGINT, np.array([10, 20, 30]), np.array([0, 1, 0], dtype=np.uint8))
+    wire = serde.serialize(Page([Block.dictionary(d, np.array([2, 2, 2, 1], dtype=np.int32))], 4))
+    raw = (struct.pack("<i", 1) + name("DICTIONARY") + struct.pack("<i", 4) + name("LONG_ARRAY") + struct.pack("<i", 2) + b"\x01" + bytes([0x40])
+           + struct.pack("<q", 30) + np.array([0, 0, 0, 1], dtype=np.int32).tobytes() + struct.pack("<qqq", 0, 0, 0))
+    expected = np.frombuffer(struct.pack("<iBiiq", 4, 0, len(raw), len(raw), 0) + raw, dtype=np.uint8)
+    assert same_wire_up_to_dictionary_ids(wire, expected)
+    rng = np.random.default_rng(11)
+    seen = set()
+    for page in dictionary_pages(rng):
+        wire = serde.serialize(page)
+        back = serde.deserialize(wire, types_of(page))
+        assert back.rows() == page.rows()
+        for lo, hi in dictionary_id_ranges(wire):
+            ident = wire[lo:hi].tobytes()
+            assert ident not in seen
+            seen.add(ident)
 
 
 def test_rejects_what_it_does_not_speak(serde):
