@@ -44,7 +44,8 @@ def test_rle_varchar_key(gpu_backend, oracle_backend):
 def test_serialized_page_of_encoded_varchar(gpu_backend, oracle_backend):
     page = q1_like_pages(np.random.default_rng(6), 1, 10_007)[0]
     g, o = PagesSerde(backend=gpu_backend), PagesSerde(backend=oracle_backend)
+    from serde_cases import same_wire_up_to_dictionary_ids
     wire = g.serialize(page)
-    assert (wire == o.serialize(page)).all()
+    assert same_wire_up_to_dictionary_ids(wire, o.serialize(page))      # DICTIONARY channels carry a per-writer instance id
     assert g.deserialize(wire, [6, 6, DOUBLE]).rows() == page.rows()
     g.close(); o.close()
