@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--cpu-rows", type=int, default=1 << 28, help="rows of the bounded sample the CPU baseline aggregates")
     ap.add_argument("--extra", type=int, default=1, help="also measure other cardinalities and the join (configs[2])")
     ap.add_argument("--extra-scale", type=float, default=0.0, help="size of the extra measurements relative to SF100 (default: rows / 600 037 902)")
+    ap.add_argument("--stream-rows", type=int, default=10_000_000_000, help="(N > 1) rows, all ranks together, streamed page by page through the fused repartition + exchange (configs[4])")
     ap.add_argument("--only", default="", help="comma separated subset of the extra measurements (names of the extra keys)")
     return ap.parse_args()
 
@@ -269,7 +270,7 @@ def run_group_by(torch, backend, page, n_rows, groups_hint, steps, warmup, devic
     return {"ms": float(np.mean(ms)), "kernel_ms": float(np.mean(kms)), "launches": int(launches), "groups": int(groups), "result": result}
 
 
-def run_partitioned_output(torch, backend, device, rows, partitions, steps, warmup, dist=None):
+def run_partitioned_output(torch, backend, device, rows, partitions, steps, warmup, dist=None, stream_rows=0):
     """configs[4] shape: 8 bigint columns, partition on column 0 (InterpretedHashGenerator + HashGenerator.getPartition); with N > 1
     ranks the partition slabs are exchanged with one all-to-all per column over NCCL."""
     from presto_b200 import BIGINT, MEM_DEVICE, PartitionedOutputOperator
@@ -322,9 +323,29 @@ def run_partitioned_output(torch, backend, device, rows, partitions, steps, warm
             if it >= warmup:
                 fms.append(e0.elapsed_time(e1))
         assert got.position_count == received, "fused exchange and all-to-all disagree on the received row count"
-        op.close(); fx.close()
         f_ms = float(np.mean(fms))
         out.update({"fused_scatter_exchange_ms": f_ms, "fused_rows_per_s": rows / (f_ms / 1000), "fused_gbs_per_gpu": 128 * rows / (f_ms / 1000) / 1e9})
+        if stream_rows > 0:
+            # configs[4] as a stream: page after page through ONE operator and ONE exchange until `stream_rows` rows (all ranks together)
+            # have been repartitioned — what a long-running PartitionedOutput stage does; every page's received rows are counted
+            world = dist.get_world_size()
+            pages = max(1, -(-stream_rows // (rows * world)))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier(); torch.cuda.synchronize()
+            e0.record(stream)
+            streamed = 0
+            for _ in range(pages):
+                streamed += fx.exchange(op, page).position_count
+            e1.record(stream)
+            torch.cuda.synchronize(); dist.barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total = torch.tensor([streamed], dtype=torch.int64, device=dev)
+            dist.all_reduce(total)
+            s_ms = float(t[0])
+            out["streamed"] = {"pages_per_rank": int(pages), "rows_all_ranks": int(pages * rows * world), "received_rows_all_ranks": int(total[0]), "ms": s_ms,
+                               "rows_per_s_all_ranks": pages * rows * world / (s_ms / 1000), "rows_per_s_per_gpu": pages * rows / (s_ms / 1000)}
+        op.close(); fx.close()
     return out
 
 
@@ -969,7 +990,7 @@ def main():
     backend.release_cached_memory()
     if world > 1 and args.extra:
         try:
-            extra["partitioned_output_all_to_all"] = run_partitioned_output(torch, backend, local, min(rows, 1 << 27), world, 2, 1, dist)
+            extra["partitioned_output_all_to_all"] = run_partitioned_output(torch, backend, local, min(rows, 1 << 27), world, 2, 1, dist, stream_rows=args.stream_rows)
         except Exception as e:
             extra["partitioned_output_all_to_all"] = {"error": str(e)[:200]}
         torch.cuda.empty_cache()

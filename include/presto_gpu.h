@@ -595,6 +595,11 @@ int32_t pg_pages_serde_create(const pg_pages_serde_config* config, pg_pages_serd
  * :584-628: referenced entries in order of first reference, remapped ids) + a per-dictionary instance id.
  * *bytes (in options.output_memory) stays valid until the next call on this serde. */
 int32_t pg_pages_serde_serialize(pg_pages_serde* serde, const pg_page* page, const uint8_t** bytes, int64_t* size);
+/* One SerializedPage per row range [row_offsets[r], row_offsets[r + 1]) of `page`, back to back in one buffer (byte_offsets: n_ranges + 1
+ * entries): what OptimizedPartitionedOutputOperator.flush :774-797 enqueues, one page per partition, when `page` / `row_offsets` are a
+ * pg_partitioned_output operator's output page and pg_partitioned_output_get_offsets.  Empty ranges give empty (0-position) pages. */
+int32_t pg_pages_serde_serialize_ranges(pg_pages_serde* serde, const pg_page* page, const int64_t* row_offsets, int32_t n_ranges,
+                                        const uint8_t** bytes, int64_t* byte_offsets);
 /* readSerializedPage + deserialize.  `memory` = where `bytes` live; `types` gives the SQL type of every channel (the wire only
  * carries encodings).  RLE / DICTIONARY channels come back as blocks of those encodings.  A CHECKSUMMED page whose CRC32 does not
  * match fails with PG_ERR_INVALID_ARGUMENT.  out->blocks (in options.output_memory) stay valid until the next call. */

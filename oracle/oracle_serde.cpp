@@ -295,6 +295,35 @@ int32_t or_pages_serde_serialize(pg_pages_serde* serde, const pg_page* page, con
 {
     OR_TRY ((oracle::PagesSerde*) serde)->serialize(page, bytes, size); OR_CATCH
 }
+// one SerializedPage per row range, back to back (OptimizedPartitionedOutputOperator.flush :774-797: one page per partition buffer)
+int32_t or_pages_serde_serialize_ranges(pg_pages_serde* serde, const pg_page* page, const int64_t* rowOffsets, int32_t nRanges, const uint8_t** bytes, int64_t* byteOffsets)
+{
+    OR_TRY
+    static thread_local std::vector<uint8_t> all;
+    all.clear();
+    byteOffsets[0] = 0;
+    for (int32_t r = 0; r < nRanges; r++) {
+        const int64_t lo = rowOffsets[r], hi = rowOffsets[r + 1];
+        if (lo < 0 || lo > hi || hi > page->position_count) throw OracleError(PG_ERR_INVALID_ARGUMENT, "row offsets must be ascending and inside the page");
+        std::vector<pg_block> blocks(page->blocks, page->blocks + page->channel_count);
+        for (pg_block& b : blocks) {
+            if (b.encoding == PG_ENC_FLAT) {
+                const int w = oracle::typeWidth(b.type);
+                if (w) b.values = (const char*) b.values + lo * w; else if (b.offsets) b.offsets += lo;
+                if (b.is_null) b.is_null += lo;
+            }
+            else if (b.encoding == PG_ENC_DICTIONARY) b.ids += lo;
+            b.position_count = hi - lo;
+        }
+        pg_page part = *page; part.blocks = blocks.data(); part.position_count = hi - lo;
+        const uint8_t* one = nullptr; int64_t size = 0;
+        ((oracle::PagesSerde*) serde)->serialize(&part, &one, &size);
+        all.insert(all.end(), one, one + size);
+        byteOffsets[r + 1] = (int64_t) all.size();
+    }
+    *bytes = all.data();
+    OR_CATCH
+}
 int32_t or_pages_serde_deserialize(pg_pages_serde* serde, const uint8_t* bytes, int64_t size, int32_t memory, const int32_t* types, int32_t n_types, pg_page* out)
 {
     OR_TRY

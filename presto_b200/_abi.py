@@ -230,6 +230,7 @@ class Backend:
         "fused_page_create": (C.c_int32, [C.POINTER(pg_fused_page_config), C.POINTER(C.c_void_p)]),
         "pages_serde_create": (C.c_int32, [C.POINTER(pg_pages_serde_config), C.POINTER(C.c_void_p)]),
         "pages_serde_serialize": (C.c_int32, [C.c_void_p, C.POINTER(pg_page), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+        "pages_serde_serialize_ranges": (C.c_int32, [C.c_void_p, C.POINTER(pg_page), C.POINTER(C.c_int64), C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
         "pages_serde_deserialize": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(pg_page)]),
         "pages_serde_destroy": (C.c_int32, [C.c_void_p]),
     }

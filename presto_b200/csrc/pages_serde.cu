@@ -199,6 +199,7 @@ class PagesSerde : public SerdeBase {
     DeviceBuffer wire, crcs, unitCounts, unitOffsets, scanTemp, dWireIn;
     std::vector<DeviceBuffer> temps;                 // aligned temporaries (compacted values, varchar ends) of one call
     PinnedBuffer hostWire, hostScratch;
+    DeviceBuffer multiWire; PinnedBuffer multiHost;     // serializeRanges: the SerializedPages of one call back to back
     // deserialized page storage
     std::vector<DeviceBuffer> outValues, outNulls, outOffsets, outIds;
     std::vector<PinnedBuffer> hostValues, hostNulls, hostOffsets, hostIds;
@@ -450,6 +451,61 @@ public:
         *size = total;
     }
 
+    // One SerializedPage per row range of `page` (range r = rows [rowOffsets[r], rowOffsets[r + 1])), back to back in one buffer: the
+    // pages OptimizedPartitionedOutputOperator.flush :774-797 hands to OutputBuffer.enqueue, one per partition, from the partitioned
+    // page (pg_partitioned_output_create's output + pg_partitioned_output_get_offsets).  byteOffsets gets nRanges + 1 entries.
+    void serializeRanges(const pg_page* page, const int64_t* rowOffsets, int32_t nRanges, const uint8_t** bytes, int64_t* byteOffsets)
+    {
+        PG_CHECK_ARG(nRanges >= 0 && rowOffsets != nullptr, "row offsets are missing");
+        const bool toHost = options.output_memory == PG_MEM_HOST;
+        std::vector<std::vector<uint8_t>> hostParts;
+        int64_t at = 0;
+        byteOffsets[0] = 0;
+        size_t capacity = 0;
+        for (int32_t r = 0; r < nRanges; r++) {
+            const int64_t lo = rowOffsets[r], hi = rowOffsets[r + 1];
+            PG_CHECK_ARG(lo >= 0 && lo <= hi && hi <= page->position_count, "row offsets must be ascending and inside the page");
+            std::vector<pg_block> blocks(page->blocks, page->blocks + page->channel_count);
+            for (pg_block& b : blocks) {
+                if (b.encoding == PG_ENC_FLAT) {
+                    const int w = typeWidth(b.type);
+                    if (w) b.values = (const char*) b.values + lo * w; else if (b.offsets) b.offsets += lo;
+                    if (b.is_null) b.is_null += lo;
+                }
+                else if (b.encoding == PG_ENC_DICTIONARY) b.ids += lo;
+                b.position_count = hi - lo;
+            }
+            pg_page part = *page; part.blocks = blocks.data(); part.position_count = hi - lo;
+            const uint8_t* one = nullptr; int64_t size = 0;
+            serialize(&part, &one, &size);
+            if (toHost) {
+                if ((size_t) (at + size) > capacity) {
+                    // grow, keeping what is there (PinnedBuffer::reserve does not preserve contents)
+                    std::vector<uint8_t> keep((const uint8_t*) multiHost.ptr, (const uint8_t*) multiHost.ptr + at);
+                    capacity = std::max<size_t>((size_t) (at + size) * 2, 4096);
+                    multiHost.reserve(capacity);
+                    if (at) memcpy(multiHost.ptr, keep.data(), (size_t) at);
+                }
+                memcpy((uint8_t*) multiHost.ptr + at, one, (size_t) size);
+            }
+            else {
+                if ((size_t) (at + size) > capacity) {
+                    DeviceBuffer bigger; bigger.accounting = &stats.device_bytes;
+                    capacity = std::max<size_t>((size_t) (at + size) * 2, 4096);
+                    bigger.reserve(capacity);
+                    if (at) PG_CUDA(cudaMemcpyAsync(bigger.ptr, multiWire.ptr, (size_t) at, cudaMemcpyDeviceToDevice, stream));
+                    PG_CUDA(cudaStreamSynchronize(stream));
+                    multiWire = std::move(bigger);
+                }
+                PG_CUDA(cudaMemcpyAsync((uint8_t*) multiWire.ptr + at, one, (size_t) size, cudaMemcpyDeviceToDevice, stream));
+                PG_CUDA(cudaStreamSynchronize(stream));
+            }
+            at += size;
+            byteOffsets[r + 1] = at;
+        }
+        *bytes = toHost ? multiHost.as<uint8_t>() : multiWire.as<uint8_t>();
+    }
+
     // ================================================================= deserialize =================================================================
     // a small window of the wire on the host (the wire itself may be device memory)
     struct WireReader {
@@ -689,6 +745,10 @@ int32_t pg_pages_serde_create(const pg_pages_serde_config* config, pg_pages_serd
 int32_t pg_pages_serde_serialize(pg_pages_serde* serde, const pg_page* page, const uint8_t** bytes, int64_t* size)
 {
     S_TRY PG_CHECK_ARG(serde && page && bytes && size, "null argument"); auto* s = (pg::PagesSerde*) serde; s->bind(); s->serialize(page, bytes, size); S_CATCH
+}
+int32_t pg_pages_serde_serialize_ranges(pg_pages_serde* serde, const pg_page* page, const int64_t* row_offsets, int32_t n_ranges, const uint8_t** bytes, int64_t* byte_offsets)
+{
+    S_TRY PG_CHECK_ARG(serde && page && bytes && byte_offsets, "null argument"); auto* s = (pg::PagesSerde*) serde; s->bind(); s->serializeRanges(page, row_offsets, n_ranges, bytes, byte_offsets); S_CATCH
 }
 int32_t pg_pages_serde_deserialize(pg_pages_serde* serde, const uint8_t* bytes, int64_t size, int32_t memory, const int32_t* types, int32_t n_types, pg_page* out)
 {

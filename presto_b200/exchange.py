@@ -114,21 +114,9 @@ def all_to_all_pages(page: Page, offsets: Sequence[int], types: Sequence[int], g
 def serialize_partitions(serde, page: Page, offsets: Sequence[int]) -> List[np.ndarray]:
     """Off-box leg of a repartition: one SerializedPage (wire bytes) per partition of a PartitionedOutputOperator output page
     (partition p = rows offsets[p]:offsets[p+1]) — what OptimizedPartitionedOutputOperator.flush hands to OutputBuffer.enqueue
-    (MB/operator/repartition/OptimizedPartitionedOutputOperator.java:774-797).  Device pages are sliced by pointer arithmetic; the
-    serde runs on the GPU."""
-    out = []
-    for p in range(len(offsets) - 1):
-        lo, hi = int(offsets[p]), int(offsets[p + 1])
-        blocks = []
-        for b in page.blocks:
-            w = TYPE_WIDTH[b.type]
-            if b.on_device:
-                nulls = b.device_ptrs["is_null"]
-                blocks.append(Block.device(b.type, hi - lo, b.device_ptrs["values"] + lo * w, (nulls + lo) if nulls else 0, keepalive=b))
-            else:
-                blocks.append(Block.from_numpy(b.type, b.values[lo:hi], None if b.is_null is None else b.is_null[lo:hi]))
-        out.append(serde.serialize(Page(blocks, hi - lo)))
-    return out
+    (MB/operator/repartition/OptimizedPartitionedOutputOperator.java:774-797).  One native call (pg_pages_serde_serialize_ranges): device
+    pages are sliced by pointer arithmetic inside the library; the serde runs on the GPU."""
+    return serde.serialize_ranges(page, offsets)
 
 
 class FusedExchange:

@@ -690,6 +690,25 @@ class PagesSerde:
             C.memmove(out.ctypes.data, ptr, size.value)
         return out
 
+    def serialize_ranges(self, page: Page, row_offsets: Sequence[int]) -> List[np.ndarray]:
+        """One SerializedPage per row range [row_offsets[r], row_offsets[r + 1]) — a PartitionedOutputOperator's output page and its
+        partition offsets give the pages OptimizedPartitionedOutputOperator.flush enqueues (one native call, the serde runs on the GPU)."""
+        cpage, keep = page.as_c()
+        n = len(row_offsets) - 1
+        offs = (C.c_int64 * (n + 1))(*[int(x) for x in row_offsets])
+        byte_offsets = (C.c_int64 * (n + 1))()
+        ptr = C.c_void_p()
+        self._b.check(self._b.pages_serde_serialize_ranges(self._h, C.byref(cpage), offs, n, C.byref(ptr), byte_offsets))
+        del keep
+        total = int(byte_offsets[n])
+        buf = np.empty(total, dtype=np.uint8)
+        if total:
+            if self._memory == abi.MEM_DEVICE:
+                self._b.check(self._b.memcpy_d2h(buf.ctypes.data, ptr, total))
+            else:
+                C.memmove(buf.ctypes.data, ptr, total)
+        return [buf[int(byte_offsets[r]):int(byte_offsets[r + 1])] for r in range(n)]
+
     def deserialize(self, data, types: Sequence[int], *, size: Optional[int] = None, memory: int = abi.MEM_HOST, copy: bool = True) -> Page:
         """``data``: numpy uint8 array (host) or an address (with ``size`` and ``memory``)."""
         if isinstance(data, np.ndarray):

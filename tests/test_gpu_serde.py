@@ -135,9 +135,30 @@ def test_partitioned_output_to_serialized_pages(gpu_backend, oracle_backend):
     wires = serialize_partitions(g, out, offs)
     ref = PartitionedOutputOperator([BIGINT, DOUBLE], parts, [0], backend=oracle_backend)
     ref.add_input(page)
-    want, woffs = ref.get_output().rows(), ref.get_offsets()
+    ref_out = ref.get_output()
+    want, woffs = ref_out.rows(), ref.get_offsets()
     o = PagesSerde(checksum_enabled=True, backend=oracle_backend)
     assert list(offs) == list(woffs)
+    ref_wires = o.serialize_ranges(ref_out, woffs)          # pg_pages_serde_serialize_ranges on both sides: byte for byte
     for p in range(parts):
         assert o.deserialize(wires[p], [BIGINT, DOUBLE]).rows() == want[woffs[p]:woffs[p + 1]]
+        assert (wires[p] == ref_wires[p]).all()
     op.close(); ref.close(); g.close(); o.close()
+
+
+def test_serialize_ranges_with_varchar_and_empty_ranges(gpu_backend, oracle_backend):
+    """Row ranges of a host page (VARCHAR + nullable BIGINT), some of them empty: every range is the SerializedPage of that slice."""
+    rng = np.random.default_rng(9)
+    n = 5000
+    strs = [None if rng.random() < 0.1 else bytes(rng.integers(97, 123, rng.integers(0, 12)).astype(np.uint8)) for _ in range(n)]
+    page = Page([Block.from_strings(strs), Block.from_numpy(BIGINT, rng.integers(-9, 9, n), (rng.random(n) < 0.2).astype(np.uint8))])
+    cuts = [0, 0, 1234, 1234, 4999, 5000]
+    g, o = PagesSerde(backend=gpu_backend), PagesSerde(backend=oracle_backend)
+    got, want = g.serialize_ranges(page, cuts), o.serialize_ranges(page, cuts)
+    rows = page.rows()
+    for r in range(len(cuts) - 1):
+        assert (got[r] == want[r]).all()
+        assert o.deserialize(got[r], [VARCHAR, BIGINT]).rows() == rows[cuts[r]:cuts[r + 1]]
+    with pytest.raises(Exception):
+        g.serialize_ranges(page, [0, 6000])
+    g.close(); o.close()

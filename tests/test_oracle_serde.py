@@ -117,3 +117,14 @@ def test_rejects_what_it_does_not_speak(serde):
         serde.deserialize(wire, [INTEGER])
     with pytest.raises(Exception, match="channel count"):
         serde.deserialize(wire, [BIGINT, BIGINT])
+
+
+def test_serialize_ranges_equals_serializing_the_slices(serde):
+    rng = np.random.default_rng(5)
+    page = random_page(rng, 1000, True)
+    cuts = [0, 10, 10, 600, 1000]
+    wires = serde.serialize_ranges(page, cuts)
+    rows = page.rows()
+    for r in range(len(cuts) - 1):
+        assert serde.deserialize(wires[r], types_of(page)).rows() == rows[cuts[r]:cuts[r + 1]]
+        assert header_of(wires[r])[0] == cuts[r + 1] - cuts[r]
