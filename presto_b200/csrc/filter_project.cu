@@ -301,11 +301,8 @@ public:
         for (size_t i = 0; i < staged.size(); i++) d.inputHasNulls[staged[i]] = cols[i].nulls != nullptr;
         const std::string ptx = generateFilterProjectPtx(d, jp.sig);
         if (!jp.sig.ok) { jp.log = jp.sig.reason; return jp; }
-        char errLog[4096]; errLog[0] = 0;
-        CUjit_option opts[2] = {CU_JIT_ERROR_LOG_BUFFER, CU_JIT_ERROR_LOG_BUFFER_SIZE_BYTES};
-        void* vals[2] = {errLog, (void*) (uintptr_t) sizeof(errLog)};
-        CUresult r = api.moduleLoadDataEx(&jp.module, ptx.c_str(), 2, opts, vals);
-        if (r != CUDA_SUCCESS) { jp.log = std::string("cuModuleLoadDataEx failed: ") + errLog; jp.module = nullptr; return jp; }
+        jp.module = getOrLoadPtxModule(options.device, ptx, &jp.log);      // shared by every operator of the same plan shape
+        if (!jp.module) return jp;
         bool fine = api.moduleGetFunction(&jp.project, jp.module, "fp_project") == CUDA_SUCCESS;
         if (filterNode >= 0) fine = fine && api.moduleGetFunction(&jp.filter, jp.module, "fp_filter") == CUDA_SUCCESS;
         jp.ok = fine;
@@ -501,7 +498,7 @@ public:
 
     ~FilterProjectOp() override
     {
-        for (auto& kv : jitCache) if (kv.second.module) { cudaStreamSynchronize(stream); DriverApi::get().moduleUnload(kv.second.module); }
+        // (the modules belong to the process-wide cache)
     }
     // 1 = the last page ran through generated PTX, 0 = through the interpreter kernels
     int usedJit() const { return jitLaunches > 0 && interpreterLaunches == 0 ? 1 : 0; }

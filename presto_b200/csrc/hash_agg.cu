@@ -945,16 +945,37 @@ __global__ void mergeStateKernel(GroupTable T, AggStateView in, uint32_t nGroups
     }
 }
 
-__global__ void collectSlotsKernel(GroupTable t, uint64_t* sortKeys, uint32_t* sortVals, unsigned int* count)
+__global__ void __launch_bounds__(256) collectSlotsKernel(GroupTable t, uint64_t* sortKeys, uint32_t* sortVals, unsigned int* count /* [0] = slots, [1..2] = OR of the first-row words */)
 {
-    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < t.capP; s += gridDim.x * blockDim.x) {
-        uint64_t f = t.firstRow[s];
-        if (f != kNoRow) {
-            unsigned int i = atomicAdd(count, 1u);
+    __shared__ unsigned int warpCount[8], blockBase;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long seen = 0;
+    const uint32_t rounds = (t.capP + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+    for (uint32_t k = 0; k < rounds; k++) {
+        const uint32_t s = k * gridDim.x * blockDim.x + blockIdx.x * blockDim.x + threadIdx.x;
+        const uint64_t f = s < t.capP ? t.firstRow[s] : kNoRow;
+        const bool live = f != kNoRow;
+        // one counter increment per CTA and round (a million groups would otherwise queue on this single address)
+        const unsigned m = __ballot_sync(0xffffffffu, live);
+        if (lane == 0) warpCount[warp] = __popc(m);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int total = 0;
+            for (int i = 0; i < 8; i++) { const unsigned int c = warpCount[i]; warpCount[i] = total; total += c; }
+            blockBase = total ? atomicAdd(count, total) : 0;
+        }
+        __syncthreads();
+        if (live) {
+            const unsigned int i = blockBase + warpCount[warp] + __popc(m & ((1u << lane) - 1));
             sortKeys[i] = f;
             sortVals[i] = s;
+            seen |= f;
         }
+        __syncthreads();
     }
+    // which bits the sort has to look at
+    for (int o = 16; o >= 1; o >>= 1) seen |= __shfl_xor_sync(0xffffffffu, seen, o);
+    if (lane == 0 && seen) { atomicOr(&count[1], (unsigned int) seen); atomicOr(&count[2], (unsigned int) (seen >> 32)); }
 }
 
 // ---- output ------------------------------------------------------------------------------------------------------------
@@ -1181,15 +1202,20 @@ static int64_t sortSlotsByFirstRow(Operator* op, const GroupTable& T, DeviceBuff
     sortKeys.reserve(capP * 8); sortVals.reserve(capP * 4); count.reserve(16);
     PG_CUDA(cudaMemsetAsync(count.ptr, 0, 16, op->stream));
     PG_LAUNCH(op, collectSlotsKernel, 1024, 256, 0, T, sortKeys.as<uint64_t>(), sortVals.as<uint32_t>(), count.as<unsigned int>());
-    unsigned int g = 0;
-    PG_CUDA(cudaMemcpyAsync(&g, count.ptr, 4, cudaMemcpyDeviceToHost, op->stream));
+    unsigned int h[3] = {0, 0, 0};
+    PG_CUDA(cudaMemcpyAsync(h, count.ptr, 12, cudaMemcpyDeviceToHost, op->stream));
     PG_CUDA(cudaStreamSynchronize(op->stream));
+    const unsigned int g = h[0];
     if (g == 0) return 0;
+    // radix passes only over the bits some first-row word has set (600 M rows: 38 of the 64)
+    const uint64_t seen = ((uint64_t) h[2] << 32) | h[1];
+    int endBit = 1;
+    while (endBit < 64 && (seen >> endBit) != 0) endBit++;
     sortKeysOut.reserve((size_t) g * 8); order.reserve((size_t) g * 4);
     size_t tempBytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, sortKeys.as<uint64_t>(), sortKeysOut.as<uint64_t>(), sortVals.as<uint32_t>(), order.as<uint32_t>(), (int) g, 0, 64, op->stream);
+    cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, sortKeys.as<uint64_t>(), sortKeysOut.as<uint64_t>(), sortVals.as<uint32_t>(), order.as<uint32_t>(), (int) g, 0, endBit, op->stream);
     temp.reserve(tempBytes);
-    cub::DeviceRadixSort::SortPairs(temp.ptr, tempBytes, sortKeys.as<uint64_t>(), sortKeysOut.as<uint64_t>(), sortVals.as<uint32_t>(), order.as<uint32_t>(), (int) g, 0, 64, op->stream);
+    cub::DeviceRadixSort::SortPairs(temp.ptr, tempBytes, sortKeys.as<uint64_t>(), sortKeysOut.as<uint64_t>(), sortVals.as<uint32_t>(), order.as<uint32_t>(), (int) g, 0, endBit, op->stream);
     op->stats.kernel_launches += 4;
     return g;
 }

@@ -133,6 +133,26 @@ const JitKernel* getOrCompileKernel(int device, const std::string& source, const
     }
 }
 
+CUmodule getOrLoadPtxModule(int device, const std::string& ptx, std::string* error)
+{
+    static std::mutex mu;
+    static std::map<std::pair<int, std::string>, CUmodule> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    const auto key = std::make_pair(device, ptx);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    DriverApi& api = DriverApi::get();
+    if (!api.ok) { if (error) *error = "libcuda.so.1 cannot be loaded"; return nullptr; }
+    char errLog[4096]; errLog[0] = 0;
+    CUjit_option opts[2] = {CU_JIT_ERROR_LOG_BUFFER, CU_JIT_ERROR_LOG_BUFFER_SIZE_BYTES};
+    void* vals[2] = {errLog, (void*) (uintptr_t) sizeof(errLog)};
+    CUmodule module = nullptr;
+    const CUresult r = api.moduleLoadDataEx(&module, ptx.c_str(), 2, opts, vals);
+    if (r != CUDA_SUCCESS) { if (error) *error = std::string("cuModuleLoadDataEx failed: ") + errLog; return nullptr; }
+    cache[key] = module;
+    return module;
+}
+
 }  // namespace pg
 
 // Host-side entry for tests: compile a generated source without a GPU (NVRTC only), returning the cubin size or the compiler log.

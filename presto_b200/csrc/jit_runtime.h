@@ -35,4 +35,9 @@ std::vector<char> compileCudaToCubin(const std::string& source, const std::strin
 struct JitKernel { CUmodule module = nullptr; CUfunction function = nullptr; int registers = 0; };
 const JitKernel* getOrCompileKernel(int device, const std::string& source, const char* entry, std::string* error);
 
+// Process-wide cache of driver-JIT modules (PTX from fp_codegen.cpp): cuModuleLoadDataEx costs ~0.3 ms per module, and every query of
+// the same plan shape generates the same PTX.  Returns nullptr + *error when the PTX does not assemble.  Modules live until the
+// process exits (like the fused pipeline modules).
+CUmodule getOrLoadPtxModule(int device, const std::string& ptx, std::string* error);
+
 }  // namespace pg

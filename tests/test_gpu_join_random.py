@@ -172,3 +172,31 @@ def test_build_outer_joins_match_oracle(gpu_backend, oracle_backend, kind, full)
     got, want = run(gpu_backend), run(oracle_backend)
     assert got == want
     assert len(want[2]) > nb // 8
+
+
+@pytest.mark.parametrize("payload", ["date", "date_int", "nullable_int"])
+@pytest.mark.parametrize("with_duplicate", [False, True])
+def test_sorted_build_of_the_dense_index(gpu_backend, oracle_backend, monkeypatch, payload, with_duplicate):
+    """Sparse unique keys in arrival order with a one-word payload (TPC-H Q3's filtered orders) are built by sorting (key - min, payload
+    word) pairs (hash_join.cu densePackPairsKernel); forced here on a small build.  NULL keys, NULL payload values, a duplicate key found
+    as two equal neighbours of the sorted keys (→ falls back to the hash table, same result)."""
+    monkeypatch.setenv("PG_JOIN_SORTED_MIN_ROWS", "1")
+    rng = np.random.default_rng(len(payload) * 2 + int(with_duplicate))
+    nb = 50_003
+    keys = (rng.choice(1 << 21, nb, replace=False).astype(np.int64) * 37) - 999        # ~1 key per 1500 values: far from the range-partitioned build
+    if with_duplicate:
+        keys[nb // 2] = keys[7]
+    knull = (rng.random(nb) < 0.02).astype(np.uint8)
+    cols = {"date": [(DATE, rng.integers(8000, 10500, nb).astype(np.int32), None)],
+            "date_int": [(DATE, rng.integers(8000, 10500, nb).astype(np.int32), None), (INTEGER, rng.integers(-5, 5, nb).astype(np.int32), None)],
+            "nullable_int": [(INTEGER, rng.integers(0, 1000, nb).astype(np.int32), (rng.random(nb) < 0.3).astype(np.uint8))]}[payload]
+    types = [BIGINT] + [c[0] for c in cols]
+    cuts = [0, nb // 3, nb]
+    build_pages = [Page([Block.from_numpy(BIGINT, keys[a:b], knull[a:b])] + [Block.from_numpy(t, v[a:b], None if m is None else m[a:b]) for t, v, m in cols]) for a, b in zip(cuts[:-1], cuts[1:])]
+    npr = 100_000
+    pk = np.where(rng.random(npr) < 0.6, keys[rng.integers(0, nb, npr)], rng.integers(int(keys.min()) - 50, int(keys.max()) + 50, npr))
+    probe_pages = [Page([Block.from_numpy(BIGINT, pk), Block.from_numpy(DOUBLE, rng.random(npr))])]
+    for jt in (JOIN_INNER, JOIN_PROBE_OUTER):
+        args = (build_pages, types, probe_pages, [BIGINT, DOUBLE], jt, list(range(1, len(types))), [0, 1])
+        got, want = join(gpu_backend, *args), join(oracle_backend, *args)
+        assert len(got) > 0 and got == want

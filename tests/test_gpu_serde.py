@@ -7,7 +7,7 @@ import struct
 import numpy as np
 import pytest
 
-from presto_b200 import BIGINT, DOUBLE, INTEGER, MEM_DEVICE, Block, Page, PagesSerde
+from presto_b200 import BIGINT, DOUBLE, INTEGER, MEM_DEVICE, VARCHAR, Block, Page, PagesSerde
 from serde_cases import dictionary_id_ranges, dictionary_pages, same_wire_up_to_dictionary_ids, HEADER, header_of, java_checksum, name, random_page, types_of
 
 pytestmark = pytest.mark.gpu
