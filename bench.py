@@ -33,6 +33,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 NCU_DRAM_BYTES_PER_ROW = 40.01   # measured, see roofline.traffic
+# the headline kernel (fused_kernel_tma, Q1 with VARCHAR(1) keys): dram__bytes_read + dram__bytes_write of one launch over 600 037 902 rows in
+# the ncu --set full capture profiles/r02_ncu_q1_fused_tma.txt (25.0448 GB + 3.6 MB).  Below the 46 algorithmic B/row because returnflag and
+# linestatus share one int32 offsets array in this synthetic table (its second read hits L2).  Quoted per run, not re-measured.
+NCU_Q1_VARCHAR_DRAM_BYTES_PER_ROW = (25.044803e9 + 3.562752e6) / 600_037_902
 ALGO_BYTES_PER_ROW = 40   # 8 (bigint key) + 4 x 8 (double inputs); output negligible
 
 
@@ -1051,7 +1055,8 @@ def main():
             "config": dict(q1_config(args, kk), parallelism=(f"{world} ranks: fused pipeline per GPU, group tables compacted on the device + ONE all-gather over NVLink + merge kernels into rank 0's operator (no intermediate pages, no row exchange)" if world > 1 else "1 GPU")),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          # dram__bytes of the fused kernel from the ncu --set full capture in profiles/ (quoted, not re-measured per run)
-                         "traffic": None, "traffic_note": "see profiles/r02_ncu_q1_fused.txt (dram__bytes_read + write of the same kernel, per launch)",
+                         "traffic": (NCU_Q1_VARCHAR_DRAM_BYTES_PER_ROW * rows if kk == "varchar" else None),
+                         "traffic_note": "dram__bytes_read + dram__bytes_write of this kernel per launch, quoted from the ncu --set full capture profiles/r02_ncu_q1_fused_tma.txt (41.74 B/row; the two key columns share one offsets array), not re-measured in this run",
                          "kernel": "fused_kernel (generated: fused_codegen.cpp + fused_agg.cuh, NVRTC sm_100a)", "peak_source": peak_kind,
                          "algorithmic_bytes_per_launch": bpr * rows, "kernel_ms": kms},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": r["launches"], "groups": len(r["result"] or []), "result": r["result"],

@@ -1991,7 +1991,7 @@ public:
         GroupTable T = table.view();
         int64_t g = sortSlotsByFirstRow(this, T, order, sortScratch);
         outGroups = g; outNext = 0;
-        stats.group_count = g;
+        stats.group_count = g; knownGroups = g;
         if (g == 0) return;
         std::vector<AggEmit> emits;
         for (auto& a : aggs) {
