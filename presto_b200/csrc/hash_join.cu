@@ -222,6 +222,68 @@ __global__ void joinEmitKernel(const __grid_constant__ EmitJoinParams P)
     }
 }
 
+// ---- VARCHAR output channels ------------------------------------------------------------------------------------------------------
+// Fixed-width output columns are written in place by the emit kernels.  A VARCHAR column (LookupJoinPageBuilder.appendRow ->
+// type.appendTo: the slice of the probe row / of the build position) follows them: the emit kernels also write, like one more 4-byte
+// column, the SOURCE index of every output row (an iota column as its "values"), and the slices are gathered through that index —
+// lengths, inclusive scan, bytes.
+__global__ void iotaU32Kernel(uint32_t* p, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) p[i] = (uint32_t) i;
+}
+__global__ void varcharIndexLengthsKernel(const int32_t* __restrict__ srcOffsets, const uint8_t* __restrict__ srcNulls, const uint32_t* __restrict__ index,
+                                          const uint8_t* __restrict__ indexNulls, int64_t m, int32_t* __restrict__ outOffsets, uint8_t* __restrict__ outNulls)
+{
+    for (int64_t o = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; o < m; o += (int64_t) gridDim.x * blockDim.x) {
+        const bool noSource = indexNulls && indexNulls[o];
+        const uint32_t i = noSource ? 0u : index[o];
+        const bool isNull = noSource || (srcNulls && srcNulls[i]);
+        outOffsets[o + 1] = isNull ? 0 : srcOffsets[i + 1] - srcOffsets[i];
+        if (outNulls) outNulls[o] = isNull ? 1 : 0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) outOffsets[0] = 0;
+}
+__global__ void varcharIndexBytesKernel(const uint8_t* __restrict__ srcBytes, const int32_t* __restrict__ srcOffsets, const uint32_t* __restrict__ index,
+                                        const int32_t* __restrict__ outOffsets, int64_t m, uint8_t* __restrict__ outBytes)
+{
+    // one warp per output row: slices are short (names, comments), lanes copy consecutive bytes
+    const int lane = threadIdx.x & 31;
+    const int64_t warpId = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5, nWarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+    for (int64_t o = warpId; o < m; o += nWarps) {
+        const int32_t dst = outOffsets[o], len = outOffsets[o + 1] - dst;
+        if (len <= 0) continue;
+        const int32_t src = srcOffsets[index[o]];
+        for (int32_t k = lane; k < len; k += 32) outBytes[dst + k] = srcBytes[src + k];
+    }
+}
+__global__ void rebaseOffsetsKernel(const int32_t* __restrict__ in, int64_t n, int32_t delta, int32_t* __restrict__ out)
+{
+    for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) out[i + 1] = in[i + 1] + delta;
+}
+
+// Gathers `m` slices of a VARCHAR column through `index` (indexNulls[o] != 0: the output row has no source, e.g. the NULL build side of an
+// outer row) into offsets / bytes / nulls buffers of the caller.  Returns the byte total (one synchronisation).
+static int64_t gatherVarcharByIndex(Operator* op, const uint8_t* srcBytes, const int32_t* srcOffsets, const uint8_t* srcNulls, const uint32_t* index,
+                                    const uint8_t* indexNulls, int64_t m, DeviceBuffer& outBytes, DeviceBuffer& outOffsets, uint8_t* outNulls, DeviceBuffer& scanTemp)
+{
+    outOffsets.reserve((size_t) (m + 1) * 4);
+    const int grid = (int) std::max<int64_t>(1, std::min<int64_t>(divUp(m, 256), (int64_t) op->numSMs * 16));
+    PG_LAUNCH(op, varcharIndexLengthsKernel, grid, 256, 0, srcOffsets, srcNulls, index, indexNulls, m, outOffsets.as<int32_t>(), outNulls);
+    size_t tb = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, tb, outOffsets.as<int32_t>() + 1, outOffsets.as<int32_t>() + 1, (int) m, op->stream);
+    scanTemp.reserve(tb);
+    cub::DeviceScan::InclusiveSum(scanTemp.ptr, tb, outOffsets.as<int32_t>() + 1, outOffsets.as<int32_t>() + 1, (int) m, op->stream);
+    op->stats.kernel_launches += 2;
+    int32_t total = 0;
+    PG_CUDA(cudaMemcpyAsync(&total, outOffsets.as<int32_t>() + m, 4, cudaMemcpyDeviceToHost, op->stream));
+    PG_CUDA(cudaStreamSynchronize(op->stream));
+    op->stats.d2h_bytes += 4;
+    PG_CHECK_ARG(total >= 0, "a VARCHAR output column exceeds 2 GB: feed smaller probe pages");
+    outBytes.reserve(std::max<size_t>((size_t) total, 16));
+    if (total > 0) PG_LAUNCH(op, varcharIndexBytesKernel, (int) std::max<int64_t>(1, std::min<int64_t>(divUp(m, 8), (int64_t) op->numSMs * 16)), 256, 0, srcBytes, srcOffsets, index, outOffsets.as<int32_t>(), m, outBytes.as<uint8_t>());
+    return total;
+}
+
 // ---- dense unique integer keys: bitmap + rank index ------------------------------------------------------------------------
 // When the build keys are unique and span a range of at most kDenseRangeFactor x n (TPC-H order keys: 150 M keys over 600 M; Q3's
 // filtered orders: ~15 M keys over the same 600 M), the
@@ -794,6 +856,9 @@ struct LookupSourceDevice {
     int64_t positionCount = 0;
     std::vector<int> types;
     std::vector<DeviceBuffer> values, nulls;       // per build channel (only channels in `kept`)
+    std::vector<DeviceBuffer> offsets;             // VARCHAR channels: int32[positionCount + 1] into values (the bytes)
+    std::vector<int64_t> varcharBytes;             // VARCHAR channels: bytes stored so far
+    bool hasVarcharOutput = false;
     std::vector<bool> hasNulls;
     std::vector<int> outputChannels;
     KeyLayout layout;
@@ -885,7 +950,7 @@ public:
         for (int k = 0; k < ls->layout.nKeys; k++) keep(ls->layout.channels[k]);
         for (int oc : ls->outputChannels) {
             PG_CHECK_ARG(oc >= 0 && oc < c->n_channels, "output channel out of range");
-            if (ls->types[oc] == PG_TYPE_VARCHAR) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR build output channels are not on the GPU path");
+            if (ls->types[oc] == PG_TYPE_VARCHAR) ls->hasVarcharOutput = true;      // (position-ordered columns + hash table: no payload rows)
             keep(oc);
         }
         if (c->filter && c->filter->filter_node >= 0) {
@@ -907,6 +972,8 @@ public:
             }
         }
         ls->values.resize(c->n_channels); ls->nulls.resize(c->n_channels); ls->hasNulls.assign(c->n_channels, false);
+        ls->offsets.resize(c->n_channels); ls->varcharBytes.assign(c->n_channels, 0);
+        for (auto& v : ls->offsets) v.accounting = &ls->deviceBytes;
         for (auto& v : ls->values) v.accounting = &ls->deviceBytes;
         for (auto& v : ls->nulls) v.accounting = &ls->deviceBytes;
         capacityRows.assign(c->n_channels, 0);
@@ -941,6 +1008,43 @@ public:
         }
     }
 
+    // PagesIndex.addPage for a VariableWidthBlock channel: the page's slices are appended to the channel's byte store, its offsets rebased
+    std::vector<int64_t> capacityVarBytes, capacityOffsets;
+    void appendVarchar(int ch, const DeviceColumn& col, int64_t n)
+    {
+        if (capacityVarBytes.empty()) { capacityVarBytes.assign(ls->types.size(), 0); capacityOffsets.assign(ls->types.size(), 0); }
+        PG_CHECK_ARG(col.offsets != nullptr, "VARCHAR block without offsets");
+        int32_t ends[2] = {0, 0};
+        PG_CUDA(cudaMemcpyAsync(&ends[0], col.offsets, 4, cudaMemcpyDeviceToHost, stream));
+        PG_CUDA(cudaMemcpyAsync(&ends[1], col.offsets + n, 4, cudaMemcpyDeviceToHost, stream));
+        PG_CUDA(cudaStreamSynchronize(stream));
+        const int64_t pageBytes = (int64_t) ends[1] - ends[0], have = ls->varcharBytes[ch], pos = ls->positionCount;
+        PG_CHECK_ARG(have + pageBytes < (int64_t(1) << 31), "a VARCHAR build channel exceeds 2 GB");
+        if (have + pageBytes > capacityVarBytes[ch]) {
+            const int64_t cap = std::max<int64_t>({have + pageBytes, capacityVarBytes[ch] * 2, 1 << 16});
+            DeviceBuffer nb; nb.accounting = &ls->deviceBytes; nb.reserve((size_t) cap);
+            if (have) PG_CUDA(cudaMemcpyAsync(nb.ptr, ls->values[ch].ptr, (size_t) have, cudaMemcpyDeviceToDevice, stream));
+            PG_CUDA(cudaStreamSynchronize(stream));
+            ls->values[ch] = std::move(nb); capacityVarBytes[ch] = cap;
+        }
+        if (pos + n + 1 > capacityOffsets[ch]) {
+            const int64_t cap = std::max<int64_t>({pos + n + 1, capacityOffsets[ch] * 2, expected + 1});
+            DeviceBuffer no; no.accounting = &ls->deviceBytes; no.reserve((size_t) cap * 4);
+            if (capacityOffsets[ch]) PG_CUDA(cudaMemcpyAsync(no.ptr, ls->offsets[ch].ptr, (size_t) (pos + 1) * 4, cudaMemcpyDeviceToDevice, stream));
+            else PG_CUDA(cudaMemsetAsync(no.ptr, 0, 4, stream));
+            DeviceBuffer nn; nn.accounting = &ls->deviceBytes; nn.reserve((size_t) cap);
+            if (pos) { if (ls->hasNulls[ch]) PG_CUDA(cudaMemcpyAsync(nn.ptr, ls->nulls[ch].ptr, (size_t) pos, cudaMemcpyDeviceToDevice, stream)); else PG_CUDA(cudaMemsetAsync(nn.ptr, 0, (size_t) pos, stream)); }
+            PG_CUDA(cudaStreamSynchronize(stream));
+            ls->offsets[ch] = std::move(no); ls->nulls[ch] = std::move(nn); capacityOffsets[ch] = cap;
+            ls->hasNulls[ch] = true;       // (a VARCHAR channel always carries its null map: one byte per position)
+        }
+        if (pageBytes) PG_CUDA(cudaMemcpyAsync(ls->values[ch].as<uint8_t>() + have, (const uint8_t*) col.values + ends[0], (size_t) pageBytes, cudaMemcpyDeviceToDevice, stream));
+        PG_LAUNCH(this, rebaseOffsetsKernel, (int) std::max<int64_t>(1, std::min<int64_t>(divUp(n, 256), (int64_t) numSMs * 8)), 256, 0, col.offsets, n, (int32_t) (have - ends[0]), ls->offsets[ch].as<int32_t>() + pos);
+        if (col.nulls) PG_CUDA(cudaMemcpyAsync(ls->nulls[ch].as<uint8_t>() + pos, col.nulls, (size_t) n, cudaMemcpyDeviceToDevice, stream));
+        else PG_CUDA(cudaMemsetAsync(ls->nulls[ch].as<uint8_t>() + pos, 0, (size_t) n, stream));
+        ls->varcharBytes[ch] = have + pageBytes;
+    }
+
     void addInput(const pg_page* page) override   // HashBuilderOperator.addInput :333-349 → PagesIndex.addPage :202-226
     {
         PG_CHECK_STATE(!finishing, "Operator is already finishing");
@@ -954,6 +1058,7 @@ public:
             int ch = kept[i];
             PG_CHECK_ARG(cols[i].type == ls->types[ch], "build channel type differs from the operator's configuration");
             int w = typeWidth(ls->types[ch]);
+            if (ls->types[ch] == PG_TYPE_VARCHAR) { appendVarchar(ch, cols[i], n); continue; }
             ensureRows(ch, ls->positionCount + n, cols[i].nulls != nullptr);
             PG_CUDA(cudaMemcpyAsync((char*) ls->values[ch].ptr + (size_t) ls->positionCount * w, cols[i].values, (size_t) n * w, cudaMemcpyDeviceToDevice, stream));
             if (ls->hasNulls[ch]) {
@@ -978,7 +1083,7 @@ public:
             ls->visited.reserve((size_t) std::max<int64_t>(n, 1));
             PG_CUDA(cudaMemsetAsync(ls->visited.ptr, 0, (size_t) std::max<int64_t>(n, 1), stream));
         }
-        if (n > 0 && !bridge->isOuter() && !ls->hasFilter() && tryBuildDense()) {
+        if (n > 0 && !bridge->isOuter() && !ls->hasFilter() && !ls->hasVarcharOutput && tryBuildDense()) {
             stats.group_count = n;
             stats.device_bytes = ls->deviceBytes;
             bridge->set(ls);
@@ -1205,6 +1310,10 @@ class LookupJoinOp : public Operator {
     int64_t pendingRows = 0;
     bool trackedByBridge = false;     // counted in bridge->liveProbes until finish() / destruction
     DeviceBuffer filterDev;           // JoinFilterProgram + its error word, rebuilt per page (the probe columns move)
+    // VARCHAR output channels (gatherVarcharByIndex): source index columns written by the emit kernels, then offsets / bytes per slot
+    std::vector<DeviceBuffer> outOffsets; std::vector<PinnedBuffer> hostOffsets; std::vector<int64_t> varBytes;
+    DeviceBuffer iotaProbe, iotaBuild, srcRow, srcPos, srcPosNull, varScan;
+    struct VarcharOut { size_t slot; bool fromBuild; int channel; };
     bool filterChannelsStaged = false;
 
 public:
@@ -1233,7 +1342,6 @@ public:
         for (int k = 0; k < layout.nKeys; k++) need(layout.channels[k]);
         for (int oc : outputChannels) {
             PG_CHECK_ARG(oc >= 0 && oc < c->n_channels, "output channel out of range");
-            if (types[oc] == PG_TYPE_VARCHAR) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR probe output channels are not on the GPU path");
             need(oc);
         }
         for (DeviceBuffer* d : {&matchHead, &counts, &offsets, &scanTemp, &unitMask}) d->accounting = &stats.device_bytes;
@@ -1339,54 +1447,77 @@ public:
 
         // pass 2: write the output columns in place
         const size_t nOut = outputChannels.size() + ls->outputChannels.size();
-        if (outValues.size() < nOut) { outValues.resize(nOut); outNulls.resize(nOut); for (auto& d : outValues) d.accounting = &stats.device_bytes; for (auto& d : outNulls) d.accounting = &stats.device_bytes; }
+        ensureOutputSlots(nOut);
         outBlocks.assign(nOut, pg_block{});
+        std::vector<bool> hasNulls(nOut, false);
+        std::vector<VarcharOut> vouts;
         EmitJoinParams E{};
         E.matchHead = matchHead.as<int32_t>(); E.offsets = offsets.as<uint32_t>(); E.links = ls->links.as<int32_t>();
-        E.n = n; E.hasDuplicates = ls->hasDuplicates; E.nProbe = (int) outputChannels.size(); E.nBuild = (int) ls->outputChannels.size();
+        E.n = n; E.hasDuplicates = ls->hasDuplicates;
         E.visited = ls->visited.as<uint8_t>();
         E.filter = filterProgram;
+        int np = 0, nb = 0;
+        bool probeVarchar = false, buildVarchar = false;
         for (size_t i = 0; i < outputChannels.size(); i++) {
             const DeviceColumn& c = colOf(outputChannels[i]);
-            JoinColumn& jc = E.probe[i];
+            outBlocks[i].type = c.type;
+            if (c.type == PG_TYPE_VARCHAR) { vouts.push_back({i, false, outputChannels[i]}); probeVarchar = true; hasNulls[i] = c.nulls != nullptr; continue; }
+            JoinColumn& jc = E.probe[np++];
             jc.width = typeWidth(c.type); jc.src = c.values; jc.srcNulls = c.nulls;
             outValues[i].reserve((size_t) total * jc.width);
             jc.dst = outValues[i].ptr; jc.dstNulls = nullptr;
-            if (c.nulls) { outNulls[i].reserve(total); jc.dstNulls = outNulls[i].as<uint8_t>(); }
-            outBlocks[i].type = c.type;
+            if (c.nulls) { outNulls[i].reserve(total); jc.dstNulls = outNulls[i].as<uint8_t>(); hasNulls[i] = true; }
         }
         for (size_t i = 0; i < ls->outputChannels.size(); i++) {
             const int ch = ls->outputChannels[i];
             const size_t o = outputChannels.size() + i;
-            JoinColumn& jc = E.build[i];
+            outBlocks[o].type = ls->types[ch];
+            const bool nullable = ls->hasNulls[ch] || joinType == PG_JOIN_PROBE_OUTER;
+            if (ls->types[ch] == PG_TYPE_VARCHAR) { vouts.push_back({o, true, ch}); buildVarchar = true; hasNulls[o] = nullable; continue; }
+            JoinColumn& jc = E.build[nb++];
             jc.width = typeWidth(ls->types[ch]); jc.src = ls->values[ch].ptr; jc.srcNulls = ls->hasNulls[ch] ? ls->nulls[ch].as<uint8_t>() : nullptr;
             outValues[o].reserve((size_t) total * jc.width);
             jc.dst = outValues[o].ptr; jc.dstNulls = nullptr;
-            if (jc.srcNulls || joinType == PG_JOIN_PROBE_OUTER) { outNulls[o].reserve(total); jc.dstNulls = outNulls[o].as<uint8_t>(); }
-            outBlocks[o].type = ls->types[ch];
+            if (nullable) { outNulls[o].reserve(total); jc.dstNulls = outNulls[o].as<uint8_t>(); hasNulls[o] = true; }
         }
+        // VARCHAR outputs: one more 4-byte column per side carries the source index of every output row
+        PG_CHECK_ARG(np + (probeVarchar ? 1 : 0) <= kMaxJoinColumns && nb + (buildVarchar ? 1 : 0) <= kMaxJoinColumns, "too many output channels");
+        if (probeVarchar) {
+            iotaProbe.reserve((size_t) n * 4); srcRow.reserve((size_t) total * 4);
+            PG_LAUNCH(this, iotaU32Kernel, grid, 256, 0, iotaProbe.as<uint32_t>(), n);
+            JoinColumn& jc = E.probe[np++];
+            jc.width = 4; jc.src = iotaProbe.ptr; jc.srcNulls = nullptr; jc.dst = srcRow.ptr; jc.dstNulls = nullptr;
+        }
+        if (buildVarchar) {
+            iotaBuild.reserve((size_t) std::max<int64_t>(ls->positionCount, 1) * 4); srcPos.reserve((size_t) total * 4);
+            PG_LAUNCH(this, iotaU32Kernel, grid, 256, 0, iotaBuild.as<uint32_t>(), ls->positionCount);
+            JoinColumn& jc = E.build[nb++];
+            jc.width = 4; jc.src = iotaBuild.ptr; jc.srcNulls = nullptr; jc.dst = srcPos.ptr; jc.dstNulls = nullptr;
+            if (joinType == PG_JOIN_PROBE_OUTER) { srcPosNull.reserve(total); jc.dstNulls = srcPosNull.as<uint8_t>(); }
+        }
+        E.nProbe = np; E.nBuild = nb;
         PG_LAUNCH(this, joinEmitKernel, grid, 256, 0, E);
-        stager.markCompute(slot);
-        const bool toHost = options.output_memory == PG_MEM_HOST;
-        if (toHost && hostValues.size() < nOut) { hostValues.resize(nOut); hostNulls.resize(nOut); }
-        for (size_t i = 0; i < nOut; i++) {
-            pg_block& b = outBlocks[i];
-            const bool hasNulls = (i < outputChannels.size() ? E.probe[i].dstNulls : E.build[i - outputChannels.size()].dstNulls) != nullptr;
-            const size_t vbytes = (size_t) total * typeWidth(b.type);
-            b.encoding = PG_ENC_FLAT; b.position_count = total; b.offsets = nullptr; b.ids = nullptr; b.dictionary_size = 0;
-            if (toHost) {
-                hostValues[i].reserve(vbytes);
-                PG_CUDA(cudaMemcpyAsync(hostValues[i].ptr, outValues[i].ptr, vbytes, cudaMemcpyDeviceToHost, stream));
-                b.values = hostValues[i].ptr; b.is_null = nullptr;
-                stats.d2h_bytes += (int64_t) vbytes;
-                if (hasNulls) { hostNulls[i].reserve(total); PG_CUDA(cudaMemcpyAsync(hostNulls[i].ptr, outNulls[i].ptr, total, cudaMemcpyDeviceToHost, stream)); b.is_null = hostNulls[i].as<uint8_t>(); stats.d2h_bytes += total; }
+        for (const VarcharOut& v : vouts) {
+            outNulls[v.slot].reserve(total);
+            uint8_t* dstNulls = hasNulls[v.slot] ? outNulls[v.slot].as<uint8_t>() : nullptr;
+            if (v.fromBuild)
+                varBytes[v.slot] = gatherVarcharByIndex(this, ls->values[v.channel].as<uint8_t>(), ls->offsets[v.channel].as<int32_t>(), ls->nulls[v.channel].as<uint8_t>(), srcPos.as<uint32_t>(),
+                                                        joinType == PG_JOIN_PROBE_OUTER ? srcPosNull.as<uint8_t>() : nullptr, total, outValues[v.slot], outOffsets[v.slot], dstNulls, varScan);
+            else {
+                const DeviceColumn& c = colOf(v.channel);
+                PG_CHECK_ARG(c.offsets != nullptr, "VARCHAR block without offsets");
+                varBytes[v.slot] = gatherVarcharByIndex(this, (const uint8_t*) c.values, c.offsets, c.nulls, srcRow.as<uint32_t>(), nullptr, total, outValues[v.slot], outOffsets[v.slot], dstNulls, varScan);
             }
-            else { b.values = outValues[i].ptr; b.is_null = hasNulls ? outNulls[i].as<uint8_t>() : nullptr; }
-            stats.output_bytes += (int64_t) vbytes;
         }
-        PG_CUDA(cudaStreamSynchronize(stream));
-        hasPending = true;
-        stats.output_positions += total;
+        stager.markCompute(slot);
+        publish(total, hasNulls);
+    }
+
+    void ensureOutputSlots(size_t nOut)
+    {
+        if (outValues.size() >= nOut) return;
+        outValues.resize(nOut); outNulls.resize(nOut); outOffsets.resize(nOut); varBytes.resize(nOut, 0);
+        for (auto* v : {&outValues, &outNulls, &outOffsets}) for (auto& d : *v) d.accounting = &stats.device_bytes;
     }
 
     // Probe of the bitmap + rank index: count per 128-row unit → scan of the unit counts → write the output columns in place.
@@ -1422,11 +1553,13 @@ public:
         pendingRows = total;
         if (total == 0) { stager.markCompute(slot); return; }
         const size_t nOut = outputChannels.size() + ls.outputChannels.size();
-        if (outValues.size() < nOut) { outValues.resize(nOut); outNulls.resize(nOut); for (auto& d : outValues) d.accounting = &stats.device_bytes; for (auto& d : outNulls) d.accounting = &stats.device_bytes; }
+        ensureOutputSlots(nOut);
         outBlocks.assign(nOut, pg_block{});
         std::vector<bool> hasNulls(nOut, false);
+        std::vector<VarcharOut> vouts;
         for (size_t i = 0; i < outputChannels.size(); i++) {
             const DeviceColumn& c = colOf(outputChannels[i]);
+            if (c.type == PG_TYPE_VARCHAR) { vouts.push_back({i, false, outputChannels[i]}); outBlocks[i].type = c.type; hasNulls[i] = c.nulls != nullptr; continue; }
             const int w = typeWidth(c.type);
             outValues[i].reserve((size_t) total * w);
             CopyColumn cc{c.values, outValues[i].ptr};
@@ -1447,10 +1580,23 @@ public:
             if (pc.width == 8) P.build8[P.nBuild8++] = f; else if (pc.width == 4) P.build4[P.nBuild4++] = f; else P.build1[P.nBuild1++] = f;
             outBlocks[o].type = ls.types[ch];
         }
+        if (!vouts.empty()) {      // the source row of every output row, as one more 4-byte probe column
+            PG_CHECK_ARG(P.nProbe4 < kMaxJoinColumns, "too many output channels");
+            iotaProbe.reserve((size_t) n * 4); srcRow.reserve((size_t) total * 4);
+            PG_LAUNCH(this, iotaU32Kernel, grid, 256, 0, iotaProbe.as<uint32_t>(), n);
+            P.probe4[P.nProbe4++] = CopyColumn{iotaProbe.ptr, srcRow.ptr};
+        }
         switch (ls.payload.strideWords) {
             case 1: PG_LAUNCH(this, denseEmitKernel<1>, grid, 256, 0, P); break;
             case 2: PG_LAUNCH(this, denseEmitKernel<2>, grid, 256, 0, P); break;
             default: PG_LAUNCH(this, denseEmitKernel<4>, grid, 256, 0, P); break;
+        }
+        for (const VarcharOut& v : vouts) {
+            const DeviceColumn& c = colOf(v.channel);
+            PG_CHECK_ARG(c.offsets != nullptr, "VARCHAR block without offsets");
+            outNulls[v.slot].reserve(total);
+            varBytes[v.slot] = gatherVarcharByIndex(this, (const uint8_t*) c.values, c.offsets, c.nulls, srcRow.as<uint32_t>(), nullptr, total, outValues[v.slot], outOffsets[v.slot],
+                                                    hasNulls[v.slot] ? outNulls[v.slot].as<uint8_t>() : nullptr, varScan);
         }
         stager.markCompute(slot);
         publish(total, hasNulls);
@@ -1461,14 +1607,21 @@ public:
     {
         const size_t nOut = outBlocks.size();
         const bool toHost = options.output_memory == PG_MEM_HOST;
-        if (toHost && hostValues.size() < nOut) { hostValues.resize(nOut); hostNulls.resize(nOut); }
+        if (toHost && hostValues.size() < nOut) { hostValues.resize(nOut); hostNulls.resize(nOut); hostOffsets.resize(nOut); }
         for (size_t i = 0; i < nOut; i++) {
             pg_block& b = outBlocks[i];
-            const size_t vbytes = (size_t) total * typeWidth(b.type);
-            b.encoding = PG_ENC_FLAT; b.position_count = total; b.offsets = nullptr; b.ids = nullptr; b.dictionary_size = 0;
+            const bool varchar = b.type == PG_TYPE_VARCHAR;
+            const size_t vbytes = varchar ? (size_t) varBytes[i] : (size_t) total * typeWidth(b.type);
+            b.encoding = PG_ENC_FLAT; b.position_count = total; b.offsets = varchar ? outOffsets[i].as<int32_t>() : nullptr; b.ids = nullptr; b.dictionary_size = 0;
             if (toHost) {
                 hostValues[i].reserve(std::max<size_t>(vbytes, 16));
-                PG_CUDA(cudaMemcpyAsync(hostValues[i].ptr, outValues[i].ptr, vbytes, cudaMemcpyDeviceToHost, stream));
+                if (vbytes) PG_CUDA(cudaMemcpyAsync(hostValues[i].ptr, outValues[i].ptr, vbytes, cudaMemcpyDeviceToHost, stream));
+                if (varchar) {
+                    hostOffsets[i].reserve((size_t) (total + 1) * 4);
+                    PG_CUDA(cudaMemcpyAsync(hostOffsets[i].ptr, outOffsets[i].ptr, (size_t) (total + 1) * 4, cudaMemcpyDeviceToHost, stream));
+                    b.offsets = hostOffsets[i].as<int32_t>();
+                    stats.d2h_bytes += (total + 1) * 4;
+                }
                 b.values = hostValues[i].ptr; b.is_null = nullptr;
                 stats.d2h_bytes += (int64_t) vbytes;
                 if (hasNulls[i]) { hostNulls[i].reserve(total); PG_CUDA(cudaMemcpyAsync(hostNulls[i].ptr, outNulls[i].ptr, total, cudaMemcpyDeviceToHost, stream)); b.is_null = hostNulls[i].as<uint8_t>(); stats.d2h_bytes += total; }
@@ -1507,6 +1660,7 @@ __global__ void outerUnvisitedKernel(const uint8_t* visited, int64_t n, uint32_t
 }
 struct OuterEmitParams {
     const uint8_t* visited; const uint32_t* offsets; int64_t n;
+    uint32_t* srcPos;          // when set: the build position of every output row (VARCHAR build channels are gathered through it)
     int32_t nProbe, nBuild;
     JoinColumn probe[kMaxJoinColumns];      // dst only: all NULL
     JoinColumn build[kMaxJoinColumns];
@@ -1516,6 +1670,7 @@ __global__ void outerEmitKernel(const __grid_constant__ OuterEmitParams P)
     for (int64_t p = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; p < P.n; p += (int64_t) gridDim.x * blockDim.x) {
         if (P.visited[p]) continue;
         const int64_t o = P.offsets[p];
+        if (P.srcPos) P.srcPos[o] = (uint32_t) p;
         for (int c = 0; c < P.nProbe; c++) writeNull(P.probe[c], o);
         for (int c = 0; c < P.nBuild; c++) copyValue(P.build[c], p, o);
     }
@@ -1529,7 +1684,8 @@ class LookupOuterOp : public Operator {
     std::vector<DeviceBuffer> outValues, outNulls;
     std::vector<PinnedBuffer> hostValues, hostNulls;
     std::vector<pg_block> outBlocks, slice;
-    DeviceBuffer flags, offsets, scanTemp;
+    DeviceBuffer flags, offsets, scanTemp, srcPos, varScan;
+    std::vector<DeviceBuffer> outOffsets; std::vector<PinnedBuffer> hostOffsets; std::vector<int64_t> varBytes;
 
 public:
     LookupOuterOp(const pg_lookup_outer_config* c, JoinBridge* b) : Operator(c->options), bridge(b)
@@ -1538,7 +1694,6 @@ public:
         PG_CHECK_ARG(b->isOuter(), "the bridge was not created for outer tracking (pg_join_bridge_set_outer)");
         PG_CHECK_ARG(c->n_probe_output_channels >= 0 && c->n_probe_output_channels <= kMaxJoinColumns, "too many probe output channels");
         probeTypes.assign(c->probe_output_types, c->probe_output_types + c->n_probe_output_channels);
-        for (int t : probeTypes) if (t == PG_TYPE_VARCHAR) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR probe output channels are not on the GPU path");
     }
     bool needsInput() override { return false; }
     void addInput(const pg_page*) override { throw Error(PG_ERR_UNSUPPORTED, "LookupOuterOperator is a source operator"); }    // :171-175
@@ -1568,41 +1723,62 @@ public:
         total = t;
         if (total == 0) return;
         const size_t nOut = probeTypes.size() + ls->outputChannels.size();
-        outValues.resize(nOut); outNulls.resize(nOut);
-        for (auto& d : outValues) d.accounting = &stats.device_bytes;
-        for (auto& d : outNulls) d.accounting = &stats.device_bytes;
+        outValues.resize(nOut); outNulls.resize(nOut); outOffsets.resize(nOut); varBytes.assign(nOut, 0);
+        for (auto* v : {&outValues, &outNulls, &outOffsets}) for (auto& d : *v) d.accounting = &stats.device_bytes;
         outBlocks.assign(nOut, pg_block{});
         OuterEmitParams E{};
         E.visited = ls->visited.as<uint8_t>(); E.offsets = offsets.as<uint32_t>(); E.n = n;
-        E.nProbe = (int) probeTypes.size(); E.nBuild = (int) ls->outputChannels.size();
         std::vector<bool> hasNulls(nOut, false);
+        std::vector<std::pair<size_t, int>> varcharBuild;      // (slot, build channel)
+        int np = 0, nb = 0;
         for (size_t i = 0; i < probeTypes.size(); i++) {
-            JoinColumn& jc = E.probe[i];
-            jc.width = typeWidth(probeTypes[i]); jc.src = nullptr; jc.srcNulls = nullptr;
-            outValues[i].reserve((size_t) total * jc.width); outNulls[i].reserve(total);
-            jc.dst = outValues[i].ptr; jc.dstNulls = outNulls[i].as<uint8_t>();
             outBlocks[i].type = probeTypes[i]; hasNulls[i] = true;
+            outNulls[i].reserve(total);
+            if (probeTypes[i] == PG_TYPE_VARCHAR) {     // an all-NULL VARCHAR column: every slice empty
+                outOffsets[i].reserve((size_t) (total + 1) * 4); outValues[i].reserve(16);
+                PG_CUDA(cudaMemsetAsync(outOffsets[i].ptr, 0, (size_t) (total + 1) * 4, stream));
+                PG_CUDA(cudaMemsetAsync(outNulls[i].ptr, 1, (size_t) total, stream));
+                continue;
+            }
+            JoinColumn& jc = E.probe[np++];
+            jc.width = typeWidth(probeTypes[i]); jc.src = nullptr; jc.srcNulls = nullptr;
+            outValues[i].reserve((size_t) total * jc.width);
+            jc.dst = outValues[i].ptr; jc.dstNulls = outNulls[i].as<uint8_t>();
         }
         for (size_t i = 0; i < ls->outputChannels.size(); i++) {
             const int ch = ls->outputChannels[i];
             const size_t o = probeTypes.size() + i;
-            JoinColumn& jc = E.build[i];
+            outBlocks[o].type = ls->types[ch];
+            if (ls->types[ch] == PG_TYPE_VARCHAR) { varcharBuild.push_back({o, ch}); hasNulls[o] = true; continue; }
+            JoinColumn& jc = E.build[nb++];
             jc.width = typeWidth(ls->types[ch]); jc.src = ls->values[ch].ptr; jc.srcNulls = ls->hasNulls[ch] ? ls->nulls[ch].as<uint8_t>() : nullptr;
             outValues[o].reserve((size_t) total * jc.width);
             jc.dst = outValues[o].ptr; jc.dstNulls = nullptr;
             if (jc.srcNulls) { outNulls[o].reserve(total); jc.dstNulls = outNulls[o].as<uint8_t>(); hasNulls[o] = true; }
-            outBlocks[o].type = ls->types[ch];
         }
+        E.nProbe = np; E.nBuild = nb;
+        if (!varcharBuild.empty()) { srcPos.reserve((size_t) total * 4); E.srcPos = srcPos.as<uint32_t>(); }
         PG_LAUNCH(this, outerEmitKernel, grid, 256, 0, E);
+        for (auto& vb : varcharBuild) {
+            outNulls[vb.first].reserve(total);
+            varBytes[vb.first] = gatherVarcharByIndex(this, ls->values[vb.second].as<uint8_t>(), ls->offsets[vb.second].as<int32_t>(), ls->nulls[vb.second].as<uint8_t>(), srcPos.as<uint32_t>(), nullptr,
+                                                      total, outValues[vb.first], outOffsets[vb.first], outNulls[vb.first].as<uint8_t>(), varScan);
+        }
         const bool toHost = options.output_memory == PG_MEM_HOST;
-        if (toHost) { hostValues.resize(nOut); hostNulls.resize(nOut); }
+        if (toHost) { hostValues.resize(nOut); hostNulls.resize(nOut); hostOffsets.resize(nOut); }
         for (size_t i = 0; i < nOut; i++) {
             pg_block& b = outBlocks[i];
-            const size_t vbytes = (size_t) total * typeWidth(b.type);
-            b.encoding = PG_ENC_FLAT; b.position_count = total; b.offsets = nullptr; b.ids = nullptr; b.dictionary_size = 0;
+            const bool varchar = b.type == PG_TYPE_VARCHAR;
+            const size_t vbytes = varchar ? (size_t) varBytes[i] : (size_t) total * typeWidth(b.type);
+            b.encoding = PG_ENC_FLAT; b.position_count = total; b.offsets = varchar ? outOffsets[i].as<int32_t>() : nullptr; b.ids = nullptr; b.dictionary_size = 0;
             if (toHost) {
                 hostValues[i].reserve(std::max<size_t>(vbytes, 16));
-                PG_CUDA(cudaMemcpyAsync(hostValues[i].ptr, outValues[i].ptr, vbytes, cudaMemcpyDeviceToHost, stream));
+                if (vbytes) PG_CUDA(cudaMemcpyAsync(hostValues[i].ptr, outValues[i].ptr, vbytes, cudaMemcpyDeviceToHost, stream));
+                if (varchar) {
+                    hostOffsets[i].reserve((size_t) (total + 1) * 4);
+                    PG_CUDA(cudaMemcpyAsync(hostOffsets[i].ptr, outOffsets[i].ptr, (size_t) (total + 1) * 4, cudaMemcpyDeviceToHost, stream));
+                    b.offsets = hostOffsets[i].as<int32_t>();
+                }
                 b.values = hostValues[i].ptr; b.is_null = nullptr;
                 stats.d2h_bytes += (int64_t) vbytes;
                 if (hasNulls[i]) { hostNulls[i].reserve(total); PG_CUDA(cudaMemcpyAsync(hostNulls[i].ptr, outNulls[i].ptr, total, cudaMemcpyDeviceToHost, stream)); b.is_null = hostNulls[i].as<uint8_t>(); stats.d2h_bytes += total; }
@@ -1622,7 +1798,8 @@ public:
         slice = outBlocks;
         for (auto& b : slice) {
             b.position_count = m;
-            b.values = (const char*) b.values + next * typeWidth(b.type);
+            if (b.type == PG_TYPE_VARCHAR) b.offsets += next;      // offsets stay absolute into the shared byte slice
+            else b.values = (const char*) b.values + next * typeWidth(b.type);
             if (b.is_null) b.is_null += next;
         }
         out->position_count = m; out->channel_count = (int32_t) slice.size(); out->memory = options.output_memory; out->blocks = slice.data();

@@ -388,6 +388,52 @@ def case_join_filter_over_both_sides(backend):
         probe.close(); builder.close(); bridge.close()
 
 
+def case_join_varchar_outputs(backend):
+    """VARCHAR channels travelling through the join (the reference's TestHashJoinOperator pages are mostly VARCHAR; here the KEYS stay BIGINT):
+    LookupJoinPageBuilder.appendRow copies the probe row's slices (:90-119) and LookupSource.appendTo the build position's.  Duplicate
+    chains (descending build position), NULL strings, empty strings, a probe page split in two, INNER / PROBE_OUTER and the outer operator."""
+    from presto_b200 import JOIN_FULL_OUTER, LookupOuterOperator
+    build_keys = [5, 7, 5, 9, None, 11]
+    build_names = [b"five-a", b"", None, b"nine", b"null-key", b"eleven, the longest of them all"]
+    probe_keys = [7, 5, 1, None, 9, 5]
+    probe_names = [b"p7", None, b"p1", b"pnull", b"", b"p5 again"]
+    bp = [Page([create_longs_block(*build_keys[:4]), create_strings_block(*build_names[:4])]), Page([create_longs_block(*build_keys[4:]), create_strings_block(*build_names[4:])])]
+    pp = [Page([create_strings_block(*probe_names[:3]), create_longs_block(*probe_keys[:3])]), Page([create_strings_block(*probe_names[3:]), create_longs_block(*probe_keys[3:])])]
+
+    def expect(outer):
+        rows = []
+        for pk, pn in zip(probe_keys, probe_names):
+            hits = [pos for pos in reversed(range(len(build_keys))) if pk is not None and build_keys[pos] == pk]
+            rows += [(pn, pk, build_names[pos], build_keys[pos]) for pos in hits]
+            if not hits and outer:
+                rows.append((pn, pk, None, None))
+        return rows
+    for jt in (JOIN_INNER, JOIN_PROBE_OUTER):
+        bridge = JoinBridge(backend=backend)
+        builder = HashBuilderOperator(bridge, [BIGINT, VARCHAR], [0], [1, 0], backend=backend)
+        to_pages(builder, bp)
+        probe = LookupJoinOperator(bridge, [VARCHAR, BIGINT], [1], [0, 1], join_type=jt, backend=backend)
+        assert rows_of(to_pages(probe, pp)) == expect(jt == JOIN_PROBE_OUTER)
+        probe.close(); builder.close(); bridge.close()
+    # FULL OUTER: the unmatched build rows (positions 4 and 5) follow with NULL probe channels, VARCHAR ones included
+    bridge = JoinBridge(backend=backend, outer=True)
+    builder = HashBuilderOperator(bridge, [BIGINT, VARCHAR], [0], [1, 0], backend=backend)
+    to_pages(builder, bp)
+    probe = LookupJoinOperator(bridge, [VARCHAR, BIGINT], [1], [0, 1], join_type=JOIN_FULL_OUTER, backend=backend)
+    outer = LookupOuterOperator(bridge, [VARCHAR, BIGINT], backend=backend, max_output_rows=1)
+    assert rows_of(to_pages(probe, pp)) == expect(True)
+    bridge.no_more_probe_operators()
+    pages = []
+    while not outer.is_finished():
+        p = outer.get_output()
+        if p is not None:
+            pages.append(p)
+    assert rows_of(pages) == [(None, None, b"null-key", None), (None, None, b"eleven, the longest of them all", 11)]
+    for op in (probe, outer, builder):
+        op.close()
+    bridge.close()
+
+
 def case_probe_outer_join_empty_lookup_source(backend):
     """testProbeOuterJoinWithEmptyLookupSource :1323+ — empty build: every probe row comes out with NULL build columns."""
     bridge = JoinBridge(backend=backend)

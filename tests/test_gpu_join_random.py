@@ -200,3 +200,45 @@ def test_sorted_build_of_the_dense_index(gpu_backend, oracle_backend, monkeypatc
         args = (build_pages, types, probe_pages, [BIGINT, DOUBLE], jt, list(range(1, len(types))), [0, 1])
         got, want = join(gpu_backend, *args), join(oracle_backend, *args)
         assert len(got) > 0 and got == want
+
+
+def _random_strings(rng, n, null_rate=0.1, max_len=12):
+    from presto_b200 import Block
+    lens = rng.integers(0, max_len + 1, n)
+    return Block.from_strings([None if rng.random() < null_rate else bytes(rng.integers(97, 123, int(k)).astype(np.uint8)) for k in lens])
+
+
+@pytest.mark.parametrize("kind", ["dense_unique", "sparse_unique", "duplicates"])
+@pytest.mark.parametrize("join_type", [JOIN_INNER, JOIN_PROBE_OUTER])
+@pytest.mark.parametrize("build_varchar", [False, True], ids=["probe_varchar_only", "varchar_on_both_sides"])
+def test_varchar_channels_through_the_join(gpu_backend, oracle_backend, kind, join_type, build_varchar):
+    """VARCHAR output channels: probe-side ones ride on either LookupSource (bitmap index for dense_unique, hash table otherwise); a VARCHAR
+    build payload keeps the position-ordered hash path.  NULL / empty strings, NULL keys, duplicate chains, several pages."""
+    from presto_b200 import VARCHAR
+    rng = np.random.default_rng(sum(map(ord, kind)) + join_type * 2 + int(build_varchar))
+    keys, nb = build_side(rng, kind, 20_000, BIGINT)
+    cut = nb // 2
+    build_pages = []
+    for s in (slice(0, cut), slice(cut, nb)):
+        m = len(keys[s])
+        blocks = [Block.from_numpy(BIGINT, keys[s], (rng.random(m) < 0.03).astype(np.uint8)), Block.from_numpy(DATE, rng.integers(8000, 9000, m).astype(np.int32))]
+        if build_varchar:
+            blocks.append(_random_strings(rng, m))
+        build_pages.append(Page(blocks))
+    build_types = [BIGINT, DATE] + ([VARCHAR] if build_varchar else [])
+    probe_pages = []
+    for _ in range(2):
+        npr = 15_000
+        pk = np.where(rng.random(npr) < 0.6, keys[rng.integers(0, nb, npr)], rng.integers(-1000, 1 << 41, npr))
+        probe_pages.append(Page([_random_strings(rng, npr), Block.from_numpy(BIGINT, pk, (rng.random(npr) < 0.05).astype(np.uint8)), _random_strings(rng, npr, null_rate=0.0, max_len=3)]))
+
+    def run(backend):
+        bridge = JoinBridge(backend=backend)
+        builder = HashBuilderOperator(bridge, build_types, [0], list(range(1, len(build_types))), backend=backend)
+        assert to_pages(builder, build_pages) == []
+        probe = LookupJoinOperator(bridge, [VARCHAR, BIGINT, VARCHAR], [1], [2, 1, 0], join_type=join_type, backend=backend)
+        rows = rows_of(to_pages(probe, probe_pages))
+        probe.close(); builder.close(); bridge.close()
+        return rows
+    got, want = run(gpu_backend), run(oracle_backend)
+    assert len(want) > 5000 and got == want

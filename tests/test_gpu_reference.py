@@ -46,6 +46,7 @@ def test_probe_outer_join_with_filter_function(gpu_backend, probe_hash, build_ha
 @pytest.mark.parametrize("probe_hash,build_hash", HASH_FLAGS)
 def test_outer_join_with_nulls_and_filter_function(gpu_backend, probe_hash, build_hash): rc.case_outer_join_with_nulls_and_filter_function(gpu_backend, probe_hash, build_hash)
 def test_join_filter_over_both_sides(gpu_backend): rc.case_join_filter_over_both_sides(gpu_backend)
+def test_join_varchar_outputs(gpu_backend): rc.case_join_varchar_outputs(gpu_backend)
 def test_probe_outer_join_empty_lookup_source(gpu_backend): rc.case_probe_outer_join_empty_lookup_source(gpu_backend)
 def test_join_duplicate_chain_order(gpu_backend): rc.case_join_duplicate_chain_order(gpu_backend)
 def test_lookup_outer_join_empty_lookup_source(gpu_backend): rc.case_lookup_outer_join_empty_lookup_source(gpu_backend)

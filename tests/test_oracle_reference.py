@@ -105,6 +105,7 @@ def test_probe_outer_join_with_filter_function(oracle_backend, probe_hash, build
 @pytest.mark.parametrize("probe_hash,build_hash", HASH_FLAGS)
 def test_outer_join_with_nulls_and_filter_function(oracle_backend, probe_hash, build_hash): rc.case_outer_join_with_nulls_and_filter_function(oracle_backend, probe_hash, build_hash)
 def test_join_filter_over_both_sides(oracle_backend): rc.case_join_filter_over_both_sides(oracle_backend)
+def test_join_varchar_outputs(oracle_backend): rc.case_join_varchar_outputs(oracle_backend)
 def test_probe_outer_join_empty_lookup_source(oracle_backend): rc.case_probe_outer_join_empty_lookup_source(oracle_backend)
 def test_join_duplicate_chain_order(oracle_backend): rc.case_join_duplicate_chain_order(oracle_backend)
 def test_lookup_outer_join_empty_lookup_source(oracle_backend): rc.case_lookup_outer_join_empty_lookup_source(oracle_backend)
