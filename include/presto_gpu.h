@@ -327,7 +327,8 @@ typedef struct pg_hash_builder_config {
     int32_t n_hash_channels;
     const int32_t* hash_channels;       /* join key channels (BIGINT / INTEGER / DATE) */
     int32_t n_output_channels;
-    const int32_t* output_channels;     /* build channels appended to join output */
+    const int32_t* output_channels;     /* build channels appended to join output (any pg_type but LONG_DECIMAL; a VARCHAR channel keeps the
+                                           position-ordered hash-table LookupSource) */
     int32_t precomputed_hash_channel;   /* $hashvalue channel or -1 */
     int64_t expected_positions;
     pg_operator_options options;
@@ -349,7 +350,7 @@ typedef struct pg_lookup_join_config {
     int32_t n_hash_channels;
     const int32_t* hash_channels;       /* probe join-key channels */
     int32_t n_output_channels;
-    const int32_t* output_channels;     /* probe channels emitted (probeOutputChannels) */
+    const int32_t* output_channels;     /* probe channels emitted (probeOutputChannels; VARCHAR slices are copied like LookupJoinPageBuilder does) */
     int32_t precomputed_hash_channel;
     pg_operator_options options;
 } pg_lookup_join_config;
