@@ -673,6 +673,7 @@ void PagesSerde::planDictionary(const pg_page* page, int c, ChannelPlan& P)
     const int64_t n = b.position_count, D = b.dictionary_size;
     PG_CHECK_ARG(D >= 0 && D < (int64_t(1) << 31) && b.ids != nullptr, "DICTIONARY block without ids");
     const bool host = page->memory == PG_MEM_HOST;
+    temps.reserve(temps.size() + 16);        // the references taken below must survive the emplace_backs that follow them
     // ids on the device
     const int32_t* ids = b.ids;
     if (host) {
