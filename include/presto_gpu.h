@@ -179,7 +179,8 @@ typedef enum {                       /* pg_operator_stats.kernel_paths */
     PG_PATH_FUSED_TIERS = 32,        /* generated fused pipeline kernel, on-chip tiers */
     PG_PATH_FUSED_DIRECT = 64,       /* generated fused pipeline kernel, HBM table */
     PG_PATH_UNFUSED_CHAIN = 128,     /* fused operator that ran its fragment operator by operator (fragment not fusable for that page) */
-    PG_PATH_FUSED_TMA = 256          /* (with FUSED_TIERS / FUSED_DIRECT) eager columns staged by a cp.async.bulk (TMA) ring */
+    PG_PATH_FUSED_TMA = 256,         /* (with FUSED_TIERS / FUSED_DIRECT) eager columns staged by a cp.async.bulk (TMA) ring */
+    PG_PATH_INTERNED_KEYS = 512      /* VARCHAR group keys without a declared length of <= 7 bytes: replaced by value ids (VarcharInterner) first */
 } pg_kernel_path;
 
 /* Options common to all operators. */

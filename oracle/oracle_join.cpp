@@ -40,11 +40,21 @@ struct LookupSource {
         if (precomputedHashChannel >= 0) return channels[precomputedHashChannel].getLong(position);
         int64_t result = 0;
         for (int hc : hashChannels) {
-            int64_t h = channels[hc].nulls[position] ? 0 : hashLong(channels[hc].getLong(position));
+            int64_t h = channels[hc].nulls[position] ? 0 : valueHash(hc, position);
             result = result * 31 + h;
         }
         return result;
     }
+    // type.hash of a build value: AbstractLongType.hash for the integer types, XxHash64 of the slice for VARCHAR
+    // (AbstractVariableWidthBlock.java:102-106)
+    int64_t valueHash(int hc, int64_t position) const
+    {
+        const Column& c = channels[hc];
+        if (c.type == PG_TYPE_VARCHAR) return xxHash64(c.data.data() + c.offsets[position], (size_t) (c.offsets[position + 1] - c.offsets[position]));
+        return hashLong(c.getLong(position));
+    }
+    // type.equalTo: slices compare by length and bytes (AbstractVariableWidthBlock.equals :108-117)
+    static bool slicesEqual(const uint8_t* a, int32_t la, const uint8_t* b, int32_t lb) { return la == lb && (la == 0 || memcmp(a, b, (size_t) la) == 0); }
     bool isPositionNull(int64_t position) const
     {
         for (int hc : hashChannels) if (channels[hc].nulls[position]) return true;
@@ -52,13 +62,24 @@ struct LookupSource {
     }
     bool positionEqualsPositionIgnoreNulls(int64_t l, int64_t r) const
     {
-        for (int hc : hashChannels) if (channels[hc].getLong(l) != channels[hc].getLong(r)) return false;
+        for (int hc : hashChannels) {
+            const Column& c = channels[hc];
+            if (c.type == PG_TYPE_VARCHAR) {
+                if (!slicesEqual(c.data.data() + c.offsets[l], c.offsets[l + 1] - c.offsets[l], c.data.data() + c.offsets[r], c.offsets[r + 1] - c.offsets[r])) return false;
+            }
+            else if (c.getLong(l) != c.getLong(r)) return false;
+        }
         return true;
     }
     bool positionEqualsRowIgnoreNulls(int64_t l, int64_t rightPosition, const std::vector<BlockView>& probeHashBlocks) const
     {
-        for (size_t i = 0; i < hashChannels.size(); i++)
-            if (channels[hashChannels[i]].getLong(l) != probeHashBlocks[i].getLong(rightPosition)) return false;
+        for (size_t i = 0; i < hashChannels.size(); i++) {
+            const Column& c = channels[hashChannels[i]];
+            if (c.type == PG_TYPE_VARCHAR) {
+                if (!slicesEqual(c.data.data() + c.offsets[l], c.offsets[l + 1] - c.offsets[l], probeHashBlocks[i].slicePtr(rightPosition), probeHashBlocks[i].sliceLength(rightPosition))) return false;
+            }
+            else if (c.getLong(l) != probeHashBlocks[i].getLong(rightPosition)) return false;
+        }
         return true;
     }
 
@@ -147,7 +168,7 @@ struct HashBuilderOperator : Operator {
         if (c->filter && c->filter->filter_node >= 0) bridge->filter = createJoinFilter(c->filter, c->n_channels);
         for (int hc : ls->hashChannels) {
             int t = ls->types[hc];
-            if (t != PG_TYPE_BIGINT && t != PG_TYPE_INTEGER && t != PG_TYPE_DATE) throw OracleError(PG_ERR_UNSUPPORTED, "join key type");
+            if (t != PG_TYPE_BIGINT && t != PG_TYPE_INTEGER && t != PG_TYPE_DATE && t != PG_TYPE_VARCHAR) throw OracleError(PG_ERR_UNSUPPORTED, "join key type");
         }
     }
     bool needsInput() override { return !finishing; }
@@ -234,7 +255,7 @@ struct LookupJoinOperator : Operator {
                 if (precomputedHashChannel >= 0) rawHash = hashBlock.getLong(position);
                 else {   // SimplePagesHashStrategy.hashRow :125-136
                     rawHash = 0;
-                    for (auto& b : probeHash) rawHash = rawHash * 31 + hashLong(b.getLong(position));
+                    for (auto& b : probeHash) rawHash = rawHash * 31 + (b.b->type == PG_TYPE_VARCHAR ? xxHash64(b.slicePtr(position), (size_t) b.sliceLength(position)) : hashLong(b.getLong(position)));
                 }
                 joinPosition = ls.getAddressIndex(position, probeHash, rawHash);
             }

@@ -81,6 +81,7 @@ class pg_operator_stats(C.Structure):
 
 PATH_AGG_FAST, PATH_AGG_WARP, PATH_AGG_MID, PATH_AGG_DIRECT, PATH_AGG_GENERIC, PATH_FUSED_TIERS, PATH_FUSED_DIRECT, PATH_UNFUSED_CHAIN = 1, 2, 4, 8, 16, 32, 64, 128
 PATH_FUSED_TMA = 256
+PATH_INTERNED_KEYS = 512
 
 
 class pg_operator_options(C.Structure):

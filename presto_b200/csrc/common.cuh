@@ -272,6 +272,52 @@ __host__ __device__ inline int64_t xxHash64Short(uint64_t lo, int len)
     return (int64_t) h;
 }
 
+// XXH64 (seed 0) of an arbitrary byte slice = VarcharType.hash (AbstractVariableWidthBlock.java:102-106 → airlift XxHash64.hash(Slice)).
+// Bytes are fetched one at a time (slices start at any alignment); the published XXH64 layout: 32-byte stripes into four lanes, then
+// 8- / 4- / 1-byte tails, then the avalanche.
+__host__ __device__ __forceinline__ uint64_t loadLe64(const uint8_t* p)
+{
+    uint64_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) v |= (uint64_t) p[i] << (8 * i);
+    return v;
+}
+__host__ __device__ inline int64_t xxHash64Bytes(const uint8_t* p, int64_t len)
+{
+    const uint64_t P1 = 0x9E3779B185EBCA87ULL, P2 = 0xC2B2AE3D27D4EB4FULL, P3 = 0x165667B19E3779F9ULL, P4 = 0x85EBCA77C2B2AE63ULL, P5 = 0x27D4EB2F165667C5ULL;
+    int64_t pos = 0;
+    uint64_t h;
+    if (len >= 32) {
+        uint64_t v[4] = {P1 + P2, P2, 0, 0 - P1};
+        for (; pos + 32 <= len; pos += 32) {
+#pragma unroll
+            for (int l = 0; l < 4; l++) {
+                uint64_t a = v[l] + loadLe64(p + pos + 8 * l) * P2;
+                v[l] = ((a << 31) | (a >> 33)) * P1;
+            }
+        }
+        h = ((v[0] << 1) | (v[0] >> 63)) + ((v[1] << 7) | (v[1] >> 57)) + ((v[2] << 12) | (v[2] >> 52)) + ((v[3] << 18) | (v[3] >> 46));
+#pragma unroll
+        for (int l = 0; l < 4; l++) {
+            uint64_t k = v[l] * P2; k = ((k << 31) | (k >> 33)) * P1;
+            h = (h ^ k) * P1 + P4;
+        }
+    }
+    else h = P5;
+    h += (uint64_t) len;
+    for (; pos + 8 <= len; pos += 8) {
+        uint64_t k = loadLe64(p + pos) * P2; k = ((k << 31) | (k >> 33)) * P1;
+        h ^= k; h = ((h << 27) | (h >> 37)) * P1 + P4;
+    }
+    if (pos + 4 <= len) {
+        const uint64_t k = (uint64_t) p[pos] | ((uint64_t) p[pos + 1] << 8) | ((uint64_t) p[pos + 2] << 16) | ((uint64_t) p[pos + 3] << 24);
+        h ^= k * P1; h = ((h << 23) | (h >> 41)) * P2 + P3; pos += 4;
+    }
+    for (; pos < len; pos++) { h ^= (uint64_t) p[pos] * P5; h = ((h << 11) | (h >> 53)) * P1; }
+    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+    return (int64_t) h;
+}
+
 // streaming 128-bit load (read-once data: do not allocate in L1)
 __device__ __forceinline__ ulonglong2 ldStream128(const void* p)
 {

@@ -20,6 +20,7 @@
 // Keys that are not one BIGINT / two 32-bit columns, NULLs, masks, bigint sums: hashAggKernel<W, MAXV> (tiers 0 / 1 / 2).
 #include "common.cuh"
 #include "group_table.cuh"
+#include "varchar_interner.h"
 #include "key_layout.h"
 #include "agg_tiers.cuh"
 #include <cub/device/device_radix_sort.cuh>
@@ -982,6 +983,7 @@ __global__ void __launch_bounds__(256) collectSlotsKernel(GroupTable t, uint64_t
 struct KeyOut {          // one output key column
     void* values; uint8_t* nulls; int32_t* lens;   // VARCHAR: lens[g] first, bytes in a second pass
     int32_t type, word, shift, bits;
+    const uint32_t* internLength; const uint64_t* internHash;   // interned VARCHAR key (varchar_interner.h): the field is the value's id
 };
 struct AggOut {
     int32_t function;      // pg_aggregate_function
@@ -1035,6 +1037,12 @@ __global__ void emitKernel(const __grid_constant__ EmitParams P)
                 case PG_TYPE_INTEGER: case PG_TYPE_DATE: ((int32_t*) ko.values)[g] = (int32_t) v; if (!isNull) th = hashLong((int64_t) (int32_t) v); break;
                 case PG_TYPE_BOOLEAN: ((uint8_t*) ko.values)[g] = (uint8_t) v; if (!isNull) th = v ? 1231 : 1237; break;
                 case PG_TYPE_VARCHAR: {
+                    if (ko.internLength) {       // id → length now, bytes gathered from the interner's pool after the scan of the lengths
+                        ko.lens[g] = isNull ? 0 : (int32_t) ko.internLength[(uint32_t) v];
+                        ((int32_t*) ko.values)[g] = (int32_t) v;
+                        if (!isNull) th = (int64_t) ko.internHash[(uint32_t) v];
+                        break;
+                    }
                     int len = isNull ? 0 : (int) (v & 0xff);
                     ko.lens[g] = len;
                     ((uint64_t*) ko.values)[g] = v >> 8;     // packed bytes, expanded by expandVarcharKernel
@@ -1237,7 +1245,8 @@ struct ResultBuilder {
     std::vector<int> outTypes;
 
     // Output schema: group keys [, $hashvalue], aggregates (HashAggregationOperator.java:357 toTypes), `g` rows in `order`.
-    void build(Operator* op, const GroupTable& T, const KeyLayout& layout, const uint32_t* order, int64_t g, bool withHash, const std::vector<AggEmit>& aggs)
+    void build(Operator* op, const GroupTable& T, const KeyLayout& layout, const uint32_t* order, int64_t g, bool withHash, const std::vector<AggEmit>& aggs,
+               const std::vector<std::unique_ptr<VarcharInterner>>* interners = nullptr)
     {
         cudaStream_t stream = op->stream;
         EmitParams E{};
@@ -1259,7 +1268,7 @@ struct ResultBuilder {
             bound = nCols * (align((size_t) g * 8 + 16) + align((size_t) g + 16)) + nVarchar * (2 * align((size_t) (g + 1) * 4) + align(scanTemp + 16) + align((size_t) g * 8 + 16))
                   + nDecimal * (align((size_t) g * 24 + 16) + align((size_t) (g + 1) * 4 + 16));
         }
-        const bool arenaMode = toHost && g > 0 && bound <= kArenaBytes;
+        const bool arenaMode = toHost && g > 0 && bound <= kArenaBytes && !layout.anyInterned();   // interned keys: byte totals are only known after the scan
         if (arenaMode) {
             arena.accounting = &op->stats.device_bytes;
             arena.reserve(bound);
@@ -1292,6 +1301,12 @@ struct ResultBuilder {
             KeyOut& ko = E.keys[k];
             ko.values = outBufs[colBufs[c].values].ptr; ko.nulls = outBufs[colBufs[c].nulls].as<uint8_t>(); ko.lens = nullptr;
             ko.type = layout.types[k]; ko.word = layout.word[k]; ko.shift = layout.shift[k]; ko.bits = layout.bits[k];
+            ko.internLength = nullptr; ko.internHash = nullptr;
+            if (layout.interned[k]) {
+                PG_CHECK_STATE(interners && (*interners)[k], "internal: interned key without its interner");
+                const InternView iv = (*interners)[k]->view();
+                ko.internLength = iv.entryLength; ko.internHash = iv.entryHash;
+            }
             if (layout.types[k] == PG_TYPE_VARCHAR) {
                 varcharLens[k] = newBuf((size_t) (g + 1) * 4);
                 zero(outBufs[varcharLens[k]].ptr, (size_t) (g + 1) * 4);
@@ -1340,6 +1355,17 @@ struct ResultBuilder {
             const int t2 = newBuf(tb);       // (lives in outBufs until the next build: no synchronisation needed to release it)
             cub::DeviceScan::ExclusiveSum(outBufs[t2].ptr, tb, outBufs[varcharLens[k]].as<int32_t>(), outBufs[offs].as<int32_t>(), (int) g + 1, stream);
             op->stats.kernel_launches += 2;
+            if (layout.interned[k]) {
+                int32_t total = 0;
+                PG_CUDA(cudaMemcpyAsync(&total, outBufs[offs].as<int32_t>() + g, 4, cudaMemcpyDeviceToHost, stream));
+                PG_CUDA(cudaStreamSynchronize(stream));
+                if (total < 0) throw Error(PG_ERR_INSUFFICIENT_RESOURCES, "VARCHAR key column of the result exceeds 2 GB");
+                const int bytesBuf = newBuf((size_t) total);
+                (*interners)[k]->gatherBytes(op, (const int32_t*) outBufs[colBufs[k].values].ptr, outBufs[colBufs[k].nulls].as<uint8_t>(), outBufs[offs].as<int32_t>(), g,
+                                             outBufs[bytesBuf].as<uint8_t>());
+                varcharBytes[k] = bytesBuf; varcharOffsets[k] = offs;
+                continue;
+            }
             int bytes = newBuf((size_t) g * 8);
             PG_LAUNCH(op, expandVarcharKernel, (int) std::min<int64_t>(divUp(g, 256), 2048), 256, 0, (const uint64_t*) outBufs[colBufs[k].values].ptr, outBufs[offs].as<int32_t>(), (int32_t) g, outBufs[bytes].as<uint8_t>());
             varcharBytes[k] = bytes; varcharOffsets[k] = offs;
@@ -1503,6 +1529,10 @@ protected:
     const std::vector<int>* inputChannels = nullptr;
     std::function<void(const std::vector<DeviceColumn>&, int64_t, const uint32_t*, uint32_t*)> fusedLaunch;
     bool lastFused = false;
+    // interned VARCHAR keys (KeyLayout::interned): one interner per such key, the id column of the chunk in flight
+    std::vector<std::unique_ptr<VarcharInterner>> interners;
+    std::vector<DeviceBuffer> internIds;
+    std::vector<DeviceColumn> internCols;
 
 public:
     explicit HashAggregationOp(const pg_hash_aggregation_config* c) : Operator(c->options), stager(this)
@@ -1529,7 +1559,27 @@ public:
         table.allocate(cap);
         hostCounters.reserve(CNT_COUNT * sizeof(unsigned int));
         bitmapA.accounting = bitmapB.accounting = &stats.device_bytes;
+        interners.resize(layout.nKeys); internIds.resize(layout.nKeys); internCols.resize(layout.nKeys);
+        for (int k = 0; k < layout.nKeys; k++)
+            if (layout.interned[k]) { interners[k].reset(new VarcharInterner(this, &stats.device_bytes)); internIds[k].accounting = &stats.device_bytes; }
         PG_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    // Interned VARCHAR keys of this chunk → id columns (MultiChannelGroupByHash compares the slices themselves, :293-358; here equal
+    // slices get equal ids first and the packed key carries the id).  Called after settle(): the previous chunk no longer needs its ids.
+    void internKeys(const std::vector<DeviceColumn>& cols, int64_t n)
+    {
+        for (int k = 0; k < layout.nKeys; k++) {
+            if (!layout.interned[k]) continue;
+            const size_t i = std::find(stagedChannels.begin(), stagedChannels.end(), layout.channels[k]) - stagedChannels.begin();
+            const DeviceColumn& src = cols[i];
+            PG_CHECK_ARG(src.type == PG_TYPE_VARCHAR, "group-by channel type differs from the operator's configuration");
+            internIds[k].reserve((size_t) n * 4 + 16);
+            interners[k]->intern(this, src, n, internIds[k].as<int32_t>(), true);
+            DeviceColumn ids; ids.type = PG_TYPE_INTEGER; ids.n = n; ids.values = internIds[k].ptr; ids.nulls = src.nulls; ids.offsets = nullptr;
+            internCols[k] = ids;
+            stats.kernel_paths |= PG_PATH_INTERNED_KEYS;
+        }
     }
 
     template <int W, int MV> void configureFor()
@@ -1739,8 +1789,8 @@ public:
         };
         std::vector<DeviceColumn> keyCols;
         for (int k = 0; k < layout.nKeys; k++) {
-            DeviceColumn kc = colOf(layout.channels[k]);
-            PG_CHECK_ARG(kc.type == layout.types[k], "group-by channel type differs from the operator's configuration");
+            DeviceColumn kc = layout.interned[k] ? internCols[k] : colOf(layout.channels[k]);
+            PG_CHECK_ARG(layout.interned[k] || kc.type == layout.types[k], "group-by channel type differs from the operator's configuration");
             int w = typeWidth(kc.type);
             if (w) kc.values = (const char*) kc.values + begin * w; else kc.offsets = kc.offsets + begin;
             if (kc.nulls) kc.nulls += begin;
@@ -1835,7 +1885,7 @@ public:
             std::vector<DeviceColumn> cols;
             int slot = stager.stage(&sub, inputChannels ? *inputChannels : stagedChannels, cols);   // PCIe copy of this chunk overlaps the previous chunk's kernel
             settle();                                              // previous chunk: counters, deferred rows, growth
-            if (!fusedLaunch) activateLazyCounts(cols);
+            if (!fusedLaunch) { activateLazyCounts(cols); internKeys(cols, m); }
             processChunk(cols, m);
             stager.markCompute(slot);
             rowsSeen += (uint64_t) m;
@@ -1912,6 +1962,7 @@ public:
     {
         PG_CHECK_ARG(buffer != nullptr && capacity >= stateBytes(maxGroups), "state buffer smaller than pg_hash_aggregation_state_bytes(max_groups)");
         PG_CHECK_STATE(!outputBuilt, "the operator has already produced output");
+        if (layout.anyInterned()) throw Error(PG_ERR_UNSUPPORTED, "aggregation states with interned VARCHAR keys (ids are private to one operator): use the page-based PARTIAL / FINAL steps");
         settle();
         uint32_t inactive = 0;
         for (size_t p = 0; p < phys.size(); p++) if (phys[p].lazy && !phys[p].active) inactive |= 1u << p;
@@ -1935,6 +1986,7 @@ public:
         PG_CHECK_ARG(buffers != nullptr && count >= 1 && count <= 200 && orderBase >= 0 && orderBase + count <= 255, "between 1 and 200 states, order tags below 255");
         PG_CHECK_ARG(stride >= stateBytes(maxGroups), "stride smaller than one state");
         PG_CHECK_STATE(needsInput(), "Operator is already finishing");
+        if (layout.anyInterned()) throw Error(PG_ERR_UNSUPPORTED, "aggregation states with interned VARCHAR keys (ids are private to one operator): use the page-based PARTIAL / FINAL steps");
         settle();
         // one strided copy brings every header; the group counts size the table, the hashes guard against a mismatched plan
         hostCounters.reserve(std::max<size_t>((size_t) count * sizeof(AggStateHeader), CNT_COUNT * sizeof(unsigned int)));
@@ -1999,7 +2051,7 @@ public:
             if (a.countCol >= 0) e.countCol = phys[a.countCol].active ? a.countCol : (a.countExact ? rowCountCol : -1);
             emits.push_back(e);
         }
-        result.build(this, T, layout, order.as<uint32_t>(), g, hashChannel >= 0, emits);
+        result.build(this, T, layout, order.as<uint32_t>(), g, hashChannel >= 0, emits, &interners);
     }
 
     bool getOutput(pg_page* out) override   // HashAggregationOperator.java:451-501
@@ -2089,6 +2141,22 @@ class GroupByHashImpl : public Operator {
     int64_t nextGroupId = 0;
     uint64_t rowsSeen = 0;
     ResultBuilder result;
+    std::vector<std::unique_ptr<VarcharInterner>> interners;     // interned VARCHAR keys (KeyLayout::interned)
+    std::vector<DeviceBuffer> internIds;
+
+    // cols[k] (one per key) with interned VARCHAR keys replaced by their id columns; insert = false only looks values up (contains)
+    std::vector<DeviceColumn> internKeys(const std::vector<DeviceColumn>& cols, int64_t n, bool insert)
+    {
+        std::vector<DeviceColumn> out = cols;
+        for (int k = 0; k < layout.nKeys; k++) {
+            if (!layout.interned[k]) continue;
+            PG_CHECK_ARG(cols[k].type == PG_TYPE_VARCHAR, "group-by channel type differs from the configuration");
+            internIds[k].reserve((size_t) n * 4 + 16);
+            interners[k]->intern(this, cols[k], n, internIds[k].as<int32_t>(), insert);
+            out[k].type = PG_TYPE_INTEGER; out[k].values = internIds[k].ptr; out[k].offsets = nullptr;
+        }
+        return out;
+    }
 
 public:
     explicit GroupByHashImpl(const pg_group_by_hash_config* c) : Operator(c->options), stager(this)
@@ -2101,6 +2169,9 @@ public:
         table.counters.reserve(CNT_COUNT * sizeof(unsigned int));
         PG_CUDA(cudaMemsetAsync(table.counters.ptr, 0, CNT_COUNT * sizeof(unsigned int), stream));
         table.allocate(std::max<uint32_t>(1024, nextPow2((uint64_t) c->expected_size * 2)));
+        interners.resize(layout.nKeys); internIds.resize(layout.nKeys);
+        for (int k = 0; k < layout.nKeys; k++)
+            if (layout.interned[k]) { interners[k].reset(new VarcharInterner(this, &stats.device_bytes)); internIds[k].accounting = &stats.device_bytes; }
         PG_CUDA(cudaStreamSynchronize(stream));
     }
     bool needsInput() override { return true; }
@@ -2171,6 +2242,7 @@ public:
             stats.input_positions += n;
             std::vector<DeviceColumn> cols;
             stager.stage(&sub, keyChannels, cols);
+            if (layout.anyInterned()) cols = internKeys(cols, n, true);
             ensureCapacity(n);
             slotOfGid.accounting = newSlots.accounting = &stats.device_bytes;
             {   // slotOfGid must hold nextGroupId + n entries, preserving what is there
@@ -2238,6 +2310,7 @@ public:
         if (page->position_count == 0) return;
         std::vector<DeviceColumn> cols;
         stager.stage(page, keyChannels, cols);
+        if (layout.anyInterned()) cols = internKeys(cols, page->position_count, false);
         lookupInto(cols, page->position_count, nullptr, flagsOut, page->memory);
         checkErrors();
     }
@@ -2247,7 +2320,7 @@ public:
     void getKeys(pg_page* out)
     {
         if (nextGroupId == 0) { out->position_count = 0; out->channel_count = 0; out->memory = options.output_memory; out->blocks = nullptr; return; }
-        result.build(this, table.view(), layout, slotOfGid.as<uint32_t>(), nextGroupId, hashChannel >= 0, {});
+        result.build(this, table.view(), layout, slotOfGid.as<uint32_t>(), nextGroupId, hashChannel >= 0, {}, &interners);
         result.slice(0, nextGroupId, options.output_memory, out);
     }
 };
@@ -2276,6 +2349,7 @@ static bool describeFragment(FusedProgramDesc& D, const std::vector<int32_t>& in
         fj.buildOutputs = v.buildOutputs; fj.strideWords = v.strideWords;
         D.joins.push_back(fj);
     }
+    if (layout.anyInterned()) { why = "VARCHAR group key without a declared length of <= 7 bytes (interned per chunk)"; return false; }
     for (int k = 0; k < layout.nKeys; k++) {
         FusedKeyField f; f.channel = layout.channels[k]; f.type = layout.types[k]; f.word = layout.word[k]; f.shift = layout.shift[k]; f.bits = layout.bits[k]; f.maxLen = layout.maxLens[k];
         D.keys.push_back(f);

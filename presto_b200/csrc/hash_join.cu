@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "fp_interp.cuh"
 #include "group_table.cuh"
+#include "varchar_interner.h"
 #include "key_layout.h"
 #include "dense_index.cuh"
 #include "operators_internal.h"
@@ -875,6 +876,10 @@ struct LookupSourceDevice {
     // JoinFilterFunction handed to the build side (HashBuilderOperator's filterFunctionFactory → JoinHash.filterFunction)
     std::vector<pg_expr_node> filterNodes; int filterNode = -1; std::vector<int> filterInputTypes; int filterBuildInputs = 0;
     bool hasFilter() const { return filterNode >= 0; }
+    // VARCHAR join keys (PagesHashStrategy compares the slices of the key channels; here they are interned to value ids when the build
+    // finishes, the packed key carries the id, and every probe page looks its slices up — an absent value cannot match)
+    std::vector<std::unique_ptr<VarcharInterner>> interners;    // per key column, null unless KeyLayout::interned
+    std::vector<DeviceBuffer> keyIds;                           // per key column: int32 id per build position
     DeviceBuffer visited;          // outer bridges: one byte per build position, set by the probes' emit kernels (OuterPositionTracker)
     PayloadLayout payload{};
     DenseIndex denseView() const { DenseIndex D{}; D.bitmap = bitmap.as<uint64_t>(); D.prefix = prefix.as<uint32_t>(); D.minKey = minKey; D.range = range; return D; }
@@ -916,8 +921,8 @@ __global__ void fillU64KernelJ(uint64_t* p, uint64_t v, size_t n)
 static void checkJoinKeyTypes(const KeyLayout& l)
 {
     for (int k = 0; k < l.nKeys; k++)
-        if (l.types[k] != PG_TYPE_BIGINT && l.types[k] != PG_TYPE_INTEGER && l.types[k] != PG_TYPE_DATE)
-            throw Error(PG_ERR_UNSUPPORTED, "join keys on the GPU path are BIGINT / INTEGER / DATE channels");
+        if (l.types[k] != PG_TYPE_BIGINT && l.types[k] != PG_TYPE_INTEGER && l.types[k] != PG_TYPE_DATE && l.types[k] != PG_TYPE_VARCHAR)
+            throw Error(PG_ERR_UNSUPPORTED, "join keys on the GPU path are BIGINT / INTEGER / DATE / VARCHAR channels");
 }
 
 class HashBuilderOp : public Operator {
@@ -1106,9 +1111,18 @@ public:
         PG_CUDA(cudaMemsetAsync(ls->counters.ptr, 0, 64, stream));
         if (n > 0) {
             std::vector<DeviceColumn> keyCols;
+            ls->interners.resize(ls->layout.nKeys); ls->keyIds.resize(ls->layout.nKeys);
             for (int k = 0; k < ls->layout.nKeys; k++) {
                 int ch = ls->layout.channels[k];
                 DeviceColumn c; c.type = ls->types[ch]; c.n = n; c.values = ls->values[ch].ptr; c.nulls = ls->hasNulls[ch] ? ls->nulls[ch].as<uint8_t>() : nullptr;
+                if (ls->layout.interned[k]) {      // the channel's slices (PagesIndex order) → one id per build position
+                    c.offsets = ls->offsets[ch].as<int32_t>();
+                    ls->interners[k].reset(new VarcharInterner(this, &ls->deviceBytes));
+                    ls->keyIds[k].accounting = &ls->deviceBytes;
+                    ls->keyIds[k].reserve((size_t) n * 4 + 16);
+                    ls->interners[k]->intern(this, c, n, ls->keyIds[k].as<int32_t>(), true);
+                    c.type = PG_TYPE_INTEGER; c.values = ls->keyIds[k].ptr; c.offsets = nullptr;
+                }
                 keyCols.push_back(c);
             }
             KeyPlan kp{};
@@ -1140,7 +1154,7 @@ public:
     // Unique keys over a small range → bitmap + rank index (see DenseIndex).  Returns false to fall back to the hash table.
     bool tryBuildDense()
     {
-        if (ls->layout.nKeys != 1) return false;
+        if (ls->layout.nKeys != 1 || ls->layout.anyInterned()) return false;
         const int64_t n = ls->positionCount;
         // payload row layout: widest columns first (natural alignment), then one null byte per nullable column
         PayloadLayout payloadLayout{};
@@ -1313,6 +1327,7 @@ class LookupJoinOp : public Operator {
     // VARCHAR output channels (gatherVarcharByIndex): source index columns written by the emit kernels, then offsets / bytes per slot
     std::vector<DeviceBuffer> outOffsets; std::vector<PinnedBuffer> hostOffsets; std::vector<int64_t> varBytes;
     DeviceBuffer iotaProbe, iotaBuild, srcRow, srcPos, srcPosNull, varScan;
+    std::vector<DeviceBuffer> probeKeyIds;      // VARCHAR key channels of the page in flight as value ids of the LookupSource's interners
     struct VarcharOut { size_t slot; bool fromBuild; int channel; };
     bool filterChannelsStaged = false;
 
@@ -1402,7 +1417,18 @@ public:
         ProbeParams P{};
         P.J = ls->view();
         std::vector<DeviceColumn> keyCols;
-        for (int k = 0; k < layout.nKeys; k++) { keyCols.push_back(colOf(layout.channels[k])); PG_CHECK_ARG(keyCols.back().type == layout.types[k], "probe key channel type differs from configuration"); }
+        for (int k = 0; k < layout.nKeys; k++) {
+            keyCols.push_back(colOf(layout.channels[k]));
+            PG_CHECK_ARG(keyCols.back().type == layout.types[k], "probe key channel type differs from configuration");
+            if (!layout.interned[k]) continue;
+            // VARCHAR key: the id the build gave this slice, -1 when the build never saw it (read-only lookup on this operator's stream)
+            if (probeKeyIds.size() < (size_t) layout.nKeys) { probeKeyIds.resize(layout.nKeys); for (auto& b : probeKeyIds) b.accounting = &stats.device_bytes; }
+            probeKeyIds[k].reserve((size_t) n * 4 + 16);
+            DeviceColumn& c = keyCols.back();
+            if (k < (int) ls->interners.size() && ls->interners[k]) ls->interners[k]->intern(this, c, n, probeKeyIds[k].as<int32_t>(), false);
+            else PG_CUDA(cudaMemsetAsync(probeKeyIds[k].ptr, 0xFF, (size_t) n * 4, stream));       // empty build: nothing matches
+            c.type = PG_TYPE_INTEGER; c.values = probeKeyIds[k].ptr; c.offsets = nullptr;
+        }
         layout.fill(P.kp, keyCols, ls->counters.as<unsigned int>() + CNT_ERROR);
         P.n = n; P.outer = joinType == PG_JOIN_PROBE_OUTER; P.hasDuplicates = ls->hasDuplicates; P.matchHead = matchHead.as<int32_t>(); P.counts = counts.as<uint32_t>();
         PG_CUDA(cudaMemsetAsync(counts.as<uint32_t>() + n, 0, 4, stream));

@@ -8,9 +8,13 @@ struct KeyLayout {
     int nKeys = 0;
     int W = 1;
     bool bigintPath = false;
+    bool anyInterned() const { for (int k = 0; k < nKeys; k++) if (interned[k]) return true; return false; }
     int types[kMaxKeyColumns] = {0};
     int channels[kMaxKeyColumns] = {0};
     int maxLens[kMaxKeyColumns] = {0};
+    // VARCHAR keys that do not fit a packed field (no declared length, or more than 7 bytes) enter the key as the 32-bit id of their
+    // value in a per-operator VarcharInterner (varchar_interner.h); the operator substitutes the id column before packing
+    bool interned[kMaxKeyColumns] = {false};
     int word[kMaxKeyColumns] = {0}, shift[kMaxKeyColumns] = {0}, bits[kMaxKeyColumns] = {0};
     int nullWord = 0, nullShift = 0;
 
@@ -29,9 +33,8 @@ struct KeyLayout {
                 case PG_TYPE_INTEGER: case PG_TYPE_DATE: bits[k] = 32; break;
                 case PG_TYPE_BOOLEAN: bits[k] = 8; break;
                 case PG_TYPE_VARCHAR:
-                    if (maxLens[k] <= 0 || maxLens[k] > 7)
-                        throw Error(PG_ERR_UNSUPPORTED, "VARCHAR group-by keys need a declared max length of 1..7 bytes on the GPU path");
-                    bits[k] = maxLens[k] <= 1 ? 16 : (maxLens[k] <= 3 ? 32 : 64);
+                    if (maxLens[k] <= 0 || maxLens[k] > 7) { interned[k] = true; bits[k] = 32; }
+                    else bits[k] = maxLens[k] <= 1 ? 16 : (maxLens[k] <= 3 ? 32 : 64);
                     break;
                 default: throw Error(PG_ERR_UNSUPPORTED, "group-by key type");
             }
@@ -56,7 +59,7 @@ struct KeyLayout {
         kp.nKeys = nKeys; kp.bigintPath = bigintPath ? 1 : 0; kp.nullWord = nullWord; kp.nullShift = nullShift; kp.errorFlag = errorFlag;
         for (int k = 0; k < nKeys; k++) {
             kp.f[k].values = cols[k].values; kp.f[k].nulls = cols[k].nulls; kp.f[k].offsets = cols[k].offsets;
-            kp.f[k].type = types[k]; kp.f[k].word = word[k]; kp.f[k].shift = shift[k]; kp.f[k].bits = bits[k]; kp.f[k].maxLen = maxLens[k];
+            kp.f[k].type = interned[k] ? PG_TYPE_INTEGER : types[k]; kp.f[k].word = word[k]; kp.f[k].shift = shift[k]; kp.f[k].bits = bits[k]; kp.f[k].maxLen = maxLens[k];
         }
     }
 };

@@ -434,31 +434,9 @@ int32_t pg_hash_local_partition(int64_t rawHash, int32_t partitionCount)
 
 int64_t pg_hash_xxhash64(const void* data, size_t len)
 {
-    // XXH64 seed 0 (airlift XxHash64.hash(Slice)); full-length host implementation
-    const uint64_t P1 = 0x9E3779B185EBCA87ULL, P2 = 0xC2B2AE3D27D4EB4FULL, P3 = 0x165667B19E3779F9ULL, P4 = 0x85EBCA77C2B2AE63ULL, P5 = 0x27D4EB2F165667C5ULL;
-    auto rot = [](uint64_t x, int r) { return (x << r) | (x >> (64 - r)); };
-    auto round = [&](uint64_t acc, uint64_t in) { acc += in * P2; acc = rot(acc, 31); return acc * P1; };
-    const uint8_t* p = (const uint8_t*) data;
-    const uint8_t* end = p + len;
-    uint64_t h;
-    if (len >= 32) {
-        uint64_t v1 = P1 + P2, v2 = P2, v3 = 0, v4 = 0 - P1;
-        while (p + 32 <= end) {
-            uint64_t a, b, c, d;
-            memcpy(&a, p, 8); memcpy(&b, p + 8, 8); memcpy(&c, p + 16, 8); memcpy(&d, p + 24, 8);
-            v1 = round(v1, a); v2 = round(v2, b); v3 = round(v3, c); v4 = round(v4, d);
-            p += 32;
-        }
-        h = rot(v1, 1) + rot(v2, 7) + rot(v3, 12) + rot(v4, 18);
-        for (uint64_t v : {v1, v2, v3, v4}) { h ^= round(0, v); h = h * P1 + P4; }
-    }
-    else h = P5;
-    h += (uint64_t) len;
-    while (p + 8 <= end) { uint64_t k; memcpy(&k, p, 8); h ^= round(0, k); h = rot(h, 27) * P1 + P4; p += 8; }
-    if (p + 4 <= end) { uint32_t k; memcpy(&k, p, 4); h ^= (uint64_t) k * P1; h = rot(h, 23) * P2 + P3; p += 4; }
-    while (p < end) { h ^= (uint64_t) (*p) * P5; h = rot(h, 11) * P1; p++; }
-    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
-    return (int64_t) h;
+    // XXH64 seed 0 (airlift XxHash64.hash(Slice)): the very function the kernels hash VARCHAR slices with (common.cuh), so the CPU
+    // tests that cross-check this entry point against the xxhash package pin the device code too
+    return pg::xxHash64Bytes((const uint8_t*) data, (int64_t) len);
 }
 
 // ---- operator protocol ------------------------------------------------------------------------------------------------

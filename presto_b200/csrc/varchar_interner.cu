@@ -1,0 +1,189 @@
+// presto_b200 — VarcharInterner (varchar_interner.h): open-addressing table of slices keyed by XXH64, values stored once in a byte
+// pool.  One thread per row: rows are short strings (group / join keys), the work per row is a hash over the bytes, one or two
+// L2-resident slot reads and one byte comparison — the page's bytes are read once from HBM (hash) and once more from L2 (compare).
+#include "varchar_interner.h"
+
+namespace pg {
+
+constexpr uint32_t kInEmpty = 0, kInLocked = 1;
+constexpr int64_t kInternChunk = int64_t(1) << 22;     // rows between two capacity checks (worst case: every row a new value)
+
+__device__ __forceinline__ bool sliceEqualsPool(const uint8_t* pool, const uint8_t* p, uint32_t len)
+{
+    // pool lines may have been filled by another SM moments ago: read them at L2 (ld.global.cg), never through this SM's L1
+    for (uint32_t i = 0; i < len; i++) if (__ldcg(pool + i) != p[i]) return false;
+    return true;
+}
+
+template <bool INSERT>
+__global__ void __launch_bounds__(256) internKernel(InternView T, const uint8_t* bytes, const int32_t* offsets, const uint8_t* nulls, int64_t n, int32_t* idsOut)
+{
+    for (int64_t row = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; row < n; row += (int64_t) gridDim.x * blockDim.x) {
+        if (nulls && nulls[row]) { idsOut[row] = 0; continue; }
+        const int32_t o = offsets[row];
+        const uint32_t len = (uint32_t) (offsets[row + 1] - o);
+        const uint8_t* p = bytes + o;
+        const uint64_t h = (uint64_t) xxHash64Bytes(p, (int64_t) len);
+        uint32_t slot = (uint32_t) h & T.mask;
+        volatile uint32_t* slots = T.slots;
+        int32_t result = -1;
+        for (uint32_t probe = 0; probe < T.cap; probe++) {
+            uint32_t st = slots[slot];
+            if (st == kInEmpty) {
+                if (!INSERT) break;
+                const uint32_t old = atomicCAS(&T.slots[slot], kInEmpty, kInLocked);
+                if (old == kInEmpty) {
+                    const uint32_t id = (uint32_t) atomicAdd(&T.counters[0], 1ULL);
+                    const uint64_t off = atomicAdd(&T.counters[1], (unsigned long long) len);
+                    for (uint32_t i = 0; i < len; i++) T.pool[off + i] = p[i];
+                    T.entryOffset[id] = off; T.entryLength[id] = len; T.entryHash[id] = h;
+                    __threadfence();
+                    slots[slot] = id + 2;          // publish: readers that saw LOCKED have been spinning on this word
+                    result = (int32_t) id;
+                    break;
+                }
+                st = old;
+            }
+            while (st == kInLocked) st = slots[slot];
+            const uint32_t id = st - 2;
+            if (__ldcg(&T.entryHash[id]) == h && __ldcg(&T.entryLength[id]) == len && sliceEqualsPool(T.pool + __ldcg(&T.entryOffset[id]), p, len)) {
+                result = (int32_t) id;
+                break;
+            }
+            slot = (slot + 1) & T.mask;
+        }
+        idsOut[row] = result;
+    }
+}
+
+__global__ void internRehashKernel(InternView T, uint64_t nEntries)
+{
+    for (uint64_t id = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; id < nEntries; id += (uint64_t) gridDim.x * blockDim.x) {
+        uint32_t slot = (uint32_t) T.entryHash[id] & T.mask;
+        while (atomicCAS(&T.slots[slot], kInEmpty, (uint32_t) id + 2) != kInEmpty) slot = (slot + 1) & T.mask;
+    }
+}
+
+__global__ void internLengthsKernel(InternView T, const int32_t* ids, const uint8_t* nulls, int64_t g, int32_t* lengthsOut)
+{
+    for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < g; i += (int64_t) gridDim.x * blockDim.x)
+        lengthsOut[i] = (nulls && nulls[i]) ? 0 : (int32_t) T.entryLength[ids[i]];
+}
+
+// one warp per value: lanes stride over its bytes (values of a few bytes cost one partly filled transaction, long ones stay coalesced)
+__global__ void internBytesKernel(InternView T, const int32_t* ids, const uint8_t* nulls, const int32_t* offsets, int64_t g, uint8_t* bytesOut)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5, warps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < g; i += warps) {
+        if (nulls && nulls[i]) continue;
+        const int32_t id = ids[i];
+        const uint8_t* src = T.pool + T.entryOffset[id];
+        const uint32_t len = T.entryLength[id];
+        uint8_t* dst = bytesOut + offsets[i];
+        for (uint32_t b = lane; b < len; b += 32) dst[b] = src[b];
+    }
+}
+
+VarcharInterner::VarcharInterner(Operator* op, int64_t* accounting)
+{
+    for (DeviceBuffer* b : {&slots, &entryOffset, &entryLength, &entryHash, &pool, &counters}) b->accounting = accounting;
+    counters.reserve(2 * sizeof(unsigned long long));
+    PG_CUDA(cudaMemsetAsync(counters.ptr, 0, 2 * sizeof(unsigned long long), op->stream));
+    host.reserve(64);
+}
+
+InternView VarcharInterner::view() const
+{
+    InternView v{};
+    v.slots = slots.as<uint32_t>(); v.cap = cap; v.mask = cap ? cap - 1 : 0;
+    v.entryOffset = entryOffset.as<uint64_t>(); v.entryLength = entryLength.as<uint32_t>(); v.entryHash = entryHash.as<uint64_t>();
+    v.pool = pool.as<uint8_t>(); v.counters = counters.as<unsigned long long>();
+    return v;
+}
+
+void VarcharInterner::readCounters(Operator* op)
+{
+    PG_CUDA(cudaMemcpyAsync(host.ptr, counters.ptr, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, op->stream));
+    PG_CUDA(cudaStreamSynchronize(op->stream));
+    nEntries = host.as<unsigned long long>()[0]; poolUsed = host.as<unsigned long long>()[1];
+    op->stats.d2h_bytes += 16;
+}
+
+// Room for `extraEntries` more values of `extraBytes` bytes in total, whatever the page holds (called between kernels; the stream is
+// synchronised before an outgrown buffer goes back to the allocator).
+void VarcharInterner::ensure(Operator* op, uint64_t extraEntries, uint64_t extraBytes)
+{
+    cudaStream_t stream = op->stream;
+    const uint64_t needEntries = nEntries + extraEntries, needBytes = poolUsed + extraBytes;
+    if (needEntries + 2 >= (1ULL << 31)) throw Error(PG_ERR_INSUFFICIENT_RESOURCES, "more than 2^31 distinct VARCHAR key values");
+    auto regrow = [&](DeviceBuffer& buf, size_t newBytes, size_t keepBytes) {
+        DeviceBuffer bigger; bigger.accounting = buf.accounting;
+        bigger.reserve(newBytes);
+        if (keepBytes) PG_CUDA(cudaMemcpyAsync(bigger.ptr, buf.ptr, keepBytes, cudaMemcpyDeviceToDevice, stream));
+        PG_CUDA(cudaStreamSynchronize(stream));
+        buf = std::move(bigger);
+    };
+    if (needEntries > entryCap) {
+        const uint64_t newCap = std::max<uint64_t>(std::max<uint64_t>(entryCap * 2, needEntries), 1024);
+        regrow(entryOffset, newCap * 8, nEntries * 8);
+        regrow(entryLength, newCap * 4, nEntries * 4);
+        regrow(entryHash, newCap * 8, nEntries * 8);
+        entryCap = newCap;
+    }
+    if (needBytes > poolCap) {
+        const uint64_t newCap = std::max<uint64_t>(std::max<uint64_t>(poolCap * 2, needBytes), 4096);
+        regrow(pool, newCap, poolUsed);
+        poolCap = newCap;
+    }
+    if (needEntries * 2 > cap) {
+        uint64_t newCap = std::max<uint32_t>(cap, 1024);
+        while (newCap < needEntries * 2) newCap <<= 1;
+        DeviceBuffer bigger; bigger.accounting = slots.accounting;
+        bigger.reserve(newCap * 4);
+        PG_CUDA(cudaMemsetAsync(bigger.ptr, 0, newCap * 4, stream));
+        PG_CUDA(cudaStreamSynchronize(stream));
+        slots = std::move(bigger);
+        cap = (uint32_t) newCap;
+        if (nEntries) PG_LAUNCH(op, internRehashKernel, (int) std::min<int64_t>(divUp((int64_t) nEntries, 256), 2048), 256, 0, view(), nEntries);
+    }
+}
+
+void VarcharInterner::intern(Operator* op, const DeviceColumn& col, int64_t n, int32_t* idsOut, bool insert)
+{
+    PG_CHECK_ARG(col.type == PG_TYPE_VARCHAR && col.offsets != nullptr, "VARCHAR key channel without offsets");
+    if (n <= 0) return;
+    cudaStream_t stream = op->stream;
+    if (!insert) {      // read-only (cap == 0: nothing was ever interned, every value is absent)
+        PG_LAUNCH(op, internKernel<false>, (int) std::min<int64_t>(divUp(n, 256), (int64_t) op->numSMs * 8), 256, 0, view(), (const uint8_t*) col.values, col.offsets,
+                  col.nulls, n, idsOut);
+        return;
+    }
+    for (int64_t begin = 0; begin < n; begin += kInternChunk) {
+        const int64_t m = std::min(kInternChunk, n - begin);
+        // what the table holds now, and how many bytes this range can add (two offsets of the page)
+        int32_t* ends = host.as<int32_t>() + 8;
+        PG_CUDA(cudaMemcpyAsync(ends, col.offsets + begin, 4, cudaMemcpyDeviceToHost, stream));
+        PG_CUDA(cudaMemcpyAsync(ends + 1, col.offsets + begin + m, 4, cudaMemcpyDeviceToHost, stream));
+        readCounters(op);
+        PG_CHECK_ARG(ends[1] >= ends[0], "VARCHAR offsets must not decrease");
+        ensure(op, (uint64_t) m, (uint64_t) (ends[1] - ends[0]));
+        PG_LAUNCH(op, internKernel<true>, (int) std::min<int64_t>(divUp(m, 256), (int64_t) op->numSMs * 8), 256, 0, view(), (const uint8_t*) col.values,
+                  col.offsets + begin, col.nulls ? col.nulls + begin : nullptr, m, idsOut + begin);
+    }
+    readCounters(op);
+}
+
+void VarcharInterner::gatherLengths(Operator* op, const int32_t* ids, const uint8_t* nulls, int64_t g, int32_t* lengthsOut)
+{
+    if (g <= 0) return;
+    PG_LAUNCH(op, internLengthsKernel, (int) std::min<int64_t>(divUp(g, 256), 2048), 256, 0, view(), ids, nulls, g, lengthsOut);
+}
+
+void VarcharInterner::gatherBytes(Operator* op, const int32_t* ids, const uint8_t* nulls, const int32_t* offsets, int64_t g, uint8_t* bytesOut)
+{
+    if (g <= 0) return;
+    PG_LAUNCH(op, internBytesKernel, (int) std::min<int64_t>(divUp(g * 32, 256), 4096), 256, 0, view(), ids, nulls, offsets, g, bytesOut);
+}
+
+}  // namespace pg

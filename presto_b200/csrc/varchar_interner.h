@@ -1,0 +1,48 @@
+// presto_b200 — VarcharInterner: VARCHAR values of any length as 32-bit ids, on the device.
+//
+// The reference keeps variable-width group / join keys as slices in its key pages and compares them byte by byte after a hash
+// match (MultiChannelGroupByHash.java:293-358 putIfAbsent → positionEqualsCurrentRow; PagesHashStrategy.positionEqualsRow for
+// joins).  The GPU tables work on fixed-width packed keys (group_table.cuh), so a VARCHAR channel that does not fit a packed
+// field is first replaced by the id of its value: equal slices ⇔ equal ids, ids are private to one interner (one operator /
+// one LookupSource), never visible in a result.  The bytes live once in the interner's pool; output key columns are gathered
+// from it.  Ids follow insertion, which depends on thread scheduling — every consumer orders its results by something else
+// (first-row ranks for group ids, build positions for join rows).
+#pragma once
+#include "common.cuh"
+
+namespace pg {
+
+struct InternView {                 // device view (kernels)
+    uint32_t* slots;                // [cap]  0 = empty, 1 = locked, id + 2 = ready
+    uint32_t cap, mask;
+    uint64_t* entryOffset;          // [entryCap] byte offset of the value in the pool
+    uint32_t* entryLength;          // [entryCap]
+    uint64_t* entryHash;            // [entryCap] XXH64 of the bytes = VarcharType.hash of the value
+    uint8_t* pool;
+    unsigned long long* counters;   // [0] entries, [1] pool bytes in use
+};
+
+class VarcharInterner {
+    DeviceBuffer slots, entryOffset, entryLength, entryHash, pool, counters;
+    PinnedBuffer host;
+    uint32_t cap = 0;
+    uint64_t entryCap = 0, poolCap = 0;
+    uint64_t nEntries = 0, poolUsed = 0;     // as of the last synchronisation
+    void ensure(Operator* op, uint64_t extraEntries, uint64_t extraBytes);
+    void readCounters(Operator* op);
+
+public:
+    // `accounting`: the device-bytes counter of whoever owns the interner (an operator's stats, a LookupSource); `op` lends its stream
+    explicit VarcharInterner(Operator* op, int64_t* accounting);
+    InternView view() const;
+    uint64_t entries() const { return nEntries; }
+    // ids of rows [0, n) of a staged FLAT VARCHAR column into idsOut (device, int32 per row).  insert = false only looks values up:
+    // an absent value gets -1 (read-only: probes of one LookupSource may look values up concurrently on their own streams).  NULL rows
+    // get 0 — the caller keeps the null map.  Runs on op->stream; inserting synchronises it.
+    void intern(Operator* op, const DeviceColumn& col, int64_t n, int32_t* idsOut, bool insert);
+    // output side: lengths[g] = length of value ids[g] (0 where nulls[g]); then, given exclusive offsets of those lengths, the bytes.
+    void gatherLengths(Operator* op, const int32_t* ids, const uint8_t* nulls, int64_t g, int32_t* lengthsOut);
+    void gatherBytes(Operator* op, const int32_t* ids, const uint8_t* nulls, const int32_t* offsets, int64_t g, uint8_t* bytesOut);
+};
+
+}  // namespace pg

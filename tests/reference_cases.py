@@ -72,11 +72,12 @@ def case_group_by_hash_get_group_ids(backend, max_group_id=MAX_GROUP_ID, tries_p
     h.close()
 
 
-def case_group_by_hash_append_to(backend):
-    """TestGroupByHash.testAppendTo :149-176 — VARCHAR keys '0'..'99' + $hashvalue come back in group-id order."""
+def case_group_by_hash_append_to(backend, max_len=7):
+    """TestGroupByHash.testAppendTo :149-176 — VARCHAR keys '0'..'99' + $hashvalue come back in group-id order.  max_len = 0 is the
+    reference's unbounded VARCHAR (on the GPU: keys interned to value ids), 7 a varchar(7) that fits a packed key field."""
     values = create_string_sequence_block(0, 100)
     hash_block = get_hash_block([values], backend)
-    h = GroupByHash([VARCHAR], [0], hash_channel=1, expected_size=100, max_lengths=[7], backend=backend)
+    h = GroupByHash([VARCHAR], [0], hash_channel=1, expected_size=100, max_lengths=[max_len], backend=backend)
     ids = h.get_group_ids(Page([values, hash_block]))
     assert list(ids) == list(range(100))
     assert h.get_group_count() == 100
@@ -112,10 +113,10 @@ def case_group_by_hash_contains(backend):
     h.close()
 
 
-def case_group_by_hash_contains_multiple_columns(backend):
+def case_group_by_hash_contains_multiple_columns(backend, max_len=7):
     """TestGroupByHash.testContainsMultipleColumns :219-234 (DOUBLE, VARCHAR)."""
     values, strings = create_double_sequence_block(0, 10), create_string_sequence_block(0, 10)
-    h = GroupByHash([DOUBLE, VARCHAR], [0, 1], hash_channel=2, expected_size=100, max_lengths=[0, 7], backend=backend)
+    h = GroupByHash([DOUBLE, VARCHAR], [0, 1], hash_channel=2, expected_size=100, max_lengths=[0, max_len], backend=backend)
     h.get_group_ids(Page([values, strings, get_hash_block([values, strings], backend)]))
     tv, ts = create_doubles_block(3.0), create_strings_block(b"3")
     assert h.contains(Page([tv, ts, get_hash_block([tv, ts], backend)]))[0]
@@ -124,11 +125,11 @@ def case_group_by_hash_contains_multiple_columns(backend):
     h.close()
 
 
-def case_group_by_hash_force_rehash(backend):
+def case_group_by_hash_force_rehash(backend, max_len=7):
     """TestGroupByHash.testForceRehash :236-250 — expectedSize 4, 100 VARCHAR keys."""
     values = create_string_sequence_block(0, 100)
     page = Page([values, get_hash_block([values], backend)])
-    h = GroupByHash([VARCHAR], [0], hash_channel=1, expected_size=4, max_lengths=[7], backend=backend)
+    h = GroupByHash([VARCHAR], [0], hash_channel=1, expected_size=4, max_lengths=[max_len], backend=backend)
     ids = h.get_group_ids(page)
     assert list(ids) == list(range(100))
     assert h.contains(page).all()
@@ -138,10 +139,11 @@ def case_group_by_hash_force_rehash(backend):
 # ---------------------------------------------------------------------------------------------------------------------
 # TestHashAggregationOperator
 # ---------------------------------------------------------------------------------------------------------------------
-def case_hash_aggregation(backend, hash_enabled: bool, number_of_rows: int = 40_000):
+def case_hash_aggregation(backend, hash_enabled: bool, number_of_rows: int = 40_000, max_len: int = 7):
     """TestHashAggregationOperator.testHashAggregation :162-217 — 3 sequence pages of 40 000 rows, VARCHAR group key;
     count(*), sum(bigint), avg(bigint), count(varchar), count(boolean).  Adaptation: max(varchar) is dropped (not on the GPU
-    path); the result is compared in group-id order (stricter than the reference's assertPagesEqualIgnoreOrder)."""
+    path); the result is compared in group-id order (stricter than the reference's assertPagesEqualIgnoreOrder).  max_len = 0: the
+    reference's unbounded VARCHAR key type."""
     b = RowPagesBuilder([VARCHAR, VARCHAR, VARCHAR, BIGINT, BOOLEAN], hash_enabled, [1], backend)
     pages = (b.add_sequence_page(number_of_rows, 100, 0, 100_000, 0, 500)
               .add_sequence_page(number_of_rows, 100, 0, 200_000, 0, 500)
@@ -149,7 +151,7 @@ def case_hash_aggregation(backend, hash_enabled: bool, number_of_rows: int = 40_
     op = HashAggregationOperator(
         [VARCHAR], [1],
         [Aggregate(AGG_COUNT_STAR), Aggregate(AGG_SUM_BIGINT, 3), Aggregate(AGG_AVG_BIGINT, 3), Aggregate(AGG_COUNT_COLUMN, 0), Aggregate(AGG_COUNT_COLUMN, 4)],
-        hash_channel=b.get_hash_channel(), expected_groups=100_000, group_max_lengths=[7], max_output_rows=16384, backend=backend)
+        hash_channel=b.get_hash_channel(), expected_groups=100_000, group_max_lengths=[max_len], max_output_rows=16384, backend=backend)
     out = to_pages(op, pages)
     assert len(out) > 1, "Expected more than one output page"
     rows = rows_of(out)
@@ -266,54 +268,63 @@ def _join(backend, build_pages, build_types, probe_pages, probe_types, join_type
     return rows
 
 
-def case_inner_join(backend, probe_hash: bool, build_hash: bool):
-    """TestHashJoinOperator.testInnerJoin :171-207 — ordered expectation."""
-    bp = RowPagesBuilder([BIGINT, BIGINT, BIGINT], build_hash, [0], backend).add_sequence_page(10, 20, 30, 40)
-    pp = RowPagesBuilder([BIGINT, BIGINT, BIGINT], probe_hash, [0], backend).add_sequence_page(1000, 0, 1000, 2000)
+def _key(key_type, v, sequence=False):
+    """The reference's join tests key on VARCHAR ("20".."29", 'a' 'b' 'c'); the BIGINT variants of the cases keep the numbers."""
+    if key_type != VARCHAR or v is None:
+        return v
+    return str(v).encode() if sequence else {1: b"a", 2: b"b", 3: b"c"}[v]
+
+
+def case_inner_join(backend, probe_hash: bool, build_hash: bool, key_type: int = BIGINT):
+    """TestHashJoinOperator.testInnerJoin :171-207 — ordered expectation (key_type VARCHAR: the reference's own column types)."""
+    bp = RowPagesBuilder([key_type, BIGINT, BIGINT], build_hash, [0], backend).add_sequence_page(10, 20, 30, 40)
+    pp = RowPagesBuilder([key_type, BIGINT, BIGINT], probe_hash, [0], backend).add_sequence_page(1000, 0, 1000, 2000)
     rows = _join(backend, bp.build(), bp.get_types(), pp.build(), pp.get_types(), JOIN_INNER, build_hash, probe_hash)
-    assert rows == [(20 + i, 1020 + i, 2020 + i, 20 + i, 30 + i, 40 + i) for i in range(10)]
+    k = lambda v: _key(key_type, v, True)
+    assert rows == [(k(20 + i), 1020 + i, 2020 + i, k(20 + i), 30 + i, 40 + i) for i in range(10)]
 
 
-def case_inner_join_with_null_probe(backend, probe_hash: bool, build_hash: bool):
+def case_inner_join_with_null_probe(backend, probe_hash: bool, build_hash: bool, key_type: int = BIGINT):
     """testInnerJoinWithNullProbe :712-750."""
-    bp = RowPagesBuilder([BIGINT], build_hash, [0], backend).row(1).row(2).row(3)
-    pp = RowPagesBuilder([BIGINT], probe_hash, [0], backend).row(1).row(None).row(None).row(1).row(2)
+    bp = RowPagesBuilder([key_type], build_hash, [0], backend).row(_key(key_type, 1)).row(_key(key_type, 2)).row(_key(key_type, 3))
+    pp = RowPagesBuilder([key_type], probe_hash, [0], backend).row(_key(key_type, 1)).row(_key(key_type, None)).row(_key(key_type, None)).row(_key(key_type, 1)).row(_key(key_type, 2))
     rows = _join(backend, bp.build(), bp.get_types(), pp.build(), pp.get_types(), JOIN_INNER, build_hash, probe_hash)
-    assert rows == [(1, 1), (1, 1), (2, 2)]
+    assert rows == [tuple(_key(key_type, v) for v in r) for r in [(1, 1), (1, 1), (2, 2)]]
 
 
-def case_inner_join_with_null_build(backend, probe_hash: bool, build_hash: bool):
+def case_inner_join_with_null_build(backend, probe_hash: bool, build_hash: bool, key_type: int = BIGINT):
     """testInnerJoinWithNullBuild :752-790 — build a,null,null,a,b ; probe a,b,c → (a,a),(a,a),(b,b)."""
-    bp = RowPagesBuilder([BIGINT], build_hash, [0], backend).row(1).row(None).row(None).row(1).row(2)
-    pp = RowPagesBuilder([BIGINT], probe_hash, [0], backend).row(1).row(2).row(3)
+    bp = RowPagesBuilder([key_type], build_hash, [0], backend).row(_key(key_type, 1)).row(_key(key_type, None)).row(_key(key_type, None)).row(_key(key_type, 1)).row(_key(key_type, 2))
+    pp = RowPagesBuilder([key_type], probe_hash, [0], backend).row(_key(key_type, 1)).row(_key(key_type, 2)).row(_key(key_type, 3))
     rows = _join(backend, bp.build(), bp.get_types(), pp.build(), pp.get_types(), JOIN_INNER, build_hash, probe_hash)
-    assert rows == [(1, 1), (1, 1), (2, 2)]
+    assert rows == [tuple(_key(key_type, v) for v in r) for r in [(1, 1), (1, 1), (2, 2)]]
 
 
-def case_inner_join_with_null_on_both_sides(backend, probe_hash: bool, build_hash: bool):
+def case_inner_join_with_null_on_both_sides(backend, probe_hash: bool, build_hash: bool, key_type: int = BIGINT):
     """testInnerJoinWithNullOnBothSides :792-830."""
-    bp = RowPagesBuilder([BIGINT], build_hash, [0], backend).row(1).row(None).row(None).row(1).row(2)
-    pp = RowPagesBuilder([BIGINT], probe_hash, [0], backend).row(1).row(2).row(None).row(3)
+    bp = RowPagesBuilder([key_type], build_hash, [0], backend).row(_key(key_type, 1)).row(_key(key_type, None)).row(_key(key_type, None)).row(_key(key_type, 1)).row(_key(key_type, 2))
+    pp = RowPagesBuilder([key_type], probe_hash, [0], backend).row(_key(key_type, 1)).row(_key(key_type, 2)).row(_key(key_type, None)).row(_key(key_type, 3))
     rows = _join(backend, bp.build(), bp.get_types(), pp.build(), pp.get_types(), JOIN_INNER, build_hash, probe_hash)
-    assert rows == [(1, 1), (1, 1), (2, 2)]
+    assert rows == [tuple(_key(key_type, v) for v in r) for r in [(1, 1), (1, 1), (2, 2)]]
 
 
-def case_probe_outer_join(backend, probe_hash: bool, build_hash: bool):
+def case_probe_outer_join(backend, probe_hash: bool, build_hash: bool, key_type: int = BIGINT):
     """testProbeOuterJoin :833-876."""
-    bp = RowPagesBuilder([BIGINT, BIGINT, BIGINT], build_hash, [0], backend).add_sequence_page(10, 20, 30, 40)
-    pp = RowPagesBuilder([BIGINT, BIGINT, BIGINT], probe_hash, [0], backend).add_sequence_page(15, 20, 1020, 2020)
+    bp = RowPagesBuilder([key_type, BIGINT, BIGINT], build_hash, [0], backend).add_sequence_page(10, 20, 30, 40)
+    pp = RowPagesBuilder([key_type, BIGINT, BIGINT], probe_hash, [0], backend).add_sequence_page(15, 20, 1020, 2020)
     rows = _join(backend, bp.build(), bp.get_types(), pp.build(), pp.get_types(), JOIN_PROBE_OUTER, build_hash, probe_hash)
-    expected = [(20 + i, 1020 + i, 2020 + i, 20 + i, 30 + i, 40 + i) for i in range(10)]
-    expected += [(30 + i, 1030 + i, 2030 + i, None, None, None) for i in range(5)]
+    k = lambda v: _key(key_type, v, True)
+    expected = [(k(20 + i), 1020 + i, 2020 + i, k(20 + i), 30 + i, 40 + i) for i in range(10)]
+    expected += [(k(30 + i), 1030 + i, 2030 + i, None, None, None) for i in range(5)]
     assert rows == expected
 
 
-def case_outer_join_with_null_on_both_sides(backend, probe_hash: bool, build_hash: bool):
+def case_outer_join_with_null_on_both_sides(backend, probe_hash: bool, build_hash: bool, key_type: int = BIGINT):
     """testOuterJoinWithNullOnBothSides :1101-1141 — probe a,b,null,c over build a,null,null,a,b."""
-    bp = RowPagesBuilder([BIGINT], build_hash, [0], backend).row(1).row(None).row(None).row(1).row(2)
-    pp = RowPagesBuilder([BIGINT], probe_hash, [0], backend).row(1).row(2).row(None).row(3)
+    bp = RowPagesBuilder([key_type], build_hash, [0], backend).row(_key(key_type, 1)).row(_key(key_type, None)).row(_key(key_type, None)).row(_key(key_type, 1)).row(_key(key_type, 2))
+    pp = RowPagesBuilder([key_type], probe_hash, [0], backend).row(_key(key_type, 1)).row(_key(key_type, 2)).row(_key(key_type, None)).row(_key(key_type, 3))
     rows = _join(backend, bp.build(), bp.get_types(), pp.build(), pp.get_types(), JOIN_PROBE_OUTER, build_hash, probe_hash)
-    assert rows == [(1, 1), (1, 1), (2, 2), (None, None), (3, None)]
+    assert rows == [tuple(_key(key_type, v) for v in r) for r in [(1, 1), (1, 1), (2, 2), (None, None), (3, None)]]
 
 
 def _join_filter(build_types, probe_types, make):

@@ -82,6 +82,22 @@ def test_product_never_imports_the_oracle():
                 assert "liboracle" not in text and "oracle_" not in text, f"{f} references the oracle"
 
 
+def test_xxhash64_of_slices_of_every_length_matches_the_xxhash_package():
+    """pg_hash_xxhash64 is common.cuh's xxHash64Bytes — the function the kernels hash VARCHAR slices with (interned group keys, $hashvalue
+    of VARCHAR keys) — compiled for the host: every length 0..100 (stripe loop, 8- / 4- / 1-byte tails) at several alignments."""
+    xxhash = pytest.importorskip("xxhash")
+    import numpy as np
+    from presto_b200._lib import load_library
+    b = load_library()
+    rng = np.random.default_rng(64)
+    data = bytes(rng.integers(0, 256, 300).astype(np.uint8))
+    for n in range(0, 101):
+        for start in (0, 1, 3, 7):
+            s = data[start:start + n]
+            want = xxhash.xxh64_intdigest(s)
+            assert b.hash_xxhash64(s, n) == (want - (1 << 64) if want >= 1 << 63 else want), (n, start)
+
+
 def test_host_hash_helpers_match_known_answers():
     """pg_hash_* host helpers (no GPU needed) against SURVEY.md §8c known answers."""
     from presto_b200._lib import load_library

@@ -8,7 +8,7 @@ from presto_b200 import (
     AGG_AVG_BIGINT, AGG_AVG_DOUBLE, AGG_COUNT_COLUMN, AGG_COUNT_STAR, AGG_SUM_BIGINT, AGG_SUM_DOUBLE, BIGINT, DATE, DOUBLE, INTEGER,
     MEM_DEVICE, STEP_FINAL, STEP_PARTIAL, VARCHAR, Aggregate, Block, HashAggregationOperator, Page, to_pages,
 )
-from util import rows_close, rows_of
+from util import page_to_device, rows_close, rows_of
 
 pytestmark = pytest.mark.gpu
 
@@ -260,3 +260,96 @@ def test_decimal_sums_random(gpu_backend, oracle_backend, groups):
         # and the oracle's FINAL accepts the GPU's states (the wire format of the intermediate column is the reference's)
         mixed = run(oracle_backend, partials, types, list(range(k)), final_aggs, step=STEP_FINAL, expected_groups=64, max_output_rows=1 << 30)
         assert sorted(mixed, key=repr) == sorted(want, key=repr)
+
+
+# ---- VARCHAR keys of any length (MultiChannelGroupByHash over VariableWidthBlock keys; GPU: interned to value ids first) -------------
+def _words(rng, count, min_len=0, max_len=40):
+    """`count` distinct byte strings, lengths spread over [min_len, max_len], sharing long prefixes (so a comparison has to read them)."""
+    out = set()
+    while len(out) < count:
+        n = int(rng.integers(min_len, max_len + 1))
+        out.add((b"presto-b200-key-prefix-" * 2)[:max(0, n - 3)] + bytes(rng.integers(97, 123, min(3, n)).astype(np.uint8)))
+    return sorted(out, key=lambda _: rng.random())
+
+
+@pytest.mark.parametrize("groups", [1, 7, 500, 60_000])
+@pytest.mark.parametrize("variant", ["plain", "nulls", "hash_channel", "two_keys", "device_pages"])
+def test_long_varchar_keys(gpu_backend, oracle_backend, groups, variant):
+    from presto_b200 import _abi as abi
+    rng = np.random.default_rng(groups * 13 + len(variant))
+    words = _words(rng, groups, 0 if groups > 1 else 12, 45)
+    n = 30_000 if groups < 10_000 else 150_000
+    pages = []
+    for _ in range(3):
+        pick = rng.integers(0, groups, n)
+        strings = [words[i] for i in pick]
+        if variant == "nulls":
+            strings = [None if rng.random() < 0.05 else s for s in strings]
+        cols = [Block.from_strings(strings), Block.from_numpy(DOUBLE, rng.random(n) * 100), Block.from_numpy(BIGINT, rng.integers(-1000, 1000, n))]
+        if variant == "two_keys":
+            cols.append(Block.from_numpy(INTEGER, (pick % 3).astype(np.int32), (rng.random(n) < 0.03).astype(np.uint8)))
+            cols.append(Block.from_strings([words[(i * 7) % groups][:5] for i in pick]))
+        pages.append(Page(cols))
+    types, chans = ([VARCHAR, INTEGER, VARCHAR], [0, 3, 4]) if variant == "two_keys" else ([VARCHAR], [0])
+    aggs = [Aggregate(AGG_SUM_DOUBLE, 1), Aggregate(AGG_SUM_BIGINT, 2), Aggregate(AGG_COUNT_COLUMN, 0), Aggregate(AGG_COUNT_STAR)]
+    kw = dict(expected_groups=64, max_output_rows=1 << 30)
+    if variant == "two_keys":
+        kw["group_max_lengths"] = [0, 0, 5]          # the third key fits a packed field, the first does not
+    want = run(oracle_backend, pages, types, chans, aggs, **kw)
+    if variant == "hash_channel":
+        # $hashvalue of a VARCHAR key = XXH64 of the slice (AbstractVariableWidthBlock.hash): precomputed on input, re-emitted on output
+        import xxhash
+        hashed = []
+        for p in pages:
+            col = p.blocks[0]
+            hv = np.array([np.uint64(xxhash.xxh64_intdigest(bytes(col.values[col.offsets[i]:col.offsets[i + 1]]))).astype(np.int64) for i in range(p.position_count)], dtype=np.int64)
+            hashed.append(Page(list(p.blocks) + [Block.from_numpy(BIGINT, hv)]))
+        got = run(gpu_backend, hashed, types, chans, aggs, hash_channel=3, **kw)
+        want = run(oracle_backend, hashed, types, chans, aggs, hash_channel=3, **kw)
+    elif variant == "device_pages":
+        op = HashAggregationOperator(types, chans, aggs, backend=gpu_backend, **kw)
+        keep = []
+        dev = [page_to_device(gpu_backend, p, keep) for p in pages]
+        got = rows_of(to_pages(op, dev))
+        assert op.get_stats()["kernel_paths"] & abi.PATH_INTERNED_KEYS
+        op.close()
+        for ptr in keep:
+            gpu_backend.device_free(ptr)
+    else:
+        got = run(gpu_backend, pages, types, chans, aggs, **kw)
+    assert len(got) == len(want)
+    rows_close(got, want)
+
+
+def test_long_varchar_keys_partial_final(gpu_backend, oracle_backend):
+    """PARTIAL → FINAL through pages with an interned key: the intermediate pages carry the slices, every operator interns its own."""
+    rng = np.random.default_rng(21)
+    words = _words(rng, 900, 9, 30)
+    pages = []
+    for _ in range(4):
+        pick = rng.integers(0, 900, 40_000)
+        pages.append(Page([Block.from_strings([words[i] for i in pick]), Block.from_numpy(DOUBLE, rng.random(40_000)), ]))
+    aggs = [Aggregate(AGG_SUM_DOUBLE, 1), Aggregate(AGG_AVG_DOUBLE, 1), Aggregate(AGG_COUNT_STAR)]
+    single = run(oracle_backend, pages, [VARCHAR], [0], aggs, expected_groups=512, max_output_rows=1 << 30)
+    partials = []
+    for half in (pages[:2], pages[2:]):
+        op = HashAggregationOperator([VARCHAR], [0], aggs, step=STEP_PARTIAL, backend=gpu_backend, expected_groups=512, max_output_rows=1 << 30)
+        partials += to_pages(op, half)
+        op.close()
+    final_aggs = [Aggregate(AGG_SUM_DOUBLE, 1), Aggregate(AGG_AVG_DOUBLE, 2), Aggregate(AGG_COUNT_STAR, 4)]
+    got = run(gpu_backend, partials, [VARCHAR], [0], final_aggs, step=STEP_FINAL, expected_groups=512, max_output_rows=1 << 30)
+    rows_close(sorted(got), sorted(single))
+
+
+def test_long_varchar_keys_many_distinct_values(gpu_backend, oracle_backend):
+    """Every row a new value over several chunks of the interner (table / pool / entry arrays grow and are re-hashed)."""
+    n = 300_000
+    pages = []
+    for p in range(2):
+        strings = [b"order-comment-%09d-%s" % (i, b"x" * (i % 23)) for i in range(p * n // 2, p * n // 2 + n)]   # the second page repeats half of the first
+        pages.append(Page([Block.from_strings(strings), Block.from_numpy(BIGINT, np.arange(n, dtype=np.int64))]))
+    aggs = [Aggregate(AGG_SUM_BIGINT, 1), Aggregate(AGG_COUNT_STAR)]
+    got = run(gpu_backend, pages, [VARCHAR], [0], aggs, expected_groups=16, max_output_rows=1 << 30)
+    want = run(oracle_backend, pages, [VARCHAR], [0], aggs, expected_groups=16, max_output_rows=1 << 30)
+    assert len(got) == n * 3 // 2
+    assert got == want

@@ -242,3 +242,53 @@ def test_varchar_channels_through_the_join(gpu_backend, oracle_backend, kind, jo
         return rows
     got, want = run(gpu_backend), run(oracle_backend)
     assert len(want) > 5000 and got == want
+
+
+# ---- VARCHAR join keys (the reference's TestHashJoinOperator keys on VARCHAR; GPU: slices interned to value ids at build time) ---------
+@pytest.mark.parametrize("shape", ["unique", "duplicates", "two_keys", "full_outer"])
+@pytest.mark.parametrize("nulls", [False, True])
+def test_varchar_join_keys_match_oracle(gpu_backend, oracle_backend, shape, nulls):
+    from presto_b200 import JOIN_FULL_OUTER, VARCHAR, LookupOuterOperator
+    rng = np.random.default_rng(len(shape) * 2 + int(nulls))
+    nb = 20_000
+    vocabulary = [b"customer#%09d-%s" % (i, b"z" * (i % 19)) for i in range(nb)]
+    vocabulary[0] = b""                                                         # the empty slice is a value, not a NULL
+    pick = rng.permutation(nb) if shape in ("unique", "full_outer") else rng.integers(0, nb // 4, nb)
+    bkeys = [vocabulary[i] for i in pick]
+    if nulls:
+        bkeys = [None if rng.random() < 0.05 else k for k in bkeys]
+    second = rng.integers(0, 3, nb).astype(np.int32)
+    pay = rng.random(nb)
+    half = nb // 2
+    build_pages = [Page([Block.from_strings(bkeys[s]), Block.from_numpy(INTEGER, second[s]), Block.from_numpy(DOUBLE, pay[s])]) for s in (slice(0, half), slice(half, nb))]
+    probe_pages = []
+    for _ in range(2):
+        npr = 30_000
+        pk = [vocabulary[i] if rng.random() < 0.7 else b"no-such-customer-%d" % i for i in rng.integers(0, nb, npr)]
+        if nulls:
+            pk = [None if rng.random() < 0.05 else k for k in pk]
+        probe_pages.append(Page([Block.from_strings(pk), Block.from_numpy(INTEGER, rng.integers(0, 3, npr).astype(np.int32)), Block.from_numpy(BIGINT, rng.integers(0, 1 << 40, npr))]))
+    key_channels = [0, 1] if shape == "two_keys" else [0]
+
+    def run(backend):
+        bridge = JoinBridge(backend=backend, outer=shape == "full_outer")
+        builder = HashBuilderOperator(bridge, [VARCHAR, INTEGER, DOUBLE], key_channels, [0, 2], backend=backend)
+        assert to_pages(builder, build_pages) == []
+        jt = JOIN_FULL_OUTER if shape == "full_outer" else (JOIN_PROBE_OUTER if nulls else JOIN_INNER)
+        probe = LookupJoinOperator(bridge, [VARCHAR, INTEGER, BIGINT], key_channels, [2, 0], join_type=jt, backend=backend)
+        rows = rows_of(to_pages(probe, probe_pages))
+        if shape == "full_outer":
+            bridge.no_more_probe_operators()
+            probe.finish()
+            outer = LookupOuterOperator(bridge, [BIGINT, VARCHAR], backend=backend)
+            while not outer.is_finished():
+                p = outer.get_output()
+                if p is not None:
+                    rows += rows_of([p])
+            outer.close()
+        probe.close(); builder.close(); bridge.close()
+        return rows
+
+    got, want = run(gpu_backend), run(oracle_backend)
+    assert len(got) == len(want) and len(got) > 0
+    assert got == want

@@ -14,10 +14,16 @@ def test_group_by_hash_append_to_multiple(gpu_backend): rc.case_group_by_hash_ap
 def test_group_by_hash_contains(gpu_backend): rc.case_group_by_hash_contains(gpu_backend)
 def test_group_by_hash_contains_multiple_columns(gpu_backend): rc.case_group_by_hash_contains_multiple_columns(gpu_backend)
 def test_group_by_hash_force_rehash(gpu_backend): rc.case_group_by_hash_force_rehash(gpu_backend)
+# the same cases with the reference's unbounded VARCHAR type: keys interned to value ids (varchar_interner.cu)
+def test_group_by_hash_append_to_unbounded_varchar(gpu_backend): rc.case_group_by_hash_append_to(gpu_backend, max_len=0)
+def test_group_by_hash_contains_multiple_columns_unbounded_varchar(gpu_backend): rc.case_group_by_hash_contains_multiple_columns(gpu_backend, max_len=0)
+def test_group_by_hash_force_rehash_unbounded_varchar(gpu_backend): rc.case_group_by_hash_force_rehash(gpu_backend, max_len=0)
 
 
 @pytest.mark.parametrize("hash_enabled", [False, True])
 def test_hash_aggregation(gpu_backend, hash_enabled): rc.case_hash_aggregation(gpu_backend, hash_enabled)
+@pytest.mark.parametrize("hash_enabled", [False, True])
+def test_hash_aggregation_unbounded_varchar_key(gpu_backend, hash_enabled): rc.case_hash_aggregation(gpu_backend, hash_enabled, max_len=0)
 def test_hash_aggregation_null_inputs(gpu_backend): rc.case_hash_aggregation_null_inputs(gpu_backend)
 def test_hash_aggregation_mask(gpu_backend): rc.case_hash_aggregation_mask(gpu_backend)
 def test_hash_aggregation_multi_key(gpu_backend): rc.case_hash_aggregation_multi_key(gpu_backend)
@@ -47,6 +53,11 @@ def test_probe_outer_join_with_filter_function(gpu_backend, probe_hash, build_ha
 def test_outer_join_with_nulls_and_filter_function(gpu_backend, probe_hash, build_hash): rc.case_outer_join_with_nulls_and_filter_function(gpu_backend, probe_hash, build_hash)
 def test_join_filter_over_both_sides(gpu_backend): rc.case_join_filter_over_both_sides(gpu_backend)
 def test_join_varchar_outputs(gpu_backend): rc.case_join_varchar_outputs(gpu_backend)
+# TestHashJoinOperator with the reference's own key type: VARCHAR join channels (GPU: interned to value ids when the build finishes)
+@pytest.mark.parametrize("probe_hash,build_hash", [(False, False), (True, True)])
+@pytest.mark.parametrize("case", ["inner_join", "inner_join_with_null_probe", "inner_join_with_null_build", "inner_join_with_null_on_both_sides",
+                                  "probe_outer_join", "outer_join_with_null_on_both_sides"])
+def test_join_varchar_keys(gpu_backend, case, probe_hash, build_hash): getattr(rc, "case_" + case)(gpu_backend, probe_hash, build_hash, key_type=rc.VARCHAR)
 def test_probe_outer_join_empty_lookup_source(gpu_backend): rc.case_probe_outer_join_empty_lookup_source(gpu_backend)
 def test_join_duplicate_chain_order(gpu_backend): rc.case_join_duplicate_chain_order(gpu_backend)
 def test_lookup_outer_join_empty_lookup_source(gpu_backend): rc.case_lookup_outer_join_empty_lookup_source(gpu_backend)

@@ -136,3 +136,22 @@ def rows_close(actual: Sequence[tuple], expected: Sequence[tuple], rel: float = 
                     assert abs(x - y) <= rel * max(abs(x), abs(y)) or x == y, f"row {i} col {j}: {x} != {y}"
             else:
                 assert x == y and type(x) is type(y), f"row {i} col {j}: {x!r} != {y!r}"
+
+
+def page_to_device(backend, page: Page, keep: list) -> Page:
+    """A host page's FLAT blocks copied into device memory (values, null map, VARCHAR offsets); `keep` collects the allocations."""
+    import ctypes as C
+
+    def up(arr):
+        p = C.c_void_p()
+        backend.check(backend.device_alloc(max(arr.nbytes, 16), C.byref(p)))
+        if arr.nbytes:
+            backend.check(backend.memcpy_h2d(p, arr.ctypes.data, arr.nbytes))
+        keep.append(p)
+        return p.value
+
+    blocks = []
+    for b in page.blocks:
+        blocks.append(Block.device(b.type, b.position_count, up(b.values), up(b.is_null) if b.is_null is not None else 0,
+                                   up(b.offsets) if b.offsets is not None else 0))
+    return Page(blocks, page.position_count)
