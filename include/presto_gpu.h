@@ -180,7 +180,8 @@ typedef enum {                       /* pg_operator_stats.kernel_paths */
     PG_PATH_FUSED_DIRECT = 64,       /* generated fused pipeline kernel, HBM table */
     PG_PATH_UNFUSED_CHAIN = 128,     /* fused operator that ran its fragment operator by operator (fragment not fusable for that page) */
     PG_PATH_FUSED_TMA = 256,         /* (with FUSED_TIERS / FUSED_DIRECT) eager columns staged by a cp.async.bulk (TMA) ring */
-    PG_PATH_INTERNED_KEYS = 512      /* VARCHAR group keys without a declared length of <= 7 bytes: replaced by value ids (VarcharInterner) first */
+    PG_PATH_INTERNED_KEYS = 512,     /* VARCHAR group keys without a declared length of <= 7 bytes: replaced by value ids (VarcharInterner) first */
+    PG_PATH_DICTIONARY_KEYS = 1024   /* (with INTERNED_KEYS) a DictionaryBlock / RLE key channel: its dictionary was interned, rows only mapped */
 } pg_kernel_path;
 
 /* Options common to all operators. */
@@ -446,6 +447,10 @@ int32_t pg_ipc_close(void* imported);
 typedef enum {
     PG_EX_INPUT = 0,      /* a = channel */
     PG_EX_CONST_BIGINT = 1, PG_EX_CONST_DOUBLE = 2, PG_EX_CONST_BOOLEAN = 3, PG_EX_CONST_NULL = 4, /* imm */
+    PG_EX_CONST_VARCHAR = 5, /* a VARCHAR literal: imm_i = address of its bytes (host memory, copied when the operator is created),
+                                reserved = its length.  VARCHAR-typed nodes are INPUT or CONST_VARCHAR; they may feed the comparisons
+                                (VarcharOperators.java:54-105: Slice.equals / Slice.compareTo = unsigned bytes, then length), BETWEEN,
+                                IS_NULL and HASH (XxHash64 of the slice); an INPUT may also be a projection (pass-through) */
     PG_EX_ADD = 10, PG_EX_SUB = 11, PG_EX_MUL = 12, PG_EX_DIV = 13, PG_EX_NEG = 14,
     PG_EX_EQ = 20, PG_EX_NE = 21, PG_EX_LT = 22, PG_EX_LE = 23, PG_EX_GT = 24, PG_EX_GE = 25,
     PG_EX_AND = 30, PG_EX_OR = 31, PG_EX_NOT = 32, PG_EX_IS_NULL = 33,

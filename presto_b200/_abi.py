@@ -42,6 +42,7 @@ STEP_SINGLE, STEP_PARTIAL, STEP_FINAL = 0, 1, 2
 JOIN_INNER, JOIN_PROBE_OUTER, JOIN_LOOKUP_OUTER, JOIN_FULL_OUTER = 0, 1, 2, 3
 # pg_expr_op
 EX_INPUT, EX_CONST_BIGINT, EX_CONST_DOUBLE, EX_CONST_BOOLEAN, EX_CONST_NULL = 0, 1, 2, 3, 4
+EX_CONST_VARCHAR = 5
 EX_ADD, EX_SUB, EX_MUL, EX_DIV, EX_NEG = 10, 11, 12, 13, 14
 EX_EQ, EX_NE, EX_LT, EX_LE, EX_GT, EX_GE = 20, 21, 22, 23, 24, 25
 EX_AND, EX_OR, EX_NOT, EX_IS_NULL = 30, 31, 32, 33
@@ -82,6 +83,7 @@ class pg_operator_stats(C.Structure):
 PATH_AGG_FAST, PATH_AGG_WARP, PATH_AGG_MID, PATH_AGG_DIRECT, PATH_AGG_GENERIC, PATH_FUSED_TIERS, PATH_FUSED_DIRECT, PATH_UNFUSED_CHAIN = 1, 2, 4, 8, 16, 32, 64, 128
 PATH_FUSED_TMA = 256
 PATH_INTERNED_KEYS = 512
+PATH_DICTIONARY_KEYS = 1024
 
 
 class pg_operator_options(C.Structure):

@@ -126,6 +126,11 @@ struct DeviceColumn {
     const void* values = nullptr;      // fixed width values, or varchar bytes
     const uint8_t* nulls = nullptr;    // byte per row or nullptr
     const int32_t* offsets = nullptr;  // varchar
+    // Only for VARCHAR channels the operator asked the stager to keep encoded (PageStager::keepEncoded): values / nulls / offsets then
+    // describe the `entries` dictionary entries (1 for RLE) and row r holds entry ids[r] (RLE: entry 0 for every row).
+    int encoding = PG_ENC_FLAT;
+    const int32_t* ids = nullptr;
+    int64_t entries = 0;
 };
 
 // ---- Operator base: MB/operator/Operator.java:20-102 ----------------------------------------------------------------
@@ -163,6 +168,9 @@ struct PageStager {
         bool computePending = false, arenaCopyPending = false;
     } slots[kSlots];
     int next = 0;
+    // VARCHAR channels that stay DictionaryBlock / RunLengthEncodedBlock on the device instead of being flattened (DeviceColumn::encoding):
+    // for consumers that work on the dictionary itself (interned group keys: MultiChannelGroupByHash's dictionary path :543-552, 628-714)
+    std::vector<int> keepEncoded;
 
     explicit PageStager(Operator* o);
     ~PageStager();

@@ -227,6 +227,9 @@ class FilterProjectOp : public Operator {
     int lastIsList = 0; int64_t lastSize = 0;
     std::map<uint64_t, JitProgram> jitCache;   // keyed by which inputs carry a null map on this page
     int64_t jitLaunches = 0, interpreterLaunches = 0;
+    DeviceBuffer literalPool;                  // bytes of the CONST_VARCHAR nodes
+    std::vector<int64_t> literalOffset;        // per node: offset of its literal in the pool (-1: not a literal)
+    bool varcharExpressions = false;           // a comparison / hash reads slices: interpreter kernels only
 
 public:
     explicit FilterProjectOp(const pg_filter_project_config* c) : Operator(c->options), stager(this)
@@ -245,7 +248,7 @@ public:
             const int p = c->projection_nodes[j];
             PG_CHECK_ARG(p >= 0 && p < c->n_nodes, "projection node out of range");
             if (nodes[p].type == PG_TYPE_VARCHAR) {
-                if (nodes[p].op != PG_EX_INPUT) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR expressions other than input references are not on the GPU path");
+                if (nodes[p].op != PG_EX_INPUT) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR projections other than input references are not on the GPU path");
                 outSlots.push_back({true, (int) varcharChannels.size()});
                 varcharChannels.push_back(nodes[p].a);
             }
@@ -253,7 +256,12 @@ public:
         }
         for (int i = 0; i < c->n_nodes; i++) {
             const pg_expr_node& n = nodes[i];
-            if (n.type == PG_TYPE_VARCHAR && n.op != PG_EX_INPUT) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR expressions other than input references are not on the GPU path");
+            if (n.type == PG_TYPE_VARCHAR && n.op != PG_EX_INPUT && n.op != PG_EX_CONST_VARCHAR)
+                throw Error(PG_ERR_UNSUPPORTED, "VARCHAR-valued expressions other than input references and literals are not on the GPU path");
+            if (n.op == PG_EX_CONST_VARCHAR) {
+                PG_CHECK_ARG(n.type == PG_TYPE_VARCHAR && n.reserved >= 0 && (n.reserved == 0 || n.imm_i != 0), "CONST_VARCHAR: imm_i = address of the bytes, reserved = length");
+                continue;
+            }
             if (n.op == PG_EX_INPUT) {
                 PG_CHECK_ARG(n.a >= 0 && n.a < c->n_input_channels, "input channel out of range");
                 PG_CHECK_ARG(inputTypes[n.a] == n.type, "input node type differs from the channel's type");
@@ -262,6 +270,32 @@ public:
             else {
                 for (int o : {n.a, n.b, n.c}) PG_CHECK_ARG(o < i, "expression nodes must be topologically ordered");
                 if (n.op == PG_EX_CAST_BIGINT) throw Error(PG_ERR_UNSUPPORTED, "CAST to BIGINT is not on the GPU path yet");
+                // VARCHAR operands: comparisons between two VARCHAR values, BETWEEN over three, IS_NULL, HASH (VarcharOperators.java:54-105,291)
+                int nVarchar = 0, nOperands = 0;
+                for (int o : {n.a, n.b, n.c}) if (o >= 0) { nOperands++; nVarchar += nodes[o].type == PG_TYPE_VARCHAR; }
+                if (nVarchar) {
+                    const bool comparison = (n.op >= PG_EX_EQ && n.op <= PG_EX_GE) || n.op == PG_EX_BETWEEN;
+                    if (!((comparison && nVarchar == nOperands) || n.op == PG_EX_IS_NULL || n.op == PG_EX_HASH))
+                        throw Error(PG_ERR_UNSUPPORTED, "VARCHAR operands: only comparisons among VARCHAR values, BETWEEN, IS NULL and the type hash are on the GPU path");
+                    if (n.op != PG_EX_IS_NULL) varcharExpressions = true;
+                }
+            }
+        }
+        {   // the literals go to the device once
+            literalOffset.assign(c->n_nodes, -1);
+            std::vector<uint8_t> bytes;
+            for (int i = 0; i < c->n_nodes; i++) {
+                if (nodes[i].op != PG_EX_CONST_VARCHAR) continue;
+                literalOffset[i] = (int64_t) bytes.size();
+                const uint8_t* src = (const uint8_t*) (uintptr_t) nodes[i].imm_i;
+                bytes.insert(bytes.end(), src, src + nodes[i].reserved);
+                nodes[i].imm_i = 0; nodes[i].a = nodes[i].b = nodes[i].c = -1;        // the caller's memory is not referenced after create
+            }
+            if (!bytes.empty()) {
+                literalPool.accounting = &stats.device_bytes;
+                literalPool.reserve(bytes.size());
+                PG_CUDA(cudaMemcpyAsync(literalPool.ptr, bytes.data(), bytes.size(), cudaMemcpyHostToDevice, stream));
+                PG_CUDA(cudaStreamSynchronize(stream));
             }
         }
         for (DeviceBuffer* d : {&counts, &offsets, &scanTemp, &errorWord, &selection}) d->accounting = &stats.device_bytes;
@@ -295,6 +329,7 @@ public:
         const char* off = getenv("PG_FP_INTERPRETER");
         DriverApi& api = DriverApi::get();
         if ((off && off[0] == '1') || !api.ok) { jp.log = "JIT disabled or libcuda not loadable"; return jp; }
+        if (varcharExpressions) { jp.log = "VARCHAR comparison / hash: interpreter kernels"; return jp; }
         FpProgramDesc d;
         d.nodes = nodes; d.inputTypes = inputTypes; d.filterNode = filterNode; d.projections = projections;
         d.inputHasNulls.assign(inputTypes.size(), false);
@@ -345,18 +380,19 @@ public:
             FpNode& d = P.nodes[i]; const pg_expr_node& s = nodes[i];
             d.op = s.op; d.type = s.type; d.a = s.a; d.b = s.b; d.c = s.c; d.isDouble = s.type == PG_TYPE_DOUBLE;
             if (s.op == PG_EX_CONST_DOUBLE) memcpy(&d.immI, &s.imm_d, 8); else d.immI = s.imm_i;
+            if (s.op == PG_EX_CONST_VARCHAR) { d.immI = (int64_t) (uintptr_t) ((const uint8_t*) literalPool.ptr + literalOffset[i]); d.len = s.reserved; d.a = d.b = d.c = -1; }
         }
         std::vector<bool> nullable(nodes.size(), false);
         for (size_t i = 0; i < staged.size(); i++) {
             PG_CHECK_ARG(cols[i].type == inputTypes[staged[i]], "input channel type differs from the operator's configuration");
-            P.inputs[staged[i]].values = cols[i].values; P.inputs[staged[i]].nulls = cols[i].nulls; P.inputs[staged[i]].type = cols[i].type;
+            P.inputs[staged[i]].values = cols[i].values; P.inputs[staged[i]].nulls = cols[i].nulls; P.inputs[staged[i]].type = cols[i].type; P.inputs[staged[i]].offsets = cols[i].offsets;
         }
         for (size_t i = 0; i < nodes.size(); i++) {
             const pg_expr_node& s = nodes[i];
             switch (s.op) {
                 case PG_EX_INPUT: nullable[i] = P.inputs[s.a].nulls != nullptr; break;
                 case PG_EX_CONST_NULL: nullable[i] = true; break;
-                case PG_EX_CONST_BIGINT: case PG_EX_CONST_DOUBLE: case PG_EX_CONST_BOOLEAN: case PG_EX_IS_NULL: case PG_EX_HASH: case PG_EX_COMBINE_HASH: nullable[i] = false; break;
+                case PG_EX_CONST_BIGINT: case PG_EX_CONST_DOUBLE: case PG_EX_CONST_BOOLEAN: case PG_EX_CONST_VARCHAR: case PG_EX_IS_NULL: case PG_EX_HASH: case PG_EX_COMBINE_HASH: nullable[i] = false; break;
                 default: nullable[i] = (s.a >= 0 && nullable[s.a]) || (s.b >= 0 && nullable[s.b]) || (s.c >= 0 && nullable[s.c]); break;
             }
         }

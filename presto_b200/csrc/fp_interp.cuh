@@ -11,10 +11,29 @@ constexpr int kMaxInputs = 32;
 
 enum { FP_ERR_OVERFLOW = 1, FP_ERR_DIV_ZERO = 2 };
 
-struct FpNode { int32_t op, type, a, b, c, isDouble; int64_t immI; };   // immI carries the double's bits for CONST_DOUBLE
-struct FpInput { const void* values; const uint8_t* nulls; int32_t type; };
+struct FpNode { int32_t op, type, a, b, c, isDouble; int64_t immI; int32_t len, pad; };   // immI: the double's bits for CONST_DOUBLE; CONST_VARCHAR: device address of the literal, len its length
+struct FpInput { const void* values; const uint8_t* nulls; int32_t type; const int32_t* offsets; };   // offsets: VARCHAR channels
 
 struct Val { uint64_t bits; bool isNull; };
+
+// VARCHAR values: bits = byte offset (low 32) | length (high 32) relative to the producing node's base — the channel's bytes for an
+// INPUT, the operator's literal pool for a CONST_VARCHAR (immI = device address of the literal, len = its length).
+__device__ __forceinline__ const uint8_t* sliceBase(const FpNode* nodes, const FpInput* inputs, int node)
+{
+    const FpNode& nd = nodes[node];
+    return nd.op == PG_EX_INPUT ? (const uint8_t*) inputs[nd.a].values : (const uint8_t*) (uintptr_t) nd.immI;
+}
+// Slice.compareTo: unsigned bytes over the common prefix, then the lengths (VarcharOperators.java:71-97)
+__device__ __forceinline__ int compareSlices(const uint8_t* p, uint32_t lp, const uint8_t* q, uint32_t lq)
+{
+    const uint32_t m = lp < lq ? lp : lq;
+    for (uint32_t i = 0; i < m; i++) { const int d = (int) p[i] - (int) q[i]; if (d) return d; }
+    return lp < lq ? -1 : (lp > lq ? 1 : 0);
+}
+__device__ __forceinline__ int compareVarchar(const FpNode* nodes, const FpInput* inputs, int na, const Val& x, int nb, const Val& y)
+{
+    return compareSlices(sliceBase(nodes, inputs, na) + (uint32_t) x.bits, (uint32_t) (x.bits >> 32), sliceBase(nodes, inputs, nb) + (uint32_t) y.bits, (uint32_t) (y.bits >> 32));
+}
 
 __device__ __forceinline__ double asDouble(const Val& v, bool isDouble) { return isDouble ? __longlong_as_double((long long) v.bits) : (double) (long long) v.bits; }
 
@@ -29,12 +48,14 @@ __device__ __forceinline__ Val evalNodeAt(const FpNode* nodes, const FpInput* in
             else switch (in.type) {
                 case PG_TYPE_BIGINT: case PG_TYPE_DOUBLE: r.bits = ldStream64((const uint64_t*) in.values + row); break;
                 case PG_TYPE_INTEGER: case PG_TYPE_DATE: r.bits = (uint64_t) (int64_t) (int32_t) ldStream32((const uint32_t*) in.values + row); break;
+                case PG_TYPE_VARCHAR: { const uint32_t o = (uint32_t) in.offsets[row]; r.bits = (uint64_t) o | ((uint64_t) ((uint32_t) in.offsets[row + 1] - o) << 32); break; }
                 default: r.bits = ((const uint8_t*) in.values)[row] != 0; break;
             }
             break;
         }
         case PG_EX_CONST_BIGINT: case PG_EX_CONST_BOOLEAN: case PG_EX_CONST_DOUBLE: r.bits = (uint64_t) nd.immI; break;
         case PG_EX_CONST_NULL: r.isNull = true; break;
+        case PG_EX_CONST_VARCHAR: r.bits = (uint64_t) (uint32_t) nd.len << 32; break;
         case PG_EX_ADD: case PG_EX_SUB: case PG_EX_MUL: case PG_EX_DIV: {
             if (x.isNull || y.isNull) { r.isNull = true; break; }
             if (nd.isDouble) {
@@ -69,7 +90,11 @@ __device__ __forceinline__ Val evalNodeAt(const FpNode* nodes, const FpInput* in
             if (x.isNull || y.isNull) { r.isNull = true; break; }
             bool res;
             const bool da = nodes[nd.a].isDouble, db = nodes[nd.b].isDouble;
-            if (da || db) {
+            if (nodes[nd.a].type == PG_TYPE_VARCHAR) {
+                const int c = compareVarchar(nodes, inputs, nd.a, x, nd.b, y);
+                res = nd.op == PG_EX_EQ ? c == 0 : nd.op == PG_EX_NE ? c != 0 : nd.op == PG_EX_LT ? c < 0 : nd.op == PG_EX_LE ? c <= 0 : nd.op == PG_EX_GT ? c > 0 : c >= 0;
+            }
+            else if (da || db) {
                 const double p = asDouble(x, da), q = asDouble(y, db);
                 res = nd.op == PG_EX_EQ ? p == q : nd.op == PG_EX_NE ? p != q : nd.op == PG_EX_LT ? p < q : nd.op == PG_EX_LE ? p <= q : nd.op == PG_EX_GT ? p > q : p >= q;
             }
@@ -84,8 +109,14 @@ __device__ __forceinline__ Val evalNodeAt(const FpNode* nodes, const FpInput* in
             const bool da = nodes[nd.a].isDouble, db = nodes[nd.b].isDouble, dc = nodes[nd.c].isDouble;
             const bool n1 = x.isNull || y.isNull, n2 = x.isNull || z.isNull;
             bool c1 = false, c2 = false;
+            if (nodes[nd.a].type == PG_TYPE_VARCHAR) {     // VarcharOperators.between :103-105
+                if (!n1) c1 = compareVarchar(nodes, inputs, nd.a, x, nd.b, y) >= 0;
+                if (!n2) c2 = compareVarchar(nodes, inputs, nd.a, x, nd.c, z) <= 0;
+            }
+            else {
             if (!n1) c1 = (da || db) ? asDouble(x, da) >= asDouble(y, db) : (long long) x.bits >= (long long) y.bits;
             if (!n2) c2 = (da || dc) ? asDouble(x, da) <= asDouble(z, dc) : (long long) x.bits <= (long long) z.bits;
+            }
             if ((!n1 && !c1) || (!n2 && !c2)) r.bits = 0;
             else if (n1 || n2) r.isNull = true;
             else r.bits = 1;
@@ -109,6 +140,7 @@ __device__ __forceinline__ Val evalNodeAt(const FpNode* nodes, const FpInput* in
             if (x.isNull) r.bits = 0;
             else if (t == PG_TYPE_DOUBLE) r.bits = (uint64_t) hashLong(doubleHashBits((int64_t) x.bits));
             else if (t == PG_TYPE_BOOLEAN) r.bits = x.bits ? 1231 : 1237;
+            else if (t == PG_TYPE_VARCHAR) r.bits = (uint64_t) xxHash64Bytes(sliceBase(nodes, inputs, nd.a) + (uint32_t) x.bits, (int64_t) (x.bits >> 32));
             else r.bits = (uint64_t) hashLong((int64_t) x.bits);
             break;
         }

@@ -9,6 +9,7 @@
 #include "fused_agg.cuh"
 #include "jit_runtime.h"
 #include "operators_internal.h"
+#include "expr_literals.h"
 #include <cub/device/device_scan.cuh>
 #include <algorithm>
 #include <map>
@@ -19,6 +20,7 @@ class FusedPageOp : public Operator {
     struct JoinCfg { JoinBridge* bridge; int joinType; std::vector<int32_t> types, hashChannels, outputChannels; int precomputedHash; };
     std::vector<int32_t> inputTypes, projections;
     std::vector<pg_expr_node> nodes;
+    ExprLiterals literals;
     int filterNode;
     std::vector<JoinCfg> joins;
     std::vector<int> rawChannels;
@@ -46,6 +48,7 @@ public:
         PG_CHECK_ARG(c->n_joins >= 0 && c->n_joins <= kFusedMaxJoins, "at most 2 joins in a fused fragment");
         inputTypes.assign(f.input_types, f.input_types + f.n_input_channels);
         nodes.assign(f.nodes, f.nodes + f.n_nodes);
+        literals.adopt(nodes);       // the unfused chain builds its FilterAndProjectOperator from `nodes` later
         filterNode = f.filter_node;
         projections.assign(f.projection_nodes, f.projection_nodes + f.n_projections);
         PG_CHECK_ARG(filterNode < f.n_nodes, "filter node out of range");

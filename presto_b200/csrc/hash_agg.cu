@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "group_table.cuh"
 #include "varchar_interner.h"
+#include "expr_literals.h"
 #include "key_layout.h"
 #include "agg_tiers.cuh"
 #include <cub/device/device_radix_sort.cuh>
@@ -1531,7 +1532,7 @@ protected:
     bool lastFused = false;
     // interned VARCHAR keys (KeyLayout::interned): one interner per such key, the id column of the chunk in flight
     std::vector<std::unique_ptr<VarcharInterner>> interners;
-    std::vector<DeviceBuffer> internIds;
+    std::vector<DeviceBuffer> internIds, internNulls;
     std::vector<DeviceColumn> internCols;
 
 public:
@@ -1559,9 +1560,17 @@ public:
         table.allocate(cap);
         hostCounters.reserve(CNT_COUNT * sizeof(unsigned int));
         bitmapA.accounting = bitmapB.accounting = &stats.device_bytes;
-        interners.resize(layout.nKeys); internIds.resize(layout.nKeys); internCols.resize(layout.nKeys);
-        for (int k = 0; k < layout.nKeys; k++)
-            if (layout.interned[k]) { interners[k].reset(new VarcharInterner(this, &stats.device_bytes)); internIds[k].accounting = &stats.device_bytes; }
+        interners.resize(layout.nKeys); internIds.resize(layout.nKeys); internNulls.resize(layout.nKeys); internCols.resize(layout.nKeys);
+        for (int k = 0; k < layout.nKeys; k++) {
+            if (!layout.interned[k]) continue;
+            interners[k].reset(new VarcharInterner(this, &stats.device_bytes));
+            internIds[k].accounting = internNulls[k].accounting = &stats.device_bytes;
+            // a key channel no accumulator reads stays DictionaryBlock / RLE on the device: its dictionary is interned, not its rows
+            bool keyOnly = true;
+            for (auto& p : phys) if (p.channel == layout.channels[k] || p.mask == layout.channels[k]) keyOnly = false;
+            for (int j = 0; j < layout.nKeys; j++) if (j != k && layout.channels[j] == layout.channels[k]) keyOnly = false;
+            if (keyOnly) stager.keepEncoded.push_back(layout.channels[k]);
+        }
         PG_CUDA(cudaStreamSynchronize(stream));
     }
 
@@ -1575,8 +1584,15 @@ public:
             const DeviceColumn& src = cols[i];
             PG_CHECK_ARG(src.type == PG_TYPE_VARCHAR, "group-by channel type differs from the operator's configuration");
             internIds[k].reserve((size_t) n * 4 + 16);
-            interners[k]->intern(this, src, n, internIds[k].as<int32_t>(), true);
             DeviceColumn ids; ids.type = PG_TYPE_INTEGER; ids.n = n; ids.values = internIds[k].ptr; ids.nulls = src.nulls; ids.offsets = nullptr;
+            if (src.encoding != PG_ENC_FLAT) {
+                uint8_t* rowNulls = nullptr;
+                if (src.nulls) { internNulls[k].reserve((size_t) n + 16); rowNulls = internNulls[k].as<uint8_t>(); }
+                interners[k]->internEncoded(this, src, n, internIds[k].as<int32_t>(), rowNulls, true);
+                ids.nulls = rowNulls;
+                stats.kernel_paths |= PG_PATH_DICTIONARY_KEYS;
+            }
+            else interners[k]->intern(this, src, n, internIds[k].as<int32_t>(), true);
             internCols[k] = ids;
             stats.kernel_paths |= PG_PATH_INTERNED_KEYS;
         }
@@ -2142,7 +2158,7 @@ class GroupByHashImpl : public Operator {
     uint64_t rowsSeen = 0;
     ResultBuilder result;
     std::vector<std::unique_ptr<VarcharInterner>> interners;     // interned VARCHAR keys (KeyLayout::interned)
-    std::vector<DeviceBuffer> internIds;
+    std::vector<DeviceBuffer> internIds, internNulls;
 
     // cols[k] (one per key) with interned VARCHAR keys replaced by their id columns; insert = false only looks values up (contains)
     std::vector<DeviceColumn> internKeys(const std::vector<DeviceColumn>& cols, int64_t n, bool insert)
@@ -2152,7 +2168,13 @@ class GroupByHashImpl : public Operator {
             if (!layout.interned[k]) continue;
             PG_CHECK_ARG(cols[k].type == PG_TYPE_VARCHAR, "group-by channel type differs from the configuration");
             internIds[k].reserve((size_t) n * 4 + 16);
-            interners[k]->intern(this, cols[k], n, internIds[k].as<int32_t>(), insert);
+            if (cols[k].encoding != PG_ENC_FLAT) {
+                uint8_t* rowNulls = nullptr;
+                if (cols[k].nulls) { internNulls[k].accounting = &stats.device_bytes; internNulls[k].reserve((size_t) n + 16); rowNulls = internNulls[k].as<uint8_t>(); }
+                interners[k]->internEncoded(this, cols[k], n, internIds[k].as<int32_t>(), rowNulls, insert);
+                out[k].nulls = rowNulls; out[k].encoding = PG_ENC_FLAT; out[k].ids = nullptr; out[k].entries = 0;
+            }
+            else interners[k]->intern(this, cols[k], n, internIds[k].as<int32_t>(), insert);
             out[k].type = PG_TYPE_INTEGER; out[k].values = internIds[k].ptr; out[k].offsets = nullptr;
         }
         return out;
@@ -2169,9 +2191,14 @@ public:
         table.counters.reserve(CNT_COUNT * sizeof(unsigned int));
         PG_CUDA(cudaMemsetAsync(table.counters.ptr, 0, CNT_COUNT * sizeof(unsigned int), stream));
         table.allocate(std::max<uint32_t>(1024, nextPow2((uint64_t) c->expected_size * 2)));
-        interners.resize(layout.nKeys); internIds.resize(layout.nKeys);
-        for (int k = 0; k < layout.nKeys; k++)
-            if (layout.interned[k]) { interners[k].reset(new VarcharInterner(this, &stats.device_bytes)); internIds[k].accounting = &stats.device_bytes; }
+        interners.resize(layout.nKeys); internIds.resize(layout.nKeys); internNulls.resize(layout.nKeys);
+        for (int k = 0; k < layout.nKeys; k++) {
+            if (!layout.interned[k]) continue;
+            interners[k].reset(new VarcharInterner(this, &stats.device_bytes)); internIds[k].accounting = &stats.device_bytes;
+            bool once = true;
+            for (int j = 0; j < layout.nKeys; j++) if (j != k && layout.channels[j] == layout.channels[k]) once = false;
+            if (once) stager.keepEncoded.push_back(layout.channels[k]);       // dictionary path: intern the dictionary, not the rows
+        }
         PG_CUDA(cudaStreamSynchronize(stream));
     }
     bool needsInput() override { return true; }
@@ -2375,6 +2402,7 @@ class FusedAggregationOp : public HashAggregationOp {
     };
     std::vector<int32_t> inputTypes, projections;
     std::vector<pg_expr_node> nodes;
+    ExprLiterals literals;
     int filterNode;
     std::vector<JoinCfg> joins;
     std::vector<int> rawChannels;                       // raw input channels the fragment reads (staged for the fused kernel)
@@ -2396,6 +2424,7 @@ public:
         PG_CHECK_ARG(c->n_joins >= 0 && c->n_joins <= kFusedMaxJoins, "at most 2 joins in a fused fragment");
         inputTypes.assign(f.input_types, f.input_types + f.n_input_channels);
         nodes.assign(f.nodes, f.nodes + f.n_nodes);
+        literals.adopt(nodes);       // the unfused chain builds its FilterAndProjectOperator from `nodes` later
         filterNode = f.filter_node;
         projections.assign(f.projection_nodes, f.projection_nodes + f.n_projections);
         PG_CHECK_ARG(filterNode < f.n_nodes, "filter node out of range");

@@ -54,6 +54,12 @@ struct Plan {
         d.input_types = keep(arena, s.input_types, s.n_input_channels);
         d.nodes = keep(arena, s.nodes, s.n_nodes);
         d.projection_nodes = keep(arena, s.projection_nodes, s.n_projections);
+        // VARCHAR literals live in the caller's memory: the copied nodes point at copies of their bytes
+        for (int i = 0; i < s.n_nodes; i++) {
+            pg_expr_node& n = const_cast<pg_expr_node&>(d.nodes[i]);
+            if (n.op != PG_EX_CONST_VARCHAR || n.reserved <= 0 || n.imm_i == 0) continue;
+            n.imm_i = (int64_t) (uintptr_t) keep(arena, (const char*) (uintptr_t) n.imm_i, (size_t) n.reserved);
+        }
     }
     void copyJoin(pg_lookup_join_config& d, const pg_lookup_join_config& s)
     {

@@ -23,7 +23,7 @@ constexpr int kMaxScatterColumns = 32;
 constexpr int kRowsPerUnit = 1024;       // rows owned by one warp (their output positions live in shared memory during pass 2)
 constexpr int kPartWarps = 8;
 
-struct HashCol { const void* values; const uint8_t* nulls; int32_t type; };
+struct HashCol { const void* values; const uint8_t* nulls; const int32_t* offsets; int32_t type; };   // offsets: VARCHAR
 
 struct PartitionIdParams {
     HashCol cols[kMaxPartChannels];
@@ -46,6 +46,10 @@ __device__ __forceinline__ int64_t typeHashOf(const HashCol& c, int64_t row)
         case PG_TYPE_BIGINT: return hashLong(((const int64_t*) c.values)[row]);
         case PG_TYPE_DOUBLE: return hashLong(doubleHashBits(((const int64_t*) c.values)[row]));
         case PG_TYPE_INTEGER: case PG_TYPE_DATE: return hashLong((int64_t) ((const int32_t*) c.values)[row]);
+        case PG_TYPE_VARCHAR: {     // VarcharType.hash → XxHash64.hash(slice)  (AbstractVariableWidthBlock.java:102-106)
+            const int32_t o = c.offsets[row];
+            return xxHash64Bytes((const uint8_t*) c.values + o, (int64_t) (c.offsets[row + 1] - o));
+        }
         default: return ((const uint8_t*) c.values)[row] ? 1231 : 1237;   // BOOLEAN
     }
 }
@@ -384,7 +388,6 @@ public:
         PG_CHECK_ARG(internalColumns <= kMaxScatterColumns, "too many channels (a VARCHAR channel counts twice)");
         for (int ch : partitionChannels) {
             PG_CHECK_ARG(ch >= 0 && ch < c->n_channels, "partition channel out of range");
-            if (types[ch] == PG_TYPE_VARCHAR) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR partition channels are not hashed on the GPU path: pass a precomputed $hashvalue channel");
         }
         PG_CHECK_ARG(hashChannel < c->n_channels && nullChannel < c->n_channels, "channel out of range");
         PG_CHECK_ARG(hashChannel >= 0 || !partitionChannels.empty() || partitionCount == 1, "no partition channels");
@@ -420,7 +423,7 @@ public:
         hist.reserve(histN * 4); base.reserve(histN * 4);
         PartitionIdParams A{};
         A.nCols = (int) partitionChannels.size();
-        for (int i = 0; i < A.nCols; i++) { const DeviceColumn& c = curCols[partitionChannels[i]]; A.cols[i].values = c.values; A.cols[i].nulls = c.nulls; A.cols[i].type = c.type; }
+        for (int i = 0; i < A.nCols; i++) { const DeviceColumn& c = curCols[partitionChannels[i]]; A.cols[i].values = c.values; A.cols[i].nulls = c.nulls; A.cols[i].offsets = c.offsets; A.cols[i].type = c.type; }
         A.precomputed = hashChannel >= 0 ? (const int64_t*) curCols[hashChannel].values : nullptr;
         A.nullChannelNulls = nullChannel >= 0 ? curCols[nullChannel].nulls : nullptr;
         A.replicateRow0 = (replicatesAnyRow && !hasAnyRowBeenReplicated) ? 1 : 0;

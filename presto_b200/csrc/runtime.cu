@@ -303,6 +303,13 @@ int PageStager::stage(const pg_page* page, const std::vector<int>& channels, std
             }
             copied = true;
         }
+        if (encoded && c.n > 0 && b.type == PG_TYPE_VARCHAR && std::find(keepEncoded.begin(), keepEncoded.end(), ch) != keepEncoded.end()) {
+            PG_CHECK_ARG(dOffsets != nullptr, "VARCHAR block without offsets");
+            c.encoding = b.encoding; c.entries = entries; c.ids = b.encoding == PG_ENC_DICTIONARY ? dIds : nullptr;
+            c.values = dValues; c.nulls = dNulls; c.offsets = dOffsets;
+            op->stats.input_bytes += c.n * 4 + (b.is_null ? c.n : 0);
+            continue;
+        }
         if (encoded && c.n > 0 && b.type == PG_TYPE_VARCHAR) {
             // lengths → inclusive scan → offsets; then the bytes (and nulls) row by row
             PG_CHECK_ARG(dOffsets != nullptr, "VARCHAR block without offsets");

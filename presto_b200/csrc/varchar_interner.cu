@@ -174,6 +174,30 @@ void VarcharInterner::intern(Operator* op, const DeviceColumn& col, int64_t n, i
     readCounters(op);
 }
 
+__global__ void internMapDictionaryKernel(const int32_t* __restrict__ entryIds, const uint8_t* __restrict__ entryNulls, const int32_t* __restrict__ ids, int64_t n,
+                                          int32_t* __restrict__ idsOut, uint8_t* __restrict__ nullsOut)
+{
+    for (int64_t row = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; row < n; row += (int64_t) gridDim.x * blockDim.x) {
+        const int32_t e = ids ? ids[row] : 0;        // RLE: the single entry
+        idsOut[row] = entryIds[e];
+        if (nullsOut) nullsOut[row] = entryNulls ? entryNulls[e] : 0;
+    }
+}
+
+void VarcharInterner::internEncoded(Operator* op, const DeviceColumn& col, int64_t n, int32_t* idsOut, uint8_t* nullsOut, bool insert)
+{
+    PG_CHECK_ARG(col.encoding != PG_ENC_FLAT && col.entries >= 1 && (col.encoding == PG_ENC_RLE || col.ids != nullptr), "not an encoded column");
+    PG_CHECK_ARG(nullsOut != nullptr || col.nulls == nullptr, "a dictionary with NULL entries needs a per-row null map");
+    if (n <= 0) return;
+    dictionaryIds.accounting = slots.accounting;
+    dictionaryIds.reserve((size_t) col.entries * 4 + 16);
+    DeviceColumn dictionary = col;
+    dictionary.encoding = PG_ENC_FLAT; dictionary.ids = nullptr; dictionary.n = col.entries;
+    intern(op, dictionary, col.entries, dictionaryIds.as<int32_t>(), insert);
+    PG_LAUNCH(op, internMapDictionaryKernel, (int) std::min<int64_t>(divUp(n, 256), (int64_t) op->numSMs * 8), 256, 0, dictionaryIds.as<int32_t>(), col.nulls, col.ids, n,
+              idsOut, nullsOut);
+}
+
 void VarcharInterner::gatherLengths(Operator* op, const int32_t* ids, const uint8_t* nulls, int64_t g, int32_t* lengthsOut)
 {
     if (g <= 0) return;

@@ -23,7 +23,7 @@ struct InternView {                 // device view (kernels)
 };
 
 class VarcharInterner {
-    DeviceBuffer slots, entryOffset, entryLength, entryHash, pool, counters;
+    DeviceBuffer slots, entryOffset, entryLength, entryHash, pool, counters, dictionaryIds;
     PinnedBuffer host;
     uint32_t cap = 0;
     uint64_t entryCap = 0, poolCap = 0;
@@ -40,6 +40,10 @@ public:
     // an absent value gets -1 (read-only: probes of one LookupSource may look values up concurrently on their own streams).  NULL rows
     // get 0 — the caller keeps the null map.  Runs on op->stream; inserting synchronises it.
     void intern(Operator* op, const DeviceColumn& col, int64_t n, int32_t* idsOut, bool insert);
+    // The same for a column the stager kept encoded (DeviceColumn::encoding): the dictionary's entries are interned once, every row takes
+    // the id of its entry — MultiChannelGroupByHash's dictionary path (:543-552, 628-714: work per dictionary entry, not per position).
+    // nullsOut (device, one byte per row, may be null when the dictionary has no null map) receives the rows' null flags.
+    void internEncoded(Operator* op, const DeviceColumn& col, int64_t n, int32_t* idsOut, uint8_t* nullsOut, bool insert);
     // output side: lengths[g] = length of value ids[g] (0 where nulls[g]); then, given exclusive offsets of those lengths, the bytes.
     void gatherLengths(Operator* op, const int32_t* ids, const uint8_t* nulls, int64_t g, int32_t* lengthsOut);
     void gatherBytes(Operator* op, const int32_t* ids, const uint8_t* nulls, const int32_t* offsets, int64_t g, uint8_t* bytesOut);

@@ -57,6 +57,7 @@ class Program:
         self.nodes: List[tuple] = []
         self.filter = -1
         self.projections: List[int] = []
+        self.literals = {}          # node index -> bytes of a VARCHAR literal (kept alive with the program)
 
     def add(self, op, type_, a=-1, b=-1, c=-1, imm_i=0, imm_d=0.0) -> Expr:
         self.nodes.append((op, type_, a, b, c, imm_i, imm_d))
@@ -68,6 +69,11 @@ class Program:
     def const(self, value, type_=None) -> Expr:
         if value is None:
             return self.add(abi.EX_CONST_NULL, type_ or abi.BIGINT)
+        if isinstance(value, (bytes, str)):
+            # a Slice constant: the node carries the address and the length of its bytes (c_nodes), the operator copies them at create
+            e = self.add(abi.EX_CONST_VARCHAR, abi.VARCHAR)
+            self.literals[e.index] = value.encode() if isinstance(value, str) else bytes(value)
+            return e
         if isinstance(value, bool):
             return self.add(abi.EX_CONST_BOOLEAN, abi.BOOLEAN, imm_i=int(value))
         if isinstance(value, float) or type_ == abi.DOUBLE:
@@ -77,6 +83,8 @@ class Program:
     def lift(self, v, like_type) -> Expr:
         if isinstance(v, Expr):
             return v
+        if isinstance(v, (bytes, str)):
+            return self.const(v)
         if isinstance(v, float):
             return self.const(v, abi.DOUBLE)
         if like_type == abi.DOUBLE and not isinstance(v, bool):
@@ -90,7 +98,14 @@ class Program:
         self.projections.extend(e.index for e in exprs)
 
     def c_nodes(self):
+        import ctypes as C
         arr = (abi.pg_expr_node * max(1, len(self.nodes)))()
+        keep = []
         for i, (op, t, a, b, c, ii, dd) in enumerate(self.nodes):
             arr[i].op, arr[i].type, arr[i].a, arr[i].b, arr[i].c, arr[i].imm_i, arr[i].imm_d = op, t, a, b, c, ii, dd
+            if op == abi.EX_CONST_VARCHAR:
+                buf = C.create_string_buffer(self.literals[i], max(1, len(self.literals[i])))
+                keep.append(buf)
+                arr[i].imm_i, arr[i].reserved = C.addressof(buf), len(self.literals[i])
+        arr._literal_buffers = keep      # the bytes live as long as the node array
         return arr

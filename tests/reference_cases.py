@@ -732,6 +732,29 @@ def case_partitioned_output_varchar_channels(backend, partition_count: int = 5, 
     op.close()
 
 
+def case_partitioned_output_varchar_partition_channels(backend, partition_count: int = 7):
+    """InterpretedHashGenerator.hashPosition :70-79 over VARCHAR partition channels (TypeUtils.hashPosition → VarcharType.hash = XxHash64 of the
+    slice, AbstractVariableWidthBlock.java:102-106; NULL → 0), combined with a BIGINT channel by CombineHashFunction: every row lands in
+    the partition the host-side restatement of the row hash names, in input order.  Slices of 0..70 bytes cross XXH64's 32-byte stripes."""
+    rng = np.random.default_rng(23)
+    n = 5000
+    s1 = [None if rng.random() < 0.1 else bytes(rng.integers(32, 127, int(rng.integers(0, 71))).astype(np.uint8)) for _ in range(n)]
+    k = rng.integers(-10**6, 10**6, n)
+    blocks = [Block.from_strings(s1), Block.from_numpy(BIGINT, k), Block.from_numpy(DOUBLE, rng.random(n))]
+    types = [VARCHAR, BIGINT, DOUBLE]
+    page = Page(blocks)
+    in_rows = page.rows()
+    for channels in ([0], [0, 1]):
+        raw = get_hash_block([blocks[c] for c in channels], backend)
+        op = PartitionedOutputOperator(types, partition_count, channels, backend=backend)
+        op.add_input(page)
+        out_rows, offsets = op.get_output().rows(), op.get_offsets()
+        parts = get_partition(raw.values, partition_count)
+        for p in range(partition_count):
+            assert out_rows[offsets[p]:offsets[p + 1]] == [in_rows[i] for i in range(n) if parts[i] == p]
+        op.close()
+
+
 def case_partitioned_output_double_zero_keys(backend):
     """DoubleType.hash → TypeUtils.doubleHashCode (PC/type/TypeUtils.java:232-238): -0.0 and +0.0 are equal keys, so they must reach the
     same partition (hash 0 → partition 0), as must every NaN payload."""
@@ -881,6 +904,64 @@ def case_page_processor_three_valued_logic(backend):
     assert [r[5] for r in rows] == [2, 6, 10, N, 4, 8, 11, 1, 6]
     assert [r[6] for r in rows] == [-1, 7, 15, N, 3, 11, 17, -3, 7]
     assert [r[7] for r in rows] == [-1, -5, -9, N, -3, -7, -10, 0, -5]
+    op.close()
+
+
+def case_page_processor_varchar_comparisons(backend, n: int = 6000):
+    """VarcharOperators.java:54-105 (equal / notEqual / lessThan … between = Slice.equals / Slice.compareTo: unsigned bytes, then length) and
+    :291 (xxHash64) inside a PageProcessor: TPC-H Q3's `c_mktsegment = 'BUILDING'` as the filter; comparisons against literals and
+    between two VARCHAR channels as BOOLEAN projections with SQL NULL semantics; the selected slices pass through.  Expectations are
+    computed here in python (bytes compare exactly like Slice.compareTo)."""
+    import xxhash
+    rng = np.random.default_rng(33)
+    segments = [b"AUTOMOBILE", b"BUILDING", b"FURNITURE", b"HOUSEHOLD", b"MACHINERY", b"", b"BUILD", b"BUILDING ", b"\xc3\xa9t\xc3\xa9", b"building"]
+    seg = [None if rng.random() < 0.1 else segments[rng.integers(len(segments))] for _ in range(n)]
+    other = [None if rng.random() < 0.1 else segments[rng.integers(len(segments))] for _ in range(n)]
+    key = rng.integers(0, 1 << 40, n)
+    page = Page([Block.from_strings(seg), Block.from_numpy(BIGINT, key), Block.from_strings(other)])
+    types = [VARCHAR, BIGINT, VARCHAR]
+
+    def tv(f, *xs):     # SQL three-valued: NULL operand → NULL
+        return None if any(x is None for x in xs) else f(*xs)
+
+    # 1. the Q3 filter; key and slice pass through
+    prog = Program(types)
+    s = prog.input(0)
+    prog.set_filter(s == b"BUILDING")
+    prog.project(prog.input(1), s)
+    op = FilterAndProjectOperator(types, prog, backend=backend)
+    rows = rows_of(to_pages(op, [page]))
+    assert rows == [(int(key[i]), b"BUILDING") for i in range(n) if seg[i] == b"BUILDING"] and len(rows) > 100
+    op.close()
+
+    # 2. every comparison as a projection (no filter), literal and column operands, BETWEEN, IS NULL, the type hash
+    prog = Program(types)
+    s, o = prog.input(0), prog.input(2)
+    prog.project(s != b"BUILDING", s < b"FURNITURE", s <= b"BUILDING", s > b"BUILD", s >= "\u00e9", s == o, s < o,
+                 s.between(b"AUTOMOBILE", b"HOUSEHOLD"), s.between(o, b"MACHINERY"), s.is_null(), s.hash(), prog.const(b"") == s)
+    op = FilterAndProjectOperator(types, prog, backend=backend)
+    rows = rows_of(to_pages(op, [page]))
+    assert len(rows) == n
+    signed = lambda h: h - (1 << 64) if h >= 1 << 63 else h
+    for i in range(n):
+        a, b = seg[i], other[i]
+        want = (tv(lambda x: x != b"BUILDING", a), tv(lambda x: x < b"FURNITURE", a), tv(lambda x: x <= b"BUILDING", a), tv(lambda x: x > b"BUILD", a),
+                tv(lambda x: x >= "\u00e9".encode(), a), tv(lambda x, y: x == y, a, b), tv(lambda x, y: x < y, a, b),
+                tv(lambda x: b"AUTOMOBILE" <= x <= b"HOUSEHOLD", a),
+                # value >= min AND value <= max with three-valued AND: FALSE wins over NULL
+                (False if (a is not None and a > b"MACHINERY") or (a is not None and b is not None and a < b) else (None if a is None or b is None else True)),
+                a is None, 0 if a is None else signed(xxhash.xxh64_intdigest(a)), tv(lambda x: x == b"", a))
+        assert rows[i] == want, (i, a, b, rows[i], want)
+    op.close()
+
+    # 3. a selective VARCHAR range filter AND a numeric predicate; three outputs including the other VARCHAR channel
+    prog = Program(types)
+    s = prog.input(0)
+    prog.set_filter((s >= b"BUILDING") & (s < b"HOUSEHOLD") & (prog.input(1) < (1 << 39)))
+    prog.project(prog.input(2), s)
+    op = FilterAndProjectOperator(types, prog, backend=backend)
+    rows = rows_of(to_pages(op, [page]))
+    assert rows == [(other[i], seg[i]) for i in range(n) if seg[i] is not None and b"BUILDING" <= seg[i] < b"HOUSEHOLD" and key[i] < (1 << 39)]
     op.close()
 
 

@@ -368,3 +368,29 @@ def test_tma_ring_path(gpu_backend, oracle_backend, key_type):
         assert not (info2["kernel_paths"] & abi.PATH_FUSED_TMA), info2
     finally:
         del os.environ["PG_FUSED_TMA"]
+
+
+def test_varchar_predicate_and_long_varchar_key_run_the_operator_chain(gpu_backend, oracle_backend):
+    """Q3's customer fragment shape — filter `mktsegment = 'BUILDING'` (VarcharOperators.equal over a Slice constant), GROUP BY a VARCHAR
+    channel of unbounded length — is outside the generated kernels' set: the fused operator runs FilterAndProject (interpreter kernels, the
+    literal adopted by the operator) → HashAggregation over interned keys, same rows as the oracle's chain."""
+    rng = np.random.default_rng(5)
+    n = 40_000
+    segments = [b"AUTOMOBILE", b"BUILDING", b"FURNITURE", b"HOUSEHOLD", b"MACHINERY"]
+    nations = [b"nation-%02d-with-a-long-name" % i for i in range(25)]
+    seg = [segments[i] for i in rng.integers(0, 5, n)]
+    nat = [None if rng.random() < 0.02 else nations[i] for i in rng.integers(0, 25, n)]
+    bal = rng.random(n) * 1e4
+    types = [VARCHAR, VARCHAR, DOUBLE]
+    page = Page([Block.from_strings(seg), Block.from_strings(nat), Block.from_numpy(DOUBLE, bal)])
+    prog = Program(types)
+    s, c, b = [prog.input(i) for i in range(3)]
+    prog.set_filter((s == b"BUILDING") & (b > 100.0))
+    prog.project(c, b)
+    args = (types, prog, [], [VARCHAR], [0], [Aggregate(AGG_SUM_DOUBLE, 1), Aggregate(AGG_COUNT_STAR)])
+    info = {}
+    got = run_fused(gpu_backend, [page, page], *args, info=info)
+    want = run_fused(oracle_backend, [page, page], *args)
+    assert len(want) == 26
+    rows_close(got, want)
+    assert info["unfused_pages"] == 2 and info["kernel_paths"] & abi.PATH_UNFUSED_CHAIN and info["kernel_paths"] & abi.PATH_INTERNED_KEYS, info

@@ -74,6 +74,7 @@ def test_min_max_aggregates(gpu_backend): rc.case_min_max_aggregates(gpu_backend
 def test_decimal_sum(gpu_backend): rc.case_decimal_sum(gpu_backend)
 def test_decimal_sum_overflow(gpu_backend): rc.case_decimal_sum_overflow(gpu_backend)
 def test_lookup_join_is_blocked_until_the_build_finishes(gpu_backend): rc.case_lookup_join_is_blocked_until_the_build_finishes(gpu_backend)
+def test_partitioned_output_varchar_partition_channels(gpu_backend): rc.case_partitioned_output_varchar_partition_channels(gpu_backend)
 def test_partitioned_output_double_zero_keys(gpu_backend): rc.case_partitioned_output_double_zero_keys(gpu_backend)
 @pytest.mark.parametrize("partition_count", [1, 2, 8, 64])
 def test_partitioned_output_local_partition_generator(gpu_backend, partition_count):
@@ -85,3 +86,4 @@ def test_page_processor_selection(gpu_backend): rc.case_page_processor_selection
 def test_page_processor_q1(gpu_backend): rc.case_page_processor_q1(gpu_backend)
 def test_page_processor_three_valued_logic(gpu_backend): rc.case_page_processor_three_valued_logic(gpu_backend)
 def test_page_processor_hash_projection(gpu_backend): rc.case_page_processor_hash_projection(gpu_backend)
+def test_page_processor_varchar_comparisons(gpu_backend): rc.case_page_processor_varchar_comparisons(gpu_backend)

@@ -127,6 +127,7 @@ def test_min_max_aggregates(oracle_backend): rc.case_min_max_aggregates(oracle_b
 def test_decimal_sum(oracle_backend): rc.case_decimal_sum(oracle_backend)
 def test_decimal_sum_overflow(oracle_backend): rc.case_decimal_sum_overflow(oracle_backend)
 def test_lookup_join_is_blocked_until_the_build_finishes(oracle_backend): rc.case_lookup_join_is_blocked_until_the_build_finishes(oracle_backend)
+def test_partitioned_output_varchar_partition_channels(oracle_backend): rc.case_partitioned_output_varchar_partition_channels(oracle_backend)
 def test_partitioned_output_double_zero_keys(oracle_backend): rc.case_partitioned_output_double_zero_keys(oracle_backend)
 @pytest.mark.parametrize("partition_count", [1, 2, 8, 64])
 def test_partitioned_output_local_partition_generator(oracle_backend, partition_count):
@@ -138,6 +139,7 @@ def test_page_processor_selection(oracle_backend): rc.case_page_processor_select
 def test_page_processor_q1(oracle_backend): rc.case_page_processor_q1(oracle_backend)
 def test_page_processor_three_valued_logic(oracle_backend): rc.case_page_processor_three_valued_logic(oracle_backend)
 def test_page_processor_hash_projection(oracle_backend): rc.case_page_processor_hash_projection(oracle_backend)
+def test_page_processor_varchar_comparisons(oracle_backend): rc.case_page_processor_varchar_comparisons(oracle_backend)
 def test_page_processor_varchar_pass_through(oracle_backend): rc.case_page_processor_varchar_pass_through(oracle_backend)
 
 
