@@ -399,8 +399,10 @@ int32_t pg_hash_semi_join_create(const pg_semi_join_config* config, pg_join_brid
  * ---------------------------------------------------------------------------------------------- */
 typedef enum {
     PG_PARTITION_HASH_GENERATOR = 0, /* HashGenerator.getPartition (MB/operator/HashGenerator.java:22-29): between tasks / GPUs */
-    PG_PARTITION_LOCAL = 1           /* LocalPartitionGenerator (MB/operator/exchange/LocalPartitionGenerator.java:43-63): LocalExchange and
+    PG_PARTITION_LOCAL = 1,          /* LocalPartitionGenerator (MB/operator/exchange/LocalPartitionGenerator.java:43-63): LocalExchange and
                                         PartitionedLookupSource inside one task; partition_count must be a power of two */
+    PG_PARTITION_ROUND_ROBIN = 2     /* RoundRobinBucketFunction (MB/sql/planner/SystemPartitioningHandle.java:282-305): row i of the operator's
+                                        input goes to bucket i mod bucket_count (the counter runs on across pages); no partition channels */
 } pg_partition_function;
 
 typedef struct pg_partitioned_output_config {
@@ -413,6 +415,11 @@ typedef struct pg_partitioned_output_config {
     int32_t replicates_any_row;         /* OptimizedPartitionedOutputOperator.java:504-512 */
     int32_t null_channel;               /* replicate rows whose null_channel is null to every partition; -1 = none */
     int32_t partition_function;         /* pg_partition_function */
+    /* BucketPartitionFunction (MB/operator/BucketPartitionFunction.java:25-54): the function above yields a BUCKET in [0, bucket_count) and
+     * bucket_to_partition[bucket] names the partition (several buckets may share one).  NULL table: bucket_count is ignored, the bucket is
+     * the partition (the identity table of SystemPartitioningHandle's hash partitioning with one bucket per partition). */
+    int32_t bucket_count;
+    const int32_t* bucket_to_partition; /* [bucket_count], values in [0, partition_count) */
     pg_operator_options options;
 } pg_partitioned_output_config;
 
@@ -581,13 +588,19 @@ int32_t pg_operator_factory_destroy(pg_operator_factory* factory);
  *                                                  RunLength,Dictionary}BlockEncoding.java, EncoderUtil.java:31-100
  * Wire bytes: [positionCount i32][markers u8][uncompressedSize i32][size i32][checksum i64] (21 bytes, little endian) then the raw
  * page: [channelCount i32] and per channel [name length i32][encoding name][positionCount i32][mayHaveNull u8][null bits, MSB first]
- * [non-null values].  Compression and encryption markers are not produced and are rejected with PG_ERR_UNSUPPORTED.
+ * [non-null values].  With compression = PG_COMPRESSION_LZ4 the raw page travels as ONE LZ4 block (the PageCompressor PagesSerdeFactory.java:75
+ * creates: airlift Lz4Compressor, block format) when that makes it at most 0.8 of its size (PagesSerde.java:118-143, MINIMUM_COMPRESSION_RATIO),
+ * marker COMPRESSED; any conforming LZ4 block is read (the bytes this encoder produces are valid LZ4, not aircompressor's byte for
+ * byte).  Encrypted pages are rejected with PG_ERR_UNSUPPORTED.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct pg_pages_serde pg_pages_serde;
 typedef struct pg_pages_serde_config {
     int32_t checksum_enabled;      /* PagesSerde.checksumEnabled: CHECKSUMMED marker + CRC32 over data, markers, positionCount, uncompressedSize */
+    int32_t compression;           /* PG_COMPRESSION_NONE / PG_COMPRESSION_LZ4: the serde's compressor (pages of either kind are always READ) */
     pg_operator_options options;   /* device; output_memory = where serialized bytes AND deserialized pages are returned; cuda_stream */
 } pg_pages_serde_config;
+#define PG_COMPRESSION_NONE 0
+#define PG_COMPRESSION_LZ4 1
 #define PG_SERIALIZED_PAGE_HEADER_BYTES 21
 #define PG_PAGE_MARKER_COMPRESSED 1
 #define PG_PAGE_MARKER_ENCRYPTED 2
@@ -596,6 +609,12 @@ typedef struct pg_pages_serde_config {
 /* The host half of the page checksum: CRC-32 (java.util.zip.CRC32) of a host buffer computed as the serde does — one CRC per
  * `chunk` bytes (0 = 4096), combined with the zero-extension operator.  Needs no GPU; exists so that the combine logic is testable. */
 int64_t pg_hash_crc32_chunked(const void* data, size_t len, size_t chunk);
+/* The LZ4 block codec of the serde run on the host (the kernels compile the same functions, csrc/lz4_codec.cuh); needs no GPU.
+ * compress: returns the compressed size, -1 when `capacity` < pg_lz4_compress_bound(n).  decompress: the decoded size, -1 for a malformed
+ * block or one that decodes to more than `capacity` bytes. */
+int64_t pg_lz4_compress_bound(int64_t n);
+int64_t pg_lz4_compress_host(const void* src, int64_t n, void* dst, int64_t capacity);
+int64_t pg_lz4_decompress_host(const void* src, int64_t n, void* dst, int64_t capacity);
 int32_t pg_pages_serde_create(const pg_pages_serde_config* config, pg_pages_serde** out);
 /* serialize(Page) + writeSerializedPage.  FLAT blocks → LONG_ARRAY / INT_ARRAY / BYTE_ARRAY / VARIABLE_WIDTH, RLE blocks → RLE,
  * DICTIONARY blocks -> DICTIONARY of the compacted dictionary (DictionaryBlockEncoding.writeBlock :34-54 over DictionaryBlock.compact

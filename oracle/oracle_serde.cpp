@@ -214,21 +214,88 @@ static void readFlat(Reader& r, const std::string& enc, int type, WireColumn& c,
 class PagesSerde {
 public:
     bool checksumEnabled;
-    std::vector<uint8_t> wire;
+    int compression = PG_COMPRESSION_NONE;
+    std::vector<uint8_t> wire, decoded;
     std::vector<WireColumn> cols; std::vector<pg_block> blocks;
-    explicit PagesSerde(bool c) : checksumEnabled(c) {}
+    explicit PagesSerde(bool c, int z = PG_COMPRESSION_NONE) : checksumEnabled(c), compression(z) {}
+
+    // ---- LZ4 block format (what io.airlift.compress.lz4.Lz4Compressor / Lz4Decompressor read and write, PagesSerdeFactory.java:75,96).
+    // aircompressor is not under /root/reference: the FORMAT is restated from its published description; which matches the encoder
+    // picks is implementation defined (parity unpinned for compressed bytes — the tests compare what streams decode to, across this
+    // encoder, the GPU's and liblz4's).  A plain single-table greedy encoder: hash of 4 bytes → last position, extend, emit.
+    static void lz4Length(std::vector<uint8_t>& out, size_t v) { v -= 15; while (v >= 255) { out.push_back(255); v -= 255; } out.push_back((uint8_t) v); }
+    static std::vector<uint8_t> lz4Compress(const uint8_t* src, size_t n)
+    {
+        std::vector<uint8_t> out;
+        std::vector<int64_t> table(1 << 14, -1);
+        size_t anchor = 0, ip = 0;
+        auto read32 = [&](size_t p) { uint32_t v; memcpy(&v, src + p, 4); return v; };
+        auto sequence = [&](size_t litEnd, size_t offset, size_t matchLen) {          // matchLen == 0: the final literals
+            const size_t lit = litEnd - anchor;
+            const size_t ml = matchLen ? matchLen - 4 : 0;
+            out.push_back((uint8_t) ((std::min<size_t>(lit, 15) << 4) | std::min<size_t>(ml, 15)));
+            if (lit >= 15) lz4Length(out, lit);
+            out.insert(out.end(), src + anchor, src + litEnd);
+            if (!matchLen) return;
+            out.push_back((uint8_t) (offset & 0xff)); out.push_back((uint8_t) (offset >> 8));
+            if (ml >= 15) lz4Length(out, ml);
+        };
+        while (n >= 13 && ip + 12 <= n) {                       // the last match starts at least 12 bytes before the end
+            const uint32_t v = read32(ip);
+            const size_t h = (v * 2654435761u) >> 18;
+            const int64_t cand = table[h];
+            table[h] = (int64_t) ip;
+            if (cand >= 0 && ip - (size_t) cand <= 65535 && read32((size_t) cand) == v) {
+                size_t len = 4;
+                while (ip + len < n - 5 && src[(size_t) cand + len] == src[ip + len]) len++;      // the last 5 bytes stay literals
+                sequence(ip, ip - (size_t) cand, len);
+                ip += len; anchor = ip;
+            }
+            else ip++;
+        }
+        sequence(n, 0, 0);
+        return out;
+    }
+    static bool lz4Decompress(const uint8_t* src, size_t n, std::vector<uint8_t>& out, size_t expect)
+    {
+        out.clear(); out.reserve(expect);
+        size_t ip = 0;
+        while (ip < n) {
+            const uint8_t token = src[ip++];
+            size_t lit = token >> 4;
+            if (lit == 15) { uint8_t b; do { if (ip >= n) return false; b = src[ip++]; lit += b; } while (b == 255); }
+            if (ip + lit > n || out.size() + lit > expect) return false;
+            out.insert(out.end(), src + ip, src + ip + lit); ip += lit;
+            if (ip >= n) break;
+            if (ip + 2 > n) return false;
+            const size_t off = src[ip] | ((size_t) src[ip + 1] << 8); ip += 2;
+            if (off == 0 || off > out.size()) return false;
+            size_t ml = token & 15;
+            if (ml == 15) { uint8_t b; do { if (ip >= n) return false; b = src[ip++]; ml += b; } while (b == 255); }
+            ml += 4;
+            if (out.size() + ml > expect) return false;
+            for (size_t i = 0; i < ml; i++) out.push_back(out[out.size() - off]);
+        }
+        return out.size() == expect;
+    }
 
     void serialize(const pg_page* page, const uint8_t** bytes, int64_t* size)
     {
         Writer raw;
         raw.i32(page->channel_count);                               // PagesSerdeUtil.writeRawPage :45-51
         for (int ch = 0; ch < page->channel_count; ch++) writeBlock(raw, page->blocks[ch]);
-        uint8_t markers = 0; int64_t checksum = 0;                  // PagesSerde.wrapSlice :118-156 without compressor / cipher
+        uint8_t markers = 0; int64_t checksum = 0;                  // PagesSerde.wrapSlice :118-156 (no cipher)
         const int32_t n = (int32_t) page->position_count, rawSize = (int32_t) raw.b.size();
-        if (checksumEnabled) { markers |= PG_PAGE_MARKER_CHECKSUMMED; checksum = pageChecksum(raw.b.data(), raw.b.size(), markers, n, rawSize); }
+        std::vector<uint8_t>* slice = &raw.b;
+        std::vector<uint8_t> compressed;
+        if (compression == PG_COMPRESSION_LZ4) {                    // :122-137: kept only when compressedSize / uncompressedSize <= 0.8
+            compressed = lz4Compress(raw.b.data(), raw.b.size());
+            if ((double) compressed.size() / (double) rawSize <= 0.8) { slice = &compressed; markers |= PG_PAGE_MARKER_COMPRESSED; }
+        }
+        if (checksumEnabled) { markers |= PG_PAGE_MARKER_CHECKSUMMED; checksum = pageChecksum(slice->data(), slice->size(), markers, n, rawSize); }
         Writer w;                                                   // PagesSerdeUtil.writeSerializedPageMetadata :70-77
-        w.i32(n); w.u8(markers); w.i32(rawSize); w.i32(rawSize); w.i64(checksum);
-        w.bytes(raw.b.data(), raw.b.size());
+        w.i32(n); w.u8(markers); w.i32(rawSize); w.i32((int32_t) slice->size()); w.i64(checksum);
+        w.bytes(slice->data(), slice->size());
         wire.swap(w.b);
         *bytes = wire.data(); *size = (int64_t) wire.size();
     }
@@ -238,11 +305,16 @@ public:
         Reader r{bytes, bytes + size};
         const int32_t positionCount = r.i32(); const uint8_t markers = r.u8();      // readSerializedPage :79-88
         const int32_t uncompressed = r.i32(), sz = r.i32(); const int64_t checksum = r.i64();
-        if (markers & (PG_PAGE_MARKER_COMPRESSED | PG_PAGE_MARKER_ENCRYPTED)) throw OracleError(PG_ERR_UNSUPPORTED, "compressed / encrypted pages are not supported");
+        if (markers & PG_PAGE_MARKER_ENCRYPTED) throw OracleError(PG_ERR_UNSUPPORTED, "encrypted pages are not supported");
         r.need(sz);
         if ((markers & PG_PAGE_MARKER_CHECKSUMMED) && pageChecksum(r.p, sz, markers, positionCount, uncompressed) != checksum)
             throw OracleError(PG_ERR_INVALID_ARGUMENT, "serialized page checksum mismatch");
         r.end = r.p + sz;
+        if (markers & PG_PAGE_MARKER_COMPRESSED) {                  // PagesSerde.deserialize :95-107
+            if (uncompressed < 0 || !lz4Decompress(r.p, (size_t) sz, decoded, (size_t) uncompressed))
+                throw OracleError(PG_ERR_INVALID_ARGUMENT, "page size changed after decompression (malformed LZ4 block)");
+            r = Reader{decoded.data(), decoded.data() + decoded.size()};
+        }
         const int32_t channels = r.i32();                                            // readRawPage :53-62
         if (channels != nTypes) throw OracleError(PG_ERR_INVALID_ARGUMENT, "channel count of the page differs from the types given");
         cols.assign(channels, WireColumn()); blocks.assign(channels, pg_block{});
@@ -289,7 +361,7 @@ extern "C" void or_set_error(const char* msg);
 extern "C" {
 int32_t or_pages_serde_create(const pg_pages_serde_config* config, pg_pages_serde** out)
 {
-    OR_TRY *out = (pg_pages_serde*) new oracle::PagesSerde(config->checksum_enabled != 0); OR_CATCH
+    OR_TRY *out = (pg_pages_serde*) new oracle::PagesSerde(config->checksum_enabled != 0, config->compression); OR_CATCH
 }
 int32_t or_pages_serde_serialize(pg_pages_serde* serde, const pg_page* page, const uint8_t** bytes, int64_t* size)
 {

@@ -137,11 +137,12 @@ class pg_partitioned_output_config(C.Structure):
     _fields_ = [
         ("n_channels", C.c_int32), ("types", _I32P), ("partition_count", C.c_int32), ("n_partition_channels", C.c_int32),
         ("partition_channels", _I32P), ("precomputed_hash_channel", C.c_int32), ("replicates_any_row", C.c_int32),
-        ("null_channel", C.c_int32), ("partition_function", C.c_int32), ("options", pg_operator_options),
+        ("null_channel", C.c_int32), ("partition_function", C.c_int32), ("bucket_count", C.c_int32), ("bucket_to_partition", _I32P),
+        ("options", pg_operator_options),
     ]
 
 
-PARTITION_HASH_GENERATOR, PARTITION_LOCAL = 0, 1
+PARTITION_HASH_GENERATOR, PARTITION_LOCAL, PARTITION_ROUND_ROBIN = 0, 1, 2
 
 
 class pg_expr_node(C.Structure):
@@ -179,10 +180,11 @@ class pg_semi_join_config(C.Structure):
 
 
 class pg_pages_serde_config(C.Structure):
-    _fields_ = [("checksum_enabled", C.c_int32), ("options", pg_operator_options)]
+    _fields_ = [("checksum_enabled", C.c_int32), ("compression", C.c_int32), ("options", pg_operator_options)]
 
 
 SERIALIZED_PAGE_HEADER_BYTES = 21
+COMPRESSION_NONE, COMPRESSION_LZ4 = 0, 1
 PAGE_MARKER_COMPRESSED, PAGE_MARKER_ENCRYPTED, PAGE_MARKER_CHECKSUMMED = 1, 2, 4
 
 
@@ -250,6 +252,9 @@ class Backend:
         "device_synchronize": (C.c_int32, []),
         "release_cached_memory": (C.c_int32, []),
         "hash_crc32_chunked": (C.c_int64, [C.c_void_p, C.c_size_t, C.c_size_t]),
+        "lz4_compress_bound": (C.c_int64, [C.c_int64]),
+        "lz4_compress_host": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
+        "lz4_decompress_host": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
         "partitioned_output_count": (C.c_int32, [C.c_void_p, C.POINTER(pg_page), C.c_void_p]),
         "partitioned_output_scatter_to": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
         "ipc_export": (C.c_int32, [C.c_void_p, C.c_void_p]),

@@ -107,6 +107,7 @@ struct Plan {
                 output = s;
                 output.types = keep(arena, s.types, s.n_channels);
                 output.partition_channels = keep(arena, s.partition_channels, s.n_partition_channels);
+                output.bucket_to_partition = s.bucket_to_partition ? keep(arena, s.bucket_to_partition, (size_t) std::max(s.bucket_count, 0)) : nullptr;
                 break;
             }
             case PG_FACTORY_FUSED_AGGREGATION: {

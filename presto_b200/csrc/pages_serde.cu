@@ -14,6 +14,7 @@
 // The host only writes / parses the fixed fields (a few dozen bytes per channel).
 #include "common.cuh"
 #include "crc32_host.h"
+#include "lz4_codec.cuh"
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <atomic>
@@ -135,6 +136,30 @@ __global__ void __launch_bounds__(128) crcChunksKernel(const uint8_t* __restrict
 
 // ---- DictionaryBlock.compact (PC/block/DictionaryBlock.java:584-628) on the device: the referenced dictionary entries, renumbered in
 // order of first reference ---------------------------------------------------------------------------------------------------------
+// ---- LZ4 block codec (lz4_codec.cuh): one thread per 8 KB segment finds / writes its sequences, one warp decodes a block ----
+constexpr int kLz4Threads = 64;
+__global__ void __launch_bounds__(kLz4Threads) lz4FindKernel(const uint8_t* __restrict__ src, int64_t n, int64_t nSegs, uint16_t* tables, lz4::Match* matches, lz4::SegmentInfo* segs)
+{
+    const int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x, T = (int64_t) gridDim.x * blockDim.x;
+    uint16_t* table = tables + t * lz4::kHashEntries;
+    for (int64_t s = t; s < nSegs; s += T) lz4::findMatches(src, n, s, table, matches + s * lz4::kMaxMatchesPerSegment, segs[s]);
+}
+__global__ void lz4PlanKernel(int64_t n, lz4::SegmentInfo* segs, int64_t nSegs, lz4::BlockInfo* block)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) lz4::planBlock(n, segs, nSegs, *block);
+}
+__global__ void __launch_bounds__(kLz4Threads) lz4EmitKernel(const uint8_t* __restrict__ src, int64_t n, int64_t nSegs, const lz4::Match* matches, const lz4::SegmentInfo* segs,
+                                                             const lz4::BlockInfo* block, uint8_t* dst)
+{
+    const int64_t t = blockIdx.x * (int64_t) blockDim.x + threadIdx.x, T = (int64_t) gridDim.x * blockDim.x;
+    for (int64_t s = t; s < nSegs; s += T) lz4::emitSegment(src, n, s, nSegs, matches + s * lz4::kMaxMatchesPerSegment, segs[s], *block, dst);
+}
+__global__ void lz4DecodeKernel(const uint8_t* src, int64_t srcLen, uint8_t* dst, int64_t dstCap, long long* result)
+{
+    const long long r = lz4::decodeBlock<true>(src, srcLen, dst, dstCap, (int) threadIdx.x, 32);
+    if (threadIdx.x == 0) *result = r;
+}
+
 __global__ void dictFillKernel(uint32_t* p, uint32_t v, int64_t n)
 {
     for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) p[i] = v;
@@ -194,6 +219,8 @@ struct SerdeBase : Operator {         // borrows the Operator plumbing (device, 
 
 class PagesSerde : public SerdeBase {
     bool checksumEnabled;
+    int compression;
+    DeviceBuffer lzTables, lzMatches, lzSegs, lzBlock, lzWire, lzRaw;      // LZ4: per-thread hash tables, match records, segment / block plans, the compressed wire, a decoded payload
     PageStager stager;
     Crc32Host crcHost;
     DeviceBuffer wire, crcs, unitCounts, unitOffsets, scanTemp, dWireIn;
@@ -268,9 +295,36 @@ class PagesSerde : public SerdeBase {
     }
 
 public:
-    explicit PagesSerde(const pg_pages_serde_config* c) : SerdeBase(c->options), checksumEnabled(c->checksum_enabled != 0), stager(this)
+    explicit PagesSerde(const pg_pages_serde_config* c) : SerdeBase(c->options), checksumEnabled(c->checksum_enabled != 0), compression(c->compression), stager(this)
     {
-        for (DeviceBuffer* d : {&wire, &crcs, &unitCounts, &unitOffsets, &scanTemp, &dWireIn}) d->accounting = &stats.device_bytes;
+        PG_CHECK_ARG(compression == PG_COMPRESSION_NONE || compression == PG_COMPRESSION_LZ4, "unknown compression");
+        for (DeviceBuffer* d : {&wire, &crcs, &unitCounts, &unitOffsets, &scanTemp, &dWireIn, &lzTables, &lzMatches, &lzSegs, &lzBlock, &lzWire, &lzRaw}) d->accounting = &stats.device_bytes;
+    }
+
+    // PagesSerde.wrapSlice :118-143: the raw page W[21, 21 + rawSize) as one LZ4 block, kept when compressed / raw <= MINIMUM_COMPRESSION_RATIO
+    // (0.8).  Returns the compressed size and leaves the block at lzWire + 21, or -1 when the page stays uncompressed.
+    int64_t tryCompress(const uint8_t* W, int64_t rawSize)
+    {
+        using namespace lz4;
+        const int64_t nSegs = segmentsOf(rawSize);
+        const int threads = (int) std::min<int64_t>(divUp(nSegs, kLz4Threads) * kLz4Threads, (int64_t) numSMs * 2 * kLz4Threads);
+        const int grid = threads / kLz4Threads;
+        lzTables.reserve((size_t) threads * kHashEntries * sizeof(uint16_t));
+        lzMatches.reserve((size_t) nSegs * kMaxMatchesPerSegment * sizeof(Match));
+        lzSegs.reserve((size_t) nSegs * sizeof(SegmentInfo));
+        lzBlock.reserve(sizeof(BlockInfo));
+        const uint8_t* raw = W + PG_SERIALIZED_PAGE_HEADER_BYTES;
+        PG_LAUNCH(this, lz4FindKernel, grid, kLz4Threads, 0, raw, rawSize, nSegs, lzTables.as<uint16_t>(), lzMatches.as<Match>(), lzSegs.as<SegmentInfo>());
+        PG_LAUNCH(this, lz4PlanKernel, 1, 32, 0, rawSize, lzSegs.as<SegmentInfo>(), nSegs, lzBlock.as<BlockInfo>());
+        BlockInfo block{};
+        PG_CUDA(cudaMemcpyAsync(&block, lzBlock.ptr, sizeof(block), cudaMemcpyDeviceToHost, stream));
+        PG_CUDA(cudaStreamSynchronize(stream));
+        stats.d2h_bytes += (int64_t) sizeof(block);
+        if ((double) block.compressedBytes / (double) rawSize > 0.8) return -1;
+        lzWire.reserve((size_t) PG_SERIALIZED_PAGE_HEADER_BYTES + block.compressedBytes + 32);
+        PG_LAUNCH(this, lz4EmitKernel, grid, kLz4Threads, 0, raw, rawSize, nSegs, lzMatches.as<Match>(), lzSegs.as<SegmentInfo>(), lzBlock.as<BlockInfo>(),
+                  lzWire.as<uint8_t>() + PG_SERIALIZED_PAGE_HEADER_BYTES);
+        return block.compressedBytes;
     }
 
     // ================================================================== serialize ==================================================================
@@ -380,9 +434,9 @@ public:
             if (P.dict) { P.idsAt = at; at += 4 * (int64_t) P.run + 24; }     // ids, dictionary instance id
             P.end = at;
         }
-        const int64_t total = at;
-        PG_CHECK_ARG(total < (int64_t(1) << 31), "serialized page exceeds 2 GB (SerializedPage sizes are 32-bit)");
-        wire.reserve((size_t) total + 32);
+        const int64_t rawTotal = at;
+        PG_CHECK_ARG(rawTotal < (int64_t(1) << 31), "serialized page exceeds 2 GB (SerializedPage sizes are 32-bit)");
+        wire.reserve((size_t) rawTotal + 32);
         uint8_t* W = wire.as<uint8_t>();
         // ---- fixed fields: assembled on the host, copied as one patch per channel ----
         hostScratch.reserve((size_t) (64 + 64 * nch));
@@ -426,17 +480,23 @@ public:
         }
         if (slot >= 0) stager.markCompute(slot);
         // ---- page metadata (PagesSerdeUtil.writeSerializedPageMetadata :70-77) ----
-        const int32_t rawSize = (int32_t) (total - PG_SERIALIZED_PAGE_HEADER_BYTES);
+        const int32_t rawSize = (int32_t) (rawTotal - PG_SERIALIZED_PAGE_HEADER_BYTES);
         {
             std::string cc = le32(nch);
             patch(PG_SERIALIZED_PAGE_HEADER_BYTES, cc);
         }
         uint8_t markers = 0; int64_t checksum = 0;
-        if (checksumEnabled) {
-            markers |= PG_PAGE_MARKER_CHECKSUMMED;
-            checksum = checksumOf(W + PG_SERIALIZED_PAGE_HEADER_BYTES, rawSize, markers, (int32_t) n, rawSize);
+        int32_t payload = rawSize;                              // bytes after the 21-byte metadata
+        int64_t total = rawTotal;
+        if (compression == PG_COMPRESSION_LZ4) {
+            const int64_t z = tryCompress(W, rawSize);
+            if (z >= 0) { markers |= PG_PAGE_MARKER_COMPRESSED; payload = (int32_t) z; W = lzWire.as<uint8_t>(); total = PG_SERIALIZED_PAGE_HEADER_BYTES + z; }
         }
-        std::string meta = le32((int32_t) n) + std::string(1, (char) markers) + le32(rawSize) + le32(rawSize) + std::string((const char*) &checksum, 8);
+        if (checksumEnabled) {                                  // over the slice that travels (compressed or not), the markers, the counts
+            markers |= PG_PAGE_MARKER_CHECKSUMMED;
+            checksum = checksumOf(W + PG_SERIALIZED_PAGE_HEADER_BYTES, payload, markers, (int32_t) n, rawSize);
+        }
+        std::string meta = le32((int32_t) n) + std::string(1, (char) markers) + le32(rawSize) + le32(payload) + std::string((const char*) &checksum, 8);
         patch(0, meta);
         stats.input_positions += n; stats.output_bytes += total;
         if (options.output_memory == PG_MEM_HOST) {
@@ -596,12 +656,31 @@ public:
         WireReader r{this, host ? bytes : nullptr, host ? nullptr : bytes, size};
         const int32_t positionCount = r.i32(); const uint8_t markers = r.u8();          // PagesSerdeUtil.readSerializedPage :79-88
         const int32_t uncompressed = r.i32(), sz = r.i32(); const int64_t checksum = r.i64();
-        if (markers & (PG_PAGE_MARKER_COMPRESSED | PG_PAGE_MARKER_ENCRYPTED)) throw Error(PG_ERR_UNSUPPORTED, "compressed / encrypted pages are not supported on the GPU path");
-        PG_CHECK_ARG(sz >= 4 && (int64_t) sz + PG_SERIALIZED_PAGE_HEADER_BYTES <= size, "serialized page is truncated");
-        const int64_t wireSize = (int64_t) sz + PG_SERIALIZED_PAGE_HEADER_BYTES;
+        if (markers & PG_PAGE_MARKER_ENCRYPTED) throw Error(PG_ERR_UNSUPPORTED, "encrypted pages are not supported on the GPU path");
+        PG_CHECK_ARG(sz >= 1 && (int64_t) sz + PG_SERIALIZED_PAGE_HEADER_BYTES <= size, "serialized page is truncated");
+        int64_t wireSize = (int64_t) sz + PG_SERIALIZED_PAGE_HEADER_BYTES;
         r.size = wireSize;
         if ((markers & PG_PAGE_MARKER_CHECKSUMMED) && checksumOf(dW + PG_SERIALIZED_PAGE_HEADER_BYTES, sz, markers, positionCount, uncompressed) != checksum)
             throw Error(PG_ERR_INVALID_ARGUMENT, "serialized page checksum mismatch");
+        if (markers & PG_PAGE_MARKER_COMPRESSED) {              // PagesSerde.deserialize :95-107: one LZ4 block → uncompressedSize bytes
+            PG_CHECK_ARG(uncompressed >= 4, "compressed page with a bad uncompressed size");
+            lzRaw.reserve((size_t) PG_SERIALIZED_PAGE_HEADER_BYTES + (size_t) uncompressed + 32);
+            lzBlock.reserve(sizeof(lz4::BlockInfo));
+            PG_LAUNCH(this, lz4DecodeKernel, 1, 32, 0, dW + PG_SERIALIZED_PAGE_HEADER_BYTES, (int64_t) sz, lzRaw.as<uint8_t>() + PG_SERIALIZED_PAGE_HEADER_BYTES, (int64_t) uncompressed,
+                      lzBlock.as<long long>());
+            long long decoded = -1;
+            PG_CUDA(cudaMemcpyAsync(&decoded, lzBlock.ptr, 8, cudaMemcpyDeviceToHost, stream));
+            PG_CUDA(cudaStreamSynchronize(stream));
+            stats.d2h_bytes += 8;
+            if (decoded != uncompressed) throw Error(PG_ERR_INVALID_ARGUMENT, "page size changed after decompression (malformed LZ4 block)");     // :104 checkState
+            // the rest of the call reads the decoded raw page: on the device, behind a metadata-sized gap so that positions keep their meaning
+            dW = lzRaw.as<uint8_t>();
+            wireSize = (int64_t) uncompressed + PG_SERIALIZED_PAGE_HEADER_BYTES;
+            const int64_t at = r.at;
+            r = WireReader{this, nullptr, dW, wireSize};
+            r.at = at;
+        }
+        PG_CHECK_ARG(wireSize >= PG_SERIALIZED_PAGE_HEADER_BYTES + 4, "serialized page is truncated");
         const int32_t channels = r.i32();                                               // readRawPage :53-62
         PG_CHECK_ARG(channels == nTypes, "channel count of the page differs from the types given");
         if ((int) outValues.size() < channels) {

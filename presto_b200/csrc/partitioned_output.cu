@@ -32,7 +32,10 @@ struct PartitionIdParams {
     const uint8_t* nullChannelNulls;     // rows whose null channel is NULL go to every partition
     int32_t replicateRow0;
     int32_t partitionCount;
-    int32_t localFunction;               // 1: LocalPartitionGenerator instead of HashGenerator.getPartition
+    int32_t localFunction;               // 1: LocalPartitionGenerator instead of HashGenerator.getPartition; 2: RoundRobinBucketFunction
+    int32_t bucketCount;                 // the function's range (= partitionCount without a bucket table)
+    const int32_t* bucketToPartition;    // BucketPartitionFunction's table, or nullptr = identity
+    uint32_t roundRobinBase;             // RoundRobinBucketFunction's counter at row 0 of this page
     int64_t n;
     int64_t units;
     uint16_t* ids;                       // [n]  partition, or partitionCount = "every partition"
@@ -70,13 +73,15 @@ __global__ void __launch_bounds__(kPartWarps * 32) partitionIdKernel(const __gri
             if (row < end) {
                 if ((P.replicateRow0 && row == 0) || (P.nullChannelNulls && P.nullChannelNulls[row])) part = PC;
                 else {
-                    int64_t rawHash;
-                    if (P.precomputed) rawHash = P.precomputed[row];
+                    int64_t rawHash = 0;
+                    if (P.localFunction == 2) part = (int) (((P.roundRobinBase + (uint32_t) row) & 0x7fffffffu) % (uint32_t) P.bucketCount);   // counter & 0x7fffffff, :297-301
                     else {
-                        rawHash = 0;   // InterpretedHashGenerator.hashPosition: CombineHashFunction.getHash(result, typeHash)
-                        for (int c = 0; c < P.nCols; c++) rawHash = (int64_t) (31ULL * (uint64_t) rawHash + (uint64_t) typeHashOf(P.cols[c], row));
+                        if (P.precomputed) rawHash = P.precomputed[row];
+                        else   // InterpretedHashGenerator.hashPosition: CombineHashFunction.getHash(result, typeHash)
+                            for (int c = 0; c < P.nCols; c++) rawHash = (int64_t) (31ULL * (uint64_t) rawHash + (uint64_t) typeHashOf(P.cols[c], row));
+                        part = P.localFunction ? localPartition(rawHash, P.bucketCount) : hashPartition(rawHash, P.bucketCount);
                     }
-                    part = P.localFunction ? localPartition(rawHash, PC) : hashPartition(rawHash, PC);
+                    if (P.bucketToPartition) part = P.bucketToPartition[part];     // BucketPartitionFunction.getPartition :49-53
                 }
                 P.ids[row] = (uint16_t) part;
             }
@@ -354,6 +359,7 @@ __global__ void varcharGatherBytesKernel(const uint8_t* inBytes, const int32_t* 
 class PartitionedOutputOp : public Operator {
     std::vector<int> types, partitionChannels, staged;
     int partitionCount, hashChannel, nullChannel, partitionFunction;
+    int bucketCount = 0; DeviceBuffer bucketTable; uint32_t roundRobinCounter = 0;
     bool replicatesAnyRow, hasAnyRowBeenReplicated = false;
     bool finishing = false, hasPending = false;
     PageStager stager;
@@ -380,9 +386,22 @@ public:
         partitionCount = c->partition_count; hashChannel = c->precomputed_hash_channel; nullChannel = c->null_channel;
         replicatesAnyRow = c->replicates_any_row != 0;
         partitionFunction = c->partition_function;
-        PG_CHECK_ARG(partitionFunction == PG_PARTITION_HASH_GENERATOR || partitionFunction == PG_PARTITION_LOCAL, "unknown partition function");
+        PG_CHECK_ARG(partitionFunction == PG_PARTITION_HASH_GENERATOR || partitionFunction == PG_PARTITION_LOCAL || partitionFunction == PG_PARTITION_ROUND_ROBIN, "unknown partition function");
+        bucketCount = partitionCount;
+        if (c->bucket_to_partition) {      // BucketPartitionFunction.java:31-36
+            PG_CHECK_ARG(c->bucket_count >= 1 && c->bucket_count <= (1 << 20), "bucket_count out of range");
+            bucketCount = c->bucket_count;
+            std::vector<int32_t> table(c->bucket_to_partition, c->bucket_to_partition + bucketCount);
+            for (int32_t p : table) PG_CHECK_ARG(p >= 0 && p < partitionCount, "bucket_to_partition entry outside [0, partition_count)");
+            bucketTable.accounting = &stats.device_bytes;
+            bucketTable.reserve((size_t) bucketCount * 4);
+            PG_CUDA(cudaMemcpyAsync(bucketTable.ptr, table.data(), (size_t) bucketCount * 4, cudaMemcpyHostToDevice, stream));
+            PG_CUDA(cudaStreamSynchronize(stream));
+        }
         if (partitionFunction == PG_PARTITION_LOCAL)
-            PG_CHECK_ARG((partitionCount & (partitionCount - 1)) == 0, "partitionCount must be a power of 2");   // LocalPartitionGenerator.java:33
+            PG_CHECK_ARG((bucketCount & (bucketCount - 1)) == 0, "partitionCount must be a power of 2");   // LocalPartitionGenerator.java:33
+        if (partitionFunction == PG_PARTITION_ROUND_ROBIN && c->null_channel >= 0)
+            throw Error(PG_ERR_UNSUPPORTED, "round-robin partitioning with a null channel (replicated rows do not advance the counter) is not on the GPU path");
         int internalColumns = 0;
         for (int t : types) { if (t == PG_TYPE_VARCHAR) { hasVarchar = true; internalColumns += 2; } else internalColumns++; }
         PG_CHECK_ARG(internalColumns <= kMaxScatterColumns, "too many channels (a VARCHAR channel counts twice)");
@@ -390,7 +409,7 @@ public:
             PG_CHECK_ARG(ch >= 0 && ch < c->n_channels, "partition channel out of range");
         }
         PG_CHECK_ARG(hashChannel < c->n_channels && nullChannel < c->n_channels, "channel out of range");
-        PG_CHECK_ARG(hashChannel >= 0 || !partitionChannels.empty() || partitionCount == 1, "no partition channels");
+        PG_CHECK_ARG(hashChannel >= 0 || !partitionChannels.empty() || partitionCount == 1 || partitionFunction == PG_PARTITION_ROUND_ROBIN, "no partition channels");
         if (hashChannel >= 0) PG_CHECK_ARG(types[hashChannel] == PG_TYPE_BIGINT, "precomputed hash channel must be BIGINT");
         for (int i = 0; i < c->n_channels; i++) staged.push_back(i);
         offsets.assign(partitionCount + 1, 0);
@@ -428,7 +447,13 @@ public:
         A.nullChannelNulls = nullChannel >= 0 ? curCols[nullChannel].nulls : nullptr;
         A.replicateRow0 = (replicatesAnyRow && !hasAnyRowBeenReplicated) ? 1 : 0;
         hasAnyRowBeenReplicated = hasAnyRowBeenReplicated || replicatesAnyRow;
-        A.partitionCount = partitionCount; A.localFunction = partitionFunction == PG_PARTITION_LOCAL ? 1 : 0; A.n = n; A.units = curUnits; A.ids = ids.as<uint16_t>(); A.hist = hist.as<uint32_t>();
+        A.bucketCount = bucketCount; A.bucketToPartition = bucketTable.as<int32_t>();
+        // RoundRobinBucketFunction keeps counting across pages; a replicated row 0 / NULL-channel row does not call the function (:504-530)
+        // (only rows that reach partitionFunction.getPartition advance it: not the replicated row 0, :504-512)
+        const uint32_t skipped = A.replicateRow0 ? 1u : 0u;
+        A.roundRobinBase = roundRobinCounter - skipped;
+        if (partitionFunction == PG_PARTITION_ROUND_ROBIN) roundRobinCounter = (uint32_t) ((roundRobinCounter + (uint64_t) n - skipped) & 0x7fffffffu);
+        A.partitionCount = partitionCount; A.localFunction = partitionFunction == PG_PARTITION_LOCAL ? 1 : (partitionFunction == PG_PARTITION_ROUND_ROBIN ? 2 : 0); A.n = n; A.units = curUnits; A.ids = ids.as<uint16_t>(); A.hist = hist.as<uint32_t>();
         PG_CUDA(cudaMemsetAsync(hist.as<uint32_t>() + histN - 1, 0, 4, stream));
         const size_t smem = (size_t) kPartWarps * partitionCount * 4;
         PG_LAUNCH(this, partitionIdKernel, launchGrid(), kPartWarps * 32, smem, A);

@@ -1,6 +1,7 @@
 // presto_b200 — runtime: device management, operator base, page staging, scalar hash helpers.
 #include "common.cuh"
 #include "crc32_host.h"
+#include "lz4_codec.cuh"
 #include <cub/device/device_scan.cuh>
 #include <map>
 #include <mutex>
@@ -437,6 +438,27 @@ int32_t pg_hash_local_partition(int64_t rawHash, int32_t partitionCount)
 {
     if (partitionCount <= 0 || (partitionCount & (partitionCount - 1)) != 0) return -1;   // checkArgument(Integer.bitCount(partitionCount) == 1)
     return pg::localPartition(rawHash, partitionCount);
+}
+
+int64_t pg_lz4_compress_bound(int64_t n) { return pg::lz4::compressBound(n); }
+int64_t pg_lz4_compress_host(const void* src, int64_t n, void* dst, int64_t capacity)
+{
+    using namespace pg::lz4;
+    if (n < 0 || capacity < compressBound(n) || n >= (int64_t(1) << 31)) return -1;
+    const int64_t nSegs = segmentsOf(n);
+    std::vector<SegmentInfo> segs((size_t) nSegs);
+    std::vector<Match> matches((size_t) nSegs * kMaxMatchesPerSegment);
+    std::vector<uint16_t> table(kHashEntries);
+    for (int64_t s = 0; s < nSegs; s++) findMatches((const uint8_t*) src, n, s, table.data(), matches.data() + s * kMaxMatchesPerSegment, segs[(size_t) s]);
+    BlockInfo block;
+    planBlock(n, segs.data(), nSegs, block);
+    for (int64_t s = 0; s < nSegs; s++) emitSegment((const uint8_t*) src, n, s, nSegs, matches.data() + s * kMaxMatchesPerSegment, segs[(size_t) s], block, (uint8_t*) dst);
+    return block.compressedBytes;
+}
+int64_t pg_lz4_decompress_host(const void* src, int64_t n, void* dst, int64_t capacity)
+{
+    if (n < 0 || capacity < 0) return -1;
+    return pg::lz4::decodeBlock<false>((const uint8_t*) src, n, (uint8_t*) dst, capacity, 0, 1);
 }
 
 int64_t pg_hash_xxhash64(const void* data, size_t len)

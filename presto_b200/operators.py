@@ -359,10 +359,13 @@ class PartitionedOutputOperator(Operator):
 
     def __init__(self, types: Sequence[int], partition_count: int, partition_channels: Sequence[int], *,
                  precomputed_hash_channel: int = -1, replicates_any_row: bool = False, null_channel: int = -1,
-                 partition_function: int = abi.PARTITION_HASH_GENERATOR, backend=None, **options):
+                 partition_function: int = abi.PARTITION_HASH_GENERATOR, bucket_to_partition: Optional[Sequence[int]] = None, backend=None, **options):
         backend = backend or _default_backend()
         cfg = abi.pg_partitioned_output_config()
         cfg.partition_function = partition_function
+        if bucket_to_partition is not None:       # BucketPartitionFunction: the function yields a bucket, the table names its partition
+            table = abi.i32_array(bucket_to_partition)
+            cfg.bucket_count, cfg.bucket_to_partition = len(bucket_to_partition), table
         ty, pc = abi.i32_array(types), abi.i32_array(partition_channels)
         cfg.n_channels, cfg.types = len(types), ty
         cfg.partition_count = partition_count
@@ -665,10 +668,11 @@ class PagesSerde:
     """PagesSerde (presto-spi/.../spi/page/PagesSerde.java:67-156) + PagesSerdeUtil.writeSerializedPage / readSerializedPage
     (:64-88): pages to and from the SerializedPage wire bytes (21-byte header + raw page)."""
 
-    def __init__(self, *, checksum_enabled: bool = False, backend=None, **options):
+    def __init__(self, *, checksum_enabled: bool = False, compression: int = abi.COMPRESSION_NONE, backend=None, **options):
         self._b = backend or _default_backend()
         cfg = abi.pg_pages_serde_config()
         cfg.checksum_enabled = int(checksum_enabled)
+        cfg.compression = compression        # COMPRESSION_LZ4: pages that shrink to <= 0.8 travel as one LZ4 block (PagesSerde.java:118-143)
         cfg.options = _options(**options)
         self._memory = cfg.options.output_memory
         self._h = C.c_void_p()

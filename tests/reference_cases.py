@@ -755,6 +755,47 @@ def case_partitioned_output_varchar_partition_channels(backend, partition_count:
         op.close()
 
 
+def case_partitioned_output_bucket_table_and_round_robin(backend):
+    """BucketPartitionFunction.java:25-54 — the bucket function's result goes through bucketToPartition (several buckets per partition, as
+    NodePartitioningManager lays buckets over nodes) — over HashBucketFunction (SystemPartitioningHandle.java:311-329) and over
+    RoundRobinBucketFunction (:282-305: a counter that runs on across pages and is not advanced by the replicated row)."""
+    from presto_b200 import _abi as abi
+    rng = np.random.default_rng(41)
+    n, buckets, partitions = 3000, 64, 5
+    table = rng.integers(0, partitions, buckets).astype(np.int32)
+    table[:partitions] = np.arange(partitions)                 # every partition is hit
+    pages = []
+    for _ in range(3):
+        pages.append(Page([Block.from_numpy(BIGINT, rng.integers(-10**9, 10**9, n)), Block.from_numpy(DOUBLE, rng.random(n))]))
+    # hash buckets
+    op = PartitionedOutputOperator([BIGINT, DOUBLE], partitions, [0], bucket_to_partition=table, backend=backend)
+    for page in pages:
+        op.add_input(page)
+        out_rows, offsets = op.get_output().rows(), op.get_offsets()
+        parts = table[get_partition(get_hash_block([page.blocks[0]], backend).values, buckets)]
+        in_rows = page.rows()
+        for p in range(partitions):
+            assert out_rows[offsets[p]:offsets[p + 1]] == [in_rows[i] for i in range(n) if parts[i] == p]
+    op.close()
+    # round robin, with and without the replicated first row
+    for replicate in (False, True):
+        op = PartitionedOutputOperator([BIGINT, DOUBLE], partitions, [], bucket_to_partition=table, partition_function=abi.PARTITION_ROUND_ROBIN,
+                                       replicates_any_row=replicate, backend=backend)
+        counter = 0
+        for k, page in enumerate(pages):
+            op.add_input(page)
+            out_rows, offsets = op.get_output().rows(), op.get_offsets()
+            in_rows = page.rows()
+            parts = np.full(n, -1)
+            for i in range(n):
+                if replicate and k == 0 and i == 0:
+                    continue                                   # goes everywhere, does not call the function
+                parts[i] = table[counter % buckets]; counter += 1
+            for p in range(partitions):
+                assert out_rows[offsets[p]:offsets[p + 1]] == [in_rows[i] for i in range(n) if parts[i] == p or parts[i] == -1]
+        op.close()
+
+
 def case_partitioned_output_double_zero_keys(backend):
     """DoubleType.hash → TypeUtils.doubleHashCode (PC/type/TypeUtils.java:232-238): -0.0 and +0.0 are equal keys, so they must reach the
     same partition (hash 0 → partition 0), as must every NaN payload."""

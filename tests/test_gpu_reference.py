@@ -75,6 +75,7 @@ def test_decimal_sum(gpu_backend): rc.case_decimal_sum(gpu_backend)
 def test_decimal_sum_overflow(gpu_backend): rc.case_decimal_sum_overflow(gpu_backend)
 def test_lookup_join_is_blocked_until_the_build_finishes(gpu_backend): rc.case_lookup_join_is_blocked_until_the_build_finishes(gpu_backend)
 def test_partitioned_output_varchar_partition_channels(gpu_backend): rc.case_partitioned_output_varchar_partition_channels(gpu_backend)
+def test_partitioned_output_bucket_table_and_round_robin(gpu_backend): rc.case_partitioned_output_bucket_table_and_round_robin(gpu_backend)
 def test_partitioned_output_double_zero_keys(gpu_backend): rc.case_partitioned_output_double_zero_keys(gpu_backend)
 @pytest.mark.parametrize("partition_count", [1, 2, 8, 64])
 def test_partitioned_output_local_partition_generator(gpu_backend, partition_count):

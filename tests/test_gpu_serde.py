@@ -162,3 +162,67 @@ def test_serialize_ranges_with_varchar_and_empty_ranges(gpu_backend, oracle_back
     with pytest.raises(Exception):
         g.serialize_ranges(page, [0, 6000])
     g.close(); o.close()
+
+
+# ---- LZ4 (PagesSerde.wrapSlice :118-143 with the PageCompressor of PagesSerdeFactory.java:75; csrc/lz4_codec.cuh) -------------------------
+def _lz4_pages():
+    rng = np.random.default_rng(12)
+    n = 60_000
+    yield "sequence", Page([Block.from_numpy(BIGINT, np.arange(n, dtype=np.int64) // 3), Block.from_numpy(INTEGER, (np.arange(n) % 11).astype(np.int32))]), True
+    yield "strings+nulls", Page([Block.from_strings([None if i % 13 == 0 else [b"BUILDING", b"AUTOMOBILE", b"", b"MACHINERY"][i % 4] for i in range(n)]),
+                                 Block.from_numpy(DOUBLE, np.round(rng.random(n) * 4) / 4, (rng.random(n) < 0.2).astype(np.uint8))]), True
+    yield "noise", Page([Block.from_numpy(DOUBLE, rng.random(n)), Block.from_numpy(BIGINT, rng.integers(-2**62, 2**62, n))]), False
+    yield "tiny", Page([Block.from_numpy(BIGINT, np.array([1, 2, 3]))]), False
+    yield "big", random_page(np.random.default_rng(5), 400_000, True), None          # several hundred 8 KB segments; whether it shrinks is the data's business
+
+
+@pytest.mark.parametrize("checksum", [False, True])
+@pytest.mark.parametrize("device_output", [False, True])
+def test_lz4_pages_cross_with_the_oracle_and_liblz4(gpu_backend, oracle_backend, checksum, device_output):
+    import pyarrow as pa
+    from presto_b200 import _abi as abi
+    kw = dict(output_memory=MEM_DEVICE) if device_output else {}
+    g = PagesSerde(checksum_enabled=checksum, compression=abi.COMPRESSION_LZ4, backend=gpu_backend, **kw)
+    g_plain = PagesSerde(checksum_enabled=checksum, backend=gpu_backend)
+    o = PagesSerde(checksum_enabled=checksum, compression=abi.COMPRESSION_LZ4, backend=oracle_backend)
+    codec = pa.Codec("lz4_raw")
+    for label, page, shrinks in _lz4_pages():
+        types = types_of(page)
+        wire = g.serialize(page)               # (copied back from the serde's output memory, host or device)
+        raw = g_plain.serialize(page)
+        position_count, markers, uncompressed, size, crc = header_of(wire)
+        compressed = bool(markers & abi.PAGE_MARKER_COMPRESSED)
+        if shrinks is not None:
+            assert compressed == shrinks, label
+        assert position_count == page.position_count and uncompressed == raw.size - HEADER and size == wire.size - HEADER, label
+        if compressed:
+            assert size <= 0.8 * uncompressed
+            assert codec.decompress(bytes(wire[HEADER:]), decompressed_size=uncompressed, asbytes=True) == bytes(raw[HEADER:]), label    # liblz4 reads the block
+        else:
+            assert (wire[HEADER:] == raw[HEADER:]).all(), label
+        if checksum:
+            assert crc == java_checksum(wire), label
+        assert o.deserialize(wire, types).rows() == page.rows(), label             # the reference-side reader
+        assert g_plain.deserialize(wire, types).rows() == page.rows(), label       # a serde without a compressor still reads compressed pages
+        wire_o = o.serialize(page)                                                  # and what the oracle's encoder writes
+        assert g_plain.deserialize(wire_o, types).rows() == page.rows(), label
+    g.close(); g_plain.close(); o.close()
+
+
+def test_lz4_block_written_by_liblz4_is_read_and_malformed_blocks_are_refused(gpu_backend):
+    import pyarrow as pa
+    from presto_b200 import PrestoException
+    from presto_b200 import _abi as abi
+    g = PagesSerde(backend=gpu_backend)
+    page = Page([Block.from_numpy(BIGINT, np.arange(30_000, dtype=np.int64) % 97), Block.from_strings([b"x" * (i % 5) for i in range(30_000)])])
+    raw = g.serialize(page)
+    z = pa.Codec("lz4_raw").compress(bytes(raw[HEADER:]), asbytes=True)
+    wire = np.frombuffer(struct.pack("<iBiiq", page.position_count, abi.PAGE_MARKER_COMPRESSED, raw.size - HEADER, len(z), 0) + z, dtype=np.uint8)
+    assert g.deserialize(wire, types_of(page)).rows() == page.rows()
+    bad = wire.copy(); bad[HEADER + 40:HEADER + 60] = 0xff
+    with pytest.raises(PrestoException):
+        g.deserialize(bad, types_of(page))
+    short = np.frombuffer(struct.pack("<iBiiq", page.position_count, abi.PAGE_MARKER_COMPRESSED, raw.size - HEADER - 1, len(z), 0) + z, dtype=np.uint8)
+    with pytest.raises(PrestoException):
+        g.deserialize(short, types_of(page))
+    g.close()

@@ -128,6 +128,7 @@ def test_decimal_sum(oracle_backend): rc.case_decimal_sum(oracle_backend)
 def test_decimal_sum_overflow(oracle_backend): rc.case_decimal_sum_overflow(oracle_backend)
 def test_lookup_join_is_blocked_until_the_build_finishes(oracle_backend): rc.case_lookup_join_is_blocked_until_the_build_finishes(oracle_backend)
 def test_partitioned_output_varchar_partition_channels(oracle_backend): rc.case_partitioned_output_varchar_partition_channels(oracle_backend)
+def test_partitioned_output_bucket_table_and_round_robin(oracle_backend): rc.case_partitioned_output_bucket_table_and_round_robin(oracle_backend)
 def test_partitioned_output_double_zero_keys(oracle_backend): rc.case_partitioned_output_double_zero_keys(oracle_backend)
 @pytest.mark.parametrize("partition_count", [1, 2, 8, 64])
 def test_partitioned_output_local_partition_generator(oracle_backend, partition_count):
