@@ -532,14 +532,18 @@ def run_join(torch, backend, device, build_rows, probe_rows, steps, warmup):
 
 def run_q3(torch, backend, device, n_orders, steps, warmup, fused=True):
     """configs[3] shape on one GPU: TPC-H Q3 filter → join → join → aggregate over device-resident tables (presto_b200/pipelines.py);
-    rows/s counts lineitem rows.  Algorithmic bytes = every input column once (28 B lineitem, 24 B orders, 12 B customer)."""
-    from presto_b200 import BIGINT, DATE, DOUBLE, INTEGER
+    rows/s counts lineitem rows.  c_mktsegment is the VARCHAR column the reference scans (filter `c_mktsegment = 'BUILDING'`).  Algorithmic
+    bytes = every input column once (28 B lineitem, 24 B orders, customer: 8 B key + 4 B offset + the segment's bytes)."""
+    from presto_b200 import BIGINT, DATE, DOUBLE, INTEGER, VARCHAR, Block, Page
     from presto_b200.pipelines import run_q3 as q3
-    from presto_b200.synthetic import q3_tables_torch
+    from presto_b200.synthetic import mktsegment_varchar_torch, q3_tables_torch
     dev = f"cuda:{device}"
     customer, orders, lineitem = q3_tables_torch(n_orders, dev)
+    seg_bytes, seg_offsets = mktsegment_varchar_torch(customer[1])
     torch.cuda.synchronize()
-    cp = [device_page(torch, list(customer), [BIGINT, INTEGER])]
+    n_cust = customer[0].numel()
+    cp = [Page([Block.device(BIGINT, n_cust, customer[0].data_ptr(), keepalive=customer[0]),
+                Block.device(VARCHAR, n_cust, seg_bytes.data_ptr(), 0, seg_offsets.data_ptr(), keepalive=(seg_bytes, seg_offsets))])]
     op = [device_page(torch, list(orders), [BIGINT, BIGINT, DATE, INTEGER])]
     lp = [device_page(torch, list(lineitem), [BIGINT, DOUBLE, DOUBLE, DATE])]
     n_li = lineitem[0].numel()
@@ -559,8 +563,8 @@ def run_q3(torch, backend, device, n_orders, steps, warmup, fused=True):
     from presto_b200.exchange import block_to_tensor
     rev = torch.cat([block_to_tensor(p.blocks[3]) for p in out]).cpu().numpy() if out else np.zeros(0)
     top = float(np.sort(rev)[-1]) if len(rev) else None
-    algo = n_li * 28 + n_orders * 24 + customer[0].numel() * 12
-    return {"orders": n_orders, "lineitem_rows": int(n_li), "joined_rows": int(stats.get("joined_rows", 0)), "groups": int(groups), "ms": ms,
+    algo = n_li * 28 + n_orders * 24 + n_cust * 12 + int(seg_bytes.numel())
+    return {"orders": n_orders, "customer_types": "BIGINT, VARCHAR (c_mktsegment = 'BUILDING')", "lineitem_rows": int(n_li), "joined_rows": int(stats.get("joined_rows", 0)), "groups": int(groups), "ms": ms,
             "lineitem_rows_per_s": n_li / (ms / 1000), "achieved_gbs": algo / (ms / 1000) / 1e9, "launches": int(stats.get("kernel_launches", 0)), "top_revenue": top,
             "fused": bool(fused), **{k: v for k, v in stats.items() if k.startswith("fused_") or k == "kernel_paths"}}
 

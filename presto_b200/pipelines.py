@@ -114,7 +114,8 @@ def run_q1(lineitem_pages: Sequence[Page], backend=None, device_resident: bool =
 def run_q3(customer: Sequence[Page], orders: Sequence[Page], lineitem: Sequence[Page], backend=None, device_resident: bool = False,
            stats: Optional[Dict] = None, fused: bool = False, **opts) -> List[Page]:
     """Q3 without the final ORDER BY / LIMIT (done on the host by the caller):
-         customer(c_custkey BIGINT, c_mktsegment INTEGER code)   → filter mktsegment = BUILDING           → build #1 (custkey)
+         customer(c_custkey BIGINT, c_mktsegment VARCHAR — the reference's type — or its INTEGER code) → filter c_mktsegment = 'BUILDING'
+                                                                                                          → build #1 (custkey)
          orders(o_orderkey, o_custkey, o_orderdate DATE, o_shippriority INTEGER) → filter o_orderdate < 1995-03-15
                → probe #1 on custkey → build #2 (orderkey; payload orderdate, shippriority)
          lineitem(l_orderkey, l_extendedprice, l_discount, l_shipdate DATE) → filter l_shipdate > 1995-03-15, project revenue = ep*(1-d)
@@ -124,11 +125,12 @@ def run_q3(customer: Sequence[Page], orders: Sequence[Page], lineitem: Sequence[
     copy = not device_resident
     o = dict(backend=backend, **opts)
     # customer → build #1
-    pc = Program([abi.BIGINT, abi.INTEGER])
+    seg_type = customer[0].blocks[1].type if customer else abi.INTEGER
+    pc = Program([abi.BIGINT, seg_type])
     ck, seg = pc.input(0), pc.input(1)
-    pc.set_filter(seg == BUILDING)
+    pc.set_filter(seg == (b"BUILDING" if seg_type == abi.VARCHAR else BUILDING))       # VarcharOperators.equal over a Slice constant
     pc.project(ck)
-    fp_c = FilterAndProjectOperator([abi.BIGINT, abi.INTEGER], pc, output_memory=mem, **o)
+    fp_c = FilterAndProjectOperator([abi.BIGINT, seg_type], pc, output_memory=mem, **o)
     bridge1 = JoinBridge(opts.get("device", 0), backend=backend)
     build1 = HashBuilderOperator(bridge1, [abi.BIGINT], [0], [], **o)
     for p in _drain(fp_c, customer, copy):
@@ -260,11 +262,12 @@ def run_q3_distributed(customer: Sequence[Page], orders: Sequence[Page], lineite
     dev = torch.device("cuda", torch.cuda.current_device())
     _TORCH = {abi.BIGINT: torch.int64, abi.DATE: torch.int32, abi.INTEGER: torch.int32, abi.DOUBLE: torch.float64}
     # ---- customer: filter, replicate the surviving keys, build #1 ----
-    pc = Program([abi.BIGINT, abi.INTEGER])
+    seg_type = customer[0].blocks[1].type if customer else abi.INTEGER
+    pc = Program([abi.BIGINT, seg_type])
     ck, seg = pc.input(0), pc.input(1)
-    pc.set_filter(seg == BUILDING)
+    pc.set_filter(seg == (b"BUILDING" if seg_type == abi.VARCHAR else BUILDING))       # VarcharOperators.equal over a Slice constant
     pc.project(ck)
-    fp_c = FilterAndProjectOperator([abi.BIGINT, abi.INTEGER], pc, output_memory=mem, **o)
+    fp_c = FilterAndProjectOperator([abi.BIGINT, seg_type], pc, output_memory=mem, **o)
     local_keys = [block_to_tensor(p.blocks[0], dev).clone() for p in _drain(fp_c, customer, False)]
     mine = torch.cat(local_keys) if local_keys else torch.empty(0, dtype=torch.int64, device=dev)
     # one fixed-shape all-gather: [count, keys...] padded to the shard size (the filter keeps ~1/5)

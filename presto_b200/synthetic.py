@@ -94,6 +94,35 @@ def q3_tables_np(n_orders: int, seed: int = 7):
     return (c_custkey, c_seg), orders, lineitem
 
 
+MKTSEGMENTS = [b"AUTOMOBILE", b"BUILDING", b"FURNITURE", b"HOUSEHOLD", b"MACHINERY"]     # TPC-H c_mktsegment's domain (dbgen dists.dss "msegmnt")
+
+
+def mktsegment_varchar_np(codes: np.ndarray):
+    """c_mktsegment as the VARCHAR column the reference scans (bytes, int32 offsets) from the 0..4 codes of q3_tables_np."""
+    lens = np.array([len(s) for s in MKTSEGMENTS], dtype=np.int64)[codes]
+    offsets = np.zeros(len(codes) + 1, dtype=np.int32)
+    np.cumsum(lens, out=offsets[1:])
+    table = np.zeros((5, 10), dtype=np.uint8)
+    for i, s in enumerate(MKTSEGMENTS):
+        table[i, :len(s)] = np.frombuffer(s, dtype=np.uint8)
+    data = table[codes][np.arange(10)[None, :] < lens[:, None]]
+    return np.ascontiguousarray(data), offsets
+
+
+def mktsegment_varchar_torch(codes):
+    """The same on the device (benchmark input only): (bytes uint8, offsets int32)."""
+    import torch
+    dev = codes.device
+    lens = torch.tensor([len(s) for s in MKTSEGMENTS], dtype=torch.int64, device=dev)[codes.long()]
+    offsets = torch.zeros(codes.numel() + 1, dtype=torch.int32, device=dev)
+    offsets[1:] = torch.cumsum(lens, 0).to(torch.int32)
+    table = torch.zeros((5, 10), dtype=torch.uint8, device=dev)
+    for i, s in enumerate(MKTSEGMENTS):
+        table[i, :len(s)] = torch.tensor(list(s), dtype=torch.uint8, device=dev)
+    data = table[codes.long()][torch.arange(10, device=dev)[None, :] < lens[:, None]]
+    return data.contiguous(), offsets
+
+
 def q3_tables_torch(n_orders: int, device, seed: int = 7):
     """The same shape generated in HBM with torch (benchmark input only)."""
     import torch

@@ -65,3 +65,28 @@ def test_q1_pipeline(gpu_backend, oracle_backend, device_resident):
     rows_close(got, want)
     for p in keep:
         gpu_backend.device_free(p)
+
+
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("device_resident", [False, True])
+def test_q3_pipeline_with_varchar_mktsegment(gpu_backend, oracle_backend, fused, device_resident):
+    """Q3 with the reference's customer types: c_mktsegment is a VARCHAR channel and the filter is `c_mktsegment = 'BUILDING'` (a Slice
+    constant through VarcharOperators.equal), not a dictionary code.  Same groups as the INTEGER-coded plan, same rows as the oracle."""
+    from presto_b200 import VARCHAR
+    from presto_b200.synthetic import mktsegment_varchar_np
+    from util import page_to_device
+    customer, orders, lineitem = q3_tables_np(30_000)
+    data, offsets = mktsegment_varchar_np(customer[1])
+    cp = [Page([Block.from_numpy(BIGINT, customer[0]), Block(VARCHAR, len(customer[0]), data, None, offsets)])]
+    coded = pages_of([BIGINT, INTEGER], customer, 1)
+    op = pages_of([BIGINT, BIGINT, DATE, INTEGER], orders, 2)
+    lp = pages_of([BIGINT, DOUBLE, DOUBLE, DATE], lineitem, 3)
+    want = rows_of(run_q3(cp, op, lp, backend=oracle_backend))
+    assert want == rows_of(run_q3(coded, op, lp, backend=oracle_backend)) and len(want) > 50
+    keep = []
+    if device_resident:
+        cp, op, lp = [[page_to_device(gpu_backend, p, keep) for p in ps] for ps in (cp, op, lp)]
+    got = rows_of(run_q3(cp, op, lp, backend=gpu_backend, device_resident=device_resident, fused=fused))
+    rows_close(got, want)
+    for p in keep:
+        gpu_backend.device_free(p)

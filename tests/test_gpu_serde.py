@@ -105,8 +105,8 @@ def test_device_resident_page_and_wire(gpu_backend, oracle_backend):
 def test_rejects_what_it_does_not_speak(gpu_backend):
     g = PagesSerde(checksum_enabled=True, backend=gpu_backend)
     wire = g.serialize(Page([Block.from_numpy(BIGINT, np.arange(100))]))
-    bad = wire.copy(); bad[4] |= 1
-    with pytest.raises(Exception, match="compressed"):
+    bad = wire.copy(); bad[4] |= 2
+    with pytest.raises(Exception, match="encrypted"):
         g.deserialize(bad, [BIGINT])
     with pytest.raises(Exception, match="truncated"):
         g.deserialize(wire[:-3], [BIGINT])

@@ -108,8 +108,11 @@ def test_dictionary_blocks_are_written_compacted(serde):
 
 def test_rejects_what_it_does_not_speak(serde):
     wire = serde.serialize(Page([Block.from_numpy(BIGINT, np.array([1]))]))
-    compressed = wire.copy(); compressed[4] = 1
-    with pytest.raises(Exception, match="compressed"):
+    encrypted = wire.copy(); encrypted[4] = 2
+    with pytest.raises(Exception, match="encrypted"):
+        serde.deserialize(encrypted, [BIGINT])
+    compressed = wire.copy(); compressed[4] = 1                     # a raw page flagged COMPRESSED is not an LZ4 block of that size
+    with pytest.raises(Exception, match="decompression"):
         serde.deserialize(compressed, [BIGINT])
     with pytest.raises(Exception, match="truncated"):
         serde.deserialize(wire[:-3], [BIGINT])
