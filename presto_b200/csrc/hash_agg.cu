@@ -984,7 +984,7 @@ __global__ void __launch_bounds__(256) collectSlotsKernel(GroupTable t, uint64_t
 struct KeyOut {          // one output key column
     void* values; uint8_t* nulls; int32_t* lens;   // VARCHAR: lens[g] first, bytes in a second pass
     int32_t type, word, shift, bits;
-    const uint32_t* internLength; const uint64_t* internHash;   // interned VARCHAR key (varchar_interner.h): the field is the value's id
+    const uint64_t* internMeta; const uint64_t* internHash;     // interned VARCHAR key (varchar_interner.h): the field is the value's id
 };
 struct AggOut {
     int32_t function;      // pg_aggregate_function
@@ -1038,8 +1038,8 @@ __global__ void emitKernel(const __grid_constant__ EmitParams P)
                 case PG_TYPE_INTEGER: case PG_TYPE_DATE: ((int32_t*) ko.values)[g] = (int32_t) v; if (!isNull) th = hashLong((int64_t) (int32_t) v); break;
                 case PG_TYPE_BOOLEAN: ((uint8_t*) ko.values)[g] = (uint8_t) v; if (!isNull) th = v ? 1231 : 1237; break;
                 case PG_TYPE_VARCHAR: {
-                    if (ko.internLength) {       // id → length now, bytes gathered from the interner's pool after the scan of the lengths
-                        ko.lens[g] = isNull ? 0 : (int32_t) ko.internLength[(uint32_t) v];
+                    if (ko.internMeta) {         // id → length now, bytes gathered from the interner's pool after the scan of the lengths
+                        ko.lens[g] = isNull ? 0 : (int32_t) internLengthOf(ko.internMeta[(uint32_t) v]);
                         ((int32_t*) ko.values)[g] = (int32_t) v;
                         if (!isNull) th = (int64_t) ko.internHash[(uint32_t) v];
                         break;
@@ -1302,11 +1302,11 @@ struct ResultBuilder {
             KeyOut& ko = E.keys[k];
             ko.values = outBufs[colBufs[c].values].ptr; ko.nulls = outBufs[colBufs[c].nulls].as<uint8_t>(); ko.lens = nullptr;
             ko.type = layout.types[k]; ko.word = layout.word[k]; ko.shift = layout.shift[k]; ko.bits = layout.bits[k];
-            ko.internLength = nullptr; ko.internHash = nullptr;
+            ko.internMeta = nullptr; ko.internHash = nullptr;
             if (layout.interned[k]) {
                 PG_CHECK_STATE(interners && (*interners)[k], "internal: interned key without its interner");
                 const InternView iv = (*interners)[k]->view();
-                ko.internLength = iv.entryLength; ko.internHash = iv.entryHash;
+                ko.internMeta = iv.entryMeta; ko.internHash = iv.entryHash;
             }
             if (layout.types[k] == PG_TYPE_VARCHAR) {
                 varcharLens[k] = newBuf((size_t) (g + 1) * 4);

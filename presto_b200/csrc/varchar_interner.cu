@@ -5,13 +5,21 @@
 
 namespace pg {
 
-constexpr uint32_t kInEmpty = 0, kInLocked = 1;
+constexpr unsigned long long kInEmpty = 0, kInLocked = 1;
 constexpr int64_t kInternChunk = int64_t(1) << 22;     // rows between two capacity checks (worst case: every row a new value)
 
-__device__ __forceinline__ bool sliceEqualsPool(const uint8_t* pool, const uint8_t* p, uint32_t len)
+// `pool8`: the value's first byte in the pool, 8-byte aligned.  Pool lines may have been filled by another SM moments ago: they are read at
+// L2 (ld.global.cg), a word at a time; the row's slice starts anywhere, its words are assembled from byte loads that hit L1.
+__device__ __forceinline__ bool sliceEqualsPool(const uint8_t* pool8, const uint8_t* p, uint32_t len)
 {
-    // pool lines may have been filled by another SM moments ago: read them at L2 (ld.global.cg), never through this SM's L1
-    for (uint32_t i = 0; i < len; i++) if (__ldcg(pool + i) != p[i]) return false;
+    uint32_t i = 0;
+    for (; i + 8 <= len; i += 8) if (__ldcg((const unsigned long long*) (pool8 + i)) != loadLe64(p + i)) return false;
+    if (i < len) {
+        const uint32_t rest = len - i;
+        uint64_t v = 0;
+        for (uint32_t k = 0; k < rest; k++) v |= (uint64_t) p[i + k] << (8 * k);
+        if ((__ldcg((const unsigned long long*) (pool8 + i)) & ((1ULL << (8 * rest)) - 1)) != v) return false;      // bytes past the value are padding
+    }
     return true;
 }
 
@@ -24,31 +32,32 @@ __global__ void __launch_bounds__(256) internKernel(InternView T, const uint8_t*
         const uint32_t len = (uint32_t) (offsets[row + 1] - o);
         const uint8_t* p = bytes + o;
         const uint64_t h = (uint64_t) xxHash64Bytes(p, (int64_t) len);
+        const unsigned long long tag = (h >> 32) << 32;
         uint32_t slot = (uint32_t) h & T.mask;
-        volatile uint32_t* slots = T.slots;
+        volatile unsigned long long* slots = T.slots;
         int32_t result = -1;
         for (uint32_t probe = 0; probe < T.cap; probe++) {
-            uint32_t st = slots[slot];
+            unsigned long long st = slots[slot];
             if (st == kInEmpty) {
                 if (!INSERT) break;
-                const uint32_t old = atomicCAS(&T.slots[slot], kInEmpty, kInLocked);
+                const unsigned long long old = atomicCAS(&T.slots[slot], (unsigned long long) kInEmpty, (unsigned long long) kInLocked);
                 if (old == kInEmpty) {
                     const uint32_t id = (uint32_t) atomicAdd(&T.counters[0], 1ULL);
-                    const uint64_t off = atomicAdd(&T.counters[1], (unsigned long long) len);
+                    const uint64_t off = atomicAdd(&T.counters[1], (unsigned long long) ((len + 7u) & ~7u));      // values start 8-byte aligned
                     for (uint32_t i = 0; i < len; i++) T.pool[off + i] = p[i];
-                    T.entryOffset[id] = off; T.entryLength[id] = len; T.entryHash[id] = h;
+                    T.entryMeta[id] = ((off >> 3) << 31) | len; T.entryHash[id] = h;
                     __threadfence();
-                    slots[slot] = id + 2;          // publish: readers that saw LOCKED have been spinning on this word
+                    slots[slot] = tag | (id + 2);          // publish: readers that saw LOCKED have been spinning on this word
                     result = (int32_t) id;
                     break;
                 }
                 st = old;
             }
             while (st == kInLocked) st = slots[slot];
-            const uint32_t id = st - 2;
-            if (__ldcg(&T.entryHash[id]) == h && __ldcg(&T.entryLength[id]) == len && sliceEqualsPool(T.pool + __ldcg(&T.entryOffset[id]), p, len)) {
-                result = (int32_t) id;
-                break;
+            if ((st & 0xffffffff00000000ULL) == tag) {
+                const uint32_t id = (uint32_t) st - 2;
+                const uint64_t meta = __ldcg(&T.entryMeta[id]);
+                if (internLengthOf(meta) == len && sliceEqualsPool(T.pool + internOffsetOf(meta), p, len)) { result = (int32_t) id; break; }
             }
             slot = (slot + 1) & T.mask;
         }
@@ -59,15 +68,16 @@ __global__ void __launch_bounds__(256) internKernel(InternView T, const uint8_t*
 __global__ void internRehashKernel(InternView T, uint64_t nEntries)
 {
     for (uint64_t id = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; id < nEntries; id += (uint64_t) gridDim.x * blockDim.x) {
-        uint32_t slot = (uint32_t) T.entryHash[id] & T.mask;
-        while (atomicCAS(&T.slots[slot], kInEmpty, (uint32_t) id + 2) != kInEmpty) slot = (slot + 1) & T.mask;
+        const uint64_t h = T.entryHash[id];
+        uint32_t slot = (uint32_t) h & T.mask;
+        while (atomicCAS(&T.slots[slot], kInEmpty, ((h >> 32) << 32) | (id + 2)) != kInEmpty) slot = (slot + 1) & T.mask;
     }
 }
 
 __global__ void internLengthsKernel(InternView T, const int32_t* ids, const uint8_t* nulls, int64_t g, int32_t* lengthsOut)
 {
     for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < g; i += (int64_t) gridDim.x * blockDim.x)
-        lengthsOut[i] = (nulls && nulls[i]) ? 0 : (int32_t) T.entryLength[ids[i]];
+        lengthsOut[i] = (nulls && nulls[i]) ? 0 : (int32_t) internLengthOf(T.entryMeta[ids[i]]);
 }
 
 // one warp per value: lanes stride over its bytes (values of a few bytes cost one partly filled transaction, long ones stay coalesced)
@@ -78,8 +88,9 @@ __global__ void internBytesKernel(InternView T, const int32_t* ids, const uint8_
     for (int64_t i = warp; i < g; i += warps) {
         if (nulls && nulls[i]) continue;
         const int32_t id = ids[i];
-        const uint8_t* src = T.pool + T.entryOffset[id];
-        const uint32_t len = T.entryLength[id];
+        const uint64_t meta = T.entryMeta[id];
+        const uint8_t* src = T.pool + internOffsetOf(meta);
+        const uint32_t len = internLengthOf(meta);
         uint8_t* dst = bytesOut + offsets[i];
         for (uint32_t b = lane; b < len; b += 32) dst[b] = src[b];
     }
@@ -87,7 +98,7 @@ __global__ void internBytesKernel(InternView T, const int32_t* ids, const uint8_
 
 VarcharInterner::VarcharInterner(Operator* op, int64_t* accounting)
 {
-    for (DeviceBuffer* b : {&slots, &entryOffset, &entryLength, &entryHash, &pool, &counters}) b->accounting = accounting;
+    for (DeviceBuffer* b : {&slots, &entryMeta, &entryHash, &pool, &counters}) b->accounting = accounting;
     counters.reserve(2 * sizeof(unsigned long long));
     PG_CUDA(cudaMemsetAsync(counters.ptr, 0, 2 * sizeof(unsigned long long), op->stream));
     host.reserve(64);
@@ -96,8 +107,8 @@ VarcharInterner::VarcharInterner(Operator* op, int64_t* accounting)
 InternView VarcharInterner::view() const
 {
     InternView v{};
-    v.slots = slots.as<uint32_t>(); v.cap = cap; v.mask = cap ? cap - 1 : 0;
-    v.entryOffset = entryOffset.as<uint64_t>(); v.entryLength = entryLength.as<uint32_t>(); v.entryHash = entryHash.as<uint64_t>();
+    v.slots = slots.as<unsigned long long>(); v.cap = cap; v.mask = cap ? cap - 1 : 0;
+    v.entryMeta = entryMeta.as<uint64_t>(); v.entryHash = entryHash.as<uint64_t>();
     v.pool = pool.as<uint8_t>(); v.counters = counters.as<unsigned long long>();
     return v;
 }
@@ -115,7 +126,7 @@ void VarcharInterner::readCounters(Operator* op)
 void VarcharInterner::ensure(Operator* op, uint64_t extraEntries, uint64_t extraBytes)
 {
     cudaStream_t stream = op->stream;
-    const uint64_t needEntries = nEntries + extraEntries, needBytes = poolUsed + extraBytes;
+    const uint64_t needEntries = nEntries + extraEntries, needBytes = poolUsed + extraBytes + 8 * extraEntries + 8;     // every value is padded to 8 bytes
     if (needEntries + 2 >= (1ULL << 31)) throw Error(PG_ERR_INSUFFICIENT_RESOURCES, "more than 2^31 distinct VARCHAR key values");
     auto regrow = [&](DeviceBuffer& buf, size_t newBytes, size_t keepBytes) {
         DeviceBuffer bigger; bigger.accounting = buf.accounting;
@@ -126,8 +137,7 @@ void VarcharInterner::ensure(Operator* op, uint64_t extraEntries, uint64_t extra
     };
     if (needEntries > entryCap) {
         const uint64_t newCap = std::max<uint64_t>(std::max<uint64_t>(entryCap * 2, needEntries), 1024);
-        regrow(entryOffset, newCap * 8, nEntries * 8);
-        regrow(entryLength, newCap * 4, nEntries * 4);
+        regrow(entryMeta, newCap * 8, nEntries * 8);
         regrow(entryHash, newCap * 8, nEntries * 8);
         entryCap = newCap;
     }
@@ -140,8 +150,8 @@ void VarcharInterner::ensure(Operator* op, uint64_t extraEntries, uint64_t extra
         uint64_t newCap = std::max<uint32_t>(cap, 1024);
         while (newCap < needEntries * 2) newCap <<= 1;
         DeviceBuffer bigger; bigger.accounting = slots.accounting;
-        bigger.reserve(newCap * 4);
-        PG_CUDA(cudaMemsetAsync(bigger.ptr, 0, newCap * 4, stream));
+        bigger.reserve(newCap * 8);
+        PG_CUDA(cudaMemsetAsync(bigger.ptr, 0, newCap * 8, stream));
         PG_CUDA(cudaStreamSynchronize(stream));
         slots = std::move(bigger);
         cap = (uint32_t) newCap;

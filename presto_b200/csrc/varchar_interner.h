@@ -13,17 +13,18 @@
 namespace pg {
 
 struct InternView {                 // device view (kernels)
-    uint32_t* slots;                // [cap]  0 = empty, 1 = locked, id + 2 = ready
+    unsigned long long* slots;      // [cap]  0 = empty, 1 = locked, (hash >> 32) << 32 | (id + 2) = ready: the tag spares a probe the entry of most other values
     uint32_t cap, mask;
-    uint64_t* entryOffset;          // [entryCap] byte offset of the value in the pool
-    uint32_t* entryLength;          // [entryCap]
+    uint64_t* entryMeta;            // [entryCap] (pool offset / 8) << 31 | length: values start 8-byte aligned in the pool
     uint64_t* entryHash;            // [entryCap] XXH64 of the bytes = VarcharType.hash of the value
     uint8_t* pool;
     unsigned long long* counters;   // [0] entries, [1] pool bytes in use
 };
+__host__ __device__ __forceinline__ uint32_t internLengthOf(uint64_t meta) { return (uint32_t) (meta & 0x7fffffffULL); }
+__host__ __device__ __forceinline__ uint64_t internOffsetOf(uint64_t meta) { return (meta >> 31) << 3; }
 
 class VarcharInterner {
-    DeviceBuffer slots, entryOffset, entryLength, entryHash, pool, counters, dictionaryIds;
+    DeviceBuffer slots, entryMeta, entryHash, pool, counters, dictionaryIds;
     PinnedBuffer host;
     uint32_t cap = 0;
     uint64_t entryCap = 0, poolCap = 0;

@@ -226,3 +226,33 @@ def test_lz4_block_written_by_liblz4_is_read_and_malformed_blocks_are_refused(gp
     with pytest.raises(PrestoException):
         g.deserialize(short, types_of(page))
     g.close()
+
+
+@pytest.mark.parametrize("decoder", ["window", "simple"])
+def test_lz4_decoders_on_blocks_of_every_shape(gpu_backend, decoder, monkeypatch):
+    """Both device decoders (shared-memory ring, plain) on blocks liblz4 wrote: runs far longer than the ring's chunk (offset 1), matches at
+    the largest offsets, literal runs longer than the input stage, many tiny sequences — payloads are handed over as VARCHAR slices of one
+    row so that the bytes are exactly these."""
+    import pyarrow as pa
+    from presto_b200 import _abi as abi
+    monkeypatch.setenv("PG_LZ4_DECODE", decoder)
+    rng = np.random.default_rng(77)
+    noise = bytes(rng.integers(0, 256, 70_000).astype(np.uint8))
+    payloads = [
+        b"\x00" * 1_000_000,                                                  # one match of ~1 MB at offset 1
+        noise[:20_000] + b"ab" * 200_000 + noise[20_000:40_000],              # offset 2, long; literals longer than the stage on both sides
+        noise[:65_535] + noise[:65_535] + noise[:100],                        # matches at offset 65535
+        noise[:60_000] + b"x" * 10 + noise[:60_000],                          # offset 60010
+        b"".join(bytes([65 + i % 7]) * (1 + i % 9) for i in range(60_000)),   # hundreds of thousands of short sequences
+        noise,                                                                # incompressible: one literal run of 70 000 bytes
+    ]
+    g = PagesSerde(backend=gpu_backend)
+    codec = pa.Codec("lz4_raw")
+    for payload in payloads:
+        page = Page([Block.from_strings([payload])])
+        raw = g.serialize(page)
+        z = codec.compress(bytes(raw[HEADER:]), asbytes=True)
+        wire = np.frombuffer(struct.pack("<iBiiq", 1, abi.PAGE_MARKER_COMPRESSED, raw.size - HEADER, len(z), 0) + z, dtype=np.uint8)
+        got = g.deserialize(wire, [VARCHAR]).rows()
+        assert len(got) == 1 and got[0][0] == payload
+    g.close()
