@@ -97,10 +97,8 @@ import ctypes as C
 dptr = C.c_void_p(); b.check(b.device_alloc(size, C.byref(dptr))); b.check(b.memcpy_h2d(dptr, wire.ctypes.data, size))
 reader = PagesSerde(backend=b, output_memory=MEM_DEVICE)
 ms_dec = timed(lambda: reader.deserialize(dptr.value, [BIGINT, BIGINT], size=int(size), memory=MEM_DEVICE, copy=False))
-os.environ["PG_LZ4_DECODE"] = "simple"
-ms_dec_simple = timed(lambda: reader.deserialize(dptr.value, [BIGINT, BIGINT], size=int(size), memory=MEM_DEVICE, copy=False), reps=1)
-del os.environ["PG_LZ4_DECODE"]
+
 raw = m * 16
 out["serde_lz4_64mb"] = {"raw_bytes": raw, "wire_bytes": int(size), "ratio": round(size / raw, 3), "serialize_plain_ms": round(ms_plain, 2), "serialize_lz4_ms": round(ms_lz, 2),
-                         "lz4_gb_s": round(raw / ms_lz / 1e6, 2), "deserialize_lz4_ms": round(ms_dec, 2), "deserialize_lz4_plain_decoder_ms": round(ms_dec_simple, 2)}
+                         "lz4_gb_s": round(raw / ms_lz / 1e6, 2), "deserialize_lz4_ms": round(ms_dec, 2)}
 print(json.dumps(out))

@@ -228,14 +228,12 @@ def test_lz4_block_written_by_liblz4_is_read_and_malformed_blocks_are_refused(gp
     g.close()
 
 
-@pytest.mark.parametrize("decoder", ["window", "simple"])
-def test_lz4_decoders_on_blocks_of_every_shape(gpu_backend, decoder, monkeypatch):
-    """Both device decoders (shared-memory ring, plain) on blocks liblz4 wrote: runs far longer than the ring's chunk (offset 1), matches at
-    the largest offsets, literal runs longer than the input stage, many tiny sequences — payloads are handed over as VARCHAR slices of one
-    row so that the bytes are exactly these."""
+def test_lz4_decoder_on_blocks_of_every_shape(gpu_backend):
+    """The device decoder on blocks liblz4 wrote: a ~1 MB match at offset 1, matches at the largest offsets, literal runs of tens of
+    kilobytes, hundreds of thousands of tiny sequences — payloads are handed over as VARCHAR slices of one row so that the bytes are
+    exactly these."""
     import pyarrow as pa
     from presto_b200 import _abi as abi
-    monkeypatch.setenv("PG_LZ4_DECODE", decoder)
     rng = np.random.default_rng(77)
     noise = bytes(rng.integers(0, 256, 70_000).astype(np.uint8))
     payloads = [
