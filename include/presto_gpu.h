@@ -246,7 +246,8 @@ typedef struct pg_hash_aggregation_config {
     int32_t n_group_channels;
     const int32_t* group_channels;      /* input channel of each group-by key */
     const int32_t* group_types;         /* pg_type of each key */
-    const int32_t* group_max_lengths;   /* VARCHAR(n): n (only short keys are on the GPU path); else 0 */
+    const int32_t* group_max_lengths;   /* VARCHAR(n) group channels: n in 1..7 packs the value into the key word; 0 (unbounded VARCHAR) or n > 7: the
+                                           channel's slices are interned into value ids on the device first (PG_PATH_INTERNED_KEYS).  Other types: 0 */
     int32_t hash_channel;               /* precomputed $hashvalue BIGINT channel or -1 */
     int32_t n_aggregates;
     const pg_aggregate* aggregates;
@@ -327,7 +328,8 @@ typedef struct pg_hash_builder_config {
     int32_t n_channels;                 /* channels of the build pages */
     const int32_t* types;               /* pg_type per channel */
     int32_t n_hash_channels;
-    const int32_t* hash_channels;       /* join key channels (BIGINT / INTEGER / DATE) */
+    const int32_t* hash_channels;       /* join key channels (BIGINT / INTEGER / DATE / VARCHAR: slices are interned into value ids when the build finishes,
+                                           probes look theirs up) */
     int32_t n_output_channels;
     const int32_t* output_channels;     /* build channels appended to join output (any pg_type but LONG_DECIMAL; a VARCHAR channel keeps the
                                            position-ordered hash-table LookupSource) */
@@ -384,7 +386,8 @@ int32_t pg_lookup_outer_create(const pg_lookup_outer_config* config, pg_join_bri
  * (MB/operator/SetBuilderOperator.java, ChannelSet.java:33-77).  The set is a pg_join_bridge fed by a
  * pg_hash_builder whose only hash channel is the set channel and which has no output channels.  Output page = every input channel
  * + one BOOLEAN channel: NULL probe value → NULL (false when the set has no rows at all); otherwise contained → true, not
- * contained → NULL when the set holds a NULL, else false.  Input channels are fixed width. */
+ * contained → NULL when the set holds a NULL, else false.  Input channels: any pg_type but LONG_DECIMAL (VARCHAR channels pass through as
+ * copied slices; a VARCHAR join channel is looked up in the set's interned values). */
 typedef struct pg_semi_join_config {
     int32_t n_channels;
     const int32_t* types;

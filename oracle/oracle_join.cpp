@@ -372,7 +372,9 @@ struct SemiJoinOperator : Operator {
                 if (setEmpty) flag.appendLong(0); else flag.appendNull();
             }
             else {
-                const bool contains = !setEmpty && set.getAddressIndex(position, probe, hashLong(probe[0].getLong(position))) >= 0;   // :170-177
+                const int64_t rawHash = probe[0].b->type == PG_TYPE_VARCHAR ? xxHash64(probe[0].slicePtr(position), (size_t) probe[0].sliceLength(position))
+                                                                            : hashLong(probe[0].getLong(position));
+                const bool contains = !setEmpty && set.getAddressIndex(position, probe, rawHash) >= 0;   // :170-177
                 if (!contains && setHasNull) flag.appendNull();               // :178-183
                 else flag.appendLong(contains ? 1 : 0);
             }

@@ -20,6 +20,7 @@
 #include "fp_interp.cuh"
 #include "group_table.cuh"
 #include "varchar_interner.h"
+#include "expr_literals.h"
 #include "key_layout.h"
 #include "dense_index.cuh"
 #include "operators_internal.h"
@@ -875,6 +876,7 @@ struct LookupSourceDevice {
     DeviceBuffer payloadRows;      // build OUTPUT columns, row-wise, in key order
     // JoinFilterFunction handed to the build side (HashBuilderOperator's filterFunctionFactory → JoinHash.filterFunction)
     std::vector<pg_expr_node> filterNodes; int filterNode = -1; std::vector<int> filterInputTypes; int filterBuildInputs = 0;
+    DeviceBuffer filterLiterals; std::vector<int64_t> filterLiteralOffset;     // bytes of the filter's VARCHAR constants, per node offset (-1: none)
     bool hasFilter() const { return filterNode >= 0; }
     // VARCHAR join keys (PagesHashStrategy compares the slices of the key channels; here they are interned to value ids when the build
     // finishes, the packed key carries the id, and every probe page looks its slices up — an absent value cannot match)
@@ -966,11 +968,30 @@ public:
             ls->filterInputTypes.assign(f.input_types, f.input_types + f.n_input_channels);
             ls->filterNode = f.filter_node; ls->filterBuildInputs = c->n_channels;
             PG_CHECK_ARG(ls->filterNodes[ls->filterNode].type == PG_TYPE_BOOLEAN, "filter must be BOOLEAN");
+            if (const char* problem = varcharUseProblem(ls->filterNodes.data(), f.n_nodes)) throw Error(PG_ERR_UNSUPPORTED, problem);
+            {   // VARCHAR constants of the filter function go to the device once; the caller's memory is not referenced after create
+                ls->filterLiteralOffset.assign(f.n_nodes, -1);
+                std::vector<uint8_t> bytes;
+                for (int i = 0; i < f.n_nodes; i++) {
+                    pg_expr_node& n = ls->filterNodes[i];
+                    if (n.op != PG_EX_CONST_VARCHAR) continue;
+                    ls->filterLiteralOffset[i] = (int64_t) bytes.size();
+                    const uint8_t* src = (const uint8_t*) (uintptr_t) n.imm_i;
+                    bytes.insert(bytes.end(), src, src + n.reserved);
+                    n.imm_i = 0; n.a = n.b = n.c = -1;
+                }
+                if (!bytes.empty()) {
+                    ls->filterLiterals.accounting = &ls->deviceBytes;
+                    ls->filterLiterals.reserve(bytes.size());
+                    PG_CUDA(cudaMemcpyAsync(ls->filterLiterals.ptr, bytes.data(), bytes.size(), cudaMemcpyHostToDevice, stream));
+                    PG_CUDA(cudaStreamSynchronize(stream));
+                }
+            }
             for (int i = 0; i < f.n_nodes; i++) {
                 const pg_expr_node& n = ls->filterNodes[i];
                 if (n.op == PG_EX_INPUT) {
                     PG_CHECK_ARG(n.a >= 0 && n.a < f.n_input_channels && ls->filterInputTypes[n.a] == n.type, "join filter: input node does not match its channel");
-                    if (n.type == PG_TYPE_VARCHAR || n.type == PG_TYPE_LONG_DECIMAL) throw Error(PG_ERR_UNSUPPORTED, "join filter inputs are fixed-width channels of at most 8 bytes on the GPU path");
+                    if (n.type == PG_TYPE_LONG_DECIMAL) throw Error(PG_ERR_UNSUPPORTED, "join filter inputs are channels of at most 8 bytes, or VARCHAR, on the GPU path");
                     if (n.a < c->n_channels) { PG_CHECK_ARG(ls->types[n.a] == n.type, "join filter: build input type differs from the build channel's"); keep(n.a); }
                 }
                 else for (int o : {n.a, n.b, n.c}) PG_CHECK_ARG(o < i, "expression nodes must be topologically ordered");
@@ -1399,11 +1420,15 @@ public:
                 FpNode& d = F.nodes[i]; const pg_expr_node& sn = ls->filterNodes[i];
                 d.op = sn.op; d.type = sn.type; d.a = sn.a; d.b = sn.b; d.c = sn.c; d.isDouble = sn.type == PG_TYPE_DOUBLE;
                 if (sn.op == PG_EX_CONST_DOUBLE) memcpy(&d.immI, &sn.imm_d, 8); else d.immI = sn.imm_i;
+                if (sn.op == PG_EX_CONST_VARCHAR) { d.immI = (int64_t) (uintptr_t) (ls->filterLiterals.as<uint8_t>() + ls->filterLiteralOffset[i]); d.len = sn.reserved; d.a = d.b = d.c = -1; }
                 if (sn.op != PG_EX_INPUT) continue;
                 FpInput& in = F.inputs[sn.a];
                 in.type = sn.type;
-                if (sn.a < F.nBuildInputs) { in.values = ls->values[sn.a].ptr; in.nulls = ls->hasNulls[sn.a] ? ls->nulls[sn.a].as<uint8_t>() : nullptr; }
-                else { const DeviceColumn& c = colOf(sn.a - F.nBuildInputs); in.values = c.values; in.nulls = c.nulls; }
+                if (sn.a < F.nBuildInputs) {
+                    in.values = ls->values[sn.a].ptr; in.nulls = ls->hasNulls[sn.a] ? ls->nulls[sn.a].as<uint8_t>() : nullptr;
+                    in.offsets = sn.type == PG_TYPE_VARCHAR ? ls->offsets[sn.a].as<int32_t>() : nullptr;
+                }
+                else { const DeviceColumn& c = colOf(sn.a - F.nBuildInputs); in.values = c.values; in.nulls = c.nulls; in.offsets = c.offsets; }
             }
             filterDev.accounting = &stats.device_bytes;
             filterDev.reserve(sizeof(JoinFilterProgram) + 16);
@@ -1906,6 +1931,9 @@ class SemiJoinOp : public Operator {
     std::vector<PinnedBuffer> hostValues, hostNulls;
     std::vector<pg_block> outBlocks;
     int64_t pendingRows = 0;
+    // VARCHAR channels: the probe key as value ids of the set's interner; pass-through slices copied by an identity gather
+    DeviceBuffer probeKeyIds, iota, varScan;
+    std::vector<DeviceBuffer> outOffsets; std::vector<PinnedBuffer> hostOffsets; std::vector<int64_t> varBytes;
 
 public:
     SemiJoinOp(const pg_semi_join_config* c, JoinBridge* b) : Operator(c->options), bridge(b), stager(this)
@@ -1915,15 +1943,17 @@ public:
         types.assign(c->types, c->types + c->n_channels);
         probeChannel = c->probe_join_channel;
         PG_CHECK_ARG(probeChannel >= 0 && probeChannel < c->n_channels, "probe join channel out of range");
-        for (int t : types) if (t == PG_TYPE_VARCHAR) throw Error(PG_ERR_UNSUPPORTED, "VARCHAR channels are not on the GPU semi-join path");
+        for (int t : types) if (t == PG_TYPE_LONG_DECIMAL) throw Error(PG_ERR_UNSUPPORTED, "Int128 channels are not on the GPU semi-join path");
         int32_t kt = types[probeChannel];
         layout.plan(1, &probeChannel, &kt, nullptr);
         checkJoinKeyTypes(layout);
         for (int i = 0; i < c->n_channels; i++) staged.push_back(i);
         const size_t nOut = types.size() + 1;
-        outValues.resize(nOut); outNulls.resize(nOut);
+        outValues.resize(nOut); outNulls.resize(nOut); outOffsets.resize(nOut); varBytes.assign(nOut, 0);
         for (auto& d : outValues) d.accounting = &stats.device_bytes;
         for (auto& d : outNulls) d.accounting = &stats.device_bytes;
+        for (auto& d : outOffsets) d.accounting = &stats.device_bytes;
+        for (DeviceBuffer* d : {&probeKeyIds, &iota, &varScan}) d->accounting = &stats.device_bytes;
     }
     bool needsInput() override { return !finishing && !hasPending && bridge->get() != nullptr; }   // "Set has not been built yet"
     bool isBlocked() override { return bridge->get() == nullptr; }
@@ -1952,6 +1982,12 @@ public:
             ProbeParams P{};
             P.J = ls->view();
             std::vector<DeviceColumn> keyCols{kc};
+            if (layout.interned[0]) {      // VARCHAR: the id the set gave this slice, -1 (no member) when the set never saw it
+                probeKeyIds.reserve((size_t) n * 4 + 16);
+                if (!ls->interners.empty() && ls->interners[0]) ls->interners[0]->intern(this, kc, n, probeKeyIds.as<int32_t>(), false);
+                else PG_CUDA(cudaMemsetAsync(probeKeyIds.ptr, 0xFF, (size_t) n * 4, stream));
+                keyCols[0].type = PG_TYPE_INTEGER; keyCols[0].values = probeKeyIds.ptr; keyCols[0].offsets = nullptr;
+            }
             layout.fill(P.kp, keyCols, ls->counters.as<unsigned int>() + CNT_ERROR);
             P.n = n;
             switch (layout.W) {
@@ -1963,23 +1999,40 @@ public:
         outBlocks.assign(flag + 1, pg_block{});
         std::vector<bool> hasNulls(flag + 1, false);
         for (size_t i = 0; i < flag; i++) {
+            outBlocks[i].type = types[i];
+            if (types[i] == PG_TYPE_VARCHAR) {      // the slices of every row, in order: an identity gather (rebased offsets, own bytes)
+                PG_CHECK_ARG(cols[i].offsets != nullptr, "VARCHAR block without offsets");
+                if (iota.capacity < (size_t) n * 4) { iota.reserve((size_t) n * 4); }
+                PG_LAUNCH(this, iotaU32Kernel, grid, 256, 0, iota.as<uint32_t>(), n);
+                outNulls[i].reserve((size_t) n);
+                hasNulls[i] = cols[i].nulls != nullptr;
+                varBytes[i] = gatherVarcharByIndex(this, (const uint8_t*) cols[i].values, cols[i].offsets, cols[i].nulls, iota.as<uint32_t>(), nullptr, n, outValues[i], outOffsets[i],
+                                                   hasNulls[i] ? outNulls[i].as<uint8_t>() : nullptr, varScan);
+                continue;
+            }
             const int w = typeWidth(types[i]);
             outValues[i].reserve((size_t) n * w);
             PG_CUDA(cudaMemcpyAsync(outValues[i].ptr, cols[i].values, (size_t) n * w, cudaMemcpyDeviceToDevice, stream));
             if (cols[i].nulls) { outNulls[i].reserve((size_t) n); PG_CUDA(cudaMemcpyAsync(outNulls[i].ptr, cols[i].nulls, (size_t) n, cudaMemcpyDeviceToDevice, stream)); hasNulls[i] = true; }
-            outBlocks[i].type = types[i];
         }
         outBlocks[flag].type = PG_TYPE_BOOLEAN; hasNulls[flag] = true;
         stager.markCompute(slot);
         const bool toHost = options.output_memory == PG_MEM_HOST;
-        if (toHost && hostValues.size() < flag + 1) { hostValues.resize(flag + 1); hostNulls.resize(flag + 1); }
+        if (toHost && hostValues.size() < flag + 1) { hostValues.resize(flag + 1); hostNulls.resize(flag + 1); hostOffsets.resize(flag + 1); }
         for (size_t i = 0; i <= flag; i++) {
             pg_block& b = outBlocks[i];
-            const size_t vbytes = (size_t) n * typeWidth(b.type);
-            b.encoding = PG_ENC_FLAT; b.position_count = n; b.offsets = nullptr; b.ids = nullptr; b.dictionary_size = 0;
+            const bool varchar = b.type == PG_TYPE_VARCHAR;
+            const size_t vbytes = varchar ? (size_t) varBytes[i] : (size_t) n * typeWidth(b.type);
+            b.encoding = PG_ENC_FLAT; b.position_count = n; b.offsets = varchar ? outOffsets[i].as<int32_t>() : nullptr; b.ids = nullptr; b.dictionary_size = 0;
             if (toHost) {
                 hostValues[i].reserve(std::max<size_t>(vbytes, 16));
-                PG_CUDA(cudaMemcpyAsync(hostValues[i].ptr, outValues[i].ptr, vbytes, cudaMemcpyDeviceToHost, stream));
+                if (vbytes) PG_CUDA(cudaMemcpyAsync(hostValues[i].ptr, outValues[i].ptr, vbytes, cudaMemcpyDeviceToHost, stream));
+                if (varchar) {
+                    hostOffsets[i].reserve((size_t) (n + 1) * 4);
+                    PG_CUDA(cudaMemcpyAsync(hostOffsets[i].ptr, outOffsets[i].ptr, (size_t) (n + 1) * 4, cudaMemcpyDeviceToHost, stream));
+                    b.offsets = hostOffsets[i].as<int32_t>();
+                    stats.d2h_bytes += (n + 1) * 4;
+                }
                 b.values = hostValues[i].ptr; b.is_null = nullptr;
                 stats.d2h_bytes += (int64_t) vbytes;
                 if (hasNulls[i]) { hostNulls[i].reserve((size_t) n); PG_CUDA(cudaMemcpyAsync(hostNulls[i].ptr, outNulls[i].ptr, (size_t) n, cudaMemcpyDeviceToHost, stream)); b.is_null = hostNulls[i].as<uint8_t>(); stats.d2h_bytes += n; }

@@ -127,7 +127,7 @@ void VarcharInterner::ensure(Operator* op, uint64_t extraEntries, uint64_t extra
 {
     cudaStream_t stream = op->stream;
     const uint64_t needEntries = nEntries + extraEntries, needBytes = poolUsed + extraBytes + 8 * extraEntries + 8;     // every value is padded to 8 bytes
-    if (needEntries + 2 >= (1ULL << 31)) throw Error(PG_ERR_INSUFFICIENT_RESOURCES, "more than 2^31 distinct VARCHAR key values");
+    if (needEntries > (1ULL << 30)) throw Error(PG_ERR_INSUFFICIENT_RESOURCES, "more than 2^30 distinct VARCHAR key values (the table's slots are indexed with 32 bits)");
     auto regrow = [&](DeviceBuffer& buf, size_t newBytes, size_t keepBytes) {
         DeviceBuffer bigger; bigger.accounting = buf.accounting;
         bigger.reserve(newBytes);

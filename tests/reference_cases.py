@@ -352,22 +352,23 @@ def case_probe_outer_join_with_filter_function(backend, probe_hash: bool, build_
     assert rows == [(25 + i, 1025 + i, 2025 + i, 25 + i, 35 + i, 45 + i) for i in range(5)]
 
 
-def case_outer_join_with_nulls_and_filter_function(backend, probe_hash: bool, build_hash: bool):
+def case_outer_join_with_nulls_and_filter_function(backend, probe_hash: bool, build_hash: bool, key_type: int = BIGINT):
     """testOuterJoinWithNullProbeAndFilterFunction :970-1011, ...NullBuild... :1056-1098, ...NullOnBothSides... :1143-1187: the filter
-    `probe.key = 'a'` (here: = 1) on top of the NULL-key rules; b -> 2, c -> 3."""
+    `probe.key = 'a'` on top of the NULL-key rules (key_type VARCHAR: the reference's own types — a VARCHAR input and a Slice constant inside
+    the JoinFilterFunction; BIGINT: a -> 1, b -> 2, c -> 3)."""
     def f(bt, pt):
-        return _join_filter(bt, pt, lambda build, probe: probe[0] == 1)
-    bp = RowPagesBuilder([BIGINT], build_hash, [0], backend).row(1).row(2).row(3)
-    pp = RowPagesBuilder([BIGINT], probe_hash, [0], backend).row(1).row(None).row(None).row(1).row(2)
+        return _join_filter(bt, pt, lambda build, probe: probe[0] == _key(key_type, 1))
+    bp = RowPagesBuilder([key_type], build_hash, [0], backend).row(_key(key_type, 1)).row(_key(key_type, 2)).row(_key(key_type, 3))
+    pp = RowPagesBuilder([key_type], probe_hash, [0], backend).row(_key(key_type, 1)).row(_key(key_type, None)).row(_key(key_type, None)).row(_key(key_type, 1)).row(_key(key_type, 2))
     rows = _join(backend, bp.build(), bp.get_types(), pp.build(), pp.get_types(), JOIN_PROBE_OUTER, build_hash, probe_hash, filter_program=f(bp.get_types(), pp.get_types()))
-    assert rows == [(1, 1), (None, None), (None, None), (1, 1), (2, None)]
-    bp = RowPagesBuilder([BIGINT], build_hash, [0], backend).row(1).row(None).row(None).row(1).row(2)
-    pp = RowPagesBuilder([BIGINT], probe_hash, [0], backend).row(1).row(2).row(3)
+    assert rows == [tuple(_key(key_type, v) for v in r) for r in [(1, 1), (None, None), (None, None), (1, 1), (2, None)]]
+    bp = RowPagesBuilder([key_type], build_hash, [0], backend).row(_key(key_type, 1)).row(_key(key_type, None)).row(_key(key_type, None)).row(_key(key_type, 1)).row(_key(key_type, 2))
+    pp = RowPagesBuilder([key_type], probe_hash, [0], backend).row(_key(key_type, 1)).row(_key(key_type, 2)).row(_key(key_type, 3))
     rows = _join(backend, bp.build(), bp.get_types(), pp.build(), pp.get_types(), JOIN_PROBE_OUTER, build_hash, probe_hash, filter_program=f(bp.get_types(), pp.get_types()))
-    assert rows == [(1, 1), (1, 1), (2, None), (3, None)]
-    pp = RowPagesBuilder([BIGINT], probe_hash, [0], backend).row(1).row(2).row(None).row(3)
+    assert rows == [tuple(_key(key_type, v) for v in r) for r in [(1, 1), (1, 1), (2, None), (3, None)]]
+    pp = RowPagesBuilder([key_type], probe_hash, [0], backend).row(_key(key_type, 1)).row(_key(key_type, 2)).row(_key(key_type, None)).row(_key(key_type, 3))
     rows = _join(backend, bp.build(), bp.get_types(), pp.build(), pp.get_types(), JOIN_PROBE_OUTER, build_hash, probe_hash, filter_program=f(bp.get_types(), pp.get_types()))
-    assert rows == [(1, 1), (1, 1), (2, None), (None, None), (3, None)]
+    assert rows == [tuple(_key(key_type, v) for v in r) for r in [(1, 1), (1, 1), (2, None), (None, None), (3, None)]]
 
 
 def case_join_filter_over_both_sides(backend):

@@ -14,18 +14,26 @@ REFERENCE_CASES = {
 }
 
 
-def run_semi_join(backend, set_values, probe_rows, set_pages=1):
+def varchar_key(v):
+    """The same cases over a VARCHAR join channel: key k becomes the slice b"key-<k>" (NULL stays NULL)."""
+    return None if v is None else b"key-%d" % v
+
+
+def run_semi_join(backend, set_values, probe_rows, set_pages=1, varchar=False):
     import numpy as np
-    from presto_b200 import BIGINT, Block, HashBuilderOperator, HashSemiJoinOperator, JoinBridge, Page, to_pages
+    from presto_b200 import BIGINT, VARCHAR, Block, HashBuilderOperator, HashSemiJoinOperator, JoinBridge, Page, to_pages
+    key_type = VARCHAR if varchar else BIGINT
+    def key_block(values):
+        return Block.from_strings([varchar_key(v) for v in values]) if varchar else Block.from_values(BIGINT, values, [v is None for v in values])
     bridge = JoinBridge(backend=backend)
-    builder = HashBuilderOperator(bridge, [BIGINT], [0], [], backend=backend)
+    builder = HashBuilderOperator(bridge, [key_type], [0], [], backend=backend)
     cuts = np.linspace(0, len(set_values), set_pages + 1).astype(int)
-    pages = [Page([Block.from_values(BIGINT, set_values[a:b], [v is None for v in set_values[a:b]])], b - a) for a, b in zip(cuts[:-1], cuts[1:])]
+    pages = [Page([key_block(set_values[a:b])], b - a) for a, b in zip(cuts[:-1], cuts[1:])]
     assert to_pages(builder, pages) == []
     width = len(probe_rows[0]) if probe_rows else 1
-    op = HashSemiJoinOperator(bridge, [BIGINT] * width, 0, backend=backend)
+    op = HashSemiJoinOperator(bridge, [key_type] + [BIGINT] * (width - 1), 0, backend=backend)
     cols = [[r[c] for r in probe_rows] for c in range(width)]
-    probe = Page([Block.from_values(BIGINT, col, [v is None for v in col]) for col in cols], len(probe_rows))
+    probe = Page([key_block(cols[0])] + [Block.from_values(BIGINT, col, [v is None for v in col]) for col in cols[1:]], len(probe_rows))
     out = [r for p in to_pages(op, [probe]) for r in p.rows()]
     op.close(); builder.close(); bridge.close()
     return out

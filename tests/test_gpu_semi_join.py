@@ -42,3 +42,26 @@ def test_random(gpu_backend, oracle_backend, kind, set_nulls):
     got = run_semi_join(gpu_backend, values, probe, set_pages=3)
     want = run_semi_join(oracle_backend, values, probe, set_pages=3)
     assert got == want and any(r[-1] is True for r in got) and any(r[-1] is False or r[-1] is None for r in got)
+
+
+# ---- VARCHAR join channel (the set's slices are interned when the SetBuilder finishes; the probe looks its slices up) -----------------
+@pytest.mark.parametrize("name", sorted(REFERENCE_CASES))
+def test_reference_case_varchar_channel(gpu_backend, name):
+    from semi_join_cases import varchar_key
+    set_values, probe, expected = REFERENCE_CASES[name]
+    assert run_semi_join(gpu_backend, set_values, probe, varchar=True) == [(varchar_key(r[0]),) + tuple(r[1:]) for r in expected]
+
+
+@pytest.mark.parametrize("set_nulls", [False, True])
+def test_random_varchar_channel(gpu_backend, oracle_backend, set_nulls):
+    rng = np.random.default_rng(40 + int(set_nulls))
+    n = 10_000
+    values = [int(v) for v in rng.integers(0, n // 3, n)]
+    if set_nulls:
+        for i in rng.integers(0, n, 30):
+            values[i] = None
+    probe = [(None if rng.random() < 0.05 else int(rng.integers(0, n // 2)), i, None if i % 5 == 0 else -i) for i in range(15_000)]
+    got = run_semi_join(gpu_backend, values, probe, set_pages=2, varchar=True)
+    want = run_semi_join(oracle_backend, values, probe, set_pages=2, varchar=True)
+    assert got == want and any(r[-1] is True for r in got) and any(r[-1] is not True for r in got)
+    assert run_semi_join(gpu_backend, [], [(1,), (None,)], varchar=True) == [(b"key-1", False), (None, False)]

@@ -109,7 +109,7 @@ def test_join_varchar_outputs(oracle_backend): rc.case_join_varchar_outputs(orac
 # TestHashJoinOperator with the reference's own key type: VARCHAR join channels (GPU: interned to value ids when the build finishes)
 @pytest.mark.parametrize("probe_hash,build_hash", [(False, False), (True, True)])
 @pytest.mark.parametrize("case", ["inner_join", "inner_join_with_null_probe", "inner_join_with_null_build", "inner_join_with_null_on_both_sides",
-                                  "probe_outer_join", "outer_join_with_null_on_both_sides"])
+                                  "probe_outer_join", "outer_join_with_null_on_both_sides", "outer_join_with_nulls_and_filter_function"])
 def test_join_varchar_keys(oracle_backend, case, probe_hash, build_hash): getattr(rc, "case_" + case)(oracle_backend, probe_hash, build_hash, key_type=rc.VARCHAR)
 def test_probe_outer_join_empty_lookup_source(oracle_backend): rc.case_probe_outer_join_empty_lookup_source(oracle_backend)
 def test_join_duplicate_chain_order(oracle_backend): rc.case_join_duplicate_chain_order(oracle_backend)
