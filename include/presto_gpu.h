@@ -181,7 +181,9 @@ typedef enum {                       /* pg_operator_stats.kernel_paths */
     PG_PATH_UNFUSED_CHAIN = 128,     /* fused operator that ran its fragment operator by operator (fragment not fusable for that page) */
     PG_PATH_FUSED_TMA = 256,         /* (with FUSED_TIERS / FUSED_DIRECT) eager columns staged by a cp.async.bulk (TMA) ring */
     PG_PATH_INTERNED_KEYS = 512,     /* VARCHAR group keys without a declared length of <= 7 bytes: replaced by value ids (VarcharInterner) first */
-    PG_PATH_DICTIONARY_KEYS = 1024   /* (with INTERNED_KEYS) a DictionaryBlock / RLE key channel: its dictionary was interned, rows only mapped */
+    PG_PATH_DICTIONARY_KEYS = 1024,  /* (with INTERNED_KEYS) a DictionaryBlock / RLE key channel: its dictionary was interned, rows only mapped */
+    PG_PATH_FP_JIT = 2048,           /* FilterAndProject: generated PTX (driver JIT) evaluated a page */
+    PG_PATH_FP_INTERPRETER = 4096    /* FilterAndProject: the interpreter kernels evaluated a page (program outside the PTX generator's set) */
 } pg_kernel_path;
 
 /* Options common to all operators. */

@@ -84,6 +84,7 @@ PATH_AGG_FAST, PATH_AGG_WARP, PATH_AGG_MID, PATH_AGG_DIRECT, PATH_AGG_GENERIC, P
 PATH_FUSED_TMA = 256
 PATH_INTERNED_KEYS = 512
 PATH_DICTIONARY_KEYS = 1024
+PATH_FP_JIT, PATH_FP_INTERPRETER = 2048, 4096
 
 
 class pg_operator_options(C.Structure):

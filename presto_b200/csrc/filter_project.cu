@@ -228,6 +228,7 @@ class FilterProjectOp : public Operator {
     std::map<uint64_t, JitProgram> jitCache;   // keyed by which inputs carry a null map on this page
     int64_t jitLaunches = 0, interpreterLaunches = 0;
     DeviceBuffer literalPool;                  // bytes of the CONST_VARCHAR nodes
+    std::vector<std::string> literalHost;      // the same per node, for the PTX generator (slice = literal compares against immediates)
     std::vector<int64_t> literalOffset;        // per node: offset of its literal in the pool (-1: not a literal)
     bool varcharExpressions = false;           // a comparison / hash reads slices: interpreter kernels only
 
@@ -289,6 +290,8 @@ public:
                 literalOffset[i] = (int64_t) bytes.size();
                 const uint8_t* src = (const uint8_t*) (uintptr_t) nodes[i].imm_i;
                 bytes.insert(bytes.end(), src, src + nodes[i].reserved);
+                if (literalHost.empty()) literalHost.resize((size_t) c->n_nodes);
+                literalHost[(size_t) i].assign((const char*) src, (size_t) nodes[i].reserved);
                 nodes[i].imm_i = 0; nodes[i].a = nodes[i].b = nodes[i].c = -1;        // the caller's memory is not referenced after create
             }
             if (!bytes.empty()) {
@@ -329,9 +332,11 @@ public:
         const char* off = getenv("PG_FP_INTERPRETER");
         DriverApi& api = DriverApi::get();
         if ((off && off[0] == '1') || !api.ok) { jp.log = "JIT disabled or libcuda not loadable"; return jp; }
-        if (varcharExpressions) { jp.log = "VARCHAR comparison / hash: interpreter kernels"; return jp; }
+        const char* vj = getenv("PG_FP_VARCHAR_JIT");
+        if (varcharExpressions && vj && vj[0] == '0') { jp.log = "VARCHAR comparison / hash: interpreter kernels (PG_FP_VARCHAR_JIT=0)"; return jp; }
         FpProgramDesc d;
         d.nodes = nodes; d.inputTypes = inputTypes; d.filterNode = filterNode; d.projections = projections;
+        d.literals = literalHost;      // slice = / <> literal is lowered to PTX; any other VARCHAR use makes the generator decline → interpreter kernels
         d.inputHasNulls.assign(inputTypes.size(), false);
         for (size_t i = 0; i < staged.size(); i++) d.inputHasNulls[staged[i]] = cols[i].nulls != nullptr;
         const std::string ptx = generateFilterProjectPtx(d, jp.sig);
@@ -352,6 +357,7 @@ public:
         CUresult r = DriverApi::get().launchKernel(f, (unsigned) grid, 1, 1, 256, 1, 1, 0, (CUstream) stream, args.data(), nullptr);
         if (r != CUDA_SUCCESS) throw Error(PG_ERR_CUDA, "cuLaunchKernel of a generated filter/project kernel failed (" + std::to_string((int) r) + ")");
         stats.kernel_launches++;
+        stats.kernel_paths |= PG_PATH_FP_JIT;
         jitLaunches++;
     }
     void inputArgs(const JitProgram& jp, const FpParams& P, std::vector<uint64_t>& v) const
@@ -359,6 +365,7 @@ public:
         v.push_back((uint64_t) P.n); v.push_back((uint64_t) P.units);
         for (int ch : jp.sig.usedInputs) {
             v.push_back((uint64_t) (uintptr_t) P.inputs[ch].values);
+            if (P.inputs[ch].type == PG_TYPE_VARCHAR) v.push_back((uint64_t) (uintptr_t) P.inputs[ch].offsets);
             if (P.inputs[ch].nulls) v.push_back((uint64_t) (uintptr_t) P.inputs[ch].nulls);
         }
     }
@@ -411,7 +418,7 @@ public:
                 v.push_back((uint64_t) (uintptr_t) P.selection); v.push_back((uint64_t) (uintptr_t) P.counts); v.push_back((uint64_t) (uintptr_t) P.error);
                 launchJit(jit.filter, grid, v);
             }
-            else { PG_LAUNCH(this, fpFilterKernel, grid, 256, 0, P); interpreterLaunches++; }
+            else { PG_LAUNCH(this, fpFilterKernel, grid, 256, 0, P); interpreterLaunches++; stats.kernel_paths |= PG_PATH_FP_INTERPRETER; }
             size_t tb = 0;
             cub::DeviceScan::ExclusiveSum(nullptr, tb, counts.as<uint32_t>(), offsets.as<uint32_t>(), (int) (P.units + 1), stream);
             scanTemp.reserve(tb);
@@ -446,7 +453,7 @@ public:
             v.push_back((uint64_t) (uintptr_t) P.selection); v.push_back((uint64_t) (uintptr_t) P.offsets); v.push_back((uint64_t) (uintptr_t) P.error);
             launchJit(jit.project, grid, v);
         }
-        else if (nOut) { PG_LAUNCH(this, fpProjectKernel, grid, 256, 0, P); interpreterLaunches++; }
+        else if (nOut) { PG_LAUNCH(this, fpProjectKernel, grid, 256, 0, P); interpreterLaunches++; stats.kernel_paths |= PG_PATH_FP_INTERPRETER; }
         // VARCHAR pass-through channels: lengths of the selected rows → output offsets (scan) → bytes
         const size_t nVc = varcharChannels.size();
         std::vector<int32_t> vcTotalBytes(nVc, 0);
@@ -574,6 +581,11 @@ int32_t pg_filter_project_explain(const pg_filter_project_config* c, uint64_t nu
         d.filterNode = c->filter_node;
         for (int j = 0; j < c->n_projections; j++)      // VARCHAR input references pass through outside the generated kernels
             if (c->nodes[c->projection_nodes[j]].type != PG_TYPE_VARCHAR) d.projections.push_back(c->projection_nodes[j]);
+        for (int i = 0; i < c->n_nodes; i++)
+            if (c->nodes[i].op == PG_EX_CONST_VARCHAR) {
+                if (d.literals.empty()) d.literals.resize((size_t) c->n_nodes);
+                d.literals[(size_t) i].assign((const char*) (uintptr_t) c->nodes[i].imm_i, (size_t) std::max(c->nodes[i].reserved, 0));
+            }
         d.inputHasNulls.assign(d.inputTypes.size(), false);
         for (size_t i = 0; i < d.inputTypes.size(); i++) d.inputHasNulls[i] = (nullableInputs >> i) & 1ULL;
         pg::FpKernelSignature sig;

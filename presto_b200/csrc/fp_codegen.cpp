@@ -11,6 +11,10 @@ struct NodeVal {
     char kind = 'i';        // 'i' int64 in a .b64 register, 'd' double bits in a .b64 register, 'b' boolean in a predicate
     std::string val;        // register holding the value
     std::string nul;        // predicate "is NULL", empty = never NULL
+    // VARCHAR: kind 's' = a slice of an input channel (val: .b64 address of its first byte, aux: .b32 length); kind 'c' = the literal of
+    // node `lit` (bytes known to the generator).  Only `slice = / <> literal` is lowered (VarcharOperators.equal / notEqual :54-65).
+    std::string aux;
+    int lit = -1;
 };
 
 struct Gen {
@@ -24,7 +28,7 @@ struct Gen {
     std::string row;        // .b64 register: row index
     std::string guard;      // predicate: this lane's row is to be evaluated (loads are predicated on it)
     std::string errOverflow, errDivZero;   // accumulated error predicates
-    std::vector<std::string> inValues, inNulls;   // per input channel: registers holding the global pointers ("" = not a parameter)
+    std::vector<std::string> inValues, inNulls, inOffsets;   // per input channel: registers holding the global pointers ("" = not a parameter)
 
     explicit Gen(const FpProgramDesc& p) : P(p) {}
     std::string r64() { return "%rd" + std::to_string(n64++); }
@@ -57,8 +61,32 @@ struct Gen {
         emit("or.pred " + acc + ", " + acc + ", " + p + ";");
     }
 
+    // slice = literal: equal lengths, then byte by byte (loads only where the lengths agree: nothing is read past the slice)
+    NodeVal compareSliceLiteral(int op, const NodeVal& s, const NodeVal& c)
+    {
+        NodeVal r; r.kind = 'b'; r.val = pr(); r.nul = s.nul;
+        if (op != PG_EX_EQ && op != PG_EX_NE) { fail = "VARCHAR ordering comparison"; return r; }
+        const std::string& bytes = P.literals[(size_t) c.lit];
+        std::string pl = pr(), pld = pr();
+        emit("setp.eq.s32 " + pl + ", " + s.aux + ", " + std::to_string(bytes.size()) + ";");
+        emit("and.pred " + pld + ", " + pl + ", " + guard + ";");
+        emit("mov.pred " + r.val + ", " + pl + ";");
+        for (size_t i = 0; i < bytes.size(); i++) {
+            std::string x = r32(), pb = pr();
+            emit("mov.b32 " + x + ", 0;");
+            emit("@" + pld + " ld.global.nc.u8 " + x + ", [" + s.val + "+" + std::to_string(i) + "];");
+            emit("setp.eq.u32 " + pb + ", " + x + ", " + std::to_string((unsigned) (unsigned char) bytes[i]) + ";");
+            emit("and.pred " + r.val + ", " + r.val + ", " + pb + ";");
+        }
+        if (op == PG_EX_NE) emit("not.pred " + r.val + ", " + r.val + ";");
+        return r;
+    }
+
     NodeVal compare(int op, const NodeVal& a, const NodeVal& b)
     {
+        if (a.kind == 's' && b.kind == 'c') return compareSliceLiteral(op, a, b);
+        if (a.kind == 'c' && b.kind == 's') return compareSliceLiteral(op, b, a);      // = and <> are symmetric
+        if (a.kind == 's' || a.kind == 'c' || b.kind == 's' || b.kind == 'c') { NodeVal r; r.kind = 'b'; r.val = pr(); fail = "VARCHAR comparison other than slice = literal"; return r; }
         NodeVal r; r.kind = 'b'; r.val = pr(); r.nul = orNull(a.nul, b.nul);
         if (a.kind == 'b' || b.kind == 'b') {
             if (a.kind != 'b' || b.kind != 'b' || (op != PG_EX_EQ && op != PG_EX_NE)) { fail = "boolean comparison"; return r; }
@@ -133,6 +161,26 @@ struct Gen {
         switch (nd.op) {
             case PG_EX_INPUT: {
                 const int ch = nd.a, t = P.inputTypes[ch];
+                if (t == PG_TYPE_VARCHAR) {       // offsets[row], offsets[row + 1] → address of the slice, its length
+                    std::string ao = r64(), o0 = r32(), o1 = r32(), o64 = r64();
+                    emit("mad.lo.u64 " + ao + ", " + row + ", 4, " + inOffsets[ch] + ";");
+                    emit("mov.b32 " + o0 + ", 0;");
+                    emit("mov.b32 " + o1 + ", 0;");
+                    emit("@" + guard + " ld.global.nc.b32 " + o0 + ", [" + ao + "];");
+                    emit("@" + guard + " ld.global.nc.b32 " + o1 + ", [" + ao + "+4];");
+                    r.kind = 's'; r.aux = r32(); r.val = r64();
+                    emit("sub.s32 " + r.aux + ", " + o1 + ", " + o0 + ";");
+                    emit("cvt.u64.u32 " + o64 + ", " + o0 + ";");
+                    emit("add.u64 " + r.val + ", " + inValues[ch] + ", " + o64 + ";");
+                    if (P.inputHasNulls[ch]) {
+                        std::string an = r64(), x = r32(); r.nul = pr();
+                        emit("add.u64 " + an + ", " + inNulls[ch] + ", " + row + ";");
+                        emit("mov.b32 " + x + ", 0;");
+                        emit("@" + guard + " ld.global.nc.u8 " + x + ", [" + an + "];");
+                        emit("setp.ne.u32 " + r.nul + ", " + x + ", 0;");
+                    }
+                    break;
+                }
                 const int w = (t == PG_TYPE_BIGINT || t == PG_TYPE_DOUBLE) ? 8 : (t == PG_TYPE_BOOLEAN ? 1 : 4);
                 std::string addr = r64();
                 emit("mad.lo.u64 " + addr + ", " + row + ", " + std::to_string(w) + ", " + inValues[ch] + ";");
@@ -165,6 +213,10 @@ struct Gen {
             case PG_EX_CONST_BIGINT: r.kind = 'i'; r.val = r64(); emit("mov.b64 " + r.val + ", " + hex64((uint64_t) nd.imm_i) + ";"); break;
             case PG_EX_CONST_DOUBLE: { uint64_t b; memcpy(&b, &nd.imm_d, 8); r.kind = 'd'; r.val = r64(); emit("mov.b64 " + r.val + ", " + hex64(b) + ";"); break; }
             case PG_EX_CONST_BOOLEAN: r.kind = 'b'; r.val = nd.imm_i ? predTrue() : predFalse(); break;
+            case PG_EX_CONST_VARCHAR:
+                if ((size_t) k >= P.literals.size() || P.literals[(size_t) k].size() > 32) { fail = "VARCHAR literal longer than 32 bytes"; break; }
+                r.kind = 'c'; r.lit = k;
+                break;
             case PG_EX_CONST_NULL:
                 r.nul = predTrue();
                 if (nd.type == PG_TYPE_BOOLEAN) { r.kind = 'b'; r.val = predFalse(); }
@@ -243,9 +295,9 @@ struct Gen {
                 emit("not.pred " + r.val + ", " + a.val + ";");
                 break;
             }
-            case PG_EX_IS_NULL: { const NodeVal a = A(); r.kind = 'b'; r.val = a.nul.empty() ? predFalse() : a.nul; break; }
+            case PG_EX_IS_NULL: { const NodeVal a = A(); if (a.kind == 'c') { fail = "IS NULL of a literal"; break; } r.kind = 'b'; r.val = a.nul.empty() ? predFalse() : a.nul; break; }
             case PG_EX_CAST_DOUBLE: { const NodeVal a = A(); r.kind = 'd'; r.nul = a.nul; r.val = asDouble(a); break; }
-            case PG_EX_HASH: r = hashOf(A(), P.nodes[nd.a].type); break;
+            case PG_EX_HASH: if (P.nodes[nd.a].type == PG_TYPE_VARCHAR) { fail = "hash of a VARCHAR value"; break; } r = hashOf(A(), P.nodes[nd.a].type); break;
             case PG_EX_COMBINE_HASH: {
                 const NodeVal a = A(), b = B();
                 if (a.kind != 'i' || b.kind != 'i') { fail = "combine_hash over non-integers"; break; }
@@ -271,6 +323,7 @@ std::string prologue(Gen& g, const std::vector<int>& usedInputs, bool filterKern
     ldp("%n", "p_n", false); ldp("%units", "p_units", false);
     for (int ch : usedInputs) {
         ldp(g.inValues[ch], "p_in" + std::to_string(ch) + "_v", true);
+        if (!g.inOffsets[ch].empty()) ldp(g.inOffsets[ch], "p_in" + std::to_string(ch) + "_o", true);
         if (!g.inNulls[ch].empty()) ldp(g.inNulls[ch], "p_in" + std::to_string(ch) + "_n", true);
     }
     (void) filterKernel;
@@ -321,7 +374,15 @@ std::string generateFilterProjectPtx(const FpProgramDesc& P, FpKernelSignature& 
     }
     sig.usedInputs.clear();
     for (size_t c = 0; c < used.size(); c++) if (used[c]) sig.usedInputs.push_back((int) c);
-    for (int ch : sig.usedInputs) if (P.inputTypes[ch] == PG_TYPE_VARCHAR) { sig.reason = "VARCHAR input"; return ""; }
+    // VARCHAR inputs: lowered only when every use is `slice = literal` / `slice <> literal` (the generator fails on anything else below);
+    // programs that merely pass VARCHAR channels through never list them here
+    for (int ch : sig.usedInputs) if (P.inputTypes[ch] == PG_TYPE_VARCHAR && P.literals.empty()) { sig.reason = "VARCHAR input"; return ""; }
+    for (int k = 0; k < nNodes; k++) {
+        const pg_expr_node& nd = P.nodes[k];
+        const bool leaf = nd.op == PG_EX_INPUT || (nd.op >= PG_EX_CONST_BIGINT && nd.op <= PG_EX_CONST_VARCHAR);
+        if (leaf || nd.op == PG_EX_EQ || nd.op == PG_EX_NE) continue;
+        for (int o : {nd.a, nd.b, nd.c}) if (o >= 0 && o < nNodes && P.nodes[o].type == PG_TYPE_VARCHAR) { sig.reason = "VARCHAR operand outside = / <>"; return ""; }
+    }
 
     std::ostringstream ptx;
     ptx << "//\n// generated by presto_b200 fp_codegen: RowExpression to PTX\n//\n.version 8.7\n.target sm_100a\n.address_size 64\n\n";
@@ -330,6 +391,7 @@ std::string generateFilterProjectPtx(const FpProgramDesc& P, FpKernelSignature& 
         s << "    .param .u64 p_n,\n    .param .u64 p_units";
         for (int ch : sig.usedInputs) {
             s << ",\n    .param .u64 p_in" << ch << "_v";
+            if (P.inputTypes[ch] == PG_TYPE_VARCHAR) s << ",\n    .param .u64 p_in" << ch << "_o";
             if (P.inputHasNulls[ch]) s << ",\n    .param .u64 p_in" << ch << "_n";
         }
         if (filterKernel) s << ",\n    .param .u64 p_sel,\n    .param .u64 p_cnt,\n    .param .u64 p_err";
@@ -344,13 +406,21 @@ std::string generateFilterProjectPtx(const FpProgramDesc& P, FpKernelSignature& 
     };
     auto newGen = [&](Gen& g) {
         g.vals.assign(nNodes, NodeVal()); g.done.assign(nNodes, false);
-        g.inValues.assign(P.inputTypes.size(), ""); g.inNulls.assign(P.inputTypes.size(), "");
-        for (int ch : sig.usedInputs) { g.inValues[ch] = "%in" + std::to_string(ch) + "v"; if (P.inputHasNulls[ch]) g.inNulls[ch] = "%in" + std::to_string(ch) + "n"; }
+        g.inValues.assign(P.inputTypes.size(), ""); g.inNulls.assign(P.inputTypes.size(), ""); g.inOffsets.assign(P.inputTypes.size(), "");
+        for (int ch : sig.usedInputs) {
+            g.inValues[ch] = "%in" + std::to_string(ch) + "v";
+            if (P.inputTypes[ch] == PG_TYPE_VARCHAR) g.inOffsets[ch] = "%in" + std::to_string(ch) + "o";
+            if (P.inputHasNulls[ch]) g.inNulls[ch] = "%in" + std::to_string(ch) + "n";
+        }
         g.row = "%row0"; g.errOverflow = "%perr_ov"; g.errDivZero = "%perr_dz";
     };
     auto inputRegDecl = [&]() {
         std::ostringstream s;
-        for (int ch : sig.usedInputs) { s << "    .reg .b64 %in" << ch << "v;\n"; if (P.inputHasNulls[ch]) s << "    .reg .b64 %in" << ch << "n;\n"; }
+        for (int ch : sig.usedInputs) {
+            s << "    .reg .b64 %in" << ch << "v;\n";
+            if (P.inputTypes[ch] == PG_TYPE_VARCHAR) s << "    .reg .b64 %in" << ch << "o;\n";
+            if (P.inputHasNulls[ch]) s << "    .reg .b64 %in" << ch << "n;\n";
+        }
         return s.str();
     };
     auto regDecl = [&](const Gen& g) {

@@ -22,11 +22,12 @@ struct FpProgramDesc {
     std::vector<bool> inputHasNulls;      // per input channel, for THIS page
     int filterNode = -1;
     std::vector<int> projections;
+    std::vector<std::string> literals;    // per node: the bytes of a PG_EX_CONST_VARCHAR (empty vector: the program has none)
 };
 
 struct FpKernelSignature {
-    // Parameter order of both kernels: n (u64), units (u64), then for every used input channel (ascending): values ptr [, nulls ptr if
-    // it has nulls]; fp_filter adds: selection, counts.  fp_project adds: for every projection: values ptr [, nulls ptr if nullable];
+    // Parameter order of both kernels: n (u64), units (u64), then for every used input channel (ascending): values ptr [, offsets ptr if
+    // the channel is VARCHAR] [, nulls ptr if it has nulls]; fp_filter adds: selection, counts.  fp_project adds: for every projection: values ptr [, nulls ptr if nullable];
     // then selection, offsets, error.
     std::vector<int> usedInputs;
     std::vector<bool> projectionNullable;

@@ -47,7 +47,18 @@ def projection_only_program():
     return types, p
 
 
-CASES = [(q1_program, ()), (q1_program, (2, 6)), (q3_lineitem_program, ()), (q3_lineitem_program, (0, 1, 2, 3)),
+def q3_customer_program():
+    """c_mktsegment = 'BUILDING' (VARCHAR slice = literal, lowered to byte compares against immediates) AND a numeric predicate; the key passes."""
+    from presto_b200 import VARCHAR
+    types = [BIGINT, VARCHAR, DOUBLE]
+    p = Program(types)
+    k, seg, bal = p.input(0), p.input(1), p.input(2)
+    p.set_filter((seg == b"BUILDING") & (bal > 0.0) & (seg != b""))
+    p.project(k, bal * 2.0)
+    return types, p
+
+
+CASES = [(q3_customer_program, ()), (q3_customer_program, (1,)), (q1_program, ()), (q1_program, (2, 6)), (q3_lineitem_program, ()), (q3_lineitem_program, (0, 1, 2, 3)),
          (integer_logic_program, ()), (integer_logic_program, (0, 1, 2, 3)), (projection_only_program, (1,))]
 
 

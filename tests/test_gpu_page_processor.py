@@ -30,6 +30,34 @@ def test_reference_cases_both_modes(gpu_backend, mode):
     rc.case_page_processor_three_valued_logic(gpu_backend)
     rc.case_page_processor_hash_projection(gpu_backend)
     rc.case_page_processor_varchar_pass_through(gpu_backend)
+    rc.case_page_processor_varchar_comparisons(gpu_backend, n=3000)
+
+
+@pytest.mark.parametrize("literal", [b"", b"A", b"BUILDING", b"a-literal-of-thirty-one-bytes..", b"thirty-three bytes: beyond the PTX lowering's limit"[:33]])
+def test_varchar_equals_literal_both_modes(gpu_backend, mode, literal):
+    """`slice = literal` / `slice <> literal` (VarcharOperators.equal / notEqual): lowered to PTX byte compares against immediates for literals
+    of up to 32 bytes (longer ones and every other VARCHAR operator run in the interpreter kernels); both lowerings, NULL slices, slices that
+    share a prefix with the literal or extend it, against python's own comparison."""
+    from presto_b200 import VARCHAR
+    from presto_b200 import _abi as abi
+    rng = np.random.default_rng(len(literal))
+    variants = [literal, literal + b"x", literal[:-1], literal[:-1] + b"~" if literal else b"~", b"", literal.lower() if literal else b"q", None]
+    n = 9000
+    col = [variants[i] for i in rng.integers(0, len(variants), n)]
+    page = Page([Block.from_strings(col), Block.from_numpy(BIGINT, np.arange(n))])
+    for negate in (False, True):
+        prog = Program([VARCHAR, BIGINT])
+        s = prog.input(0)
+        prog.set_filter((s != literal) if negate else (s == literal))
+        prog.project(prog.input(1), s.is_null())
+        op = FilterAndProjectOperator([VARCHAR, BIGINT], prog, backend=gpu_backend)
+        rows = rows_of(to_pages(op, [page]))
+        paths = op.get_stats()["kernel_paths"]
+        op.close()
+        want = [(i, False) for i in range(n) if col[i] is not None and ((col[i] != literal) if negate else (col[i] == literal))]
+        assert rows == want and len(rows) > 500
+        expect_jit = mode == "ptx" and len(literal) <= 32
+        assert bool(paths & abi.PATH_FP_JIT) == expect_jit and bool(paths & abi.PATH_FP_INTERPRETER) == (not expect_jit), (paths, mode, literal)
 
 
 def random_program(rng, types):
