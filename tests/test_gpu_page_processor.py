@@ -35,9 +35,9 @@ def test_reference_cases_both_modes(gpu_backend, mode):
 
 @pytest.mark.parametrize("literal", [b"", b"A", b"BUILDING", b"a-literal-of-thirty-one-bytes..", b"thirty-three bytes: beyond the PTX lowering's limit"[:33]])
 def test_varchar_equals_literal_both_modes(gpu_backend, mode, literal):
-    """`slice = literal` / `slice <> literal` (VarcharOperators.equal / notEqual): lowered to PTX byte compares against immediates for literals
-    of up to 32 bytes (longer ones and every other VARCHAR operator run in the interpreter kernels); both lowerings, NULL slices, slices that
-    share a prefix with the literal or extend it, against python's own comparison."""
+    """`slice = literal` / `slice <> literal` (VarcharOperators.equal / notEqual) with NULL slices, slices that share a prefix with the literal
+    or extend it, against python's own comparison.  With PG_FP_VARCHAR_JIT=1 the "ptx" mode lowers literals of up to 32 bytes to PTX byte
+    compares against immediates (opt-in: not yet run on a GPU); otherwise both modes use the interpreter kernels."""
     from presto_b200 import VARCHAR
     from presto_b200 import _abi as abi
     rng = np.random.default_rng(len(literal))
@@ -56,8 +56,11 @@ def test_varchar_equals_literal_both_modes(gpu_backend, mode, literal):
         op.close()
         want = [(i, False) for i in range(n) if col[i] is not None and ((col[i] != literal) if negate else (col[i] == literal))]
         assert rows == want and len(rows) > 500
-        expect_jit = mode == "ptx" and len(literal) <= 32
-        assert bool(paths & abi.PATH_FP_JIT) == expect_jit and bool(paths & abi.PATH_FP_INTERPRETER) == (not expect_jit), (paths, mode, literal)
+        # the PTX lowering of slice = literal is opt-in (PG_FP_VARCHAR_JIT=1: written after the round's last GPU run); by default both modes
+        # evaluate VARCHAR predicates in the interpreter kernels
+        if os.environ.get("PG_FP_VARCHAR_JIT") == "1":
+            expect_jit = mode == "ptx" and len(literal) <= 32
+            assert bool(paths & abi.PATH_FP_JIT) == expect_jit and bool(paths & abi.PATH_FP_INTERPRETER) == (not expect_jit), (paths, mode, literal)
 
 
 def random_program(rng, types):
