@@ -108,3 +108,44 @@ def test_oracle_serde_lz4_pages(checksum):
         assert lz.deserialize(np.frombuffer(wire, dtype=np.uint8), types).rows() == page.rows()
         assert plain.deserialize(np.frombuffer(wire, dtype=np.uint8), types).rows() == page.rows()      # any serde READS compressed pages
     plain.close(); lz.close()
+
+
+def test_corrupted_blocks_never_write_out_of_bounds(lib):
+    """Fuzz: blocks with random byte flips / truncations decode to something or are refused, but never past the capacity (the output
+    buffer is followed by a guard pattern) — the bounds checks of decodeBlock are the kernel's."""
+    codec = pa.Codec("lz4_raw")
+    rng = np.random.default_rng(2024)
+    guard = b"\xa5" * 64
+    for trial in range(300):
+        n = int(rng.integers(1, 5000))
+        alphabet = int(rng.integers(1, 40))
+        data = bytes(rng.integers(0, alphabet, n).astype(np.uint8))
+        z = bytearray(codec.compress(data, asbytes=True))
+        for _ in range(int(rng.integers(1, 6))):
+            z[int(rng.integers(0, len(z)))] = int(rng.integers(0, 256))
+        if rng.random() < 0.3:
+            z = z[:int(rng.integers(1, len(z) + 1))]
+        cap = int(rng.integers(0, n + 10))
+        out = C.create_string_buffer(cap + len(guard))
+        C.memmove(C.addressof(out) + cap, guard, len(guard))
+        got = lib.lz4_decompress_host(bytes(z), len(z), out, cap)
+        assert -1 <= got <= cap
+        assert out.raw[cap:cap + len(guard)] == guard, trial
+
+
+def test_random_structured_data_round_trips_through_both_codecs(lib):
+    codec = pa.Codec("lz4_raw")
+    rng = np.random.default_rng(99)
+    for trial in range(60):
+        pieces = []
+        for _ in range(int(rng.integers(1, 30))):
+            kind = rng.integers(0, 4)
+            m = int(rng.integers(1, 6000))
+            if kind == 0: pieces.append(bytes(rng.integers(0, 256, m).astype(np.uint8)))
+            elif kind == 1: pieces.append(bytes([int(rng.integers(0, 256))]) * m)
+            elif kind == 2 and pieces: pieces.append(pieces[int(rng.integers(0, len(pieces)))][:m])
+            else: pieces.append((b"%d|" % int(rng.integers(0, 1000))) * (m // 4 + 1))
+        data = b"".join(pieces)
+        z = compress(lib, data)
+        assert codec.decompress(z, decompressed_size=len(data), asbytes=True) == data
+        assert decompress(lib, codec.compress(data, asbytes=True), len(data)) == data
