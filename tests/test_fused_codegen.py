@@ -104,3 +104,22 @@ def test_page_sink_fragment_compiles():
     src = FusedPageOperator.explain(types, p2, [join([BIGINT, DOUBLE, BIGINT], [0], [0, 1, 2])], [[DOUBLE, INTEGER]], nullable_inputs=[2])
     assert "P.outNulls[2]" in src and "P.outValues[4]" in src and "errOv" in src
     assert compile_check(src) > 10_000
+
+
+def test_fragments_outside_the_generated_set_say_why():
+    """Declined fragments run operator by operator on the GPU; the explain entry points name the reason (what `get_info()["reason"]` reports at
+    run time): an unbounded VARCHAR group key (interned per chunk), a VARCHAR comparison in the page processor."""
+    types = [VARCHAR, VARCHAR, DOUBLE]
+    prog = Program(types)
+    s, c, v = [prog.input(i) for i in range(3)]
+    prog.set_filter(v > 1.0)
+    prog.project(c, v)
+    with pytest.raises(PrestoException, match="interned"):
+        FusedAggregationOperator.explain(types, prog, [], [], [VARCHAR], [0], [Aggregate(AGG_SUM_DOUBLE, 1)])          # no declared length: value ids first
+    assert "fused_kernel" in FusedAggregationOperator.explain(types, prog, [], [], [VARCHAR], [0], [Aggregate(AGG_SUM_DOUBLE, 1)], group_max_lengths=[7])
+    prog = Program(types)
+    s, c, v = [prog.input(i) for i in range(3)]
+    prog.set_filter(s == b"BUILDING")
+    prog.project(c, v)
+    with pytest.raises(PrestoException, match="VARCHAR comparison"):
+        FusedAggregationOperator.explain(types, prog, [], [], [VARCHAR], [0], [Aggregate(AGG_SUM_DOUBLE, 1)], group_max_lengths=[7])
