@@ -1007,6 +1007,37 @@ def case_page_processor_varchar_comparisons(backend, n: int = 6000):
     op.close()
 
 
+def case_varchar_operators(backend):
+    """TestVarcharOperators.java:60-127 (testEqual … testBetween): the reference's own expectations for `=`, `<>`, `<`, `<=`, `>`, `>=` and
+    BETWEEN over 'foo' / 'bar', evaluated through a PageProcessor over VARCHAR channels (and once against Slice constants)."""
+    a = Block.from_strings([b"foo", b"foo", b"bar", b"bar"])
+    b = Block.from_strings([b"foo", b"bar", b"foo", b"bar"])
+    T, F = True, False
+    expected = {                                             # rows: ('foo','foo'), ('foo','bar'), ('bar','foo'), ('bar','bar')
+        "eq": [T, F, F, T], "ne": [F, T, T, F], "lt": [F, F, T, F], "le": [T, F, T, T], "gt": [F, T, F, F], "ge": [T, T, F, T],
+    }
+    prog = Program([VARCHAR, VARCHAR])
+    x, y = prog.input(0), prog.input(1)
+    prog.project(x == y, x != y, x < y, x <= y, x > y, x >= y)
+    op = FilterAndProjectOperator([VARCHAR, VARCHAR], prog, backend=backend)
+    rows = rows_of(to_pages(op, [Page([a, b])]))
+    op.close()
+    for j, name in enumerate(["eq", "ne", "lt", "le", "gt", "ge"]):
+        assert [r[j] for r in rows] == expected[name], name
+    # BETWEEN :113-127: value BETWEEN min AND max for the eight combinations, value and bounds as channels
+    value = Block.from_strings([b"foo"] * 4 + [b"bar"] * 4)
+    lo = Block.from_strings([b"foo", b"foo", b"bar", b"bar"] * 2)
+    hi = Block.from_strings([b"foo", b"bar", b"foo", b"bar"] * 2)
+    prog = Program([VARCHAR, VARCHAR, VARCHAR])
+    v, l, h = [prog.input(i) for i in range(3)]
+    prog.project(v.between(l, h), v.between(b"bar", b"foo"))
+    op = FilterAndProjectOperator([VARCHAR, VARCHAR, VARCHAR], prog, backend=backend)
+    rows = rows_of(to_pages(op, [Page([value, lo, hi])]))
+    op.close()
+    assert [r[0] for r in rows] == [T, F, T, F, F, F, T, T]
+    assert [r[1] for r in rows] == [T] * 8                                   # 'foo' and 'bar' are both BETWEEN 'bar' AND 'foo'
+
+
 def case_page_processor_hash_projection(backend):
     """The $hashvalue projection HashGenerationOptimizer.java:975-987 injects: combine_hash(combine_hash(0, hash(a)), hash(b))."""
     a = Block.from_values(BIGINT, [1, 2, None, 42])

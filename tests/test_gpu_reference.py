@@ -93,3 +93,5 @@ def test_page_processor_q1(gpu_backend): rc.case_page_processor_q1(gpu_backend)
 def test_page_processor_three_valued_logic(gpu_backend): rc.case_page_processor_three_valued_logic(gpu_backend)
 def test_page_processor_hash_projection(gpu_backend): rc.case_page_processor_hash_projection(gpu_backend)
 def test_page_processor_varchar_comparisons(gpu_backend): rc.case_page_processor_varchar_comparisons(gpu_backend)
+@unverified_on_gpu
+def test_varchar_operators(gpu_backend): rc.case_varchar_operators(gpu_backend)

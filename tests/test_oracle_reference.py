@@ -141,6 +141,7 @@ def test_page_processor_q1(oracle_backend): rc.case_page_processor_q1(oracle_bac
 def test_page_processor_three_valued_logic(oracle_backend): rc.case_page_processor_three_valued_logic(oracle_backend)
 def test_page_processor_hash_projection(oracle_backend): rc.case_page_processor_hash_projection(oracle_backend)
 def test_page_processor_varchar_comparisons(oracle_backend): rc.case_page_processor_varchar_comparisons(oracle_backend)
+def test_varchar_operators(oracle_backend): rc.case_varchar_operators(oracle_backend)
 def test_page_processor_varchar_pass_through(oracle_backend): rc.case_page_processor_varchar_pass_through(oracle_backend)
 
 
