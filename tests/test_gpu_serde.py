@@ -254,3 +254,21 @@ def test_lz4_decoder_on_blocks_of_every_shape(gpu_backend):
         got = g.deserialize(wire, [VARCHAR]).rows()
         assert len(got) == 1 and got[0][0] == payload
     g.close()
+
+
+from conftest import unverified_on_gpu
+
+
+@unverified_on_gpu
+def test_reference_sizes_hold_with_the_lz4_codec(gpu_backend):
+    """TestPagesSerde :82-127 runs its size expectations for every CompressionCodec, LZ4 included: pages this small stay uncompressed."""
+    from presto_b200 import _abi as abi
+    g = PagesSerde(compression=abi.COMPRESSION_LZ4, backend=gpu_backend)
+    assert g.serialize(Page([Block.from_numpy(BIGINT, np.array([123]))])).size == 52
+    assert g.serialize(Page([Block.from_numpy(BIGINT, np.array([123, 456]))])).size == 60
+    assert g.serialize(Page([Block.from_strings([])], 0)).size == 52
+    assert g.serialize(Page([Block.from_strings([b"alice", b"bob"])])).size == 52 + 9 + 7
+    names = Block.from_strings([b"alice", b"bob", b"charlie", b"dave"])
+    page = Page([names, names, names])
+    assert g.deserialize(g.serialize(page), [VARCHAR, VARCHAR, VARCHAR]).rows() == page.rows()
+    g.close()

@@ -131,3 +131,20 @@ def test_serialize_ranges_equals_serializing_the_slices(serde):
     for r in range(len(cuts) - 1):
         assert serde.deserialize(wires[r], types_of(page)).rows() == rows[cuts[r]:cuts[r + 1]]
         assert header_of(wires[r])[0] == cuts[r + 1] - cuts[r]
+
+
+def test_reference_sizes_and_round_trip_hold_with_the_lz4_codec(oracle_backend):
+    """TestPagesSerde runs testBigintSerializedSize / testVarcharSerializedSize / testRoundTrip for every CompressionCodec, LZ4 included, and
+    expects the SAME sizes (:82-127): pages this small do not reach MINIMUM_COMPRESSION_RATIO and travel uncompressed."""
+    from presto_b200 import _abi as abi
+    s = PagesSerde(compression=abi.COMPRESSION_LZ4, backend=oracle_backend)
+    assert s.serialize(Page([Block.from_numpy(BIGINT, np.array([123]))])).size == 35 + 17
+    assert s.serialize(Page([Block.from_numpy(BIGINT, np.array([123, 456]))])).size == 35 + 17 + 8
+    assert s.serialize(Page([Block.from_strings([])], 0)).size == 52
+    assert s.serialize(Page([Block.from_strings([b"alice"])])).size == 52 + 9
+    assert s.serialize(Page([Block.from_strings([b"alice", b"bob"])])).size == 52 + 9 + 7
+    names = Block.from_strings([b"alice", b"bob", b"charlie", b"dave"])                  # testRoundTrip :58-80
+    page = Page([names, names, names])
+    wire = s.serialize(page)
+    assert s.deserialize(wire, [6, 6, 6]).rows() == page.rows()
+    s.close()
