@@ -1027,6 +1027,20 @@ def main():
                                       "roofline_frac": ALGO_BYTES_PER_ROW * n / (rr["kernel_ms"] / 1000) / 1e9 / peak}
             return out
 
+        def varchar_and_lz4_paths():
+            """The paths added at the end of round 2 — interned VARCHAR group keys, VARCHAR join keys, a VARCHAR predicate, the LZ4 wire — timed by
+            profiles/new_paths_r02.py in a process of its own (wall clock around synchronous C-ABI calls over device-resident pages; a failure
+            there cannot take this line down)."""
+            import subprocess
+            script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "new_paths_r02.py")
+            env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local)))
+            r = subprocess.run([sys.executable, script, "--rows", str(max(200_000, int(8_000_000 * scale)))], capture_output=True, text=True, timeout=300, env=env)
+            if r.returncode != 0:
+                raise RuntimeError((r.stderr or r.stdout)[-200:])
+            out = json.loads(r.stdout.strip().splitlines()[-1])
+            out["timing"] = "wall clock around synchronous C-ABI calls, best of 3, separate process"
+            return out
+
         for name, fn in [
             ("q3_pipeline", lambda: run_q3(torch, backend, local, int(150_000_000 * scale), 3, 2)),
             ("q1_pipeline_integer_keys", lambda: run_q1_pipeline(torch, backend, local, int(Q1_SF100_ROWS * scale), 3, 2)),
@@ -1037,6 +1051,7 @@ def main():
             ("serialized_page_8_bigint_cols", lambda: run_serialized_page(torch, backend, local, int((1 << 24) * scale), 3, 2)),
             ("q1_pipeline_unfused", lambda: run_q1_pipeline(torch, backend, local, int(Q1_SF100_ROWS * scale), 2, 1, fused=False)),
             ("q3_pipeline_unfused", lambda: run_q3(torch, backend, local, int(150_000_000 * scale), 2, 1, fused=False)),
+            ("varchar_and_lz4_paths", varchar_and_lz4_paths),
         ]:
             if only and name not in only:
                 continue

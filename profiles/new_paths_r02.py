@@ -46,8 +46,8 @@ def strings_block(words, pick):
 
 
 keep = []
-n = 20_000_000
-for groups in (100, 100_000):
+n = int(sys.argv[sys.argv.index("--rows") + 1]) if "--rows" in sys.argv else 20_000_000
+for groups in (100, min(100_000, n // 20)):
     words = [b"customer-name-%08d-x" % i for i in range(groups)]            # 23-byte keys
     page = page_to_device(b, Page([strings_block(words, rng.integers(0, groups, n)), Block.from_numpy(DOUBLE, rng.random(n))]), keep)
     def agg():
@@ -55,10 +55,10 @@ for groups in (100, 100_000):
         res = to_pages(op, [page]); assert sum(p.position_count for p in res) == groups
         op.close()
     ms = timed(agg)
-    out[f"group_by_varchar23_{groups}_groups"] = {"rows": n, "ms": round(ms, 2), "g_rows_s": round(n / ms / 1e6, 2), "bytes_per_row": 23 + 4 + 8}
+    out[f"group_by_varchar23_{'few' if groups == 100 else 'many'}_groups"] = {"rows": n, "groups": groups, "ms": round(ms, 2), "g_rows_s": round(n / ms / 1e6, 2), "bytes_per_row": 23 + 4 + 8}
 
 # VARCHAR join: 1 M unique build keys, 20 M probe rows (70 % hits)
-nb = 1_000_000
+nb = min(1_000_000, n // 8)
 words = [b"order-%09d" % i for i in range(nb)]
 build = page_to_device(b, Page([strings_block(words, rng.permutation(nb)), Block.from_numpy(BIGINT, np.arange(nb))]), keep)
 probe_words = words + [b"missing-%07d" % i for i in range(nb // 2)]
@@ -72,7 +72,7 @@ def join():
     pr.close(); hb.close(); bridge.close()
     return rows
 ms = timed(join)
-out["join_varchar15_1m_build_20m_probe"] = {"ms": round(ms, 2), "probe_g_rows_s": round(n / ms / 1e6, 2), "output_rows": join()}
+out["join_varchar15"] = {"build_rows": nb, "probe_rows": n, "ms": round(ms, 2), "probe_g_rows_s": round(n / ms / 1e6, 2), "output_rows": join()}
 
 # VARCHAR predicate: c_mktsegment = 'BUILDING' over 20 M rows, key passes through
 segs = [b"AUTOMOBILE", b"BUILDING", b"FURNITURE", b"HOUSEHOLD", b"MACHINERY"]
@@ -85,7 +85,7 @@ ms = timed(filt)
 out["filter_mktsegment_eq_building"] = {"rows": n, "ms": round(ms, 2), "g_rows_s": round(n / ms / 1e6, 2)}
 
 # LZ4 serde: a 64 MB compressible page (BIGINT sequence // 3 + small-domain INTEGER) and its decode
-m = 4_000_000
+m = min(4_000_000, n // 2)
 page = page_to_device(b, Page([Block.from_numpy(BIGINT, np.arange(m, dtype=np.int64) // 3), Block.from_numpy(BIGINT, rng.integers(0, 50, m))]), keep)
 lz = PagesSerde(compression=abi.COMPRESSION_LZ4, backend=b, output_memory=MEM_DEVICE)
 plain = PagesSerde(backend=b, output_memory=MEM_DEVICE)
@@ -99,6 +99,6 @@ reader = PagesSerde(backend=b, output_memory=MEM_DEVICE)
 ms_dec = timed(lambda: reader.deserialize(dptr.value, [BIGINT, BIGINT], size=int(size), memory=MEM_DEVICE, copy=False))
 
 raw = m * 16
-out["serde_lz4_64mb"] = {"raw_bytes": raw, "wire_bytes": int(size), "ratio": round(size / raw, 3), "serialize_plain_ms": round(ms_plain, 2), "serialize_lz4_ms": round(ms_lz, 2),
+out["serde_lz4"] = {"raw_bytes": raw, "wire_bytes": int(size), "ratio": round(size / raw, 3), "serialize_plain_ms": round(ms_plain, 2), "serialize_lz4_ms": round(ms_lz, 2),
                          "lz4_gb_s": round(raw / ms_lz / 1e6, 2), "deserialize_lz4_ms": round(ms_dec, 2)}
 print(json.dumps(out))
