@@ -380,7 +380,7 @@ std::string generateFilterProjectPtx(const FpProgramDesc& P, FpKernelSignature& 
     for (int k = 0; k < nNodes; k++) {
         const pg_expr_node& nd = P.nodes[k];
         const bool leaf = nd.op == PG_EX_INPUT || (nd.op >= PG_EX_CONST_BIGINT && nd.op <= PG_EX_CONST_VARCHAR);
-        if (leaf || nd.op == PG_EX_EQ || nd.op == PG_EX_NE) continue;
+        if (leaf || nd.op == PG_EX_EQ || nd.op == PG_EX_NE || nd.op == PG_EX_IS_NULL) continue;
         for (int o : {nd.a, nd.b, nd.c}) if (o >= 0 && o < nNodes && P.nodes[o].type == PG_TYPE_VARCHAR) { sig.reason = "VARCHAR operand outside = / <>"; return ""; }
     }
 
