@@ -10,13 +10,27 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "unverified: GPU test of code written after the round's last GPU run (see unverified_on_gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    """Tests of code that has not run on a GPU yet go LAST: whatever they do to the device cannot disturb a test that has been green."""
+    items.sort(key=lambda item: 1 if item.get_closest_marker("unverified") else 0)
 
 
 def unverified_on_gpu(fn):
     """GPU tests of code written after the round's last GPU run (the gpurun budget was spent): they have passed with the oracle standing
-    in for the device (test logic) and the code they exercise compiles for sm_100a, but they have not run on a B200 yet.  Opt in with
-    PG_TEST_UNVERIFIED=1; the default `pytest -m gpu` run holds only tests that have been green on the hardware."""
-    return pytest.mark.skipif(os.environ.get("PG_TEST_UNVERIFIED") != "1", reason="written after the last GPU run; set PG_TEST_UNVERIFIED=1")(fn)
+    in for the device (test logic) and the code they exercise compiles for sm_100a (generated PTX is also executed on the CPU by
+    tests/ptx_interp.py), but they have not run on a B200 yet.  They run at the END of the session (pytest_collection_modifyitems) and are
+    non-strict xfail: a first run on hardware that goes wrong shows as `x` and breaks nothing that has been green; a run that goes right
+    shows as XPASS — the evidence that the code works on the device.  PG_TEST_UNVERIFIED=0 skips them, =1 makes them ordinary tests."""
+    mode = os.environ.get("PG_TEST_UNVERIFIED", "")
+    fn = pytest.mark.unverified(fn)
+    if mode == "0":
+        return pytest.mark.skip(reason="written after the last GPU run; PG_TEST_UNVERIFIED=0")(fn)
+    if mode == "1":
+        return fn
+    return pytest.mark.xfail(strict=False, reason="written after the round's last GPU run: first run on hardware (XPASS = it works on the device)")(fn)
 
 
 @pytest.fixture(scope="session")

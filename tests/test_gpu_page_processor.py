@@ -8,6 +8,7 @@ import pytest
 
 import reference_cases as rc
 from presto_b200 import BIGINT, BOOLEAN, DATE, DOUBLE, INTEGER, Block, FilterAndProjectOperator, Page, Program, to_pages
+from conftest import unverified_on_gpu
 from util import rows_close, rows_of
 
 pytestmark = pytest.mark.gpu
@@ -61,6 +62,16 @@ def test_varchar_equals_literal_both_modes(gpu_backend, mode, literal):
         if os.environ.get("PG_FP_VARCHAR_JIT") == "1":
             expect_jit = mode == "ptx" and len(literal) <= 32
             assert bool(paths & abi.PATH_FP_JIT) == expect_jit and bool(paths & abi.PATH_FP_INTERPRETER) == (not expect_jit), (paths, mode, literal)
+
+
+@unverified_on_gpu
+@pytest.mark.parametrize("literal", [b"", b"BUILDING", b"a-literal-of-thirty-one-bytes.."])
+def test_varchar_equals_literal_ptx_lowering_on_the_device(gpu_backend, literal, monkeypatch):
+    """The PTX lowering of `slice = literal` (opt-in: PG_FP_VARCHAR_JIT=1) through the driver JIT on the device; on the CPU the same PTX is
+    executed by tests/ptx_interp.py against the oracle (tests/test_ptx_semantics.py)."""
+    monkeypatch.setenv("PG_FP_VARCHAR_JIT", "1")
+    monkeypatch.setenv("PG_FP_INTERPRETER", "0")
+    test_varchar_equals_literal_both_modes(gpu_backend, "ptx", literal)
 
 
 def random_program(rng, types):
