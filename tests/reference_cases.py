@@ -327,6 +327,28 @@ def case_outer_join_with_null_on_both_sides(backend, probe_hash: bool, build_has
     assert rows == [tuple(_key(key_type, v) for v in r) for r in [(1, 1), (1, 1), (2, 2), (None, None), (3, None)]]
 
 
+def case_outer_join_with_null_probe(backend, probe_hash: bool, build_hash: bool, key_type: int = BIGINT):
+    """testOuterJoinWithNullProbe :927-968 — build a,b,c ; probe a,null,null,a,b (PROBE_OUTER): NULL probe keys come out with a NULL build side."""
+    bp = RowPagesBuilder([key_type], build_hash, [0], backend).row(_key(key_type, 1)).row(_key(key_type, 2)).row(_key(key_type, 3))
+    pp = RowPagesBuilder([key_type], probe_hash, [0], backend).row(_key(key_type, 1)).row(None).row(None).row(_key(key_type, 1)).row(_key(key_type, 2))
+    rows = _join(backend, bp.build(), bp.get_types(), pp.build(), pp.get_types(), JOIN_PROBE_OUTER, build_hash, probe_hash)
+    assert rows == [tuple(_key(key_type, v) for v in r) for r in [(1, 1), (None, None), (None, None), (1, 1), (2, 2)]]
+
+
+def case_outer_join_with_null_build(backend, probe_hash: bool, build_hash: bool, key_type: int = BIGINT):
+    """testOuterJoinWithNullBuild :1014-1054 — build a,null,null,a,b ; probe a,b,c (PROBE_OUTER) → (a,a),(a,a),(b,b),(c,null)."""
+    bp = RowPagesBuilder([key_type], build_hash, [0], backend).row(_key(key_type, 1)).row(None).row(None).row(_key(key_type, 1)).row(_key(key_type, 2))
+    pp = RowPagesBuilder([key_type], probe_hash, [0], backend).row(_key(key_type, 1)).row(_key(key_type, 2)).row(_key(key_type, 3))
+    rows = _join(backend, bp.build(), bp.get_types(), pp.build(), pp.get_types(), JOIN_PROBE_OUTER, build_hash, probe_hash)
+    assert rows == [tuple(_key(key_type, v) for v in r) for r in [(1, 1), (1, 1), (2, 2), (3, None)]]
+
+
+def case_inner_join_with_non_empty_lookup_source_and_empty_probe(backend, key_type: int = BIGINT):
+    """testInnerJoinWithNonEmptyLookupSourceAndEmptyProbe :1414-1452 — build a,b,null,c ; no probe page at all: no output, the operator finishes."""
+    bp = RowPagesBuilder([key_type], False, [0], backend).row(_key(key_type, 1)).row(_key(key_type, 2)).row(None).row(_key(key_type, 3))
+    assert _join(backend, bp.build(), bp.get_types(), [], [key_type], JOIN_INNER, False, False) == []
+
+
 def _join_filter(build_types, probe_types, make):
     """A JoinFilterFunction: a Program over the build channels followed by the probe channels (createJoinSourcesLayout); `make(build,
     probe)` gets the two lists of input expressions and returns the BOOLEAN filter."""

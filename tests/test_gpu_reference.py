@@ -63,6 +63,13 @@ def test_join_varchar_keys(gpu_backend, case, probe_hash, build_hash): getattr(r
 @unverified_on_gpu
 @pytest.mark.parametrize("probe_hash,build_hash", [(False, False), (True, True)])
 def test_join_varchar_filter_function(gpu_backend, probe_hash, build_hash): rc.case_outer_join_with_nulls_and_filter_function(gpu_backend, probe_hash, build_hash, key_type=rc.VARCHAR)
+@unverified_on_gpu
+@pytest.mark.parametrize("key_type", [rc.BIGINT, rc.VARCHAR])
+@pytest.mark.parametrize("probe_hash,build_hash", [(False, False), (True, True)])
+def test_outer_join_with_null_probe_and_null_build(gpu_backend, probe_hash, build_hash, key_type):
+    rc.case_outer_join_with_null_probe(gpu_backend, probe_hash, build_hash, key_type)
+    rc.case_outer_join_with_null_build(gpu_backend, probe_hash, build_hash, key_type)
+    rc.case_inner_join_with_non_empty_lookup_source_and_empty_probe(gpu_backend, key_type)
 def test_probe_outer_join_empty_lookup_source(gpu_backend): rc.case_probe_outer_join_empty_lookup_source(gpu_backend)
 def test_join_duplicate_chain_order(gpu_backend): rc.case_join_duplicate_chain_order(gpu_backend)
 def test_lookup_outer_join_empty_lookup_source(gpu_backend): rc.case_lookup_outer_join_empty_lookup_source(gpu_backend)

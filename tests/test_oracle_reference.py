@@ -111,6 +111,12 @@ def test_join_varchar_outputs(oracle_backend): rc.case_join_varchar_outputs(orac
 @pytest.mark.parametrize("case", ["inner_join", "inner_join_with_null_probe", "inner_join_with_null_build", "inner_join_with_null_on_both_sides",
                                   "probe_outer_join", "outer_join_with_null_on_both_sides", "outer_join_with_nulls_and_filter_function"])
 def test_join_varchar_keys(oracle_backend, case, probe_hash, build_hash): getattr(rc, "case_" + case)(oracle_backend, probe_hash, build_hash, key_type=rc.VARCHAR)
+@pytest.mark.parametrize("key_type", [rc.BIGINT, rc.VARCHAR])
+@pytest.mark.parametrize("probe_hash,build_hash", [(False, False), (True, True)])
+def test_outer_join_with_null_probe_and_null_build(oracle_backend, probe_hash, build_hash, key_type):
+    rc.case_outer_join_with_null_probe(oracle_backend, probe_hash, build_hash, key_type)
+    rc.case_outer_join_with_null_build(oracle_backend, probe_hash, build_hash, key_type)
+    rc.case_inner_join_with_non_empty_lookup_source_and_empty_probe(oracle_backend, key_type)
 def test_probe_outer_join_empty_lookup_source(oracle_backend): rc.case_probe_outer_join_empty_lookup_source(oracle_backend)
 def test_join_duplicate_chain_order(oracle_backend): rc.case_join_duplicate_chain_order(oracle_backend)
 def test_lookup_outer_join_empty_lookup_source(oracle_backend): rc.case_lookup_outer_join_empty_lookup_source(oracle_backend)
